@@ -1,0 +1,173 @@
+#!/usr/bin/env python3
+"""Derive tests/golden/reference_goldens.json from the reference's own test goldens.
+
+Run in the build container only (it reads /root/reference/test/polydeal/*.output,
+which does not exist on the GPU box).  The .output files are parsed into
+structured records (polytopes, faces, (cell, face) lists, DoF indices, sparsity
+rows, invariants); tests/test_oracle_goldens.py rebuilds each scenario with the
+CPU oracle and compares against these records.  Nothing from the reference's
+sources is copied; only the numbers its tests print.
+"""
+import json
+import os
+import re
+import sys
+
+REF = "/root/reference/test/polydeal"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_goldens.json")
+
+
+def lines(name):
+    with open(os.path.join(REF, name)) as f:
+        return [l.rstrip("\n") for l in f]
+
+
+def parse_sparsity(name):
+    rows = []
+    for l in lines(name):
+        nums = [int(t) for t in l.strip("[]").split(",")]
+        rows.append(nums)  # [row, col0, col1, ...]
+    return rows
+
+
+def parse_neighbors_faces(name):
+    polys, cur, face = [], None, None
+    pend_cell = None
+    for l in lines(name):
+        if m := re.match(r"Polytope with idx: (\d+)", l):
+            cur = {"index": int(m[1]), "n_faces": None, "faces": {}}
+            polys.append(cur)
+        elif m := re.match(r"Number of faces for the agglomeration: (\d+)", l):
+            cur["n_faces"] = int(m[1])
+        elif m := re.match(r"Agglomerated face with idx: (\d+)", l):
+            face = cur["faces"].setdefault(m[1], [])
+        elif m := re.match(r"deal.II cell idx: (\d+)", l):
+            pend_cell = int(m[1])
+        elif m := re.match(r"deal.II face idx: (\d+)", l):
+            face.append([pend_cell, int(m[1])])
+    return polys
+
+
+def parse_nofn(name):
+    out, cur = [], None
+    for l in lines(name):
+        if m := re.match(r"Cell with idx: (\d+)", l):
+            cur = {"master": int(m[1]), "nofn": []}
+            out.append(cur)
+        elif m := re.match(r"Number of faces for this cell: (\d+)", l):
+            cur["n_faces"] = int(m[1])
+        elif m := re.match(r"Neighbor of neighbor for \((\d+),(\d+)\) = (\d+)", l):
+            cur["nofn"].append(int(m[3]))
+    return out
+
+
+def parse_continuous_face(name):
+    scenarios, polys, cur, face = [], [], None, None
+    pend = {}
+    for l in lines(name):
+        if m := re.match(r"Master cell index = (\d+)", l):
+            cur = {"master": int(m[1]), "faces": []}
+            polys.append(cur)
+        elif m := re.match(r"Number of agglomerated faces = (\d+)", l):
+            cur["n_faces"] = int(m[1])
+        elif m := re.match(r"Agglomerate face index = (\d+)", l):
+            face = {"f": int(m[1]), "neighbor": None, "nofn": None, "subfaces": []}
+            cur["faces"].append(face)
+        elif m := re.match(r"Neighbor(?: polytope index)? = (\d+)", l):
+            face["neighbor"] = int(m[1])
+        elif m := re.match(r"Neighbor of neighbor = (\d+)", l):
+            face["nofn"] = int(m[1])
+        elif m := re.match(r"deal.II cell index = (\d+)", l):
+            pend = {"cell": int(m[1])}
+        elif m := re.match(r"Local face idx = (\d+)", l):
+            pend["face"] = int(m[1])
+        elif m := re.match(r"Neighboring master cell index = (\d+)", l):
+            face["subfaces"].append([pend["cell"], pend["face"], int(m[1])])
+        elif m := re.match(r"Perimeter = (\S+)", l):
+            scenarios.append({"polytopes": polys, "perimeter": float(m[1])})
+            polys = []
+    return scenarios
+
+
+def parse_hp_structure(name):
+    out, cur, mode = [], None, None
+    for l in lines(name):
+        if m := re.match(r"Cell with global index: (\d+) has global DoF indices:", l):
+            cur = {"master": int(m[1]), "dofs": [], "vertices": []}
+            out.append(cur)
+            mode = "dofs"
+        elif l.strip() == "and vertices:":
+            mode = "verts"
+        elif l.strip():
+            if mode == "dofs":
+                cur["dofs"].append(int(l))
+            else:
+                cur["vertices"].append([float(t) for t in l.split()])
+    return out
+
+
+def parse_reinit_cell_face_02(name):
+    out, cur = [], None
+    for l in lines(name):
+        if m := re.match(r"Cell with index (\d+) has (\d+) faces", l):
+            cur = {"master": int(m[1]), "n_faces": int(m[2]), "faces": []}
+            out.append(cur)
+        elif m := re.match(r"Neighbor index= (\d+)", l):
+            cur["faces"].append(int(m[1]))  # master cell index of neighbour
+        elif re.match(r"Face with idx: (\d+) is a boundary face", l):
+            cur["faces"].append(-1)
+    return out
+
+
+def parse_polytope_iterator(name):
+    out, cur = [], None
+    for l in lines(name):
+        if l.startswith("Looping backwards"):
+            break
+        if m := re.match(r"Global DoF indices for polytope (\d+)", l):
+            cur = {"index": int(m[1]), "dofs": []}
+            out.append(cur)
+        elif re.match(r"^\d+$", l.strip()) and cur is not None:
+            cur["dofs"].append(int(l))
+    return out
+
+
+def floats_after(name, pat):
+    return [float(m[1]) for l in lines(name) if (m := re.search(pat, l))]
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit("reference tree not present; goldens can only be regenerated in the build container")
+    g = {
+        "_provenance": "parsed from /root/reference/test/polydeal/*.output by tests/golden/make_golden.py",
+        "sparsity_agglomerated_tria": parse_sparsity("sparsity_agglomerated_tria.output"),
+        "agglomerated_neighbors_01": parse_neighbors_faces("agglomerated_neighbors_01.output"),
+        "agglomerated_neighbors_02": parse_neighbors_faces("agglomerated_neighbors_02.output"),
+        "agglomerated_neighbors_03": parse_nofn("agglomerated_neighbors_03.output"),
+        "continuous_face_01": parse_continuous_face("continuous_face_01.output"),
+        "hp_structure_01": parse_hp_structure("hp_structure_01.output"),
+        "reinit_cell_face_02": parse_reinit_cell_face_02("reinit_cell_face_02.output"),
+        "polytope_iterator": parse_polytope_iterator("polytope_iterator.output"),
+        "fe_space_on_bbox": floats_after("fe_space_on_bbox.output", r"Sum is: (\S+)"),
+        "reinit_cell_face_01": floats_after("reinit_cell_face_01.output", r" is (\S+)$"),
+        "agg_handler_bbox_test": [
+            [float(t) for t in l.split("=")[1].split()] for l in lines("agg_handler_bbox_test.output")
+        ],
+        "aggl_handler_master_and_slaves_01": floats_after(
+            "aggl_handler_master_and_slaves_01.output", r"associated value: (\S+)"
+        ),
+        "poisson_sanity_check_01": {
+            "x": floats_after("poisson_sanity_check_01.output", r"f\(x,y\)=x:(\S+)"),
+            "xplusy": floats_after("poisson_sanity_check_01.output", r"f\(x,y\)=x\+y:(\S+)"),
+            "one": floats_after("poisson_sanity_check_01.output", r"Test with 1: (\S+)"),
+        },
+        "poisson": floats_after("poisson.output", r"(\d\.\d+)"),
+    }
+    with open(OUT, "w") as f:
+        json.dump(g, f, separators=(",", ":"))
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

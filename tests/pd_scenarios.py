@@ -1,0 +1,102 @@
+"""Mesh + agglomeration scenarios taken from the reference's own tests
+(/root/reference/test/polydeal/*.cc); shared by the oracle tests and the
+product parity tests so both are driven with identical inputs."""
+from __future__ import annotations
+
+
+def standard_8x8_agglomerates():
+    """[-1,1]^2 refined 3x; {3,6,9,12,13},{15,36,37},{57,60,54},{25,19,22} + singletons
+    (test/polydeal/agglomerated_neighbors_01.cc:30-107, sparsity_agglomerated_tria.cc:30-107,
+    fe_space_on_bbox.cc, reinit_cell_face_01.cc).  collect_cells_for_agglomeration sorts
+    into active-cell order (include/poly_utils.h:532-538)."""
+    groups = [[3, 6, 9, 12, 13], [15, 36, 37], [57, 60, 54], [25, 19, 22]]
+    return _with_singletons(groups, 64)
+
+
+def _with_singletons(groups, n_cells):
+    flagged = {c for g in groups for c in g}
+    out = [sorted(g) for g in groups]
+    out += [[c] for c in range(n_cells) if c not in flagged]
+    return out
+
+
+def blocks_2x2_of_4x4():
+    """[-1,1]^2 refined 2x, {0..3},{4..7},{8..11},{12..15}
+    (agglomerated_neighbors_02.cc, hp_structure_01.cc, minimal_SIP_Poisson.cc)."""
+    return [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11], [12, 13, 14, 15]]
+
+
+def polytope_iterator_agglomerates():
+    """[-1,1]^2 refined 6x with seven 2-cell agglomerates (polytope_iterator.cc:142-230,
+    same sets as test/polydeal/poisson.cc:153-232)."""
+    groups = [[3235, 3238], [831, 874], [1226, 1227], [2279, 2278], [3760, 3761], [3648, 3306], [3765, 3764]]
+    return _with_singletons(groups, 4096)
+
+
+def block_partition(dim, n, b, order=0):
+    """Uniform b^dim blocks of an n^dim structured grid (the `blocks` shape of
+    SURVEY 8d): list of cell lists, cells in active-cell order."""
+    import numpy as np
+
+    idx = np.arange(n**dim)
+    if dim == 2:
+        i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+        k = np.zeros_like(i)
+    else:
+        i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    if order == 0:
+        levels = n.bit_length() - 1
+        cell = np.zeros_like(i)
+        for l in range(levels):
+            cell |= ((i >> l) & 1) << (dim * l)
+            cell |= ((j >> l) & 1) << (dim * l + 1)
+            if dim == 3:
+                cell |= ((k >> l) & 1) << (dim * l + 2)
+    else:
+        cell = (k * n + j) * n + i
+    nb = n // b
+    part = ((k // b) * nb + (j // b)) * nb + (i // b)
+    groups = [[] for _ in range(nb**dim)]
+    order_ = np.argsort(cell)
+    for c, p in zip(cell[order_], part[order_]):
+        groups[p].append(int(c))
+    del idx
+    return groups
+
+
+def random_partition(n_cells, nbr, n_parts, seed):
+    """Connected random agglomerates by seeded region growing on the face-adjacency
+    graph -- stand-in for METIS partitions (inputs, never outputs)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    part = -np.ones(n_cells, dtype=np.int64)
+    seeds = rng.choice(n_cells, size=n_parts, replace=False)
+    frontier = [[int(s)] for s in seeds]
+    for p, s in enumerate(seeds):
+        part[s] = p
+    remaining = n_cells - n_parts
+    while remaining > 0:
+        progressed = False
+        for p in rng.permutation(n_parts):
+            fr = frontier[p]
+            while fr:
+                c = fr[int(rng.integers(len(fr)))]
+                free = [int(x) for x in nbr[c] if x >= 0 and part[x] < 0]
+                if not free:
+                    fr.remove(c)
+                    continue
+                x = free[int(rng.integers(len(free)))]
+                part[x] = p
+                fr.append(x)
+                remaining -= 1
+                progressed = True
+                break
+        if not progressed:
+            break
+    assert remaining == 0
+    groups = [[] for _ in range(n_parts)]
+    for c in range(n_cells):
+        groups[part[c]].append(c)
+    return groups

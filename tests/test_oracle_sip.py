@@ -1,0 +1,181 @@
+"""SIP arithmetic of the CPU oracle, pinned through the reference tests' own
+invariants: minimal_SIP_Poisson equality, poisson_sanity_check
+energies, exact_solutions exactness on distorted grids (2-D and 3-D)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import pd_scenarios as sc
+from oracle import pyoracle as po
+
+
+def handler(dim, n_refine, groups, p, nq, lo=-1.0, hi=1.0, distort=None, fe_kind=po.FE_DGQ):
+    grid = po.Grid.hyper_cube(dim, lo, hi, n_refine)
+    if distort:
+        grid.distort_random(*distort)
+    ah = po.AgglomerationHandler(grid)
+    for g in groups:
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(nq)
+    ah.distribute_agglomerated_dofs(fe_kind, p)
+    return grid, ah
+
+
+def interpolate(ah, fun):
+    """VectorTools::interpolate on the box mapping: nodal values at the DGQ support
+    points of each polytope's bounding box."""
+    p = round(ah.n_dofs_per_cell ** (1.0 / ah.dim)) - 1
+    nodes = po.gauss_lobatto_nodes(p + 1)
+    u = np.zeros(ah.n_dofs)
+    for k in range(ah.n_polytopes):
+        lo, hi = ah.bbox(k)
+        dofs = ah.get_dof_indices(k)
+        for i, dof in enumerate(dofs):
+            idx = [(i // (p + 1) ** d) % (p + 1) for d in range(ah.dim)]
+            x = lo + nodes[idx] * (hi - lo)
+            u[dof] = fun(x)
+    return u
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_minimal_sip_poisson(dim):
+    """test/polydeal/minimal_SIP_Poisson.cc:101,247-253,308,490-508: the matrix on
+    2x2-cell (2^3-cell) agglomerates equals the one on the coarser standard grid to 1e-13.
+    DGQ1, QGauss(3), penalty 20, h_f = 1, visit by index()."""
+    if dim == 2:
+        _, ah_a = handler(2, 2, sc.blocks_2x2_of_4x4(), 1, 3)
+        _, ah_s = handler(2, 1, [[c] for c in range(4)], 1, 3)
+    else:
+        _, ah_a = handler(3, 1, [list(range(8))], 1, 3)
+        _, ah_s = handler(3, 0, [[0]], 1, 3)
+    kw = dict(penalty_constant=20.0, h_rule=po.H_CONSTANT, h_const=1.0, visit_rule=po.VISIT_BY_INDEX)
+    A = po.assemble_dg_matrix(ah_a, **kw).scipy().toarray()
+    S = po.assemble_dg_matrix(ah_s, **kw).scipy().toarray()
+    assert A.shape == S.shape
+    assert np.abs(A - S).max() < 1e-13
+    assert np.abs(A - A.T).max() < 1e-13
+
+
+@pytest.mark.parametrize("n_parts", [50, 100, 120])
+def test_poisson_sanity_check(n_parts, goldens):
+    """test/polydeal/poisson_sanity_check_01.cc:158-164,261-266,420-450: on ANY
+    agglomeration of [0,1]^2 64x64 (the reference uses METIS; partition independent),
+    boundary terms dropped, penalty 10 max(1/hA,1/hB): x'Ax = 1, (x+y)'A(x+y) = 2, 1'A1 ~ 0."""
+    grid = po.Grid.hyper_cube(2, 0.0, 1.0, 6)
+    _, _, nbr = grid.arrays()
+    groups = sc.random_partition(grid.n_cells, nbr, n_parts, seed=n_parts)
+    ah = po.AgglomerationHandler(grid)
+    for g in groups:
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(3)
+    ah.distribute_agglomerated_dofs(po.FE_DGQ, 1)
+    A = po.assemble_dg_matrix(ah, penalty_constant=10.0, h_rule=po.H_MAX_INVERSE_DIAMETER, with_boundary=False).scipy()
+    ux = interpolate(ah, lambda x: x[0])
+    uxy = interpolate(ah, lambda x: x[0] + x[1])
+    one = np.ones(ah.n_dofs)
+    g = goldens["poisson_sanity_check_01"]
+    assert ux @ (A @ ux) == pytest.approx(g["x"][0], abs=1e-11)
+    assert uxy @ (A @ uxy) == pytest.approx(g["xplusy"][0], abs=1e-11)
+    assert abs(one @ (A @ one)) < 1e-11
+    assert abs(A - A.T).max() < 1e-12
+
+
+def solve_poisson(ah, p, exact, rhs_f, penalty_constant=10.0):
+    """The assembly loop of test/polydeal/exact_solutions.cc:400-640 written against the
+    oracle's reinit tables (matrix from the oracle's assembler; Dirichlet data and
+    forcing added here): penalty = C/diameter(visitor)."""
+    A = po.assemble_dg_matrix(ah, penalty_constant=penalty_constant, visit_rule=po.VISIT_BY_INDEX).scipy()
+    b = np.zeros(ah.n_dofs)
+    vol = bdry = 0.0
+    for k in range(ah.n_polytopes):
+        fev = ah.reinit(k)
+        dofs = ah.get_dof_indices(k)
+        vol += fev.JxW.sum()
+        f = np.array([rhs_f(x) for x in fev.points])
+        b[dofs] += fev.values @ (f * fev.JxW)
+        for fc in range(ah.n_faces(k)):
+            if ah.at_boundary(k, fc):
+                ff = ah.reinit(k, fc)
+                bdry += ff.JxW.sum()
+                g = np.array([exact(x) for x in ff.points])
+                pen = penalty_constant / ah.diameter(k)
+                gn = np.einsum("iqd,qd->iq", ff.grads, ff.normals)
+                b[dofs] += (pen * ff.values - gn) @ (g * ff.JxW)
+    u = spla.spsolve(A.tocsc(), b)
+    # L2 and H1-semi errors with the same agglomerated quadrature
+    l2 = h1 = 0.0
+    eps = 1e-6
+    for k in range(ah.n_polytopes):
+        fev = ah.reinit(k)
+        uk = u[ah.get_dof_indices(k)]
+        uh = uk @ fev.values
+        gh = np.einsum("i,iqd->qd", uk, fev.grads)
+        ue = np.array([exact(x) for x in fev.points])
+        ge = np.array([[(exact(x + eps * e) - exact(x - eps * e)) / (2 * eps) for e in np.eye(ah.dim)] for x in fev.points])
+        l2 += ((uh - ue) ** 2 * fev.JxW).sum()
+        h1 += (((gh - ge) ** 2).sum(axis=1) * fev.JxW).sum()
+    return vol, bdry, np.sqrt(l2), np.sqrt(h1)
+
+
+@pytest.mark.parametrize("kind", ["linear", "quadratic"])
+def test_exact_solutions_distorted_2d(kind):
+    """test/polydeal/exact_solutions.cc:31,296-311,470-476,552-555,638-648: randomly
+    distorted 4x4 grid in 2x2 blocks; u = x+y-1 (DGQ1) and x^2+y^2-1 (DGQ2) are reproduced
+    to 1e-14-ish; sum of volume JxW = 1, boundary JxW = 4.  (deal.II's distort_random
+    stream is not reproducible, so a seeded distortion of our own is used.)"""
+    p = 1 if kind == "linear" else 2
+    exact = (lambda x: x[0] + x[1] - 1.0) if p == 1 else (lambda x: x[0] ** 2 + x[1] ** 2 - 1.0)
+    rhs = (lambda x: 0.0) if p == 1 else (lambda x: -4.0)
+    _, ah = handler(2, 2, sc.blocks_2x2_of_4x4(), p, 2 * p + 1, lo=0.0, hi=1.0, distort=(0.25, 7))
+    vol, bdry, l2, h1 = solve_poisson(ah, p, exact, rhs)
+    assert vol == pytest.approx(1.0, abs=1e-14)
+    assert bdry == pytest.approx(4.0, abs=1e-14)
+    assert l2 < 1e-13
+    assert h1 < 1e-7  # finite-difference gradient of the exact solution limits this one
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_exact_solutions_3d_invariants(dim):
+    """test/polydeal/exact_solutions_distributed.cc:45,182-211,299,669 run serially:
+    [0,1]^d refined 3x, DGQ1, penalty 10/h: vol = 1, boundary measure = 2d, linear
+    solution exact."""
+    n = 8
+    groups = sc.block_partition(dim, n, 2)
+    _, ah = handler(dim, 3, groups, 1, 3, lo=0.0, hi=1.0)
+    exact = (lambda x: x.sum() - 1.0)
+    vol, bdry, l2, _ = solve_poisson(ah, 1, exact, lambda x: 0.0)
+    assert vol == pytest.approx(1.0, abs=1e-13)
+    assert bdry == pytest.approx(2.0 * dim, abs=1e-13)
+    assert l2 < 1e-12
+
+
+def test_threaded_assembly_is_consistent():
+    grid = po.Grid.hyper_cube(3, 0.0, 1.0, 3)
+    ah = po.AgglomerationHandler(grid)
+    for g in sc.block_partition(3, 8, 2):
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(3)
+    ah.distribute_agglomerated_dofs(po.FE_DGQ, 2)
+    a1 = po.assemble_dg_matrix(ah, degree=2, n_threads=1).values()
+    a4 = po.assemble_dg_matrix(ah, degree=2, n_threads=4).values()
+    assert np.abs(a1 - a4).max() <= 1e-12 * np.abs(a1).max()
+
+
+def test_fine_mesh_penalty_rule_matches_monodomain_emulation():
+    """include/utils.h:861-866,906-909 on Cartesian singletons: sigma_F = p(p+1)(1/h_m+1/h_p),
+    boundary 4 p(p+1)/h -- same SIP form, so constants are in the null space without boundary
+    terms and the matrix is SPD with them."""
+    p = 2
+    grid = po.Grid.hyper_cube(3, 0.0, 1.0, 2)
+    ah = po.AgglomerationHandler(grid)
+    for c in range(grid.n_cells):
+        ah.define_agglomerate([c])
+    ah.initialize_fe_values(p + 1)
+    ah.distribute_agglomerated_dofs(po.FE_DGQ, p)
+    A0 = po.assemble_dg_matrix(ah, penalty_constant=p * (p + 1.0), h_rule=po.H_NORMAL_EXTENT, with_boundary=False).scipy()
+    assert np.abs(A0 @ np.ones(ah.n_dofs)).max() < 1e-11
+    A = po.assemble_dg_matrix(ah, penalty_constant=p * (p + 1.0), h_rule=po.H_NORMAL_EXTENT).scipy()
+    assert abs(A - A.T).max() < 1e-12
+    w = np.linalg.eigvalsh(A.toarray())
+    assert w.min() > 0
