@@ -1,0 +1,257 @@
+/* =============================================================================
+ * polydeal_b200.h -- C ABI of the B200-native SIP-DG hot path for agglomerated
+ * polytopes (assembly + operator apply).
+ *
+ * The reference (polyDEAL) has no FFI layer: its seam is C++.
+ * The entry points below are what a binding on the reference side would call
+ * (INTEGRATION.md shows the C++ shim).  Each one cites the reference interface
+ * it replaces (paths relative to /root/reference).
+ *
+ * Conventions: every function returns an int status (PD_OK = 0, negative =
+ * error; pd_last_error() gives the message of the last failure on the calling
+ * thread).  No exceptions cross the ABI.  All pointers are caller owned unless
+ * stated.  One handle is single-threaded, like the reference's handler
+ * (include/agglomeration_handler.h:841-851: reinit* invalidates the previous
+ * result); separate handles may be used concurrently.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with
+ * PD_ERR_NO_DEVICE.
+ *
+ * Two layers:
+ *   pd_*   device core: takes the flattened agglomeration (SoA arrays) and
+ *          runs the sm_100a kernels.
+ *   pdh_*  host mirror of AgglomerationHandler / AgglomerationAccessor /
+ *          MappingBox / PolyUtils::assemble_dg_matrix that produces that
+ *          flattened form with the reference's numbering.
+ * ========================================================================== */
+#ifndef POLYDEAL_B200_H
+#define POLYDEAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_OK 0
+#define PD_ERR_INVALID (-1)     /* bad argument / inconsistent descriptor        */
+#define PD_ERR_CUDA (-2)        /* a CUDA runtime call or kernel failed          */
+#define PD_ERR_UNSUPPORTED (-3) /* (dim, degree, FE) combination has no kernel   */
+#define PD_ERR_NO_DEVICE (-4)   /* no CUDA device: there is no CPU fallback      */
+#define PD_ERR_STATE (-5)       /* call order violated (e.g. vmult before assemble) */
+
+#define PD_INVALID_UINT 0xFFFFFFFFu /* numbers::invalid_unsigned_int */
+
+typedef struct pd_handle pd_handle;     /* device-resident flattened agglomeration */
+typedef struct pdh_grid pdh_grid;       /* background hypercube mesh               */
+typedef struct pdh_handler pdh_handler; /* host mirror of AgglomerationHandler<dim> */
+
+const char *pd_last_error(void);
+/* number of CUDA devices visible (0 => every compute call fails loudly) */
+int pd_device_count(void);
+
+/* -----------------------------------------------------------------------------
+ * Flattened agglomeration (what `AgglomerationHandler` + `PolytopeCache` hold,
+ * include/agglomeration_handler.h:600-851, as SoA arrays).  Host pointers.
+ * -------------------------------------------------------------------------- */
+typedef struct pd_mesh_desc
+{
+  int32_t dim;       /* 2 or 3 */
+  int32_t fe_degree; /* p of FE_DGQ<dim>(p): (p+1)^dim DoFs on the bounding box   */
+  int32_t n_q1d;      /* QGauss<dim>(n_q1d) on every sub-cell    (initialize_fe_values,
+                         source/agglomeration_handler.cc:212-236) */
+  int32_t n_q1d_face; /* QGauss<dim-1>(n_q1d_face) on every sub-face */
+
+  /* background mesh, deal.II conventions (vertices lexicographic in a cell) */
+  int64_t        n_verts;
+  const double  *verts;      /* [n_verts][dim] */
+  int64_t        n_cells;
+  const int32_t *cell_verts; /* [n_cells][2^dim] */
+
+  /* polytopes, in define_agglomerate order (= polytope->index()) */
+  int32_t        n_polytopes;
+  const int64_t *poly_subcell_ptr; /* [n_polytopes+1] CSR                              */
+  const int32_t *poly_subcell_idx; /* sub-cells, slaves first, master last
+                                      (include/agglomeration_accessor.h:562-569)      */
+  const double  *bbox;             /* [n_polytopes][2*dim]: lo[dim] then hi[dim]
+                                      (source/agglomeration_handler.cc:476-491)       */
+  const int32_t *dof_block;        /* [n_polytopes] first global DoF / n_dofs_per_cell:
+                                      DoF blocks follow the master's active-cell index */
+
+  /* polytope faces as a work list.  One entry per boundary face of a polytope
+   * (polyB = -1) and one per interior interface, listed from the VISITING side A
+   * (include/poly_utils.h:2089).  Sub-faces are (cell, local face) pairs of A's
+   * sub-cells in the reference's interface order
+   * (source/agglomeration_handler.cc:1375-1397,1442-1463,1606-1609). */
+  int32_t        n_ifaces;
+  const int32_t *iface_polyA;   /* [n_ifaces] */
+  const int32_t *iface_polyB;   /* [n_ifaces], -1 on the boundary */
+  const int64_t *iface_sub_ptr; /* [n_ifaces+1] */
+  const int32_t *sub_cell;      /* [n_subfaces] */
+  const int32_t *sub_face;      /* [n_subfaces] local face 0..2*dim-1 */
+  const double  *sub_sigma;     /* [n_subfaces] penalty (C/h as the caller's rule says) */
+
+  /* block-CSR pattern = create_agglomeration_sparsity_pattern
+   * (source/agglomeration_handler.cc:910-1022) in units of n x n blocks, block
+   * columns ascending.  Scalar CSR follows: row b*n+i holds, for every block k of
+   * block row b in order, columns bcol[k]*n + (0..n-1). */
+  int32_t        n_block_rows;
+  const int64_t *brow_ptr; /* [n_block_rows+1] */
+  const int32_t *bcol_idx; /* [n_blocks] */
+} pd_mesh_desc;
+
+typedef struct pd_coefficients
+{
+  double stiffness; /* sigma: scales grad-grad AND all face terms
+                       (include/utils.h:1628-1636)                     */
+  double mass;      /* f: adds f * phi_i phi_j  (reaction c / chi*C_m/dt,
+                       examples/diffusion_reaction.cc:489-506)          */
+} pd_coefficients;
+
+/* assemble flags */
+#define PD_ASSEMBLE_VOLUME 1u   /* include/poly_utils.h:2038-2052 */
+#define PD_ASSEMBLE_BOUNDARY 2u /* include/poly_utils.h:2060-2085 */
+#define PD_ASSEMBLE_INTERIOR 4u /* include/poly_utils.h:1870-1926, 2086-2132 */
+#define PD_ASSEMBLE_ALL 7u
+
+/* vmult modes */
+#define PD_VMULT_BLOCK_CSR 0   /* y = A x with the assembled matrix */
+#define PD_VMULT_MATRIX_FREE 1 /* y = A x recomputed from the quadrature data           */
+
+/* Create the device-resident copy.  Replaces the state built by
+ * AgglomerationHandler::define_agglomerate / distribute_agglomerated_dofs /
+ * setup_connectivity_of_agglomeration (source/agglomeration_handler.cc:45-104,
+ * 326-379, 495-527).  The descriptor is copied; it may be freed afterwards. */
+int pd_create(const pd_mesh_desc *desc, pd_handle **out);
+int pd_destroy(pd_handle *h);
+
+/* Re-send every descriptor array host->device into the existing buffers (same
+ * sizes as at pd_create).  This is the per-step host->device leg of the
+ * end-to-end path. */
+int pd_upload(pd_handle *h, const pd_mesh_desc *desc);
+
+/* Use a caller stream (cudaStream_t passed as void*); NULL = the handle's own. */
+int pd_set_stream(pd_handle *h, void *cuda_stream);
+int pd_synchronize(pd_handle *h);
+
+/* agglomerated_quadrature + the geometry half of reinit_master on the device
+ * (source/agglomeration_handler.cc:622-707, 1139-1165): fills the volume
+ * q-points/JxW of every polytope and the face q-points/normals/JxW of every
+ * interface.  Called implicitly by pd_assemble when stale. */
+int pd_build_quadrature(pd_handle *h);
+
+/* PolyUtils::assemble_dg_matrix (include/poly_utils.h:2000-2195).  Result: the
+ * scalar-CSR value array of the reference pattern (ascending columns), kept on
+ * the device inside the handle. */
+int pd_assemble(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
+
+int64_t pd_n_dofs(const pd_handle *h);
+int64_t pd_nnz(const pd_handle *h);
+int32_t pd_n_dofs_per_cell(const pd_handle *h);
+/* device pointer to the matrix values (length pd_nnz) */
+int pd_matrix_values_device(pd_handle *h, double **dev_values);
+/* device->host copy of the matrix values (the per-step device->host leg) */
+int pd_matrix_values_to_host(pd_handle *h, double *host_values);
+/* scalar CSR pattern of the result: rowptr[n_dofs+1], cols[nnz] (host) */
+int pd_matrix_pattern_to_host(pd_handle *h, int64_t *rowptr, int32_t *cols);
+
+/* vmult: what LinearOperatorMG::vmult / TrilinosWrappers::SparseMatrix::vmult do
+ * on agglomerated levels (include/multigrid_amg.h:345-355,
+ * include/linear_operator_for_mg.h:295).  src/dst are DEVICE pointers of
+ * pd_n_dofs doubles.  vmult_add accumulates into dst. */
+int pd_vmult(pd_handle *h, int mode, const double *src_dev, double *dst_dev);
+int pd_vmult_add(pd_handle *h, int mode, const double *src_dev, double *dst_dev);
+/* same with HOST buffers (pinned or pageable): H2D, apply, D2H */
+int pd_vmult_host(pd_handle *h, int mode, const double *src_host, double *dst_host);
+/* inverse of the matrix diagonal, entries below 1e-10 kept as they are
+ * (include/utils.h:797-814); device pointer of pd_n_dofs doubles */
+int pd_diagonal_inverse(pd_handle *h, double *dst_dev);
+
+/* Debug/parity access to device-resident arrays.  name in: "vol_qpt" [dim][Q],
+ * "vol_jxw" [Q], "face_qpt" [dim][Qf], "face_normal" [dim][Qf], "face_jxw" [Qf].
+ * Returns the element count through *count when host_out is NULL. */
+int pd_copy_array(pd_handle *h, const char *name, double *host_out, int64_t *count);
+
+/* number of kernel launches issued through this handle so far */
+int64_t pd_launch_count(const pd_handle *h);
+/* device time (ms) of the dominant assembly kernels of the LAST pd_assemble,
+ * measured with CUDA events on the handle's stream: [0] volume, [1] faces,
+ * [2] reduce, [3] quadrature */
+int pd_last_kernel_ms(pd_handle *h, float *ms4);
+
+/* -----------------------------------------------------------------------------
+ * Host mirror of the reference classes
+ * -------------------------------------------------------------------------- */
+/* GridGenerator::hyper_cube + refine_global (order 0: hierarchical = Morton cell
+ * order, needs n = 2^k) or subdivided_hyper_rectangle (order 1: lexicographic) */
+int pdh_grid_create_structured(int32_t dim, const int32_t *n, const double *lo, const double *hi,
+                               int32_t order, pdh_grid **out);
+/* any hypercube mesh in deal.II conventions; nbr[n_cells][2*dim] = neighbouring
+ * cell behind each local face (-1 on the boundary), standard orientation */
+int pdh_grid_create(int32_t dim, int64_t n_verts, const double *verts, int64_t n_cells,
+                    const int32_t *cell_verts, const int32_t *nbr, pdh_grid **out);
+int pdh_grid_destroy(pdh_grid *g);
+int64_t pdh_grid_n_cells(const pdh_grid *g);
+int64_t pdh_grid_n_verts(const pdh_grid *g);
+/* overwrite vertex coordinates (e.g. GridTools::distort_random done by the caller) */
+int pdh_grid_set_vertices(pdh_grid *g, const double *verts);
+int pdh_grid_get_arrays(const pdh_grid *g, double *verts, int32_t *cell_verts, int32_t *nbr);
+
+/* AgglomerationHandler<dim>(cached_tria)  (source/agglomeration_handler.cc:20-40) */
+int pdh_handler_create(pdh_grid *g, pdh_handler **out);
+int pdh_handler_destroy(pdh_handler *ah);
+/* define_agglomerate(cells): cells[0] is the master; returns polytope index or <0
+ * (source/agglomeration_handler.cc:45-104) */
+int32_t pdh_define_agglomerate(pdh_handler *ah, const int32_t *cells, int32_t n);
+/* initialize_fe_values(QGauss<dim>(nq_cell), ..., QGauss<dim-1>(nq_face)) (:210-236) */
+int pdh_initialize_fe_values(pdh_handler *ah, int32_t nq_cell, int32_t nq_face);
+/* distribute_agglomerated_dofs(FE_DGQ<dim>(degree))  (:326-379); fe_kind 0 = FE_DGQ */
+int pdh_distribute_agglomerated_dofs(pdh_handler *ah, int32_t fe_kind, int32_t degree);
+
+int32_t  pdh_n_polytopes(const pdh_handler *ah);
+int64_t  pdh_n_dofs(const pdh_handler *ah);
+int32_t  pdh_n_dofs_per_cell(const pdh_handler *ah);
+/* AgglomerationAccessor (include/agglomeration_accessor.h:41-299) by polytope index */
+int32_t  pdh_master_cell(const pdh_handler *ah, int32_t poly);
+int32_t  pdh_n_background_cells(const pdh_handler *ah, int32_t poly);
+int      pdh_get_agglomerate(const pdh_handler *ah, int32_t poly, int32_t *cells);
+uint32_t pdh_n_faces(const pdh_handler *ah, int32_t poly);
+int32_t  pdh_at_boundary(const pdh_handler *ah, int32_t poly, uint32_t f);
+int32_t  pdh_neighbor(const pdh_handler *ah, int32_t poly, uint32_t f); /* -1: boundary */
+uint32_t pdh_neighbor_of_agglomerated_neighbor(const pdh_handler *ah, int32_t poly, uint32_t f);
+/* get_interface().at({id, neighbour id}): fills (cell, local face) pairs, returns count */
+int32_t  pdh_interface(const pdh_handler *ah, int32_t poly, uint32_t f, int32_t *cells,
+                       int32_t *faces, int32_t cap);
+int      pdh_get_dof_indices(const pdh_handler *ah, int32_t poly, uint32_t *dofs);
+int      pdh_bounding_box(const pdh_handler *ah, int32_t poly, double *lo, double *hi);
+double   pdh_diameter(const pdh_handler *ah, int32_t poly);
+double   pdh_volume(const pdh_handler *ah, int32_t poly);
+/* create_agglomeration_sparsity_pattern (:910-1022): scalar CSR, ascending columns */
+int64_t  pdh_sparsity_nnz(const pdh_handler *ah);
+int      pdh_create_agglomeration_sparsity_pattern(const pdh_handler *ah, int64_t *rowptr, int32_t *cols);
+
+/* penalty rules found in the reference */
+#define PD_H_DIAMETER_OF_VISITOR 0  /* C / polytope->diameter()       include/poly_utils.h:2057   */
+#define PD_H_MAX_INVERSE_DIAMETER 1 /* C max(1/hA,1/hB)  test/polydeal/poisson_sanity_check_01.cc:261 */
+#define PD_H_CONSTANT 2             /* C / h_const       test/polydeal/minimal_SIP_Poisson.cc:308 */
+#define PD_H_NORMAL_EXTENT 3        /* C (1/hn_A + 1/hn_B), boundary 4C/hn  include/utils.h:861-866,906-909 */
+#define PD_VISIT_BY_ID 0            /* polytope->id() < neighbour->id()        include/poly_utils.h:2089 */
+#define PD_VISIT_BY_INDEX 1         /* polytope->index() < neighbour->index()  examples/poisson.cc:841   */
+
+typedef struct pdh_flatten_params
+{
+  double  penalty_constant; /* C; <0 => library default 10 (p+dim)(p+1), include/poly_utils.h:2018 */
+  int32_t h_rule;
+  double  h_const;
+  int32_t visit_rule;
+} pdh_flatten_params;
+
+/* Flatten the agglomeration into a descriptor whose arrays stay owned by (and
+ * valid as long as) the handler. */
+int pdh_flatten(pdh_handler *ah, const pdh_flatten_params *prm, pd_mesh_desc *out);
+/* pdh_flatten + pd_create in one call */
+int pdh_create_device(pdh_handler *ah, const pdh_flatten_params *prm, pd_handle **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYDEAL_B200_H */
