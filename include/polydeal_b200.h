@@ -178,6 +178,11 @@ int64_t pd_launch_count(const pd_handle *h);
  * [2] reduce, [3] quadrature */
 int pd_last_kernel_ms(pd_handle *h, float *ms4);
 
+/* The 1-D tables the kernels use: QGauss<1>(n) on [0,1] and the Gauss-Lobatto
+ * support points of FE_DGQ(degree).  Host-only; lets a CPU test-suite check them. */
+int pd_quadrature_rule_1d(int n, double *x, double *w);
+int pd_dgq_nodes_1d(int degree, double *nodes);
+
 /* -----------------------------------------------------------------------------
  * Host mirror of the reference classes
  * -------------------------------------------------------------------------- */

@@ -1,0 +1,735 @@
+// -----------------------------------------------------------------------------
+// pd_api.cu -- C ABI of the device core (include/polydeal_b200.h, pd_* part).
+// -----------------------------------------------------------------------------
+#include "pd_host.hpp"
+#include "pd_internal.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <string>
+
+namespace pd
+{
+  static thread_local std::string g_last_error;
+  void
+  set_last_error(const std::string &m)
+  {
+    g_last_error = m;
+  }
+
+  // Gauss-Legendre on [0,1]: Newton on P_n from the Chebyshev guess, symmetric
+  // pairs computed once and mirrored
+  void
+  make_gauss_1d(const int n, Quad1D &q)
+  {
+    if (n < 1 || n > 8)
+      throw Error(PD_ERR_INVALID, "QGauss: 1 <= n <= 8 points per direction supported");
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int i = 0; i < (n + 1) / 2; ++i)
+      {
+        long double z = cosl(pi * (i + 0.75L) / (n + 0.5L)), pp = 1;
+        for (int it = 0; it < 64; ++it)
+          {
+            long double p1 = 1, p2 = 0;
+            for (int j = 1; j <= n; ++j)
+              {
+                const long double p3 = p2;
+                p2                   = p1;
+                p1                   = ((2 * j - 1) * z * p2 - (j - 1) * p3) / j;
+              }
+            pp                   = n * (z * p1 - p2) / (z * z - 1);
+            const long double dz = p1 / pp;
+            z -= dz;
+            if (fabsl(dz) < 1e-19L)
+              break;
+          }
+        // z > 0 is the upper root of the pair
+        const long double w = 1 / ((1 - z * z) * pp * pp); // weight on [0,1]
+        q.x[n - 1 - i]      = (double)((1 + z) / 2);
+        q.x[i]              = (double)((1 - z) / 2);
+        q.w[i] = q.w[n - 1 - i] = (double)w;
+      }
+    if (n % 2)
+      q.x[n / 2] = 0.5;
+  }
+
+  // Gauss-Lobatto nodes of FE_DGQ(p) on [0,1] in closed form
+  void
+  make_basis_1d(const int p, Basis1D &b)
+  {
+    std::memset(&b, 0, sizeof(b));
+    switch (p)
+      {
+        case 0:
+          b.node[0] = 0.5;
+          break;
+        case 1:
+          b.node[0] = 0;
+          b.node[1] = 1;
+          break;
+        case 2:
+          b.node[0] = 0;
+          b.node[1] = 0.5;
+          b.node[2] = 1;
+          break;
+        case 3:
+          {
+            const long double s = sqrtl(5.0L) / 10;
+            b.node[0]           = 0;
+            b.node[1]           = (double)(0.5L - s);
+            b.node[2]           = (double)(0.5L + s);
+            b.node[3]           = 1;
+            break;
+          }
+        case 4:
+          {
+            const long double s = sqrtl(3.0L / 7.0L) / 2;
+            b.node[0]           = 0;
+            b.node[1]           = (double)(0.5L - s);
+            b.node[2]           = 0.5;
+            b.node[3]           = (double)(0.5L + s);
+            b.node[4]           = 1;
+            break;
+          }
+        case 5:
+          {
+            const long double r = 2 * sqrtl(7.0L) / 21;
+            const long double s1 = sqrtl(1.0L / 3 - r) / 2, s2 = sqrtl(1.0L / 3 + r) / 2;
+            b.node[0] = 0;
+            b.node[1] = (double)(0.5L - s2);
+            b.node[2] = (double)(0.5L - s1);
+            b.node[3] = (double)(0.5L + s1);
+            b.node[4] = (double)(0.5L + s2);
+            b.node[5] = 1;
+            break;
+          }
+        default:
+          throw Error(PD_ERR_UNSUPPORTED, "FE_DGQ degree must be in [0,5]");
+      }
+    for (int a = 0; a <= p; ++a)
+      {
+        double w = 1;
+        for (int c = 0; c <= p; ++c)
+          if (c != a)
+            w /= (b.node[a] - b.node[c]);
+        b.wprod[a] = w;
+      }
+  }
+
+  template <class F>
+  static int
+  guarded(F &&f)
+  {
+    try
+      {
+        f();
+        return PD_OK;
+      }
+    catch (const Error &e)
+      {
+        set_last_error(e.what());
+        return e.code;
+      }
+    catch (const CudaError &e)
+      {
+        set_last_error(std::string("CUDA: ") + cudaGetErrorString(e.e) + " in `" + e.what + "` (line " +
+                       std::to_string(e.line) + ")");
+        return e.e == cudaErrorNotSupported ? PD_ERR_UNSUPPORTED : PD_ERR_CUDA;
+      }
+    catch (const std::exception &e)
+      {
+        set_last_error(e.what());
+        return PD_ERR_INVALID;
+      }
+  }
+
+  static void
+  require_device()
+  {
+    int         n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      {
+        cudaGetLastError();
+        throw Error(PD_ERR_NO_DEVICE,
+                    "polydeal_b200: no CUDA device visible; this path has no CPU fallback (sm_100a kernels only)");
+      }
+  }
+
+  template <class T>
+  static void
+  h2d(DevBuf<T> &b, const T *src, size_t n, cudaStream_t s)
+  {
+    if (n)
+      PD_CUDA(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+
+  static void
+  validate(const pd_mesh_desc &d)
+  {
+    auto need = [](bool ok, const char *m) {
+      if (!ok)
+        throw Error(PD_ERR_INVALID, std::string("pd_mesh_desc: ") + m);
+    };
+    need(d.dim == 2 || d.dim == 3, "dim must be 2 or 3");
+    need(d.fe_degree >= 0 && d.fe_degree <= 5, "fe_degree out of range");
+    need(d.n_q1d >= 1 && d.n_q1d <= 8 && d.n_q1d_face >= 1 && d.n_q1d_face <= 8, "n_q1d out of range");
+    need(d.n_verts > 0 && d.verts, "no vertices");
+    need(d.n_cells > 0 && d.cell_verts, "no cells");
+    need(d.n_polytopes > 0 && d.poly_subcell_ptr && d.poly_subcell_idx && d.bbox && d.dof_block, "no polytopes");
+    need(d.n_ifaces >= 0 && (d.n_ifaces == 0 || (d.iface_polyA && d.iface_polyB && d.iface_sub_ptr)), "bad interface list");
+    need(d.n_block_rows == d.n_polytopes && d.brow_ptr && d.bcol_idx, "block pattern must have one row per polytope");
+    need(d.poly_subcell_ptr[0] == 0, "poly_subcell_ptr[0] != 0");
+    for (int32_t p = 0; p < d.n_polytopes; ++p)
+      {
+        need(d.poly_subcell_ptr[p + 1] > d.poly_subcell_ptr[p], "empty polytope");
+        need(d.dof_block[p] >= 0 && d.dof_block[p] < d.n_polytopes, "dof_block out of range");
+        for (int k = 0; k < d.dim; ++k)
+          need(d.bbox[(size_t)p * 2 * d.dim + d.dim + k] > d.bbox[(size_t)p * 2 * d.dim + k], "degenerate bounding box");
+      }
+    const int64_t ns = d.poly_subcell_ptr[d.n_polytopes];
+    for (int64_t s = 0; s < ns; ++s)
+      need(d.poly_subcell_idx[s] >= 0 && d.poly_subcell_idx[s] < d.n_cells, "sub-cell index out of range");
+    for (int32_t f = 0; f < d.n_ifaces; ++f)
+      {
+        need(d.iface_polyA[f] >= 0 && d.iface_polyA[f] < d.n_polytopes, "iface_polyA out of range");
+        need(d.iface_polyB[f] >= -1 && d.iface_polyB[f] < d.n_polytopes, "iface_polyB out of range");
+        need(d.iface_sub_ptr[f + 1] >= d.iface_sub_ptr[f], "iface_sub_ptr not monotone");
+      }
+    const int64_t nsf = d.n_ifaces ? d.iface_sub_ptr[d.n_ifaces] : 0;
+    need(nsf == 0 || (d.sub_cell && d.sub_face && d.sub_sigma), "missing sub-face arrays");
+    for (int64_t s = 0; s < nsf; ++s)
+      {
+        need(d.sub_cell[s] >= 0 && d.sub_cell[s] < d.n_cells, "sub_cell out of range");
+        need(d.sub_face[s] >= 0 && d.sub_face[s] < 2 * d.dim, "sub_face out of range");
+      }
+  }
+
+  static int64_t
+  find_block(const pd_mesh_desc &d, const int32_t brow, const int32_t bcol)
+  {
+    const int32_t *b = d.bcol_idx + d.brow_ptr[brow], *e = d.bcol_idx + d.brow_ptr[brow + 1];
+    const int32_t *p = std::lower_bound(b, e, bcol);
+    if (p == e || *p != bcol)
+      throw Error(PD_ERR_INVALID, "pd_mesh_desc: block (" + std::to_string(brow) + "," + std::to_string(bcol) +
+                                    ") needed by an interface is not in the block pattern");
+    return p - b;
+  }
+
+  static void
+  upload_descriptor(pd_handle *h, const pd_mesh_desc &d)
+  {
+    cudaStream_t s = h->stream;
+    h2d(h->verts, d.verts, (size_t)d.n_verts * d.dim, s);
+    h2d(h->cell_verts, d.cell_verts, (size_t)d.n_cells << d.dim, s);
+    h2d(h->subcell_ptr, d.poly_subcell_ptr, (size_t)d.n_polytopes + 1, s);
+    h2d(h->subcell_idx, d.poly_subcell_idx, (size_t)h->n_subcells, s);
+    h2d(h->bbox, d.bbox, (size_t)d.n_polytopes * 2 * d.dim, s);
+    h2d(h->dof_block, d.dof_block, (size_t)d.n_polytopes, s);
+    h2d(h->ifA, d.iface_polyA, (size_t)d.n_ifaces, s);
+    h2d(h->ifB, d.iface_polyB, (size_t)d.n_ifaces, s);
+    h2d(h->if_sub_ptr, d.iface_sub_ptr, (size_t)d.n_ifaces + 1, s);
+    h2d(h->sub_cell, d.sub_cell, (size_t)h->n_subfaces, s);
+    h2d(h->sub_face, d.sub_face, (size_t)h->n_subfaces, s);
+    h2d(h->sub_sigma, d.sub_sigma, (size_t)h->n_subfaces, s);
+    h2d(h->brow_ptr, d.brow_ptr, (size_t)d.n_block_rows + 1, s);
+    h2d(h->bcol, d.bcol_idx, (size_t)h->n_blocks, s);
+    h->quad_valid = false;
+    h->assembled  = false;
+  }
+
+  static void
+  create(const pd_mesh_desc &d, pd_handle **out)
+  {
+    require_device();
+    validate(d);
+    if (!assemble_supported(d.dim, d.fe_degree))
+      throw Error(PD_ERR_UNSUPPORTED, "no sm_100a kernel for FE_DGQ<" + std::to_string(d.dim) + ">(" +
+                                        std::to_string(d.fe_degree) + "); supported: 2-D p=1..4, 3-D p=1..3");
+    pd_handle *h = new pd_handle;
+    try
+      {
+        h->dim    = d.dim;
+        h->degree = d.fe_degree;
+        h->n1     = d.fe_degree + 1;
+        h->n      = 1;
+        for (int k = 0; k < d.dim; ++k)
+          h->n *= h->n1;
+        h->nq1  = d.n_q1d;
+        h->nq1f = d.n_q1d_face;
+        h->nqc  = 1;
+        h->nqf  = 1;
+        for (int k = 0; k < d.dim; ++k)
+          h->nqc *= h->nq1;
+        for (int k = 0; k + 1 < d.dim; ++k)
+          h->nqf *= h->nq1f;
+        make_basis_1d(h->degree, h->basis);
+        make_gauss_1d(h->nq1, h->quad);
+        make_gauss_1d(h->nq1f, h->quadf);
+        h->n_verts    = d.n_verts;
+        h->n_cells    = d.n_cells;
+        h->np         = d.n_polytopes;
+        h->n_ifaces   = d.n_ifaces;
+        h->n_subcells = d.poly_subcell_ptr[d.n_polytopes];
+        h->n_subfaces = d.n_ifaces ? d.iface_sub_ptr[d.n_ifaces] : 0;
+        h->Q          = h->n_subcells * h->nqc;
+        h->Qf         = h->n_subfaces * h->nqf;
+        h->n_blocks   = d.brow_ptr[d.n_block_rows];
+        h->n_dofs     = (int64_t)h->np * h->n;
+        h->nnz        = h->n_blocks * h->n * h->n;
+        int dev       = 0;
+        PD_CUDA(cudaGetDevice(&dev));
+        PD_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+        PD_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        for (auto &e : h->ev)
+          PD_CUDA(cudaEventCreate(&e));
+
+        h->verts.alloc((size_t)d.n_verts * d.dim);
+        h->cell_verts.alloc((size_t)d.n_cells << d.dim);
+        h->subcell_ptr.alloc((size_t)h->np + 1);
+        h->subcell_idx.alloc((size_t)h->n_subcells);
+        h->bbox.alloc((size_t)h->np * 2 * d.dim);
+        h->dof_block.alloc((size_t)h->np);
+        h->ifA.alloc((size_t)h->n_ifaces);
+        h->ifB.alloc((size_t)h->n_ifaces);
+        h->if_sub_ptr.alloc((size_t)h->n_ifaces + 1);
+        h->sub_cell.alloc((size_t)h->n_subfaces);
+        h->sub_face.alloc((size_t)h->n_subfaces);
+        h->sub_sigma.alloc((size_t)h->n_subfaces);
+        h->brow_ptr.alloc((size_t)h->np + 1);
+        h->bcol.alloc((size_t)h->n_blocks);
+        if (h->n_ifaces == 0)
+          {
+            // keep a valid pointer for the one-element ptr array
+            const int64_t zero = 0;
+            PD_CUDA(cudaMemcpy(h->if_sub_ptr.p, &zero, sizeof(zero), cudaMemcpyHostToDevice));
+          }
+        upload_descriptor(h, d);
+
+        h->h_brow_ptr.assign(d.brow_ptr, d.brow_ptr + h->np + 1);
+        h->h_bcol.assign(d.bcol_idx, d.bcol_idx + h->n_blocks);
+        h->h_dof_block.assign(d.dof_block, d.dof_block + h->np);
+
+        // ---- derived index data ------------------------------------------------
+        const int64_t        nn = (int64_t)h->n * h->n;
+        std::vector<int32_t> row_stride(h->np);
+        for (int32_t b = 0; b < h->np; ++b)
+          row_stride[b] = (int32_t)(d.brow_ptr[b + 1] - d.brow_ptr[b]) * h->n;
+        std::vector<int64_t> diag_base(h->np);
+        std::vector<char>    seen_block(h->np, 0);
+        for (int32_t p = 0; p < h->np; ++p)
+          {
+            const int32_t b = d.dof_block[p];
+            if (seen_block[b])
+              throw Error(PD_ERR_INVALID, "pd_mesh_desc: dof_block is not a permutation");
+            seen_block[b] = 1;
+            diag_base[p]  = d.brow_ptr[b] * nn + find_block(d, b, b) * h->n;
+          }
+        std::vector<int64_t> baseAB(h->n_ifaces, -1), baseBA(h->n_ifaces, -1);
+        std::vector<int64_t> padj_ptr(h->np + 1, 0);
+        for (int32_t f = 0; f < h->n_ifaces; ++f)
+          {
+            const int32_t pa = d.iface_polyA[f], pb = d.iface_polyB[f];
+            ++padj_ptr[pa + 1];
+            if (pb >= 0)
+              {
+                if (pb == pa)
+                  throw Error(PD_ERR_INVALID, "pd_mesh_desc: interface joins a polytope with itself");
+                ++padj_ptr[pb + 1];
+                const int32_t ba = d.dof_block[pa], bb = d.dof_block[pb];
+                baseAB[f] = d.brow_ptr[ba] * nn + find_block(d, ba, bb) * h->n;
+                baseBA[f] = d.brow_ptr[bb] * nn + find_block(d, bb, ba) * h->n;
+              }
+          }
+        for (int32_t p = 0; p < h->np; ++p)
+          padj_ptr[p + 1] += padj_ptr[p];
+        std::vector<int64_t> padj(padj_ptr[h->np]), cursor(padj_ptr.begin(), padj_ptr.end() - 1);
+        for (int32_t f = 0; f < h->n_ifaces; ++f)
+          {
+            padj[cursor[d.iface_polyA[f]]++] = (int64_t)f * 2;
+            if (d.iface_polyB[f] >= 0)
+              padj[cursor[d.iface_polyB[f]]++] = (int64_t)f * 2 + 1;
+          }
+        // volume work items: whole sub-cells, sized so that every SM gets several
+        const int64_t        target = std::max<int64_t>(512, (h->Q + (int64_t)h->sm_count * 8 - 1) / ((int64_t)h->sm_count * 8));
+        std::vector<int32_t> item_poly;
+        std::vector<int64_t> item_q0, item_q1, poly_item_ptr(h->np + 1, 0);
+        for (int32_t p = 0; p < h->np; ++p)
+          {
+            const int64_t c0 = d.poly_subcell_ptr[p], c1 = d.poly_subcell_ptr[p + 1];
+            const int64_t qp = (c1 - c0) * h->nqc;
+            const int64_t nchunk = std::max<int64_t>(1, std::min<int64_t>(c1 - c0, (qp + target - 1) / target));
+            for (int64_t k = 0; k < nchunk; ++k)
+              {
+                const int64_t a = c0 + (c1 - c0) * k / nchunk, b = c0 + (c1 - c0) * (k + 1) / nchunk;
+                item_poly.push_back(p);
+                item_q0.push_back(a * h->nqc);
+                item_q1.push_back(b * h->nqc);
+              }
+            poly_item_ptr[p + 1] = (int64_t)item_poly.size();
+          }
+        h->n_vitems = (int32_t)item_poly.size();
+
+        auto put32 = [&](DevBuf<int32_t> &b, const std::vector<int32_t> &v) {
+          b.alloc(v.size());
+          if (!v.empty())
+            PD_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        };
+        auto put64 = [&](DevBuf<int64_t> &b, const std::vector<int64_t> &v) {
+          b.alloc(v.size());
+          if (!v.empty())
+            PD_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        };
+        put32(h->row_stride, row_stride);
+        put64(h->diag_base, diag_base);
+        put64(h->if_baseAB, baseAB);
+        put64(h->if_baseBA, baseBA);
+        put64(h->padj_ptr, padj_ptr);
+        put64(h->padj, padj);
+        put32(h->vitem_poly, item_poly);
+        put64(h->vitem_q0, item_q0);
+        put64(h->vitem_q1, item_q1);
+        put64(h->poly_vitem_ptr, poly_item_ptr);
+
+        h->vq_x.alloc((size_t)h->Q * d.dim);
+        h->vq_w.alloc((size_t)h->Q);
+        h->fq_x.alloc((size_t)h->Qf * d.dim);
+        h->fq_n.alloc((size_t)h->Qf * d.dim);
+        h->fq_w.alloc((size_t)h->Qf);
+        h->vol_partial.alloc((size_t)h->n_vitems * nn);
+        h->face_diag.alloc((size_t)h->n_ifaces * 2 * nn);
+        h->values.alloc((size_t)h->nnz);
+        PD_CUDA(cudaStreamSynchronize(h->stream));
+      }
+    catch (...)
+      {
+        for (auto &e : h->ev)
+          if (e)
+            cudaEventDestroy(e);
+        if (h->own_stream)
+          cudaStreamDestroy(h->own_stream);
+        delete h;
+        throw;
+      }
+    *out = h;
+  }
+} // namespace pd
+
+using namespace pd;
+
+extern "C"
+{
+  const char *
+  pd_last_error(void)
+  {
+    return g_last_error.c_str();
+  }
+
+  int
+  pd_device_count(void)
+  {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+      {
+        cudaGetLastError();
+        return 0;
+      }
+    return n;
+  }
+
+  int
+  pd_create(const pd_mesh_desc *desc, pd_handle **out)
+  {
+    return guarded([&] {
+      if (!desc || !out)
+        throw Error(PD_ERR_INVALID, "pd_create: null argument");
+      *out = nullptr;
+      create(*desc, out);
+    });
+  }
+
+  int
+  pd_destroy(pd_handle *h)
+  {
+    return guarded([&] {
+      if (!h)
+        return;
+      cudaStreamSynchronize(h->stream);
+      for (auto &e : h->ev)
+        if (e)
+          cudaEventDestroy(e);
+      if (h->own_stream)
+        cudaStreamDestroy(h->own_stream);
+      delete h;
+    });
+  }
+
+  int
+  pd_upload(pd_handle *h, const pd_mesh_desc *d)
+  {
+    return guarded([&] {
+      if (!h || !d)
+        throw Error(PD_ERR_INVALID, "pd_upload: null argument");
+      const int64_t nsc = d->poly_subcell_ptr[d->n_polytopes];
+      const int64_t nsf = d->n_ifaces ? d->iface_sub_ptr[d->n_ifaces] : 0;
+      if (d->dim != h->dim || d->fe_degree != h->degree || d->n_q1d != h->nq1 || d->n_q1d_face != h->nq1f ||
+          d->n_verts != h->n_verts || d->n_cells != h->n_cells || d->n_polytopes != h->np ||
+          d->n_ifaces != h->n_ifaces || nsc != h->n_subcells || nsf != h->n_subfaces ||
+          d->brow_ptr[d->n_block_rows] != h->n_blocks)
+        throw Error(PD_ERR_INVALID, "pd_upload: descriptor sizes differ from the ones the handle was created with");
+      upload_descriptor(h, *d);
+    });
+  }
+
+  int
+  pd_set_stream(pd_handle *h, void *cuda_stream)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      PD_CUDA(cudaStreamSynchronize(h->stream));
+      h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    });
+  }
+
+  int
+  pd_synchronize(pd_handle *h)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      PD_CUDA(cudaStreamSynchronize(h->stream));
+    });
+  }
+
+  int
+  pd_build_quadrature(pd_handle *h)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      launch_quadrature(h);
+      h->quad_valid = true;
+    });
+  }
+
+  int
+  pd_assemble(pd_handle *h, uint32_t flags, const pd_coefficients *coef)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      pd_coefficients c{1.0, 0.0};
+      if (coef)
+        c = *coef;
+      PD_CUDA(cudaEventRecord(h->ev[4], h->stream));
+      const bool built = !h->quad_valid;
+      if (built)
+        {
+          launch_quadrature(h);
+          h->quad_valid = true;
+        }
+      launch_assemble(h, flags, c);
+      h->assembled  = true;
+      h->last_ms[3] = built ? -1.f : 0.f; // resolved lazily in pd_last_kernel_ms
+    });
+  }
+
+  int64_t
+  pd_n_dofs(const pd_handle *h)
+  {
+    return h ? h->n_dofs : 0;
+  }
+  int64_t
+  pd_nnz(const pd_handle *h)
+  {
+    return h ? h->nnz : 0;
+  }
+  int32_t
+  pd_n_dofs_per_cell(const pd_handle *h)
+  {
+    return h ? h->n : 0;
+  }
+
+  int
+  pd_matrix_values_device(pd_handle *h, double **dev_values)
+  {
+    return guarded([&] {
+      if (!h || !dev_values)
+        throw Error(PD_ERR_INVALID, "null argument");
+      *dev_values = h->values.p;
+    });
+  }
+
+  int
+  pd_matrix_values_to_host(pd_handle *h, double *host_values)
+  {
+    return guarded([&] {
+      if (!h || !host_values)
+        throw Error(PD_ERR_INVALID, "null argument");
+      if (!h->assembled)
+        throw Error(PD_ERR_STATE, "pd_matrix_values_to_host: pd_assemble has not been called");
+      PD_CUDA(cudaMemcpyAsync(host_values, h->values.p, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+      PD_CUDA(cudaStreamSynchronize(h->stream));
+    });
+  }
+
+  int
+  pd_matrix_pattern_to_host(pd_handle *h, int64_t *rowptr, int32_t *cols)
+  {
+    return guarded([&] {
+      if (!h || !rowptr || !cols)
+        throw Error(PD_ERR_INVALID, "null argument");
+      const int n = h->n;
+      int64_t   k = 0;
+      rowptr[0]   = 0;
+      for (int32_t b = 0; b < h->np; ++b)
+        for (int i = 0; i < n; ++i)
+          {
+            for (int64_t e = h->h_brow_ptr[b]; e < h->h_brow_ptr[b + 1]; ++e)
+              for (int j = 0; j < n; ++j)
+                cols[k++] = h->h_bcol[e] * n + j;
+            rowptr[(int64_t)b * n + i + 1] = k;
+          }
+    });
+  }
+
+  static void
+  vmult_impl(pd_handle *h, int mode, const double *src, double *dst, bool add)
+  {
+    if (!h || !src || !dst)
+      throw Error(PD_ERR_INVALID, "pd_vmult: null argument");
+    if (mode == PD_VMULT_BLOCK_CSR)
+      {
+        if (!h->assembled)
+          throw Error(PD_ERR_STATE, "pd_vmult(BLOCK_CSR): pd_assemble has not been called");
+        launch_spmv(h, src, dst, add);
+      }
+    else
+      throw Error(PD_ERR_UNSUPPORTED, "pd_vmult: matrix-free mode is not built yet in this round");
+  }
+
+  int
+  pd_vmult(pd_handle *h, int mode, const double *src_dev, double *dst_dev)
+  {
+    return guarded([&] { vmult_impl(h, mode, src_dev, dst_dev, false); });
+  }
+
+  int
+  pd_vmult_add(pd_handle *h, int mode, const double *src_dev, double *dst_dev)
+  {
+    return guarded([&] { vmult_impl(h, mode, src_dev, dst_dev, true); });
+  }
+
+  int
+  pd_vmult_host(pd_handle *h, int mode, const double *src_host, double *dst_host)
+  {
+    return guarded([&] {
+      if (!h || !src_host || !dst_host)
+        throw Error(PD_ERR_INVALID, "pd_vmult_host: null argument");
+      if (h->vec_a.n != (size_t)h->n_dofs)
+        {
+          h->vec_a.alloc((size_t)h->n_dofs);
+          h->vec_b.alloc((size_t)h->n_dofs);
+        }
+      PD_CUDA(cudaMemcpyAsync(h->vec_a.p, src_host, sizeof(double) * h->n_dofs, cudaMemcpyHostToDevice, h->stream));
+      vmult_impl(h, mode, h->vec_a.p, h->vec_b.p, false);
+      PD_CUDA(cudaMemcpyAsync(dst_host, h->vec_b.p, sizeof(double) * h->n_dofs, cudaMemcpyDeviceToHost, h->stream));
+      PD_CUDA(cudaStreamSynchronize(h->stream));
+    });
+  }
+
+  int
+  pd_diagonal_inverse(pd_handle *h, double *dst_dev)
+  {
+    return guarded([&] {
+      if (!h || !dst_dev)
+        throw Error(PD_ERR_INVALID, "null argument");
+      if (!h->assembled)
+        throw Error(PD_ERR_STATE, "pd_diagonal_inverse: pd_assemble has not been called");
+      launch_diagonal_inverse(h, dst_dev);
+    });
+  }
+
+  int
+  pd_copy_array(pd_handle *h, const char *name, double *host_out, int64_t *count)
+  {
+    return guarded([&] {
+      if (!h || !name)
+        throw Error(PD_ERR_INVALID, "null argument");
+      const std::string s(name);
+      const double     *p = nullptr;
+      int64_t           n = 0;
+      if (s == "vol_qpt")
+        p = h->vq_x.p, n = h->Q * h->dim;
+      else if (s == "vol_jxw")
+        p = h->vq_w.p, n = h->Q;
+      else if (s == "face_qpt")
+        p = h->fq_x.p, n = h->Qf * h->dim;
+      else if (s == "face_normal")
+        p = h->fq_n.p, n = h->Qf * h->dim;
+      else if (s == "face_jxw")
+        p = h->fq_w.p, n = h->Qf;
+      else
+        throw Error(PD_ERR_INVALID, "pd_copy_array: unknown array '" + s + "'");
+      if (count)
+        *count = n;
+      if (host_out)
+        {
+          if (!h->quad_valid)
+            throw Error(PD_ERR_STATE, "pd_copy_array: quadrature has not been built");
+          PD_CUDA(cudaMemcpyAsync(host_out, p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+          PD_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    });
+  }
+
+  int64_t
+  pd_launch_count(const pd_handle *h)
+  {
+    return h ? h->launches : 0;
+  }
+
+  int
+  pd_last_kernel_ms(pd_handle *h, float *ms4)
+  {
+    return guarded([&] {
+      if (!h || !ms4)
+        throw Error(PD_ERR_INVALID, "null argument");
+      if (!h->assembled)
+        throw Error(PD_ERR_STATE, "pd_last_kernel_ms: pd_assemble has not been called");
+      PD_CUDA(cudaEventSynchronize(h->ev[3]));
+      PD_CUDA(cudaEventElapsedTime(&ms4[0], h->ev[0], h->ev[1]));
+      PD_CUDA(cudaEventElapsedTime(&ms4[1], h->ev[1], h->ev[2]));
+      PD_CUDA(cudaEventElapsedTime(&ms4[2], h->ev[2], h->ev[3]));
+      PD_CUDA(cudaEventElapsedTime(&ms4[3], h->ev[4], h->ev[0]));
+    });
+  }
+
+  // exposed so the CPU-only test-suite can check the rule tables the kernels use
+  int
+  pd_quadrature_rule_1d(int n, double *x, double *w)
+  {
+    return guarded([&] {
+      Quad1D q;
+      make_gauss_1d(n, q);
+      for (int i = 0; i < n; ++i)
+        {
+          x[i] = q.x[i];
+          w[i] = q.w[i];
+        }
+    });
+  }
+
+  int
+  pd_dgq_nodes_1d(int degree, double *nodes)
+  {
+    return guarded([&] {
+      Basis1D b;
+      make_basis_1d(degree, b);
+      for (int i = 0; i <= degree; ++i)
+        nodes[i] = b.node[i];
+    });
+  }
+}

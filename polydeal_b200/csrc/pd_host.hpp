@@ -1,0 +1,555 @@
+// -----------------------------------------------------------------------------
+// pd_host.hpp -- host mirror of the reference's polytopal-mesh layer.
+//
+// Produces, with the reference's numbering, the flattened agglomeration the
+// device kernels consume.  Names follow the reference:
+//   AgglomerationHandler  include/agglomeration_handler.h:171-575,
+//                         source/agglomeration_handler.cc
+//   accessor queries      include/agglomeration_accessor.h:41-299
+//   MappingBox            source/mapping_box.cc:194-224, 923-972
+// Unlike the reference (std::map / std::set keyed on CellId pairs, one heap
+// object per reinit) everything is flat CSR built in two linear sweeps.
+// No arithmetic of the hot path runs here: quadrature, basis evaluation and
+// the SIP terms are computed by the CUDA kernels only.
+// -----------------------------------------------------------------------------
+#pragma once
+#include "../../include/polydeal_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace pd
+{
+  struct Error : std::runtime_error
+  {
+    int code;
+    Error(int c, const std::string &m)
+      : std::runtime_error(m)
+      , code(c)
+    {}
+  };
+
+  // ---------------------------------------------------------------------------
+  // Background mesh (quads / hexes, deal.II vertex and face numbering)
+  // ---------------------------------------------------------------------------
+  struct Grid
+  {
+    int                  dim = 0;
+    std::vector<double>  verts;      // [n_verts][dim]
+    std::vector<int32_t> cell_verts; // [n_cells][2^dim]
+    std::vector<int32_t> nbr;        // [n_cells][2*dim]
+
+    int64_t
+    n_cells() const
+    {
+      return (int64_t)(cell_verts.size() >> dim);
+    }
+    int64_t
+    n_verts() const
+    {
+      return (int64_t)(verts.size() / dim);
+    }
+
+    // interleave the bits of (i,j,k): position of a cell in the hierarchical
+    // (refine_global) ordering of a 2^L grid
+    static inline uint64_t
+    morton(const int dim, const int levels, const uint32_t i, const uint32_t j, const uint32_t k)
+    {
+      uint64_t m = 0;
+      for (int l = 0; l < levels; ++l)
+        {
+          m |= (uint64_t)((i >> l) & 1u) << (dim * l);
+          m |= (uint64_t)((j >> l) & 1u) << (dim * l + 1);
+          if (dim == 3)
+            m |= (uint64_t)((k >> l) & 1u) << (dim * l + 2);
+        }
+      return m;
+    }
+
+    void
+    make_structured(const int dim_, const int32_t *n, const double *lo, const double *hi, const int order)
+    {
+      if (dim_ != 2 && dim_ != 3)
+        throw Error(PD_ERR_INVALID, "dim must be 2 or 3");
+      dim             = dim_;
+      const int64_t nx = n[0], ny = n[1], nz = dim == 3 ? n[2] : 1;
+      if (nx < 1 || ny < 1 || nz < 1)
+        throw Error(PD_ERR_INVALID, "grid sizes must be positive");
+      int levels = 0;
+      if (order == 0)
+        {
+          while ((int64_t(1) << levels) < nx)
+            ++levels;
+          if ((int64_t(1) << levels) != nx || ny != nx || (dim == 3 && nz != nx))
+            throw Error(PD_ERR_INVALID, "hierarchical (Morton) order needs n = 2^k in every direction");
+        }
+      const int64_t vx = nx + 1, vy = ny + 1, vz = dim == 3 ? nz + 1 : 1;
+      verts.resize((size_t)(vx * vy * vz) * dim);
+      const double inv[3] = {1.0 / nx, 1.0 / ny, 1.0 / nz};
+      for (int64_t k = 0; k < vz; ++k)
+        for (int64_t j = 0; j < vy; ++j)
+          for (int64_t i = 0; i < vx; ++i)
+            {
+              double      *x      = &verts[(size_t)((k * vy + j) * vx + i) * dim];
+              const int64_t ijk[3] = {i, j, k};
+              for (int d = 0; d < dim; ++d)
+                x[d] = lo[d] + (hi[d] - lo[d]) * ((double)ijk[d] * inv[d]);
+            }
+      const int     vpc = 1 << dim, fpc = 2 * dim;
+      const int64_t nc  = nx * ny * nz;
+      cell_verts.resize((size_t)nc * vpc);
+      nbr.resize((size_t)nc * fpc);
+      auto id = [&](int64_t i, int64_t j, int64_t k) -> int64_t {
+        return order == 0 ? (int64_t)morton(dim, levels, (uint32_t)i, (uint32_t)j, (uint32_t)k) :
+                            (k * ny + j) * nx + i;
+      };
+      for (int64_t k = 0; k < nz; ++k)
+        for (int64_t j = 0; j < ny; ++j)
+          for (int64_t i = 0; i < nx; ++i)
+            {
+              const int64_t c = id(i, j, k);
+              for (int v = 0; v < vpc; ++v)
+                cell_verts[(size_t)c * vpc + v] =
+                  (int32_t)(((k + ((v >> 2) & 1)) * vy + (j + ((v >> 1) & 1))) * vx + (i + (v & 1)));
+              int32_t *b = &nbr[(size_t)c * fpc];
+              b[0]       = i ? (int32_t)id(i - 1, j, k) : -1;
+              b[1]       = i + 1 < nx ? (int32_t)id(i + 1, j, k) : -1;
+              b[2]       = j ? (int32_t)id(i, j - 1, k) : -1;
+              b[3]       = j + 1 < ny ? (int32_t)id(i, j + 1, k) : -1;
+              if (dim == 3)
+                {
+                  b[4] = k ? (int32_t)id(i, j, k - 1) : -1;
+                  b[5] = k + 1 < nz ? (int32_t)id(i, j, k + 1) : -1;
+                }
+            }
+    }
+  };
+
+  // ---------------------------------------------------------------------------
+  // AgglomerationHandler mirror
+  // ---------------------------------------------------------------------------
+  class AgglomerationHandler
+  {
+  public:
+    explicit AgglomerationHandler(Grid *g)
+      : grid(g)
+      , dim(g->dim)
+      , poly_of_cell((size_t)g->n_cells(), -1)
+    {
+      if (g->n_cells() == 0)
+        throw Error(PD_ERR_INVALID, "The triangulation must not be empty upon calling this function.");
+      subcell_ptr.push_back(0);
+    }
+
+    // source/agglomeration_handler.cc:45-104.  cells[0] becomes the master.
+    int32_t
+    define_agglomerate(const int32_t *cells, const int32_t n)
+    {
+      if (n <= 0)
+        throw Error(PD_ERR_INVALID, "No cells to be agglomerated.");
+      const int32_t p = (int32_t)masters.size();
+      for (int32_t i = 0; i < n; ++i)
+        {
+          if (cells[i] < 0 || cells[i] >= grid->n_cells())
+            throw Error(PD_ERR_INVALID, "cell index out of range in define_agglomerate");
+          if (poly_of_cell[cells[i]] >= 0)
+            throw Error(PD_ERR_INVALID, "cell " + std::to_string(cells[i]) + " already belongs to an agglomerate");
+        }
+      masters.push_back(cells[0]);
+      // stored order = the accessor's get_agglomerate(): slaves first, master last
+      for (int32_t i = 1; i < n; ++i)
+        subcell_idx.push_back(cells[i]);
+      subcell_idx.push_back(cells[0]);
+      subcell_ptr.push_back((int64_t)subcell_idx.size());
+      for (int32_t i = 0; i < n; ++i)
+        poly_of_cell[cells[i]] = p;
+      // bounding box of all vertices of all cells (:476-491)
+      double b[6];
+      for (int d = 0; d < dim; ++d)
+        {
+          b[d]       = std::numeric_limits<double>::infinity();
+          b[dim + d] = -std::numeric_limits<double>::infinity();
+        }
+      const int vpc = 1 << dim;
+      for (int32_t i = 0; i < n; ++i)
+        for (int v = 0; v < vpc; ++v)
+          {
+            const double *x = &grid->verts[(size_t)grid->cell_verts[(size_t)cells[i] * vpc + v] * dim];
+            for (int d = 0; d < dim; ++d)
+              {
+                b[d]       = std::min(b[d], x[d]);
+                b[dim + d] = std::max(b[dim + d], x[d]);
+              }
+          }
+      bbox.insert(bbox.end(), b, b + 2 * dim);
+      connectivity_ready = false;
+      return p;
+    }
+
+    void
+    initialize_fe_values(const int32_t nq_cell, const int32_t nq_face)
+    {
+      if (nq_cell < 1 || nq_face < 1 || nq_cell > 8 || nq_face > 8)
+        throw Error(PD_ERR_INVALID, "number of Gauss points per direction must be in [1,8]");
+      n_q1d      = nq_cell;
+      n_q1d_face = nq_face;
+    }
+
+    // :326-379 -- DoFs (hp: FE on masters, FE_Nothing on slaves => consecutive
+    // blocks in active-cell order of the masters) + connectivity
+    void
+    distribute_agglomerated_dofs(const int32_t fe_kind, const int32_t degree)
+    {
+      if (fe_kind != 0)
+        throw Error(PD_ERR_UNSUPPORTED, "Currently, this interface supports only DGQ bases on the device path.");
+      if (degree < 0 || degree > 5)
+        throw Error(PD_ERR_UNSUPPORTED, "FE_DGQ degree must be in [0,5]");
+      if (masters.empty())
+        throw Error(PD_ERR_STATE, "No agglomeration has been performed.");
+      fe_degree     = degree;
+      dofs_per_cell = 1;
+      for (int d = 0; d < dim; ++d)
+        dofs_per_cell *= degree + 1;
+      // rank of each master among all masters by active cell index
+      std::vector<int32_t> order(masters.size());
+      for (size_t i = 0; i < order.size(); ++i)
+        order[i] = (int32_t)i;
+      std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return masters[a] < masters[b]; });
+      dof_block.resize(masters.size());
+      block_to_poly.resize(masters.size());
+      for (size_t r = 0; r < order.size(); ++r)
+        {
+          dof_block[order[r]] = (int32_t)r;
+          block_to_poly[r]    = order[r];
+        }
+      setup_connectivity_of_agglomeration();
+    }
+
+    // --- accessor-like queries ------------------------------------------------
+    int32_t
+    n_polytopes() const
+    {
+      return (int32_t)masters.size();
+    }
+    int64_t
+    n_dofs() const
+    {
+      return (int64_t)masters.size() * dofs_per_cell;
+    }
+    void
+    check_poly(const int32_t p) const
+    {
+      if (p < 0 || p >= n_polytopes())
+        throw Error(PD_ERR_INVALID, "polytope index out of range");
+    }
+    void
+    check_face(const int32_t p, const uint32_t f) const
+    {
+      check_poly(p);
+      require_connectivity();
+      if (f >= n_faces(p))
+        throw Error(PD_ERR_INVALID, "face index out of range"); // reference: std::map::at -> std::out_of_range
+    }
+    void
+    require_connectivity() const
+    {
+      if (!connectivity_ready)
+        throw Error(PD_ERR_STATE,
+                    "The DoFHandler associated to the agglomeration has not been initialized. "
+                    "It's likely that you forgot to distribute the DoFs.");
+    }
+    uint32_t
+    n_faces(const int32_t p) const
+    {
+      return (uint32_t)(face_ptr[p + 1] - face_ptr[p]);
+    }
+    bool
+    at_boundary(const int32_t p, const uint32_t f) const
+    {
+      return face_nbr[face_ptr[p] + f] < 0;
+    }
+    int32_t
+    neighbor(const int32_t p, const uint32_t f) const
+    {
+      return face_nbr[face_ptr[p] + f];
+    }
+    uint32_t
+    neighbor_of_agglomerated_neighbor(const int32_t p, const uint32_t f) const
+    {
+      return face_nofn[face_ptr[p] + f];
+    }
+    double
+    diameter(const int32_t p) const
+    {
+      const double *b = &bbox[(size_t)p * 2 * dim];
+      double        s = 0;
+      for (int d = 0; d < dim; ++d)
+        s += (b[dim + d] - b[d]) * (b[dim + d] - b[d]);
+      return std::sqrt(s);
+    }
+    double
+    volume(const int32_t p) const
+    {
+      const double *b = &bbox[(size_t)p * 2 * dim];
+      double        v = 1;
+      for (int d = 0; d < dim; ++d)
+        v *= (b[dim + d] - b[d]);
+      return v;
+    }
+
+    // block-CSR pattern (:910-1022): diagonal + one block per neighbouring polytope
+    void
+    block_pattern(std::vector<int64_t> &brow_ptr, std::vector<int32_t> &bcol) const
+    {
+      require_connectivity();
+      const int32_t np = n_polytopes();
+      brow_ptr.assign(np + 1, 0);
+      bcol.clear();
+      std::vector<int32_t> row;
+      for (int32_t b = 0; b < np; ++b)
+        {
+          const int32_t p = block_to_poly[b];
+          row.clear();
+          row.push_back(b);
+          for (uint32_t f = 0; f < n_faces(p); ++f)
+            if (!at_boundary(p, f))
+              row.push_back(dof_block[neighbor(p, f)]);
+          std::sort(row.begin(), row.end());
+          bcol.insert(bcol.end(), row.begin(), row.end());
+          brow_ptr[b + 1] = (int64_t)bcol.size();
+        }
+    }
+
+    // Fill a descriptor; the arrays it points to live in this object.
+    void
+    flatten(const pdh_flatten_params &prm, pd_mesh_desc &d)
+    {
+      require_connectivity();
+      if (n_q1d <= 0)
+        throw Error(PD_ERR_STATE, "initialize_fe_values() must be called before flattening");
+      const double C =
+        prm.penalty_constant >= 0 ? prm.penalty_constant : 10.0 * (fe_degree + dim) * (fe_degree + 1);
+      fl_polyA.clear();
+      fl_polyB.clear();
+      fl_sub_ptr.assign(1, 0);
+      fl_sub_cell.clear();
+      fl_sub_face.clear();
+      fl_sub_sigma.clear();
+      const int32_t np = n_polytopes();
+      for (int32_t p = 0; p < np; ++p)
+        {
+          const double hp = diameter(p);
+          for (uint32_t f = 0; f < n_faces(p); ++f)
+            {
+              const int32_t q = neighbor(p, f);
+              if (q >= 0)
+                {
+                  const bool visit = prm.visit_rule == PD_VISIT_BY_ID ? masters[p] < masters[q] : p < q;
+                  if (!visit)
+                    continue;
+                }
+              fl_polyA.push_back(p);
+              fl_polyB.push_back(q);
+              const int64_t fi = face_ptr[p] + f;
+              for (int64_t s = face_sub_ptr[fi]; s < face_sub_ptr[fi + 1]; ++s)
+                {
+                  fl_sub_cell.push_back(sub_cell[s]);
+                  fl_sub_face.push_back(sub_face[s]);
+                  double sigma;
+                  switch (prm.h_rule)
+                    {
+                      case PD_H_MAX_INVERSE_DIAMETER:
+                        sigma = q >= 0 ? C * std::max(1.0 / hp, 1.0 / diameter(q)) : C / hp;
+                        break;
+                      case PD_H_CONSTANT:
+                        sigma = C / prm.h_const;
+                        break;
+                      case PD_H_NORMAL_EXTENT:
+                        {
+                          const int     nd = sub_face[s] / 2;
+                          const double *ba = &bbox[(size_t)p * 2 * dim];
+                          const double  ia = 1.0 / (ba[dim + nd] - ba[nd]);
+                          if (q >= 0)
+                            {
+                              const double *bb = &bbox[(size_t)q * 2 * dim];
+                              sigma            = C * (ia + 1.0 / (bb[dim + nd] - bb[nd]));
+                            }
+                          else
+                            sigma = 4.0 * C * ia;
+                          break;
+                        }
+                      default:
+                        sigma = C / hp;
+                    }
+                  fl_sub_sigma.push_back(sigma);
+                }
+              fl_sub_ptr.push_back((int64_t)fl_sub_cell.size());
+            }
+        }
+      block_pattern(fl_brow_ptr, fl_bcol);
+
+      d                  = pd_mesh_desc{};
+      d.dim              = dim;
+      d.fe_degree        = fe_degree;
+      d.n_q1d            = n_q1d;
+      d.n_q1d_face       = n_q1d_face;
+      d.n_verts          = grid->n_verts();
+      d.verts            = grid->verts.data();
+      d.n_cells          = grid->n_cells();
+      d.cell_verts       = grid->cell_verts.data();
+      d.n_polytopes      = np;
+      d.poly_subcell_ptr = subcell_ptr.data();
+      d.poly_subcell_idx = subcell_idx.data();
+      d.bbox             = bbox.data();
+      d.dof_block        = dof_block.data();
+      d.n_ifaces         = (int32_t)fl_polyA.size();
+      d.iface_polyA      = fl_polyA.data();
+      d.iface_polyB      = fl_polyB.data();
+      d.iface_sub_ptr    = fl_sub_ptr.data();
+      d.sub_cell         = fl_sub_cell.data();
+      d.sub_face         = fl_sub_face.data();
+      d.sub_sigma        = fl_sub_sigma.data();
+      d.n_block_rows     = np;
+      d.brow_ptr         = fl_brow_ptr.data();
+      d.bcol_idx         = fl_bcol.data();
+    }
+
+    Grid     *grid;
+    int       dim;
+    int32_t   fe_degree = -1, dofs_per_cell = 0, n_q1d = 0, n_q1d_face = 0;
+    bool      connectivity_ready = false;
+
+    std::vector<int32_t> poly_of_cell; // -1: cell not agglomerated
+    std::vector<int32_t> masters;      // master cell of each polytope (define order)
+    std::vector<int64_t> subcell_ptr;
+    std::vector<int32_t> subcell_idx;
+    std::vector<double>  bbox;
+    std::vector<int32_t> dof_block, block_to_poly;
+
+    // polytope faces in the reference's discovery order
+    std::vector<int64_t>  face_ptr;     // [np+1]
+    std::vector<int32_t>  face_nbr;     // neighbour polytope or -1 (boundary)
+    std::vector<uint32_t> face_nofn;    // neighbor_of_agglomerated_neighbor
+    std::vector<int64_t>  face_sub_ptr; // [n_faces_total+1]
+    std::vector<int32_t>  sub_cell, sub_face;
+
+  private:
+    // Face enumeration with the ordering of
+    // source/agglomeration_handler.cc:1253-1645: walk the sub-cells (slaves...,
+    // master) and their local faces; the first sight of a neighbouring polytope
+    // opens the next face index; all physical-boundary sub-faces share one face.
+    // The (cell, face) list of an interface is recorded in the traversal order of
+    // whichever of the two polytopes is set up FIRST (define order) and mirrored
+    // for the other one -- which is what the reference's global visited set
+    // yields (:1370-1397).
+    void
+    setup_connectivity_of_agglomeration()
+    {
+      for (int64_t c = 0; c < grid->n_cells(); ++c)
+        if (poly_of_cell[c] < 0)
+          throw Error(PD_ERR_INVALID,
+                      "cell " + std::to_string(c) +
+                        " belongs to no agglomerate (define singletons with define_agglomerate({cell}))");
+      const int32_t np  = n_polytopes();
+      const int     fpc = 2 * dim;
+      face_ptr.assign(np + 1, 0);
+      face_nbr.clear();
+      std::vector<int32_t>              stamp(np, -1), slot(np, -1);
+      std::vector<std::vector<int32_t>> own_cells, own_faces; // per global face, own traversal order
+      for (int32_t p = 0; p < np; ++p)
+        {
+          const int64_t f0       = (int64_t)face_nbr.size();
+          int32_t       bnd_slot = -1;
+          for (int64_t s = subcell_ptr[p]; s < subcell_ptr[p + 1]; ++s)
+            {
+              const int32_t c = subcell_idx[s];
+              for (int f = 0; f < fpc; ++f)
+                {
+                  const int32_t nc = grid->nbr[(size_t)c * fpc + f];
+                  int32_t       fs;
+                  if (nc < 0)
+                    {
+                      if (bnd_slot < 0)
+                        {
+                          bnd_slot = (int32_t)(face_nbr.size() - f0);
+                          face_nbr.push_back(-1);
+                          own_cells.emplace_back();
+                          own_faces.emplace_back();
+                        }
+                      fs = bnd_slot;
+                    }
+                  else
+                    {
+                      const int32_t q = poly_of_cell[nc];
+                      if (q == p)
+                        continue;
+                      if (stamp[q] != p)
+                        {
+                          stamp[q] = p;
+                          slot[q]  = (int32_t)(face_nbr.size() - f0);
+                          face_nbr.push_back(q);
+                          own_cells.emplace_back();
+                          own_faces.emplace_back();
+                        }
+                      fs = slot[q];
+                    }
+                  own_cells[f0 + fs].push_back(c);
+                  own_faces[f0 + fs].push_back(f);
+                }
+            }
+          face_ptr[p + 1] = (int64_t)face_nbr.size();
+        }
+      // neighbor_of_agglomerated_neighbor
+      const int64_t nf = (int64_t)face_nbr.size();
+      face_nofn.assign(nf, PD_INVALID_UINT);
+      for (int32_t p = 0; p < np; ++p)
+        for (int64_t fi = face_ptr[p]; fi < face_ptr[p + 1]; ++fi)
+          {
+            const int32_t q = face_nbr[fi];
+            if (q < 0)
+              continue;
+            for (int64_t gi = face_ptr[q]; gi < face_ptr[q + 1]; ++gi)
+              if (face_nbr[gi] == p)
+                {
+                  face_nofn[fi] = (uint32_t)(gi - face_ptr[q]);
+                  break;
+                }
+          }
+      // sub-face lists: own order if this side is set up first, else mirrored
+      face_sub_ptr.assign(nf + 1, 0);
+      sub_cell.clear();
+      sub_face.clear();
+      for (int32_t p = 0; p < np; ++p)
+        for (int64_t fi = face_ptr[p]; fi < face_ptr[p + 1]; ++fi)
+          {
+            const int32_t q = face_nbr[fi];
+            if (q < 0 || p < q)
+              {
+                sub_cell.insert(sub_cell.end(), own_cells[fi].begin(), own_cells[fi].end());
+                sub_face.insert(sub_face.end(), own_faces[fi].begin(), own_faces[fi].end());
+              }
+            else
+              {
+                const int64_t gi = face_ptr[q] + face_nofn[fi];
+                for (size_t k = 0; k < own_cells[gi].size(); ++k)
+                  {
+                    const int32_t c = own_cells[gi][k], f = own_faces[gi][k];
+                    sub_cell.push_back(grid->nbr[(size_t)c * fpc + f]);
+                    sub_face.push_back(f ^ 1); // neighbor_of_neighbor, standard orientation
+                  }
+              }
+            face_sub_ptr[fi + 1] = (int64_t)sub_cell.size();
+          }
+      connectivity_ready = true;
+    }
+
+    // storage behind flatten()
+    std::vector<int32_t> fl_polyA, fl_polyB, fl_sub_cell, fl_sub_face, fl_bcol;
+    std::vector<int64_t> fl_sub_ptr, fl_brow_ptr;
+    std::vector<double>  fl_sub_sigma;
+  };
+} // namespace pd

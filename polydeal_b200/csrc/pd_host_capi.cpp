@@ -1,0 +1,364 @@
+// -----------------------------------------------------------------------------
+// pd_host_capi.cpp -- C ABI of the host mirror (include/polydeal_b200.h, pdh_*).
+// -----------------------------------------------------------------------------
+#include "pd_host.hpp"
+
+#include <cstring>
+#include <memory>
+
+namespace pd
+{
+  void set_last_error(const std::string &m);
+}
+
+struct pdh_grid
+{
+  pd::Grid g;
+};
+struct pdh_handler
+{
+  std::unique_ptr<pd::AgglomerationHandler> ah;
+};
+
+namespace
+{
+  template <class F>
+  int
+  guarded(F &&f)
+  {
+    try
+      {
+        f();
+        return PD_OK;
+      }
+    catch (const pd::Error &e)
+      {
+        pd::set_last_error(e.what());
+        return e.code;
+      }
+    catch (const std::exception &e)
+      {
+        pd::set_last_error(e.what());
+        return PD_ERR_INVALID;
+      }
+  }
+  pd::AgglomerationHandler &
+  H(const pdh_handler *ah)
+  {
+    if (!ah || !ah->ah)
+      throw pd::Error(PD_ERR_INVALID, "null handler");
+    return *ah->ah;
+  }
+} // namespace
+
+extern "C"
+{
+  int
+  pdh_grid_create_structured(int32_t dim, const int32_t *n, const double *lo, const double *hi, int32_t order, pdh_grid **out)
+  {
+    return guarded([&] {
+      if (!n || !lo || !hi || !out)
+        throw pd::Error(PD_ERR_INVALID, "null argument");
+      std::unique_ptr<pdh_grid> g(new pdh_grid);
+      g->g.make_structured(dim, n, lo, hi, order);
+      *out = g.release();
+    });
+  }
+
+  int
+  pdh_grid_create(int32_t dim, int64_t n_verts, const double *verts, int64_t n_cells, const int32_t *cell_verts,
+                  const int32_t *nbr, pdh_grid **out)
+  {
+    return guarded([&] {
+      if (!verts || !cell_verts || !nbr || !out || (dim != 2 && dim != 3) || n_verts <= 0 || n_cells <= 0)
+        throw pd::Error(PD_ERR_INVALID, "pdh_grid_create: bad argument");
+      std::unique_ptr<pdh_grid> g(new pdh_grid);
+      g->g.dim = dim;
+      g->g.verts.assign(verts, verts + n_verts * dim);
+      g->g.cell_verts.assign(cell_verts, cell_verts + (n_cells << dim));
+      g->g.nbr.assign(nbr, nbr + n_cells * 2 * dim);
+      for (int32_t v : g->g.cell_verts)
+        if (v < 0 || v >= n_verts)
+          throw pd::Error(PD_ERR_INVALID, "pdh_grid_create: vertex index out of range");
+      for (int32_t c : g->g.nbr)
+        if (c < -1 || c >= n_cells)
+          throw pd::Error(PD_ERR_INVALID, "pdh_grid_create: neighbour index out of range");
+      *out = g.release();
+    });
+  }
+
+  int
+  pdh_grid_destroy(pdh_grid *g)
+  {
+    delete g;
+    return PD_OK;
+  }
+  int64_t
+  pdh_grid_n_cells(const pdh_grid *g)
+  {
+    return g ? g->g.n_cells() : 0;
+  }
+  int64_t
+  pdh_grid_n_verts(const pdh_grid *g)
+  {
+    return g ? g->g.n_verts() : 0;
+  }
+  int
+  pdh_grid_set_vertices(pdh_grid *g, const double *verts)
+  {
+    return guarded([&] {
+      if (!g || !verts)
+        throw pd::Error(PD_ERR_INVALID, "null argument");
+      std::memcpy(g->g.verts.data(), verts, g->g.verts.size() * sizeof(double));
+    });
+  }
+  int
+  pdh_grid_get_arrays(const pdh_grid *g, double *verts, int32_t *cell_verts, int32_t *nbr)
+  {
+    return guarded([&] {
+      if (!g)
+        throw pd::Error(PD_ERR_INVALID, "null argument");
+      if (verts)
+        std::memcpy(verts, g->g.verts.data(), g->g.verts.size() * sizeof(double));
+      if (cell_verts)
+        std::memcpy(cell_verts, g->g.cell_verts.data(), g->g.cell_verts.size() * sizeof(int32_t));
+      if (nbr)
+        std::memcpy(nbr, g->g.nbr.data(), g->g.nbr.size() * sizeof(int32_t));
+    });
+  }
+
+  int
+  pdh_handler_create(pdh_grid *g, pdh_handler **out)
+  {
+    return guarded([&] {
+      if (!g || !out)
+        throw pd::Error(PD_ERR_INVALID, "null argument");
+      std::unique_ptr<pdh_handler> h(new pdh_handler);
+      h->ah.reset(new pd::AgglomerationHandler(&g->g));
+      *out = h.release();
+    });
+  }
+  int
+  pdh_handler_destroy(pdh_handler *ah)
+  {
+    delete ah;
+    return PD_OK;
+  }
+  int32_t
+  pdh_define_agglomerate(pdh_handler *ah, const int32_t *cells, int32_t n)
+  {
+    int32_t r  = -1;
+    const int e = guarded([&] { r = H(ah).define_agglomerate(cells, n); });
+    return e == PD_OK ? r : e;
+  }
+  int
+  pdh_initialize_fe_values(pdh_handler *ah, int32_t nq_cell, int32_t nq_face)
+  {
+    return guarded([&] { H(ah).initialize_fe_values(nq_cell, nq_face); });
+  }
+  int
+  pdh_distribute_agglomerated_dofs(pdh_handler *ah, int32_t fe_kind, int32_t degree)
+  {
+    return guarded([&] { H(ah).distribute_agglomerated_dofs(fe_kind, degree); });
+  }
+  int32_t
+  pdh_n_polytopes(const pdh_handler *ah)
+  {
+    return ah && ah->ah ? ah->ah->n_polytopes() : 0;
+  }
+  int64_t
+  pdh_n_dofs(const pdh_handler *ah)
+  {
+    return ah && ah->ah ? ah->ah->n_dofs() : 0;
+  }
+  int32_t
+  pdh_n_dofs_per_cell(const pdh_handler *ah)
+  {
+    return ah && ah->ah ? ah->ah->dofs_per_cell : 0;
+  }
+  int32_t
+  pdh_master_cell(const pdh_handler *ah, int32_t poly)
+  {
+    int32_t r  = -1;
+    const int e = guarded([&] {
+      H(ah).check_poly(poly);
+      r = H(ah).masters[poly];
+    });
+    return e == PD_OK ? r : e;
+  }
+  int32_t
+  pdh_n_background_cells(const pdh_handler *ah, int32_t poly)
+  {
+    int32_t r  = -1;
+    const int e = guarded([&] {
+      H(ah).check_poly(poly);
+      r = (int32_t)(H(ah).subcell_ptr[poly + 1] - H(ah).subcell_ptr[poly]);
+    });
+    return e == PD_OK ? r : e;
+  }
+  int
+  pdh_get_agglomerate(const pdh_handler *ah, int32_t poly, int32_t *cells)
+  {
+    return guarded([&] {
+      auto &h = H(ah);
+      h.check_poly(poly);
+      std::copy(h.subcell_idx.begin() + h.subcell_ptr[poly], h.subcell_idx.begin() + h.subcell_ptr[poly + 1], cells);
+    });
+  }
+  uint32_t
+  pdh_n_faces(const pdh_handler *ah, int32_t poly)
+  {
+    uint32_t r = PD_INVALID_UINT;
+    guarded([&] {
+      auto &h = H(ah);
+      h.check_poly(poly);
+      h.require_connectivity();
+      r = h.n_faces(poly);
+    });
+    return r;
+  }
+  int32_t
+  pdh_at_boundary(const pdh_handler *ah, int32_t poly, uint32_t f)
+  {
+    int32_t r  = -1;
+    const int e = guarded([&] {
+      H(ah).check_face(poly, f);
+      r = H(ah).at_boundary(poly, f) ? 1 : 0;
+    });
+    return e == PD_OK ? r : e;
+  }
+  int32_t
+  pdh_neighbor(const pdh_handler *ah, int32_t poly, uint32_t f)
+  {
+    int32_t r = -1;
+    guarded([&] {
+      H(ah).check_face(poly, f);
+      r = H(ah).neighbor(poly, f);
+    });
+    return r;
+  }
+  uint32_t
+  pdh_neighbor_of_agglomerated_neighbor(const pdh_handler *ah, int32_t poly, uint32_t f)
+  {
+    uint32_t r = PD_INVALID_UINT;
+    guarded([&] {
+      H(ah).check_face(poly, f);
+      r = H(ah).neighbor_of_agglomerated_neighbor(poly, f);
+    });
+    return r;
+  }
+  int32_t
+  pdh_interface(const pdh_handler *ah, int32_t poly, uint32_t f, int32_t *cells, int32_t *faces, int32_t cap)
+  {
+    int32_t r  = -1;
+    const int e = guarded([&] {
+      auto &h = H(ah);
+      h.check_face(poly, f);
+      const int64_t fi = h.face_ptr[poly] + f;
+      const int64_t s0 = h.face_sub_ptr[fi], s1 = h.face_sub_ptr[fi + 1];
+      for (int64_t s = s0; s < s1 && s - s0 < cap; ++s)
+        {
+          cells[s - s0] = h.sub_cell[s];
+          faces[s - s0] = h.sub_face[s];
+        }
+      r = (int32_t)(s1 - s0);
+    });
+    return e == PD_OK ? r : e;
+  }
+  int
+  pdh_get_dof_indices(const pdh_handler *ah, int32_t poly, uint32_t *dofs)
+  {
+    return guarded([&] {
+      auto &h = H(ah);
+      h.check_poly(poly);
+      if (h.dofs_per_cell <= 0)
+        throw pd::Error(PD_ERR_STATE, "DoFs have not been distributed");
+      for (int32_t i = 0; i < h.dofs_per_cell; ++i)
+        dofs[i] = (uint32_t)(h.dof_block[poly] * h.dofs_per_cell + i);
+    });
+  }
+  int
+  pdh_bounding_box(const pdh_handler *ah, int32_t poly, double *lo, double *hi)
+  {
+    return guarded([&] {
+      auto &h = H(ah);
+      h.check_poly(poly);
+      for (int d = 0; d < h.dim; ++d)
+        {
+          lo[d] = h.bbox[(size_t)poly * 2 * h.dim + d];
+          hi[d] = h.bbox[(size_t)poly * 2 * h.dim + h.dim + d];
+        }
+    });
+  }
+  double
+  pdh_diameter(const pdh_handler *ah, int32_t poly)
+  {
+    double r = -1;
+    guarded([&] {
+      H(ah).check_poly(poly);
+      r = H(ah).diameter(poly);
+    });
+    return r;
+  }
+  double
+  pdh_volume(const pdh_handler *ah, int32_t poly)
+  {
+    double r = -1;
+    guarded([&] {
+      H(ah).check_poly(poly);
+      r = H(ah).volume(poly);
+    });
+    return r;
+  }
+  int64_t
+  pdh_sparsity_nnz(const pdh_handler *ah)
+  {
+    int64_t r = -1;
+    guarded([&] {
+      std::vector<int64_t> bp;
+      std::vector<int32_t> bc;
+      H(ah).block_pattern(bp, bc);
+      r = (int64_t)bc.size() * H(ah).dofs_per_cell * H(ah).dofs_per_cell;
+    });
+    return r;
+  }
+  int
+  pdh_create_agglomeration_sparsity_pattern(const pdh_handler *ah, int64_t *rowptr, int32_t *cols)
+  {
+    return guarded([&] {
+      auto                &h = H(ah);
+      std::vector<int64_t> bp;
+      std::vector<int32_t> bc;
+      h.block_pattern(bp, bc);
+      const int n = h.dofs_per_cell;
+      int64_t   k = 0;
+      rowptr[0]   = 0;
+      for (int32_t b = 0; b < h.n_polytopes(); ++b)
+        for (int i = 0; i < n; ++i)
+          {
+            for (int64_t e = bp[b]; e < bp[b + 1]; ++e)
+              for (int j = 0; j < n; ++j)
+                cols[k++] = bc[e] * n + j;
+            rowptr[(int64_t)b * n + i + 1] = k;
+          }
+    });
+  }
+  int
+  pdh_flatten(pdh_handler *ah, const pdh_flatten_params *prm, pd_mesh_desc *out)
+  {
+    return guarded([&] {
+      if (!prm || !out)
+        throw pd::Error(PD_ERR_INVALID, "null argument");
+      H(ah).flatten(*prm, *out);
+    });
+  }
+  int
+  pdh_create_device(pdh_handler *ah, const pdh_flatten_params *prm, pd_handle **out)
+  {
+    pd_mesh_desc d;
+    const int    e = pdh_flatten(ah, prm, &d);
+    if (e != PD_OK)
+      return e;
+    return pd_create(&d, out);
+  }
+}

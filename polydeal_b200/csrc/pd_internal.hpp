@@ -1,0 +1,129 @@
+// -----------------------------------------------------------------------------
+// pd_internal.hpp -- device-side state behind a pd_handle and launch prototypes.
+// -----------------------------------------------------------------------------
+#pragma once
+#include "../../include/polydeal_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pd
+{
+  void set_last_error(const std::string &m);
+
+  struct CudaError
+  {
+    cudaError_t e;
+    const char *what;
+    int         line;
+  };
+
+#define PD_CUDA(call)                                             \
+  do                                                              \
+    {                                                             \
+      cudaError_t e__ = (call);                                   \
+      if (e__ != cudaSuccess)                                     \
+        throw ::pd::CudaError{e__, #call, __LINE__};              \
+    }                                                             \
+  while (0)
+
+  // 1-D Lagrange basis of FE_DGQ(p) on the Gauss-Lobatto nodes of [0,1]
+  // (deal.II FE_DGQ; accepted by source/agglomeration_handler.cc:331-332),
+  // in product form  l_a(x) = w_a prod_{b != a} (x - x_b)
+  struct Basis1D
+  {
+    double node[6];
+    double wprod[6];
+  };
+  // Gauss-Legendre rule on [0,1] (deal.II QGauss<1>)
+  struct Quad1D
+  {
+    double x[8];
+    double w[8];
+  };
+  void make_basis_1d(int degree, Basis1D &b);
+  void make_gauss_1d(int n, Quad1D &q);
+
+  template <class T>
+  struct DevBuf
+  {
+    T     *p = nullptr;
+    size_t n = 0;
+    void
+    alloc(size_t count)
+    {
+      release();
+      n = count;
+      if (count)
+        PD_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void
+    release()
+    {
+      if (p)
+        cudaFree(p);
+      p = nullptr;
+      n = 0;
+    }
+    ~DevBuf()
+    {
+      release();
+    }
+    DevBuf()                          = default;
+    DevBuf(const DevBuf &)            = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+  };
+} // namespace pd
+
+struct pd_handle
+{
+  int     dim = 0, degree = 0, n1 = 0, n = 0; // n = dofs per polytope
+  int     nq1 = 0, nq1f = 0, nqc = 0, nqf = 0;
+  int64_t n_verts = 0, n_cells = 0, n_subcells = 0, n_subfaces = 0;
+  int32_t np = 0, n_ifaces = 0;
+  int64_t Q = 0, Qf = 0; // total volume / face quadrature points
+  int64_t n_blocks = 0, nnz = 0, n_dofs = 0;
+  int32_t n_vitems = 0;
+
+  pd::Basis1D basis{};
+  pd::Quad1D  quad{}, quadf{};
+
+  // descriptor arrays
+  pd::DevBuf<double>  verts, bbox, sub_sigma;
+  pd::DevBuf<int32_t> cell_verts, subcell_idx, dof_block, ifA, ifB, sub_cell, sub_face, bcol;
+  pd::DevBuf<int64_t> subcell_ptr, if_sub_ptr, brow_ptr;
+  // derived index data
+  pd::DevBuf<int64_t> diag_base, if_baseAB, if_baseBA, vitem_q0, vitem_q1, poly_vitem_ptr, padj_ptr, padj;
+  pd::DevBuf<int32_t> row_stride, vitem_poly; // row_stride[b] = (#blocks in block row b) * n
+  // quadrature (SoA by coordinate)
+  pd::DevBuf<double> vq_x, vq_w, fq_x, fq_n, fq_w;
+  // work buffers and result
+  pd::DevBuf<double> vol_partial, face_diag, values;
+  pd::DevBuf<double> vec_a, vec_b; // staging for pd_vmult_host
+
+  std::vector<int64_t> h_brow_ptr;
+  std::vector<int32_t> h_bcol, h_dof_block;
+
+  cudaStream_t stream     = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t  ev[5]      = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float        last_ms[4] = {0, 0, 0, 0};
+  bool         quad_valid = false, assembled = false;
+  int64_t      launches   = 0;
+  int          sm_count   = 148;
+};
+
+namespace pd
+{
+  // pd_geometry.cu
+  void launch_quadrature(pd_handle *h);
+  // pd_assemble.cu
+  void launch_assemble(pd_handle *h, uint32_t flags, const pd_coefficients &coef);
+  bool assemble_supported(int dim, int degree);
+  // pd_vmult.cu
+  void launch_spmv(pd_handle *h, const double *src, double *dst, bool add);
+  void launch_diagonal_inverse(pd_handle *h, double *dst);
+} // namespace pd

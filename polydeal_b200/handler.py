@@ -1,0 +1,327 @@
+"""Python mirror of the reference surface for the hot path.
+
+Names, argument meaning and error behaviour follow
+  AgglomerationHandler   /root/reference/include/agglomeration_handler.h:171-575
+  AgglomerationAccessor  /root/reference/include/agglomeration_accessor.h:41-299
+  PolyUtils::assemble_dg_matrix  /root/reference/include/poly_utils.h:2000-2195
+  LinearOperatorMG::vmult / m() / n()  /root/reference/include/linear_operator_for_mg.h:295-357
+Everything forwards to the C ABI; polytopes are addressed by `polytope->index()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Grid:
+    """Background quad/hex mesh in deal.II conventions."""
+
+    def __init__(self, handle, dim):
+        self._h, self.dim = handle, dim
+
+    @staticmethod
+    def structured(dim, n, lo, hi, order=0):
+        n = np.ascontiguousarray(np.broadcast_to(n, (dim,)), dtype=np.int32)
+        lo = np.ascontiguousarray(np.broadcast_to(lo, (dim,)), dtype=np.float64)
+        hi = np.ascontiguousarray(np.broadcast_to(hi, (dim,)), dtype=np.float64)
+        h = C.c_void_p()
+        K.check(K.lib().pdh_grid_create_structured(dim, _ptr(n), _ptr(lo), _ptr(hi), order, C.byref(h)))
+        return Grid(h, dim)
+
+    @staticmethod
+    def hyper_cube(dim, a, b, n_refine):
+        """GridGenerator::hyper_cube(tria, a, b); tria.refine_global(n_refine)."""
+        return Grid.structured(dim, 1 << n_refine, a, b, order=0)
+
+    @staticmethod
+    def from_arrays(verts, cell_verts, nbr):
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        cell_verts = np.ascontiguousarray(cell_verts, dtype=np.int32)
+        nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+        dim = verts.shape[1]
+        h = C.c_void_p()
+        K.check(K.lib().pdh_grid_create(dim, verts.shape[0], _ptr(verts), cell_verts.shape[0], _ptr(cell_verts), _ptr(nbr), C.byref(h)))
+        return Grid(h, dim)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and K._lib is not None:
+            K._lib.pdh_grid_destroy(self._h)
+            self._h = None
+
+    @property
+    def n_cells(self):
+        return K.lib().pdh_grid_n_cells(self._h)
+
+    @property
+    def n_verts(self):
+        return K.lib().pdh_grid_n_verts(self._h)
+
+    def arrays(self):
+        v = np.empty((self.n_verts, self.dim))
+        cv = np.empty((self.n_cells, 1 << self.dim), dtype=np.int32)
+        nb = np.empty((self.n_cells, 2 * self.dim), dtype=np.int32)
+        K.check(K.lib().pdh_grid_get_arrays(self._h, _ptr(v), _ptr(cv), _ptr(nb)))
+        return v, cv, nb
+
+    def set_vertices(self, verts):
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        assert verts.shape == (self.n_verts, self.dim)
+        K.check(K.lib().pdh_grid_set_vertices(self._h, _ptr(verts)))
+
+
+class AgglomerationHandler:
+    def __init__(self, grid: Grid):
+        self.grid, self.dim = grid, grid.dim
+        self._h = C.c_void_p()
+        K.check(K.lib().pdh_handler_create(grid._h, C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and K._lib is not None:
+            K._lib.pdh_handler_destroy(self._h)
+            self._h = None
+
+    def define_agglomerate(self, cells):
+        a = np.ascontiguousarray(cells, dtype=np.int32)
+        r = K.lib().pdh_define_agglomerate(self._h, _ptr(a), len(a))
+        if r < 0:
+            K.check(r)
+        return r
+
+    def initialize_fe_values(self, nq_cell, nq_face=None):
+        K.check(K.lib().pdh_initialize_fe_values(self._h, nq_cell, nq_face if nq_face is not None else nq_cell))
+
+    def distribute_agglomerated_dofs(self, fe_kind, degree):
+        K.check(K.lib().pdh_distribute_agglomerated_dofs(self._h, fe_kind, degree))
+
+    n_polytopes = property(lambda s: K.lib().pdh_n_polytopes(s._h))
+    n_dofs = property(lambda s: K.lib().pdh_n_dofs(s._h))
+    n_dofs_per_cell = property(lambda s: K.lib().pdh_n_dofs_per_cell(s._h))
+
+    def _int(self, r):
+        if r < -1:
+            K.check(r)
+        return r
+
+    def master_cell(self, p):
+        r = K.lib().pdh_master_cell(self._h, p)
+        if r < 0:
+            K.check(r)
+        return r
+
+    def get_agglomerate(self, p):
+        n = K.lib().pdh_n_background_cells(self._h, p)
+        if n < 0:
+            K.check(n)
+        out = np.empty(n, dtype=np.int32)
+        K.check(K.lib().pdh_get_agglomerate(self._h, p, _ptr(out)))
+        return out
+
+    def n_faces(self, p):
+        r = K.lib().pdh_n_faces(self._h, p)
+        if r == K.INVALID_UINT:
+            raise K.PolydealError(K.PD_ERR_INVALID, K.lib().pd_last_error().decode())
+        return r
+
+    def at_boundary(self, p, f):
+        r = K.lib().pdh_at_boundary(self._h, p, f)
+        if r < 0:
+            K.check(r)
+        return bool(r)
+
+    def neighbor(self, p, f):
+        if f >= self.n_faces(p):
+            raise K.PolydealError(K.PD_ERR_INVALID, "face index out of range")
+        return K.lib().pdh_neighbor(self._h, p, f)
+
+    def neighbor_of_agglomerated_neighbor(self, p, f):
+        if f >= self.n_faces(p):
+            raise K.PolydealError(K.PD_ERR_INVALID, "face index out of range")
+        return K.lib().pdh_neighbor_of_agglomerated_neighbor(self._h, p, f)
+
+    def interface(self, p, f):
+        n = K.lib().pdh_interface(self._h, p, f, None, None, 0)
+        if n < 0:
+            K.check(n)
+        c, fa = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        K.lib().pdh_interface(self._h, p, f, _ptr(c), _ptr(fa), n)
+        return list(zip(c.tolist(), fa.tolist()))
+
+    def get_dof_indices(self, p):
+        out = np.empty(self.n_dofs_per_cell, dtype=np.uint32)
+        K.check(K.lib().pdh_get_dof_indices(self._h, p, _ptr(out)))
+        return out
+
+    def bbox(self, p):
+        lo, hi = np.empty(self.dim), np.empty(self.dim)
+        K.check(K.lib().pdh_bounding_box(self._h, p, _ptr(lo), _ptr(hi)))
+        return lo, hi
+
+    def diameter(self, p):
+        return K.lib().pdh_diameter(self._h, p)
+
+    def volume(self, p):
+        return K.lib().pdh_volume(self._h, p)
+
+    def create_agglomeration_sparsity_pattern(self):
+        nnz = K.lib().pdh_sparsity_nnz(self._h)
+        if nnz < 0:
+            raise K.PolydealError(K.PD_ERR_STATE, K.lib().pd_last_error().decode())
+        rp = np.empty(self.n_dofs + 1, dtype=np.int64)
+        cols = np.empty(nnz, dtype=np.int32)
+        K.check(K.lib().pdh_create_agglomeration_sparsity_pattern(self._h, _ptr(rp), _ptr(cols)))
+        return rp, cols
+
+    def flatten(self, penalty_constant=-1.0, h_rule=K.H_DIAMETER_OF_VISITOR, h_const=1.0, visit_rule=K.VISIT_BY_ID):
+        """The flattened agglomeration as a pd_mesh_desc (arrays owned by this handler)."""
+        prm = K.FlattenParams(penalty_constant, h_rule, h_const, visit_rule)
+        d = K.MeshDesc()
+        K.check(K.lib().pdh_flatten(self._h, C.byref(prm), C.byref(d)))
+        return d
+
+
+class SIPOperator:
+    """Device-resident SIP operator: assembled block-CSR matrix + apply.
+
+    Plays the role of the matrix/LinearOperatorMG the reference's solvers call
+    (vmult / vmult_add / Tvmult / m / n / get_matrix_diagonal_inverse)."""
+
+    def __init__(self, desc: K.MeshDesc, keepalive=None):
+        self._keep = keepalive
+        self.desc = desc
+        self._h = C.c_void_p()
+        K.check(K.lib().pd_create(C.byref(desc), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and K._lib is not None:
+            K._lib.pd_destroy(self._h)
+            self._h = None
+
+    def upload(self, desc=None):
+        K.check(K.lib().pd_upload(self._h, C.byref(desc if desc is not None else self.desc)))
+
+    def set_stream(self, cuda_stream_ptr):
+        K.check(K.lib().pd_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        K.check(K.lib().pd_synchronize(self._h))
+
+    def build_quadrature(self):
+        K.check(K.lib().pd_build_quadrature(self._h))
+
+    def assemble(self, flags=K.ASSEMBLE_ALL, stiffness=1.0, mass=0.0):
+        c = K.Coefficients(stiffness, mass)
+        K.check(K.lib().pd_assemble(self._h, flags, C.byref(c)))
+
+    def m(self):
+        return K.lib().pd_n_dofs(self._h)
+
+    n = m
+
+    @property
+    def nnz(self):
+        return K.lib().pd_nnz(self._h)
+
+    @property
+    def n_dofs_per_cell(self):
+        return K.lib().pd_n_dofs_per_cell(self._h)
+
+    def values_device_ptr(self):
+        p = C.c_void_p()
+        K.check(K.lib().pd_matrix_values_device(self._h, C.byref(p)))
+        return p.value
+
+    def values(self, out=None):
+        if out is None:
+            out = np.empty(self.nnz)
+        K.check(K.lib().pd_matrix_values_to_host(self._h, _ptr(out)))
+        return out
+
+    def values_to_host_ptr(self, host_ptr):
+        K.check(K.lib().pd_matrix_values_to_host(self._h, C.c_void_p(host_ptr)))
+
+    def pattern(self):
+        rp = np.empty(self.m() + 1, dtype=np.int64)
+        cols = np.empty(self.nnz, dtype=np.int32)
+        K.check(K.lib().pd_matrix_pattern_to_host(self._h, _ptr(rp), _ptr(cols)))
+        return rp, cols
+
+    def scipy(self):
+        import scipy.sparse as sp
+
+        rp, cols = self.pattern()
+        return sp.csr_matrix((self.values(), cols, rp), shape=(self.m(), self.m()))
+
+    # --- apply: device pointers (ints, e.g. torch.Tensor.data_ptr()) or host numpy arrays
+    def vmult_ptr(self, dst_ptr, src_ptr, mode=K.VMULT_BLOCK_CSR, add=False):
+        fn = K.lib().pd_vmult_add if add else K.lib().pd_vmult
+        K.check(fn(self._h, mode, C.c_void_p(src_ptr), C.c_void_p(dst_ptr)))
+
+    def vmult(self, dst, src, mode=K.VMULT_BLOCK_CSR):
+        """dst = A src.  torch CUDA tensors (float64, contiguous) stay on the device;
+        numpy arrays go through pd_vmult_host (H2D, apply, D2H)."""
+        if isinstance(src, np.ndarray):
+            assert src.dtype == np.float64 and dst.dtype == np.float64 and src.flags.c_contiguous and dst.flags.c_contiguous
+            assert src.size == self.m() and dst.size == self.m()
+            K.check(K.lib().pd_vmult_host(self._h, mode, _ptr(src), _ptr(dst)))
+        else:
+            self._check_tensor(src), self._check_tensor(dst)
+            self.vmult_ptr(dst.data_ptr(), src.data_ptr(), mode)
+        return dst
+
+    def vmult_add(self, dst, src, mode=K.VMULT_BLOCK_CSR):
+        self._check_tensor(src), self._check_tensor(dst)
+        self.vmult_ptr(dst.data_ptr(), src.data_ptr(), mode, add=True)
+        return dst
+
+    # the SIP operator is symmetric (include/utils.h:431-445 does the same)
+    Tvmult = vmult
+    Tvmult_add = vmult_add
+
+    def vmult_host_ptr(self, dst_host_ptr, src_host_ptr, mode=K.VMULT_BLOCK_CSR):
+        K.check(K.lib().pd_vmult_host(self._h, mode, C.c_void_p(src_host_ptr), C.c_void_p(dst_host_ptr)))
+
+    def get_matrix_diagonal_inverse(self, out):
+        self._check_tensor(out)
+        K.check(K.lib().pd_diagonal_inverse(self._h, C.c_void_p(out.data_ptr())))
+        return out
+
+    def _check_tensor(self, t):
+        import torch
+
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == self.m()):
+            raise K.PolydealError(K.PD_ERR_INVALID, "vector must be a contiguous float64 CUDA tensor of length m()")
+
+    def copy_array(self, name):
+        cnt = C.c_int64()
+        K.check(K.lib().pd_copy_array(self._h, name.encode(), None, C.byref(cnt)))
+        out = np.empty(cnt.value)
+        K.check(K.lib().pd_copy_array(self._h, name.encode(), _ptr(out), C.byref(cnt)))
+        return out
+
+    @property
+    def launch_count(self):
+        return K.lib().pd_launch_count(self._h)
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 4)()
+        K.check(K.lib().pd_last_kernel_ms(self._h, ms))
+        return {"volume": ms[0], "faces": ms[1], "reduce": ms[2], "quadrature": ms[3]}
+
+
+def assemble_dg_matrix(ah: AgglomerationHandler, penalty_constant=-1.0, h_rule=K.H_DIAMETER_OF_VISITOR, h_const=1.0,
+                       visit_rule=K.VISIT_BY_ID, with_boundary=True, stiffness_coeff=1.0, mass_coeff=0.0) -> SIPOperator:
+    """PolyUtils::assemble_dg_matrix(system_matrix, fe_dg, ah): flattens the handler,
+    creates the device copy and assembles.  penalty_constant < 0 selects the library's
+    10 (p+dim)(p+1)."""
+    desc = ah.flatten(penalty_constant, h_rule, h_const, visit_rule)
+    op = SIPOperator(desc, keepalive=ah)
+    flags = K.ASSEMBLE_ALL if with_boundary else (K.ASSEMBLE_VOLUME | K.ASSEMBLE_INTERIOR)
+    op.assemble(flags, stiffness_coeff, mass_coeff)
+    return op

@@ -1,0 +1,269 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs, plus the reference tests' invariants evaluated on the GPU result.
+
+Tolerance (north_star): 1e-12 relative in fp64, applied per matrix block entry relative
+to the block's largest entry and per vmult output relative to max|y|."""
+import numpy as np
+import pytest
+
+import pd_scenarios as sc
+from oracle import pyoracle as po
+from pd_helpers import assert_blocks_close, groups_for, oracle_handler, product_handler, src_vector
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def gpu():
+    import polydeal_b200 as pdl
+
+    return pdl
+
+
+def both(dim, n, shape, p, nq=None, order=0, distort=None, lo=0.0, hi=1.0, seed=1):
+    nq = nq if nq is not None else p + 1
+    ogrid = po.Grid(dim, n, lo, hi, order)
+    groups = groups_for(shape, dim, n, ogrid, seed)
+    _, oah = oracle_handler(dim, n, groups, p, nq, lo=lo, hi=hi, order=order, distort=distort)
+    _, pah = product_handler(oah.grid, groups, p, nq)
+    return oah, pah
+
+
+# ----------------------------------------------------------------------------------
+# row 1: agglomerated quadrature (source/agglomeration_handler.cc:622-707, 1139-1165)
+# ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,n,shape,nq,distort", [
+    (2, 8, "random7", 2, None), (2, 8, "random7", 3, (0.25, 5)),
+    (3, 4, "random6", 2, None), (3, 4, "blocks2", 3, (0.2, 9)),
+])
+def test_quadrature_matches_oracle(dim, n, shape, nq, distort):
+    pdl = gpu()
+    oah, pah = both(dim, n, shape, 1, nq=nq, distort=distort)
+    op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+    op.build_quadrature()
+    Q = sum(len(oah.get_agglomerate(p)) for p in range(oah.n_polytopes)) * nq**dim
+    x = op.copy_array("vol_qpt").reshape(dim, Q)
+    w = op.copy_array("vol_jxw")
+    k = 0
+    for p in range(oah.n_polytopes):
+        fev = oah.reinit(p)
+        np.testing.assert_allclose(x[:, k:k + fev.n_q].T, fev.points, rtol=0, atol=4e-16)
+        np.testing.assert_allclose(w[k:k + fev.n_q], fev.JxW, rtol=1e-14, atol=0)
+        k += fev.n_q
+    assert k == Q
+    # faces: the flattened work list, visited from A
+    d = op.desc
+    A = np.ctypeslib.as_array(d.iface_polyA, (d.n_ifaces,))
+    B = np.ctypeslib.as_array(d.iface_polyB, (d.n_ifaces,))
+    Qf = int(np.ctypeslib.as_array(d.iface_sub_ptr, (d.n_ifaces + 1,))[-1]) * nq ** (dim - 1)
+    fx = op.copy_array("face_qpt").reshape(dim, Qf)
+    fn = op.copy_array("face_normal").reshape(dim, Qf)
+    fw = op.copy_array("face_jxw")
+    k = 0
+    for a, b in zip(A, B):
+        f = next(f for f in range(oah.n_faces(a)) if oah.neighbor(a, f) == b)
+        ff = oah.reinit(a, f)
+        np.testing.assert_allclose(fx[:, k:k + ff.n_q].T, ff.points, rtol=0, atol=4e-16)
+        np.testing.assert_allclose(fn[:, k:k + ff.n_q].T, ff.normals, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(fw[k:k + ff.n_q], ff.JxW, rtol=1e-14, atol=0)
+        k += ff.n_q
+    assert k == Qf
+
+
+# ----------------------------------------------------------------------------------
+# rows 2-9: assembled matrix, per block entry
+# ----------------------------------------------------------------------------------
+CASES = [
+    # dim, n, shape, p, nq, distort, kwargs
+    (2, 16, "blocks4", 1, 2, None, {}),                       # config A shape (reduced)
+    (2, 16, "random13", 1, 3, None, {}),
+    (2, 8, "random5", 2, 3, (0.2, 3), {}),
+    (2, 8, "blocks2", 3, 4, None, {}),
+    (2, 8, "random4", 4, 5, None, {}),
+    (3, 8, "blocks4", 1, 2, None, {}),
+    (3, 8, "blocks4", 2, 3, None, {}),                        # config B / D shape (reduced)
+    (3, 8, "random12", 2, 3, None, {}),
+    (3, 4, "random5", 2, 3, (0.15, 4), {}),
+    (3, 8, "blocks4", 3, 4, None, {}),                        # config C shape (reduced)
+    (3, 4, "random3", 3, 4, None, {}),
+    (3, 4, "singletons", 2, 3, None, dict(penalty_constant=6.0, h_rule=3)),  # fine-mesh LaplaceOperatorDG penalty
+    (3, 8, "blocks4", 2, 3, None, dict(mass_coeff=0.5, penalty_constant=40.0)),  # config D: reaction c=0.5, C=10p^2
+    (2, 8, "random6", 1, 3, None, dict(penalty_constant=10.0, h_rule=1, with_boundary=False)),  # sanity-check rule
+    (3, 4, "random4", 1, 2, None, dict(stiffness_coeff=1e-4, mass_coeff=1.5e4, with_boundary=False)),  # monodomain f M + sigma K
+    (2, 8, "random6", 2, 3, None, dict(visit_rule=1)),        # examples/poisson.cc: visit by index()
+]
+
+
+@pytest.mark.parametrize("dim,n,shape,p,nq,distort,kw", CASES)
+def test_assembled_matrix_matches_oracle(dim, n, shape, p, nq, distort, kw):
+    pdl = gpu()
+    oah, pah = both(dim, n, shape, p, nq=nq, distort=distort)
+    okw = dict(kw)
+    okw.setdefault("penalty_constant", None)
+    ref = po.assemble_dg_matrix(oah, degree=p, n_threads=4, **okw)
+    pkw = dict(kw)
+    pkw.setdefault("penalty_constant", -1.0)
+    op = pdl.assemble_dg_matrix(pah, **pkw)
+    rp, cols = op.pattern()
+    orp, ocols, ovals = ref.csr()
+    np.testing.assert_array_equal(rp, orp)      # sparsity bit exact
+    np.testing.assert_array_equal(cols, ocols)
+    vals = op.values()
+    assert np.isfinite(vals).all()
+    assert_blocks_close(vals, ovals, oah.n_dofs_per_cell, rp, TOL)
+    # vmult with the assembled matrix, device vectors and host vectors
+    import torch
+
+    x = src_vector(op.m())
+    yref = ref.vmult(x)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    op.vmult(yd, xd)
+    torch.cuda.synchronize()
+    op.synchronize()
+    scale = np.abs(yref).max()
+    assert np.abs(yd.cpu().numpy() - yref).max() <= TOL * scale
+    yh = np.empty_like(x)
+    op.vmult(yh, x)
+    assert np.abs(yh - yref).max() <= TOL * scale
+    op.vmult_add(yd, xd)
+    op.synchronize()
+    assert np.abs(yd.cpu().numpy() - 2 * yref).max() <= 2 * TOL * scale
+    dinv = torch.empty_like(xd)
+    op.get_matrix_diagonal_inverse(dinv)
+    op.synchronize()
+    diag = ref.scipy().diagonal()
+    np.testing.assert_allclose(dinv.cpu().numpy(), np.where(np.abs(diag) > 1e-10, 1.0 / diag, diag), rtol=1e-11)
+
+
+def test_assemble_flags_split_the_matrix():
+    """volume + boundary + interior parts add up to the full matrix."""
+    pdl = gpu()
+    from polydeal_b200 import ASSEMBLE_BOUNDARY, ASSEMBLE_INTERIOR, ASSEMBLE_VOLUME
+
+    oah, pah = both(3, 4, "random5", 2, nq=3)
+    op = pdl.assemble_dg_matrix(pah)
+    full = op.values().copy()
+    parts = np.zeros_like(full)
+    for fl in (ASSEMBLE_VOLUME, ASSEMBLE_BOUNDARY, ASSEMBLE_INTERIOR):
+        op.assemble(fl)
+        parts += op.values()
+    assert np.abs(parts - full).max() <= 1e-13 * np.abs(full).max()
+
+
+# ----------------------------------------------------------------------------------
+# the reference tests' own invariants, evaluated on the GPU result
+# ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+def test_minimal_sip_poisson_on_gpu(dim):
+    """test/polydeal/minimal_SIP_Poisson.cc: agglomerated == standard matrix to 1e-13."""
+    pdl = gpu()
+    kw = dict(penalty_constant=20.0, h_rule=pdl.H_CONSTANT, h_const=1.0, visit_rule=pdl.VISIT_BY_INDEX)
+    if dim == 2:
+        ga, gs = sc.blocks_2x2_of_4x4(), [[c] for c in range(4)]
+        na, ns = 4, 2
+    else:
+        ga, gs = [list(range(8))], [[0]]
+        na, ns = 2, 1
+    mats = []
+    for n, groups in ((na, ga), (ns, gs)):
+        ogrid = po.Grid(dim, n, -1.0, 1.0, 0)
+        _, pah = product_handler(ogrid, groups, 1, 3)
+        mats.append(pdl.assemble_dg_matrix(pah, **kw).scipy().toarray())
+    assert np.abs(mats[0] - mats[1]).max() < 1e-13
+
+
+def interpolate(pah, fun, p):
+    nodes = po.gauss_lobatto_nodes(p + 1)
+    u = np.zeros(pah.n_dofs)
+    for k in range(pah.n_polytopes):
+        lo, hi = pah.bbox(k)
+        for i, dof in enumerate(pah.get_dof_indices(k)):
+            idx = [(i // (p + 1) ** d) % (p + 1) for d in range(pah.dim)]
+            u[dof] = fun(lo + nodes[idx] * (hi - lo))
+    return u
+
+
+@pytest.mark.parametrize("n_parts", [50, 120])
+def test_poisson_sanity_check_on_gpu(n_parts, goldens):
+    """test/polydeal/poisson_sanity_check_01.cc: x'Ax = 1, (x+y)'A(x+y) = 2, 1'A1 ~ 1e-14."""
+    pdl = gpu()
+    ogrid = po.Grid(2, 64, 0.0, 1.0, 0)
+    groups = groups_for(f"random{n_parts}", 2, 64, ogrid, seed=n_parts)
+    _, pah = product_handler(ogrid, groups, 1, 3)
+    A = pdl.assemble_dg_matrix(pah, penalty_constant=10.0, h_rule=pdl.H_MAX_INVERSE_DIAMETER, with_boundary=False).scipy()
+    ux, uxy, one = interpolate(pah, lambda x: x[0], 1), interpolate(pah, lambda x: x[0] + x[1], 1), np.ones(pah.n_dofs)
+    g = goldens["poisson_sanity_check_01"]
+    assert ux @ (A @ ux) == pytest.approx(g["x"][0], abs=1e-11)
+    assert uxy @ (A @ uxy) == pytest.approx(g["xplusy"][0], abs=1e-11)
+    assert abs(one @ (A @ one)) < 1e-11
+    assert abs(A - A.T).max() < 1e-12
+
+
+# ----------------------------------------------------------------------------------
+# full BASELINE sizes through size-independent properties
+# ----------------------------------------------------------------------------------
+def test_config_b_full_size_properties():
+    """Config B (64^3 hexes, 512 polyhedra of 8^3 cells, DGQ2, QGauss(3)): too big for the
+    scalar oracle in seconds, so: symmetry, constants in the kernel of the boundary-free
+    operator, energy of u = x equals |Omega| = 1, and translation invariance (all interior
+    polytopes of the uniform `blocks` shape carry identical diagonal blocks)."""
+    pdl = gpu()
+    import torch
+
+    grid = pdl.Grid.hyper_cube(3, 0.0, 1.0, 6)
+    ah = pdl.AgglomerationHandler(grid)
+    for g in sc.block_partition(3, 64, 8):
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(3)
+    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, 2)
+    op = pdl.assemble_dg_matrix(ah, with_boundary=False)
+    A = op.scipy()
+    assert A.shape == (13824, 13824)
+    scale = abs(A).max()
+    assert abs(A - A.T).max() <= 1e-12 * scale
+    one = np.ones(op.m())
+    assert np.abs(A @ one).max() <= 1e-10 * scale
+    ux = interpolate(ah, lambda x: x[0], 2)
+    assert ux @ (A @ ux) == pytest.approx(1.0, abs=1e-10)
+    # interior polytopes: identical diagonal blocks
+    n = 27
+    D = A.toarray().reshape(512, n, 512, n)
+    blocks = sc.block_partition(3, 64, 8)
+    interior = [p for p in range(512) if all(not ah.at_boundary(p, f) for f in range(ah.n_faces(p)))]
+    assert len(interior) == 216
+    b0 = ah.get_dof_indices(interior[0])[0] // n
+    ref_block = D[b0, :, b0, :]
+    for p in interior[1:]:
+        b = ah.get_dof_indices(p)[0] // n
+        assert np.abs(D[b, :, b, :] - ref_block).max() <= 1e-11 * np.abs(ref_block).max()
+    del blocks
+    # vmult agrees with the assembled matrix applied on the host
+    x = src_vector(op.m())
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    op.vmult(yd, xd)
+    op.synchronize()
+    y = A @ x
+    assert np.abs(yd.cpu().numpy() - y).max() <= 1e-12 * np.abs(y).max()
+
+
+def test_edge_cases():
+    """single polytope covering the mesh (no interior faces), singleton polytopes only
+    (every face a 1-sub-face interface), and a two-polytope split."""
+    pdl = gpu()
+    for dim, n, shape, p in [(2, 4, "blocks4", 2), (3, 2, "singletons", 1), (2, 4, "random2", 1)]:
+        oah, pah = both(dim, n, shape, p)
+        ref = po.assemble_dg_matrix(oah, degree=p)
+        op = pdl.assemble_dg_matrix(pah)
+        rp, _ = op.pattern()
+        assert_blocks_close(op.values(), ref.values(), oah.n_dofs_per_cell, rp, TOL)
+
+
+def test_unsupported_degree_fails_loudly():
+    pdl = gpu()
+    ogrid = po.Grid(3, 2, 0.0, 1.0, 0)
+    _, pah = product_handler(ogrid, [[c] for c in range(8)], 4, 5)
+    with pytest.raises(pdl.PolydealError, match="no sm_100a kernel"):
+        pdl.assemble_dg_matrix(pah)

@@ -1,0 +1,194 @@
+"""CPU-only tests of the product's host side: the C-ABI library loads and exports
+every declared symbol, the host mirror of AgglomerationHandler reproduces the
+reference goldens and agrees bit-exactly with the oracle on irregular partitions,
+and compute entry points fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pd_scenarios as sc
+import polydeal_b200 as pdl
+from oracle import pyoracle as po
+from pd_helpers import groups_for, oracle_handler, product_handler
+from polydeal_b200 import _capi as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "polydeal_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pdh?_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) > 50
+    L = C.CDLL(K.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(K.SIGNATURES), declared ^ set(K.SIGNATURES)
+
+
+def test_rule_tables_match_oracle():
+    for n in range(1, 9):
+        x, w = np.empty(n), np.empty(n)
+        K.check(K.lib().pd_quadrature_rule_1d(n, x.ctypes.data, w.ctypes.data))
+        xo, wo = po.gauss_1d(n)
+        np.testing.assert_allclose(x, xo, rtol=0, atol=2e-16)
+        np.testing.assert_allclose(w, wo, rtol=0, atol=2e-16)
+    for p in range(1, 6):
+        x = np.empty(p + 1)
+        K.check(K.lib().pd_dgq_nodes_1d(p, x.ctypes.data))
+        np.testing.assert_allclose(x, po.gauss_lobatto_nodes(p + 1), rtol=0, atol=2e-16)
+
+
+def product_from_groups(dim, n_refine, groups, p=1, nq=2, lo=-1.0, hi=1.0):
+    grid = pdl.Grid.hyper_cube(dim, lo, hi, n_refine)
+    ah = pdl.AgglomerationHandler(grid)
+    for g in groups:
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(nq)
+    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, p)
+    return grid, ah
+
+
+def test_sparsity_agglomerated_tria_golden(goldens):
+    """test/polydeal/sparsity_agglomerated_tria.cc through the product's host mirror."""
+    _, ah = product_from_groups(2, 3, sc.standard_8x8_agglomerates())
+    rp, cols = ah.create_agglomeration_sparsity_pattern()
+    gold = goldens["sparsity_agglomerated_tria"]
+    assert ah.n_dofs == len(gold)
+    for r, row in enumerate(gold):
+        assert cols[rp[r]:rp[r + 1]].tolist() == row[1:]
+
+
+@pytest.mark.parametrize("name,n_refine,which", [("agglomerated_neighbors_01", 3, "std"), ("agglomerated_neighbors_02", 2, "blocks")])
+def test_agglomerated_neighbors_goldens(goldens, name, n_refine, which):
+    groups = sc.standard_8x8_agglomerates() if which == "std" else sc.blocks_2x2_of_4x4()
+    _, ah = product_from_groups(2, n_refine, groups)
+    for g in goldens[name]:
+        p = g["index"]
+        assert ah.n_faces(p) == g["n_faces"]
+        for f in range(g["n_faces"]):
+            if ah.at_boundary(p, f):
+                assert str(f) not in g["faces"]
+            else:
+                assert [list(t) for t in ah.interface(p, f)] == g["faces"][str(f)]
+
+
+def test_nofn_and_dofs_goldens(goldens):
+    _, ah = product_from_groups(2, 2, sc.blocks_2x2_of_4x4())
+    for p, g in enumerate(goldens["agglomerated_neighbors_03"]):
+        assert ah.master_cell(p) == g["master"]
+        assert [ah.neighbor_of_agglomerated_neighbor(p, f) for f in range(g["n_faces"])] == g["nofn"]
+    for p, g in enumerate(goldens["hp_structure_01"]):
+        assert ah.get_dof_indices(p).tolist() == g["dofs"]
+    _, ah = product_from_groups(2, 6, sc.polytope_iterator_agglomerates())
+    for g in goldens["polytope_iterator"]:
+        assert ah.n_faces(g["index"]) == 6
+        assert ah.get_dof_indices(g["index"]).tolist() == g["dofs"]
+
+
+def test_bbox_golden(goldens):
+    g = goldens["agg_handler_bbox_test"]
+    for dim, cells, (lo, hi) in [(2, [3, 6, 9, 12, 13], g[0:2]), (3, [30, 58], g[2:4])]:
+        grid = pdl.Grid.hyper_cube(dim, -1, 1, 2)
+        ah = pdl.AgglomerationHandler(grid)
+        p = ah.define_agglomerate(cells)
+        blo, bhi = ah.bbox(p)
+        assert blo.tolist() == lo and bhi.tolist() == hi
+
+
+@pytest.mark.parametrize("dim,n,shape,order", [(2, 16, "random23", 0), (2, 12, "random17", 1), (3, 8, "random40", 0), (3, 8, "blocks2", 0), (3, 6, "random11", 1)])
+def test_host_mirror_matches_oracle_bit_exactly(dim, n, shape, order):
+    """Numbering, face enumeration, aligned sub-face lists, nofn, sparsity: identical to
+    the oracle's literal restatement on irregular agglomerates."""
+    ogrid = po.Grid(dim, n, 0.0, 1.0, order)
+    groups = groups_for(shape, dim, n, ogrid, seed=dim * 100 + n)
+    _, oah = oracle_handler(dim, n, groups, 1, 2, order=order)
+    _, pah = product_handler(oah.grid, groups, 1, 2)
+    assert pah.n_polytopes == oah.n_polytopes and pah.n_dofs == oah.n_dofs
+    for p in range(oah.n_polytopes):
+        assert pah.master_cell(p) == oah.master_cell(p)
+        assert pah.get_agglomerate(p).tolist() == oah.get_agglomerate(p).tolist()
+        assert pah.get_dof_indices(p).tolist() == oah.get_dof_indices(p).tolist()
+        assert pah.n_faces(p) == oah.n_faces(p)
+        assert pah.diameter(p) == oah.diameter(p) and pah.volume(p) == oah.volume(p)
+        np.testing.assert_array_equal(np.concatenate(pah.bbox(p)), np.concatenate(oah.bbox(p)))
+        for f in range(oah.n_faces(p)):
+            assert pah.at_boundary(p, f) == oah.at_boundary(p, f)
+            assert pah.neighbor(p, f) == oah.neighbor(p, f)
+            assert pah.neighbor_of_agglomerated_neighbor(p, f) == oah.neighbor_of_agglomerated_neighbor(p, f)
+            assert pah.interface(p, f) == oah.interface(p, f)
+    rp, cols = pah.create_agglomeration_sparsity_pattern()
+    orp, ocols = oah.create_agglomeration_sparsity_pattern()
+    np.testing.assert_array_equal(rp, orp)
+    np.testing.assert_array_equal(cols, ocols)
+
+
+def test_flatten_descriptor_is_consistent():
+    ogrid = po.Grid(3, 4, 0.0, 1.0, 0)
+    groups = groups_for("random9", 3, 4, ogrid, seed=3)
+    _, oah = oracle_handler(3, 4, groups, 2, 3)
+    _, pah = product_handler(oah.grid, groups, 2, 3)
+    d = pah.flatten()
+    assert (d.dim, d.fe_degree, d.n_q1d, d.n_q1d_face, d.n_polytopes) == (3, 2, 3, 3, 9)
+    A = np.ctypeslib.as_array(d.iface_polyA, (d.n_ifaces,))
+    B = np.ctypeslib.as_array(d.iface_polyB, (d.n_ifaces,))
+    sub_ptr = np.ctypeslib.as_array(d.iface_sub_ptr, (d.n_ifaces + 1,))
+    sigma = np.ctypeslib.as_array(d.sub_sigma, (sub_ptr[-1],))
+    # every interior pair appears once, from the side with the smaller master id (poly_utils.h:2089)
+    pairs = set()
+    for a, b in zip(A, B):
+        if b >= 0:
+            assert pah.master_cell(a) < pah.master_cell(b)
+            assert (a, b) not in pairs and (b, a) not in pairs
+            pairs.add((a, b))
+    n_int = sum(1 for p in range(9) for f in range(pah.n_faces(p)) if not pah.at_boundary(p, f))
+    assert 2 * len(pairs) == n_int
+    # library penalty: 10 (p+dim)(p+1) / diameter(visitor)
+    for k, a in enumerate(A):
+        np.testing.assert_allclose(sigma[sub_ptr[k]:sub_ptr[k + 1]], 10.0 * (2 + 3) * 3 / pah.diameter(a), rtol=1e-15)
+
+
+def test_error_behaviour():
+    grid = pdl.Grid.hyper_cube(2, 0, 1, 2)
+    ah = pdl.AgglomerationHandler(grid)
+    with pytest.raises(pdl.PolydealError, match="No cells to be agglomerated"):
+        ah.define_agglomerate([])
+    ah.define_agglomerate([0, 1])
+    with pytest.raises(pdl.PolydealError, match="already belongs"):
+        ah.define_agglomerate([1, 2])
+    with pytest.raises(pdl.PolydealError, match="belongs to no agglomerate"):
+        ah.distribute_agglomerated_dofs(pdl.FE_DGQ, 1)
+    for c in range(2, 16):
+        ah.define_agglomerate([c])
+    with pytest.raises(pdl.PolydealError, match="forgot to distribute"):
+        ah.n_faces(0)
+    with pytest.raises(pdl.PolydealError, match="only DGQ"):
+        ah.distribute_agglomerated_dofs(1, 1)
+    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, 1)
+    with pytest.raises(pdl.PolydealError, match="face index out of range"):
+        ah.neighbor(0, 99)
+    with pytest.raises(pdl.PolydealError, match="initialize_fe_values"):
+        ah.flatten()
+    with pytest.raises(pdl.PolydealError, match="Morton"):
+        pdl.Grid.structured(2, 6, 0, 1, order=0)
+
+
+@pytest.mark.skipif(K.lib().pd_device_count() > 0, reason="GPU present: the loud-failure path is for CPU-only hosts")
+def test_compute_fails_loudly_without_gpu():
+    _, ah = product_from_groups(2, 2, sc.blocks_2x2_of_4x4())
+    with pytest.raises(pdl.PolydealError, match="no CPU fallback") as e:
+        pdl.assemble_dg_matrix(ah)
+    assert e.value.code == K.PD_ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    """The product path must not route through oracle/ (task rule)."""
+    pkg = os.path.join(ROOT, "polydeal_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".hpp", ".h", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and False, os.path.join(dirpath, f)
