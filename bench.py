@@ -1,0 +1,395 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path on B200.
+
+Workload (BASELINE.json configs[1]): unit cube, 64^3 hexes, 512
+polyhedra of 8^3 cells (the `blocks` shape an R-tree of fan-out 8 extracts at level 3),
+FE_DGQ<3>(2), QGauss(3), SIP assembly of stiffness + penalty + boundary terms with the
+library penalty C = 10 (p+dim)(p+1) = 150 (include/poly_utils.h:2018-2019).
+A step = agglomerated quadrature + volume + face + diagonal-gather kernels, from the
+flattened agglomeration resident in HBM to the finished scalar-CSR values in HBM.
+
+Metric: polytope DoFs assembled per second (whole job, all ranks).  The companion
+metric of BASELINE.json, SIP vmult GDoF/s, is reported in the "vmult" object.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+  python bench.py --impl reference ...   times the CPU oracle restating the reference's
+                                         assembly on the host cores (the reference itself
+                                         needs deal.II and cannot be built here)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+METRIC = "polytope DoFs assembled/s"
+UNIT = "DoF/s"
+DIM, N_CELLS_1D, BLOCK, DEGREE, NQ = 3, 64, 8, 2, 3
+WORKLOAD = "B: unit cube 64^3 hexes -> 512 polyhedra (8^3 blocks, R-tree level 3), FE_DGQ(2), QGauss(3), SIP stiffness+penalty+boundary, C=150"
+
+
+def block_groups(n, b):
+    import pd_scenarios as sc
+
+    return sc.block_partition(DIM, n, b)
+
+
+def read_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            peaks["hbm_gbs"] = float(json.load(open(p))["hbm_gbs"])
+            peaks["hbm_src"] = "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    peaks["fp64_tflops"] = 37.1
+    peaks["fp64_src"] = "fallback 37.1 (nominal 148 SM x 64 FMA/clk x 1.965 GHz)"
+    p = os.path.join(ROOT, "profiles", "FP64_PEAK.json")
+    if os.path.exists(p):
+        try:
+            peaks["fp64_tflops"] = float(json.load(open(p))["fp64_tflops"])
+            peaks["fp64_src"] = "measured DMMA m8n8k4 (profiles/FP64_PEAK.json; MEASURED_PEAKS.json has no FP64 figure)"
+        except Exception:
+            pass
+    return peaks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        load = [v for v in sm if mx and v > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def pinned_copy_of_desc(desc):
+    """Copy every descriptor array into pinned host memory; returns (new desc, keepalive, bytes)."""
+    import torch
+
+    from polydeal_b200 import _capi as K
+
+    d = K.MeshDesc()
+    keep, total = [], 0
+    nsc = desc.poly_subcell_ptr[desc.n_polytopes]
+    nsf = desc.iface_sub_ptr[desc.n_ifaces] if desc.n_ifaces else 0
+    nblk = desc.brow_ptr[desc.n_block_rows]
+    sizes = {
+        "verts": desc.n_verts * desc.dim, "cell_verts": desc.n_cells << desc.dim,
+        "poly_subcell_ptr": desc.n_polytopes + 1, "poly_subcell_idx": nsc, "bbox": desc.n_polytopes * 2 * desc.dim,
+        "dof_block": desc.n_polytopes, "iface_polyA": desc.n_ifaces, "iface_polyB": desc.n_ifaces,
+        "iface_sub_ptr": desc.n_ifaces + 1, "sub_cell": nsf, "sub_face": nsf, "sub_sigma": nsf,
+        "brow_ptr": desc.n_block_rows + 1, "bcol_idx": nblk,
+    }
+    for name, ctype in K.MeshDesc._fields_:
+        v = getattr(desc, name)
+        if name in sizes:
+            n = int(sizes[name])
+            elem = ctype._type_
+            dt = {C.c_double: torch.float64, C.c_int32: torch.int32, C.c_int64: torch.int64}[elem]
+            t = torch.empty(max(n, 1), dtype=dt).pin_memory()
+            src = np.ctypeslib.as_array(v, (n,)) if n else np.zeros(0)
+            t[:n].copy_(torch.from_numpy(np.array(src)))
+            keep.append(t)
+            total += n * C.sizeof(elem)
+            setattr(d, name, C.cast(t.data_ptr(), ctype))
+        else:
+            setattr(d, name, v)
+    return d, keep, total
+
+
+def run_gpu(args):
+    import torch
+
+    import polydeal_b200 as pdl
+    from polydeal_b200 import _capi as K
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- build the agglomeration (host, untimed) --------------------------------------
+    # Weak scaling: every rank owns one config-B box (64^3 cells, 512 polyhedra); the path
+    # shards over polytopes with no data-path collective in assembly.
+    grid = pdl.Grid.hyper_cube(DIM, 0.0, 1.0, N_CELLS_1D.bit_length() - 1)
+    ah = pdl.AgglomerationHandler(grid)
+    for g in block_groups(N_CELLS_1D, BLOCK):
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(NQ)
+    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, DEGREE)
+    desc0 = ah.flatten()  # library penalty, visit by id
+    desc, keep, h2d_bytes = pinned_copy_of_desc(desc0)
+    op = pdl.SIPOperator(desc, keepalive=(ah, keep))
+    # all work and all timing events go to ONE explicit non-default stream (the legacy
+    # default stream has handle 0, which pd_set_stream reads as "use the handle's own")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    op.set_stream(stream.cuda_stream)
+    n_dofs = op.m()
+    n = op.n_dofs_per_cell
+    Q = int(desc.poly_subcell_ptr[desc.n_polytopes]) * NQ**DIM
+    nnz = op.nnz
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2
+
+    def step_device():
+        # a step starts from the flattened agglomeration: the quadrature is rebuilt every step
+        op.invalidate_quadrature()
+        op.assemble()
+
+    # device-resident timing -----------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = op.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kms = {"volume": [], "faces": [], "reduce": [], "quadrature": []}
+    torch.cuda.synchronize()
+    for s in range(args.steps):
+        flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+        ev[s][0].record(stream)
+        step_device()
+        ev[s][1].record(stream)
+        ev[s][1].synchronize()
+        for k, v in op.last_kernel_ms().items():
+            kms[k].append(v)
+    torch.cuda.synchronize()
+    launches = op.launch_count - launches0
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # end-to-end: host buffers in (pinned), matrix values out (pinned), every step
+    out_host = torch.empty(nnz, dtype=torch.float64).pin_memory()
+    for _ in range(min(3, args.warmup)):
+        op.upload()
+        op.assemble()
+        op.values_to_host_ptr(out_host.data_ptr())
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    e2e_ev[0].record(stream)
+    for _ in range(args.steps):
+        op.upload()
+        op.assemble()
+        op.values_to_host_ptr(out_host.data_ptr())
+    e2e_ev[1].record(stream)
+    torch.cuda.synchronize()
+    t_e2e_ms = max(e2e_ev[0].elapsed_time(e2e_ev[1]), (time.perf_counter() - t0) * 1e3)
+    checksum = float(out_host.sum())
+
+    # vmult with the assembled matrix (device vectors), L2 flushed between applies
+    x = torch.from_numpy(np.sin(0.37 * np.arange(n_dofs)) + 0.01 * (np.arange(n_dofs) % 7)).cuda()
+    y = torch.empty_like(x)
+    for _ in range(3):
+        op.vmult(y, x)
+    vm = []
+    for _ in range(max(args.steps, 5)):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        op.vmult(y, x)
+        b.record(stream)
+        b.synchronize()
+        vm.append(a.elapsed_time(b))
+    t_vm_ms = statistics.mean(vm)
+
+    times = torch.tensor([t_ms, t_e2e_ms, t_vm_ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_ms, t_e2e_ms, t_vm_ms = (float(v) for v in times.cpu())
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peaks = read_peaks()
+    ms_per_step = t_ms / args.steps
+    value = world * n_dofs / (ms_per_step * 1e-3)
+    e2e_value = world * n_dofs / (t_e2e_ms / args.steps * 1e-3)
+    # dominant kernel: the volume contraction.  Algorithmic flops per launch =
+    # 2 n^2 dim Q; bytes = 8 (dim+1) Q read + 8 n^2 per polytope written.
+    vol_ms = statistics.mean(kms["volume"])
+    flops = 2.0 * n * n * DIM * Q
+    achieved = flops / (vol_ms * 1e-3) / 1e12
+    vol_bytes = 8.0 * (DIM + 1) * Q + 8.0 * n * n * desc.n_polytopes
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("k_volume_bytes_per_launch")
+        except Exception:
+            traffic = None
+    nblocks = int(desc.brow_ptr[desc.n_block_rows])
+    vm_bytes = 8.0 * n * n * nblocks + 4.0 * nblocks + 16.0 * n_dofs
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_dofs_per_gpu": n_dofs, "n_polytopes_per_gpu": int(desc.n_polytopes),
+                   "volume_q_points_per_gpu": Q, "sharding": f"{world} x one box per rank, no assembly collective",
+                   "l2": "flushed (512 MiB memset) between timed steps; inputs 226 MB > L2 as well",
+                   "step": "quadrature + volume + faces + diagonal gather, all device kernels"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": nnz * 8,
+                "api": "pd_upload + pd_assemble + pd_matrix_values_to_host (pinned host buffers)", "checksum": checksum},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "k_volume<3,2> (FP64 DMMA contraction)", "achieved": achieved,
+                     "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["fp64_tflops"],
+                     "traffic": traffic, "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": vol_bytes,
+                     "kernel_ms": vol_ms, "peak_source": peaks["fp64_src"],
+                     "hbm_frac_of_same_kernel": vol_bytes / (vol_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        "kernel_ms": {k: statistics.mean(v) for k, v in kms.items()},
+        "vmult": {"metric": "SIP vmult GDoF/s (block-CSR apply of the assembled operator)",
+                  "value": world * n_dofs / (t_vm_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t_vm_ms,
+                  "roofline": {"bound": "hbm", "achieved": vm_bytes / (t_vm_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                               "unit": "GB/s", "frac": vm_bytes / (t_vm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                               "peak_source": peaks["hbm_src"]}},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(full=True)
+    print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+def oracle_config_b():
+    from oracle import pyoracle as po
+    from pd_helpers import oracle_handler
+
+    groups = block_groups(N_CELLS_1D, BLOCK)
+    _, oah = oracle_handler(DIM, N_CELLS_1D, groups, DEGREE, NQ)
+    return po, oah
+
+
+def cpu_baseline(full, stride=None, oah=None, po=None):
+    """The CPU oracle (port of include/poly_utils.h:2000-2195, faithful cost: tables
+    re-evaluated per polytope and per face, scalar q*i*j loops) on all host cores."""
+    if oah is None:
+        po, oah = oracle_config_b()
+    cores = os.cpu_count() or 1
+    stride = stride or (1 if full else 4)
+    m = po.assemble_dg_matrix(oah, degree=DEGREE, n_threads=cores, poly_stride=stride, poly_offset=0)
+    n_poly = len(range(0, oah.n_polytopes, stride))
+    dofs = n_poly * oah.n_dofs_per_cell
+    return {"value": dofs / m.seconds, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_poly} of {oah.n_polytopes} polytopes of config B (every {stride}th), {m.seconds:.2f} s, "
+                      "oracle CPU restatement of assemble_dg_matrix, not polyDEAL/deal.II itself", "seconds": m.seconds}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    po, oah = oracle_config_b()
+    cores = os.cpu_count() or 1
+    stride = 4
+    for _ in range(args.warmup):
+        cpu_baseline(False, stride, oah, po)
+    t, dofs, last = 0.0, 0, None
+    for _ in range(args.steps):
+        last = cpu_baseline(False, stride, oah, po)
+        t += last["seconds"]
+        dofs += len(range(0, oah.n_polytopes, stride)) * oah.n_dofs_per_cell
+    value = dofs / t
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm: oracle port of the reference assembly on the host cores; "
+                   "polyDEAL itself needs deal.II/Trilinos/MPI and cannot be built in this image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

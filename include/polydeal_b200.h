@@ -138,6 +138,9 @@ int pd_synchronize(pd_handle *h);
  * q-points/JxW of every polytope and the face q-points/normals/JxW of every
  * interface.  Called implicitly by pd_assemble when stale. */
 int pd_build_quadrature(pd_handle *h);
+/* mark the device quadrature stale (vertices changed through pd_upload do this
+ * implicitly): the next pd_assemble rebuilds it */
+int pd_invalidate_quadrature(pd_handle *h);
 
 /* PolyUtils::assemble_dg_matrix (include/poly_utils.h:2000-2195).  Result: the
  * scalar-CSR value array of the reference pattern (ascending columns), kept on

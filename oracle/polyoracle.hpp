@@ -1131,6 +1131,10 @@ namespace po
     double stiffness_coeff  = 1.; // sigma: scales volume gradient AND all face terms
     double mass_coeff       = 0.; // f:     + f * phi_i phi_j
     int    n_threads        = 1;
+    // bounded sampling for CPU-baseline timing: only polytopes p with
+    // p % poly_stride == poly_offset do their (visiting) work
+    int    poly_stride      = 1;
+    int    poly_offset      = 0;
   };
 
   struct CSRMatrix
@@ -1194,14 +1198,21 @@ namespace po
       locks[br].clear(std::memory_order_release);
     };
 
-    auto work = [&](const int p_begin, const int p_end) {
+    std::atomic<int> next_poly{0};
+    auto work = [&](const int p_begin_unused, const int p_end_unused) {
+      (void)p_begin_unused;
+      (void)p_end_unused;
       std::vector<double>       cell_matrix((size_t)n * n), M11((size_t)n * n),
         M12((size_t)n * n), M21((size_t)n * n), M22((size_t)n * n);
       std::vector<unsigned int> ldi(n), ldin(n);
       FEValuesTable             av, f0, f1;
       const double              sc = prm.stiffness_coeff;
-      for (int p = p_begin; p < p_end; ++p)
+      // dynamic schedule: the visiting polytope does all the work of an interface,
+      // so static ranges would be badly balanced
+      for (int p = next_poly.fetch_add(1); p < np; p = next_poly.fetch_add(1))
         {
+          if (p % prm.poly_stride != prm.poly_offset)
+            continue;
           std::fill(cell_matrix.begin(), cell_matrix.end(), 0.);
           ah.reinit(p, av);
           for (int q = 0; q < av.n_q; ++q)

@@ -326,6 +326,8 @@ extern "C"
     double stiffness_coeff;
     double mass_coeff;
     int    n_threads;
+    int    poly_stride;
+    int    poly_offset;
   };
 
   void *
@@ -341,6 +343,8 @@ extern "C"
     prm.stiffness_coeff  = p->stiffness_coeff;
     prm.mass_coeff       = p->mass_coeff;
     prm.n_threads        = p->n_threads;
+    prm.poly_stride      = p->poly_stride > 0 ? p->poly_stride : 1;
+    prm.poly_offset      = p->poly_offset;
     const auto t0        = std::chrono::steady_clock::now();
     if (guard([&] { assemble_dg_matrix(*static_cast<Handler *>(ah), prm, M->A); }))
       {

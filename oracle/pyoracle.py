@@ -44,6 +44,8 @@ class _Params(C.Structure):
         ("stiffness_coeff", C.c_double),
         ("mass_coeff", C.c_double),
         ("n_threads", C.c_int),
+        ("poly_stride", C.c_int),
+        ("poly_offset", C.c_int),
     ]
 
 
@@ -369,13 +371,16 @@ def assemble_dg_matrix(
     mass_coeff=0.0,
     n_threads=1,
     degree=None,
+    poly_stride=1,
+    poly_offset=0,
 ) -> Matrix:
     """PolyUtils::assemble_dg_matrix (include/poly_utils.h:2000-2195); the
     default penalty is the library's 10 (p+dim)(p+1) (:2018-2019)."""
     if penalty_constant is None:
         assert degree is not None
         penalty_constant = 10.0 * (degree + ah.dim) * (degree + 1)
-    prm = _Params(penalty_constant, h_rule, h_const, visit_rule, int(with_boundary), stiffness_coeff, mass_coeff, n_threads)
+    prm = _Params(penalty_constant, h_rule, h_const, visit_rule, int(with_boundary), stiffness_coeff, mass_coeff, n_threads,
+                  poly_stride, poly_offset)
     sec = C.c_double(0.0)
     h = lib().po_assemble_dg_matrix(ah.h, C.byref(prm), C.byref(sec))
     if not h:

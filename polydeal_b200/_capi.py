@@ -49,6 +49,7 @@ SIGNATURES = {
     "pd_set_stream": (C.c_int, [vp, vp]),
     "pd_synchronize": (C.c_int, [vp]),
     "pd_build_quadrature": (C.c_int, [vp]),
+    "pd_invalidate_quadrature": (C.c_int, [vp]),
     "pd_assemble": (C.c_int, [vp, u32, P(Coefficients)]),
     "pd_n_dofs": (i64, [vp]),
     "pd_nnz": (i64, [vp]),

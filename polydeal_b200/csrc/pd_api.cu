@@ -236,6 +236,13 @@ namespace pd
     h2d(h->bcol, d.bcol_idx, (size_t)h->n_blocks, s);
     h->quad_valid = false;
     h->assembled  = false;
+    // the volume schedule depends on poly_subcell_ptr only: rebuild it when that changed
+    if (h->h_subcell_ptr.size() != (size_t)d.n_polytopes + 1 ||
+        std::memcmp(h->h_subcell_ptr.data(), d.poly_subcell_ptr, sizeof(int64_t) * ((size_t)d.n_polytopes + 1)) != 0)
+      {
+        h->h_subcell_ptr.assign(d.poly_subcell_ptr, d.poly_subcell_ptr + d.n_polytopes + 1);
+        h->vol_plan_tq = 0;
+      }
   }
 
   static void
@@ -351,26 +358,6 @@ namespace pd
             if (d.iface_polyB[f] >= 0)
               padj[cursor[d.iface_polyB[f]]++] = (int64_t)f * 2 + 1;
           }
-        // volume work items: whole sub-cells, sized so that every SM gets several
-        const int64_t        target = std::max<int64_t>(512, (h->Q + (int64_t)h->sm_count * 8 - 1) / ((int64_t)h->sm_count * 8));
-        std::vector<int32_t> item_poly;
-        std::vector<int64_t> item_q0, item_q1, poly_item_ptr(h->np + 1, 0);
-        for (int32_t p = 0; p < h->np; ++p)
-          {
-            const int64_t c0 = d.poly_subcell_ptr[p], c1 = d.poly_subcell_ptr[p + 1];
-            const int64_t qp = (c1 - c0) * h->nqc;
-            const int64_t nchunk = std::max<int64_t>(1, std::min<int64_t>(c1 - c0, (qp + target - 1) / target));
-            for (int64_t k = 0; k < nchunk; ++k)
-              {
-                const int64_t a = c0 + (c1 - c0) * k / nchunk, b = c0 + (c1 - c0) * (k + 1) / nchunk;
-                item_poly.push_back(p);
-                item_q0.push_back(a * h->nqc);
-                item_q1.push_back(b * h->nqc);
-              }
-            poly_item_ptr[p + 1] = (int64_t)item_poly.size();
-          }
-        h->n_vitems = (int32_t)item_poly.size();
-
         auto put32 = [&](DevBuf<int32_t> &b, const std::vector<int32_t> &v) {
           b.alloc(v.size());
           if (!v.empty())
@@ -387,17 +374,12 @@ namespace pd
         put64(h->if_baseBA, baseBA);
         put64(h->padj_ptr, padj_ptr);
         put64(h->padj, padj);
-        put32(h->vitem_poly, item_poly);
-        put64(h->vitem_q0, item_q0);
-        put64(h->vitem_q1, item_q1);
-        put64(h->poly_vitem_ptr, poly_item_ptr);
 
         h->vq_x.alloc((size_t)h->Q * d.dim);
         h->vq_w.alloc((size_t)h->Q);
         h->fq_x.alloc((size_t)h->Qf * d.dim);
         h->fq_n.alloc((size_t)h->Qf * d.dim);
         h->fq_w.alloc((size_t)h->Qf);
-        h->vol_partial.alloc((size_t)h->n_vitems * nn);
         h->face_diag.alloc((size_t)h->n_ifaces * 2 * nn);
         h->values.alloc((size_t)h->nnz);
         PD_CUDA(cudaStreamSynchronize(h->stream));
@@ -511,6 +493,16 @@ extern "C"
         throw Error(PD_ERR_INVALID, "null handle");
       launch_quadrature(h);
       h->quad_valid = true;
+    });
+  }
+
+  int
+  pd_invalidate_quadrature(pd_handle *h)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      h->quad_valid = false;
     });
   }
 

@@ -30,6 +30,7 @@
 // columns): block row b, local row i, block k, local column j at
 //   brow_ptr[b]*n*n + i*(nb_b*n) + k*n + j.
 // -----------------------------------------------------------------------------
+#include "pd_host.hpp"
 #include "pd_internal.hpp"
 
 namespace pd
@@ -49,10 +50,12 @@ namespace pd
       static constexpr int N   = ipow(N1, DIM);
       static constexpr int NT8 = (N + 7) / 8; // 8x8 MMA tiles per side
       static constexpr int NP  = NT8 * 8;
+      static constexpr int NU  = ipow(N1, DIM - 1); // generator units per point
       // Row stride (doubles) of operand panels.  A fragment load touches 4 rows x
       // 8 consecutive doubles; with stride = 4, 8 or 12 (mod 16) the four rows
       // cover every bank pair exactly twice => 2 wavefronts, the minimum for 256 B.
       static constexpr int STRIDE = (NP % 16 == 0) ? NP + 8 : NP;
+      static constexpr int NTRI   = NT8 * (NT8 + 1) / 2;
     };
 
     __device__ __forceinline__ void
@@ -66,7 +69,7 @@ namespace pd
     __device__ __forceinline__ void
     cta_sync()
     {
-      // plain barrier 0; issued from role-specialised code paths, hence PTX
+      // barrier 0, issued from role-specialised code paths, hence PTX
       asm volatile("bar.sync 0;\n" ::: "memory");
     }
 
@@ -103,13 +106,13 @@ namespace pd
       const double  *bbox;
       const int32_t *item_poly;
       const int64_t *item_q0, *item_q1;
-      int32_t        n_items;
-      double        *partial; // [n_items][N][N]
+      const int32_t *cta_item_ptr; // [grid+1] items of every persistent CTA
+      double        *partial;      // [n_items][N][N]
       double         stiffness, mass;
       Basis1D        basis;
     };
 
-    template <int NT8, int NROLE, int ROLE>
+    template <int NROLE, int ROLE>
     __device__ __forceinline__ constexpr bool
     vol_role_owns_row(const int I)
     {
@@ -117,200 +120,274 @@ namespace pd
       return NROLE == 1 ? true : ((((I & 3) == 0) || ((I & 3) == 3)) == (ROLE == 0));
     }
 
-    template <int DIM, int DEG, bool MASS, int TQ, int NWARPS, int NROLE, int ROLE>
+    __device__ __forceinline__ constexpr int
+    tri_index(const int NT8, const int I, const int J) // I <= J
+    {
+      return I * NT8 - (I * (I - 1)) / 2 + (J - I);
+    }
+
+    // Volume kernel, software-pipelined.  Per stage of TQ = 32 points (lane = point):
+    //   table warps : 1-D Lagrange tables of stage s+2 (+ prefetch of the raw x, JxW of s+3)
+    //   gen warps   : operand rows of stage s+1 from the tables of s+1
+    //   all warps   : DMMA contraction of stage s
+    // then ONE barrier.  The phases of different warps overlap on the SM's pipes
+    // (DMMA vs LSU/FP64), so the tensor pipe does not wait for the generator.
+    //
+    // Shared-memory layout (all accesses bank-conflict free):
+    //   T[buf][d][2][N1][TQ]   tables, point fastest
+    //   G[buf][i][RS]          operand panel, DOF-major, row index r = c*TQ + q fastest,
+    //                          RS = 4 (mod 16): a fragment load (8 dofs x 4 rows) touches
+    //                          every bank pair once per half-warp
+    //   WC[3][R]               JxW * coefficient per row
+    template <int DIM, int DEG, bool MASS, int NWARPS, int NROLE, int ROLE>
     __device__ __forceinline__ void
     volume_body(const VolArgs &A, double *smem)
     {
       using C              = Cfg<DIM, DEG>;
-      constexpr int N1     = C::N1, N = C::N, NT8 = C::NT8, NP = C::NP, STRIDE = C::STRIDE;
+      constexpr int TQ     = 32;
+      constexpr int N1     = C::N1, N = C::N, NT8 = C::NT8, NP = C::NP, NU = C::NU, NTRI = C::NTRI;
       constexpr int NC     = DIM + (MASS ? 1 : 0);
       constexpr int R      = TQ * NC;
+      constexpr int RS     = ((R + 11) / 16) * 16 + 4; // >= R, = 4 (mod 16)
       constexpr int KSPLIT = NWARPS / NROLE;
       constexpr int NTHR   = NWARPS * 32;
-      static_assert(R % 4 == 0, "panel rows must be a multiple of the MMA k");
-      static_assert(TQ * DIM <= NTHR, "one thread per (point, direction) in the table phase");
+      constexpr int NTABW  = DIM;            // table warps: one per direction
+      constexpr int NGENW  = NWARPS - NTABW; // generator warps
+      constexpr int TSZ    = DIM * 2 * N1 * TQ;
+      constexpr int GSZ    = NP * RS;
+      static_assert(RS >= R && RS % 16 == 4, "panel row stride");
+      static_assert(NGENW >= 1, "need generator warps");
 
-      double *G  = smem;                        // [R][STRIDE] operand panel
-      double *WC = G + R * STRIDE;              // [R] JxW * coefficient of the row
-      double *T  = WC + R;                      // [TQ][DIM][2][N1] 1-D tables
-      double *S  = smem;                        // [NP][NP+1] aliases G after the main loop
+      double *Gb = smem;               // [2][GSZ]
+      double *Tb = Gb + 2 * GSZ;       // [2][TSZ]
+      double *WC = Tb + 2 * TSZ;       // [3][R]
+      double *S  = smem;               // [KSPLIT][NTRI][64] epilogue slabs alias the panels
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
       const int g = lane >> 2, t = lane & 3;
       const int kpart = warp / NROLE;
+      const bool tabw = warp >= NGENW; // warp-uniform role
+      const int  td   = tabw ? warp - NGENW : 0;
 
-      // columns >= N of the panel are never written by the generator: clear once
-      for (int i = tid; i < R * STRIDE; i += NTHR)
-        G[i] = 0.;
+      const int item_begin = A.cta_item_ptr[blockIdx.x], item_end = A.cta_item_ptr[blockIdx.x + 1];
 
-      for (int item = blockIdx.x; item < A.n_items; item += gridDim.x)
+      for (int item = item_begin; item < item_end; ++item)
         {
-          const int      poly = A.item_poly[item];
-          const int64_t  q0 = A.item_q0[item], q1 = A.item_q1[item];
-          const double  *bb = A.bbox + (int64_t)poly * 2 * DIM;
-          double         acc[NT8][NT8][2];
+          const int     poly = A.item_poly[item];
+          const int64_t q0 = A.item_q0[item], q1 = A.item_q1[item];
+          const int     nst = (int)((q1 - q0 + TQ - 1) / TQ);
+          const double *bb  = A.bbox + (int64_t)poly * 2 * DIM;
+          double        acc[NT8][NT8][2];
 #pragma unroll
           for (int I = 0; I < NT8; ++I)
 #pragma unroll
             for (int J = 0; J < NT8; ++J)
               acc[I][J][0] = acc[I][J][1] = 0.;
 
-          for (int64_t qt = q0; qt < q1; qt += TQ)
-            {
-              cta_sync(); // previous MMA phase done with G / T / WC
-              // ---- phase 1: 1-D tables, one thread per (direction, point)
-              if (tid < TQ * DIM)
-                {
-                  const int     d = tid / TQ, q = tid - d * TQ;
-                  const int64_t gq = qt + q;
-                  const double  lo = bb[d], hi = bb[DIM + d];
-                  const double  x  = gq < q1 ? A.vq_x[(int64_t)d * A.Q + gq] : lo;
-                  // BoundingBox::real_to_unit, covariant scaling by 1/h
-                  const double xhat = (x - lo) / (hi - lo);
-                  double       L[N1], dL[N1];
-                  lagrange<N1>(A.basis, xhat, 1. / (hi - lo), L, dL);
-                  double *Tq = T + (q * DIM + d) * 2 * N1;
+          const double lo = bb[td], hi = bb[DIM + td];
+          const double inv_h = 1. / (hi - lo);
+          double       x_pre = lo, w_pre = 0.; // raw data of the next stage to tabulate
+          int          s_pre = 0;              // stage x_pre belongs to
+
+          auto prefetch = [&](const int s) {
+            const int64_t gq = q0 + (int64_t)s * TQ + lane;
+            x_pre = lo;
+            w_pre = 0.;
+            if (s < nst && gq < q1)
+              {
+                x_pre = A.vq_x[(int64_t)td * A.Q + gq];
+                if (td == 0)
+                  w_pre = A.vq_w[gq];
+              }
+            s_pre = s;
+          };
+          // tables of stage s from the prefetched registers (table warps only)
+          auto tables = [&](const int s) {
+            const double x = x_pre, w = w_pre;
+            prefetch(s + 1);
+            if (s >= nst)
+              return;
+            // BoundingBox::real_to_unit, covariant scaling by 1/h
+            const double xhat = (x - lo) / (hi - lo);
+            double       L[N1], dL[N1];
+            lagrange<N1>(A.basis, xhat, inv_h, L, dL);
+            double *Tq = Tb + (s & 1) * TSZ + td * 2 * N1 * TQ + lane;
 #pragma unroll
-                  for (int a = 0; a < N1; ++a)
-                    {
-                      Tq[a]      = L[a];
-                      Tq[N1 + a] = dL[a];
-                    }
-                  if (d == 0)
-                    {
-                      const double w = gq < q1 ? A.vq_w[gq] : 0.;
+            for (int a = 0; a < N1; ++a)
+              {
+                Tq[a * TQ]        = L[a];
+                Tq[(N1 + a) * TQ] = dL[a];
+              }
+            if (td == 0)
+              {
+                double *wc = WC + (s % 3) * R + lane;
 #pragma unroll
-                      for (int c = 0; c < DIM; ++c)
-                        WC[q * NC + c] = w * A.stiffness;
-                      if (MASS)
-                        WC[q * NC + DIM] = w * A.mass;
-                    }
-                }
-              cta_sync();
-              // ---- phase 2: rows g_d(q)[i] (and phi(q)[i]) of the operand panel
-              for (int idx = tid; idx < TQ * N; idx += NTHR)
-                {
-                  const int     q  = idx / N, i = idx - q * N;
-                  const double *Tq = T + q * DIM * 2 * N1;
-                  double       *Gq = G + (q * NC) * STRIDE + i;
-                  if constexpr (DIM == 2)
-                    {
-                      const int    a = i % N1, b = i / N1;
-                      const double lx = Tq[a], dx = Tq[N1 + a], ly = Tq[2 * N1 + b], dy = Tq[3 * N1 + b];
-                      Gq[0]          = dx * ly;
-                      Gq[STRIDE]     = lx * dy;
-                      if (MASS)
-                        Gq[2 * STRIDE] = lx * ly;
-                    }
-                  else
-                    {
-                      const int    a = i % N1, b = (i / N1) % N1, c = i / (N1 * N1);
-                      const double lx = Tq[a], dx = Tq[N1 + a], ly = Tq[2 * N1 + b], dy = Tq[3 * N1 + b],
-                                   lz = Tq[4 * N1 + c], dz = Tq[5 * N1 + c];
-                      const double lxy = lx * ly;
-                      Gq[0]            = dx * ly * lz;
-                      Gq[STRIDE]       = lx * dy * lz;
-                      Gq[2 * STRIDE]   = lxy * dz;
-                      if (MASS)
-                        Gq[3 * STRIDE] = lxy * lz;
-                    }
-                }
-              cta_sync();
-              // ---- phase 3: C += sum_r wc_r G_r G_r^T on the upper triangle of tiles
-#pragma unroll 2
-              for (int ks = kpart; ks < R / 4; ks += KSPLIT)
-                {
-                  const int     r   = ks * 4 + t;
-                  const double *row = G + r * STRIDE + g;
-                  const double  wc  = WC[r];
-                  double        a[NT8], b[NT8];
+                for (int c = 0; c < DIM; ++c)
+                  wc[c * TQ] = w * A.stiffness;
+                if (MASS)
+                  wc[DIM * TQ] = w * A.mass;
+              }
+          };
+          // operand rows of stage s (generator warps only): one warp-unit = all 32 points
+          // for one (b[,c]) pair; the y/z products are formed once and swept over a
+          auto generate = [&](const int s) {
+            if (s >= nst)
+              return;
+            const double *Tq = Tb + (s & 1) * TSZ + lane;
+            double       *Gq = Gb + (s & 1) * GSZ + lane;
+            for (int wu = warp; wu < NU; wu += NGENW)
+              {
+                if constexpr (DIM == 2)
+                  {
+                    const double ly = Tq[(2 * N1 + wu) * TQ], dy = Tq[(3 * N1 + wu) * TQ];
 #pragma unroll
-                  for (int I = 0; I < NT8; ++I)
-                    {
-                      a[I] = row[8 * I];
-                      b[I] = a[I] * wc;
-                    }
-#pragma unroll
-                  for (int I = 0; I < NT8; ++I)
-                    if (vol_role_owns_row<NT8, NROLE, ROLE>(I))
+                    for (int a = 0; a < N1; ++a)
                       {
-#pragma unroll
-                        for (int J = I; J < NT8; ++J)
-                          dmma884(acc[I][J][0], acc[I][J][1], a[I], b[J]);
+                        const double lx = Tq[a * TQ], dx = Tq[(N1 + a) * TQ];
+                        double      *o  = Gq + (wu * N1 + a) * RS;
+                        o[0]            = dx * ly;
+                        o[TQ]           = lx * dy;
+                        if (MASS)
+                          o[2 * TQ] = lx * ly;
                       }
-                }
+                  }
+                else
+                  {
+                    const int    b = wu % N1, c = wu / N1;
+                    const double ly = Tq[(2 * N1 + b) * TQ], dy = Tq[(3 * N1 + b) * TQ];
+                    const double lz = Tq[(4 * N1 + c) * TQ], dz = Tq[(5 * N1 + c) * TQ];
+                    const double yz = ly * lz, dyz = dy * lz, ydz = ly * dz;
+#pragma unroll
+                    for (int a = 0; a < N1; ++a)
+                      {
+                        const double lx = Tq[a * TQ], dx = Tq[(N1 + a) * TQ];
+                        double      *o  = Gq + (wu * N1 + a) * RS;
+                        o[0]            = dx * yz;
+                        o[TQ]           = lx * dyz;
+                        o[2 * TQ]       = lx * ydz;
+                        if (MASS)
+                          o[3 * TQ] = lx * yz;
+                      }
+                  }
+              }
+          };
+          // C += sum_r wc_r G_r G_r^T on the upper triangle of tiles, rows of this k-part
+          auto contract = [&](const int s) {
+            const double *Gs = Gb + (s & 1) * GSZ + g * RS + t;
+            const double *ws = WC + (s % 3) * R + t;
+#pragma unroll 3
+            for (int ks = kpart; ks < R / 4; ks += KSPLIT)
+              {
+                const double wc = ws[ks * 4];
+                double       a[NT8], b[NT8];
+#pragma unroll
+                for (int I = 0; I < NT8; ++I)
+                  {
+                    a[I] = Gs[8 * I * RS + ks * 4];
+                    b[I] = a[I] * wc;
+                  }
+#pragma unroll
+                for (int I = 0; I < NT8; ++I)
+                  if (vol_role_owns_row<NROLE, ROLE>(I))
+                    {
+#pragma unroll
+                      for (int J = I; J < NT8; ++J)
+                        dmma884(acc[I][J][0], acc[I][J][1], a[I], b[J]);
+                    }
+              }
+          };
+
+          // ---- pipeline fill
+          cta_sync(); // previous item's epilogue is done with the aliased slabs
+          if (tabw)
+            {
+              prefetch(0);
+              tables(0);
             }
-          // ---- reduce the k-split partial tiles through shared memory
-          constexpr int SS = NP + 1;
           cta_sync();
-          for (int round = 0; round < KSPLIT; ++round)
+          if (tabw)
+            tables(1);
+          else
+            generate(0);
+          cta_sync();
+          // ---- steady state: one barrier per stage
+          for (int s = 0; s < nst; ++s)
             {
-              if (kpart == round)
-                {
-#pragma unroll
-                  for (int I = 0; I < NT8; ++I)
-                    if (vol_role_owns_row<NT8, NROLE, ROLE>(I))
-                      {
-#pragma unroll
-                        for (int J = I; J < NT8; ++J)
-                          {
-                            double *s = S + (8 * I + g) * SS + 8 * J + 2 * t;
-                            if (round == 0)
-                              {
-                                s[0] = acc[I][J][0];
-                                s[1] = acc[I][J][1];
-                              }
-                            else
-                              {
-                                s[0] += acc[I][J][0];
-                                s[1] += acc[I][J][1];
-                              }
-                          }
-                      }
-                }
+              if (tabw)
+                tables(s + 2);
+              else
+                generate(s + 1);
+              contract(s);
               cta_sync();
             }
+          (void)s_pre;
+          // ---- every k-part writes its partial tiles into its own slab, one barrier,
+          //      then all threads sum the slabs while writing the n x n partial block
+#pragma unroll
+          for (int I = 0; I < NT8; ++I)
+            if (vol_role_owns_row<NROLE, ROLE>(I))
+              {
+#pragma unroll
+                for (int J = I; J < NT8; ++J)
+                  {
+                    double *sl = S + (kpart * NTRI + tri_index(NT8, I, J)) * 64 + g * 8 + 2 * t;
+                    sl[0]      = acc[I][J][0];
+                    sl[1]      = acc[I][J][1];
+                  }
+              }
+          cta_sync();
           double *out = A.partial + (int64_t)item * N * N;
           for (int idx = tid; idx < N * N; idx += NTHR)
             {
-              const int i = idx / N, j = idx - i * N;
-              out[idx]    = (i >> 3) <= (j >> 3) ? S[i * SS + j] : S[j * SS + i];
+              int i = idx / N, j = idx - i * N;
+              if ((i >> 3) > (j >> 3))
+                {
+                  const int sw = i;
+                  i            = j;
+                  j            = sw;
+                }
+              const double *sl = S + tri_index(NT8, i >> 3, j >> 3) * 64 + (i & 7) * 8 + (j & 7);
+              double        v  = 0.;
+#pragma unroll
+              for (int k = 0; k < KSPLIT; ++k)
+                v += sl[k * NTRI * 64];
+              out[idx] = v;
             }
-          cta_sync();
-          // S aliased the panel: restore the zero padding columns
-          for (int i = tid; i < R * STRIDE; i += NTHR)
-            G[i] = 0.;
         }
     }
 
-    template <int DIM, int DEG, bool MASS, int TQ, int NWARPS>
-    __global__ void __launch_bounds__(NWARPS * 32, 2)
+    template <int DIM, int DEG, bool MASS, int NWARPS>
+    __global__ void __launch_bounds__(NWARPS * 32, NWARPS == 8 ? 2 : 1)
     k_volume(const VolArgs A)
     {
       extern __shared__ double smem[];
       constexpr int NROLE = Cfg<DIM, DEG>::NT8 >= 8 ? 2 : 1;
       if constexpr (NROLE == 1)
-        volume_body<DIM, DEG, MASS, TQ, NWARPS, 1, 0>(A, smem);
+        volume_body<DIM, DEG, MASS, NWARPS, 1, 0>(A, smem);
       else
         {
           if (((threadIdx.x >> 5) & 1) == 0)
-            volume_body<DIM, DEG, MASS, TQ, NWARPS, 2, 0>(A, smem);
+            volume_body<DIM, DEG, MASS, NWARPS, 2, 0>(A, smem);
           else
-            volume_body<DIM, DEG, MASS, TQ, NWARPS, 2, 1>(A, smem);
+            volume_body<DIM, DEG, MASS, NWARPS, 2, 1>(A, smem);
         }
     }
 
-    template <int DIM, int DEG, bool MASS, int TQ>
+    template <int DIM, int DEG, bool MASS, int NWARPS>
     constexpr size_t
     volume_smem_bytes()
     {
-      using C          = Cfg<DIM, DEG>;
-      constexpr int NC = DIM + (MASS ? 1 : 0);
-      constexpr int R  = TQ * NC;
-      size_t        a  = (size_t)R * C::STRIDE + R + (size_t)TQ * DIM * 2 * C::N1;
-      size_t        s  = (size_t)C::NP * (C::NP + 1);
+      using C             = Cfg<DIM, DEG>;
+      constexpr int TQ    = 32;
+      constexpr int NC    = DIM + (MASS ? 1 : 0);
+      constexpr int R     = TQ * NC;
+      constexpr int RS    = ((R + 11) / 16) * 16 + 4;
+      constexpr int NROLE = C::NT8 >= 8 ? 2 : 1;
+      size_t        a     = (size_t)2 * C::NP * RS + (size_t)2 * DIM * 2 * C::N1 * TQ + 3 * R;
+      size_t        s     = (size_t)(NWARPS / NROLE) * C::NTRI * 64;
       return sizeof(double) * (a > s ? a : s);
     }
 
+    // -------------------------------------------------------------------------
     // -------------------------------------------------------------------------
     // face kernel
     // -------------------------------------------------------------------------
@@ -333,38 +410,47 @@ namespace pd
       Basis1D        basis;
     };
 
-    template <int DIM, int DEG, int TQ, int ISPLIT, int KSPLIT>
-    __global__ void __launch_bounds__(4 * ISPLIT * KSPLIT * 32, 1)
+    // Warp roles.  Interior interface: 4 quadrants (Z side, V side) x ISPLIT row groups
+    // x KSPLIT k-parts, each warp MI x NT8 tiles.  Boundary face: only the (0,0)
+    // quadrant exists, so the quadrant index becomes an extra 4-way k-split.
+    template <int DIM, int DEG, int TQ, int ISPLIT, int KSPLIT, int MINB>
+    __global__ void __launch_bounds__(4 * ISPLIT * KSPLIT * 32, MINB)
     k_faces(const FaceArgs A)
     {
       using C              = Cfg<DIM, DEG>;
-      constexpr int N1     = C::N1, N = C::N, NT8 = C::NT8, NP = C::NP;
+      constexpr int N1     = C::N1, N = C::N, NT8 = C::NT8, NP = C::NP, NU = C::NU;
       constexpr int NP2    = 2 * NP;
       constexpr int STRIDE = (NP2 % 16 == 0) ? NP2 + 8 : NP2;
       constexpr int NWARPS = 4 * ISPLIT * KSPLIT;
       constexpr int NTHR   = NWARPS * 32;
       constexpr int MI     = NT8 / ISPLIT;
-      constexpr int SS     = NP2 + 1;
+      constexpr int SS     = NP2 + 1;          // slab row stride
+      constexpr int SLAB   = NP2 * SS;         // doubles per k-part slab (interior)
+      constexpr int KB     = 4 * KSPLIT;       // k-parts of a boundary face
+      constexpr int SSB    = NP + 1;
+      constexpr int SLABB  = NP * SSB;
       static_assert(NT8 % ISPLIT == 0, "row split must divide the tile count");
       static_assert(TQ % 4 == 0, "panel rows must be a multiple of the MMA k");
       static_assert(2 * TQ * DIM <= NTHR, "one thread per (side, direction, point)");
 
       extern __shared__ double smem[];
-      double *Zp = smem;                  // [TQ][STRIDE]  Z rows (side 0 | side 1)
-      double *Vp = Zp + TQ * STRIDE;      // [TQ][STRIDE]  V rows
-      double *WC = Vp + TQ * STRIDE;      // [TQ] JxW * sigma_coefficient
-      double *SG = WC + TQ;               // [TQ] penalty per point
-      double *T  = SG + TQ;               // [TQ][2 sides][DIM][2][N1]
-      double *S  = smem;                  // [NP2][SS] aliases the panels in the epilogue
+      double *Zp = smem;             // [TQ][STRIDE]  Z rows (side 0 | side 1)
+      double *Vp = Zp + TQ * STRIDE; // [TQ][STRIDE]  V rows
+      double *WC = Vp + TQ * STRIDE; // [TQ] JxW * coefficient
+      double *SG = WC + TQ;          // [TQ] sigma / 2 per point
+      double *T  = SG + TQ;          // [TQ][2 sides][DIM][2][N1]
+      double *S  = smem;             // epilogue slabs alias the panels
 
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
       const int g = lane >> 2, t = lane & 3;
-      const int quad = warp & 3, qa = quad >> 1, qb = quad & 1;
+      const int quad  = warp & 3;
       const int isub  = (warp >> 2) % ISPLIT;
       const int kpart = (warp >> 2) / ISPLIT;
 
-      for (int i = tid; i < 2 * TQ * STRIDE; i += NTHR)
-        smem[i] = 0.;
+      const bool tab   = tid < 2 * TQ * DIM;
+      const int  tside = tab ? tid / (TQ * DIM) : 0;
+      const int  trem  = tid - tside * TQ * DIM;
+      const int  td = tab ? trem / TQ : 0, tq = tab ? trem - td * TQ : 0;
 
       for (int f = blockIdx.x; f < A.n_ifaces; f += gridDim.x)
         {
@@ -374,9 +460,14 @@ namespace pd
             continue;
           const int64_t s0 = A.if_sub_ptr[f], s1 = A.if_sub_ptr[f + 1];
           const int64_t q0 = s0 * A.nqf, q1 = s1 * A.nqf;
-          const double *bba = A.bbox + (int64_t)pa * 2 * DIM;
-          const double *bbb = A.bbox + (int64_t)(interior ? pb : pa) * 2 * DIM;
-          const bool    active = interior || quad == 0; // boundary: only the (0,0) quadrant
+          const double *bbt = A.bbox + (int64_t)((tside && interior) ? pb : pa) * 2 * DIM;
+          const double  lo = bbt[td], hi = bbt[DIM + td];
+          const double  inv_h = 1. / (hi - lo);
+          // interior: (qa, qb) quadrant, k-part kpart of KSPLIT; boundary: quadrant (0,0),
+          // k-part kpart*4 + quad of KB
+          const int qa = interior ? (quad >> 1) : 0, qb = interior ? (quad & 1) : 0;
+          const int kp = interior ? kpart : kpart * 4 + quad;
+          const int kn = interior ? KSPLIT : KB;
 
           double acc[MI][NT8][2];
 #pragma unroll
@@ -385,131 +476,129 @@ namespace pd
             for (int J = 0; J < NT8; ++J)
               acc[I][J][0] = acc[I][J][1] = 0.;
 
+          double x_next = lo, n_next = 0., w_next = 0., sg_next = 0.;
+          if (tab && q0 + tq < q1)
+            {
+              x_next = A.fq_x[(int64_t)td * A.Qf + q0 + tq];
+              n_next = A.fq_n[(int64_t)td * A.Qf + q0 + tq];
+              if (tside == 0 && td == 0)
+                {
+                  w_next  = A.fq_w[q0 + tq];
+                  sg_next = A.sub_sigma[(q0 + tq) / A.nqf];
+                }
+            }
+
           for (int64_t qt = q0; qt < q1; qt += TQ)
             {
               __syncthreads();
               // ---- phase 1: per (side, direction, point): l_a, l_a' * n_d / h_d
-              if (tid < 2 * TQ * DIM)
+              if (tab)
                 {
-                  const int     side = tid / (TQ * DIM);
-                  const int     rem  = tid - side * TQ * DIM;
-                  const int     d = rem / TQ, q = rem - d * TQ;
-                  const int64_t gq = qt + q;
-                  const double *bb = side ? bbb : bba;
-                  const double  lo = bb[d], hi = bb[DIM + d];
-                  const bool    ok = gq < q1;
-                  const double  x  = ok ? A.fq_x[(int64_t)d * A.Qf + gq] : lo;
-                  const double  nd = ok ? A.fq_n[(int64_t)d * A.Qf + gq] : 0.;
-                  const double  xhat = (x - lo) / (hi - lo);
-                  double        L[N1], dL[N1];
-                  lagrange<N1>(A.basis, xhat, nd * (1. / (hi - lo)), L, dL);
-                  double *Tq = T + ((q * 2 + side) * DIM + d) * 2 * N1;
+                  const double x = x_next, nd = n_next, w = w_next, sg = sg_next;
+                  const int64_t gq = qt + TQ + tq;
+                  x_next = lo;
+                  n_next = w_next = sg_next = 0.;
+                  if (gq < q1)
+                    {
+                      x_next = A.fq_x[(int64_t)td * A.Qf + gq];
+                      n_next = A.fq_n[(int64_t)td * A.Qf + gq];
+                      if (tside == 0 && td == 0)
+                        {
+                          w_next  = A.fq_w[gq];
+                          sg_next = A.sub_sigma[gq / A.nqf];
+                        }
+                    }
+                  const double xhat = (x - lo) / (hi - lo);
+                  double       L[N1], dL[N1];
+                  lagrange<N1>(A.basis, xhat, nd * inv_h, L, dL);
+                  double *Tq = T + ((tq * 2 + tside) * DIM + td) * 2 * N1;
 #pragma unroll
                   for (int a = 0; a < N1; ++a)
                     {
                       Tq[a]      = L[a];
                       Tq[N1 + a] = dL[a];
                     }
-                  if (side == 0 && d == 0)
+                  if (tside == 0 && td == 0)
                     {
-                      WC[q] = ok ? A.fq_w[gq] * A.stiffness : 0.;
-                      SG[q] = ok ? A.sub_sigma[gq / A.nqf] : 0.;
+                      WC[tq] = w * A.stiffness;
+                      SG[tq] = 0.5 * sg;
                     }
                 }
               __syncthreads();
               // ---- phase 2: V and Z rows.  interior: V = [phi0 ; -phi1],
               //      Z = sigma/2 V - [dn0 ; dn1]/2.  boundary: V = phi0, Z = sigma/2 phi0 - dn0.
-              for (int idx = tid; idx < TQ * 2 * N; idx += NTHR)
+              const int nside = interior ? 2 : 1;
+              for (int u = tid; u < TQ * nside * NU; u += NTHR)
                 {
-                  const int q = idx / (2 * N), rem = idx - q * 2 * N;
-                  const int side = rem / N, i = rem - side * N;
-                  if (side == 1 && !interior)
-                    continue;
+                  const int     q = u / (nside * NU), rem = u - q * nside * NU;
+                  const int     side = rem / NU, bc = rem - side * NU;
                   const double *Tq = T + (q * 2 + side) * DIM * 2 * N1;
-                  double        v, dn;
+                  const double  hs = SG[q];
+                  const double  sgn = side ? -1. : 1.;
+                  const double  dscale = interior ? 0.5 : 1.;
+                  double       *vp = Vp + q * STRIDE + side * NP + bc * N1;
+                  double       *zp = Zp + q * STRIDE + side * NP + bc * N1;
+                  double        s1, s2;
                   if constexpr (DIM == 2)
                     {
-                      const int a = i % N1, b = i / N1;
-                      v  = Tq[a] * Tq[2 * N1 + b];
-                      dn = Tq[N1 + a] * Tq[2 * N1 + b] + Tq[a] * Tq[3 * N1 + b];
+                      s1 = Tq[2 * N1 + bc];
+                      s2 = Tq[3 * N1 + bc];
                     }
                   else
                     {
-                      const int    a = i % N1, b = (i / N1) % N1, c = i / (N1 * N1);
-                      const double lx = Tq[a], ly = Tq[2 * N1 + b], lz = Tq[4 * N1 + c];
-                      v  = lx * ly * lz;
-                      dn = Tq[N1 + a] * ly * lz + lx * (Tq[3 * N1 + b] * lz + ly * Tq[5 * N1 + c]);
+                      const int    b = bc % N1, c = bc / N1;
+                      const double ly = Tq[2 * N1 + b], dy = Tq[3 * N1 + b], lz = Tq[4 * N1 + c], dz = Tq[5 * N1 + c];
+                      s1 = ly * lz;
+                      s2 = dy * lz + ly * dz;
                     }
-                  const double hs = 0.5 * SG[q];
-                  const int    col = side * NP + i;
-                  if (interior)
+#pragma unroll
+                  for (int a = 0; a < N1; ++a)
                     {
-                      const double V = side ? -v : v;
-                      Vp[q * STRIDE + col] = V;
-                      Zp[q * STRIDE + col] = hs * V - 0.5 * dn;
-                    }
-                  else
-                    {
-                      Vp[q * STRIDE + col] = v;
-                      Zp[q * STRIDE + col] = hs * v - dn;
+                      const double lx = Tq[a], dx = Tq[N1 + a];
+                      const double v  = lx * s1;
+                      const double dn = dx * s1 + lx * s2;
+                      const double V  = sgn * v;
+                      vp[a]           = V;
+                      zp[a]           = hs * V - dscale * dn;
                     }
                 }
               __syncthreads();
               // ---- phase 3: T_(qa,qb) += sum_q wc Z_qa V_qb^T
-              if (active)
+              for (int ks = kp; ks < TQ / 4; ks += kn)
                 {
-                  // boundary faces: the four quadrant warps of an (isub,kpart) group would be
-                  // idle except quadrant 0; acceptable, boundary faces are a surface term
-                  for (int ks = kpart; ks < TQ / 4; ks += KSPLIT)
-                    {
-                      const int     r  = ks * 4 + t;
-                      const double  wc = WC[r];
-                      const double *zr = Zp + r * STRIDE + qa * NP + isub * MI * 8 + g;
-                      const double *vr = Vp + r * STRIDE + qb * NP + g;
-                      double        a[MI], b[NT8];
+                  const int     r  = ks * 4 + t;
+                  const double  wc = WC[r];
+                  const double *zr = Zp + r * STRIDE + qa * NP + isub * MI * 8 + g;
+                  const double *vr = Vp + r * STRIDE + qb * NP + g;
+                  double        a[MI], b[NT8];
 #pragma unroll
-                      for (int I = 0; I < MI; ++I)
-                        a[I] = zr[8 * I];
+                  for (int I = 0; I < MI; ++I)
+                    a[I] = zr[8 * I];
 #pragma unroll
-                      for (int J = 0; J < NT8; ++J)
-                        b[J] = vr[8 * J] * wc;
-#pragma unroll
-                      for (int I = 0; I < MI; ++I)
-#pragma unroll
-                        for (int J = 0; J < NT8; ++J)
-                          dmma884(acc[I][J][0], acc[I][J][1], a[I], b[J]);
-                    }
-                }
-            }
-          // ---- epilogue: T -> shared, M = T + T^T -> global
-          __syncthreads();
-          for (int round = 0; round < KSPLIT; ++round)
-            {
-              if (kpart == round && active)
-                {
+                  for (int J = 0; J < NT8; ++J)
+                    b[J] = vr[8 * J] * wc;
 #pragma unroll
                   for (int I = 0; I < MI; ++I)
 #pragma unroll
                     for (int J = 0; J < NT8; ++J)
-                      {
-                        double *s = S + (qa * NP + (isub * MI + I) * 8 + g) * SS + qb * NP + 8 * J + 2 * t;
-                        if (round == 0)
-                          {
-                            s[0] = acc[I][J][0];
-                            s[1] = acc[I][J][1];
-                          }
-                        else
-                          {
-                            s[0] += acc[I][J][0];
-                            s[1] += acc[I][J][1];
-                          }
-                      }
+                      dmma884(acc[I][J][0], acc[I][J][1], a[I], b[J]);
                 }
-              __syncthreads();
             }
+          // ---- epilogue: k-part slabs -> M = T + T^T -> global
+          __syncthreads();
           double *fd = A.face_diag + (int64_t)f * 2 * N * N;
           if (interior)
             {
+#pragma unroll
+              for (int I = 0; I < MI; ++I)
+#pragma unroll
+                for (int J = 0; J < NT8; ++J)
+                  {
+                    double *s = S + kp * SLAB + (qa * NP + (isub * MI + I) * 8 + g) * SS + qb * NP + 8 * J + 2 * t;
+                    s[0]      = acc[I][J][0];
+                    s[1]      = acc[I][J][1];
+                  }
+              __syncthreads();
               const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
               const int     strideA = A.row_stride[A.dof_block[pa]], strideB = A.row_stride[A.dof_block[pb]];
               for (int idx = tid; idx < 4 * N * N; idx += NTHR)
@@ -517,7 +606,10 @@ namespace pd
                   const int which = idx / (N * N), rem = idx - which * N * N;
                   const int i = rem / N, j = rem - i * N;
                   const int ri = (which >> 1) * NP + i, cj = (which & 1) * NP + j;
-                  const double m = S[ri * SS + cj] + S[cj * SS + ri];
+                  double    m = 0.;
+#pragma unroll
+                  for (int k = 0; k < KSPLIT; ++k)
+                    m += S[k * SLAB + ri * SS + cj] + S[k * SLAB + cj * SS + ri];
                   if (which == 0)
                     fd[rem] = m;
                   else if (which == 3)
@@ -530,19 +622,30 @@ namespace pd
             }
           else
             {
+#pragma unroll
+              for (int I = 0; I < MI; ++I)
+#pragma unroll
+                for (int J = 0; J < NT8; ++J)
+                  {
+                    double *s = S + kp * SLABB + ((isub * MI + I) * 8 + g) * SSB + 8 * J + 2 * t;
+                    s[0]      = acc[I][J][0];
+                    s[1]      = acc[I][J][1];
+                  }
+              __syncthreads();
               for (int idx = tid; idx < N * N; idx += NTHR)
                 {
                   const int i = idx / N, j = idx - i * N;
-                  fd[idx]     = S[i * SS + j] + S[j * SS + i];
+                  double    m = 0.;
+#pragma unroll
+                  for (int k = 0; k < KB; ++k)
+                    m += S[k * SLABB + i * SSB + j] + S[k * SLABB + j * SSB + i];
+                  fd[idx] = m;
                 }
             }
-          __syncthreads();
-          for (int i = tid; i < 2 * TQ * STRIDE; i += NTHR)
-            smem[i] = 0.;
         }
     }
 
-    template <int DIM, int DEG, int TQ>
+    template <int DIM, int DEG, int TQ, int KSPLIT>
     constexpr size_t
     face_smem_bytes()
     {
@@ -550,7 +653,9 @@ namespace pd
       constexpr int NP2    = 2 * C::NP;
       constexpr int STRIDE = (NP2 % 16 == 0) ? NP2 + 8 : NP2;
       size_t        a      = (size_t)2 * TQ * STRIDE + 2 * TQ + (size_t)TQ * 2 * DIM * 2 * C::N1;
-      size_t        s      = (size_t)NP2 * (NP2 + 1);
+      size_t        s      = (size_t)KSPLIT * NP2 * (NP2 + 1);
+      size_t        sb     = (size_t)4 * KSPLIT * C::NP * (C::NP + 1);
+      s                    = s > sb ? s : sb;
       return sizeof(double) * (a > s ? a : s);
     }
 
@@ -611,37 +716,100 @@ namespace pd
         PD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     }
 
-    template <int DIM, int DEG, bool MASS, int TQ>
+    // Stage-balanced persistent schedule: the stages (TQ points of one polytope) of all
+    // polytopes are dealt to `grid` CTAs in equal contiguous shares; an item is a maximal
+    // run of one polytope's stages inside one share.  Every CTA does the same amount of
+    // MMA work whatever the polytope sizes are (METIS shapes vary in #sub-cells).
+    void
+    plan_volume(pd_handle *h, const int tq, const int grid)
+    {
+      if (h->vol_plan_tq == tq && h->vol_plan_grid == grid)
+        return;
+      const std::vector<int64_t> &sub = h->h_subcell_ptr;
+      std::vector<int64_t> stage_ptr(h->np + 1, 0);
+      for (int32_t p = 0; p < h->np; ++p)
+        stage_ptr[p + 1] = stage_ptr[p] + ((sub[p + 1] - sub[p]) * h->nqc + tq - 1) / tq;
+      const int64_t        S = stage_ptr[h->np];
+      std::vector<int32_t> item_poly, cta_ptr(grid + 1, 0);
+      std::vector<int64_t> q0, q1, poly_item_ptr(h->np + 1, 0);
+      // items are emitted polytope-major so that a polytope's partials are contiguous;
+      // a polytope's stage range is cut wherever a CTA share boundary falls inside it
+      std::vector<int32_t> item_cta;
+      for (int32_t p = 0; p < h->np; ++p)
+        {
+          int64_t s = stage_ptr[p];
+          while (s < stage_ptr[p + 1])
+            {
+              const int64_t c   = std::min<int64_t>(grid - 1, (s * grid) / std::max<int64_t>(S, 1));
+              // first stage of CTA c+1 = smallest s' with floor(s' grid / S) >= c+1
+              int64_t end = ((c + 1) * S + grid - 1) / grid;
+              end         = std::min(end, stage_ptr[p + 1]);
+              if (end <= s)
+                end = s + 1;
+              const int64_t base = sub[p] * h->nqc;
+              item_poly.push_back(p);
+              item_cta.push_back((int32_t)c);
+              q0.push_back(base + (s - stage_ptr[p]) * tq);
+              q1.push_back(std::min(base + (end - stage_ptr[p]) * tq, sub[p + 1] * h->nqc));
+              s = end;
+            }
+          poly_item_ptr[p + 1] = (int64_t)item_poly.size();
+        }
+      // items are already sorted by CTA (shares are contiguous in stage order)
+      for (size_t i = 0; i < item_cta.size(); ++i)
+        ++cta_ptr[item_cta[i] + 1];
+      for (int c = 0; c < grid; ++c)
+        cta_ptr[c + 1] += cta_ptr[c];
+      h->n_vitems = (int32_t)item_poly.size();
+      auto put = [](auto &buf, const auto &v) {
+        buf.alloc(v.size());
+        if (!v.empty())
+          PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+      };
+      put(h->vitem_poly, item_poly);
+      put(h->vitem_q0, q0);
+      put(h->vitem_q1, q1);
+      put(h->poly_vitem_ptr, poly_item_ptr);
+      put(h->cta_item_ptr, cta_ptr);
+      h->vol_partial.alloc((size_t)h->n_vitems * h->n * h->n);
+      h->vol_plan_tq   = tq;
+      h->vol_plan_grid = grid;
+    }
+
+    template <int DIM, int DEG, bool MASS>
     void
     run_volume(pd_handle *h, const pd_coefficients &coef)
     {
-      constexpr int NWARPS = 8;
-      VolArgs       a;
-      a.vq_x      = h->vq_x.p;
-      a.vq_w      = h->vq_w.p;
-      a.Q         = h->Q;
-      a.bbox      = h->bbox.p;
-      a.item_poly = h->vitem_poly.p;
-      a.item_q0   = h->vitem_q0.p;
-      a.item_q1   = h->vitem_q1.p;
-      a.n_items   = h->n_vitems;
-      a.partial   = h->vol_partial.p;
-      a.stiffness = coef.stiffness;
-      a.mass      = coef.mass;
-      a.basis     = h->basis;
-      auto           kern  = k_volume<DIM, DEG, MASS, TQ, NWARPS>;
-      constexpr size_t smem = volume_smem_bytes<DIM, DEG, MASS, TQ>();
+      constexpr int    TQ     = 32;
+      constexpr int    NWARPS = Cfg<DIM, DEG>::NT8 >= 8 ? 16 : 8;
+      auto             kern   = k_volume<DIM, DEG, MASS, NWARPS>;
+      constexpr size_t smem   = volume_smem_bytes<DIM, DEG, MASS, NWARPS>();
       set_smem(kern, smem);
       int per_sm = 1;
       PD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NWARPS * 32, smem));
       if (per_sm < 1)
         per_sm = 1;
-      const int grid = std::min<int64_t>(h->n_vitems, (int64_t)h->sm_count * per_sm);
+      const int64_t total_stages = (h->Q + TQ - 1) / TQ + h->np;
+      const int     grid         = (int)std::max<int64_t>(1, std::min<int64_t>(total_stages / 4 + 1, (int64_t)h->sm_count * per_sm));
+      plan_volume(h, TQ, grid);
+      VolArgs a;
+      a.vq_x         = h->vq_x.p;
+      a.vq_w         = h->vq_w.p;
+      a.Q            = h->Q;
+      a.bbox         = h->bbox.p;
+      a.item_poly    = h->vitem_poly.p;
+      a.item_q0      = h->vitem_q0.p;
+      a.item_q1      = h->vitem_q1.p;
+      a.cta_item_ptr = h->cta_item_ptr.p;
+      a.partial      = h->vol_partial.p;
+      a.stiffness    = coef.stiffness;
+      a.mass         = coef.mass;
+      a.basis        = h->basis;
       kern<<<grid, NWARPS * 32, smem, h->stream>>>(a);
       ++h->launches;
     }
 
-    template <int DIM, int DEG, int TQ, int ISPLIT, int KSPLIT>
+    template <int DIM, int DEG, int TQ, int ISPLIT, int KSPLIT, int MINB>
     void
     run_faces(pd_handle *h, const pd_coefficients &coef, const uint32_t flags)
     {
@@ -666,9 +834,9 @@ namespace pd
       a.stiffness  = coef.stiffness;
       a.flags      = flags;
       a.basis      = h->basis;
-      auto             kern  = k_faces<DIM, DEG, TQ, ISPLIT, KSPLIT>;
-      constexpr size_t smem  = face_smem_bytes<DIM, DEG, TQ>();
-      constexpr int    nthr  = 4 * ISPLIT * KSPLIT * 32;
+      auto             kern = k_faces<DIM, DEG, TQ, ISPLIT, KSPLIT, MINB>;
+      constexpr size_t smem = face_smem_bytes<DIM, DEG, TQ, KSPLIT>();
+      constexpr int    nthr = 4 * ISPLIT * KSPLIT * 32;
       set_smem(kern, smem);
       int per_sm = 1;
       PD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthr, smem));
@@ -679,22 +847,24 @@ namespace pd
       ++h->launches;
     }
 
-    template <int DIM, int DEG, int TQV, int TQF, int ISPLIT, int KSPLIT>
+    template <int DIM, int DEG, int TQV, int TQF, int ISPLIT, int KSPLIT, int MINB>
     void
     run_all(pd_handle *h, const uint32_t flags, const pd_coefficients &coef)
     {
       PD_CUDA(cudaEventRecord(h->ev[0], h->stream));
-      if ((flags & PD_ASSEMBLE_VOLUME) && h->n_vitems > 0)
+      if ((flags & PD_ASSEMBLE_VOLUME) && h->Q > 0)
         {
           if (coef.mass != 0.)
-            run_volume<DIM, DEG, true, TQV>(h, coef);
+            run_volume<DIM, DEG, true>(h, coef);
           else
-            run_volume<DIM, DEG, false, TQV>(h, coef);
+            run_volume<DIM, DEG, false>(h, coef);
         }
       PD_CUDA(cudaEventRecord(h->ev[1], h->stream));
       if ((flags & (PD_ASSEMBLE_BOUNDARY | PD_ASSEMBLE_INTERIOR)) && h->n_ifaces > 0)
-        run_faces<DIM, DEG, TQF, ISPLIT, KSPLIT>(h, coef, flags);
+        run_faces<DIM, DEG, TQF, ISPLIT, KSPLIT, MINB>(h, coef, flags);
       PD_CUDA(cudaEventRecord(h->ev[2], h->stream));
+      if (h->vol_plan_tq == 0) // volume never planned (flags without VOLUME): empty item lists
+        plan_volume(h, 32, 1);
       ReduceArgs r;
       r.poly_vitem_ptr = h->poly_vitem_ptr.p;
       r.partial        = h->vol_partial.p;
@@ -736,14 +906,14 @@ namespace pd
     const int key = h->dim * 10 + h->degree;
     switch (key)
       {
-        //                 DIM DEG TQV TQF ISPLIT KSPLIT
-        case 21: run_all<2, 1, 64, 32, 1, 2>(h, flags, coef); break;
-        case 22: run_all<2, 2, 64, 32, 1, 2>(h, flags, coef); break;
-        case 23: run_all<2, 3, 64, 32, 1, 2>(h, flags, coef); break;
-        case 24: run_all<2, 4, 64, 32, 1, 2>(h, flags, coef); break;
-        case 31: run_all<3, 1, 64, 32, 1, 2>(h, flags, coef); break;
-        case 32: run_all<3, 2, 64, 32, 1, 2>(h, flags, coef); break;
-        case 33: run_all<3, 3, 32, 16, 4, 1>(h, flags, coef); break;
+        //                 DIM DEG TQV TQF ISPLIT KSPLIT MINB
+        case 21: run_all<2, 1, 64, 32, 1, 2, 2>(h, flags, coef); break;
+        case 22: run_all<2, 2, 64, 32, 1, 2, 2>(h, flags, coef); break;
+        case 23: run_all<2, 3, 64, 32, 1, 2, 2>(h, flags, coef); break;
+        case 24: run_all<2, 4, 64, 32, 1, 2, 2>(h, flags, coef); break;
+        case 31: run_all<3, 1, 64, 32, 1, 2, 2>(h, flags, coef); break;
+        case 32: run_all<3, 2, 64, 32, 1, 2, 2>(h, flags, coef); break;
+        case 33: run_all<3, 3, 32, 16, 4, 1, 1>(h, flags, coef); break;
         default:
           throw CudaError{cudaErrorNotSupported, "no assembly kernel for this (dim, degree)", __LINE__};
       }

@@ -98,13 +98,15 @@ struct pd_handle
   // derived index data
   pd::DevBuf<int64_t> diag_base, if_baseAB, if_baseBA, vitem_q0, vitem_q1, poly_vitem_ptr, padj_ptr, padj;
   pd::DevBuf<int32_t> row_stride, vitem_poly; // row_stride[b] = (#blocks in block row b) * n
+  pd::DevBuf<int32_t> cta_item_ptr;           // volume items of every persistent CTA
+  int                 vol_plan_tq = 0, vol_plan_grid = 0; // schedule the item lists were built for
   // quadrature (SoA by coordinate)
   pd::DevBuf<double> vq_x, vq_w, fq_x, fq_n, fq_w;
   // work buffers and result
   pd::DevBuf<double> vol_partial, face_diag, values;
   pd::DevBuf<double> vec_a, vec_b; // staging for pd_vmult_host
 
-  std::vector<int64_t> h_brow_ptr;
+  std::vector<int64_t> h_brow_ptr, h_subcell_ptr;
   std::vector<int32_t> h_bcol, h_dof_block;
 
   cudaStream_t stream     = nullptr;

@@ -215,6 +215,9 @@ class SIPOperator:
     def build_quadrature(self):
         K.check(K.lib().pd_build_quadrature(self._h))
 
+    def invalidate_quadrature(self):
+        K.check(K.lib().pd_invalidate_quadrature(self._h))
+
     def assemble(self, flags=K.ASSEMBLE_ALL, stiffness=1.0, mass=0.0):
         c = K.Coefficients(stiffness, mass)
         K.check(K.lib().pd_assemble(self._h, flags, C.byref(c)))
