@@ -273,6 +273,18 @@ namespace pd
         make_basis_1d(h->degree, h->basis);
         make_gauss_1d(h->nq1, h->quad);
         make_gauss_1d(h->nq1f, h->quadf);
+        {
+          double r[32];
+          for (int i = 0; i < 8; ++i)
+            {
+              r[i]      = h->quad.x[i];
+              r[8 + i]  = h->quad.w[i];
+              r[16 + i] = h->quadf.x[i];
+              r[24 + i] = h->quadf.w[i];
+            }
+          h->rules.alloc(32);
+          PD_CUDA(cudaMemcpy(h->rules.p, r, sizeof(r), cudaMemcpyHostToDevice));
+        }
         h->n_verts    = d.n_verts;
         h->n_cells    = d.n_cells;
         h->np         = d.n_polytopes;

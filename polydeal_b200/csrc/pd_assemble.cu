@@ -410,35 +410,44 @@ namespace pd
       Basis1D        basis;
     };
 
-    // Warp roles.  Interior interface: 4 quadrants (Z side, V side) x ISPLIT row groups
-    // x KSPLIT k-parts, each warp MI x NT8 tiles.  Boundary face: only the (0,0)
-    // quadrant exists, so the quadrant index becomes an extra 4-way k-split.
-    template <int DIM, int DEG, int TQ, int ISPLIT, int KSPLIT, int MINB>
+    // Face kernel, software-pipelined like the volume kernel (stage = 32 points, lane =
+    // point, one barrier per stage):
+    //   table tasks (side, direction): l_a and l_a' n_d / h_d of stage s+2
+    //   generator units (side, b[,c]): V and Z columns of stage s+1
+    //   all warps: DMMA contraction of stage s
+    // Warp roles in the contraction.  Interior interface: 4 quadrants (Z side, V side) x
+    // ISPLIT row groups x KSPLIT k-parts, each warp MI x NT8 tiles.  Boundary face: only
+    // the (0,0) quadrant exists, so the quadrant index becomes an extra 4-way k-split.
+    // Panels are DOF-major with row stride 36 = 4 (mod 16): conflict-free stores
+    // (lane = point) and fragment loads.
+    template <int DIM, int DEG, int ISPLIT, int KSPLIT, int MINB>
     __global__ void __launch_bounds__(4 * ISPLIT * KSPLIT * 32, MINB)
     k_faces(const FaceArgs A)
     {
       using C              = Cfg<DIM, DEG>;
+      constexpr int TQ     = 32;
+      constexpr int RS     = 36;
       constexpr int N1     = C::N1, N = C::N, NT8 = C::NT8, NP = C::NP, NU = C::NU;
       constexpr int NP2    = 2 * NP;
-      constexpr int STRIDE = (NP2 % 16 == 0) ? NP2 + 8 : NP2;
       constexpr int NWARPS = 4 * ISPLIT * KSPLIT;
       constexpr int NTHR   = NWARPS * 32;
       constexpr int MI     = NT8 / ISPLIT;
-      constexpr int SS     = NP2 + 1;          // slab row stride
-      constexpr int SLAB   = NP2 * SS;         // doubles per k-part slab (interior)
-      constexpr int KB     = 4 * KSPLIT;       // k-parts of a boundary face
+      constexpr int SS     = NP2 + 1;    // slab row stride
+      constexpr int SLAB   = NP2 * SS;   // doubles per k-part slab (interior)
+      constexpr int KB     = 4 * KSPLIT; // k-parts of a boundary face
       constexpr int SSB    = NP + 1;
       constexpr int SLABB  = NP * SSB;
+      constexpr int NTAB   = 2 * DIM;    // table tasks
+      constexpr int PSZ    = NP2 * RS;   // one panel (Z or V) of one buffer
+      constexpr int TSZ    = 2 * DIM * 2 * N1 * TQ;
       static_assert(NT8 % ISPLIT == 0, "row split must divide the tile count");
-      static_assert(TQ % 4 == 0, "panel rows must be a multiple of the MMA k");
-      static_assert(2 * TQ * DIM <= NTHR, "one thread per (side, direction, point)");
+      static_assert(NTAB <= NWARPS, "one warp per table task");
 
       extern __shared__ double smem[];
-      double *Zp = smem;             // [TQ][STRIDE]  Z rows (side 0 | side 1)
-      double *Vp = Zp + TQ * STRIDE; // [TQ][STRIDE]  V rows
-      double *WC = Vp + TQ * STRIDE; // [TQ] JxW * coefficient
-      double *SG = WC + TQ;          // [TQ] sigma / 2 per point
-      double *T  = SG + TQ;          // [TQ][2 sides][DIM][2][N1]
+      double *Pb = smem;             // [2 bufs][Z,V][NP2][RS]
+      double *Tb = Pb + 4 * PSZ;     // [2 bufs][side][d][2][N1][TQ]
+      double *WC = Tb + 2 * TSZ;     // [3][TQ] JxW * coefficient
+      double *SG = WC + 3 * TQ;      // [2][TQ] sigma / 2
       double *S  = smem;             // epilogue slabs alias the panels
 
       const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -446,11 +455,10 @@ namespace pd
       const int quad  = warp & 3;
       const int isub  = (warp >> 2) % ISPLIT;
       const int kpart = (warp >> 2) / ISPLIT;
-
-      const bool tab   = tid < 2 * TQ * DIM;
-      const int  tside = tab ? tid / (TQ * DIM) : 0;
-      const int  trem  = tid - tside * TQ * DIM;
-      const int  td = tab ? trem / TQ : 0, tq = tab ? trem - td * TQ : 0;
+      const bool tabw  = warp < NTAB;
+      const int  tside = tabw ? warp / DIM : 0, td = tabw ? warp % DIM : 0;
+      const bool lead  = tabw && warp == 0; // task (side 0, d 0) also carries JxW and sigma
+      const int  first_unit = (warp - NTAB + NWARPS) % NWARPS;
 
       for (int f = blockIdx.x; f < A.n_ifaces; f += gridDim.x)
         {
@@ -460,14 +468,18 @@ namespace pd
             continue;
           const int64_t s0 = A.if_sub_ptr[f], s1 = A.if_sub_ptr[f + 1];
           const int64_t q0 = s0 * A.nqf, q1 = s1 * A.nqf;
+          const int     nst = (int)((q1 - q0 + TQ - 1) / TQ);
           const double *bbt = A.bbox + (int64_t)((tside && interior) ? pb : pa) * 2 * DIM;
           const double  lo = bbt[td], hi = bbt[DIM + td];
           const double  inv_h = 1. / (hi - lo);
+          const bool    tab_active = tabw && (interior || tside == 0);
           // interior: (qa, qb) quadrant, k-part kpart of KSPLIT; boundary: quadrant (0,0),
           // k-part kpart*4 + quad of KB
           const int qa = interior ? (quad >> 1) : 0, qb = interior ? (quad & 1) : 0;
           const int kp = interior ? kpart : kpart * 4 + quad;
           const int kn = interior ? KSPLIT : KB;
+          const int nunits = (interior ? 2 : 1) * NU;
+          const double dscale = interior ? 0.5 : 1.;
 
           double acc[MI][NT8][2];
 #pragma unroll
@@ -476,116 +488,128 @@ namespace pd
             for (int J = 0; J < NT8; ++J)
               acc[I][J][0] = acc[I][J][1] = 0.;
 
-          double x_next = lo, n_next = 0., w_next = 0., sg_next = 0.;
-          if (tab && q0 + tq < q1)
-            {
-              x_next = A.fq_x[(int64_t)td * A.Qf + q0 + tq];
-              n_next = A.fq_n[(int64_t)td * A.Qf + q0 + tq];
-              if (tside == 0 && td == 0)
-                {
-                  w_next  = A.fq_w[q0 + tq];
-                  sg_next = A.sub_sigma[(q0 + tq) / A.nqf];
-                }
-            }
-
-          for (int64_t qt = q0; qt < q1; qt += TQ)
-            {
-              __syncthreads();
-              // ---- phase 1: per (side, direction, point): l_a, l_a' * n_d / h_d
-              if (tab)
-                {
-                  const double x = x_next, nd = n_next, w = w_next, sg = sg_next;
-                  const int64_t gq = qt + TQ + tq;
-                  x_next = lo;
-                  n_next = w_next = sg_next = 0.;
-                  if (gq < q1)
-                    {
-                      x_next = A.fq_x[(int64_t)td * A.Qf + gq];
-                      n_next = A.fq_n[(int64_t)td * A.Qf + gq];
-                      if (tside == 0 && td == 0)
-                        {
-                          w_next  = A.fq_w[gq];
-                          sg_next = A.sub_sigma[gq / A.nqf];
-                        }
-                    }
-                  const double xhat = (x - lo) / (hi - lo);
-                  double       L[N1], dL[N1];
-                  lagrange<N1>(A.basis, xhat, nd * inv_h, L, dL);
-                  double *Tq = T + ((tq * 2 + tside) * DIM + td) * 2 * N1;
+          double x_pre = lo, n_pre = 0., w_pre = 0., sg_pre = 0.;
+          auto   prefetch = [&](const int s) {
+            const int64_t gq = q0 + (int64_t)s * TQ + lane;
+            x_pre = lo;
+            n_pre = w_pre = sg_pre = 0.;
+            if (s < nst && gq < q1)
+              {
+                x_pre = A.fq_x[(int64_t)td * A.Qf + gq];
+                n_pre = A.fq_n[(int64_t)td * A.Qf + gq];
+                if (lead)
+                  {
+                    w_pre  = A.fq_w[gq];
+                    sg_pre = A.sub_sigma[gq / A.nqf];
+                  }
+              }
+          };
+          auto tables = [&](const int s) {
+            const double x = x_pre, nd = n_pre, w = w_pre, sg = sg_pre;
+            prefetch(s + 1);
+            if (s >= nst)
+              return;
+            const double xhat = (x - lo) / (hi - lo);
+            double       L[N1], dL[N1];
+            lagrange<N1>(A.basis, xhat, nd * inv_h, L, dL);
+            double *Tq = Tb + (s & 1) * TSZ + (tside * DIM + td) * 2 * N1 * TQ + lane;
 #pragma unroll
-                  for (int a = 0; a < N1; ++a)
-                    {
-                      Tq[a]      = L[a];
-                      Tq[N1 + a] = dL[a];
-                    }
-                  if (tside == 0 && td == 0)
-                    {
-                      WC[tq] = w * A.stiffness;
-                      SG[tq] = 0.5 * sg;
-                    }
-                }
-              __syncthreads();
-              // ---- phase 2: V and Z rows.  interior: V = [phi0 ; -phi1],
-              //      Z = sigma/2 V - [dn0 ; dn1]/2.  boundary: V = phi0, Z = sigma/2 phi0 - dn0.
-              const int nside = interior ? 2 : 1;
-              for (int u = tid; u < TQ * nside * NU; u += NTHR)
-                {
-                  const int     q = u / (nside * NU), rem = u - q * nside * NU;
-                  const int     side = rem / NU, bc = rem - side * NU;
-                  const double *Tq = T + (q * 2 + side) * DIM * 2 * N1;
-                  const double  hs = SG[q];
-                  const double  sgn = side ? -1. : 1.;
-                  const double  dscale = interior ? 0.5 : 1.;
-                  double       *vp = Vp + q * STRIDE + side * NP + bc * N1;
-                  double       *zp = Zp + q * STRIDE + side * NP + bc * N1;
-                  double        s1, s2;
-                  if constexpr (DIM == 2)
-                    {
-                      s1 = Tq[2 * N1 + bc];
-                      s2 = Tq[3 * N1 + bc];
-                    }
-                  else
-                    {
-                      const int    b = bc % N1, c = bc / N1;
-                      const double ly = Tq[2 * N1 + b], dy = Tq[3 * N1 + b], lz = Tq[4 * N1 + c], dz = Tq[5 * N1 + c];
-                      s1 = ly * lz;
-                      s2 = dy * lz + ly * dz;
-                    }
+            for (int a = 0; a < N1; ++a)
+              {
+                Tq[a * TQ]        = L[a];
+                Tq[(N1 + a) * TQ] = dL[a];
+              }
+            if (lead)
+              {
+                WC[(s % 3) * TQ + lane] = w * A.stiffness;
+                SG[(s & 1) * TQ + lane] = 0.5 * sg;
+              }
+          };
+          // V and Z columns.  interior: V = [phi0 ; -phi1], Z = sigma/2 V - [dn0 ; dn1]/2.
+          // boundary: V = phi0, Z = sigma/2 phi0 - dn0.
+          auto generate = [&](const int s) {
+            if (s >= nst)
+              return;
+            const double hs = SG[(s & 1) * TQ + lane];
+            double      *Zp = Pb + (s & 1) * 2 * PSZ + lane;
+            double      *Vp = Zp + PSZ;
+            for (int wu = first_unit; wu < nunits; wu += NWARPS)
+              {
+                const int     side = wu / NU, bc = wu - side * NU;
+                const double *Tq   = Tb + (s & 1) * TSZ + side * DIM * 2 * N1 * TQ + lane;
+                const double  sgn  = side ? -1. : 1.;
+                double        s1, s2;
+                if constexpr (DIM == 2)
+                  {
+                    s1 = Tq[(2 * N1 + bc) * TQ];
+                    s2 = Tq[(3 * N1 + bc) * TQ];
+                  }
+                else
+                  {
+                    const int    b = bc % N1, c = bc / N1;
+                    const double ly = Tq[(2 * N1 + b) * TQ], dy = Tq[(3 * N1 + b) * TQ];
+                    const double lz = Tq[(4 * N1 + c) * TQ], dz = Tq[(5 * N1 + c) * TQ];
+                    s1 = ly * lz;
+                    s2 = dy * lz + ly * dz;
+                  }
 #pragma unroll
-                  for (int a = 0; a < N1; ++a)
-                    {
-                      const double lx = Tq[a], dx = Tq[N1 + a];
-                      const double v  = lx * s1;
-                      const double dn = dx * s1 + lx * s2;
-                      const double V  = sgn * v;
-                      vp[a]           = V;
-                      zp[a]           = hs * V - dscale * dn;
-                    }
-                }
-              __syncthreads();
-              // ---- phase 3: T_(qa,qb) += sum_q wc Z_qa V_qb^T
-              for (int ks = kp; ks < TQ / 4; ks += kn)
-                {
-                  const int     r  = ks * 4 + t;
-                  const double  wc = WC[r];
-                  const double *zr = Zp + r * STRIDE + qa * NP + isub * MI * 8 + g;
-                  const double *vr = Vp + r * STRIDE + qb * NP + g;
-                  double        a[MI], b[NT8];
+                for (int a = 0; a < N1; ++a)
+                  {
+                    const double lx = Tq[a * TQ], dx = Tq[(N1 + a) * TQ];
+                    const double v  = lx * s1;
+                    const double dn = dx * s1 + lx * s2;
+                    const double V  = sgn * v;
+                    const int    col = side * NP + bc * N1 + a;
+                    Vp[col * RS]     = V;
+                    Zp[col * RS]     = hs * V - dscale * dn;
+                  }
+              }
+          };
+          // T_(qa,qb) += sum_q wc Z_qa V_qb^T
+          auto contract = [&](const int s) {
+            const double *Zs = Pb + (s & 1) * 2 * PSZ + (qa * NP + isub * MI * 8 + g) * RS + t;
+            const double *Vs = Pb + (s & 1) * 2 * PSZ + PSZ + (qb * NP + g) * RS + t;
+            const double *ws = WC + (s % 3) * TQ + t;
+            for (int ks = kp; ks < TQ / 4; ks += kn)
+              {
+                const double wc = ws[ks * 4];
+                double       a[MI], b[NT8];
 #pragma unroll
-                  for (int I = 0; I < MI; ++I)
-                    a[I] = zr[8 * I];
+                for (int I = 0; I < MI; ++I)
+                  a[I] = Zs[8 * I * RS + ks * 4];
+#pragma unroll
+                for (int J = 0; J < NT8; ++J)
+                  b[J] = Vs[8 * J * RS + ks * 4] * wc;
+#pragma unroll
+                for (int I = 0; I < MI; ++I)
 #pragma unroll
                   for (int J = 0; J < NT8; ++J)
-                    b[J] = vr[8 * J] * wc;
-#pragma unroll
-                  for (int I = 0; I < MI; ++I)
-#pragma unroll
-                    for (int J = 0; J < NT8; ++J)
-                      dmma884(acc[I][J][0], acc[I][J][1], a[I], b[J]);
-                }
+                    dmma884(acc[I][J][0], acc[I][J][1], a[I], b[J]);
+              }
+          };
+
+          // ---- pipeline fill
+          __syncthreads(); // previous interface's epilogue is done with the aliased slabs
+          if (tab_active)
+            {
+              prefetch(0);
+              tables(0);
+            }
+          __syncthreads();
+          if (tab_active)
+            tables(1);
+          generate(0);
+          __syncthreads();
+          // ---- steady state
+          for (int s = 0; s < nst; ++s)
+            {
+              if (tab_active)
+                tables(s + 2);
+              generate(s + 1);
+              contract(s);
+              __syncthreads();
             }
           // ---- epilogue: k-part slabs -> M = T + T^T -> global
-          __syncthreads();
           double *fd = A.face_diag + (int64_t)f * 2 * N * N;
           if (interior)
             {
@@ -594,9 +618,9 @@ namespace pd
 #pragma unroll
                 for (int J = 0; J < NT8; ++J)
                   {
-                    double *s = S + kp * SLAB + (qa * NP + (isub * MI + I) * 8 + g) * SS + qb * NP + 8 * J + 2 * t;
-                    s[0]      = acc[I][J][0];
-                    s[1]      = acc[I][J][1];
+                    double *sl = S + kp * SLAB + (qa * NP + (isub * MI + I) * 8 + g) * SS + qb * NP + 8 * J + 2 * t;
+                    sl[0]      = acc[I][J][0];
+                    sl[1]      = acc[I][J][1];
                   }
               __syncthreads();
               const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
@@ -627,9 +651,9 @@ namespace pd
 #pragma unroll
                 for (int J = 0; J < NT8; ++J)
                   {
-                    double *s = S + kp * SLABB + ((isub * MI + I) * 8 + g) * SSB + 8 * J + 2 * t;
-                    s[0]      = acc[I][J][0];
-                    s[1]      = acc[I][J][1];
+                    double *sl = S + kp * SLABB + ((isub * MI + I) * 8 + g) * SSB + 8 * J + 2 * t;
+                    sl[0]      = acc[I][J][0];
+                    sl[1]      = acc[I][J][1];
                   }
               __syncthreads();
               for (int idx = tid; idx < N * N; idx += NTHR)
@@ -645,17 +669,17 @@ namespace pd
         }
     }
 
-    template <int DIM, int DEG, int TQ, int KSPLIT>
+    template <int DIM, int DEG, int KSPLIT>
     constexpr size_t
     face_smem_bytes()
     {
-      using C              = Cfg<DIM, DEG>;
-      constexpr int NP2    = 2 * C::NP;
-      constexpr int STRIDE = (NP2 % 16 == 0) ? NP2 + 8 : NP2;
-      size_t        a      = (size_t)2 * TQ * STRIDE + 2 * TQ + (size_t)TQ * 2 * DIM * 2 * C::N1;
-      size_t        s      = (size_t)KSPLIT * NP2 * (NP2 + 1);
-      size_t        sb     = (size_t)4 * KSPLIT * C::NP * (C::NP + 1);
-      s                    = s > sb ? s : sb;
+      using C           = Cfg<DIM, DEG>;
+      constexpr int TQ  = 32, RS = 36;
+      constexpr int NP2 = 2 * C::NP;
+      size_t        a   = (size_t)4 * NP2 * RS + (size_t)2 * 2 * DIM * 2 * C::N1 * TQ + 5 * TQ;
+      size_t        s   = (size_t)KSPLIT * NP2 * (NP2 + 1);
+      size_t        sb  = (size_t)4 * KSPLIT * C::NP * (C::NP + 1);
+      s                 = s > sb ? s : sb;
       return sizeof(double) * (a > s ? a : s);
     }
 
@@ -809,7 +833,7 @@ namespace pd
       ++h->launches;
     }
 
-    template <int DIM, int DEG, int TQ, int ISPLIT, int KSPLIT, int MINB>
+    template <int DIM, int DEG, int ISPLIT, int KSPLIT, int MINB>
     void
     run_faces(pd_handle *h, const pd_coefficients &coef, const uint32_t flags)
     {
@@ -834,8 +858,8 @@ namespace pd
       a.stiffness  = coef.stiffness;
       a.flags      = flags;
       a.basis      = h->basis;
-      auto             kern = k_faces<DIM, DEG, TQ, ISPLIT, KSPLIT, MINB>;
-      constexpr size_t smem = face_smem_bytes<DIM, DEG, TQ, KSPLIT>();
+      auto             kern = k_faces<DIM, DEG, ISPLIT, KSPLIT, MINB>;
+      constexpr size_t smem = face_smem_bytes<DIM, DEG, KSPLIT>();
       constexpr int    nthr = 4 * ISPLIT * KSPLIT * 32;
       set_smem(kern, smem);
       int per_sm = 1;
@@ -847,7 +871,7 @@ namespace pd
       ++h->launches;
     }
 
-    template <int DIM, int DEG, int TQV, int TQF, int ISPLIT, int KSPLIT, int MINB>
+    template <int DIM, int DEG, int ISPLIT, int KSPLIT, int MINB>
     void
     run_all(pd_handle *h, const uint32_t flags, const pd_coefficients &coef)
     {
@@ -861,7 +885,7 @@ namespace pd
         }
       PD_CUDA(cudaEventRecord(h->ev[1], h->stream));
       if ((flags & (PD_ASSEMBLE_BOUNDARY | PD_ASSEMBLE_INTERIOR)) && h->n_ifaces > 0)
-        run_faces<DIM, DEG, TQF, ISPLIT, KSPLIT, MINB>(h, coef, flags);
+        run_faces<DIM, DEG, ISPLIT, KSPLIT, MINB>(h, coef, flags);
       PD_CUDA(cudaEventRecord(h->ev[2], h->stream));
       if (h->vol_plan_tq == 0) // volume never planned (flags without VOLUME): empty item lists
         plan_volume(h, 32, 1);
@@ -906,14 +930,14 @@ namespace pd
     const int key = h->dim * 10 + h->degree;
     switch (key)
       {
-        //                 DIM DEG TQV TQF ISPLIT KSPLIT MINB
-        case 21: run_all<2, 1, 64, 32, 1, 2, 2>(h, flags, coef); break;
-        case 22: run_all<2, 2, 64, 32, 1, 2, 2>(h, flags, coef); break;
-        case 23: run_all<2, 3, 64, 32, 1, 2, 2>(h, flags, coef); break;
-        case 24: run_all<2, 4, 64, 32, 1, 2, 2>(h, flags, coef); break;
-        case 31: run_all<3, 1, 64, 32, 1, 2, 2>(h, flags, coef); break;
-        case 32: run_all<3, 2, 64, 32, 1, 2, 2>(h, flags, coef); break;
-        case 33: run_all<3, 3, 32, 16, 4, 1, 1>(h, flags, coef); break;
+        //                 DIM DEG ISPLIT KSPLIT MINB
+        case 21: run_all<2, 1, 1, 2, 2>(h, flags, coef); break;
+        case 22: run_all<2, 2, 1, 2, 2>(h, flags, coef); break;
+        case 23: run_all<2, 3, 1, 2, 2>(h, flags, coef); break;
+        case 24: run_all<2, 4, 1, 2, 2>(h, flags, coef); break;
+        case 31: run_all<3, 1, 1, 2, 2>(h, flags, coef); break;
+        case 32: run_all<3, 2, 1, 2, 2>(h, flags, coef); break;
+        case 33: run_all<3, 3, 4, 1, 1>(h, flags, coef); break;
         default:
           throw CudaError{cudaErrorNotSupported, "no assembly kernel for this (dim, degree)", __LINE__};
       }

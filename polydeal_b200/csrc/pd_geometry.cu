@@ -16,6 +16,8 @@
 // -----------------------------------------------------------------------------
 #include "pd_internal.hpp"
 
+#include <algorithm>
+
 namespace pd
 {
   namespace
@@ -92,46 +94,74 @@ namespace pd
         }
     }
 
+    // The 1-D rules live in a small device array (x[8], w[8]): indexing a kernel
+    // PARAMETER array with a runtime index makes the compiler copy the whole struct to
+    // local memory in every thread (16 STL + LDLs per point, seen in the SASS).
+    // One block handles CPB consecutive sub-cells: their vertices are fetched ONCE into
+    // shared memory (one thread per vertex), then one thread computes one point.
     template <int DIM>
     __global__ void __launch_bounds__(256)
     k_volume_quadrature(const double *__restrict__ verts,
                         const int32_t *__restrict__ cell_verts,
                         const int32_t *__restrict__ subcell_idx,
+                        const int64_t n_subcells,
                         const int64_t n_points,
                         const int     nq1,
                         const int     nqc,
-                        const Quad1D  quad,
+                        const int     cpb,
+                        const double *__restrict__ rule,
                         double *__restrict__ vq_x,
                         double *__restrict__ vq_w)
     {
-      const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-      if (idx >= n_points)
-        return;
-      const int64_t s = idx / nqc;
-      int           q = (int)(idx - s * nqc);
-      CellVerts<DIM> cv;
-      load_cell<DIM>(verts, cell_verts, subcell_idx[s], cv);
-      double xi[DIM], w = 1.;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) // x fastest (tensor QGauss<dim>)
+      constexpr int VPC = 1 << DIM;
+      extern __shared__ double sv[]; // [cpb][VPC][DIM]
+      __shared__ double        sq[16];
+      if (threadIdx.x < 16)
+        sq[threadIdx.x] = __ldg(&rule[threadIdx.x]);
+      const int64_t slot0 = (int64_t)blockIdx.x * cpb;
+      const int     nslot = (int)min((int64_t)cpb, n_subcells - slot0);
+      for (int tv = threadIdx.x; tv < nslot * VPC; tv += blockDim.x)
         {
-          const int a = q % nq1;
-          q /= nq1;
-          xi[d] = quad.x[a];
-          w *= quad.w[a];
-        }
-      double x[DIM], J[DIM][DIM];
-      q1_map<DIM>(cv, xi, x, J);
-      double det;
-      if constexpr (DIM == 2)
-        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-      else
-        det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
-              J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+          const int     sl = tv / VPC, v = tv - sl * VPC;
+          const int64_t vi = cell_verts[(int64_t)subcell_idx[slot0 + sl] * VPC + v];
 #pragma unroll
-      for (int d = 0; d < DIM; ++d)
-        vq_x[(int64_t)d * n_points + idx] = x[d];
-      vq_w[idx] = w * det;
+          for (int d = 0; d < DIM; ++d)
+            sv[tv * DIM + d] = __ldg(&verts[vi * DIM + d]);
+        }
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nslot * nqc; idx += blockDim.x)
+        {
+          const int      sl = idx / nqc;
+          int            q  = idx - sl * nqc;
+          CellVerts<DIM> cv;
+#pragma unroll
+          for (int v = 0; v < VPC; ++v)
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+              cv.x[v][d] = sv[(sl * VPC + v) * DIM + d];
+          double xi[DIM], w = 1.;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) // x fastest (tensor QGauss<dim>)
+            {
+              const int a = q % nq1;
+              q /= nq1;
+              xi[d] = sq[a];
+              w *= sq[8 + a];
+            }
+          double x[DIM], J[DIM][DIM];
+          q1_map<DIM>(cv, xi, x, J);
+          double det;
+          if constexpr (DIM == 2)
+            det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+          else
+            det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                  J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+          const int64_t o = slot0 * nqc + idx;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+            vq_x[(int64_t)d * n_points + o] = x[d];
+          vq_w[o] = w * det;
+        }
     }
 
     // Face rule projected as deal.II does: the face coordinate(s) run along the
@@ -146,11 +176,15 @@ namespace pd
                       const int64_t n_points,
                       const int     nq1,
                       const int     nqf,
-                      const Quad1D  quad,
+                      const double *__restrict__ rule,
                       double *__restrict__ fq_x,
                       double *__restrict__ fq_n,
                       double *__restrict__ fq_w)
     {
+      __shared__ double sq[16];
+      if (threadIdx.x < 16)
+        sq[threadIdx.x] = __ldg(&rule[threadIdx.x]);
+      __syncthreads();
       const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
       if (idx >= n_points)
         return;
@@ -166,20 +200,20 @@ namespace pd
       if constexpr (DIM == 2)
         {
           t0 = 1 - nd;
-          w  = quad.w[q];
+          w  = sq[8 + q];
 #pragma unroll
           for (int d = 0; d < DIM; ++d)
-            xi[d] = d == nd ? side : quad.x[q];
+            xi[d] = d == nd ? side : sq[q];
         }
       else
         {
           t0          = (nd + 1) % 3;
           t1          = (nd + 2) % 3;
           const int a = q % nq1, b = q / nq1;
-          w           = quad.w[a] * quad.w[b];
+          w           = sq[8 + a] * sq[8 + b];
 #pragma unroll
           for (int d = 0; d < DIM; ++d)
-            xi[d] = d == nd ? side : (d == t0 ? quad.x[a] : quad.x[b]);
+            xi[d] = d == nd ? side : (d == t0 ? sq[a] : sq[b]);
         }
       double x[DIM], J[DIM][DIM];
       q1_map<DIM>(cv, xi, x, J);
@@ -250,13 +284,17 @@ namespace pd
     const int tb = 256;
     if (h->Q > 0)
       {
-        const unsigned nb = (unsigned)((h->Q + tb - 1) / tb);
+        const int      cpb  = std::max(1, tb / h->nqc);
+        const unsigned nb   = (unsigned)((h->n_subcells + cpb - 1) / cpb);
+        const size_t   smem = sizeof(double) * cpb * (1 << h->dim) * h->dim;
         if (h->dim == 2)
-          k_volume_quadrature<2><<<nb, tb, 0, h->stream>>>(h->verts.p, h->cell_verts.p, h->subcell_idx.p, h->Q, h->nq1,
-                                                          h->nqc, h->quad, h->vq_x.p, h->vq_w.p);
+          k_volume_quadrature<2><<<nb, tb, smem, h->stream>>>(h->verts.p, h->cell_verts.p, h->subcell_idx.p,
+                                                             h->n_subcells, h->Q, h->nq1, h->nqc, cpb, h->rules.p,
+                                                             h->vq_x.p, h->vq_w.p);
         else
-          k_volume_quadrature<3><<<nb, tb, 0, h->stream>>>(h->verts.p, h->cell_verts.p, h->subcell_idx.p, h->Q, h->nq1,
-                                                          h->nqc, h->quad, h->vq_x.p, h->vq_w.p);
+          k_volume_quadrature<3><<<nb, tb, smem, h->stream>>>(h->verts.p, h->cell_verts.p, h->subcell_idx.p,
+                                                             h->n_subcells, h->Q, h->nq1, h->nqc, cpb, h->rules.p,
+                                                             h->vq_x.p, h->vq_w.p);
         ++h->launches;
       }
     if (h->Qf > 0)
@@ -264,11 +302,11 @@ namespace pd
         const unsigned nb = (unsigned)((h->Qf + tb - 1) / tb);
         if (h->dim == 2)
           k_face_quadrature<2><<<nb, tb, 0, h->stream>>>(h->verts.p, h->cell_verts.p, h->sub_cell.p, h->sub_face.p,
-                                                        h->Qf, h->nq1f, h->nqf, h->quadf, h->fq_x.p, h->fq_n.p,
+                                                        h->Qf, h->nq1f, h->nqf, h->rules.p + 16, h->fq_x.p, h->fq_n.p,
                                                         h->fq_w.p);
         else
           k_face_quadrature<3><<<nb, tb, 0, h->stream>>>(h->verts.p, h->cell_verts.p, h->sub_cell.p, h->sub_face.p,
-                                                        h->Qf, h->nq1f, h->nqf, h->quadf, h->fq_x.p, h->fq_n.p,
+                                                        h->Qf, h->nq1f, h->nqf, h->rules.p + 16, h->fq_x.p, h->fq_n.p,
                                                         h->fq_w.p);
         ++h->launches;
       }

@@ -93,6 +93,7 @@ struct pd_handle
 
   // descriptor arrays
   pd::DevBuf<double>  verts, bbox, sub_sigma;
+  pd::DevBuf<double>  rules; // [32]: cell rule x[8], w[8], face rule x[8], w[8]
   pd::DevBuf<int32_t> cell_verts, subcell_idx, dof_block, ifA, ifB, sub_cell, sub_face, bcol;
   pd::DevBuf<int64_t> subcell_ptr, if_sub_ptr, brow_ptr;
   // derived index data
