@@ -356,7 +356,7 @@ namespace pd
     }
 
     template <int DIM, int DEG, bool MASS, int NWARPS>
-    __global__ void __launch_bounds__(NWARPS * 32, NWARPS == 8 ? 2 : 1)
+    __global__ void __launch_bounds__(NWARPS * 32, NWARPS == 8 ? 3 : 1)
     k_volume(const VolArgs A)
     {
       extern __shared__ double smem[];

@@ -6,13 +6,16 @@
 // reinit_master (:1139-1165): for every sub-cell of every polytope the Gauss
 // points and JxW under the Q1 map, for every sub-face of every interface the
 // Gauss points, outward normals and surface JxW.  The reference does this with
-// one deal.II FEValues::reinit per sub-cell / sub-face on the host; here one
-// thread computes one quadrature point and the results are written as SoA
-// streams that the assembly kernels read fully coalesced.
+// one deal.II FEValues::reinit per sub-cell / sub-face on the host.
 //
-// HBM-bound: reads 2^dim vertices per sub-cell (L1/L2 hits after the first
-// point of the cell), writes 8(dim+1) B per volume point and 8(2 dim+1) B per
-// face point.
+// Here a WARP takes a run of consecutive sub-cells (sub-faces).  Phase 1: one
+// lane per (cell, coordinate) gathers the 2^dim vertices and turns them into
+// the multilinear coefficients of x_d(xi) = sum_m c_m prod_{k in m} xi_k by
+// successive differencing (exactly zero mixed terms on Cartesian cells).
+// Phase 2: one thread per quadrature point evaluates x and dx/dxi by nested
+// multiplication (11 FMAs per coordinate) and writes the SoA streams fully
+// coalesced.  HBM-bound by design: 8(dim+1) B per volume point and 8(2dim+1) B
+// per face point written, 2^dim vertices per cell read once.
 // -----------------------------------------------------------------------------
 #include "pd_internal.hpp"
 
@@ -22,85 +25,75 @@ namespace pd
 {
   namespace
   {
-    template <int DIM>
-    struct CellVerts
-    {
-      double x[1 << DIM][DIM];
-    };
-
+    // c[m], m = bit mask of the unit coordinates in the monomial, for ONE coordinate
     template <int DIM>
     __device__ __forceinline__ void
-    load_cell(const double *__restrict__ verts, const int32_t *__restrict__ cell_verts, const int32_t cell, CellVerts<DIM> &cv)
+    multilinear_coefficients(double (&c)[1 << DIM])
     {
       constexpr int VPC = 1 << DIM;
 #pragma unroll
-      for (int v = 0; v < VPC; ++v)
-        {
-          const int64_t vi = cell_verts[(int64_t)cell * VPC + v];
+      for (int d = 0; d < DIM; ++d)
 #pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            cv.x[v][d] = __ldg(&verts[vi * DIM + d]);
-        }
+        for (int v = 0; v < VPC; ++v)
+          if (v & (1 << d))
+            c[v] -= c[v ^ (1 << d)];
     }
 
-    // x(xi) and J[a][b] = dx_a/dxi_b of the multilinear map
+    // value and gradient w.r.t. xi of one coordinate from its coefficients (shared memory)
     template <int DIM>
     __device__ __forceinline__ void
-    q1_map(const CellVerts<DIM> &cv, const double (&xi)[DIM], double (&x)[DIM], double (&J)[DIM][DIM])
+    multilinear_eval(const double *c, const double (&xi)[DIM], double &x, double (&dx)[DIM])
     {
-      constexpr int VPC = 1 << DIM;
-#pragma unroll
-      for (int a = 0; a < DIM; ++a)
+      if constexpr (DIM == 2)
         {
-          x[a] = 0.;
-#pragma unroll
-          for (int b = 0; b < DIM; ++b)
-            J[a][b] = 0.;
+          const double a0 = fma(c[1], xi[0], c[0]), a1 = fma(c[3], xi[0], c[2]);
+          x     = fma(a1, xi[1], a0);
+          dx[0] = fma(c[3], xi[1], c[1]);
+          dx[1] = a1;
         }
-#pragma unroll
-      for (int v = 0; v < VPC; ++v)
+      else
         {
-          double f[DIM], s[DIM];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            {
-              const bool up = (v >> d) & 1;
-              f[d]          = up ? xi[d] : 1. - xi[d];
-              s[d]          = up ? 1. : -1.;
-            }
-          double N = 1.;
-#pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            N *= f[d];
-          double dN[DIM];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            {
-              double g = s[d];
-#pragma unroll
-              for (int e = 0; e < DIM; ++e)
-                if (e != d)
-                  g *= f[e];
-              dN[d] = g;
-            }
-#pragma unroll
-          for (int a = 0; a < DIM; ++a)
-            {
-              x[a] += N * cv.x[v][a];
-#pragma unroll
-              for (int b = 0; b < DIM; ++b)
-                J[a][b] += dN[b] * cv.x[v][a];
-            }
+          const double a0 = fma(c[1], xi[0], c[0]), a1 = fma(c[3], xi[0], c[2]);
+          const double a2 = fma(c[5], xi[0], c[4]), a3 = fma(c[7], xi[0], c[6]);
+          const double b0 = fma(a1, xi[1], a0), b1 = fma(a3, xi[1], a2);
+          x     = fma(b1, xi[2], b0);
+          dx[2] = b1;
+          dx[1] = fma(a3, xi[2], a1);
+          dx[0] = fma(fma(c[7], xi[1], c[5]), xi[2], fma(c[3], xi[1], c[1]));
         }
     }
 
-    // The 1-D rules live in a small device array (x[8], w[8]): indexing a kernel
-    // PARAMETER array with a runtime index makes the compiler copy the whole struct to
-    // local memory in every thread (16 STL + LDLs per point, seen in the SASS).
-    // One block handles CPB consecutive sub-cells: their vertices are fetched ONCE into
-    // shared memory (one thread per vertex), then one thread computes one point.
+    // phase 1 shared by both kernels, per WARP (no block barrier: every warp is an
+    // independent latency chain, which is what hides the index -> vertex gather):
+    // lanes < nslot*DIM compute the coefficients of (slot, coordinate) into sc[slot][d][2^dim]
     template <int DIM>
-    __global__ void __launch_bounds__(256)
+    __device__ __forceinline__ void
+    stage_coefficients(const double *__restrict__ verts,
+                       const int32_t *__restrict__ cell_verts,
+                       const int32_t *__restrict__ cells, // cell index of every slot of this warp
+                       const int nslot,
+                       double   *sc)
+    {
+      constexpr int VPC = 1 << DIM;
+      const int     lane = threadIdx.x & 31;
+      for (int tv = lane; tv < nslot * DIM; tv += 32)
+        {
+          const int      sl = tv / DIM, d = tv - sl * DIM;
+          const int32_t *cv = cell_verts + (int64_t)cells[sl] * VPC;
+          double         c[VPC];
+#pragma unroll
+          for (int v = 0; v < VPC; ++v)
+            c[v] = __ldg(&verts[(int64_t)cv[v] * DIM + d]);
+          multilinear_coefficients<DIM>(c);
+#pragma unroll
+          for (int v = 0; v < VPC; ++v)
+            sc[tv * VPC + v] = c[v];
+        }
+      __syncwarp();
+    }
+
+    template <int DIM>
+    __global__ void __launch_bounds__(256, 4)
     k_volume_quadrature(const double *__restrict__ verts,
                         const int32_t *__restrict__ cell_verts,
                         const int32_t *__restrict__ subcell_idx,
@@ -109,37 +102,28 @@ namespace pd
                         const int     nq1,
                         const int     nqc,
                         const int     cpb,
-                        const double *__restrict__ rule,
+                        const double *__restrict__ rule, // x[8], w[8]
                         double *__restrict__ vq_x,
                         double *__restrict__ vq_w)
     {
       constexpr int VPC = 1 << DIM;
-      extern __shared__ double sv[]; // [cpb][VPC][DIM]
+      extern __shared__ double sc_all[]; // [warps][cpb][DIM][VPC], cpb = cells per WARP
       __shared__ double        sq[16];
       if (threadIdx.x < 16)
         sq[threadIdx.x] = __ldg(&rule[threadIdx.x]);
-      const int64_t slot0 = (int64_t)blockIdx.x * cpb;
-      const int     nslot = (int)min((int64_t)cpb, n_subcells - slot0);
-      for (int tv = threadIdx.x; tv < nslot * VPC; tv += blockDim.x)
-        {
-          const int     sl = tv / VPC, v = tv - sl * VPC;
-          const int64_t vi = cell_verts[(int64_t)subcell_idx[slot0 + sl] * VPC + v];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            sv[tv * DIM + d] = __ldg(&verts[vi * DIM + d]);
-        }
       __syncthreads();
-      for (int idx = threadIdx.x; idx < nslot * nqc; idx += blockDim.x)
+      const int     lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+      double       *sc   = sc_all + warp * cpb * DIM * VPC;
+      const int64_t slot0 = ((int64_t)blockIdx.x * nwarp + warp) * cpb;
+      if (slot0 >= n_subcells)
+        return;
+      const int nslot = (int)min((int64_t)cpb, n_subcells - slot0);
+      stage_coefficients<DIM>(verts, cell_verts, subcell_idx + slot0, nslot, sc);
+      for (int idx = lane; idx < nslot * nqc; idx += 32)
         {
-          const int      sl = idx / nqc;
-          int            q  = idx - sl * nqc;
-          CellVerts<DIM> cv;
-#pragma unroll
-          for (int v = 0; v < VPC; ++v)
-#pragma unroll
-            for (int d = 0; d < DIM; ++d)
-              cv.x[v][d] = sv[(sl * VPC + v) * DIM + d];
-          double xi[DIM], w = 1.;
+          const int sl = idx / nqc;
+          int       q  = idx - sl * nqc;
+          double    xi[DIM], w = 1.;
 #pragma unroll
           for (int d = 0; d < DIM; ++d) // x fastest (tensor QGauss<dim>)
             {
@@ -149,7 +133,9 @@ namespace pd
               w *= sq[8 + a];
             }
           double x[DIM], J[DIM][DIM];
-          q1_map<DIM>(cv, xi, x, J);
+#pragma unroll
+          for (int d = 0; d < DIM; ++d)
+            multilinear_eval<DIM>(sc + (sl * DIM + d) * VPC, xi, x[d], J[d]);
           double det;
           if constexpr (DIM == 2)
             det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
@@ -168,113 +154,134 @@ namespace pd
     // free axes, 3-D faces 0/1 -> (y,z), 2/3 -> (z,x), 4/5 -> (x,y), first face
     // coordinate fastest.
     template <int DIM>
-    __global__ void __launch_bounds__(256)
+    __global__ void __launch_bounds__(256, 4)
     k_face_quadrature(const double *__restrict__ verts,
                       const int32_t *__restrict__ cell_verts,
                       const int32_t *__restrict__ sub_cell,
                       const int32_t *__restrict__ sub_face,
+                      const int64_t n_subfaces,
                       const int64_t n_points,
                       const int     nq1,
                       const int     nqf,
+                      const int     spb,
                       const double *__restrict__ rule,
                       double *__restrict__ fq_x,
                       double *__restrict__ fq_n,
                       double *__restrict__ fq_w)
     {
-      __shared__ double sq[16];
+      constexpr int VPC = 1 << DIM;
+      extern __shared__ double sc_all[]; // [warps][spb][DIM][VPC], spb = sub-faces per WARP
+      __shared__ double        sq[16];
       if (threadIdx.x < 16)
         sq[threadIdx.x] = __ldg(&rule[threadIdx.x]);
       __syncthreads();
-      const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-      if (idx >= n_points)
+      const int     lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+      double       *sc   = sc_all + warp * spb * DIM * VPC;
+      const int64_t slot0 = ((int64_t)blockIdx.x * nwarp + warp) * spb;
+      if (slot0 >= n_subfaces)
         return;
-      const int64_t s  = idx / nqf;
-      const int     q  = (int)(idx - s * nqf);
-      const int     f  = sub_face[s];
-      const int     nd = f >> 1;
-      const double  side = (f & 1) ? 1. : 0.;
-      CellVerts<DIM> cv;
-      load_cell<DIM>(verts, cell_verts, sub_cell[s], cv);
-      double xi[DIM], w;
-      int    t0, t1 = 0;
-      if constexpr (DIM == 2)
+      const int nslot = (int)min((int64_t)spb, n_subfaces - slot0);
+      stage_coefficients<DIM>(verts, cell_verts, sub_cell + slot0, nslot, sc);
+      for (int idx = lane; idx < nslot * nqf; idx += 32)
         {
-          t0 = 1 - nd;
-          w  = sq[8 + q];
+          const int    sl = idx / nqf, q = idx - sl * nqf;
+          const int    f  = sub_face[slot0 + sl];
+          const int    nd = f >> 1;
+          const double side = (f & 1) ? 1. : 0.;
+          double       xi[DIM], w;
+          int          t0, t1 = 0;
+          if constexpr (DIM == 2)
+            {
+              t0 = 1 - nd;
+              w  = sq[8 + q];
+#pragma unroll
+              for (int d = 0; d < DIM; ++d)
+                xi[d] = d == nd ? side : sq[q];
+            }
+          else
+            {
+              t0          = (nd + 1) % 3;
+              t1          = (nd + 2) % 3;
+              const int a = q % nq1, b = q / nq1;
+              w           = sq[8 + a] * sq[8 + b];
+#pragma unroll
+              for (int d = 0; d < DIM; ++d)
+                xi[d] = d == nd ? side : (d == t0 ? sq[a] : sq[b]);
+            }
+          double x[DIM], J[DIM][DIM];
 #pragma unroll
           for (int d = 0; d < DIM; ++d)
-            xi[d] = d == nd ? side : sq[q];
-        }
-      else
-        {
-          t0          = (nd + 1) % 3;
-          t1          = (nd + 2) % 3;
-          const int a = q % nq1, b = q / nq1;
-          w           = sq[8 + a] * sq[8 + b];
+            multilinear_eval<DIM>(sc + (sl * DIM + d) * VPC, xi, x[d], J[d]);
+          // tangents = columns t0 (, t1) of J; outward side fixed by the sign of the
+          // component along dx/dxi_nd
+          double nrm[DIM], jn[DIM];
+          if constexpr (DIM == 2)
+            {
+              double tx = 0., ty = 0.;
 #pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            xi[d] = d == nd ? side : (d == t0 ? sq[a] : sq[b]);
-        }
-      double x[DIM], J[DIM][DIM];
-      q1_map<DIM>(cv, xi, x, J);
-      double nrm[DIM];
-      if constexpr (DIM == 2)
-        {
-          double tx = 0., ty = 0.;
+              for (int e = 0; e < DIM; ++e)
+                {
+                  if (e == t0)
+                    {
+                      tx = J[0][e];
+                      ty = J[1][e];
+                    }
+                  if (e == nd)
+                    {
+                      jn[0] = J[0][e];
+                      jn[1] = J[1][e];
+                    }
+                }
+              nrm[0] = ty;
+              nrm[1] = -tx;
+            }
+          else
+            {
+              double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
 #pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            if (d == t0)
-              {
-                tx = J[0][d];
-                ty = J[1][d];
-              }
-          nrm[0] = ty;
-          nrm[1] = -tx;
-        }
-      else
-        {
-          double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+              for (int e = 0; e < DIM; ++e)
+                {
+                  if (e == t0)
+                    {
+                      a[0] = J[0][e];
+                      a[1] = J[1][e];
+                      a[2] = J[2][e];
+                    }
+                  if (e == t1)
+                    {
+                      b[0] = J[0][e];
+                      b[1] = J[1][e];
+                      b[2] = J[2][e];
+                    }
+                  if (e == nd)
+                    {
+                      jn[0] = J[0][e];
+                      jn[1] = J[1][e];
+                      jn[2] = J[2][e];
+                    }
+                }
+              nrm[0] = a[1] * b[2] - a[2] * b[1];
+              nrm[1] = a[2] * b[0] - a[0] * b[2];
+              nrm[2] = a[0] * b[1] - a[1] * b[0];
+            }
+          double len2 = 0., dotp = 0.;
 #pragma unroll
           for (int d = 0; d < DIM; ++d)
             {
-              if (d == t0)
-                {
-                  a[0] = J[0][d];
-                  a[1] = J[1][d];
-                  a[2] = J[2][d];
-                }
-              if (d == t1)
-                {
-                  b[0] = J[0][d];
-                  b[1] = J[1][d];
-                  b[2] = J[2][d];
-                }
+              len2 += nrm[d] * nrm[d];
+              dotp += nrm[d] * jn[d];
             }
-          nrm[0] = a[1] * b[2] - a[2] * b[1];
-          nrm[1] = a[2] * b[0] - a[0] * b[2];
-          nrm[2] = a[0] * b[1] - a[1] * b[0];
-        }
-      double len2 = 0., dotp = 0.;
+          const double  len = sqrt(len2);
+          const double  sgn = ((dotp > 0.) == (side > 0.5)) ? 1. : -1.;
+          const int64_t o   = slot0 * nqf + idx;
 #pragma unroll
-      for (int d = 0; d < DIM; ++d)
-        {
-          len2 += nrm[d] * nrm[d];
-          double jn = 0.;
-#pragma unroll
-          for (int e = 0; e < DIM; ++e)
-            if (e == nd)
-              jn = J[d][e];
-          dotp += nrm[d] * jn;
+          for (int d = 0; d < DIM; ++d)
+            {
+              fq_x[(int64_t)d * n_points + o] = x[d];
+              fq_n[(int64_t)d * n_points + o] = sgn * nrm[d] / len;
+            }
+          fq_w[o] = w * len;
         }
-      const double len = sqrt(len2);
-      const double sgn = ((dotp > 0.) == (side > 0.5)) ? 1. : -1.;
-#pragma unroll
-      for (int d = 0; d < DIM; ++d)
-        {
-          fq_x[(int64_t)d * n_points + idx] = x[d];
-          fq_n[(int64_t)d * n_points + idx] = sgn * nrm[d] / len;
-        }
-      fq_w[idx] = w * len;
     }
   } // namespace
 
@@ -284,9 +291,12 @@ namespace pd
     const int tb = 256;
     if (h->Q > 0)
       {
-        const int      cpb  = std::max(1, tb / h->nqc);
-        const unsigned nb   = (unsigned)((h->n_subcells + cpb - 1) / cpb);
-        const size_t   smem = sizeof(double) * cpb * (1 << h->dim) * h->dim;
+        // cells per warp: one lane per (cell, coordinate) gathers vertices, so 32/dim cells share ONE
+        // index->vertex latency round trip (the kernel is latency-bound otherwise)
+        const int      cpb  = 32 / h->dim;
+        const int64_t  per_block = (int64_t)cpb * (tb / 32);
+        const unsigned nb   = (unsigned)((h->n_subcells + per_block - 1) / per_block);
+        const size_t   smem = sizeof(double) * per_block * (1 << h->dim) * h->dim;
         if (h->dim == 2)
           k_volume_quadrature<2><<<nb, tb, smem, h->stream>>>(h->verts.p, h->cell_verts.p, h->subcell_idx.p,
                                                              h->n_subcells, h->Q, h->nq1, h->nqc, cpb, h->rules.p,
@@ -299,15 +309,18 @@ namespace pd
       }
     if (h->Qf > 0)
       {
-        const unsigned nb = (unsigned)((h->Qf + tb - 1) / tb);
+        const int      spb  = 32 / h->dim; // sub-faces per warp
+        const int64_t  per_block = (int64_t)spb * (tb / 32);
+        const unsigned nb   = (unsigned)((h->n_subfaces + per_block - 1) / per_block);
+        const size_t   smem = sizeof(double) * per_block * (1 << h->dim) * h->dim;
         if (h->dim == 2)
-          k_face_quadrature<2><<<nb, tb, 0, h->stream>>>(h->verts.p, h->cell_verts.p, h->sub_cell.p, h->sub_face.p,
-                                                        h->Qf, h->nq1f, h->nqf, h->rules.p + 16, h->fq_x.p, h->fq_n.p,
-                                                        h->fq_w.p);
+          k_face_quadrature<2><<<nb, tb, smem, h->stream>>>(h->verts.p, h->cell_verts.p, h->sub_cell.p, h->sub_face.p,
+                                                           h->n_subfaces, h->Qf, h->nq1f, h->nqf, spb,
+                                                           h->rules.p + 16, h->fq_x.p, h->fq_n.p, h->fq_w.p);
         else
-          k_face_quadrature<3><<<nb, tb, 0, h->stream>>>(h->verts.p, h->cell_verts.p, h->sub_cell.p, h->sub_face.p,
-                                                        h->Qf, h->nq1f, h->nqf, h->rules.p + 16, h->fq_x.p, h->fq_n.p,
-                                                        h->fq_w.p);
+          k_face_quadrature<3><<<nb, tb, smem, h->stream>>>(h->verts.p, h->cell_verts.p, h->sub_cell.p, h->sub_face.p,
+                                                           h->n_subfaces, h->Qf, h->nq1f, h->nqf, spb,
+                                                           h->rules.p + 16, h->fq_x.p, h->fq_n.p, h->fq_w.p);
         ++h->launches;
       }
     PD_CUDA(cudaGetLastError());

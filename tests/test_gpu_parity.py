@@ -48,7 +48,7 @@ def test_quadrature_matches_oracle(dim, n, shape, nq, distort):
     k = 0
     for p in range(oah.n_polytopes):
         fev = oah.reinit(p)
-        np.testing.assert_allclose(x[:, k:k + fev.n_q].T, fev.points, rtol=0, atol=4e-16)
+        np.testing.assert_allclose(x[:, k:k + fev.n_q].T, fev.points, rtol=0, atol=1e-15)
         np.testing.assert_allclose(w[k:k + fev.n_q], fev.JxW, rtol=1e-14, atol=0)
         k += fev.n_q
     assert k == Q
@@ -64,7 +64,7 @@ def test_quadrature_matches_oracle(dim, n, shape, nq, distort):
     for a, b in zip(A, B):
         f = next(f for f in range(oah.n_faces(a)) if oah.neighbor(a, f) == b)
         ff = oah.reinit(a, f)
-        np.testing.assert_allclose(fx[:, k:k + ff.n_q].T, ff.points, rtol=0, atol=4e-16)
+        np.testing.assert_allclose(fx[:, k:k + ff.n_q].T, ff.points, rtol=0, atol=1e-15)
         np.testing.assert_allclose(fn[:, k:k + ff.n_q].T, ff.normals, rtol=0, atol=1e-15)
         np.testing.assert_allclose(fw[k:k + ff.n_q], ff.JxW, rtol=1e-14, atol=0)
         k += ff.n_q
