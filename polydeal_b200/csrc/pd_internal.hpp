@@ -117,6 +117,7 @@ struct pd_handle
   bool         quad_valid = false, assembled = false;
   int64_t      launches   = 0;
   int          sm_count   = 148;
+  int64_t      max_row_len = -1; // longest scalar row (doubles), computed lazily for the SpMV dispatch
 };
 
 namespace pd

@@ -5,19 +5,95 @@
 // LinearOperatorMG::vmult -> TrilinosWrappers::SparseMatrix::vmult
 // (include/multigrid_amg.h:345-355, include/linear_operator_for_mg.h:295;
 // CG at examples/diffusion_reaction.cc:721-724), and the inverse diagonal of
-// include/utils.h:797-814.
+// include/utils.h:797-814.  The reference's SpMV is scalar CRS and ignores the
+// block structure.
 //
 // HBM-bound: 8 n^2 B per block + 4 B per block index + 16 B per DoF.  The value
-// array is the scalar CSR of the reference pattern, so a scalar row is one
-// contiguous run of nb*n doubles: one warp streams one row with unit-stride
-// loads; the source vector is gathered per block (n contiguous doubles).
+// array is the scalar CSR of the reference pattern, so a block row is ONE
+// contiguous run of n * (nb*n) doubles.  A CTA takes a block row: it gathers the
+// nb source blocks once into shared memory laid out exactly like a matrix row
+// (xs[k*n + j] = x[bcol[k]*n + j]), then every warp streams whole rows with
+// unit-stride loads and multiplies against xs -- no index arithmetic and no
+// gather in the inner loop, two rows in flight per warp for memory-level
+// parallelism.
 // -----------------------------------------------------------------------------
 #include "pd_internal.hpp"
+
+#include <algorithm>
 
 namespace pd
 {
   namespace
   {
+    constexpr int SPMV_THREADS = 256;
+    constexpr int SPMV_MAX_ROW = 4096; // doubles of shared memory for the gathered source row
+
+    template <bool ADD>
+    __global__ void __launch_bounds__(SPMV_THREADS)
+    k_spmv_block_row(const double *__restrict__ vals,
+                     const int64_t *__restrict__ brow_ptr,
+                     const int32_t *__restrict__ bcol,
+                     const int      n,
+                     const int32_t  n_block_rows,
+                     const double *__restrict__ x,
+                     double *__restrict__ y)
+    {
+      __shared__ double xs[SPMV_MAX_ROW];
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = SPMV_THREADS / 32;
+      for (int b = blockIdx.x; b < n_block_rows; b += gridDim.x)
+        {
+          const int64_t kb  = brow_ptr[b];
+          const int     nb  = (int)(brow_ptr[b + 1] - kb);
+          const int     len = nb * n;
+          __syncthreads(); // previous block row is done with xs
+          for (int e = threadIdx.x; e < len; e += SPMV_THREADS)
+            {
+              const int k = e / n, j = e - k * n;
+              xs[e]       = __ldg(&x[(int64_t)bcol[kb + k] * n + j]);
+            }
+          __syncthreads();
+          const double *rows = vals + kb * n * n;
+          // RPW rows in flight per warp: short rows (n = 27: 189 doubles) need the
+          // memory-level parallelism, long rows (n = 64) are fine either way
+          constexpr int RPW = 4;
+          for (int i = warp; i < n; i += RPW * nwarp)
+            {
+              const double *r[RPW];
+              double        s[RPW];
+#pragma unroll
+              for (int u = 0; u < RPW; ++u)
+                {
+                  const int iu = i + u * nwarp;
+                  r[u]         = rows + (int64_t)(iu < n ? iu : i) * len;
+                  s[u]         = 0.;
+                }
+              for (int e = lane; e < len; e += 32)
+                {
+                  const double xe = xs[e];
+#pragma unroll
+                  for (int u = 0; u < RPW; ++u)
+                    s[u] += r[u][e] * xe;
+                }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < RPW; ++u)
+                  s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+              if (lane == 0)
+                {
+#pragma unroll
+                  for (int u = 0; u < RPW; ++u)
+                    if (i + u * nwarp < n)
+                      {
+                        const int64_t row = (int64_t)b * n + i + u * nwarp;
+                        y[row]            = ADD ? y[row] + s[u] : s[u];
+                      }
+                }
+            }
+        }
+    }
+
+    // fallback for block rows that do not fit the shared-memory row buffer
     template <bool ADD>
     __global__ void __launch_bounds__(256)
     k_spmv_warp_per_row(const double *__restrict__ vals,
@@ -76,16 +152,36 @@ namespace pd
   void
   launch_spmv(pd_handle *h, const double *src, double *dst, const bool add)
   {
-    const int     tb   = 256;
-    const int64_t rows = h->n_dofs;
-    const int64_t want = (rows * 32 + tb - 1) / tb;
-    const int     grid = (int)std::min<int64_t>(want, (int64_t)h->sm_count * 16);
-    if (add)
-      k_spmv_warp_per_row<true><<<grid, tb, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->row_stride.p, h->n,
-                                                           rows, src, dst);
+    if (h->max_row_len < 0)
+      {
+        int64_t m = 0;
+        for (int32_t b = 0; b < h->np; ++b)
+          m = std::max<int64_t>(m, (h->h_brow_ptr[b + 1] - h->h_brow_ptr[b]) * h->n);
+        h->max_row_len = m;
+      }
+    if (h->max_row_len <= SPMV_MAX_ROW)
+      {
+        const int grid = (int)std::min<int64_t>(h->np, (int64_t)h->sm_count * 8);
+        if (add)
+          k_spmv_block_row<true><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n, h->np,
+                                                                      src, dst);
+        else
+          k_spmv_block_row<false><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n, h->np,
+                                                                       src, dst);
+      }
     else
-      k_spmv_warp_per_row<false><<<grid, tb, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->row_stride.p,
-                                                            h->n, rows, src, dst);
+      {
+        const int     tb   = 256;
+        const int64_t rows = h->n_dofs;
+        const int64_t want = (rows * 32 + tb - 1) / tb;
+        const int     grid = (int)std::min<int64_t>(want, (int64_t)h->sm_count * 16);
+        if (add)
+          k_spmv_warp_per_row<true><<<grid, tb, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->row_stride.p,
+                                                               h->n, rows, src, dst);
+        else
+          k_spmv_warp_per_row<false><<<grid, tb, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->row_stride.p,
+                                                                h->n, rows, src, dst);
+      }
     ++h->launches;
     PD_CUDA(cudaGetLastError());
   }

@@ -1,0 +1,156 @@
+#!/usr/bin/env python3
+"""Run one SURVEY 8d configuration (blocks shape) on one GPU: assembly kernel times,
+rooflines, size-independent parity properties and vmult timing.  Prints one JSON line.
+
+  python tools/run_config.py A|B|C|D [--steps K] [--check]
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+CONFIGS = {
+    # name: dim, cells per direction, block edge, degree, n_q1d, penalty constant (None = library), mass
+    "A": dict(dim=2, n=256, b=16, p=1, nq=2, C=None, mass=0.0),
+    "B": dict(dim=3, n=64, b=8, p=2, nq=3, C=None, mass=0.0),
+    "C": dict(dim=3, n=128, b=4, p=3, nq=4, C=None, mass=0.0),
+    "D": dict(dim=3, n=256, b=4, p=2, nq=3, C=40.0, mass=0.5),
+    "D8": dict(dim=3, n=128, b=4, p=2, nq=3, C=40.0, mass=0.5),  # one eighth of D (per-GPU share at 8 GPUs)
+}
+
+
+def fast_block_groups(dim, n, b):
+    """block_partition without Python loops over cells: cells in Morton (active) order."""
+    ax = np.arange(n, dtype=np.int64)
+    if dim == 2:
+        i, j = np.meshgrid(ax, ax, indexing="ij")
+        k = np.zeros_like(i)
+    else:
+        i, j, k = np.meshgrid(ax, ax, ax, indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    cell = np.zeros_like(i)
+    for l in range(n.bit_length() - 1):
+        cell |= ((i >> l) & 1) << (dim * l)
+        cell |= ((j >> l) & 1) << (dim * l + 1)
+        if dim == 3:
+            cell |= ((k >> l) & 1) << (dim * l + 2)
+    nb = n // b
+    part = ((k // b) * nb + (j // b)) * nb + (i // b)
+    order = np.lexsort((cell, part))
+    cells_sorted = cell[order].astype(np.int32)
+    per = b**dim
+    return cells_sorted.reshape(nb**dim, per)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    import torch
+
+    import polydeal_b200 as pdl
+
+    dim, n, b, p, nq = cfg["dim"], cfg["n"], cfg["b"], cfg["p"], cfg["nq"]
+    t0 = time.time()
+    grid = pdl.Grid.hyper_cube(dim, 0.0, 1.0, n.bit_length() - 1)
+    ah = pdl.AgglomerationHandler(grid)
+    for g in fast_block_groups(dim, n, b):
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(nq)
+    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, p)
+    desc = ah.flatten(penalty_constant=-1.0 if cfg["C"] is None else cfg["C"])
+    t_host = time.time() - t0
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    op = pdl.SIPOperator(desc, keepalive=ah)
+    op.set_stream(stream.cuda_stream)
+    N, nd = op.m(), op.n_dofs_per_cell
+    Q = int(desc.poly_subcell_ptr[desc.n_polytopes]) * nq**dim
+    Qf = int(desc.iface_sub_ptr[desc.n_ifaces]) * nq ** (dim - 1)
+    nblocks = int(desc.brow_ptr[desc.n_block_rows])
+    kms = {"volume": [], "faces": [], "reduce": [], "quadrature": []}
+    tot = []
+    for s in range(args.steps + 2):
+        op.invalidate_quadrature()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        op.assemble(stiffness=1.0, mass=cfg["mass"])
+        e.record(stream)
+        e.synchronize()
+        if s >= 2:
+            tot.append(a.elapsed_time(e))
+            for k, v in op.last_kernel_ms().items():
+                kms[k].append(v)
+    x = torch.from_numpy(np.sin(0.37 * np.arange(N)) + 0.01 * (np.arange(N) % 7)).cuda()
+    y = torch.empty_like(x)
+    vm = []
+    for s in range(args.steps + 2):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        op.vmult(y, x)
+        e.record(stream)
+        e.synchronize()
+        if s >= 2:
+            vm.append(a.elapsed_time(e))
+    ncomp = dim + (1 if cfg["mass"] else 0)
+    vol_flops = 2.0 * nd * nd * ncomp * Q
+    n_int = int(sum(1 for f in range(desc.n_ifaces) if desc.iface_polyB[f] >= 0)) if desc.n_ifaces < 4_000_000 else None
+    vol_ms, vm_ms = statistics.mean(kms["volume"]), statistics.mean(vm)
+    vm_bytes = 8.0 * nd * nd * nblocks + 4.0 * nblocks + 16.0 * N
+    out = {
+        "config": args.config, "dim": dim, "cells": n**dim, "polytopes": int(desc.n_polytopes), "degree": p, "n_dofs": N,
+        "volume_points": Q, "face_points": Qf, "n_blocks": nblocks, "matrix_GB": nblocks * nd * nd * 8 / 1e9,
+        "host_setup_s": t_host, "assemble_ms": statistics.mean(tot), "kernel_ms": {k: statistics.mean(v) for k, v in kms.items()},
+        "dofs_per_s": N / (statistics.mean(tot) * 1e-3),
+        "volume_tflops_algorithmic": vol_flops / (vol_ms * 1e-3) / 1e12, "volume_frac_fp64_peak": vol_flops / (vol_ms * 1e-3) / 1e12 / 37.1,
+        "vmult_ms": vm_ms, "vmult_gdofs": N / (vm_ms * 1e-3) / 1e9, "vmult_GBs": vm_bytes / (vm_ms * 1e-3) / 1e9,
+        "vmult_frac_hbm": vm_bytes / (vm_ms * 1e-3) / 1e9 / 6543.4, "interior_ifaces": n_int,
+        "mem_GB": torch.cuda.max_memory_allocated() / 1e9,
+    }
+    if args.check:
+        # size-independent properties: constants in the kernel of the boundary-free stiffness operator
+        # (checked through vmult), symmetry through x'Ay = y'Ax, energy of u = x_0 equals |Omega| = 1
+        op.assemble(flags=pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR, stiffness=1.0, mass=0.0)
+        one = torch.ones_like(x)
+        op.vmult(y, one)
+        stream.synchronize()
+        op.synchronize()
+        scale = float(torch.max(torch.abs(torch.from_numpy(op.values()[: 10 * nd * nd]))))
+        out["max_abs_A_one_over_scale"] = float(y.abs().max()) / scale
+        z = torch.from_numpy(np.cos(0.11 * np.arange(N))).cuda()
+        ax_, az_ = torch.empty_like(x), torch.empty_like(x)
+        op.vmult(ax_, x)
+        op.vmult(az_, z)
+        stream.synchronize()
+        out["sym_rel"] = abs(float(z @ ax_) - float(x @ az_)) / abs(float(z @ ax_))
+        # u = x_0 interpolated at the DGQ support points of every bbox
+        nodes = np.empty(p + 1)
+        from polydeal_b200 import _capi as K
+
+        K.check(K.lib().pd_dgq_nodes_1d(p, nodes.ctypes.data))
+        bbox = np.ctypeslib.as_array(desc.bbox, (desc.n_polytopes, 2 * dim))
+        blk = np.ctypeslib.as_array(desc.dof_block, (desc.n_polytopes,))
+        i = np.arange(nd)
+        u = np.empty(N)
+        ux = bbox[:, 0:1] + nodes[i % (p + 1)][None, :] * (bbox[:, dim:dim + 1] - bbox[:, 0:1])
+        u.reshape(-1, nd)[blk] = ux
+        ud = torch.from_numpy(u).cuda()
+        op.vmult(y, ud)
+        stream.synchronize()
+        out["energy_u_eq_x"] = float(ud @ y)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
