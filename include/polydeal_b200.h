@@ -162,6 +162,14 @@ int pd_matrix_pattern_to_host(pd_handle *h, int64_t *rowptr, int32_t *cols);
  * include/linear_operator_for_mg.h:295).  src/dst are DEVICE pointers of
  * pd_n_dofs doubles.  vmult_add accumulates into dst. */
 int pd_vmult(pd_handle *h, int mode, const double *src_dev, double *dst_dev);
+/* Operator of the MATRIX_FREE apply: which terms (PD_ASSEMBLE_* flags) and the
+ * coefficients, e.g. flags = VOLUME|INTERIOR, {sigma, chi*Cm/dt} for
+ * MonodomainOperatorDG (include/utils.h:1131-1134, 1565-1659: no boundary term).
+ * Default: all terms, {1, 0} = LaplaceOperatorDG (include/utils.h:819-925). */
+int pd_set_operator(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
+/* 1 when the sum-factorised matrix-free apply exists for this handle: every
+ * polytope is one axis-aligned cell (the reference's fine-mesh MatrixFree case) */
+int pd_matrix_free_available(const pd_handle *h);
 int pd_vmult_add(pd_handle *h, int mode, const double *src_dev, double *dst_dev);
 /* same with HOST buffers (pinned or pageable): H2D, apply, D2H */
 int pd_vmult_host(pd_handle *h, int mode, const double *src_host, double *dst_host);

@@ -394,6 +394,7 @@ namespace pd
         h->fq_w.alloc((size_t)h->Qf);
         h->face_diag.alloc((size_t)h->n_ifaces * 2 * nn);
         h->values.alloc((size_t)h->nnz);
+        setup_fine_operator(h, d);
         PD_CUDA(cudaStreamSynchronize(h->stream));
       }
     catch (...)
@@ -610,8 +611,33 @@ extern "C"
           throw Error(PD_ERR_STATE, "pd_vmult(BLOCK_CSR): pd_assemble has not been called");
         launch_spmv(h, src, dst, add);
       }
+    else if (mode == PD_VMULT_MATRIX_FREE)
+      {
+        if (!h->mf_ready)
+          throw Error(PD_ERR_UNSUPPORTED,
+                      "pd_vmult(MATRIX_FREE): available when every polytope is a single axis-aligned cell (the "
+                      "fine-mesh LaplaceOperatorDG / MonodomainOperatorDG case); use PD_VMULT_BLOCK_CSR on agglomerates");
+        launch_fine_operator(h, src, dst, add);
+      }
     else
-      throw Error(PD_ERR_UNSUPPORTED, "pd_vmult: matrix-free mode is not built yet in this round");
+      throw Error(PD_ERR_INVALID, "pd_vmult: unknown mode");
+  }
+
+  int
+  pd_set_operator(pd_handle *h, uint32_t flags, const pd_coefficients *coef)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      h->op_flags = flags;
+      h->op_coef  = coef ? *coef : pd_coefficients{1.0, 0.0};
+    });
+  }
+
+  int
+  pd_matrix_free_available(const pd_handle *h)
+  {
+    return h && h->mf_ready ? 1 : 0;
   }
 
   int

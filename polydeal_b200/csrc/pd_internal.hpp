@@ -106,6 +106,12 @@ struct pd_handle
   // work buffers and result
   pd::DevBuf<double> vol_partial, face_diag, values;
   pd::DevBuf<double> vec_a, vec_b; // staging for pd_vmult_host
+  // matrix-free fine-mesh operator (every polytope = one Cartesian cell), pd_finemesh.cu
+  bool                mf_ready = false;
+  pd::DevBuf<double>  mf_tables, mf_cell_h, mf_sigma;
+  pd::DevBuf<int32_t> mf_nbr;
+  pd_coefficients     op_coef{1.0, 0.0}; // operator of the matrix-free apply
+  uint32_t            op_flags = PD_ASSEMBLE_ALL;
 
   std::vector<int64_t> h_brow_ptr, h_subcell_ptr;
   std::vector<int32_t> h_bcol, h_dof_block;
@@ -127,6 +133,9 @@ namespace pd
   // pd_assemble.cu
   void launch_assemble(pd_handle *h, uint32_t flags, const pd_coefficients &coef);
   bool assemble_supported(int dim, int degree);
+  // pd_finemesh.cu
+  void setup_fine_operator(pd_handle *h, const pd_mesh_desc &d);
+  void launch_fine_operator(pd_handle *h, const double *src, double *dst, bool add);
   // pd_vmult.cu
   void launch_spmv(pd_handle *h, const double *src, double *dst, bool add);
   void launch_diagonal_inverse(pd_handle *h, double *dst);

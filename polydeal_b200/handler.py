@@ -222,6 +222,15 @@ class SIPOperator:
         c = K.Coefficients(stiffness, mass)
         K.check(K.lib().pd_assemble(self._h, flags, C.byref(c)))
 
+    def set_operator(self, flags=K.ASSEMBLE_ALL, stiffness=1.0, mass=0.0):
+        """Operator of the matrix-free apply (pd_set_operator)."""
+        c = K.Coefficients(stiffness, mass)
+        K.check(K.lib().pd_set_operator(self._h, flags, C.byref(c)))
+
+    @property
+    def matrix_free_available(self):
+        return bool(K.lib().pd_matrix_free_available(self._h))
+
     def m(self):
         return K.lib().pd_n_dofs(self._h)
 

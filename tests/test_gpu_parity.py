@@ -267,3 +267,70 @@ def test_unsupported_degree_fails_loudly():
     _, pah = product_handler(ogrid, [[c] for c in range(8)], 4, 5)
     with pytest.raises(pdl.PolydealError, match="no sm_100a kernel"):
         pdl.assemble_dg_matrix(pah)
+
+
+# ----------------------------------------------------------------------------------
+# rows 10-11: matrix-free sum-factorised SIP on the fine mesh
+# (LaplaceOperatorDG include/utils.h:819-925, MonodomainOperatorDG :1565-1659).
+# Checker: the oracle's matrix of the same form on singleton polytopes (the emulation
+# the reference itself documents at examples/monodomain_DG3D.cc:1470-1498) times x.
+# ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,n,p,order,hi,kw", [
+    (2, (8, 8), 1, 0, 1.0, {}),
+    (2, (6, 5), 2, 1, (1.0, 0.7), {}),
+    (2, (4, 4), 3, 0, 1.0, {}),
+    (2, (4, 3), 4, 1, (2.0, 1.0), {}),
+    (3, (4, 4, 4), 1, 0, 1.0, {}),
+    (3, (4, 4, 4), 2, 0, 1.0, {}),
+    (3, (3, 4, 5), 2, 1, (1.0, 0.8, 1.3), {}),
+    (3, (2, 2, 2), 3, 0, 1.0, {}),
+    (3, (4, 4, 4), 1, 0, 1.0, dict(with_boundary=False, stiffness_coeff=1e-4, mass_coeff=1.5e4)),   # monodomain, BDF2
+    (3, (3, 3, 3), 2, 1, 1.0, dict(with_boundary=False, stiffness_coeff=1e-4, mass_coeff=1.0e4)),  # monodomain, BDF1
+])
+def test_fine_mesh_matrix_free_vmult(dim, n, p, order, hi, kw):
+    pdl = gpu()
+    import torch
+
+    ogrid = po.Grid(dim, n, 0.0, hi, order)
+    groups = [[c] for c in range(ogrid.n_cells)]
+    oah = po.AgglomerationHandler(ogrid)
+    for g in groups:
+        oah.define_agglomerate(g)
+    oah.initialize_fe_values(p + 1)
+    oah.distribute_agglomerated_dofs(po.FE_DGQ, p)
+    _, pah = product_handler(ogrid, groups, p, p + 1)
+    C = max(p, 1) * (p + 1.0)  # include/utils.h:866
+    ref = po.assemble_dg_matrix(oah, penalty_constant=C, h_rule=po.H_NORMAL_EXTENT, n_threads=4, **kw)
+    op = pdl.SIPOperator(pah.flatten(penalty_constant=C, h_rule=pdl.H_NORMAL_EXTENT), keepalive=pah)
+    assert op.matrix_free_available
+    flags = pdl.ASSEMBLE_ALL if kw.get("with_boundary", True) else (pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR)
+    op.set_operator(flags, kw.get("stiffness_coeff", 1.0), kw.get("mass_coeff", 0.0))
+    x = src_vector(op.m())
+    yref = ref.vmult(x)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros_like(xd)
+    op.vmult(yd, xd, mode=pdl.VMULT_MATRIX_FREE)
+    op.synchronize()
+    scale = np.abs(yref).max()
+    assert np.abs(yd.cpu().numpy() - yref).max() <= TOL * scale
+    op.vmult_add(yd, xd, mode=pdl.VMULT_MATRIX_FREE)
+    op.synchronize()
+    assert np.abs(yd.cpu().numpy() - 2 * yref).max() <= 2 * TOL * scale
+    # and it is the same operator as the assembled one on the GPU
+    op.assemble(flags, kw.get("stiffness_coeff", 1.0), kw.get("mass_coeff", 0.0))
+    yb = torch.empty_like(xd)
+    op.vmult(yb, xd, mode=pdl.VMULT_BLOCK_CSR)
+    op.synchronize()
+    assert np.abs(yb.cpu().numpy() - yref).max() <= TOL * scale
+
+
+def test_matrix_free_refused_on_agglomerates():
+    pdl = gpu()
+    import torch
+
+    _, pah = both(3, 4, "blocks2", 1)
+    op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+    assert not op.matrix_free_available
+    x = torch.zeros(op.m(), dtype=torch.float64, device="cuda")
+    with pytest.raises(pdl.PolydealError, match="single axis-aligned cell"):
+        op.vmult(torch.empty_like(x), x, mode=pdl.VMULT_MATRIX_FREE)
