@@ -246,6 +246,21 @@ namespace pd
   }
 
   static void
+  ensure_assembly_buffers(pd_handle *h)
+  {
+    if (h->values.p || h->nnz == 0)
+      return;
+    const size_t nn = (size_t)h->n * h->n;
+    h->vq_x.alloc((size_t)h->Q * h->dim);
+    h->vq_w.alloc((size_t)h->Q);
+    h->fq_x.alloc((size_t)h->Qf * h->dim);
+    h->fq_n.alloc((size_t)h->Qf * h->dim);
+    h->fq_w.alloc((size_t)h->Qf);
+    h->face_diag.alloc((size_t)h->n_ifaces * 2 * nn);
+    h->values.alloc((size_t)h->nnz);
+  }
+
+  static void
   create(const pd_mesh_desc &d, pd_handle **out)
   {
     require_device();
@@ -387,13 +402,9 @@ namespace pd
         put64(h->padj_ptr, padj_ptr);
         put64(h->padj, padj);
 
-        h->vq_x.alloc((size_t)h->Q * d.dim);
-        h->vq_w.alloc((size_t)h->Q);
-        h->fq_x.alloc((size_t)h->Qf * d.dim);
-        h->fq_n.alloc((size_t)h->Qf * d.dim);
-        h->fq_w.alloc((size_t)h->Qf);
-        h->face_diag.alloc((size_t)h->n_ifaces * 2 * nn);
-        h->values.alloc((size_t)h->nnz);
+        // quadrature streams, work buffers and the matrix are allocated on first use
+        // (ensure_assembly_buffers): a handle used only for the matrix-free apply never
+        // pays for them
         setup_fine_operator(h, d);
         PD_CUDA(cudaStreamSynchronize(h->stream));
       }
@@ -504,6 +515,7 @@ extern "C"
     return guarded([&] {
       if (!h)
         throw Error(PD_ERR_INVALID, "null handle");
+      ensure_assembly_buffers(h);
       launch_quadrature(h);
       h->quad_valid = true;
     });
@@ -528,6 +540,7 @@ extern "C"
       pd_coefficients c{1.0, 0.0};
       if (coef)
         c = *coef;
+      ensure_assembly_buffers(h);
       PD_CUDA(cudaEventRecord(h->ev[4], h->stream));
       const bool built = !h->quad_valid;
       if (built)
@@ -563,6 +576,7 @@ extern "C"
     return guarded([&] {
       if (!h || !dev_values)
         throw Error(PD_ERR_INVALID, "null argument");
+      ensure_assembly_buffers(h);
       *dev_values = h->values.p;
     });
   }

@@ -84,6 +84,15 @@ namespace pd
 
       for (int i = threadIdx.x; i < 3 * N1 * N1 + 4 * N1; i += blockDim.x)
         tab[i] = A.tables[i];
+      __syncthreads();
+      // all shared arrays are private to a cell slot: when a slot is (part of) one warp the
+      // phases only need warp-level ordering
+      auto group_sync = [] {
+        if constexpr (GS <= 32)
+          __syncwarp();
+        else
+          __syncthreads();
+      };
 
       const int  slot = threadIdx.x / GS, l = threadIdx.x % GS;
       const bool lane_ok = l < N;
@@ -103,7 +112,7 @@ namespace pd
         {
           const int  cell = c0 + slot;
           const bool ok   = lane_ok && cell < A.n_cells;
-          __syncthreads(); // previous batch done with shared arrays (also orders the table load)
+          group_sync(); // previous batch done with this slot's shared arrays
           double h[DIM];
           int    nb[NFC];
 #pragma unroll
@@ -128,7 +137,7 @@ namespace pd
               for (int f = 0; f < NFC; ++f)
                 sN[slot][f][l] = nb[f] >= 0 ? A.x[(int64_t)nb[f] * N + l] : 0.;
             }
-          __syncthreads();
+          group_sync();
           double vol = 1.;
 #pragma unroll
           for (int d = 0; d < DIM; ++d)
@@ -182,7 +191,7 @@ namespace pd
                 sT[slot][f][0][e] = av;
                 sT[slot][f][1][e] = bv;
               }
-          __syncthreads();
+          group_sync();
           // ---- surface mass (Mf x Mf) on the face arrays, times the face area
           if constexpr (DIM == 3)
             {
@@ -197,7 +206,7 @@ namespace pd
                       s += Mf[a * N1 + t] * sT[slot][f][w][t + b * N1];
                     (w ? sB : sA)[slot][f][e] = s;
                   }
-              __syncthreads();
+              group_sync();
               if (cell < A.n_cells)
                 for (int m = l; m < NFC * 2 * NF; m += GS)
                   {
@@ -209,7 +218,7 @@ namespace pd
                       s += Mf[b * N1 + t] * (w ? sB : sA)[slot][f][a + t * N1];
                     sT[slot][f][w][e] = s * (vol / h[d]);
                   }
-              __syncthreads();
+              group_sync();
             }
           else
             {
@@ -223,14 +232,14 @@ namespace pd
                       s += Mf[e * N1 + t] * sT[slot][f][w][t];
                     (w ? sB : sA)[slot][f][e] = s * (vol / h[d]);
                   }
-              __syncthreads();
+              group_sync();
               if (cell < A.n_cells)
                 for (int m = l; m < NFC * 2 * NF; m += GS)
                   {
                     const int f = m / (2 * NF), w = (m / NF) & 1, e = m % NF;
                     sT[slot][f][w][e] = (w ? sB : sA)[slot][f][e];
                   }
-              __syncthreads();
+              group_sync();
             }
 
           // ---- cell term by 1-D contractions.  3-D:
@@ -251,7 +260,7 @@ namespace pd
                   sW[slot][0][l] = contract(Mh, sU[slot], 2); // Mz U
                   sW[slot][1][l] = contract(Sh, sU[slot], 2); // Sz U
                 }
-              __syncthreads();
+              group_sync();
               double yz = 0.;
               if (ok)
                 {
@@ -261,7 +270,7 @@ namespace pd
                   sW[slot][3][l]   = A.stiffness * ((vol / (h[1] * h[1])) * syz + (vol / (h[2] * h[2])) * mysz) +
                                    A.mass * vol * yz;
                 }
-              __syncthreads();
+              group_sync();
               if (ok && vol_on)
                 acc = A.stiffness * (vol / (h[0] * h[0])) * contract(Sh, sW[slot][2], 0) + contract(Mh, sW[slot][3], 0);
             }
@@ -272,7 +281,7 @@ namespace pd
                   sW[slot][0][l] = contract(Mh, sU[slot], 1); // My U
                   sW[slot][1][l] = A.stiffness * (vol / (h[1] * h[1])) * contract(Sh, sU[slot], 1); // Sy U
                 }
-              __syncthreads();
+              group_sync();
               if (ok && vol_on)
                 {
                   const double sx = contract(Sh, sW[slot][0], 0), mx_my = contract(Mh, sW[slot][0], 0);

@@ -24,6 +24,11 @@ CONFIGS = {
     "C": dict(dim=3, n=128, b=4, p=3, nq=4, C=None, mass=0.0),
     "D": dict(dim=3, n=256, b=4, p=2, nq=3, C=40.0, mass=0.5),
     "D8": dict(dim=3, n=128, b=4, p=2, nq=3, C=40.0, mass=0.5),  # one eighth of D (per-GPU share at 8 GPUs)
+    # fine-mesh matrix-free operators (every cell its own element), examples/matrix_free_agglo.cc: 64^3, DGQ2
+    "F1": dict(dim=3, n=64, b=1, p=1, nq=2, C=2.0, mass=0.0, fine=True),
+    "F2": dict(dim=3, n=64, b=1, p=2, nq=3, C=6.0, mass=0.0, fine=True),
+    "F3": dict(dim=3, n=64, b=1, p=3, nq=4, C=12.0, mass=0.0, fine=True),
+    "F2L": dict(dim=3, n=128, b=1, p=2, nq=3, C=6.0, mass=0.0, fine=True),
 }
 
 
@@ -69,7 +74,9 @@ def main():
         ah.define_agglomerate(g)
     ah.initialize_fe_values(nq)
     ah.distribute_agglomerated_dofs(pdl.FE_DGQ, p)
-    desc = ah.flatten(penalty_constant=-1.0 if cfg["C"] is None else cfg["C"])
+    fine = cfg.get("fine", False)
+    desc = ah.flatten(penalty_constant=-1.0 if cfg["C"] is None else cfg["C"],
+                      h_rule=pdl.H_NORMAL_EXTENT if fine else pdl.H_DIAMETER_OF_VISITOR)
     t_host = time.time() - t0
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -79,6 +86,26 @@ def main():
     Q = int(desc.poly_subcell_ptr[desc.n_polytopes]) * nq**dim
     Qf = int(desc.iface_sub_ptr[desc.n_ifaces]) * nq ** (dim - 1)
     nblocks = int(desc.brow_ptr[desc.n_block_rows])
+    if fine:
+        x = torch.from_numpy(np.sin(0.37 * np.arange(N)) + 0.01 * (np.arange(N) % 7)).cuda()
+        y = torch.empty_like(x)
+        flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+        vm = []
+        for s in range(args.steps + 3):
+            flush.zero_()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            op.vmult(y, x, mode=pdl.VMULT_MATRIX_FREE)
+            e.record(stream)
+            e.synchronize()
+            if s >= 3:
+                vm.append(a.elapsed_time(e))
+        ms = statistics.mean(vm)
+        print(json.dumps({"config": args.config, "cells": n**dim, "degree": p, "n_dofs": N, "host_setup_s": t_host,
+                          "mf_vmult_ms": ms, "mf_vmult_gdofs": N / (ms * 1e-3) / 1e9,
+                          "mf_GBs_algorithmic_16B_per_dof": 16.0 * N / (ms * 1e-3) / 1e9,
+                          "frac_hbm": 16.0 * N / (ms * 1e-3) / 1e9 / 6543.4, "l2": "flushed between applies"}))
+        return
     kms = {"volume": [], "faces": [], "reduce": [], "quadrature": []}
     tot = []
     for s in range(args.steps + 2):
