@@ -97,6 +97,16 @@ typedef struct pd_mesh_desc
   int32_t        n_block_rows;
   const int64_t *brow_ptr; /* [n_block_rows+1] */
   const int32_t *bcol_idx; /* [n_blocks] */
+
+  /* Sharding (one rank of a partition by polytopes; an agglomerate never straddles ranks,
+   * source/agglomeration_handler.cc:83-87).  0 = everything is owned.  Otherwise polytopes
+   * [0, n_owned) are owned and [n_owned, n_polytopes) are GHOSTS: no sub-cells, only bbox and
+   * dof_block (>= n_owned), the role of recv_ghosted_bbox / recv_ghost_dofs
+   * (include/agglomeration_handler.h:525-548).  Rows exist for owned polytopes only
+   * (n_block_rows = n_owned); column block indices run over owned + ghost.  An interface
+   * (A owned, B ghost) is listed from the OWNED side whatever the visiting rule says (the SIP
+   * form is symmetric under swapping sides with the normal flipped) with the sigma of the rule. */
+  int32_t n_owned_polytopes;
 } pd_mesh_desc;
 
 typedef struct pd_coefficients
@@ -147,7 +157,8 @@ int pd_invalidate_quadrature(pd_handle *h);
  * the device inside the handle. */
 int pd_assemble(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
 
-int64_t pd_n_dofs(const pd_handle *h);
+int64_t pd_n_dofs(const pd_handle *h);        /* rows = owned DoFs */
+int64_t pd_n_source_dofs(const pd_handle *h); /* length of vmult source vectors = owned + ghost DoFs */
 int64_t pd_nnz(const pd_handle *h);
 int32_t pd_n_dofs_per_cell(const pd_handle *h);
 /* device pointer to the matrix values (length pd_nnz) */
@@ -264,6 +275,23 @@ typedef struct pdh_flatten_params
 /* Flatten the agglomeration into a descriptor whose arrays stay owned by (and
  * valid as long as) the handler. */
 int pdh_flatten(pdh_handler *ah, const pdh_flatten_params *prm, pd_mesh_desc *out);
+/* One rank's share of a partition of the polytopes (owner[p] = rank of polytope p, all
+ * polytopes of the handler): owned polytopes + the ghost polytopes adjacent to them, as a
+ * descriptor with n_owned_polytopes set, plus the global block numbers needed to build the
+ * halo exchange.  Local block r of an owned polytope <-> owned_global_block[r] (ascending);
+ * ghost k (local block n_owned + k) <-> ghost_global_block[k], owned by ghost_owner[k];
+ * ghosts are grouped by owner rank (ascending) and ordered by global block inside a group.
+ * Arrays stay owned by the handler. */
+typedef struct pdh_local_info
+{
+  int32_t        n_owned, n_ghost;
+  const int32_t *owned_global_block; /* [n_owned] */
+  const int32_t *ghost_global_block; /* [n_ghost] */
+  const int32_t *ghost_owner;        /* [n_ghost] */
+  const int32_t *local_poly_global;  /* [n_owned + n_ghost] global polytope index of local polytope */
+} pdh_local_info;
+int pdh_flatten_local(pdh_handler *ah, const pdh_flatten_params *prm, const int32_t *owner, int32_t rank,
+                      pd_mesh_desc *out, pdh_local_info *info);
 /* pdh_flatten + pd_create in one call */
 int pdh_create_device(pdh_handler *ah, const pdh_flatten_params *prm, pd_handle **out);
 

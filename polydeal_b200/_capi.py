@@ -29,11 +29,17 @@ class MeshDesc(C.Structure):
         ("n_ifaces", i32), ("iface_polyA", P(i32)), ("iface_polyB", P(i32)), ("iface_sub_ptr", P(i64)),
         ("sub_cell", P(i32)), ("sub_face", P(i32)), ("sub_sigma", P(f64)),
         ("n_block_rows", i32), ("brow_ptr", P(i64)), ("bcol_idx", P(i32)),
+        ("n_owned_polytopes", i32),
     ]
 
 
 class Coefficients(C.Structure):
     _fields_ = [("stiffness", f64), ("mass", f64)]
+
+
+class LocalInfo(C.Structure):
+    _fields_ = [("n_owned", i32), ("n_ghost", i32), ("owned_global_block", P(i32)), ("ghost_global_block", P(i32)),
+                ("ghost_owner", P(i32)), ("local_poly_global", P(i32))]
 
 
 class FlattenParams(C.Structure):
@@ -52,6 +58,7 @@ SIGNATURES = {
     "pd_invalidate_quadrature": (C.c_int, [vp]),
     "pd_assemble": (C.c_int, [vp, u32, P(Coefficients)]),
     "pd_n_dofs": (i64, [vp]),
+    "pd_n_source_dofs": (i64, [vp]),
     "pd_nnz": (i64, [vp]),
     "pd_n_dofs_per_cell": (i32, [vp]),
     "pd_matrix_values_device": (C.c_int, [vp, P(vp)]),
@@ -98,6 +105,7 @@ SIGNATURES = {
     "pdh_sparsity_nnz": (i64, [vp]),
     "pdh_create_agglomeration_sparsity_pattern": (C.c_int, [vp, vp, vp]),
     "pdh_flatten": (C.c_int, [vp, P(FlattenParams), P(MeshDesc)]),
+    "pdh_flatten_local": (C.c_int, [vp, P(FlattenParams), vp, i32, P(MeshDesc), P(LocalInfo)]),
     "pdh_create_device": (C.c_int, [vp, P(FlattenParams), P(vp)]),
 }
 

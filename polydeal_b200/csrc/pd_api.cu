@@ -178,11 +178,22 @@ namespace pd
     need(d.n_cells > 0 && d.cell_verts, "no cells");
     need(d.n_polytopes > 0 && d.poly_subcell_ptr && d.poly_subcell_idx && d.bbox && d.dof_block, "no polytopes");
     need(d.n_ifaces >= 0 && (d.n_ifaces == 0 || (d.iface_polyA && d.iface_polyB && d.iface_sub_ptr)), "bad interface list");
-    need(d.n_block_rows == d.n_polytopes && d.brow_ptr && d.bcol_idx, "block pattern must have one row per polytope");
+    const int32_t n_own = d.n_owned_polytopes > 0 ? d.n_owned_polytopes : d.n_polytopes;
+    need(n_own <= d.n_polytopes, "n_owned_polytopes exceeds n_polytopes");
+    need(d.n_block_rows == n_own && d.brow_ptr && d.bcol_idx, "block pattern must have one row per owned polytope");
     need(d.poly_subcell_ptr[0] == 0, "poly_subcell_ptr[0] != 0");
     for (int32_t p = 0; p < d.n_polytopes; ++p)
       {
-        need(d.poly_subcell_ptr[p + 1] > d.poly_subcell_ptr[p], "empty polytope");
+        if (p < n_own)
+          {
+            need(d.poly_subcell_ptr[p + 1] > d.poly_subcell_ptr[p], "empty polytope");
+            need(d.dof_block[p] < n_own, "owned polytopes must carry the first n_owned block indices");
+          }
+        else
+          {
+            need(d.poly_subcell_ptr[p + 1] == d.poly_subcell_ptr[p], "ghost polytopes carry no sub-cells");
+            need(d.dof_block[p] >= n_own, "ghost polytopes must carry block indices >= n_owned");
+          }
         need(d.dof_block[p] >= 0 && d.dof_block[p] < d.n_polytopes, "dof_block out of range");
         for (int k = 0; k < d.dim; ++k)
           need(d.bbox[(size_t)p * 2 * d.dim + d.dim + k] > d.bbox[(size_t)p * 2 * d.dim + k], "degenerate bounding box");
@@ -192,7 +203,7 @@ namespace pd
       need(d.poly_subcell_idx[s] >= 0 && d.poly_subcell_idx[s] < d.n_cells, "sub-cell index out of range");
     for (int32_t f = 0; f < d.n_ifaces; ++f)
       {
-        need(d.iface_polyA[f] >= 0 && d.iface_polyA[f] < d.n_polytopes, "iface_polyA out of range");
+        need(d.iface_polyA[f] >= 0 && d.iface_polyA[f] < n_own, "iface_polyA must be an owned polytope");
         need(d.iface_polyB[f] >= -1 && d.iface_polyB[f] < d.n_polytopes, "iface_polyB out of range");
         need(d.iface_sub_ptr[f + 1] >= d.iface_sub_ptr[f], "iface_sub_ptr not monotone");
       }
@@ -303,13 +314,14 @@ namespace pd
         h->n_verts    = d.n_verts;
         h->n_cells    = d.n_cells;
         h->np         = d.n_polytopes;
+        h->np_own     = d.n_owned_polytopes > 0 ? d.n_owned_polytopes : d.n_polytopes;
         h->n_ifaces   = d.n_ifaces;
         h->n_subcells = d.poly_subcell_ptr[d.n_polytopes];
         h->n_subfaces = d.n_ifaces ? d.iface_sub_ptr[d.n_ifaces] : 0;
         h->Q          = h->n_subcells * h->nqc;
         h->Qf         = h->n_subfaces * h->nqf;
         h->n_blocks   = d.brow_ptr[d.n_block_rows];
-        h->n_dofs     = (int64_t)h->np * h->n;
+        h->n_dofs     = (int64_t)h->np_own * h->n; // rows; source vectors have np * n entries (owned + ghost)
         h->nnz        = h->n_blocks * h->n * h->n;
         int dev       = 0;
         PD_CUDA(cudaGetDevice(&dev));
@@ -331,7 +343,7 @@ namespace pd
         h->sub_cell.alloc((size_t)h->n_subfaces);
         h->sub_face.alloc((size_t)h->n_subfaces);
         h->sub_sigma.alloc((size_t)h->n_subfaces);
-        h->brow_ptr.alloc((size_t)h->np + 1);
+        h->brow_ptr.alloc((size_t)h->np_own + 1);
         h->bcol.alloc((size_t)h->n_blocks);
         if (h->n_ifaces == 0)
           {
@@ -341,16 +353,20 @@ namespace pd
           }
         upload_descriptor(h, d);
 
-        h->h_brow_ptr.assign(d.brow_ptr, d.brow_ptr + h->np + 1);
+        h->h_brow_ptr.assign(d.brow_ptr, d.brow_ptr + h->np_own + 1);
         h->h_bcol.assign(d.bcol_idx, d.bcol_idx + h->n_blocks);
         h->h_dof_block.assign(d.dof_block, d.dof_block + h->np);
 
         // ---- derived index data ------------------------------------------------
         const int64_t        nn = (int64_t)h->n * h->n;
-        std::vector<int32_t> row_stride(h->np);
-        for (int32_t b = 0; b < h->np; ++b)
+        // Rows exist for OWNED polytopes only.  An interface whose B side is a ghost
+        // polytope (owned by another rank) contributes M11 and M12 to A's row; its M21 / M22
+        // belong to the other rank, which evaluates the same interface itself.
+        const int32_t        n_own = h->np_own;
+        std::vector<int32_t> row_stride(n_own);
+        for (int32_t b = 0; b < n_own; ++b)
           row_stride[b] = (int32_t)(d.brow_ptr[b + 1] - d.brow_ptr[b]) * h->n;
-        std::vector<int64_t> diag_base(h->np);
+        std::vector<int64_t> diag_base(n_own);
         std::vector<char>    seen_block(h->np, 0);
         for (int32_t p = 0; p < h->np; ++p)
           {
@@ -358,10 +374,11 @@ namespace pd
             if (seen_block[b])
               throw Error(PD_ERR_INVALID, "pd_mesh_desc: dof_block is not a permutation");
             seen_block[b] = 1;
-            diag_base[p]  = d.brow_ptr[b] * nn + find_block(d, b, b) * h->n;
+            if (p < n_own)
+              diag_base[p] = d.brow_ptr[b] * nn + find_block(d, b, b) * h->n;
           }
         std::vector<int64_t> baseAB(h->n_ifaces, -1), baseBA(h->n_ifaces, -1);
-        std::vector<int64_t> padj_ptr(h->np + 1, 0);
+        std::vector<int64_t> padj_ptr(n_own + 1, 0);
         for (int32_t f = 0; f < h->n_ifaces; ++f)
           {
             const int32_t pa = d.iface_polyA[f], pb = d.iface_polyB[f];
@@ -370,19 +387,22 @@ namespace pd
               {
                 if (pb == pa)
                   throw Error(PD_ERR_INVALID, "pd_mesh_desc: interface joins a polytope with itself");
-                ++padj_ptr[pb + 1];
                 const int32_t ba = d.dof_block[pa], bb = d.dof_block[pb];
                 baseAB[f] = d.brow_ptr[ba] * nn + find_block(d, ba, bb) * h->n;
-                baseBA[f] = d.brow_ptr[bb] * nn + find_block(d, bb, ba) * h->n;
+                if (pb < n_own)
+                  {
+                    ++padj_ptr[pb + 1];
+                    baseBA[f] = d.brow_ptr[bb] * nn + find_block(d, bb, ba) * h->n;
+                  }
               }
           }
-        for (int32_t p = 0; p < h->np; ++p)
+        for (int32_t p = 0; p < n_own; ++p)
           padj_ptr[p + 1] += padj_ptr[p];
-        std::vector<int64_t> padj(padj_ptr[h->np]), cursor(padj_ptr.begin(), padj_ptr.end() - 1);
+        std::vector<int64_t> padj(padj_ptr[n_own]), cursor(padj_ptr.begin(), padj_ptr.end() - 1);
         for (int32_t f = 0; f < h->n_ifaces; ++f)
           {
             padj[cursor[d.iface_polyA[f]]++] = (int64_t)f * 2;
-            if (d.iface_polyB[f] >= 0)
+            if (d.iface_polyB[f] >= 0 && d.iface_polyB[f] < n_own)
               padj[cursor[d.iface_polyB[f]]++] = (int64_t)f * 2 + 1;
           }
         auto put32 = [&](DevBuf<int32_t> &b, const std::vector<int32_t> &v) {
@@ -481,6 +501,7 @@ extern "C"
       const int64_t nsf = d->n_ifaces ? d->iface_sub_ptr[d->n_ifaces] : 0;
       if (d->dim != h->dim || d->fe_degree != h->degree || d->n_q1d != h->nq1 || d->n_q1d_face != h->nq1f ||
           d->n_verts != h->n_verts || d->n_cells != h->n_cells || d->n_polytopes != h->np ||
+          (d->n_owned_polytopes > 0 ? d->n_owned_polytopes : d->n_polytopes) != h->np_own ||
           d->n_ifaces != h->n_ifaces || nsc != h->n_subcells || nsf != h->n_subfaces ||
           d->brow_ptr[d->n_block_rows] != h->n_blocks)
         throw Error(PD_ERR_INVALID, "pd_upload: descriptor sizes differ from the ones the handle was created with");
@@ -564,6 +585,11 @@ extern "C"
   {
     return h ? h->nnz : 0;
   }
+  int64_t
+  pd_n_source_dofs(const pd_handle *h)
+  {
+    return h ? (int64_t)h->np * h->n : 0;
+  }
   int32_t
   pd_n_dofs_per_cell(const pd_handle *h)
   {
@@ -603,7 +629,7 @@ extern "C"
       const int n = h->n;
       int64_t   k = 0;
       rowptr[0]   = 0;
-      for (int32_t b = 0; b < h->np; ++b)
+      for (int32_t b = 0; b < h->np_own; ++b)
         for (int i = 0; i < n; ++i)
           {
             for (int64_t e = h->h_brow_ptr[b]; e < h->h_brow_ptr[b + 1]; ++e)
@@ -672,12 +698,13 @@ extern "C"
     return guarded([&] {
       if (!h || !src_host || !dst_host)
         throw Error(PD_ERR_INVALID, "pd_vmult_host: null argument");
-      if (h->vec_a.n != (size_t)h->n_dofs)
+      const size_t n_src = (size_t)h->np * h->n;
+      if (h->vec_a.n != n_src)
         {
-          h->vec_a.alloc((size_t)h->n_dofs);
+          h->vec_a.alloc(n_src);
           h->vec_b.alloc((size_t)h->n_dofs);
         }
-      PD_CUDA(cudaMemcpyAsync(h->vec_a.p, src_host, sizeof(double) * h->n_dofs, cudaMemcpyHostToDevice, h->stream));
+      PD_CUDA(cudaMemcpyAsync(h->vec_a.p, src_host, sizeof(double) * n_src, cudaMemcpyHostToDevice, h->stream));
       vmult_impl(h, mode, h->vec_a.p, h->vec_b.p, false);
       PD_CUDA(cudaMemcpyAsync(dst_host, h->vec_b.p, sizeof(double) * h->n_dofs, cudaMemcpyDeviceToHost, h->stream));
       PD_CUDA(cudaStreamSynchronize(h->stream));

@@ -624,7 +624,8 @@ namespace pd
                   }
               __syncthreads();
               const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
-              const int     strideA = A.row_stride[A.dof_block[pa]], strideB = A.row_stride[A.dof_block[pb]];
+              const int     strideA = A.row_stride[A.dof_block[pa]];
+              const int     strideB = baseBA >= 0 ? A.row_stride[A.dof_block[pb]] : 0;
               for (int idx = tid; idx < 4 * N * N; idx += NTHR)
                 {
                   const int which = idx / (N * N), rem = idx - which * N * N;
@@ -640,7 +641,7 @@ namespace pd
                     fd[N * N + rem] = m;
                   else if (which == 1)
                     A.values[baseAB + (int64_t)i * strideA + j] = m;
-                  else
+                  else if (baseBA >= 0) // B is a ghost polytope: its rows live on another rank
                     A.values[baseBA + (int64_t)i * strideB + j] = m;
                 }
             }
@@ -900,10 +901,10 @@ namespace pd
       r.dof_block      = h->dof_block.p;
       r.row_stride     = h->row_stride.p;
       r.values         = h->values.p;
-      r.np             = h->np;
+      r.np             = h->np_own;
       r.n              = h->n;
       r.flags          = flags;
-      const int grid   = std::min<int64_t>(h->np, (int64_t)h->sm_count * 8);
+      const int grid   = std::min<int64_t>(h->np_own, (int64_t)h->sm_count * 8);
       k_reduce_diag<<<grid, 256, 0, h->stream>>>(r);
       ++h->launches;
       PD_CUDA(cudaEventRecord(h->ev[3], h->stream));

@@ -340,10 +340,10 @@ namespace pd
   setup_fine_operator(pd_handle *h, const pd_mesh_desc &d)
   {
     h->mf_ready = false;
-    if (h->n_subcells != h->np)
+    if (h->n_subcells != h->np_own)
       return;
     const int dim = d.dim, vpc = 1 << dim, nfc = 2 * dim;
-    for (int32_t p = 0; p < h->np; ++p)
+    for (int32_t p = 0; p < h->np_own; ++p)
       {
         const int32_t  c  = d.poly_subcell_idx[d.poly_subcell_ptr[p]];
         const double  *bb = d.bbox + (size_t)p * 2 * dim;
@@ -355,9 +355,11 @@ namespace pd
                 return; // not an axis-aligned box in reference orientation
           }
       }
-    std::vector<double>  cell_h((size_t)h->np * dim), sigma((size_t)h->np * nfc, 0.);
-    std::vector<int32_t> nbr((size_t)h->np * nfc, -1);
-    std::vector<char>    seen((size_t)h->np * nfc, 0);
+    // extents for owned AND ghost cells (a neighbour's normal derivative needs its 1/h);
+    // neighbour / penalty rows for owned cells only
+    std::vector<double>  cell_h((size_t)h->np * dim), sigma((size_t)h->np_own * nfc, 0.);
+    std::vector<int32_t> nbr((size_t)h->np_own * nfc, -1);
+    std::vector<char>    seen((size_t)h->np_own * nfc, 0);
     for (int32_t p = 0; p < h->np; ++p)
       for (int k = 0; k < dim; ++k)
         cell_h[(size_t)d.dof_block[p] * dim + k] = d.bbox[(size_t)p * 2 * dim + dim + k] - d.bbox[(size_t)p * 2 * dim + k];
@@ -371,7 +373,7 @@ namespace pd
             nbr[(size_t)ba * nfc + lf]   = b >= 0 ? d.dof_block[b] : -1;
             sigma[(size_t)ba * nfc + lf] = d.sub_sigma[s];
             seen[(size_t)ba * nfc + lf]  = 1;
-            if (b >= 0)
+            if (b >= 0 && b < h->np_own)
               {
                 const int32_t bb = d.dof_block[b];
                 nbr[(size_t)bb * nfc + (lf ^ 1)]   = ba;
@@ -433,7 +435,7 @@ namespace pd
     a.sigma     = h->mf_sigma.p;
     a.x         = src;
     a.y         = dst;
-    a.n_cells   = h->np;
+    a.n_cells   = h->np_own;
     a.stiffness = h->op_coef.stiffness;
     a.mass      = h->op_coef.mass;
     a.flags     = h->op_flags;
@@ -441,7 +443,7 @@ namespace pd
     const int key = h->dim * 10 + h->degree;
     auto      go  = [&](auto kern, const int gs) {
       const int     cpb  = 256 / gs;
-      const int64_t want = ((int64_t)h->np + cpb - 1) / cpb;
+      const int64_t want = ((int64_t)h->np_own + cpb - 1) / cpb;
       const int     grid = (int)std::min<int64_t>(want, (int64_t)h->sm_count * 16);
       kern<<<grid, 256, 0, h->stream>>>(a);
     };

@@ -418,6 +418,191 @@ namespace pd
       d.bcol_idx         = fl_bcol.data();
     }
 
+    // Flatten the piece of the agglomeration one rank needs (owner-computes-rows):
+    // its owned polytopes (define order; local block order = global block order
+    // restricted to the owned ones), then the ghost polytopes adjacent to them, grouped
+    // by owning rank and ordered by global block inside a group -- so that the ghost
+    // section of a source vector is the concatenation of what each peer sends.
+    // Replaces setup_ghost_polytopes / exchange_interface_values
+    // (source/agglomeration_handler.cc:531-618, 1026-1091): instead of shipping basis
+    // values and gradients at the face points, the ghost's bounding box and DoF block are
+    // enough, because the owning side re-evaluates the ghost basis itself.
+    void
+    flatten_local(const pdh_flatten_params &prm, const int32_t *owner, const int32_t rank, pd_mesh_desc &d,
+                  pdh_local_info &info)
+    {
+      require_connectivity();
+      if (n_q1d <= 0)
+        throw Error(PD_ERR_STATE, "initialize_fe_values() must be called before flattening");
+      const double C =
+        prm.penalty_constant >= 0 ? prm.penalty_constant : 10.0 * (fe_degree + dim) * (fe_degree + 1);
+      const int32_t np = n_polytopes();
+      lc_poly_global.clear();
+      std::vector<int32_t> g2l(np, -1);
+      for (int32_t p = 0; p < np; ++p)
+        if (owner[p] == rank)
+          {
+            g2l[p] = (int32_t)lc_poly_global.size();
+            lc_poly_global.push_back(p);
+          }
+      const int32_t n_own = (int32_t)lc_poly_global.size();
+      if (n_own == 0)
+        throw Error(PD_ERR_INVALID, "rank " + std::to_string(rank) + " owns no polytope");
+      // ghosts: neighbours owned elsewhere, sorted by (owner, global block)
+      std::vector<int32_t> ghosts;
+      for (int32_t lp = 0; lp < n_own; ++lp)
+        {
+          const int32_t p = lc_poly_global[lp];
+          for (uint32_t f = 0; f < n_faces(p); ++f)
+            {
+              const int32_t q = neighbor(p, f);
+              if (q >= 0 && owner[q] != rank && g2l[q] == -1)
+                {
+                  g2l[q] = -2; // mark
+                  ghosts.push_back(q);
+                }
+            }
+        }
+      std::sort(ghosts.begin(), ghosts.end(), [&](int32_t a, int32_t b) {
+        return owner[a] != owner[b] ? owner[a] < owner[b] : dof_block[a] < dof_block[b];
+      });
+      for (const int32_t q : ghosts)
+        {
+          g2l[q] = (int32_t)lc_poly_global.size();
+          lc_poly_global.push_back(q);
+        }
+      const int32_t n_loc = (int32_t)lc_poly_global.size(), n_ghost = n_loc - n_own;
+      // local block numbering
+      std::vector<int32_t> own_sorted(lc_poly_global.begin(), lc_poly_global.begin() + n_own);
+      std::sort(own_sorted.begin(), own_sorted.end(), [&](int32_t a, int32_t b) { return dof_block[a] < dof_block[b]; });
+      lc_dof_block.assign(n_loc, 0);
+      lc_owned_global_block.resize(n_own);
+      for (int32_t r = 0; r < n_own; ++r)
+        {
+          lc_dof_block[g2l[own_sorted[r]]] = r;
+          lc_owned_global_block[r]          = dof_block[own_sorted[r]];
+        }
+      lc_ghost_global_block.resize(n_ghost);
+      lc_ghost_owner.resize(n_ghost);
+      for (int32_t k = 0; k < n_ghost; ++k)
+        {
+          lc_dof_block[n_own + k]  = n_own + k;
+          lc_ghost_global_block[k] = dof_block[ghosts[k]];
+          lc_ghost_owner[k]        = owner[ghosts[k]];
+        }
+      // sub-cells, bounding boxes
+      lc_subcell_ptr.assign(1, 0);
+      lc_subcell_idx.clear();
+      lc_bbox.clear();
+      for (int32_t lp = 0; lp < n_loc; ++lp)
+        {
+          const int32_t p = lc_poly_global[lp];
+          if (lp < n_own)
+            lc_subcell_idx.insert(lc_subcell_idx.end(), subcell_idx.begin() + subcell_ptr[p],
+                                  subcell_idx.begin() + subcell_ptr[p + 1]);
+          lc_subcell_ptr.push_back((int64_t)lc_subcell_idx.size());
+          lc_bbox.insert(lc_bbox.end(), bbox.begin() + (size_t)p * 2 * dim, bbox.begin() + (size_t)(p + 1) * 2 * dim);
+        }
+      // faces: always listed from the owned side; sigma by the reference's rule
+      lc_polyA.clear();
+      lc_polyB.clear();
+      lc_sub_ptr.assign(1, 0);
+      lc_sub_cell.clear();
+      lc_sub_face.clear();
+      lc_sub_sigma.clear();
+      std::vector<std::vector<int32_t>> rows(n_own);
+      for (int32_t lp = 0; lp < n_own; ++lp)
+        {
+          const int32_t p = lc_poly_global[lp];
+          rows[lc_dof_block[lp]].push_back(lc_dof_block[lp]);
+          for (uint32_t f = 0; f < n_faces(p); ++f)
+            {
+              const int32_t q = neighbor(p, f);
+              if (q >= 0)
+                rows[lc_dof_block[lp]].push_back(lc_dof_block[g2l[q]]);
+              const bool p_visits = q < 0 || (prm.visit_rule == PD_VISIT_BY_ID ? masters[p] < masters[q] : p < q);
+              if (q >= 0 && owner[q] == rank && !p_visits)
+                continue; // both owned: listed once, from the visiting side
+              const double h_visitor = p_visits ? diameter(p) : diameter(q);
+              lc_polyA.push_back(lp);
+              lc_polyB.push_back(q >= 0 ? g2l[q] : -1);
+              const int64_t fi = face_ptr[p] + f;
+              for (int64_t s = face_sub_ptr[fi]; s < face_sub_ptr[fi + 1]; ++s)
+                {
+                  lc_sub_cell.push_back(sub_cell[s]);
+                  lc_sub_face.push_back(sub_face[s]);
+                  double sigma;
+                  switch (prm.h_rule)
+                    {
+                      case PD_H_MAX_INVERSE_DIAMETER:
+                        sigma = q >= 0 ? C * std::max(1.0 / diameter(p), 1.0 / diameter(q)) : C / diameter(p);
+                        break;
+                      case PD_H_CONSTANT:
+                        sigma = C / prm.h_const;
+                        break;
+                      case PD_H_NORMAL_EXTENT:
+                        {
+                          const int     nd = sub_face[s] / 2;
+                          const double *ba = &bbox[(size_t)p * 2 * dim];
+                          const double  ia = 1.0 / (ba[dim + nd] - ba[nd]);
+                          if (q >= 0)
+                            {
+                              const double *bb = &bbox[(size_t)q * 2 * dim];
+                              sigma            = C * (ia + 1.0 / (bb[dim + nd] - bb[nd]));
+                            }
+                          else
+                            sigma = 4.0 * C * ia;
+                          break;
+                        }
+                      default:
+                        sigma = C / h_visitor;
+                    }
+                  lc_sub_sigma.push_back(sigma);
+                }
+              lc_sub_ptr.push_back((int64_t)lc_sub_cell.size());
+            }
+        }
+      lc_brow_ptr.assign(1, 0);
+      lc_bcol.clear();
+      for (int32_t b = 0; b < n_own; ++b)
+        {
+          std::sort(rows[b].begin(), rows[b].end());
+          lc_bcol.insert(lc_bcol.end(), rows[b].begin(), rows[b].end());
+          lc_brow_ptr.push_back((int64_t)lc_bcol.size());
+        }
+      d                   = pd_mesh_desc{};
+      d.dim               = dim;
+      d.fe_degree         = fe_degree;
+      d.n_q1d             = n_q1d;
+      d.n_q1d_face        = n_q1d_face;
+      d.n_verts           = grid->n_verts();
+      d.verts             = grid->verts.data();
+      d.n_cells           = grid->n_cells();
+      d.cell_verts        = grid->cell_verts.data();
+      d.n_polytopes       = n_loc;
+      d.n_owned_polytopes = n_own;
+      d.poly_subcell_ptr  = lc_subcell_ptr.data();
+      d.poly_subcell_idx  = lc_subcell_idx.data();
+      d.bbox              = lc_bbox.data();
+      d.dof_block         = lc_dof_block.data();
+      d.n_ifaces          = (int32_t)lc_polyA.size();
+      d.iface_polyA       = lc_polyA.data();
+      d.iface_polyB       = lc_polyB.data();
+      d.iface_sub_ptr     = lc_sub_ptr.data();
+      d.sub_cell          = lc_sub_cell.data();
+      d.sub_face          = lc_sub_face.data();
+      d.sub_sigma         = lc_sub_sigma.data();
+      d.n_block_rows      = n_own;
+      d.brow_ptr          = lc_brow_ptr.data();
+      d.bcol_idx          = lc_bcol.data();
+      info.n_owned            = n_own;
+      info.n_ghost            = n_ghost;
+      info.owned_global_block = lc_owned_global_block.data();
+      info.ghost_global_block = lc_ghost_global_block.data();
+      info.ghost_owner        = lc_ghost_owner.data();
+      info.local_poly_global  = lc_poly_global.data();
+    }
+
     Grid     *grid;
     int       dim;
     int32_t   fe_degree = -1, dofs_per_cell = 0, n_q1d = 0, n_q1d_face = 0;
@@ -547,6 +732,11 @@ namespace pd
       connectivity_ready = true;
     }
 
+    // storage behind flatten_local()
+    std::vector<int32_t> lc_poly_global, lc_dof_block, lc_owned_global_block, lc_ghost_global_block, lc_ghost_owner,
+      lc_subcell_idx, lc_polyA, lc_polyB, lc_sub_cell, lc_sub_face, lc_bcol;
+    std::vector<int64_t> lc_subcell_ptr, lc_sub_ptr, lc_brow_ptr;
+    std::vector<double>  lc_bbox, lc_sub_sigma;
     // storage behind flatten()
     std::vector<int32_t> fl_polyA, fl_polyB, fl_sub_cell, fl_sub_face, fl_bcol;
     std::vector<int64_t> fl_sub_ptr, fl_brow_ptr;

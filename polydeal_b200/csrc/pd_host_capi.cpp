@@ -353,6 +353,16 @@ extern "C"
     });
   }
   int
+  pdh_flatten_local(pdh_handler *ah, const pdh_flatten_params *prm, const int32_t *owner, int32_t rank, pd_mesh_desc *out,
+                    pdh_local_info *info)
+  {
+    return guarded([&] {
+      if (!prm || !out || !owner || !info)
+        throw pd::Error(PD_ERR_INVALID, "null argument");
+      H(ah).flatten_local(*prm, owner, rank, *out, *info);
+    });
+  }
+  int
   pdh_create_device(pdh_handler *ah, const pdh_flatten_params *prm, pd_handle **out)
   {
     pd_mesh_desc d;

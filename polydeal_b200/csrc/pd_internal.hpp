@@ -83,7 +83,7 @@ struct pd_handle
   int     dim = 0, degree = 0, n1 = 0, n = 0; // n = dofs per polytope
   int     nq1 = 0, nq1f = 0, nqc = 0, nqf = 0;
   int64_t n_verts = 0, n_cells = 0, n_subcells = 0, n_subfaces = 0;
-  int32_t np = 0, n_ifaces = 0;
+  int32_t np = 0, np_own = 0, n_ifaces = 0; // np_own owned polytopes (rows) + ghosts = np
   int64_t Q = 0, Qf = 0; // total volume / face quadrature points
   int64_t n_blocks = 0, nnz = 0, n_dofs = 0;
   int32_t n_vitems = 0;

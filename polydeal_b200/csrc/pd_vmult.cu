@@ -155,19 +155,19 @@ namespace pd
     if (h->max_row_len < 0)
       {
         int64_t m = 0;
-        for (int32_t b = 0; b < h->np; ++b)
+        for (int32_t b = 0; b < h->np_own; ++b)
           m = std::max<int64_t>(m, (h->h_brow_ptr[b + 1] - h->h_brow_ptr[b]) * h->n);
         h->max_row_len = m;
       }
     if (h->max_row_len <= SPMV_MAX_ROW)
       {
-        const int grid = (int)std::min<int64_t>(h->np, (int64_t)h->sm_count * 8);
+        const int grid = (int)std::min<int64_t>(h->np_own, (int64_t)h->sm_count * 8);
         if (add)
-          k_spmv_block_row<true><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n, h->np,
-                                                                      src, dst);
+          k_spmv_block_row<true><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n,
+                                                                      h->np_own, src, dst);
         else
-          k_spmv_block_row<false><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n, h->np,
-                                                                       src, dst);
+          k_spmv_block_row<false><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n,
+                                                                       h->np_own, src, dst);
       }
     else
       {
@@ -189,9 +189,9 @@ namespace pd
   void
   launch_diagonal_inverse(pd_handle *h, double *dst)
   {
-    const int64_t nd = (int64_t)h->np * h->n;
+    const int64_t nd = (int64_t)h->np_own * h->n;
     k_diag_inverse<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>(h->values.p, h->diag_base.p, h->dof_block.p,
-                                                                      h->row_stride.p, h->n, h->np, dst);
+                                                                      h->row_stride.p, h->n, h->np_own, dst);
     ++h->launches;
     PD_CUDA(cudaGetLastError());
   }

@@ -1,0 +1,158 @@
+"""Sharding of the hot path over GPUs: one process per GPU, polytopes as the unit.
+
+Reference: MPI domain decomposition in which an agglomerate never straddles ranks
+(/root/reference/source/agglomeration_handler.cc:83-87); ghost metadata travels once
+(setup_ghost_polytopes / exchange_interface_values, :531-618, 1026-1091) and the vector
+ghost values travel in every vmult (LinearAlgebra::distributed::Vector inside
+MatrixFree::loop, include/utils.h:466-472; Trilinos import for the matrix-based vmult).
+
+Here:
+ * assembly is owner-computes-rows: every rank evaluates its cut interfaces itself from the
+   ghost polytope's bounding box + DoF block (one-time ghost geometry), so there is NO
+   data-path collective in assembly and no reverse matrix communication;
+ * vmult has one exchange step per apply: the coefficient blocks of the ghost polytopes,
+   grouped send/recv per peer (torch.distributed P2P batch = ncclGroupStart/ncclSend/ncclRecv/
+   ncclGroupEnd over NVLink), received straight into the ghost section of the source vector.
+
+Every rank holds the (host-side, replicated) AgglomerationHandler of the whole mesh, so the
+exchange plan is computed locally without any setup communication.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as K
+from .handler import AgglomerationHandler, SIPOperator, _ptr
+
+
+def partition_by_blocks(ah: AgglomerationHandler, n_ranks: int) -> np.ndarray:
+    """owner[p]: contiguous, equally sized ranges of the global DoF-block order (a slab
+    decomposition on lexicographic grids, a space-filling-curve one on Morton grids)."""
+    np_ = ah.n_polytopes
+    n = ah.n_dofs_per_cell
+    block = np.array([int(ah.get_dof_indices(p)[0]) // n for p in range(np_)], dtype=np.int64)
+    owner = np.empty(np_, dtype=np.int32)
+    owner[:] = (block * n_ranks) // np_
+    return owner
+
+
+def partition_by_coordinate(ah: AgglomerationHandler, n_ranks: int, axis: int) -> np.ndarray:
+    """owner[p] by the bounding-box centre along `axis`: equal-count slabs."""
+    np_ = ah.n_polytopes
+    centre = np.array([0.5 * (ah.bbox(p)[0][axis] + ah.bbox(p)[1][axis]) for p in range(np_)])
+    order = np.argsort(centre, kind="stable")
+    owner = np.empty(np_, dtype=np.int32)
+    owner[order] = (np.arange(np_) * n_ranks) // np_
+    return owner
+
+
+class LocalPart:
+    """The local descriptor of one rank + the index maps of the halo exchange."""
+
+    def __init__(self, ah: AgglomerationHandler, owner: np.ndarray, rank: int, penalty_constant=-1.0,
+                 h_rule=K.H_DIAMETER_OF_VISITOR, h_const=1.0, visit_rule=K.VISIT_BY_ID):
+        owner = np.ascontiguousarray(owner, dtype=np.int32)
+        assert owner.shape == (ah.n_polytopes,)
+        self.ah, self.owner, self.rank = ah, owner, rank
+        self.n = ah.n_dofs_per_cell
+        prm = K.FlattenParams(penalty_constant, h_rule, h_const, visit_rule)
+        self.desc, info = K.MeshDesc(), K.LocalInfo()
+        K.check(K.lib().pdh_flatten_local(ah._h, C.byref(prm), _ptr(owner), rank, C.byref(self.desc), C.byref(info)))
+        self.n_owned, self.n_ghost = info.n_owned, info.n_ghost
+        as_np = lambda p, m: np.ctypeslib.as_array(p, (m,)).copy() if m else np.zeros(0, dtype=np.int32)
+        self.owned_global_block = as_np(info.owned_global_block, self.n_owned)
+        self.ghost_global_block = as_np(info.ghost_global_block, self.n_ghost)
+        self.ghost_owner = as_np(info.ghost_owner, self.n_ghost)
+        self.local_poly_global = as_np(info.local_poly_global, self.n_owned + self.n_ghost)
+        # ---- exchange plan, computed without communication from the replicated handler ----
+        n_ranks = int(owner.max()) + 1
+        self.n_ranks = n_ranks
+        # what I receive: my ghost section is grouped by owner rank
+        self.recv_counts = np.bincount(self.ghost_owner, minlength=n_ranks).astype(np.int64)
+        # what I send to peer s: my owned polytopes adjacent to a polytope owned by s, by global block
+        nbrs = [[ah.neighbor(int(p), f) for f in range(ah.n_faces(int(p)))] for p in self.local_poly_global[: self.n_owned]]
+        need = [set() for _ in range(n_ranks)]
+        for lp, p in enumerate(self.local_poly_global[: self.n_owned]):
+            gb = int(ah.get_dof_indices(int(p))[0]) // self.n
+            for q in nbrs[lp]:
+                if q >= 0 and owner[q] != rank:
+                    need[owner[q]].add(gb)
+        self.send_blocks = []  # per peer: local owned block indices, in the order the peer stores them
+        for s in range(n_ranks):
+            gbs = np.array(sorted(need[s]), dtype=np.int64)
+            self.send_blocks.append(np.searchsorted(self.owned_global_block, gbs).astype(np.int64))
+        self.send_counts = np.array([len(b) for b in self.send_blocks], dtype=np.int64)
+
+    @property
+    def n_owned_dofs(self):
+        return self.n_owned * self.n
+
+    @property
+    def n_local_dofs(self):
+        return (self.n_owned + self.n_ghost) * self.n
+
+    def owned_global_dofs(self):
+        return (self.owned_global_block[:, None] * self.n + np.arange(self.n)[None, :]).ravel()
+
+    def ghost_global_dofs(self):
+        return (self.ghost_global_block[:, None] * self.n + np.arange(self.n)[None, :]).ravel()
+
+
+def exchange_ghost_values(part: LocalPart, x_full, group=None):
+    """update_ghost_values(): fill the ghost section of `x_full` (torch tensor, length
+    (n_owned + n_ghost) * n, CPU for gloo or CUDA for nccl) from the owning ranks."""
+    import torch
+    import torch.distributed as dist
+
+    n = part.n
+    xo = x_full[: part.n_owned * n].view(part.n_owned, n)
+    xg = x_full[part.n_owned * n:].view(part.n_ghost, n)
+    ops, keep = [], []
+    off = 0
+    for s in range(part.n_ranks):
+        cnt = int(part.recv_counts[s])
+        if cnt:
+            ops.append(dist.P2POp(dist.irecv, xg[off:off + cnt], s, group))
+        off += cnt
+    for s in range(part.n_ranks):
+        if len(part.send_blocks[s]):
+            idx = torch.as_tensor(part.send_blocks[s], device=x_full.device)
+            buf = xo.index_select(0, idx).contiguous()  # pack
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, s, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return x_full
+
+
+class DistributedSIPOperator:
+    """One rank's share of the SIP operator: local assembly with ghost interfaces and a
+    vmult that exchanges the ghost-polytope coefficients first."""
+
+    def __init__(self, ah: AgglomerationHandler, owner, rank: int, group=None, **flatten_kw):
+        self.part = LocalPart(ah, owner, rank, **flatten_kw)
+        self.op = SIPOperator(self.part.desc, keepalive=(ah, self.part))
+        self.group = group
+        self._x_full = None
+
+    def assemble(self, flags=K.ASSEMBLE_ALL, stiffness=1.0, mass=0.0):
+        self.op.assemble(flags, stiffness, mass)
+
+    def m(self):
+        return self.part.n_owned_dofs
+
+    def vmult(self, dst, src, mode=K.VMULT_BLOCK_CSR, exchange=True):
+        """dst (owned DoFs) = A_local [src ; ghosts].  `src` holds the owned DoFs."""
+        import torch
+
+        p = self.part
+        if self._x_full is None or self._x_full.device != src.device:
+            self._x_full = torch.empty(p.n_local_dofs, dtype=torch.float64, device=src.device)
+        self._x_full[: p.n_owned_dofs].copy_(src)
+        if exchange and p.n_ranks > 1:
+            exchange_ghost_values(p, self._x_full, self.group)
+        self.op.vmult_ptr(dst.data_ptr(), self._x_full.data_ptr(), mode)
+        return dst

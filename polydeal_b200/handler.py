@@ -237,6 +237,11 @@ class SIPOperator:
     n = m
 
     @property
+    def n_source_dofs(self):
+        """Length of vmult source vectors: owned + ghost DoFs (== m() without sharding)."""
+        return K.lib().pd_n_source_dofs(self._h)
+
+    @property
     def nnz(self):
         return K.lib().pd_nnz(self._h)
 
@@ -268,7 +273,7 @@ class SIPOperator:
         import scipy.sparse as sp
 
         rp, cols = self.pattern()
-        return sp.csr_matrix((self.values(), cols, rp), shape=(self.m(), self.m()))
+        return sp.csr_matrix((self.values(), cols, rp), shape=(self.m(), self.n_source_dofs))
 
     # --- apply: device pointers (ints, e.g. torch.Tensor.data_ptr()) or host numpy arrays
     def vmult_ptr(self, dst_ptr, src_ptr, mode=K.VMULT_BLOCK_CSR, add=False):

@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""Multi-process check of the sharded path on real GPUs (one rank per GPU, NCCL):
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port 29511 tests/run_distributed_check.py
+Every rank assembles its share, then y = A x through DistributedSIPOperator.vmult with the
+NCCL ghost exchange; compared with the CPU oracle's global result on the same input."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import polydeal_b200 as pdl
+from oracle import pyoracle as po
+from pd_helpers import groups_for, oracle_handler, product_handler, src_vector
+from polydeal_b200 import distributed as pdd
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    worst = 0.0
+    for dim, n, shape, p in [(3, 8, "blocks2", 2), (3, 8, "random40", 1), (2, 16, "random23", 3)]:
+        ogrid = po.Grid(dim, n, 0.0, 1.0, 1)
+        groups = groups_for(shape, dim, n, ogrid, 5)
+        _, oah = oracle_handler(dim, n, groups, p, p + 1, order=1)
+        _, pah = product_handler(oah.grid, groups, p, p + 1)
+        A = po.assemble_dg_matrix(oah, degree=p, n_threads=4).scipy().tocsr()
+        x = src_vector(A.shape[0])
+        y = A @ x
+        owner = pdd.partition_by_blocks(pah, world)
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            dop = pdd.DistributedSIPOperator(pah, owner, rank)
+            dop.op.set_stream(stream.cuda_stream)
+            dop.assemble()
+            rows = dop.part.owned_global_dofs()
+            xs = torch.from_numpy(x[rows]).cuda()
+            yd = torch.empty_like(xs)
+            dop.vmult(yd, xs)
+            stream.synchronize()
+        err = float(np.abs(yd.cpu().numpy() - y[rows]).max() / np.abs(y).max())
+        t = torch.tensor([err], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst = max(worst, float(t))
+        if rank == 0:
+            print(f"case dim={dim} n={n} {shape} p={p}: world={world} max rel err {float(t):.2e}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    assert worst <= 1e-12, worst
+    if rank == 0:
+        print("DISTRIBUTED CHECK OK")
+
+
+if __name__ == "__main__":
+    main()

@@ -334,3 +334,63 @@ def test_matrix_free_refused_on_agglomerates():
     x = torch.zeros(op.m(), dtype=torch.float64, device="cuda")
     with pytest.raises(pdl.PolydealError, match="single axis-aligned cell"):
         op.vmult(torch.empty_like(x), x, mode=pdl.VMULT_MATRIX_FREE)
+
+
+# ----------------------------------------------------------------------------------
+# row (e): sharded assembly + vmult, the ranks emulated one after the other on ONE GPU
+# (B200_PROFILING.md: with fewer GPUs than ranks, emulate; the real multi-process path is
+# tests/run_distributed_check.py under torchrun and the gloo tests on CPU).
+# ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,dim,n,shape,p,kw", [
+    (2, 2, 8, "blocks2", 1, {}),
+    (3, 2, 8, "random9", 2, {}),
+    (2, 3, 4, "random7", 2, dict(visit_rule=1)),
+    (4, 3, 4, "blocks2", 1, dict(penalty_constant=10.0, h_rule=1)),
+    (2, 3, 4, "singletons", 2, dict(penalty_constant=6.0, h_rule=3)),
+])
+def test_sharded_assembly_and_vmult_match_serial(world, dim, n, shape, p, kw):
+    pdl = gpu()
+    import torch
+
+    from polydeal_b200 import distributed as pdd
+
+    oah, pah = both(dim, n, shape, p, order=1)
+    okw = dict(kw)
+    okw.setdefault("penalty_constant", None)
+    A = po.assemble_dg_matrix(oah, degree=p, n_threads=4, **okw).scipy().tocsr()
+    nd = oah.n_dofs_per_cell
+    x = src_vector(A.shape[0])
+    y = A @ x
+    owner = pdd.partition_by_blocks(pah, world)
+    pkw = dict(kw)
+    pkw.setdefault("penalty_constant", -1.0)
+    seen_rows = 0
+    for rank in range(world):
+        part = pdd.LocalPart(pah, owner, rank, **pkw)
+        op = pdl.SIPOperator(part.desc, keepalive=(pah, part))
+        op.assemble()
+        rows = part.owned_global_dofs()
+        cols = np.concatenate([rows, part.ghost_global_dofs()])
+        ref = A[rows][:, cols].tocsr()
+        ref.sort_indices()
+        got = op.scipy()
+        assert got.shape == (len(rows), len(cols))
+        got.sort_indices()
+        np.testing.assert_array_equal(got.indptr, ref.indptr)
+        np.testing.assert_array_equal(got.indices, ref.indices)
+        rp, _ = op.pattern()
+        assert_blocks_close(op.values(), ref.data, nd, rp, TOL)
+        # vmult with the ghost section filled from the global vector (= what the exchange delivers)
+        xd = torch.from_numpy(x[cols]).cuda()
+        yd = torch.empty(len(rows), dtype=torch.float64, device="cuda")
+        op.vmult_ptr(yd.data_ptr(), xd.data_ptr())
+        op.synchronize()
+        assert np.abs(yd.cpu().numpy() - y[rows]).max() <= TOL * np.abs(y).max()
+        if op.matrix_free_available:
+            op.set_operator()
+            ym = torch.empty_like(yd)
+            op.vmult_ptr(ym.data_ptr(), xd.data_ptr(), mode=pdl.VMULT_MATRIX_FREE)
+            op.synchronize()
+            assert np.abs(ym.cpu().numpy() - y[rows]).max() <= TOL * np.abs(y).max()
+        seen_rows += len(rows)
+    assert seen_rows == A.shape[0]
