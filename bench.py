@@ -46,6 +46,16 @@ def block_groups(n, b):
     return sc.block_partition(DIM, n, b)
 
 
+def lex_block_groups(nx, ny, nz, b):
+    """b^3 blocks of an nx x ny x nz lexicographic grid, cells of a block in active-cell order."""
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    cell = (k * ny + j) * nx + i
+    part = ((k // b) * (ny // b) + (j // b)) * (nx // b) + (i // b)
+    order = np.lexsort((cell, part))
+    return cell[order].astype(np.int32).reshape(-1, b**3)
+
+
 def read_peaks():
     peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)"}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -175,15 +185,33 @@ def run_gpu(args):
     # ---- build the agglomeration (host, untimed) --------------------------------------
     # Weak scaling: every rank owns one config-B box (64^3 cells, 512 polyhedra); the path
     # shards over polytopes with no data-path collective in assembly.
-    grid = pdl.Grid.hyper_cube(DIM, 0.0, 1.0, N_CELLS_1D.bit_length() - 1)
-    ah = pdl.AgglomerationHandler(grid)
-    for g in block_groups(N_CELLS_1D, BLOCK):
-        ah.define_agglomerate(g)
-    ah.initialize_fe_values(NQ)
-    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, DEGREE)
-    desc0 = ah.flatten()  # library penalty, visit by id
+    part = None
+    if world == 1:
+        grid = pdl.Grid.hyper_cube(DIM, 0.0, 1.0, N_CELLS_1D.bit_length() - 1)
+        ah = pdl.AgglomerationHandler(grid)
+        for g in block_groups(N_CELLS_1D, BLOCK):
+            ah.define_agglomerate(g)
+        ah.initialize_fe_values(NQ)
+        ah.distribute_agglomerated_dofs(pdl.FE_DGQ, DEGREE)
+        desc0 = ah.flatten()  # library penalty, visit by id
+    else:
+        # N boxes stacked along z: [0,1]^2 x [0,N], 64 x 64 x 64N cubic cells, 8^3 blocks,
+        # sharded into z-slabs of 512 polyhedra; the cut interfaces are evaluated by both
+        # neighbours from one-time ghost geometry (owner-computes-rows)
+        from polydeal_b200 import distributed as pdd
+
+        nz = N_CELLS_1D * world
+        grid = pdl.Grid.structured(DIM, (N_CELLS_1D, N_CELLS_1D, nz), 0.0, (1.0, 1.0, float(world)), order=1)
+        ah = pdl.AgglomerationHandler(grid)
+        for g in lex_block_groups(N_CELLS_1D, N_CELLS_1D, nz, BLOCK):
+            ah.define_agglomerate(g)
+        ah.initialize_fe_values(NQ)
+        ah.distribute_agglomerated_dofs(pdl.FE_DGQ, DEGREE)
+        owner = pdd.partition_by_blocks(ah, world)
+        part = pdd.LocalPart(ah, owner, rank)
+        desc0 = part.desc
     desc, keep, h2d_bytes = pinned_copy_of_desc(desc0)
-    op = pdl.SIPOperator(desc, keepalive=(ah, keep))
+    op = pdl.SIPOperator(desc, keepalive=(ah, keep, part))
     # all work and all timing events go to ONE explicit non-default stream (the legacy
     # default stream has handle 0, which pd_set_stream reads as "use the handle's own")
     stream = torch.cuda.Stream()
@@ -250,16 +278,24 @@ def run_gpu(args):
     checksum = float(out_host.sum())
 
     # vmult with the assembled matrix (device vectors), L2 flushed between applies
-    x = torch.from_numpy(np.sin(0.37 * np.arange(n_dofs)) + 0.01 * (np.arange(n_dofs) % 7)).cuda()
-    y = torch.empty_like(x)
+    n_src = op.n_source_dofs
+    x = torch.from_numpy(np.sin(0.37 * np.arange(n_src)) + 0.01 * (np.arange(n_src) % 7)).cuda()
+    y = torch.empty(n_dofs, dtype=torch.float64, device="cuda")
+
+    def apply():
+        if part is not None:
+            # one exchange step per apply: ghost-polytope coefficients, grouped NCCL send/recv
+            pdd.exchange_ghost_values(part, x)
+        op.vmult_ptr(y.data_ptr(), x.data_ptr())
+
     for _ in range(3):
-        op.vmult(y, x)
+        apply()
     vm = []
     for _ in range(max(args.steps, 5)):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        op.vmult(y, x)
+        apply()
         b.record(stream)
         b.synchronize()
         vm.append(a.elapsed_time(b))
@@ -283,7 +319,7 @@ def run_gpu(args):
     vol_ms = statistics.mean(kms["volume"])
     flops = 2.0 * n * n * DIM * Q
     achieved = flops / (vol_ms * 1e-3) / 1e12
-    vol_bytes = 8.0 * (DIM + 1) * Q + 8.0 * n * n * desc.n_polytopes
+    vol_bytes = 8.0 * (DIM + 1) * Q + 8.0 * n * n * (n_dofs // n)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -298,7 +334,11 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_dofs_per_gpu": n_dofs, "n_polytopes_per_gpu": int(desc.n_polytopes),
-                   "volume_q_points_per_gpu": Q, "sharding": f"{world} x one box per rank, no assembly collective",
+                   "volume_q_points_per_gpu": Q,
+                   "sharding": "single GPU" if world == 1 else
+                   f"[0,1]^2 x [0,{world}] in {world} z-slabs of 512 polyhedra, cut interfaces evaluated by both sides "
+                   "from ghost bbox + DoF block (no assembly collective); vmult exchanges ghost blocks over NCCL",
+                   "ghost_polytopes_per_gpu": int(desc.n_polytopes - n_dofs // n),
                    "l2": "flushed (512 MiB memset) between timed steps; inputs 226 MB > L2 as well",
                    "step": "quadrature + volume + faces + diagonal gather, all device kernels"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": nnz * 8,
@@ -311,7 +351,8 @@ def run_gpu(args):
                      "kernel_ms": vol_ms, "peak_source": peaks["fp64_src"],
                      "hbm_frac_of_same_kernel": vol_bytes / (vol_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
         "kernel_ms": {k: statistics.mean(v) for k, v in kms.items()},
-        "vmult": {"metric": "SIP vmult GDoF/s (block-CSR apply of the assembled operator)",
+        "vmult": {"metric": "SIP vmult GDoF/s (block-CSR apply of the assembled operator"
+                            + (", incl. NCCL ghost exchange)" if world > 1 else ")"),
                   "value": world * n_dofs / (t_vm_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t_vm_ms,
                   "roofline": {"bound": "hbm", "achieved": vm_bytes / (t_vm_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": vm_bytes / (t_vm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
