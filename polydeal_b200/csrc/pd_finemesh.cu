@@ -60,29 +60,36 @@ namespace pd
 
     // One thread per DoF, GS threads per cell (GS = N rounded up to a power of two),
     // CPB cells per block, persistent over cell batches.
+    //
+    // On a Cartesian cell the SIP operator is
+    //   sum_d  M (x) ... (x) L_d (x) ... (x) M   +  f vol  M (x) M (x) M
+    // where L_d is the 1-D DG stencil along d: three (N1 x N1) matrices acting on the
+    // cell's own line of DoFs and on the lines of its two neighbours along d,
+    //   B_own   = (a/h) Sh + sum_s a [ sig e_s e_s^T - sn/(2h) (e_s d_s^T + d_s e_s^T) ]
+    //   B_nbr,s = a [ -sig e_s e_s'^T - sn/(2 h_N) e_s d_s'^T + sn/(2h) d_s e_s'^T ],  s' = 1-s
+    // (boundary face: a [ pen e_s e_s^T - sn/h (e_s d_s^T + d_s e_s^T) ], no neighbour part),
+    // a = vol/h the face area, sn = -1/+1 the outward normal sign, and M the 1-D mass
+    // (cell and face Gauss rules coincide).  15 one-dimensional contractions per cell in 3-D.
     template <int DIM, int DEG>
-    __global__ void __launch_bounds__(256)
+    __global__ void __launch_bounds__(256, 4) // latency-bound: occupancy beats spill-free code here (measured)
     k_fine_sip(const FineArgs A)
     {
       constexpr int N1  = DEG + 1;
       constexpr int N   = ipow_(N1, DIM);
-      constexpr int NF  = ipow_(N1, DIM - 1); // DoFs of a face trace
       constexpr int GS  = N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : (N <= 32 ? 32 : (N <= 64 ? 64 : 128))));
       constexpr int CPB = 256 / GS;
       constexpr int NFC = 2 * DIM; // faces per cell
+      constexpr int NM  = N1 * N1;
 
-      __shared__ double tab[3 * N1 * N1 + 4 * N1];
-      __shared__ double sU[CPB][N];        // own coefficients
-      __shared__ double sN[CPB][NFC][N];   // neighbours' coefficients
-      __shared__ double sA[CPB][NFC][NF];  // coefficient of v(face)
-      __shared__ double sB[CPB][NFC][NF];  // coefficient of dn v(face)
-      __shared__ double sW[CPB][4][N];     // contraction work arrays
-      __shared__ double sT[CPB][NFC][2][NF];
+      __shared__ double tab[3 * NM + 4 * N1];
+      __shared__ double sU[CPB][N];           // own coefficients
+      __shared__ double sN[CPB][NFC][N];      // neighbours' coefficients
+      __shared__ double sW[CPB][4][N];        // contraction work arrays
 
-      const double *Mh = tab, *Sh = tab + N1 * N1, *Mf = tab + 2 * N1 * N1;
-      const double *e0 = tab + 3 * N1 * N1, *d0 = e0 + 2 * N1; // e0,e1 contiguous; d0,d1 contiguous
+      const double *Mh = tab, *Sh = tab + NM;
+      const double *e0 = tab + 3 * NM, *d0 = e0 + 2 * N1; // e0,e1 contiguous; d0,d1 contiguous
 
-      for (int i = threadIdx.x; i < 3 * N1 * N1 + 4 * N1; i += blockDim.x)
+      for (int i = threadIdx.x; i < 3 * NM + 4 * N1; i += blockDim.x)
         tab[i] = A.tables[i];
       __syncthreads();
       // all shared arrays are private to a cell slot: when a slot is (part of) one warp the
@@ -107,144 +114,32 @@ namespace pd
           }
       }
       constexpr int stride[3] = {1, N1, N1 * N1};
+      const bool    vol_on = (A.flags & PD_ASSEMBLE_VOLUME) != 0;
 
       for (int c0 = blockIdx.x * CPB; c0 < A.n_cells; c0 += gridDim.x * CPB)
         {
-          const int  cell = c0 + slot;
-          const bool ok   = lane_ok && cell < A.n_cells;
+          const int  cell  = c0 + slot;
+          const bool cell_ok = cell < A.n_cells;
+          const bool ok    = lane_ok && cell_ok;
           group_sync(); // previous batch done with this slot's shared arrays
-          double h[DIM];
-          int    nb[NFC];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            h[d] = 1.;
-#pragma unroll
-          for (int f = 0; f < NFC; ++f)
-            nb[f] = -1;
-          if (cell < A.n_cells)
-            {
-#pragma unroll
-              for (int d = 0; d < DIM; ++d)
-                h[d] = A.cell_h[(int64_t)cell * DIM + d];
-#pragma unroll
-              for (int f = 0; f < NFC; ++f)
-                nb[f] = A.nbr[(int64_t)cell * NFC + f];
-            }
           if (ok)
             {
               sU[slot][l] = A.x[(int64_t)cell * N + l];
 #pragma unroll
               for (int f = 0; f < NFC; ++f)
-                sN[slot][f][l] = nb[f] >= 0 ? A.x[(int64_t)nb[f] * N + l] : 0.;
+                {
+                  const int nb   = A.nbr[(int64_t)cell * NFC + f];
+                  sN[slot][f][l] = nb >= 0 ? A.x[(int64_t)nb * N + l] : 0.;
+                }
             }
-          group_sync();
-          double vol = 1.;
+          double vol = 1., h[DIM];
 #pragma unroll
           for (int d = 0; d < DIM; ++d)
-            vol *= h[d];
-
-          // ---- face traces: own value/normal derivative and the neighbour's, on every face
-          if (cell < A.n_cells)
-            for (int m = l; m < NFC * NF; m += GS)
-              {
-                const int f = m / NF, e = m - f * NF;
-                const int d = f >> 1, s = f & 1;
-                // base index of face entry e: dims other than d, in increasing order
-                int base = 0, r = e;
-#pragma unroll
-                for (int dd = 0; dd < DIM; ++dd)
-                  if (dd != d)
-                    {
-                      base += (r % N1) * stride[dd];
-                      r /= N1;
-                    }
-                const double *ev_own = e0 + s * N1, *dv_own = d0 + s * N1;             // own side s
-                const double *ev_nb = e0 + (1 - s) * N1, *dv_nb = d0 + (1 - s) * N1;   // neighbour: opposite side
-                double        u = 0., du = 0., p = 0., dp = 0.;
-#pragma unroll
-                for (int t = 0; t < N1; ++t)
-                  {
-                    const double a = sU[slot][base + t * stride[d]], b = sN[slot][f][base + t * stride[d]];
-                    u += ev_own[t] * a;
-                    du += dv_own[t] * a;
-                    p += ev_nb[t] * b;
-                    dp += dv_nb[t] * b;
-                  }
-                const double sn  = s ? 1. : -1.;
-                const double ih  = 1. / h[d];
-                const double sg  = A.sigma[(int64_t)cell * NFC + f];
-                double       av, bv;
-                if (nb[f] >= 0)
-                  {
-                    // neighbour extent along d equals... not necessarily ours: carried in sigma only;
-                    // its normal derivative needs 1/h of the NEIGHBOUR
-                    const double ihn = 1. / A.cell_h[(int64_t)nb[f] * DIM + d];
-                    const double jmp = u - p;
-                    av               = (A.flags & PD_ASSEMBLE_INTERIOR) ? sg * jmp - 0.5 * sn * (du * ih + dp * ihn) : 0.;
-                    bv               = (A.flags & PD_ASSEMBLE_INTERIOR) ? -0.5 * jmp : 0.;
-                  }
-                else
-                  {
-                    av = (A.flags & PD_ASSEMBLE_BOUNDARY) ? sg * u - sn * du * ih : 0.;
-                    bv = (A.flags & PD_ASSEMBLE_BOUNDARY) ? -u : 0.;
-                  }
-                sT[slot][f][0][e] = av;
-                sT[slot][f][1][e] = bv;
-              }
+            {
+              h[d] = cell_ok ? A.cell_h[(int64_t)cell * DIM + d] : 1.;
+              vol *= h[d];
+            }
           group_sync();
-          // ---- surface mass (Mf x Mf) on the face arrays, times the face area
-          if constexpr (DIM == 3)
-            {
-              if (cell < A.n_cells)
-                for (int m = l; m < NFC * 2 * NF; m += GS)
-                  {
-                    const int f = m / (2 * NF), w = (m / NF) & 1, e = m % NF;
-                    const int a = e % N1, b = e / N1;
-                    double    s = 0.;
-#pragma unroll
-                    for (int t = 0; t < N1; ++t)
-                      s += Mf[a * N1 + t] * sT[slot][f][w][t + b * N1];
-                    (w ? sB : sA)[slot][f][e] = s;
-                  }
-              group_sync();
-              if (cell < A.n_cells)
-                for (int m = l; m < NFC * 2 * NF; m += GS)
-                  {
-                    const int f = m / (2 * NF), w = (m / NF) & 1, e = m % NF;
-                    const int a = e % N1, b = e / N1, d = f >> 1;
-                    double    s = 0.;
-#pragma unroll
-                    for (int t = 0; t < N1; ++t)
-                      s += Mf[b * N1 + t] * (w ? sB : sA)[slot][f][a + t * N1];
-                    sT[slot][f][w][e] = s * (vol / h[d]);
-                  }
-              group_sync();
-            }
-          else
-            {
-              if (cell < A.n_cells)
-                for (int m = l; m < NFC * 2 * NF; m += GS)
-                  {
-                    const int f = m / (2 * NF), w = (m / NF) & 1, e = m % NF, d = f >> 1;
-                    double    s = 0.;
-#pragma unroll
-                    for (int t = 0; t < N1; ++t)
-                      s += Mf[e * N1 + t] * sT[slot][f][w][t];
-                    (w ? sB : sA)[slot][f][e] = s * (vol / h[d]);
-                  }
-              group_sync();
-              if (cell < A.n_cells)
-                for (int m = l; m < NFC * 2 * NF; m += GS)
-                  {
-                    const int f = m / (2 * NF), w = (m / NF) & 1, e = m % NF;
-                    sT[slot][f][w][e] = (w ? sB : sA)[slot][f][e];
-                  }
-              group_sync();
-            }
-
-          // ---- cell term by 1-D contractions.  3-D:
-          //   c0 Sx(My Mz U) + Mx[ c1 Sy(Mz U) + c2 My(Sz U) + f vol My Mz U ],  c_d = vol / h_d^2
-          double acc = 0.;
           auto contract = [&](const double *Mat, const double *src, const int d) {
             double s = 0.;
 #pragma unroll
@@ -252,62 +147,125 @@ namespace pd
               s += Mat[idx[d] * N1 + t] * src[l + (t - idx[d]) * stride[d]];
             return s;
           };
-          const bool vol_on = (A.flags & PD_ASSEMBLE_VOLUME) != 0;
+          // ---- 1-D stencil along every direction, per lane.  The face parts of the stencil
+          //      matrices are rank one / two (outer products of e_s, d_s), so each lane forms
+          //      the traces of its own line (and of the neighbours' lines) and lifts them.
+          double st[DIM];
+          if (ok)
+            {
+#pragma unroll
+              for (int d = 0; d < DIM; ++d)
+                {
+                  const int     i    = idx[d];
+                  const double *u    = sU[slot] + l - i * stride[d];
+                  const double  ih   = 1. / h[d], a = vol * ih;
+                  double        su   = 0.;
+                  double        tu[2] = {0., 0.}, du[2] = {0., 0.};
+#pragma unroll
+                  for (int t = 0; t < N1; ++t)
+                    {
+                      const double ut = u[t * stride[d]];
+                      su += Sh[i * N1 + t] * ut;
+                      tu[0] += e0[t] * ut;
+                      tu[1] += e0[N1 + t] * ut;
+                      du[0] += d0[t] * ut;
+                      du[1] += d0[N1 + t] * ut;
+                    }
+                  double acc_d = vol_on ? a * ih * su : 0.;
+#pragma unroll
+                  for (int s = 0; s < 2; ++s)
+                    {
+                      const int     f  = 2 * d + s;
+                      const int     nb = A.nbr[(int64_t)cell * NFC + f];
+                      const double  sg = A.sigma[(int64_t)cell * NFC + f], sn = s ? 1. : -1.;
+                      const double *es = e0 + s * N1, *ds = d0 + s * N1;
+                      double        av = 0., bv = 0.;
+                      if (nb >= 0)
+                        {
+                          if (A.flags & PD_ASSEMBLE_INTERIOR)
+                            {
+                              const double *un  = sN[slot][f] + l - i * stride[d];
+                              const double *eo  = e0 + (1 - s) * N1, *dd = d0 + (1 - s) * N1;
+                              const double  ihn = 1. / A.cell_h[(int64_t)nb * DIM + d];
+                              double        tn = 0., dn = 0.;
+#pragma unroll
+                              for (int t = 0; t < N1; ++t)
+                                {
+                                  const double nt = un[t * stride[d]];
+                                  tn += eo[t] * nt;
+                                  dn += dd[t] * nt;
+                                }
+                              const double jmp = tu[s] - tn;
+                              av               = sg * jmp - 0.5 * sn * (du[s] * ih + dn * ihn);
+                              bv               = -0.5 * jmp;
+                            }
+                        }
+                      else if (A.flags & PD_ASSEMBLE_BOUNDARY)
+                        {
+                          av = sg * tu[s] - sn * du[s] * ih;
+                          bv = -tu[s];
+                        }
+                      acc_d += a * (es[i] * av + sn * ih * ds[i] * bv);
+                    }
+                  st[d] = A.stiffness * acc_d;
+                }
+            }
+          // ---- masses in the other directions:
+          //   3-D: My(Mz W0) + Mx[ Mz W1 + My( W2 + f vol Mz U ) ];  2-D: My W0 + Mx( W1 + f vol My U )
+          double acc = 0.;
           if constexpr (DIM == 3)
             {
               if (ok)
                 {
-                  sW[slot][0][l] = contract(Mh, sU[slot], 2); // Mz U
-                  sW[slot][1][l] = contract(Sh, sU[slot], 2); // Sz U
+                  sW[slot][0][l] = st[0];
+                  sW[slot][1][l] = st[1];
                 }
               group_sync();
-              double yz = 0.;
+              double t0 = 0., t1 = 0., t2 = 0.;
               if (ok)
                 {
-                  yz = contract(Mh, sW[slot][0], 1);                                         // My Mz U
-                  const double syz = contract(Sh, sW[slot][0], 1), mysz = contract(Mh, sW[slot][1], 1);
-                  sW[slot][2][l]   = yz;
-                  sW[slot][3][l]   = A.stiffness * ((vol / (h[1] * h[1])) * syz + (vol / (h[2] * h[2])) * mysz) +
-                                   A.mass * vol * yz;
+                  t0 = contract(Mh, sW[slot][0], 2);
+                  t1 = contract(Mh, sW[slot][1], 2);
+                  t2 = st[2] + (vol_on && A.mass != 0. ? A.mass * vol * contract(Mh, sU[slot], 2) : 0.);
                 }
               group_sync();
-              if (ok && vol_on)
-                acc = A.stiffness * (vol / (h[0] * h[0])) * contract(Sh, sW[slot][2], 0) + contract(Mh, sW[slot][3], 0);
+              if (ok)
+                {
+                  sW[slot][2][l] = t0;
+                  sW[slot][3][l] = t2;
+                }
+              group_sync();
+              double t4 = 0.;
+              if (ok)
+                {
+                  acc = contract(Mh, sW[slot][2], 1);
+                  t4  = t1 + contract(Mh, sW[slot][3], 1);
+                }
+              group_sync();
+              if (ok)
+                sW[slot][0][l] = t4;
+              group_sync();
+              if (ok)
+                acc += contract(Mh, sW[slot][0], 0);
             }
           else
             {
               if (ok)
+                sW[slot][0][l] = st[0];
+              group_sync();
+              double t1 = 0.;
+              if (ok)
                 {
-                  sW[slot][0][l] = contract(Mh, sU[slot], 1); // My U
-                  sW[slot][1][l] = A.stiffness * (vol / (h[1] * h[1])) * contract(Sh, sU[slot], 1); // Sy U
+                  acc = contract(Mh, sW[slot][0], 1);
+                  t1  = st[1] + (vol_on && A.mass != 0. ? A.mass * vol * contract(Mh, sU[slot], 1) : 0.);
+                  sW[slot][1][l] = t1;
                 }
               group_sync();
-              if (ok && vol_on)
-                {
-                  const double sx = contract(Sh, sW[slot][0], 0), mx_my = contract(Mh, sW[slot][0], 0);
-                  acc = A.stiffness * (vol / (h[0] * h[0])) * sx + contract(Mh, sW[slot][1], 0) + A.mass * vol * mx_my;
-                }
+              if (ok)
+                acc += contract(Mh, sW[slot][1], 0);
             }
-          // ---- lift the face terms: v(face) = e_s[i_d], dn v(face) = sn d_s[i_d] / h_d
           if (ok)
             {
-              double fa = 0.;
-#pragma unroll
-              for (int f = 0; f < NFC; ++f)
-                {
-                  const int d = f >> 1, s = f & 1;
-                  int       e = 0, mul = 1;
-#pragma unroll
-                  for (int dd = 0; dd < DIM; ++dd)
-                    if (dd != d)
-                      {
-                        e += idx[dd] * mul;
-                        mul *= N1;
-                      }
-                  const double sn = s ? 1. : -1.;
-                  fa += (e0 + s * N1)[idx[d]] * sT[slot][f][0][e] + sn * (d0 + s * N1)[idx[d]] / h[d] * sT[slot][f][1][e];
-                }
-              acc += A.stiffness * fa;
               double *yp = A.y + (int64_t)cell * N + l;
               *yp        = A.add ? *yp + acc : acc;
             }
@@ -340,8 +298,8 @@ namespace pd
   setup_fine_operator(pd_handle *h, const pd_mesh_desc &d)
   {
     h->mf_ready = false;
-    if (h->n_subcells != h->np_own)
-      return;
+    if (h->n_subcells != h->np_own || h->nq1 != h->nq1f)
+      return; // (the stencil form needs the cell and face Gauss rules to coincide, as in MatrixFree)
     const int dim = d.dim, vpc = 1 << dim, nfc = 2 * dim;
     for (int32_t p = 0; p < h->np_own; ++p)
       {
