@@ -394,3 +394,50 @@ def test_sharded_assembly_and_vmult_match_serial(world, dim, n, shape, p, kw):
             assert np.abs(ym.cpu().numpy() - y[rows]).max() <= TOL * np.abs(y).max()
         seen_rows += len(rows)
     assert seen_rows == A.shape[0]
+
+
+def test_poisson_golden_l2_error_on_gpu(goldens):
+    """test/polydeal/poisson.cc / poisson.output: L2 error 0.00647702 with the matrix assembled
+    by the CUDA path (RHS and error functional from the checker's tables, direct solve on the
+    host), and the same system solved by CG running on the GPU through pd_vmult."""
+    pdl = gpu()
+    import scipy.sparse.linalg as spla
+    import torch
+
+    from test_oracle_sip import poisson_golden_problem, poisson_rhs_and_error
+
+    grid, oah, kw = poisson_golden_problem()
+    groups = [oah.get_agglomerate(p).tolist()[-1:] + oah.get_agglomerate(p).tolist()[:-1] for p in range(oah.n_polytopes)]
+    _, pah = product_handler(grid, groups, 1, 3)
+    op = pdl.assemble_dg_matrix(pah, penalty_constant=20.0, h_rule=pdl.H_CONSTANT, h_const=2.0 / 64,
+                                visit_rule=pdl.VISIT_BY_INDEX)
+    b, l2_error = poisson_rhs_and_error(grid, oah)
+    u = spla.spsolve(op.scipy().tocsc(), b)
+    assert l2_error(u) == pytest.approx(goldens["poisson"][0], abs=5e-9)
+    # conjugate gradients on the device: the loop SolverCG runs around vmult in the reference
+    # (examples/diffusion_reaction.cc:721-724), Jacobi-preconditioned with pd_diagonal_inverse
+    bd = torch.from_numpy(b).cuda()
+    x = torch.zeros_like(bd)
+    dinv = torch.empty_like(bd)
+    op.get_matrix_diagonal_inverse(dinv)
+    op.synchronize()
+    r = bd.clone()
+    z = dinv * r
+    p_ = z.clone()
+    Ap = torch.empty_like(bd)
+    rz = torch.dot(r, z)
+    for it in range(5000):
+        torch.cuda.synchronize()
+        op.vmult(Ap, p_)
+        op.synchronize()
+        alpha = rz / torch.dot(p_, Ap)
+        x += alpha * p_
+        r -= alpha * Ap
+        if float(torch.linalg.norm(r)) < 1e-12 * float(torch.linalg.norm(bd)):
+            break
+        z = dinv * r
+        rz_new = torch.dot(r, z)
+        p_ = z + (rz_new / rz) * p_
+        rz = rz_new
+    assert it < 4999
+    assert l2_error(x.cpu().numpy()) == pytest.approx(goldens["poisson"][0], abs=5e-9)

@@ -179,3 +179,50 @@ def test_fine_mesh_penalty_rule_matches_monodomain_emulation():
     assert abs(A - A.T).max() < 1e-12
     w = np.linalg.eigvalsh(A.toarray())
     assert w.min() > 0
+
+
+def poisson_golden_problem():
+    """test/polydeal/poisson.cc:107,122-123,153-232,316,357: [-1,1]^2 refined 6x, seven 2-cell
+    agglomerates + singletons, DGQ1, QGauss(3), penalty 20 / h_f with h_f = measure of a cell
+    face = 2/64, visited by index(), f = 8 pi^2 sin(2 pi x) sin(2 pi y), homogeneous Dirichlet."""
+    groups = sc.polytope_iterator_agglomerates()
+    grid, ah = handler(2, 6, groups, 1, 3, lo=-1.0, hi=1.0)
+    kw = dict(penalty_constant=20.0, h_rule=po.H_CONSTANT, h_const=2.0 / 64, visit_rule=po.VISIT_BY_INDEX)
+    return grid, ah, kw
+
+
+def poisson_rhs_and_error(grid, ah):
+    """RHS vector and the error functional of the reference test: the polytopal solution is
+    interpolated to the fine DGQ1 space (exact, it is bilinear on every sub-cell) and
+    integrate_difference runs with QGauss(degree) = ONE point per cell (poisson.cc:output_results)."""
+    f = lambda x: 8 * np.pi**2 * np.sin(2 * np.pi * x[:, 0]) * np.sin(2 * np.pi * x[:, 1])
+    b = np.zeros(ah.n_dofs)
+    for k in range(ah.n_polytopes):
+        fev = ah.reinit(k)
+        b[ah.get_dof_indices(k)] += fev.values @ (f(fev.points) * fev.JxW)
+
+    def l2_error(u):
+        err2 = 0.0
+        for k in range(ah.n_polytopes):
+            lo, hi = ah.bbox(k)
+            uk = u[ah.get_dof_indices(k)]
+            for c in ah.get_agglomerate(k):
+                v = grid.cell_vertices(int(c))
+                xc = v.mean(axis=0)
+                area = (v[:, 0].max() - v[:, 0].min()) * (v[:, 1].max() - v[:, 1].min())
+                phi, _ = po.fe_evaluate(po.FE_DGQ, 2, 1, (xc - lo) / (hi - lo))
+                exact = np.sin(2 * np.pi * xc[0]) * np.sin(2 * np.pi * xc[1])
+                err2 += (uk @ phi - exact) ** 2 * area
+        return np.sqrt(err2)
+
+    return b, l2_error
+
+
+def test_poisson_golden_l2_error(goldens):
+    """The one end-to-end NUMBER the reference pins for this path: L2 error 0.00647702
+    (test/polydeal/poisson.output).  Matrix from the oracle, direct solve."""
+    grid, ah, kw = poisson_golden_problem()
+    A = po.assemble_dg_matrix(ah, n_threads=4, **kw).scipy().tocsc()
+    b, l2_error = poisson_rhs_and_error(grid, ah)
+    u = spla.spsolve(A, b)
+    assert l2_error(u) == pytest.approx(goldens["poisson"][0], abs=5e-9)  # golden printed with 6 digits
