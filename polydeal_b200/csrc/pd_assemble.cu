@@ -570,7 +570,11 @@ namespace pd
             const double *Zs = Pb + (s & 1) * 2 * PSZ + (qa * NP + isub * MI * 8 + g) * RS + t;
             const double *Vs = Pb + (s & 1) * 2 * PSZ + PSZ + (qb * NP + g) * RS + t;
             const double *ws = WC + (s % 3) * TQ + t;
-            for (int ks = kp; ks < TQ / 4; ks += kn)
+            // the last stage of an interface is usually partial (e.g. 144 points = 4.5 stages):
+            // skip the k-steps that only hold padding rows
+            const int64_t left = q1 - (q0 + (int64_t)s * TQ);
+            const int     nk   = left >= TQ ? TQ / 4 : (int)((left + 3) / 4);
+            for (int ks = kp; ks < nk; ks += kn)
               {
                 const double wc = ws[ks * 4];
                 double       a[MI], b[NT8];

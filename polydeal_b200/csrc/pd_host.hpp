@@ -575,10 +575,40 @@ namespace pd
       d.fe_degree         = fe_degree;
       d.n_q1d             = n_q1d;
       d.n_q1d_face        = n_q1d_face;
-      d.n_verts           = grid->n_verts();
-      d.verts             = grid->verts.data();
-      d.n_cells           = grid->n_cells();
-      d.cell_verts        = grid->cell_verts.data();
+      // the rank only needs the cells of its own polytopes (interfaces are listed from the
+      // owned side): compress the mesh to them and renumber cells and vertices locally
+      {
+        const int            vpc = 1 << dim;
+        std::vector<int32_t> cell_l(grid->n_cells(), -1), vert_l(grid->n_verts(), -1);
+        lc_cell_verts.clear();
+        lc_verts.clear();
+        int32_t n_lc = 0, n_lv = 0;
+        for (int32_t &c : lc_subcell_idx)
+          {
+            if (cell_l[c] < 0)
+              {
+                cell_l[c] = n_lc++;
+                for (int v = 0; v < vpc; ++v)
+                  {
+                    const int32_t gv = grid->cell_verts[(size_t)c * vpc + v];
+                    if (vert_l[gv] < 0)
+                      {
+                        vert_l[gv] = n_lv++;
+                        lc_verts.insert(lc_verts.end(), grid->verts.begin() + (size_t)gv * dim,
+                                        grid->verts.begin() + (size_t)(gv + 1) * dim);
+                      }
+                    lc_cell_verts.push_back(vert_l[gv]);
+                  }
+              }
+            c = cell_l[c];
+          }
+        for (int32_t &c : lc_sub_cell)
+          c = cell_l[c]; // always an owned cell
+        d.n_verts    = n_lv;
+        d.verts      = lc_verts.data();
+        d.n_cells    = n_lc;
+        d.cell_verts = lc_cell_verts.data();
+      }
       d.n_polytopes       = n_loc;
       d.n_owned_polytopes = n_own;
       d.poly_subcell_ptr  = lc_subcell_ptr.data();
@@ -736,7 +766,8 @@ namespace pd
     std::vector<int32_t> lc_poly_global, lc_dof_block, lc_owned_global_block, lc_ghost_global_block, lc_ghost_owner,
       lc_subcell_idx, lc_polyA, lc_polyB, lc_sub_cell, lc_sub_face, lc_bcol;
     std::vector<int64_t> lc_subcell_ptr, lc_sub_ptr, lc_brow_ptr;
-    std::vector<double>  lc_bbox, lc_sub_sigma;
+    std::vector<double>  lc_bbox, lc_sub_sigma, lc_verts;
+    std::vector<int32_t> lc_cell_verts;
     // storage behind flatten()
     std::vector<int32_t> fl_polyA, fl_polyB, fl_sub_cell, fl_sub_face, fl_bcol;
     std::vector<int64_t> fl_sub_ptr, fl_brow_ptr;
