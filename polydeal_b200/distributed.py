@@ -102,26 +102,41 @@ class LocalPart:
 
 def exchange_ghost_values(part: LocalPart, x_full, group=None):
     """update_ghost_values(): fill the ghost section of `x_full` (torch tensor, length
-    (n_owned + n_ghost) * n, CPU for gloo or CUDA for nccl) from the owning ranks."""
+    (n_owned + n_ghost) * n, CPU for gloo or CUDA for nccl) from the owning ranks.
+
+    One pack kernel (index_select with the concatenated per-peer send lists, cached on the
+    device) and one exchange that receives straight into the ghost section: a single
+    all_to_all_single on NCCL (one grouped ncclSend/ncclRecv per peer), P2P batches on gloo."""
     import torch
     import torch.distributed as dist
 
     n = part.n
     xo = x_full[: part.n_owned * n].view(part.n_owned, n)
     xg = x_full[part.n_owned * n:].view(part.n_ghost, n)
-    ops, keep = [], []
-    off = 0
+    cache = part.__dict__.setdefault("_xchg", {})
+    key = (x_full.device.type, x_full.device.index)
+    if key not in cache:
+        idx = np.concatenate(part.send_blocks) if part.n_ranks else np.zeros(0, dtype=np.int64)
+        cache[key] = (torch.as_tensor(idx, device=x_full.device),
+                      torch.empty((len(idx), n), dtype=x_full.dtype, device=x_full.device))
+    idx, sendbuf = cache[key]
+    if len(idx):
+        torch.index_select(xo, 0, idx, out=sendbuf)  # pack
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(xg, sendbuf, output_split_sizes=part.recv_counts.tolist(),
+                               input_split_sizes=part.send_counts.tolist(), group=group)
+        return x_full
+    ops, off_r, off_s = [], 0, 0
     for s in range(part.n_ranks):
         cnt = int(part.recv_counts[s])
         if cnt:
-            ops.append(dist.P2POp(dist.irecv, xg[off:off + cnt], s, group))
-        off += cnt
+            ops.append(dist.P2POp(dist.irecv, xg[off_r:off_r + cnt], s, group))
+        off_r += cnt
     for s in range(part.n_ranks):
-        if len(part.send_blocks[s]):
-            idx = torch.as_tensor(part.send_blocks[s], device=x_full.device)
-            buf = xo.index_select(0, idx).contiguous()  # pack
-            keep.append(buf)
-            ops.append(dist.P2POp(dist.isend, buf, s, group))
+        cnt = int(part.send_counts[s])
+        if cnt:
+            ops.append(dist.P2POp(dist.isend, sendbuf[off_s:off_s + cnt], s, group))
+        off_s += cnt
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
