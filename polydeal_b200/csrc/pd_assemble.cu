@@ -139,7 +139,11 @@ namespace pd
     //                          RS = 4 (mod 16): a fragment load (8 dofs x 4 rows) touches
     //                          every bank pair once per half-warp
     //   WC[3][R]               JxW * coefficient per row
-    template <int DIM, int DEG, bool MASS, int NWARPS, int NROLE, int ROLE>
+    // SQ: the row weight w_q * coefficient (>= 0) is folded into the operand rows as its square
+    // root by the generator, so the contraction is pure LDS + DMMA (the profile of the first
+    // version showed a DMUL b = a * wc in front of almost every DMMA, on the same FP64 pipe).
+    // !SQ (a negative coefficient): rows unscaled, b = a * wc in the contraction.
+    template <int DIM, int DEG, bool MASS, bool SQ, int NWARPS, int NROLE, int ROLE>
     __device__ __forceinline__ void
     volume_body(const VolArgs &A, double *smem)
     {
@@ -222,9 +226,9 @@ namespace pd
                 double *wc = WC + (s % 3) * R + lane;
 #pragma unroll
                 for (int c = 0; c < DIM; ++c)
-                  wc[c * TQ] = w * A.stiffness;
+                  wc[c * TQ] = SQ ? sqrt(w * A.stiffness) : w * A.stiffness;
                 if (MASS)
-                  wc[DIM * TQ] = w * A.mass;
+                  wc[DIM * TQ] = SQ ? sqrt(w * A.mass) : w * A.mass;
               }
           };
           // operand rows of stage s (generator warps only): one warp-unit = all 32 points
@@ -234,11 +238,15 @@ namespace pd
               return;
             const double *Tq = Tb + (s & 1) * TSZ + lane;
             double       *Gq = Gb + (s & 1) * GSZ + lane;
+            // sqrt(w * coefficient) of this lane's point: gradient rows / mass row
+            const double sg = SQ ? WC[(s % 3) * R + lane] : 1.;
+            const double sm = (SQ && MASS) ? WC[(s % 3) * R + DIM * TQ + lane] : 1.;
             for (int wu = warp; wu < NU; wu += NGENW)
               {
                 if constexpr (DIM == 2)
                   {
-                    const double ly = Tq[(2 * N1 + wu) * TQ], dy = Tq[(3 * N1 + wu) * TQ];
+                    const double ly0 = Tq[(2 * N1 + wu) * TQ];
+                    const double ly = ly0 * sg, dy = Tq[(3 * N1 + wu) * TQ] * sg, lym = ly0 * sm;
 #pragma unroll
                     for (int a = 0; a < N1; ++a)
                       {
@@ -247,7 +255,7 @@ namespace pd
                         o[0]            = dx * ly;
                         o[TQ]           = lx * dy;
                         if (MASS)
-                          o[2 * TQ] = lx * ly;
+                          o[2 * TQ] = lx * lym;
                       }
                   }
                 else
@@ -255,7 +263,8 @@ namespace pd
                     const int    b = wu % N1, c = wu / N1;
                     const double ly = Tq[(2 * N1 + b) * TQ], dy = Tq[(3 * N1 + b) * TQ];
                     const double lz = Tq[(4 * N1 + c) * TQ], dz = Tq[(5 * N1 + c) * TQ];
-                    const double yz = ly * lz, dyz = dy * lz, ydz = ly * dz;
+                    const double yz0 = ly * lz;
+                    const double yz = yz0 * sg, dyz = dy * lz * sg, ydz = ly * dz * sg, yzm = yz0 * sm;
 #pragma unroll
                     for (int a = 0; a < N1; ++a)
                       {
@@ -265,7 +274,7 @@ namespace pd
                         o[TQ]           = lx * dyz;
                         o[2 * TQ]       = lx * ydz;
                         if (MASS)
-                          o[3 * TQ] = lx * yz;
+                          o[3 * TQ] = lx * yzm;
                       }
                   }
               }
@@ -277,22 +286,37 @@ namespace pd
 #pragma unroll 3
             for (int ks = kpart; ks < R / 4; ks += KSPLIT)
               {
-                const double wc = ws[ks * 4];
-                double       a[NT8], b[NT8];
+                double a[NT8];
 #pragma unroll
                 for (int I = 0; I < NT8; ++I)
+                  a[I] = Gs[8 * I * RS + ks * 4];
+                if constexpr (SQ)
                   {
-                    a[I] = Gs[8 * I * RS + ks * 4];
-                    b[I] = a[I] * wc;
+#pragma unroll
+                    for (int I = 0; I < NT8; ++I)
+                      if (vol_role_owns_row<NROLE, ROLE>(I))
+                        {
+#pragma unroll
+                          for (int J = I; J < NT8; ++J)
+                            dmma884(acc[I][J][0], acc[I][J][1], a[I], a[J]);
+                        }
                   }
+                else
+                  {
+                    const double wc = ws[ks * 4];
+                    double       b[NT8];
 #pragma unroll
-                for (int I = 0; I < NT8; ++I)
-                  if (vol_role_owns_row<NROLE, ROLE>(I))
-                    {
+                    for (int I = 0; I < NT8; ++I)
+                      b[I] = a[I] * wc;
 #pragma unroll
-                      for (int J = I; J < NT8; ++J)
-                        dmma884(acc[I][J][0], acc[I][J][1], a[I], b[J]);
-                    }
+                    for (int I = 0; I < NT8; ++I)
+                      if (vol_role_owns_row<NROLE, ROLE>(I))
+                        {
+#pragma unroll
+                          for (int J = I; J < NT8; ++J)
+                            dmma884(acc[I][J][0], acc[I][J][1], a[I], b[J]);
+                        }
+                  }
               }
           };
 
@@ -355,20 +379,20 @@ namespace pd
         }
     }
 
-    template <int DIM, int DEG, bool MASS, int NWARPS>
+    template <int DIM, int DEG, bool MASS, bool SQ, int NWARPS>
     __global__ void __launch_bounds__(NWARPS * 32, NWARPS == 8 ? 3 : 1)
     k_volume(const VolArgs A)
     {
       extern __shared__ double smem[];
       constexpr int NROLE = Cfg<DIM, DEG>::NT8 >= 8 ? 2 : 1;
       if constexpr (NROLE == 1)
-        volume_body<DIM, DEG, MASS, NWARPS, 1, 0>(A, smem);
+        volume_body<DIM, DEG, MASS, SQ, NWARPS, 1, 0>(A, smem);
       else
         {
           if (((threadIdx.x >> 5) & 1) == 0)
-            volume_body<DIM, DEG, MASS, NWARPS, 2, 0>(A, smem);
+            volume_body<DIM, DEG, MASS, SQ, NWARPS, 2, 0>(A, smem);
           else
-            volume_body<DIM, DEG, MASS, NWARPS, 2, 1>(A, smem);
+            volume_body<DIM, DEG, MASS, SQ, NWARPS, 2, 1>(A, smem);
         }
     }
 
@@ -531,6 +555,7 @@ namespace pd
             if (s >= nst)
               return;
             const double hs = SG[(s & 1) * TQ + lane];
+            const double wq = WC[(s % 3) * TQ + lane];
             double      *Zp = Pb + (s & 1) * 2 * PSZ + lane;
             double      *Vp = Zp + PSZ;
             for (int wu = first_unit; wu < nunits; wu += NWARPS)
@@ -560,7 +585,7 @@ namespace pd
                     const double dn = dx * s1 + lx * s2;
                     const double V  = sgn * v;
                     const int    col = side * NP + bc * N1 + a;
-                    Vp[col * RS]     = V;
+                    Vp[col * RS]     = V * wq; // JxW * coefficient folded into the V operand
                     Zp[col * RS]     = hs * V - dscale * dn;
                   }
               }
@@ -569,21 +594,19 @@ namespace pd
           auto contract = [&](const int s) {
             const double *Zs = Pb + (s & 1) * 2 * PSZ + (qa * NP + isub * MI * 8 + g) * RS + t;
             const double *Vs = Pb + (s & 1) * 2 * PSZ + PSZ + (qb * NP + g) * RS + t;
-            const double *ws = WC + (s % 3) * TQ + t;
             // the last stage of an interface is usually partial (e.g. 144 points = 4.5 stages):
             // skip the k-steps that only hold padding rows
             const int64_t left = q1 - (q0 + (int64_t)s * TQ);
             const int     nk   = left >= TQ ? TQ / 4 : (int)((left + 3) / 4);
             for (int ks = kp; ks < nk; ks += kn)
               {
-                const double wc = ws[ks * 4];
-                double       a[MI], b[NT8];
+                double a[MI], b[NT8];
 #pragma unroll
                 for (int I = 0; I < MI; ++I)
                   a[I] = Zs[8 * I * RS + ks * 4];
 #pragma unroll
                 for (int J = 0; J < NT8; ++J)
-                  b[J] = Vs[8 * J * RS + ks * 4] * wc;
+                  b[J] = Vs[8 * J * RS + ks * 4];
 #pragma unroll
                 for (int I = 0; I < MI; ++I)
 #pragma unroll
@@ -805,13 +828,13 @@ namespace pd
       h->vol_plan_grid = grid;
     }
 
-    template <int DIM, int DEG, bool MASS>
+    template <int DIM, int DEG, bool MASS, bool SQ>
     void
     run_volume(pd_handle *h, const pd_coefficients &coef)
     {
       constexpr int    TQ     = 32;
       constexpr int    NWARPS = Cfg<DIM, DEG>::NT8 >= 8 ? 16 : 8;
-      auto             kern   = k_volume<DIM, DEG, MASS, NWARPS>;
+      auto             kern   = k_volume<DIM, DEG, MASS, SQ, NWARPS>;
       constexpr size_t smem   = volume_smem_bytes<DIM, DEG, MASS, NWARPS>();
       set_smem(kern, smem);
       int per_sm = 1;
@@ -883,10 +906,13 @@ namespace pd
       PD_CUDA(cudaEventRecord(h->ev[0], h->stream));
       if ((flags & PD_ASSEMBLE_VOLUME) && h->Q > 0)
         {
+          // non-negative coefficients (every use in the reference): weights folded into the
+          // operands as square roots; otherwise the signed variant
+          const bool sq = coef.stiffness >= 0. && coef.mass >= 0.;
           if (coef.mass != 0.)
-            run_volume<DIM, DEG, true>(h, coef);
+            sq ? run_volume<DIM, DEG, true, true>(h, coef) : run_volume<DIM, DEG, true, false>(h, coef);
           else
-            run_volume<DIM, DEG, false>(h, coef);
+            sq ? run_volume<DIM, DEG, false, true>(h, coef) : run_volume<DIM, DEG, false, false>(h, coef);
         }
       PD_CUDA(cudaEventRecord(h->ev[1], h->stream));
       if ((flags & (PD_ASSEMBLE_BOUNDARY | PD_ASSEMBLE_INTERIOR)) && h->n_ifaces > 0)

@@ -92,6 +92,8 @@ CASES = [
     (2, 8, "random6", 1, 3, None, dict(penalty_constant=10.0, h_rule=1, with_boundary=False)),  # sanity-check rule
     (3, 4, "random4", 1, 2, None, dict(stiffness_coeff=1e-4, mass_coeff=1.5e4, with_boundary=False)),  # monodomain f M + sigma K
     (2, 8, "random6", 2, 3, None, dict(visit_rule=1)),        # examples/poisson.cc: visit by index()
+    (3, 4, "random4", 2, 3, None, dict(mass_coeff=-0.3)),     # negative coefficient: signed-weight kernel variant
+    (2, 8, "random5", 1, 2, None, dict(mass_coeff=-2.0)),
 ]
 
 
