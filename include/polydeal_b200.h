@@ -188,6 +188,24 @@ int pd_vmult_host(pd_handle *h, int mode, const double *src_host, double *dst_ho
  * (include/utils.h:797-814); device pointer of pd_n_dofs doubles */
 int pd_diagonal_inverse(pd_handle *h, double *dst_dev);
 
+/* --- the immediate callers of vmult, device resident (single-rank handles) ------------------
+ * Preconditioned conjugate gradients around pd_vmult: what SolverCG does in
+ * examples/diffusion_reaction.cc:709-724 / examples/matrix_free_agglo.cc:377-384.
+ * jacobi != 0 preconditions with the inverse diagonal (needs pd_assemble).  x_dev holds the
+ * initial guess on entry.  Stops when |r| <= rel_tol |b| (checked every 8 iterations: the
+ * iteration body is replayed from a CUDA graph) or after max_iter. */
+int pd_cg_solve(pd_handle *h, int mode, const double *b_dev, double *x_dev, int max_iter, double rel_tol,
+                int jacobi, int *iterations, double *relative_residual);
+/* largest eigenvalue of D^-1 A by n_iterations of the power method (the bound
+ * PreconditionChebyshev needs; deal.II estimates it with eig_cg_n_iterations CG steps) */
+int pd_estimate_lambda_max(pd_handle *h, int mode, int n_iterations, double *lambda_max);
+/* PreconditionChebyshev with a Jacobi inner preconditioner as used for the multigrid smoothers
+ * (examples/matrix_free_agglo.cc:264-319: degree 3, smoothing_range 20): `degree` steps of the
+ * Chebyshev recurrence on [lambda_max/smoothing_range, lambda_max]; degree - 1 operator applies
+ * when zero_initial_guess != 0. */
+int pd_chebyshev_smooth(pd_handle *h, int mode, int degree, double lambda_max, double smoothing_range,
+                        const double *b_dev, double *x_dev, int zero_initial_guess);
+
 /* Debug/parity access to device-resident arrays.  name in: "vol_qpt" [dim][Q],
  * "vol_jxw" [Q], "face_qpt" [dim][Qf], "face_normal" [dim][Qf], "face_jxw" [Qf].
  * Returns the element count through *count when host_out is NULL. */

@@ -482,6 +482,8 @@ extern "C"
       if (!h)
         return;
       cudaStreamSynchronize(h->stream);
+      if (h->cg_graph_exec)
+        cudaGraphExecDestroy(h->cg_graph_exec);
       for (auto &e : h->ev)
         if (e)
           cudaEventDestroy(e);
@@ -640,6 +642,18 @@ extern "C"
     });
   }
 
+  static void vmult_impl(pd_handle *h, int mode, const double *src, double *dst, bool add);
+}
+namespace pd
+{
+  void
+  vmult_dispatch(pd_handle *h, int mode, const double *src, double *dst, bool add)
+  {
+    vmult_impl(h, mode, src, dst, add);
+  }
+} // namespace pd
+extern "C"
+{
   static void
   vmult_impl(pd_handle *h, int mode, const double *src, double *dst, bool add)
   {
@@ -708,6 +722,38 @@ extern "C"
       vmult_impl(h, mode, h->vec_a.p, h->vec_b.p, false);
       PD_CUDA(cudaMemcpyAsync(dst_host, h->vec_b.p, sizeof(double) * h->n_dofs, cudaMemcpyDeviceToHost, h->stream));
       PD_CUDA(cudaStreamSynchronize(h->stream));
+    });
+  }
+
+  int
+  pd_cg_solve(pd_handle *h, int mode, const double *b_dev, double *x_dev, int max_iter, double rel_tol, int jacobi,
+              int *iterations, double *relative_residual)
+  {
+    return guarded([&] {
+      if (!h || !b_dev || !x_dev)
+        throw Error(PD_ERR_INVALID, "pd_cg_solve: null argument");
+      solver_cg(h, mode, b_dev, x_dev, max_iter, rel_tol, jacobi, iterations, relative_residual);
+    });
+  }
+
+  int
+  pd_estimate_lambda_max(pd_handle *h, int mode, int n_iterations, double *lambda_max)
+  {
+    return guarded([&] {
+      if (!h || !lambda_max || n_iterations < 1)
+        throw Error(PD_ERR_INVALID, "pd_estimate_lambda_max: bad argument");
+      *lambda_max = solver_lambda_max(h, mode, n_iterations);
+    });
+  }
+
+  int
+  pd_chebyshev_smooth(pd_handle *h, int mode, int degree, double lambda_max, double smoothing_range, const double *b_dev,
+                      double *x_dev, int zero_initial_guess)
+  {
+    return guarded([&] {
+      if (!h || !b_dev || !x_dev)
+        throw Error(PD_ERR_INVALID, "pd_chebyshev_smooth: null argument");
+      solver_chebyshev(h, mode, degree, lambda_max, smoothing_range, b_dev, x_dev, zero_initial_guess);
     });
   }
 

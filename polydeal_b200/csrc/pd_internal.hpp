@@ -112,6 +112,12 @@ struct pd_handle
   pd::DevBuf<int32_t> mf_nbr;
   pd_coefficients     op_coef{1.0, 0.0}; // operator of the matrix-free apply
   uint32_t            op_flags = PD_ASSEMBLE_ALL;
+  // device-resident solvers around vmult (pd_solver.cu)
+  pd::DevBuf<double> sv_r, sv_z, sv_p, sv_Ap, sv_dinv, sv_partial, sv_scal;
+  cudaGraphExec_t    cg_graph_exec   = nullptr;
+  int                cg_graph_mode   = -1, cg_graph_jacobi = -1;
+  const double      *cg_graph_x      = nullptr, *cg_graph_b = nullptr;
+  int64_t            cg_launches_per_chunk = 0;
 
   std::vector<int64_t> h_brow_ptr, h_subcell_ptr;
   std::vector<int32_t> h_bcol, h_dof_block;
@@ -136,6 +142,12 @@ namespace pd
   // pd_finemesh.cu
   void setup_fine_operator(pd_handle *h, const pd_mesh_desc &d);
   void launch_fine_operator(pd_handle *h, const double *src, double *dst, bool add);
+  // pd_solver.cu
+  void   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,
+                   int *iters_out, double *relres_out);
+  double solver_lambda_max(pd_handle *h, int mode, int n_iter);
+  void   solver_chebyshev(pd_handle *h, int mode, int degree, double lambda_max, double smoothing_range, const double *b,
+                          double *x, int zero_initial_guess);
   // pd_vmult.cu
   void launch_spmv(pd_handle *h, const double *src, double *dst, bool add);
   void launch_diagonal_inverse(pd_handle *h, double *dst);

@@ -1,0 +1,354 @@
+// -----------------------------------------------------------------------------
+// pd_solver.cu -- the immediate callers of vmult, device resident.
+//
+// Reference: SolverCG around the operator (examples/diffusion_reaction.cc:
+// 709-724, examples/matrix_free_agglo.cc:377-384) and PreconditionChebyshev
+// with a Jacobi (inverse-diagonal) inner preconditioner as multigrid smoother
+// (examples/matrix_free_agglo.cc:264-319; inverse diagonal include/utils.h:
+// 797-814).  Both are deal.II classes; what is restated here is the textbook
+// algorithm they implement:
+//   * preconditioned conjugate gradients (Hestenes-Stiefel),
+//   * the Chebyshev three-term recurrence on [lambda_max / range, lambda_max]
+//     (Saad, Iterative Methods, Alg. 12.1; the form used by deal.II),
+//   * a power iteration on D^-1 A for lambda_max (deal.II estimates it with a
+//     few CG/Lanczos steps; either way it is an input of the smoother).
+// Parity unpinned against deal.II's own iterates (no golden in the reference);
+// tests compare with a numpy restatement and with direct solves.
+//
+// Everything stays on the device: scalars (alpha, beta, residual norms) live in
+// device memory, the vector updates are fused around the two dot products, the
+// dot products are deterministic two-stage reductions, and the body of a CG
+// iteration is captured once in a CUDA graph and replayed (the loop is
+// launch-bound at config-B sizes: one SpMV + 5 tiny kernels).
+// -----------------------------------------------------------------------------
+#include "pd_host.hpp"
+#include "pd_internal.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace pd
+{
+  void vmult_dispatch(pd_handle *h, int mode, const double *src, double *dst, bool add); // pd_api.cu
+
+  namespace
+  {
+    constexpr int RB = 256;  // reduction block
+    constexpr int RG = 296;  // reduction grid (2 per SM)
+
+    // partial[k][block] = sum over this block's grid-stride share of a_k[i] * b_k[i], k < NK
+    template <int NK>
+    __device__ __forceinline__ void
+    block_reduce_store(double (&s)[NK], double *partial)
+    {
+      __shared__ double sh[NK][RB / 32];
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+        {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+          if ((threadIdx.x & 31) == 0)
+            sh[k][threadIdx.x >> 5] = s[k];
+        }
+      __syncthreads();
+      if (threadIdx.x < NK)
+        {
+          double t = 0.;
+#pragma unroll
+          for (int w = 0; w < RB / 32; ++w)
+            t += sh[threadIdx.x][w];
+          partial[threadIdx.x * RG + blockIdx.x] = t;
+        }
+    }
+
+    // scal[dst_k] = sum_b partial[k][b]  (fixed order => deterministic)
+    __global__ void
+    k_finalize(const double *__restrict__ partial, double *scal, const int nk, const int dst0)
+    {
+      const int k = threadIdx.x;
+      if (k < nk)
+        {
+          double t = 0.;
+          for (int b = 0; b < RG; ++b)
+            t += partial[k * RG + b];
+          scal[dst0 + k] = t;
+        }
+    }
+
+    // scalars: [0] rz  [1] pAp  [2] rz_new  [3] rr  [4] bb
+    __global__ void __launch_bounds__(RB)
+    k_dot_pAp(const double *__restrict__ p, const double *__restrict__ Ap, const int64_t n, double *partial)
+    {
+      double s[1] = {0.};
+      for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
+        s[0] += p[i] * Ap[i];
+      block_reduce_store<1>(s, partial);
+    }
+
+    // x += alpha p ; r -= alpha Ap ; z = dinv r (or r) ; partial <- (r.z, r.r);  alpha = rz / pAp
+    __global__ void __launch_bounds__(RB)
+    k_cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, const double *__restrict__ p,
+                const double *__restrict__ Ap, const double *__restrict__ dinv, const double *__restrict__ scal,
+                const int64_t n, double *partial)
+    {
+      const double alpha = scal[1] != 0. ? scal[0] / scal[1] : 0.; // converged exactly: stay put
+      double       s[2]  = {0., 0.};
+      for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
+        {
+          x[i] += alpha * p[i];
+          const double ri = r[i] - alpha * Ap[i];
+          r[i]            = ri;
+          const double zi = dinv ? dinv[i] * ri : ri;
+          z[i]            = zi;
+          s[0] += ri * zi;
+          s[1] += ri * ri;
+        }
+      block_reduce_store<2>(s, partial);
+    }
+
+    // p = z + beta p, beta = rz_new / rz ; then rz <- rz_new (by block 0 after the grid is done is
+    // not possible without a sync, so the swap is a separate tiny kernel)
+    __global__ void __launch_bounds__(RB)
+    k_cg_direction(double *__restrict__ p, const double *__restrict__ z, const double *__restrict__ scal, const int64_t n)
+    {
+      const double beta = scal[0] != 0. ? scal[2] / scal[0] : 0.;
+      for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
+        p[i] = z[i] + beta * p[i];
+    }
+    __global__ void
+    k_cg_roll(double *scal)
+    {
+      scal[0] = scal[2];
+    }
+
+    // r = b - Ax (Ax given) ; z = dinv r ; p = z ; partial <- (r.z, r.r, b.b)
+    __global__ void __launch_bounds__(RB)
+    k_cg_init(const double *__restrict__ b, const double *__restrict__ Ax, double *__restrict__ r, double *__restrict__ z,
+              double *__restrict__ p, const double *__restrict__ dinv, const int64_t n, double *partial)
+    {
+      double s[3] = {0., 0., 0.};
+      for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
+        {
+          const double ri = b[i] - Ax[i];
+          r[i]            = ri;
+          const double zi = dinv ? dinv[i] * ri : ri;
+          z[i]            = zi;
+          p[i]            = zi;
+          s[0] += ri * zi;
+          s[1] += ri * ri;
+          s[2] += b[i] * b[i];
+        }
+      block_reduce_store<3>(s, partial);
+    }
+
+    // Chebyshev step: d = c1 d + c2 dinv (b - Ax) ; x += d     (Ax == nullptr: zero start, Ax = 0)
+    __global__ void __launch_bounds__(RB)
+    k_cheb_step(double *__restrict__ x, double *__restrict__ d, const double *__restrict__ b, const double *__restrict__ Ax,
+                const double *__restrict__ dinv, const double c1, const double c2, const int64_t n, const int first)
+    {
+      for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)gridDim.x * RB)
+        {
+          const double res = b[i] - (Ax ? Ax[i] : 0.);
+          const double di  = (first ? 0. : c1 * d[i]) + c2 * dinv[i] * res;
+          d[i]             = di;
+          x[i]             = (first && !Ax ? 0. : x[i]) + di;
+        }
+    }
+
+    // power iteration on D^-1 A:  w = dinv (A v) ; partial <- (w.w, v.w)
+    __global__ void __launch_bounds__(RB)
+    k_power(const double *__restrict__ Av, const double *__restrict__ dinv, const double *__restrict__ v,
+            double *__restrict__ w, const int64_t n, double *partial)
+    {
+      double s[2] = {0., 0.};
+      for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
+        {
+          const double wi = dinv[i] * Av[i];
+          w[i]            = wi;
+          s[0] += wi * wi;
+          s[1] += v[i] * wi;
+        }
+      block_reduce_store<2>(s, partial);
+    }
+    __global__ void __launch_bounds__(RB)
+    k_scale_from(double *__restrict__ v, const double *__restrict__ w, const double *__restrict__ scal, const int64_t n)
+    {
+      const double inv = rsqrt(scal[0]);
+      for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)gridDim.x * RB)
+        v[i] = w[i] * inv;
+    }
+    __global__ void __launch_bounds__(RB)
+    k_fill_guess(double *__restrict__ v, const int64_t n)
+    {
+      // deterministic, non-constant start vector with zero mean tendency
+      for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)gridDim.x * RB)
+        v[i] = (double)((i % 11) - 5) + 0.5;
+    }
+
+    void
+    ensure_work(pd_handle *h)
+    {
+      const size_t n = (size_t)h->n_dofs, ns = (size_t)h->np * h->n;
+      if (h->sv_r.n != n)
+        {
+          h->sv_r.alloc(n);
+          h->sv_z.alloc(n);
+          h->sv_Ap.alloc(n);
+          h->sv_dinv.alloc(n);
+          h->sv_p.alloc(ns); // search direction is a vmult source: owned + ghost length
+          h->sv_partial.alloc(4 * RG);
+          h->sv_scal.alloc(8);
+          PD_CUDA(cudaMemsetAsync(h->sv_p.p, 0, sizeof(double) * ns, h->stream));
+        }
+    }
+  } // namespace
+
+  void
+  solver_cg(pd_handle *h, const int mode, const double *b, double *x, const int max_iter, const double rel_tol,
+            const int jacobi, int *iters_out, double *relres_out)
+  {
+    if (h->np != h->np_own)
+      throw Error(PD_ERR_UNSUPPORTED, "pd_cg_solve: single-rank handles only (no ghost polytopes)");
+    ensure_work(h);
+    const int64_t n = h->n_dofs;
+    cudaStream_t  s = h->stream;
+    double       *r = h->sv_r.p, *z = h->sv_z.p, *p = h->sv_p.p, *Ap = h->sv_Ap.p, *partial = h->sv_partial.p,
+           *scal = h->sv_scal.p;
+    const double *dinv = nullptr;
+    if (jacobi)
+      {
+        launch_diagonal_inverse(h, h->sv_dinv.p);
+        dinv = h->sv_dinv.p;
+      }
+    vmult_dispatch(h, mode, x, Ap, false);
+    k_cg_init<<<RG, RB, 0, s>>>(b, Ap, r, z, p, dinv, n, partial);
+    k_finalize<<<1, 32, 0, s>>>(partial, scal, 3, 2); // scal[2] = rz, [3] = rr, [4] = bb
+    k_cg_roll<<<1, 1, 0, s>>>(scal);
+    h->launches += 3;
+    double hs[5];
+    PD_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    PD_CUDA(cudaStreamSynchronize(s));
+    const double bnorm = std::sqrt(hs[4] > 0 ? hs[4] : 1.);
+    double       relres = std::sqrt(hs[3]) / bnorm;
+    int          it     = 0;
+    // one iteration = SpMV + 5 small kernels; captured once and replayed in chunks
+    constexpr int CHUNK = 8;
+    if (!h->cg_graph_exec || h->cg_graph_mode != mode || h->cg_graph_jacobi != jacobi)
+      {
+        if (h->cg_graph_exec)
+          {
+            cudaGraphExecDestroy(h->cg_graph_exec);
+            h->cg_graph_exec = nullptr;
+          }
+        cudaGraph_t graph = nullptr;
+        PD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int64_t l0 = h->launches;
+        for (int k = 0; k < CHUNK; ++k)
+          {
+            vmult_dispatch(h, mode, p, Ap, false);
+            k_dot_pAp<<<RG, RB, 0, s>>>(p, Ap, n, partial);
+            k_finalize<<<1, 32, 0, s>>>(partial, scal, 1, 1);
+            k_cg_update<<<RG, RB, 0, s>>>(x, r, z, p, Ap, dinv, scal, n, partial);
+            k_finalize<<<1, 32, 0, s>>>(partial, scal, 2, 2);
+            k_cg_direction<<<RG, RB, 0, s>>>(p, z, scal, n);
+            k_cg_roll<<<1, 1, 0, s>>>(scal);
+          }
+        h->cg_launches_per_chunk = (h->launches - l0) + 6 * CHUNK;
+        h->launches              = l0;
+        PD_CUDA(cudaStreamEndCapture(s, &graph));
+        PD_CUDA(cudaGraphInstantiate(&h->cg_graph_exec, graph, 0));
+        PD_CUDA(cudaGraphDestroy(graph));
+        h->cg_graph_mode   = mode;
+        h->cg_graph_jacobi = jacobi;
+        h->cg_graph_x      = x;
+        h->cg_graph_b      = b;
+      }
+    else if (h->cg_graph_x != x)
+      {
+        // the graph bakes in the x pointer: different vector => rebuild next time
+        cudaGraphExecDestroy(h->cg_graph_exec);
+        h->cg_graph_exec = nullptr;
+        solver_cg(h, mode, b, x, max_iter, rel_tol, jacobi, iters_out, relres_out);
+        return;
+      }
+    while (it < max_iter && relres > rel_tol)
+      {
+        PD_CUDA(cudaGraphLaunch(h->cg_graph_exec, s));
+        h->launches += h->cg_launches_per_chunk;
+        it += CHUNK;
+        PD_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, s));
+        PD_CUDA(cudaStreamSynchronize(s));
+        relres = std::sqrt(hs[3]) / bnorm;
+        if (!(relres == relres))
+          throw Error(PD_ERR_CUDA, "pd_cg_solve: residual became NaN (operator not positive definite?)");
+      }
+    if (iters_out)
+      *iters_out = it;
+    if (relres_out)
+      *relres_out = relres;
+  }
+
+  double
+  solver_lambda_max(pd_handle *h, const int mode, const int n_iter)
+  {
+    if (h->np != h->np_own)
+      throw Error(PD_ERR_UNSUPPORTED, "pd_estimate_lambda_max: single-rank handles only");
+    ensure_work(h);
+    const int64_t n = h->n_dofs;
+    cudaStream_t  s = h->stream;
+    double       *v = h->sv_p.p, *w = h->sv_z.p, *Av = h->sv_Ap.p, *partial = h->sv_partial.p, *scal = h->sv_scal.p;
+    launch_diagonal_inverse(h, h->sv_dinv.p);
+    k_fill_guess<<<RG, RB, 0, s>>>(v, n);
+    double lambda = 0.;
+    for (int it = 0; it < n_iter; ++it)
+      {
+        vmult_dispatch(h, mode, v, Av, false);
+        k_power<<<RG, RB, 0, s>>>(Av, h->sv_dinv.p, v, w, n, partial);
+        k_finalize<<<1, 32, 0, s>>>(partial, scal, 2, 0);
+        k_scale_from<<<RG, RB, 0, s>>>(v, w, scal, n);
+        h->launches += 3;
+      }
+    double hs[2];
+    PD_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    PD_CUDA(cudaStreamSynchronize(s));
+    // last iterate: v was normalised before the product, so |D^-1 A v| estimates lambda_max
+    lambda = std::sqrt(hs[0]);
+    return lambda;
+  }
+
+  void
+  solver_chebyshev(pd_handle *h, const int mode, const int degree, const double lambda_max, const double smoothing_range,
+                   const double *b, double *x, const int zero_initial_guess)
+  {
+    if (h->np != h->np_own)
+      throw Error(PD_ERR_UNSUPPORTED, "pd_chebyshev_smooth: single-rank handles only");
+    if (degree < 1 || !(lambda_max > 0.) || !(smoothing_range > 1.))
+      throw Error(PD_ERR_INVALID, "pd_chebyshev_smooth: need degree >= 1, lambda_max > 0, smoothing_range > 1");
+    ensure_work(h);
+    const int64_t n = h->n_dofs;
+    cudaStream_t  s = h->stream;
+    double       *d = h->sv_z.p, *Ax = h->sv_Ap.p;
+    launch_diagonal_inverse(h, h->sv_dinv.p);
+    const double lmin = lambda_max / smoothing_range;
+    const double theta = 0.5 * (lambda_max + lmin), delta = 0.5 * (lambda_max - lmin);
+    const double sigma1 = theta / delta;
+    double       rho    = 1. / sigma1;
+    const int    grid   = (int)std::min<int64_t>((n + RB - 1) / RB, 148 * 8);
+    // step 0: d = 1/theta D^-1 (b - A x0), x = x0 + d
+    if (!zero_initial_guess)
+      vmult_dispatch(h, mode, x, Ax, false);
+    k_cheb_step<<<grid, RB, 0, s>>>(x, d, b, zero_initial_guess ? nullptr : Ax, h->sv_dinv.p, 0., 1. / theta, n, 1);
+    ++h->launches;
+    for (int k = 1; k < degree; ++k)
+      {
+        const double rho_new = 1. / (2. * sigma1 - rho);
+        vmult_dispatch(h, mode, x, Ax, false);
+        k_cheb_step<<<grid, RB, 0, s>>>(x, d, b, Ax, h->sv_dinv.p, rho_new * rho, 2. * rho_new / delta, n, 0);
+        ++h->launches;
+        rho = rho_new;
+      }
+    PD_CUDA(cudaGetLastError());
+  }
+} // namespace pd

@@ -309,6 +309,27 @@ class SIPOperator:
         K.check(K.lib().pd_diagonal_inverse(self._h, C.c_void_p(out.data_ptr())))
         return out
 
+    def cg_solve(self, x, b, max_iter=1000, rel_tol=1e-10, jacobi=True, mode=K.VMULT_BLOCK_CSR):
+        """SolverCG around vmult, device resident (pd_cg_solve).  Returns (iterations, relative residual)."""
+        self._check_tensor(x), self._check_tensor(b)
+        it, rr = C.c_int(0), C.c_double(0.0)
+        K.check(K.lib().pd_cg_solve(self._h, mode, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), max_iter, rel_tol,
+                                    int(jacobi), C.byref(it), C.byref(rr)))
+        return it.value, rr.value
+
+    def estimate_lambda_max(self, n_iterations=20, mode=K.VMULT_BLOCK_CSR):
+        lam = C.c_double(0.0)
+        K.check(K.lib().pd_estimate_lambda_max(self._h, mode, n_iterations, C.byref(lam)))
+        return lam.value
+
+    def chebyshev_smooth(self, x, b, degree, lambda_max, smoothing_range=20.0, zero_initial_guess=True,
+                         mode=K.VMULT_BLOCK_CSR):
+        """PreconditionChebyshev (Jacobi inner preconditioner) as a smoother (pd_chebyshev_smooth)."""
+        self._check_tensor(x), self._check_tensor(b)
+        K.check(K.lib().pd_chebyshev_smooth(self._h, mode, degree, lambda_max, smoothing_range, C.c_void_p(b.data_ptr()),
+                                            C.c_void_p(x.data_ptr()), int(zero_initial_guess)))
+        return x
+
     def _check_tensor(self, t):
         import torch
 

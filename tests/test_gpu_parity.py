@@ -443,3 +443,84 @@ def test_poisson_golden_l2_error_on_gpu(goldens):
         rz = rz_new
     assert it < 4999
     assert l2_error(x.cpu().numpy()) == pytest.approx(goldens["poisson"][0], abs=5e-9)
+
+
+# ----------------------------------------------------------------------------------
+# the callers of vmult on the device (CG, Chebyshev smoother, lambda_max)
+# ----------------------------------------------------------------------------------
+def numpy_chebyshev(A, dinv, b, x0, degree, lam_max, rng):
+    """Saad Alg. 12.1 on [lam_max/rng, lam_max] with Jacobi inner preconditioner (the recurrence
+    deal.II's PreconditionChebyshev runs)."""
+    lmin = lam_max / rng
+    theta, delta = 0.5 * (lam_max + lmin), 0.5 * (lam_max - lmin)
+    sigma1 = theta / delta
+    rho = 1.0 / sigma1
+    x = x0.copy()
+    d = dinv * (b - A @ x) / theta
+    x += d
+    for _ in range(1, degree):
+        rho_new = 1.0 / (2 * sigma1 - rho)
+        d = rho_new * rho * d + 2 * rho_new / delta * dinv * (b - A @ x)
+        x += d
+        rho = rho_new
+    return x
+
+
+def test_device_cg_chebyshev_and_lambda_max(goldens):
+    pdl = gpu()
+    import scipy.sparse.linalg as spla
+    import torch
+
+    from test_oracle_sip import poisson_golden_problem, poisson_rhs_and_error
+
+    grid, oah, kw = poisson_golden_problem()
+    groups = [oah.get_agglomerate(p).tolist()[-1:] + oah.get_agglomerate(p).tolist()[:-1] for p in range(oah.n_polytopes)]
+    _, pah = product_handler(grid, groups, 1, 3)
+    op = pdl.assemble_dg_matrix(pah, penalty_constant=20.0, h_rule=pdl.H_CONSTANT, h_const=2.0 / 64,
+                                visit_rule=pdl.VISIT_BY_INDEX)
+    A = op.scipy().tocsr()
+    b, l2_error = poisson_rhs_and_error(grid, oah)
+    bd = torch.from_numpy(b).cuda()
+    # --- CG (Jacobi), CUDA-graph replayed, against the golden and a numpy PCG iteration count
+    x = torch.zeros_like(bd)
+    iters, relres = op.cg_solve(x, bd, max_iter=4000, rel_tol=1e-12, jacobi=True)
+    op.synchronize()
+    assert relres <= 1e-12 and iters < 4000
+    assert l2_error(x.cpu().numpy()) == pytest.approx(goldens["poisson"][0], abs=5e-9)
+    dinv = 1.0 / A.diagonal()
+    xr, r = np.zeros_like(b), b.copy()
+    z = dinv * r
+    p_, rz, k = z.copy(), r @ z, 0
+    while np.linalg.norm(r) > 1e-12 * np.linalg.norm(b):
+        Ap = A @ p_
+        alpha = rz / (p_ @ Ap)
+        xr += alpha * p_
+        r -= alpha * Ap
+        z = dinv * r
+        rz, rz_old = r @ z, rz
+        p_ = z + (rz / rz_old) * p_
+        k += 1
+    # same algorithm => same iteration count up to rounding in the dot products (a few per
+    # cent at 1e-12) and the 8-iteration check interval of the device loop
+    assert abs(iters - k) <= 0.05 * k + 8
+    # second solve with the same vectors replays the cached graph
+    x.zero_()
+    iters2, _ = op.cg_solve(x, bd, max_iter=4000, rel_tol=1e-12, jacobi=True)
+    assert iters2 == iters
+    # unpreconditioned variant
+    x2 = torch.zeros_like(bd)
+    it3, rr3 = op.cg_solve(x2, bd, max_iter=8000, rel_tol=1e-10, jacobi=False)
+    assert rr3 <= 1e-10 and np.abs(x2.cpu().numpy() - xr).max() <= 1e-7 * np.abs(xr).max()
+    # --- lambda_max(D^-1 A) by power iteration: a lower bound converging to the true value
+    lam_true = float(spla.eigs(spla.aslinearoperator(A.multiply(dinv[:, None]).tocsr()), k=1, which="LM",
+                               return_eigenvectors=False)[0].real)
+    lam = op.estimate_lambda_max(60)
+    assert 0.9 * lam_true <= lam <= lam_true * (1 + 1e-10)
+    # --- Chebyshev smoother (degree 3, range 20 as in examples/matrix_free_agglo.cc:306-308)
+    for zero_guess in (True, False):
+        x0 = np.zeros_like(b) if zero_guess else np.cos(0.1 * np.arange(len(b)))
+        want = numpy_chebyshev(A, dinv, b, x0, 3, 1.2 * lam, 20.0)
+        xs = torch.from_numpy(x0.copy()).cuda()
+        op.chebyshev_smooth(xs, bd, 3, 1.2 * lam, 20.0, zero_initial_guess=zero_guess)
+        op.synchronize()
+        assert np.abs(xs.cpu().numpy() - want).max() <= 1e-12 * np.abs(want).max()
