@@ -178,9 +178,16 @@ int pd_vmult(pd_handle *h, int mode, const double *src_dev, double *dst_dev);
  * MonodomainOperatorDG (include/utils.h:1131-1134, 1565-1659: no boundary term).
  * Default: all terms, {1, 0} = LaplaceOperatorDG (include/utils.h:819-925). */
 int pd_set_operator(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
-/* 1 when the sum-factorised matrix-free apply exists for this handle: every
- * polytope is one axis-aligned cell (the reference's fine-mesh MatrixFree case) */
+/* PD_VMULT_MATRIX_FREE picks one of two kernels:
+ *  - every polytope is one axis-aligned cell (the reference's fine-mesh MatrixFree case,
+ *    pd_matrix_free_available() == 1): the sum-factorised 1-D stencil kernel;
+ *  - genuine agglomerates: the basis is regenerated at the agglomerated quadrature points
+ *    (the same operand rows the assembly contracts) and applied to the polytope's coefficients --
+ *    no matrix memory, ~12 n flops per volume point; the block-CSR apply is the faster one
+ *    whenever the matrix fits.
+ * pd_force_generic_matrix_free(h, 1) selects the second kernel on fine meshes too (testing). */
 int pd_matrix_free_available(const pd_handle *h);
+int pd_force_generic_matrix_free(pd_handle *h, int on);
 int pd_vmult_add(pd_handle *h, int mode, const double *src_dev, double *dst_dev);
 /* same with HOST buffers (pinned or pageable): H2D, apply, D2H */
 int pd_vmult_host(pd_handle *h, int mode, const double *src_host, double *dst_host);

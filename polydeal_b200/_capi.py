@@ -67,6 +67,7 @@ SIGNATURES = {
     "pd_vmult": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_set_operator": (C.c_int, [vp, u32, P(Coefficients)]),
     "pd_matrix_free_available": (C.c_int, [vp]),
+    "pd_force_generic_matrix_free": (C.c_int, [vp, C.c_int]),
     "pd_vmult_add": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_vmult_host": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_diagonal_inverse": (C.c_int, [vp, vp]),

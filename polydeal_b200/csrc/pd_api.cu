@@ -257,16 +257,24 @@ namespace pd
   }
 
   static void
-  ensure_assembly_buffers(pd_handle *h)
+  ensure_quadrature_buffers(pd_handle *h)
   {
-    if (h->values.p || h->nnz == 0)
+    if (h->vq_w.p || h->Q == 0)
       return;
-    const size_t nn = (size_t)h->n * h->n;
     h->vq_x.alloc((size_t)h->Q * h->dim);
     h->vq_w.alloc((size_t)h->Q);
     h->fq_x.alloc((size_t)h->Qf * h->dim);
     h->fq_n.alloc((size_t)h->Qf * h->dim);
     h->fq_w.alloc((size_t)h->Qf);
+  }
+
+  static void
+  ensure_assembly_buffers(pd_handle *h)
+  {
+    ensure_quadrature_buffers(h);
+    if (h->values.p || h->nnz == 0)
+      return;
+    const size_t nn = (size_t)h->n * h->n;
     h->face_diag.alloc((size_t)h->n_ifaces * 2 * nn);
     h->values.alloc((size_t)h->nnz);
   }
@@ -667,11 +675,19 @@ extern "C"
       }
     else if (mode == PD_VMULT_MATRIX_FREE)
       {
-        if (!h->mf_ready)
-          throw Error(PD_ERR_UNSUPPORTED,
-                      "pd_vmult(MATRIX_FREE): available when every polytope is a single axis-aligned cell (the "
-                      "fine-mesh LaplaceOperatorDG / MonodomainOperatorDG case); use PD_VMULT_BLOCK_CSR on agglomerates");
-        launch_fine_operator(h, src, dst, add);
+        if (h->mf_ready && !h->force_generic_mf)
+          launch_fine_operator(h, src, dst, add); // fine Cartesian mesh: sum-factorised stencil kernel
+        else
+          {
+            // agglomerated polytopes: regenerate the basis at the agglomerated quadrature points
+            ensure_quadrature_buffers(h);
+            if (!h->quad_valid)
+              {
+                launch_quadrature(h);
+                h->quad_valid = true;
+              }
+            launch_poly_apply(h, src, dst, add);
+          }
       }
     else
       throw Error(PD_ERR_INVALID, "pd_vmult: unknown mode");
@@ -692,6 +708,16 @@ extern "C"
   pd_matrix_free_available(const pd_handle *h)
   {
     return h && h->mf_ready ? 1 : 0;
+  }
+
+  int
+  pd_force_generic_matrix_free(pd_handle *h, int on)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      h->force_generic_mf = on != 0;
+    });
   }
 
   int

@@ -107,9 +107,10 @@ struct pd_handle
   pd::DevBuf<double> vol_partial, face_diag, values;
   pd::DevBuf<double> vec_a, vec_b; // staging for pd_vmult_host
   // matrix-free fine-mesh operator (every polytope = one Cartesian cell), pd_finemesh.cu
-  bool                mf_ready = false;
+  bool                mf_ready = false, force_generic_mf = false;
   pd::DevBuf<double>  mf_tables, mf_cell_h, mf_sigma;
   pd::DevBuf<int32_t> mf_nbr;
+  pd::DevBuf<double>  mf_vol_partial, mf_face_partial; // polytopal matrix-free apply (pd_polyapply.cu)
   pd_coefficients     op_coef{1.0, 0.0}; // operator of the matrix-free apply
   uint32_t            op_flags = PD_ASSEMBLE_ALL;
   // device-resident solvers around vmult (pd_solver.cu)
@@ -142,6 +143,8 @@ namespace pd
   // pd_finemesh.cu
   void setup_fine_operator(pd_handle *h, const pd_mesh_desc &d);
   void launch_fine_operator(pd_handle *h, const double *src, double *dst, bool add);
+  // pd_polyapply.cu
+  void launch_poly_apply(pd_handle *h, const double *src, double *dst, bool add);
   // pd_solver.cu
   void   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,
                    int *iters_out, double *relres_out);

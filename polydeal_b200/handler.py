@@ -227,6 +227,9 @@ class SIPOperator:
         c = K.Coefficients(stiffness, mass)
         K.check(K.lib().pd_set_operator(self._h, flags, C.byref(c)))
 
+    def force_generic_matrix_free(self, on=True):
+        K.check(K.lib().pd_force_generic_matrix_free(self._h, int(on)))
+
     @property
     def matrix_free_available(self):
         return bool(K.lib().pd_matrix_free_available(self._h))

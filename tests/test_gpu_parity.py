@@ -326,16 +326,43 @@ def test_fine_mesh_matrix_free_vmult(dim, n, p, order, hi, kw):
     assert np.abs(yb.cpu().numpy() - yref).max() <= TOL * scale
 
 
-def test_matrix_free_refused_on_agglomerates():
+@pytest.mark.parametrize("dim,n,shape,p,nq,distort,kw", [
+    (2, 16, "blocks4", 1, 2, None, {}),
+    (2, 8, "random5", 2, 3, (0.2, 3), {}),
+    (2, 8, "random4", 4, 5, None, {}),
+    (3, 8, "blocks4", 2, 3, None, {}),
+    (3, 8, "random12", 2, 3, None, dict(mass_coeff=0.5, penalty_constant=40.0)),
+    (3, 4, "random3", 3, 4, None, {}),
+    (3, 4, "random4", 1, 2, None, dict(stiffness_coeff=1e-4, mass_coeff=1.5e4, with_boundary=False)),
+    (3, 4, "singletons", 2, 3, None, dict(penalty_constant=6.0, h_rule=3)),
+])
+def test_polytopal_matrix_free_vmult(dim, n, shape, p, nq, distort, kw):
+    """PD_VMULT_MATRIX_FREE on genuine agglomerates: the basis is regenerated at the agglomerated
+    quadrature points and applied; same operator as the assembled one (checker: oracle matrix)."""
     pdl = gpu()
     import torch
 
-    _, pah = both(3, 4, "blocks2", 1)
-    op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
-    assert not op.matrix_free_available
-    x = torch.zeros(op.m(), dtype=torch.float64, device="cuda")
-    with pytest.raises(pdl.PolydealError, match="single axis-aligned cell"):
-        op.vmult(torch.empty_like(x), x, mode=pdl.VMULT_MATRIX_FREE)
+    oah, pah = both(dim, n, shape, p, nq=nq, distort=distort)
+    okw = dict(kw)
+    okw.setdefault("penalty_constant", None)
+    ref = po.assemble_dg_matrix(oah, degree=p, n_threads=4, **okw)
+    fkw = {k: v for k, v in kw.items() if k in ("penalty_constant", "h_rule", "visit_rule")}
+    fkw.setdefault("penalty_constant", -1.0)
+    op = pdl.SIPOperator(pah.flatten(**fkw), keepalive=pah)
+    op.force_generic_matrix_free(True)
+    flags = pdl.ASSEMBLE_ALL if kw.get("with_boundary", True) else (pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR)
+    op.set_operator(flags, kw.get("stiffness_coeff", 1.0), kw.get("mass_coeff", 0.0))
+    x = src_vector(op.m())
+    yref = ref.vmult(x)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros_like(xd)
+    op.vmult(yd, xd, mode=pdl.VMULT_MATRIX_FREE)
+    op.synchronize()
+    scale = np.abs(yref).max()
+    assert np.abs(yd.cpu().numpy() - yref).max() <= TOL * scale
+    op.vmult_add(yd, xd, mode=pdl.VMULT_MATRIX_FREE)
+    op.synchronize()
+    assert np.abs(yd.cpu().numpy() - 2 * yref).max() <= 2 * TOL * scale
 
 
 # ----------------------------------------------------------------------------------
@@ -388,8 +415,9 @@ def test_sharded_assembly_and_vmult_match_serial(world, dim, n, shape, p, kw):
         op.vmult_ptr(yd.data_ptr(), xd.data_ptr())
         op.synchronize()
         assert np.abs(yd.cpu().numpy() - y[rows]).max() <= TOL * np.abs(y).max()
-        if op.matrix_free_available:
-            op.set_operator()
+        op.set_operator()
+        for force in ([False, True] if op.matrix_free_available else [True]):
+            op.force_generic_matrix_free(force)
             ym = torch.empty_like(yd)
             op.vmult_ptr(ym.data_ptr(), xd.data_ptr(), mode=pdl.VMULT_MATRIX_FREE)
             op.synchronize()
