@@ -145,6 +145,31 @@ def main():
         "vmult_frac_hbm": vm_bytes / (vm_ms * 1e-3) / 1e9 / 6543.4, "interior_ifaces": n_int,
         "mem_GB": torch.cuda.max_memory_allocated() / 1e9,
     }
+    # matrix-free polytopal apply of the same operator (no matrix memory)
+    op.set_operator(pdl.ASSEMBLE_ALL, 1.0, cfg["mass"])
+    mf = []
+    for s in range(args.steps + 2):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        op.vmult(y, x, mode=pdl.VMULT_MATRIX_FREE)
+        e.record(stream)
+        e.synchronize()
+        if s >= 2:
+            mf.append(a.elapsed_time(e))
+    out["mf_poly_vmult_ms"] = statistics.mean(mf)
+    out["mf_poly_vmult_gdofs"] = N / (statistics.mean(mf) * 1e-3) / 1e9
+    # CG iteration rate through the CUDA-graph loop (block-CSR)
+    b_ = torch.ones_like(x)
+    x_ = torch.zeros_like(x)
+    op.cg_solve(x_, b_, max_iter=8, rel_tol=0.0)
+    x_.zero_()
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    it, rr = op.cg_solve(x_, b_, max_iter=96, rel_tol=0.0)
+    e.record(stream)
+    e.synchronize()
+    out["cg_ms_per_iteration"] = a.elapsed_time(e) / max(it, 1)
+    out["cg_iterations_timed"] = it
     if args.check:
         # size-independent properties: constants in the kernel of the boundary-free stiffness operator
         # (checked through vmult), symmetry through x'Ay = y'Ax, energy of u = x_0 equals |Omega| = 1
