@@ -21,17 +21,20 @@
 // there are no atomics and the result is deterministic.  On Cartesian cells all
 // geometry factors are per-direction scalars and the operator is a sum of
 // Kronecker products of the 1-D matrices
-//   Mh = int l_i l_j,  Sh = int l_i' l_j'   (the cell Gauss rule)
-//   Mf = int l_i l_j                        (the face Gauss rule)
+//   Mh = int l_i l_j,  Sh = int l_i' l_j'   (the Gauss rule; cell and face rules coincide)
 //   e0/e1 = l_i(0)/l_i(1),  d0/d1 = l_i'(0)/l_i'(1)
-// applied by 1-D contractions through shared memory.
+// applied LINE by line: one thread owns one line of N1 DoFs along one direction,
+// keeps it in registers and multiplies by the tables as constant-bank operands
+// (the first version, one thread per DoF with every operand fetched from shared
+// memory, was shared-memory-bandwidth bound at 2.6x the time).
 //
-// HBM-bound by design: 16 B per DoF (read src once, write dst once; neighbour
-// reads are L1/L2 hits), O(1) geometry per cell.
+// Algorithmic traffic 16 B per DoF (read src once, write dst once; neighbour reads
+// are L1/L2 hits) plus 64 B per (cell, direction) of folded stencil record.
 // -----------------------------------------------------------------------------
 #include "pd_internal.hpp"
 
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 namespace pd
@@ -44,228 +47,262 @@ namespace pd
       return e == 0 ? 1 : b * ipow_(b, e - 1);
     }
 
+    // 1-D tables, passed BY VALUE as kernel parameters: every index is a compile-time constant
+    // after unrolling, so each entry is a constant-bank operand of its DFMA (no load at all).
+    template <int N1>
+    struct FineTables
+    {
+      double Mh[N1 * N1], Sh[N1 * N1], e[2][N1], d[2][N1];
+    };
+
+    // What one line of DoFs along direction d of one cell needs to know about the cell
+    // (a = vol/h_d the face area, sg the face penalty): the geometry record built at set-up
+    //   cV = a/h_d,  P[s] = a sg_s,  Q[s] = a / (2 h_d(neighbour_s))   (0 at the boundary)
+    struct alignas(16) FineGeo
+    {
+      int32_t nb[2]; // neighbour block along -d / +d, -1 = boundary
+      double  cV;
+      double  P[2];
+      double  Q[2];
+    };
+    static_assert(sizeof(FineGeo) == 6 * sizeof(double), "records travel in a double buffer");
+
+    // ... and the record the kernel reads: the operator's coefficient and term flags folded
+    // in (k_fine_fold, once per pd_set_operator), so the apply kernel has no per-face logic:
+    //   cVol = c cV (volume term on),  cD[s] = c cV/2 (interior) | c cV (boundary),
+    //   P[s], Q[s] scaled by c; everything of a switched-off face term is zero.
+    struct alignas(16) FineRec
+    {
+      int32_t nb[2];
+      double  cVol;
+      double  cD[2];
+      double  P[2];
+      double  Q[2];
+    };
+    static_assert(sizeof(FineRec) == 64, "four 16-byte loads");
+
+    __global__ void
+    k_fine_fold(const FineGeo *geo, FineRec *rec, const int64_t n, const double c, const uint32_t flags)
+    {
+      const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (i >= n)
+        return;
+      const FineGeo g = geo[i];
+      FineRec       r;
+      r.cVol = (flags & PD_ASSEMBLE_VOLUME) ? c * g.cV : 0.;
+      for (int s = 0; s < 2; ++s)
+        {
+          const bool inner = g.nb[s] >= 0;
+          const bool on    = (flags & (inner ? PD_ASSEMBLE_INTERIOR : PD_ASSEMBLE_BOUNDARY)) != 0;
+          r.nb[s]          = g.nb[s];
+          r.cD[s]          = on ? c * (inner ? 0.5 * g.cV : g.cV) : 0.;
+          r.P[s]           = on ? c * g.P[s] : 0.;
+          r.Q[s]           = on ? c * g.Q[s] : 0.;
+        }
+      rec[i] = r;
+    }
+
+    template <int N1>
     struct FineArgs
     {
-      const double  *tables; // Mh[N1*N1], Sh[N1*N1], Mf[N1*N1], e0[N1], e1[N1], d0[N1], d1[N1]
-      const double  *cell_h; // [n_cells][DIM]   extents, block order
-      const int32_t *nbr;    // [n_cells][2*DIM] neighbour block, -1 = boundary
-      const double  *sigma;  // [n_cells][2*DIM] penalty of the face
+      FineTables<N1> T;
+      const FineRec *rec;  // [n_cells][DIM], block order
+      const double  *vol;  // [n_cells]
+      const double  *zero; // N zeros: what a missing neighbour reads
       const double  *x;
       double        *y;
       int32_t        n_cells;
-      double         stiffness, mass;
-      uint32_t       flags;
+      double         mass; // 0 when the volume term is off
       int            add;
     };
 
-    // One thread per DoF, GS threads per cell (GS = N rounded up to a power of two),
-    // CPB cells per block, persistent over cell batches.
-    //
+    constexpr int
+    pow2_at_least(const int v)
+    {
+      int g = 4;
+      while (g < v)
+        g *= 2;
+      return g;
+    }
+
     // On a Cartesian cell the SIP operator is
     //   sum_d  M (x) ... (x) L_d (x) ... (x) M   +  f vol  M (x) M (x) M
-    // where L_d is the 1-D DG stencil along d: three (N1 x N1) matrices acting on the
-    // cell's own line of DoFs and on the lines of its two neighbours along d,
-    //   B_own   = (a/h) Sh + sum_s a [ sig e_s e_s^T - sn/(2h) (e_s d_s^T + d_s e_s^T) ]
-    //   B_nbr,s = a [ -sig e_s e_s'^T - sn/(2 h_N) e_s d_s'^T + sn/(2h) d_s e_s'^T ],  s' = 1-s
-    // (boundary face: a [ pen e_s e_s^T - sn/h (e_s d_s^T + d_s e_s^T) ], no neighbour part),
-    // a = vol/h the face area, sn = -1/+1 the outward normal sign, and M the 1-D mass
-    // (cell and face Gauss rules coincide).  15 one-dimensional contractions per cell in 3-D.
-    template <int DIM, int DEG>
-    __global__ void __launch_bounds__(256, 4) // latency-bound: occupancy beats spill-free code here (measured)
-    k_fine_sip(const FineArgs A)
+    // where L_d is the 1-D DG stencil along d acting on the cell's own line of DoFs and on
+    // the lines of its two neighbours along d (the face parts are rank one / two: outer
+    // products of the end values e_s and end derivatives d_s), and M the 1-D mass (cell and
+    // face Gauss rules coincide).  The mass term is folded into the last direction's stencil,
+    //   M (x) M (x) (L_z + f vol M).
+    //
+    // One thread per LINE: thread (d, j) of a cell owns line j along direction d.  It reads
+    // its own line and the two neighbour lines straight from the vector (L1/L2 hits for the
+    // neighbours), applies L_d entirely in registers with the tables as constant operands,
+    // and writes the N1 results to the cell's work array W_d in shared memory; the DIM-1
+    // remaining mass contractions of W_d are again one line per thread, in place, and the
+    // DoF lanes finally sum W_0..W_{DIM-1}.  GS threads per cell (a power of two covering
+    // both the DIM*N1^(DIM-1) lines and the N DoFs), 256/GS cells per block, grid-stride.
+    template <int DIM, int DEG, int MINB>
+    __global__ void __launch_bounds__(256, MINB) k_fine_sip(const __grid_constant__ FineArgs<DEG + 1> A)
     {
       constexpr int N1  = DEG + 1;
       constexpr int N   = ipow_(N1, DIM);
-      constexpr int GS  = N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : (N <= 32 ? 32 : (N <= 64 ? 64 : 128))));
+      constexpr int NL  = N / N1;   // lines per direction
+      constexpr int NT  = DIM * NL; // line tasks per cell
+      constexpr int GS  = pow2_at_least(N > NT ? N : NT);
       constexpr int CPB = 256 / GS;
-      constexpr int NFC = 2 * DIM; // faces per cell
-      constexpr int NM  = N1 * N1;
 
-      __shared__ double tab[3 * NM + 4 * N1];
-      __shared__ double sU[CPB][N];           // own coefficients
-      __shared__ double sN[CPB][NFC][N];      // neighbours' coefficients
-      __shared__ double sW[CPB][4][N];        // contraction work arrays
+      constexpr int NP  = N | 1; // odd row length: the DIM work arrays of a cell start on different banks
+      __shared__ double sW[CPB][DIM][NP];
 
-      const double *Mh = tab, *Sh = tab + NM;
-      const double *e0 = tab + 3 * NM, *d0 = e0 + 2 * N1; // e0,e1 contiguous; d0,d1 contiguous
-
-      for (int i = threadIdx.x; i < 3 * NM + 4 * N1; i += blockDim.x)
-        tab[i] = A.tables[i];
-      __syncthreads();
-      // all shared arrays are private to a cell slot: when a slot is (part of) one warp the
-      // phases only need warp-level ordering
-      auto group_sync = [] {
+      const int  slot = threadIdx.x / GS, l = threadIdx.x % GS;
+      // a cell's work arrays are private to its GS threads: warp-level ordering when a cell
+      // is (part of) one warp, a named barrier per cell slot otherwise
+      auto group_sync = [slot] {
         if constexpr (GS <= 32)
           __syncwarp();
         else
-          __syncthreads();
+          asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(GS) : "memory");
       };
 
-      const int  slot = threadIdx.x / GS, l = threadIdx.x % GS;
-      const bool lane_ok = l < N;
-      int        idx[DIM];
+      const bool task_ok = l < NT;
+      const int  d = task_ok ? l / NL : 0, j = l % NL;
+      // line j along direction dd: first DoF and stride
+      auto line = [](const int dd, const int jj, int &base, int &stride) {
+        stride = dd == 0 ? 1 : (dd == 1 ? N1 : N1 * N1);
+        base   = dd == 0 ? jj * N1 : (dd == 1 ? (jj % N1) + (jj / N1) * N1 * N1 : jj);
+      };
+      // loop-invariant offsets: the line in the vector / in W_d, and the lines of the mass passes
+      int off[N1], offk[DIM > 1 ? DIM - 1 : 1][N1];
       {
-        int r = l;
+        int base, stride;
+        line(d, j, base, stride);
 #pragma unroll
-        for (int d = 0; d < DIM; ++d)
+        for (int t = 0; t < N1; ++t)
+          off[t] = base + t * stride;
+#pragma unroll
+        for (int k = 1; k < DIM; ++k)
           {
-            idx[d] = r % N1;
-            r /= N1;
-          }
-      }
-      constexpr int stride[3] = {1, N1, N1 * N1};
-      const bool    vol_on = (A.flags & PD_ASSEMBLE_VOLUME) != 0;
-
-      for (int c0 = blockIdx.x * CPB; c0 < A.n_cells; c0 += gridDim.x * CPB)
-        {
-          const int  cell  = c0 + slot;
-          const bool cell_ok = cell < A.n_cells;
-          const bool ok    = lane_ok && cell_ok;
-          group_sync(); // previous batch done with this slot's shared arrays
-          if (ok)
-            {
-              sU[slot][l] = A.x[(int64_t)cell * N + l];
-#pragma unroll
-              for (int f = 0; f < NFC; ++f)
-                {
-                  const int nb   = A.nbr[(int64_t)cell * NFC + f];
-                  sN[slot][f][l] = nb >= 0 ? A.x[(int64_t)nb * N + l] : 0.;
-                }
-            }
-          double vol = 1., h[DIM];
-#pragma unroll
-          for (int d = 0; d < DIM; ++d)
-            {
-              h[d] = cell_ok ? A.cell_h[(int64_t)cell * DIM + d] : 1.;
-              vol *= h[d];
-            }
-          group_sync();
-          auto contract = [&](const double *Mat, const double *src, const int d) {
-            double s = 0.;
+            line((d + k) % DIM, j, base, stride);
 #pragma unroll
             for (int t = 0; t < N1; ++t)
-              s += Mat[idx[d] * N1 + t] * src[l + (t - idx[d]) * stride[d]];
-            return s;
-          };
-          // ---- 1-D stencil along every direction, per lane.  The face parts of the stencil
-          //      matrices are rank one / two (outer products of e_s, d_s), so each lane forms
-          //      the traces of its own line (and of the neighbours' lines) and lifts them.
-          double st[DIM];
-          if (ok)
+              offk[k - 1][t] = base + t * stride;
+          }
+      }
+      double *const  wd     = &sW[slot][d][0];
+      const bool     mass_on = A.mass != 0.;
+      const double   mass_d = d == DIM - 1 ? A.mass : 0.;
+      const FineRec *recp   = A.rec + d;
+
+      // the neighbour indices of the NEXT cell are fetched one iteration ahead, so the two
+      // dependent long-latency steps (record -> neighbour lines) overlap across iterations
+      int       cell = blockIdx.x * CPB + slot;
+      const int step = gridDim.x * CPB;
+      int2      nbn  = make_int2(-1, -1);
+      if (cell < A.n_cells && task_ok)
+        nbn = *reinterpret_cast<const int2 *>(recp + (int64_t)cell * DIM);
+
+      for (int c0 = blockIdx.x * CPB; c0 < A.n_cells; c0 += step, cell += step)
+        {
+          const bool cell_ok = cell < A.n_cells;
+          double     out[N1];
+#pragma unroll
+          for (int i = 0; i < N1; ++i)
+            out[i] = 0.;
+          const int2 nb = nbn;
+          if (cell + step < A.n_cells && task_ok)
+            nbn = *reinterpret_cast<const int2 *>(recp + (int64_t)(cell + step) * DIM);
+          if (cell_ok && task_ok)
             {
+              // all loads are unconditional (a missing neighbour reads zeros), so they are
+              // issued back to back
+              const double *xc  = A.x + (int64_t)cell * N;
+              const double *xn0 = nb.x >= 0 ? A.x + (int64_t)nb.x * N : A.zero;
+              const double *xn1 = nb.y >= 0 ? A.x + (int64_t)nb.y * N : A.zero;
+              double        u[N1], nv[2][N1];
 #pragma unroll
-              for (int d = 0; d < DIM; ++d)
+              for (int t = 0; t < N1; ++t)
                 {
-                  const int     i    = idx[d];
-                  const double *u    = sU[slot] + l - i * stride[d];
-                  const double  ih   = 1. / h[d], a = vol * ih;
-                  double        su   = 0.;
-                  double        tu[2] = {0., 0.}, du[2] = {0., 0.};
+                  u[t]     = xc[off[t]];
+                  nv[0][t] = xn0[off[t]];
+                  nv[1][t] = xn1[off[t]];
+                }
+              const FineRec r = recp[(int64_t)cell * DIM];
+              // traces of the own line and of the neighbours' facing ends
+              double tu[2] = {0., 0.}, du[2] = {0., 0.}, tn[2] = {0., 0.}, dn[2] = {0., 0.};
 #pragma unroll
-                  for (int t = 0; t < N1; ++t)
-                    {
-                      const double ut = u[t * stride[d]];
-                      su += Sh[i * N1 + t] * ut;
-                      tu[0] += e0[t] * ut;
-                      tu[1] += e0[N1 + t] * ut;
-                      du[0] += d0[t] * ut;
-                      du[1] += d0[N1 + t] * ut;
-                    }
-                  double acc_d = vol_on ? a * ih * su : 0.;
+              for (int t = 0; t < N1; ++t)
+                {
 #pragma unroll
                   for (int s = 0; s < 2; ++s)
                     {
-                      const int     f  = 2 * d + s;
-                      const int     nb = A.nbr[(int64_t)cell * NFC + f];
-                      const double  sg = A.sigma[(int64_t)cell * NFC + f], sn = s ? 1. : -1.;
-                      const double *es = e0 + s * N1, *ds = d0 + s * N1;
-                      double        av = 0., bv = 0.;
-                      if (nb >= 0)
-                        {
-                          if (A.flags & PD_ASSEMBLE_INTERIOR)
-                            {
-                              const double *un  = sN[slot][f] + l - i * stride[d];
-                              const double *eo  = e0 + (1 - s) * N1, *dd = d0 + (1 - s) * N1;
-                              const double  ihn = 1. / A.cell_h[(int64_t)nb * DIM + d];
-                              double        tn = 0., dn = 0.;
-#pragma unroll
-                              for (int t = 0; t < N1; ++t)
-                                {
-                                  const double nt = un[t * stride[d]];
-                                  tn += eo[t] * nt;
-                                  dn += dd[t] * nt;
-                                }
-                              const double jmp = tu[s] - tn;
-                              av               = sg * jmp - 0.5 * sn * (du[s] * ih + dn * ihn);
-                              bv               = -0.5 * jmp;
-                            }
-                        }
-                      else if (A.flags & PD_ASSEMBLE_BOUNDARY)
-                        {
-                          av = sg * tu[s] - sn * du[s] * ih;
-                          bv = -tu[s];
-                        }
-                      acc_d += a * (es[i] * av + sn * ih * ds[i] * bv);
+                      tu[s] += A.T.e[s][t] * u[t];
+                      du[s] += A.T.d[s][t] * u[t];
+                      tn[s] += A.T.e[1 - s][t] * nv[s][t];
+                      dn[s] += A.T.d[1 - s][t] * nv[s][t];
                     }
-                  st[d] = A.stiffness * acc_d;
+                }
+              // av = P [u] - sn (cD du + Q dn),  bv = -sn cD [u]   (sn = -1 / +1)
+              const double j0 = tu[0] - tn[0], j1 = tu[1] - tn[1];
+              const double a0 = r.P[0] * j0 + (r.cD[0] * du[0] + r.Q[0] * dn[0]), b0 = r.cD[0] * j0;
+              const double a1 = r.P[1] * j1 - (r.cD[1] * du[1] + r.Q[1] * dn[1]), b1 = -r.cD[1] * j1;
+#pragma unroll
+              for (int i = 0; i < N1; ++i)
+                {
+                  double sv = 0.;
+#pragma unroll
+                  for (int t = 0; t < N1; ++t)
+                    sv += A.T.Sh[i * N1 + t] * u[t];
+                  out[i] = r.cVol * sv + A.T.e[0][i] * a0 + A.T.e[1][i] * a1 + A.T.d[0][i] * b0 + A.T.d[1][i] * b1;
+                }
+              if (mass_on) // kernel-uniform
+                {
+                  const double mv = mass_d * A.vol[cell];
+#pragma unroll
+                  for (int i = 0; i < N1; ++i)
+                    {
+                      double sm = 0.;
+#pragma unroll
+                      for (int t = 0; t < N1; ++t)
+                        sm += A.T.Mh[i * N1 + t] * u[t];
+                      out[i] += mv * sm;
+                    }
                 }
             }
-          // ---- masses in the other directions:
-          //   3-D: My(Mz W0) + Mx[ Mz W1 + My( W2 + f vol Mz U ) ];  2-D: My W0 + Mx( W1 + f vol My U )
-          double acc = 0.;
-          if constexpr (DIM == 3)
+          group_sync(); // the previous cell's final sum has read this slot's work arrays
+          if (task_ok)
             {
-              if (ok)
-                {
-                  sW[slot][0][l] = st[0];
-                  sW[slot][1][l] = st[1];
-                }
-              group_sync();
-              double t0 = 0., t1 = 0., t2 = 0.;
-              if (ok)
-                {
-                  t0 = contract(Mh, sW[slot][0], 2);
-                  t1 = contract(Mh, sW[slot][1], 2);
-                  t2 = st[2] + (vol_on && A.mass != 0. ? A.mass * vol * contract(Mh, sU[slot], 2) : 0.);
-                }
-              group_sync();
-              if (ok)
-                {
-                  sW[slot][2][l] = t0;
-                  sW[slot][3][l] = t2;
-                }
-              group_sync();
-              double t4 = 0.;
-              if (ok)
-                {
-                  acc = contract(Mh, sW[slot][2], 1);
-                  t4  = t1 + contract(Mh, sW[slot][3], 1);
-                }
-              group_sync();
-              if (ok)
-                sW[slot][0][l] = t4;
-              group_sync();
-              if (ok)
-                acc += contract(Mh, sW[slot][0], 0);
+#pragma unroll
+              for (int i = 0; i < N1; ++i)
+                wd[off[i]] = out[i];
             }
-          else
+          group_sync();
+          // ---- masses along the other directions, in place, one line per thread
+#pragma unroll
+          for (int k = 1; k < DIM; ++k)
             {
-              if (ok)
-                sW[slot][0][l] = st[0];
-              group_sync();
-              double t1 = 0.;
-              if (ok)
+              if (task_ok)
                 {
-                  acc = contract(Mh, sW[slot][0], 1);
-                  t1  = st[1] + (vol_on && A.mass != 0. ? A.mass * vol * contract(Mh, sU[slot], 1) : 0.);
-                  sW[slot][1][l] = t1;
+                  double v[N1];
+#pragma unroll
+                  for (int t = 0; t < N1; ++t)
+                    v[t] = wd[offk[k - 1][t]];
+#pragma unroll
+                  for (int i = 0; i < N1; ++i)
+                    {
+                      double sm = 0.;
+#pragma unroll
+                      for (int t = 0; t < N1; ++t)
+                        sm += A.T.Mh[i * N1 + t] * v[t];
+                      wd[offk[k - 1][i]] = sm;
+                    }
                 }
               group_sync();
-              if (ok)
-                acc += contract(Mh, sW[slot][1], 0);
             }
-          if (ok)
+          if (cell_ok && l < N)
             {
+              double acc = 0.;
+#pragma unroll
+              for (int dd = 0; dd < DIM; ++dd)
+                acc += sW[slot][dd][l];
               double *yp = A.y + (int64_t)cell * N + l;
               *yp        = A.add ? *yp + acc : acc;
             }
@@ -343,10 +380,34 @@ namespace pd
     for (char s : seen)
       if (!s)
         return; // a cell face without an interface entry: not a conforming singleton mesh
-    // 1-D tables
-    const int           n1 = h->n1;
-    std::vector<double> tab(3 * n1 * n1 + 4 * n1, 0.), L(n1), dL(n1);
-    double             *Mh = tab.data(), *Sh = Mh + n1 * n1, *Mf = Sh + n1 * n1, *e0 = Mf + n1 * n1, *d0 = e0 + 2 * n1;
+    // the per-(cell, direction) stencil records
+    std::vector<double> rec((size_t)h->np_own * dim * 6), vol((size_t)h->np_own);
+    for (int32_t c = 0; c < h->np_own; ++c)
+      {
+        double v = 1.;
+        for (int k = 0; k < dim; ++k)
+          v *= cell_h[(size_t)c * dim + k];
+        vol[c] = v;
+        for (int k = 0; k < dim; ++k)
+          {
+            FineGeo      r;
+            const double hk = cell_h[(size_t)c * dim + k], a = v / hk;
+            r.cV = a / hk;
+            for (int s = 0; s < 2; ++s)
+              {
+                const int32_t nb = nbr[(size_t)c * nfc + 2 * k + s];
+                r.nb[s]          = nb;
+                r.P[s]           = a * sigma[(size_t)c * nfc + 2 * k + s];
+                r.Q[s]           = nb >= 0 ? 0.5 * a / cell_h[(size_t)nb * dim + k] : 0.;
+              }
+            std::memcpy(rec.data() + ((size_t)c * dim + k) * 6, &r, sizeof r);
+          }
+      }
+    // 1-D tables: Mh, Sh, e0|e1, d0|d1
+    const int n1 = h->n1;
+    h->mf_tab_host.assign(2 * n1 * n1 + 4 * n1, 0.);
+    std::vector<double> L(n1), dL(n1);
+    double             *Mh = h->mf_tab_host.data(), *Sh = Mh + n1 * n1, *e0 = Sh + n1 * n1, *d0 = e0 + 2 * n1;
     for (int q = 0; q < h->nq1; ++q)
       {
         lagrange_host(h->basis, n1, h->quad.x[q], L.data(), dL.data());
@@ -357,23 +418,18 @@ namespace pd
               Sh[i * n1 + j] += h->quad.w[q] * dL[i] * dL[j];
             }
       }
-    for (int q = 0; q < h->nq1f; ++q)
-      {
-        lagrange_host(h->basis, n1, h->quadf.x[q], L.data(), dL.data());
-        for (int i = 0; i < n1; ++i)
-          for (int j = 0; j < n1; ++j)
-            Mf[i * n1 + j] += h->quadf.w[q] * L[i] * L[j];
-      }
     lagrange_host(h->basis, n1, 0., e0, d0);
     lagrange_host(h->basis, n1, 1., e0 + n1, d0 + n1);
     auto put = [](auto &buf, const auto &v) {
       buf.alloc(v.size());
       PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
     };
-    put(h->mf_tables, tab);
-    put(h->mf_cell_h, cell_h);
-    put(h->mf_nbr, nbr);
-    put(h->mf_sigma, sigma);
+    put(h->mf_geo, rec);
+    put(h->mf_vol, vol);
+    h->mf_rec.alloc((size_t)h->np_own * dim * 8);
+    h->mf_zero.alloc((size_t)h->n);
+    PD_CUDA(cudaMemset(h->mf_zero.p, 0, (size_t)h->n * sizeof(double)));
+    h->mf_rec_valid = false;
     h->mf_ready = true;
   }
 
@@ -383,37 +439,55 @@ namespace pd
     return (dim == 2 && degree >= 1 && degree <= 4) || (dim == 3 && degree >= 1 && degree <= 3);
   }
 
+  namespace
+  {
+    template <int DIM, int DEG, int MINB>
+    void
+    launch_fine(pd_handle *h, const double *src, double *dst, const bool add)
+    {
+      constexpr int N1 = DEG + 1, N = ipow_(N1, DIM), NT = DIM * (N / N1);
+      constexpr int GS = pow2_at_least(N > NT ? N : NT), CPB = 256 / GS;
+      FineArgs<N1>  a;
+      static_assert(sizeof(a.T) == (2 * N1 * N1 + 4 * N1) * sizeof(double), "table layout");
+      std::memcpy(&a.T, h->mf_tab_host.data(), sizeof(a.T));
+      const bool vol_on = (h->op_flags & PD_ASSEMBLE_VOLUME) != 0;
+      if (!h->mf_rec_valid || h->mf_rec_flags != h->op_flags || h->mf_rec_coef != h->op_coef.stiffness)
+        {
+          const int64_t n = (int64_t)h->np_own * DIM;
+          k_fine_fold<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<const FineGeo *>(h->mf_geo.p),
+                                                                        reinterpret_cast<FineRec *>(h->mf_rec.p), n,
+                                                                        h->op_coef.stiffness, h->op_flags);
+          h->mf_rec_valid = true;
+          h->mf_rec_flags = h->op_flags;
+          h->mf_rec_coef  = h->op_coef.stiffness;
+          ++h->launches;
+        }
+      a.rec      = reinterpret_cast<const FineRec *>(h->mf_rec.p);
+      a.vol      = h->mf_vol.p;
+      a.zero     = h->mf_zero.p;
+      a.x        = src;
+      a.y        = dst;
+      a.n_cells  = h->np_own;
+      a.mass     = vol_on ? h->op_coef.mass : 0.;
+      a.add      = add ? 1 : 0;
+      const int64_t want = ((int64_t)h->np_own + CPB - 1) / CPB;
+      const int     grid = (int)std::min<int64_t>(want, (int64_t)h->sm_count * 4 * MINB);
+      k_fine_sip<DIM, DEG, MINB><<<grid, 256, 0, h->stream>>>(a);
+    }
+  } // namespace
+
   void
   launch_fine_operator(pd_handle *h, const double *src, double *dst, const bool add)
   {
-    FineArgs a;
-    a.tables    = h->mf_tables.p;
-    a.cell_h    = h->mf_cell_h.p;
-    a.nbr       = h->mf_nbr.p;
-    a.sigma     = h->mf_sigma.p;
-    a.x         = src;
-    a.y         = dst;
-    a.n_cells   = h->np_own;
-    a.stiffness = h->op_coef.stiffness;
-    a.mass      = h->op_coef.mass;
-    a.flags     = h->op_flags;
-    a.add       = add ? 1 : 0;
-    const int key = h->dim * 10 + h->degree;
-    auto      go  = [&](auto kern, const int gs) {
-      const int     cpb  = 256 / gs;
-      const int64_t want = ((int64_t)h->np_own + cpb - 1) / cpb;
-      const int     grid = (int)std::min<int64_t>(want, (int64_t)h->sm_count * 16);
-      kern<<<grid, 256, 0, h->stream>>>(a);
-    };
-    switch (key)
+    switch (h->dim * 10 + h->degree)
       {
-        case 21: go(k_fine_sip<2, 1>, 4); break;
-        case 22: go(k_fine_sip<2, 2>, 16); break;
-        case 23: go(k_fine_sip<2, 3>, 16); break;
-        case 24: go(k_fine_sip<2, 4>, 32); break;
-        case 31: go(k_fine_sip<3, 1>, 8); break;
-        case 32: go(k_fine_sip<3, 2>, 32); break;
-        case 33: go(k_fine_sip<3, 3>, 64); break;
+        case 21: launch_fine<2, 1, 4>(h, src, dst, add); break;
+        case 22: launch_fine<2, 2, 3>(h, src, dst, add); break;
+        case 23: launch_fine<2, 3, 3>(h, src, dst, add); break;
+        case 24: launch_fine<2, 4, 2>(h, src, dst, add); break;
+        case 31: launch_fine<3, 1, 4>(h, src, dst, add); break;
+        case 32: launch_fine<3, 2, 3>(h, src, dst, add); break;
+        case 33: launch_fine<3, 3, 2>(h, src, dst, add); break;
         default:
           throw CudaError{cudaErrorNotSupported, "no fine-mesh operator kernel for this (dim, degree)", __LINE__};
       }

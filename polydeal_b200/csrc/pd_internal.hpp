@@ -108,8 +108,11 @@ struct pd_handle
   pd::DevBuf<double> vec_a, vec_b; // staging for pd_vmult_host
   // matrix-free fine-mesh operator (every polytope = one Cartesian cell), pd_finemesh.cu
   bool                mf_ready = false, force_generic_mf = false;
-  pd::DevBuf<double>  mf_tables, mf_cell_h, mf_sigma;
-  pd::DevBuf<int32_t> mf_nbr;
+  pd::DevBuf<double>  mf_geo, mf_rec, mf_vol, mf_zero; // per (cell, direction) geometry / folded stencil records, cell volumes (pd_finemesh.cu)
+  bool                mf_rec_valid = false;
+  uint32_t            mf_rec_flags = 0;
+  double              mf_rec_coef  = 0.;
+  std::vector<double> mf_tab_host;    // 1-D tables Mh, Sh, e0|e1, d0|d1 (passed as kernel parameters)
   pd::DevBuf<double>  mf_vol_partial, mf_face_partial; // polytopal matrix-free apply (pd_polyapply.cu)
   pd_coefficients     op_coef{1.0, 0.0}; // operator of the matrix-free apply
   uint32_t            op_flags = PD_ASSEMBLE_ALL;
