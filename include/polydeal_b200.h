@@ -126,6 +126,7 @@ typedef struct pd_coefficients
 /* vmult modes */
 #define PD_VMULT_BLOCK_CSR 0   /* y = A x with the assembled matrix */
 #define PD_VMULT_MATRIX_FREE 1 /* y = A x recomputed from the quadrature data           */
+#define PD_VMULT_MAPPED_FINE 2 /* fine mesh of general hexes, mapped FE_DGQ basis (below)  */
 
 /* Create the device-resident copy.  Replaces the state built by
  * AgglomerationHandler::define_agglomerate / distribute_agglomerated_dofs /
@@ -188,6 +189,17 @@ int pd_set_operator(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
  * pd_force_generic_matrix_free(h, 1) selects the second kernel on fine meshes too (testing). */
 int pd_matrix_free_available(const pd_handle *h);
 int pd_force_generic_matrix_free(pd_handle *h, int on);
+/* PD_VMULT_MAPPED_FINE: the reference's fine-mesh MatrixFree operators on GENERAL (Q1-mapped,
+ * distorted) cells -- LaplaceOperatorDG / MonodomainOperatorDG with the standard mapped
+ * FE_DGQ(p) basis, n_q_points_1d = p+1 and the penalty of include/utils.h:861-866, 906-909
+ * (max(p,1)(p+1) (|n J_m^-1| + |n J_p^-1|) at face point 0; 4 max(p,1)(p+1) |n J^-1| on the
+ * boundary), computed here from the cell vertices: the descriptor's sub_sigma / bbox are NOT
+ * used, and on distorted cells this is a different operator from the bounding-box-basis one
+ * that pd_assemble / PD_VMULT_MATRIX_FREE apply (they coincide on Cartesian cells with the
+ * normal-extent penalty rule).  Terms and coefficients come from pd_set_operator.
+ * Available (== 1) when every polytope is one cell, the handle has no ghost polytopes, the
+ * cell and face rules are QGauss(p+1) and neighbouring cells are in standard orientation. */
+int pd_mapped_fine_available(const pd_handle *h);
 int pd_vmult_add(pd_handle *h, int mode, const double *src_dev, double *dst_dev);
 /* same with HOST buffers (pinned or pageable): H2D, apply, D2H */
 int pd_vmult_host(pd_handle *h, int mode, const double *src_host, double *dst_host);

@@ -1369,4 +1369,197 @@ namespace po
           t.join();
       }
   }
+  // ---------------------------------------------------------------------------
+  // Fine-mesh (non-agglomerated) SIP operator with the standard MAPPED FE_DGQ(p)
+  // basis, phi_i(x) = phihat_i(F_K^{-1}(x)), F_K the Q1 map of the cell:
+  //   y = (mass M + stiffness K_SIP) x
+  // Restates the matrix-based assembly of /root/reference/examples/monodomain_DG3D.cc:1374-1622
+  // (cell term :1408-1449; interior faces visited from the smaller active-cell index
+  // :1459-1460, M11/M12/M21/M22 :1514-1575; penalty = pc (|J0^{-1}[nd0] . n| + |J1^{-1}[nd1] . n|)
+  // at face quadrature point 0, :1470-1498, which the reference documents as the emulation of
+  // the matrix-free sigmaF of include/utils.h:861-866) applied to a vector, plus the boundary
+  // term of LaplaceOperatorDG::local_apply_boundary (include/utils.h:895-925):
+  //   (4 pc |J^{-1}[nd] . n| u - dn u) v - u dn v,   pc = max(p,1)(p+1).
+  // DoFs: n per cell in active-cell order.  Neighbouring cells are assumed to be in standard
+  // orientation (opposite local face, aligned tangential axes); checked point by point.
+  // PARITY UNPINNED: no reference test fixes numbers for this operator.
+  // ---------------------------------------------------------------------------
+  inline void
+  mapped_fine_vmult(const Grid   &g,
+                    const int     degree,
+                    const int     nq,
+                    const double  stiffness,
+                    const double  mass,
+                    const bool    with_volume,
+                    const bool    with_boundary,
+                    const bool    with_interior,
+                    const double *x,
+                    double       *y)
+  {
+    const int     dim = g.dim;
+    FiniteElement fe;
+    fe.init(FE_DGQ, dim, degree);
+    const int n = fe.n_dofs;
+    Quad1D    q;
+    gauss_1d(nq, q.x, q.w);
+    const double pc = std::max(degree, 1) * (degree + 1.0);
+    std::fill(y, y + (size_t)g.n_cells() * n, 0.);
+
+    // basis of `cell` at reference point xi: values, physical gradients, J^{-1}
+    std::vector<double> gh(n * dim);
+    auto eval = [&](const int cell, const double *xi, double *val, double *grad, double *Jinv, double *xr) {
+      double J[9];
+      q1_map(g, cell, xi, xr, J);
+      const double dt = det(dim, J);
+      if (dim == 2)
+        {
+          Jinv[0] = J[3] / dt;
+          Jinv[1] = -J[1] / dt;
+          Jinv[2] = -J[2] / dt;
+          Jinv[3] = J[0] / dt;
+        }
+      else
+        {
+          Jinv[0] = (J[4] * J[8] - J[5] * J[7]) / dt;
+          Jinv[1] = (J[2] * J[7] - J[1] * J[8]) / dt;
+          Jinv[2] = (J[1] * J[5] - J[2] * J[4]) / dt;
+          Jinv[3] = (J[5] * J[6] - J[3] * J[8]) / dt;
+          Jinv[4] = (J[0] * J[8] - J[2] * J[6]) / dt;
+          Jinv[5] = (J[2] * J[3] - J[0] * J[5]) / dt;
+          Jinv[6] = (J[3] * J[7] - J[4] * J[6]) / dt;
+          Jinv[7] = (J[1] * J[6] - J[0] * J[7]) / dt;
+          Jinv[8] = (J[0] * J[4] - J[1] * J[3]) / dt;
+        }
+      fe.evaluate(xi, val, gh.data());
+      // grad phi = J^{-T} gradhat phi :  (d/dx_a) = sum_b (dxi_b/dx_a) d/dxi_b = sum_b Jinv[b][a] ...
+      for (int i = 0; i < n; ++i)
+        for (int a = 0; a < dim; ++a)
+          {
+            double s = 0.;
+            for (int b = 0; b < dim; ++b)
+              s += Jinv[b * dim + a] * gh[i * dim + b];
+            grad[i * dim + a] = s;
+          }
+      return dt;
+    };
+
+    std::vector<double> v0(n), g0(n * dim), v1(n), g1(n * dim);
+    const int           nz = dim == 3 ? nq : 1;
+    for (int c = 0; c < g.n_cells(); ++c)
+      {
+        const double *xc = x + (size_t)c * n;
+        double       *yc = y + (size_t)c * n;
+        if (with_volume)
+          for (int kz = 0; kz < nz; ++kz)
+            for (int ky = 0; ky < nq; ++ky)
+              for (int kx = 0; kx < nq; ++kx)
+                {
+                  const double xi[3] = {q.x[kx], q.x[ky], dim == 3 ? q.x[kz] : 0.};
+                  double       Ji[9], xr[3];
+                  const double dt  = eval(c, xi, v0.data(), g0.data(), Ji, xr);
+                  const double jxw = q.w[kx] * q.w[ky] * (dim == 3 ? q.w[kz] : 1.) * dt;
+                  double       u = 0., gu[3] = {0, 0, 0};
+                  for (int j = 0; j < n; ++j)
+                    {
+                      u += v0[j] * xc[j];
+                      for (int a = 0; a < dim; ++a)
+                        gu[a] += g0[j * dim + a] * xc[j];
+                    }
+                  for (int i = 0; i < n; ++i)
+                    {
+                      double s = 0.;
+                      for (int a = 0; a < dim; ++a)
+                        s += g0[i * dim + a] * gu[a];
+                      yc[i] += (stiffness * s + mass * v0[i] * u) * jxw;
+                    }
+                }
+        for (int f = 0; f < 2 * dim; ++f)
+          {
+            const int nbc = g.neighbor(c, f);
+            if (nbc >= 0 && !(with_interior && c < nbc))
+              continue;
+            if (nbc < 0 && !with_boundary)
+              continue;
+            std::vector<double> pts, jxw, nrm;
+            face_quadrature(g, c, f, q, pts, jxw, nrm);
+            const int    nd = f / 2, nqf = (int)jxw.size();
+            const double side = (f % 2) ? 1. : 0.;
+            int          t0, t1 = -1;
+            if (dim == 2)
+              t0 = 1 - nd;
+            else
+              {
+                t0 = (nd + 1) % 3;
+                t1 = (nd + 2) % 3;
+              }
+            double        pen = 0.;
+            const double *xn  = nbc >= 0 ? x + (size_t)nbc * n : nullptr;
+            double       *yn  = nbc >= 0 ? y + (size_t)nbc * n : nullptr;
+            for (int k = 0; k < nqf; ++k)
+              {
+                double xi[3] = {0, 0, 0}, xo[3] = {0, 0, 0};
+                xi[nd]       = side;
+                xi[t0]       = q.x[k % nq];
+                if (dim == 3)
+                  xi[t1] = q.x[k / nq];
+                for (int a = 0; a < 3; ++a)
+                  xo[a] = xi[a];
+                xo[nd] = 1. - side;
+                double        J0i[9], J1i[9], xr0[3], xr1[3];
+                const double *nv = nrm.data() + (size_t)k * dim;
+                eval(c, xi, v0.data(), g0.data(), J0i, xr0);
+                if (nbc >= 0)
+                  {
+                    eval(nbc, xo, v1.data(), g1.data(), J1i, xr1);
+                    for (int a = 0; a < dim; ++a)
+                      if (std::fabs(xr0[a] - xr1[a]) > 1e-12 * (1. + std::fabs(xr0[a])))
+                        throw std::runtime_error("mapped_fine_vmult: neighbouring cells are not in standard orientation");
+                  }
+                if (k == 0)
+                  {
+                    double h0 = 0., h1 = 0.;
+                    for (int a = 0; a < dim; ++a)
+                      {
+                        h0 += J0i[nd * dim + a] * nv[a];
+                        if (nbc >= 0)
+                          h1 += J1i[nd * dim + a] * nv[a];
+                      }
+                    pen = nbc >= 0 ? pc * (std::fabs(h0) + std::fabs(h1)) : 4. * pc * std::fabs(h0);
+                  }
+                double u0 = 0., u1 = 0., dn0 = 0., dn1 = 0.;
+                for (int j = 0; j < n; ++j)
+                  {
+                    u0 += v0[j] * xc[j];
+                    for (int a = 0; a < dim; ++a)
+                      dn0 += g0[j * dim + a] * nv[a] * xc[j];
+                    if (nbc >= 0)
+                      {
+                        u1 += v1[j] * xn[j];
+                        for (int a = 0; a < dim; ++a)
+                          dn1 += g1[j * dim + a] * nv[a] * xn[j];
+                      }
+                  }
+                const double w = stiffness * jxw[k];
+                for (int i = 0; i < n; ++i)
+                  {
+                    double gn0 = 0., gn1 = 0.;
+                    for (int a = 0; a < dim; ++a)
+                      {
+                        gn0 += g0[i * dim + a] * nv[a];
+                        if (nbc >= 0)
+                          gn1 += g1[i * dim + a] * nv[a];
+                      }
+                    if (nbc >= 0)
+                      {
+                        // rows of M11 x0 + M12 x1 and of M21 x0 + M22 x1
+                        yc[i] += w * (-0.5 * gn0 * (u0 - u1) - 0.5 * (dn0 + dn1) * v0[i] + pen * v0[i] * (u0 - u1));
+                        yn[i] += w * (-0.5 * gn1 * (u0 - u1) + 0.5 * (dn0 + dn1) * v1[i] - pen * v1[i] * (u0 - u1));
+                      }
+                    else
+                      yc[i] += w * ((pen * u0 - dn0) * v0[i] - u0 * gn0);
+                  }
+              }
+          }
+      }
+  }
 } // namespace po

@@ -386,4 +386,13 @@ extern "C"
   {
     spmv(static_cast<Matrix *>(M)->A, x, y, n_threads);
   }
+  int
+  po_mapped_fine_vmult(void *g, int degree, int nq, double stiffness, double mass, int with_volume, int with_boundary,
+                       int with_interior, const double *x, double *y)
+  {
+    return guard([&] {
+      mapped_fine_vmult(*static_cast<Grid *>(g), degree, nq, stiffness, mass, with_volume != 0, with_boundary != 0,
+                        with_interior != 0, x, y);
+    });
+  }
 }

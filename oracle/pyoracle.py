@@ -104,6 +104,7 @@ def lib():
             "po_matrix_nnz": (i64, [vp]),
             "po_matrix_copy": (None, [vp, P(i64), P(i32), P(f64)]),
             "po_matrix_vmult": (None, [vp, P(f64), P(f64), i32]),
+            "po_mapped_fine_vmult": (i32, [vp, i32, i32, f64, f64, i32, i32, i32, P(f64), P(f64)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -386,3 +387,15 @@ def assemble_dg_matrix(
     if not h:
         raise RuntimeError(_err())
     return Matrix(h, sec.value)
+
+
+def mapped_fine_vmult(grid: Grid, degree, nq, x, stiffness=1.0, mass=0.0, volume=True, boundary=True, interior=True):
+    """y = (mass M + stiffness K_SIP) x of the fine-mesh operator with the mapped FE_DGQ basis
+    (LaplaceOperatorDG / MonodomainOperatorDG semantics, include/utils.h:819-925, 1565-1659;
+    matrix-based twin examples/monodomain_DG3D.cc:1374-1622)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    if lib().po_mapped_fine_vmult(grid.h, degree, nq, stiffness, mass, int(volume), int(boundary), int(interior),
+                                  _p(x, C.c_double), _p(y, C.c_double)) != 0:
+        raise RuntimeError(_err())
+    return y

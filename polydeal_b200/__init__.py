@@ -9,7 +9,7 @@ library or a GPU is missing.
 from . import _capi
 from ._capi import (ASSEMBLE_ALL, ASSEMBLE_BOUNDARY, ASSEMBLE_INTERIOR, ASSEMBLE_VOLUME, H_CONSTANT,
                     H_DIAMETER_OF_VISITOR, H_MAX_INVERSE_DIAMETER, H_NORMAL_EXTENT, INVALID_UINT, VISIT_BY_ID,
-                    VISIT_BY_INDEX, VMULT_BLOCK_CSR, VMULT_MATRIX_FREE, PolydealError)
+                    VISIT_BY_INDEX, VMULT_BLOCK_CSR, VMULT_MATRIX_FREE, VMULT_MAPPED_FINE, PolydealError)
 from .handler import AgglomerationHandler, Grid, SIPOperator, assemble_dg_matrix
 
 FE_DGQ = 0
@@ -18,5 +18,5 @@ __all__ = [
     "AgglomerationHandler", "Grid", "SIPOperator", "assemble_dg_matrix", "PolydealError", "FE_DGQ",
     "ASSEMBLE_ALL", "ASSEMBLE_BOUNDARY", "ASSEMBLE_INTERIOR", "ASSEMBLE_VOLUME",
     "H_CONSTANT", "H_DIAMETER_OF_VISITOR", "H_MAX_INVERSE_DIAMETER", "H_NORMAL_EXTENT",
-    "VISIT_BY_ID", "VISIT_BY_INDEX", "VMULT_BLOCK_CSR", "VMULT_MATRIX_FREE", "INVALID_UINT",
+    "VISIT_BY_ID", "VISIT_BY_INDEX", "VMULT_BLOCK_CSR", "VMULT_MATRIX_FREE", "VMULT_MAPPED_FINE", "INVALID_UINT",
 ]

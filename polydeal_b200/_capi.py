@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpolydeal_b200.so")
 PD_OK, PD_ERR_INVALID, PD_ERR_CUDA, PD_ERR_UNSUPPORTED, PD_ERR_NO_DEVICE, PD_ERR_STATE = 0, -1, -2, -3, -4, -5
 INVALID_UINT = 0xFFFFFFFF
 ASSEMBLE_VOLUME, ASSEMBLE_BOUNDARY, ASSEMBLE_INTERIOR, ASSEMBLE_ALL = 1, 2, 4, 7
-VMULT_BLOCK_CSR, VMULT_MATRIX_FREE = 0, 1
+VMULT_BLOCK_CSR, VMULT_MATRIX_FREE, VMULT_MAPPED_FINE = 0, 1, 2
 H_DIAMETER_OF_VISITOR, H_MAX_INVERSE_DIAMETER, H_CONSTANT, H_NORMAL_EXTENT = 0, 1, 2, 3
 VISIT_BY_ID, VISIT_BY_INDEX = 0, 1
 
@@ -68,6 +68,7 @@ SIGNATURES = {
     "pd_set_operator": (C.c_int, [vp, u32, P(Coefficients)]),
     "pd_matrix_free_available": (C.c_int, [vp]),
     "pd_force_generic_matrix_free": (C.c_int, [vp, C.c_int]),
+    "pd_mapped_fine_available": (C.c_int, [vp]),
     "pd_vmult_add": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_vmult_host": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_diagonal_inverse": (C.c_int, [vp, vp]),

@@ -434,6 +434,7 @@ namespace pd
         // (ensure_assembly_buffers): a handle used only for the matrix-free apply never
         // pays for them
         setup_fine_operator(h, d);
+        setup_mapped_operator(h, d);
         PD_CUDA(cudaStreamSynchronize(h->stream));
       }
     catch (...)
@@ -689,6 +690,14 @@ extern "C"
             launch_poly_apply(h, src, dst, add);
           }
       }
+    else if (mode == PD_VMULT_MAPPED_FINE)
+      {
+        if (!h->mp_ready)
+          throw Error(PD_ERR_STATE,
+                      "pd_vmult(MAPPED_FINE): needs one cell per polytope, no ghosts, QGauss(p+1) on cells and faces "
+                      "and neighbouring cells in standard orientation");
+        launch_mapped_operator(h, src, dst, add);
+      }
     else
       throw Error(PD_ERR_INVALID, "pd_vmult: unknown mode");
   }
@@ -708,6 +717,12 @@ extern "C"
   pd_matrix_free_available(const pd_handle *h)
   {
     return h && h->mf_ready ? 1 : 0;
+  }
+
+  int
+  pd_mapped_fine_available(const pd_handle *h)
+  {
+    return h && h->mp_ready ? 1 : 0;
   }
 
   int

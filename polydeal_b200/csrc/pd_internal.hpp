@@ -113,6 +113,11 @@ struct pd_handle
   uint32_t            mf_rec_flags = 0;
   double              mf_rec_coef  = 0.;
   std::vector<double> mf_tab_host;    // 1-D tables Mh, Sh, e0|e1, d0|d1 (passed as kernel parameters)
+  // matrix-free fine-mesh operator on general (Q1-mapped) cells with the mapped basis, pd_mappedfine.cu
+  bool                mp_ready = false, mp_geo_valid = false;
+  std::vector<double> mp_tab_host; // V | V^T | Dt | e0 e1 | d0 d1
+  pd::DevBuf<int32_t> mp_cellv, mp_nbr;
+  pd::DevBuf<double>  mp_dt, mp_cgeo, mp_fgeo, mp_sigma, mp_xg, mp_yg, mp_zero;
   pd::DevBuf<double>  mf_vol_partial, mf_face_partial; // polytopal matrix-free apply (pd_polyapply.cu)
   pd_coefficients     op_coef{1.0, 0.0}; // operator of the matrix-free apply
   uint32_t            op_flags = PD_ASSEMBLE_ALL;
@@ -146,6 +151,9 @@ namespace pd
   // pd_finemesh.cu
   void setup_fine_operator(pd_handle *h, const pd_mesh_desc &d);
   void launch_fine_operator(pd_handle *h, const double *src, double *dst, bool add);
+  // pd_mappedfine.cu
+  void setup_mapped_operator(pd_handle *h, const pd_mesh_desc &d);
+  void launch_mapped_operator(pd_handle *h, const double *src, double *dst, bool add);
   // pd_polyapply.cu
   void launch_poly_apply(pd_handle *h, const double *src, double *dst, bool add);
   // pd_solver.cu

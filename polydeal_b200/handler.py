@@ -75,6 +75,32 @@ class Grid:
         assert verts.shape == (self.n_verts, self.dim)
         K.check(K.lib().pdh_grid_set_vertices(self._h, _ptr(verts)))
 
+    def distort_random(self, factor, seed):
+        """GridTools::distort_random(factor, tria, keep_boundary = true): every interior vertex
+        moves by a uniform random vector of at most factor * (shortest incident edge) per
+        coordinate.  (numpy's PCG64 stream: like deal.II's own boost RNG, not reproducible
+        elsewhere; distorted-mesh checks are therefore made on the same vertex array.)"""
+        v, cv, nb = self.arrays()
+        dim, vpc = self.dim, 1 << self.dim
+        minlen = np.full(self.n_verts, np.inf)
+        for d in range(dim):
+            for a in range(vpc):
+                b = a ^ (1 << d)
+                if b < a:
+                    continue
+                ln = np.linalg.norm(v[cv[:, a]] - v[cv[:, b]], axis=1)
+                np.minimum.at(minlen, cv[:, a], ln)
+                np.minimum.at(minlen, cv[:, b], ln)
+        on_boundary = np.zeros(self.n_verts, dtype=bool)
+        for f in range(2 * dim):
+            cells = np.nonzero(nb[:, f] < 0)[0]
+            for a in range(vpc):
+                if ((a >> (f // 2)) & 1) == f % 2:
+                    on_boundary[cv[cells, a]] = True
+        u = np.random.default_rng(seed).uniform(-1.0, 1.0, size=v.shape)
+        v[~on_boundary] += (u * (factor * minlen)[:, None])[~on_boundary]
+        self.set_vertices(v)
+
 
 class AgglomerationHandler:
     def __init__(self, grid: Grid):
@@ -233,6 +259,11 @@ class SIPOperator:
     @property
     def matrix_free_available(self):
         return bool(K.lib().pd_matrix_free_available(self._h))
+
+    @property
+    def mapped_fine_available(self):
+        """VMULT_MAPPED_FINE (mapped FE_DGQ basis on general hexes) can be applied."""
+        return bool(K.lib().pd_mapped_fine_available(self._h))
 
     def m(self):
         return K.lib().pd_n_dofs(self._h)

@@ -326,6 +326,67 @@ def test_fine_mesh_matrix_free_vmult(dim, n, p, order, hi, kw):
     assert np.abs(yb.cpu().numpy() - yref).max() <= TOL * scale
 
 
+@pytest.mark.parametrize("dim,n,p,order,distort,kw", [
+    (2, 8, 1, 0, (0.25, 11), {}),
+    (2, 6, 2, 1, (0.2, 5), dict(stiffness=1.3, mass=0.7)),
+    (2, 5, 3, 1, (0.2, 7), {}),
+    (2, 4, 4, 0, (0.15, 2), dict(boundary=False)),
+    (3, 4, 1, 0, (0.2, 20251018), dict(stiffness=1e-4, mass=1.5e4, boundary=False)),  # monodomain, config E
+    (3, 4, 2, 0, (0.2, 20251018), {}),
+    (3, 3, 2, 1, (0.25, 1), dict(interior=False)),
+    (3, 3, 3, 1, (0.2, 9), dict(mass=2.0)),
+    (3, 4, 2, 0, None, {}),  # Cartesian: also equals the stencil kernel
+])
+def test_mapped_fine_mesh_vmult(dim, n, p, order, distort, kw):
+    """PD_VMULT_MAPPED_FINE: LaplaceOperatorDG / MonodomainOperatorDG semantics with the mapped
+    FE_DGQ basis on distorted cells (include/utils.h:819-925, 1565-1659); checker: the oracle's
+    restatement of the matrix-based twin (examples/monodomain_DG3D.cc:1374-1622)."""
+    pdl = gpu()
+    import torch
+
+    ogrid = po.Grid(dim, n, 0.0, 1.0, order)
+    if distort:
+        ogrid.distort_random(*distort)
+    groups = [[c] for c in range(ogrid.n_cells)]
+    _, pah = product_handler(ogrid, groups, p, p + 1)
+    op = pdl.SIPOperator(pah.flatten(penalty_constant=max(p, 1) * (p + 1.0), h_rule=pdl.H_NORMAL_EXTENT), keepalive=pah)
+    assert op.mapped_fine_available
+    flags = pdl.ASSEMBLE_VOLUME
+    if kw.get("boundary", True):
+        flags |= pdl.ASSEMBLE_BOUNDARY
+    if kw.get("interior", True):
+        flags |= pdl.ASSEMBLE_INTERIOR
+    op.set_operator(flags, kw.get("stiffness", 1.0), kw.get("mass", 0.0))
+    x = src_vector(op.m())
+    yref = po.mapped_fine_vmult(ogrid, p, p + 1, x, **kw)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros_like(xd)
+    op.vmult(yd, xd, mode=pdl.VMULT_MAPPED_FINE)
+    op.synchronize()
+    scale = np.abs(yref).max()
+    assert np.abs(yd.cpu().numpy() - yref).max() <= TOL * scale
+    op.vmult_add(yd, xd, mode=pdl.VMULT_MAPPED_FINE)
+    op.synchronize()
+    assert np.abs(yd.cpu().numpy() - 2 * yref).max() <= 2 * TOL * scale
+    if distort is None:
+        ys = torch.empty_like(xd)
+        op.vmult(ys, xd, mode=pdl.VMULT_MATRIX_FREE)
+        op.synchronize()
+        assert np.abs(ys.cpu().numpy() - yref).max() <= TOL * scale
+
+
+def test_mapped_fine_mesh_unavailable_on_agglomerates():
+    pdl = gpu()
+    import torch
+
+    oah, pah = both(2, 8, "blocks2", 1, nq=2)
+    op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+    assert not op.mapped_fine_available
+    x = torch.zeros(op.m(), dtype=torch.float64, device="cuda")
+    with pytest.raises(pdl.PolydealError):
+        op.vmult(torch.empty_like(x), x, mode=pdl.VMULT_MAPPED_FINE)
+
+
 @pytest.mark.parametrize("dim,n,shape,p,nq,distort,kw", [
     (2, 16, "blocks4", 1, 2, None, {}),
     (2, 8, "random5", 2, 3, (0.2, 3), {}),

@@ -8,6 +8,7 @@ import scipy.sparse.linalg as spla
 
 import pd_scenarios as sc
 from oracle import pyoracle as po
+from pd_helpers import oracle_handler, src_vector
 
 
 def handler(dim, n_refine, groups, p, nq, lo=-1.0, hi=1.0, distort=None, fe_kind=po.FE_DGQ):
@@ -226,3 +227,35 @@ def test_poisson_golden_l2_error(goldens):
     b, l2_error = poisson_rhs_and_error(grid, ah)
     u = spla.spsolve(A, b)
     assert l2_error(u) == pytest.approx(goldens["poisson"][0], abs=5e-9)  # golden printed with 6 digits
+
+
+@pytest.mark.parametrize("dim,n,p", [(2, 4, 1), (2, 4, 2), (2, 3, 3), (3, 2, 1), (3, 3, 2)])
+def test_mapped_fine_operator_equals_polytope_assembly_on_cartesian_cells(dim, n, p):
+    """The oracle's mapped-basis fine-mesh operator (unpinned by reference tests) against the
+    pinned polytope assembly: on Cartesian cells with one cell per polytope and the
+    normal-extent penalty max(p,1)(p+1)(1/h_m + 1/h_p) they are the same matrix."""
+    grid, ah = oracle_handler(dim, n, [[c] for c in range(n**dim)], p, p + 1, order=1)
+    x = src_vector(ah.n_dofs)
+    pc = max(p, 1) * (p + 1.0)
+    y = po.mapped_fine_vmult(grid, p, p + 1, x, stiffness=1.3, mass=0.7)
+    M = po.assemble_dg_matrix(ah, penalty_constant=pc, h_rule=po.H_NORMAL_EXTENT, stiffness_coeff=1.3, mass_coeff=0.7)
+    y2 = M.vmult(x)
+    assert np.abs(y - y2).max() <= 1e-13 * np.abs(y2).max()
+
+
+@pytest.mark.parametrize("dim,n,p", [(2, 5, 2), (3, 3, 1), (3, 3, 2)])
+def test_mapped_fine_operator_invariants_on_distorted_cells(dim, n, p):
+    """Symmetry, constants in the kernel of the interior part, positivity (SIP with the
+    reference's penalty is coercive), mass = volume."""
+    grid = po.Grid(dim, n, 0.0, 1.0, 1)
+    grid.distort_random(0.25, 4)
+    N = grid.n_cells * (p + 1) ** dim
+    rng = np.random.default_rng(0)
+    x, z = rng.standard_normal(N), rng.standard_normal(N)
+    A = lambda v, **kw: po.mapped_fine_vmult(grid, p, p + 1, v, **kw)
+    assert abs(z @ A(x) - x @ A(z)) <= 1e-12 * abs(z @ A(x))
+    one = np.ones(N)
+    assert np.abs(A(one, boundary=False)).max() <= 1e-12
+    assert x @ A(x) > 0
+    vol = one @ po.mapped_fine_vmult(grid, p, p + 1, one, stiffness=0.0, mass=1.0, boundary=False, interior=False)
+    assert abs(vol - 1.0) <= 1e-13
