@@ -7,7 +7,7 @@
 //   Utils::MatrixFreeOperators::LaplaceOperatorDG::{local_apply, local_apply_face,
 //     local_apply_boundary}                              include/utils.h:819-925
 //   MonodomainOperatorDG (f M + sigma K, no boundary)     include/utils.h:1565-1659
-//   matrix-based twin (the oracle follows it)             examples/monodomain_DG3D.cc:1374-1622
+//   matrix-based twin of the same operator                examples/monodomain_DG3D.cc:1374-1622
 // with n_q_points_1d = p+1 and the face penalty
 //   sigma_F = max(p,1)(p+1) (|n . J_m^{-1}|_normal + |n . J_p^{-1}|_normal)  at face point 0,
 //   boundary 2 * 2 * max(p,1)(p+1) |n . J^{-1}|_normal.
