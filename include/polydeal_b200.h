@@ -149,6 +149,27 @@ int pd_synchronize(pd_handle *h);
  * q-points/JxW of every polytope and the face q-points/normals/JxW of every
  * interface.  Called implicitly by pd_assemble when stale. */
 int pd_build_quadrature(pd_handle *h);
+/* the agglomerated quadrature, structure of arrays: vol_x [dim][Q], vol_jxw [Q] with the points
+ * of polytope p at poly_subcell_ptr[p] * n_q^dim ...; face_x / face_n [dim][Qf], face_jxw [Qf]
+ * with the points of sub-face s at s * n_q^(dim-1) ...  (built on demand).  Callers evaluate
+ * their data (right-hand side f, Dirichlet values g, exact solution) at these points. */
+int64_t pd_n_quadrature_points(const pd_handle *h, int faces);
+int pd_quadrature_device(pd_handle *h, const double **vol_x, const double **vol_jxw, const double **face_x,
+                         const double **face_n, const double **face_jxw);
+int pd_quadrature_to_host(pd_handle *h, double *vol_x, double *vol_jxw, double *face_x, double *face_n,
+                          double *face_jxw);
+/* Right-hand side over polytopes (examples/poisson.cc:745-761, examples/diffusion_reaction.cc:
+ * 550-556): rhs_i = sum_q f_q phi_i w_q  +  stiffness * sum_{boundary q} (sigma g_q phi_i -
+ * (grad phi_i . n) g_q) w_q, sigma the boundary sub-face penalty of the descriptor.
+ * f_vol_dev [Q] and g_face_dev [Qf] (only boundary points are read) are device arrays of
+ * values at the quadrature points; either may be NULL.  rhs_dev: pd_n_dofs doubles. */
+int pd_assemble_rhs(pd_handle *h, const double *f_vol_dev, const double *g_face_dev, double stiffness,
+                    double *rhs_dev);
+/* PolyUtils::compute_global_error (include/poly_utils.h:1647-1750): L2 norm and H1 seminorm of
+ * u_h - u over the agglomerated quadrature; exact_dev [Q], exact_grad_dev [dim][Q] (may be NULL
+ * together with h1_seminorm).  Owned polytopes only: a sharded caller sums the squares. */
+int pd_error_norms(pd_handle *h, const double *u_dev, const double *exact_dev, const double *exact_grad_dev,
+                   double *l2, double *h1_seminorm);
 /* mark the device quadrature stale (vertices changed through pd_upload do this
  * implicitly): the next pd_assemble rebuilds it */
 int pd_invalidate_quadrature(pd_handle *h);

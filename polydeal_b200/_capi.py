@@ -69,6 +69,11 @@ SIGNATURES = {
     "pd_matrix_free_available": (C.c_int, [vp]),
     "pd_force_generic_matrix_free": (C.c_int, [vp, C.c_int]),
     "pd_mapped_fine_available": (C.c_int, [vp]),
+    "pd_n_quadrature_points": (C.c_int64, [vp, C.c_int]),
+    "pd_quadrature_device": (C.c_int, [vp] + [C.POINTER(C.c_void_p)] * 5),
+    "pd_quadrature_to_host": (C.c_int, [vp] + [C.c_void_p] * 5),
+    "pd_assemble_rhs": (C.c_int, [vp, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "pd_error_norms": (C.c_int, [vp, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pd_vmult_add": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_vmult_host": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_diagonal_inverse": (C.c_int, [vp, vp]),

@@ -252,7 +252,18 @@ namespace pd
         std::memcmp(h->h_subcell_ptr.data(), d.poly_subcell_ptr, sizeof(int64_t) * ((size_t)d.n_polytopes + 1)) != 0)
       {
         h->h_subcell_ptr.assign(d.poly_subcell_ptr, d.poly_subcell_ptr + d.n_polytopes + 1);
-        h->vol_plan_tq = 0;
+        h->vol_plan_tq   = 0;
+        h->pw_plan_valid = false;
+      }
+    if (h->h_if_sub_ptr.size() != (size_t)d.n_ifaces + 1 ||
+        (d.n_ifaces > 0 &&
+         std::memcmp(h->h_if_sub_ptr.data(), d.iface_sub_ptr, sizeof(int64_t) * ((size_t)d.n_ifaces + 1)) != 0))
+      {
+        if (d.n_ifaces > 0)
+          h->h_if_sub_ptr.assign(d.iface_sub_ptr, d.iface_sub_ptr + d.n_ifaces + 1);
+        else
+          h->h_if_sub_ptr.assign(1, 0);
+        h->pw_plan_valid = false;
       }
   }
 
@@ -553,6 +564,97 @@ extern "C"
     });
   }
 
+  static void
+  need_quadrature(pd_handle *h)
+  {
+    ensure_quadrature_buffers(h);
+    if (!h->quad_valid)
+      {
+        launch_quadrature(h);
+        h->quad_valid = true;
+      }
+  }
+
+  int64_t
+  pd_n_quadrature_points(const pd_handle *h, int faces)
+  {
+    return h ? (faces ? h->Qf : h->Q) : 0;
+  }
+
+  int
+  pd_quadrature_device(pd_handle *h, const double **vol_x, const double **vol_jxw, const double **face_x,
+                       const double **face_n, const double **face_jxw)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      need_quadrature(h);
+      if (vol_x)
+        *vol_x = h->vq_x.p;
+      if (vol_jxw)
+        *vol_jxw = h->vq_w.p;
+      if (face_x)
+        *face_x = h->fq_x.p;
+      if (face_n)
+        *face_n = h->fq_n.p;
+      if (face_jxw)
+        *face_jxw = h->fq_w.p;
+    });
+  }
+
+  int
+  pd_quadrature_to_host(pd_handle *h, double *vol_x, double *vol_jxw, double *face_x, double *face_n, double *face_jxw)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      need_quadrature(h);
+      auto get = [&](double *dst, const double *src, const size_t count) {
+        if (dst && count)
+          PD_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      };
+      get(vol_x, h->vq_x.p, (size_t)h->Q * h->dim);
+      get(vol_jxw, h->vq_w.p, (size_t)h->Q);
+      get(face_x, h->fq_x.p, (size_t)h->Qf * h->dim);
+      get(face_n, h->fq_n.p, (size_t)h->Qf * h->dim);
+      get(face_jxw, h->fq_w.p, (size_t)h->Qf);
+      PD_CUDA(cudaStreamSynchronize(h->stream));
+    });
+  }
+
+  int
+  pd_assemble_rhs(pd_handle *h, const double *f_vol_dev, const double *g_face_dev, double stiffness, double *rhs_dev)
+  {
+    return guarded([&] {
+      if (!h || !rhs_dev)
+        throw Error(PD_ERR_INVALID, "pd_assemble_rhs: null argument");
+      need_quadrature(h);
+      launch_poly_rhs(h, f_vol_dev, g_face_dev, stiffness, rhs_dev);
+    });
+  }
+
+  int
+  pd_error_norms(pd_handle *h, const double *u_dev, const double *exact_dev, const double *exact_grad_dev, double *l2,
+                 double *h1_seminorm)
+  {
+    return guarded([&] {
+      if (!h || !u_dev || !exact_dev || !l2)
+        throw Error(PD_ERR_INVALID, "pd_error_norms: null argument");
+      if (h1_seminorm && !exact_grad_dev)
+        throw Error(PD_ERR_INVALID, "pd_error_norms: the H1 seminorm needs the exact gradient");
+      need_quadrature(h);
+      if (h->sv_scal.n < 8)
+        h->sv_scal.alloc(8);
+      launch_poly_error(h, u_dev, exact_dev, h1_seminorm ? exact_grad_dev : nullptr, h->sv_scal.p);
+      double e[2];
+      PD_CUDA(cudaMemcpyAsync(e, h->sv_scal.p, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+      PD_CUDA(cudaStreamSynchronize(h->stream));
+      *l2 = std::sqrt(e[0]);
+      if (h1_seminorm)
+        *h1_seminorm = std::sqrt(e[1]);
+    });
+  }
+
   int
   pd_invalidate_quadrature(pd_handle *h)
   {
@@ -681,12 +783,7 @@ extern "C"
         else
           {
             // agglomerated polytopes: regenerate the basis at the agglomerated quadrature points
-            ensure_quadrature_buffers(h);
-            if (!h->quad_valid)
-              {
-                launch_quadrature(h);
-                h->quad_valid = true;
-              }
+            need_quadrature(h);
             launch_poly_apply(h, src, dst, add);
           }
       }

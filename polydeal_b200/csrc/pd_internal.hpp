@@ -118,7 +118,15 @@ struct pd_handle
   std::vector<double> mp_tab_host; // V | V^T | Dt | e0 e1 | d0 d1
   pd::DevBuf<int32_t> mp_cellv, mp_nbr;
   pd::DevBuf<double>  mp_dt, mp_cgeo, mp_fgeo, mp_sigma, mp_xg, mp_yg, mp_zero;
-  pd::DevBuf<double>  mf_vol_partial, mf_face_partial; // polytopal matrix-free apply (pd_polyapply.cu)
+  pd::DevBuf<double>  mf_vol_partial, mf_face_partial;
+  bool                pw_plan_valid = false; // work items of the point-wise kernels (pd_polyapply.cu)
+  int32_t             pw_n_items    = 0;
+  pd::DevBuf<int32_t> pw_item_poly;
+  pd::DevBuf<int64_t> pw_item_q0, pw_item_q1, pw_poly_item_ptr;
+  int32_t             pw_n_fitems = 0;
+  pd::DevBuf<int32_t> pw_fitem_iface;
+  pd::DevBuf<int64_t> pw_fitem_q0, pw_fitem_q1, pw_iface_item_ptr;
+  std::vector<int64_t> h_if_sub_ptr; // polytopal matrix-free apply (pd_polyapply.cu)
   pd_coefficients     op_coef{1.0, 0.0}; // operator of the matrix-free apply
   uint32_t            op_flags = PD_ASSEMBLE_ALL;
   // device-resident solvers around vmult (pd_solver.cu)
@@ -156,6 +164,8 @@ namespace pd
   void launch_mapped_operator(pd_handle *h, const double *src, double *dst, bool add);
   // pd_polyapply.cu
   void launch_poly_apply(pd_handle *h, const double *src, double *dst, bool add);
+  void launch_poly_rhs(pd_handle *h, const double *f_vol, const double *g_face, double stiffness, double *rhs);
+  void launch_poly_error(pd_handle *h, const double *u, const double *exact, const double *exact_grad, double *out2_dev);
   // pd_solver.cu
   void   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,
                    int *iters_out, double *relres_out);

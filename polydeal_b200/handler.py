@@ -351,6 +351,55 @@ class SIPOperator:
                                     int(jacobi), C.byref(it), C.byref(rr)))
         return it.value, rr.value
 
+    # ---- data at the agglomerated quadrature points: right-hand side and error norms ----
+    def n_quadrature_points(self, faces=False):
+        return int(K.lib().pd_n_quadrature_points(self._h, int(faces)))
+
+    def quadrature(self):
+        """Device views (torch, no copy) of the agglomerated quadrature:
+        dict(vol_x [dim, Q], vol_jxw [Q], face_x [dim, Qf], face_n [dim, Qf], face_jxw [Qf])."""
+        import torch
+
+        ptrs = [C.c_void_p() for _ in range(5)]
+        K.check(K.lib().pd_quadrature_device(self._h, *[C.byref(p) for p in ptrs]))
+        Q, Qf, dim = self.n_quadrature_points(), self.n_quadrature_points(True), self.desc.dim
+
+        def view(ptr, shape):
+            n = int(np.prod(shape))
+            if n == 0:
+                return torch.zeros(shape, dtype=torch.float64, device="cuda")
+            iface = {"shape": tuple(shape), "typestr": "<f8", "data": (ptr.value, False), "version": 2}
+            holder = type("_DevView", (), {"__cuda_array_interface__": iface})()
+            return torch.as_tensor(holder, device="cuda")
+
+        names = ["vol_x", "vol_jxw", "face_x", "face_n", "face_jxw"]
+        shapes = [(dim, Q), (Q,), (dim, Qf), (dim, Qf), (Qf,)]
+        return {k: view(p, sh) for k, p, sh in zip(names, ptrs, shapes)}
+
+    def assemble_rhs(self, rhs, f_vol=None, g_face=None, stiffness=1.0):
+        """rhs_i = sum_q f_q phi_i w_q + stiffness * boundary Dirichlet terms (pd_assemble_rhs);
+        f_vol [Q] / g_face [Qf] are CUDA tensors of values at the quadrature points."""
+        self._check_tensor(rhs)
+        if f_vol is not None:
+            self._check_tensor(f_vol, self.n_quadrature_points())
+        if g_face is not None:
+            self._check_tensor(g_face, self.n_quadrature_points(True))
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        K.check(K.lib().pd_assemble_rhs(self._h, ptr(f_vol), ptr(g_face), float(stiffness), ptr(rhs)))
+        return rhs
+
+    def error_norms(self, u, exact, exact_grad=None):
+        """PolyUtils::compute_global_error: (L2, H1-seminorm or None) of u_h - u (pd_error_norms)."""
+        Q = self.n_quadrature_points()
+        self._check_tensor(u, K.lib().pd_n_source_dofs(self._h)), self._check_tensor(exact, Q)
+        l2, h1 = C.c_double(0.0), C.c_double(0.0)
+        if exact_grad is not None:
+            self._check_tensor(exact_grad, Q * self.desc.dim)
+        K.check(K.lib().pd_error_norms(self._h, C.c_void_p(u.data_ptr()), C.c_void_p(exact.data_ptr()),
+                                       C.c_void_p(exact_grad.data_ptr()) if exact_grad is not None else None,
+                                       C.byref(l2), C.byref(h1) if exact_grad is not None else None))
+        return l2.value, (h1.value if exact_grad is not None else None)
+
     def estimate_lambda_max(self, n_iterations=20, mode=K.VMULT_BLOCK_CSR):
         lam = C.c_double(0.0)
         K.check(K.lib().pd_estimate_lambda_max(self._h, mode, n_iterations, C.byref(lam)))
@@ -364,11 +413,12 @@ class SIPOperator:
                                             C.c_void_p(x.data_ptr()), int(zero_initial_guess)))
         return x
 
-    def _check_tensor(self, t):
+    def _check_tensor(self, t, numel=None):
         import torch
 
-        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == self.m()):
-            raise K.PolydealError(K.PD_ERR_INVALID, "vector must be a contiguous float64 CUDA tensor of length m()")
+        numel = self.m() if numel is None else numel
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == numel):
+            raise K.PolydealError(K.PD_ERR_INVALID, f"expected a contiguous float64 CUDA tensor of {numel} entries")
 
     def copy_array(self, name):
         cnt = C.c_int64()

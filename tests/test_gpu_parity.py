@@ -326,6 +326,66 @@ def test_fine_mesh_matrix_free_vmult(dim, n, p, order, hi, kw):
     assert np.abs(yb.cpu().numpy() - yref).max() <= TOL * scale
 
 
+@pytest.mark.parametrize("dim,n,shape,p,nq,distort", [
+    (2, 8, "random5", 1, 2, None),
+    (2, 8, "blocks4", 2, 4, (0.2, 3)),
+    (2, 8, "random4", 4, 5, None),
+    (3, 4, "random6", 1, 3, None),
+    (3, 4, "blocks2", 2, 3, (0.15, 8)),
+    (3, 4, "random3", 3, 4, None),
+])
+def test_rhs_and_error_functionals(dim, n, shape, p, nq, distort):
+    """pd_assemble_rhs (examples/poisson.cc:745-761 + Dirichlet terms of diffusion_reaction.cc:550-556)
+    and pd_error_norms (PolyUtils::compute_global_error, include/poly_utils.h:1647-1750) against
+    the oracle's reinit() tables."""
+    pdl = gpu()
+    import torch
+
+    oah, pah = both(dim, n, shape, p, nq=nq, distort=distort)
+    C = 10.0 * (p + dim) * (p + 1)
+    op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+    f = lambda x: np.sin(1.3 * x[..., 0] + 0.2) * np.cos(0.7 * x[..., 1]) + (x[..., 2] ** 2 if dim == 3 else 0.0)
+    g = lambda x: 1.0 + x[..., 0] - 0.5 * x[..., 1] ** 2
+    gradg = lambda x: np.stack([np.ones_like(x[..., 0]), -x[..., 1]] + ([np.zeros_like(x[..., 0])] if dim == 3 else []), axis=-1)
+    # ---- oracle side
+    N = oah.n_dofs
+    b_ref = np.zeros(N)
+    uh = src_vector(N) * 0.1
+    l2_ref = h1_ref = 0.0
+    for k in range(oah.n_polytopes):
+        fev = oah.reinit(k)
+        dofs = oah.get_dof_indices(k)
+        b_ref[dofs] += fev.values @ (f(fev.points) * fev.JxW)
+        uq = uh[dofs] @ fev.values
+        gq = np.einsum("i,iqd->qd", uh[dofs], fev.grads)
+        l2_ref += np.sum((uq - g(fev.points)) ** 2 * fev.JxW)
+        h1_ref += np.sum(np.sum((gq - gradg(fev.points)) ** 2, axis=1) * fev.JxW)
+        for fc in range(oah.n_faces(k)):
+            if oah.at_boundary(k, fc):
+                fv = oah.reinit(k, fc)
+                sig = C / oah.diameter(k)
+                gn = np.einsum("iqd,qd->iq", fv.grads, fv.normals)
+                b_ref[dofs] += 0.7 * ((sig * fv.values - gn) @ (g(fv.points) * fv.JxW))
+    # ---- device side: data evaluated at the device quadrature points
+    q = op.quadrature()
+    vx = q["vol_x"].T.cpu().numpy()
+    fx = q["face_x"].T.cpu().numpy()
+    assert abs(q["vol_jxw"].sum().item() - 1.0) < 1e-12
+    fq = torch.from_numpy(np.ascontiguousarray(f(vx))).cuda()
+    gq = torch.from_numpy(np.ascontiguousarray(g(fx))).cuda()
+    rhs = torch.empty(N, dtype=torch.float64, device="cuda")
+    op.assemble_rhs(rhs, fq, gq, stiffness=0.7)
+    op.synchronize()
+    assert np.abs(rhs.cpu().numpy() - b_ref).max() <= TOL * np.abs(b_ref).max()
+    ex = torch.from_numpy(np.ascontiguousarray(g(vx))).cuda()
+    exg = torch.from_numpy(np.ascontiguousarray(gradg(vx).T)).cuda()
+    l2, h1 = op.error_norms(torch.from_numpy(uh).cuda(), ex, exg)
+    assert abs(l2 - np.sqrt(l2_ref)) <= 1e-12 * np.sqrt(l2_ref)
+    assert abs(h1 - np.sqrt(h1_ref)) <= 1e-12 * np.sqrt(h1_ref)
+    l2_only, none = op.error_norms(torch.from_numpy(uh).cuda(), ex)
+    assert none is None and l2_only == l2
+
+
 @pytest.mark.parametrize("dim,n,p,order,distort,kw", [
     (2, 8, 1, 0, (0.25, 11), {}),
     (2, 6, 2, 1, (0.2, 5), dict(stiffness=1.3, mass=0.7)),
