@@ -592,6 +592,23 @@ def test_poisson_golden_l2_error_on_gpu(goldens):
         rz = rz_new
     assert it < 4999
     assert l2_error(x.cpu().numpy()) == pytest.approx(goldens["poisson"][0], abs=5e-9)
+    # and end to end on the device: right-hand side by pd_assemble_rhs from f evaluated at the
+    # device quadrature points (examples/poisson.cc:745-761), pd_cg_solve, golden functional
+    q = op.quadrature()
+    vx = q["vol_x"]
+    fq = (8 * np.pi**2) * torch.sin(2 * np.pi * vx[0]) * torch.sin(2 * np.pi * vx[1])
+    rhs = torch.empty_like(bd)
+    op.assemble_rhs(rhs, fq.contiguous())
+    op.synchronize()
+    assert np.abs(rhs.cpu().numpy() - b).max() <= TOL * np.abs(b).max()
+    xs = torch.zeros_like(bd)
+    iters, relres = op.cg_solve(xs, rhs, max_iter=5000, rel_tol=1e-12)
+    assert relres <= 1e-12
+    assert l2_error(xs.cpu().numpy()) == pytest.approx(goldens["poisson"][0], abs=5e-9)
+    # PolyUtils::compute_global_error of the same solution (full agglomerated quadrature)
+    exact = (torch.sin(2 * np.pi * vx[0]) * torch.sin(2 * np.pi * vx[1])).contiguous()
+    l2_full, _ = op.error_norms(xs, exact)
+    assert 0.5 * goldens["poisson"][0] < l2_full < 2.0 * goldens["poisson"][0]
 
 
 # ----------------------------------------------------------------------------------
