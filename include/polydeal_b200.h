@@ -170,6 +170,29 @@ int pd_assemble_rhs(pd_handle *h, const double *f_vol_dev, const double *g_face_
  * together with h1_seminorm).  Owned polytopes only: a sharded caller sums the squares. */
 int pd_error_norms(pd_handle *h, const double *u_dev, const double *exact_dev, const double *exact_grad_dev,
                    double *l2, double *h1_seminorm);
+/* --- level transfers (the step either side of vmult in the V-cycle) ---------------------------
+ * P evaluates a polytope's function at the FE_DGQ support points of a child element,
+ * local_matrix(i, j) = phi^parent_j(p_i), applied on the fly (no transfer matrix is stored):
+ *  pd_transfer_create          child = polytope of a FINER agglomeration level (another handle on
+ *                              the same mesh and FE), points = the nodes of the child's bounding
+ *                              box: Utils::fill_injection_matrix (include/utils.h:95-270).
+ *                              parent_of_fine[q] = the coarse polytope that contains fine
+ *                              polytope q (polytope->children(), inverted).
+ *  pd_transfer_create_to_cells child = every mesh cell of a polytope, points = its Q1-mapped nodes:
+ *                              PolyUtils::fill_interpolation_matrix (include/poly_utils.h:1469-1634);
+ *                              fine DoFs = n per cell in active-cell order.
+ *  prolongate  y_fine (+)= P x_coarse      (MGTransferAgglomeration::prolongate[_and_add])
+ *  restrict    x_coarse (+)= P^T y_fine    (restrict_and_add, source/multigrid_amg.cc:66-110)
+ * Both handles must outlive the transfer.  Vectors are device pointers. */
+typedef struct pd_transfer pd_transfer;
+int pd_transfer_create(pd_handle *coarse, pd_handle *fine, const int32_t *parent_of_fine, pd_transfer **out);
+int pd_transfer_create_to_cells(pd_handle *h, pd_transfer **out);
+void pd_transfer_destroy(pd_transfer *t);
+int64_t pd_transfer_m(const pd_transfer *t); /* fine DoFs (rows of P) */
+int64_t pd_transfer_n(const pd_transfer *t); /* coarse DoFs */
+int pd_transfer_prolongate(pd_transfer *t, const double *src_coarse_dev, double *dst_fine_dev, int add);
+int pd_transfer_restrict(pd_transfer *t, const double *src_fine_dev, double *dst_coarse_dev, int add);
+
 /* mark the device quadrature stale (vertices changed through pd_upload do this
  * implicitly): the next pd_assemble rebuilds it */
 int pd_invalidate_quadrature(pd_handle *h);

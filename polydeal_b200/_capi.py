@@ -69,6 +69,13 @@ SIGNATURES = {
     "pd_matrix_free_available": (C.c_int, [vp]),
     "pd_force_generic_matrix_free": (C.c_int, [vp, C.c_int]),
     "pd_mapped_fine_available": (C.c_int, [vp]),
+    "pd_transfer_create": (C.c_int, [vp, vp, C.c_void_p, C.POINTER(vp)]),
+    "pd_transfer_create_to_cells": (C.c_int, [vp, C.POINTER(vp)]),
+    "pd_transfer_destroy": (None, [vp]),
+    "pd_transfer_m": (C.c_int64, [vp]),
+    "pd_transfer_n": (C.c_int64, [vp]),
+    "pd_transfer_prolongate": (C.c_int, [vp, vp, vp, C.c_int]),
+    "pd_transfer_restrict": (C.c_int, [vp, vp, vp, C.c_int]),
     "pd_n_quadrature_points": (C.c_int64, [vp, C.c_int]),
     "pd_quadrature_device": (C.c_int, [vp] + [C.POINTER(C.c_void_p)] * 5),
     "pd_quadrature_to_host": (C.c_int, [vp] + [C.c_void_p] * 5),

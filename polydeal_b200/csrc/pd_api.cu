@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <string>
 
 namespace pd
@@ -652,6 +653,116 @@ extern "C"
       *l2 = std::sqrt(e[0]);
       if (h1_seminorm)
         *h1_seminorm = std::sqrt(e[1]);
+    });
+  }
+
+  static void
+  finish_transfer(pd_transfer *t, const std::vector<int32_t> &parent, const std::vector<int32_t> &blk)
+  {
+    pd_handle *h  = t->coarse;
+    t->n_children = (int32_t)parent.size();
+    std::vector<int64_t> pc_ptr((size_t)h->np_own + 1, 0);
+    for (const int32_t p : parent)
+      {
+        if (p < 0 || p >= h->np_own)
+          throw Error(PD_ERR_INVALID, "pd_transfer: parent polytope out of range");
+        ++pc_ptr[p + 1];
+      }
+    for (int32_t p = 0; p < h->np_own; ++p)
+      pc_ptr[p + 1] += pc_ptr[p];
+    std::vector<int32_t> pc_idx(parent.size());
+    std::vector<int64_t> fill(pc_ptr.begin(), pc_ptr.end() - 1);
+    for (size_t c = 0; c < parent.size(); ++c)
+      pc_idx[fill[parent[c]]++] = (int32_t)c;
+    auto put = [](auto &buf, const auto &v) {
+      buf.alloc(v.size());
+      if (!v.empty())
+        PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+    };
+    put(t->parent, parent);
+    put(t->child_blk, blk);
+    put(t->pc_ptr, pc_ptr);
+    put(t->pc_idx, pc_idx);
+    t->partial.alloc(parent.size() * (size_t)h->n);
+  }
+
+  int
+  pd_transfer_create(pd_handle *coarse, pd_handle *fine, const int32_t *parent_of_fine, pd_transfer **out)
+  {
+    return guarded([&] {
+      if (!coarse || !fine || !parent_of_fine || !out)
+        throw Error(PD_ERR_INVALID, "pd_transfer_create: null argument");
+      if (coarse->dim != fine->dim || coarse->degree != fine->degree)
+        throw Error(PD_ERR_INVALID, "pd_transfer_create: the two levels must use the same FE_DGQ space");
+      std::unique_ptr<pd_transfer> t(new pd_transfer);
+      t->coarse      = coarse;
+      t->kind        = 0;
+      t->child_bbox  = fine->bbox.p;
+      t->n_fine_dofs = (int64_t)fine->np_own * fine->n;
+      std::vector<int32_t> parent(parent_of_fine, parent_of_fine + fine->np_own);
+      std::vector<int32_t> blk(fine->h_dof_block.begin(), fine->h_dof_block.begin() + fine->np_own);
+      finish_transfer(t.get(), parent, blk);
+      *out = t.release();
+    });
+  }
+
+  int
+  pd_transfer_create_to_cells(pd_handle *h, pd_transfer **out)
+  {
+    return guarded([&] {
+      if (!h || !out)
+        throw Error(PD_ERR_INVALID, "pd_transfer_create_to_cells: null argument");
+      std::unique_ptr<pd_transfer> t(new pd_transfer);
+      t->coarse      = h;
+      t->kind        = 1;
+      t->n_fine_dofs = h->n_cells * h->n;
+      const int64_t        ns = h->h_subcell_ptr[h->np_own];
+      std::vector<int32_t> cells((size_t)ns), parent((size_t)ns);
+      if (ns)
+        PD_CUDA(cudaMemcpy(cells.data(), h->subcell_idx.p, sizeof(int32_t) * (size_t)ns, cudaMemcpyDeviceToHost));
+      for (int32_t p = 0; p < h->np_own; ++p)
+        for (int64_t k = h->h_subcell_ptr[p]; k < h->h_subcell_ptr[p + 1]; ++k)
+          parent[(size_t)k] = p;
+      finish_transfer(t.get(), parent, cells);
+      *out = t.release();
+    });
+  }
+
+  void
+  pd_transfer_destroy(pd_transfer *t)
+  {
+    delete t;
+  }
+
+  int64_t
+  pd_transfer_m(const pd_transfer *t)
+  {
+    return t ? t->n_fine_dofs : 0;
+  }
+
+  int64_t
+  pd_transfer_n(const pd_transfer *t)
+  {
+    return t ? (int64_t)t->coarse->np_own * t->coarse->n : 0;
+  }
+
+  int
+  pd_transfer_prolongate(pd_transfer *t, const double *src_coarse_dev, double *dst_fine_dev, int add)
+  {
+    return guarded([&] {
+      if (!t || !src_coarse_dev || !dst_fine_dev)
+        throw Error(PD_ERR_INVALID, "pd_transfer_prolongate: null argument");
+      launch_transfer(t->coarse, *t, false, src_coarse_dev, dst_fine_dev, add != 0);
+    });
+  }
+
+  int
+  pd_transfer_restrict(pd_transfer *t, const double *src_fine_dev, double *dst_coarse_dev, int add)
+  {
+    return guarded([&] {
+      if (!t || !src_fine_dev || !dst_coarse_dev)
+        throw Error(PD_ERR_INVALID, "pd_transfer_restrict: null argument");
+      launch_transfer(t->coarse, *t, true, src_fine_dev, dst_coarse_dev, add != 0);
     });
   }
 

@@ -149,6 +149,19 @@ struct pd_handle
   int64_t      max_row_len = -1; // longest scalar row (doubles), computed lazily for the SpMV dispatch
 };
 
+// level transfer between a handle's polytopal space and a finer space (pd_polyapply.cu)
+struct pd_transfer
+{
+  pd_handle          *coarse     = nullptr;
+  int                 kind       = 0; // 0: finer agglomeration level, 1: the mesh cells
+  int32_t             n_children = 0;
+  int64_t             n_fine_dofs = 0;
+  pd::DevBuf<int32_t> parent, child_blk, pc_idx;
+  pd::DevBuf<int64_t> pc_ptr;
+  pd::DevBuf<double>  partial;
+  const double       *child_bbox = nullptr; // kind 0: the finer handle's bounding boxes (device)
+};
+
 namespace pd
 {
   // pd_geometry.cu
@@ -165,6 +178,7 @@ namespace pd
   // pd_polyapply.cu
   void launch_poly_apply(pd_handle *h, const double *src, double *dst, bool add);
   void launch_poly_rhs(pd_handle *h, const double *f_vol, const double *g_face, double stiffness, double *rhs);
+  void launch_transfer(pd_handle *h, const pd_transfer &t, bool transpose, const double *src, double *dst, bool add);
   void launch_poly_error(pd_handle *h, const double *u, const double *exact, const double *exact_grad, double *out2_dev);
   // pd_solver.cu
   void   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,

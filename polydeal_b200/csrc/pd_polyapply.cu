@@ -734,7 +734,207 @@ namespace pd
       PD_CUDA(cudaGetLastError());
     }
 
-#define PD_DISPATCH(FN, ...)                                                                                       \
+    // ---- level transfers ------------------------------------------------
+    // P evaluates the parent polytope's function at the support points of a child element:
+    //   kind 0  child = polytope of a finer agglomeration level, points = the FE_DGQ nodes of
+    //           ITS bounding box                     (fill_injection_matrix, include/utils.h:95-270)
+    //   kind 1  child = one mesh cell, points = its Q1-mapped FE_DGQ nodes
+    //           (fill_interpolation_matrix, include/poly_utils.h:1469-1634)
+    // local_matrix(i, j) = phi^parent_j(p_i): rows = child DoFs.  Applied on the fly, one warp
+    // per child, lane = support point: prolongation is a pure evaluation (no reduction),
+    // restriction (P^T, MGTransferAgglomeration::restrict_and_add, source/multigrid_amg.cc:
+    // 92-108) integrates the child's values as point weights and sums a parent's children in
+    // list order.
+    struct TransferArgs
+    {
+      int            kind;
+      int32_t        n_children;
+      const int32_t *parent;     // [child] parent polytope (coarse handle numbering)
+      const int32_t *child_blk;  // [child] DoF block in the fine vector
+      const double  *child_bbox; // kind 0: [child][2 dim]
+      const int32_t *child_cv;   // kind 1: the mesh's cell_verts, [cell][2^dim] vertex ids
+      const double  *verts;
+      const double  *bbox;       // coarse bounding boxes
+      const int32_t *dof_block;  // coarse DoF blocks
+      const double  *src;
+      double        *dst;     // prolongation: fine vector
+      double        *partial; // restriction: [child][N]
+      int            add;
+      Basis1D        basis;
+    };
+
+    template <int DIM, int DEG, bool TRANSPOSE, int GZ>
+    __global__ void __launch_bounds__(NW * 32, 2) k_pw_transfer(const TransferArgs A)
+    {
+      using C           = Cfg<DIM, DEG>;
+      constexpr int N1  = C::N1, N = C::N;
+      constexpr int NS  = N1 / GZ, NI = N / N1, NA = NS * NI;
+      constexpr int PTS = 32 / GZ;
+      __shared__ double Us[NW][N];
+
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pt = lane % PTS, part = lane / PTS;
+      double   *U = Us[warp];
+      for (int c = blockIdx.x * NW + warp; c < A.n_children; c += gridDim.x * NW)
+        {
+          const int     K  = A.parent[c];
+          const double *bb = A.bbox + (int64_t)K * 2 * DIM;
+          __syncwarp();
+          if (!TRANSPOSE)
+            for (int i = lane; i < N; i += 32)
+              U[i] = A.src[(int64_t)A.dof_block[K] * N + i];
+          __syncwarp();
+          double acc[NA];
+#pragma unroll
+          for (int k = 0; k < NA; ++k)
+            acc[k] = 0.;
+          for (int ib = 0; ib < N; ib += PTS)
+            {
+              const int  i  = ib + pt;
+              const bool ok = i < N;
+              // support point i of the child
+              double xi[DIM], x[DIM];
+              {
+                int r = ok ? i : 0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                  {
+                    const int a = r % N1;
+                    r /= N1;
+                    xi[d] = A.basis.node[0];
+#pragma unroll
+                    for (int t = 1; t < N1; ++t)
+                      if (a == t)
+                        xi[d] = A.basis.node[t];
+                  }
+              }
+              if (A.kind == 0)
+                {
+                  const double *cb = A.child_bbox + (int64_t)c * 2 * DIM;
+#pragma unroll
+                  for (int d = 0; d < DIM; ++d)
+                    x[d] = cb[d] + xi[d] * (cb[DIM + d] - cb[d]);
+                }
+              else
+                {
+                  const int32_t *cv = A.child_cv + (int64_t)A.child_blk[c] * (1 << DIM); // the child IS mesh cell child_blk[c]
+#pragma unroll
+                  for (int d = 0; d < DIM; ++d)
+                    x[d] = 0.;
+#pragma unroll
+                  for (int v = 0; v < (1 << DIM); ++v)
+                    {
+                      double w = 1.;
+#pragma unroll
+                      for (int d = 0; d < DIM; ++d)
+                        w *= ((v >> d) & 1) ? xi[d] : 1. - xi[d];
+                      const double *X = A.verts + (int64_t)cv[v] * DIM;
+#pragma unroll
+                      for (int d = 0; d < DIM; ++d)
+                        x[d] += w * X[d];
+                    }
+                }
+              PointTab<DIM, N1> T;
+              point_tables<DIM, N1>(A.basis, bb, x, T);
+              double ls[NS], dls[NS];
+              my_slices<DIM, N1, GZ>(T, part, ls, dls);
+              if constexpr (!TRANSPOSE)
+                {
+                  double u, g[DIM];
+                  eval_slices<DIM, N1, NS>(T, ls, dls, U + part * NA, u, g);
+#pragma unroll
+                  for (int o = PTS; o < 32; o <<= 1)
+                    u += __shfl_xor_sync(0xffffffffu, u, o);
+                  if (ok && part == 0)
+                    {
+                      double *yp = A.dst + (int64_t)A.child_blk[c] * N + i;
+                      *yp        = A.add ? *yp + u : u;
+                    }
+                }
+              else
+                {
+                  const double yv    = ok ? A.src[(int64_t)A.child_blk[c] * N + i] : 0.;
+                  double       f[DIM] = {};
+                  integrate_slices<DIM, N1, NS, false>(T, ls, dls, f, yv, acc);
+                }
+            }
+          if constexpr (TRANSPOSE)
+            warp_reduce_store<NA, PTS>(acc, A.partial + (int64_t)c * N, lane);
+        }
+    }
+
+    struct TransferGatherArgs
+    {
+      const int64_t *pc_ptr; // children of every coarse polytope
+      const int32_t *pc_idx;
+      const double  *partial;
+      const int32_t *dof_block;
+      double        *y;
+      int32_t        np, n;
+      int            add;
+    };
+
+    __global__ void __launch_bounds__(256)
+    k_transfer_gather(const TransferGatherArgs A)
+    {
+      const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      if (idx >= (int64_t)A.np * A.n)
+        return;
+      const int p = (int)(idx / A.n), i = (int)(idx - (int64_t)p * A.n);
+      double    s = 0.;
+      for (int64_t k = A.pc_ptr[p]; k < A.pc_ptr[p + 1]; ++k)
+        s += A.partial[(int64_t)A.pc_idx[k] * A.n + i];
+      double *yp = A.y + (int64_t)A.dof_block[p] * A.n + i;
+      *yp        = A.add ? *yp + s : s;
+    }
+
+    template <int DIM, int DEG>
+    void
+    run_transfer(pd_handle *h, const pd_transfer &t, const bool transpose, const double *src, double *dst, const bool add)
+    {
+      constexpr int GZ = lanes_per_point<DIM, DEG>();
+      TransferArgs  a;
+      a.kind       = t.kind;
+      a.n_children = t.n_children;
+      a.parent     = t.parent.p;
+      a.child_blk  = t.child_blk.p;
+      a.child_bbox = t.child_bbox;
+      a.child_cv   = h->cell_verts.p;
+      a.verts      = h->verts.p;
+      a.bbox       = h->bbox.p;
+      a.dof_block  = h->dof_block.p;
+      a.src        = src;
+      a.dst        = dst;
+      a.partial    = t.partial.p;
+      a.add        = add ? 1 : 0;
+      a.basis      = h->basis;
+      const int grid = (int)std::min<int64_t>((t.n_children + NW - 1) / NW, (int64_t)h->sm_count * 2);
+      if (t.n_children > 0)
+        {
+          if (transpose)
+            k_pw_transfer<DIM, DEG, true, GZ><<<grid, NW * 32, 0, h->stream>>>(a);
+          else
+            k_pw_transfer<DIM, DEG, false, GZ><<<grid, NW * 32, 0, h->stream>>>(a);
+          ++h->launches;
+        }
+      if (transpose)
+        {
+          TransferGatherArgs g;
+          g.pc_ptr    = t.pc_ptr.p;
+          g.pc_idx    = t.pc_idx.p;
+          g.partial   = t.partial.p;
+          g.dof_block = h->dof_block.p;
+          g.y         = dst;
+          g.np        = h->np_own;
+          g.n         = h->n;
+          g.add       = add ? 1 : 0;
+          const int64_t nd = (int64_t)h->np_own * h->n;
+          k_transfer_gather<<<(unsigned)((nd + 255) / 256), 256, 0, h->stream>>>(g);
+          ++h->launches;
+        }
+      PD_CUDA(cudaGetLastError());
+    }
+
+#define PD_DISPATCH(FN, ...)                                                                                      \
   switch (h->dim * 10 + h->degree)                                                                                 \
     {                                                                                                              \
       case 21: FN<2, 1>(__VA_ARGS__); break;                                                                       \
@@ -759,6 +959,12 @@ namespace pd
   launch_poly_rhs(pd_handle *h, const double *f_vol, const double *g_face, const double stiffness, double *rhs)
   {
     PD_DISPATCH(run_rhs, h, f_vol, g_face, stiffness, rhs);
+  }
+
+  void
+  launch_transfer(pd_handle *h, const pd_transfer &t, const bool transpose, const double *src, double *dst, const bool add)
+  {
+    PD_DISPATCH(run_transfer, h, t, transpose, src, dst, add);
   }
 
   void

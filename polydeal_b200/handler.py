@@ -447,3 +447,61 @@ def assemble_dg_matrix(ah: AgglomerationHandler, penalty_constant=-1.0, h_rule=K
     flags = K.ASSEMBLE_ALL if with_boundary else (K.ASSEMBLE_VOLUME | K.ASSEMBLE_INTERIOR)
     op.assemble(flags, stiffness_coeff, mass_coeff)
     return op
+
+
+class Transfer:
+    """Level transfer applied on the fly (pd_transfer_*): `Transfer(coarse_op, fine_op, parent)` is
+    Utils::fill_injection_matrix between two agglomeration levels (include/utils.h:95-270),
+    `Transfer.to_cells(op)` is PolyUtils::fill_interpolation_matrix onto the mesh's FE_DGQ space
+    (include/poly_utils.h:1469-1634).  prolongate / restrict_and_add as in MGTransferAgglomeration
+    (source/multigrid_amg.cc:66-110)."""
+
+    def __init__(self, coarse: SIPOperator, fine: SIPOperator = None, parent_of_fine=None, _to_cells=False):
+        self._h = C.c_void_p()
+        self._keep = (coarse, fine)
+        if _to_cells:
+            K.check(K.lib().pd_transfer_create_to_cells(coarse._h, C.byref(self._h)))
+        else:
+            parent = np.ascontiguousarray(parent_of_fine, dtype=np.int32)
+            assert parent.shape == (fine.desc.n_owned_polytopes or fine.desc.n_polytopes,)
+            K.check(K.lib().pd_transfer_create(coarse._h, fine._h, _ptr(parent), C.byref(self._h)))
+
+    @staticmethod
+    def to_cells(op: SIPOperator):
+        return Transfer(op, _to_cells=True)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and K._lib is not None:
+            K._lib.pd_transfer_destroy(self._h)
+            self._h = None
+
+    def m(self):
+        return int(K.lib().pd_transfer_m(self._h))
+
+    def n(self):
+        return int(K.lib().pd_transfer_n(self._h))
+
+    def _check(self, t, numel):
+        import torch
+
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == numel):
+            raise K.PolydealError(K.PD_ERR_INVALID, f"expected a contiguous float64 CUDA tensor of {numel} entries")
+
+    def prolongate(self, dst_fine, src_coarse, add=False):
+        self._check(dst_fine, self.m()), self._check(src_coarse, self.n())
+        K.check(K.lib().pd_transfer_prolongate(self._h, C.c_void_p(src_coarse.data_ptr()), C.c_void_p(dst_fine.data_ptr()), int(add)))
+        return dst_fine
+
+    def prolongate_and_add(self, dst_fine, src_coarse):
+        return self.prolongate(dst_fine, src_coarse, add=True)
+
+    def restrict_and_add(self, dst_coarse, src_fine):
+        return self.restrict(dst_coarse, src_fine, add=True)
+
+    def restrict(self, dst_coarse, src_fine, add=False):
+        self._check(dst_coarse, self.n()), self._check(src_fine, self.m())
+        K.check(K.lib().pd_transfer_restrict(self._h, C.c_void_p(src_fine.data_ptr()), C.c_void_p(dst_coarse.data_ptr()), int(add)))
+        return dst_coarse
+
+    vmult = prolongate
+    Tvmult = restrict

@@ -690,3 +690,135 @@ def test_device_cg_chebyshev_and_lambda_max(goldens):
         op.chebyshev_smooth(xs, bd, 3, 1.2 * lam, 20.0, zero_initial_guess=zero_guess)
         op.synchronize()
         assert np.abs(xs.cpu().numpy() - want).max() <= 1e-12 * np.abs(want).max()
+
+
+# ----------------------------------------------------------------------------------
+# "next" row N2: level transfers (include/utils.h:95-270, include/poly_utils.h:1469-1634,
+# source/multigrid_amg.cc:66-110)
+# ----------------------------------------------------------------------------------
+def _dgq_unit_support_points(dim, p):
+    g = po.gauss_lobatto_nodes(p + 1)
+    return np.array([[g[(i // (p + 1) ** d) % (p + 1)] for d in range(dim)] for i in range((p + 1) ** dim)])  # x fastest
+
+
+def _nested_levels(dim, n, p, coarse_shape, fine_shape, distort=None, seed=1):
+    """Two agglomeration levels of the same mesh, the fine one nested in the coarse one."""
+    ogrid = po.Grid(dim, n, 0.0, 1.0, 0)
+    if distort:
+        ogrid.distort_random(*distort)
+    fine_groups = groups_for(fine_shape, dim, n, ogrid, seed)
+    if coarse_shape.startswith("blocks"):
+        coarse_groups = groups_for(coarse_shape, dim, n, ogrid, seed)
+    else:  # unions of consecutive fine groups: irregular, still nested
+        k = int(coarse_shape[5:])
+        coarse_groups = [sum((list(g) for g in fine_groups[i:i + k]), []) for i in range(0, len(fine_groups), k)]
+    cell_to_coarse = {}
+    for K_, g in enumerate(coarse_groups):
+        for c in g:
+            cell_to_coarse[int(c)] = K_
+    parent = np.array([cell_to_coarse[int(g[0])] for g in fine_groups], dtype=np.int32)
+    for q, g in enumerate(fine_groups):
+        assert all(cell_to_coarse[int(c)] == parent[q] for c in g)
+    return ogrid, coarse_groups, fine_groups, parent
+
+
+@pytest.mark.parametrize("dim,n,p,coarse,fine,distort", [
+    (2, 8, 1, "blocks4", "blocks2", None),
+    (2, 8, 2, "union3", "random4", (0.2, 3)),
+    (2, 8, 4, "blocks4", "blocks2", None),
+    (3, 4, 1, "union2", "random5", None),
+    (3, 4, 2, "blocks4", "blocks2", (0.15, 2)),
+    (3, 4, 3, "blocks2", "singletons", None),
+])
+def test_injection_between_agglomeration_levels(dim, n, p, coarse, fine, distort):
+    pdl = gpu()
+    import torch
+
+    ogrid, cg, fg, parent = _nested_levels(dim, n, p, coarse, fine, distort)
+    ops, oahs = [], []
+    for groups in (cg, fg):
+        _, oah = oracle_handler(dim, n, groups, p, p + 1, distort=distort)
+        _, pah = product_handler(oah.grid, groups, p, p + 1)
+        ops.append(pdl.SIPOperator(pah.flatten(), keepalive=pah))
+        oahs.append(oah)
+    (cop, fop), (coah, foah) = ops, oahs
+    T = pdl.Transfer(cop, fop, parent)
+    nd = (p + 1) ** dim
+    assert (T.m(), T.n()) == (foah.n_dofs, coah.n_dofs)
+    # checker: the injection matrix of the reference, entry by entry
+    usp = _dgq_unit_support_points(dim, p)
+    P = np.zeros((foah.n_dofs, coah.n_dofs))
+    for q in range(foah.n_polytopes):
+        flo, fhi = foah.bbox(q)
+        clo, chi = coah.bbox(int(parent[q]))
+        rows, cols = foah.get_dof_indices(q), coah.get_dof_indices(int(parent[q]))
+        for i in range(nd):
+            real = flo + usp[i] * (fhi - flo)  # fine_bbox.unit_to_real
+            phi, _ = po.fe_evaluate(po.FE_DGQ, dim, p, (real - clo) / (chi - clo))  # coarse_bbox.real_to_unit
+            P[rows[i], cols] = phi
+    x = src_vector(coah.n_dofs)
+    y = np.cos(0.11 * np.arange(foah.n_dofs)) + 0.3
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    out_f = torch.full((foah.n_dofs,), 7.0, dtype=torch.float64, device="cuda")
+    T.prolongate(out_f, xd)
+    ref = P @ x
+    assert np.abs(out_f.cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
+    T.prolongate_and_add(out_f, xd)
+    assert np.abs(out_f.cpu().numpy() - 2 * ref).max() <= 2 * TOL * np.abs(ref).max()
+    out_c = torch.full((coah.n_dofs,), -3.0, dtype=torch.float64, device="cuda")
+    T.restrict(out_c, yd)
+    ref = P.T @ y
+    assert np.abs(out_c.cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
+    T.restrict_and_add(out_c, yd)
+    assert np.abs(out_c.cpu().numpy() - 2 * ref).max() <= 2 * TOL * np.abs(ref).max()
+    # test/polydeal/distributed_injection_01: a polynomial of the space is reproduced exactly
+    # (interpolate on the coarse level, inject, compare with the interpolant on the fine level)
+    f = lambda X: X.sum(axis=-1) - 1.0 if p == 1 else (X**2).sum(axis=-1) - 1.0
+    def interpolant(oah):
+        v = np.zeros(oah.n_dofs)
+        for k in range(oah.n_polytopes):
+            lo, hi = oah.bbox(k)
+            v[oah.get_dof_indices(k)] = f(lo + usp * (hi - lo))
+        return v
+    T.prolongate(out_f, torch.from_numpy(interpolant(coah)).cuda())
+    assert np.abs(out_f.cpu().numpy() - interpolant(foah)).max() <= 1e-13
+
+
+@pytest.mark.parametrize("dim,n,p,shape,distort", [
+    (2, 8, 1, "random5", (0.25, 4)),
+    (2, 8, 3, "blocks4", None),
+    (3, 4, 2, "random6", (0.2, 6)),
+    (3, 4, 3, "blocks2", None),
+])
+def test_interpolation_to_the_fine_mesh_space(dim, n, p, shape, distort):
+    pdl = gpu()
+    import torch
+
+    oah, pah = both(dim, n, shape, p, distort=distort)
+    op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+    T = pdl.Transfer.to_cells(op)
+    nd = (p + 1) ** dim
+    n_cells = oah.grid.n_cells
+    assert (T.m(), T.n()) == (n_cells * nd, oah.n_dofs)
+    usp = _dgq_unit_support_points(dim, p)
+    P = np.zeros((n_cells * nd, oah.n_dofs))
+    for k in range(oah.n_polytopes):
+        lo, hi = oah.bbox(k)
+        cols = oah.get_dof_indices(k)
+        for c in oah.get_agglomerate(k):
+            V = oah.grid.cell_vertices(int(c))
+            for i in range(nd):
+                w = np.array([np.prod([usp[i][d] if (v >> d) & 1 else 1 - usp[i][d] for d in range(dim)]) for v in range(1 << dim)])
+                real = w @ V  # the Q1-mapped support point of the fine cell
+                phi, _ = po.fe_evaluate(po.FE_DGQ, dim, p, (real - lo) / (hi - lo))
+                P[int(c) * nd + i, cols] = phi
+    x = src_vector(oah.n_dofs)
+    y = np.cos(0.13 * np.arange(n_cells * nd)) - 0.2
+    out_f = torch.empty(n_cells * nd, dtype=torch.float64, device="cuda")
+    T.prolongate(out_f, torch.from_numpy(x).cuda())
+    ref = P @ x
+    assert np.abs(out_f.cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
+    out_c = torch.empty(oah.n_dofs, dtype=torch.float64, device="cuda")
+    T.restrict(out_c, torch.from_numpy(y).cuda())
+    ref = P.T @ y
+    assert np.abs(out_c.cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
