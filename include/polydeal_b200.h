@@ -56,7 +56,7 @@ int pd_device_count(void);
 typedef struct pd_mesh_desc
 {
   int32_t dim;       /* 2 or 3 */
-  int32_t fe_degree; /* p of FE_DGQ<dim>(p): (p+1)^dim DoFs on the bounding box   */
+  int32_t fe_degree; /* p of the element on the bounding box, see fe_kind at the end */
   int32_t n_q1d;      /* QGauss<dim>(n_q1d) on every sub-cell    (initialize_fe_values,
                          source/agglomeration_handler.cc:212-236) */
   int32_t n_q1d_face; /* QGauss<dim-1>(n_q1d_face) on every sub-face */
@@ -107,6 +107,15 @@ typedef struct pd_mesh_desc
    * (A owned, B ghost) is listed from the OWNED side whatever the visiting rule says (the SIP
    * form is symmetric under swapping sides with the normal flipped) with the sigma of the rule. */
   int32_t n_owned_polytopes;
+
+  /* element family on the bounding box (source/agglomeration_handler.cc:331-337):
+   *  PD_FE_DGQ      FE_DGQ<dim>(p): tensor Lagrange basis on the Gauss-Lobatto nodes, (p+1)^dim DoFs
+   *  PD_FE_AGGLODGP FE_AggloDGP<dim>(p) (source/fe_agglodgp.cc:28-57): products of L2[0,1]-
+   *                 orthonormal Legendre polynomials of total degree <= p, C(p+dim, dim) DoFs,
+   *                 last coordinate outermost / first fastest.  Assembly and the block-CSR apply;
+   *                 the point-wise matrix-free kernels are FE_DGQ only.
+   * Last member, so that zero-initialised descriptors of older callers mean FE_DGQ. */
+  int32_t fe_kind;
 } pd_mesh_desc;
 
 typedef struct pd_coefficients
@@ -124,6 +133,9 @@ typedef struct pd_coefficients
 #define PD_ASSEMBLE_ALL 7u
 
 /* vmult modes */
+#define PD_FE_DGQ 0
+#define PD_FE_AGGLODGP 1
+
 #define PD_VMULT_BLOCK_CSR 0   /* y = A x with the assembled matrix */
 #define PD_VMULT_MATRIX_FREE 1 /* y = A x recomputed from the quadrature data           */
 #define PD_VMULT_MAPPED_FINE 2 /* fine mesh of general hexes, mapped FE_DGQ basis (below)  */
@@ -312,7 +324,7 @@ int pdh_handler_destroy(pdh_handler *ah);
 int32_t pdh_define_agglomerate(pdh_handler *ah, const int32_t *cells, int32_t n);
 /* initialize_fe_values(QGauss<dim>(nq_cell), ..., QGauss<dim-1>(nq_face)) (:210-236) */
 int pdh_initialize_fe_values(pdh_handler *ah, int32_t nq_cell, int32_t nq_face);
-/* distribute_agglomerated_dofs(FE_DGQ<dim>(degree))  (:326-379); fe_kind 0 = FE_DGQ */
+/* distribute_agglomerated_dofs(fe)  (:326-379); fe_kind PD_FE_DGQ or PD_FE_AGGLODGP */
 int pdh_distribute_agglomerated_dofs(pdh_handler *ah, int32_t fe_kind, int32_t degree);
 
 int32_t  pdh_n_polytopes(const pdh_handler *ah);

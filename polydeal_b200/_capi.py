@@ -29,7 +29,7 @@ class MeshDesc(C.Structure):
         ("n_ifaces", i32), ("iface_polyA", P(i32)), ("iface_polyB", P(i32)), ("iface_sub_ptr", P(i64)),
         ("sub_cell", P(i32)), ("sub_face", P(i32)), ("sub_sigma", P(f64)),
         ("n_block_rows", i32), ("brow_ptr", P(i64)), ("bcol_idx", P(i32)),
-        ("n_owned_polytopes", i32),
+        ("n_owned_polytopes", i32), ("fe_kind", i32),
     ]
 
 

@@ -296,18 +296,24 @@ namespace pd
   {
     require_device();
     validate(d);
-    if (!assemble_supported(d.dim, d.fe_degree))
-      throw Error(PD_ERR_UNSUPPORTED, "no sm_100a kernel for FE_DGQ<" + std::to_string(d.dim) + ">(" +
-                                        std::to_string(d.fe_degree) + "); supported: 2-D p=1..4, 3-D p=1..3");
+    if (!assemble_supported(d.dim, d.fe_degree, d.fe_kind))
+      throw Error(PD_ERR_UNSUPPORTED, std::string("no sm_100a kernel for ") +
+                                        (d.fe_kind == PD_FE_AGGLODGP ? "FE_AggloDGP<" : "FE_DGQ<") + std::to_string(d.dim) +
+                                        ">(" + std::to_string(d.fe_degree) + "); supported: 2-D p=1..4, 3-D p=1..3");
     pd_handle *h = new pd_handle;
     try
       {
         h->dim    = d.dim;
         h->degree = d.fe_degree;
         h->n1     = d.fe_degree + 1;
-        h->n      = 1;
-        for (int k = 0; k < d.dim; ++k)
-          h->n *= h->n1;
+        h->fe_kind = d.fe_kind;
+        h->n       = 1;
+        if (d.fe_kind == PD_FE_DGQ)
+          for (int k = 0; k < d.dim; ++k)
+            h->n *= h->n1;
+        else
+          for (int k = 1; k <= d.dim; ++k)
+            h->n = h->n * (d.fe_degree + k) / k;
         h->nq1  = d.n_q1d;
         h->nq1f = d.n_q1d_face;
         h->nqc  = 1;
@@ -445,8 +451,11 @@ namespace pd
         // quadrature streams, work buffers and the matrix are allocated on first use
         // (ensure_assembly_buffers): a handle used only for the matrix-free apply never
         // pays for them
-        setup_fine_operator(h, d);
-        setup_mapped_operator(h, d);
+        if (h->fe_kind == PD_FE_DGQ)
+          {
+            setup_fine_operator(h, d);
+            setup_mapped_operator(h, d);
+          }
         PD_CUDA(cudaStreamSynchronize(h->stream));
       }
     catch (...)
@@ -522,7 +531,7 @@ extern "C"
         throw Error(PD_ERR_INVALID, "pd_upload: null argument");
       const int64_t nsc = d->poly_subcell_ptr[d->n_polytopes];
       const int64_t nsf = d->n_ifaces ? d->iface_sub_ptr[d->n_ifaces] : 0;
-      if (d->dim != h->dim || d->fe_degree != h->degree || d->n_q1d != h->nq1 || d->n_q1d_face != h->nq1f ||
+      if (d->dim != h->dim || d->fe_degree != h->degree || d->fe_kind != h->fe_kind || d->n_q1d != h->nq1 || d->n_q1d_face != h->nq1f ||
           d->n_verts != h->n_verts || d->n_cells != h->n_cells || d->n_polytopes != h->np ||
           (d->n_owned_polytopes > 0 ? d->n_owned_polytopes : d->n_polytopes) != h->np_own ||
           d->n_ifaces != h->n_ifaces || nsc != h->n_subcells || nsf != h->n_subfaces ||
@@ -629,6 +638,8 @@ extern "C"
     return guarded([&] {
       if (!h || !rhs_dev)
         throw Error(PD_ERR_INVALID, "pd_assemble_rhs: null argument");
+      if (h->fe_kind != PD_FE_DGQ)
+        throw Error(PD_ERR_UNSUPPORTED, "pd_assemble_rhs: FE_DGQ only");
       need_quadrature(h);
       launch_poly_rhs(h, f_vol_dev, g_face_dev, stiffness, rhs_dev);
     });
@@ -641,6 +652,8 @@ extern "C"
     return guarded([&] {
       if (!h || !u_dev || !exact_dev || !l2)
         throw Error(PD_ERR_INVALID, "pd_error_norms: null argument");
+      if (h->fe_kind != PD_FE_DGQ)
+        throw Error(PD_ERR_UNSUPPORTED, "pd_error_norms: FE_DGQ only");
       if (h1_seminorm && !exact_grad_dev)
         throw Error(PD_ERR_INVALID, "pd_error_norms: the H1 seminorm needs the exact gradient");
       need_quadrature(h);
@@ -692,6 +705,8 @@ extern "C"
     return guarded([&] {
       if (!coarse || !fine || !parent_of_fine || !out)
         throw Error(PD_ERR_INVALID, "pd_transfer_create: null argument");
+      if (coarse->fe_kind != PD_FE_DGQ || fine->fe_kind != PD_FE_DGQ)
+        throw Error(PD_ERR_UNSUPPORTED, "pd_transfer_create: FE_DGQ only");
       if (coarse->dim != fine->dim || coarse->degree != fine->degree)
         throw Error(PD_ERR_INVALID, "pd_transfer_create: the two levels must use the same FE_DGQ space");
       std::unique_ptr<pd_transfer> t(new pd_transfer);
@@ -712,6 +727,8 @@ extern "C"
     return guarded([&] {
       if (!h || !out)
         throw Error(PD_ERR_INVALID, "pd_transfer_create_to_cells: null argument");
+      if (h->fe_kind != PD_FE_DGQ)
+        throw Error(PD_ERR_UNSUPPORTED, "pd_transfer_create_to_cells: FE_DGQ only");
       std::unique_ptr<pd_transfer> t(new pd_transfer);
       t->coarse      = h;
       t->kind        = 1;
@@ -887,6 +904,8 @@ extern "C"
           throw Error(PD_ERR_STATE, "pd_vmult(BLOCK_CSR): pd_assemble has not been called");
         launch_spmv(h, src, dst, add);
       }
+    else if (h->fe_kind != PD_FE_DGQ)
+      throw Error(PD_ERR_UNSUPPORTED, "the matrix-free applies are implemented for FE_DGQ only; use PD_VMULT_BLOCK_CSR");
     else if (mode == PD_VMULT_MATRIX_FREE)
       {
         if (h->mf_ready && !h->force_generic_mf)

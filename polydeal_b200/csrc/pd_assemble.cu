@@ -156,7 +156,7 @@ namespace pd
             // BoundingBox::real_to_unit, covariant scaling by 1/h
             const double xhat = (x - lo) / (hi - lo);
             double       L[N1], dL[N1];
-            lagrange<N1>(A.basis, xhat, inv_h, L, dL);
+            basis_1d<C>(A.basis, xhat, inv_h, L, dL);
             double *Tq = Tb + (s & 1) * TSZ + td * 2 * N1 * TQ + lane;
 #pragma unroll
             for (int a = 0; a < N1; ++a)
@@ -190,11 +190,14 @@ namespace pd
                   {
                     const double ly0 = Tq[(2 * N1 + wu) * TQ];
                     const double ly = ly0 * sg, dy = Tq[(3 * N1 + wu) * TQ] * sg, lym = ly0 * sm;
+                    const int    row0 = C::unit_base(wu), cnt = C::unit_count(wu);
 #pragma unroll
                     for (int a = 0; a < N1; ++a)
                       {
+                        if (a >= cnt)
+                          break;
                         const double lx = Tq[a * TQ], dx = Tq[(N1 + a) * TQ];
-                        double      *o  = Gq + (wu * N1 + a) * RS;
+                        double      *o  = Gq + (row0 + a) * RS;
                         o[0]            = dx * ly;
                         o[TQ]           = lx * dy;
                         if (MASS)
@@ -208,11 +211,14 @@ namespace pd
                     const double lz = Tq[(4 * N1 + c) * TQ], dz = Tq[(5 * N1 + c) * TQ];
                     const double yz0 = ly * lz;
                     const double yz = yz0 * sg, dyz = dy * lz * sg, ydz = ly * dz * sg, yzm = yz0 * sm;
+                    const int    row0 = C::unit_base(wu), cnt = C::unit_count(wu);
 #pragma unroll
                     for (int a = 0; a < N1; ++a)
                       {
+                        if (a >= cnt)
+                          break;
                         const double lx = Tq[a * TQ], dx = Tq[(N1 + a) * TQ];
-                        double      *o  = Gq + (wu * N1 + a) * RS;
+                        double      *o  = Gq + (row0 + a) * RS;
                         o[0]            = dx * yz;
                         o[TQ]           = lx * dyz;
                         o[2 * TQ]       = lx * ydz;
@@ -478,7 +484,7 @@ namespace pd
               return;
             const double xhat = (x - lo) / (hi - lo);
             double       L[N1], dL[N1];
-            lagrange<N1>(A.basis, xhat, nd * inv_h, L, dL);
+            basis_1d<C>(A.basis, xhat, nd * inv_h, L, dL);
             double *Tq = Tb + (s & 1) * TSZ + (tside * DIM + td) * 2 * N1 * TQ + lane;
 #pragma unroll
             for (int a = 0; a < N1; ++a)
@@ -520,14 +526,17 @@ namespace pd
                     s1 = ly * lz;
                     s2 = dy * lz + ly * dz;
                   }
+                const int row0 = C::unit_base(bc), cnt = C::unit_count(bc);
 #pragma unroll
                 for (int a = 0; a < N1; ++a)
                   {
+                    if (a >= cnt)
+                      break;
                     const double lx = Tq[a * TQ], dx = Tq[(N1 + a) * TQ];
                     const double v  = lx * s1;
                     const double dn = dx * s1 + lx * s2;
                     const double V  = sgn * v;
-                    const int    col = side * NP + bc * N1 + a;
+                    const int    col = side * NP + row0 + a;
                     Vp[col * RS]     = V * wq; // JxW * coefficient folded into the V operand
                     Zp[col * RS]     = hs * V - dscale * dn;
                   }
@@ -892,8 +901,10 @@ namespace pd
   }
 
   bool
-  assemble_supported(const int dim, const int degree)
+  assemble_supported(const int dim, const int degree, const int fe_kind)
   {
+    if (fe_kind != PD_FE_DGQ && fe_kind != PD_FE_AGGLODGP)
+      return false;
     if (dim == 2)
       return degree >= 1 && degree <= 4;
     if (dim == 3)
@@ -907,10 +918,17 @@ namespace pd
     // off-diagonal blocks are only written by interior interfaces: clear when skipped
     if (!(flags & PD_ASSEMBLE_INTERIOR))
       PD_CUDA(cudaMemsetAsync(h->values.p, 0, sizeof(double) * h->nnz, h->stream));
-    const int key = h->dim * 10 + h->degree;
+    const int key = h->fe_kind * 100 + h->dim * 10 + h->degree;
     switch (key)
       {
         //                 DIM DEG ISPLIT KSPLIT MINB
+        case 121: run_all<2, DGP_BASE + 1, 1, 2, 2>(h, flags, coef); break; // FE_AggloDGP
+        case 122: run_all<2, DGP_BASE + 2, 1, 2, 2>(h, flags, coef); break;
+        case 123: run_all<2, DGP_BASE + 3, 1, 2, 2>(h, flags, coef); break;
+        case 124: run_all<2, DGP_BASE + 4, 1, 2, 2>(h, flags, coef); break;
+        case 131: run_all<3, DGP_BASE + 1, 1, 2, 2>(h, flags, coef); break;
+        case 132: run_all<3, DGP_BASE + 2, 1, 2, 2>(h, flags, coef); break;
+        case 133: run_all<3, DGP_BASE + 3, 1, 2, 2>(h, flags, coef); break;
         case 21: run_all<2, 1, 1, 2, 2>(h, flags, coef); break;
         case 22: run_all<2, 2, 1, 2, 2>(h, flags, coef); break;
         case 23: run_all<2, 3, 1, 2, 2>(h, flags, coef); break;

@@ -204,16 +204,23 @@ namespace pd
     void
     distribute_agglomerated_dofs(const int32_t fe_kind, const int32_t degree)
     {
-      if (fe_kind != 0)
-        throw Error(PD_ERR_UNSUPPORTED, "Currently, this interface supports only DGQ bases on the device path.");
+      // the reference accepts FE_DGQ, FE_AggloDGP (and FE_SimplexDGP, not on this path),
+      // source/agglomeration_handler.cc:331-337
+      if (fe_kind != PD_FE_DGQ && fe_kind != PD_FE_AGGLODGP)
+        throw Error(PD_ERR_UNSUPPORTED, "Currently, this interface supports only DGQ and DGP bases.");
       if (degree < 0 || degree > 5)
-        throw Error(PD_ERR_UNSUPPORTED, "FE_DGQ degree must be in [0,5]");
+        throw Error(PD_ERR_UNSUPPORTED, "the polynomial degree must be in [0,5]");
       if (masters.empty())
         throw Error(PD_ERR_STATE, "No agglomeration has been performed.");
       fe_degree     = degree;
+      this->fe_kind = fe_kind;
       dofs_per_cell = 1;
-      for (int d = 0; d < dim; ++d)
-        dofs_per_cell *= degree + 1;
+      if (fe_kind == PD_FE_DGQ)
+        for (int d = 0; d < dim; ++d)
+          dofs_per_cell *= degree + 1;
+      else // C(p + dim, dim)
+        for (int d = 1; d <= dim; ++d)
+          dofs_per_cell = dofs_per_cell * (degree + d) / d;
       // rank of each master among all masters by active cell index
       std::vector<int32_t> order(masters.size());
       for (size_t i = 0; i < order.size(); ++i)
@@ -395,6 +402,7 @@ namespace pd
       d                  = pd_mesh_desc{};
       d.dim              = dim;
       d.fe_degree        = fe_degree;
+      d.fe_kind          = fe_kind;
       d.n_q1d            = n_q1d;
       d.n_q1d_face       = n_q1d_face;
       d.n_verts          = grid->n_verts();
@@ -573,6 +581,7 @@ namespace pd
       d                   = pd_mesh_desc{};
       d.dim               = dim;
       d.fe_degree         = fe_degree;
+      d.fe_kind           = fe_kind;
       d.n_q1d             = n_q1d;
       d.n_q1d_face        = n_q1d_face;
       // the rank only needs the cells of its own polytopes (interfaces are listed from the
@@ -635,7 +644,7 @@ namespace pd
 
     Grid     *grid;
     int       dim;
-    int32_t   fe_degree = -1, dofs_per_cell = 0, n_q1d = 0, n_q1d_face = 0;
+    int32_t   fe_degree = -1, fe_kind = 0, dofs_per_cell = 0, n_q1d = 0, n_q1d_face = 0;
     bool      connectivity_ready = false;
 
     std::vector<int32_t> poly_of_cell; // -1: cell not agglomerated

@@ -81,6 +81,7 @@ namespace pd
 struct pd_handle
 {
   int     dim = 0, degree = 0, n1 = 0, n = 0; // n = dofs per polytope
+  int     fe_kind = PD_FE_DGQ;
   int     nq1 = 0, nq1f = 0, nqc = 0, nqf = 0;
   int64_t n_verts = 0, n_cells = 0, n_subcells = 0, n_subfaces = 0;
   int32_t np = 0, np_own = 0, n_ifaces = 0; // np_own owned polytopes (rows) + ghosts = np
@@ -168,7 +169,7 @@ namespace pd
   void launch_quadrature(pd_handle *h);
   // pd_assemble.cu
   void launch_assemble(pd_handle *h, uint32_t flags, const pd_coefficients &coef);
-  bool assemble_supported(int dim, int degree);
+  bool assemble_supported(int dim, int degree, int fe_kind);
   // pd_finemesh.cu
   void setup_fine_operator(pd_handle *h, const pd_mesh_desc &d);
   void launch_fine_operator(pd_handle *h, const double *src, double *dst, bool add);

@@ -503,5 +503,9 @@ class Transfer:
         K.check(K.lib().pd_transfer_restrict(self._h, C.c_void_p(src_fine.data_ptr()), C.c_void_p(dst_coarse.data_ptr()), int(add)))
         return dst_coarse
 
+    def synchronize(self):
+        """Transfers run on the coarse operator's stream."""
+        self._keep[0].synchronize()
+
     vmult = prolongate
     Tvmult = restrict

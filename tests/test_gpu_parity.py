@@ -761,15 +761,19 @@ def test_injection_between_agglomeration_levels(dim, n, p, coarse, fine, distort
     xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
     out_f = torch.full((foah.n_dofs,), 7.0, dtype=torch.float64, device="cuda")
     T.prolongate(out_f, xd)
+    T.synchronize()
     ref = P @ x
     assert np.abs(out_f.cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
     T.prolongate_and_add(out_f, xd)
+    T.synchronize()
     assert np.abs(out_f.cpu().numpy() - 2 * ref).max() <= 2 * TOL * np.abs(ref).max()
     out_c = torch.full((coah.n_dofs,), -3.0, dtype=torch.float64, device="cuda")
     T.restrict(out_c, yd)
+    T.synchronize()
     ref = P.T @ y
     assert np.abs(out_c.cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
     T.restrict_and_add(out_c, yd)
+    T.synchronize()
     assert np.abs(out_c.cpu().numpy() - 2 * ref).max() <= 2 * TOL * np.abs(ref).max()
     # test/polydeal/distributed_injection_01: a polynomial of the space is reproduced exactly
     # (interpolate on the coarse level, inject, compare with the interpolant on the fine level)
@@ -781,6 +785,7 @@ def test_injection_between_agglomeration_levels(dim, n, p, coarse, fine, distort
             v[oah.get_dof_indices(k)] = f(lo + usp * (hi - lo))
         return v
     T.prolongate(out_f, torch.from_numpy(interpolant(coah)).cuda())
+    T.synchronize()
     assert np.abs(out_f.cpu().numpy() - interpolant(foah)).max() <= 1e-13
 
 
@@ -816,9 +821,59 @@ def test_interpolation_to_the_fine_mesh_space(dim, n, p, shape, distort):
     y = np.cos(0.13 * np.arange(n_cells * nd)) - 0.2
     out_f = torch.empty(n_cells * nd, dtype=torch.float64, device="cuda")
     T.prolongate(out_f, torch.from_numpy(x).cuda())
+    T.synchronize()
     ref = P @ x
     assert np.abs(out_f.cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
     out_c = torch.empty(oah.n_dofs, dtype=torch.float64, device="cuda")
     T.restrict(out_c, torch.from_numpy(y).cuda())
+    T.synchronize()
     ref = P.T @ y
     assert np.abs(out_c.cpu().numpy() - ref).max() <= TOL * np.abs(ref).max()
+
+
+# ----------------------------------------------------------------------------------
+# row 5 / "next" row N4: FE_AggloDGP on the bounding box (source/fe_agglodgp.cc:28-57)
+# ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,n,shape,p,nq,distort,kw", [
+    (2, 8, "blocks4", 1, 2, None, {}),
+    (2, 8, "random5", 2, 3, (0.2, 3), {}),
+    (2, 8, "random4", 3, 4, None, dict(mass_coeff=0.5)),
+    (2, 8, "blocks2", 4, 5, None, {}),
+    (3, 4, "random6", 1, 2, None, {}),
+    (3, 4, "blocks2", 2, 3, (0.15, 2), dict(mass_coeff=2.0, stiffness_coeff=0.3)),
+    (3, 4, "random3", 3, 4, None, {}),
+    (3, 4, "singletons", 2, 3, None, dict(with_boundary=False)),
+])
+def test_assembly_with_fe_agglodgp(dim, n, shape, p, nq, distort, kw):
+    """assemble_dg_matrix with FE_AggloDGP<dim>(p): C(p+dim, dim) Legendre products per polytope."""
+    pdl = gpu()
+    import math
+    import torch
+
+    ogrid = po.Grid(dim, n, 0.0, 1.0, 0)
+    groups = groups_for(shape, dim, n, ogrid, 1)
+    _, oah = oracle_handler(dim, n, groups, p, nq, distort=distort, fe_kind=po.FE_AGGLODGP)
+    v, cv, nb = oah.grid.arrays()
+    pah = pdl.AgglomerationHandler(pdl.Grid.from_arrays(v, cv, nb))
+    for g_ in groups:
+        pah.define_agglomerate(g_)
+    pah.initialize_fe_values(nq)
+    pah.distribute_agglomerated_dofs(pdl.FE_AGGLODGP, p)
+    nd = math.comb(p + dim, dim)
+    assert pah.n_dofs_per_cell == oah.n_dofs_per_cell == nd
+    ref = po.assemble_dg_matrix(oah, degree=p, n_threads=4, **kw)
+    op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+    flags = pdl.ASSEMBLE_ALL if kw.get("with_boundary", True) else (pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR)
+    op.assemble(flags, kw.get("stiffness_coeff", 1.0), kw.get("mass_coeff", 0.0))
+    rowptr, cols = op.pattern()
+    rp, rc, rv = ref.csr()
+    assert np.array_equal(rowptr, rp) and np.array_equal(cols, rc)  # sparsity bit-exact
+    assert_blocks_close(op.values(), rv, nd, rowptr)
+    x = src_vector(op.m())
+    y = torch.empty(op.m(), dtype=torch.float64, device="cuda")
+    op.vmult(y, torch.from_numpy(x).cuda())
+    op.synchronize()
+    yref = ref.vmult(x)
+    assert np.abs(y.cpu().numpy() - yref).max() <= TOL * np.abs(yref).max()
+    with pytest.raises(pdl.PolydealError):
+        op.vmult(y, torch.from_numpy(x).cuda(), mode=pdl.VMULT_MATRIX_FREE)

@@ -165,8 +165,8 @@ def test_error_behaviour():
         ah.define_agglomerate([c])
     with pytest.raises(pdl.PolydealError, match="forgot to distribute"):
         ah.n_faces(0)
-    with pytest.raises(pdl.PolydealError, match="only DGQ"):
-        ah.distribute_agglomerated_dofs(1, 1)
+    with pytest.raises(pdl.PolydealError, match="only DGQ and DGP"):
+        ah.distribute_agglomerated_dofs(2, 1)  # FE_SimplexDGP is not on this path
     ah.distribute_agglomerated_dofs(pdl.FE_DGQ, 1)
     with pytest.raises(pdl.PolydealError, match="face index out of range"):
         ah.neighbor(0, 99)
@@ -192,3 +192,28 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".hpp", ".h", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and False, os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 3), (3, 1), (3, 2)])
+def test_fe_agglodgp_numbering_and_sparsity_match_the_oracle(dim, p):
+    """FE_AggloDGP<dim>(p): C(p+dim, dim) DoFs per polytope, same block numbering and pattern rules."""
+    import math
+
+    n = 4
+    ogrid = po.Grid(dim, n, 0.0, 1.0, 0)
+    groups = groups_for("random3", dim, n, ogrid, 2)
+    _, oah = oracle_handler(dim, n, groups, p, p + 1, fe_kind=po.FE_AGGLODGP)
+    v, cv, nb = oah.grid.arrays()
+    pah = pdl.AgglomerationHandler(pdl.Grid.from_arrays(v, cv, nb))
+    for g in groups:
+        pah.define_agglomerate(g)
+    pah.initialize_fe_values(p + 1)
+    pah.distribute_agglomerated_dofs(pdl.FE_AGGLODGP, p)
+    assert pah.n_dofs_per_cell == oah.n_dofs_per_cell == math.comb(p + dim, dim)
+    assert pah.n_dofs == oah.n_dofs
+    for k in range(oah.n_polytopes):
+        assert np.array_equal(pah.get_dof_indices(k), oah.get_dof_indices(k))
+    rp, cols = pah.create_agglomeration_sparsity_pattern()
+    orp, ocols = oah.create_agglomeration_sparsity_pattern()
+    assert np.array_equal(rp, orp) and np.array_equal(cols, ocols)
+    assert pah.flatten().fe_kind == pdl.FE_AGGLODGP
