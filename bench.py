@@ -282,29 +282,46 @@ def run_gpu(args):
     x = torch.from_numpy(np.sin(0.37 * np.arange(n_src)) + 0.01 * (np.arange(n_src) % 7)).cuda()
     y = torch.empty(n_dofs, dtype=torch.float64, device="cuda")
 
-    def apply():
+    # one exchange step per apply (ghost-polytope coefficients): over NVLink peer memory
+    # (csrc/pd_peer.cu: publish + pull kernels, flag handshake) and, for comparison, NCCL
+    peer = pdd.PeerExchange(part, op) if part is not None else None
+
+    def apply(use_peer=True):
         if part is not None:
-            # one exchange step per apply: ghost-polytope coefficients, grouped NCCL send/recv
-            pdd.exchange_ghost_values(part, x)
+            if use_peer:
+                peer.exchange(x)
+            else:
+                pdd.exchange_ghost_values(part, x)
         op.vmult_ptr(y.data_ptr(), x.data_ptr())
 
-    for _ in range(3):
-        apply()
-    vm = []
-    for _ in range(max(args.steps, 5)):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        apply()
-        b.record(stream)
-        b.synchronize()
-        vm.append(a.elapsed_time(b))
-    t_vm_ms = statistics.mean(vm)
+    def time_apply(use_peer):
+        for _ in range(3):
+            apply(use_peer)
+        vm = []
+        for _ in range(max(args.steps, 5)):
+            flush.zero_()
+            if dist:
+                dist.barrier()  # ranks enter the timed apply together, as in a solver iteration
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            apply(use_peer)
+            b.record(stream)
+            b.synchronize()
+            vm.append(a.elapsed_time(b))
+        return statistics.mean(vm)
 
-    times = torch.tensor([t_ms, t_e2e_ms, t_vm_ms], dtype=torch.float64, device="cuda")
+    t_vm_ms = time_apply(True)
+    t_vm_nccl_ms = time_apply(False) if part is not None else t_vm_ms
+    if peer is not None:
+        assert peer.ok(), "peer exchange timed out"
+
+    times = torch.tensor([t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_ms, t_e2e_ms, t_vm_ms = (float(v) for v in times.cpu())
+    t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms = (float(v) for v in times.cpu())
+    if peer is not None:
+        dist.barrier()  # nobody unmaps while a neighbour may still pull
+        peer.close()
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -337,7 +354,7 @@ def run_gpu(args):
                    "volume_q_points_per_gpu": Q,
                    "sharding": "single GPU" if world == 1 else
                    f"[0,1]^2 x [0,{world}] in {world} z-slabs of 512 polyhedra, cut interfaces evaluated by both sides "
-                   "from ghost bbox + DoF block (no assembly collective); vmult exchanges ghost blocks over NCCL",
+                   "from ghost bbox + DoF block (no assembly collective); vmult pulls ghost blocks over NVLink peer memory",
                    "ghost_polytopes_per_gpu": int(desc.n_polytopes - n_dofs // n),
                    "l2": "flushed (512 MiB memset) between timed steps; inputs 226 MB > L2 as well",
                    "step": "quadrature + volume + faces + diagonal gather, all device kernels"},
@@ -352,12 +369,15 @@ def run_gpu(args):
                      "hbm_frac_of_same_kernel": vol_bytes / (vol_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
         "kernel_ms": {k: statistics.mean(v) for k, v in kms.items()},
         "vmult": {"metric": "SIP vmult GDoF/s (block-CSR apply of the assembled operator"
-                            + (", incl. NCCL ghost exchange)" if world > 1 else ")"),
+                            + (", incl. the ghost exchange over NVLink peer memory)" if world > 1 else ")"),
                   "value": world * n_dofs / (t_vm_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t_vm_ms,
                   "roofline": {"bound": "hbm", "achieved": vm_bytes / (t_vm_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": vm_bytes / (t_vm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                "peak_source": peaks["hbm_src"]}},
     }
+    if world > 1:
+        out["vmult"]["ms_with_nccl_exchange"] = t_vm_nccl_ms
+        out["vmult"]["exchange"] = "publish + pull kernels over CUDA-IPC peer memory, epoch-flag handshake (pd_peer_*); NCCL all_to_all_single timed beside it"
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(full=True)
     print(json.dumps(out))

@@ -205,6 +205,28 @@ int64_t pd_transfer_n(const pd_transfer *t); /* coarse DoFs */
 int pd_transfer_prolongate(pd_transfer *t, const double *src_coarse_dev, double *dst_fine_dev, int add);
 int pd_transfer_restrict(pd_transfer *t, const double *src_fine_dev, double *dst_coarse_dev, int add);
 
+/* --- ghost exchange of the sharded vmult over NVLink peer memory ------------------------------
+ * One process per GPU on one node.  Instead of a message per apply (update_ghost_values() inside
+ * MatrixFree::loop, include/utils.h:466-472), every rank publishes the blocks its neighbours need
+ * into a buffer they have mapped through CUDA IPC and pulls its ghost blocks with loads over
+ * NVLink; ordering is an epoch-flag handshake in the same memory, double buffered (pd_peer.cu).
+ * Plan (all in polytope blocks): send_ptr[world+1] / send_blocks = my owned blocks needed by
+ * each peer; recv_ptr[world+1] = my ghost section grouped by owner rank; remote_offset[s] = where
+ * my segment starts in rank s's send list (= s's send_ptr[my rank]).
+ *   pd_peer_create -> pd_peer_export (pd_peer_handle_bytes() bytes) -> all-gather the handles by
+ *   any means (once) -> pd_peer_connect([world][bytes]) -> pd_peer_exchange(x_full) before every
+ *   pd_vmult: fills the ghost section of x_full (length pd_n_source_dofs) on the handle's stream.
+ * pd_peer_status != PD_OK after a synchronize means a neighbour did not arrive within ~2 s. */
+typedef struct pd_peer pd_peer;
+int pd_peer_create(pd_handle *h, int rank, int world, const int64_t *send_ptr, const int32_t *send_blocks,
+                   const int64_t *recv_ptr, const int64_t *remote_offset, pd_peer **out);
+int pd_peer_handle_bytes(void);
+int pd_peer_export(pd_peer *p, void *handles_out);
+int pd_peer_connect(pd_peer *p, const void *all_handles);
+int pd_peer_exchange(pd_peer *p, double *x_full_dev);
+int pd_peer_status(pd_peer *p);
+void pd_peer_destroy(pd_peer *p);
+
 /* mark the device quadrature stale (vertices changed through pd_upload do this
  * implicitly): the next pd_assemble rebuilds it */
 int pd_invalidate_quadrature(pd_handle *h);

@@ -76,6 +76,13 @@ SIGNATURES = {
     "pd_transfer_n": (C.c_int64, [vp]),
     "pd_transfer_prolongate": (C.c_int, [vp, vp, vp, C.c_int]),
     "pd_transfer_restrict": (C.c_int, [vp, vp, vp, C.c_int]),
+    "pd_peer_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(vp)]),
+    "pd_peer_handle_bytes": (C.c_int, []),
+    "pd_peer_export": (C.c_int, [vp, C.c_void_p]),
+    "pd_peer_connect": (C.c_int, [vp, C.c_void_p]),
+    "pd_peer_exchange": (C.c_int, [vp, C.c_void_p]),
+    "pd_peer_status": (C.c_int, [vp]),
+    "pd_peer_destroy": (None, [vp]),
     "pd_n_quadrature_points": (C.c_int64, [vp, C.c_int]),
     "pd_quadrature_device": (C.c_int, [vp] + [C.POINTER(C.c_void_p)] * 5),
     "pd_quadrature_to_host": (C.c_int, [vp] + [C.c_void_p] * 5),

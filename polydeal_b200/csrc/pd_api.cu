@@ -784,6 +784,47 @@ extern "C"
   }
 
   int
+  pd_peer_create(pd_handle *h, int rank, int world, const int64_t *send_ptr, const int32_t *send_blocks,
+                 const int64_t *recv_ptr, const int64_t *remote_offset, pd_peer **out)
+  {
+    return guarded([&] {
+      if (!out)
+        throw Error(PD_ERR_INVALID, "pd_peer_create: null argument");
+      *out = peer_create(h, rank, world, send_ptr, send_blocks, recv_ptr, remote_offset);
+    });
+  }
+  int
+  pd_peer_handle_bytes(void)
+  {
+    return peer_handle_bytes();
+  }
+  int
+  pd_peer_export(pd_peer *p, void *handles_out)
+  {
+    return guarded([&] { peer_export(p, handles_out); });
+  }
+  int
+  pd_peer_connect(pd_peer *p, const void *all_handles)
+  {
+    return guarded([&] { peer_connect(p, all_handles); });
+  }
+  int
+  pd_peer_exchange(pd_peer *p, double *x_full_dev)
+  {
+    return guarded([&] { peer_exchange(p, x_full_dev); });
+  }
+  int
+  pd_peer_status(pd_peer *p)
+  {
+    return peer_status(p);
+  }
+  void
+  pd_peer_destroy(pd_peer *p)
+  {
+    peer_destroy(p);
+  }
+
+  int
   pd_invalidate_quadrature(pd_handle *h)
   {
     return guarded([&] {

@@ -150,6 +150,7 @@ struct pd_handle
   int64_t      max_row_len = -1; // longest scalar row (doubles), computed lazily for the SpMV dispatch
 };
 
+struct pd_peer;
 // level transfer between a handle's polytopal space and a finer space (pd_polyapply.cu)
 struct pd_transfer
 {
@@ -187,6 +188,15 @@ namespace pd
   double solver_lambda_max(pd_handle *h, int mode, int n_iter);
   void   solver_chebyshev(pd_handle *h, int mode, int degree, double lambda_max, double smoothing_range, const double *b,
                           double *x, int zero_initial_guess);
+  // pd_peer.cu (all throw; the extern "C" wrappers live in pd_api.cu)
+  pd_peer *peer_create(pd_handle *h, int rank, int world, const int64_t *send_ptr, const int32_t *send_blocks,
+                       const int64_t *recv_ptr, const int64_t *remote_offset);
+  int      peer_handle_bytes();
+  void     peer_export(pd_peer *p, void *handles_out);
+  void     peer_connect(pd_peer *p, const void *all_handles);
+  void     peer_exchange(pd_peer *p, double *x_full_dev);
+  int      peer_status(pd_peer *p);
+  void     peer_destroy(pd_peer *p);
   // pd_vmult.cu
   void launch_spmv(pd_handle *h, const double *src, double *dst, bool add);
   void launch_diagonal_inverse(pd_handle *h, double *dst);

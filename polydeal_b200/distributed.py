@@ -143,6 +143,57 @@ def exchange_ghost_values(part: LocalPart, x_full, group=None):
     return x_full
 
 
+class PeerExchange:
+    """update_ghost_values() over NVLink peer memory (pd_peer_*, csrc/pd_peer.cu): every rank
+    publishes the blocks its neighbours need into an IPC-mapped buffer and pulls its ghost blocks
+    with plain loads, ordered by an epoch-flag handshake -- two small kernels on the operator's
+    stream per apply, no NCCL call on the data path.  Setup (once) all-gathers the send counts
+    and the CUDA IPC handles through `torch.distributed`."""
+
+    def __init__(self, part: LocalPart, op: SIPOperator, group=None):
+        import torch.distributed as dist
+
+        self.part, self.op = part, op
+        world, rank = part.n_ranks, part.rank
+        if dist.get_world_size(group) != world:
+            raise ValueError("the partition has a different number of ranks than the process group")
+        send_ptr = np.zeros(world + 1, dtype=np.int64)
+        send_ptr[1:] = np.cumsum(part.send_counts)
+        recv_ptr = np.zeros(world + 1, dtype=np.int64)
+        recv_ptr[1:] = np.cumsum(part.recv_counts)
+        send_blocks = np.ascontiguousarray(np.concatenate(part.send_blocks) if world else np.zeros(0), dtype=np.int32)
+        all_ptr = [None] * world
+        dist.all_gather_object(all_ptr, send_ptr.tolist(), group=group)
+        remote_off = np.array([all_ptr[s][rank] for s in range(world)], dtype=np.int64)
+        for s in range(world):  # what s sends me is what I expect from s
+            assert all_ptr[s][rank + 1] - all_ptr[s][rank] == part.recv_counts[s]
+        self._h = C.c_void_p()
+        K.check(K.lib().pd_peer_create(op._h, rank, world, _ptr(send_ptr), _ptr(send_blocks), _ptr(recv_ptr),
+                                       _ptr(remote_off), C.byref(self._h)))
+        nb = K.lib().pd_peer_handle_bytes()
+        mine = (C.c_char * nb)()
+        K.check(K.lib().pd_peer_export(self._h, mine))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine), group=group)
+        blob = b"".join(handles)
+        K.check(K.lib().pd_peer_connect(self._h, blob))
+        dist.barrier(group=group)  # every rank has mapped its neighbours before anyone publishes
+
+    def exchange(self, x_full):
+        K.check(K.lib().pd_peer_exchange(self._h, C.c_void_p(x_full.data_ptr())))
+        return x_full
+
+    def ok(self):
+        return K.lib().pd_peer_status(self._h) == 0
+
+    def close(self):
+        if getattr(self, "_h", None) and K._lib is not None:
+            K._lib.pd_peer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
 class DistributedSIPOperator:
     """One rank's share of the SIP operator: local assembly with ghost interfaces and a
     vmult that exchanges the ghost-polytope coefficients first."""
@@ -152,6 +203,12 @@ class DistributedSIPOperator:
         self.op = SIPOperator(self.part.desc, keepalive=(ah, self.part))
         self.group = group
         self._x_full = None
+        self.peer = None
+
+    def enable_peer_exchange(self):
+        """Switch the ghost exchange of vmult from NCCL to NVLink peer memory (collective call)."""
+        self.peer = PeerExchange(self.part, self.op, self.group)
+        return self
 
     def assemble(self, flags=K.ASSEMBLE_ALL, stiffness=1.0, mass=0.0):
         self.op.assemble(flags, stiffness, mass)
@@ -168,6 +225,9 @@ class DistributedSIPOperator:
             self._x_full = torch.empty(p.n_local_dofs, dtype=torch.float64, device=src.device)
         self._x_full[: p.n_owned_dofs].copy_(src)
         if exchange and p.n_ranks > 1:
-            exchange_ghost_values(p, self._x_full, self.group)
+            if self.peer is not None:
+                self.peer.exchange(self._x_full)
+            else:
+                exchange_ghost_values(p, self._x_full, self.group)
         self.op.vmult_ptr(dst.data_ptr(), self._x_full.data_ptr(), mode)
         return dst

@@ -3,7 +3,8 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port 29511 tests/run_distributed_check.py
 Every rank assembles its share, then y = A x through DistributedSIPOperator.vmult with the
-NCCL ghost exchange; compared with the CPU oracle's global result on the same input."""
+NCCL ghost exchange and with the NVLink peer-memory exchange; compared with the CPU oracle's
+global result on the same input."""
 import os
 import sys
 
@@ -45,7 +46,24 @@ def main():
             yd = torch.empty_like(xs)
             dop.vmult(yd, xs)
             stream.synchronize()
-        err = float(np.abs(yd.cpu().numpy() - y[rows]).max() / np.abs(y).max())
+            err = float(np.abs(yd.cpu().numpy() - y[rows]).max() / np.abs(y).max())
+            # the same through NVLink peer memory (pd_peer_*): several applies back to back with a
+            # changing source exercise the double-buffered epochs; ranks deliberately out of step
+            dop.enable_peer_exchange()
+            for k in range(1, 7):
+                if (rank + k) % 3 == 0:
+                    torch.cuda._sleep(2_000_000)
+                dop.vmult(yd, xs * float(k))
+                if k % 2 == 0:
+                    stream.synchronize()
+                    e2 = float(np.abs(yd.cpu().numpy() - k * y[rows]).max() / (k * np.abs(y).max()))
+                    err = max(err, e2)
+            stream.synchronize()
+            assert dop.peer.ok(), "a neighbour did not publish in time"
+            e2 = float(np.abs(yd.cpu().numpy() - 6 * y[rows]).max() / (6 * np.abs(y).max()))
+            err = max(err, e2)
+            dist.barrier()
+            dop.peer.close()
         t = torch.tensor([err], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         worst = max(worst, float(t))
