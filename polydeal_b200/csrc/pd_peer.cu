@@ -11,8 +11,8 @@
 // flag handshake in the same peer memory (no host, no NCCL call on the data path):
 //   publish(e)  pack my send blocks into export[e & 1]; the last CTA to finish fences
 //               (system scope) and stores the epoch e into flags[my rank] ON every neighbour
-//   pull(e)     CTAs spin (bounded) until flags[owner] >= e, then copy the owner's segment of
-//               its export[e & 1] into my ghost section
+//   pull(e)     every CTA spins (bounded) until flags[owner] >= e for the ranks I receive from,
+//               then the grid copies their segments of export[e & 1] into my ghost section
 // Double buffering removes the write-after-read hazard: a rank cannot publish epoch e + 2 into
 // the buffer a neighbour still reads for epoch e, because its own pull of epoch e + 1 waited
 // for that neighbour's publish(e + 1), which follows the neighbour's pull(e) in stream order
@@ -48,8 +48,8 @@ struct pd_peer
   std::vector<unsigned long long *> peer_flags;
   pd::DevBuf<double *>              d_peer_export;
   pd::DevBuf<unsigned long long *>  d_peer_flags;
-  pd::DevBuf<int32_t>               d_neighbours; // ranks I send to
-  int                               n_neighbours = 0;
+  pd::DevBuf<int32_t>               d_neighbours, d_owners; // ranks I send to / receive from
+  int                               n_neighbours = 0, n_owners = 0;
   bool                              connected    = false;
 };
 
@@ -91,31 +91,31 @@ namespace pd
     __global__ void
     k_peer_pull(double *ghost, const int32_t *owner_of_block, const int64_t *src_block, const int64_t n_recv, const int n,
                 double *const *peer_export, const int parity, volatile unsigned long long *flags, const int world,
-                const unsigned long long epoch)
+                const unsigned long long epoch, const int32_t *owners, const int n_owners)
     {
-      // one CTA per ghost block (grid-stride): wait for the owner's epoch, then copy n doubles
-      for (int64_t b = blockIdx.x; b < n_recv; b += gridDim.x)
+      // every CTA waits (bounded) until all the ranks I receive from have published this epoch,
+      // then the whole grid copies element-wise: wide, coalesced loads over NVLink
+      if ((int)threadIdx.x < n_owners)
         {
-          const int owner = owner_of_block[b];
-          if (threadIdx.x == 0)
+          const int       owner = owners[threadIdx.x];
+          const long long t0    = clock64();
+          while (flags[owner] < epoch)
             {
-              const long long t0 = clock64();
-              while (flags[owner] < epoch)
+              if (clock64() - t0 > 4000000000ll) // ~2 s: the peer is gone; report, do not hang
                 {
-                  if (clock64() - t0 > 4000000000ll) // ~2 s: the peer is gone; report, do not hang
-                    {
-                      flags[world] = 1ull;
-                      break;
-                    }
-                  __nanosleep(100);
+                  flags[world] = 1ull;
+                  break;
                 }
-              __threadfence_system();
+              __nanosleep(64);
             }
-          __syncthreads();
-          const double *src = peer_export[owner] + (src_block[b] * 2 + parity) * n;
-          for (int i = threadIdx.x; i < n; i += blockDim.x)
-            ghost[b * n + i] = __ldcg(src + i);
-          __syncthreads();
+          __threadfence_system();
+        }
+      __syncthreads();
+      const int64_t total = n_recv * n;
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        {
+          const int64_t b = i / n;
+          ghost[i]        = __ldcg(peer_export[owner_of_block[b]] + (src_block[b] * 2 + parity) * n + (i - b * n));
         }
     }
   } // namespace
@@ -146,7 +146,7 @@ namespace pd
         if (!v.empty())
           PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
       };
-      std::vector<int32_t> sb(send_blocks, send_blocks + p->n_send), owner((size_t)p->n_recv), nbrs;
+      std::vector<int32_t> sb(send_blocks, send_blocks + p->n_send), owner((size_t)p->n_recv), nbrs, owners;
       std::vector<int64_t> src((size_t)p->n_recv);
       for (int s = 0; s < world; ++s)
         {
@@ -157,12 +157,16 @@ namespace pd
             }
           if (send_ptr[s + 1] > send_ptr[s])
             nbrs.push_back(s);
+          if (recv_ptr[s + 1] > recv_ptr[s])
+            owners.push_back(s);
         }
       put(p->send_blocks, sb);
       put(p->recv_owner_of_block, owner);
       put(p->recv_src_block, src);
       put(p->d_neighbours, nbrs);
+      put(p->d_owners, owners);
       p->n_neighbours = (int)nbrs.size();
+      p->n_owners     = (int)owners.size();
       // IPC-exportable allocations (plain cudaMalloc)
       const size_t exp_count = (size_t)std::max<int64_t>(1, 2 * p->n_send * h->n);
       PD_CUDA(cudaMalloc((void **)&p->export_buf, exp_count * sizeof(double)));
@@ -251,10 +255,10 @@ namespace pd
         }
       if (p->n_recv > 0)
         {
-          const int grid = (int)std::min<int64_t>(p->n_recv, (int64_t)h->sm_count * 8);
-          k_peer_pull<<<grid, 64, 0, h->stream>>>(x_full_dev + (int64_t)h->np_own * n, p->recv_owner_of_block.p,
-                                                  p->recv_src_block.p, p->n_recv, n, p->d_peer_export.p, (int)parity, p->flags,
-                                                  p->world, (unsigned long long)p->epoch);
+          const int grid = (int)std::min<int64_t>((p->n_recv * n + 255) / 256, (int64_t)h->sm_count * 4);
+          k_peer_pull<<<grid, 256, 0, h->stream>>>(x_full_dev + (int64_t)h->np_own * n, p->recv_owner_of_block.p,
+                                                   p->recv_src_block.p, p->n_recv, n, p->d_peer_export.p, (int)parity, p->flags,
+                                                   p->world, (unsigned long long)p->epoch, p->d_owners.p, p->n_owners);
           ++h->launches;
         }
       PD_CUDA(cudaGetLastError());
