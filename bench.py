@@ -314,11 +314,27 @@ def run_gpu(args):
     t_vm_nccl_ms = time_apply(False) if part is not None else t_vm_ms
     if peer is not None:
         assert peer.ok(), "peer exchange timed out"
+    # the loop around vmult: Jacobi-preconditioned CG, device resident (CUDA graph); sharded: ghost exchange
+    # and dot-product all-reduce over peer memory inside the graph.  96 iterations, no convergence test.
+    bcg = torch.from_numpy(np.cos(0.23 * np.arange(n_dofs)) + 0.1).cuda()
+    xcg = torch.zeros_like(bcg)
+    solve = (lambda: peer.cg_solve(xcg, bcg, max_iter=96, rel_tol=0.0)) if peer is not None else \
+            (lambda: op.cg_solve(xcg, bcg, max_iter=96, rel_tol=0.0))
+    solve()
+    xcg.zero_()
+    if dist:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    cg_iters, _ = solve()
+    b.record(stream)
+    b.synchronize()
+    t_cg_ms = a.elapsed_time(b) / max(cg_iters, 1)
 
-    times = torch.tensor([t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms], dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms, t_cg_ms], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms = (float(v) for v in times.cpu())
+    t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms, t_cg_ms = (float(v) for v in times.cpu())
     if peer is not None:
         dist.barrier()  # nobody unmaps while a neighbour may still pull
         peer.close()
@@ -375,6 +391,9 @@ def run_gpu(args):
                                "unit": "GB/s", "frac": vm_bytes / (t_vm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                "peak_source": peaks["hbm_src"]}},
     }
+    out["vmult"]["cg_ms_per_iteration"] = t_cg_ms
+    out["vmult"]["cg"] = ("Jacobi-PCG around the block-CSR vmult, CUDA-graph replayed"
+                          + ("; ghost exchange + dot-product all-reduce over NVLink peer memory inside the graph" if world > 1 else ""))
     if world > 1:
         out["vmult"]["ms_with_nccl_exchange"] = t_vm_nccl_ms
         out["vmult"]["exchange"] = "publish + pull kernels over CUDA-IPC peer memory, epoch-flag handshake (pd_peer_*); NCCL all_to_all_single timed beside it"

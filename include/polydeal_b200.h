@@ -225,6 +225,15 @@ int pd_peer_export(pd_peer *p, void *handles_out);
 int pd_peer_connect(pd_peer *p, const void *all_handles);
 int pd_peer_exchange(pd_peer *p, double *x_full_dev);
 int pd_peer_status(pd_peer *p);
+/* sum of `count` <= 4 doubles (device memory, in place) over all ranks: one warp, stores into every
+ * rank's mapped buffer + flag handshake; the result is bitwise identical on all ranks */
+int pd_peer_allreduce(pd_peer *p, double *scalars_dev, int count);
+/* pd_cg_solve on a sharded handle (collective call): b_dev / x_dev hold the OWNED DoFs; the
+ * ghost exchange of every apply and the all-reduce of every dot product run over peer memory
+ * inside the replayed CUDA graph (MPI_Allreduce + update_ghost_values in the reference's
+ * SolverCG on LinearAlgebra::distributed::Vector).  Residual norms are global. */
+int pd_cg_solve_sharded(pd_peer *p, int mode, const double *b_dev, double *x_dev, int max_iter, double rel_tol,
+                        int jacobi, int *iterations, double *relative_residual);
 void pd_peer_destroy(pd_peer *p);
 
 /* mark the device quadrature stale (vertices changed through pd_upload do this

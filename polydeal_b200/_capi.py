@@ -82,6 +82,9 @@ SIGNATURES = {
     "pd_peer_connect": (C.c_int, [vp, C.c_void_p]),
     "pd_peer_exchange": (C.c_int, [vp, C.c_void_p]),
     "pd_peer_status": (C.c_int, [vp]),
+    "pd_peer_allreduce": (C.c_int, [vp, C.c_void_p, C.c_int]),
+    "pd_cg_solve_sharded": (C.c_int, [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "pd_peer_destroy": (None, [vp]),
     "pd_n_quadrature_points": (C.c_int64, [vp, C.c_int]),
     "pd_quadrature_device": (C.c_int, [vp] + [C.POINTER(C.c_void_p)] * 5),

@@ -1046,6 +1046,25 @@ extern "C"
   }
 
   int
+  pd_cg_solve_sharded(pd_peer *peer, int mode, const double *b_dev, double *x_dev, int max_iter, double rel_tol,
+                      int jacobi, int *iterations, double *relative_residual)
+  {
+    return guarded([&] {
+      if (!peer || !b_dev || !x_dev)
+        throw Error(PD_ERR_INVALID, "pd_cg_solve_sharded: null argument");
+      solver_cg(peer_handle(peer), mode, b_dev, x_dev, max_iter, rel_tol, jacobi, iterations, relative_residual, peer);
+      if (peer_status(peer) != PD_OK)
+        throw Error(PD_ERR_STATE, "pd_cg_solve_sharded: a rank did not arrive at a collective within the time-out");
+    });
+  }
+
+  int
+  pd_peer_allreduce(pd_peer *p, double *scalars_dev, int count)
+  {
+    return guarded([&] { peer_allreduce(p, scalars_dev, 0, count); });
+  }
+
+  int
   pd_estimate_lambda_max(pd_handle *h, int mode, int n_iterations, double *lambda_max)
   {
     return guarded([&] {

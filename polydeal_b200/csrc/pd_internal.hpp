@@ -78,6 +78,7 @@ namespace pd
   };
 } // namespace pd
 
+struct pd_peer;
 struct pd_handle
 {
   int     dim = 0, degree = 0, n1 = 0, n = 0; // n = dofs per polytope
@@ -134,6 +135,7 @@ struct pd_handle
   pd::DevBuf<double> sv_r, sv_z, sv_p, sv_Ap, sv_dinv, sv_partial, sv_scal;
   cudaGraphExec_t    cg_graph_exec   = nullptr;
   int                cg_graph_mode   = -1, cg_graph_jacobi = -1;
+  pd_peer           *cg_graph_peer   = nullptr;
   const double      *cg_graph_x      = nullptr, *cg_graph_b = nullptr;
   int64_t            cg_launches_per_chunk = 0;
 
@@ -150,7 +152,6 @@ struct pd_handle
   int64_t      max_row_len = -1; // longest scalar row (doubles), computed lazily for the SpMV dispatch
 };
 
-struct pd_peer;
 // level transfer between a handle's polytopal space and a finer space (pd_polyapply.cu)
 struct pd_transfer
 {
@@ -184,7 +185,7 @@ namespace pd
   void launch_poly_error(pd_handle *h, const double *u, const double *exact, const double *exact_grad, double *out2_dev);
   // pd_solver.cu
   void   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,
-                   int *iters_out, double *relres_out);
+                   int *iters_out, double *relres_out, pd_peer *peer = nullptr);
   double solver_lambda_max(pd_handle *h, int mode, int n_iter);
   void   solver_chebyshev(pd_handle *h, int mode, int degree, double lambda_max, double smoothing_range, const double *b,
                           double *x, int zero_initial_guess);
@@ -195,6 +196,8 @@ namespace pd
   void     peer_export(pd_peer *p, void *handles_out);
   void     peer_connect(pd_peer *p, const void *all_handles);
   void     peer_exchange(pd_peer *p, double *x_full_dev);
+  void     peer_allreduce(pd_peer *p, double *scal_dev, int dst0, int nk);
+  pd_handle *peer_handle(pd_peer *p);
   int      peer_status(pd_peer *p);
   void     peer_destroy(pd_peer *p);
   // pd_vmult.cu

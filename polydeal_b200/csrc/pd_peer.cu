@@ -1,26 +1,30 @@
 // -----------------------------------------------------------------------------
-// pd_peer.cu -- the ghost exchange of the sharded vmult over NVLink peer memory.
+// pd_peer.cu -- the collectives of the sharded operator over NVLink peer memory:
+// the ghost exchange of vmult and the all-reduce of the solver's dot products.
 //
 // Reference: LinearAlgebra::distributed::Vector::update_ghost_values() inside
 // MatrixFree::loop (include/utils.h:466-472) / the Trilinos import of the matrix-based
-// vmult: the coefficient blocks of the ghost polytopes travel before every apply.
+// vmult -- the coefficient blocks of the ghost polytopes travel before every apply -- and the
+// MPI_Allreduce inside every dot product of SolverCG on distributed vectors.
 //
-// With one process per GPU on an NVSwitch node there is no need for a message: every rank
-// PUBLISHES the blocks its neighbours need into a buffer that they have mapped through CUDA
-// IPC, and every rank PULLS its ghost blocks with ordinary loads over NVLink.  Ordering is a
-// flag handshake in the same peer memory (no host, no NCCL call on the data path):
-//   publish(e)  pack my send blocks into export[e & 1]; the last CTA to finish fences
-//               (system scope) and stores the epoch e into flags[my rank] ON every neighbour
-//   pull(e)     every CTA spins (bounded) until flags[owner] >= e for the ranks I receive from,
-//               then the grid copies their segments of export[e & 1] into my ghost section
-// Double buffering removes the write-after-read hazard: a rank cannot publish epoch e + 2 into
-// the buffer a neighbour still reads for epoch e, because its own pull of epoch e + 1 waited
-// for that neighbour's publish(e + 1), which follows the neighbour's pull(e) in stream order
-// (adjacency is symmetric).
-// Two small kernels per apply on the handle's stream, a few microseconds, instead of a NCCL
-// all-to-all whose latency dominates a latency-bound vmult.
-// A spin that does not see its flag within ~2 s raises the error word (reported by
-// pd_peer_status) and moves on instead of hanging the GPU.
+// With one process per GPU on an NVSwitch node there is no need for a message.  Every rank
+// owns ONE buffer allocated with cudaMalloc that all the others map through CUDA IPC:
+//   [ flags[world] | error word | red_flags[world] | red_vals[world][2][4] | export[n_send][2][n] ]
+// Ghost exchange, two small kernels on the operator's stream:
+//   publish  e = epoch + 1; pack my send blocks into export[.][e & 1]; the last CTA to finish
+//            fences (system scope) and stores e into flags[my rank] ON every neighbour
+//   pull     every CTA spins (bounded) until flags[owner] >= e for the ranks I receive from,
+//            then the grid copies their segments into my ghost section with loads over NVLink
+// All-reduce of up to 4 scalars, one warp: store my values into red_vals[my rank][e & 1] ON every
+// rank, fence, store e into red_flags[my rank] there; spin until every rank's flag reached e;
+// sum in rank order (every rank gets bitwise the same result).
+// Double buffering removes the write-after-read hazard: a rank cannot write epoch e + 2 into
+// the slot a peer still reads for epoch e, because its own wait of epoch e + 1 needed that
+// peer's store of e + 1, which follows the peer's read of e in stream order.
+// The epochs live in device memory, so the kernels carry no host state and a whole solver
+// iteration (exchange + SpMV + dot products + all-reduce) replays from a CUDA graph.
+// A spin that does not see its flag within ~2 s raises the error word (pd_peer_status) and
+// moves on instead of hanging the GPU.
 // -----------------------------------------------------------------------------
 #include "pd_internal.hpp"
 #include "pd_host.hpp"
@@ -29,46 +33,91 @@
 #include <memory>
 #include <vector>
 
+namespace
+{
+  using u64 = unsigned long long;
+  constexpr int RED_MAX = 4; // scalars per all-reduce
+
+  // byte offsets of the fixed-size regions inside every rank's IPC buffer
+  __host__ __device__ inline size_t
+  off_flags(int)
+  {
+    return 0;
+  }
+  __host__ __device__ inline size_t
+  off_red_flags(const int world)
+  {
+    return (size_t)(world + 1) * sizeof(u64);
+  }
+  __host__ __device__ inline size_t
+  off_red_vals(const int world)
+  {
+    return off_red_flags(world) + (size_t)world * sizeof(u64);
+  }
+  __host__ __device__ inline size_t
+  off_export(const int world)
+  {
+    return off_red_vals(world) + (size_t)world * 2 * RED_MAX * sizeof(double);
+  }
+} // namespace
+
 struct pd_peer
 {
-  pd_handle *h     = nullptr;
-  int        rank  = 0, world = 1;
-  int64_t    epoch = 0;
-  // plan
-  std::vector<int64_t> send_ptr, recv_ptr, remote_off; // in blocks
-  pd::DevBuf<int32_t>  send_blocks, send_peer_of_block, recv_owner_of_block;
-  pd::DevBuf<int64_t>  recv_src_block; // position of every ghost block inside its owner's export buffer
+  pd_handle *h    = nullptr;
+  int        rank = 0, world = 1;
+  // plan (in polytope blocks)
+  std::vector<int64_t> send_ptr, recv_ptr;
+  pd::DevBuf<int32_t>  send_blocks, recv_owner_of_block, d_neighbours, d_owners;
+  pd::DevBuf<int64_t>  recv_src_block; // position of every ghost block inside its owner's send list
   int64_t              n_send = 0, n_recv = 0;
-  // IPC memory of this rank
-  double             *export_buf = nullptr; // [n_send][2 parities][n]
-  unsigned long long *flags      = nullptr; // [world] epochs written by the peers; [world] = error word
-  unsigned int       *counter    = nullptr; // last-CTA ticket
-  // mapped memory of the peers
-  std::vector<double *>             peer_export;
-  std::vector<unsigned long long *> peer_flags;
-  pd::DevBuf<double *>              d_peer_export;
-  pd::DevBuf<unsigned long long *>  d_peer_flags;
-  pd::DevBuf<int32_t>               d_neighbours, d_owners; // ranks I send to / receive from
-  int                               n_neighbours = 0, n_owners = 0;
-  bool                              connected    = false;
+  int                  n_neighbours = 0, n_owners = 0;
+  // this rank's IPC buffer and device-side state
+  char         *ipc     = nullptr;
+  u64          *epochs  = nullptr; // [0] exchange epoch, [1] all-reduce epoch
+  unsigned int *counter = nullptr; // last-CTA ticket of publish
+  // the peers' buffers as mapped here ([rank] = own)
+  std::vector<char *> peer_base;
+  pd::DevBuf<char *>  d_peer_base;
+  bool                connected = false;
 };
 
 namespace pd
 {
   namespace
   {
-    __global__ void
-    k_peer_publish(const double *x, const int32_t *send_blocks, const int64_t n_send, const int n, const int parity, double *exp,
-                   unsigned long long *const *peer_flags, const int32_t *neighbours, const int n_neighbours, const int rank,
-                   const unsigned long long epoch, unsigned int *counter)
+    constexpr long long SPIN_CYCLES = 4000000000ll; // ~2 s
+
+    __device__ __forceinline__ void
+    wait_for(volatile u64 *flag, const u64 epoch, volatile u64 *error_word)
     {
-      const int64_t total = n_send * n;
+      const long long t0 = clock64();
+      while (*flag < epoch)
+        {
+          if (clock64() - t0 > SPIN_CYCLES) // the peer is gone: report, do not hang
+            {
+              *error_word = 1ull;
+              break;
+            }
+          __nanosleep(64);
+        }
+    }
+
+    __global__ void
+    k_peer_publish(const double *x, const int32_t *send_blocks, const int64_t n_send, const int n, char *const *peer_base,
+                   const int32_t *neighbours, const int n_neighbours, const int rank, const int world, u64 *epochs,
+                   unsigned int *counter)
+    {
+      const u64     e      = *(volatile u64 *)epochs + 1;
+      const int     parity = (int)(e & 1);
+      double       *exp    = reinterpret_cast<double *>(peer_base[rank] + off_export(world));
+      const int64_t total  = n_send * n;
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         {
-          const int64_t b = i / n;
+          const int64_t b                         = i / n;
           exp[(b * 2 + parity) * n + (i - b * n)] = x[(int64_t)send_blocks[b] * n + (i - b * n)];
         }
-      // last CTA to finish announces the epoch to every neighbour
+      // the last CTA to finish announces the epoch to every neighbour (all CTAs have read `epochs`
+      // before taking their ticket, so bumping it here is safe)
       __shared__ bool last;
       __threadfence();
       __syncthreads();
@@ -80,189 +129,227 @@ namespace pd
           __threadfence_system();
           for (int k = threadIdx.x; k < n_neighbours; k += blockDim.x)
             {
-              volatile unsigned long long *f = peer_flags[neighbours[k]] + rank;
-              *f                             = epoch;
+              volatile u64 *f = reinterpret_cast<u64 *>(peer_base[neighbours[k]] + off_flags(world)) + rank;
+              *f              = e;
             }
           if (threadIdx.x == 0)
-            *counter = 0;
+            {
+              *counter  = 0;
+              epochs[0] = e;
+            }
         }
     }
 
     __global__ void
     k_peer_pull(double *ghost, const int32_t *owner_of_block, const int64_t *src_block, const int64_t n_recv, const int n,
-                double *const *peer_export, const int parity, volatile unsigned long long *flags, const int world,
-                const unsigned long long epoch, const int32_t *owners, const int n_owners)
+                char *const *peer_base, const int rank, const int world, const u64 *epochs, const int32_t *owners,
+                const int n_owners)
     {
-      // every CTA waits (bounded) until all the ranks I receive from have published this epoch,
-      // then the whole grid copies element-wise: wide, coalesced loads over NVLink
+      const u64     e      = *(volatile const u64 *)epochs; // bumped by the publish in front of me
+      const int     parity = (int)(e & 1);
+      volatile u64 *flags  = reinterpret_cast<u64 *>(peer_base[rank] + off_flags(world));
       if ((int)threadIdx.x < n_owners)
         {
-          const int       owner = owners[threadIdx.x];
-          const long long t0    = clock64();
-          while (flags[owner] < epoch)
-            {
-              if (clock64() - t0 > 4000000000ll) // ~2 s: the peer is gone; report, do not hang
-                {
-                  flags[world] = 1ull;
-                  break;
-                }
-              __nanosleep(64);
-            }
+          wait_for(flags + owners[threadIdx.x], e, flags + world);
           __threadfence_system();
         }
       __syncthreads();
       const int64_t total = n_recv * n;
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         {
-          const int64_t b = i / n;
-          ghost[i]        = __ldcg(peer_export[owner_of_block[b]] + (src_block[b] * 2 + parity) * n + (i - b * n));
+          const int64_t b   = i / n;
+          const double *exp = reinterpret_cast<const double *>(peer_base[owner_of_block[b]] + off_export(world));
+          ghost[i]          = __ldcg(exp + (src_block[b] * 2 + parity) * n + (i - b * n));
         }
+    }
+
+    // scal[dst0 .. dst0+nk) <- sum over ranks, one warp
+    __global__ void
+    k_peer_allreduce(double *scal, const int dst0, const int nk, char *const *peer_base, const int rank, const int world,
+                     u64 *epochs)
+    {
+      const int lane   = threadIdx.x;
+      const u64 e      = *(volatile u64 *)(epochs + 1) + 1;
+      const int parity = (int)(e & 1);
+      double    v[RED_MAX];
+#pragma unroll
+      for (int k = 0; k < RED_MAX; ++k)
+        v[k] = k < nk ? scal[dst0 + k] : 0.;
+      for (int r = lane; r < world; r += 32)
+        {
+          volatile double *dst =
+            reinterpret_cast<double *>(peer_base[r] + off_red_vals(world)) + ((size_t)rank * 2 + parity) * RED_MAX;
+#pragma unroll
+          for (int k = 0; k < RED_MAX; ++k)
+            dst[k] = v[k];
+          __threadfence_system();
+          volatile u64 *f = reinterpret_cast<u64 *>(peer_base[r] + off_red_flags(world)) + rank;
+          *f              = e;
+        }
+      __syncwarp();
+      volatile u64 *my_flags = reinterpret_cast<u64 *>(peer_base[rank] + off_red_flags(world));
+      volatile u64 *err      = reinterpret_cast<u64 *>(peer_base[rank] + off_flags(world)) + world;
+      for (int s = lane; s < world; s += 32)
+        wait_for(my_flags + s, e, err);
+      __threadfence_system();
+      __syncwarp();
+      if (lane < nk)
+        {
+          const volatile double *vals = reinterpret_cast<const double *>(peer_base[rank] + off_red_vals(world));
+          double                 t    = 0.;
+          for (int s = 0; s < world; ++s) // rank order: the same bits on every rank
+            t += vals[((size_t)s * 2 + parity) * RED_MAX + lane];
+          scal[dst0 + lane] = t;
+        }
+      __syncwarp();
+      if (lane == 0)
+        epochs[1] = e;
     }
   } // namespace
-} // namespace pd
 
-namespace pd
-{
   pd_peer *
-  peer_create(pd_handle *h, int rank, int world, const int64_t *send_ptr, const int32_t *send_blocks,
-              const int64_t *recv_ptr, const int64_t *remote_offset)
+  peer_create(pd_handle *h, int rank, int world, const int64_t *send_ptr, const int32_t *send_blocks, const int64_t *recv_ptr,
+              const int64_t *remote_offset)
   {
-    {
-      if (!h || !send_ptr || !recv_ptr || !remote_offset || rank < 0 || rank >= world)
-        throw Error(PD_ERR_INVALID, "pd_peer_create: bad argument");
-      std::unique_ptr<pd_peer> p(new pd_peer);
-      p->h     = h;
-      p->rank  = rank;
-      p->world = world;
-      p->send_ptr.assign(send_ptr, send_ptr + world + 1);
-      p->recv_ptr.assign(recv_ptr, recv_ptr + world + 1);
-      p->remote_off.assign(remote_offset, remote_offset + world);
-      p->n_send = send_ptr[world];
-      p->n_recv = recv_ptr[world];
-      if (p->n_recv != (int64_t)(h->np - h->np_own))
-        throw Error(PD_ERR_INVALID, "pd_peer_create: the receive plan does not cover the ghost polytopes of the handle");
-      auto put = [](auto &buf, const auto &v) {
-        buf.alloc(v.size());
-        if (!v.empty())
-          PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
-      };
-      std::vector<int32_t> sb(send_blocks, send_blocks + p->n_send), owner((size_t)p->n_recv), nbrs, owners;
-      std::vector<int64_t> src((size_t)p->n_recv);
-      for (int s = 0; s < world; ++s)
-        {
-          for (int64_t k = recv_ptr[s]; k < recv_ptr[s + 1]; ++k)
-            {
-              owner[(size_t)k] = s;
-              src[(size_t)k]   = remote_offset[s] + (k - recv_ptr[s]);
-            }
-          if (send_ptr[s + 1] > send_ptr[s])
-            nbrs.push_back(s);
-          if (recv_ptr[s + 1] > recv_ptr[s])
-            owners.push_back(s);
-        }
-      put(p->send_blocks, sb);
-      put(p->recv_owner_of_block, owner);
-      put(p->recv_src_block, src);
-      put(p->d_neighbours, nbrs);
-      put(p->d_owners, owners);
-      p->n_neighbours = (int)nbrs.size();
-      p->n_owners     = (int)owners.size();
-      // IPC-exportable allocations (plain cudaMalloc)
-      const size_t exp_count = (size_t)std::max<int64_t>(1, 2 * p->n_send * h->n);
-      PD_CUDA(cudaMalloc((void **)&p->export_buf, exp_count * sizeof(double)));
-      PD_CUDA(cudaMemset(p->export_buf, 0, exp_count * sizeof(double)));
-      PD_CUDA(cudaMalloc((void **)&p->flags, (size_t)(world + 1) * sizeof(unsigned long long)));
-      PD_CUDA(cudaMemset(p->flags, 0, (size_t)(world + 1) * sizeof(unsigned long long)));
-      PD_CUDA(cudaMalloc((void **)&p->counter, sizeof(unsigned int)));
-      PD_CUDA(cudaMemset(p->counter, 0, sizeof(unsigned int)));
-      return p.release();
-    }
+    if (!h || !send_ptr || !recv_ptr || !remote_offset || rank < 0 || rank >= world || world > 32)
+      throw Error(PD_ERR_INVALID, "pd_peer_create: bad argument (1 <= world <= 32)");
+    std::unique_ptr<pd_peer> p(new pd_peer);
+    p->h     = h;
+    p->rank  = rank;
+    p->world = world;
+    p->send_ptr.assign(send_ptr, send_ptr + world + 1);
+    p->recv_ptr.assign(recv_ptr, recv_ptr + world + 1);
+    p->n_send = send_ptr[world];
+    p->n_recv = recv_ptr[world];
+    if (p->n_recv != (int64_t)(h->np - h->np_own))
+      throw Error(PD_ERR_INVALID, "pd_peer_create: the receive plan does not cover the ghost polytopes of the handle");
+    auto put = [](auto &buf, const auto &v) {
+      buf.alloc(v.size());
+      if (!v.empty())
+        PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+    };
+    std::vector<int32_t> sb(send_blocks, send_blocks + p->n_send), owner((size_t)p->n_recv), nbrs, owners;
+    std::vector<int64_t> src((size_t)p->n_recv);
+    for (int s = 0; s < world; ++s)
+      {
+        for (int64_t k = recv_ptr[s]; k < recv_ptr[s + 1]; ++k)
+          {
+            owner[(size_t)k] = s;
+            src[(size_t)k]   = remote_offset[s] + (k - recv_ptr[s]);
+          }
+        if (send_ptr[s + 1] > send_ptr[s])
+          nbrs.push_back(s);
+        if (recv_ptr[s + 1] > recv_ptr[s])
+          owners.push_back(s);
+      }
+    put(p->send_blocks, sb);
+    put(p->recv_owner_of_block, owner);
+    put(p->recv_src_block, src);
+    put(p->d_neighbours, nbrs);
+    put(p->d_owners, owners);
+    p->n_neighbours = (int)nbrs.size();
+    p->n_owners     = (int)owners.size();
+    // the IPC-exportable buffer (plain cudaMalloc) and the local device state
+    const size_t bytes = off_export(world) + (size_t)std::max<int64_t>(1, 2 * p->n_send * h->n) * sizeof(double);
+    PD_CUDA(cudaMalloc((void **)&p->ipc, bytes));
+    PD_CUDA(cudaMemset(p->ipc, 0, bytes));
+    PD_CUDA(cudaMalloc((void **)&p->epochs, 2 * sizeof(u64)));
+    PD_CUDA(cudaMemset(p->epochs, 0, 2 * sizeof(u64)));
+    PD_CUDA(cudaMalloc((void **)&p->counter, sizeof(unsigned int)));
+    PD_CUDA(cudaMemset(p->counter, 0, sizeof(unsigned int)));
+    return p.release();
   }
 
   int
   peer_handle_bytes()
   {
-    return 2 * (int)sizeof(cudaIpcMemHandle_t);
+    return (int)sizeof(cudaIpcMemHandle_t);
   }
 
   void
   peer_export(pd_peer *p, void *handles_out)
   {
-    {
-      if (!p || !handles_out)
-        throw Error(PD_ERR_INVALID, "pd_peer_export: null argument");
-      cudaIpcMemHandle_t hd[2];
-      PD_CUDA(cudaIpcGetMemHandle(&hd[0], p->export_buf));
-      PD_CUDA(cudaIpcGetMemHandle(&hd[1], p->flags));
-      std::memcpy(handles_out, hd, sizeof hd);
-    }
+    if (!p || !handles_out)
+      throw Error(PD_ERR_INVALID, "pd_peer_export: null argument");
+    cudaIpcMemHandle_t hd;
+    PD_CUDA(cudaIpcGetMemHandle(&hd, p->ipc));
+    std::memcpy(handles_out, &hd, sizeof hd);
   }
 
   void
   peer_connect(pd_peer *p, const void *all_handles)
   {
-    {
-      if (!p || !all_handles)
-        throw Error(PD_ERR_INVALID, "pd_peer_connect: null argument");
-      const auto *hd = static_cast<const cudaIpcMemHandle_t *>(all_handles);
-      p->peer_export.assign(p->world, nullptr);
-      p->peer_flags.assign(p->world, nullptr);
-      for (int s = 0; s < p->world; ++s)
-        {
-          if (s == p->rank)
-            {
-              p->peer_export[s] = p->export_buf;
-              p->peer_flags[s]  = p->flags;
-              continue;
-            }
-          const bool need = p->send_ptr[s + 1] > p->send_ptr[s] || p->recv_ptr[s + 1] > p->recv_ptr[s];
-          if (!need)
+    if (!p || !all_handles)
+      throw Error(PD_ERR_INVALID, "pd_peer_connect: null argument");
+    const auto *hd = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    p->peer_base.assign(p->world, nullptr);
+    for (int s = 0; s < p->world; ++s)
+      {
+        if (s == p->rank)
+          {
+            p->peer_base[s] = p->ipc;
             continue;
-          void *a = nullptr, *b = nullptr;
-          PD_CUDA(cudaIpcOpenMemHandle(&a, hd[2 * s], cudaIpcMemLazyEnablePeerAccess));
-          PD_CUDA(cudaIpcOpenMemHandle(&b, hd[2 * s + 1], cudaIpcMemLazyEnablePeerAccess));
-          p->peer_export[s] = static_cast<double *>(a);
-          p->peer_flags[s]  = static_cast<unsigned long long *>(b);
-        }
-      p->d_peer_export.alloc(p->world);
-      p->d_peer_flags.alloc(p->world);
-      PD_CUDA(cudaMemcpy(p->d_peer_export.p, p->peer_export.data(), sizeof(double *) * p->world, cudaMemcpyHostToDevice));
-      PD_CUDA(cudaMemcpy(p->d_peer_flags.p, p->peer_flags.data(), sizeof(unsigned long long *) * p->world,
-                         cudaMemcpyHostToDevice));
-      p->connected = true;
-    }
+          }
+        void *a = nullptr; // every rank is mapped: the all-reduce talks to all of them
+        PD_CUDA(cudaIpcOpenMemHandle(&a, hd[s], cudaIpcMemLazyEnablePeerAccess));
+        p->peer_base[s] = static_cast<char *>(a);
+      }
+    p->d_peer_base.alloc(p->world);
+    PD_CUDA(cudaMemcpy(p->d_peer_base.p, p->peer_base.data(), sizeof(char *) * p->world, cudaMemcpyHostToDevice));
+    p->connected = true;
+  }
+
+  static void
+  require_connected(const pd_peer *p, const char *who)
+  {
+    if (!p)
+      throw Error(PD_ERR_INVALID, std::string(who) + ": null argument");
+    if (!p->connected)
+      throw Error(PD_ERR_STATE, std::string(who) + ": pd_peer_connect has not been called");
   }
 
   void
   peer_exchange(pd_peer *p, double *x_full_dev)
   {
-    {
-      if (!p || !x_full_dev)
-        throw Error(PD_ERR_INVALID, "pd_peer_exchange: null argument");
-      if (!p->connected)
-        throw Error(PD_ERR_STATE, "pd_peer_exchange: pd_peer_connect has not been called");
-      pd_handle    *h      = p->h;
-      const int     n      = h->n;
-      const int64_t parity = (++p->epoch) & 1;
-      if (p->n_send > 0 || p->n_neighbours > 0)
-        {
-          const int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (p->n_send * n + 255) / 256), h->sm_count);
-          k_peer_publish<<<grid, 256, 0, h->stream>>>(x_full_dev, p->send_blocks.p, p->n_send, n, (int)parity,
-                                                      p->export_buf, p->d_peer_flags.p,
-                                                      p->d_neighbours.p, p->n_neighbours, p->rank,
-                                                      (unsigned long long)p->epoch, p->counter);
-          ++h->launches;
-        }
-      if (p->n_recv > 0)
-        {
-          const int grid = (int)std::min<int64_t>((p->n_recv * n + 255) / 256, (int64_t)h->sm_count * 4);
-          k_peer_pull<<<grid, 256, 0, h->stream>>>(x_full_dev + (int64_t)h->np_own * n, p->recv_owner_of_block.p,
-                                                   p->recv_src_block.p, p->n_recv, n, p->d_peer_export.p, (int)parity, p->flags,
-                                                   p->world, (unsigned long long)p->epoch, p->d_owners.p, p->n_owners);
-          ++h->launches;
-        }
-      PD_CUDA(cudaGetLastError());
-    }
+    require_connected(p, "pd_peer_exchange");
+    if (!x_full_dev)
+      throw Error(PD_ERR_INVALID, "pd_peer_exchange: null argument");
+    pd_handle *h = p->h;
+    const int  n = h->n;
+    if (p->n_neighbours > 0)
+      {
+        const int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (p->n_send * n + 255) / 256), h->sm_count);
+        k_peer_publish<<<grid, 256, 0, h->stream>>>(x_full_dev, p->send_blocks.p, p->n_send, n, p->d_peer_base.p,
+                                                    p->d_neighbours.p, p->n_neighbours, p->rank, p->world, p->epochs,
+                                                    p->counter);
+        ++h->launches;
+      }
+    if (p->n_recv > 0)
+      {
+        const int grid = (int)std::min<int64_t>((p->n_recv * n + 255) / 256, (int64_t)h->sm_count * 4);
+        k_peer_pull<<<grid, 256, 0, h->stream>>>(x_full_dev + (int64_t)h->np_own * n, p->recv_owner_of_block.p,
+                                                 p->recv_src_block.p, p->n_recv, n, p->d_peer_base.p, p->rank, p->world,
+                                                 p->epochs, p->d_owners.p, p->n_owners);
+        ++h->launches;
+      }
+    PD_CUDA(cudaGetLastError());
+  }
+
+  void
+  peer_allreduce(pd_peer *p, double *scal_dev, const int dst0, const int nk)
+  {
+    require_connected(p, "pd_peer_allreduce");
+    if (!scal_dev || nk < 1 || nk > RED_MAX)
+      throw Error(PD_ERR_INVALID, "pd_peer_allreduce: 1..4 scalars");
+    k_peer_allreduce<<<1, 32, 0, p->h->stream>>>(scal_dev, dst0, nk, p->d_peer_base.p, p->rank, p->world, p->epochs);
+    ++p->h->launches;
+    PD_CUDA(cudaGetLastError());
+  }
+
+  pd_handle *
+  peer_handle(pd_peer *p)
+  {
+    return p ? p->h : nullptr;
   }
 
   int
@@ -270,8 +357,9 @@ namespace pd
   {
     if (!p)
       return PD_ERR_INVALID;
-    unsigned long long e = 0;
-    if (cudaMemcpy(&e, p->flags + p->world, sizeof e, cudaMemcpyDeviceToHost) != cudaSuccess)
+    u64 e = 0;
+    if (cudaMemcpy(&e, p->ipc + off_flags(p->world) + (size_t)p->world * sizeof(u64), sizeof e, cudaMemcpyDeviceToHost) !=
+        cudaSuccess)
       return PD_ERR_CUDA;
     return e ? PD_ERR_STATE : PD_OK;
   }
@@ -281,16 +369,11 @@ namespace pd
   {
     if (!p)
       return;
-    for (int s = 0; s < p->world; ++s)
-      if (s != p->rank)
-        {
-          if (s < (int)p->peer_export.size() && p->peer_export[s])
-            cudaIpcCloseMemHandle(p->peer_export[s]);
-          if (s < (int)p->peer_flags.size() && p->peer_flags[s])
-            cudaIpcCloseMemHandle(p->peer_flags[s]);
-        }
-    cudaFree(p->export_buf);
-    cudaFree(p->flags);
+    for (int s = 0; s < (int)p->peer_base.size(); ++s)
+      if (s != p->rank && p->peer_base[s])
+        cudaIpcCloseMemHandle(p->peer_base[s]);
+    cudaFree(p->ipc);
+    cudaFree(p->epochs);
     cudaFree(p->counter);
     delete p;
   }

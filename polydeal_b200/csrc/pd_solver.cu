@@ -205,13 +205,28 @@ namespace pd
     }
   } // namespace
 
+  // With `peer` (a sharded handle): the search direction's ghost blocks are pulled over NVLink
+  // before every apply and every dot product is summed over the ranks by the peer-memory
+  // all-reduce (pd_peer.cu) -- all inside the replayed graph, no NCCL and no host in the loop.
+  // The reduced scalars are bitwise identical on all ranks, so every rank takes the same path.
   void
   solver_cg(pd_handle *h, const int mode, const double *b, double *x, const int max_iter, const double rel_tol,
-            const int jacobi, int *iters_out, double *relres_out)
+            const int jacobi, int *iters_out, double *relres_out, pd_peer *peer)
   {
-    if (h->np != h->np_own)
-      throw Error(PD_ERR_UNSUPPORTED, "pd_cg_solve: single-rank handles only (no ghost polytopes)");
+    if (h->np != h->np_own && !peer)
+      throw Error(PD_ERR_UNSUPPORTED, "pd_cg_solve: a handle with ghost polytopes needs pd_cg_solve_sharded");
+    if (peer && peer_handle(peer) != h)
+      throw Error(PD_ERR_INVALID, "pd_cg_solve_sharded: the peer object belongs to another handle");
     ensure_work(h);
+    auto apply = [&](double *src_full, double *dst) {
+      if (peer)
+        peer_exchange(peer, src_full);
+      vmult_dispatch(h, mode, src_full, dst, false);
+    };
+    auto reduce = [&](const int dst0, const int nk) {
+      if (peer)
+        peer_allreduce(peer, h->sv_scal.p, dst0, nk);
+    };
     const int64_t n = h->n_dofs;
     cudaStream_t  s = h->stream;
     double       *r = h->sv_r.p, *z = h->sv_z.p, *p = h->sv_p.p, *Ap = h->sv_Ap.p, *partial = h->sv_partial.p,
@@ -222,9 +237,17 @@ namespace pd
         launch_diagonal_inverse(h, h->sv_dinv.p);
         dinv = h->sv_dinv.p;
       }
-    vmult_dispatch(h, mode, x, Ap, false);
+    if (peer)
+      {
+        // x holds the owned DoFs only: stage it in the (owned + ghost) direction buffer
+        PD_CUDA(cudaMemcpyAsync(p, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        apply(p, Ap);
+      }
+    else
+      vmult_dispatch(h, mode, x, Ap, false);
     k_cg_init<<<RG, RB, 0, s>>>(b, Ap, r, z, p, dinv, n, partial);
     k_finalize<<<1, 32, 0, s>>>(partial, scal, 3, 2); // scal[2] = rz, [3] = rr, [4] = bb
+    reduce(2, 3);
     k_cg_roll<<<1, 1, 0, s>>>(scal);
     h->launches += 3;
     double hs[5];
@@ -235,7 +258,7 @@ namespace pd
     int          it     = 0;
     // one iteration = SpMV + 5 small kernels; captured once and replayed in chunks
     constexpr int CHUNK = 8;
-    if (!h->cg_graph_exec || h->cg_graph_mode != mode || h->cg_graph_jacobi != jacobi)
+    if (!h->cg_graph_exec || h->cg_graph_mode != mode || h->cg_graph_jacobi != jacobi || h->cg_graph_peer != peer)
       {
         if (h->cg_graph_exec)
           {
@@ -247,11 +270,13 @@ namespace pd
         const int64_t l0 = h->launches;
         for (int k = 0; k < CHUNK; ++k)
           {
-            vmult_dispatch(h, mode, p, Ap, false);
+            apply(p, Ap);
             k_dot_pAp<<<RG, RB, 0, s>>>(p, Ap, n, partial);
             k_finalize<<<1, 32, 0, s>>>(partial, scal, 1, 1);
+            reduce(1, 1);
             k_cg_update<<<RG, RB, 0, s>>>(x, r, z, p, Ap, dinv, scal, n, partial);
             k_finalize<<<1, 32, 0, s>>>(partial, scal, 2, 2);
+            reduce(2, 2);
             k_cg_direction<<<RG, RB, 0, s>>>(p, z, scal, n);
             k_cg_roll<<<1, 1, 0, s>>>(scal);
           }
@@ -262,6 +287,7 @@ namespace pd
         PD_CUDA(cudaGraphDestroy(graph));
         h->cg_graph_mode   = mode;
         h->cg_graph_jacobi = jacobi;
+        h->cg_graph_peer   = peer;
         h->cg_graph_x      = x;
         h->cg_graph_b      = b;
       }
@@ -270,7 +296,7 @@ namespace pd
         // the graph bakes in the x pointer: different vector => rebuild next time
         cudaGraphExecDestroy(h->cg_graph_exec);
         h->cg_graph_exec = nullptr;
-        solver_cg(h, mode, b, x, max_iter, rel_tol, jacobi, iters_out, relres_out);
+        solver_cg(h, mode, b, x, max_iter, rel_tol, jacobi, iters_out, relres_out, peer);
         return;
       }
     while (it < max_iter && relres > rel_tol)

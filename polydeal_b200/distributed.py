@@ -186,6 +186,20 @@ class PeerExchange:
     def ok(self):
         return K.lib().pd_peer_status(self._h) == 0
 
+    def allreduce(self, scalars):
+        """In-place sum over the ranks of a CUDA float64 tensor of at most 4 entries."""
+        assert scalars.is_cuda and scalars.numel() <= 4
+        K.check(K.lib().pd_peer_allreduce(self._h, C.c_void_p(scalars.data_ptr()), scalars.numel()))
+        return scalars
+
+    def cg_solve(self, x, b, max_iter=1000, rel_tol=1e-10, jacobi=True, mode=K.VMULT_BLOCK_CSR):
+        """SolverCG on the sharded operator, device resident on every rank (pd_cg_solve_sharded);
+        x, b hold the owned DoFs.  Returns (iterations, global relative residual)."""
+        it, rr = C.c_int(0), C.c_double(0.0)
+        K.check(K.lib().pd_cg_solve_sharded(self._h, mode, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), max_iter,
+                                            rel_tol, int(jacobi), C.byref(it), C.byref(rr)))
+        return it.value, rr.value
+
     def close(self):
         if getattr(self, "_h", None) and K._lib is not None:
             K._lib.pd_peer_destroy(self._h)

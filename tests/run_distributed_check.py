@@ -27,6 +27,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     worst = 0.0
+    solve_ref, cg_info = None, []
     for dim, n, shape, p in [(3, 8, "blocks2", 2), (3, 8, "random40", 1), (2, 16, "random23", 3)]:
         ogrid = po.Grid(dim, n, 0.0, 1.0, 1)
         groups = groups_for(shape, dim, n, ogrid, 5)
@@ -62,13 +63,31 @@ def main():
             assert dop.peer.ok(), "a neighbour did not publish in time"
             e2 = float(np.abs(yd.cpu().numpy() - 6 * y[rows]).max() / (6 * np.abs(y).max()))
             err = max(err, e2)
+            # peer-memory all-reduce, then the sharded CG (exchange + all-reduce inside the CUDA graph)
+            t4 = torch.tensor([1.0 + rank, 0.5 * rank, -2.0, 1e-3 * (rank + 1)], dtype=torch.float64, device="cuda")
+            dop.peer.allreduce(t4)
+            stream.synchronize()
+            ranks = np.arange(world)
+            ref4 = [np.sum(1.0 + ranks), np.sum(0.5 * ranks), -2.0 * world, np.sum(1e-3 * (ranks + 1))]
+            assert np.allclose(t4.cpu().numpy(), ref4, rtol=1e-15, atol=0), (t4, ref4)
+            if solve_ref is None:
+                solve_ref = {}
+            bs = torch.from_numpy(y[rows]).cuda()  # b = A x  =>  the solution is x
+            xs0 = torch.zeros_like(bs)
+            iters, relres = dop.peer.cg_solve(xs0, bs, max_iter=4000, rel_tol=1e-11)
+            stream.synchronize()
+            assert relres <= 1e-11, (iters, relres)
+            e3 = float(np.abs(xs0.cpu().numpy() - x[rows]).max() / np.abs(x).max())
+            assert e3 <= 1e-7, e3
+            cg_info.append((iters, relres, e3))
             dist.barrier()
             dop.peer.close()
         t = torch.tensor([err], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         worst = max(worst, float(t))
         if rank == 0:
-            print(f"case dim={dim} n={n} {shape} p={p}: world={world} max rel err {float(t):.2e}", flush=True)
+            print(f"case dim={dim} n={n} {shape} p={p}: world={world} max rel err {float(t):.2e}; sharded CG "
+                  f"{cg_info[-1][0]} its, relres {cg_info[-1][1]:.1e}, solution err {cg_info[-1][2]:.1e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     assert worst <= 1e-12, worst
