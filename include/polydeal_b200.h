@@ -253,6 +253,10 @@ int32_t pd_n_dofs_per_cell(const pd_handle *h);
 int pd_matrix_values_device(pd_handle *h, double **dev_values);
 /* device->host copy of the matrix values (the per-step device->host leg) */
 int pd_matrix_values_to_host(pd_handle *h, double *host_values);
+/* the same without the final stream synchronisation (pinned host memory; complete after
+ * pd_synchronize): lets a caller that assembles many matrices double-buffer two handles on two
+ * streams, so that the download of one overlaps the upload and the kernels of the next */
+int pd_matrix_values_to_host_async(pd_handle *h, double *host_values_pinned);
 /* scalar CSR pattern of the result: rowptr[n_dofs+1], cols[nnz] (host) */
 int pd_matrix_pattern_to_host(pd_handle *h, int64_t *rowptr, int32_t *cols);
 

@@ -63,6 +63,7 @@ SIGNATURES = {
     "pd_n_dofs_per_cell": (i32, [vp]),
     "pd_matrix_values_device": (C.c_int, [vp, P(vp)]),
     "pd_matrix_values_to_host": (C.c_int, [vp, vp]),
+    "pd_matrix_values_to_host_async": (C.c_int, [vp, vp]),
     "pd_matrix_pattern_to_host": (C.c_int, [vp, vp, vp]),
     "pd_vmult": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_set_operator": (C.c_int, [vp, u32, P(Coefficients)]),

@@ -903,6 +903,18 @@ extern "C"
   }
 
   int
+  pd_matrix_values_to_host_async(pd_handle *h, double *host_values_pinned)
+  {
+    return guarded([&] {
+      if (!h || !host_values_pinned)
+        throw Error(PD_ERR_INVALID, "null argument");
+      if (!h->assembled)
+        throw Error(PD_ERR_STATE, "pd_matrix_values_to_host_async: pd_assemble has not been called");
+      PD_CUDA(cudaMemcpyAsync(host_values_pinned, h->values.p, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->stream));
+    });
+  }
+
+  int
   pd_matrix_pattern_to_host(pd_handle *h, int64_t *rowptr, int32_t *cols)
   {
     return guarded([&] {

@@ -294,8 +294,10 @@ class SIPOperator:
         K.check(K.lib().pd_matrix_values_to_host(self._h, _ptr(out)))
         return out
 
-    def values_to_host_ptr(self, host_ptr):
-        K.check(K.lib().pd_matrix_values_to_host(self._h, C.c_void_p(host_ptr)))
+    def values_to_host_ptr(self, host_ptr, wait=True):
+        """D2H of the CSR values into (pinned) host memory; wait=False returns without synchronising."""
+        fn = K.lib().pd_matrix_values_to_host if wait else K.lib().pd_matrix_values_to_host_async
+        K.check(fn(self._h, C.c_void_p(host_ptr)))
 
     def pattern(self):
         rp = np.empty(self.m() + 1, dtype=np.int64)
