@@ -24,8 +24,18 @@ from polydeal_b200 import distributed as pdd
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # PD_CHECK_SAME_DEVICE=1: all ranks share GPU 0 (CUDA IPC works between processes on one device;
+    # their kernels are time-sliced), rendezvous over gloo -- lets a single-GPU test run exercise the
+    # peer-memory collectives.  NCCL cannot put two ranks on one GPU, so its path is skipped there.
+    same = os.environ.get("PD_CHECK_SAME_DEVICE") == "1"
+    if same:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if same:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    red_dev = "cpu" if same else "cuda"
     worst = 0.0
     solve_ref, cg_info = None, []
     for dim, n, shape, p in [(3, 8, "blocks2", 2), (3, 8, "random40", 1), (2, 16, "random23", 3)]:
@@ -45,9 +55,11 @@ def main():
             rows = dop.part.owned_global_dofs()
             xs = torch.from_numpy(x[rows]).cuda()
             yd = torch.empty_like(xs)
-            dop.vmult(yd, xs)
-            stream.synchronize()
-            err = float(np.abs(yd.cpu().numpy() - y[rows]).max() / np.abs(y).max())
+            err = 0.0
+            if not same:
+                dop.vmult(yd, xs)
+                stream.synchronize()
+                err = float(np.abs(yd.cpu().numpy() - y[rows]).max() / np.abs(y).max())
             # the same through NVLink peer memory (pd_peer_*): several applies back to back with a
             # changing source exercise the double-buffered epochs; ranks deliberately out of step
             dop.enable_peer_exchange()
@@ -82,7 +94,7 @@ def main():
             cg_info.append((iters, relres, e3))
             dist.barrier()
             dop.peer.close()
-        t = torch.tensor([err], device="cuda")
+        t = torch.tensor([err], device=red_dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         worst = max(worst, float(t))
         if rank == 0:

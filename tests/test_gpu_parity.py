@@ -3,6 +3,8 @@ same seeded inputs, plus the reference tests' invariants evaluated on the GPU re
 
 Tolerance (north_star): 1e-12 relative in fp64, applied per matrix block entry relative
 to the block's largest entry and per vmult output relative to max|y|."""
+import os
+
 import numpy as np
 import pytest
 
@@ -877,3 +879,27 @@ def test_assembly_with_fe_agglodgp(dim, n, shape, p, nq, distort, kw):
     assert np.abs(y.cpu().numpy() - yref).max() <= TOL * np.abs(yref).max()
     with pytest.raises(pdl.PolydealError):
         op.vmult(y, torch.from_numpy(x).cuda(), mode=pdl.VMULT_MATRIX_FREE)
+
+
+# ----------------------------------------------------------------------------------
+# multi-rank collectives over peer memory, on ONE GPU: two processes share the device
+# ----------------------------------------------------------------------------------
+def test_peer_memory_collectives_two_processes_one_gpu():
+    """pd_peer_* (ghost exchange, all-reduce) and pd_cg_solve_sharded between two PROCESSES that share
+    cuda:0 (CUDA IPC + epoch flags; the kernels of the two contexts are time-sliced).  The same script
+    runs one rank per GPU under torchrun with NCCL (tests/run_distributed_check.py)."""
+    gpu()
+    import socket
+    import subprocess
+    import sys
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PD_CHECK_SAME_DEVICE="1", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "tests", "run_distributed_check.py")],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "DISTRIBUTED CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
