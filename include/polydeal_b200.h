@@ -234,6 +234,11 @@ int pd_peer_allreduce(pd_peer *p, double *scalars_dev, int count);
  * SolverCG on LinearAlgebra::distributed::Vector).  Residual norms are global. */
 int pd_cg_solve_sharded(pd_peer *p, int mode, const double *b_dev, double *x_dev, int max_iter, double rel_tol,
                         int jacobi, int *iterations, double *relative_residual);
+/* pd_estimate_lambda_max / pd_chebyshev_smooth on a sharded handle (collective calls).  The
+ * smoother's x_full_dev is a vmult source: pd_n_source_dofs long, owned DoFs first; b_dev owned. */
+int pd_estimate_lambda_max_sharded(pd_peer *p, int mode, int n_iterations, double *lambda_max);
+int pd_chebyshev_smooth_sharded(pd_peer *p, int mode, int degree, double lambda_max, double smoothing_range,
+                                const double *b_dev, double *x_full_dev, int zero_initial_guess);
 void pd_peer_destroy(pd_peer *p);
 
 /* mark the device quadrature stale (vertices changed through pd_upload do this

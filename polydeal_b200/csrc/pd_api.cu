@@ -1087,6 +1087,28 @@ extern "C"
   }
 
   int
+  pd_estimate_lambda_max_sharded(pd_peer *peer, int mode, int n_iterations, double *lambda_max)
+  {
+    return guarded([&] {
+      if (!peer || !lambda_max || n_iterations < 1)
+        throw Error(PD_ERR_INVALID, "pd_estimate_lambda_max_sharded: bad argument");
+      *lambda_max = solver_lambda_max(peer_handle(peer), mode, n_iterations, peer);
+    });
+  }
+
+  int
+  pd_chebyshev_smooth_sharded(pd_peer *peer, int mode, int degree, double lambda_max, double smoothing_range,
+                              const double *b_dev, double *x_full_dev, int zero_initial_guess)
+  {
+    return guarded([&] {
+      if (!peer || !b_dev || !x_full_dev)
+        throw Error(PD_ERR_INVALID, "pd_chebyshev_smooth_sharded: null argument");
+      solver_chebyshev(peer_handle(peer), mode, degree, lambda_max, smoothing_range, b_dev, x_full_dev, zero_initial_guess,
+                       peer);
+    });
+  }
+
+  int
   pd_chebyshev_smooth(pd_handle *h, int mode, int degree, double lambda_max, double smoothing_range, const double *b_dev,
                       double *x_dev, int zero_initial_guess)
   {

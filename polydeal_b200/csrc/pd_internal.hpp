@@ -186,9 +186,9 @@ namespace pd
   // pd_solver.cu
   void   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,
                    int *iters_out, double *relres_out, pd_peer *peer = nullptr);
-  double solver_lambda_max(pd_handle *h, int mode, int n_iter);
+  double solver_lambda_max(pd_handle *h, int mode, int n_iter, pd_peer *peer = nullptr);
   void   solver_chebyshev(pd_handle *h, int mode, int degree, double lambda_max, double smoothing_range, const double *b,
-                          double *x, int zero_initial_guess);
+                          double *x, int zero_initial_guess, pd_peer *peer = nullptr);
   // pd_peer.cu (all throw; the extern "C" wrappers live in pd_api.cu)
   pd_peer *peer_create(pd_handle *h, int rank, int world, const int64_t *send_ptr, const int32_t *send_blocks,
                        const int64_t *recv_ptr, const int64_t *remote_offset);

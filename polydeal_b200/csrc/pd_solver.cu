@@ -317,10 +317,12 @@ namespace pd
   }
 
   double
-  solver_lambda_max(pd_handle *h, const int mode, const int n_iter)
+  solver_lambda_max(pd_handle *h, const int mode, const int n_iter, pd_peer *peer)
   {
-    if (h->np != h->np_own)
-      throw Error(PD_ERR_UNSUPPORTED, "pd_estimate_lambda_max: single-rank handles only");
+    if (h->np != h->np_own && !peer)
+      throw Error(PD_ERR_UNSUPPORTED, "pd_estimate_lambda_max: a handle with ghost polytopes needs the sharded call");
+    if (peer && peer_handle(peer) != h)
+      throw Error(PD_ERR_INVALID, "pd_estimate_lambda_max_sharded: the peer object belongs to another handle");
     ensure_work(h);
     const int64_t n = h->n_dofs;
     cudaStream_t  s = h->stream;
@@ -330,9 +332,13 @@ namespace pd
     double lambda = 0.;
     for (int it = 0; it < n_iter; ++it)
       {
+        if (peer)
+          peer_exchange(peer, v);
         vmult_dispatch(h, mode, v, Av, false);
         k_power<<<RG, RB, 0, s>>>(Av, h->sv_dinv.p, v, w, n, partial);
         k_finalize<<<1, 32, 0, s>>>(partial, scal, 2, 0);
+        if (peer)
+          peer_allreduce(peer, scal, 0, 2);
         k_scale_from<<<RG, RB, 0, s>>>(v, w, scal, n);
         h->launches += 3;
       }
@@ -344,12 +350,16 @@ namespace pd
     return lambda;
   }
 
+  // sharded (peer != null): x is a vmult source, i.e. it has the (owned + ghost) length
+  // pd_n_source_dofs; its ghost section is refreshed over peer memory before every apply.
   void
   solver_chebyshev(pd_handle *h, const int mode, const int degree, const double lambda_max, const double smoothing_range,
-                   const double *b, double *x, const int zero_initial_guess)
+                   const double *b, double *x, const int zero_initial_guess, pd_peer *peer)
   {
-    if (h->np != h->np_own)
-      throw Error(PD_ERR_UNSUPPORTED, "pd_chebyshev_smooth: single-rank handles only");
+    if (h->np != h->np_own && !peer)
+      throw Error(PD_ERR_UNSUPPORTED, "pd_chebyshev_smooth: a handle with ghost polytopes needs the sharded call");
+    if (peer && peer_handle(peer) != h)
+      throw Error(PD_ERR_INVALID, "pd_chebyshev_smooth_sharded: the peer object belongs to another handle");
     if (degree < 1 || !(lambda_max > 0.) || !(smoothing_range > 1.))
       throw Error(PD_ERR_INVALID, "pd_chebyshev_smooth: need degree >= 1, lambda_max > 0, smoothing_range > 1");
     ensure_work(h);
@@ -363,14 +373,19 @@ namespace pd
     double       rho    = 1. / sigma1;
     const int    grid   = (int)std::min<int64_t>((n + RB - 1) / RB, 148 * 8);
     // step 0: d = 1/theta D^-1 (b - A x0), x = x0 + d
-    if (!zero_initial_guess)
+    auto apply = [&] {
+      if (peer)
+        peer_exchange(peer, x);
       vmult_dispatch(h, mode, x, Ax, false);
+    };
+    if (!zero_initial_guess)
+      apply();
     k_cheb_step<<<grid, RB, 0, s>>>(x, d, b, zero_initial_guess ? nullptr : Ax, h->sv_dinv.p, 0., 1. / theta, n, 1);
     ++h->launches;
     for (int k = 1; k < degree; ++k)
       {
         const double rho_new = 1. / (2. * sigma1 - rho);
-        vmult_dispatch(h, mode, x, Ax, false);
+        apply();
         k_cheb_step<<<grid, RB, 0, s>>>(x, d, b, Ax, h->sv_dinv.p, rho_new * rho, 2. * rho_new / delta, n, 0);
         ++h->launches;
         rho = rho_new;

@@ -192,6 +192,19 @@ class PeerExchange:
         K.check(K.lib().pd_peer_allreduce(self._h, C.c_void_p(scalars.data_ptr()), scalars.numel()))
         return scalars
 
+    def estimate_lambda_max(self, n_iterations=20, mode=K.VMULT_BLOCK_CSR):
+        lam = C.c_double(0.0)
+        K.check(K.lib().pd_estimate_lambda_max_sharded(self._h, mode, n_iterations, C.byref(lam)))
+        return lam.value
+
+    def chebyshev_smooth(self, x_full, b, degree, lambda_max, smoothing_range=20.0, zero_initial_guess=True,
+                         mode=K.VMULT_BLOCK_CSR):
+        """PreconditionChebyshev on the sharded operator; x_full has the (owned + ghost) length."""
+        K.check(K.lib().pd_chebyshev_smooth_sharded(self._h, mode, degree, lambda_max, smoothing_range,
+                                                    C.c_void_p(b.data_ptr()), C.c_void_p(x_full.data_ptr()),
+                                                    int(zero_initial_guess)))
+        return x_full
+
     def cg_solve(self, x, b, max_iter=1000, rel_tol=1e-10, jacobi=True, mode=K.VMULT_BLOCK_CSR):
         """SolverCG on the sharded operator, device resident on every rank (pd_cg_solve_sharded);
         x, b hold the owned DoFs.  Returns (iterations, global relative residual)."""

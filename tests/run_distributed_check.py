@@ -92,6 +92,32 @@ def main():
             e3 = float(np.abs(xs0.cpu().numpy() - x[rows]).max() / np.abs(x).max())
             assert e3 <= 1e-7, e3
             cg_info.append((iters, relres, e3))
+            # sharded lambda_max (power iteration on D^-1 A) and Chebyshev smoother vs numpy on the global matrix
+            dinv_g = 1.0 / A.diagonal()
+            lam = dop.peer.estimate_lambda_max(40)
+            import scipy.sparse as sp
+            import scipy.sparse.linalg as spla
+            Dh = sp.diags(np.sqrt(dinv_g))
+            lam_true = float(spla.eigsh(Dh @ A @ Dh, k=1, which="LA", return_eigenvectors=False)[0])
+            assert 0.8 * lam_true <= lam <= 1.0001 * lam_true, (lam, lam_true)
+            lmax, rng_ = 1.2 * lam_true, 20.0
+            lmin = lmax / rng_
+            theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+            sigma1 = theta / delta
+            rho = 1.0 / sigma1
+            xg = np.zeros_like(y)
+            dg = dinv_g * y / theta
+            xg += dg
+            for _ in range(1, 4):
+                rho_new = 1.0 / (2 * sigma1 - rho)
+                dg = rho_new * rho * dg + 2 * rho_new / delta * dinv_g * (y - A @ xg)
+                xg += dg
+                rho = rho_new
+            xfull = torch.zeros(dop.part.n_local_dofs, dtype=torch.float64, device="cuda")
+            dop.peer.chebyshev_smooth(xfull, bs, 4, lmax, rng_, zero_initial_guess=True)
+            stream.synchronize()
+            e4 = float(np.abs(xfull[: len(rows)].cpu().numpy() - xg[rows]).max() / np.abs(xg).max())
+            assert e4 <= 1e-12, e4
             dist.barrier()
             dop.peer.close()
         t = torch.tensor([err], device=red_dev)
