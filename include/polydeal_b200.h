@@ -224,6 +224,9 @@ int pd_peer_handle_bytes(void);
 int pd_peer_export(pd_peer *p, void *handles_out);
 int pd_peer_connect(pd_peer *p, const void *all_handles);
 int pd_peer_exchange(pd_peer *p, double *x_full_dev);
+/* pd_peer_exchange + pd_vmult in one call; with the fine-mesh stencil kernel the cells that need no
+ * ghost data are applied while the ghost blocks travel on a second stream */
+int pd_peer_vmult(pd_peer *p, int mode, double *x_full_dev, double *dst_dev, int add);
 int pd_peer_status(pd_peer *p);
 /* sum of `count` <= 4 doubles (device memory, in place) over all ranks: one warp, stores into every
  * rank's mapped buffer + flag handshake; the result is bitwise identical on all ranks */

@@ -82,6 +82,7 @@ SIGNATURES = {
     "pd_peer_export": (C.c_int, [vp, C.c_void_p]),
     "pd_peer_connect": (C.c_int, [vp, C.c_void_p]),
     "pd_peer_exchange": (C.c_int, [vp, C.c_void_p]),
+    "pd_peer_vmult": (C.c_int, [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "pd_peer_status": (C.c_int, [vp]),
     "pd_peer_allreduce": (C.c_int, [vp, C.c_void_p, C.c_int]),
     "pd_estimate_lambda_max_sharded": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),

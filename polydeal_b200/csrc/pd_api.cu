@@ -814,6 +814,11 @@ extern "C"
     return guarded([&] { peer_exchange(p, x_full_dev); });
   }
   int
+  pd_peer_vmult(pd_peer *p, int mode, double *x_full_dev, double *dst_dev, int add)
+  {
+    return guarded([&] { peer_vmult(p, mode, x_full_dev, dst_dev, add != 0); });
+  }
+  int
   pd_peer_status(pd_peer *p)
   {
     return peer_status(p);

@@ -112,6 +112,7 @@ namespace pd
       const double  *x;
       double        *y;
       int32_t        n_cells;
+      const int32_t *list; // optional: the cells to process (interior / boundary split of a sharded apply)
       double         mass; // 0 when the volume term is off
       int            add;
     };
@@ -194,22 +195,26 @@ namespace pd
 
       // the neighbour indices of the NEXT cell are fetched one iteration ahead, so the two
       // dependent long-latency steps (record -> neighbour lines) overlap across iterations
-      int       cell = blockIdx.x * CPB + slot;
+      // work index -> cell (identity unless a cell list is given)
+      auto cell_of = [&](const int idx) { return idx < A.n_cells ? (A.list ? A.list[idx] : idx) : -1; };
+      int       idx  = blockIdx.x * CPB + slot;
       const int step = gridDim.x * CPB;
+      int       cell = cell_of(idx), cell_next = cell_of(idx + step);
       int2      nbn  = make_int2(-1, -1);
-      if (cell < A.n_cells && task_ok)
+      if (cell >= 0 && task_ok)
         nbn = *reinterpret_cast<const int2 *>(recp + (int64_t)cell * DIM);
 
-      for (int c0 = blockIdx.x * CPB; c0 < A.n_cells; c0 += step, cell += step)
+      for (int c0 = blockIdx.x * CPB; c0 < A.n_cells;
+           c0 += step, idx += step, cell = cell_next, cell_next = cell_of(idx + step))
         {
-          const bool cell_ok = cell < A.n_cells;
+          const bool cell_ok = cell >= 0;
           double     out[N1];
 #pragma unroll
           for (int i = 0; i < N1; ++i)
             out[i] = 0.;
           const int2 nb = nbn;
-          if (cell + step < A.n_cells && task_ok)
-            nbn = *reinterpret_cast<const int2 *>(recp + (int64_t)(cell + step) * DIM);
+          if (cell_next >= 0 && task_ok)
+            nbn = *reinterpret_cast<const int2 *>(recp + (int64_t)cell_next * DIM);
           if (cell_ok && task_ok)
             {
               // all loads are unconditional (a missing neighbour reads zeros), so they are
@@ -426,6 +431,22 @@ namespace pd
     };
     put(h->mf_geo, rec);
     put(h->mf_vol, vol);
+    // sharded handles: cells whose neighbours are all owned can be applied while the ghost blocks travel
+    h->mf_list_interior.release();
+    h->mf_list_boundary.release();
+    if (h->np != h->np_own)
+      {
+        std::vector<int32_t> inner, outer;
+        for (int32_t c = 0; c < h->np_own; ++c)
+          {
+            bool ghost = false;
+            for (int f = 0; f < nfc; ++f)
+              ghost = ghost || nbr[(size_t)c * nfc + f] >= h->np_own;
+            (ghost ? outer : inner).push_back(c);
+          }
+        put(h->mf_list_interior, inner);
+        put(h->mf_list_boundary, outer);
+      }
     h->mf_rec.alloc((size_t)h->np_own * dim * 8);
     h->mf_zero.alloc((size_t)h->n);
     PD_CUDA(cudaMemset(h->mf_zero.p, 0, (size_t)h->n * sizeof(double)));
@@ -443,7 +464,7 @@ namespace pd
   {
     template <int DIM, int DEG, int MINB>
     void
-    launch_fine(pd_handle *h, const double *src, double *dst, const bool add)
+    launch_fine(pd_handle *h, const double *src, double *dst, const bool add, const int part)
     {
       constexpr int N1 = DEG + 1, N = ipow_(N1, DIM), NT = DIM * (N / N1);
       constexpr int GS = pow2_at_least(N > NT ? N : NT), CPB = 256 / GS;
@@ -467,27 +488,31 @@ namespace pd
       a.zero     = h->mf_zero.p;
       a.x        = src;
       a.y        = dst;
-      a.n_cells  = h->np_own;
-      a.mass     = vol_on ? h->op_coef.mass : 0.;
-      a.add      = add ? 1 : 0;
-      const int64_t want = ((int64_t)h->np_own + CPB - 1) / CPB;
+      // part 0: all owned cells; 1: cells without ghost neighbours; 2: cells with ghost neighbours
+      a.n_cells = part == 0 ? h->np_own : (part == 1 ? (int32_t)h->mf_list_interior.n : (int32_t)h->mf_list_boundary.n);
+      a.list    = part == 0 ? nullptr : (part == 1 ? h->mf_list_interior.p : h->mf_list_boundary.p);
+      a.mass    = vol_on ? h->op_coef.mass : 0.;
+      a.add     = add ? 1 : 0;
+      if (a.n_cells == 0)
+        return;
+      const int64_t want = ((int64_t)a.n_cells + CPB - 1) / CPB;
       const int     grid = (int)std::min<int64_t>(want, (int64_t)h->sm_count * 4 * MINB);
       k_fine_sip<DIM, DEG, MINB><<<grid, 256, 0, h->stream>>>(a);
     }
   } // namespace
 
   void
-  launch_fine_operator(pd_handle *h, const double *src, double *dst, const bool add)
+  launch_fine_operator(pd_handle *h, const double *src, double *dst, const bool add, const int part)
   {
     switch (h->dim * 10 + h->degree)
       {
-        case 21: launch_fine<2, 1, 4>(h, src, dst, add); break;
-        case 22: launch_fine<2, 2, 3>(h, src, dst, add); break;
-        case 23: launch_fine<2, 3, 3>(h, src, dst, add); break;
-        case 24: launch_fine<2, 4, 2>(h, src, dst, add); break;
-        case 31: launch_fine<3, 1, 4>(h, src, dst, add); break;
-        case 32: launch_fine<3, 2, 3>(h, src, dst, add); break;
-        case 33: launch_fine<3, 3, 2>(h, src, dst, add); break;
+        case 21: launch_fine<2, 1, 4>(h, src, dst, add, part); break;
+        case 22: launch_fine<2, 2, 3>(h, src, dst, add, part); break;
+        case 23: launch_fine<2, 3, 3>(h, src, dst, add, part); break;
+        case 24: launch_fine<2, 4, 2>(h, src, dst, add, part); break;
+        case 31: launch_fine<3, 1, 4>(h, src, dst, add, part); break;
+        case 32: launch_fine<3, 2, 3>(h, src, dst, add, part); break;
+        case 33: launch_fine<3, 3, 2>(h, src, dst, add, part); break;
         default:
           throw CudaError{cudaErrorNotSupported, "no fine-mesh operator kernel for this (dim, degree)", __LINE__};
       }

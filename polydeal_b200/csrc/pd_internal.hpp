@@ -110,6 +110,7 @@ struct pd_handle
   pd::DevBuf<double> vec_a, vec_b; // staging for pd_vmult_host
   // matrix-free fine-mesh operator (every polytope = one Cartesian cell), pd_finemesh.cu
   bool                mf_ready = false, force_generic_mf = false;
+  pd::DevBuf<int32_t> mf_list_interior, mf_list_boundary; // sharded: cells without / with ghost neighbours
   pd::DevBuf<double>  mf_geo, mf_rec, mf_vol, mf_zero; // per (cell, direction) geometry / folded stencil records, cell volumes (pd_finemesh.cu)
   bool                mf_rec_valid = false;
   uint32_t            mf_rec_flags = 0;
@@ -174,7 +175,7 @@ namespace pd
   bool assemble_supported(int dim, int degree, int fe_kind);
   // pd_finemesh.cu
   void setup_fine_operator(pd_handle *h, const pd_mesh_desc &d);
-  void launch_fine_operator(pd_handle *h, const double *src, double *dst, bool add);
+  void launch_fine_operator(pd_handle *h, const double *src, double *dst, bool add, int part = 0);
   // pd_mappedfine.cu
   void setup_mapped_operator(pd_handle *h, const pd_mesh_desc &d);
   void launch_mapped_operator(pd_handle *h, const double *src, double *dst, bool add);
@@ -196,6 +197,7 @@ namespace pd
   void     peer_export(pd_peer *p, void *handles_out);
   void     peer_connect(pd_peer *p, const void *all_handles);
   void     peer_exchange(pd_peer *p, double *x_full_dev);
+  void     peer_vmult(pd_peer *p, int mode, double *x_full_dev, double *dst, bool add);
   void     peer_allreduce(pd_peer *p, double *scal_dev, int dst0, int nk);
   pd_handle *peer_handle(pd_peer *p);
   int      peer_status(pd_peer *p);

@@ -29,6 +29,7 @@
 #include "pd_internal.hpp"
 #include "pd_host.hpp"
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -79,6 +80,9 @@ struct pd_peer
   std::vector<char *> peer_base;
   pd::DevBuf<char *>  d_peer_base;
   bool                connected = false;
+  // a second stream for the exchange, so that work which needs no ghost data overlaps it
+  cudaStream_t aux     = nullptr;
+  cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace pd
@@ -257,6 +261,14 @@ namespace pd
     PD_CUDA(cudaMemset(p->epochs, 0, 2 * sizeof(u64)));
     PD_CUDA(cudaMalloc((void **)&p->counter, sizeof(unsigned int)));
     PD_CUDA(cudaMemset(p->counter, 0, sizeof(unsigned int)));
+    {
+      // highest priority: the small exchange kernels must get SM slots next to a resident grid-stride kernel
+      int lo = 0, hi = 0;
+      PD_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      PD_CUDA(cudaStreamCreateWithPriority(&p->aux, cudaStreamNonBlocking, hi));
+    }
+    PD_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    PD_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     return p.release();
   }
 
@@ -308,18 +320,17 @@ namespace pd
       throw Error(PD_ERR_STATE, std::string(who) + ": pd_peer_connect has not been called");
   }
 
-  void
-  peer_exchange(pd_peer *p, double *x_full_dev)
+  void vmult_dispatch(pd_handle *h, int mode, const double *src, double *dst, bool add); // pd_api.cu
+
+  static void
+  exchange_on(pd_peer *p, double *x_full_dev, cudaStream_t stream)
   {
-    require_connected(p, "pd_peer_exchange");
-    if (!x_full_dev)
-      throw Error(PD_ERR_INVALID, "pd_peer_exchange: null argument");
     pd_handle *h = p->h;
     const int  n = h->n;
     if (p->n_neighbours > 0)
       {
         const int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (p->n_send * n + 255) / 256), h->sm_count);
-        k_peer_publish<<<grid, 256, 0, h->stream>>>(x_full_dev, p->send_blocks.p, p->n_send, n, p->d_peer_base.p,
+        k_peer_publish<<<grid, 256, 0, stream>>>(x_full_dev, p->send_blocks.p, p->n_send, n, p->d_peer_base.p,
                                                     p->d_neighbours.p, p->n_neighbours, p->rank, p->world, p->epochs,
                                                     p->counter);
         ++h->launches;
@@ -327,12 +338,49 @@ namespace pd
     if (p->n_recv > 0)
       {
         const int grid = (int)std::min<int64_t>((p->n_recv * n + 255) / 256, (int64_t)h->sm_count * 4);
-        k_peer_pull<<<grid, 256, 0, h->stream>>>(x_full_dev + (int64_t)h->np_own * n, p->recv_owner_of_block.p,
+        k_peer_pull<<<grid, 256, 0, stream>>>(x_full_dev + (int64_t)h->np_own * n, p->recv_owner_of_block.p,
                                                  p->recv_src_block.p, p->n_recv, n, p->d_peer_base.p, p->rank, p->world,
                                                  p->epochs, p->d_owners.p, p->n_owners);
         ++h->launches;
       }
     PD_CUDA(cudaGetLastError());
+  }
+
+  void
+  peer_exchange(pd_peer *p, double *x_full_dev)
+  {
+    require_connected(p, "pd_peer_exchange");
+    if (!x_full_dev)
+      throw Error(PD_ERR_INVALID, "pd_peer_exchange: null argument");
+    exchange_on(p, x_full_dev, p->h->stream);
+  }
+
+  // update_ghost_values() + vmult.  On a fine Cartesian mesh (stencil kernel) the cells whose
+  // neighbours are all owned are applied on the operator's stream WHILE the ghost blocks travel
+  // on a second stream; the cells next to a cut follow once the pull has finished.
+  void
+  peer_vmult(pd_peer *p, const int mode, double *x_full_dev, double *dst, const bool add)
+  {
+    require_connected(p, "pd_peer_vmult");
+    if (!x_full_dev || !dst)
+      throw Error(PD_ERR_INVALID, "pd_peer_vmult: null argument");
+    pd_handle *h = p->h;
+    static const bool no_split = getenv("PD_PEER_NO_SPLIT") != nullptr; // A/B switch for measurements
+    const bool split = !no_split && mode == PD_VMULT_MATRIX_FREE && h->mf_ready && !h->force_generic_mf && h->fe_kind == PD_FE_DGQ &&
+                       h->np != h->np_own && h->mf_list_interior.n > 0 && h->mf_list_boundary.n > 0;
+    if (!split)
+      {
+        exchange_on(p, x_full_dev, h->stream);
+        vmult_dispatch(h, mode, x_full_dev, dst, add);
+        return;
+      }
+    PD_CUDA(cudaEventRecord(p->ev_fork, h->stream));
+    PD_CUDA(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
+    exchange_on(p, x_full_dev, p->aux);
+    PD_CUDA(cudaEventRecord(p->ev_join, p->aux));
+    launch_fine_operator(h, x_full_dev, dst, add, 1);
+    PD_CUDA(cudaStreamWaitEvent(h->stream, p->ev_join, 0));
+    launch_fine_operator(h, x_full_dev, dst, add, 2);
   }
 
   void
@@ -372,6 +420,12 @@ namespace pd
     for (int s = 0; s < (int)p->peer_base.size(); ++s)
       if (s != p->rank && p->peer_base[s])
         cudaIpcCloseMemHandle(p->peer_base[s]);
+    if (p->aux)
+      cudaStreamDestroy(p->aux);
+    if (p->ev_fork)
+      cudaEventDestroy(p->ev_fork);
+    if (p->ev_join)
+      cudaEventDestroy(p->ev_join);
     cudaFree(p->ipc);
     cudaFree(p->epochs);
     cudaFree(p->counter);

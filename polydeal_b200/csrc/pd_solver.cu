@@ -220,8 +220,9 @@ namespace pd
     ensure_work(h);
     auto apply = [&](double *src_full, double *dst) {
       if (peer)
-        peer_exchange(peer, src_full);
-      vmult_dispatch(h, mode, src_full, dst, false);
+        peer_vmult(peer, mode, src_full, dst, false);
+      else
+        vmult_dispatch(h, mode, src_full, dst, false);
     };
     auto reduce = [&](const int dst0, const int nk) {
       if (peer)

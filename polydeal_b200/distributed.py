@@ -183,6 +183,12 @@ class PeerExchange:
         K.check(K.lib().pd_peer_exchange(self._h, C.c_void_p(x_full.data_ptr())))
         return x_full
 
+    def vmult(self, dst, x_full, mode=K.VMULT_BLOCK_CSR, add=False):
+        """exchange + vmult in one call (pd_peer_vmult): overlaps the exchange with the cells that need
+        no ghost data when the fine-mesh stencil kernel applies."""
+        K.check(K.lib().pd_peer_vmult(self._h, mode, C.c_void_p(x_full.data_ptr()), C.c_void_p(dst.data_ptr()), int(add)))
+        return dst
+
     def ok(self):
         return K.lib().pd_peer_status(self._h) == 0
 
@@ -253,8 +259,7 @@ class DistributedSIPOperator:
         self._x_full[: p.n_owned_dofs].copy_(src)
         if exchange and p.n_ranks > 1:
             if self.peer is not None:
-                self.peer.exchange(self._x_full)
-            else:
-                exchange_ghost_values(p, self._x_full, self.group)
+                return self.peer.vmult(dst, self._x_full, mode)
+            exchange_ghost_values(p, self._x_full, self.group)
         self.op.vmult_ptr(dst.data_ptr(), self._x_full.data_ptr(), mode)
         return dst
