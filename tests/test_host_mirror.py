@@ -217,3 +217,21 @@ def test_fe_agglodgp_numbering_and_sparsity_match_the_oracle(dim, p):
     orp, ocols = oah.create_agglomeration_sparsity_pattern()
     assert np.array_equal(rp, orp) and np.array_equal(cols, ocols)
     assert pah.flatten().fe_kind == pdl.FE_AGGLODGP
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/polydeal_b200.h is C99 and the library is callable from a plain C program:
+    tests/c_abi/c_abi_smoke.c walks the host mirror and checks the no-GPU answer of pd_create."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "c_abi_smoke")
+    lib_dir = os.path.dirname(K.LIB_PATH)
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "c_abi_smoke.c"), "-L", lib_dir, "-lpolydeal_b200",
+                    "-Wl,-rpath," + lib_dir, "-o", exe], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C ABI OK" in r.stdout, r.stdout + r.stderr
