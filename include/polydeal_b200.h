@@ -305,6 +305,12 @@ int pd_vmult_host(pd_handle *h, int mode, const double *src_host, double *dst_ho
 /* inverse of the matrix diagonal, entries below 1e-10 kept as they are
  * (include/utils.h:797-814); device pointer of pd_n_dofs doubles */
 int pd_diagonal_inverse(pd_handle *h, double *dst_dev);
+/* the same for the operator a vmult mode applies.  Matrix-free modes need no assembled matrix: the
+ * operator is applied to sums of unit vectors over independent sets of polytopes (greedy colouring of
+ * the block pattern), n_dofs_per_cell * n_colours applies, cached until pd_set_operator changes
+ * (MatrixFreeTools::compute_diagonal in the reference, include/utils.h:929-1100).  pd_cg_solve with
+ * jacobi != 0, pd_chebyshev_smooth and pd_estimate_lambda_max use it for their mode. */
+int pd_diagonal_inverse_of(pd_handle *h, int mode, double *dst_dev);
 
 /* --- the immediate callers of vmult, device resident (single-rank handles) ------------------
  * Preconditioned conjugate gradients around pd_vmult: what SolverCG does in

@@ -98,6 +98,7 @@ SIGNATURES = {
     "pd_vmult_add": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_vmult_host": (C.c_int, [vp, C.c_int, vp, vp]),
     "pd_diagonal_inverse": (C.c_int, [vp, vp]),
+    "pd_diagonal_inverse_of": (C.c_int, [vp, C.c_int, vp]),
     "pd_cg_solve": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, f64, C.c_int, P(C.c_int), P(f64)]),
     "pd_estimate_lambda_max": (C.c_int, [vp, C.c_int, C.c_int, P(f64)]),
     "pd_chebyshev_smooth": (C.c_int, [vp, C.c_int, C.c_int, f64, f64, vp, vp, C.c_int]),

@@ -1137,6 +1137,18 @@ extern "C"
   }
 
   int
+  pd_diagonal_inverse_of(pd_handle *h, int mode, double *dst_dev)
+  {
+    return guarded([&] {
+      if (!h || !dst_dev)
+        throw Error(PD_ERR_INVALID, "null argument");
+      if (mode != PD_VMULT_BLOCK_CSR && h->fe_kind != PD_FE_DGQ)
+        throw Error(PD_ERR_UNSUPPORTED, "the matrix-free applies are implemented for FE_DGQ only");
+      solver_diagonal_inverse(h, mode, dst_dev);
+    });
+  }
+
+  int
   pd_copy_array(pd_handle *h, const char *name, double *host_out, int64_t *count)
   {
     return guarded([&] {

@@ -137,6 +137,13 @@ struct pd_handle
   cudaGraphExec_t    cg_graph_exec   = nullptr;
   int                cg_graph_mode   = -1, cg_graph_jacobi = -1;
   pd_peer           *cg_graph_peer   = nullptr;
+  // inverse diagonal of the matrix-free operators (pd_solver.cu)
+  pd::DevBuf<int32_t> mfd_colour;
+  pd::DevBuf<double>  mfd_dinv;
+  int                 mfd_n_colours = 0, mfd_mode = -1;
+  bool                mfd_valid = false;
+  uint32_t            mfd_flags = 0;
+  double              mfd_coef[2] = {0., 0.};
   const double      *cg_graph_x      = nullptr, *cg_graph_b = nullptr;
   int64_t            cg_launches_per_chunk = 0;
 
@@ -187,6 +194,7 @@ namespace pd
   // pd_solver.cu
   void   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,
                    int *iters_out, double *relres_out, pd_peer *peer = nullptr);
+  void   solver_diagonal_inverse(pd_handle *h, int mode, double *dst);
   double solver_lambda_max(pd_handle *h, int mode, int n_iter, pd_peer *peer = nullptr);
   void   solver_chebyshev(pd_handle *h, int mode, int degree, double lambda_max, double smoothing_range, const double *b,
                           double *x, int zero_initial_guess, pd_peer *peer = nullptr);

@@ -187,6 +187,31 @@ namespace pd
         v[i] = (double)((i % 11) - 5) + 0.5;
     }
 
+    // x = sum over the blocks of one colour of the unit vector of local DoF i
+    __global__ void __launch_bounds__(RB)
+    k_unit_of_colour(double *__restrict__ x, const int32_t *__restrict__ colour, const int c, const int i, const int n,
+                     const int64_t n_own, const int64_t n_src)
+    {
+      for (int64_t k = (int64_t)blockIdx.x * RB + threadIdx.x; k < n_src; k += (int64_t)gridDim.x * RB)
+        {
+          const int64_t b = k / n;
+          x[k]            = (k < n_own && colour[b] == c && k - b * n == i) ? 1. : 0.;
+        }
+    }
+    // dinv[b n + i] = 1 / y[b n + i] for the blocks of that colour (entries below 1e-10 kept,
+    // include/utils.h:797-814)
+    __global__ void __launch_bounds__(RB)
+    k_take_diagonal(const double *__restrict__ y, const int32_t *__restrict__ colour, const int c, const int i, const int n,
+                    const int64_t n_blocks, double *__restrict__ dinv)
+    {
+      for (int64_t b = (int64_t)blockIdx.x * RB + threadIdx.x; b < n_blocks; b += (int64_t)gridDim.x * RB)
+        if (colour[b] == c)
+          {
+            const double d  = y[b * n + i];
+            dinv[b * n + i] = fabs(d) > 1e-10 ? 1. / d : d;
+          }
+    }
+
     void
     ensure_work(pd_handle *h)
     {
@@ -209,6 +234,72 @@ namespace pd
   // before every apply and every dot product is summed over the ranks by the peer-memory
   // all-reduce (pd_peer.cu) -- all inside the replayed graph, no NCCL and no host in the loop.
   // The reduced scalars are bitwise identical on all ranks, so every rank takes the same path.
+  // get_matrix_diagonal_inverse() of whatever operator `mode` applies (include/utils.h:797-814, 929-1100).
+  // BLOCK_CSR: read off the assembled matrix.  Matrix-free modes: the operator is applied to sums of unit
+  // vectors over an independent set of polytopes (greedy colouring of the block pattern, host, once), so
+  // every diagonal entry is isolated exactly: n * n_colours applies, cached per (mode, flags, coefficients).
+  void
+  solver_diagonal_inverse(pd_handle *h, const int mode, double *dst)
+  {
+    if (mode == PD_VMULT_BLOCK_CSR || h->np != h->np_own)
+      {
+        // sharded handles: the assembled diagonal (equal to the matrix-free operator's on Cartesian cells)
+        if (!h->assembled)
+          throw Error(PD_ERR_STATE, "the inverse diagonal needs pd_assemble (block-CSR mode or a sharded handle)");
+        launch_diagonal_inverse(h, dst);
+        return;
+      }
+    ensure_work(h);
+    const int64_t n_own = h->n_dofs, n_src = (int64_t)h->np * h->n;
+    cudaStream_t  s = h->stream;
+    if (!(h->mfd_valid && h->mfd_mode == mode && h->mfd_flags == h->op_flags && h->mfd_coef[0] == h->op_coef.stiffness &&
+          h->mfd_coef[1] == h->op_coef.mass))
+      {
+        if (h->mfd_colour.n != (size_t)h->np_own)
+          {
+            std::vector<int32_t> colour((size_t)h->np_own, -1);
+            int                  n_colours = 0;
+            std::vector<char>    used;
+            for (int32_t b = 0; b < h->np_own; ++b)
+              {
+                used.assign((size_t)n_colours + 1, 0);
+                for (int64_t e = h->h_brow_ptr[b]; e < h->h_brow_ptr[b + 1]; ++e)
+                  {
+                    const int32_t nb = h->h_bcol[e];
+                    if (nb != b && nb < h->np_own && colour[nb] >= 0)
+                      used[colour[nb]] = 1;
+                  }
+                int c = 0;
+                while (used[c])
+                  ++c;
+                colour[b] = c;
+                n_colours = std::max(n_colours, c + 1);
+              }
+            h->mfd_colour.alloc(colour.size());
+            PD_CUDA(cudaMemcpy(h->mfd_colour.p, colour.data(), colour.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            h->mfd_n_colours = n_colours;
+            h->mfd_dinv.alloc((size_t)n_own);
+          }
+        double   *x = h->sv_p.p, *y = h->sv_Ap.p;
+        const int grid = (int)std::min<int64_t>((n_src + RB - 1) / RB, 148 * 8);
+        for (int c = 0; c < h->mfd_n_colours; ++c)
+          for (int i = 0; i < h->n; ++i)
+            {
+              k_unit_of_colour<<<grid, RB, 0, s>>>(x, h->mfd_colour.p, c, i, h->n, n_own, n_src);
+              vmult_dispatch(h, mode, x, y, false);
+              k_take_diagonal<<<grid, RB, 0, s>>>(y, h->mfd_colour.p, c, i, h->n, h->np_own, h->mfd_dinv.p);
+              h->launches += 2;
+            }
+        PD_CUDA(cudaGetLastError());
+        h->mfd_valid   = true;
+        h->mfd_mode    = mode;
+        h->mfd_flags   = h->op_flags;
+        h->mfd_coef[0] = h->op_coef.stiffness;
+        h->mfd_coef[1] = h->op_coef.mass;
+      }
+    PD_CUDA(cudaMemcpyAsync(dst, h->mfd_dinv.p, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, s));
+  }
+
   void
   solver_cg(pd_handle *h, const int mode, const double *b, double *x, const int max_iter, const double rel_tol,
             const int jacobi, int *iters_out, double *relres_out, pd_peer *peer)
@@ -235,7 +326,7 @@ namespace pd
     const double *dinv = nullptr;
     if (jacobi)
       {
-        launch_diagonal_inverse(h, h->sv_dinv.p);
+        solver_diagonal_inverse(h, mode, h->sv_dinv.p);
         dinv = h->sv_dinv.p;
       }
     if (peer)
@@ -328,7 +419,7 @@ namespace pd
     const int64_t n = h->n_dofs;
     cudaStream_t  s = h->stream;
     double       *v = h->sv_p.p, *w = h->sv_z.p, *Av = h->sv_Ap.p, *partial = h->sv_partial.p, *scal = h->sv_scal.p;
-    launch_diagonal_inverse(h, h->sv_dinv.p);
+    solver_diagonal_inverse(h, mode, h->sv_dinv.p);
     k_fill_guess<<<RG, RB, 0, s>>>(v, n);
     double lambda = 0.;
     for (int it = 0; it < n_iter; ++it)
@@ -367,7 +458,7 @@ namespace pd
     const int64_t n = h->n_dofs;
     cudaStream_t  s = h->stream;
     double       *d = h->sv_z.p, *Ax = h->sv_Ap.p;
-    launch_diagonal_inverse(h, h->sv_dinv.p);
+    solver_diagonal_inverse(h, mode, h->sv_dinv.p);
     const double lmin = lambda_max / smoothing_range;
     const double theta = 0.5 * (lambda_max + lmin), delta = 0.5 * (lambda_max - lmin);
     const double sigma1 = theta / delta;

@@ -340,9 +340,11 @@ class SIPOperator:
     def vmult_host_ptr(self, dst_host_ptr, src_host_ptr, mode=K.VMULT_BLOCK_CSR):
         K.check(K.lib().pd_vmult_host(self._h, mode, C.c_void_p(src_host_ptr), C.c_void_p(dst_host_ptr)))
 
-    def get_matrix_diagonal_inverse(self, out):
+    def get_matrix_diagonal_inverse(self, out, mode=K.VMULT_BLOCK_CSR):
+        """Inverse diagonal of the operator `mode` applies (pd_diagonal_inverse_of); matrix-free modes
+        need no assembled matrix."""
         self._check_tensor(out)
-        K.check(K.lib().pd_diagonal_inverse(self._h, C.c_void_p(out.data_ptr())))
+        K.check(K.lib().pd_diagonal_inverse_of(self._h, mode, C.c_void_p(out.data_ptr())))
         return out
 
     def cg_solve(self, x, b, max_iter=1000, rel_tol=1e-10, jacobi=True, mode=K.VMULT_BLOCK_CSR):

@@ -903,3 +903,48 @@ def test_peer_memory_collectives_two_processes_one_gpu():
                         os.path.join(root, "tests", "run_distributed_check.py")],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "DISTRIBUTED CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("kind", ["polytopal", "fine", "mapped"])
+def test_matrix_free_inverse_diagonal_and_jacobi_cg(kind):
+    """get_matrix_diagonal_inverse() of the matrix-free operators without an assembled matrix
+    (MatrixFreeTools::compute_diagonal, include/utils.h:929-1100): unit vectors over independent sets of
+    polytopes; then Jacobi-CG and the Chebyshev machinery run on the matrix-free operator alone."""
+    pdl = gpu()
+    import torch
+
+    if kind == "polytopal":
+        oah, pah = both(3, 4, "random6", 2, nq=3)
+        op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+        mode = pdl.VMULT_MATRIX_FREE
+        A = po.assemble_dg_matrix(oah, degree=2, n_threads=4).scipy().tocsr()
+        apply_ref = lambda v: A @ v
+        diag_ref = A.diagonal()
+    else:
+        dim, n, p = (3, 3, 2) if kind == "fine" else (2, 5, 2)
+        ogrid = po.Grid(dim, n, 0.0, 1.0, 1)
+        if kind == "mapped":
+            ogrid.distort_random(0.2, 3)
+        groups = [[c] for c in range(ogrid.n_cells)]
+        _, pah = product_handler(ogrid, groups, p, p + 1)
+        C_ = max(p, 1) * (p + 1.0)
+        op = pdl.SIPOperator(pah.flatten(penalty_constant=C_, h_rule=pdl.H_NORMAL_EXTENT), keepalive=pah)
+        mode = pdl.VMULT_MATRIX_FREE if kind == "fine" else pdl.VMULT_MAPPED_FINE
+        apply_ref = lambda v: po.mapped_fine_vmult(ogrid, p, p + 1, v)
+        N_ = ogrid.n_cells * (p + 1) ** dim
+        diag_ref = np.array([apply_ref(np.eye(1, N_, k).ravel())[k] for k in range(N_)])
+    N = op.m()
+    dinv = torch.empty(N, dtype=torch.float64, device="cuda")
+    op.get_matrix_diagonal_inverse(dinv, mode=mode)
+    op.synchronize()
+    got = 1.0 / dinv.cpu().numpy()
+    assert np.abs(got - diag_ref).max() <= TOL * np.abs(diag_ref).max()
+    # Jacobi-preconditioned CG on the matrix-free operator: b = A x*  =>  x*
+    xs = src_vector(N)
+    b = torch.from_numpy(apply_ref(xs)).cuda()
+    x = torch.zeros_like(b)
+    iters, relres = op.cg_solve(x, b, max_iter=3000, rel_tol=1e-11, jacobi=True, mode=mode)
+    assert relres <= 1e-11
+    assert np.abs(x.cpu().numpy() - xs).max() <= 1e-7 * np.abs(xs).max()
+    lam = op.estimate_lambda_max(30, mode=mode)
+    assert lam > 0
