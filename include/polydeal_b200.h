@@ -112,8 +112,9 @@ typedef struct pd_mesh_desc
    *  PD_FE_DGQ      FE_DGQ<dim>(p): tensor Lagrange basis on the Gauss-Lobatto nodes, (p+1)^dim DoFs
    *  PD_FE_AGGLODGP FE_AggloDGP<dim>(p) (source/fe_agglodgp.cc:28-57): products of L2[0,1]-
    *                 orthonormal Legendre polynomials of total degree <= p, C(p+dim, dim) DoFs,
-   *                 last coordinate outermost / first fastest.  Assembly and the block-CSR apply;
-   *                 the point-wise matrix-free kernels are FE_DGQ only.
+   *                 last coordinate outermost / first fastest.  Assembly, block-CSR apply, the
+   *                 polytopal matrix-free apply, right-hand side and error norms; the fine-mesh
+   *                 operators and the level transfers are FE_DGQ notions (nodal support points).
    * Last member, so that zero-initialised descriptors of older callers mean FE_DGQ. */
   int32_t fe_kind;
 } pd_mesh_desc;

@@ -638,8 +638,6 @@ extern "C"
     return guarded([&] {
       if (!h || !rhs_dev)
         throw Error(PD_ERR_INVALID, "pd_assemble_rhs: null argument");
-      if (h->fe_kind != PD_FE_DGQ)
-        throw Error(PD_ERR_UNSUPPORTED, "pd_assemble_rhs: FE_DGQ only");
       need_quadrature(h);
       launch_poly_rhs(h, f_vol_dev, g_face_dev, stiffness, rhs_dev);
     });
@@ -652,8 +650,6 @@ extern "C"
     return guarded([&] {
       if (!h || !u_dev || !exact_dev || !l2)
         throw Error(PD_ERR_INVALID, "pd_error_norms: null argument");
-      if (h->fe_kind != PD_FE_DGQ)
-        throw Error(PD_ERR_UNSUPPORTED, "pd_error_norms: FE_DGQ only");
       if (h1_seminorm && !exact_grad_dev)
         throw Error(PD_ERR_INVALID, "pd_error_norms: the H1 seminorm needs the exact gradient");
       need_quadrature(h);
@@ -962,8 +958,8 @@ extern "C"
           throw Error(PD_ERR_STATE, "pd_vmult(BLOCK_CSR): pd_assemble has not been called");
         launch_spmv(h, src, dst, add);
       }
-    else if (h->fe_kind != PD_FE_DGQ)
-      throw Error(PD_ERR_UNSUPPORTED, "the matrix-free applies are implemented for FE_DGQ only; use PD_VMULT_BLOCK_CSR");
+    else if (h->fe_kind != PD_FE_DGQ && mode != PD_VMULT_MATRIX_FREE)
+      throw Error(PD_ERR_UNSUPPORTED, "the fine-mesh matrix-free operators are defined for FE_DGQ only");
     else if (mode == PD_VMULT_MATRIX_FREE)
       {
         if (h->mf_ready && !h->force_generic_mf)
@@ -1142,8 +1138,8 @@ extern "C"
     return guarded([&] {
       if (!h || !dst_dev)
         throw Error(PD_ERR_INVALID, "null argument");
-      if (mode != PD_VMULT_BLOCK_CSR && h->fe_kind != PD_FE_DGQ)
-        throw Error(PD_ERR_UNSUPPORTED, "the matrix-free applies are implemented for FE_DGQ only");
+      if (mode == PD_VMULT_MAPPED_FINE && h->fe_kind != PD_FE_DGQ)
+        throw Error(PD_ERR_UNSUPPORTED, "the fine-mesh matrix-free operators are defined for FE_DGQ only");
       solver_diagonal_inverse(h, mode, dst_dev);
     });
   }

@@ -48,7 +48,7 @@ namespace pd
       double L[DIM][N1], dL[DIM][N1]; // l_a(xhat_d), l_a'(xhat_d) / h_d
     };
 
-    template <int DIM, int N1>
+    template <int DIM, int N1, bool DGP = false>
     __device__ __forceinline__ void
     point_tables(const Basis1D &B, const double *bb, const double (&x)[DIM], PointTab<DIM, N1> &T)
     {
@@ -56,7 +56,10 @@ namespace pd
       for (int d = 0; d < DIM; ++d)
         {
           const double ih = 1. / (bb[DIM + d] - bb[d]);
-          lagrange<N1>(B, (x[d] - bb[d]) * ih, ih, T.L[d], T.dL[d]);
+          if constexpr (DGP) // FE_AggloDGP: orthonormal Legendre factors
+            legendre01<N1>((x[d] - bb[d]) * ih, ih, T.L[d], T.dL[d]);
+          else
+            lagrange<N1>(B, (x[d] - bb[d]) * ih, ih, T.L[d], T.dL[d]);
         }
     }
 
@@ -82,7 +85,7 @@ namespace pd
     }
 
     // u_h and grad u_h at the point, summed over this lane's slices; Us = first owned slice
-    template <int DIM, int N1, int NS>
+    template <int DIM, int N1, int NS, bool DGP = false>
     __device__ __forceinline__ void
     eval_slices(const PointTab<DIM, N1> &T, const double (&ls)[NS], const double (&dls)[NS], const double *Us, double &u,
                 double (&g)[DIM])
@@ -91,7 +94,58 @@ namespace pd
 #pragma unroll
       for (int d = 0; d < DIM; ++d)
         g[d] = 0.;
-      if constexpr (DIM == 3)
+      if constexpr (DGP)
+        {
+          // FE_AggloDGP: the DoFs (a, b[, c]) with a + b [+ c] <= p, last index outermost, first fastest
+          constexpr int P   = N1 - 1;
+          int           idx = 0; // compile-time after unrolling
+          if constexpr (DIM == 3)
+            {
+#pragma unroll
+              for (int c = 0; c <= P; ++c)
+                {
+                  double Yv = 0., Yd = 0., Yx = 0.;
+#pragma unroll
+                  for (int b = 0; b <= P - c; ++b)
+                    {
+                      double X0 = 0., X1 = 0.;
+#pragma unroll
+                      for (int a = 0; a <= P - b - c; ++a)
+                        {
+                          const double v = *(const volatile double *)&Us[idx++];
+                          X0 += T.L[0][a] * v;
+                          X1 += T.dL[0][a] * v;
+                        }
+                      Yv += T.L[1][b] * X0;
+                      Yd += T.dL[1][b] * X0;
+                      Yx += T.L[1][b] * X1;
+                    }
+                  u += T.L[2][c] * Yv;
+                  g[0] += T.L[2][c] * Yx;
+                  g[1] += T.L[2][c] * Yd;
+                  g[2] += T.dL[2][c] * Yv;
+                }
+            }
+          else
+            {
+#pragma unroll
+              for (int b = 0; b <= P; ++b)
+                {
+                  double X0 = 0., X1 = 0.;
+#pragma unroll
+                  for (int a = 0; a <= P - b; ++a)
+                    {
+                      const double v = *(const volatile double *)&Us[idx++];
+                      X0 += T.L[0][a] * v;
+                      X1 += T.dL[0][a] * v;
+                    }
+                  u += T.L[1][b] * X0;
+                  g[0] += T.L[1][b] * X1;
+                  g[1] += T.dL[1][b] * X0;
+                }
+            }
+        }
+      else if constexpr (DIM == 3)
         {
 #pragma unroll
           for (int cc = 0; cc < NS; ++cc)
@@ -139,12 +193,62 @@ namespace pd
     }
 
     // acc_i += fm phi_i + f . grad phi_i for the DoFs of this lane's slices
-    template <int DIM, int N1, int NS, bool GRAD>
+    template <int DIM, int N1, int NS, bool GRAD, bool DGP = false>
     __device__ __forceinline__ void
     integrate_slices(const PointTab<DIM, N1> &T, const double (&ls)[NS], const double (&dls)[NS], const double (&f)[DIM],
                      const double fm, double *acc)
     {
-      if constexpr (DIM == 3)
+      if constexpr (DGP)
+        {
+          constexpr int P   = N1 - 1;
+          int           idx = 0;
+          if constexpr (DIM == 3)
+            {
+#pragma unroll
+              for (int c = 0; c <= P; ++c)
+#pragma unroll
+                for (int b = 0; b <= P - c; ++b)
+                  {
+                    const double yz = T.L[1][b] * T.L[2][c];
+                    double       A = 0., Bv = fm * yz;
+                    if constexpr (GRAD)
+                      {
+                        A = f[0] * yz;
+                        Bv += f[1] * (T.dL[1][b] * T.L[2][c]) + f[2] * (T.L[1][b] * T.dL[2][c]);
+                      }
+#pragma unroll
+                    for (int a = 0; a <= P - b - c; ++a, ++idx)
+                      {
+                        double t = acc[idx] + T.L[0][a] * Bv;
+                        if constexpr (GRAD)
+                          t += T.dL[0][a] * A;
+                        acc[idx] = t;
+                      }
+                  }
+            }
+          else
+            {
+#pragma unroll
+              for (int b = 0; b <= P; ++b)
+                {
+                  double A = 0., Bv = fm * T.L[1][b];
+                  if constexpr (GRAD)
+                    {
+                      A = f[0] * T.L[1][b];
+                      Bv += f[1] * T.dL[1][b];
+                    }
+#pragma unroll
+                  for (int a = 0; a <= P - b; ++a, ++idx)
+                    {
+                      double t = acc[idx] + T.L[0][a] * Bv;
+                      if constexpr (GRAD)
+                        t += T.dL[0][a] * A;
+                      acc[idx] = t;
+                    }
+                }
+            }
+        }
+      else if constexpr (DIM == 3)
         {
 #pragma unroll
           for (int cc = 0; cc < NS; ++cc)
@@ -233,9 +337,9 @@ namespace pd
     {
       using C           = Cfg<DIM, DEG>;
       constexpr int N1  = C::N1, N = C::N;
-      constexpr int NS  = N1 / GZ, NI = N / N1, NA = NS * NI;
+      constexpr int NS  = N1 / GZ, NA = C::DGP ? N : NS * (N / N1);
       constexpr int PTS = 32 / GZ;
-      static_assert(N1 % GZ == 0 && GZ * NA == N, "slices must tile the last index");
+      static_assert(N1 % GZ == 0 && GZ * NA == N && (!C::DGP || GZ == 1), "slices must tile the last index");
       __shared__ double Us[NW][N];
 
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pt = lane % PTS, part = lane / PTS;
@@ -265,13 +369,13 @@ namespace pd
                 x[d] = ok ? A.vq_x[(int64_t)d * A.Q + q] : bb[d];
               const double      w = ok ? A.vq_w[q] : 0.;
               PointTab<DIM, N1> T;
-              point_tables<DIM, N1>(A.basis, bb, x, T);
+              point_tables<DIM, N1, C::DGP>(A.basis, bb, x, T);
               double ls[NS], dls[NS];
               my_slices<DIM, N1, GZ>(T, part, ls, dls);
               double u = 0., g[DIM];
               if constexpr (MODE != MODE_RHS)
                 {
-                  eval_slices<DIM, N1, NS>(T, ls, dls, U + part * NA, u, g);
+                  eval_slices<DIM, N1, NS, C::DGP>(T, ls, dls, U + part * NA, u, g);
 #pragma unroll
                   for (int o = PTS; o < 32; o <<= 1)
                     {
@@ -287,12 +391,12 @@ namespace pd
 #pragma unroll
                   for (int d = 0; d < DIM; ++d)
                     f[d] = w * A.stiffness * g[d];
-                  integrate_slices<DIM, N1, NS, true>(T, ls, dls, f, MASS ? w * A.mass * u : 0., acc);
+                  integrate_slices<DIM, N1, NS, true, C::DGP>(T, ls, dls, f, MASS ? w * A.mass * u : 0., acc);
                 }
               else if constexpr (MODE == MODE_RHS)
                 {
                   double f[DIM] = {};
-                  integrate_slices<DIM, N1, NS, false>(T, ls, dls, f, ok ? w * A.data0[q] : 0., acc);
+                  integrate_slices<DIM, N1, NS, false, C::DGP>(T, ls, dls, f, ok ? w * A.data0[q] : 0., acc);
                 }
               else if (ok && part == 0)
                 {
@@ -344,7 +448,7 @@ namespace pd
     {
       using C           = Cfg<DIM, DEG>;
       constexpr int N1  = C::N1, N = C::N;
-      constexpr int NS  = N1 / GZ, NI = N / N1, NA = NS * NI;
+      constexpr int NS  = N1 / GZ, NA = C::DGP ? N : NS * (N / N1);
       constexpr int PTS = 32 / (2 * GZ);
       __shared__ double Us[NW][2 * N];
 
@@ -393,14 +497,14 @@ namespace pd
               const double      w  = ok ? A.fq_w[q] * A.stiffness : 0.;
               const double      sg = ok ? A.sub_sigma[q / A.nqf] : 0.;
               PointTab<DIM, N1> T;
-              point_tables<DIM, N1>(A.basis, bb, x, T);
+              point_tables<DIM, N1, C::DGP>(A.basis, bb, x, T);
               double ls[NS], dls[NS];
               my_slices<DIM, N1, GZ>(T, part, ls, dls);
               double fv[DIM], fm;
               if constexpr (MODE == MODE_APPLY)
                 {
                   double u, g[DIM];
-                  eval_slices<DIM, N1, NS>(T, ls, dls, U + side * N + part * NA, u, g);
+                  eval_slices<DIM, N1, NS, C::DGP>(T, ls, dls, U + side * N + part * NA, u, g);
                   double dn = 0.;
 #pragma unroll
                   for (int d = 0; d < DIM; ++d)
@@ -442,7 +546,7 @@ namespace pd
 #pragma unroll
               for (int d = 0; d < DIM; ++d)
                 fv[d] *= w;
-              integrate_slices<DIM, N1, NS, true>(T, ls, dls, fv, fm, acc);
+              integrate_slices<DIM, N1, NS, true, C::DGP>(T, ls, dls, fv, fm, acc);
             }
           // lane groups are (side, part): group g holds the DoFs side * N + part * NA + [0, NA)
           warp_reduce_store<NA, PTS>(acc, out, lane);
@@ -647,7 +751,7 @@ namespace pd
     constexpr int
     lanes_per_point()
     {
-      return (DEG + 1) % 2 == 0 && Cfg<DIM, DEG>::N > 32 ? 2 : 1;
+      return !Cfg<DIM, DEG>::DGP && Cfg<DIM, DEG>::N1 % 2 == 0 && Cfg<DIM, DEG>::N > 32 ? 2 : 1;
     }
 
     template <int DIM, int DEG>
@@ -768,7 +872,7 @@ namespace pd
     {
       using C           = Cfg<DIM, DEG>;
       constexpr int N1  = C::N1, N = C::N;
-      constexpr int NS  = N1 / GZ, NI = N / N1, NA = NS * NI;
+      constexpr int NS  = N1 / GZ, NA = C::DGP ? N : NS * (N / N1);
       constexpr int PTS = 32 / GZ;
       __shared__ double Us[NW][N];
 
@@ -834,13 +938,13 @@ namespace pd
                     }
                 }
               PointTab<DIM, N1> T;
-              point_tables<DIM, N1>(A.basis, bb, x, T);
+              point_tables<DIM, N1, C::DGP>(A.basis, bb, x, T);
               double ls[NS], dls[NS];
               my_slices<DIM, N1, GZ>(T, part, ls, dls);
               if constexpr (!TRANSPOSE)
                 {
                   double u, g[DIM];
-                  eval_slices<DIM, N1, NS>(T, ls, dls, U + part * NA, u, g);
+                  eval_slices<DIM, N1, NS, C::DGP>(T, ls, dls, U + part * NA, u, g);
 #pragma unroll
                   for (int o = PTS; o < 32; o <<= 1)
                     u += __shfl_xor_sync(0xffffffffu, u, o);
@@ -854,7 +958,7 @@ namespace pd
                 {
                   const double yv    = ok ? A.src[(int64_t)A.child_blk[c] * N + i] : 0.;
                   double       f[DIM] = {};
-                  integrate_slices<DIM, N1, NS, false>(T, ls, dls, f, yv, acc);
+                  integrate_slices<DIM, N1, NS, false, C::DGP>(T, ls, dls, f, yv, acc);
                 }
             }
           if constexpr (TRANSPOSE)
@@ -949,16 +1053,33 @@ namespace pd
     }
   } // namespace
 
+#define PD_DISPATCH_FE(FN, ...)                                                                                    \
+  if (h->fe_kind == PD_FE_AGGLODGP)                                                                                \
+    switch (h->dim * 10 + h->degree)                                                                               \
+      {                                                                                                            \
+        case 21: FN<2, DGP_BASE + 1>(__VA_ARGS__); break;                                                          \
+        case 22: FN<2, DGP_BASE + 2>(__VA_ARGS__); break;                                                          \
+        case 23: FN<2, DGP_BASE + 3>(__VA_ARGS__); break;                                                          \
+        case 24: FN<2, DGP_BASE + 4>(__VA_ARGS__); break;                                                          \
+        case 31: FN<3, DGP_BASE + 1>(__VA_ARGS__); break;                                                          \
+        case 32: FN<3, DGP_BASE + 2>(__VA_ARGS__); break;                                                          \
+        case 33: FN<3, DGP_BASE + 3>(__VA_ARGS__); break;                                                          \
+        default:                                                                                                   \
+          throw CudaError{cudaErrorNotSupported, "no point-wise FE_AggloDGP kernel for this (dim, degree)", __LINE__}; \
+      }                                                                                                            \
+  else                                                                                                             \
+    PD_DISPATCH(FN, __VA_ARGS__)
+
   void
   launch_poly_apply(pd_handle *h, const double *src, double *dst, const bool add)
   {
-    PD_DISPATCH(run_apply, h, src, dst, add);
+    PD_DISPATCH_FE(run_apply, h, src, dst, add);
   }
 
   void
   launch_poly_rhs(pd_handle *h, const double *f_vol, const double *g_face, const double stiffness, double *rhs)
   {
-    PD_DISPATCH(run_rhs, h, f_vol, g_face, stiffness, rhs);
+    PD_DISPATCH_FE(run_rhs, h, f_vol, g_face, stiffness, rhs);
   }
 
   void
@@ -970,6 +1091,6 @@ namespace pd
   void
   launch_poly_error(pd_handle *h, const double *u, const double *exact, const double *exact_grad, double *out2_dev)
   {
-    PD_DISPATCH(run_error, h, u, exact, exact_grad, out2_dev);
+    PD_DISPATCH_FE(run_error, h, u, exact, exact_grad, out2_dev);
   }
 } // namespace pd

@@ -877,8 +877,29 @@ def test_assembly_with_fe_agglodgp(dim, n, shape, p, nq, distort, kw):
     op.synchronize()
     yref = ref.vmult(x)
     assert np.abs(y.cpu().numpy() - yref).max() <= TOL * np.abs(yref).max()
+    # the point-wise kernels on the Legendre basis: matrix-free apply, right-hand side, error norms
+    op.set_operator(flags, kw.get("stiffness_coeff", 1.0), kw.get("mass_coeff", 0.0))
+    op.vmult(y, torch.from_numpy(x).cuda(), mode=pdl.VMULT_MATRIX_FREE)
+    op.synchronize()
+    assert np.abs(y.cpu().numpy() - yref).max() <= TOL * np.abs(yref).max()
+    f = lambda X: np.sin(1.1 * X[..., 0]) + X[..., 1] ** 2
+    b_ref, l2_ref = np.zeros(oah.n_dofs), 0.0
+    uh = 0.1 * x
+    for k in range(oah.n_polytopes):
+        fev = oah.reinit(k)
+        dofs = oah.get_dof_indices(k)
+        b_ref[dofs] += fev.values @ (f(fev.points) * fev.JxW)
+        l2_ref += np.sum((uh[dofs] @ fev.values - f(fev.points)) ** 2 * fev.JxW)
+    q = op.quadrature()
+    fq = torch.from_numpy(np.ascontiguousarray(f(q["vol_x"].T.cpu().numpy()))).cuda()
+    rhs = torch.empty(op.m(), dtype=torch.float64, device="cuda")
+    op.assemble_rhs(rhs, fq)
+    op.synchronize()
+    assert np.abs(rhs.cpu().numpy() - b_ref).max() <= TOL * np.abs(b_ref).max()
+    l2, _ = op.error_norms(torch.from_numpy(uh).cuda(), fq)
+    assert abs(l2 - np.sqrt(l2_ref)) <= 1e-12 * np.sqrt(l2_ref)
     with pytest.raises(pdl.PolydealError):
-        op.vmult(y, torch.from_numpy(x).cuda(), mode=pdl.VMULT_MATRIX_FREE)
+        op.vmult(y, torch.from_numpy(x).cuda(), mode=pdl.VMULT_MAPPED_FINE)
 
 
 # ----------------------------------------------------------------------------------
