@@ -132,6 +132,18 @@ def parse_polytope_iterator(name):
     return out
 
 
+def parse_neighbor_lists(name, header):
+    """'<header> i has n faces' followed by 'Neighbor is: k' for every non-boundary face, in face order."""
+    out, cur = [], None
+    for l in lines(name):
+        if m := re.match(header + r" (\d+) has (\d+) faces", l):
+            cur = {"id": int(m[1]), "n_faces": int(m[2]), "neighbors": []}
+            out.append(cur)
+        elif m := re.match(r"Neighbor is: (\d+)", l):
+            cur["neighbors"].append(int(m[1]))
+    return out
+
+
 def floats_after(name, pat):
     return [float(m[1]) for l in lines(name) if (m := re.search(pat, l))]
 
@@ -146,6 +158,11 @@ def main():
         "agglomerated_neighbors_02": parse_neighbors_faces("agglomerated_neighbors_02.output"),
         "agglomerated_neighbors_03": parse_nofn("agglomerated_neighbors_03.output"),
         "continuous_face_01": parse_continuous_face("continuous_face_01.output"),
+        "continuous_face_02": parse_continuous_face("continuous_face_02.output"),
+        "continuous_face_03": parse_continuous_face("continuous_face_03.output"),
+        "continuous_face_distorted_grid": parse_continuous_face("continuous_face_distorted_grid.output"),
+        "reinit_cell_face_master_master": parse_neighbor_lists("reinit_cell_face_master_master.output", "Polytope with index"),
+        "reinit_cell_face_quad_pts": parse_neighbor_lists("reinit_cell_face_quad_pts.output", "Cell with index"),
         "hp_structure_01": parse_hp_structure("hp_structure_01.output"),
         "reinit_cell_face_02": parse_reinit_cell_face_02("reinit_cell_face_02.output"),
         "polytope_iterator": parse_polytope_iterator("polytope_iterator.output"),
@@ -161,6 +178,16 @@ def main():
             "x": floats_after("poisson_sanity_check_01.output", r"f\(x,y\)=x:(\S+)"),
             "xplusy": floats_after("poisson_sanity_check_01.output", r"f\(x,y\)=x\+y:(\S+)"),
             "one": floats_after("poisson_sanity_check_01.output", r"Test with 1: (\S+)"),
+        },
+        "poisson_sanity_check_02": {
+            "step": floats_after("poisson_sanity_check_02.output", r"Step function = (\S+)"),
+            "v": floats_after("poisson_sanity_check_02.output", r"V function = (\S+)"),
+        },
+        "poisson_sanity_check_03": {
+            "n_subdomains": floats_after("poisson_sanity_check_03.output", r"N subdomains: (\S+)"),
+            "x": floats_after("poisson_sanity_check_03.output", r"f\(x,y\)=x:(\S+)"),
+            "xplusy": floats_after("poisson_sanity_check_03.output", r"f\(x,y\)=x\+y:(\S+)"),
+            "one": floats_after("poisson_sanity_check_03.output", r"Test with 1: (\S+)"),
         },
         "poisson": floats_after("poisson.output", r"(\d\.\d+)"),
     }

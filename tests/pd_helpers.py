@@ -68,3 +68,44 @@ def assert_blocks_close(got, ref, n, rowptr, tol=1e-12):
         worst = max(worst, err)
     assert worst <= tol, f"worst block-relative error {worst:.3e} > {tol}"
     return worst
+
+
+def check_continuous_face_scenario(ah, gold, reinit=True):
+    """The walk of test/polydeal/continuous_face_0x.cc (perimeter_test, test_neighbors, test_face_qpoints)
+    against one parsed golden scenario.  `ah` is the oracle handler or the product's host mirror (which
+    has no reinit: reinit=False skips perimeter and q-point alignment)."""
+    perimeter = 0.0
+    assert ah.n_polytopes == len(gold["polytopes"])
+    for p, g in enumerate(gold["polytopes"]):
+        assert ah.master_cell(p) == g["master"]
+        assert ah.n_faces(p) == g["n_faces"]
+        for f, gf in enumerate(g["faces"]):
+            if ah.at_boundary(p, f):
+                assert gf["neighbor"] is None
+                if reinit:
+                    perimeter += ah.reinit(p, f).JxW.sum()
+            else:
+                nb = ah.neighbor(p, f)
+                assert nb == gf["neighbor"]
+                nofn = ah.neighbor_of_agglomerated_neighbor(p, f)
+                assert nofn == gf["nofn"]
+                assert ah.neighbor(nb, nofn) == p
+                if gf["subfaces"]:  # continuous_face_03 prints neighbour / nofn only
+                    assert [[c, lf, ah.master_cell(nb)] for c, lf in ah.interface(p, f)] == gf["subfaces"]
+                if reinit:
+                    f0, f1 = ah.reinit_interface(p, nb, f, nofn)
+                    assert np.abs(f0.points - f1.points).max() < 1e-15
+    if reinit:
+        assert abs(perimeter - gold["perimeter"]) <= 1e-13
+
+
+def check_neighbor_lists(ah, gold, by_master):
+    """'<polytope> has n faces' + the neighbour of every non-boundary face in face order
+    (reinit_cell_face_master_master: polytope indices; reinit_cell_face_quad_pts: master cell indices)."""
+    assert ah.n_polytopes == len(gold)
+    for p, g in enumerate(gold):
+        assert (ah.master_cell(p) if by_master else p) == g["id"]
+        assert ah.n_faces(p) == g["n_faces"]
+        got = [ah.master_cell(ah.neighbor(p, f)) if by_master else ah.neighbor(p, f)
+               for f in range(g["n_faces"]) if not ah.at_boundary(p, f)]
+        assert got == g["neighbors"]

@@ -100,3 +100,70 @@ def random_partition(n_cells, nbr, n_parts, seed):
     for c in range(n_cells):
         groups[part[c]].append(c)
     return groups
+
+
+# ---- more fixtures of the reference's face tests (inputs fully specified in the .cc files) ----
+def continuous_face_02_cases():
+    """test/polydeal/continuous_face_02.cc test0/test1/test2 on [-1,1]^2 refined twice."""
+    return [
+        [list(range(0, 8)), list(range(8, 12)), [12], [13], [14], [15]],
+        [list(range(0, 8)), list(range(8, 12)), list(range(12, 16))],
+        [[3, 6, 9, 12], [0, 1, 4, 5], [2, 8, 10], [11, 14, 15], [7, 13]],
+    ]
+
+
+def continuous_face_03_groups():
+    """test/polydeal/continuous_face_03.cc: 8x8 cells; every unflagged cell first (active order), then
+    {36,37,38,39}, {18,24,25}, {3,6}."""
+    agg = [[36, 37, 38, 39], [18, 24, 25], [3, 6]]
+    flagged = {c for g in agg for c in g}
+    return [[c] for c in range(64) if c not in flagged] + agg
+
+
+def continuous_face_distorted_cases():
+    """test/polydeal/continuous_face_distorted_grid.cc test0/test1 (4x4 cells, distort_random(0.25))."""
+    return [[list(range(0, 8)), list(range(8, 16))], [list(range(0, 4)), list(range(4, 8)), list(range(8, 12)), list(range(12, 16))]]
+
+
+def reinit_cell_face_master_master_groups():
+    return [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11], [12], [13], [14], [15]]
+
+
+def reinit_cell_face_quad_pts_groups():
+    """{3,6,9}, {36,37}, {25,19} first, then every other cell of the 8x8 grid in active order."""
+    agg = [[3, 6, 9], [36, 37], [19, 25]]
+    flagged = {c for g in agg for c in g}
+    return agg + [[c] for c in range(64) if c not in flagged]
+
+
+def partition_from_continuous_face_golden(scenario, n_cells, nbr):
+    """Recover the (METIS) partition a continuous_face scenario was run on from its own golden: every
+    cell that touches an interface is listed on its polytope's side; the remaining cells have all their
+    neighbours in their own polytope, so a flood fill assigns them.  Returns groups in polytope order
+    (cells ascending = active order), or None if the golden does not determine the partition."""
+    owner = [-1] * n_cells
+    for p, poly in enumerate(scenario["polytopes"]):
+        owner[poly["master"]] = p
+        for face in poly["faces"]:
+            for cell, _lf, _nm in face["subfaces"]:
+                if owner[cell] not in (-1, p):
+                    return None
+                owner[cell] = p
+    changed = True
+    while changed:
+        changed = False
+        for c in range(n_cells):
+            if owner[c] >= 0:
+                continue
+            cand = {owner[n] for n in nbr[c] if n >= 0 and owner[n] >= 0}
+            # an unlisted cell is interior to its polytope: any assigned neighbour that is itself unlisted-or-
+            # same-polytope decides; if two different polytopes touch it, it would have been listed
+            if len(cand) == 1:
+                owner[c] = cand.pop()
+                changed = True
+    if min(owner) < 0:
+        return None
+    groups = [[] for _ in scenario["polytopes"]]
+    for c, p in enumerate(owner):
+        groups[p].append(c)
+    return groups

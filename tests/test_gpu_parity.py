@@ -969,3 +969,49 @@ def test_matrix_free_inverse_diagonal_and_jacobi_cg(kind):
     assert np.abs(x.cpu().numpy() - xs).max() <= 1e-7 * np.abs(xs).max()
     lam = op.estimate_lambda_max(30, mode=mode)
     assert lam > 0
+
+
+# ----------------------------------------------------------------------------------
+# the reference's exactness tests, entirely on the device: exact_solutions.cc, exact_solutions_dgp.cc,
+# continuous_face_exact_solution.cc, disconnected_exact_solution.cc
+# ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("fe,kind,shape", [
+    ("dgq", "linear", "blocks"), ("dgq", "quadratic", "blocks"),
+    ("dgp", "linear", "blocks"), ("dgp", "quadratic", "blocks"),
+    ("dgq", "quadratic", "disconnected"), ("dgp", "quadratic", "disconnected"),
+])
+def test_exact_solutions_on_the_device(fe, kind, shape):
+    """Distorted 4x4 grid of [0,1]^2, penalty 10 / diameter, Dirichlet data from the exact solution:
+    assembly, right-hand side (volume + boundary terms), Jacobi-CG and the error norms all run on the GPU;
+    "Linear: OK" / "Quadratic: OK" = volume 1, perimeter 4, L2 error and H1 seminorm at round-off."""
+    pdl = gpu()
+    import torch
+
+    p = 1 if kind == "linear" else 2
+    groups = sc.blocks_2x2_of_4x4() if shape == "blocks" else [[0, 1, 2, 3], [12, 13, 14, 15], [4, 5, 6, 7], [8, 9, 10], [11]]
+    grid = pdl.Grid.hyper_cube(2, 0.0, 1.0, 2)
+    grid.distort_random(0.25, 5)
+    ah = pdl.AgglomerationHandler(grid)
+    for g in groups:
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(2 * p + 1)
+    ah.distribute_agglomerated_dofs(pdl.FE_DGQ if fe == "dgq" else pdl.FE_AGGLODGP, p)
+    op = pdl.SIPOperator(ah.flatten(penalty_constant=10.0, visit_rule=pdl.VISIT_BY_INDEX), keepalive=ah)
+    op.assemble()
+    q = op.quadrature()
+    assert abs(q["vol_jxw"].sum().item() - 1.0) < 1e-14
+    vx, fx = q["vol_x"], q["face_x"]
+    if p == 1:
+        exact = lambda X: X[0] + X[1] - 1.0
+        grad = lambda X: torch.stack([torch.ones_like(X[0]), torch.ones_like(X[0])])
+        f = torch.zeros_like(vx[0])
+    else:
+        exact = lambda X: X[0] ** 2 + X[1] ** 2 - 1.0
+        grad = lambda X: torch.stack([2 * X[0], 2 * X[1]])
+        f = torch.full_like(vx[0], -4.0)
+    rhs = torch.empty(op.m(), dtype=torch.float64, device="cuda")
+    op.assemble_rhs(rhs, f.contiguous(), exact(fx).contiguous())
+    x = torch.zeros_like(rhs)
+    iters, relres = op.cg_solve(x, rhs, max_iter=5000, rel_tol=1e-14)
+    l2, h1 = op.error_norms(x, exact(vx).contiguous(), grad(vx).contiguous())
+    assert l2 < 1e-11 and h1 < 1e-10, (l2, h1, iters, relres)

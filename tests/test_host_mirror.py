@@ -235,3 +235,33 @@ def test_c_abi_from_plain_c(tmp_path):
                     "-Wl,-rpath," + lib_dir, "-o", exe], check=True, capture_output=True, text=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "C ABI OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_more_face_goldens_through_the_host_mirror(goldens):
+    """continuous_face_02 (incl. the METIS scenario recovered from its golden), continuous_face_03,
+    continuous_face_distorted_grid, reinit_cell_face_master_master, reinit_cell_face_quad_pts: face
+    numbering, neighbours, nofn and aligned (cell, face) lists from the product's host mirror."""
+    from pd_helpers import check_continuous_face_scenario, check_neighbor_lists
+
+    for groups, gold in zip(sc.continuous_face_02_cases(), goldens["continuous_face_02"][:3]):
+        _, ah = product_from_groups(2, 2, groups)
+        check_continuous_face_scenario(ah, gold, reinit=False)
+    metis = goldens["continuous_face_02"][3]
+    nbr = pdl.Grid.hyper_cube(2, -1.0, 1.0, 3).arrays()[2].tolist()
+    _, ah = product_from_groups(2, 3, sc.partition_from_continuous_face_golden(metis, 64, nbr))
+    check_continuous_face_scenario(ah, metis, reinit=False)
+    _, ah = product_from_groups(2, 3, sc.continuous_face_03_groups())
+    check_continuous_face_scenario(ah, goldens["continuous_face_03"][0], reinit=False)
+    for groups, gold in zip(sc.continuous_face_distorted_cases(), goldens["continuous_face_distorted_grid"]):
+        grid = pdl.Grid.hyper_cube(2, -1.0, 1.0, 2)
+        grid.distort_random(0.25, 7)
+        ah = pdl.AgglomerationHandler(grid)
+        for g in groups:
+            ah.define_agglomerate(g)
+        ah.initialize_fe_values(1)
+        ah.distribute_agglomerated_dofs(pdl.FE_DGQ, 1)
+        check_continuous_face_scenario(ah, gold, reinit=False)
+    _, ah = product_from_groups(2, 2, sc.reinit_cell_face_master_master_groups())
+    check_neighbor_lists(ah, goldens["reinit_cell_face_master_master"], by_master=False)
+    _, ah = product_from_groups(2, 3, sc.reinit_cell_face_quad_pts_groups())
+    check_neighbor_lists(ah, goldens["reinit_cell_face_quad_pts"], by_master=True)

@@ -108,6 +108,51 @@ def test_continuous_face_01(goldens):
         assert perimeter == pytest.approx(gold["perimeter"], abs=1e-14)
 
 
+def test_continuous_face_02_03_and_distorted(goldens):
+    """continuous_face_02 (test0-2 + the METIS scenario, whose partition is recovered from the golden
+    itself), continuous_face_03 (58 polytopes on 8x8) and continuous_face_distorted_grid (same topology on a
+    distorted grid; boundary vertices stay put, so the perimeter is still 8)."""
+    from pd_helpers import check_continuous_face_scenario
+
+    for groups, gold in zip(sc.continuous_face_02_cases(), goldens["continuous_face_02"][:3]):
+        _, ah = make_handler(2, 2, groups, nq=1)
+        check_continuous_face_scenario(ah, gold)
+    metis = goldens["continuous_face_02"][3]
+    grid = po.Grid.hyper_cube(2, -1.0, 1.0, 3)
+    groups = sc.partition_from_continuous_face_golden(metis, 64, grid.arrays()[2].tolist())
+    assert groups is not None and len(groups) == 10 and sorted(c for g in groups for c in g) == list(range(64))
+    _, ah = make_handler(2, 3, groups, nq=1)
+    check_continuous_face_scenario(ah, metis)
+    _, ah = make_handler(2, 3, sc.continuous_face_03_groups(), nq=1)
+    check_continuous_face_scenario(ah, goldens["continuous_face_03"][0])
+    for groups, gold in zip(sc.continuous_face_distorted_cases(), goldens["continuous_face_distorted_grid"]):
+        grid = po.Grid.hyper_cube(2, -1.0, 1.0, 2)
+        grid.distort_random(0.25, 7)
+        ah = po.AgglomerationHandler(grid)
+        for g in groups:
+            ah.define_agglomerate(g)
+        ah.initialize_fe_values(1)
+        ah.distribute_agglomerated_dofs(po.FE_DGQ, 1)
+        check_continuous_face_scenario(ah, gold)
+
+
+def test_reinit_cell_face_master_master_and_quad_pts(goldens):
+    """reinit_cell_face_master_master.cc (polytope indices of the neighbours per face) and
+    reinit_cell_face_quad_pts.cc (master cells of the neighbours, q-points seen from both sides coincide)."""
+    from pd_helpers import check_neighbor_lists
+
+    _, ah = make_handler(2, 2, sc.reinit_cell_face_master_master_groups(), nq=1)
+    check_neighbor_lists(ah, goldens["reinit_cell_face_master_master"], by_master=False)
+    _, ah = make_handler(2, 3, sc.reinit_cell_face_quad_pts_groups(), nq=1)
+    check_neighbor_lists(ah, goldens["reinit_cell_face_quad_pts"], by_master=True)
+    for p in range(ah.n_polytopes):
+        for f in range(ah.n_faces(p)):
+            if not ah.at_boundary(p, f):
+                nb = ah.neighbor(p, f)
+                f0, f1 = ah.reinit_interface(p, nb, f, ah.neighbor_of_agglomerated_neighbor(p, f))
+                assert np.abs(f0.points - f1.points).max() < 1e-15
+
+
 def test_reinit_cell_face_02(goldens):
     """test/polydeal/reinit_cell_face_02.cc: {3,6,9},{15,36,37},{57,60,54},{25,19,22}
     + singletons; neighbour master indices per face, boundary faces flagged."""

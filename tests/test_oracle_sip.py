@@ -82,6 +82,44 @@ def test_poisson_sanity_check(n_parts, goldens):
     assert abs(A - A.T).max() < 1e-12
 
 
+def test_poisson_sanity_check_02(goldens):
+    """test/polydeal/poisson_sanity_check_02.cc (input fully specified): [0,1]^2 in 2x2 cells, agglomerates
+    {0,2} and {1,3} (two columns), DGQ1, QGauss(3), boundary terms zeroed, penalty 10 max(1/hA, 1/hB):
+    the interpolated step function (a ramp on the left polytope) has energy 2, |x - 1/2| has energy 1."""
+    _, ah = handler(2, 1, [[0, 2], [1, 3]], 1, 3, lo=0.0, hi=1.0)
+    A = po.assemble_dg_matrix(ah, penalty_constant=10.0, h_rule=po.H_MAX_INVERSE_DIAMETER, with_boundary=False).scipy()
+    step = interpolate(ah, lambda x: 0.0 if x[0] < 0.5 else 1.0)
+    vfun = interpolate(ah, lambda x: abs(x[0] - 0.5))
+    g = goldens["poisson_sanity_check_02"]
+    assert step @ (A @ step) == pytest.approx(g["step"][0], abs=1e-13)
+    assert vfun @ (A @ vfun) == pytest.approx(g["v"][0], abs=1e-13)
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_poisson_sanity_check_03(k, goldens):
+    """test/polydeal/poisson_sanity_check_03.cc: the same invariants on an UNSTRUCTURED mesh (t3.msh, read
+    by GridIn -- not reproducible here) split by METIS into 50 ... 800 agglomerates.  The numbers it prints
+    (1, 2, ~1e-14) do not depend on mesh or partition; stand-in: a randomly distorted 64x64 grid with the
+    same agglomerate counts."""
+    g = goldens["poisson_sanity_check_03"]
+    n_parts = int(g["n_subdomains"][k])
+    grid = po.Grid.hyper_cube(2, 0.0, 1.0, 6)
+    grid.distort_random(0.3, 100 + k)
+    groups = sc.random_partition(grid.n_cells, grid.arrays()[2], n_parts, seed=n_parts)
+    ah = po.AgglomerationHandler(grid)
+    for gr in groups:
+        ah.define_agglomerate(gr)
+    ah.initialize_fe_values(3)
+    ah.distribute_agglomerated_dofs(po.FE_DGQ, 1)
+    A = po.assemble_dg_matrix(ah, penalty_constant=10.0, h_rule=po.H_MAX_INVERSE_DIAMETER, with_boundary=False).scipy()
+    ux = interpolate(ah, lambda x: x[0])
+    uxy = interpolate(ah, lambda x: x[0] + x[1])
+    one = np.ones(ah.n_dofs)
+    assert ux @ (A @ ux) == pytest.approx(g["x"][k], abs=1e-11)
+    assert uxy @ (A @ uxy) == pytest.approx(g["xplusy"][k], abs=1e-11)
+    assert abs(one @ (A @ one)) < 1e-10 and abs(g["one"][k]) < 1e-12
+
+
 def solve_poisson(ah, p, exact, rhs_f, penalty_constant=10.0):
     """The assembly loop of test/polydeal/exact_solutions.cc:400-640 written against the
     oracle's reinit tables (matrix from the oracle's assembler; Dirichlet data and
@@ -134,6 +172,59 @@ def test_exact_solutions_distorted_2d(kind):
     assert bdry == pytest.approx(4.0, abs=1e-14)
     assert l2 < 1e-13
     assert h1 < 1e-7  # finite-difference gradient of the exact solution limits this one
+
+
+@pytest.mark.parametrize("kind", ["linear", "quadratic"])
+def test_exact_solutions_dgp(kind):
+    """test/polydeal/exact_solutions_dgp.cc:26,278-283,304-306,321-348: the same problem with
+    FE_AggloDGP(1) / FE_AggloDGP(2) (Legendre basis of total degree p on the bounding boxes): "Linear: OK",
+    "Quadratic: OK" = volume 1, boundary 4, L2 and H1 errors below 1e-14."""
+    p = 1 if kind == "linear" else 2
+    exact = (lambda x: x[0] + x[1] - 1.0) if p == 1 else (lambda x: x[0] ** 2 + x[1] ** 2 - 1.0)
+    rhs = (lambda x: 0.0) if p == 1 else (lambda x: -4.0)
+    _, ah = handler(2, 2, sc.blocks_2x2_of_4x4(), p, 2 * p + 1, lo=0.0, hi=1.0, distort=(0.25, 7), fe_kind=po.FE_AGGLODGP)
+    assert ah.n_dofs_per_cell == (3 if p == 1 else 6)
+    vol, bdry, l2, h1 = solve_poisson(ah, p, exact, rhs)
+    assert vol == pytest.approx(1.0, abs=1e-14) and bdry == pytest.approx(4.0, abs=1e-14)
+    assert l2 < 1e-13 and h1 < 1e-7
+
+
+@pytest.mark.parametrize("kind", ["linear", "quadratic"])
+def test_disconnected_exact_solution(kind):
+    """test/polydeal/disconnected_exact_solution.cc:343-377: define_agglomerate_with_check splits
+    {0,1,2,3,12,13,14,15} and {4,...,10} into their face-connected components (the two blocks of the second
+    set touch in a corner only), {11} stays: "Number of generated agglomerates: 5", one of them L-shaped;
+    linear / quadratic solutions are still reproduced (continuous_face_exact_solution.cc is the same problem
+    on the four 2x2 blocks, covered by test_exact_solutions_distorted_2d)."""
+    grid = po.Grid.hyper_cube(2, 0.0, 1.0, 2)
+    nbr = grid.arrays()[2]
+
+    def components(cells):  # source/agglomeration_handler.cc:174-207
+        cells, seen, out = list(cells), set(), []
+        for c in cells:
+            if c in seen:
+                continue
+            comp, stack = [], [c]
+            seen.add(c)
+            while stack:
+                a = stack.pop()
+                comp.append(a)
+                for b in nbr[a]:
+                    if b in cells and b not in seen:
+                        seen.add(int(b))
+                        stack.append(int(b))
+            out.append(sorted(comp))
+        return out
+
+    groups = components([0, 1, 2, 3, 12, 13, 14, 15]) + components([4, 5, 6, 7, 8, 9, 10]) + components([11])
+    assert len(groups) == 5 and [8, 9, 10] in groups
+    p = 1 if kind == "linear" else 2
+    exact = (lambda x: x[0] + x[1] - 1.0) if p == 1 else (lambda x: x[0] ** 2 + x[1] ** 2 - 1.0)
+    rhs = (lambda x: 0.0) if p == 1 else (lambda x: -4.0)
+    _, ah = handler(2, 2, groups, p, 2 * p + 1, lo=0.0, hi=1.0, distort=(0.25, 11))
+    vol, bdry, l2, h1 = solve_poisson(ah, p, exact, rhs)
+    assert vol == pytest.approx(1.0, abs=1e-14) and bdry == pytest.approx(4.0, abs=1e-14)
+    assert l2 < 1e-13 and h1 < 1e-7
 
 
 @pytest.mark.parametrize("dim", [2, 3])
