@@ -144,6 +144,22 @@ def parse_neighbor_lists(name, header):
     return out
 
 
+def parse_ghosted(name):
+    """'Polytope with local index i from rank r' followed, for every face whose neighbour lives on another
+    rank, by a block of numbers (bbox corners or DoF indices)."""
+    out, cur, block = [], None, None
+    for l in lines(name):
+        if m := re.match(r"Polytope with local index (\d+) from rank (\d+)", l):
+            cur = {"local_index": int(m[1]), "rank": int(m[2]), "ghosts": []}
+            out.append(cur)
+        elif l.startswith("Neighboring bbox") or l.startswith("DoFs indices"):
+            block = []
+            cur["ghosts"].append(block)
+        elif cur is not None and re.match(r"^[-0-9. e]+$", l.strip()) and l.strip():
+            block.append([float(t) for t in l.split()])
+    return out
+
+
 def floats_after(name, pat):
     return [float(m[1]) for l in lines(name) if (m := re.search(pat, l))]
 
@@ -163,6 +179,12 @@ def main():
         "continuous_face_distorted_grid": parse_continuous_face("continuous_face_distorted_grid.output"),
         "reinit_cell_face_master_master": parse_neighbor_lists("reinit_cell_face_master_master.output", "Polytope with index"),
         "reinit_cell_face_quad_pts": parse_neighbor_lists("reinit_cell_face_quad_pts.output", "Cell with index"),
+        "ghosted_bbox_01": parse_ghosted("ghosted_bbox_01.with_mpi=true.with_p4est=true.mpirun=3.output"),
+        "ghosted_dofs_01": parse_ghosted("ghosted_dofs_01.with_mpi=true.with_p4est=true.mpirun=3.output"),
+        "sparsity_distributed_tria": [
+            [int(t) for t in re.match(r"\((\d+),(\d+)\)", l).groups()]
+            for l in lines("sparsity_distributed_tria.with_mpi=true.with_p4est=true.mpirun=3.output") if l.startswith("(")
+        ],
         "hp_structure_01": parse_hp_structure("hp_structure_01.output"),
         "reinit_cell_face_02": parse_reinit_cell_face_02("reinit_cell_face_02.output"),
         "polytope_iterator": parse_polytope_iterator("polytope_iterator.output"),

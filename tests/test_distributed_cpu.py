@@ -108,3 +108,72 @@ def test_sharding_host_logic_gloo(world, dim, n, shape, p):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, dim, n, shape, p, results), nprocs=world, join=True)
     assert dict(results) == {r: "ok" for r in range(world)}
+
+
+def test_distributed_reference_goldens(goldens):
+    """ghosted_bbox_01 / ghosted_dofs_01 / sparsity_distributed_tria (mpirun=3): [0,1]^2 refined twice on a
+    parallel::distributed (p4est = Morton ranges) triangulation, agglomerates {0,1},{2,3} on rank 0,
+    {4,5},{6,7},{8,9},{10,11} on rank 1, {12,13},{14,15} on rank 2.  What the reference prints about the ghosted
+    neighbours -- bounding boxes seen from rank 1, DoF indices seen from rank 0, rank 0's rows of the
+    distributed sparsity pattern -- must be what the local descriptor of that rank carries."""
+    sys.path.insert(0, ROOT)
+    import polydeal_b200 as pdl
+    from polydeal_b200 import distributed as pdd
+
+    owner = np.array([0, 0, 1, 1, 1, 1, 2, 2], dtype=np.int32)
+
+    def handler(degree):
+        grid = pdl.Grid.hyper_cube(2, 0.0, 1.0, 2)
+        ah = pdl.AgglomerationHandler(grid)
+        for k in range(8):
+            ah.define_agglomerate([2 * k, 2 * k + 1])
+        ah.initialize_fe_values(2 * degree + 1)
+        ah.distribute_agglomerated_dofs(pdl.FE_DGQ, degree)
+        return ah
+
+    def ghost_walk(ah, part, rank):
+        """(local index, [local index of the ghost polytope behind every face whose neighbour is remote])"""
+        loc = {int(g): i for i, g in enumerate(part.local_poly_global)}
+        first = int(np.nonzero(owner == rank)[0][0])
+        out = []
+        for p in np.nonzero(owner == rank)[0]:
+            ghosts = [loc[ah.neighbor(int(p), f)] for f in range(ah.n_faces(int(p)))
+                      if not ah.at_boundary(int(p), f) and owner[ah.neighbor(int(p), f)] != rank]
+            out.append((int(p) - first, ghosts))
+        return out
+
+    # ghosted_bbox_01: FE_DGQ(0), seen from rank 1
+    ah = handler(0)
+    part = pdd.LocalPart(ah, owner, 1)
+    bbox = np.ctypeslib.as_array(part.desc.bbox, (part.n_owned + part.n_ghost, 2, 2))
+    gold = goldens["ghosted_bbox_01"]
+    walk = ghost_walk(ah, part, 1)
+    assert len(walk) == len(gold)
+    for (li, ghosts), g in zip(walk, gold):
+        assert (li, 1) == (g["local_index"], g["rank"]) and len(ghosts) == len(g["ghosts"])
+        for lp, corners in zip(ghosts, g["ghosts"]):
+            assert lp >= part.n_owned  # carried as a ghost
+            assert bbox[lp].tolist() == corners
+    # ghosted_dofs_01: FE_DGQ(1), seen from rank 0
+    ah = handler(1)
+    part = pdd.LocalPart(ah, owner, 0)
+    gdofs = part.ghost_global_dofs().reshape(part.n_ghost, part.n)
+    gold = goldens["ghosted_dofs_01"]
+    walk = ghost_walk(ah, part, 0)
+    assert len(walk) == len(gold)
+    for (li, ghosts), g in zip(walk, gold):
+        assert (li, 0) == (g["local_index"], g["rank"]) and len(ghosts) == len(g["ghosts"])
+        for lp, dofs in zip(ghosts, g["ghosts"]):
+            assert gdofs[lp - part.n_owned].tolist() == [int(d[0]) for d in dofs]
+    # sparsity_distributed_tria: rank 0's rows of the distributed pattern, from the LOCAL descriptor
+    d = part.desc
+    brow = np.ctypeslib.as_array(d.brow_ptr, (d.n_block_rows + 1,))
+    bcol = np.ctypeslib.as_array(d.bcol_idx, (int(brow[-1]),))
+    gblock = np.concatenate([part.owned_global_block, part.ghost_global_block])
+    got = set()
+    for b in range(d.n_block_rows):
+        for e in range(brow[b], brow[b + 1]):
+            for i in range(part.n):
+                for j in range(part.n):
+                    got.add((int(gblock[b]) * part.n + i, int(gblock[bcol[e]]) * part.n + j))
+    assert got == {tuple(rc) for rc in goldens["sparsity_distributed_tria"]}
