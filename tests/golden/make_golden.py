@@ -211,6 +211,12 @@ def main():
             "xplusy": floats_after("poisson_sanity_check_03.output", r"f\(x,y\)=x\+y:(\S+)"),
             "one": floats_after("poisson_sanity_check_03.output", r"Test with 1: (\S+)"),
         },
+        "coarse_operator_from_matrix_free": {
+            "fine": floats_after("coarse_operator_from_matrix_free.with_mpi=true.with_p4est=true.mpirun=3.output",
+                                 r"induced by fine operator: (\S+)"),
+            "agglomerated": floats_after("coarse_operator_from_matrix_free.with_mpi=true.with_p4est=true.mpirun=3.output",
+                                         r"induced by agglomerated operator: (\S+)"),
+        },
         "poisson": floats_after("poisson.output", r"(\d\.\d+)"),
     }
     with open(OUT, "w") as f:

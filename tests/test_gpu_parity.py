@@ -1015,3 +1015,62 @@ def test_exact_solutions_on_the_device(fe, kind, shape):
     iters, relres = op.cg_solve(x, rhs, max_iter=5000, rel_tol=1e-14)
     l2, h1 = op.error_norms(x, exact(vx).contiguous(), grad(vx).contiguous())
     assert l2 < 1e-11 and h1 < 1e-10, (l2, h1, iters, relres)
+
+
+def test_coarse_operator_from_matrix_free(goldens):
+    """test/polydeal/coarse_operator_from_matrix_free.cc: the Galerkin coarse operator P^T A P of the fine-mesh
+    MATRIX-FREE cell Laplacian (MatrixFreeProjector::compute_level_matrices), P = fill_interpolation_matrix.
+    <v, A v> on the fine mesh and <v_c, P^T A P v_c> on the agglomerates agree and equal 0, 1, 2 for
+    v = 1, x, x + y (the reference prints them for an R-tree and a gmsh agglomeration; the numbers are
+    partition independent -- 66 random connected agglomerates of the 64x64 grid here).  Everything on the GPU:
+    prolongate, matrix-free apply (volume term only), restrict."""
+    pdl = gpu()
+    import torch
+
+    g = goldens["coarse_operator_from_matrix_free"]
+    p = 1
+    ogrid = po.Grid(2, 64, 0.0, 1.0, 0)
+    _, pah_fine = product_handler(ogrid, [[c] for c in range(ogrid.n_cells)], p, p + 1)
+    fine = pdl.SIPOperator(pah_fine.flatten(penalty_constant=2.0, h_rule=pdl.H_NORMAL_EXTENT), keepalive=pah_fine)
+    fine.set_operator(pdl.ASSEMBLE_VOLUME, 1.0, 0.0)  # the test's operator has no face terms
+    assert fine.matrix_free_available
+    groups = groups_for("random66", 2, 64, ogrid, 4)
+    _, pah = product_handler(ogrid, groups, p, p + 1)
+    coarse = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+    P = pdl.Transfer.to_cells(coarse)
+    assert (P.m(), P.n()) == (16384, 264) and fine.m() == 16384  # "Injection matrix has size: (16384,264)"
+    usp = _dgq_unit_support_points(2, p)
+    verts, cv, _ = ogrid.arrays()
+
+    def interpolate_fine(f):
+        out = np.empty(fine.m())
+        for c in range(ogrid.n_cells):
+            lo, hi = verts[cv[c]].min(axis=0), verts[cv[c]].max(axis=0)
+            out[c * 4:(c + 1) * 4] = f(lo + usp * (hi - lo))
+        return out
+
+    def interpolate_coarse(f):
+        out = np.empty(coarse.m())
+        for k in range(pah.n_polytopes):
+            lo, hi = pah.bbox(k)
+            out[pah.get_dof_indices(k)] = f(lo + usp * (hi - lo))
+        return out
+
+    funcs = [lambda X: np.ones(len(X)), lambda X: X[:, 0], lambda X: X[:, 0] + X[:, 1]]
+    for f, gf, gc in zip(funcs, g["fine"][::2], g["agglomerated"][::2]):
+        vf = torch.from_numpy(interpolate_fine(f)).cuda()
+        Av = torch.empty_like(vf)
+        fine.vmult(Av, vf, mode=pdl.VMULT_MATRIX_FREE)
+        fine.synchronize()
+        assert abs(float(vf @ Av) - gf) <= 1e-11
+        vc = torch.from_numpy(interpolate_coarse(f)).cuda()
+        Pv = torch.empty_like(vf)
+        P.prolongate(Pv, vc)
+        P.synchronize()
+        APv = torch.empty_like(vf)
+        fine.vmult(APv, Pv, mode=pdl.VMULT_MATRIX_FREE)
+        fine.synchronize()
+        PtAPv = torch.empty_like(vc)
+        P.restrict(PtAPv, APv)
+        P.synchronize()
+        assert abs(float(vc @ PtAPv) - round(gc)) <= 1e-11 and abs(gc - round(gc)) < 1e-12
