@@ -63,17 +63,23 @@ namespace pd
         }
     }
 
-    // scal[dst_k] = sum_b partial[k][b]  (fixed order => deterministic)
+    // scal[dst_k] = sum_b partial[k][b]: one warp, lane l adds b = l, l + 32, ... and the lanes meet in a
+    // fixed butterfly => deterministic, and ten dependent loads instead of RG (this tiny kernel was 2 of the
+    // 7 launches of a CG iteration and, summing serially, its slowest)
     __global__ void
     k_finalize(const double *__restrict__ partial, double *scal, const int nk, const int dst0)
     {
-      const int k = threadIdx.x;
-      if (k < nk)
+      const int lane = threadIdx.x;
+      for (int k = 0; k < nk; ++k)
         {
           double t = 0.;
-          for (int b = 0; b < RG; ++b)
+          for (int b = lane; b < RG; b += 32)
             t += partial[k * RG + b];
-          scal[dst0 + k] = t;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0)
+            scal[dst0 + k] = t;
         }
     }
 
