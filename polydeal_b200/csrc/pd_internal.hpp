@@ -134,6 +134,7 @@ struct pd_handle
   uint32_t            op_flags = PD_ASSEMBLE_ALL;
   // device-resident solvers around vmult (pd_solver.cu)
   pd::DevBuf<double> sv_r, sv_z, sv_p, sv_Ap, sv_dinv, sv_partial, sv_scal;
+  pd::DevBuf<unsigned int> sv_ticket; // last-CTA ticket of the fused dot-product kernels
   cudaGraphExec_t    cg_graph_exec   = nullptr;
   int                cg_graph_mode   = -1, cg_graph_jacobi = -1;
   pd_peer           *cg_graph_peer   = nullptr;

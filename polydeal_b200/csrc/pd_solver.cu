@@ -19,7 +19,8 @@
 // device memory, the vector updates are fused around the two dot products, the
 // dot products are deterministic two-stage reductions, and the body of a CG
 // iteration is captured once in a CUDA graph and replayed (the loop is
-// launch-bound at config-B sizes: one SpMV + 5 tiny kernels).
+// launch-bound at config-B sizes: one SpMV + 3 small kernels; the dot products are finalised by the
+// last CTA of the kernel that produces them, so there is no separate reduction launch).
 // -----------------------------------------------------------------------------
 #include "pd_host.hpp"
 #include "pd_internal.hpp"
@@ -37,12 +38,15 @@ namespace pd
     constexpr int RB = 256;  // reduction block
     constexpr int RG = 296;  // reduction grid (2 per SM)
 
-    // partial[k][block] = sum over this block's grid-stride share of a_k[i] * b_k[i], k < NK
+    // partial[k][block] = sum over this block's grid-stride share of a_k[i] * b_k[i], k < NK; the LAST CTA
+    // to arrive (ticket) then sums the RG partials of every k in a fixed order -- lane l adds b = l, l + 32,
+    // ..., fixed butterfly -- into scal[dst0 + k]: deterministic, and no separate finalize launch.
     template <int NK>
     __device__ __forceinline__ void
-    block_reduce_store(double (&s)[NK], double *partial)
+    block_reduce_store(double (&s)[NK], double *partial, double *scal, const int dst0, unsigned int *ticket)
     {
       __shared__ double sh[NK][RB / 32];
+      __shared__ bool   last;
 #pragma unroll
       for (int k = 0; k < NK; ++k)
         {
@@ -60,44 +64,47 @@ namespace pd
           for (int w = 0; w < RB / 32; ++w)
             t += sh[threadIdx.x][w];
           partial[threadIdx.x * RG + blockIdx.x] = t;
+          __threadfence();
         }
-    }
-
-    // scal[dst_k] = sum_b partial[k][b]: one warp, lane l adds b = l, l + 32, ... and the lanes meet in a
-    // fixed butterfly => deterministic, and ten dependent loads instead of RG (this tiny kernel was 2 of the
-    // 7 launches of a CG iteration and, summing serially, its slowest)
-    __global__ void
-    k_finalize(const double *__restrict__ partial, double *scal, const int nk, const int dst0)
-    {
-      const int lane = threadIdx.x;
-      for (int k = 0; k < nk; ++k)
+      __syncthreads();
+      if (threadIdx.x == 0)
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+      __syncthreads();
+      if (last && threadIdx.x < 32)
         {
-          double t = 0.;
-          for (int b = lane; b < RG; b += 32)
-            t += partial[k * RG + b];
+          __threadfence();
+          for (int k = 0; k < NK; ++k)
+            {
+              double t = 0.;
+              for (int b = threadIdx.x; b < RG; b += 32)
+                t += __ldcg(partial + k * RG + b);
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-            t += __shfl_xor_sync(0xffffffffu, t, o);
-          if (lane == 0)
-            scal[dst0 + k] = t;
+              for (int o = 16; o > 0; o >>= 1)
+                t += __shfl_xor_sync(0xffffffffu, t, o);
+              if (threadIdx.x == 0)
+                scal[dst0 + k] = t;
+            }
+          if (threadIdx.x == 0)
+            *ticket = 0;
         }
     }
 
     // scalars: [0] rz  [1] pAp  [2] rz_new  [3] rr  [4] bb
     __global__ void __launch_bounds__(RB)
-    k_dot_pAp(const double *__restrict__ p, const double *__restrict__ Ap, const int64_t n, double *partial)
+    k_dot_pAp(const double *__restrict__ p, const double *__restrict__ Ap, const int64_t n, double *partial, double *scal,
+              unsigned int *ticket)
     {
       double s[1] = {0.};
       for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
         s[0] += p[i] * Ap[i];
-      block_reduce_store<1>(s, partial);
+      block_reduce_store<1>(s, partial, scal, 1, ticket); // scal[1] = pAp
     }
 
     // x += alpha p ; r -= alpha Ap ; z = dinv r (or r) ; partial <- (r.z, r.r);  alpha = rz / pAp
     __global__ void __launch_bounds__(RB)
     k_cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, const double *__restrict__ p,
-                const double *__restrict__ Ap, const double *__restrict__ dinv, const double *__restrict__ scal,
-                const int64_t n, double *partial)
+                const double *__restrict__ Ap, const double *__restrict__ dinv, double *scal, const int64_t n,
+                double *partial, unsigned int *ticket)
     {
       const double alpha = scal[1] != 0. ? scal[0] / scal[1] : 0.; // converged exactly: stay put
       double       s[2]  = {0., 0.};
@@ -111,17 +118,24 @@ namespace pd
           s[0] += ri * zi;
           s[1] += ri * ri;
         }
-      block_reduce_store<2>(s, partial);
+      block_reduce_store<2>(s, partial, scal, 2, ticket); // scal[2] = rz_new, scal[3] = rr
     }
 
-    // p = z + beta p, beta = rz_new / rz ; then rz <- rz_new (by block 0 after the grid is done is
-    // not possible without a sync, so the swap is a separate tiny kernel)
+    // p = z + beta p, beta = rz_new / rz; the last CTA to finish rolls rz <- rz_new (every CTA has read
+    // both before it takes its ticket)
     __global__ void __launch_bounds__(RB)
-    k_cg_direction(double *__restrict__ p, const double *__restrict__ z, const double *__restrict__ scal, const int64_t n)
+    k_cg_direction(double *__restrict__ p, const double *__restrict__ z, double *scal, const int64_t n, unsigned int *ticket)
     {
-      const double beta = scal[0] != 0. ? scal[2] / scal[0] : 0.;
+      const double rz = scal[0], rz_new = scal[2];
+      const double beta = rz != 0. ? rz_new / rz : 0.;
       for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
         p[i] = z[i] + beta * p[i];
+      __syncthreads();
+      if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1)
+        {
+          scal[0] = rz_new;
+          *ticket = 0;
+        }
     }
     __global__ void
     k_cg_roll(double *scal)
@@ -132,7 +146,8 @@ namespace pd
     // r = b - Ax (Ax given) ; z = dinv r ; p = z ; partial <- (r.z, r.r, b.b)
     __global__ void __launch_bounds__(RB)
     k_cg_init(const double *__restrict__ b, const double *__restrict__ Ax, double *__restrict__ r, double *__restrict__ z,
-              double *__restrict__ p, const double *__restrict__ dinv, const int64_t n, double *partial)
+              double *__restrict__ p, const double *__restrict__ dinv, const int64_t n, double *partial, double *scal,
+              unsigned int *ticket)
     {
       double s[3] = {0., 0., 0.};
       for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
@@ -146,7 +161,7 @@ namespace pd
           s[1] += ri * ri;
           s[2] += b[i] * b[i];
         }
-      block_reduce_store<3>(s, partial);
+      block_reduce_store<3>(s, partial, scal, 2, ticket); // scal[2] = rz, [3] = rr, [4] = bb
     }
 
     // Chebyshev step: d = c1 d + c2 dinv (b - Ax) ; x += d     (Ax == nullptr: zero start, Ax = 0)
@@ -166,7 +181,7 @@ namespace pd
     // power iteration on D^-1 A:  w = dinv (A v) ; partial <- (w.w, v.w)
     __global__ void __launch_bounds__(RB)
     k_power(const double *__restrict__ Av, const double *__restrict__ dinv, const double *__restrict__ v,
-            double *__restrict__ w, const int64_t n, double *partial)
+            double *__restrict__ w, const int64_t n, double *partial, double *scal, unsigned int *ticket)
     {
       double s[2] = {0., 0.};
       for (int64_t i = (int64_t)blockIdx.x * RB + threadIdx.x; i < n; i += (int64_t)RG * RB)
@@ -176,7 +191,7 @@ namespace pd
           s[0] += wi * wi;
           s[1] += v[i] * wi;
         }
-      block_reduce_store<2>(s, partial);
+      block_reduce_store<2>(s, partial, scal, 0, ticket);
     }
     __global__ void __launch_bounds__(RB)
     k_scale_from(double *__restrict__ v, const double *__restrict__ w, const double *__restrict__ scal, const int64_t n)
@@ -231,6 +246,8 @@ namespace pd
           h->sv_p.alloc(ns); // search direction is a vmult source: owned + ghost length
           h->sv_partial.alloc(4 * RG);
           h->sv_scal.alloc(8);
+          h->sv_ticket.alloc(1);
+          PD_CUDA(cudaMemsetAsync(h->sv_ticket.p, 0, sizeof(unsigned int), h->stream));
           PD_CUDA(cudaMemsetAsync(h->sv_p.p, 0, sizeof(double) * ns, h->stream));
         }
     }
@@ -343,18 +360,18 @@ namespace pd
       }
     else
       vmult_dispatch(h, mode, x, Ap, false);
-    k_cg_init<<<RG, RB, 0, s>>>(b, Ap, r, z, p, dinv, n, partial);
-    k_finalize<<<1, 32, 0, s>>>(partial, scal, 3, 2); // scal[2] = rz, [3] = rr, [4] = bb
+    unsigned int *ticket = h->sv_ticket.p;
+    k_cg_init<<<RG, RB, 0, s>>>(b, Ap, r, z, p, dinv, n, partial, scal, ticket);
     reduce(2, 3);
     k_cg_roll<<<1, 1, 0, s>>>(scal);
-    h->launches += 3;
+    h->launches += 2;
     double hs[5];
     PD_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, s));
     PD_CUDA(cudaStreamSynchronize(s));
     const double bnorm = std::sqrt(hs[4] > 0 ? hs[4] : 1.);
     double       relres = std::sqrt(hs[3]) / bnorm;
     int          it     = 0;
-    // one iteration = SpMV + 5 small kernels; captured once and replayed in chunks
+    // one iteration = SpMV + dot, update, direction (3 kernels); captured once and replayed in chunks
     constexpr int CHUNK = 8;
     if (!h->cg_graph_exec || h->cg_graph_mode != mode || h->cg_graph_jacobi != jacobi || h->cg_graph_peer != peer)
       {
@@ -369,16 +386,13 @@ namespace pd
         for (int k = 0; k < CHUNK; ++k)
           {
             apply(p, Ap);
-            k_dot_pAp<<<RG, RB, 0, s>>>(p, Ap, n, partial);
-            k_finalize<<<1, 32, 0, s>>>(partial, scal, 1, 1);
+            k_dot_pAp<<<RG, RB, 0, s>>>(p, Ap, n, partial, scal, ticket);
             reduce(1, 1);
-            k_cg_update<<<RG, RB, 0, s>>>(x, r, z, p, Ap, dinv, scal, n, partial);
-            k_finalize<<<1, 32, 0, s>>>(partial, scal, 2, 2);
+            k_cg_update<<<RG, RB, 0, s>>>(x, r, z, p, Ap, dinv, scal, n, partial, ticket);
             reduce(2, 2);
-            k_cg_direction<<<RG, RB, 0, s>>>(p, z, scal, n);
-            k_cg_roll<<<1, 1, 0, s>>>(scal);
+            k_cg_direction<<<RG, RB, 0, s>>>(p, z, scal, n, ticket);
           }
-        h->cg_launches_per_chunk = (h->launches - l0) + 6 * CHUNK;
+        h->cg_launches_per_chunk = (h->launches - l0) + 3 * CHUNK;
         h->launches              = l0;
         PD_CUDA(cudaStreamEndCapture(s, &graph));
         PD_CUDA(cudaGraphInstantiate(&h->cg_graph_exec, graph, 0));
@@ -433,12 +447,11 @@ namespace pd
         if (peer)
           peer_exchange(peer, v);
         vmult_dispatch(h, mode, v, Av, false);
-        k_power<<<RG, RB, 0, s>>>(Av, h->sv_dinv.p, v, w, n, partial);
-        k_finalize<<<1, 32, 0, s>>>(partial, scal, 2, 0);
+        k_power<<<RG, RB, 0, s>>>(Av, h->sv_dinv.p, v, w, n, partial, scal, h->sv_ticket.p);
         if (peer)
           peer_allreduce(peer, scal, 0, 2);
         k_scale_from<<<RG, RB, 0, s>>>(v, w, scal, n);
-        h->launches += 3;
+        h->launches += 2;
       }
     double hs[2];
     PD_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, s));
