@@ -120,7 +120,7 @@ struct pd_handle
   bool                mp_ready = false, mp_geo_valid = false;
   std::vector<double> mp_tab_host; // V | V^T | Dt | e0 e1 | d0 d1
   pd::DevBuf<int32_t> mp_cellv, mp_nbr;
-  pd::DevBuf<double>  mp_dt, mp_cgeo, mp_fgeo, mp_sigma, mp_xg, mp_yg, mp_zero;
+  pd::DevBuf<double>  mp_dt, mp_cgeo, mp_fgeo, mp_sigma, mp_xg, mp_zero;
   pd::DevBuf<double>  mf_vol_partial, mf_face_partial;
   bool                pw_plan_valid = false; // work items of the point-wise kernels (pd_polyapply.cu)
   int32_t             pw_n_items    = 0;

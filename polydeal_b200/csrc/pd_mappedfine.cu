@@ -61,6 +61,7 @@ namespace pd
       double Dt[N1 * N1]; // Dt[q][r] = l~_r'(x_q)        collocation derivative
       double e[2][N1];    // e[s][q]  = l~_q(s)           trace at the face s = 0 / 1
       double d[2][N1];    // d[s][q]  = l~_q'(s)
+      double Vt[N1 * N1]; // Vt[i][q] = l_i(x_q): back to the nodal test functions
     };
 
     template <int N1>
@@ -74,7 +75,8 @@ namespace pd
       const int32_t   *nbr;     // [cell][2 DIM]
       const double    *zero;
       const double    *xg;
-      double          *yg;
+      double          *y; // nodal result (the basis change back is fused into this kernel)
+      int              add;
       int32_t          n_cells;
       double           stiffness, mass;
       uint32_t         flags;
@@ -294,7 +296,38 @@ namespace pd
               acc *= A.stiffness;
               if (mass != 0.)
                 acc += mass * A.cgeo[(int64_t)cell * (NG + 1) * N + NG * N + l] * A.xg[(int64_t)cell * N + l];
-              A.yg[(int64_t)cell * N + l] = acc;
+              sT[slot][0][0][0][l] = acc; // the face-trace arrays are free now: N <= DIM * 4 * NF doubles
+            }
+          group_sync();
+          // ---- back to the nodal basis: y = (V^T (x) ... (x) V^T) y~, one line per thread and direction pass
+          double *yq = &sT[slot][0][0][0][0];
+#pragma unroll
+          for (int pass = 0; pass < DIM; ++pass)
+            {
+              if (cell_ok && l < NF)
+                {
+                  const int stride = pass == 0 ? 1 : (pass == 1 ? N1 : N1 * N1);
+                  const int base   = pass == 0 ? l * N1 : (pass == 1 ? (l % N1) + (l / N1) * N1 * N1 : l);
+                  double    v[N1];
+#pragma unroll
+                  for (int t = 0; t < N1; ++t)
+                    v[t] = yq[base + t * stride];
+#pragma unroll
+                  for (int i = 0; i < N1; ++i)
+                    {
+                      double sm = 0.;
+#pragma unroll
+                      for (int t = 0; t < N1; ++t)
+                        sm += A.T.Vt[i * N1 + t] * v[t];
+                      yq[base + i * stride] = sm;
+                    }
+                }
+              group_sync();
+            }
+          if (cell_ok && l < N)
+            {
+              double *yp = A.y + (int64_t)cell * N + l;
+              *yp        = A.add ? *yp + yq[l] : yq[l];
             }
         }
     }
@@ -571,8 +604,9 @@ namespace pd
       {
         constexpr int  GS = pow2_at_least(N > NT ? N : NT), CPB = 256 / GS;
         MappedArgs<N1> a;
-        static_assert(sizeof(a.T) == (N1 * N1 + 4 * N1) * sizeof(double), "table layout");
-        std::memcpy(&a.T, h->mp_tab_host.data() + 2 * N1 * N1, sizeof(a.T));
+        static_assert(sizeof(a.T) == (2 * N1 * N1 + 4 * N1) * sizeof(double), "table layout");
+        std::memcpy(&a.T, h->mp_tab_host.data() + 2 * N1 * N1, (N1 * N1 + 4 * N1) * sizeof(double)); // Dt | e | d
+        std::memcpy(a.T.Vt, h->mp_tab_host.data() + N1 * N1, N1 * N1 * sizeof(double));
         a.dt_rows   = h->mp_dt.p;
         a.cgeo      = h->mp_cgeo.p;
         a.fgeo      = h->mp_fgeo.p;
@@ -580,7 +614,8 @@ namespace pd
         a.nbr       = h->mp_nbr.p;
         a.zero      = h->mp_zero.p;
         a.xg        = h->mp_xg.p;
-        a.yg        = h->mp_yg.p;
+        a.y         = dst;
+        a.add       = add ? 1 : 0;
         a.n_cells   = h->np_own;
         a.stiffness = h->op_coef.stiffness;
         a.mass      = h->op_coef.mass;
@@ -588,19 +623,7 @@ namespace pd
         const int64_t want = ((int64_t)h->np_own + CPB - 1) / CPB;
         k_mapped_sip<DIM, DEG, MINB><<<(int)std::min<int64_t>(want, (int64_t)sm * 4 * MINB), 256, 0, h->stream>>>(a);
       }
-      // 3. back: test against the nodal basis, y = (V^T (x) ...) y~
-      {
-        constexpr int  GS = pow2_at_least(N), CPB = 256 / GS;
-        ChangeArgs<N1> c;
-        std::memcpy(c.M, h->mp_tab_host.data() + N1 * N1, sizeof(c.M)); // V^T
-        c.src     = h->mp_yg.p;
-        c.dst     = dst;
-        c.n_cells = h->np_own;
-        c.add     = add ? 1 : 0;
-        const int64_t want = ((int64_t)h->np_own + CPB - 1) / CPB;
-        k_basis_change<DIM, DEG><<<(int)std::min<int64_t>(want, (int64_t)sm * 32), 256, 0, h->stream>>>(c);
-      }
-      h->launches += 3;
+      h->launches += 2;
     }
   } // namespace
 
@@ -691,7 +714,6 @@ namespace pd
         h->mp_fgeo.alloc((size_t)nc * dim * 2 * (1 + 2 * dim) * NF);
         h->mp_sigma.alloc((size_t)nc * 2 * dim);
         h->mp_xg.alloc((size_t)nc * N);
-        h->mp_yg.alloc((size_t)nc * N);
         h->mp_zero.alloc((size_t)N);
         PD_CUDA(cudaMemsetAsync(h->mp_zero.p, 0, (size_t)N * sizeof(double), h->stream));
         GeoArgs g;
