@@ -308,11 +308,11 @@ def run_gpu(args):
     peer = pdd.PeerExchange(part, op) if part is not None else None
 
     def apply(use_peer=True):
+        if part is not None and use_peer:
+            peer.vmult(y, x)  # pd_peer_vmult: block rows without ghost columns run while the ghost blocks travel
+            return
         if part is not None:
-            if use_peer:
-                peer.exchange(x)
-            else:
-                pdd.exchange_ghost_values(part, x)
+            pdd.exchange_ghost_values(part, x)
         op.vmult_ptr(y.data_ptr(), x.data_ptr())
 
     def time_apply(use_peer):

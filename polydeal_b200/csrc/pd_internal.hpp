@@ -110,6 +110,7 @@ struct pd_handle
   pd::DevBuf<double> vec_a, vec_b; // staging for pd_vmult_host
   // matrix-free fine-mesh operator (every polytope = one Cartesian cell), pd_finemesh.cu
   bool                mf_ready = false, force_generic_mf = false;
+  pd::DevBuf<int32_t> spmv_list_interior, spmv_list_boundary; // sharded: block rows without / with ghost columns
   pd::DevBuf<int32_t> mf_list_interior, mf_list_boundary; // sharded: cells without / with ghost neighbours
   pd::DevBuf<double>  mf_geo, mf_rec, mf_vol, mf_zero; // per (cell, direction) geometry / folded stencil records, cell volumes (pd_finemesh.cu)
   bool                mf_rec_valid = false;
@@ -212,6 +213,7 @@ namespace pd
   int      peer_status(pd_peer *p);
   void     peer_destroy(pd_peer *p);
   // pd_vmult.cu
-  void launch_spmv(pd_handle *h, const double *src, double *dst, bool add);
+  void launch_spmv(pd_handle *h, const double *src, double *dst, bool add, int part = 0);
+  bool spmv_can_split(pd_handle *h);
   void launch_diagonal_inverse(pd_handle *h, double *dst);
 } // namespace pd

@@ -35,13 +35,15 @@ namespace pd
                      const int32_t *__restrict__ bcol,
                      const int      n,
                      const int32_t  n_block_rows,
+                     const int32_t *__restrict__ row_list, // optional: the block rows to process
                      const double *__restrict__ x,
                      double *__restrict__ y)
     {
       __shared__ double xs[SPMV_MAX_ROW];
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = SPMV_THREADS / 32;
-      for (int b = blockIdx.x; b < n_block_rows; b += gridDim.x)
+      for (int bi = blockIdx.x; bi < n_block_rows; bi += gridDim.x)
         {
+          const int     b   = row_list ? row_list[bi] : bi;
           const int64_t kb  = brow_ptr[b];
           const int     nb  = (int)(brow_ptr[b + 1] - kb);
           const int     len = nb * n;
@@ -149,9 +151,45 @@ namespace pd
     }
   } // namespace
 
-  void
-  launch_spmv(pd_handle *h, const double *src, double *dst, const bool add)
+  bool
+  spmv_can_split(pd_handle *h)
   {
+    if (h->max_row_len < 0)
+      {
+        int64_t m = 0;
+        for (int32_t b = 0; b < h->np_own; ++b)
+          m = std::max<int64_t>(m, (h->h_brow_ptr[b + 1] - h->h_brow_ptr[b]) * h->n);
+        h->max_row_len = m;
+      }
+    return h->assembled && h->np != h->np_own && h->max_row_len <= SPMV_MAX_ROW;
+  }
+
+  void
+  launch_spmv(pd_handle *h, const double *src, double *dst, const bool add, const int part)
+  {
+    // part 0: all block rows; 1: rows without ghost columns; 2: rows with ghost columns (sharded handles)
+    if (part != 0 && h->spmv_list_interior.n + h->spmv_list_boundary.n != (size_t)h->np_own)
+      {
+        std::vector<int32_t> inner, outer;
+        for (int32_t b = 0; b < h->np_own; ++b)
+          {
+            bool ghost = false;
+            for (int64_t e = h->h_brow_ptr[b]; e < h->h_brow_ptr[b + 1]; ++e)
+              ghost = ghost || h->h_bcol[e] >= h->np_own;
+            (ghost ? outer : inner).push_back(b);
+          }
+        auto put = [](auto &buf, const auto &v) {
+          buf.alloc(v.size());
+          if (!v.empty())
+            PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+        };
+        put(h->spmv_list_interior, inner);
+        put(h->spmv_list_boundary, outer);
+      }
+    const int32_t *list   = part == 0 ? nullptr : (part == 1 ? h->spmv_list_interior.p : h->spmv_list_boundary.p);
+    const int32_t  n_rows = part == 0 ? h->np_own : (int32_t)(part == 1 ? h->spmv_list_interior.n : h->spmv_list_boundary.n);
+    if (n_rows == 0)
+      return;
     if (h->max_row_len < 0)
       {
         int64_t m = 0;
@@ -161,16 +199,18 @@ namespace pd
       }
     if (h->max_row_len <= SPMV_MAX_ROW)
       {
-        const int grid = (int)std::min<int64_t>(h->np_own, (int64_t)h->sm_count * 8);
+        const int grid = (int)std::min<int64_t>(n_rows, (int64_t)h->sm_count * 8);
         if (add)
-          k_spmv_block_row<true><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n,
-                                                                      h->np_own, src, dst);
+          k_spmv_block_row<true><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n, n_rows,
+                                                                      list, src, dst);
         else
-          k_spmv_block_row<false><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n,
-                                                                       h->np_own, src, dst);
+          k_spmv_block_row<false><<<grid, SPMV_THREADS, 0, h->stream>>>(h->values.p, h->brow_ptr.p, h->bcol.p, h->n, n_rows,
+                                                                       list, src, dst);
       }
     else
       {
+        if (part == 2)
+          return; // the fallback kernel has no row list: part 1 did all rows (callers order 1 after the exchange)
         const int     tb   = 256;
         const int64_t rows = h->n_dofs;
         const int64_t want = (rows * 32 + tb - 1) / tb;
