@@ -370,7 +370,8 @@ namespace pd
                        h->np != h->np_own && h->mf_list_interior.n > 0 && h->mf_list_boundary.n > 0;
     // block-CSR: worth the extra launch + event only when the apply is long enough to hide the exchange behind
     // (measured on config B, a 16 us apply: 37 us unsplit, 39 us split)
-    const bool split_csr = !no_split && mode == PD_VMULT_BLOCK_CSR && h->nnz > (int64_t)16 * 1024 * 1024 && spmv_can_split(h);
+    static const int64_t csr_min = getenv("PD_PEER_CSR_SPLIT_MIN_NNZ") ? atoll(getenv("PD_PEER_CSR_SPLIT_MIN_NNZ")) : (int64_t)16 * 1024 * 1024;
+    const bool split_csr = !no_split && mode == PD_VMULT_BLOCK_CSR && h->nnz > csr_min && spmv_can_split(h);
     if (!split && !split_csr)
       {
         exchange_on(p, x_full_dev, h->stream);

@@ -918,7 +918,9 @@ def test_peer_memory_collectives_two_processes_one_gpu():
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PD_CHECK_SAME_DEVICE="1", OMP_NUM_THREADS="2")
+    # PD_PEER_CSR_SPLIT_MIN_NNZ=0: also take the interior / boundary split of the block-CSR apply, which is
+    # reserved for large matrices by default
+    env = dict(os.environ, PD_CHECK_SAME_DEVICE="1", OMP_NUM_THREADS="2", PD_PEER_CSR_SPLIT_MIN_NNZ="0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(root, "tests", "run_distributed_check.py")],
