@@ -160,6 +160,16 @@ def parse_ghosted(name):
     return out
 
 
+def parse_cell_face_pairs(name):
+    out, cell = [], None
+    for l in lines(name):
+        if m := re.match(r"deal.II cell index = (\d+)", l):
+            cell = int(m[1])
+        elif m := re.match(r"Local face idx = (\d+)", l):
+            out.append([cell, int(m[1])])
+    return out
+
+
 def floats_after(name, pat):
     return [float(m[1]) for l in lines(name) if (m := re.search(pat, l))]
 
@@ -185,6 +195,10 @@ def main():
             [int(t) for t in re.match(r"\((\d+),(\d+)\)", l).groups()]
             for l in lines("sparsity_distributed_tria.with_mpi=true.with_p4est=true.mpirun=3.output") if l.startswith("(")
         ],
+        "locally_owned_polytope": {
+            k: parse_cell_face_pairs(f"locally_owned_polytope_{k}.with_mpi=true.with_p4est=true.mpirun=3.output")
+            for k in ("02", "03", "04")
+        },
         "hp_structure_01": parse_hp_structure("hp_structure_01.output"),
         "reinit_cell_face_02": parse_reinit_cell_face_02("reinit_cell_face_02.output"),
         "polytope_iterator": parse_polytope_iterator("polytope_iterator.output"),

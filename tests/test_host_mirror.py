@@ -265,3 +265,24 @@ def test_more_face_goldens_through_the_host_mirror(goldens):
     check_neighbor_lists(ah, goldens["reinit_cell_face_master_master"], by_master=False)
     _, ah = product_from_groups(2, 3, sc.reinit_cell_face_quad_pts_groups())
     check_neighbor_lists(ah, goldens["reinit_cell_face_quad_pts"], by_master=True)
+
+
+def test_locally_owned_polytope_goldens(goldens):
+    """locally_owned_polytope_02/03/04 (mpirun=3, p4est keeps refinement families together: rank 0 owns cells
+    0-3 of the 4x4 grid): the (cell, local face) lists of every interface of the polytopes rank 0 owns, towards
+    local and ghosted neighbours alike, in face order."""
+    cases = {
+        "02": [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11], [12, 13, 14, 15]],
+        "03": [[2 * k, 2 * k + 1] for k in range(8)],
+        "04": [[c] for c in range(16)],
+    }
+    for key, groups in cases.items():
+        _, ah = product_from_groups(2, 2, groups, lo=0.0, hi=1.0)
+        got = []
+        for p, g in enumerate(groups):
+            if max(g) > 3:  # not on rank 0
+                continue
+            for f in range(ah.n_faces(p)):
+                if not ah.at_boundary(p, f):
+                    got += [[c, lf] for c, lf in ah.interface(p, f)]
+        assert got == goldens["locally_owned_polytope"][key], key
