@@ -231,6 +231,10 @@ def main():
             "agglomerated": floats_after("coarse_operator_from_matrix_free.with_mpi=true.with_p4est=true.mpirun=3.output",
                                          r"induced by agglomerated operator: (\S+)"),
         },
+        "distributed_poisson_sanity_check_01": {
+            "x": floats_after("distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x: (\S+)"),
+            "xplusy": floats_after("distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x\+y: (\S+)"),
+        },
         "poisson": floats_after("poisson.output", r"(\d\.\d+)"),
     }
     with open(OUT, "w") as f:

@@ -1076,3 +1076,41 @@ def test_coarse_operator_from_matrix_free(goldens):
         P.restrict(PtAPv, APv)
         P.synchronize()
         assert abs(float(vc @ PtAPv) - round(gc)) <= 1e-11 and abs(gc - round(gc)) < 1e-12
+
+
+def test_distributed_poisson_sanity_check(goldens):
+    """test/polydeal/distributed_poisson_sanity_check_01 (mpirun=3): the energies 1 and 2 of x and x + y summed
+    over the ranks of a SHARDED assembly (owner-computes-rows, cut interfaces evaluated from the ghost polytope's
+    bounding box), three ranks emulated on one GPU; boundary terms dropped, penalty 10 max(1/hA, 1/hB)."""
+    pdl = gpu()
+    import torch
+
+    from polydeal_b200 import distributed as pdd
+
+    g = goldens["distributed_poisson_sanity_check_01"]
+    ogrid = po.Grid(2, 32, 0.0, 1.0, 0)
+    groups = groups_for("random40", 2, 32, ogrid, 9)
+    _, pah = product_handler(ogrid, groups, 1, 3)
+    usp = _dgq_unit_support_points(2, 1)
+    funcs = {"x": lambda X: X[:, 0], "xplusy": lambda X: X[:, 0] + X[:, 1], "one": lambda X: np.ones(len(X))}
+    u = {k: np.empty(pah.n_dofs) for k in funcs}
+    for k_ in range(pah.n_polytopes):
+        lo, hi = pah.bbox(k_)
+        for name, f in funcs.items():
+            u[name][pah.get_dof_indices(k_)] = f(lo + usp * (hi - lo))
+    owner = pdd.partition_by_blocks(pah, 3)
+    energy = {k: 0.0 for k in funcs}
+    for rank in range(3):
+        part = pdd.LocalPart(pah, owner, rank, penalty_constant=10.0, h_rule=pdl.H_MAX_INVERSE_DIAMETER)
+        op = pdl.SIPOperator(part.desc, keepalive=(pah, part))
+        op.assemble(pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR)
+        rows = part.owned_global_dofs()
+        cols = np.concatenate([rows, part.ghost_global_dofs()])
+        for name in funcs:
+            xd = torch.from_numpy(u[name][cols]).cuda()
+            yd = torch.empty(len(rows), dtype=torch.float64, device="cuda")
+            op.vmult_ptr(yd.data_ptr(), xd.data_ptr())
+            op.synchronize()
+            energy[name] += float(u[name][rows] @ yd.cpu().numpy())
+    assert abs(energy["x"] - g["x"][0]) <= 1e-11 and abs(energy["xplusy"] - g["xplusy"][0]) <= 1e-11
+    assert abs(energy["one"]) <= 1e-11
