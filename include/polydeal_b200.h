@@ -435,6 +435,14 @@ typedef struct pdh_local_info
 } pdh_local_info;
 int pdh_flatten_local(pdh_handler *ah, const pdh_flatten_params *prm, const int32_t *owner, int32_t rank,
                       pd_mesh_desc *out, pdh_local_info *info);
+/* Graph partitioning with METIS (libmetis_static.a of the CUDA toolkit, 64-bit indices), called like
+ * deal.II's SparsityTools::partition: default options, PartGraphRecursive for n_parts <= 8, PartGraphKway
+ * above.  Two uses on this path, both INPUTS of it: the METIS agglomeration shape
+ * (GridTools::partition_triangulation on the cell face-adjacency graph, examples/poisson.cc) and the
+ * distribution of polytopes over GPUs (vertex weight = sub-cells of the polytope, edge weight = shared
+ * sub-faces).  CSR graph without self loops, both directions listed; weights may be NULL. */
+int pdh_partition_graph(int64_t n_vertices, const int64_t *xadj, const int64_t *adjncy, const int64_t *vertex_weights,
+                        const int64_t *edge_weights, int32_t n_parts, int32_t *part_out);
 /* pdh_flatten + pd_create in one call */
 int pdh_create_device(pdh_handler *ah, const pdh_flatten_params *prm, pd_handle **out);
 

@@ -53,6 +53,18 @@ namespace
 
 extern "C"
 {
+  // METIS 5 API of the CUDA toolkit's libmetis_static.a: idx_t = int64_t, real_t = float
+  int METIS_SetDefaultOptions(int64_t *options);
+  int METIS_PartGraphKway(int64_t *nvtxs, int64_t *ncon, int64_t *xadj, int64_t *adjncy, int64_t *vwgt, int64_t *vsize,
+                          int64_t *adjwgt, int64_t *nparts, float *tpwgts, float *ubvec, int64_t *options, int64_t *objval,
+                          int64_t *part);
+  int METIS_PartGraphRecursive(int64_t *nvtxs, int64_t *ncon, int64_t *xadj, int64_t *adjncy, int64_t *vwgt, int64_t *vsize,
+                               int64_t *adjwgt, int64_t *nparts, float *tpwgts, float *ubvec, int64_t *options,
+                               int64_t *objval, int64_t *part);
+}
+
+extern "C"
+{
   int
   pdh_grid_create_structured(int32_t dim, const int32_t *n, const double *lo, const double *hi, int32_t order, pdh_grid **out)
   {
@@ -370,5 +382,37 @@ extern "C"
     if (e != PD_OK)
       return e;
     return pd_create(&d, out);
+  }
+
+  // Graph partitioning with METIS (the 64-bit-index build shipped with the CUDA toolkit as
+  // libmetis_static.a), called the way deal.II's SparsityTools::partition does
+  // (include/poly_utils.h:603-606, GridTools::partition_triangulation in the examples and tests):
+  // default options, METIS_PartGraphRecursive for nparts <= 8, METIS_PartGraphKway above.
+  int
+  pdh_partition_graph(int64_t n_vertices, const int64_t *xadj, const int64_t *adjncy, const int64_t *vertex_weights,
+                      const int64_t *edge_weights, int32_t n_parts, int32_t *part_out)
+  {
+    return guarded([&] {
+      if (n_vertices <= 0 || !xadj || !adjncy || !part_out || n_parts < 1)
+        throw pd::Error(PD_ERR_INVALID, "pdh_partition_graph: bad argument");
+      if (n_parts == 1)
+        {
+          std::fill(part_out, part_out + n_vertices, 0);
+          return;
+        }
+      int64_t              nv = n_vertices, ncon = 1, np = n_parts, objval = 0;
+      std::vector<int64_t> part((size_t)n_vertices), options(40);
+      METIS_SetDefaultOptions(options.data());
+      auto *xa = const_cast<int64_t *>(xadj), *ad = const_cast<int64_t *>(adjncy);
+      auto *vw = const_cast<int64_t *>(vertex_weights), *ew = const_cast<int64_t *>(edge_weights);
+      const int rc = n_parts <= 8 ? METIS_PartGraphRecursive(&nv, &ncon, xa, ad, vw, nullptr, ew, &np, nullptr, nullptr,
+                                                             options.data(), &objval, part.data()) :
+                                    METIS_PartGraphKway(&nv, &ncon, xa, ad, vw, nullptr, ew, &np, nullptr, nullptr,
+                                                        options.data(), &objval, part.data());
+      if (rc != 1)
+        throw pd::Error(PD_ERR_INVALID, "pdh_partition_graph: METIS returned error " + std::to_string(rc));
+      for (int64_t v = 0; v < n_vertices; ++v)
+        part_out[v] = (int32_t)part[(size_t)v];
+    });
   }
 }

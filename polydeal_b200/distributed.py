@@ -48,6 +48,27 @@ def partition_by_coordinate(ah: AgglomerationHandler, n_ranks: int, axis: int) -
     return owner
 
 
+def partition_by_metis(ah: AgglomerationHandler, n_ranks: int) -> np.ndarray:
+    """owner[p] from a METIS partition of the polytope adjacency graph, vertex weight = number of sub-cells
+    (volume work), edge weight = number of shared sub-faces (ghost traffic): SURVEY 8e."""
+    from .handler import partition_graph
+
+    np_ = ah.n_polytopes
+    rows, cols, wts = [], [], []
+    for p in range(np_):
+        for f in range(ah.n_faces(p)):
+            if not ah.at_boundary(p, f):
+                rows.append(p)
+                cols.append(ah.neighbor(p, f))
+                wts.append(len(ah.interface(p, f)))
+    rows, cols, wts = np.array(rows, dtype=np.int64), np.array(cols, dtype=np.int64), np.array(wts, dtype=np.int64)
+    order = np.lexsort((cols, rows))
+    xadj = np.zeros(np_ + 1, dtype=np.int64)
+    xadj[1:] = np.cumsum(np.bincount(rows, minlength=np_))
+    vw = np.array([len(ah.get_agglomerate(p)) for p in range(np_)], dtype=np.int64)
+    return partition_graph(xadj, cols[order], n_ranks, vw, wts[order]).astype(np.int32)
+
+
 class LocalPart:
     """The local descriptor of one rank + the index maps of the halo exchange."""
 

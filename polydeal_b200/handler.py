@@ -102,6 +102,32 @@ class Grid:
         self.set_vertices(v)
 
 
+def partition_graph(xadj, adjncy, n_parts, vertex_weights=None, edge_weights=None):
+    """METIS through the C ABI (pdh_partition_graph): part[v] in [0, n_parts)."""
+    xadj = np.ascontiguousarray(xadj, dtype=np.int64)
+    adjncy = np.ascontiguousarray(adjncy, dtype=np.int64)
+    vw = None if vertex_weights is None else np.ascontiguousarray(vertex_weights, dtype=np.int64)
+    ew = None if edge_weights is None else np.ascontiguousarray(edge_weights, dtype=np.int64)
+    part = np.empty(len(xadj) - 1, dtype=np.int32)
+    K.check(K.lib().pdh_partition_graph(len(xadj) - 1, _ptr(xadj), _ptr(adjncy), _ptr(vw) if vw is not None else None,
+                                        _ptr(ew) if ew is not None else None, int(n_parts), _ptr(part)))
+    return part
+
+
+def metis_agglomerates(grid: "Grid", n_parts: int):
+    """GridTools::partition_triangulation(n_parts, tria, SparsityTools::Partitioner::metis) followed by one
+    agglomerate per subdomain (examples/poisson.cc, test/polydeal/continuous_face_02.cc test3): METIS on the
+    face-adjacency graph of the cells.  Returns the cell lists in subdomain order, cells ascending."""
+    _, _, nbr = grid.arrays()
+    mask = nbr >= 0
+    xadj = np.zeros(grid.n_cells + 1, dtype=np.int64)
+    xadj[1:] = np.cumsum(mask.sum(axis=1))
+    part = partition_graph(xadj, nbr[mask], n_parts)
+    order = np.argsort(part, kind="stable")
+    counts = np.bincount(part, minlength=n_parts)
+    return [g.tolist() for g in np.split(order.astype(np.int32), np.cumsum(counts)[:-1]) if len(g)]
+
+
 class AgglomerationHandler:
     def __init__(self, grid: Grid):
         self.grid, self.dim = grid, grid.dim

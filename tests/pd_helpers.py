@@ -41,6 +41,11 @@ def groups_for(shape, dim, n, ogrid, seed=0):
     if shape.startswith("random"):
         _, _, nbr = ogrid.arrays()
         return sc.random_partition(ogrid.n_cells, nbr, int(shape[6:]), seed)
+    if shape.startswith("metis"):  # GridTools::partition_triangulation(k, tria, metis): the reference's main shape
+        import polydeal_b200 as pdl
+
+        v, cv, nbr = ogrid.arrays()
+        return pdl.metis_agglomerates(pdl.Grid.from_arrays(v, cv, nbr), int(shape[5:]))
     raise ValueError(shape)
 
 

@@ -286,3 +286,33 @@ def test_locally_owned_polytope_goldens(goldens):
                 if not ah.at_boundary(p, f):
                     got += [[c, lf] for c, lf in ah.interface(p, f)]
         assert got == goldens["locally_owned_polytope"][key], key
+
+
+def test_metis_agglomeration_and_sharding():
+    """pdh_partition_graph (METIS of the CUDA toolkit, called like deal.II's SparsityTools::partition): the METIS
+    agglomeration shape of the reference's examples and the METIS distribution of polytopes over ranks.  METIS
+    versions differ, so partitions are inputs of the path, never outputs to match: checked here are the
+    contracts (every cell / polytope exactly once, all parts used, balance, mostly face-connected parts)."""
+    from polydeal_b200 import distributed as pdd
+
+    for dim, n_ref, k in [(2, 4, 10), (2, 6, 256), (3, 3, 40)]:
+        grid = pdl.Grid.hyper_cube(dim, 0.0, 1.0, n_ref)
+        groups = pdl.metis_agglomerates(grid, k)
+        assert len(groups) == k
+        assert sorted(c for g in groups for c in g) == list(range(grid.n_cells))
+        sizes = np.array([len(g) for g in groups])
+        assert sizes.max() <= 1.35 * grid.n_cells / k + 1
+        ah = pdl.AgglomerationHandler(grid)
+        for g in groups:
+            ah.define_agglomerate(g)
+        ah.initialize_fe_values(2)
+        ah.distribute_agglomerated_dofs(pdl.FE_DGQ, 1)
+        for world in (2, 8):
+            owner = pdd.partition_by_metis(ah, world)
+            cnt = np.bincount(owner, minlength=world)
+            assert owner.shape == (k,) and cnt.min() > 0 and cnt.max() <= 1.5 * k / world + 1
+            parts = [pdd.LocalPart(ah, owner, r) for r in range(world)]
+            assert sum(p.n_owned for p in parts) == k
+            for r, p in enumerate(parts):  # what r expects from s is what s sends to r
+                for s_ in range(world):
+                    assert p.recv_counts[s_] == parts[s_].send_counts[r]
