@@ -32,8 +32,11 @@
 // are L1/L2 hits) plus 64 B per (cell, direction) of folded stencil record.
 // -----------------------------------------------------------------------------
 #include "pd_internal.hpp"
+#include "pd_fine_cell.hpp"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -314,6 +317,170 @@ namespace pd
         }
     }
 
+    // ---------------------------------------------------------------------------------------
+    // The tiled kernel: ONE THREAD PER CELL, coefficients staged in shared memory.
+    //
+    // ncu on k_fine_sip (profiles/ncu_r01_fine_sip_summary.txt) shows the line-per-thread kernel
+    // bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 92 %: 61 global + 73 shared
+    // wavefronts per DGQ2 cell, every 8-byte access of a line a separate wavefront share), with
+    // HBM at 13 % and the FP64 pipe at 29 %.  Here a CTA takes TILE consecutive cells, copies
+    // their coefficients and those of the neighbours outside the tile (the "halo", tile plan of
+    // pd_fine_cell.hpp) into shared memory with cp.async (no registers, everything in flight at
+    // once), and thread i then applies the whole operator to cell i in registers
+    // (pd::fine::cell_apply): its reads are row reads of an [slot][N] array with N odd -> bank
+    // conflict free, 16 useful doubles per wavefront, and there is no exchange between threads.
+    // Results go back through the own slots so that the global stores are coalesced.
+    // Per DGQ2 cell on a Morton-ordered mesh: ~35 wavefronts instead of 134.
+    // ---------------------------------------------------------------------------------------
+    template <int N1>
+    struct TileArgs
+    {
+      fine::TileTables<N1> T;
+      const FineRec       *rec;
+      const double        *vol;
+      const double        *x;
+      double              *y;
+      const int32_t       *seq;      // cells in processing order (nullptr: 0 .. n_seq-1)
+      const int32_t       *tile_ptr; // [n_tiles + 1] into halo
+      const int32_t       *halo;
+      const uint16_t      *nslot; // [n_seq][2 DIM]
+      int32_t              n_seq, zslot;
+      double               mass;
+      int                  add;
+    };
+
+    __device__ __forceinline__ void
+    cp_async8(void *smem, const void *gmem)
+    {
+      const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+    }
+    __device__ __forceinline__ void
+    cp_async16(void *smem, const void *gmem)
+    {
+      const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+    }
+    __device__ __forceinline__ void
+    cp_async_wait_all()
+    {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+
+    constexpr int FINE_TILE = 64;
+
+    constexpr size_t
+    round16(const size_t v)
+    {
+      return (v + 15) / 16 * 16;
+    }
+    // shared memory of a tile CTA: values [(zslot+1)][N] | records [TILE][DIM*64+16] | slot -> cell [zslot]
+    constexpr size_t
+    tile_smem_bytes(const int dim, const int n, const int zslot)
+    {
+      return round16((size_t)(zslot + 1) * n * sizeof(double)) + (size_t)FINE_TILE * (dim * 64 + 16) + round16((size_t)zslot * 4);
+    }
+
+    template <int DIM, int DEG>
+    __global__ void __launch_bounds__(FINE_TILE, 4) k_fine_tile(const __grid_constant__ TileArgs<DEG + 1> A)
+    {
+      constexpr int N1  = DEG + 1;
+      constexpr int N   = ipow_(N1, DIM);
+      constexpr int NFC = 2 * DIM;
+      constexpr int RS  = DIM * 64 + 16; // record row of a cell, padded: 16-byte reads of consecutive threads hit distinct banks
+      constexpr int SPW = 32 / N;        // slots a warp copies per step
+      constexpr int NW  = FINE_TILE / 32;
+      static_assert(N <= 32, "one warp step copies at least one cell");
+
+      extern __shared__ __align__(16) unsigned char smem[];
+      double        *S  = reinterpret_cast<double *>(smem);
+      unsigned char *sR = smem + round16((size_t)(A.zslot + 1) * N * sizeof(double));
+      int32_t       *sC = reinterpret_cast<int32_t *>(sR + FINE_TILE * RS);
+
+      const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+      const int s0 = blockIdx.x * FINE_TILE, n_own = min(FINE_TILE, A.n_seq - s0);
+      const int h0 = A.tile_ptr[blockIdx.x], n_slots = n_own + (A.tile_ptr[blockIdx.x + 1] - h0);
+
+      for (int i = tid; i < n_slots; i += FINE_TILE)
+        sC[i] = i < n_own ? (A.seq ? A.seq[s0 + i] : s0 + i) : A.halo[h0 + i - n_own];
+      if (tid < N)
+        S[(size_t)A.zslot * N + tid] = 0.;
+      // what this thread's cell needs beside the staged data
+      const bool mine = tid < n_own;
+      uint32_t   ns[NFC];
+      double     mv = 0.;
+      if (mine)
+        {
+          const uint16_t *np = A.nslot + (size_t)(s0 + tid) * NFC;
+#pragma unroll
+          for (int f = 0; f < NFC; ++f)
+            ns[f] = np[f];
+          if (A.mass != 0.)
+            mv = A.mass * A.vol[A.seq ? A.seq[s0 + tid] : s0 + tid];
+        }
+      __syncthreads();
+      // ---- stage coefficients (own + halo) and the own cells' records, asynchronously
+      const int  sub = lane / N, e = lane % N;
+      const bool copier = sub < SPW;
+#pragma unroll 4
+      for (int slot = warp * SPW + sub; slot < n_slots; slot += NW * SPW)
+        if (copier)
+          cp_async8(S + (size_t)slot * N + e, A.x + (int64_t)sC[slot] * N + e);
+      for (int i = tid; i < n_own * DIM * 4; i += FINE_TILE)
+        {
+          const int slot = i / (DIM * 4), c = i % (DIM * 4);
+          cp_async16(sR + slot * RS + c * 16, reinterpret_cast<const unsigned char *>(A.rec) + ((int64_t)sC[slot] * DIM * 4 + c) * 16);
+        }
+      cp_async_wait_all();
+      __syncthreads();
+      // ---- one cell per thread, in registers
+      double out[N];
+      if (mine)
+        {
+          double u[N];
+#pragma unroll
+          for (int k = 0; k < N; ++k)
+            u[k] = S[tid * N + k];
+          const double *nbp[NFC];
+#pragma unroll
+          for (int f = 0; f < NFC; ++f)
+            nbp[f] = S + ns[f] * N;
+          const unsigned char *myrec = sR + tid * RS;
+          fine::cell_apply<DIM, N1>(
+            A.T, u, [&](const int d, const int s, const int k) { return nbp[2 * d + s][k]; },
+            [&](const int d) {
+              const unsigned char *r  = myrec + d * 64;
+              const double2        cd = *reinterpret_cast<const double2 *>(r + 16);
+              const double2        pp = *reinterpret_cast<const double2 *>(r + 32);
+              const double2        qq = *reinterpret_cast<const double2 *>(r + 48);
+              fine::LineCoef       c;
+              c.cVol  = *reinterpret_cast<const double *>(r + 8);
+              c.cD[0] = cd.x, c.cD[1] = cd.y;
+              c.P[0] = pp.x, c.P[1] = pp.y;
+              c.Q[0] = qq.x, c.Q[1] = qq.y;
+              return c;
+            },
+            mv, out);
+        }
+      __syncthreads(); // every read of the staged coefficients is done: the own slots become the output staging
+      if (mine)
+        {
+#pragma unroll
+          for (int k = 0; k < N; ++k)
+            S[tid * N + k] = out[k];
+        }
+      __syncthreads();
+#pragma unroll 4
+      for (int slot = warp * SPW + sub; slot < n_own; slot += NW * SPW)
+        if (copier)
+          {
+            double *yp = A.y + (int64_t)sC[slot] * N + e;
+            const double v = S[(size_t)slot * N + e];
+            *yp            = A.add ? *yp + v : v;
+          }
+    }
+
+
     // host: l_a(x), l_a'(x)
     void
     lagrange_host(const Basis1D &B, const int n1, const double x, double *L, double *dL)
@@ -447,6 +614,104 @@ namespace pd
         put(h->mf_list_interior, inner);
         put(h->mf_list_boundary, outer);
       }
+    // ---- the tiled kernel: premultiplied tables and one tile plan per cell sequence
+    for (auto &t : h->mf_tiles)
+      t.ok = false;
+    {
+      const char *env = std::getenv("PD_FINE_KERNEL");
+      h->mf_kernel    = (env && std::strcmp(env, "line") == 0) ? 1 : 0;
+    }
+    if (h->mf_kernel == 0 && h->n <= 27)
+      {
+        // X = Mh^-1 B by Gaussian elimination with partial pivoting (Mh is SPD, n1 <= 5)
+        auto solve = [n1](const double *M, const double *B, const int ncol, double *X) {
+          std::vector<double> a(M, M + n1 * n1), b(B, B + n1 * ncol);
+          for (int k = 0; k < n1; ++k)
+            {
+              int piv = k;
+              for (int r = k + 1; r < n1; ++r)
+                if (std::fabs(a[r * n1 + k]) > std::fabs(a[piv * n1 + k]))
+                  piv = r;
+              for (int c = 0; c < n1; ++c)
+                std::swap(a[k * n1 + c], a[piv * n1 + c]);
+              for (int c = 0; c < ncol; ++c)
+                std::swap(b[k * ncol + c], b[piv * ncol + c]);
+              for (int r = k + 1; r < n1; ++r)
+                {
+                  const double f = a[r * n1 + k] / a[k * n1 + k];
+                  for (int c = k; c < n1; ++c)
+                    a[r * n1 + c] -= f * a[k * n1 + c];
+                  for (int c = 0; c < ncol; ++c)
+                    b[r * ncol + c] -= f * b[k * ncol + c];
+                }
+            }
+          for (int k = n1 - 1; k >= 0; --k)
+            for (int c = 0; c < ncol; ++c)
+              {
+                double v = b[k * ncol + c];
+                for (int r = k + 1; r < n1; ++r)
+                  v -= a[k * n1 + r] * X[r * ncol + c];
+                X[k * ncol + c] = v / a[k * n1 + k];
+              }
+        };
+        // layout of fine::TileTables: Mh | Shp | ep[2] | dp[2] | d[2]
+        h->mf_tile_tab_host.assign(2 * n1 * n1 + 6 * n1, 0.);
+        double *tM = h->mf_tile_tab_host.data(), *tS = tM + n1 * n1, *tE = tS + n1 * n1, *tDp = tE + 2 * n1, *tD = tDp + 2 * n1;
+        std::copy(Mh, Mh + n1 * n1, tM);
+        solve(Mh, Sh, n1, tS);
+        std::vector<double> rhs(n1 * 4), sol(n1 * 4); // columns e0, e1, d0, d1
+        for (int i = 0; i < n1; ++i)
+          {
+            rhs[i * 4 + 0] = e0[i], rhs[i * 4 + 1] = e0[n1 + i];
+            rhs[i * 4 + 2] = d0[i], rhs[i * 4 + 3] = d0[n1 + i];
+          }
+        solve(Mh, rhs.data(), 4, sol.data());
+        for (int i = 0; i < n1; ++i)
+          {
+            tE[i] = sol[i * 4 + 0], tE[n1 + i] = sol[i * 4 + 1];
+            tDp[i] = sol[i * 4 + 2], tDp[n1 + i] = sol[i * 4 + 3];
+            tD[i] = d0[i], tD[n1 + i] = d0[n1 + i];
+          }
+        // the unit-vector traces cell_apply relies on (FE_DGQ(p >= 1): nodes on both ends)
+        bool unit = true;
+        for (int i = 0; i < n1; ++i)
+          unit = unit && std::fabs(e0[i] - (i == 0 ? 1. : 0.)) < 1e-14 && std::fabs(e0[n1 + i] - (i == n1 - 1 ? 1. : 0.)) < 1e-14;
+        std::vector<int32_t> inner, outer;
+        if (h->np != h->np_own)
+          for (int32_t c = 0; c < h->np_own; ++c)
+            {
+              bool ghost = false;
+              for (int f = 0; f < nfc; ++f)
+                ghost = ghost || nbr[(size_t)c * nfc + f] >= h->np_own;
+              (ghost ? outer : inner).push_back(c);
+            }
+        for (int part = 0; unit && part < 3; ++part)
+          {
+            const std::vector<int32_t> *seq = part == 0 ? nullptr : (part == 1 ? &inner : &outer);
+            const int32_t               n_seq = seq ? (int32_t)seq->size() : h->np_own;
+            if (n_seq == 0)
+              continue;
+            fine::TilePlan plan;
+            try
+              {
+                plan = fine::build_tile_plan(n_seq, seq ? seq->data() : nullptr, nbr.data(), nfc, h->np, FINE_TILE);
+              }
+            catch (const std::exception &)
+              {
+                continue;
+              }
+            if (tile_smem_bytes(dim, h->n, plan.zslot) > 200 * 1024)
+              continue; // an ordering without locality: the line-per-thread kernel takes this sequence
+            auto &t = h->mf_tiles[part];
+            put(t.tile_ptr, plan.tile_ptr);
+            put(t.nslot, plan.nslot);
+            if (plan.halo.empty())
+              plan.halo.push_back(0);
+            put(t.halo, plan.halo);
+            t.n_tiles = plan.n_tiles, t.zslot = plan.zslot, t.n_seq = n_seq;
+            t.ok = true;
+          }
+      }
     h->mf_rec.alloc((size_t)h->np_own * dim * 8);
     h->mf_zero.alloc((size_t)h->n);
     PD_CUDA(cudaMemset(h->mf_zero.p, 0, (size_t)h->n * sizeof(double)));
@@ -462,16 +727,11 @@ namespace pd
 
   namespace
   {
-    template <int DIM, int DEG, int MINB>
+    // the operator's coefficient and term flags folded into the stencil records (once per pd_set_operator)
+    template <int DIM>
     void
-    launch_fine(pd_handle *h, const double *src, double *dst, const bool add, const int part)
+    fold_fine_records(pd_handle *h)
     {
-      constexpr int N1 = DEG + 1, N = ipow_(N1, DIM), NT = DIM * (N / N1);
-      constexpr int GS = pow2_at_least(N > NT ? N : NT), CPB = 256 / GS;
-      FineArgs<N1>  a;
-      static_assert(sizeof(a.T) == (2 * N1 * N1 + 4 * N1) * sizeof(double), "table layout");
-      std::memcpy(&a.T, h->mf_tab_host.data(), sizeof(a.T));
-      const bool vol_on = (h->op_flags & PD_ASSEMBLE_VOLUME) != 0;
       if (!h->mf_rec_valid || h->mf_rec_flags != h->op_flags || h->mf_rec_coef != h->op_coef.stiffness)
         {
           const int64_t n = (int64_t)h->np_own * DIM;
@@ -483,6 +743,19 @@ namespace pd
           h->mf_rec_coef  = h->op_coef.stiffness;
           ++h->launches;
         }
+    }
+
+    template <int DIM, int DEG, int MINB>
+    void
+    launch_fine(pd_handle *h, const double *src, double *dst, const bool add, const int part)
+    {
+      constexpr int N1 = DEG + 1, N = ipow_(N1, DIM), NT = DIM * (N / N1);
+      constexpr int GS = pow2_at_least(N > NT ? N : NT), CPB = 256 / GS;
+      FineArgs<N1>  a;
+      static_assert(sizeof(a.T) == (2 * N1 * N1 + 4 * N1) * sizeof(double), "table layout");
+      std::memcpy(&a.T, h->mf_tab_host.data(), sizeof(a.T));
+      const bool vol_on = (h->op_flags & PD_ASSEMBLE_VOLUME) != 0;
+      fold_fine_records<DIM>(h);
       a.rec      = reinterpret_cast<const FineRec *>(h->mf_rec.p);
       a.vol      = h->mf_vol.p;
       a.zero     = h->mf_zero.p;
@@ -499,13 +772,52 @@ namespace pd
       const int     grid = (int)std::min<int64_t>(want, (int64_t)h->sm_count * 4 * MINB);
       k_fine_sip<DIM, DEG, MINB><<<grid, 256, 0, h->stream>>>(a);
     }
+    template <int DIM, int DEG>
+    void
+    launch_fine_tiled(pd_handle *h, const double *src, double *dst, const bool add, const int part)
+    {
+      constexpr int     N1 = DEG + 1;
+      const auto       &t  = h->mf_tiles[part];
+      TileArgs<N1>      a;
+      static_assert(sizeof(a.T) == (2 * N1 * N1 + 6 * N1) * sizeof(double), "table layout");
+      std::memcpy(&a.T, h->mf_tile_tab_host.data(), sizeof(a.T));
+      fold_fine_records<DIM>(h);
+      const bool vol_on = (h->op_flags & PD_ASSEMBLE_VOLUME) != 0;
+      a.rec      = reinterpret_cast<const FineRec *>(h->mf_rec.p);
+      a.vol      = h->mf_vol.p;
+      a.x        = src;
+      a.y        = dst;
+      a.seq      = part == 0 ? nullptr : (part == 1 ? h->mf_list_interior.p : h->mf_list_boundary.p);
+      a.tile_ptr = t.tile_ptr.p;
+      a.halo     = t.halo.p;
+      a.nslot    = t.nslot.p;
+      a.n_seq    = t.n_seq;
+      a.zslot    = t.zslot;
+      a.mass     = vol_on ? h->op_coef.mass : 0.;
+      a.add      = add ? 1 : 0;
+      const size_t smem = tile_smem_bytes(DIM, ipow_(N1, DIM), t.zslot);
+      static size_t smem_set = 0; // per instantiation
+      if (smem > smem_set)
+        {
+          PD_CUDA(cudaFuncSetAttribute(k_fine_tile<DIM, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          smem_set = smem;
+        }
+      k_fine_tile<DIM, DEG><<<t.n_tiles, FINE_TILE, smem, h->stream>>>(a);
+    }
   } // namespace
 
   void
   launch_fine_operator(pd_handle *h, const double *src, double *dst, const bool add, const int part)
   {
-    switch (h->dim * 10 + h->degree)
+    const bool tiled = h->mf_kernel == 0 && h->mf_tiles[part].ok;
+    switch ((tiled ? 100 : 0) + h->dim * 10 + h->degree)
       {
+        case 121: launch_fine_tiled<2, 1>(h, src, dst, add, part); break;
+        case 122: launch_fine_tiled<2, 2>(h, src, dst, add, part); break;
+        case 123: launch_fine_tiled<2, 3>(h, src, dst, add, part); break;
+        case 124: launch_fine_tiled<2, 4>(h, src, dst, add, part); break;
+        case 131: launch_fine_tiled<3, 1>(h, src, dst, add, part); break;
+        case 132: launch_fine_tiled<3, 2>(h, src, dst, add, part); break;
         case 21: launch_fine<2, 1, 4>(h, src, dst, add, part); break;
         case 22: launch_fine<2, 2, 3>(h, src, dst, add, part); break;
         case 23: launch_fine<2, 3, 3>(h, src, dst, add, part); break;

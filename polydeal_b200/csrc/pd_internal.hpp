@@ -117,6 +117,18 @@ struct pd_handle
   uint32_t            mf_rec_flags = 0;
   double              mf_rec_coef  = 0.;
   std::vector<double> mf_tab_host;    // 1-D tables Mh, Sh, e0|e1, d0|d1 (passed as kernel parameters)
+  // tiled variant (one thread per cell, coefficients staged in shared memory): the tile plans of the three
+  // cell sequences (all owned cells, interior list, boundary list) and the premultiplied 1-D tables
+  struct FineTiles
+  {
+    pd::DevBuf<int32_t>  tile_ptr, halo;
+    pd::DevBuf<uint16_t> nslot;
+    int32_t              n_tiles = 0, zslot = 0, n_seq = 0;
+    bool                 ok = false;
+  };
+  FineTiles           mf_tiles[3];
+  std::vector<double> mf_tile_tab_host; // Mh | Mh^-1 Sh | Mh^-1 e0,e1 | Mh^-1 d0,d1 | d0,d1
+  int                 mf_kernel = 0;    // 0: tiled where available, 1: line-per-thread always (PD_FINE_KERNEL=line)
   // matrix-free fine-mesh operator on general (Q1-mapped) cells with the mapped basis, pd_mappedfine.cu
   bool                mp_ready = false, mp_geo_valid = false;
   std::vector<double> mp_tab_host; // V | V^T | Dt | e0 e1 | d0 d1

@@ -1,0 +1,72 @@
+// Test-only host instantiation of the tiled fine-mesh kernel's per-cell arithmetic and tile plan
+// (polydeal_b200/csrc/pd_fine_cell.hpp), compiled by tests/test_fine_tile_host.py with g++ and
+// compared with a dense Kronecker restatement in numpy.  Not part of the product library.
+#include "../../polydeal_b200/csrc/pd_fine_cell.hpp"
+
+#include <cstring>
+
+namespace
+{
+  template <int DIM, int N1>
+  void
+  run(const double *tab, const double *u, const double *nb, const double *coef, const double mv, double *out)
+  {
+    constexpr int               N = pd::fine::ipow(N1, DIM);
+    pd::fine::TileTables<N1>    T;
+    static_assert(sizeof(T) == (2 * N1 * N1 + 6 * N1) * sizeof(double), "table layout");
+    std::memcpy(&T, tab, sizeof(T));
+    pd::fine::cell_apply<DIM, N1>(
+      T, u, [&](const int d, const int s, const int e) { return nb[(2 * d + s) * N + e]; },
+      [&](const int d) {
+        pd::fine::LineCoef c;
+        std::memcpy(&c, coef + 7 * d, sizeof(c));
+        return c;
+      },
+      mv, out);
+  }
+} // namespace
+
+extern "C"
+{
+  // tab: Mh | Mh^-1 Sh | Mh^-1 e0,e1 | Mh^-1 d0,d1 | d0,d1;  nb[2 dim][N];  coef[dim][7] = cVol, cD0, cD1, P0, P1, Q0, Q1
+  int
+  fine_cell_host(const int dim, const int n1, const double *tab, const double *u, const double *nb, const double *coef,
+                 const double mv, double *out)
+  {
+    switch (dim * 10 + n1)
+      {
+        case 22: run<2, 2>(tab, u, nb, coef, mv, out); return 0;
+        case 23: run<2, 3>(tab, u, nb, coef, mv, out); return 0;
+        case 24: run<2, 4>(tab, u, nb, coef, mv, out); return 0;
+        case 25: run<2, 5>(tab, u, nb, coef, mv, out); return 0;
+        case 32: run<3, 2>(tab, u, nb, coef, mv, out); return 0;
+        case 33: run<3, 3>(tab, u, nb, coef, mv, out); return 0;
+        default: return -1;
+      }
+  }
+
+  // outputs sized by the caller: tile_ptr[n_tiles + 1], nslot[n_seq * nfc], halo[halo_cap]
+  int
+  fine_tile_plan_host(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
+                      const int tile, int32_t *n_tiles, int32_t *zslot, int32_t *tile_ptr, int32_t *halo, const int64_t halo_cap,
+                      int64_t *n_halo, uint16_t *nslot)
+  {
+    try
+      {
+        const pd::fine::TilePlan p = pd::fine::build_tile_plan(n_seq, seq, nbr, nfc, n_cells_total, tile);
+        *n_tiles                   = p.n_tiles;
+        *zslot                     = p.zslot;
+        *n_halo                    = (int64_t)p.halo.size();
+        if ((int64_t)p.halo.size() > halo_cap)
+          return -2;
+        std::memcpy(tile_ptr, p.tile_ptr.data(), p.tile_ptr.size() * sizeof(int32_t));
+        std::memcpy(halo, p.halo.data(), p.halo.size() * sizeof(int32_t));
+        std::memcpy(nslot, p.nslot.data(), p.nslot.size() * sizeof(uint16_t));
+        return 0;
+      }
+    catch (const std::exception &)
+      {
+        return -1;
+      }
+  }
+}

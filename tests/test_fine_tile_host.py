@@ -1,0 +1,160 @@
+"""Host-side checks of the tiled fine-mesh SIP kernel (polydeal_b200/csrc/pd_fine_cell.hpp): the per-cell
+arithmetic cell_apply (premultiplied stencils M^-1 L_d + mass passes, LaplaceOperatorDG / MonodomainOperatorDG
+include/utils.h:819-925, 1565-1659) against a dense Kronecker restatement, and the tile plan (own / halo / zero
+slots) against its contract.  The templates are compiled here with g++ (tests/csrc/fine_cell_host.cpp); the GPU
+parity of the kernel itself is tests/test_gpu_parity.py::test_fine_mesh_matrix_free_vmult."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("fine_cell") / "libfine_cell_host.so"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", str(out),
+                           os.path.join(HERE, "csrc", "fine_cell_host.cpp")])
+    return C.CDLL(str(out))
+
+
+def gll_nodes(p):
+    return {1: [0.0, 1.0], 2: [0.0, 0.5, 1.0], 3: [0.0, 0.5 - np.sqrt(5) / 10, 0.5 + np.sqrt(5) / 10, 1.0],
+            4: [0.0, 0.5 - np.sqrt(21) / 14, 0.5, 0.5 + np.sqrt(21) / 14, 1.0]}[p]
+
+
+def tables_1d(p):
+    """Mh, Sh, e[2], d[2] of FE_DGQ(p) on [0,1] with QGauss(p+1)."""
+    nodes = np.array(gll_nodes(p))
+    n1 = p + 1
+    polys = []
+    for a in range(n1):
+        c = np.poly1d([1.0])
+        for b in range(n1):
+            if b != a:
+                c = c * np.poly1d([1.0, -nodes[b]]) / (nodes[a] - nodes[b])
+        polys.append(c)
+    xg, wg = np.polynomial.legendre.leggauss(n1)
+    xg, wg = 0.5 * (xg + 1.0), 0.5 * wg
+    L = np.array([[pl(x) for x in xg] for pl in polys])
+    dL = np.array([[pl.deriv()(x) for x in xg] for pl in polys])
+    Mh = (L * wg) @ L.T
+    Sh = (dL * wg) @ dL.T
+    e = np.array([[pl(s) for pl in polys] for s in (0.0, 1.0)])
+    d = np.array([[pl.deriv()(s) for pl in polys] for s in (0.0, 1.0)])
+    return Mh, Sh, e, d
+
+
+def kron_dir(mats):
+    """x fastest: kron(A_z, A_y, A_x)"""
+    out = np.array([[1.0]])
+    for m in mats:
+        out = np.kron(m, out)
+    return out
+
+
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 2), (2, 3), (2, 4), (3, 1), (3, 2)])
+def test_cell_apply_equals_dense_kronecker_form(lib, dim, p):
+    rng = np.random.default_rng(7 * dim + p)
+    n1, N = p + 1, (p + 1) ** dim
+    Mh, Sh, e, d = tables_1d(p)
+    tab = np.concatenate([Mh.ravel(), np.linalg.solve(Mh, Sh).ravel(), np.linalg.solve(Mh, e.T).T.ravel(),
+                          np.linalg.solve(Mh, d.T).T.ravel(), d.ravel()])
+    for trial in range(4):
+        u = rng.standard_normal(N)
+        nb = rng.standard_normal((2 * dim, N))
+        coef = rng.uniform(0.2, 2.0, (dim, 7))  # cVol, cD0, cD1, P0, P1, Q0, Q1
+        if trial == 1:  # a boundary face: no neighbour, Q = 0
+            nb[0] = 0.0
+            coef[0, 5] = 0.0
+        if trial == 2:  # face terms switched off in one direction
+            coef[dim - 1, 1:] = 0.0
+        mv = 0.0 if trial == 0 else 1.7
+        # dense form of the line stencils (pd_finemesh.cu: a_s, b_s of k_fine_sip)
+        ref = mv * kron_dir([Mh] * dim) @ u
+        e0, e1, d0, d1 = e[0], e[1], d[0], d[1]
+        for k in range(dim):
+            cV, cD0, cD1, P0, P1, Q0, Q1 = coef[k]
+            own = (cV * Sh + np.outer(e0, P0 * e0 + cD0 * d0) + np.outer(d0, cD0 * e0)
+                   + np.outer(e1, P1 * e1 - cD1 * d1) + np.outer(d1, -cD1 * e1))
+            n0 = np.outer(e0, -P0 * e1 + Q0 * d1) + np.outer(d0, -cD0 * e1)
+            n1m = np.outer(e1, -P1 * e0 - Q1 * d0) + np.outer(d1, cD1 * e0)
+            place = lambda m: kron_dir([m if kk == k else Mh for kk in range(dim)])
+            ref = ref + place(own) @ u + place(n0) @ nb[2 * k] + place(n1m) @ nb[2 * k + 1]
+        out = np.empty(N)
+        dp = lambda a: a.ctypes.data_as(C.c_void_p)
+        nbc, coefc = np.ascontiguousarray(nb), np.ascontiguousarray(coef)
+        assert lib.fine_cell_host(dim, n1, dp(tab), dp(u), dp(nbc), dp(coefc), C.c_double(mv), dp(out)) == 0
+        assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def grid_neighbours(shape, order):
+    """neighbour table [cell][2 dim] of a Cartesian grid, cells numbered lexicographically or in Morton order"""
+    dim = len(shape)
+    idx = np.arange(int(np.prod(shape))).reshape(shape[::-1])  # [z][y][x]
+    coords = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, dim)
+    if order == "morton":
+        key = np.zeros(len(coords), dtype=np.int64)
+        for b in range(10):
+            for k in range(dim):
+                key |= ((coords[:, k] >> b) & 1) << (b * dim + k)
+        perm = np.argsort(key, kind="stable")
+    else:
+        perm = np.lexsort([coords[:, k] for k in range(dim)])
+    coords = coords[perm]
+    num = {tuple(c): i for i, c in enumerate(coords)}
+    nbr = -np.ones((len(coords), 2 * dim), dtype=np.int32)
+    for i, c in enumerate(coords):
+        for k in range(dim):
+            for s, step in enumerate((-1, 1)):
+                cc = list(c)
+                cc[k] += step
+                if 0 <= cc[k] < shape[k]:
+                    nbr[i, 2 * k + s] = num[tuple(cc)]
+    return nbr
+
+
+@pytest.mark.parametrize("shape,order,tile,with_list", [
+    ((8, 8, 8), "morton", 64, False), ((5, 7, 3), "lex", 64, False), ((16, 16), "morton", 64, False),
+    ((6, 6, 6), "lex", 16, True), ((3, 2), "lex", 64, False), ((8, 8, 8), "morton", 64, True),
+])
+def test_tile_plan_contract(lib, shape, order, tile, with_list):
+    nbr = grid_neighbours(shape, order)
+    n_cells, nfc = nbr.shape
+    seq = None
+    if with_list:  # an arbitrary sub-sequence, like the interior / boundary lists of a sharded apply
+        seq = np.ascontiguousarray(np.arange(n_cells, dtype=np.int32)[::-1][::2])
+    n_seq = n_cells if seq is None else len(seq)
+    n_tiles_max = (n_seq + tile - 1) // tile
+    tile_ptr = np.zeros(n_tiles_max + 1, dtype=np.int32)
+    halo = np.zeros(n_seq * nfc + 1, dtype=np.int32)
+    nslot = np.zeros(n_seq * nfc, dtype=np.uint16)
+    n_tiles, zslot, n_halo = C.c_int32(), C.c_int32(), C.c_int64()
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.fine_tile_plan_host(n_seq, dp(seq) if seq is not None else None, dp(nbr), nfc, n_cells, tile, C.byref(n_tiles),
+                                 C.byref(zslot), dp(tile_ptr), dp(halo), C.c_int64(len(halo)), C.byref(n_halo), dp(nslot))
+    assert rc == 0 and n_tiles.value == n_tiles_max and tile_ptr[-1] == n_halo.value
+    cells = np.arange(n_cells, dtype=np.int32) if seq is None else seq
+    max_slots = 0
+    for k in range(n_tiles.value):
+        own = cells[k * tile:(k + 1) * tile]
+        hl = halo[tile_ptr[k]:tile_ptr[k + 1]]
+        slots = np.concatenate([own, hl])
+        assert len(set(slots.tolist())) == len(slots)  # every cell staged once
+        max_slots = max(max_slots, len(slots))
+        for i, c in enumerate(own):
+            for f in range(nfc):
+                s = nslot[(k * tile + i) * nfc + f]
+                if nbr[c, f] < 0:
+                    assert s == zslot.value
+                else:
+                    assert s < len(slots) and slots[s] == nbr[c, f]
+        # no halo cell that nobody needs
+        needed = {int(nbr[c, f]) for c in own for f in range(nfc) if nbr[c, f] >= 0} - set(own.tolist())
+        assert needed == set(hl.tolist())
+    assert zslot.value == max_slots
+    if order == "morton" and not with_list and shape == (8, 8, 8):
+        assert max_slots == 64 + 48  # a 4x4x4 corner block and its three inner faces

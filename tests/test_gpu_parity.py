@@ -288,6 +288,10 @@ def test_unsupported_degree_fails_loudly():
     (3, (4, 4, 4), 2, 0, 1.0, {}),
     (3, (3, 4, 5), 2, 1, (1.0, 0.8, 1.3), {}),
     (3, (2, 2, 2), 3, 0, 1.0, {}),
+    (3, (8, 8, 8), 2, 0, 1.0, {}),                  # tiled kernel: eight 4x4x4 Morton tiles with halos
+    (3, (6, 5, 7), 1, 1, (1.0, 0.9, 1.2), {}),      # ... lexicographic order: pencils with large halos, ragged last tile
+    (2, (16, 16), 3, 0, 1.0, {}),
+    (2, (20, 13), 2, 1, (1.0, 0.6), dict(with_boundary=False, stiffness_coeff=0.3, mass_coeff=2.0)),
     (3, (4, 4, 4), 1, 0, 1.0, dict(with_boundary=False, stiffness_coeff=1e-4, mass_coeff=1.5e4)),   # monodomain, BDF2
     (3, (3, 3, 3), 2, 1, 1.0, dict(with_boundary=False, stiffness_coeff=1e-4, mass_coeff=1.0e4)),  # monodomain, BDF1
 ])
@@ -326,6 +330,36 @@ def test_fine_mesh_matrix_free_vmult(dim, n, p, order, hi, kw):
     op.vmult(yb, xd, mode=pdl.VMULT_BLOCK_CSR)
     op.synchronize()
     assert np.abs(yb.cpu().numpy() - yref).max() <= TOL * scale
+
+
+@pytest.mark.parametrize("dim,n,p,order", [(3, (16, 16, 16), 2, 0), (3, (12, 10, 9), 1, 1), (2, (40, 33), 4, 1), (2, (32, 32), 1, 0)])
+def test_fine_mesh_tiled_kernel_equals_line_kernel(dim, n, p, order, monkeypatch):
+    """The two kernels behind PD_VMULT_MATRIX_FREE on a fine Cartesian mesh -- k_fine_tile (one thread per cell,
+    coefficients staged in shared memory; the default) and k_fine_sip (one thread per line; PD_FINE_KERNEL=line,
+    and the only one for 3-D DGQ3) -- on meshes of many tiles, Laplace and monodomain coefficients, vmult and vmult_add."""
+    pdl = gpu()
+    import torch
+
+    ogrid = po.Grid(dim, n, 0.0, 1.0, order)
+    groups = [[c] for c in range(ogrid.n_cells)]
+    C = max(p, 1) * (p + 1.0)
+    ops = {}
+    for kernel in ("tile", "line"):
+        monkeypatch.setenv("PD_FINE_KERNEL", kernel)
+        _, pah = product_handler(ogrid, groups, p, p + 1)
+        ops[kernel] = pdl.SIPOperator(pah.flatten(penalty_constant=C, h_rule=pdl.H_NORMAL_EXTENT), keepalive=pah)
+        assert ops[kernel].matrix_free_available
+    x = torch.from_numpy(src_vector(ops["tile"].m())).cuda()
+    for flags, sc, mc in [(pdl.ASSEMBLE_ALL, 1.0, 0.0), (pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR, 1e-4, 1.5e4)]:
+        y = {}
+        for kernel, op in ops.items():
+            op.set_operator(flags, sc, mc)
+            y[kernel] = torch.full_like(x, 0.25)
+            op.vmult(y[kernel], x, mode=pdl.VMULT_MATRIX_FREE)
+            op.vmult_add(y[kernel], x, mode=pdl.VMULT_MATRIX_FREE)
+            op.synchronize()
+        scale = y["line"].abs().max().item()
+        assert scale > 0 and (y["tile"] - y["line"]).abs().max().item() <= TOL * scale
 
 
 @pytest.mark.parametrize("dim,n,shape,p,nq,distort", [
