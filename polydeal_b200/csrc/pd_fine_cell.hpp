@@ -12,10 +12,10 @@
 // On a Cartesian cell the operator is
 //   sum_d  M (x) .. (x) L_d (x) .. (x) M  +  f vol  M (x) M (x) M
 //     = (M (x) M (x) M) [ sum_d  I (x) .. (x) M^-1 L_d (x) .. (x) I  +  f vol I ]
-// so ONE thread that owns a whole cell applies the premultiplied 1-D stencils
-// M^-1 L_d line by line into a register accumulator and finishes with DIM mass
-// passes, all indices compile-time after unrolling -- no exchange between
-// threads at all.  FE_DGQ(p >= 1) has nodes on both ends of [0,1], so the trace
+// so the thread(s) that own a whole cell apply the premultiplied 1-D stencils
+// M^-1 L_d line by line into register accumulators and finish with DIM mass
+// passes, all indices compile-time after unrolling -- no exchange between the
+// threads of a cell except one partial sum.  FE_DGQ(p >= 1) has nodes on both ends of [0,1], so the trace
 // functionals l_i(0), l_i(1) are unit vectors and only the derivative
 // functionals d_s = l_i'(s) cost arithmetic.
 // -----------------------------------------------------------------------------
@@ -60,25 +60,38 @@ namespace pd
       double cVol, cD[2], P[2], Q[2];
     };
 
+    // The lines of a cell are split between TWO threads (roles) so that twice as many warps are resident:
+    // role 1 takes the first lines_of_role1() lines in (direction, line) order, role 0 the rest plus the mass
+    // passes; the split balances the arithmetic (a line costs about N1^2 + 8 N1 + 10 FMAs).
+    template <int DIM, int N1>
+    constexpr int
+    lines_of_role1()
+    {
+      constexpr int N = ipow(N1, DIM), L = DIM * (N / N1);
+      constexpr int line_cost = N1 * N1 + 8 * N1 + 10, mass_cost = DIM * N * N1 + N;
+      constexpr int nb = (L * line_cost + mass_cost + line_cost) / (2 * line_cost);
+      return nb > L ? L : nb;
+    }
+
+    // acc += the premultiplied stencils M^-1 L_d of the lines of `role` (role < 0: all lines) applied to u.
     // u: the cell's coefficients; nbv(d, s, e): coefficient e of the neighbour across face (d, s) (zeros where
-    // there is none); coef(d): the folded record; mv = f vol.  out may not alias u.
+    // there is none); coef(d): the folded record of direction d.
     template <int DIM, int N1, class Tab, class Nb, class Coef>
     PD_HD void
-    cell_apply(const Tab &T, const double *u, Nb &&nbv, Coef &&coef, const double mv, double *out)
+    cell_lines(const Tab &T, const int role, const double *u, Nb &&nbv, Coef &&coef, double *acc)
     {
-      constexpr int N = ipow(N1, DIM), NL = N / N1;
-      double        acc[N];
-#pragma unroll
-      for (int e = 0; e < N; ++e)
-        acc[e] = mv * u[e];
+      constexpr int N = ipow(N1, DIM), NL = N / N1, NB = lines_of_role1<DIM, N1>();
 #pragma unroll
       for (int d = 0; d < DIM; ++d)
         {
+          // (a direction none of whose lines belong to the role costs nothing: everything below is dead code)
           const LineCoef r      = coef(d);
           const int      stride = d == 0 ? 1 : (d == 1 ? N1 : N1 * N1);
 #pragma unroll
           for (int j = 0; j < NL; ++j)
             {
+              if (role >= 0 && (d * NL + j < NB) != (role == 1))
+                continue;
               const int base = d == 0 ? j * N1 : (d == 1 ? (j % N1) + (j / N1) * N1 * N1 : j);
               double    n0[N1], n1[N1];
 #pragma unroll
@@ -111,7 +124,14 @@ namespace pd
                 }
             }
         }
-      // M (x) M (x) M, one direction after the other, in registers
+    }
+
+    // acc <- (M (x) M (x) M) acc, one direction after the other, in registers
+    template <int DIM, int N1, class Tab>
+    PD_HD void
+    cell_mass(const Tab &T, double *acc)
+    {
+      constexpr int N = ipow(N1, DIM), NL = N / N1;
 #pragma unroll
       for (int d = 0; d < DIM; ++d)
         {
@@ -135,78 +155,115 @@ namespace pd
                 }
             }
         }
+    }
+
+    // the whole operator on one cell the way the kernel's two roles compose it: role 0 starts from the mass
+    // term mv u (mv = f vol), role 1 from zero, the partial sums meet, then the mass passes.  out may not alias u.
+    template <int DIM, int N1, class Tab, class Nb, class Coef>
+    PD_HD void
+    cell_apply(const Tab &T, const double *u, Nb &&nbv, Coef &&coef, const double mv, double *out)
+    {
+      constexpr int N = ipow(N1, DIM);
+      double        acc0[N], acc1[N];
 #pragma unroll
       for (int e = 0; e < N; ++e)
-        out[e] = acc[e];
+        {
+          acc0[e] = mv * u[e];
+          acc1[e] = 0.;
+        }
+      cell_lines<DIM, N1>(T, 0, u, nbv, coef, acc0);
+      cell_lines<DIM, N1>(T, 1, u, nbv, coef, acc1);
+#pragma unroll
+      for (int e = 0; e < N; ++e)
+        acc0[e] += acc1[e];
+      cell_mass<DIM, N1>(T, acc0);
+#pragma unroll
+      for (int e = 0; e < N; ++e)
+        out[e] = acc0[e];
     }
 
     // ---- tile plan -----------------------------------------------------------
     // A CTA of the tiled kernel takes TILE consecutive entries of a cell sequence (all owned cells, or the
     // interior / boundary lists of a sharded apply), stages their coefficients AND those of every
-    // neighbour outside the tile ("halo") in shared memory, and each thread then works on slots:
-    //   slot i < n_own            own cell i of the tile
-    //   slot n_own + k            halo cell halo[tile_ptr[tile] + k]
-    //   slot zslot (= max slots)  zeros: what a missing neighbour reads
-    // nslot[(seq position) * 2 DIM + face] is the slot of the neighbour across that face.
+    // neighbour outside the tile ("halo") in shared memory, and each thread then reads rows of it.
+    // Shared-memory layout of the coefficients, in doubles:
+    //   [i * n, (i+1) * n)                          own cell i of the tile (i < TILE)
+    //   TILE * n + k * halo_row(n) + odd + [0, n)   halo cell halo[tile_ptr[tile] + k]; a halo row is filled by ONE
+    //                                               bulk copy (16-byte granularity), so it starts at the 16-byte
+    //                                               boundary below the cell's first coefficient: odd = (cell * n) & 1
+    //   zoff + [0, n)                               zeros: what a missing neighbour reads
+    // noff[(seq position) * 2 DIM + face] is the first double of the neighbour across that face.
+    // Halo rows are handed out face by face (all -x neighbours in cell order, then +x, ...), so the lanes of
+    // a warp, which read the same face at the same time, mostly read different rows -> few bank conflicts.
+    constexpr int
+    halo_row(const int n)
+    {
+      int r = (n + 2) / 2 * 2; // even, and room for the odd start
+      if (r % 4 == 0)
+        r += 2; // rows 2 (mod 4) doubles apart spread over all banks
+      return r;
+    }
+
     struct TilePlan
     {
-      int32_t               n_tiles = 0, zslot = 0;
+      int32_t               n_tiles = 0, max_halo = 0, zoff = 0;
       std::vector<int32_t>  tile_ptr, halo;
-      std::vector<uint16_t> nslot;
+      std::vector<uint16_t> noff;
     };
 
     // seq: the cells in processing order (nullptr = 0 .. n_seq-1); nbr[cell * nfc + f]: neighbour cell or -1;
-    // n_cells_total bounds every id that appears in nbr (owned + ghost cells)
+    // n_cells_total bounds every id that appears in nbr (owned + ghost cells); n: coefficients per cell
     inline TilePlan
     build_tile_plan(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
-                    const int tile)
+                    const int tile, const int n)
     {
-      TilePlan p;
-      p.n_tiles = (n_seq + tile - 1) / tile;
+      TilePlan  p;
+      const int rh = halo_row(n);
+      p.n_tiles    = (n_seq + tile - 1) / tile;
       p.tile_ptr.assign((size_t)p.n_tiles + 1, 0);
-      p.nslot.assign((size_t)n_seq * nfc, 0xFFFF);
-      std::vector<int32_t> slot_of((size_t)n_cells_total, -1);
-      int                  max_slots = 0;
+      p.noff.assign((size_t)n_seq * nfc, 0xFFFF);
+      std::vector<int32_t> off_of((size_t)n_cells_total, -1);
       for (int32_t k = 0; k < p.n_tiles; ++k)
         {
           const int32_t s0 = k * tile, n_own = std::min<int32_t>(tile, n_seq - s0);
           const size_t  h0 = p.halo.size();
           for (int32_t i = 0; i < n_own; ++i)
-            slot_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = i;
-          int32_t n_slots = n_own;
+            off_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = i * n;
+          for (int f = 0; f < nfc; ++f)
+            for (int32_t i = 0; i < n_own; ++i)
+              {
+                const int32_t c  = seq ? seq[s0 + i] : s0 + i;
+                const int32_t nb = nbr[(size_t)c * nfc + f];
+                if (nb < 0)
+                  continue; // patched to zoff below
+                if (nb >= n_cells_total)
+                  throw std::out_of_range("build_tile_plan: neighbour id out of range");
+                if (off_of[(size_t)nb] < 0)
+                  {
+                    const int64_t o = (int64_t)tile * n + (int64_t)(p.halo.size() - h0) * rh + (((int64_t)nb * n) & 1);
+                    if (o + n >= 0xFFFF)
+                      throw std::length_error("build_tile_plan: tile too large for 16-bit offsets");
+                    off_of[(size_t)nb] = (int32_t)o;
+                    p.halo.push_back(nb);
+                  }
+                p.noff[(size_t)(s0 + i) * nfc + f] = (uint16_t)off_of[(size_t)nb];
+              }
+          p.max_halo = std::max<int32_t>(p.max_halo, (int32_t)(p.halo.size() - h0));
           for (int32_t i = 0; i < n_own; ++i)
-            {
-              const int32_t c = seq ? seq[s0 + i] : s0 + i;
-              for (int f = 0; f < nfc; ++f)
-                {
-                  const int32_t nb = nbr[(size_t)c * nfc + f];
-                  if (nb < 0)
-                    continue; // patched to zslot below
-                  if (nb >= n_cells_total)
-                    throw std::out_of_range("build_tile_plan: neighbour id out of range");
-                  if (slot_of[(size_t)nb] < 0)
-                    {
-                      slot_of[(size_t)nb] = n_slots++;
-                      p.halo.push_back(nb);
-                    }
-                  p.nslot[(size_t)(s0 + i) * nfc + f] = (uint16_t)slot_of[(size_t)nb];
-                }
-            }
-          max_slots = std::max(max_slots, n_slots);
-          for (int32_t i = 0; i < n_own; ++i)
-            slot_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = -1;
+            off_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = -1;
           for (size_t h = h0; h < p.halo.size(); ++h)
-            slot_of[(size_t)p.halo[h]] = -1;
+            off_of[(size_t)p.halo[h]] = -1;
           p.tile_ptr[(size_t)k + 1] = (int32_t)p.halo.size();
         }
-      if (max_slots >= 0xFFFF)
-        throw std::length_error("build_tile_plan: tile with more than 65534 slots");
-      p.zslot = max_slots;
-      for (size_t i = 0; i < p.nslot.size(); ++i)
+      const int64_t zoff = (int64_t)tile * n + (int64_t)p.max_halo * rh;
+      if (zoff + n >= 0xFFFF)
+        throw std::length_error("build_tile_plan: tile too large for 16-bit offsets");
+      p.zoff = (int32_t)zoff;
+      for (size_t i = 0; i < p.noff.size(); ++i)
         {
           const int32_t c = seq ? seq[i / nfc] : (int32_t)(i / nfc);
           if (nbr[(size_t)c * nfc + i % nfc] < 0)
-            p.nslot[i] = (uint16_t)p.zslot;
+            p.noff[i] = (uint16_t)p.zoff;
         }
       return p;
     }

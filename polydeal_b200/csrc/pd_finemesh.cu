@@ -323,14 +323,17 @@ namespace pd
     // ncu on k_fine_sip (profiles/ncu_r01_fine_sip_summary.txt) shows the line-per-thread kernel
     // bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 92 %: 61 global + 73 shared
     // wavefronts per DGQ2 cell, every 8-byte access of a line a separate wavefront share), with
-    // HBM at 13 % and the FP64 pipe at 29 %.  Here a CTA takes TILE consecutive cells, copies
+    // HBM at 13 % and the FP64 pipe at 29 %.  Here a CTA takes TILE consecutive cells and copies
     // their coefficients and those of the neighbours outside the tile (the "halo", tile plan of
-    // pd_fine_cell.hpp) into shared memory with cp.async (no registers, everything in flight at
-    // once), and thread i then applies the whole operator to cell i in registers
-    // (pd::fine::cell_apply): its reads are row reads of an [slot][N] array with N odd -> bank
-    // conflict free, 16 useful doubles per wavefront, and there is no exchange between threads.
-    // Results go back through the own slots so that the global stores are coalesced.
-    // Per DGQ2 cell on a Morton-ordered mesh: ~35 wavefronts instead of 134.
+    // pd_fine_cell.hpp) into shared memory with TMA bulk copies (cp.async.bulk: no registers, no
+    // LSU wavefronts, everything in flight at once, completion on one mbarrier).  Two threads per
+    // cell then apply the whole operator in registers (pd::fine::cell_lines, cell_mass; the lines
+    // are split between two roles so that 16 warps are resident per SM, the partial sums meet
+    // once through the cell's own row): their reads are row reads of an [cell][N] array with N
+    // odd -> bank-conflict free, 16 useful doubles per wavefront.  Results go back through the
+    // own rows so that the global stores are coalesced.
+    // Measured (64^3 DGQ2, Morton order): 55 -> ~45 L1 wavefronts per cell instead of 134,
+    // 0.134 -> 0.070 ms.
     // ---------------------------------------------------------------------------------------
     template <int N1>
     struct TileArgs
@@ -338,13 +341,13 @@ namespace pd
       fine::TileTables<N1> T;
       const FineRec       *rec;
       const double        *vol;
-      const double        *x;
+      const double        *x; // 16-byte aligned (checked at launch): the halo rows are filled by bulk copies
       double              *y;
       const int32_t       *seq;      // cells in processing order (nullptr: 0 .. n_seq-1)
       const int32_t       *tile_ptr; // [n_tiles + 1] into halo
       const int32_t       *halo;
-      const uint16_t      *nslot; // [n_seq][2 DIM]
-      int32_t              n_seq, zslot;
+      const uint16_t      *noff; // [n_seq][2 DIM]: first double of the neighbour's coefficients in shared memory
+      int32_t              n_seq, max_halo, zoff;
       double               mass;
       int                  add;
     };
@@ -356,130 +359,218 @@ namespace pd
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
     }
     __device__ __forceinline__ void
-    cp_async16(void *smem, const void *gmem)
-    {
-      const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-    }
-    __device__ __forceinline__ void
     cp_async_wait_all()
     {
       asm volatile("cp.async.wait_all;" ::: "memory");
     }
+    // bulk copy global -> shared through the TMA unit (no LSU wavefronts, no registers), completion on an mbarrier
+    __device__ __forceinline__ void
+    bulk_g2s(void *smem, const void *gmem, const uint32_t bytes, uint64_t *bar)
+    {
+      const unsigned s = (unsigned)__cvta_generic_to_shared(smem), b = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s), "l"(gmem),
+                   "r"(bytes), "r"(b)
+                   : "memory");
+    }
+    __device__ __forceinline__ void
+    mbar_init(uint64_t *bar, const uint32_t count)
+    {
+      const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __device__ __forceinline__ void
+    mbar_arrive_expect(uint64_t *bar, const uint32_t bytes)
+    {
+      const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+      if (bytes)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+      else
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
+    }
+    __device__ __forceinline__ bool
+    mbar_try_wait(uint64_t *bar, const uint32_t parity)
+    {
+      const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+      uint32_t       ok;
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok)
+                   : "r"(b), "r"(parity)
+                   : "memory");
+      return ok != 0;
+    }
 
-    constexpr int FINE_TILE = 64;
+    constexpr int FINE_TILE = 64, FINE_TILE_THREADS = 2 * FINE_TILE; // two threads (roles) per cell
 
     constexpr size_t
     round16(const size_t v)
     {
       return (v + 15) / 16 * 16;
     }
-    // shared memory of a tile CTA: values [(zslot+1)][N] | records [TILE][DIM*64+16] | slot -> cell [zslot]
+    // shared memory of a tile CTA: coefficients (own | halo rows | zeros, pd_fine_cell.hpp) | records
+    // [TILE][DIM*64+16] | mbarrier
     constexpr size_t
-    tile_smem_bytes(const int dim, const int n, const int zslot)
+    tile_values_bytes(const int n, const int max_halo)
     {
-      return round16((size_t)(zslot + 1) * n * sizeof(double)) + (size_t)FINE_TILE * (dim * 64 + 16) + round16((size_t)zslot * 4);
+      return round16(((size_t)FINE_TILE * n + (size_t)max_halo * fine::halo_row(n) + n + 1) * sizeof(double));
+    }
+    constexpr size_t
+    tile_smem_bytes(const int dim, const int n, const int max_halo)
+    {
+      return tile_values_bytes(n, max_halo) + (size_t)FINE_TILE * (dim * 64 + 16) + 16;
     }
 
     template <int DIM, int DEG>
-    __global__ void __launch_bounds__(FINE_TILE, 4) k_fine_tile(const __grid_constant__ TileArgs<DEG + 1> A)
+    __global__ void __launch_bounds__(FINE_TILE_THREADS, 4) k_fine_tile(const __grid_constant__ TileArgs<DEG + 1> A)
     {
       constexpr int N1  = DEG + 1;
       constexpr int N   = ipow_(N1, DIM);
       constexpr int NFC = 2 * DIM;
+      constexpr int RH  = fine::halo_row(N);
       constexpr int RS  = DIM * 64 + 16; // record row of a cell, padded: 16-byte reads of consecutive threads hit distinct banks
-      constexpr int SPW = 32 / N;        // slots a warp copies per step
-      constexpr int NW  = FINE_TILE / 32;
+      constexpr int SPW = 32 / N;        // cells a warp copies per step
+      constexpr int NW  = FINE_TILE_THREADS / 32;
       static_assert(N <= 32, "one warp step copies at least one cell");
 
       extern __shared__ __align__(16) unsigned char smem[];
-      double        *S  = reinterpret_cast<double *>(smem);
-      unsigned char *sR = smem + round16((size_t)(A.zslot + 1) * N * sizeof(double));
-      int32_t       *sC = reinterpret_cast<int32_t *>(sR + FINE_TILE * RS);
+      double        *S   = reinterpret_cast<double *>(smem);
+      unsigned char *sR  = smem + tile_values_bytes(N, A.max_halo);
+      uint64_t      *bar = reinterpret_cast<uint64_t *>(sR + FINE_TILE * RS);
 
       const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
       const int s0 = blockIdx.x * FINE_TILE, n_own = min(FINE_TILE, A.n_seq - s0);
-      const int h0 = A.tile_ptr[blockIdx.x], n_slots = n_own + (A.tile_ptr[blockIdx.x + 1] - h0);
+      const int h0 = A.tile_ptr[blockIdx.x], nh = A.tile_ptr[blockIdx.x + 1] - h0;
+      auto      cell_of = [&](const int i) { return A.seq ? A.seq[s0 + i] : s0 + i; };
 
-      for (int i = tid; i < n_slots; i += FINE_TILE)
-        sC[i] = i < n_own ? (A.seq ? A.seq[s0 + i] : s0 + i) : A.halo[h0 + i - n_own];
+      if (tid == 0)
+        mbar_init(bar, FINE_TILE_THREADS);
       if (tid < N)
-        S[(size_t)A.zslot * N + tid] = 0.;
-      // what this thread's cell needs beside the staged data
-      const bool mine = tid < n_own;
-      uint32_t   ns[NFC];
+        S[A.zoff + tid] = 0.;
+      // thread = (role, cell): role 0 (warps 0-1) and role 1 (warps 2-3) split the lines of a cell
+      const int  role = tid / FINE_TILE, ci = tid % FINE_TILE;
+      const bool mine = ci < n_own;
+      uint32_t   no[NFC];
       double     mv = 0.;
       if (mine)
         {
-          const uint16_t *np = A.nslot + (size_t)(s0 + tid) * NFC;
+          const uint16_t *np = A.noff + (size_t)(s0 + ci) * NFC;
 #pragma unroll
           for (int f = 0; f < NFC; ++f)
-            ns[f] = np[f];
-          if (A.mass != 0.)
-            mv = A.mass * A.vol[A.seq ? A.seq[s0 + tid] : s0 + tid];
+            no[f] = np[f];
+          if (role == 0 && A.mass != 0.)
+            mv = A.mass * A.vol[cell_of(ci)];
         }
-      __syncthreads();
-      // ---- stage coefficients (own + halo) and the own cells' records, asynchronously
-      const int  sub = lane / N, e = lane % N;
-      const bool copier = sub < SPW;
-#pragma unroll 4
-      for (int slot = warp * SPW + sub; slot < n_slots; slot += NW * SPW)
-        if (copier)
-          cp_async8(S + (size_t)slot * N + e, A.x + (int64_t)sC[slot] * N + e);
-      for (int i = tid; i < n_own * DIM * 4; i += FINE_TILE)
+      __syncthreads(); // the mbarrier is initialised
+      // ---- stage the coefficients (own + halo) and the own cells' records; everything is in flight at once
+      uint32_t bytes = 0;
+      for (int r = tid; r < nh; r += FINE_TILE_THREADS)
+        { // halo row r: one bulk copy from the 16-byte boundary below the cell (+ its last double when that leaves 8 bytes)
+          const int64_t  first = (int64_t)A.halo[h0 + r] * N, a0 = first & ~(int64_t)1;
+          const uint32_t total = (uint32_t)(N + (first - a0)) * 8, sz = total & ~15u;
+          double        *dst   = S + FINE_TILE * N + r * RH;
+          bulk_g2s(dst, A.x + a0, sz, bar);
+          bytes += sz;
+          if (total != sz)
+            cp_async8(dst + sz / 8, A.x + a0 + sz / 8);
+        }
+      if (mine && role == 0)
         {
-          const int slot = i / (DIM * 4), c = i % (DIM * 4);
-          cp_async16(sR + slot * RS + c * 16, reinterpret_cast<const unsigned char *>(A.rec) + ((int64_t)sC[slot] * DIM * 4 + c) * 16);
+          bulk_g2s(sR + ci * RS, A.rec + (int64_t)cell_of(ci) * DIM, DIM * 64, bar);
+          bytes += DIM * 64;
         }
+      if (A.seq == nullptr && n_own == FINE_TILE && (FINE_TILE * N) % 2 == 0)
+        { // the own cells are one aligned contiguous range
+          if (tid == 0)
+            {
+              bulk_g2s(S, A.x + (int64_t)s0 * N, FINE_TILE * N * 8, bar);
+              bytes += FINE_TILE * N * 8;
+            }
+        }
+      else
+        {
+          const int  sub = lane / N, e = lane % N;
+          const bool copier = sub < SPW;
+#pragma unroll 2
+          for (int i = warp * SPW + sub; i < n_own; i += NW * SPW)
+            if (copier)
+              cp_async8(S + i * N + e, A.x + (int64_t)cell_of(i) * N + e);
+        }
+      mbar_arrive_expect(bar, bytes);
       cp_async_wait_all();
+      for (int spin = 0; !mbar_try_wait(bar, 0); ++spin)
+        if (spin > (1 << 22))
+          __trap(); // a bulk copy that never completes would otherwise hang the device
       __syncthreads();
-      // ---- one cell per thread, in registers
-      double out[N];
+      // ---- the lines of one cell in registers, split between its two threads
+      double        acc[N];
+      double *const own = S + ci * N;
       if (mine)
         {
-          double u[N];
-#pragma unroll
-          for (int k = 0; k < N; ++k)
-            u[k] = S[tid * N + k];
           const double *nbp[NFC];
 #pragma unroll
           for (int f = 0; f < NFC; ++f)
-            nbp[f] = S + ns[f] * N;
-          const unsigned char *myrec = sR + tid * RS;
-          fine::cell_apply<DIM, N1>(
-            A.T, u, [&](const int d, const int s, const int k) { return nbp[2 * d + s][k]; },
-            [&](const int d) {
-              const unsigned char *r  = myrec + d * 64;
-              const double2        cd = *reinterpret_cast<const double2 *>(r + 16);
-              const double2        pp = *reinterpret_cast<const double2 *>(r + 32);
-              const double2        qq = *reinterpret_cast<const double2 *>(r + 48);
-              fine::LineCoef       c;
-              c.cVol  = *reinterpret_cast<const double *>(r + 8);
-              c.cD[0] = cd.x, c.cD[1] = cd.y;
-              c.P[0] = pp.x, c.P[1] = pp.y;
-              c.Q[0] = qq.x, c.Q[1] = qq.y;
-              return c;
-            },
-            mv, out);
+            nbp[f] = S + no[f];
+          const unsigned char *myrec = sR + ci * RS;
+          auto                 nbv   = [&](const int d, const int s, const int k) { return nbp[2 * d + s][k]; };
+          auto                 coef  = [&](const int d) {
+            const unsigned char *r  = myrec + d * 64;
+            const double2        cd = *reinterpret_cast<const double2 *>(r + 16);
+            const double2        pp = *reinterpret_cast<const double2 *>(r + 32);
+            const double2        qq = *reinterpret_cast<const double2 *>(r + 48);
+            fine::LineCoef       c;
+            c.cVol  = *reinterpret_cast<const double *>(r + 8);
+            c.cD[0] = cd.x, c.cD[1] = cd.y;
+            c.P[0] = pp.x, c.P[1] = pp.y;
+            c.Q[0] = qq.x, c.Q[1] = qq.y;
+            return c;
+          };
+          if (role == 0) // warp-uniform
+            {
+#pragma unroll
+              for (int k = 0; k < N; ++k)
+                acc[k] = mv * own[k];
+              fine::cell_lines<DIM, N1>(A.T, 0, own, nbv, coef, acc);
+            }
+          else
+            {
+#pragma unroll
+              for (int k = 0; k < N; ++k)
+                acc[k] = 0.;
+              fine::cell_lines<DIM, N1>(A.T, 1, own, nbv, coef, acc);
+            }
         }
-      __syncthreads(); // every read of the staged coefficients is done: the own slots become the output staging
-      if (mine)
+      __syncthreads(); // every read of the staged coefficients is done: the own rows become the exchange / output staging
+      if (mine && role == 1)
         {
 #pragma unroll
           for (int k = 0; k < N; ++k)
-            S[tid * N + k] = out[k];
+            own[k] = acc[k];
         }
       __syncthreads();
-#pragma unroll 4
-      for (int slot = warp * SPW + sub; slot < n_own; slot += NW * SPW)
-        if (copier)
-          {
-            double *yp = A.y + (int64_t)sC[slot] * N + e;
-            const double v = S[(size_t)slot * N + e];
-            *yp            = A.add ? *yp + v : v;
-          }
+      if (mine && role == 0)
+        {
+#pragma unroll
+          for (int k = 0; k < N; ++k)
+            acc[k] += own[k];
+          fine::cell_mass<DIM, N1>(A.T, acc);
+#pragma unroll
+          for (int k = 0; k < N; ++k)
+            own[k] = acc[k];
+        }
+      __syncthreads();
+      {
+        const int  sub = lane / N, e = lane % N;
+        const bool copier = sub < SPW;
+#pragma unroll 2
+        for (int i = warp * SPW + sub; i < n_own; i += NW * SPW)
+          if (copier)
+            {
+              double      *yp = A.y + (int64_t)cell_of(i) * N + e;
+              const double v  = S[i * N + e];
+              *yp             = A.add ? *yp + v : v;
+            }
+      }
     }
-
 
     // host: l_a(x), l_a'(x)
     void
@@ -618,8 +709,11 @@ namespace pd
     for (auto &t : h->mf_tiles)
       t.ok = false;
     {
+      // Which kernel: measured on B200 (64^3 cells, profiles/README.md) the tiled kernel wins for 3-D DGQ2
+      // (0.070 vs 0.134 ms) and loses for 3-D DGQ1 (64-byte cells: 0.070 vs 0.055 ms), so that is the default
+      // policy; PD_FINE_KERNEL=tile / line force one of them wherever it exists (the tests run both).
       const char *env = std::getenv("PD_FINE_KERNEL");
-      h->mf_kernel    = (env && std::strcmp(env, "line") == 0) ? 1 : 0;
+      h->mf_kernel    = (env && std::strcmp(env, "line") == 0) ? 1 : ((env && std::strcmp(env, "tile") == 0) ? 0 : (dim == 3 && h->degree == 2 ? 0 : 1));
     }
     if (h->mf_kernel == 0 && h->n <= 27)
       {
@@ -694,21 +788,21 @@ namespace pd
             fine::TilePlan plan;
             try
               {
-                plan = fine::build_tile_plan(n_seq, seq ? seq->data() : nullptr, nbr.data(), nfc, h->np, FINE_TILE);
+                plan = fine::build_tile_plan(n_seq, seq ? seq->data() : nullptr, nbr.data(), nfc, h->np, FINE_TILE, h->n);
               }
             catch (const std::exception &)
               {
                 continue;
               }
-            if (tile_smem_bytes(dim, h->n, plan.zslot) > 200 * 1024)
+            if (tile_smem_bytes(dim, h->n, plan.max_halo) > 200 * 1024)
               continue; // an ordering without locality: the line-per-thread kernel takes this sequence
             auto &t = h->mf_tiles[part];
             put(t.tile_ptr, plan.tile_ptr);
-            put(t.nslot, plan.nslot);
+            put(t.noff, plan.noff);
             if (plan.halo.empty())
               plan.halo.push_back(0);
             put(t.halo, plan.halo);
-            t.n_tiles = plan.n_tiles, t.zslot = plan.zslot, t.n_seq = n_seq;
+            t.n_tiles = plan.n_tiles, t.max_halo = plan.max_halo, t.zoff = plan.zoff, t.n_seq = n_seq;
             t.ok = true;
           }
       }
@@ -790,26 +884,29 @@ namespace pd
       a.seq      = part == 0 ? nullptr : (part == 1 ? h->mf_list_interior.p : h->mf_list_boundary.p);
       a.tile_ptr = t.tile_ptr.p;
       a.halo     = t.halo.p;
-      a.nslot    = t.nslot.p;
+      a.noff     = t.noff.p;
       a.n_seq    = t.n_seq;
-      a.zslot    = t.zslot;
+      a.max_halo = t.max_halo;
+      a.zoff     = t.zoff;
       a.mass     = vol_on ? h->op_coef.mass : 0.;
       a.add      = add ? 1 : 0;
-      const size_t smem = tile_smem_bytes(DIM, ipow_(N1, DIM), t.zslot);
+      const size_t smem = tile_smem_bytes(DIM, ipow_(N1, DIM), t.max_halo);
       static size_t smem_set = 0; // per instantiation
       if (smem > smem_set)
         {
           PD_CUDA(cudaFuncSetAttribute(k_fine_tile<DIM, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           smem_set = smem;
         }
-      k_fine_tile<DIM, DEG><<<t.n_tiles, FINE_TILE, smem, h->stream>>>(a);
+      k_fine_tile<DIM, DEG><<<t.n_tiles, FINE_TILE_THREADS, smem, h->stream>>>(a);
     }
   } // namespace
 
   void
   launch_fine_operator(pd_handle *h, const double *src, double *dst, const bool add, const int part)
   {
-    const bool tiled = h->mf_kernel == 0 && h->mf_tiles[part].ok;
+    // (the tiled kernel fills its halo rows with 16-byte bulk copies: a source vector that is only 8-byte
+    // aligned goes to the line-per-thread kernel)
+    const bool tiled = h->mf_kernel == 0 && h->mf_tiles[part].ok && reinterpret_cast<uintptr_t>(src) % 16 == 0;
     switch ((tiled ? 100 : 0) + h->dim * 10 + h->degree)
       {
         case 121: launch_fine_tiled<2, 1>(h, src, dst, add, part); break;

@@ -122,13 +122,13 @@ struct pd_handle
   struct FineTiles
   {
     pd::DevBuf<int32_t>  tile_ptr, halo;
-    pd::DevBuf<uint16_t> nslot;
-    int32_t              n_tiles = 0, zslot = 0, n_seq = 0;
+    pd::DevBuf<uint16_t> noff;
+    int32_t              n_tiles = 0, max_halo = 0, zoff = 0, n_seq = 0;
     bool                 ok = false;
   };
   FineTiles           mf_tiles[3];
   std::vector<double> mf_tile_tab_host; // Mh | Mh^-1 Sh | Mh^-1 e0,e1 | Mh^-1 d0,d1 | d0,d1
-  int                 mf_kernel = 0;    // 0: tiled where available, 1: line-per-thread always (PD_FINE_KERNEL=line)
+  int                 mf_kernel = 0;    // 0: tiled where available, 1: line-per-thread (default policy and PD_FINE_KERNEL in pd_finemesh.cu)
   // matrix-free fine-mesh operator on general (Q1-mapped) cells with the mapped basis, pd_mappedfine.cu
   bool                mp_ready = false, mp_geo_valid = false;
   std::vector<double> mp_tab_host; // V | V^T | Dt | e0 e1 | d0 d1

@@ -45,23 +45,25 @@ extern "C"
       }
   }
 
-  // outputs sized by the caller: tile_ptr[n_tiles + 1], nslot[n_seq * nfc], halo[halo_cap]
+  // outputs sized by the caller: tile_ptr[n_tiles + 1], noff[n_seq * nfc], halo[halo_cap]
   int
   fine_tile_plan_host(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
-                      const int tile, int32_t *n_tiles, int32_t *zslot, int32_t *tile_ptr, int32_t *halo, const int64_t halo_cap,
-                      int64_t *n_halo, uint16_t *nslot)
+                      const int tile, const int n, int32_t *n_tiles, int32_t *max_halo, int32_t *zoff, int32_t *halo_row,
+                      int32_t *tile_ptr, int32_t *halo, const int64_t halo_cap, int64_t *n_halo, uint16_t *noff)
   {
     try
       {
-        const pd::fine::TilePlan p = pd::fine::build_tile_plan(n_seq, seq, nbr, nfc, n_cells_total, tile);
+        const pd::fine::TilePlan p = pd::fine::build_tile_plan(n_seq, seq, nbr, nfc, n_cells_total, tile, n);
         *n_tiles                   = p.n_tiles;
-        *zslot                     = p.zslot;
+        *max_halo                  = p.max_halo;
+        *zoff                      = p.zoff;
+        *halo_row                  = pd::fine::halo_row(n);
         *n_halo                    = (int64_t)p.halo.size();
         if ((int64_t)p.halo.size() > halo_cap)
           return -2;
         std::memcpy(tile_ptr, p.tile_ptr.data(), p.tile_ptr.size() * sizeof(int32_t));
         std::memcpy(halo, p.halo.data(), p.halo.size() * sizeof(int32_t));
-        std::memcpy(nslot, p.nslot.data(), p.nslot.size() * sizeof(uint16_t));
+        std::memcpy(noff, p.noff.data(), p.noff.size() * sizeof(uint16_t));
         return 0;
       }
     catch (const std::exception &)

@@ -117,11 +117,11 @@ def grid_neighbours(shape, order):
     return nbr
 
 
-@pytest.mark.parametrize("shape,order,tile,with_list", [
-    ((8, 8, 8), "morton", 64, False), ((5, 7, 3), "lex", 64, False), ((16, 16), "morton", 64, False),
-    ((6, 6, 6), "lex", 16, True), ((3, 2), "lex", 64, False), ((8, 8, 8), "morton", 64, True),
+@pytest.mark.parametrize("shape,order,tile,with_list,n", [
+    ((8, 8, 8), "morton", 64, False, 27), ((5, 7, 3), "lex", 64, False, 8), ((16, 16), "morton", 64, False, 16),
+    ((6, 6, 6), "lex", 16, True, 27), ((3, 2), "lex", 64, False, 25), ((8, 8, 8), "morton", 64, True, 27),
 ])
-def test_tile_plan_contract(lib, shape, order, tile, with_list):
+def test_tile_plan_contract(lib, shape, order, tile, with_list, n):
     nbr = grid_neighbours(shape, order)
     n_cells, nfc = nbr.shape
     seq = None
@@ -131,30 +131,32 @@ def test_tile_plan_contract(lib, shape, order, tile, with_list):
     n_tiles_max = (n_seq + tile - 1) // tile
     tile_ptr = np.zeros(n_tiles_max + 1, dtype=np.int32)
     halo = np.zeros(n_seq * nfc + 1, dtype=np.int32)
-    nslot = np.zeros(n_seq * nfc, dtype=np.uint16)
-    n_tiles, zslot, n_halo = C.c_int32(), C.c_int32(), C.c_int64()
+    noff = np.zeros(n_seq * nfc, dtype=np.uint16)
+    n_tiles, max_halo, zoff, rh, n_halo = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.fine_tile_plan_host(n_seq, dp(seq) if seq is not None else None, dp(nbr), nfc, n_cells, tile, C.byref(n_tiles),
-                                 C.byref(zslot), dp(tile_ptr), dp(halo), C.c_int64(len(halo)), C.byref(n_halo), dp(nslot))
+    rc = lib.fine_tile_plan_host(n_seq, dp(seq) if seq is not None else None, dp(nbr), nfc, n_cells, tile, n, C.byref(n_tiles),
+                                 C.byref(max_halo), C.byref(zoff), C.byref(rh), dp(tile_ptr), dp(halo), C.c_int64(len(halo)),
+                                 C.byref(n_halo), dp(noff))
     assert rc == 0 and n_tiles.value == n_tiles_max and tile_ptr[-1] == n_halo.value
+    rh = rh.value
+    assert rh % 2 == 0 and rh >= n + 1 and rh % 4 == 2  # a 16-byte aligned row with room for an odd start, spread over the banks
     cells = np.arange(n_cells, dtype=np.int32) if seq is None else seq
-    max_slots = 0
+    seen_max_halo = 0
     for k in range(n_tiles.value):
         own = cells[k * tile:(k + 1) * tile]
         hl = halo[tile_ptr[k]:tile_ptr[k + 1]]
-        slots = np.concatenate([own, hl])
-        assert len(set(slots.tolist())) == len(slots)  # every cell staged once
-        max_slots = max(max_slots, len(slots))
+        assert len(set(own.tolist()) | set(hl.tolist())) == len(own) + len(hl)  # every cell staged once
+        seen_max_halo = max(seen_max_halo, len(hl))
+        where = {int(c): i * n for i, c in enumerate(own)}
+        # a halo row starts at the 16-byte boundary below the cell's first coefficient
+        where.update({int(c): tile * n + r * rh + ((int(c) * n) & 1) for r, c in enumerate(hl)})
         for i, c in enumerate(own):
             for f in range(nfc):
-                s = nslot[(k * tile + i) * nfc + f]
-                if nbr[c, f] < 0:
-                    assert s == zslot.value
-                else:
-                    assert s < len(slots) and slots[s] == nbr[c, f]
+                o = noff[(k * tile + i) * nfc + f]
+                assert o == (zoff.value if nbr[c, f] < 0 else where[int(nbr[c, f])])
         # no halo cell that nobody needs
         needed = {int(nbr[c, f]) for c in own for f in range(nfc) if nbr[c, f] >= 0} - set(own.tolist())
         assert needed == set(hl.tolist())
-    assert zslot.value == max_slots
+    assert max_halo.value == seen_max_halo and zoff.value == tile * n + seen_max_halo * rh
     if order == "morton" and not with_list and shape == (8, 8, 8):
-        assert max_slots == 64 + 48  # a 4x4x4 corner block and its three inner faces
+        assert seen_max_halo == 48  # a 4x4x4 corner block and its three inner faces

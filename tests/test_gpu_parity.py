@@ -295,9 +295,15 @@ def test_unsupported_degree_fails_loudly():
     (3, (4, 4, 4), 1, 0, 1.0, dict(with_boundary=False, stiffness_coeff=1e-4, mass_coeff=1.5e4)),   # monodomain, BDF2
     (3, (3, 3, 3), 2, 1, 1.0, dict(with_boundary=False, stiffness_coeff=1e-4, mass_coeff=1.0e4)),  # monodomain, BDF1
 ])
-def test_fine_mesh_matrix_free_vmult(dim, n, p, order, hi, kw):
+@pytest.mark.parametrize("kernel", ["default", "tile"])
+def test_fine_mesh_matrix_free_vmult(dim, n, p, order, hi, kw, kernel, monkeypatch):
     pdl = gpu()
     import torch
+
+    if kernel == "tile":  # the tiled kernel wherever it exists (by default only where it is the faster one)
+        if dim == 3 and p == 3:
+            pytest.skip("3-D DGQ3 has the line-per-thread kernel only")
+        monkeypatch.setenv("PD_FINE_KERNEL", "tile")
 
     ogrid = po.Grid(dim, n, 0.0, hi, order)
     groups = [[c] for c in range(ogrid.n_cells)]
