@@ -419,11 +419,61 @@ def run_gpu(args):
     if world > 1:
         out["vmult"]["ms_with_nccl_exchange"] = t_vm_nccl_ms
         out["vmult"]["exchange"] = "publish + pull kernels over CUDA-IPC peer memory, epoch-flag handshake (pd_peer_*); NCCL all_to_all_single timed beside it"
+    if world == 1 and not args.no_mf_vmult:
+        out["mf_vmult"] = mf_vmult_fine_mesh(stream, flush, peaks, max(args.steps, 5))
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(full=True)
     print(json.dumps(out))
     if dist:
         dist.destroy_process_group()
+
+
+def mf_vmult_fine_mesh(stream, flush, peaks, steps):
+    """The second metric of BASELINE.json: the matrix-free sum-factorised SIP vmult of
+    examples/matrix_free_agglo.cc -- Utils::MatrixFreeOperators::LaplaceOperatorDG (include/utils.h:819-925) on
+    the fine hex mesh, hyper_cube refined 6x = 64^3 cells, FE_DGQ(2), 7.08 M DoFs -- through
+    pd_vmult(PD_VMULT_MATRIX_FREE), device vectors, L2 flushed between applies, CUDA events on the launch
+    stream.  Separate from the timed assembly steps above.  (Sharded: tools/run_fine_mf_scaling.py.)"""
+    import torch
+
+    import polydeal_b200 as pdl
+
+    n, p = 64, 2
+    grid = pdl.Grid.hyper_cube(3, 0.0, 1.0, 6)
+    ah = pdl.AgglomerationHandler(grid)
+    for c in range(n**3):
+        ah.define_agglomerate([c])
+    ah.initialize_fe_values(p + 1)
+    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, p)
+    op = pdl.SIPOperator(ah.flatten(penalty_constant=p * (p + 1.0), h_rule=pdl.H_NORMAL_EXTENT), keepalive=ah)
+    op.set_stream(stream.cuda_stream)
+    assert op.matrix_free_available
+    op.set_operator(pdl.ASSEMBLE_ALL, 1.0, 0.0)
+    N = op.m()
+    x = torch.from_numpy(np.sin(0.37 * np.arange(N)) + 0.01 * (np.arange(N) % 7)).cuda()
+    y = torch.empty_like(x)
+    l0 = op.launch_count
+    for _ in range(3):
+        op.vmult(y, x, mode=pdl.VMULT_MATRIX_FREE)
+    per_apply = (op.launch_count - l0 - 1) // 3  # the first apply also folds the stencil records
+    ms = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        op.vmult(y, x, mode=pdl.VMULT_MATRIX_FREE)
+        b.record(stream)
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    t = statistics.mean(ms)
+    nbytes = 16.0 * N + 3 * 64.0 * n**3  # read src + write dst (16 B/DoF, SURVEY 8d) + one 64-byte stencil record per (cell, direction)
+    return {"metric": "matrix-free SIP vmult GDoF/s (LaplaceOperatorDG on the fine mesh, examples/matrix_free_agglo.cc: 64^3 hexes, FE_DGQ(2))",
+            "value": N / (t * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t, "n_dofs": N, "applies": steps, "gpu_launches_per_apply": int(per_apply),
+            "kernel": "k_fine_tile<3,2> (one cell per thread pair, coefficients + halo staged in shared memory by TMA bulk copies)",
+            "checksum": float(y.sum()),
+            "roofline": {"bound": "hbm", "achieved": nbytes / (t * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": nbytes / (t * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_src"],
+                         "algorithmic_bytes_per_launch": nbytes}}
 
 
 def oracle_config_b():
@@ -485,6 +535,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mf-vmult", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

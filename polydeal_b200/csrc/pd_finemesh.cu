@@ -689,13 +689,43 @@ namespace pd
     };
     put(h->mf_geo, rec);
     put(h->mf_vol, vol);
+    // Processing order: the cells sorted along the Morton curve through their centres, so that consecutive
+    // cells are neighbours in space whatever the caller's numbering (a hyper_cube + refine_global mesh already
+    // is in this order); the tiled kernel's tiles then are compact blocks with a small halo.
+    std::vector<int32_t> morton_order((size_t)h->np_own);
+    {
+      std::vector<double> ctr((size_t)h->np_own * dim), lo(dim, 1e300), hmin(dim, 1e300);
+      for (int32_t p = 0; p < h->np_own; ++p)
+        for (int k = 0; k < dim; ++k)
+          {
+            const double a = d.bbox[(size_t)p * 2 * dim + k], b = d.bbox[(size_t)p * 2 * dim + dim + k];
+            ctr[(size_t)d.dof_block[p] * dim + k] = 0.5 * (a + b);
+            lo[k]   = std::min(lo[k], a);
+            hmin[k] = std::min(hmin[k], b - a);
+          }
+      std::vector<uint64_t> key((size_t)h->np_own, 0);
+      for (int32_t c = 0; c < h->np_own; ++c)
+        for (int k = 0; k < dim; ++k)
+          {
+            const uint64_t q = (uint64_t)std::min(2097151., std::floor((ctr[(size_t)c * dim + k] - lo[k]) / hmin[k]));
+            for (int b = 0; b < 21; ++b)
+              key[c] |= ((q >> b) & 1u) << (b * dim + k);
+          }
+      for (int32_t c = 0; c < h->np_own; ++c)
+        morton_order[c] = c;
+      std::stable_sort(morton_order.begin(), morton_order.end(), [&](const int32_t a, const int32_t b) { return key[a] < key[b]; });
+    }
+    bool identity_order = true;
+    for (int32_t c = 0; c < h->np_own; ++c)
+      identity_order = identity_order && morton_order[c] == c;
     // sharded handles: cells whose neighbours are all owned can be applied while the ghost blocks travel
     h->mf_list_interior.release();
     h->mf_list_boundary.release();
+    h->mf_seq_all.release();
+    std::vector<int32_t> inner, outer;
     if (h->np != h->np_own)
       {
-        std::vector<int32_t> inner, outer;
-        for (int32_t c = 0; c < h->np_own; ++c)
+        for (const int32_t c : morton_order)
           {
             bool ghost = false;
             for (int f = 0; f < nfc; ++f)
@@ -770,18 +800,9 @@ namespace pd
         bool unit = true;
         for (int i = 0; i < n1; ++i)
           unit = unit && std::fabs(e0[i] - (i == 0 ? 1. : 0.)) < 1e-14 && std::fabs(e0[n1 + i] - (i == n1 - 1 ? 1. : 0.)) < 1e-14;
-        std::vector<int32_t> inner, outer;
-        if (h->np != h->np_own)
-          for (int32_t c = 0; c < h->np_own; ++c)
-            {
-              bool ghost = false;
-              for (int f = 0; f < nfc; ++f)
-                ghost = ghost || nbr[(size_t)c * nfc + f] >= h->np_own;
-              (ghost ? outer : inner).push_back(c);
-            }
         for (int part = 0; unit && part < 3; ++part)
           {
-            const std::vector<int32_t> *seq = part == 0 ? nullptr : (part == 1 ? &inner : &outer);
+            const std::vector<int32_t> *seq = part == 0 ? (identity_order ? nullptr : &morton_order) : (part == 1 ? &inner : &outer);
             const int32_t               n_seq = seq ? (int32_t)seq->size() : h->np_own;
             if (n_seq == 0)
               continue;
@@ -794,8 +815,8 @@ namespace pd
               {
                 continue;
               }
-            if (tile_smem_bytes(dim, h->n, plan.max_halo) > 200 * 1024)
-              continue; // an ordering without locality: the line-per-thread kernel takes this sequence
+            if (tile_smem_bytes(dim, h->n, plan.max_halo) > 56 * 1024)
+              continue; // tiles with large halos (four CTAs no longer fit an SM): the line-per-thread kernel takes this sequence
             auto &t = h->mf_tiles[part];
             put(t.tile_ptr, plan.tile_ptr);
             put(t.noff, plan.noff);
@@ -804,6 +825,8 @@ namespace pd
             put(t.halo, plan.halo);
             t.n_tiles = plan.n_tiles, t.max_halo = plan.max_halo, t.zoff = plan.zoff, t.n_seq = n_seq;
             t.ok = true;
+            if (part == 0 && seq)
+              put(h->mf_seq_all, morton_order);
           }
       }
     h->mf_rec.alloc((size_t)h->np_own * dim * 8);
@@ -881,7 +904,8 @@ namespace pd
       a.vol      = h->mf_vol.p;
       a.x        = src;
       a.y        = dst;
-      a.seq      = part == 0 ? nullptr : (part == 1 ? h->mf_list_interior.p : h->mf_list_boundary.p);
+      a.seq      = part == 0 ? h->mf_seq_all.p /* nullptr: the cells are numbered along the curve already */ :
+                               (part == 1 ? h->mf_list_interior.p : h->mf_list_boundary.p);
       a.tile_ptr = t.tile_ptr.p;
       a.halo     = t.halo.p;
       a.noff     = t.noff.p;

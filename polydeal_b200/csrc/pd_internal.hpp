@@ -111,7 +111,8 @@ struct pd_handle
   // matrix-free fine-mesh operator (every polytope = one Cartesian cell), pd_finemesh.cu
   bool                mf_ready = false, force_generic_mf = false;
   pd::DevBuf<int32_t> spmv_list_interior, spmv_list_boundary; // sharded: block rows without / with ghost columns
-  pd::DevBuf<int32_t> mf_list_interior, mf_list_boundary; // sharded: cells without / with ghost neighbours
+  pd::DevBuf<int32_t> mf_list_interior, mf_list_boundary; // sharded: cells without / with ghost neighbours (Morton order)
+  pd::DevBuf<int32_t> mf_seq_all;                         // all owned cells in Morton order (empty: already numbered that way)
   pd::DevBuf<double>  mf_geo, mf_rec, mf_vol, mf_zero; // per (cell, direction) geometry / folded stencil records, cell volumes (pd_finemesh.cu)
   bool                mf_rec_valid = false;
   uint32_t            mf_rec_flags = 0;
