@@ -204,28 +204,36 @@ namespace pd
       return r;
     }
 
+    // Tiles are runs of at most TILE consecutive sequence entries that share a block key (cells of one aligned
+    // 4x4x4 / 8x8 block of the Morton curve): a list that leaves cells out (the interior / boundary split of a
+    // sharded apply) then still gets compact tiles, only smaller ones.
     struct TilePlan
     {
       int32_t               n_tiles = 0, max_halo = 0, zoff = 0;
-      std::vector<int32_t>  tile_ptr, halo;
+      std::vector<int32_t>  tile_first, tile_ptr, halo; // [n_tiles + 1]: first sequence entry / first halo cell of a tile
       std::vector<uint16_t> noff;
     };
 
-    // seq: the cells in processing order (nullptr = 0 .. n_seq-1); nbr[cell * nfc + f]: neighbour cell or -1;
+    // seq: the cells in processing order (nullptr = 0 .. n_seq-1); block_key[i]: block of sequence entry i
+    // (nullptr: tiles of `tile` consecutive entries); nbr[cell * nfc + f]: neighbour cell or -1;
     // n_cells_total bounds every id that appears in nbr (owned + ghost cells); n: coefficients per cell
     inline TilePlan
-    build_tile_plan(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
-                    const int tile, const int n)
+    build_tile_plan(const int32_t n_seq, const int32_t *seq, const uint64_t *block_key, const int32_t *nbr, const int nfc,
+                    const int32_t n_cells_total, const int tile, const int n)
     {
       TilePlan  p;
       const int rh = halo_row(n);
-      p.n_tiles    = (n_seq + tile - 1) / tile;
+      p.tile_first.push_back(0);
+      for (int32_t i = 1; i <= n_seq; ++i)
+        if (i == n_seq || i - p.tile_first.back() == tile || (block_key && block_key[i] != block_key[i - 1]))
+          p.tile_first.push_back(i);
+      p.n_tiles = (int32_t)p.tile_first.size() - 1;
       p.tile_ptr.assign((size_t)p.n_tiles + 1, 0);
       p.noff.assign((size_t)n_seq * nfc, 0xFFFF);
       std::vector<int32_t> off_of((size_t)n_cells_total, -1);
       for (int32_t k = 0; k < p.n_tiles; ++k)
         {
-          const int32_t s0 = k * tile, n_own = std::min<int32_t>(tile, n_seq - s0);
+          const int32_t s0 = p.tile_first[k], n_own = p.tile_first[k + 1] - s0;
           const size_t  h0 = p.halo.size();
           for (int32_t i = 0; i < n_own; ++i)
             off_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = i * n;

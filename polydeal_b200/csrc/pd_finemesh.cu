@@ -344,7 +344,8 @@ namespace pd
       const double        *x; // 16-byte aligned (checked at launch): the halo rows are filled by bulk copies
       double              *y;
       const int32_t       *seq;      // cells in processing order (nullptr: 0 .. n_seq-1)
-      const int32_t       *tile_ptr; // [n_tiles + 1] into halo
+      const int32_t       *tile_first; // [n_tiles + 1]: first sequence entry of a tile (at most FINE_TILE entries)
+      const int32_t       *tile_ptr;   // [n_tiles + 1] into halo
       const int32_t       *halo;
       const uint16_t      *noff; // [n_seq][2 DIM]: first double of the neighbour's coefficients in shared memory
       int32_t              n_seq, max_halo, zoff;
@@ -438,7 +439,7 @@ namespace pd
       uint64_t      *bar = reinterpret_cast<uint64_t *>(sR + FINE_TILE * RS);
 
       const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-      const int s0 = blockIdx.x * FINE_TILE, n_own = min(FINE_TILE, A.n_seq - s0);
+      const int s0 = A.tile_first[blockIdx.x], n_own = A.tile_first[blockIdx.x + 1] - s0;
       const int h0 = A.tile_ptr[blockIdx.x], nh = A.tile_ptr[blockIdx.x + 1] - h0;
       auto      cell_of = [&](const int i) { return A.seq ? A.seq[s0 + i] : s0 + i; };
 
@@ -478,7 +479,7 @@ namespace pd
           bulk_g2s(sR + ci * RS, A.rec + (int64_t)cell_of(ci) * DIM, DIM * 64, bar);
           bytes += DIM * 64;
         }
-      if (A.seq == nullptr && n_own == FINE_TILE && (FINE_TILE * N) % 2 == 0)
+      if (A.seq == nullptr && n_own == FINE_TILE && (s0 * N) % 2 == 0)
         { // the own cells are one aligned contiguous range
           if (tid == 0)
             {
@@ -692,7 +693,8 @@ namespace pd
     // Processing order: the cells sorted along the Morton curve through their centres, so that consecutive
     // cells are neighbours in space whatever the caller's numbering (a hyper_cube + refine_global mesh already
     // is in this order); the tiled kernel's tiles then are compact blocks with a small halo.
-    std::vector<int32_t> morton_order((size_t)h->np_own);
+    std::vector<int32_t>  morton_order((size_t)h->np_own);
+    std::vector<uint64_t> key((size_t)h->np_own, 0);
     {
       std::vector<double> ctr((size_t)h->np_own * dim), lo(dim, 1e300), hmin(dim, 1e300);
       for (int32_t p = 0; p < h->np_own; ++p)
@@ -703,7 +705,6 @@ namespace pd
             lo[k]   = std::min(lo[k], a);
             hmin[k] = std::min(hmin[k], b - a);
           }
-      std::vector<uint64_t> key((size_t)h->np_own, 0);
       for (int32_t c = 0; c < h->np_own; ++c)
         for (int k = 0; k < dim; ++k)
           {
@@ -806,10 +807,15 @@ namespace pd
             const int32_t               n_seq = seq ? (int32_t)seq->size() : h->np_own;
             if (n_seq == 0)
               continue;
+            // block of a sequence entry: the aligned 4x4x4 (3-D) / 8x8 (2-D) block of the curve, FINE_TILE cells
+            const int             block_bits = dim == 3 ? 2 : (dim == 2 ? 3 : 6);
+            std::vector<uint64_t> bkey((size_t)n_seq);
+            for (int32_t i = 0; i < n_seq; ++i)
+              bkey[i] = key[seq ? (*seq)[i] : i] >> (block_bits * dim);
             fine::TilePlan plan;
             try
               {
-                plan = fine::build_tile_plan(n_seq, seq ? seq->data() : nullptr, nbr.data(), nfc, h->np, FINE_TILE, h->n);
+                plan = fine::build_tile_plan(n_seq, seq ? seq->data() : nullptr, bkey.data(), nbr.data(), nfc, h->np, FINE_TILE, h->n);
               }
             catch (const std::exception &)
               {
@@ -818,6 +824,7 @@ namespace pd
             if (tile_smem_bytes(dim, h->n, plan.max_halo) > 56 * 1024)
               continue; // tiles with large halos (four CTAs no longer fit an SM): the line-per-thread kernel takes this sequence
             auto &t = h->mf_tiles[part];
+            put(t.tile_first, plan.tile_first);
             put(t.tile_ptr, plan.tile_ptr);
             put(t.noff, plan.noff);
             if (plan.halo.empty())
@@ -906,6 +913,7 @@ namespace pd
       a.y        = dst;
       a.seq      = part == 0 ? h->mf_seq_all.p /* nullptr: the cells are numbered along the curve already */ :
                                (part == 1 ? h->mf_list_interior.p : h->mf_list_boundary.p);
+      a.tile_first = t.tile_first.p;
       a.tile_ptr = t.tile_ptr.p;
       a.halo     = t.halo.p;
       a.noff     = t.noff.p;

@@ -45,15 +45,19 @@ extern "C"
       }
   }
 
-  // outputs sized by the caller: tile_ptr[n_tiles + 1], noff[n_seq * nfc], halo[halo_cap]
+  // outputs sized by the caller: tile_first[n_seq + 1], tile_ptr[n_seq + 1], noff[n_seq * nfc], halo[halo_cap]
   int
-  fine_tile_plan_host(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
-                      const int tile, const int n, int32_t *n_tiles, int32_t *max_halo, int32_t *zoff, int32_t *halo_row,
-                      int32_t *tile_ptr, int32_t *halo, const int64_t halo_cap, int64_t *n_halo, uint16_t *noff)
+  fine_tile_plan_host(const int32_t n_seq, const int32_t *seq, const uint64_t *block_key, const int32_t *nbr, const int nfc,
+                      const int32_t n_cells_total, const int tile, const int n, int32_t *n_tiles, int32_t *max_halo, int32_t *zoff,
+                      int32_t *halo_row, int32_t *tile_first, int32_t *tile_ptr, int32_t *halo, const int64_t halo_cap,
+                      int64_t *n_halo, uint16_t *noff)
   {
     try
       {
-        const pd::fine::TilePlan p = pd::fine::build_tile_plan(n_seq, seq, nbr, nfc, n_cells_total, tile, n);
+        const pd::fine::TilePlan p = pd::fine::build_tile_plan(n_seq, seq, block_key, nbr, nfc, n_cells_total, tile, n);
+        if ((int64_t)p.halo.size() > halo_cap)
+          return -2;
+        std::memcpy(tile_first, p.tile_first.data(), p.tile_first.size() * sizeof(int32_t));
         *n_tiles                   = p.n_tiles;
         *max_halo                  = p.max_halo;
         *zoff                      = p.zoff;

@@ -117,33 +117,49 @@ def grid_neighbours(shape, order):
     return nbr
 
 
-@pytest.mark.parametrize("shape,order,tile,with_list,n", [
-    ((8, 8, 8), "morton", 64, False, 27), ((5, 7, 3), "lex", 64, False, 8), ((16, 16), "morton", 64, False, 16),
-    ((6, 6, 6), "lex", 16, True, 27), ((3, 2), "lex", 64, False, 25), ((8, 8, 8), "morton", 64, True, 27),
+@pytest.mark.parametrize("shape,order,tile,with_list,n,blocks", [
+    ((8, 8, 8), "morton", 64, False, 27, True), ((5, 7, 3), "lex", 64, False, 8, False), ((16, 16), "morton", 64, False, 16, True),
+    ((6, 6, 6), "lex", 16, True, 27, False), ((3, 2), "lex", 64, False, 25, False), ((8, 8, 8), "morton", 64, True, 27, True),
+    ((8, 8, 8), "morton", 64, "interior", 27, True),
 ])
-def test_tile_plan_contract(lib, shape, order, tile, with_list, n):
+def test_tile_plan_contract(lib, shape, order, tile, with_list, n, blocks):
     nbr = grid_neighbours(shape, order)
     n_cells, nfc = nbr.shape
+    dim = len(shape)
     seq = None
-    if with_list:  # an arbitrary sub-sequence, like the interior / boundary lists of a sharded apply
-        seq = np.ascontiguousarray(np.arange(n_cells, dtype=np.int32)[::-1][::2])
+    if with_list == "interior":  # what a sharded apply does first: the cells that touch no boundary, in curve order
+        seq = np.ascontiguousarray(np.nonzero((nbr >= 0).all(axis=1))[0].astype(np.int32))
+    elif with_list:  # an arbitrary sub-sequence
+        seq = np.ascontiguousarray(np.arange(n_cells, dtype=np.int32)[::2])
     n_seq = n_cells if seq is None else len(seq)
-    n_tiles_max = (n_seq + tile - 1) // tile
-    tile_ptr = np.zeros(n_tiles_max + 1, dtype=np.int32)
+    cells = np.arange(n_cells, dtype=np.int32) if seq is None else seq
+    key = None
+    if blocks:  # Morton-numbered cells: the aligned block of 64 = cell id >> 6
+        key = np.ascontiguousarray((cells >> 6).astype(np.uint64))
+    tile_first = np.zeros(n_seq + 1, dtype=np.int32)
+    tile_ptr = np.zeros(n_seq + 1, dtype=np.int32)
     halo = np.zeros(n_seq * nfc + 1, dtype=np.int32)
     noff = np.zeros(n_seq * nfc, dtype=np.uint16)
     n_tiles, max_halo, zoff, rh, n_halo = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = lib.fine_tile_plan_host(n_seq, dp(seq) if seq is not None else None, dp(nbr), nfc, n_cells, tile, n, C.byref(n_tiles),
-                                 C.byref(max_halo), C.byref(zoff), C.byref(rh), dp(tile_ptr), dp(halo), C.c_int64(len(halo)),
-                                 C.byref(n_halo), dp(noff))
-    assert rc == 0 and n_tiles.value == n_tiles_max and tile_ptr[-1] == n_halo.value
+    rc = lib.fine_tile_plan_host(n_seq, dp(seq) if seq is not None else None, dp(key) if key is not None else None, dp(nbr), nfc,
+                                 n_cells, tile, n, C.byref(n_tiles), C.byref(max_halo), C.byref(zoff), C.byref(rh), dp(tile_first),
+                                 dp(tile_ptr), dp(halo), C.c_int64(len(halo)), C.byref(n_halo), dp(noff))
+    assert rc == 0
+    nt = n_tiles.value
+    assert tile_first[0] == 0 and tile_first[nt] == n_seq and tile_ptr[nt] == n_halo.value
     rh = rh.value
     assert rh % 2 == 0 and rh >= n + 1 and rh % 4 == 2  # a 16-byte aligned row with room for an odd start, spread over the banks
-    cells = np.arange(n_cells, dtype=np.int32) if seq is None else seq
     seen_max_halo = 0
-    for k in range(n_tiles.value):
-        own = cells[k * tile:(k + 1) * tile]
+    for k in range(nt):
+        s0, s1 = tile_first[k], tile_first[k + 1]
+        assert 0 < s1 - s0 <= tile
+        own = cells[s0:s1]
+        if key is None:
+            assert s1 - s0 == tile or k == nt - 1
+        else:  # a tile never straddles two blocks, and a block is not cut unless it is full
+            assert len(set(key[s0:s1].tolist())) == 1
+            assert s1 == n_seq or key[s1] != key[s0] or s1 - s0 == tile
         hl = halo[tile_ptr[k]:tile_ptr[k + 1]]
         assert len(set(own.tolist()) | set(hl.tolist())) == len(own) + len(hl)  # every cell staged once
         seen_max_halo = max(seen_max_halo, len(hl))
@@ -152,11 +168,13 @@ def test_tile_plan_contract(lib, shape, order, tile, with_list, n):
         where.update({int(c): tile * n + r * rh + ((int(c) * n) & 1) for r, c in enumerate(hl)})
         for i, c in enumerate(own):
             for f in range(nfc):
-                o = noff[(k * tile + i) * nfc + f]
+                o = noff[(s0 + i) * nfc + f]
                 assert o == (zoff.value if nbr[c, f] < 0 else where[int(nbr[c, f])])
         # no halo cell that nobody needs
         needed = {int(nbr[c, f]) for c in own for f in range(nfc) if nbr[c, f] >= 0} - set(own.tolist())
         assert needed == set(hl.tolist())
     assert max_halo.value == seen_max_halo and zoff.value == tile * n + seen_max_halo * rh
-    if order == "morton" and not with_list and shape == (8, 8, 8):
-        assert seen_max_halo == 48  # a 4x4x4 corner block and its three inner faces
+    if order == "morton" and shape == (8, 8, 8) and with_list is False:
+        assert nt == 8 and seen_max_halo == 48  # a 4x4x4 corner block and its three inner faces
+    if with_list == "interior":  # 6^3 interior cells: the eight 3x3x3 corners of the blocks, compact halos
+        assert nt == 8 and seen_max_halo <= 96
