@@ -235,6 +235,15 @@ def main():
             "x": floats_after("distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x: (\S+)"),
             "xplusy": floats_after("distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x\+y: (\S+)"),
         },
+        "distributed_poisson_sanity_check_02": {
+            "x": floats_after("distributed_poisson_sanity_check_02.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x: (\S+)"),
+            "xplusy": floats_after("distributed_poisson_sanity_check_02.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x\+y: (\S+)"),
+        },
+        "fully_distributed_poisson_sanity_check_01": {
+            "n_cells": floats_after("fully_distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"Number of cells: (\S+)"),
+            "x": floats_after("fully_distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x: (\S+)"),
+            "xplusy": floats_after("fully_distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x\+y: (\S+)"),
+        },
         "poisson": floats_after("poisson.output", r"(\d\.\d+)"),
     }
     with open(OUT, "w") as f:

@@ -1118,30 +1118,23 @@ def test_coarse_operator_from_matrix_free(goldens):
         assert abs(float(vc @ PtAPv) - round(gc)) <= 1e-11 and abs(gc - round(gc)) < 1e-12
 
 
-def test_distributed_poisson_sanity_check(goldens):
-    """test/polydeal/distributed_poisson_sanity_check_01 (mpirun=3): the energies 1 and 2 of x and x + y summed
-    over the ranks of a SHARDED assembly (owner-computes-rows, cut interfaces evaluated from the ghost polytope's
-    bounding box), three ranks emulated on one GPU; boundary terms dropped, penalty 10 max(1/hA, 1/hB)."""
-    pdl = gpu()
+def _sharded_energies(pdl, pah, owner, funcs, **penalty):
+    """sum over the ranks of u_owned . (A_rank u) for a SHARDED assembly (owner-computes-rows, cut interfaces
+    evaluated from the ghost polytope's bounding box), the ranks emulated one after the other on one GPU;
+    volume + interior-face terms only, as in the reference's sanity checks."""
     import torch
 
     from polydeal_b200 import distributed as pdd
 
-    g = goldens["distributed_poisson_sanity_check_01"]
-    ogrid = po.Grid(2, 32, 0.0, 1.0, 0)
-    groups = groups_for("random40", 2, 32, ogrid, 9)
-    _, pah = product_handler(ogrid, groups, 1, 3)
     usp = _dgq_unit_support_points(2, 1)
-    funcs = {"x": lambda X: X[:, 0], "xplusy": lambda X: X[:, 0] + X[:, 1], "one": lambda X: np.ones(len(X))}
     u = {k: np.empty(pah.n_dofs) for k in funcs}
     for k_ in range(pah.n_polytopes):
         lo, hi = pah.bbox(k_)
         for name, f in funcs.items():
             u[name][pah.get_dof_indices(k_)] = f(lo + usp * (hi - lo))
-    owner = pdd.partition_by_blocks(pah, 3)
     energy = {k: 0.0 for k in funcs}
-    for rank in range(3):
-        part = pdd.LocalPart(pah, owner, rank, penalty_constant=10.0, h_rule=pdl.H_MAX_INVERSE_DIAMETER)
+    for rank in range(int(owner.max()) + 1):
+        part = pdd.LocalPart(pah, owner, rank, **penalty)
         op = pdl.SIPOperator(part.desc, keepalive=(pah, part))
         op.assemble(pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR)
         rows = part.owned_global_dofs()
@@ -1152,5 +1145,71 @@ def test_distributed_poisson_sanity_check(goldens):
             op.vmult_ptr(yd.data_ptr(), xd.data_ptr())
             op.synchronize()
             energy[name] += float(u[name][rows] @ yd.cpu().numpy())
+    return energy
+
+
+_SANITY_FUNCS = {"x": lambda X: X[:, 0], "xplusy": lambda X: X[:, 0] + X[:, 1], "one": lambda X: np.ones(len(X))}
+
+
+def test_distributed_poisson_sanity_check(goldens):
+    """test/polydeal/distributed_poisson_sanity_check_01 (mpirun=3): the energies 1 and 2 of x and x + y summed
+    over the ranks of a sharded assembly, three ranks; boundary terms dropped, penalty 10 max(1/hA, 1/hB)."""
+    pdl = gpu()
+    from polydeal_b200 import distributed as pdd
+
+    g = goldens["distributed_poisson_sanity_check_01"]
+    ogrid = po.Grid(2, 32, 0.0, 1.0, 0)
+    groups = groups_for("random40", 2, 32, ogrid, 9)
+    _, pah = product_handler(ogrid, groups, 1, 3)
+    energy = _sharded_energies(pdl, pah, pdd.partition_by_blocks(pah, 3), _SANITY_FUNCS, penalty_constant=10.0,
+                               h_rule=pdl.H_MAX_INVERSE_DIAMETER)
+    assert abs(energy["x"] - g["x"][0]) <= 1e-11 and abs(energy["xplusy"] - g["xplusy"][0]) <= 1e-11
+    assert abs(energy["one"]) <= 1e-11
+
+
+def test_distributed_poisson_sanity_check_02(goldens):
+    """test/polydeal/distributed_poisson_sanity_check_02 (mpirun=3): [0,1]^2 refined 6x, every rank agglomerates ALL
+    of its locally owned cells into one polytope (p4est: three contiguous pieces of the Morton curve, 1365-1366
+    cells each), DGQ1, QGauss(3), penalty 1/1; three polytopes, one per rank (:115-156, 230-231)."""
+    pdl = gpu()
+    g = goldens["distributed_poisson_sanity_check_02"]
+    ogrid = po.Grid(2, 64, 0.0, 1.0, 0)
+    n = ogrid.n_cells
+    cuts = [n * r // 3 for r in range(4)]
+    groups = [list(range(cuts[r], cuts[r + 1])) for r in range(3)]
+    _, pah = product_handler(ogrid, groups, 1, 3)
+    energy = _sharded_energies(pdl, pah, np.arange(3, dtype=np.int32), _SANITY_FUNCS, penalty_constant=1.0,
+                               h_rule=pdl.H_CONSTANT, h_const=1.0)
+    assert abs(energy["x"] - g["x"][0]) <= 1e-11 and abs(energy["xplusy"] - g["xplusy"][0]) <= 1e-11
+    assert abs(energy["one"]) <= 1e-11
+
+
+def test_fully_distributed_poisson_sanity_check_01(goldens):
+    """test/polydeal/fully_distributed_poisson_sanity_check_01 (mpirun=3): [0,1]^2 refined 4x (256 cells), ranks =
+    strips floor(3 x_centre) (:48-66), METIS into 10 agglomerates inside every rank's region
+    (PolyUtils::partition_locally_owned_regions, include/poly_utils.h:629-704), DGQ1, QGauss(3), penalty 1/1.
+    METIS versions differ, so the partition is an input; the golden energies do not depend on it."""
+    pdl = gpu()
+    g = goldens["fully_distributed_poisson_sanity_check_01"]
+    ogrid = po.Grid(2, 16, 0.0, 1.0, 0)
+    assert ogrid.n_cells == int(g["n_cells"][0])
+    v, cv, nbr = ogrid.arrays()
+    centre_x = v[cv].mean(axis=1)[:, 0]
+    rank_of_cell = np.floor(centre_x * 3).astype(np.int32)
+    groups, owner = [], []
+    for r in range(3):
+        cells = np.nonzero(rank_of_cell == r)[0]
+        local = -np.ones(ogrid.n_cells, dtype=np.int64)
+        local[cells] = np.arange(len(cells))
+        adj = [[local[q] for q in nbr[c] if q >= 0 and local[q] >= 0] for c in cells]  # face graph of the owned region
+        xadj = np.concatenate([[0], np.cumsum([len(a) for a in adj])])
+        part = pdl.partition_graph(xadj, np.concatenate(adj), 10)
+        for k in range(10):
+            if (part == k).any():
+                groups.append(cells[part == k].tolist())
+                owner.append(r)
+    _, pah = product_handler(ogrid, groups, 1, 3)
+    energy = _sharded_energies(pdl, pah, np.array(owner, dtype=np.int32), _SANITY_FUNCS, penalty_constant=1.0,
+                               h_rule=pdl.H_CONSTANT, h_const=1.0)
     assert abs(energy["x"] - g["x"][0]) <= 1e-11 and abs(energy["xplusy"] - g["xplusy"][0]) <= 1e-11
     assert abs(energy["one"]) <= 1e-11

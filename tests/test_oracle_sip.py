@@ -95,6 +95,46 @@ def test_poisson_sanity_check_02(goldens):
     assert vfun @ (A @ vfun) == pytest.approx(g["v"][0], abs=1e-13)
 
 
+@pytest.mark.parametrize("name", ["distributed_poisson_sanity_check_02", "fully_distributed_poisson_sanity_check_01"])
+def test_distributed_poisson_sanity_checks(name, goldens):
+    """test/polydeal/distributed_poisson_sanity_check_02.cc (mpirun=3; [0,1]^2 refined 6x, one agglomerate per rank =
+    all of its cells, i.e. three contiguous pieces of the Morton curve, :115-156) and
+    fully_distributed_poisson_sanity_check_01.cc (256 cells, strips floor(3 x_centre), 10 agglomerates inside every
+    strip, :48-66,166-177): DGQ1, QGauss(3), no boundary terms, penalty 1/1 (:230-231 / :249-250).  The golden
+    energies 1 and 2 are sums over the ranks, so the serial oracle on the same agglomeration must print them too;
+    the sharded GPU assembly is checked against the same goldens in tests/test_gpu_parity.py."""
+    g = goldens[name]
+    if name == "distributed_poisson_sanity_check_02":
+        grid = po.Grid.hyper_cube(2, 0.0, 1.0, 6)
+        n = grid.n_cells
+        groups = [list(range(n * r // 3, n * (r + 1) // 3)) for r in range(3)]
+    else:
+        grid = po.Grid.hyper_cube(2, 0.0, 1.0, 4)
+        assert grid.n_cells == int(g["n_cells"][0])
+        v, cv, nbr = grid.arrays()
+        strip = np.floor(v[cv].mean(axis=1)[:, 0] * 3).astype(int)
+        groups = []
+        for r in range(3):
+            cells = np.nonzero(strip == r)[0]
+            local = -np.ones(grid.n_cells, dtype=np.int64)
+            local[cells] = np.arange(len(cells))
+            sub_nbr = np.where(nbr[cells] >= 0, local[np.maximum(nbr[cells], 0)], -1)
+            groups += [[int(cells[i]) for i in gr] for gr in sc.random_partition(len(cells), sub_nbr, 10, seed=r)]
+        assert len(groups) == 30
+    ah = po.AgglomerationHandler(grid)
+    for gr in groups:
+        ah.define_agglomerate(gr)
+    ah.initialize_fe_values(3)
+    ah.distribute_agglomerated_dofs(po.FE_DGQ, 1)
+    A = po.assemble_dg_matrix(ah, penalty_constant=1.0, h_rule=po.H_CONSTANT, h_const=1.0, with_boundary=False).scipy()
+    ux = interpolate(ah, lambda x: x[0])
+    uxy = interpolate(ah, lambda x: x[0] + x[1])
+    one = np.ones(ah.n_dofs)
+    assert ux @ (A @ ux) == pytest.approx(g["x"][0], abs=1e-11)
+    assert uxy @ (A @ uxy) == pytest.approx(g["xplusy"][0], abs=1e-11)
+    assert abs(one @ (A @ one)) < 1e-11
+
+
 @pytest.mark.parametrize("k", range(6))
 def test_poisson_sanity_check_03(k, goldens):
     """test/polydeal/poisson_sanity_check_03.cc: the same invariants on an UNSTRUCTURED mesh (t3.msh, read
