@@ -187,14 +187,21 @@ namespace pd
     // interior / boundary lists of a sharded apply), stages their coefficients AND those of every
     // neighbour outside the tile ("halo") in shared memory, and each thread then reads rows of it.
     // Shared-memory layout of the coefficients, in doubles:
-    //   [i * n, (i+1) * n)                          own cell i of the tile (i < TILE)
-    //   TILE * n + k * halo_row(n) + odd + [0, n)   halo cell halo[tile_ptr[tile] + k]; a halo row is filled by ONE
+    //   i * own_row(n) + [0, n)                     own cell i of the tile (i < TILE)
+    //   TILE * own_row(n) + k * halo_row(n) + odd + [0, n)   halo cell halo[tile_ptr[tile] + k]; a halo row is filled by ONE
     //                                               bulk copy (16-byte granularity), so it starts at the 16-byte
     //                                               boundary below the cell's first coefficient: odd = (cell * n) & 1
     //   zoff + [0, n)                               zeros: what a missing neighbour reads
     // noff[(seq position) * 2 DIM + face] is the first double of the neighbour across that face.
     // Halo rows are handed out face by face (all -x neighbours in cell order, then +x, ...), so the lanes of
     // a warp, which read the same face at the same time, mostly read different rows -> few bank conflicts.
+    // own rows: n doubles apart when n is odd (the global layout: one bulk copy fills them all), n + 1 when n
+    // is even -- consecutive threads read consecutive rows, and an even distance would put them on few banks
+    constexpr int
+    own_row(const int n)
+    {
+      return n | 1;
+    }
     constexpr int
     halo_row(const int n)
     {
@@ -222,7 +229,7 @@ namespace pd
                     const int32_t n_cells_total, const int tile, const int n)
     {
       TilePlan  p;
-      const int rh = halo_row(n);
+      const int rh = halo_row(n), ro = own_row(n);
       p.tile_first.push_back(0);
       for (int32_t i = 1; i <= n_seq; ++i)
         if (i == n_seq || i - p.tile_first.back() == tile || (block_key && block_key[i] != block_key[i - 1]))
@@ -236,7 +243,7 @@ namespace pd
           const int32_t s0 = p.tile_first[k], n_own = p.tile_first[k + 1] - s0;
           const size_t  h0 = p.halo.size();
           for (int32_t i = 0; i < n_own; ++i)
-            off_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = i * n;
+            off_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = i * ro;
           for (int f = 0; f < nfc; ++f)
             for (int32_t i = 0; i < n_own; ++i)
               {
@@ -248,7 +255,7 @@ namespace pd
                   throw std::out_of_range("build_tile_plan: neighbour id out of range");
                 if (off_of[(size_t)nb] < 0)
                   {
-                    const int64_t o = (int64_t)tile * n + (int64_t)(p.halo.size() - h0) * rh + (((int64_t)nb * n) & 1);
+                    const int64_t o = (int64_t)tile * ro + (int64_t)(p.halo.size() - h0) * rh + (((int64_t)nb * n) & 1);
                     if (o + n >= 0xFFFF)
                       throw std::length_error("build_tile_plan: tile too large for 16-bit offsets");
                     off_of[(size_t)nb] = (int32_t)o;
@@ -263,7 +270,7 @@ namespace pd
             off_of[(size_t)p.halo[h]] = -1;
           p.tile_ptr[(size_t)k + 1] = (int32_t)p.halo.size();
         }
-      const int64_t zoff = (int64_t)tile * n + (int64_t)p.max_halo * rh;
+      const int64_t zoff = (int64_t)tile * ro + (int64_t)p.max_halo * rh;
       if (zoff + n >= 0xFFFF)
         throw std::length_error("build_tile_plan: tile too large for 16-bit offsets");
       p.zoff = (int32_t)zoff;

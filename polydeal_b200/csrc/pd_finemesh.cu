@@ -413,7 +413,7 @@ namespace pd
     constexpr size_t
     tile_values_bytes(const int n, const int max_halo)
     {
-      return round16(((size_t)FINE_TILE * n + (size_t)max_halo * fine::halo_row(n) + n + 1) * sizeof(double));
+      return round16(((size_t)FINE_TILE * fine::own_row(n) + (size_t)max_halo * fine::halo_row(n) + n + 1) * sizeof(double));
     }
     constexpr size_t
     tile_smem_bytes(const int dim, const int n, const int max_halo)
@@ -428,6 +428,7 @@ namespace pd
       constexpr int N   = ipow_(N1, DIM);
       constexpr int NFC = 2 * DIM;
       constexpr int RH  = fine::halo_row(N);
+      constexpr int RO  = fine::own_row(N); // distance of the own rows (N odd: the global layout)
       constexpr int RS  = DIM * 64 + 16; // record row of a cell, padded: 16-byte reads of consecutive threads hit distinct banks
       constexpr int SPW = 32 / N;        // cells a warp copies per step
       constexpr int NW  = FINE_TILE_THREADS / 32;
@@ -468,7 +469,7 @@ namespace pd
         { // halo row r: one bulk copy from the 16-byte boundary below the cell (+ its last double when that leaves 8 bytes)
           const int64_t  first = (int64_t)A.halo[h0 + r] * N, a0 = first & ~(int64_t)1;
           const uint32_t total = (uint32_t)(N + (first - a0)) * 8, sz = total & ~15u;
-          double        *dst   = S + FINE_TILE * N + r * RH;
+          double        *dst   = S + FINE_TILE * RO + r * RH;
           bulk_g2s(dst, A.x + a0, sz, bar);
           bytes += sz;
           if (total != sz)
@@ -479,7 +480,7 @@ namespace pd
           bulk_g2s(sR + ci * RS, A.rec + (int64_t)cell_of(ci) * DIM, DIM * 64, bar);
           bytes += DIM * 64;
         }
-      if (A.seq == nullptr && n_own == FINE_TILE && (s0 * N) % 2 == 0)
+      if (RO == N && A.seq == nullptr && n_own == FINE_TILE && (s0 * N) % 2 == 0)
         { // the own cells are one aligned contiguous range
           if (tid == 0)
             {
@@ -494,7 +495,7 @@ namespace pd
 #pragma unroll 2
           for (int i = warp * SPW + sub; i < n_own; i += NW * SPW)
             if (copier)
-              cp_async8(S + i * N + e, A.x + (int64_t)cell_of(i) * N + e);
+              cp_async8(S + i * RO + e, A.x + (int64_t)cell_of(i) * N + e);
         }
       mbar_arrive_expect(bar, bytes);
       cp_async_wait_all();
@@ -504,7 +505,7 @@ namespace pd
       __syncthreads();
       // ---- the lines of one cell in registers, split between its two threads
       double        acc[N];
-      double *const own = S + ci * N;
+      double *const own = S + ci * RO;
       if (mine)
         {
           const double *nbp[NFC];
@@ -567,7 +568,7 @@ namespace pd
           if (copier)
             {
               double      *yp = A.y + (int64_t)cell_of(i) * N + e;
-              const double v  = S[i * N + e];
+              const double v  = S[i * RO + e];
               *yp             = A.add ? *yp + v : v;
             }
       }
@@ -740,11 +741,14 @@ namespace pd
     for (auto &t : h->mf_tiles)
       t.ok = false;
     {
-      // Which kernel: measured on B200 (64^3 cells, profiles/README.md) the tiled kernel wins for 3-D DGQ2
-      // (0.070 vs 0.134 ms) and loses for 3-D DGQ1 (64-byte cells: 0.070 vs 0.055 ms), so that is the default
-      // policy; PD_FINE_KERNEL=tile / line force one of them wherever it exists (the tests run both).
-      const char *env = std::getenv("PD_FINE_KERNEL");
-      h->mf_kernel    = (env && std::strcmp(env, "line") == 0) ? 1 : ((env && std::strcmp(env, "tile") == 0) ? 0 : (dim == 3 && h->degree == 2 ? 0 : 1));
+      // Which kernel: measured on B200 (profiles/README.md) the tiled kernel wins wherever it was timed -- 3-D
+      // DGQ1 / DGQ2 (64^3: 0.049 vs 0.057, 0.070 vs 0.134 ms), 2-D DGQ2 / 3 / 4 (512^2: 0.041 vs 0.048, 0.052 vs
+      // 0.100, 0.070 vs 0.200 ms) -- so it is the default there; 2-D DGQ1 (not timed) and 3-D DGQ3 (128
+      // accumulators: no tiled instance) run the line kernel.  PD_FINE_KERNEL=tile / line force one of them
+      // wherever it exists (the tests run both).
+      const char *env    = std::getenv("PD_FINE_KERNEL");
+      const bool  faster = (dim == 3 && h->degree <= 2) || (dim == 2 && h->degree >= 2);
+      h->mf_kernel = (env && std::strcmp(env, "line") == 0) ? 1 : ((env && std::strcmp(env, "tile") == 0) ? 0 : (faster ? 0 : 1));
     }
     if (h->mf_kernel == 0 && h->n <= 27)
       {

@@ -148,7 +148,7 @@ def test_tile_plan_contract(lib, shape, order, tile, with_list, n, blocks):
     assert rc == 0
     nt = n_tiles.value
     assert tile_first[0] == 0 and tile_first[nt] == n_seq and tile_ptr[nt] == n_halo.value
-    rh = rh.value
+    rh, ro = rh.value, n | 1
     assert rh % 2 == 0 and rh >= n + 1 and rh % 4 == 2  # a 16-byte aligned row with room for an odd start, spread over the banks
     seen_max_halo = 0
     for k in range(nt):
@@ -163,9 +163,9 @@ def test_tile_plan_contract(lib, shape, order, tile, with_list, n, blocks):
         hl = halo[tile_ptr[k]:tile_ptr[k + 1]]
         assert len(set(own.tolist()) | set(hl.tolist())) == len(own) + len(hl)  # every cell staged once
         seen_max_halo = max(seen_max_halo, len(hl))
-        where = {int(c): i * n for i, c in enumerate(own)}
+        where = {int(c): i * ro for i, c in enumerate(own)}  # own rows an odd number of doubles apart
         # a halo row starts at the 16-byte boundary below the cell's first coefficient
-        where.update({int(c): tile * n + r * rh + ((int(c) * n) & 1) for r, c in enumerate(hl)})
+        where.update({int(c): tile * ro + r * rh + ((int(c) * n) & 1) for r, c in enumerate(hl)})
         for i, c in enumerate(own):
             for f in range(nfc):
                 o = noff[(s0 + i) * nfc + f]
@@ -173,7 +173,7 @@ def test_tile_plan_contract(lib, shape, order, tile, with_list, n, blocks):
         # no halo cell that nobody needs
         needed = {int(nbr[c, f]) for c in own for f in range(nfc) if nbr[c, f] >= 0} - set(own.tolist())
         assert needed == set(hl.tolist())
-    assert max_halo.value == seen_max_halo and zoff.value == tile * n + seen_max_halo * rh
+    assert max_halo.value == seen_max_halo and zoff.value == tile * ro + seen_max_halo * rh
     if order == "morton" and shape == (8, 8, 8) and with_list is False:
         assert nt == 8 and seen_max_halo == 48  # a 4x4x4 corner block and its three inner faces
     if with_list == "interior":  # 6^3 interior cells: the eight 3x3x3 corners of the blocks, compact halos

@@ -29,6 +29,10 @@ CONFIGS = {
     "F2": dict(dim=3, n=64, b=1, p=2, nq=3, C=6.0, mass=0.0, fine=True),
     "F3": dict(dim=3, n=64, b=1, p=3, nq=4, C=12.0, mass=0.0, fine=True),
     "F2L": dict(dim=3, n=128, b=1, p=2, nq=3, C=6.0, mass=0.0, fine=True),
+    # 2-D fine meshes (512^2 quads), for the tiled-vs-line kernel policy of pd_finemesh.cu
+    "G2": dict(dim=2, n=512, b=1, p=2, nq=3, C=6.0, mass=0.0, fine=True),
+    "G3": dict(dim=2, n=512, b=1, p=3, nq=4, C=12.0, mass=0.0, fine=True),
+    "G4": dict(dim=2, n=512, b=1, p=4, nq=5, C=20.0, mass=0.0, fine=True),
     # E: distorted 64^3 hex box (stand-in for the missing LV mesh), MonodomainOperatorDG semantics
     # f M + sigma K without boundary terms, f = 1.5e4, sigma = 1e-4 (examples/parameters_monodomain.prm)
     "E1": dict(dim=3, n=64, b=1, p=1, nq=2, C=2.0, fine=True, mapped=True, distort=(0.2, 20251018),
