@@ -9,7 +9,10 @@ A step = agglomerated quadrature + volume + face + diagonal-gather kernels, from
 flattened agglomeration resident in HBM to the finished scalar-CSR values in HBM.
 
 Metric: polytope DoFs assembled per second (whole job, all ranks).  The companion
-metric of BASELINE.json, SIP vmult GDoF/s, is reported in the "vmult" object.
+metric of BASELINE.json, SIP vmult GDoF/s, is reported twice: "vmult" = the block-CSR
+apply of the matrix just assembled (what the reference's solvers call on agglomerated
+levels), "mf_vmult" (N = 1) = the matrix-free sum-factorised LaplaceOperatorDG on the
+64^3 DGQ2 fine mesh of examples/matrix_free_agglo.cc, each with its own HBM roofline.
 
   python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
   python bench.py --impl reference ...   times the CPU oracle restating the reference's
