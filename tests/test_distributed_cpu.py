@@ -177,3 +177,88 @@ def test_distributed_reference_goldens(goldens):
                 for j in range(part.n):
                     got.add((int(gblock[b]) * part.n + i, int(gblock[bcol[e]]) * part.n + j))
     assert got == {tuple(rc) for rc in goldens["sparsity_distributed_tria"]}
+
+
+def _subface_midpoints(desc, f):
+    """geometric identity of the sub-faces of local interface f: the mid-points of their vertices, in list order"""
+    dim = desc.dim
+    vpc = 1 << dim
+    verts = np.ctypeslib.as_array(desc.verts, (desc.n_verts, dim))
+    cv = np.ctypeslib.as_array(desc.cell_verts, (desc.n_cells, vpc))
+    ptr = np.ctypeslib.as_array(desc.iface_sub_ptr, (desc.n_ifaces + 1,))
+    sc_ = np.ctypeslib.as_array(desc.sub_cell, (int(ptr[-1]),))
+    sf = np.ctypeslib.as_array(desc.sub_face, (int(ptr[-1]),))
+    out = []
+    for s in range(ptr[f], ptr[f + 1]):
+        axis, side = int(sf[s]) // 2, int(sf[s]) % 2  # deal.II face numbering: 2 * direction + side
+        face_verts = [v for v in range(vpc) if ((v >> axis) & 1) == side]
+        out.append(verts[cv[sc_[s]][face_verts]].mean(axis=0))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("name,n_ref,groups,owner", [
+    # reinit_ghosted_neighbor_01.cc:62-118: K0 | K1, K2 | K3 on ranks 0 | 1 | 2
+    ("reinit_ghosted_neighbor_01", 2, [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11], [12, 13, 14, 15]], [0, 1, 1, 2]),
+    # reinit_ghosted_neighbor_02.cc:69-146 and locally_owned_polytope_05.cc:68-150: eight two-cell polytopes
+    ("reinit_ghosted_neighbor_02", 2, [[2 * k, 2 * k + 1] for k in range(8)], [0, 0, 1, 1, 1, 1, 2, 2]),
+    # locally_owned_polytope_01.cc:43-53 (mpirun=2): every cell its own polytope, two ranks of eight cells
+    ("locally_owned_polytope_01", 2, [[c] for c in range(16)], [0] * 8 + [1] * 8),
+])
+def test_cut_interfaces_seen_from_both_ranks(name, n_ref, groups, owner):
+    """test/polydeal/reinit_ghosted_neighbor_01/02 (mpirun=3, golden "Ok"): on an interface cut by the partition the
+    face quadrature points and JxW a rank computes must be those its neighbour rank holds for the same interface
+    (source/agglomeration_handler.cc:531-618 ships them; here BOTH ranks evaluate the interface from their local
+    descriptor, so the check is that the two descriptors list the same sub-faces in the same order -- the
+    quadrature is generated from exactly these lists).  locally_owned_polytope_01 (mpirun=2): every rank owns eight
+    polytopes with local indices 0..7; locally_owned_polytope_05 (mpirun=3, golden "Ok"): owned volumes sum to 1 and
+    owned boundary faces to 4 (:163-210)."""
+    sys.path.insert(0, ROOT)
+    import polydeal_b200 as pdl
+    from polydeal_b200 import distributed as pdd
+
+    owner = np.array(owner, dtype=np.int32)
+    grid = pdl.Grid.hyper_cube(2, 0.0, 1.0, n_ref)
+    ah = pdl.AgglomerationHandler(grid)
+    for g in groups:
+        ah.define_agglomerate(g)
+    ah.initialize_fe_values(1)  # FE_DGQ(0), QGauss(1) as in the reference tests
+    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, 0)
+    world = int(owner.max()) + 1
+    # every cut interface, from both sides (the descriptor arrays belong to the handler and are rewritten by the
+    # next flatten, so each rank's view is read before the next one is made)
+    seen = {}
+    volume = perimeter = 0.0
+    for r in range(world):
+        part = pdd.LocalPart(ah, owner, r)
+        # ownership: every polytope exactly once, local indices 0 .. n_owned-1 in the global order
+        assert part.local_poly_global[: part.n_owned].tolist() == np.nonzero(owner == r)[0].tolist()
+        if name == "locally_owned_polytope_01":
+            assert part.n_owned == 8
+        d = part.desc
+        A = np.ctypeslib.as_array(d.iface_polyA, (d.n_ifaces,))
+        B = np.ctypeslib.as_array(d.iface_polyB, (d.n_ifaces,))
+        glob = part.local_poly_global
+        for f in range(d.n_ifaces):
+            mid = _subface_midpoints(d, f)
+            if B[f] < 0:
+                if A[f] < part.n_owned:  # boundary face of an owned polytope: sum of JxW = its length
+                    sub = mid.shape[0]
+                    perimeter += sub * (0.5 ** n_ref)
+                continue
+            key = tuple(sorted((int(glob[A[f]]), int(glob[B[f]]))))  # whichever side a rank lists first
+            if owner[key[0]] != owner[key[1]]:
+                seen.setdefault(key, {})[r] = mid
+        for lp in range(part.n_owned):
+            lo, hi = ah.bbox(int(glob[lp]))
+            volume += len(ah.get_agglomerate(int(glob[lp]))) * 0.25 ** n_ref
+    n_cut = 0
+    for key, views in seen.items():
+        assert set(views) == {int(owner[key[0]]), int(owner[key[1]])}, key  # both owners carry the interface
+        a, b = views.values()
+        assert a.shape == b.shape and np.abs(a - b).max() < 1e-15, key  # same sub-faces, same order
+        n_cut += 1
+    # every face between polytopes of different ranks was found
+    want = {(p, ah.neighbor(p, f)) for p in range(ah.n_polytopes) for f in range(ah.n_faces(p))
+            if not ah.at_boundary(p, f) and owner[p] != owner[ah.neighbor(p, f)]}
+    assert {tuple(sorted(k)) for k in seen} == {tuple(sorted(k)) for k in want} and n_cut == len(want) // 2
+    assert abs(volume - 1.0) < 1e-15 and abs(perimeter - 4.0) < 1e-15
