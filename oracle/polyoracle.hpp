@@ -380,11 +380,37 @@ namespace po
     {
       return nbr[(size_t)c * 2 * dim + f];
     }
-    // structured grids only: the neighbour sees us through the opposite face
-    static int
-    neighbor_of_neighbor(const int f)
+    // cell->neighbor_of_neighbor(f) of deal.II: the face through which the neighbour across face f sees
+    // this cell.  The opposite face on structured grids; on unstructured meshes (GridIn) the neighbour may
+    // be rotated, so look it up.
+    int
+    neighbor_of_neighbor(const int c, const int f) const
     {
-      return f ^ 1;
+      const int q = neighbor(c, f);
+      if (q >= 0 && neighbor(q, f ^ 1) == c)
+        return f ^ 1;
+      for (int g = 0; q >= 0 && g < 2 * dim; ++g)
+        if (neighbor(q, g) == c)
+          return g;
+      throw std::runtime_error("Grid::neighbor_of_neighbor: the neighbour table is not symmetric");
+    }
+
+    // any conforming quadrilateral / hexahedral mesh from its arrays (vertices of a cell in deal.II's
+    // lexicographic order, faces 2 * direction + side); the boundary vertices are found from the faces
+    void
+    build_from_arrays(const int dim_, const int n_verts_, const double *v, const int n_cells_, const int *cv, const int *nb)
+    {
+      dim = dim_;
+      verts.assign(v, v + (size_t)n_verts_ * dim);
+      cell_verts.assign(cv, cv + ((size_t)n_cells_ << dim));
+      nbr.assign(nb, nb + (size_t)n_cells_ * 2 * dim);
+      vert_on_boundary.assign((size_t)n_verts_, 0);
+      for (int c = 0; c < n_cells_; ++c)
+        for (int f = 0; f < 2 * dim; ++f)
+          if (nbr[(size_t)c * 2 * dim + f] < 0)
+            for (int k = 0; k < (1 << dim); ++k)
+              if (((k >> (f / 2)) & 1) == (f % 2))
+                vert_on_boundary[(size_t)cell_verts[((size_t)c << dim) + k]] = 1;
     }
 
     // Build an nx*ny*nz structured grid on [lo,hi].  order==0: deal.II
@@ -870,7 +896,7 @@ namespace po
                   if (!are_cells_agglomerated(cell, neighboring_cell))
                     {
                       const int master_of_neighbor = master_of_cell[neighboring_cell];
-                      const int nof = Grid::neighbor_of_neighbor(f);
+                      const int nof = grid->neighbor_of_neighbor(cell, f);
                       const int neighbor_polytope_index =
                         master2polygon.at(master_of_neighbor);
                       const int neighbor_polytope_id = master_of_neighbor;

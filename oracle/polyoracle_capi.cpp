@@ -86,6 +86,17 @@ extern "C"
       }
     return g;
   }
+  void *
+  po_grid_from_arrays(int dim, int n_verts, const double *verts, int n_cells, const int *cell_verts, const int *nbr)
+  {
+    Grid *g = new Grid;
+    if (guard([&] { g->build_from_arrays(dim, n_verts, verts, n_cells, cell_verts, nbr); }))
+      {
+        delete g;
+        return nullptr;
+      }
+    return g;
+  }
   void
   po_grid_free(void *g)
   {

@@ -66,6 +66,7 @@ def lib():
             "po_fe_n_dofs": (i32, [i32, i32, i32]),
             "po_fe_evaluate": (None, [i32, i32, i32, P(f64), P(f64), P(f64)]),
             "po_grid_structured": (vp, [i32, P(i32), P(f64), P(f64), i32]),
+            "po_grid_from_arrays": (vp, [i32, i32, P(f64), i32, P(i32), P(i32)]),
             "po_grid_free": (None, [vp]),
             "po_grid_distort_random": (None, [vp, f64, C.c_uint64]),
             "po_grid_dim": (i32, [vp]),
@@ -162,6 +163,22 @@ class Grid:
     @staticmethod
     def hyper_cube(dim, a, b, n_refine):
         return Grid(dim, 1 << n_refine, a, b, order=0)
+
+    @staticmethod
+    def from_arrays(verts, cell_verts, nbr):
+        """Any conforming quad / hex mesh (what GridIn would read): vertices of a cell in deal.II's lexicographic
+        order, nbr[c, 2 * direction + side] = neighbour or -1.  Neighbours may be rotated against each other."""
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        cell_verts = np.ascontiguousarray(cell_verts, dtype=np.int32)
+        nbr = np.ascontiguousarray(nbr, dtype=np.int32)
+        g = Grid.__new__(Grid)
+        g.dim = verts.shape[1]
+        g.h = lib().po_grid_from_arrays(g.dim, len(verts), _p(verts, C.c_double), len(cell_verts), _p(cell_verts, C.c_int),
+                                        _p(nbr, C.c_int))
+        if not g.h:
+            raise RuntimeError(_err())
+        g.n, g.order = None, None
+        return g
 
     def __del__(self):
         if getattr(self, "h", None) and _lib is not None:

@@ -54,6 +54,21 @@ namespace pd
       return (int64_t)(verts.size() / dim);
     }
 
+    // cell->neighbor_of_neighbor(f): the face through which the neighbour across face f sees cell c -- the opposite
+    // face on structured grids; looked up on unstructured meshes, where neighbours may be rotated against each other
+    int32_t
+    neighbor_of_neighbor(const int32_t c, const int f) const
+    {
+      const int     fpc = 2 * dim;
+      const int32_t q   = nbr[(size_t)c * fpc + f];
+      if (q >= 0 && nbr[(size_t)q * fpc + (f ^ 1)] == c)
+        return f ^ 1;
+      for (int g = 0; q >= 0 && g < fpc; ++g)
+        if (nbr[(size_t)q * fpc + g] == c)
+          return g;
+      throw Error(PD_ERR_INVALID, "Grid: the neighbour table is not symmetric");
+    }
+
     // interleave the bits of (i,j,k): position of a cell in the hierarchical
     // (refine_global) ordering of a 2^L grid
     static inline uint64_t
@@ -762,8 +777,9 @@ namespace pd
                 for (size_t k = 0; k < own_cells[gi].size(); ++k)
                   {
                     const int32_t c = own_cells[gi][k], f = own_faces[gi][k];
-                    sub_cell.push_back(grid->nbr[(size_t)c * fpc + f]);
-                    sub_face.push_back(f ^ 1); // neighbor_of_neighbor, standard orientation
+                    const int32_t nc = grid->nbr[(size_t)c * fpc + f];
+                    sub_cell.push_back(nc);
+                    sub_face.push_back(grid->neighbor_of_neighbor(c, f));
                   }
               }
             face_sub_ptr[fi + 1] = (int64_t)sub_cell.size();

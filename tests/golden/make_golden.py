@@ -174,6 +174,35 @@ def floats_after(name, pat):
     return [float(m[1]) for l in lines(name) if (m := re.search(pat, l))]
 
 
+def parse_gmsh_quads(path):
+    """vertices (x, y) and 4-node quadrilaterals (gmsh's counter-clockwise node order, 0-based, renumbered
+    compactly) of a gmsh 4.1 ASCII file -- the input grid of fully_distributed_poisson_sanity_check_02.cc."""
+    toks = open(path).read().split("\n")
+    i = toks.index("$Nodes") + 1
+    n_blocks, n_nodes = int(toks[i].split()[0]), int(toks[i].split()[1])
+    i += 1
+    coords = {}
+    for _ in range(n_blocks):
+        nb = int(toks[i].split()[3])
+        tags = [int(toks[i + 1 + k]) for k in range(nb)]
+        for k, t in enumerate(tags):
+            coords[t] = [float(v) for v in toks[i + 1 + nb + k].split()[:2]]
+        i += 1 + 2 * nb
+    assert len(coords) == n_nodes
+    i = toks.index("$Elements") + 1
+    n_blocks = int(toks[i].split()[0])
+    i += 1
+    quads = []
+    for _ in range(n_blocks):
+        _, _, etype, nb = (int(v) for v in toks[i].split())
+        if etype == 3:
+            quads += [[int(v) for v in toks[i + 1 + k].split()[1:5]] for k in range(nb)]
+        i += 1 + nb
+    used = sorted({t for q in quads for t in q})
+    new = {t: k for k, t in enumerate(used)}
+    return {"verts": [coords[t] for t in used], "quads": [[new[t] for t in q] for q in quads]}
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference tree not present; goldens can only be regenerated in the build container")
@@ -243,6 +272,12 @@ def main():
             "n_cells": floats_after("fully_distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"Number of cells: (\S+)"),
             "x": floats_after("fully_distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x: (\S+)"),
             "xplusy": floats_after("fully_distributed_poisson_sanity_check_01.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x\+y: (\S+)"),
+        },
+        "fully_distributed_poisson_sanity_check_02": {
+            "n_cells": floats_after("fully_distributed_poisson_sanity_check_02.with_mpi=true.with_p4est=true.mpirun=3.output", r"Number of cells: (\S+)"),
+            "x": floats_after("fully_distributed_poisson_sanity_check_02.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x: (\S+)"),
+            "xplusy": floats_after("fully_distributed_poisson_sanity_check_02.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x\+y: (\S+)"),
+            "input_grid": parse_gmsh_quads(os.path.join(REF, "input_grids", "square.msh")),
         },
         "poisson": floats_after("poisson.output", r"(\d\.\d+)"),
     }

@@ -3,6 +3,8 @@
 product parity tests so both are driven with identical inputs."""
 from __future__ import annotations
 
+import numpy as np
+
 
 def standard_8x8_agglomerates():
     """[-1,1]^2 refined 3x; {3,6,9,12,13},{15,36,37},{57,60,54},{25,19,22} + singletons
@@ -167,3 +169,73 @@ def partition_from_continuous_face_golden(scenario, n_cells, nbr):
     for c, p in enumerate(owner):
         groups[p].append(c)
     return groups
+
+
+def quad_mesh_from_gmsh(verts, quads_ccw, n_refine=0):
+    """(verts, cell_verts, nbr) of an unstructured quadrilateral mesh the way deal.II's GridIn + refine_global hand
+    it over: gmsh lists a quad counter-clockwise, deal.II lexicographically with consistently directed edges; faces
+    0: x-, 1: x+, 2: y-, 3: y+ of the reference cell; children of a refined cell in the order of its vertices.
+    Neighbouring cells are in general rotated against each other (no opposite-face rule), but an edge has the same
+    direction seen from both sides, as in every 2-D deal.II triangulation."""
+    verts = [tuple(map(float, v)) for v in verts]
+    # GridTools::consistently_order_cells (what GridIn does in 2-D): every edge gets ONE direction, the same seen
+    # from both of its cells, and the opposite edges of a quad are parallel; found by walking the chains of
+    # opposite edges.  direction[(a, b)] = True means a -> b for the edge {a, b}, a < b.
+    cells_of_edge = {}
+    for qi, q in enumerate(quads_ccw):
+        for k in range(4):
+            a, b = q[k], q[(k + 1) % 4]
+            cells_of_edge.setdefault((min(a, b), max(a, b)), []).append(qi)
+    direction = {}
+    for start in cells_of_edge:
+        if start in direction:
+            continue
+        direction[start] = True
+        stack = [start]
+        while stack:
+            e = stack.pop()
+            tail, head = e if direction[e] else e[::-1]
+            for qi in cells_of_edge[e]:
+                q = quads_ccw[qi]
+                k = next(k for k in range(4) if {q[k], q[(k + 1) % 4]} == set(e))
+                # the opposite edge runs q[k+3] -> q[k+2] when this one runs q[k] -> q[k+1]
+                o_tail, o_head = (q[(k + 3) % 4], q[(k + 2) % 4]) if q[k] == tail else (q[(k + 2) % 4], q[(k + 3) % 4])
+                o = (min(o_tail, o_head), max(o_tail, o_head))
+                if o not in direction:
+                    direction[o] = o_tail < o_head
+                    stack.append(o)
+                else:
+                    assert direction[o] == (o_tail < o_head), "mesh is not orientable"
+    starts_at = lambda a, b: direction[(min(a, b), max(a, b))] == (a < b)
+    cells = []
+    for q in quads_ccw:
+        k = next(k for k in range(4) if starts_at(q[k], q[(k + 1) % 4]) and starts_at(q[k], q[(k + 3) % 4]))
+        cells.append([q[k], q[(k + 1) % 4], q[(k + 3) % 4], q[(k + 2) % 4]])  # lexicographic, counter-clockwise = positive
+    for _ in range(n_refine):
+        mid, new_cells = {}, []
+
+        def midpoint(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in mid:
+                verts.append(tuple(0.5 * (verts[a][k] + verts[b][k]) for k in range(2)))
+                mid[key] = len(verts) - 1
+            return mid[key]
+
+        for v0, v1, v2, v3 in cells:
+            m01, m02, m13, m23 = midpoint(v0, v1), midpoint(v0, v2), midpoint(v1, v3), midpoint(v2, v3)
+            verts.append(tuple(0.25 * (verts[v0][k] + verts[v1][k] + verts[v2][k] + verts[v3][k]) for k in range(2)))
+            c = len(verts) - 1
+            new_cells += [[v0, m01, m02, c], [m01, v1, c, m13], [m02, c, v2, m23], [c, m13, m23, v3]]
+        cells = new_cells
+    face_verts = [(0, 2), (1, 3), (0, 1), (2, 3)]
+    edge = {}
+    for ci, cv in enumerate(cells):
+        for f, (a, b) in enumerate(face_verts):
+            edge.setdefault((min(cv[a], cv[b]), max(cv[a], cv[b])), []).append((ci, f))
+    nbr = -np.ones((len(cells), 4), dtype=np.int32)
+    for sides in edge.values():
+        assert len(sides) <= 2
+        if len(sides) == 2:
+            (c0, f0), (c1, f1) = sides
+            nbr[c0, f0], nbr[c1, f1] = c1, c0
+    return np.array(verts), np.array(cells, dtype=np.int32), nbr

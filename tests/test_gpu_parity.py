@@ -1213,3 +1213,47 @@ def test_fully_distributed_poisson_sanity_check_01(goldens):
                                h_rule=pdl.H_CONSTANT, h_const=1.0)
     assert abs(energy["x"] - g["x"][0]) <= 1e-11 and abs(energy["xplusy"] - g["xplusy"][0]) <= 1e-11
     assert abs(energy["one"]) <= 1e-11
+
+
+def test_assembly_on_an_unstructured_mesh(goldens):
+    """The input grid of test/polydeal/fully_distributed_poisson_sanity_check_02.cc (input_grids/square.msh refined
+    once, 364 quadrilaterals read the way GridIn hands them over: neighbours rotated against each other), 30
+    agglomerates, DGQ2: the GPU-assembled SIP matrix against the oracle per block entry, and the golden energies of
+    x and x + y (1 and 2, no boundary terms, penalty 1/1) with the GPU matrix."""
+    pdl = gpu()
+    import torch
+
+    g = goldens["fully_distributed_poisson_sanity_check_02"]
+    v, cv, nbr = sc.quad_mesh_from_gmsh(g["input_grid"]["verts"], g["input_grid"]["quads"], n_refine=1)
+    groups = sc.random_partition(len(nbr), nbr, 30, seed=5)
+    handlers = []
+    for mod, grid in ((po, po.Grid.from_arrays(v, cv, nbr)), (pdl, pdl.Grid.from_arrays(v, cv, nbr))):
+        ah = mod.AgglomerationHandler(grid)
+        for gr in groups:
+            ah.define_agglomerate(gr)
+        ah.initialize_fe_values(3)
+        ah.distribute_agglomerated_dofs(mod.FE_DGQ, 2)
+        handlers.append(ah)
+    oah, pah = handlers
+    ref = po.assemble_dg_matrix(oah, degree=2, n_threads=4)
+    op = pdl.assemble_dg_matrix(pah)
+    rp, cols = op.pattern()
+    orp, ocols, ovals = ref.csr()
+    np.testing.assert_array_equal(rp, orp)
+    np.testing.assert_array_equal(cols, ocols)
+    assert_blocks_close(op.values(), ovals, oah.n_dofs_per_cell, rp, TOL)
+    # the sanity-check invariants with the GPU operator
+    kw = dict(penalty_constant=1.0, h_rule=pdl.H_CONSTANT, h_const=1.0)
+    op = pdl.SIPOperator(pah.flatten(**kw), keepalive=pah)
+    op.assemble(pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR)
+    usp = _dgq_unit_support_points(2, 2)
+    for name, f in (("x", lambda X: X[:, 0]), ("xplusy", lambda X: X[:, 0] + X[:, 1])):
+        u = np.empty(pah.n_dofs)
+        for k_ in range(pah.n_polytopes):
+            lo, hi = pah.bbox(k_)
+            u[pah.get_dof_indices(k_)] = f(lo + usp * (hi - lo))
+        xd = torch.from_numpy(u).cuda()
+        yd = torch.empty_like(xd)
+        op.vmult(yd, xd)
+        op.synchronize()
+        assert abs(float(u @ yd.cpu().numpy()) - g[name][0]) <= 1e-11

@@ -316,3 +316,85 @@ def test_metis_agglomeration_and_sharding():
             for r, p in enumerate(parts):  # what r expects from s is what s sends to r
                 for s_ in range(world):
                     assert p.recv_counts[s_] == parts[s_].send_counts[r]
+
+
+def test_host_mirror_on_an_unstructured_mesh(goldens):
+    """The input grid of test/polydeal/fully_distributed_poisson_sanity_check_02.cc (input_grids/square.msh refined once:
+    364 quadrilaterals, neighbours rotated against each other -- no opposite-face rule, cell->neighbor_of_neighbor
+    looked up), 30 agglomerates: numbering, face enumeration, aligned sub-face lists, nofn and sparsity of the host
+    mirror are those of the oracle's literal restatement, and the flattened descriptor lists every cut from both
+    ranks with the same sub-faces in the same order."""
+    from polydeal_b200 import distributed as pdd
+
+    g = goldens["fully_distributed_poisson_sanity_check_02"]
+    v, cv, nbr = sc.quad_mesh_from_gmsh(g["input_grid"]["verts"], g["input_grid"]["quads"], n_refine=1)
+    assert len(cv) == int(g["n_cells"][0])
+    rank_groups = sc.random_partition(len(nbr), nbr, 3, seed=0)
+    groups, owner = [], []
+    for r, cells in enumerate(rank_groups):
+        cells = np.array(sorted(cells))
+        local = -np.ones(len(nbr), dtype=np.int64)
+        local[cells] = np.arange(len(cells))
+        sub_nbr = np.where(nbr[cells] >= 0, local[np.maximum(nbr[cells], 0)], -1)
+        for gr in sc.random_partition(len(cells), sub_nbr, 10, seed=1 + r):
+            groups.append([int(cells[i]) for i in gr])
+            owner.append(r)
+    oah = po.AgglomerationHandler(po.Grid.from_arrays(v, cv, nbr))
+    pah = pdl.AgglomerationHandler(pdl.Grid.from_arrays(v, cv, nbr))
+    for ah, kind in ((oah, po.FE_DGQ), (pah, pdl.FE_DGQ)):
+        for gr in groups:
+            ah.define_agglomerate(gr)
+        ah.initialize_fe_values(3)
+        ah.distribute_agglomerated_dofs(kind, 1)
+    assert pah.n_polytopes == oah.n_polytopes == 30 and pah.n_dofs == oah.n_dofs
+    rotated = 0
+    for p in range(oah.n_polytopes):
+        assert pah.master_cell(p) == oah.master_cell(p)
+        assert pah.get_agglomerate(p).tolist() == oah.get_agglomerate(p).tolist()
+        assert pah.get_dof_indices(p).tolist() == oah.get_dof_indices(p).tolist()
+        assert pah.n_faces(p) == oah.n_faces(p)
+        np.testing.assert_array_equal(np.concatenate(pah.bbox(p)), np.concatenate(oah.bbox(p)))
+        for f in range(oah.n_faces(p)):
+            assert pah.at_boundary(p, f) == oah.at_boundary(p, f)
+            assert pah.neighbor(p, f) == oah.neighbor(p, f)
+            assert pah.neighbor_of_agglomerated_neighbor(p, f) == oah.neighbor_of_agglomerated_neighbor(p, f)
+            assert pah.interface(p, f) == oah.interface(p, f)
+            if not pah.at_boundary(p, f):  # the two sides list the same sub-faces, each through its own cell
+                q, nofn = pah.neighbor(p, f), pah.neighbor_of_agglomerated_neighbor(p, f)
+                mine, theirs = pah.interface(p, f), pah.interface(q, nofn)
+                assert len(mine) == len(theirs)
+                for (c, lf), (c2, lf2) in zip(mine, theirs):
+                    assert nbr[c, lf] == c2 and nbr[c2, lf2] == c
+                    rotated += lf2 != (lf ^ 1)
+    assert rotated > 0  # the mesh does exercise the general neighbor_of_neighbor
+    rp, cols = pah.create_agglomeration_sparsity_pattern()
+    orp, ocols = oah.create_agglomeration_sparsity_pattern()
+    np.testing.assert_array_equal(rp, orp)
+    np.testing.assert_array_equal(cols, ocols)
+    # local descriptors of the three ranks: every cut interface from both owners, same sub-faces in the same order
+    owner = np.array(owner, dtype=np.int32)
+    seen = {}
+    for r in range(3):
+        part = pdd.LocalPart(pah, owner, r, penalty_constant=1.0, h_rule=pdl.H_CONSTANT, h_const=1.0)
+        d = part.desc
+        A = np.ctypeslib.as_array(d.iface_polyA, (d.n_ifaces,))
+        B = np.ctypeslib.as_array(d.iface_polyB, (d.n_ifaces,))
+        ptr = np.ctypeslib.as_array(d.iface_sub_ptr, (d.n_ifaces + 1,))
+        sub_c = np.ctypeslib.as_array(d.sub_cell, (int(ptr[-1]),))
+        sub_f = np.ctypeslib.as_array(d.sub_face, (int(ptr[-1]),))
+        verts = np.ctypeslib.as_array(d.verts, (d.n_verts, 2))
+        lcv = np.ctypeslib.as_array(d.cell_verts, (d.n_cells, 4))
+        glob = part.local_poly_global
+        for f in range(d.n_ifaces):
+            if B[f] < 0 or owner[glob[A[f]]] == owner[glob[B[f]]]:
+                continue
+            mids = []
+            for s_ in range(ptr[f], ptr[f + 1]):
+                axis, side = int(sub_f[s_]) // 2, int(sub_f[s_]) % 2
+                mids.append(verts[lcv[sub_c[s_]][[k for k in range(4) if ((k >> axis) & 1) == side]]].mean(axis=0))
+            seen.setdefault(tuple(sorted((int(glob[A[f]]), int(glob[B[f]])))), {})[r] = np.array(mids)
+    assert seen
+    for key, views in seen.items():
+        assert set(views) == {int(owner[key[0]]), int(owner[key[1]])}, key
+        a, b = views.values()
+        assert a.shape == b.shape and np.abs(a - b).max() < 1e-15, key

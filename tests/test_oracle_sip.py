@@ -390,3 +390,64 @@ def test_mapped_fine_operator_invariants_on_distorted_cells(dim, n, p):
     assert x @ A(x) > 0
     vol = one @ po.mapped_fine_vmult(grid, p, p + 1, one, stiffness=0.0, mass=1.0, boundary=False, interior=False)
     assert abs(vol - 1.0) <= 1e-13
+
+
+def _unstructured_square(goldens):
+    """the input grid of fully_distributed_poisson_sanity_check_02.cc:124-129 (input_grids/square.msh, 91 quads,
+    parsed into tests/golden by make_golden.py), refined once: 364 cells, neighbours rotated against each other"""
+    g = goldens["fully_distributed_poisson_sanity_check_02"]
+    v, cv, nbr = sc.quad_mesh_from_gmsh(g["input_grid"]["verts"], g["input_grid"]["quads"], n_refine=1)
+    assert len(cv) == int(g["n_cells"][0])
+    # it IS unstructured: some neighbour does not see the cell through the opposite face
+    assert any(nbr[nbr[c, f], f ^ 1] != c for c in range(len(cv)) for f in range(4) if nbr[c, f] >= 0)
+    return v, cv, nbr
+
+
+def _rank_then_agglomerates(nbr, n_ranks, n_local, seed=0):
+    """GridTools::partition_triangulation(n_ranks) then PolyUtils::partition_locally_owned_regions(n_local): both
+    METIS in the reference (partition = input of the path); here seeded graph growing on the same graphs"""
+    rank_groups = sc.random_partition(len(nbr), nbr, n_ranks, seed=seed)
+    groups, owner = [], []
+    for r, cells in enumerate(rank_groups):
+        cells = np.array(sorted(cells))
+        local = -np.ones(len(nbr), dtype=np.int64)
+        local[cells] = np.arange(len(cells))
+        sub_nbr = np.where(nbr[cells] >= 0, local[np.maximum(nbr[cells], 0)], -1)
+        for gr in sc.random_partition(len(cells), sub_nbr, n_local, seed=seed + 1 + r):
+            groups.append([int(cells[i]) for i in gr])
+            owner.append(r)
+    return groups, owner
+
+
+def test_fully_distributed_poisson_sanity_check_02_unstructured(goldens):
+    """test/polydeal/fully_distributed_poisson_sanity_check_02.cc (mpirun=3): the sanity-check energies on an
+    UNSTRUCTURED quadrilateral mesh read by GridIn (square.msh refined once = 364 cells), three ranks, ten
+    agglomerates per rank, DGQ1, QGauss(3), no boundary terms, penalty 1/1: x'Ax = 1, (x+y)'A(x+y) = 2."""
+    g = goldens["fully_distributed_poisson_sanity_check_02"]
+    v, cv, nbr = _unstructured_square(goldens)
+    groups, owner = _rank_then_agglomerates(nbr, 3, 10)
+    assert len(groups) == 30
+    grid = po.Grid.from_arrays(v, cv, nbr)
+    ah = po.AgglomerationHandler(grid)
+    for gr in groups:
+        ah.define_agglomerate(gr)
+    ah.initialize_fe_values(3)
+    ah.distribute_agglomerated_dofs(po.FE_DGQ, 1)
+    # volume and boundary quadrature see the unit square
+    assert sum(ah.reinit(k).JxW.sum() for k in range(ah.n_polytopes)) == pytest.approx(1.0, abs=1e-14)
+    assert sum(ah.reinit(k, f).JxW.sum() for k in range(ah.n_polytopes) for f in range(ah.n_faces(k))
+               if ah.at_boundary(k, f)) == pytest.approx(4.0, abs=1e-14)
+    # the two sides of every interface meet in the same quadrature points (test/polydeal/reinit_cell_face_quad_pts.cc)
+    for k in range(ah.n_polytopes):
+        for f in range(ah.n_faces(k)):
+            if not ah.at_boundary(k, f) and k < ah.neighbor(k, f):
+                q = ah.neighbor(k, f)
+                a, b = ah.reinit_interface(k, q, f, ah.neighbor_of_agglomerated_neighbor(k, f))
+                assert np.abs(a.points - b.points).max() < 1e-15 and np.abs(a.normals + b.normals).max() < 1e-14
+    A = po.assemble_dg_matrix(ah, penalty_constant=1.0, h_rule=po.H_CONSTANT, h_const=1.0, with_boundary=False).scipy()
+    ux = interpolate(ah, lambda x: x[0])
+    uxy = interpolate(ah, lambda x: x[0] + x[1])
+    one = np.ones(ah.n_dofs)
+    assert ux @ (A @ ux) == pytest.approx(g["x"][0], abs=1e-11)
+    assert uxy @ (A @ uxy) == pytest.approx(g["xplusy"][0], abs=1e-11)
+    assert abs(one @ (A @ one)) < 1e-11 and abs(A - A.T).max() < 1e-12
