@@ -178,3 +178,38 @@ def test_tile_plan_contract(lib, shape, order, tile, with_list, n, blocks):
         assert nt == 8 and seen_max_halo == 48  # a 4x4x4 corner block and its three inner faces
     if with_list == "interior":  # 6^3 interior cells: the eight 3x3x3 corners of the blocks, compact halos
         assert nt == 8 and seen_max_halo <= 96
+
+
+@pytest.mark.parametrize("n", [4, 8, 9, 16, 25, 27])
+def test_halo_bulk_copies_are_aligned_and_in_bounds(n):
+    """The arithmetic k_fine_tile uses to fill a halo row with ONE 16-byte-granular bulk copy (pd_finemesh.cu,
+    stage of the halo: first = cell * n doubles, copy from the 16-byte boundary below it, a trailing 8-byte copy
+    when 8 bytes are left), restated here and checked for every cell of a vector, the last one included:
+    source and destination 16-byte aligned, size a positive multiple of 16, nothing read past the vector, nothing
+    written past the row, and coefficient k of the cell lands where the tile plan's offset (odd start) says.
+    (compute-sanitizer is not available on the GPU pool; this is the bounds check of our own.)"""
+    tile, n_cells = 64, 37
+    ro, rh = n | 1, None
+    rh = (n + 2) // 2 * 2
+    if rh % 4 == 0:
+        rh += 2
+    vector_bytes = n_cells * n * 8
+    for hid in range(n_cells):
+        first = hid * n
+        a0 = first & ~1
+        total = (n + first - a0) * 8
+        sz = total & ~15
+        tail = total - sz
+        assert (a0 * 8) % 16 == 0 and sz > 0 and sz % 16 == 0 and tail in (0, 8)
+        assert a0 * 8 + sz + tail <= vector_bytes  # the last cell does not read past the end of the vector
+        for r in (0, 1, 95):
+            dst = (tile * ro + r * rh) * 8
+            assert dst % 16 == 0 and sz + tail <= rh * 8  # stays inside its row
+        odd = (hid * n) & 1  # what build_tile_plan adds to the row's offset
+        assert first - a0 == odd
+        # row[j] = x[a0 + j]  =>  row[odd + k] = x[first + k]
+        assert all(a0 + odd + k == first + k for k in range(n)) and (odd + n) * 8 <= sz + tail
+    # the contiguous own range of a full tile: 16-byte aligned start and size whenever own rows are n doubles apart
+    if ro == n:
+        for t in range(5):
+            assert (t * tile * n * 8) % 16 == 0 and (tile * n * 8) % 16 == 0
