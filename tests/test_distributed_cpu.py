@@ -35,7 +35,7 @@ def _build(dim, n, shape, p, seed=3):
     return po, oah, pah
 
 
-def _worker(rank, world, port, dim, n, shape, p, results):
+def _worker(rank, world, port, dim, n, shape, p, results, partitioner="blocks"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -43,7 +43,10 @@ def _worker(rank, world, port, dim, n, shape, p, results):
         from polydeal_b200 import distributed as pdd
 
         po, oah, pah = _build(dim, n, shape, p)
-        owner = pdd.partition_by_blocks(pah, world)
+        # blocks: contiguous ranges of the DoF-block order; metis: METIS on the polytope adjacency graph,
+        # ownership then is scattered over the numbering
+        owner = pdd.partition_by_blocks(pah, world) if partitioner == "blocks" else pdd.partition_by_metis(pah, world)
+        assert len(set(owner.tolist())) == world
         part = pdd.LocalPart(pah, owner, rank)
         nd = part.n
         # every polytope is owned exactly once; local block order = global order restricted
@@ -101,12 +104,13 @@ def _worker(rank, world, port, dim, n, shape, p, results):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,dim,n,shape,p", [(2, 2, 8, "blocks2", 1), (2, 3, 4, "random9", 1), (3, 2, 8, "random11", 2)])
-def test_sharding_host_logic_gloo(world, dim, n, shape, p):
+@pytest.mark.parametrize("world,dim,n,shape,p,partitioner", [(2, 2, 8, "blocks2", 1, "blocks"), (2, 3, 4, "random9", 1, "blocks"),
+                                                             (3, 2, 8, "random11", 2, "blocks"), (2, 2, 8, "random12", 1, "metis")])
+def test_sharding_host_logic_gloo(world, dim, n, shape, p, partitioner):
     mgr = mp.Manager()
     results = mgr.dict()
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, dim, n, shape, p, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, dim, n, shape, p, results, partitioner), nprocs=world, join=True)
     assert dict(results) == {r: "ok" for r in range(world)}
 
 
