@@ -318,7 +318,7 @@ namespace pd
     }
 
     // ---------------------------------------------------------------------------------------
-    // The tiled kernel: ONE THREAD PER CELL, coefficients staged in shared memory.
+    // The tiled kernel: ONE CELL PER THREAD PAIR, coefficients staged in shared memory.
     //
     // ncu on k_fine_sip (profiles/ncu_r01_fine_sip_summary.txt) shows the line-per-thread kernel
     // bound by the L1 data pipe (l1tex__data_pipe_lsu_wavefronts 92 %: 61 global + 73 shared
@@ -329,11 +329,11 @@ namespace pd
     // LSU wavefronts, everything in flight at once, completion on one mbarrier).  Two threads per
     // cell then apply the whole operator in registers (pd::fine::cell_lines, cell_mass; the lines
     // are split between two roles so that 16 warps are resident per SM, the partial sums meet
-    // once through the cell's own row): their reads are row reads of an [cell][N] array with N
-    // odd -> bank-conflict free, 16 useful doubles per wavefront.  Results go back through the
+    // once through the cell's own row): their reads are row reads of an [cell][row] array with
+    // an odd row length -> bank-conflict free, 16 useful doubles per wavefront.  Results go back through the
     // own rows so that the global stores are coalesced.
-    // Measured (64^3 DGQ2, Morton order): 55 -> ~45 L1 wavefronts per cell instead of 134,
-    // 0.134 -> 0.070 ms.
+    // Measured (64^3 DGQ2, Morton order, profiles/ncu_r01_fine_tile_summary.txt): 31 shared + ~6
+    // global L1 wavefronts per cell instead of 134, 0.134 -> 0.070 ms.
     // ---------------------------------------------------------------------------------------
     template <int N1>
     struct TileArgs
