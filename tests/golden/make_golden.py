@@ -203,6 +203,31 @@ def parse_gmsh_quads(path):
     return {"verts": [coords[t] for t in used], "quads": [[new[t] for t in q] for q in quads]}
 
 
+def parse_ucd_quads(path):
+    """vertices and quadrilaterals (counter-clockwise node order, 0-based) of a UCD (.inp) file -- circle-grid.inp of
+    unstructured_grid.cc."""
+    rows = [l.split() for l in open(path).read().split("\n") if l.strip() and not l.startswith("#")]
+    n_verts, n_cells = int(rows[0][0]), int(rows[0][1])
+    tag = {int(r[0]): k for k, r in enumerate(rows[1:1 + n_verts])}
+    verts = [[float(r[1]), float(r[2])] for r in rows[1:1 + n_verts]]
+    quads = [[tag[int(t)] for t in r[3:7]] for r in rows[1 + n_verts:1 + n_verts + n_cells] if r[2] == "quad"]
+    return {"verts": verts, "quads": quads}
+
+
+def parse_unstructured_grid(name):
+    """blocks 'Number of faces ... normals ... Perimeter' of unstructured_grid.output"""
+    out, cur = [], None
+    for l in lines(name):
+        if m := re.match(r"Number of faces of this cell: (\d+)", l):
+            cur = {"n_faces": int(m.group(1)), "normals": []}
+            out.append(cur)
+        elif m := re.match(r"For face with index f =(\d+) the normal is (\S+) (\S+)", l):
+            cur["normals"].append([float(m.group(2)), float(m.group(3))])
+        elif m := re.match(r"Perimeter of agglomeration.* is (\S+)", l):
+            cur["perimeter"] = float(m.group(1))
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference tree not present; goldens can only be regenerated in the build container")
@@ -278,6 +303,10 @@ def main():
             "x": floats_after("fully_distributed_poisson_sanity_check_02.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x: (\S+)"),
             "xplusy": floats_after("fully_distributed_poisson_sanity_check_02.with_mpi=true.with_p4est=true.mpirun=3.output", r"f\(x,y\)=x\+y: (\S+)"),
             "input_grid": parse_gmsh_quads(os.path.join(REF, "input_grids", "square.msh")),
+        },
+        "unstructured_grid": {
+            "blocks": parse_unstructured_grid("unstructured_grid.output"),
+            "circle_grid": parse_ucd_quads(os.path.join(REF, "circle-grid.inp")),
         },
         "poisson": floats_after("poisson.output", r"(\d\.\d+)"),
     }

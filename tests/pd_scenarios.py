@@ -207,6 +207,13 @@ def quad_mesh_from_gmsh(verts, quads_ccw, n_refine=0):
                 else:
                     assert direction[o] == (o_tail < o_head), "mesh is not orientable"
     starts_at = lambda a, b: direction[(min(a, b), max(a, b))] == (a < b)
+    # a file whose cells already are consistently directed keeps its vertex order (deal.II reorders only if it must)
+    as_given, consistent = {}, True
+    for q in quads_ccw:
+        for a, b in ((q[0], q[3]), (q[1], q[2]), (q[0], q[1]), (q[3], q[2])):  # lines 0..3 of (n0 n1 n3 n2)
+            consistent = consistent and as_given.setdefault((min(a, b), max(a, b)), a < b) == (a < b)
+    if consistent:
+        starts_at = lambda a, b: as_given[(min(a, b), max(a, b))] == (a < b)
     cells = []
     for q in quads_ccw:
         k = next(k for k in range(4) if starts_at(q[k], q[(k + 1) % 4]) and starts_at(q[k], q[(k + 3) % 4]))
@@ -239,3 +246,49 @@ def quad_mesh_from_gmsh(verts, quads_ccw, n_refine=0):
             (c0, f0), (c1, f1) = sides
             nbr[c0, f0], nbr[c1, f1] = c1, c0
     return np.array(verts), np.array(cells, dtype=np.int32), nbr
+
+
+def hyper_ball_2d_refined_once():
+    """GridGenerator::hyper_ball<2>(tria) (centre 0, radius 1: the five-cell disc, inner square of half width
+    1 / (sqrt 2 (1 + sqrt 2)), SphericalManifold on the boundary) followed by refine_global(1), as in
+    test/polydeal/unstructured_grid.cc:30-32.  deal.II behaviours restated (pinned by that test's golden): the new
+    vertex of a boundary line lies on the circle, the one of an interior line at its mid-point, the one of a cell at
+    the transfinite interpolation of its 4 vertices (weight -1/4) and 4 new line vertices (+1/2)."""
+    a, r = 1.0 / (1.0 + np.sqrt(2.0)), 1.0 / np.sqrt(2.0)
+    verts = [(-r, -r), (r, -r), (-r * a, -r * a), (r * a, -r * a), (-r * a, r * a), (r * a, r * a), (-r, r), (r, r)]
+    cells = [[0, 1, 2, 3], [0, 2, 6, 4], [2, 3, 4, 5], [1, 7, 3, 5], [6, 4, 7, 5]]
+    face_verts = [(0, 2), (1, 3), (0, 1), (2, 3)]
+    n_cells_at = {}
+    for c in cells:
+        for i, j in face_verts:
+            key = (min(c[i], c[j]), max(c[i], c[j]))
+            n_cells_at[key] = n_cells_at.get(key, 0) + 1
+    mid = {}
+
+    def midpoint(p, q):
+        key = (min(p, q), max(p, q))
+        if key not in mid:
+            m = 0.5 * (np.array(verts[p]) + np.array(verts[q]))
+            if n_cells_at[key] == 1:  # boundary line: SphericalManifold
+                m = m / np.linalg.norm(m)
+            verts.append(tuple(m))
+            mid[key] = len(verts) - 1
+        return mid[key]
+
+    children = []
+    for v0, v1, v2, v3 in cells:
+        m01, m02, m13, m23 = midpoint(v0, v1), midpoint(v0, v2), midpoint(v1, v3), midpoint(v2, v3)
+        P = lambda i: np.array(verts[i])
+        verts.append(tuple(-0.25 * (P(v0) + P(v1) + P(v2) + P(v3)) + 0.5 * (P(m01) + P(m02) + P(m13) + P(m23))))
+        c = len(verts) - 1
+        children += [[v0, m01, m02, c], [m01, v1, c, m13], [m02, c, v2, m23], [c, m13, m23, v3]]
+    edge = {}
+    for ci, cv in enumerate(children):
+        for f, (i, j) in enumerate(face_verts):
+            edge.setdefault((min(cv[i], cv[j]), max(cv[i], cv[j])), []).append((ci, f))
+    nbr = -np.ones((len(children), 4), dtype=np.int32)
+    for sides in edge.values():
+        if len(sides) == 2:
+            (c0, f0), (c1, f1) = sides
+            nbr[c0, f0], nbr[c1, f1] = c1, c0
+    return np.array(verts), np.array(children, dtype=np.int32), nbr

@@ -398,3 +398,44 @@ def test_host_mirror_on_an_unstructured_mesh(goldens):
         assert set(views) == {int(owner[key[0]]), int(owner[key[1]])}, key
         a, b = views.values()
         assert a.shape == b.shape and np.abs(a - b).max() < 1e-15, key
+
+
+@pytest.mark.parametrize("which", ["circle-grid.inp", "hyper_ball"])
+def test_unstructured_grid_golden_through_the_host_mirror(goldens, which):
+    """test/polydeal/unstructured_grid.cc through the product's host mirror: the two-cell polytope has the golden
+    number of faces, and numbering, face enumeration, neighbours, nofn, aligned sub-face lists and sparsity are those
+    of the oracle (which reproduces the golden's normals and perimeter, tests/test_oracle_goldens.py)."""
+    g = goldens["unstructured_grid"]
+    if which == "circle-grid.inp":
+        gold, pair = g["blocks"][0], (25, 44)
+        v, cv, nbr = sc.quad_mesh_from_gmsh(g["circle_grid"]["verts"], g["circle_grid"]["quads"], n_refine=1)
+    else:
+        gold, pair = g["blocks"][1], (5, 8)
+        v, cv, nbr = sc.hyper_ball_2d_refined_once()
+    oah = po.AgglomerationHandler(po.Grid.from_arrays(v, cv, nbr))
+    pah = pdl.AgglomerationHandler(pdl.Grid.from_arrays(v, cv, nbr))
+    for ah, kind in ((oah, po.FE_DGQ), (pah, pdl.FE_DGQ)):
+        ah.define_agglomerate(list(pair))
+        for c in range(len(cv)):
+            if c not in pair:
+                ah.define_agglomerate([c])
+        ah.initialize_fe_values(1, 1)
+        ah.distribute_agglomerated_dofs(kind, 1)
+    assert pah.n_faces(0) == gold["n_faces"] and pah.get_agglomerate(0).tolist() == [pair[1], pair[0]]  # slave, master
+    assert pah.n_polytopes == oah.n_polytopes and pah.n_dofs == oah.n_dofs
+    for p in range(oah.n_polytopes):
+        assert pah.master_cell(p) == oah.master_cell(p)
+        assert pah.get_dof_indices(p).tolist() == oah.get_dof_indices(p).tolist()
+        assert pah.n_faces(p) == oah.n_faces(p)
+        np.testing.assert_array_equal(np.concatenate(pah.bbox(p)), np.concatenate(oah.bbox(p)))
+        for f in range(oah.n_faces(p)):
+            assert pah.at_boundary(p, f) == oah.at_boundary(p, f)
+            assert pah.neighbor(p, f) == oah.neighbor(p, f)
+            assert pah.neighbor_of_agglomerated_neighbor(p, f) == oah.neighbor_of_agglomerated_neighbor(p, f)
+            assert pah.interface(p, f) == oah.interface(p, f)
+    rp, cols = pah.create_agglomeration_sparsity_pattern()
+    orp, ocols = oah.create_agglomeration_sparsity_pattern()
+    np.testing.assert_array_equal(rp, orp)
+    np.testing.assert_array_equal(cols, ocols)
+    d = pah.flatten()
+    assert d.n_polytopes == oah.n_polytopes and d.n_ifaces > 0

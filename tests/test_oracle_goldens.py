@@ -253,3 +253,34 @@ def test_agglodgp_is_orthonormal(dim, p, n):
     V = np.array([po.fe_evaluate(po.FE_AGGLODGP, dim, p, x)[0] for x in pts])
     np.testing.assert_allclose(V.T @ (wts[:, None] * V), np.eye(n), atol=1e-13)
     np.testing.assert_allclose(V[:, 0], 1.0, atol=1e-15)
+
+
+@pytest.mark.parametrize("which", ["circle-grid.inp", "hyper_ball"])
+def test_unstructured_grid_golden(goldens, which):
+    """test/polydeal/unstructured_grid.cc: normals[0] of every face of the one polytope made of two cells, and its
+    perimeter, on (i) circle-grid.inp read by GridIn::read_ucd and refined once, cells {25, 44} (:116-196, the block
+    with six faces) and (ii) GridGenerator::hyper_ball refined once, cells {8, 5} (:28-110, five faces).  Pins, on
+    meshes whose neighbours are rotated against each other: the vertex order GridIn hands over, the child order of
+    refine_global, the new-vertex rules of the spherical manifold, the face enumeration and the outward normals."""
+    g = goldens["unstructured_grid"]
+    if which == "circle-grid.inp":
+        gold, pair = g["blocks"][0], (25, 44)
+        v, cv, nbr = sc.quad_mesh_from_gmsh(g["circle_grid"]["verts"], g["circle_grid"]["quads"], n_refine=1)
+    else:
+        gold, pair = g["blocks"][1], (5, 8)
+        v, cv, nbr = sc.hyper_ball_2d_refined_once()
+    ah = po.AgglomerationHandler(po.Grid.from_arrays(v, cv, nbr))
+    ah.define_agglomerate(list(pair))
+    for c in range(len(cv)):
+        if c not in pair:
+            ah.define_agglomerate([c])
+    ah.initialize_fe_values(1, 1)  # QGauss<2>(1), faces QGauss<1>(1)
+    ah.distribute_agglomerated_dofs(po.FE_DGQ, 1)
+    # the only polytope with that many faces is the agglomerated one
+    assert [k for k in range(ah.n_polytopes) if ah.n_faces(k) == gold["n_faces"]] == [0]
+    perimeter = 0.0
+    for f, n_gold in enumerate(gold["normals"]):
+        fv = ah.reinit(0, f)
+        perimeter += fv.JxW.sum()
+        assert np.abs(fv.normals[0] - np.array(n_gold)).max() < 5e-7 * max(1.0, np.abs(n_gold).max()), (f, fv.normals[0])
+    assert perimeter == pytest.approx(gold["perimeter"], rel=5e-6)
