@@ -137,15 +137,17 @@ def test_distributed_poisson_sanity_checks(name, goldens):
 
 @pytest.mark.parametrize("k", range(6))
 def test_poisson_sanity_check_03(k, goldens):
-    """test/polydeal/poisson_sanity_check_03.cc: the same invariants on an UNSTRUCTURED mesh (t3.msh, read
-    by GridIn -- not reproducible here) split by METIS into 50 ... 800 agglomerates.  The numbers it prints
-    (1, 2, ~1e-14) do not depend on mesh or partition; stand-in: a randomly distorted 64x64 grid with the
-    same agglomerate counts."""
+    """test/polydeal/poisson_sanity_check_03.cc:105-116: the same invariants on the UNSTRUCTURED mesh t3.msh (identical
+    to test/polydeal/input_grids/square.msh, parsed into tests/golden), read by GridIn and refined three times (5824
+    quadrilaterals), split into 50 ... 800 agglomerates (METIS in the reference: the partition is an input, the numbers
+    1, 2, ~1e-14 do not depend on it)."""
     g = goldens["poisson_sanity_check_03"]
     n_parts = int(g["n_subdomains"][k])
-    grid = po.Grid.hyper_cube(2, 0.0, 1.0, 6)
-    grid.distort_random(0.3, 100 + k)
-    groups = sc.random_partition(grid.n_cells, grid.arrays()[2], n_parts, seed=n_parts)
+    mesh = goldens["fully_distributed_poisson_sanity_check_02"]["input_grid"]
+    v, cv, nbr = sc.quad_mesh_from_gmsh(mesh["verts"], mesh["quads"], n_refine=3)
+    assert len(cv) == 91 * 64
+    grid = po.Grid.from_arrays(v, cv, nbr)
+    groups = sc.random_partition(grid.n_cells, nbr, n_parts, seed=n_parts)
     ah = po.AgglomerationHandler(grid)
     for gr in groups:
         ah.define_agglomerate(gr)
