@@ -439,3 +439,40 @@ def test_unstructured_grid_golden_through_the_host_mirror(goldens, which):
     np.testing.assert_array_equal(cols, ocols)
     d = pah.flatten()
     assert d.n_polytopes == oah.n_polytopes and d.n_ifaces > 0
+
+
+@pytest.mark.parametrize("mesh,n_refine", [("square.msh", 0), ("square.msh", 1), ("circle-grid.inp", 0), ("circle-grid.inp", 2), ("hyper_ball", 1)])
+def test_host_mirror_matches_oracle_on_random_agglomerations_of_unstructured_meshes(goldens, mesh, n_refine):
+    """face enumeration, neighbours, nofn, aligned sub-face lists and sparsity on random connected agglomerations of
+    the reference tests' unstructured input grids (neighbours rotated against each other), host mirror vs oracle;
+    and the oracle's matrix keeps the constants in its kernel."""
+    if mesh == "square.msh":
+        src = goldens["fully_distributed_poisson_sanity_check_02"]["input_grid"]
+        v, cv, nbr = sc.quad_mesh_from_gmsh(src["verts"], src["quads"], n_refine=n_refine)
+    elif mesh == "circle-grid.inp":
+        src = goldens["unstructured_grid"]["circle_grid"]
+        v, cv, nbr = sc.quad_mesh_from_gmsh(src["verts"], src["quads"], n_refine=n_refine)
+    else:
+        v, cv, nbr = sc.hyper_ball_2d_refined_once()
+    for seed in range(3):
+        groups = sc.random_partition(len(cv), nbr, max(2, len(cv) // (3 + 2 * seed)), seed=seed)
+        oah = po.AgglomerationHandler(po.Grid.from_arrays(v, cv, nbr))
+        pah = pdl.AgglomerationHandler(pdl.Grid.from_arrays(v, cv, nbr))
+        for ah, kind in ((oah, po.FE_DGQ), (pah, pdl.FE_DGQ)):
+            for gr in groups:
+                ah.define_agglomerate(gr)
+            ah.initialize_fe_values(2)
+            ah.distribute_agglomerated_dofs(kind, 1)
+        for p in range(oah.n_polytopes):
+            assert pah.n_faces(p) == oah.n_faces(p)
+            for f in range(oah.n_faces(p)):
+                assert pah.neighbor(p, f) == oah.neighbor(p, f) and pah.interface(p, f) == oah.interface(p, f)
+                assert pah.neighbor_of_agglomerated_neighbor(p, f) == oah.neighbor_of_agglomerated_neighbor(p, f)
+        rp, cols = pah.create_agglomeration_sparsity_pattern()
+        orp, ocols = oah.create_agglomeration_sparsity_pattern()
+        np.testing.assert_array_equal(rp, orp)
+        np.testing.assert_array_equal(cols, ocols)
+        A = po.assemble_dg_matrix(oah, penalty_constant=10.0, h_rule=po.H_MAX_INVERSE_DIAMETER, with_boundary=False).scipy()
+        one = np.ones(oah.n_dofs)
+        assert abs(A - A.T).max() < 1e-12 and abs(one @ (A @ one)) < 1e-10
+        assert pah.flatten().n_polytopes == oah.n_polytopes
