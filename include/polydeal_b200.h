@@ -38,6 +38,8 @@ extern "C" {
 #define PD_ERR_UNSUPPORTED (-3) /* (dim, degree, FE) combination has no kernel   */
 #define PD_ERR_NO_DEVICE (-4)   /* no CUDA device: there is no CPU fallback      */
 #define PD_ERR_STATE (-5)       /* call order violated (e.g. vmult before assemble) */
+#define PD_NOT_CONVERGED 1      /* pd_cg_solve*: tolerance not reached within max_iter; the iterate, the iteration
+                                   count and the residual are valid (SolverCG throws NoConvergence there)          */
 
 #define PD_INVALID_UINT 0xFFFFFFFFu /* numbers::invalid_unsigned_int */
 
@@ -148,12 +150,25 @@ typedef struct pd_coefficients
 int pd_create(const pd_mesh_desc *desc, pd_handle **out);
 int pd_destroy(pd_handle *h);
 
-/* Re-send every descriptor array host->device into the existing buffers (same
- * sizes as at pd_create).  This is the per-step host->device leg of the
- * end-to-end path. */
+/* Re-send every descriptor array host->device into the existing buffers.  This is the
+ * per-step host->device leg of the end-to-end path (a mesh whose vertices move, new
+ * penalties).  The TOPOLOGY must be the one of pd_create: sizes, poly_subcell_ptr,
+ * dof_block, the interface list (iface_polyA/B, iface_sub_ptr) and the block pattern are
+ * compared with the handle's copies and a difference is PD_ERR_INVALID (create a new
+ * handle).  verts, bbox, sub_sigma and the range-checked index arrays cell_verts,
+ * poly_subcell_idx, sub_cell, sub_face may change: the quadrature, the assembled matrix
+ * and the cached inverse diagonals are invalidated, and on fine meshes the stencil /
+ * mapped-geometry tables of the matrix-free operators are re-derived when they differ. */
 int pd_upload(pd_handle *h, const pd_mesh_desc *desc);
 
-/* Use a caller stream (cudaStream_t passed as void*); NULL = the handle's own. */
+/* Stream contract: every device call of a handle is enqueued on ONE stream and nothing else
+ * orders it against the caller's work.  By default that is a stream the handle creates
+ * (cudaStreamNonBlocking: NOT ordered with the legacy default stream); a caller that
+ * produces src / consumes dst on its own stream must either hand that stream over here or
+ * synchronise itself.  cuda_stream: a cudaStream_t passed as void*; NULL = back to the
+ * handle's own stream; the legacy default stream is named by cudaStreamLegacy
+ * ((void*)0x1), the per-thread default stream by cudaStreamPerThread ((void*)0x2).
+ * Synchronises the previous stream; invalidates captured solver graphs. */
 int pd_set_stream(pd_handle *h, void *cuda_stream);
 int pd_synchronize(pd_handle *h);
 
@@ -318,7 +333,12 @@ int pd_diagonal_inverse_of(pd_handle *h, int mode, double *dst_dev);
  * examples/diffusion_reaction.cc:709-724 / examples/matrix_free_agglo.cc:377-384.
  * jacobi != 0 preconditions with the inverse diagonal (needs pd_assemble).  x_dev holds the
  * initial guess on entry.  Stops when |r| <= rel_tol |b| (checked every 8 iterations: the
- * iteration body is replayed from a CUDA graph) or after max_iter. */
+ * iteration body is replayed from a CUDA graph; *iterations is the number actually run,
+ * never more than max_iter) and returns PD_OK, or returns PD_NOT_CONVERGED after max_iter.
+ * rel_tol <= 0: exactly max_iter iterations without a convergence test (PD_OK).
+ * The captured graphs are keyed on everything they bake in (mode, jacobi, x_dev, b_dev,
+ * operator terms / coefficients, stream, uploads), so changing any of it between two
+ * solves is safe. */
 int pd_cg_solve(pd_handle *h, int mode, const double *b_dev, double *x_dev, int max_iter, double rel_tol,
                 int jacobi, int *iterations, double *relative_residual);
 /* largest eigenvalue of D^-1 A by n_iterations of the power method (the bound

@@ -1199,15 +1199,149 @@ namespace po
     return s; // this is already the inverse extent
   }
 
+  // penalty of a boundary point / an interior point seen from the visitor p (SURVEY 8c zoo)
+  inline double
+  boundary_penalty(const Handler &ah, const AssembleParams &prm, const int p, const double *nrm)
+  {
+    switch (prm.h_rule)
+      {
+        case H_CONSTANT:
+          return prm.penalty_constant / prm.h_const;
+        case H_NORMAL_EXTENT:
+          return 4. * prm.penalty_constant * normal_extent(ah, p, nrm);
+        default:
+          return prm.penalty_constant / ah.diameter(p);
+      }
+  }
+  inline double
+  interior_penalty(const Handler &ah, const AssembleParams &prm, const int p, const int nbp, const double *nrm)
+  {
+    switch (prm.h_rule)
+      {
+        case H_MAX_INVERSE_DIAMETER:
+          return prm.penalty_constant * std::max(1. / ah.diameter(p), 1. / ah.diameter(nbp));
+        case H_CONSTANT:
+          return prm.penalty_constant / prm.h_const;
+        case H_NORMAL_EXTENT:
+          return prm.penalty_constant * (normal_extent(ah, p, nrm) + normal_extent(ah, nbp, nrm));
+        default:
+          return prm.penalty_constant / ah.diameter(p);
+      }
+  }
+
+  // volume term (include/poly_utils.h:2038-2052) plus the boundary faces of polytope p
+  // (:2060-2085) into cell_matrix (n x n, zeroed here)
+  inline void
+  cell_and_boundary_matrix(const Handler        &ah,
+                           const AssembleParams &prm,
+                           const int             p,
+                           FEValuesTable        &av,
+                           FEValuesTable        &f0,
+                           std::vector<double>  &cell_matrix)
+  {
+    const int    n   = ah.fe.n_dofs;
+    const int    dim = ah.dim;
+    const double sc  = prm.stiffness_coeff;
+    std::fill(cell_matrix.begin(), cell_matrix.end(), 0.);
+    ah.reinit(p, av);
+    for (int q = 0; q < av.n_q; ++q)
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+          {
+            const double *gi = av.shape_grad(i, q), *gj = av.shape_grad(j, q);
+            double        gg = gi[0] * gj[0] + gi[1] * gj[1];
+            if (dim == 3)
+              gg += gi[2] * gj[2];
+            double v = sc * gg;
+            if (prm.mass_coeff != 0.)
+              v += prm.mass_coeff * av.shape_value(i, q) * av.shape_value(j, q);
+            cell_matrix[(size_t)i * n + j] += v * av.jxw[q];
+          }
+    if (!prm.with_boundary)
+      return;
+    const unsigned nf = ah.n_faces(p);
+    for (unsigned f = 0; f < nf; ++f)
+      {
+        if (!ah.at_boundary(p, f))
+          continue;
+        ah.reinit_face(p, f, f0);
+        for (int q = 0; q < f0.n_q; ++q)
+          {
+            const double *nrm = &f0.normals[(size_t)q * dim];
+            const double  pen = boundary_penalty(ah, prm, p, nrm);
+            for (int i = 0; i < n; ++i)
+              for (int j = 0; j < n; ++j)
+                cell_matrix[(size_t)i * n + j] +=
+                  sc *
+                  (-f0.shape_value(i, q) * dotn(dim, f0.shape_grad(j, q), nrm) -
+                   dotn(dim, f0.shape_grad(i, q), nrm) * f0.shape_value(j, q) +
+                   pen * f0.shape_value(i, q) * f0.shape_value(j, q)) *
+                  f0.jxw[q];
+          }
+      }
+  }
+
+  // the four blocks of interface (p, neighbor(p, f)) seen from the visitor p:
+  // reinit_interface + assemble_local_jumps_and_averages (include/poly_utils.h:1870-1926)
+  inline void
+  interface_matrices(const Handler        &ah,
+                     const AssembleParams &prm,
+                     const int             p,
+                     const unsigned        f,
+                     FEValuesTable        &f0,
+                     FEValuesTable        &f1,
+                     std::vector<double>  &M11,
+                     std::vector<double>  &M12,
+                     std::vector<double>  &M21,
+                     std::vector<double>  &M22)
+  {
+    const int      n    = ah.fe.n_dofs;
+    const int      dim  = ah.dim;
+    const double   sc   = prm.stiffness_coeff;
+    const int      nbp  = ah.neighbor(p, f);
+    const unsigned nofn = ah.neighbor_of_agglomerated_neighbor(p, f);
+    ah.reinit_interface(p, nbp, f, nofn, f0, f1);
+    std::fill(M11.begin(), M11.end(), 0.);
+    std::fill(M12.begin(), M12.end(), 0.);
+    std::fill(M21.begin(), M21.end(), 0.);
+    std::fill(M22.begin(), M22.end(), 0.);
+    for (int q = 0; q < f0.n_q; ++q)
+      {
+        const double *nrm = &f0.normals[(size_t)q * dim];
+        const double  pen = interior_penalty(ah, prm, p, nbp, nrm);
+        // include/poly_utils.h:1884-1925
+        for (int i = 0; i < n; ++i)
+          for (int j = 0; j < n; ++j)
+            {
+              const double g0i = dotn(dim, f0.shape_grad(i, q), nrm);
+              const double g0j = dotn(dim, f0.shape_grad(j, q), nrm);
+              const double g1i = dotn(dim, f1.shape_grad(i, q), nrm);
+              const double g1j = dotn(dim, f1.shape_grad(j, q), nrm);
+              const double v0i = f0.shape_value(i, q), v0j = f0.shape_value(j, q);
+              const double v1i = f1.shape_value(i, q), v1j = f1.shape_value(j, q);
+              const size_t ij  = (size_t)i * n + j;
+              M11[ij] += sc * (-0.5 * g0i * v0j - 0.5 * g0j * v0i + pen * v0i * v0j) * f0.jxw[q];
+              M12[ij] += sc * (0.5 * g0i * v1j - 0.5 * g1j * v0i - pen * v0i * v1j) * f1.jxw[q];
+              M21[ij] += sc * (-0.5 * g1i * v0j + 0.5 * g0j * v1i - pen * v1i * v0j) * f1.jxw[q];
+              M22[ij] += sc * (0.5 * g1i * v1j + 0.5 * g1j * v1i + pen * v1i * v1j) * f1.jxw[q];
+            }
+      }
+  }
+
+  inline bool
+  visits(const Handler &ah, const AssembleParams &prm, const int p, const int nbp)
+  {
+    return prm.visit_rule == VISIT_BY_ID ? ah.master_cell(p) < ah.master_cell(nbp) : p < nbp;
+  }
+
   inline void
   assemble_dg_matrix(const Handler &ah, const AssembleParams &prm, CSRMatrix &A)
   {
     ah.sparsity_pattern(A.rowptr, A.cols);
     A.vals.assign(A.cols.size(), 0.);
-    const int n   = ah.fe.n_dofs;
-    const int dim = ah.dim;
-    const int np  = ah.n_polytopes();
-    const int nb  = ah.n_dofs / n;
+    const int n  = ah.fe.n_dofs;
+    const int np = ah.n_polytopes();
+    const int nb = ah.n_dofs / n;
     // one spin lock per block row so the threaded variant stays race free
     std::unique_ptr<std::atomic_flag[]> locks(new std::atomic_flag[nb]);
     for (int i = 0; i < nb; ++i)
@@ -1225,132 +1359,33 @@ namespace po
     };
 
     std::atomic<int> next_poly{0};
-    auto work = [&](const int p_begin_unused, const int p_end_unused) {
-      (void)p_begin_unused;
-      (void)p_end_unused;
+    auto work = [&]() {
       std::vector<double>       cell_matrix((size_t)n * n), M11((size_t)n * n),
         M12((size_t)n * n), M21((size_t)n * n), M22((size_t)n * n);
       std::vector<unsigned int> ldi(n), ldin(n);
       FEValuesTable             av, f0, f1;
-      const double              sc = prm.stiffness_coeff;
       // dynamic schedule: the visiting polytope does all the work of an interface,
       // so static ranges would be badly balanced
       for (int p = next_poly.fetch_add(1); p < np; p = next_poly.fetch_add(1))
         {
           if (p % prm.poly_stride != prm.poly_offset)
             continue;
-          std::fill(cell_matrix.begin(), cell_matrix.end(), 0.);
-          ah.reinit(p, av);
-          for (int q = 0; q < av.n_q; ++q)
-            for (int i = 0; i < n; ++i)
-              for (int j = 0; j < n; ++j)
-                {
-                  const double *gi = av.shape_grad(i, q), *gj = av.shape_grad(j, q);
-                  double        gg = gi[0] * gj[0] + gi[1] * gj[1];
-                  if (dim == 3)
-                    gg += gi[2] * gj[2];
-                  double v = sc * gg;
-                  if (prm.mass_coeff != 0.)
-                    v += prm.mass_coeff * av.shape_value(i, q) * av.shape_value(j, q);
-                  cell_matrix[(size_t)i * n + j] += v * av.jxw[q];
-                }
+          cell_and_boundary_matrix(ah, prm, p, av, f0, cell_matrix);
           ah.get_dof_indices(p, ldi.data());
-          const unsigned nf   = ah.n_faces(p);
-          const double   h_p  = ah.diameter(p);
+          const unsigned nf = ah.n_faces(p);
           for (unsigned f = 0; f < nf; ++f)
             {
               if (ah.at_boundary(p, f))
-                {
-                  if (!prm.with_boundary)
-                    continue;
-                  ah.reinit_face(p, f, f0);
-                  for (int q = 0; q < f0.n_q; ++q)
-                    {
-                      const double *nrm = &f0.normals[(size_t)q * dim];
-                      double        pen;
-                      switch (prm.h_rule)
-                        {
-                          case H_CONSTANT:
-                            pen = prm.penalty_constant / prm.h_const;
-                            break;
-                          case H_NORMAL_EXTENT:
-                            pen = 4. * prm.penalty_constant * normal_extent(ah, p, nrm);
-                            break;
-                          default:
-                            pen = prm.penalty_constant / h_p;
-                        }
-                      for (int i = 0; i < n; ++i)
-                        for (int j = 0; j < n; ++j)
-                          cell_matrix[(size_t)i * n + j] +=
-                            sc *
-                            (-f0.shape_value(i, q) * dotn(dim, f0.shape_grad(j, q), nrm) -
-                             dotn(dim, f0.shape_grad(i, q), nrm) * f0.shape_value(j, q) +
-                             pen * f0.shape_value(i, q) * f0.shape_value(j, q)) *
-                            f0.jxw[q];
-                    }
-                }
-              else
-                {
-                  const int  nbp = ah.neighbor(p, f);
-                  const bool visit =
-                    prm.visit_rule == VISIT_BY_ID ?
-                      ah.master_cell(p) < ah.master_cell(nbp) :
-                      p < nbp;
-                  if (!visit)
-                    continue;
-                  const unsigned nofn = ah.neighbor_of_agglomerated_neighbor(p, f);
-                  ah.reinit_interface(p, nbp, f, nofn, f0, f1);
-                  std::fill(M11.begin(), M11.end(), 0.);
-                  std::fill(M12.begin(), M12.end(), 0.);
-                  std::fill(M21.begin(), M21.end(), 0.);
-                  std::fill(M22.begin(), M22.end(), 0.);
-                  for (int q = 0; q < f0.n_q; ++q)
-                    {
-                      const double *nrm = &f0.normals[(size_t)q * dim];
-                      double        pen;
-                      switch (prm.h_rule)
-                        {
-                          case H_MAX_INVERSE_DIAMETER:
-                            pen = prm.penalty_constant *
-                                  std::max(1. / h_p, 1. / ah.diameter(nbp));
-                            break;
-                          case H_CONSTANT:
-                            pen = prm.penalty_constant / prm.h_const;
-                            break;
-                          case H_NORMAL_EXTENT:
-                            pen = prm.penalty_constant * (normal_extent(ah, p, nrm) +
-                                                          normal_extent(ah, nbp, nrm));
-                            break;
-                          default:
-                            pen = prm.penalty_constant / h_p;
-                        }
-                      // include/poly_utils.h:1884-1925
-                      for (int i = 0; i < n; ++i)
-                        for (int j = 0; j < n; ++j)
-                          {
-                            const double g0i = dotn(dim, f0.shape_grad(i, q), nrm);
-                            const double g0j = dotn(dim, f0.shape_grad(j, q), nrm);
-                            const double g1i = dotn(dim, f1.shape_grad(i, q), nrm);
-                            const double g1j = dotn(dim, f1.shape_grad(j, q), nrm);
-                            const double v0i = f0.shape_value(i, q), v0j = f0.shape_value(j, q);
-                            const double v1i = f1.shape_value(i, q), v1j = f1.shape_value(j, q);
-                            const size_t ij  = (size_t)i * n + j;
-                            M11[ij] += sc * (-0.5 * g0i * v0j - 0.5 * g0j * v0i + pen * v0i * v0j) *
-                                       f0.jxw[q];
-                            M12[ij] += sc * (0.5 * g0i * v1j - 0.5 * g1j * v0i - pen * v0i * v1j) *
-                                       f1.jxw[q];
-                            M21[ij] += sc * (-0.5 * g1i * v0j + 0.5 * g0j * v1i - pen * v1i * v0j) *
-                                       f1.jxw[q];
-                            M22[ij] += sc * (0.5 * g1i * v1j + 0.5 * g1j * v1i + pen * v1i * v1j) *
-                                       f1.jxw[q];
-                          }
-                    }
-                  ah.get_dof_indices(nbp, ldin.data());
-                  scatter(M11, ldi.data(), ldi.data());
-                  scatter(M12, ldi.data(), ldin.data());
-                  scatter(M21, ldin.data(), ldi.data());
-                  scatter(M22, ldin.data(), ldin.data());
-                }
+                continue;
+              const int nbp = ah.neighbor(p, f);
+              if (!visits(ah, prm, p, nbp))
+                continue;
+              interface_matrices(ah, prm, p, f, f0, f1, M11, M12, M21, M22);
+              ah.get_dof_indices(nbp, ldin.data());
+              scatter(M11, ldi.data(), ldi.data());
+              scatter(M12, ldi.data(), ldin.data());
+              scatter(M21, ldin.data(), ldi.data());
+              scatter(M22, ldin.data(), ldin.data());
             }
           scatter(cell_matrix, ldi.data(), ldi.data());
         }
@@ -1358,12 +1393,104 @@ namespace po
 
     const int nt = std::max(1, std::min(prm.n_threads, np));
     if (nt == 1)
-      work(0, np);
+      work();
     else
       {
         std::vector<std::thread> th;
         for (int t = 0; t < nt; ++t)
-          th.emplace_back(work, (int)((int64_t)np * t / nt), (int)((int64_t)np * (t + 1) / nt));
+          th.emplace_back(work);
+        for (auto &t : th)
+          t.join();
+      }
+  }
+
+  // The COMPLETE block rows of a few polytopes (parity checks at sizes where the whole matrix is
+  // out of reach for a scalar CPU code): for polytope p its volume and boundary terms, and for
+  // every interior face the interface evaluated from its VISITING side exactly as assemble_dg_matrix
+  // does -- p keeps M11, M12 if it visits, M22, M21 if its neighbour does.  Row layout = the scalar
+  // CSR rows of the reference pattern: block columns ascending; entry (i, k, j) of polytope s at
+  // ptr[s] n^2 + i (nb_s n) + k n + j, nb_s = ptr[s+1] - ptr[s].
+  struct BlockRows
+  {
+    std::vector<int64_t> ptr;
+    std::vector<int>     bcol;
+    std::vector<double>  vals;
+  };
+  inline void
+  assemble_block_rows(const Handler &ah, const AssembleParams &prm, const int *polys, const int n_polys, BlockRows &R)
+  {
+    const int n = ah.fe.n_dofs;
+    R.ptr.assign(n_polys + 1, 0);
+    std::vector<std::vector<std::pair<int, unsigned>>> cols(n_polys); // (block column, face or ~0u for the diagonal)
+    std::vector<unsigned int>                          ldi(n);
+    for (int s = 0; s < n_polys; ++s)
+      {
+        const int p = polys[s];
+        ah.get_dof_indices(p, ldi.data());
+        cols[s].push_back({(int)(ldi[0] / n), ~0u});
+        for (unsigned f = 0; f < ah.n_faces(p); ++f)
+          if (!ah.at_boundary(p, f))
+            {
+              ah.get_dof_indices(ah.neighbor(p, f), ldi.data());
+              cols[s].push_back({(int)(ldi[0] / n), f});
+            }
+        std::sort(cols[s].begin(), cols[s].end());
+        R.ptr[s + 1] = R.ptr[s] + (int64_t)cols[s].size();
+      }
+    R.bcol.resize(R.ptr[n_polys]);
+    R.vals.assign((size_t)R.ptr[n_polys] * n * n, 0.);
+    for (int s = 0; s < n_polys; ++s)
+      for (size_t k = 0; k < cols[s].size(); ++k)
+        R.bcol[R.ptr[s] + k] = cols[s][k].first;
+    std::atomic<int> next{0};
+    auto             work = [&]() {
+      std::vector<double> cell_matrix((size_t)n * n), M11((size_t)n * n), M12((size_t)n * n), M21((size_t)n * n),
+        M22((size_t)n * n);
+      FEValuesTable av, f0, f1;
+      for (int s = next.fetch_add(1); s < n_polys; s = next.fetch_add(1))
+        {
+          const int     p   = polys[s];
+          const int64_t nbk = R.ptr[s + 1] - R.ptr[s];
+          double       *row = &R.vals[(size_t)R.ptr[s] * n * n];
+          auto          add = [&](const size_t k, const std::vector<double> &M) {
+            for (int i = 0; i < n; ++i)
+              for (int j = 0; j < n; ++j)
+                row[(size_t)i * nbk * n + k * n + j] += M[(size_t)i * n + j];
+          };
+          size_t kd = 0;
+          while (cols[s][kd].second != ~0u)
+            ++kd;
+          cell_and_boundary_matrix(ah, prm, p, av, f0, cell_matrix);
+          add(kd, cell_matrix);
+          for (size_t k = 0; k < cols[s].size(); ++k)
+            {
+              const unsigned f = cols[s][k].second;
+              if (f == ~0u)
+                continue;
+              const int nbp = ah.neighbor(p, f);
+              if (visits(ah, prm, p, nbp))
+                {
+                  interface_matrices(ah, prm, p, f, f0, f1, M11, M12, M21, M22);
+                  add(kd, M11);
+                  add(k, M12);
+                }
+              else
+                {
+                  interface_matrices(ah, prm, nbp, ah.neighbor_of_agglomerated_neighbor(p, f), f0, f1, M11, M12, M21, M22);
+                  add(kd, M22);
+                  add(k, M21);
+                }
+            }
+        }
+    };
+    const int nt = std::max(1, std::min(prm.n_threads, n_polys));
+    if (nt == 1)
+      work();
+    else
+      {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t)
+          th.emplace_back(work);
         for (auto &t : th)
           t.join();
       }

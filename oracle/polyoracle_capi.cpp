@@ -366,6 +366,34 @@ extern "C"
       *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return M;
   }
+  // complete block rows of the listed polytopes (assemble_block_rows): returns the number of blocks;
+  // bcol / vals may be null to query sizes (vals: n_blocks * n^2 doubles)
+  int64_t
+  po_assemble_block_rows(void *ah, const po_assemble_params *p, const int *polys, int n_polys, int64_t *ptr, int *bcol,
+                         double *vals, double *seconds)
+  {
+    AssembleParams prm;
+    prm.penalty_constant = p->penalty_constant;
+    prm.h_rule           = p->h_rule;
+    prm.h_const          = p->h_const;
+    prm.visit_rule       = p->visit_rule;
+    prm.with_boundary    = p->with_boundary;
+    prm.stiffness_coeff  = p->stiffness_coeff;
+    prm.mass_coeff       = p->mass_coeff;
+    prm.n_threads        = p->n_threads;
+    BlockRows  R;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (guard([&] { assemble_block_rows(*static_cast<Handler *>(ah), prm, polys, n_polys, R); }))
+      return -1;
+    if (seconds)
+      *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::copy(R.ptr.begin(), R.ptr.end(), ptr);
+    if (bcol)
+      std::copy(R.bcol.begin(), R.bcol.end(), bcol);
+    if (vals)
+      std::copy(R.vals.begin(), R.vals.end(), vals);
+    return R.ptr.back();
+  }
   void
   po_matrix_free(void *M)
   {

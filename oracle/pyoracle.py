@@ -100,6 +100,7 @@ def lib():
             "po_ah_sparsity_nnz": (i64, [vp]),
             "po_ah_sparsity": (None, [vp, P(i64), P(i32)]),
             "po_assemble_dg_matrix": (vp, [vp, P(_Params), P(f64)]),
+            "po_assemble_block_rows": (i64, [vp, P(_Params), P(i32), i32, P(i64), P(i32), P(f64), P(f64)]),
             "po_matrix_free": (None, [vp]),
             "po_matrix_n_rows": (i64, [vp]),
             "po_matrix_nnz": (i64, [vp]),
@@ -404,6 +405,33 @@ def assemble_dg_matrix(
     if not h:
         raise RuntimeError(_err())
     return Matrix(h, sec.value)
+
+
+def assemble_block_rows(ah: AgglomerationHandler, polys, penalty_constant=None, h_rule=H_DIAMETER_OF_VISITOR, h_const=1.0,
+                        visit_rule=VISIT_BY_ID, with_boundary=True, stiffness_coeff=1.0, mass_coeff=0.0, n_threads=1,
+                        degree=None):
+    """The complete block rows of the polytopes `polys` (every interface evaluated from its visiting side as
+    PolyUtils::assemble_dg_matrix does, include/poly_utils.h:2086-2132): parity checks at sizes where the whole
+    matrix is out of reach for the scalar oracle.  Returns (ptr, bcol, rows, seconds): polytope s has block columns
+    bcol[ptr[s]:ptr[s+1]] (ascending) and rows[s] of shape (n, nb_s * n) = its scalar CSR rows."""
+    if penalty_constant is None:
+        assert degree is not None
+        penalty_constant = 10.0 * (degree + ah.dim) * (degree + 1)
+    prm = _Params(penalty_constant, h_rule, h_const, visit_rule, int(with_boundary), stiffness_coeff, mass_coeff, n_threads, 1, 0)
+    polys = np.ascontiguousarray(polys, dtype=np.int32)
+    n = ah.n_dofs_per_cell
+    ptr = np.empty(len(polys) + 1, dtype=np.int64)
+    nblk = sum(1 + sum(1 for f in range(ah.n_faces(int(p))) if not ah.at_boundary(int(p), f)) for p in polys)
+    bcol = np.empty(nblk, dtype=np.int32)
+    vals = np.empty(nblk * n * n)
+    sec = C.c_double(0.0)
+    got = lib().po_assemble_block_rows(ah.h, C.byref(prm), _p(polys, C.c_int), len(polys), _p(ptr, C.c_int64), _p(bcol, C.c_int),
+                                       _p(vals, C.c_double), C.byref(sec))
+    if got < 0:
+        raise RuntimeError(_err())
+    assert got == nblk
+    rows = [vals[ptr[s] * n * n: ptr[s + 1] * n * n].reshape(n, -1) for s in range(len(polys))]
+    return ptr, bcol, rows, sec.value
 
 
 def mapped_fine_vmult(grid: Grid, degree, nq, x, stiffness=1.0, mass=0.0, volume=True, boundary=True, interior=True):

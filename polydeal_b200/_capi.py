@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpolydeal_b200.so")
 
 PD_OK, PD_ERR_INVALID, PD_ERR_CUDA, PD_ERR_UNSUPPORTED, PD_ERR_NO_DEVICE, PD_ERR_STATE = 0, -1, -2, -3, -4, -5
+PD_NOT_CONVERGED = 1
 INVALID_UINT = 0xFFFFFFFF
 ASSEMBLE_VOLUME, ASSEMBLE_BOUNDARY, ASSEMBLE_INTERIOR, ASSEMBLE_ALL = 1, 2, 4, 7
 VMULT_BLOCK_CSR, VMULT_MATRIX_FREE, VMULT_MAPPED_FINE = 0, 1, 2
@@ -170,5 +171,7 @@ def lib():
 
 
 def check(code):
-    if code != PD_OK:
+    """Negative = error (raises); positive = a status the caller interprets (PD_NOT_CONVERGED)."""
+    if code < 0:
         raise PolydealError(code, lib().pd_last_error().decode())
+    return code

@@ -4,10 +4,14 @@
 #include "pd_host.hpp"
 #include "pd_internal.hpp"
 
+#include <algorithm>
+#include <array>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 
 namespace pd
 {
@@ -142,6 +146,11 @@ namespace pd
         set_last_error(e.what());
         return PD_ERR_INVALID;
       }
+    catch (...)
+      {
+        set_last_error("unknown exception");
+        return PD_ERR_INVALID;
+      }
   }
 
   static void
@@ -163,6 +172,47 @@ namespace pd
   {
     if (n)
       PD_CUDA(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+
+  // every entry of a[0..n) inside [lo, hi)?  (the large index arrays: a few threads, one pass)
+  static bool
+  all_in_range(const int32_t *a, const int64_t n, const int64_t lo, const int64_t hi)
+  {
+    auto scan = [&](int64_t b, int64_t e) {
+      int32_t mn = INT32_MAX, mx = INT32_MIN;
+      for (int64_t i = b; i < e; ++i)
+        {
+          mn = std::min(mn, a[i]);
+          mx = std::max(mx, a[i]);
+        }
+      return e <= b || ((int64_t)mn >= lo && (int64_t)mx < hi);
+    };
+    if (n < (int64_t)1 << 20)
+      return scan(0, n);
+    constexpr int            NT = 4;
+    std::array<char, NT>     ok{};
+    std::vector<std::thread> th;
+    for (int t = 0; t < NT; ++t)
+      th.emplace_back([&, t] { ok[t] = scan(n * t / NT, n * (t + 1) / NT); });
+    for (auto &t : th)
+      t.join();
+    return std::all_of(ok.begin(), ok.end(), [](char c) { return c != 0; });
+  }
+
+  // the arrays pd_upload may change without a new handle: coordinates and penalties only
+  static void
+  validate_large_arrays(const pd_mesh_desc &d)
+  {
+    auto need = [](bool ok, const char *m) {
+      if (!ok)
+        throw Error(PD_ERR_INVALID, std::string("pd_mesh_desc: ") + m);
+    };
+    need(all_in_range(d.cell_verts, d.n_cells << d.dim, 0, d.n_verts), "cell_verts out of range");
+    need(all_in_range(d.poly_subcell_idx, d.poly_subcell_ptr[d.n_polytopes], 0, d.n_cells), "sub-cell index out of range");
+    const int64_t nsf = d.n_ifaces ? d.iface_sub_ptr[d.n_ifaces] : 0;
+    need(nsf == 0 || (d.sub_cell && d.sub_face && d.sub_sigma), "missing sub-face arrays");
+    need(all_in_range(d.sub_cell, nsf, 0, d.n_cells), "sub_cell out of range");
+    need(all_in_range(d.sub_face, nsf, 0, 2 * d.dim), "sub_face out of range");
   }
 
   static void
@@ -199,22 +249,13 @@ namespace pd
         for (int k = 0; k < d.dim; ++k)
           need(d.bbox[(size_t)p * 2 * d.dim + d.dim + k] > d.bbox[(size_t)p * 2 * d.dim + k], "degenerate bounding box");
       }
-    const int64_t ns = d.poly_subcell_ptr[d.n_polytopes];
-    for (int64_t s = 0; s < ns; ++s)
-      need(d.poly_subcell_idx[s] >= 0 && d.poly_subcell_idx[s] < d.n_cells, "sub-cell index out of range");
     for (int32_t f = 0; f < d.n_ifaces; ++f)
       {
         need(d.iface_polyA[f] >= 0 && d.iface_polyA[f] < n_own, "iface_polyA must be an owned polytope");
         need(d.iface_polyB[f] >= -1 && d.iface_polyB[f] < d.n_polytopes, "iface_polyB out of range");
         need(d.iface_sub_ptr[f + 1] >= d.iface_sub_ptr[f], "iface_sub_ptr not monotone");
       }
-    const int64_t nsf = d.n_ifaces ? d.iface_sub_ptr[d.n_ifaces] : 0;
-    need(nsf == 0 || (d.sub_cell && d.sub_face && d.sub_sigma), "missing sub-face arrays");
-    for (int64_t s = 0; s < nsf; ++s)
-      {
-        need(d.sub_cell[s] >= 0 && d.sub_cell[s] < d.n_cells, "sub_cell out of range");
-        need(d.sub_face[s] >= 0 && d.sub_face[s] < 2 * d.dim, "sub_face out of range");
-      }
+    validate_large_arrays(d);
   }
 
   static int64_t
@@ -248,24 +289,44 @@ namespace pd
     h2d(h->bcol, d.bcol_idx, (size_t)h->n_blocks, s);
     h->quad_valid = false;
     h->assembled  = false;
-    // the volume schedule depends on poly_subcell_ptr only: rebuild it when that changed
-    if (h->h_subcell_ptr.size() != (size_t)d.n_polytopes + 1 ||
-        std::memcmp(h->h_subcell_ptr.data(), d.poly_subcell_ptr, sizeof(int64_t) * ((size_t)d.n_polytopes + 1)) != 0)
+    h->mfd_valid  = false; // cached inverse diagonal of the matrix-free operators
+    ++h->op_generation;    // graphs captured around the old state are stale
+  }
+
+  // 64-bit mix of the arrays the fine-mesh operators are derived from (pd_upload re-derives them on change)
+  static uint64_t
+  hash_bytes(uint64_t hsh, const void *p, const size_t bytes)
+  {
+    const uint64_t *w = static_cast<const uint64_t *>(p);
+    const size_t    n = bytes / 8;
+    uint64_t        a = hsh, b = 0x9e3779b97f4a7c15ull, c = 0xc2b2ae3d27d4eb4full, d = 0x165667b19e3779f9ull;
+    size_t          i = 0;
+    for (; i + 4 <= n; i += 4)
       {
-        h->h_subcell_ptr.assign(d.poly_subcell_ptr, d.poly_subcell_ptr + d.n_polytopes + 1);
-        h->vol_plan_tq   = 0;
-        h->pw_plan_valid = false;
+        a = (a ^ w[i]) * 0x100000001b3ull;
+        b = (b ^ w[i + 1]) * 0x100000001b3ull;
+        c = (c ^ w[i + 2]) * 0x100000001b3ull;
+        d = (d ^ w[i + 3]) * 0x100000001b3ull;
       }
-    if (h->h_if_sub_ptr.size() != (size_t)d.n_ifaces + 1 ||
-        (d.n_ifaces > 0 &&
-         std::memcmp(h->h_if_sub_ptr.data(), d.iface_sub_ptr, sizeof(int64_t) * ((size_t)d.n_ifaces + 1)) != 0))
-      {
-        if (d.n_ifaces > 0)
-          h->h_if_sub_ptr.assign(d.iface_sub_ptr, d.iface_sub_ptr + d.n_ifaces + 1);
-        else
-          h->h_if_sub_ptr.assign(1, 0);
-        h->pw_plan_valid = false;
-      }
+    for (; i < n; ++i)
+      a = (a ^ w[i]) * 0x100000001b3ull;
+    const unsigned char *t = static_cast<const unsigned char *>(p) + n * 8;
+    for (size_t k = 0; k < bytes % 8; ++k)
+      a = (a ^ t[k]) * 0x100000001b3ull;
+    return a ^ (b << 1) ^ (c << 2) ^ (d << 3);
+  }
+  static uint64_t
+  fine_geometry_hash(const pd_handle *h, const pd_mesh_desc &d)
+  {
+    uint64_t x = 0xcbf29ce484222325ull;
+    x = hash_bytes(x, d.verts, sizeof(double) * (size_t)d.n_verts * d.dim);
+    x = hash_bytes(x, d.cell_verts, sizeof(int32_t) * ((size_t)d.n_cells << d.dim));
+    x = hash_bytes(x, d.poly_subcell_idx, sizeof(int32_t) * (size_t)h->n_subcells);
+    x = hash_bytes(x, d.bbox, sizeof(double) * (size_t)d.n_polytopes * 2 * d.dim);
+    x = hash_bytes(x, d.sub_cell, sizeof(int32_t) * (size_t)h->n_subfaces);
+    x = hash_bytes(x, d.sub_face, sizeof(int32_t) * (size_t)h->n_subfaces);
+    x = hash_bytes(x, d.sub_sigma, sizeof(double) * (size_t)h->n_subfaces);
+    return x;
   }
 
   static void
@@ -289,6 +350,8 @@ namespace pd
     const size_t nn = (size_t)h->n * h->n;
     h->face_diag.alloc((size_t)h->n_ifaces * 2 * nn);
     h->values.alloc((size_t)h->nnz);
+    // pattern blocks no interface covers (a caller's wider pattern) stay zero
+    PD_CUDA(cudaMemsetAsync(h->values.p, 0, sizeof(double) * (size_t)h->nnz, h->stream));
   }
 
   static void
@@ -382,6 +445,15 @@ namespace pd
         h->h_brow_ptr.assign(d.brow_ptr, d.brow_ptr + h->np_own + 1);
         h->h_bcol.assign(d.bcol_idx, d.bcol_idx + h->n_blocks);
         h->h_dof_block.assign(d.dof_block, d.dof_block + h->np);
+        h->h_subcell_ptr.assign(d.poly_subcell_ptr, d.poly_subcell_ptr + d.n_polytopes + 1);
+        if (d.n_ifaces > 0)
+          {
+            h->h_if_sub_ptr.assign(d.iface_sub_ptr, d.iface_sub_ptr + d.n_ifaces + 1);
+            h->h_ifA.assign(d.iface_polyA, d.iface_polyA + d.n_ifaces);
+            h->h_ifB.assign(d.iface_polyB, d.iface_polyB + d.n_ifaces);
+          }
+        else
+          h->h_if_sub_ptr.assign(1, 0);
 
         // ---- derived index data ------------------------------------------------
         const int64_t        nn = (int64_t)h->n * h->n;
@@ -405,6 +477,12 @@ namespace pd
           }
         std::vector<int64_t> baseAB(h->n_ifaces, -1), baseBA(h->n_ifaces, -1);
         std::vector<int64_t> padj_ptr(n_own + 1, 0);
+        std::vector<char>    slot_taken((size_t)h->n_blocks, 0); // an off-diagonal block has exactly one writer
+        auto                 take = [&](const int64_t slot) {
+          if (slot_taken[(size_t)slot])
+            throw Error(PD_ERR_INVALID, "pd_mesh_desc: two interfaces join the same pair of polytopes");
+          slot_taken[(size_t)slot] = 1;
+        };
         for (int32_t f = 0; f < h->n_ifaces; ++f)
           {
             const int32_t pa = d.iface_polyA[f], pb = d.iface_polyB[f];
@@ -414,11 +492,15 @@ namespace pd
                 if (pb == pa)
                   throw Error(PD_ERR_INVALID, "pd_mesh_desc: interface joins a polytope with itself");
                 const int32_t ba = d.dof_block[pa], bb = d.dof_block[pb];
-                baseAB[f] = d.brow_ptr[ba] * nn + find_block(d, ba, bb) * h->n;
+                const int64_t kab = find_block(d, ba, bb);
+                take(d.brow_ptr[ba] + kab);
+                baseAB[f] = d.brow_ptr[ba] * nn + kab * h->n;
                 if (pb < n_own)
                   {
                     ++padj_ptr[pb + 1];
-                    baseBA[f] = d.brow_ptr[bb] * nn + find_block(d, bb, ba) * h->n;
+                    const int64_t kba = find_block(d, bb, ba);
+                    take(d.brow_ptr[bb] + kba);
+                    baseBA[f] = d.brow_ptr[bb] * nn + kba * h->n;
                   }
               }
           }
@@ -455,6 +537,8 @@ namespace pd
           {
             setup_fine_operator(h, d);
             setup_mapped_operator(h, d);
+            if (h->n_subcells == h->np_own)
+              h->fine_geo_hash = fine_geometry_hash(h, d);
           }
         PD_CUDA(cudaStreamSynchronize(h->stream));
       }
@@ -514,6 +598,8 @@ extern "C"
       cudaStreamSynchronize(h->stream);
       if (h->cg_graph_exec)
         cudaGraphExecDestroy(h->cg_graph_exec);
+      if (h->cg_graph1_exec)
+        cudaGraphExecDestroy(h->cg_graph1_exec);
       for (auto &e : h->ev)
         if (e)
           cudaEventDestroy(e);
@@ -529,15 +615,45 @@ extern "C"
     return guarded([&] {
       if (!h || !d)
         throw Error(PD_ERR_INVALID, "pd_upload: null argument");
-      const int64_t nsc = d->poly_subcell_ptr[d->n_polytopes];
-      const int64_t nsf = d->n_ifaces ? d->iface_sub_ptr[d->n_ifaces] : 0;
+      if (!d->verts || !d->cell_verts || !d->poly_subcell_ptr || !d->poly_subcell_idx || !d->bbox || !d->dof_block ||
+          !d->brow_ptr || !d->bcol_idx || (d->n_ifaces > 0 && (!d->iface_polyA || !d->iface_polyB || !d->iface_sub_ptr)))
+        throw Error(PD_ERR_INVALID, "pd_upload: null array in the descriptor");
       if (d->dim != h->dim || d->fe_degree != h->degree || d->fe_kind != h->fe_kind || d->n_q1d != h->nq1 || d->n_q1d_face != h->nq1f ||
           d->n_verts != h->n_verts || d->n_cells != h->n_cells || d->n_polytopes != h->np ||
           (d->n_owned_polytopes > 0 ? d->n_owned_polytopes : d->n_polytopes) != h->np_own ||
-          d->n_ifaces != h->n_ifaces || nsc != h->n_subcells || nsf != h->n_subfaces ||
-          d->brow_ptr[d->n_block_rows] != h->n_blocks)
+          d->n_ifaces != h->n_ifaces || d->n_block_rows != h->np_own)
         throw Error(PD_ERR_INVALID, "pd_upload: descriptor sizes differ from the ones the handle was created with");
+      // the TOPOLOGY (polytope -> sub-cell ranges, DoF blocks, interface list, block pattern) is what every derived
+      // table of the handle was built from: it must be the one of pd_create.  Coordinates, bounding boxes,
+      // penalties and the (range-checked) cell / sub-cell / sub-face index arrays may change.
+      auto same = [](const auto &v, const auto *p) { return v.empty() || std::memcmp(v.data(), p, v.size() * sizeof(v[0])) == 0; };
+      if (!same(h->h_subcell_ptr, d->poly_subcell_ptr) || !same(h->h_dof_block, d->dof_block) ||
+          !same(h->h_brow_ptr, d->brow_ptr) || !same(h->h_bcol, d->bcol_idx) ||
+          (d->n_ifaces > 0 && (!same(h->h_if_sub_ptr, d->iface_sub_ptr) || !same(h->h_ifA, d->iface_polyA) ||
+                               !same(h->h_ifB, d->iface_polyB))))
+        throw Error(PD_ERR_INVALID,
+                    "pd_upload: the topology (sub-cell ranges, dof_block, interface list, block pattern) differs from "
+                    "pd_create's; only coordinates, bounding boxes, penalties and cell indices may change -- create a new handle");
+      validate_large_arrays(*d);
+      for (int32_t p = 0; p < d->n_polytopes; ++p)
+        for (int k = 0; k < d->dim; ++k)
+          if (!(d->bbox[(size_t)p * 2 * d->dim + d->dim + k] > d->bbox[(size_t)p * 2 * d->dim + k]))
+            throw Error(PD_ERR_INVALID, "pd_upload: degenerate bounding box");
       upload_descriptor(h, *d);
+      // fine-mesh operators (every polytope one cell): geometry tables, stencil records and tile plans are derived
+      // from the coordinates and penalties -- re-derive them when those changed
+      if (h->fe_kind == PD_FE_DGQ && h->n_subcells == h->np_own)
+        {
+          const uint64_t hsh = fine_geometry_hash(h, *d);
+          if (hsh != h->fine_geo_hash)
+            {
+              h->mf_rec_valid = false;
+              h->mp_geo_valid = false;
+              setup_fine_operator(h, *d);
+              setup_mapped_operator(h, *d);
+              h->fine_geo_hash = hsh;
+            }
+        }
     });
   }
 
@@ -549,6 +665,7 @@ extern "C"
         throw Error(PD_ERR_INVALID, "null handle");
       PD_CUDA(cudaStreamSynchronize(h->stream));
       h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+      ++h->op_generation;
     });
   }
 
@@ -991,6 +1108,7 @@ extern "C"
         throw Error(PD_ERR_INVALID, "null handle");
       h->op_flags = flags;
       h->op_coef  = coef ? *coef : pd_coefficients{1.0, 0.0};
+      ++h->op_generation;
     });
   }
 
@@ -1013,6 +1131,7 @@ extern "C"
       if (!h)
         throw Error(PD_ERR_INVALID, "null handle");
       h->force_generic_mf = on != 0;
+      ++h->op_generation;
     });
   }
 
@@ -1051,24 +1170,29 @@ extern "C"
   pd_cg_solve(pd_handle *h, int mode, const double *b_dev, double *x_dev, int max_iter, double rel_tol, int jacobi,
               int *iterations, double *relative_residual)
   {
-    return guarded([&] {
+    bool      converged = true;
+    const int rc        = guarded([&] {
       if (!h || !b_dev || !x_dev)
         throw Error(PD_ERR_INVALID, "pd_cg_solve: null argument");
-      solver_cg(h, mode, b_dev, x_dev, max_iter, rel_tol, jacobi, iterations, relative_residual);
+      converged = solver_cg(h, mode, b_dev, x_dev, max_iter, rel_tol, jacobi, iterations, relative_residual);
     });
+    return rc != PD_OK ? rc : (converged ? PD_OK : PD_NOT_CONVERGED);
   }
 
   int
   pd_cg_solve_sharded(pd_peer *peer, int mode, const double *b_dev, double *x_dev, int max_iter, double rel_tol,
                       int jacobi, int *iterations, double *relative_residual)
   {
-    return guarded([&] {
+    bool      converged = true;
+    const int rc        = guarded([&] {
       if (!peer || !b_dev || !x_dev)
         throw Error(PD_ERR_INVALID, "pd_cg_solve_sharded: null argument");
-      solver_cg(peer_handle(peer), mode, b_dev, x_dev, max_iter, rel_tol, jacobi, iterations, relative_residual, peer);
+      converged =
+        solver_cg(peer_handle(peer), mode, b_dev, x_dev, max_iter, rel_tol, jacobi, iterations, relative_residual, peer);
       if (peer_status(peer) != PD_OK)
         throw Error(PD_ERR_STATE, "pd_cg_solve_sharded: a rank did not arrive at a collective within the time-out");
     });
+    return rc != PD_OK ? rc : (converged ? PD_OK : PD_NOT_CONVERGED);
   }
 
   int
@@ -1094,6 +1218,8 @@ extern "C"
       if (!peer || !lambda_max || n_iterations < 1)
         throw Error(PD_ERR_INVALID, "pd_estimate_lambda_max_sharded: bad argument");
       *lambda_max = solver_lambda_max(peer_handle(peer), mode, n_iterations, peer);
+      if (peer_status(peer) != PD_OK)
+        throw Error(PD_ERR_STATE, "pd_estimate_lambda_max_sharded: a rank did not arrive at a collective within the time-out");
     });
   }
 

@@ -163,7 +163,13 @@ struct pd_handle
   int64_t            cg_launches_per_chunk = 0;
 
   std::vector<int64_t> h_brow_ptr, h_subcell_ptr;
-  std::vector<int32_t> h_bcol, h_dof_block;
+  std::vector<int32_t> h_bcol, h_dof_block, h_ifA, h_ifB;
+  uint64_t             fine_geo_hash = 0; // fine meshes: hash of the arrays the stencil / mapped operators derive from
+  // bumped by everything a captured solver graph bakes in (operator terms and coefficients, kernel choice,
+  // stream, work buffers, uploads); part of the graph cache key (pd_solver.cu)
+  uint64_t             op_generation = 0;
+  uint64_t             cg_graph_generation = ~0ull;
+  cudaGraphExec_t      cg_graph1_exec = nullptr; // one iteration: the tail below a chunk
 
   cudaStream_t stream     = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -207,7 +213,7 @@ namespace pd
   void launch_transfer(pd_handle *h, const pd_transfer &t, bool transpose, const double *src, double *dst, bool add);
   void launch_poly_error(pd_handle *h, const double *u, const double *exact, const double *exact_grad, double *out2_dev);
   // pd_solver.cu
-  void   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,
+  bool   solver_cg(pd_handle *h, int mode, const double *b, double *x, int max_iter, double rel_tol, int jacobi,
                    int *iters_out, double *relres_out, pd_peer *peer = nullptr);
   void   solver_diagonal_inverse(pd_handle *h, int mode, double *dst);
   double solver_lambda_max(pd_handle *h, int mode, int n_iter, pd_peer *peer = nullptr);

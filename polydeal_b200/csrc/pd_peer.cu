@@ -327,8 +327,9 @@ namespace pd
   {
     pd_handle *h = p->h;
     const int  n = h->n;
-    if (p->n_neighbours > 0)
-      {
+    // always launched: it is also what advances the epoch the pull reads (a rank that only receives
+    // must still step its parity)
+    {
         const int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (p->n_send * n + 255) / 256), h->sm_count);
         k_peer_publish<<<grid, 256, 0, stream>>>(x_full_dev, p->send_blocks.p, p->n_send, n, p->d_peer_base.p,
                                                     p->d_neighbours.p, p->n_neighbours, p->rank, p->world, p->epochs,

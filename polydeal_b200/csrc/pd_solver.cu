@@ -247,6 +247,7 @@ namespace pd
           h->sv_partial.alloc(4 * RG);
           h->sv_scal.alloc(8);
           h->sv_ticket.alloc(1);
+          ++h->op_generation; // captured graphs point into the old buffers
           PD_CUDA(cudaMemsetAsync(h->sv_ticket.p, 0, sizeof(unsigned int), h->stream));
           PD_CUDA(cudaMemsetAsync(h->sv_p.p, 0, sizeof(double) * ns, h->stream));
         }
@@ -323,7 +324,9 @@ namespace pd
     PD_CUDA(cudaMemcpyAsync(dst, h->mfd_dinv.p, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, s));
   }
 
-  void
+  // returns false when the tolerance was not reached within max_iter iterations (SolverCG throws
+  // SolverControl::NoConvergence there; the C ABI reports PD_NOT_CONVERGED with the iterate kept)
+  bool
   solver_cg(pd_handle *h, const int mode, const double *b, double *x, const int max_iter, const double rel_tol,
             const int jacobi, int *iters_out, double *relres_out, pd_peer *peer)
   {
@@ -371,51 +374,75 @@ namespace pd
     const double bnorm = std::sqrt(hs[4] > 0 ? hs[4] : 1.);
     double       relres = std::sqrt(hs[3]) / bnorm;
     int          it     = 0;
-    // one iteration = SpMV + dot, update, direction (3 kernels); captured once and replayed in chunks
+    // one iteration = SpMV + dot, update, direction (3 kernels); captured once and replayed: a graph of CHUNK
+    // iterations and a graph of one iteration for the tail, so that exactly min(max_iter, needed rounded up to
+    // the check interval) iterations run.  The graphs bake in the operator (terms, coefficients, kernel choice
+    // are kernel parameters / template choices of the captured launches), the stream, the work buffers and
+    // the x / b pointers: all of that is in the cache key (op_generation is bumped by pd_set_operator,
+    // pd_force_generic_matrix_free, pd_upload, pd_set_stream and every reallocation of the work buffers).
     constexpr int CHUNK = 8;
-    if (!h->cg_graph_exec || h->cg_graph_mode != mode || h->cg_graph_jacobi != jacobi || h->cg_graph_peer != peer)
+    const bool    stale = !h->cg_graph_exec || h->cg_graph_mode != mode || h->cg_graph_jacobi != jacobi ||
+                       h->cg_graph_peer != peer || h->cg_graph_x != x || h->cg_graph_b != b ||
+                       h->cg_graph_generation != h->op_generation;
+    if (stale)
       {
-        if (h->cg_graph_exec)
-          {
-            cudaGraphExecDestroy(h->cg_graph_exec);
-            h->cg_graph_exec = nullptr;
-          }
-        cudaGraph_t graph = nullptr;
-        PD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        const int64_t l0 = h->launches;
-        for (int k = 0; k < CHUNK; ++k)
-          {
-            apply(p, Ap);
-            k_dot_pAp<<<RG, RB, 0, s>>>(p, Ap, n, partial, scal, ticket);
-            reduce(1, 1);
-            k_cg_update<<<RG, RB, 0, s>>>(x, r, z, p, Ap, dinv, scal, n, partial, ticket);
-            reduce(2, 2);
-            k_cg_direction<<<RG, RB, 0, s>>>(p, z, scal, n, ticket);
-          }
-        h->cg_launches_per_chunk = (h->launches - l0) + 3 * CHUNK;
-        h->launches              = l0;
-        PD_CUDA(cudaStreamEndCapture(s, &graph));
-        PD_CUDA(cudaGraphInstantiate(&h->cg_graph_exec, graph, 0));
-        PD_CUDA(cudaGraphDestroy(graph));
-        h->cg_graph_mode   = mode;
-        h->cg_graph_jacobi = jacobi;
-        h->cg_graph_peer   = peer;
-        h->cg_graph_x      = x;
-        h->cg_graph_b      = b;
+        for (cudaGraphExec_t *g : {&h->cg_graph_exec, &h->cg_graph1_exec})
+          if (*g)
+            {
+              cudaGraphExecDestroy(*g);
+              *g = nullptr;
+            }
+        auto capture = [&](const int n_iter, cudaGraphExec_t *exec) {
+          cudaGraph_t   graph = nullptr;
+          const int64_t l0    = h->launches;
+          PD_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+          try
+            {
+              for (int k = 0; k < n_iter; ++k)
+                {
+                  apply(p, Ap);
+                  k_dot_pAp<<<RG, RB, 0, s>>>(p, Ap, n, partial, scal, ticket);
+                  reduce(1, 1);
+                  k_cg_update<<<RG, RB, 0, s>>>(x, r, z, p, Ap, dinv, scal, n, partial, ticket);
+                  reduce(2, 2);
+                  k_cg_direction<<<RG, RB, 0, s>>>(p, z, scal, n, ticket);
+                }
+            }
+          catch (...)
+            {
+              cudaStreamEndCapture(s, &graph); // never leave the stream in capture mode
+              if (graph)
+                cudaGraphDestroy(graph);
+              h->launches = l0;
+              throw;
+            }
+          const int64_t per_iter = (h->launches - l0) / n_iter + 3;
+          h->launches            = l0;
+          PD_CUDA(cudaStreamEndCapture(s, &graph));
+          const cudaError_t e = cudaGraphInstantiate(exec, graph, 0);
+          cudaGraphDestroy(graph);
+          PD_CUDA(e);
+          return per_iter;
+        };
+        const int64_t per_iter   = capture(CHUNK, &h->cg_graph_exec);
+        h->cg_launches_per_chunk = per_iter * CHUNK;
+        capture(1, &h->cg_graph1_exec);
+        h->cg_graph_mode       = mode;
+        h->cg_graph_jacobi     = jacobi;
+        h->cg_graph_peer       = peer;
+        h->cg_graph_x          = x;
+        h->cg_graph_b          = b;
+        h->cg_graph_generation = h->op_generation;
       }
-    else if (h->cg_graph_x != x)
+    // rel_tol <= 0: no convergence test, exactly max_iter iterations (timing runs)
+    while (it < max_iter && (rel_tol <= 0. || relres > rel_tol))
       {
-        // the graph bakes in the x pointer: different vector => rebuild next time
-        cudaGraphExecDestroy(h->cg_graph_exec);
-        h->cg_graph_exec = nullptr;
-        solver_cg(h, mode, b, x, max_iter, rel_tol, jacobi, iters_out, relres_out, peer);
-        return;
-      }
-    while (it < max_iter && relres > rel_tol)
-      {
-        PD_CUDA(cudaGraphLaunch(h->cg_graph_exec, s));
-        h->launches += h->cg_launches_per_chunk;
-        it += CHUNK;
+        const bool chunk = max_iter - it >= CHUNK;
+        PD_CUDA(cudaGraphLaunch(chunk ? h->cg_graph_exec : h->cg_graph1_exec, s));
+        h->launches += chunk ? h->cg_launches_per_chunk : h->cg_launches_per_chunk / CHUNK;
+        it += chunk ? CHUNK : 1;
+        if (rel_tol <= 0. && it < max_iter)
+          continue;
         PD_CUDA(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, s));
         PD_CUDA(cudaStreamSynchronize(s));
         relres = std::sqrt(hs[3]) / bnorm;
@@ -426,6 +453,7 @@ namespace pd
       *iters_out = it;
     if (relres_out)
       *relres_out = relres;
+    return rel_tol <= 0. || relres <= rel_tol;
   }
 
   double

@@ -201,12 +201,14 @@ class PeerExchange:
         dist.barrier(group=group)  # every rank has mapped its neighbours before anyone publishes
 
     def exchange(self, x_full):
+        self.op._bind_torch_stream()
         K.check(K.lib().pd_peer_exchange(self._h, C.c_void_p(x_full.data_ptr())))
         return x_full
 
     def vmult(self, dst, x_full, mode=K.VMULT_BLOCK_CSR, add=False):
         """exchange + vmult in one call (pd_peer_vmult): overlaps the exchange with the cells that need
         no ghost data when the fine-mesh stencil kernel applies."""
+        self.op._bind_torch_stream()
         K.check(K.lib().pd_peer_vmult(self._h, mode, C.c_void_p(x_full.data_ptr()), C.c_void_p(dst.data_ptr()), int(add)))
         return dst
 
@@ -216,6 +218,7 @@ class PeerExchange:
     def allreduce(self, scalars):
         """In-place sum over the ranks of a CUDA float64 tensor of at most 4 entries."""
         assert scalars.is_cuda and scalars.numel() <= 4
+        self.op._bind_torch_stream()
         K.check(K.lib().pd_peer_allreduce(self._h, C.c_void_p(scalars.data_ptr()), scalars.numel()))
         return scalars
 
@@ -227,6 +230,7 @@ class PeerExchange:
     def chebyshev_smooth(self, x_full, b, degree, lambda_max, smoothing_range=20.0, zero_initial_guess=True,
                          mode=K.VMULT_BLOCK_CSR):
         """PreconditionChebyshev on the sharded operator; x_full has the (owned + ghost) length."""
+        self.op._bind_torch_stream()
         K.check(K.lib().pd_chebyshev_smooth_sharded(self._h, mode, degree, lambda_max, smoothing_range,
                                                     C.c_void_p(b.data_ptr()), C.c_void_p(x_full.data_ptr()),
                                                     int(zero_initial_guess)))
@@ -236,8 +240,10 @@ class PeerExchange:
         """SolverCG on the sharded operator, device resident on every rank (pd_cg_solve_sharded);
         x, b hold the owned DoFs.  Returns (iterations, global relative residual)."""
         it, rr = C.c_int(0), C.c_double(0.0)
-        K.check(K.lib().pd_cg_solve_sharded(self._h, mode, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), max_iter,
-                                            rel_tol, int(jacobi), C.byref(it), C.byref(rr)))
+        self.op._bind_torch_stream()
+        rc = K.check(K.lib().pd_cg_solve_sharded(self._h, mode, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), max_iter,
+                                                 rel_tol, int(jacobi), C.byref(it), C.byref(rr)))
+        self.last_cg_converged = rc != K.PD_NOT_CONVERGED
         return it.value, rr.value
 
     def close(self):
@@ -277,6 +283,7 @@ class DistributedSIPOperator:
         p = self.part
         if self._x_full is None or self._x_full.device != src.device:
             self._x_full = torch.empty(p.n_local_dofs, dtype=torch.float64, device=src.device)
+        self.op._bind_torch_stream()  # the copy above, the exchange and the apply all on torch's current stream
         self._x_full[: p.n_owned_dofs].copy_(src)
         if exchange and p.n_ranks > 1:
             if self.peer is not None:

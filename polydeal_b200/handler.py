@@ -259,7 +259,21 @@ class SIPOperator:
         K.check(K.lib().pd_upload(self._h, C.byref(desc if desc is not None else self.desc)))
 
     def set_stream(self, cuda_stream_ptr):
-        K.check(K.lib().pd_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+        """Enqueue every device call of this operator on the given cudaStream_t (an int).  0 is read as the
+        legacy default stream (cudaStreamLegacy), which is what torch's default stream is."""
+        ptr = int(cuda_stream_ptr) or 1  # cudaStreamLegacy == (cudaStream_t)0x1
+        K.check(K.lib().pd_set_stream(self._h, C.c_void_p(ptr)))
+        self._bound_stream = ptr
+
+    def _bind_torch_stream(self):
+        """The torch-tensor entry points run on torch's CURRENT stream, so that they are ordered with the
+        caller's tensor work like any torch op (the handle's own stream is cudaStreamNonBlocking and would
+        race with it).  Re-bound only when the current stream changed (pd_set_stream synchronises)."""
+        import torch
+
+        ptr = int(torch.cuda.current_stream().cuda_stream) or 1
+        if getattr(self, "_bound_stream", None) != ptr:
+            self.set_stream(ptr)
 
     def synchronize(self):
         K.check(K.lib().pd_synchronize(self._h))
@@ -351,11 +365,13 @@ class SIPOperator:
             K.check(K.lib().pd_vmult_host(self._h, mode, _ptr(src), _ptr(dst)))
         else:
             self._check_tensor(src), self._check_tensor(dst)
+            self._bind_torch_stream()
             self.vmult_ptr(dst.data_ptr(), src.data_ptr(), mode)
         return dst
 
     def vmult_add(self, dst, src, mode=K.VMULT_BLOCK_CSR):
         self._check_tensor(src), self._check_tensor(dst)
+        self._bind_torch_stream()
         self.vmult_ptr(dst.data_ptr(), src.data_ptr(), mode, add=True)
         return dst
 
@@ -370,15 +386,19 @@ class SIPOperator:
         """Inverse diagonal of the operator `mode` applies (pd_diagonal_inverse_of); matrix-free modes
         need no assembled matrix."""
         self._check_tensor(out)
+        self._bind_torch_stream()
         K.check(K.lib().pd_diagonal_inverse_of(self._h, mode, C.c_void_p(out.data_ptr())))
         return out
 
     def cg_solve(self, x, b, max_iter=1000, rel_tol=1e-10, jacobi=True, mode=K.VMULT_BLOCK_CSR):
-        """SolverCG around vmult, device resident (pd_cg_solve).  Returns (iterations, relative residual)."""
+        """SolverCG around vmult, device resident (pd_cg_solve).  Returns (iterations, relative residual);
+        `last_cg_converged` is False when the tolerance was not reached within max_iter (PD_NOT_CONVERGED)."""
         self._check_tensor(x), self._check_tensor(b)
+        self._bind_torch_stream()
         it, rr = C.c_int(0), C.c_double(0.0)
-        K.check(K.lib().pd_cg_solve(self._h, mode, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), max_iter, rel_tol,
-                                    int(jacobi), C.byref(it), C.byref(rr)))
+        rc = K.check(K.lib().pd_cg_solve(self._h, mode, C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), max_iter, rel_tol,
+                                         int(jacobi), C.byref(it), C.byref(rr)))
+        self.last_cg_converged = rc != K.PD_NOT_CONVERGED
         return it.value, rr.value
 
     # ---- data at the agglomerated quadrature points: right-hand side and error norms ----
@@ -391,6 +411,7 @@ class SIPOperator:
         import torch
 
         ptrs = [C.c_void_p() for _ in range(5)]
+        self._bind_torch_stream()
         K.check(K.lib().pd_quadrature_device(self._h, *[C.byref(p) for p in ptrs]))
         Q, Qf, dim = self.n_quadrature_points(), self.n_quadrature_points(True), self.desc.dim
 
@@ -415,6 +436,7 @@ class SIPOperator:
         if g_face is not None:
             self._check_tensor(g_face, self.n_quadrature_points(True))
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self._bind_torch_stream()
         K.check(K.lib().pd_assemble_rhs(self._h, ptr(f_vol), ptr(g_face), float(stiffness), ptr(rhs)))
         return rhs
 
@@ -425,6 +447,7 @@ class SIPOperator:
         l2, h1 = C.c_double(0.0), C.c_double(0.0)
         if exact_grad is not None:
             self._check_tensor(exact_grad, Q * self.desc.dim)
+        self._bind_torch_stream()
         K.check(K.lib().pd_error_norms(self._h, C.c_void_p(u.data_ptr()), C.c_void_p(exact.data_ptr()),
                                        C.c_void_p(exact_grad.data_ptr()) if exact_grad is not None else None,
                                        C.byref(l2), C.byref(h1) if exact_grad is not None else None))
@@ -439,6 +462,7 @@ class SIPOperator:
                          mode=K.VMULT_BLOCK_CSR):
         """PreconditionChebyshev (Jacobi inner preconditioner) as a smoother (pd_chebyshev_smooth)."""
         self._check_tensor(x), self._check_tensor(b)
+        self._bind_torch_stream()
         K.check(K.lib().pd_chebyshev_smooth(self._h, mode, degree, lambda_max, smoothing_range, C.c_void_p(b.data_ptr()),
                                             C.c_void_p(x.data_ptr()), int(zero_initial_guess)))
         return x
@@ -519,6 +543,7 @@ class Transfer:
 
     def prolongate(self, dst_fine, src_coarse, add=False):
         self._check(dst_fine, self.m()), self._check(src_coarse, self.n())
+        self._keep[0]._bind_torch_stream()
         K.check(K.lib().pd_transfer_prolongate(self._h, C.c_void_p(src_coarse.data_ptr()), C.c_void_p(dst_fine.data_ptr()), int(add)))
         return dst_fine
 
@@ -530,6 +555,7 @@ class Transfer:
 
     def restrict(self, dst_coarse, src_fine, add=False):
         self._check(dst_coarse, self.n()), self._check(src_fine, self.m())
+        self._keep[0]._bind_torch_stream()
         K.check(K.lib().pd_transfer_restrict(self._h, C.c_void_p(src_fine.data_ptr()), C.c_void_p(dst_coarse.data_ptr()), int(add)))
         return dst_coarse
 

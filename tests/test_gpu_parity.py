@@ -1257,3 +1257,147 @@ def test_assembly_on_an_unstructured_mesh(goldens):
         op.vmult(yd, xd)
         op.synchronize()
         assert abs(float(u @ yd.cpu().numpy()) - g[name][0]) <= 1e-11
+
+
+# ----------------------------------------------------------------------------------
+# state the handle caches around the operator: solver graphs, uploads, streams
+# ----------------------------------------------------------------------------------
+def test_cg_after_set_operator_uses_the_new_operator():
+    """The replayed CG graph bakes the matrix-free operator in (coefficients are kernel parameters): a second
+    solve on the SAME x / b after pd_set_operator must iterate with the new operator, and max_iter is exact."""
+    pdl = gpu()
+    import torch
+
+    n, p = 4, 2
+    ogrid = po.Grid(3, n, 0.0, 1.0, 0)
+    groups = [[c] for c in range(ogrid.n_cells)]
+    oah = po.AgglomerationHandler(ogrid)
+    for g in groups:
+        oah.define_agglomerate(g)
+    oah.initialize_fe_values(p + 1)
+    oah.distribute_agglomerated_dofs(po.FE_DGQ, p)
+    _, pah = product_handler(ogrid, groups, p, p + 1)
+    C = p * (p + 1.0)
+    op = pdl.SIPOperator(pah.flatten(penalty_constant=C, h_rule=pdl.H_NORMAL_EXTENT), keepalive=pah)
+    b = torch.from_numpy(np.cos(0.3 * np.arange(op.m())) + 0.2).cuda()
+    x = torch.zeros_like(b)
+    sols = {}
+    for mass in (0.0, 50.0, 0.0):
+        op.set_operator(pdl.ASSEMBLE_ALL, 1.0, mass)
+        x.zero_()
+        it, rr = op.cg_solve(x, b, max_iter=2000, rel_tol=1e-11, jacobi=True, mode=pdl.VMULT_MATRIX_FREE)
+        assert op.last_cg_converged and rr <= 1e-11
+        A = po.assemble_dg_matrix(oah, penalty_constant=C, h_rule=po.H_NORMAL_EXTENT, mass_coeff=mass).scipy().tocsc()
+        import scipy.sparse.linalg as spla
+
+        want = spla.spsolve(A, b.cpu().numpy())
+        torch.cuda.synchronize()
+        assert np.abs(x.cpu().numpy() - want).max() <= 1e-8 * np.abs(want).max(), mass
+        sols[mass] = it
+    # the iteration budget is exact and a missed tolerance is reported, not silently accepted
+    x.zero_()
+    it, rr = op.cg_solve(x, b, max_iter=5, rel_tol=1e-14, jacobi=True, mode=pdl.VMULT_MATRIX_FREE)
+    assert it == 5 and not op.last_cg_converged and rr > 1e-14
+    x.zero_()
+    it, rr = op.cg_solve(x, b, max_iter=19, rel_tol=0.0, jacobi=True, mode=pdl.VMULT_MATRIX_FREE)
+    assert it == 19 and op.last_cg_converged
+
+
+def test_upload_rederives_the_fine_mesh_operator_and_rejects_new_topology():
+    """pd_upload with moved vertices / bounding boxes: the matrix-free fine-mesh operator (stencil records,
+    tile plan, cached inverse diagonal) follows; a descriptor with another topology is refused."""
+    pdl = gpu()
+    import torch
+
+    p = 2
+    C = p * (p + 1.0)
+
+    def build(hi):
+        ogrid = po.Grid(3, (4, 4, 4), 0.0, hi, 1)
+        groups = [[c] for c in range(ogrid.n_cells)]
+        oah = po.AgglomerationHandler(ogrid)
+        for g in groups:
+            oah.define_agglomerate(g)
+        oah.initialize_fe_values(p + 1)
+        oah.distribute_agglomerated_dofs(po.FE_DGQ, p)
+        _, pah = product_handler(ogrid, groups, p, p + 1)
+        return oah, pah, pah.flatten(penalty_constant=C, h_rule=pdl.H_NORMAL_EXTENT)
+
+    oah1, pah1, d1 = build((1.0, 1.0, 1.0))
+    oah2, pah2, d2 = build((1.0, 0.7, 1.9))  # same topology, other coordinates / boxes / penalties
+    op = pdl.SIPOperator(d1, keepalive=(pah1, pah2))
+    x = src_vector(op.m())
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    dinv = torch.empty_like(xd)
+    for oah, desc in ((oah1, d1), (oah2, d2), (oah1, d1)):
+        op.upload(desc)
+        ref = po.assemble_dg_matrix(oah, penalty_constant=C, h_rule=po.H_NORMAL_EXTENT)
+        op.vmult(yd, xd, mode=pdl.VMULT_MATRIX_FREE)
+        torch.cuda.synchronize()
+        yref = ref.vmult(x)
+        assert np.abs(yd.cpu().numpy() - yref).max() <= TOL * np.abs(yref).max()
+        op.get_matrix_diagonal_inverse(dinv, mode=pdl.VMULT_MATRIX_FREE)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(dinv.cpu().numpy(), 1.0 / ref.scipy().diagonal(), rtol=1e-11)
+        op.assemble()
+        rp, _ = op.pattern()
+        assert_blocks_close(op.values(), ref.values(), 27, rp, TOL)
+    # another topology: refused, the handle keeps working
+    ogrid = po.Grid(3, (4, 4, 4), 0.0, 1.0, 1)
+    groups = [[c] for c in range(ogrid.n_cells)]
+    groups[0], groups[5] = groups[5], groups[0]  # polytope order (hence dof_block / interface list) differs
+    _, pah3 = product_handler(ogrid, groups, p, p + 1)
+    d3 = pah3.flatten(penalty_constant=C, h_rule=pdl.H_NORMAL_EXTENT)
+    with pytest.raises(pdl.PolydealError, match="topology"):
+        op.upload(d3)
+    bad = pah1.flatten(penalty_constant=C, h_rule=pdl.H_NORMAL_EXTENT)
+    cv = np.ctypeslib.as_array(bad.cell_verts, (bad.n_cells * 8,)).copy()
+    cv[17] = bad.n_verts + 3
+    import ctypes as Cc
+
+    bad.cell_verts = cv.ctypes.data_as(Cc.POINTER(Cc.c_int32))
+    with pytest.raises(pdl.PolydealError, match="cell_verts out of range"):
+        op.upload(bad)
+    with pytest.raises(pdl.PolydealError, match="cell_verts out of range"):
+        pdl.SIPOperator(bad, keepalive=pah1)
+
+
+def test_duplicate_interfaces_are_rejected():
+    pdl = gpu()
+    import ctypes as Cc
+
+    oah, pah = both(2, 4, "blocks2", 1)
+    d = pah.flatten()
+    A = np.ctypeslib.as_array(d.iface_polyA, (d.n_ifaces,)).copy()
+    B = np.ctypeslib.as_array(d.iface_polyB, (d.n_ifaces,)).copy()
+    interior = np.nonzero(B >= 0)[0]
+    A[interior[1]], B[interior[1]] = A[interior[0]], B[interior[0]]  # the same pair listed twice
+    d.iface_polyA = A.ctypes.data_as(Cc.POINTER(Cc.c_int32))
+    d.iface_polyB = B.ctypes.data_as(Cc.POINTER(Cc.c_int32))
+    with pytest.raises(pdl.PolydealError, match="two interfaces join the same pair"):
+        pdl.SIPOperator(d, keepalive=pah)
+
+
+def test_torch_entry_points_follow_the_current_stream():
+    """vmult with torch tensors is ordered with the caller's tensor work on torch's current stream (the handle's
+    own stream is non-blocking): produce the source on a side stream right before the apply, no synchronisation."""
+    pdl = gpu()
+    import torch
+
+    oah, pah = both(3, 8, "blocks4", 2)
+    ref = po.assemble_dg_matrix(oah, degree=2, n_threads=4)
+    op = pdl.assemble_dg_matrix(pah)
+    x = src_vector(op.m())
+    yref = ref.vmult(x)
+    xh = torch.from_numpy(x).pin_memory()
+    for stream in (torch.cuda.Stream(), torch.cuda.default_stream(), torch.cuda.Stream()):
+        with torch.cuda.stream(stream):
+            big = torch.zeros(64 * 1024 * 1024, dtype=torch.float64, device="cuda")  # keeps the stream busy
+            big += 1.0
+            xd = torch.zeros(op.m(), dtype=torch.float64, device="cuda")
+            xd.copy_(xh, non_blocking=True)
+            yd = torch.empty_like(xd)
+            op.vmult(yd, xd)
+            yh = yd.cpu()  # stream-ordered D2H on the same stream
+        assert np.abs(yh.numpy() - yref).max() <= TOL * np.abs(yref).max()
