@@ -1,28 +1,34 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the hot path on B200.
 
-Workload (BASELINE.json configs[1]): unit cube, 64^3 hexes, 512
-polyhedra of 8^3 cells (the `blocks` shape an R-tree of fan-out 8 extracts at level 3),
-FE_DGQ<3>(2), QGauss(3), SIP assembly of stiffness + penalty + boundary terms with the
-library penalty C = 10 (p+dim)(p+1) = 150 (include/poly_utils.h:2018-2019).
-A step = agglomerated quadrature + volume + face + diagonal-gather kernels, from the
-flattened agglomeration resident in HBM to the finished scalar-CSR values in HBM.
+Workload (BASELINE.json configs[2], SURVEY 8d config C -- the largest configuration of `configs` whose matrix fits
+one GPU): unit cube, 128^3 hexes agglomerated into 32 768 polyhedra of 4^3 cells, FE_DGQ<3>(3), QGauss(4), SIP
+assembly of stiffness + penalty + boundary terms with the library penalty C = 10 (p+dim)(p+1) = 240
+(include/poly_utils.h:2018-2019): 2 097 152 DoFs, 134 M volume and 26 M face quadrature points, 7.3 GB of matrix.
+N > 1 (weak scaling): N such cubes stacked along z, the polytope adjacency graph partitioned into N parts by METIS
+(vertex weight = sub-cells, edge weight = shared sub-faces); every rank assembles its own rows, cut
+interfaces from one-time ghost geometry (no data-path collective in assembly); vmult exchanges ghost-polytope
+coefficients over NVLink peer memory.
 
-Metric: polytope DoFs assembled per second (whole job, all ranks).  The companion
-metric of BASELINE.json, SIP vmult GDoF/s, is reported twice: "vmult" = the block-CSR
-apply of the matrix just assembled (what the reference's solvers call on agglomerated
-levels), "mf_vmult" (N = 1) = the matrix-free sum-factorised LaplaceOperatorDG on the
-64^3 DGQ2 fine mesh of examples/matrix_free_agglo.cc, each with its own HBM roofline.
+A step = agglomerated quadrature + volume + face + diagonal-gather kernels, from the flattened agglomeration
+resident in HBM to the finished scalar-CSR values in HBM.  Metric: polytope DoFs assembled per second (whole job).
+The companion metric of BASELINE.json, SIP vmult GDoF/s, rides in the same line at every N:
+  "vmult"         block-CSR apply of the matrix just assembled (what the reference's solvers call on agglomerated
+                  levels) incl. the ghost exchange, and the CG iteration around it,
+  "poly_mf_vmult" the matrix-free apply on the same polytopes,
+  "mf_vmult"      the matrix-free sum-factorised LaplaceOperatorDG on the fine mesh of examples/matrix_free_agglo.cc
+                  (64^3 hexes, FE_DGQ(2), per GPU; N > 1: METIS partition of the cells, ghost exchange overlapped),
+each with its HBM roofline; "rooflines" carries one block per kernel of the step.  N = 1 adds configs B and D.
 
   python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
-  python bench.py --impl reference ...   times the CPU oracle restating the reference's
-                                         assembly on the host cores (the reference itself
-                                         needs deal.II and cannot be built here)
+  python bench.py --impl reference ...   times the CPU oracle restating the reference's assembly on the host cores
+                                         (the reference itself needs deal.II and cannot be built here)
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import statistics
@@ -32,31 +38,33 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 
 import numpy as np
 
+from pd_workloads import CONFIGS, build_handler
+
 METRIC = "polytope DoFs assembled/s"
 UNIT = "DoF/s"
-DIM, N_CELLS_1D, BLOCK, DEGREE, NQ = 3, 64, 8, 2, 3
-WORKLOAD = "B: unit cube 64^3 hexes -> 512 polyhedra (8^3 blocks, R-tree level 3), FE_DGQ(2), QGauss(3), SIP stiffness+penalty+boundary, C=150"
+CFG = CONFIGS["C"]
+DIM, DEGREE, NQ = CFG["dim"], CFG["p"], CFG["nq"]
+N_POLY_PER_GPU = (CFG["n"] // CFG["b"]) ** 3
+N_DOFS_PER_GPU = N_POLY_PER_GPU * (DEGREE + 1) ** DIM
+WORKLOAD = ("C: unit cube 128^3 hexes -> 32768 polyhedra (4^3 blocks) per GPU, FE_DGQ(3), QGauss(4), SIP "
+            "stiffness+penalty+boundary, C=240 (BASELINE configs[2]; N>1: N cubes stacked along z, polytope graph "
+            "METIS-partitioned into N parts)")
+REF_STRIDE = 128  # --impl reference: every 128th polytope per step (256 polytopes, ~2 s on 16 cores)
+CPU_STRIDE = 32   # cpu_baseline of the GPU arm: every 32nd polytope (1024 polytopes, ~10 s)
 
 
-def block_groups(n, b):
-    import pd_scenarios as sc
-
-    return sc.block_partition(DIM, n, b)
-
-
-def lex_block_groups(nx, ny, nz, b):
-    """b^3 blocks of an nx x ny x nz lexicographic grid, cells of a block in active-cell order."""
-    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
-    i, j, k = i.ravel(), j.ravel(), k.ravel()
-    cell = (k * ny + j) * nx + i
-    part = ((k // b) * (ny // b) + (j // b)) * (nx // b) + (i // b)
-    order = np.lexsort((cell, part))
-    return cell[order].astype(np.int32).reshape(-1, b**3)
+def config_dict():
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "n_dofs_per_gpu": N_DOFS_PER_GPU, "n_polytopes_per_gpu": N_POLY_PER_GPU,
+            "volume_q_points_per_gpu": N_POLY_PER_GPU * CFG["b"] ** 3 * NQ**DIM,
+            "l2": "inputs larger than L2 (4.3 GB of quadrature points per step); additionally flushed (512 MiB memset) between timed steps",
+            "step": "quadrature + volume + faces + diagonal gather, all device kernels"}
 
 
 def read_peaks():
@@ -129,6 +137,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(local):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs of the GPU's NUMA node: eight ranks share the
+    host links otherwise.  Returns a short description for the JSON line."""
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(local)
+        bus = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return f"gpu {bus}: no NUMA affinity reported"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return f"gpu {bus} -> NUMA node {node}, {len(allowed)} cpus"
+    except Exception as e:  # containers without sysfs topology
+        return f"not pinned ({type(e).__name__})"
+
+
 def pinned_copy_of_desc(desc):
     """Copy every descriptor array into pinned host memory; returns (new desc, keepalive, bytes)."""
     import torch
@@ -164,21 +195,108 @@ def pinned_copy_of_desc(desc):
     return d, keep, total
 
 
+def src_values(n, offset=0):
+    i = np.arange(offset, offset + n, dtype=np.float64)
+    return np.sin(0.37 * i) + 0.01 * (np.arange(offset, offset + n) % 7)
+
+
+class Timer:
+    """CUDA-event timing on the launch stream; ranks enter together (barrier) when sharded."""
+
+    def __init__(self, stream, dist):
+        self.stream, self.dist = stream, dist
+
+    def per_call_ms(self, fn, reps, warm=3):
+        import torch
+
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(self.stream)
+        for _ in range(reps):
+            fn()
+        b.record(self.stream)
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
+
+def hbm_block(name, nbytes, ms, peaks, **extra):
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return dict(kernel=name, bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                algorithmic_bytes_per_launch=nbytes, kernel_ms=ms, peak_source=peaks["hbm_src"], **extra)
+
+
+def tensor_block(name, flops, ms, peaks, **extra):
+    ach = flops / (ms * 1e-3) / 1e12
+    return dict(kernel=name, bound="tensor", achieved=ach, peak=peaks["fp64_tflops"], unit="TFLOP/s",
+                frac=ach / peaks["fp64_tflops"], algorithmic_flops_per_launch=flops, kernel_ms=ms,
+                peak_source=peaks["fp64_src"], **extra)
+
+
+def traffic_of(kernel_key):
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            return json.load(open(tp)).get(kernel_key)
+        except Exception:
+            return None
+    return None
+
+
+def assembly_rooflines(desc, n, nq, kms, peaks, mass=False):
+    """One roofline block per kernel of the assembly step (algorithmic flops / bytes)."""
+    dim = desc.dim
+    n_own = desc.n_owned_polytopes or desc.n_polytopes
+    Q = int(desc.poly_subcell_ptr[desc.n_polytopes]) * nq**dim
+    B = np.ctypeslib.as_array(desc.iface_polyB, (desc.n_ifaces,))
+    sp = np.ctypeslib.as_array(desc.iface_sub_ptr, (desc.n_ifaces + 1,))
+    nsub = np.diff(sp)
+    qf_int = int(nsub[B >= 0].sum()) * nq ** (dim - 1)
+    qf_bnd = int(nsub[B < 0].sum()) * nq ** (dim - 1)
+    n_int, n_bnd = int((B >= 0).sum()), int((B < 0).sum())
+    ncomp = dim + (1 if mass else 0)
+    out = []
+    out.append(tensor_block(f"k_volume<{dim},{desc.fe_degree}> (FP64 DMMA contraction, upper tiles only)",
+                            2.0 * n * n * ncomp * Q, kms["volume"], peaks,
+                            algorithmic_bytes_per_launch=8.0 * (dim + 1) * Q + 8.0 * n * n * n_own,
+                            note="algorithmic flops = 2 n^2 dim Q (SURVEY 8d); the kernel issues only the upper triangle of 8x8 "
+                                 "tiles, so frac may exceed 1; frac_issued counts the DMMA flops actually issued",
+                            frac_issued=None))
+    out.append(tensor_block(f"k_faces<{dim},{desc.fe_degree}> (T + T^T form, FP64 DMMA)",
+                            24.0 * n * n * qf_int + 6.0 * n * n * qf_bnd, kms["faces"], peaks,
+                            algorithmic_bytes_per_launch=8.0 * (2 * dim + 1) * (qf_int + qf_bnd) + 8.0 * n * n * (4 * n_int + n_bnd),
+                            note="algorithmic flops = 24 n^2 per interior face point + 6 n^2 per boundary point (SURVEY 8d); "
+                                 "the T + T^T form issues a third of that"))
+    if kms.get("quadrature", 0) > 0:
+        qbytes = 8.0 * (dim + 1) * Q + 8.0 * (2 * dim + 1) * (qf_int + qf_bnd) + (4.0 * 2**dim + 8.0 * dim) * desc.n_cells
+        out.append(hbm_block("k_volume_quadrature + k_face_quadrature", qbytes, kms["quadrature"], peaks))
+    vol_items = None
+    rbytes = 8.0 * n * n * (2 * n_own + 2 * n_int + n_bnd)
+    out.append(hbm_block("k_reduce_diag (gather of the diagonal blocks)", rbytes, kms["reduce"], peaks,
+                         note="reads >= one volume partial per polytope + M11/M22/boundary parts, writes the diagonal block"))
+    del vol_items
+    return out
+
+
 def run_gpu(args):
     import torch
 
     import polydeal_b200 as pdl
-    from polydeal_b200 import _capi as K
+    from polydeal_b200 import distributed as pdd
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    affinity0 = os.sched_getaffinity(0)
+    numa = pin_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -186,44 +304,25 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- build the agglomeration (host, untimed) --------------------------------------
-    # Weak scaling: every rank owns one config-B box (64^3 cells, 512 polyhedra); the path
-    # shards over polytopes with no data-path collective in assembly.
+    t_host0 = time.time()
+    ah = build_handler(pdl, CFG, world)
     part = None
     if world == 1:
-        grid = pdl.Grid.hyper_cube(DIM, 0.0, 1.0, N_CELLS_1D.bit_length() - 1)
-        ah = pdl.AgglomerationHandler(grid)
-        for g in block_groups(N_CELLS_1D, BLOCK):
-            ah.define_agglomerate(g)
-        ah.initialize_fe_values(NQ)
-        ah.distribute_agglomerated_dofs(pdl.FE_DGQ, DEGREE)
         desc0 = ah.flatten()  # library penalty, visit by id
     else:
-        # N boxes stacked along z: [0,1]^2 x [0,N], 64 x 64 x 64N cubic cells, 8^3 blocks,
-        # sharded into z-slabs of 512 polyhedra; the cut interfaces are evaluated by both
-        # neighbours from one-time ghost geometry (owner-computes-rows)
-        from polydeal_b200 import distributed as pdd
-
-        nz = N_CELLS_1D * world
-        grid = pdl.Grid.structured(DIM, (N_CELLS_1D, N_CELLS_1D, nz), 0.0, (1.0, 1.0, float(world)), order=1)
-        ah = pdl.AgglomerationHandler(grid)
-        for g in lex_block_groups(N_CELLS_1D, N_CELLS_1D, nz, BLOCK):
-            ah.define_agglomerate(g)
-        ah.initialize_fe_values(NQ)
-        ah.distribute_agglomerated_dofs(pdl.FE_DGQ, DEGREE)
-        owner = pdd.partition_by_blocks(ah, world)
+        owner = pdd.partition_by_metis(ah, world)
         part = pdd.LocalPart(ah, owner, rank)
         desc0 = part.desc
+    t_host = time.time() - t_host0
     desc, keep, h2d_bytes = pinned_copy_of_desc(desc0)
     op = pdl.SIPOperator(desc, keepalive=(ah, keep, part))
-    # all work and all timing events go to ONE explicit non-default stream (the legacy
-    # default stream has handle 0, which pd_set_stream reads as "use the handle's own")
+    # all work and all timing events go to ONE explicit non-default stream
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
     op.set_stream(stream.cuda_stream)
+    timer = Timer(stream, dist)
     n_dofs = op.m()
     n = op.n_dofs_per_cell
-    Q = int(desc.poly_subcell_ptr[desc.n_polytopes]) * NQ**DIM
     nnz = op.nnz
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2
 
@@ -232,7 +331,7 @@ def run_gpu(args):
         op.invalidate_quadrature()
         op.assemble()
 
-    # device-resident timing -----------------------------------------------------------
+    # ---- device-resident timing --------------------------------------------------------
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
@@ -259,11 +358,14 @@ def run_gpu(args):
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
-    # end-to-end: host buffers in (pinned), matrix values out (pinned), every step.  A caller that
-    # assembles a sequence of matrices double-buffers two handles on two streams, so that the
-    # download of step i overlaps the upload and the kernels of step i+1 (PCIe is full duplex);
-    # every step still uploads its whole descriptor and delivers its whole matrix inside the timed
-    # region.  The strictly serial variant (one handle, synchronous download) is timed beside it.
+    kms = {k: statistics.mean(v) for k, v in kms.items()}
+
+    # ---- end to end: host buffers in (pinned), matrix values out (pinned), every step ---------------------------
+    # A caller that assembles a sequence of matrices double-buffers two handles on two streams, so that the download
+    # of step i overlaps the upload and the kernels of step i+1 (PCIe is full duplex); every step still uploads its
+    # whole descriptor and delivers its whole matrix inside the timed region.  The strictly serial variant (one
+    # handle, synchronous download) is timed beside it.
+    e2e_steps = max(2, min(args.steps, 6))
     out_host = torch.empty(nnz, dtype=torch.float64).pin_memory()
     out_host2 = torch.empty(nnz, dtype=torch.float64).pin_memory()
     stream2 = torch.cuda.Stream()
@@ -287,65 +389,62 @@ def run_gpu(args):
         op2.synchronize()
 
     def timed(fn):
-        fn(min(3, args.warmup))
+        fn(2)
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
         t0 = time.perf_counter()
-        fn(args.steps)
+        fn(e2e_steps)
         torch.cuda.synchronize()
-        return (time.perf_counter() - t0) * 1e3
+        return (time.perf_counter() - t0) * 1e3 / e2e_steps
 
     t_e2e_serial_ms = timed(e2e_serial)
     t_e2e_ms = timed(e2e_pipelined)
     assert torch.equal(out_host, out_host2)  # both handles delivered the same matrix
-    checksum = float(out_host.sum())
+    checksum = float(out_host[:: max(1, nnz // 4_000_000)].sum())
+    del out_host2, op2, pair
+    gc.collect()
 
-    # vmult with the assembled matrix (device vectors), L2 flushed between applies
+    # ---- vmult with the assembled matrix: back-to-back applies (the 7.3 GB matrix does not fit L2) ---------------
     n_src = op.n_source_dofs
-    x = torch.from_numpy(np.sin(0.37 * np.arange(n_src)) + 0.01 * (np.arange(n_src) % 7)).cuda()
+    x = torch.from_numpy(src_values(n_src)).cuda()
     y = torch.empty(n_dofs, dtype=torch.float64, device="cuda")
-
-    # one exchange step per apply (ghost-polytope coefficients): over NVLink peer memory
-    # (csrc/pd_peer.cu: publish + pull kernels, flag handshake) and, for comparison, NCCL
     peer = pdd.PeerExchange(part, op) if part is not None else None
+    reps = max(args.steps, 10)
 
-    def apply(use_peer=True):
-        if part is not None and use_peer:
+    def apply_csr():
+        if peer is not None:
             peer.vmult(y, x)  # pd_peer_vmult: block rows without ghost columns run while the ghost blocks travel
-            return
-        if part is not None:
+        else:
+            op.vmult_ptr(y.data_ptr(), x.data_ptr())
+
+    t_vm_ms = timer.per_call_ms(apply_csr, reps)
+    t_vm_nccl_ms = t_vm_ms
+    if part is not None:
+        def apply_nccl():
             pdd.exchange_ghost_values(part, x)
-        op.vmult_ptr(y.data_ptr(), x.data_ptr())
+            op.vmult_ptr(y.data_ptr(), x.data_ptr())
+        t_vm_nccl_ms = timer.per_call_ms(apply_nccl, reps)
+    # the polytopal matrix-free apply of the same operator (no matrix memory)
+    op.set_operator(pdl.ASSEMBLE_ALL, 1.0, 0.0)
 
-    def time_apply(use_peer):
-        for _ in range(3):
-            apply(use_peer)
-        vm = []
-        for _ in range(max(args.steps, 5)):
-            flush.zero_()
-            if dist:
-                dist.barrier()  # ranks enter the timed apply together, as in a solver iteration
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            apply(use_peer)
-            b.record(stream)
-            b.synchronize()
-            vm.append(a.elapsed_time(b))
-        return statistics.mean(vm)
+    def apply_pmf():
+        if peer is not None:
+            peer.vmult(y, x, mode=pdl.VMULT_MATRIX_FREE)
+        else:
+            op.vmult_ptr(y.data_ptr(), x.data_ptr(), mode=pdl.VMULT_MATRIX_FREE)
 
-    t_vm_ms = time_apply(True)
-    t_vm_nccl_ms = time_apply(False) if part is not None else t_vm_ms
-    if peer is not None:
-        assert peer.ok(), "peer exchange timed out"
+    t_pmf_ms = timer.per_call_ms(apply_pmf, max(3, reps // 3), warm=2)
+    pmf_checksum = float(y.sum())
     # the loop around vmult: Jacobi-preconditioned CG, device resident (CUDA graph); sharded: ghost exchange
-    # and dot-product all-reduce over peer memory inside the graph.  96 iterations, no convergence test.
+    # and dot-product all-reduce over peer memory inside the graph.  24 iterations, no convergence test.
     bcg = torch.from_numpy(np.cos(0.23 * np.arange(n_dofs)) + 0.1).cuda()
     xcg = torch.zeros_like(bcg)
-    solve = (lambda: peer.cg_solve(xcg, bcg, max_iter=96, rel_tol=0.0)) if peer is not None else \
-            (lambda: op.cg_solve(xcg, bcg, max_iter=96, rel_tol=0.0))
+    solve = (lambda: peer.cg_solve(xcg, bcg, max_iter=24, rel_tol=0.0)) if peer is not None else \
+            (lambda: op.cg_solve(xcg, bcg, max_iter=24, rel_tol=0.0))
     solve()
     xcg.zero_()
+    torch.cuda.synchronize()
     if dist:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -354,14 +453,32 @@ def run_gpu(args):
     b.record(stream)
     b.synchronize()
     t_cg_ms = a.elapsed_time(b) / max(cg_iters, 1)
-
-    times = torch.tensor([t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms, t_cg_ms, t_e2e_serial_ms], dtype=torch.float64, device="cuda")
-    if dist:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms, t_cg_ms, t_e2e_serial_ms = (float(v) for v in times.cpu())
     if peer is not None:
+        assert peer.ok(), "peer exchange timed out"
         dist.barrier()  # nobody unmaps while a neighbour may still pull
         peer.close()
+    nblocks = int(desc.brow_ptr[desc.n_block_rows])
+    roofs = assembly_rooflines(desc, n, NQ, kms, read_peaks()) if rank == 0 else None
+    n_ghost_poly = int(desc.n_polytopes - n_dofs // n)
+    n_poly_own = n_dofs // n
+    del op, x, y, bcg, xcg, keep, desc, desc0, part, out_host, ah, peer
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---- the second metric's own path: matrix-free fine-mesh SIP vmult, sharded like the polytopes ---------------
+    mf = None if args.no_mf_vmult else mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, 2, reps)
+    mf3 = None
+    if world == 1 and not args.no_mf_vmult:
+        mf3 = mf_vmult_fine_mesh(pdl, pdd, stream, timer, 1, 0, None, 3, reps)
+
+    counts = torch.tensor([float(n_dofs)], dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms, t_cg_ms, t_e2e_serial_ms, t_pmf_ms,
+                          mf["ms"] if mf else 0.0], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    t_ms, t_e2e_ms, t_vm_ms, t_vm_nccl_ms, t_cg_ms, t_e2e_serial_ms, t_pmf_ms, t_mf_ms = (float(v) for v in times.cpu())
+    total_dofs = float(counts.cpu()[0])
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -369,161 +486,234 @@ def run_gpu(args):
 
     peaks = read_peaks()
     ms_per_step = t_ms / args.steps
-    value = world * n_dofs / (ms_per_step * 1e-3)
-    e2e_value = world * n_dofs / (t_e2e_ms / args.steps * 1e-3)
-    # dominant kernel: the volume contraction.  Algorithmic flops per launch =
-    # 2 n^2 dim Q; bytes = 8 (dim+1) Q read + 8 n^2 per polytope written.
-    vol_ms = statistics.mean(kms["volume"])
-    flops = 2.0 * n * n * DIM * Q
-    achieved = flops / (vol_ms * 1e-3) / 1e12
-    vol_bytes = 8.0 * (DIM + 1) * Q + 8.0 * n * n * (n_dofs // n)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("k_volume_bytes_per_launch")
-        except Exception:
-            traffic = None
-    nblocks = int(desc.brow_ptr[desc.n_block_rows])
+    value = total_dofs / (ms_per_step * 1e-3)
+    e2e_value = total_dofs / (t_e2e_ms * 1e-3)
+    vol = roofs[0]
+    vol["traffic"] = traffic_of("k_volume_C_bytes_per_launch")
+    n_tiles = (n + 7) // 8
+    vol["frac_issued"] = vol["frac"] * (n_tiles * (n_tiles + 1) / 2) / (n_tiles * n_tiles)
     vm_bytes = 8.0 * n * n * nblocks + 4.0 * nblocks + 16.0 * n_dofs
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_dofs_per_gpu": n_dofs, "n_polytopes_per_gpu": int(desc.n_polytopes),
-                   "volume_q_points_per_gpu": Q,
-                   "sharding": "single GPU" if world == 1 else
-                   f"[0,1]^2 x [0,{world}] in {world} z-slabs of 512 polyhedra, cut interfaces evaluated by both sides "
-                   "from ghost bbox + DoF block (no assembly collective); vmult pulls ghost blocks over NVLink peer memory",
-                   "ghost_polytopes_per_gpu": int(desc.n_polytopes - n_dofs // n),
-                   "l2": "flushed (512 MiB memset) between timed steps; inputs 226 MB > L2 as well",
-                   "step": "quadrature + volume + faces + diagonal gather, all device kernels"},
+        "config": config_dict(),
+        "sharding": {"how": "single GPU" if world == 1 else
+                     f"[0,1]^2 x [0,{world}], {N_POLY_PER_GPU * world} polyhedra, METIS k-way on the polytope adjacency graph "
+                     "(vertex weight sub-cells, edge weight shared sub-faces); cut interfaces evaluated by both sides from "
+                     "ghost bbox + DoF block (no assembly collective); vmult ghost blocks over NVLink peer memory",
+                     "rank0_owned_polytopes": n_poly_own, "rank0_ghost_polytopes": n_ghost_poly,
+                     "total_dofs": total_dofs, "host_setup_s": t_host, "numa": numa},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": nnz * 8,
-                "api": "pd_upload + pd_assemble + pd_matrix_values_to_host_async per step, two handles double-buffered on two streams (pinned host buffers); wall clock over all steps",
-                "checksum": checksum, "serial_one_handle_value": world * n_dofs * args.steps / (t_e2e_serial_ms * 1e-3)},
+                "api": "pd_upload + pd_assemble + pd_matrix_values_to_host_async per step, two handles double-buffered on two "
+                       "streams (pinned host buffers, rank pinned to the GPU's NUMA node); wall clock, max over ranks",
+                "steps": e2e_steps, "checksum": checksum,
+                "serial_one_handle_value": total_dofs / (t_e2e_serial_ms * 1e-3)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "k_volume<3,2> (FP64 DMMA contraction)", "achieved": achieved,
-                     "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["fp64_tflops"],
-                     "traffic": traffic, "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": vol_bytes,
-                     "kernel_ms": vol_ms, "peak_source": peaks["fp64_src"],
-                     "hbm_frac_of_same_kernel": vol_bytes / (vol_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-        "kernel_ms": {k: statistics.mean(v) for k, v in kms.items()},
+        "roofline": {k: vol[k] for k in vol if k != "kernel"} | {"kernel": vol["kernel"]},
+        "rooflines": roofs,
+        "kernel_ms": kms,
         "vmult": {"metric": "SIP vmult GDoF/s (block-CSR apply of the assembled operator"
                             + (", incl. the ghost exchange over NVLink peer memory)" if world > 1 else ")"),
-                  "value": world * n_dofs / (t_vm_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t_vm_ms,
-                  "roofline": {"bound": "hbm", "achieved": vm_bytes / (t_vm_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                               "unit": "GB/s", "frac": vm_bytes / (t_vm_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                               "peak_source": peaks["hbm_src"]}},
+                  "value": total_dofs / (t_vm_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t_vm_ms,
+                  "timing": f"{reps} applies back to back (matrix 7.3 GB per GPU > L2), CUDA events, max over ranks",
+                  "roofline": hbm_block("k_spmv_block_row", vm_bytes, t_vm_ms, peaks),
+                  "cg_ms_per_iteration": t_cg_ms,
+                  "cg": "Jacobi-PCG around the block-CSR vmult, CUDA-graph replayed"
+                        + ("; ghost exchange + dot-product all-reduce over NVLink peer memory inside the graph" if world > 1 else "")},
+        "poly_mf_vmult": {"metric": "matrix-free SIP vmult on the agglomerated polytopes, GDoF/s",
+                          "value": total_dofs / (t_pmf_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t_pmf_ms,
+                          "checksum_rank0": pmf_checksum},
     }
-    out["vmult"]["cg_ms_per_iteration"] = t_cg_ms
-    out["vmult"]["cg"] = ("Jacobi-PCG around the block-CSR vmult, CUDA-graph replayed"
-                          + ("; ghost exchange + dot-product all-reduce over NVLink peer memory inside the graph" if world > 1 else ""))
     if world > 1:
         out["vmult"]["ms_with_nccl_exchange"] = t_vm_nccl_ms
-        out["vmult"]["exchange"] = "publish + pull kernels over CUDA-IPC peer memory, epoch-flag handshake (pd_peer_*); NCCL all_to_all_single timed beside it"
-    if world == 1 and not args.no_mf_vmult:
-        out["mf_vmult"] = mf_vmult_fine_mesh(stream, flush, peaks, max(args.steps, 5))
+        out["vmult"]["exchange"] = ("publish + pull kernels over CUDA-IPC peer memory, epoch-flag handshake (pd_peer_*); "
+                                    "NCCL all_to_all_single timed beside it")
+    if mf:
+        mf["ms"] = t_mf_ms
+        mf["value"] = mf["total_dofs"] / (t_mf_ms * 1e-3) / 1e9
+        mf["roofline"] = hbm_block(mf.pop("kernel"), 16.0 * mf["n_dofs_per_gpu"], t_mf_ms, peaks,
+                                   note="algorithmic bytes = 16 B/DoF (read src, write dst; SURVEY 8d); per GPU")
+        out["mf_vmult"] = mf
+    if mf3:
+        mf3["roofline"] = hbm_block(mf3.pop("kernel"), 16.0 * mf3["n_dofs_per_gpu"], mf3["ms"], peaks)
+        out["mf_vmult_dgq3"] = mf3
+    if world == 1 and not args.no_extra_configs:
+        out["config_B"] = run_extra_config(pdl, "B", stream, peaks, steps=max(args.steps, 10))
+        out["config_D"] = run_extra_config(pdl, "D", stream, peaks, steps=3)
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline(full=True)
+        os.sched_setaffinity(0, affinity0)  # the CPU arm gets every core of the box
+        out["cpu_baseline"] = cpu_baseline(CPU_STRIDE)
     print(json.dumps(out))
     if dist:
         dist.destroy_process_group()
 
 
-def mf_vmult_fine_mesh(stream, flush, peaks, steps):
-    """The second metric of BASELINE.json: the matrix-free sum-factorised SIP vmult of
-    examples/matrix_free_agglo.cc -- Utils::MatrixFreeOperators::LaplaceOperatorDG (include/utils.h:819-925) on
-    the fine hex mesh, hyper_cube refined 6x = 64^3 cells, FE_DGQ(2), 7.08 M DoFs -- through
-    pd_vmult(PD_VMULT_MATRIX_FREE), device vectors, L2 flushed between applies, CUDA events on the launch
-    stream.  Separate from the timed assembly steps above.  (Sharded: tools/run_fine_mf_scaling.py.)"""
+def mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, p, reps):
+    """The second metric of BASELINE.json: the matrix-free sum-factorised SIP vmult of examples/matrix_free_agglo.cc --
+    Utils::MatrixFreeOperators::LaplaceOperatorDG (include/utils.h:819-925) on the fine hex mesh, 64^3 cells of
+    FE_DGQ(p) per GPU -- through pd_vmult(PD_VMULT_MATRIX_FREE) / pd_peer_vmult, device vectors, `reps` applies back to
+    back (163 MB of vectors per GPU > L2), CUDA events on the launch stream.  N > 1: N cubes stacked along z, the
+    cells METIS-partitioned, ghost cells pulled over NVLink while the interior cells are applied."""
     import torch
 
-    import polydeal_b200 as pdl
-
-    n, p = 64, 2
-    grid = pdl.Grid.hyper_cube(3, 0.0, 1.0, 6)
-    ah = pdl.AgglomerationHandler(grid)
-    for c in range(n**3):
-        ah.define_agglomerate([c])
-    ah.initialize_fe_values(p + 1)
-    ah.distribute_agglomerated_dofs(pdl.FE_DGQ, p)
-    op = pdl.SIPOperator(ah.flatten(penalty_constant=p * (p + 1.0), h_rule=pdl.H_NORMAL_EXTENT), keepalive=ah)
+    cfg = dict(dim=3, n=64, b=1, p=p, nq=p + 1)
+    ah = build_handler(pdl, cfg, world)
+    pen = dict(penalty_constant=max(p, 1) * (p + 1.0), h_rule=pdl.H_NORMAL_EXTENT)
+    part = peer = None
+    if world == 1:
+        op = pdl.SIPOperator(ah.flatten(**pen), keepalive=ah)
+    else:
+        owner = pdd.partition_by_metis(ah, world)
+        part = pdd.LocalPart(ah, owner, rank, **pen)
+        op = pdl.SIPOperator(part.desc, keepalive=(ah, part))
     op.set_stream(stream.cuda_stream)
     assert op.matrix_free_available
     op.set_operator(pdl.ASSEMBLE_ALL, 1.0, 0.0)
-    N = op.m()
-    x = torch.from_numpy(np.sin(0.37 * np.arange(N)) + 0.01 * (np.arange(N) % 7)).cuda()
-    y = torch.empty_like(x)
+    N, ns = op.m(), op.n_source_dofs
+    x = torch.from_numpy(src_values(ns)).cuda()
+    y = torch.empty(N, dtype=torch.float64, device="cuda")
+    if part is not None:
+        peer = pdd.PeerExchange(part, op)
     l0 = op.launch_count
-    for _ in range(3):
-        op.vmult(y, x, mode=pdl.VMULT_MATRIX_FREE)
-    per_apply = (op.launch_count - l0 - 1) // 3  # the first apply also folds the stencil records
-    ms = []
-    for _ in range(steps):
+
+    def apply():
+        if peer is not None:
+            peer.vmult(y, x, mode=pdl.VMULT_MATRIX_FREE)
+        else:
+            op.vmult_ptr(y.data_ptr(), x.data_ptr(), mode=pdl.VMULT_MATRIX_FREE)
+
+    apply()
+    l1 = op.launch_count
+    apply()
+    per_apply = op.launch_count - l1
+    ms = timer.per_call_ms(apply, reps)
+    total = torch.tensor([float(N)], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    res = {"metric": f"matrix-free SIP vmult GDoF/s (LaplaceOperatorDG on the fine mesh, examples/matrix_free_agglo.cc: 64^3 hexes "
+                     f"per GPU, FE_DGQ({p}))" + (", incl. the ghost exchange over NVLink peer memory" if world > 1 else ""),
+           "value": float(total.cpu()[0]) / (ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": ms, "n_dofs_per_gpu": N,
+           "total_dofs": float(total.cpu()[0]), "applies": reps, "gpu_launches_per_apply": int(per_apply),
+           "kernel": os.environ.get("PD_FINE_KERNEL", "default") + f" fine-mesh kernel, FE_DGQ<3>({p})",
+           "checksum_rank0": float(y.sum())}
+    del l0
+    if peer is not None:
+        assert peer.ok(), "peer exchange timed out"
+        dist.barrier()
+        peer.close()
+    return res
+
+
+def run_extra_config(pdl, name, stream, peaks, steps):
+    """Assembly + block-CSR vmult of another SURVEY 8d configuration on one GPU (extra keys of the N = 1 line)."""
+    import torch
+
+    cfg = CONFIGS[name]
+    t0 = time.time()
+    ah = build_handler(pdl, cfg, 1)
+    desc = ah.flatten(penalty_constant=-1.0 if cfg["C"] is None else cfg["C"])
+    t_host = time.time() - t0
+    op = pdl.SIPOperator(desc, keepalive=ah)
+    op.set_stream(stream.cuda_stream)
+    N, n = op.m(), op.n_dofs_per_cell
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    kms, tot = {"volume": [], "faces": [], "reduce": [], "quadrature": []}, []
+    for s in range(steps + 2):
         flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        op.invalidate_quadrature()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        op.vmult(y, x, mode=pdl.VMULT_MATRIX_FREE)
-        b.record(stream)
-        b.synchronize()
-        ms.append(a.elapsed_time(b))
-    t = statistics.mean(ms)
-    nbytes = 16.0 * N + 3 * 64.0 * n**3  # read src + write dst (16 B/DoF, SURVEY 8d) + one 64-byte stencil record per (cell, direction)
-    return {"metric": "matrix-free SIP vmult GDoF/s (LaplaceOperatorDG on the fine mesh, examples/matrix_free_agglo.cc: 64^3 hexes, FE_DGQ(2))",
-            "value": N / (t * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t, "n_dofs": N, "applies": steps, "gpu_launches_per_apply": int(per_apply),
-            "kernel": "k_fine_tile<3,2> (one cell per thread pair, coefficients + halo staged in shared memory by TMA bulk copies)",
-            "checksum": float(y.sum()),
-            "roofline": {"bound": "hbm", "achieved": nbytes / (t * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": nbytes / (t * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_src"],
-                         "algorithmic_bytes_per_launch": nbytes}}
+        op.assemble(stiffness=1.0, mass=cfg["mass"])
+        e.record(stream)
+        e.synchronize()
+        if s >= 2:
+            tot.append(a.elapsed_time(e))
+            for k, v in op.last_kernel_ms().items():
+                kms[k].append(v)
+    kms = {k: statistics.mean(v) for k, v in kms.items()}
+    x = torch.from_numpy(src_values(N)).cuda()
+    y = torch.empty_like(x)
+    vm = []
+    for s in range(steps + 2):
+        flush.zero_()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        op.vmult_ptr(y.data_ptr(), x.data_ptr())
+        e.record(stream)
+        e.synchronize()
+        if s >= 2:
+            vm.append(a.elapsed_time(e))
+    nblocks = int(desc.brow_ptr[desc.n_block_rows])
+    ms, vm_ms = statistics.mean(tot), statistics.mean(vm)
+    res = {"workload": f"{name}: {cfg['n']}^{cfg['dim']} cells -> {desc.n_polytopes} polytopes ({cfg['b']}^{cfg['dim']} blocks), "
+                       f"FE_DGQ({cfg['p']}), QGauss({cfg['nq']})" + (", + reaction c=0.5, C=40" if cfg["mass"] else ""),
+           "n_dofs": N, "assemble_ms": ms, "dofs_per_s": N / (ms * 1e-3), "kernel_ms": kms, "host_setup_s": t_host,
+           "rooflines": assembly_rooflines(desc, n, cfg["nq"], kms, peaks, mass=bool(cfg["mass"])),
+           "vmult_ms": vm_ms, "vmult_gdofs": N / (vm_ms * 1e-3) / 1e9,
+           "vmult_roofline": hbm_block("k_spmv_block_row", 8.0 * n * n * nblocks + 4.0 * nblocks + 16.0 * N, vm_ms, peaks),
+           "l2": "flushed between steps / applies"}
+    del op, x, y, flush
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
 
 
-def oracle_config_b():
-    from oracle import pyoracle as po
-    from pd_helpers import oracle_handler
-
-    groups = block_groups(N_CELLS_1D, BLOCK)
-    _, oah = oracle_handler(DIM, N_CELLS_1D, groups, DEGREE, NQ)
-    return po, oah
+_ORACLE = {}
 
 
-def cpu_baseline(full, stride=None, oah=None, po=None):
-    """The CPU oracle (port of include/poly_utils.h:2000-2195, faithful cost: tables
-    re-evaluated per polytope and per face, scalar q*i*j loops) on all host cores."""
-    if oah is None:
-        po, oah = oracle_config_b()
-    cores = os.cpu_count() or 1
-    stride = stride or (1 if full else 4)
-    m = po.assemble_dg_matrix(oah, degree=DEGREE, n_threads=cores, poly_stride=stride, poly_offset=0)
-    n_poly = len(range(0, oah.n_polytopes, stride))
+def oracle_config_c():
+    """The oracle's handler of config C (built once per process)."""
+    if "ah" not in _ORACLE:
+        from oracle import pyoracle as po
+        from pd_workloads import morton_block_groups
+
+        grid = po.Grid(DIM, CFG["n"], 0.0, 1.0, 0)
+        oah = po.AgglomerationHandler(grid)
+        for g in morton_block_groups(DIM, CFG["n"], CFG["b"]):
+            oah.define_agglomerate(g)
+        oah.initialize_fe_values(NQ)
+        oah.distribute_agglomerated_dofs(po.FE_DGQ, DEGREE)
+        _ORACLE["ah"], _ORACLE["po"] = oah, po
+    return _ORACLE["po"], _ORACLE["ah"]
+
+
+def cpu_baseline(stride, offset=5):
+    """The CPU oracle (port of include/poly_utils.h:2000-2195, faithful cost: tables re-evaluated per polytope and
+    per face, scalar q*i*j loops) on all host cores, on every `stride`-th polytope of config C; the local matrices
+    are computed in full and summed into a sink instead of a 7.3 GB global matrix."""
+    po, oah = oracle_config_c()
+    cores = len(os.sched_getaffinity(0)) or 1
+    m = po.assemble_dg_matrix(oah, degree=DEGREE, n_threads=cores, poly_stride=stride, poly_offset=offset, discard_scatter=True)
+    n_poly = len(range(offset, oah.n_polytopes, stride))
     dofs = n_poly * oah.n_dofs_per_cell
     return {"value": dofs / m.seconds, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_poly} of {oah.n_polytopes} polytopes of config B (every {stride}th), {m.seconds:.2f} s, "
-                      "oracle CPU restatement of assemble_dg_matrix, not polyDEAL/deal.II itself", "seconds": m.seconds}
+            "sample": f"{n_poly} of {oah.n_polytopes} polytopes of config C (every {stride}th: volume + boundary + visited "
+                      f"interfaces), {m.seconds:.2f} s, oracle CPU restatement of assemble_dg_matrix without the global scatter, "
+                      "not polyDEAL/deal.II itself", "seconds": m.seconds, "dofs": dofs, "checksum": float(m.values()[0])}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    po, oah = oracle_config_b()
-    cores = os.cpu_count() or 1
-    stride = 4
+    cores = len(os.sched_getaffinity(0)) or 1
     for _ in range(args.warmup):
-        cpu_baseline(False, stride, oah, po)
+        cpu_baseline(REF_STRIDE)
     t, dofs, last = 0.0, 0, None
-    for _ in range(args.steps):
-        last = cpu_baseline(False, stride, oah, po)
+    for s in range(args.steps):
+        last = cpu_baseline(REF_STRIDE, offset=5 + (s % 64))
         t += last["seconds"]
-        dofs += len(range(0, oah.n_polytopes, stride)) * oah.n_dofs_per_cell
+        dofs += last["dofs"]
     value = dofs / t
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: oracle port of the reference assembly on the host cores; "
-                   "polyDEAL itself needs deal.II/Trilinos/MPI and cannot be built in this image"},
+        "config": config_dict(),
+        "note": "CPU arm: oracle port of the reference assembly on the host cores, each step a bounded sample of the workload; "
+                "polyDEAL itself needs deal.II/Trilinos/MPI and cannot be built in this image",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": last["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -539,6 +729,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mf-vmult", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

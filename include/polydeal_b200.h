@@ -392,6 +392,8 @@ int pdh_handler_destroy(pdh_handler *ah);
 /* define_agglomerate(cells): cells[0] is the master; returns polytope index or <0
  * (source/agglomeration_handler.cc:45-104) */
 int32_t pdh_define_agglomerate(pdh_handler *ah, const int32_t *cells, int32_t n);
+/* the same for many agglomerates in one call: group g = cells[ptr[g] .. ptr[g+1]) (define order = group order) */
+int pdh_define_agglomerates(pdh_handler *ah, int32_t n_groups, const int64_t *ptr, const int32_t *cells);
 /* initialize_fe_values(QGauss<dim>(nq_cell), ..., QGauss<dim-1>(nq_face)) (:210-236) */
 int pdh_initialize_fe_values(pdh_handler *ah, int32_t nq_cell, int32_t nq_face);
 /* distribute_agglomerated_dofs(fe)  (:326-379); fe_kind PD_FE_DGQ or PD_FE_AGGLODGP */
@@ -463,6 +465,11 @@ int pdh_flatten_local(pdh_handler *ah, const pdh_flatten_params *prm, const int3
  * sub-faces).  CSR graph without self loops, both directions listed; weights may be NULL. */
 int pdh_partition_graph(int64_t n_vertices, const int64_t *xadj, const int64_t *adjncy, const int64_t *vertex_weights,
                         const int64_t *edge_weights, int32_t n_parts, int32_t *part_out);
+/* The polytope adjacency graph in the CSR form pdh_partition_graph takes (vertex weight = sub-cells of
+ * the polytope, edge weight = shared sub-faces; neighbours in face order).  Returns the number of directed edges
+ * (or < 0); any output may be NULL (call once with NULLs for the size). */
+int64_t pdh_polytope_graph(const pdh_handler *ah, int64_t *xadj, int64_t *adjncy, int64_t *vertex_weights,
+                           int64_t *edge_weights);
 /* pdh_flatten + pd_create in one call */
 int pdh_create_device(pdh_handler *ah, const pdh_flatten_params *prm, pd_handle **out);
 

@@ -339,6 +339,7 @@ extern "C"
     int    n_threads;
     int    poly_stride;
     int    poly_offset;
+    int    discard_scatter;
   };
 
   void *
@@ -356,6 +357,7 @@ extern "C"
     prm.n_threads        = p->n_threads;
     prm.poly_stride      = p->poly_stride > 0 ? p->poly_stride : 1;
     prm.poly_offset      = p->poly_offset;
+    prm.discard_scatter  = p->discard_scatter;
     const auto t0        = std::chrono::steady_clock::now();
     if (guard([&] { assemble_dg_matrix(*static_cast<Handler *>(ah), prm, M->A); }))
       {

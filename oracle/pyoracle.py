@@ -46,6 +46,7 @@ class _Params(C.Structure):
         ("n_threads", C.c_int),
         ("poly_stride", C.c_int),
         ("poly_offset", C.c_int),
+        ("discard_scatter", C.c_int),
     ]
 
 
@@ -392,6 +393,7 @@ def assemble_dg_matrix(
     degree=None,
     poly_stride=1,
     poly_offset=0,
+    discard_scatter=False,
 ) -> Matrix:
     """PolyUtils::assemble_dg_matrix (include/poly_utils.h:2000-2195); the
     default penalty is the library's 10 (p+dim)(p+1) (:2018-2019)."""
@@ -399,7 +401,7 @@ def assemble_dg_matrix(
         assert degree is not None
         penalty_constant = 10.0 * (degree + ah.dim) * (degree + 1)
     prm = _Params(penalty_constant, h_rule, h_const, visit_rule, int(with_boundary), stiffness_coeff, mass_coeff, n_threads,
-                  poly_stride, poly_offset)
+                  poly_stride, poly_offset, int(discard_scatter))
     sec = C.c_double(0.0)
     h = lib().po_assemble_dg_matrix(ah.h, C.byref(prm), C.byref(sec))
     if not h:
@@ -417,7 +419,7 @@ def assemble_block_rows(ah: AgglomerationHandler, polys, penalty_constant=None, 
     if penalty_constant is None:
         assert degree is not None
         penalty_constant = 10.0 * (degree + ah.dim) * (degree + 1)
-    prm = _Params(penalty_constant, h_rule, h_const, visit_rule, int(with_boundary), stiffness_coeff, mass_coeff, n_threads, 1, 0)
+    prm = _Params(penalty_constant, h_rule, h_const, visit_rule, int(with_boundary), stiffness_coeff, mass_coeff, n_threads, 1, 0, 0)
     polys = np.ascontiguousarray(polys, dtype=np.int32)
     n = ah.n_dofs_per_cell
     ptr = np.empty(len(polys) + 1, dtype=np.int64)

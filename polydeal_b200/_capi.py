@@ -138,6 +138,8 @@ SIGNATURES = {
     "pdh_sparsity_nnz": (i64, [vp]),
     "pdh_create_agglomeration_sparsity_pattern": (C.c_int, [vp, vp, vp]),
     "pdh_flatten": (C.c_int, [vp, P(FlattenParams), P(MeshDesc)]),
+    "pdh_define_agglomerates": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pdh_polytope_graph": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdh_partition_graph": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pdh_flatten_local": (C.c_int, [vp, P(FlattenParams), vp, i32, P(MeshDesc), P(LocalInfo)]),
     "pdh_create_device": (C.c_int, [vp, P(FlattenParams), P(vp)]),

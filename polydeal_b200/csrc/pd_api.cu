@@ -600,6 +600,8 @@ extern "C"
         cudaGraphExecDestroy(h->cg_graph_exec);
       if (h->cg_graph1_exec)
         cudaGraphExecDestroy(h->cg_graph1_exec);
+      if (h->ev_order)
+        cudaEventDestroy(h->ev_order);
       for (auto &e : h->ev)
         if (e)
           cudaEventDestroy(e);

@@ -164,6 +164,47 @@ extern "C"
     return e == PD_OK ? r : e;
   }
   int
+  pdh_define_agglomerates(pdh_handler *ah, int32_t n_groups, const int64_t *ptr, const int32_t *cells)
+  {
+    return guarded([&] {
+      if (!ptr || !cells || n_groups < 0)
+        throw pd::Error(PD_ERR_INVALID, "pdh_define_agglomerates: bad argument");
+      for (int32_t g = 0; g < n_groups; ++g)
+        H(ah).define_agglomerate(cells + ptr[g], (int32_t)(ptr[g + 1] - ptr[g]));
+    });
+  }
+  int64_t
+  pdh_polytope_graph(const pdh_handler *ah, int64_t *xadj, int64_t *adjncy, int64_t *vertex_weights, int64_t *edge_weights)
+  {
+    int64_t   n_edges = -1;
+    const int e       = guarded([&] {
+      const pd::AgglomerationHandler &a = H(ah);
+      a.require_connectivity();
+      const int32_t np = a.n_polytopes();
+      int64_t       k  = 0;
+      for (int32_t p = 0; p < np; ++p)
+        {
+          if (xadj)
+            xadj[p] = k;
+          if (vertex_weights)
+            vertex_weights[p] = a.subcell_ptr[p + 1] - a.subcell_ptr[p];
+          for (uint32_t f = 0; f < a.n_faces(p); ++f)
+            if (!a.at_boundary(p, f))
+              {
+                if (adjncy)
+                  adjncy[k] = a.neighbor(p, f);
+                if (edge_weights)
+                  edge_weights[k] = a.face_sub_ptr[a.face_ptr[p] + f + 1] - a.face_sub_ptr[a.face_ptr[p] + f];
+                ++k;
+              }
+        }
+      if (xadj)
+        xadj[np] = k;
+      n_edges = k;
+    });
+    return e == PD_OK ? n_edges : e;
+  }
+  int
   pdh_initialize_fe_values(pdh_handler *ah, int32_t nq_cell, int32_t nq_face)
   {
     return guarded([&] { H(ah).initialize_fe_values(nq_cell, nq_face); });

@@ -174,6 +174,7 @@ struct pd_handle
   cudaStream_t stream     = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t  ev[5]      = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t  ev_order   = nullptr; // orders the own stream behind a caller stream that cannot capture (pd_solver.cu)
   float        last_ms[4] = {0, 0, 0, 0};
   bool         quad_valid = false, assembled = false;
   int64_t      launches   = 0;

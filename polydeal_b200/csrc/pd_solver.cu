@@ -334,6 +334,31 @@ namespace pd
       throw Error(PD_ERR_UNSUPPORTED, "pd_cg_solve: a handle with ghost polytopes needs pd_cg_solve_sharded");
     if (peer && peer_handle(peer) != h)
       throw Error(PD_ERR_INVALID, "pd_cg_solve_sharded: the peer object belongs to another handle");
+    // stream capture is not available on the legacy / per-thread default streams: run the solve on the handle's
+    // own stream, ordered behind the caller's work by an event (the solve ends with a synchronisation of its
+    // stream, so the caller's stream needs no dependency in the other direction)
+    struct OwnStreamScope
+    {
+      pd_handle   *h;
+      cudaStream_t saved;
+      explicit OwnStreamScope(pd_handle *h_)
+        : h(h_)
+        , saved(h_->stream)
+      {
+        if (saved == cudaStreamLegacy || saved == cudaStreamPerThread || saved == nullptr)
+          {
+            if (!h->ev_order)
+              PD_CUDA(cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming));
+            PD_CUDA(cudaEventRecord(h->ev_order, saved));
+            PD_CUDA(cudaStreamWaitEvent(h->own_stream, h->ev_order, 0));
+            h->stream = h->own_stream;
+          }
+      }
+      ~OwnStreamScope()
+      {
+        h->stream = saved;
+      }
+    } own_stream_scope(h);
     ensure_work(h);
     auto apply = [&](double *src_full, double *dst) {
       if (peer)

@@ -53,20 +53,8 @@ def partition_by_metis(ah: AgglomerationHandler, n_ranks: int) -> np.ndarray:
     (volume work), edge weight = number of shared sub-faces (ghost traffic): SURVEY 8e."""
     from .handler import partition_graph
 
-    np_ = ah.n_polytopes
-    rows, cols, wts = [], [], []
-    for p in range(np_):
-        for f in range(ah.n_faces(p)):
-            if not ah.at_boundary(p, f):
-                rows.append(p)
-                cols.append(ah.neighbor(p, f))
-                wts.append(len(ah.interface(p, f)))
-    rows, cols, wts = np.array(rows, dtype=np.int64), np.array(cols, dtype=np.int64), np.array(wts, dtype=np.int64)
-    order = np.lexsort((cols, rows))
-    xadj = np.zeros(np_ + 1, dtype=np.int64)
-    xadj[1:] = np.cumsum(np.bincount(rows, minlength=np_))
-    vw = np.array([len(ah.get_agglomerate(p)) for p in range(np_)], dtype=np.int64)
-    return partition_graph(xadj, cols[order], n_ranks, vw, wts[order]).astype(np.int32)
+    xadj, adjncy, vw, ew = ah.polytope_graph()
+    return partition_graph(xadj, adjncy, n_ranks, vw, ew).astype(np.int32)
 
 
 class LocalPart:
@@ -93,17 +81,19 @@ class LocalPart:
         # what I receive: my ghost section is grouped by owner rank
         self.recv_counts = np.bincount(self.ghost_owner, minlength=n_ranks).astype(np.int64)
         # what I send to peer s: my owned polytopes adjacent to a polytope owned by s, by global block
-        nbrs = [[ah.neighbor(int(p), f) for f in range(ah.n_faces(int(p)))] for p in self.local_poly_global[: self.n_owned]]
-        need = [set() for _ in range(n_ranks)]
-        for lp, p in enumerate(self.local_poly_global[: self.n_owned]):
-            gb = int(ah.get_dof_indices(int(p))[0]) // self.n
-            for q in nbrs[lp]:
-                if q >= 0 and owner[q] != rank:
-                    need[owner[q]].add(gb)
-        self.send_blocks = []  # per peer: local owned block indices, in the order the peer stores them
+        xadj, adjncy, _, _ = ah.polytope_graph()
+        own = self.local_poly_global[: self.n_owned].astype(np.int64)
+        deg = xadj[own + 1] - xadj[own]
+        local_block = np.ctypeslib.as_array(self.desc.dof_block, (self.n_owned + self.n_ghost,))[: self.n_owned].astype(np.int64)
+        src_local = np.repeat(local_block, deg)  # local block (row) of the owned end of every edge
+        idx = np.repeat(xadj[own], deg) + (np.arange(int(deg.sum()), dtype=np.int64) - np.repeat(np.cumsum(deg) - deg, deg))
+        nb_owner = owner[adjncy[idx]]
+        self.send_blocks = []  # per peer: local owned block indices, in the order the peer stores them (global block)
         for s in range(n_ranks):
-            gbs = np.array(sorted(need[s]), dtype=np.int64)
-            self.send_blocks.append(np.searchsorted(self.owned_global_block, gbs).astype(np.int64))
+            if s == rank:
+                self.send_blocks.append(np.zeros(0, dtype=np.int64))
+                continue
+            self.send_blocks.append(np.unique(src_local[nb_owner == s]))  # owned_global_block ascends with the local block
         self.send_counts = np.array([len(b) for b in self.send_blocks], dtype=np.int64)
 
     @property

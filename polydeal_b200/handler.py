@@ -146,6 +146,28 @@ class AgglomerationHandler:
             K.check(r)
         return r
 
+    def define_agglomerates(self, groups):
+        """define_agglomerate for every cell list of `groups` (a 2-D integer array or a list of lists), in order."""
+        if isinstance(groups, np.ndarray) and groups.ndim == 2:
+            ptr = np.arange(groups.shape[0] + 1, dtype=np.int64) * groups.shape[1]
+            cells = np.ascontiguousarray(groups, dtype=np.int32).ravel()
+        else:
+            ptr = np.zeros(len(groups) + 1, dtype=np.int64)
+            ptr[1:] = np.cumsum([len(g) for g in groups])
+            cells = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=np.int32) for g in groups]), dtype=np.int32)
+        K.check(K.lib().pdh_define_agglomerates(self._h, len(ptr) - 1, _ptr(ptr), _ptr(cells)))
+
+    def polytope_graph(self):
+        """(xadj, adjncy, vertex_weights, edge_weights) of the polytope adjacency graph (pdh_polytope_graph)."""
+        ne = K.lib().pdh_polytope_graph(self._h, None, None, None, None)
+        if ne < 0:
+            K.check(int(ne))
+        np_ = self.n_polytopes
+        xadj, adj = np.empty(np_ + 1, dtype=np.int64), np.empty(ne, dtype=np.int64)
+        vw, ew = np.empty(np_, dtype=np.int64), np.empty(ne, dtype=np.int64)
+        K.lib().pdh_polytope_graph(self._h, _ptr(xadj), _ptr(adj), _ptr(vw), _ptr(ew))
+        return xadj, adj, vw, ew
+
     def initialize_fe_values(self, nq_cell, nq_face=None):
         K.check(K.lib().pdh_initialize_fe_values(self._h, nq_cell, nq_face if nq_face is not None else nq_cell))
 

@@ -24,24 +24,14 @@ TOL = 1e-12
 
 
 def fast_block_groups(dim, n, b):
-    """b^dim blocks of the Morton-ordered n^dim grid without Python loops over cells."""
-    ax = np.arange(n, dtype=np.int64)
-    if dim == 2:
-        i, j = np.meshgrid(ax, ax, indexing="ij")
-        k = np.zeros_like(i)
-    else:
-        i, j, k = np.meshgrid(ax, ax, ax, indexing="ij")
-    i, j, k = i.ravel(), j.ravel(), k.ravel()
-    cell = np.zeros_like(i)
-    for l in range(n.bit_length() - 1):
-        cell |= ((i >> l) & 1) << (dim * l)
-        cell |= ((j >> l) & 1) << (dim * l + 1)
-        if dim == 3:
-            cell |= ((k >> l) & 1) << (dim * l + 2)
-    nb = n // b
-    part = ((k // b) * nb + (j // b)) * nb + (i // b)
-    order = np.lexsort((cell, part))
-    return cell[order].astype(np.int32).reshape(nb**dim, b**dim)
+    """b^dim blocks of the Morton-ordered n^dim grid without Python loops over cells (tools/pd_workloads.py)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from pd_workloads import morton_block_groups
+
+    return morton_block_groups(dim, n, b)
 
 
 def handlers(dim, n, groups, p, nq):
