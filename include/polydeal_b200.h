@@ -186,6 +186,39 @@ int pd_quadrature_device(pd_handle *h, const double **vol_x, const double **vol_
                          const double **face_n, const double **face_jxw);
 int pd_quadrature_to_host(pd_handle *h, double *vol_x, double *vol_jxw, double *face_x, double *face_n,
                           double *face_jxw);
+/* --- the reinit() family: the FEValues tables of ONE polytope / polytope face -------------------
+ * What AgglomerationHandler::reinit(polytope), reinit(polytope, f) and reinit_interface return
+ * (include/agglomeration_handler.h:431-452, source/agglomeration_handler.cc:729-906): the element on
+ * the bounding box (MappingBox, source/mapping_box.cc:393-439: value phihat(xhat), gradient
+ * grad-hat / h_bbox) at the agglomerated quadrature.  The assembly kernels generate these tables on
+ * the fly; these entry points materialise them so that the reference's hand-written loops
+ * (examples/poisson.cc:745-905) can be pointed at the library.  Output pointers are HOST or DEVICE
+ * memory (any may be NULL); the tables are complete when the call returns, and -- as in the
+ * reference, where reinit* invalidates the previous FEValues -- one call at a time per handle.
+ * Layout = the FEValues accessors, Q = number of points of the item, n = pd_n_dofs_per_cell:
+ *   values[i * Q + q] = shape_value(i, q)       grads[(i * Q + q) * dim + d] = shape_grad(i, q)[d]
+ *   jxw[q] = JxW(q)    points[q * dim + d] = quadrature_point(q)[d]    normals[q * dim + d] = normal_vector(q)[d]
+ * Faces are addressed through the flattened work list: interface `iface` (pdh_face_work_item maps a
+ * polytope's face number to it), side 0 = the listing polytope iface_polyA with its outward normal,
+ * side 1 = iface_polyB at the SAME (aligned) points with its own outward normal = -n_A and its own
+ * bounding box -- the pair reinit_interface returns. */
+int64_t pd_reinit_n_points(const pd_handle *h, int32_t poly);        /* Q of an owned polytope, < 0: error */
+int64_t pd_reinit_iface_n_points(const pd_handle *h, int32_t iface); /* Q of an interface / boundary face */
+int pd_reinit_polytope(pd_handle *h, int32_t poly, double *values, double *grads, double *jxw, double *points);
+int pd_reinit_face(pd_handle *h, int32_t iface, int32_t side, double *values, double *grads, double *jxw,
+                   double *points, double *normals);
+int pd_reinit_interface(pd_handle *h, int32_t iface, double *values0, double *grads0, double *values1, double *grads1,
+                        double *jxw, double *points, double *normals);
+/* AgglomerationHandler::agglomerated_quadrature (source/agglomeration_handler.cc:622-707) of one polytope:
+ * the Quadrature<dim> the reference builds holds the points in bounding-box UNIT coordinates and the
+ * physical JxW as weights; real_points are the same points before BoundingBox::real_to_unit. */
+int pd_agglomerated_quadrature(pd_handle *h, int32_t poly, double *unit_points, double *jxw, double *real_points);
+/* The element families on the unit cell at arbitrary points (unit_points [n_points][dim], host or device):
+ * FE_DGQ<dim>(degree) / FE_AggloDGP<dim>(degree) shape values [n][n_points] and gradients [n][n_points][dim]
+ * (source/fe_agglodgp.cc:28-57; deal.II FE_DGQ).  Needs a CUDA device like every compute entry point. */
+int pd_fe_evaluate(int32_t fe_kind, int32_t dim, int32_t degree, int64_t n_points, const double *unit_points,
+                   double *values, double *grads);
+
 /* Right-hand side over polytopes (examples/poisson.cc:745-761, examples/diffusion_reaction.cc:
  * 550-556): rhs_i = sum_q f_q phi_i w_q  +  stiffness * sum_{boundary q} (sigma g_q phi_i -
  * (grad phi_i . n) g_q) w_q, sigma the boundary sub-face penalty of the descriptor.
@@ -440,6 +473,14 @@ typedef struct pdh_flatten_params
 /* Flatten the agglomeration into a descriptor whose arrays stay owned by (and
  * valid as long as) the handler. */
 int pdh_flatten(pdh_handler *ah, const pdh_flatten_params *prm, pd_mesh_desc *out);
+/* Where face f of polytope `poly` (the reference's face numbering, n_faces / neighbor / at_boundary) sits in
+ * the work list of the LAST pdh_flatten: *iface = its entry, *side = 0 if `poly` is the listing (visiting)
+ * polytope iface_polyA, 1 if it is iface_polyB.  Feeds pd_reinit_face / pd_reinit_interface. */
+int pdh_face_work_item(const pdh_handler *ah, int32_t poly, uint32_t f, int32_t *iface, int32_t *side);
+/* MappingBox / BoundingBox of a polytope (source/mapping_box.cc:923-972, agglomeration_handler.cc:698-704):
+ * xhat = (x - lo) / (hi - lo) and back, n points [n][dim]. */
+int pdh_real_to_unit(const pdh_handler *ah, int32_t poly, int64_t n, const double *real_points, double *unit_points);
+int pdh_unit_to_real(const pdh_handler *ah, int32_t poly, int64_t n, const double *unit_points, double *real_points);
 /* One rank's share of a partition of the polytopes (owner[p] = rank of polytope p, all
  * polytopes of the handler): owned polytopes + the ghost polytopes adjacent to them, as a
  * descriptor with n_owned_polytopes set, plus the global block numbers needed to build the

@@ -103,6 +103,13 @@ SIGNATURES = {
     "pd_cg_solve": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, f64, C.c_int, P(C.c_int), P(f64)]),
     "pd_estimate_lambda_max": (C.c_int, [vp, C.c_int, C.c_int, P(f64)]),
     "pd_chebyshev_smooth": (C.c_int, [vp, C.c_int, C.c_int, f64, f64, vp, vp, C.c_int]),
+    "pd_reinit_n_points": (i64, [vp, i32]),
+    "pd_reinit_iface_n_points": (i64, [vp, i32]),
+    "pd_reinit_polytope": (C.c_int, [vp, i32, vp, vp, vp, vp]),
+    "pd_reinit_face": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp]),
+    "pd_reinit_interface": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "pd_agglomerated_quadrature": (C.c_int, [vp, i32, vp, vp, vp]),
+    "pd_fe_evaluate": (C.c_int, [i32, i32, i32, i64, vp, vp, vp]),
     "pd_copy_array": (C.c_int, [vp, C.c_char_p, vp, P(i64)]),
     "pd_launch_count": (i64, [vp]),
     "pd_last_kernel_ms": (C.c_int, [vp, P(C.c_float)]),
@@ -138,6 +145,9 @@ SIGNATURES = {
     "pdh_sparsity_nnz": (i64, [vp]),
     "pdh_create_agglomeration_sparsity_pattern": (C.c_int, [vp, vp, vp]),
     "pdh_flatten": (C.c_int, [vp, P(FlattenParams), P(MeshDesc)]),
+    "pdh_face_work_item": (C.c_int, [vp, i32, u32, P(i32), P(i32)]),
+    "pdh_real_to_unit": (C.c_int, [vp, i32, i64, vp, vp]),
+    "pdh_unit_to_real": (C.c_int, [vp, i32, i64, vp, vp]),
     "pdh_define_agglomerates": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "pdh_polytope_graph": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdh_partition_graph": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -287,6 +287,7 @@ namespace pd
     h2d(h->sub_sigma, d.sub_sigma, (size_t)h->n_subfaces, s);
     h2d(h->brow_ptr, d.brow_ptr, (size_t)d.n_block_rows + 1, s);
     h2d(h->bcol, d.bcol_idx, (size_t)h->n_blocks, s);
+    h->h_bbox.assign(d.bbox, d.bbox + (size_t)d.n_polytopes * 2 * d.dim);
     h->quad_valid = false;
     h->assembled  = false;
     h->mfd_valid  = false; // cached inverse diagonal of the matrix-free operators
@@ -942,6 +943,90 @@ extern "C"
   pd_peer_destroy(pd_peer *p)
   {
     peer_destroy(p);
+  }
+
+  // ---- the reinit() family (pd_reinit.cu) ----
+  int64_t
+  pd_reinit_n_points(const pd_handle *h, int32_t poly)
+  {
+    int64_t   n = -1;
+    const int e = guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      n = reinit_n_points(h, poly);
+    });
+    return e == PD_OK ? n : e;
+  }
+  int64_t
+  pd_reinit_iface_n_points(const pd_handle *h, int32_t iface)
+  {
+    int64_t   n = -1;
+    const int e = guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      n = reinit_iface_n_points(h, iface);
+    });
+    return e == PD_OK ? n : e;
+  }
+  int
+  pd_reinit_polytope(pd_handle *h, int32_t poly, double *values, double *grads, double *jxw, double *points)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      reinit_n_points(h, poly); // range check
+      need_quadrature(h);
+      reinit_polytope(h, poly, values, grads, jxw, points, nullptr);
+    });
+  }
+  int
+  pd_agglomerated_quadrature(pd_handle *h, int32_t poly, double *unit_points, double *jxw, double *real_points)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      reinit_n_points(h, poly);
+      need_quadrature(h);
+      reinit_polytope(h, poly, nullptr, nullptr, jxw, real_points, unit_points);
+    });
+  }
+  int
+  pd_reinit_face(pd_handle *h, int32_t iface, int32_t side, double *values, double *grads, double *jxw, double *points,
+                 double *normals)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      reinit_iface_n_points(h, iface);
+      need_quadrature(h);
+      reinit_iface(h, iface, side, values, grads, jxw, points, normals);
+    });
+  }
+  int
+  pd_reinit_interface(pd_handle *h, int32_t iface, double *values0, double *grads0, double *values1, double *grads1,
+                      double *jxw, double *points, double *normals)
+  {
+    return guarded([&] {
+      if (!h)
+        throw Error(PD_ERR_INVALID, "null handle");
+      reinit_iface_n_points(h, iface);
+      if (h->h_ifB[iface] < 0)
+        throw Error(PD_ERR_INVALID, "pd_reinit_interface: a boundary face has no second side (use pd_reinit_face)");
+      need_quadrature(h);
+      reinit_iface(h, iface, 0, values0, grads0, jxw, points, normals);
+      reinit_iface(h, iface, 1, values1, grads1, nullptr, nullptr, nullptr);
+    });
+  }
+  int
+  pd_fe_evaluate(int32_t fe_kind, int32_t dim, int32_t degree, int64_t n_points, const double *unit_points, double *values,
+                 double *grads)
+  {
+    return guarded([&] {
+      require_device();
+      if (!unit_points && n_points > 0)
+        throw Error(PD_ERR_INVALID, "pd_fe_evaluate: null argument");
+      fe_evaluate(fe_kind, dim, degree, n_points, unit_points, values, grads);
+    });
   }
 
   int

@@ -362,6 +362,7 @@ namespace pd
       fl_sub_face.clear();
       fl_sub_sigma.clear();
       const int32_t np = n_polytopes();
+      fl_face_item.assign((size_t)face_ptr[np], -1);
       for (int32_t p = 0; p < np; ++p)
         {
           const double hp = diameter(p);
@@ -373,7 +374,9 @@ namespace pd
                   const bool visit = prm.visit_rule == PD_VISIT_BY_ID ? masters[p] < masters[q] : p < q;
                   if (!visit)
                     continue;
+                  fl_face_item[(size_t)(face_ptr[q] + neighbor_of_agglomerated_neighbor(p, f))] = 2 * (int64_t)fl_polyA.size() + 1;
                 }
+              fl_face_item[(size_t)(face_ptr[p] + f)] = 2 * (int64_t)fl_polyA.size();
               fl_polyA.push_back(p);
               fl_polyB.push_back(q);
               const int64_t fi = face_ptr[p] + f;
@@ -656,6 +659,19 @@ namespace pd
       info.ghost_owner        = lc_ghost_owner.data();
       info.local_poly_global  = lc_poly_global.data();
     }
+
+    // polytope face -> (entry of the last flatten's work list, side)
+    void
+    face_work_item(const int32_t p, const uint32_t f, int32_t &iface, int32_t &side) const
+    {
+      check_face(p, f);
+      if (fl_face_item.size() != (size_t)face_ptr[n_polytopes()])
+        throw Error(PD_ERR_STATE, "pdh_face_work_item: pdh_flatten has not been called");
+      const int64_t v = fl_face_item[(size_t)(face_ptr[p] + f)];
+      iface           = (int32_t)(v >> 1);
+      side            = (int32_t)(v & 1);
+    }
+    std::vector<int64_t> fl_face_item;
 
     Grid     *grid;
     int       dim;

@@ -205,6 +205,40 @@ extern "C"
     return e == PD_OK ? n_edges : e;
   }
   int
+  pdh_face_work_item(const pdh_handler *ah, int32_t poly, uint32_t f, int32_t *iface, int32_t *side)
+  {
+    return guarded([&] {
+      if (!iface || !side)
+        throw pd::Error(PD_ERR_INVALID, "pdh_face_work_item: null argument");
+      H(ah).face_work_item(poly, f, *iface, *side);
+    });
+  }
+  static int
+  box_map(const pdh_handler *ah, int32_t poly, int64_t n, const double *in, double *out, bool to_unit)
+  {
+    return guarded([&] {
+      const pd::AgglomerationHandler &a = H(ah);
+      a.check_poly(poly);
+      if ((!in || !out) && n > 0)
+        throw pd::Error(PD_ERR_INVALID, "null argument");
+      const int     dim = a.dim;
+      const double *b   = &a.bbox[(size_t)poly * 2 * dim];
+      for (int64_t q = 0; q < n; ++q)
+        for (int d = 0; d < dim; ++d)
+          out[q * dim + d] = to_unit ? (in[q * dim + d] - b[d]) / (b[dim + d] - b[d]) : b[d] + in[q * dim + d] * (b[dim + d] - b[d]);
+    });
+  }
+  int
+  pdh_real_to_unit(const pdh_handler *ah, int32_t poly, int64_t n, const double *real_points, double *unit_points)
+  {
+    return box_map(ah, poly, n, real_points, unit_points, true);
+  }
+  int
+  pdh_unit_to_real(const pdh_handler *ah, int32_t poly, int64_t n, const double *unit_points, double *real_points)
+  {
+    return box_map(ah, poly, n, unit_points, real_points, false);
+  }
+  int
   pdh_initialize_fe_values(pdh_handler *ah, int32_t nq_cell, int32_t nq_face)
   {
     return guarded([&] { H(ah).initialize_fe_values(nq_cell, nq_face); });

@@ -164,6 +164,8 @@ struct pd_handle
 
   std::vector<int64_t> h_brow_ptr, h_subcell_ptr;
   std::vector<int32_t> h_bcol, h_dof_block, h_ifA, h_ifB;
+  std::vector<double>  h_bbox;          // bounding boxes (reinit tables, pd_reinit.cu)
+  pd::DevBuf<double>   reinit_scratch;  // tables of one polytope / face before they go to the caller
   uint64_t             fine_geo_hash = 0; // fine meshes: hash of the arrays the stencil / mapped operators derive from
   // bumped by everything a captured solver graph bakes in (operator terms and coefficients, kernel choice,
   // stream, work buffers, uploads); part of the graph cache key (pd_solver.cu)
@@ -232,6 +234,15 @@ namespace pd
   pd_handle *peer_handle(pd_peer *p);
   int      peer_status(pd_peer *p);
   void     peer_destroy(pd_peer *p);
+  // pd_reinit.cu
+  int64_t reinit_n_points(const pd_handle *h, int32_t poly);
+  int64_t reinit_iface_n_points(const pd_handle *h, int32_t iface);
+  void    reinit_polytope(pd_handle *h, int32_t poly, double *values, double *grads, double *jxw, double *points,
+                          double *unit_points);
+  void    reinit_iface(pd_handle *h, int32_t iface, int side, double *values, double *grads, double *jxw, double *points,
+                       double *normals);
+  void    fe_evaluate(int fe_kind, int dim, int degree, int64_t n_points, const double *unit_points, double *values,
+                      double *grads);
   // pd_vmult.cu
   void launch_spmv(pd_handle *h, const double *src, double *dst, bool add, int part = 0);
   bool spmv_can_split(pd_handle *h);

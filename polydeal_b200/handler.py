@@ -243,6 +243,25 @@ class AgglomerationHandler:
     def volume(self, p):
         return K.lib().pdh_volume(self._h, p)
 
+    def face_work_item(self, p, f):
+        """(iface, side) of face f of polytope p in the work list of the last flatten() (pdh_face_work_item)."""
+        i, s = C.c_int32(-1), C.c_int32(-1)
+        K.check(K.lib().pdh_face_work_item(self._h, p, f, C.byref(i), C.byref(s)))
+        return i.value, s.value
+
+    def real_to_unit(self, p, points):
+        """BoundingBox::real_to_unit of polytope p's box (MappingBox::transform_real_to_unit_cell)."""
+        x = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
+        out = np.empty_like(x)
+        K.check(K.lib().pdh_real_to_unit(self._h, p, len(x), _ptr(x), _ptr(out)))
+        return out
+
+    def unit_to_real(self, p, points):
+        x = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, self.dim)
+        out = np.empty_like(x)
+        K.check(K.lib().pdh_unit_to_real(self._h, p, len(x), _ptr(x), _ptr(out)))
+        return out
+
     def create_agglomeration_sparsity_pattern(self):
         nnz = K.lib().pdh_sparsity_nnz(self._h)
         if nnz < 0:
@@ -258,6 +277,29 @@ class AgglomerationHandler:
         d = K.MeshDesc()
         K.check(K.lib().pdh_flatten(self._h, C.byref(prm), C.byref(d)))
         return d
+
+
+class FEValuesTables:
+    """What `reinit*` returns in the reference (FEValues / FEImmersedSurfaceValues), as arrays."""
+
+    def __init__(self, values, grads, jxw, points, normals):
+        self.values, self.grads, self.JxW, self.points, self.normals = values, grads, jxw, points, normals
+        self.n_q = len(jxw)
+
+    def shape_value(self, i, q):
+        return self.values[i, q]
+
+    def shape_grad(self, i, q):
+        return self.grads[i, q]
+
+
+def fe_evaluate(fe_kind, dim, degree, unit_points):
+    """FE_DGQ / FE_AggloDGP on the unit cell: (values [n, Q], grads [n, Q, dim]) at unit_points [Q, dim] (pd_fe_evaluate)."""
+    x = np.ascontiguousarray(unit_points, dtype=np.float64).reshape(-1, dim)
+    n = (degree + 1) ** dim if fe_kind == 0 else int(np.prod([degree + k for k in range(1, dim + 1)]) // np.prod(range(1, dim + 1)))
+    v, g = np.empty((n, len(x))), np.empty((n, len(x), dim))
+    K.check(K.lib().pd_fe_evaluate(fe_kind, dim, degree, len(x), _ptr(x), _ptr(v), _ptr(g)))
+    return v, g
 
 
 class SIPOperator:
@@ -474,6 +516,42 @@ class SIPOperator:
                                        C.c_void_p(exact_grad.data_ptr()) if exact_grad is not None else None,
                                        C.byref(l2), C.byref(h1) if exact_grad is not None else None))
         return l2.value, (h1.value if exact_grad is not None else None)
+
+    # ---- the reinit() family: FEValues tables of one polytope / face, as numpy arrays on the host ----
+    def reinit(self, poly):
+        """ah.reinit(polytope): FEValuesTables(values [n, Q], grads [n, Q, dim], JxW [Q], points [Q, dim])."""
+        Q = K.lib().pd_reinit_n_points(self._h, poly)
+        if Q < 0:
+            K.check(int(Q))
+        n, dim = self.n_dofs_per_cell, self.desc.dim
+        t = FEValuesTables(np.empty((n, Q)), np.empty((n, Q, dim)), np.empty(Q), np.empty((Q, dim)), None)
+        K.check(K.lib().pd_reinit_polytope(self._h, poly, _ptr(t.values), _ptr(t.grads), _ptr(t.JxW), _ptr(t.points)))
+        return t
+
+    def reinit_face(self, iface, side=0):
+        """ah.reinit(polytope, f) with (iface, side) = AgglomerationHandler.face_work_item(polytope, f)."""
+        Q = K.lib().pd_reinit_iface_n_points(self._h, iface)
+        if Q < 0:
+            K.check(int(Q))
+        n, dim = self.n_dofs_per_cell, self.desc.dim
+        t = FEValuesTables(np.empty((n, Q)), np.empty((n, Q, dim)), np.empty(Q), np.empty((Q, dim)), np.empty((Q, dim)))
+        K.check(K.lib().pd_reinit_face(self._h, iface, side, _ptr(t.values), _ptr(t.grads), _ptr(t.JxW), _ptr(t.points),
+                                       _ptr(t.normals)))
+        return t
+
+    def reinit_interface(self, iface):
+        """ah.reinit_interface(...): the pair (side 0, side 1) at aligned points, each with its own outward normal."""
+        return self.reinit_face(iface, 0), self.reinit_face(iface, 1)
+
+    def agglomerated_quadrature(self, poly):
+        """(unit points [Q, dim], JxW [Q], real points [Q, dim]) of polytope `poly` (pd_agglomerated_quadrature)."""
+        Q = K.lib().pd_reinit_n_points(self._h, poly)
+        if Q < 0:
+            K.check(int(Q))
+        dim = self.desc.dim
+        u, w, x = np.empty((Q, dim)), np.empty(Q), np.empty((Q, dim))
+        K.check(K.lib().pd_agglomerated_quadrature(self._h, poly, _ptr(u), _ptr(w), _ptr(x)))
+        return u, w, x
 
     def estimate_lambda_max(self, n_iterations=20, mode=K.VMULT_BLOCK_CSR):
         lam = C.c_double(0.0)

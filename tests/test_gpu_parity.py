@@ -1401,3 +1401,128 @@ def test_torch_entry_points_follow_the_current_stream():
             op.vmult(yd, xd)
             yh = yd.cpu()  # stream-ordered D2H on the same stream
         assert np.abs(yh.numpy() - yref).max() <= TOL * np.abs(yref).max()
+
+
+# ----------------------------------------------------------------------------------
+# row (b): the reinit() family through the C ABI (include/agglomeration_handler.h:431-452)
+# ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,n,shape,p,nq,distort,fe", [
+    (2, 8, "random7", 1, 2, None, "dgq"), (2, 8, "random5", 3, 4, (0.2, 5), "dgq"), (3, 4, "random6", 2, 3, None, "dgq"),
+    (3, 4, "blocks2", 3, 4, (0.15, 9), "dgq"), (2, 8, "random6", 2, 3, None, "dgp"), (3, 4, "random5", 2, 3, None, "dgp"),
+])
+def test_reinit_tables_match_oracle(dim, n, shape, p, nq, distort, fe):
+    """reinit(polytope), reinit(polytope, f) and reinit_interface: values, gradients, JxW, points and normals of
+    every polytope and every polytope face against the oracle's tables; two-sided alignment of the interface points
+    (test/polydeal/reinit_cell_face_quad_pts); agglomerated_quadrature in bbox unit coordinates."""
+    pdl = gpu()
+    kind = po.FE_AGGLODGP if fe == "dgp" else po.FE_DGQ
+    ogrid = po.Grid(dim, n, 0.0, 1.0, 0)
+    groups = groups_for(shape, dim, n, ogrid, 3)
+    _, oah = oracle_handler(dim, n, groups, p, nq, distort=distort, fe_kind=kind)
+    v, cv, nb = oah.grid.arrays()
+    pah = pdl.AgglomerationHandler(pdl.Grid.from_arrays(v, cv, nb))
+    for g in groups:
+        pah.define_agglomerate(g)
+    pah.initialize_fe_values(nq)
+    pah.distribute_agglomerated_dofs(pdl.FE_AGGLODGP if fe == "dgp" else pdl.FE_DGQ, p)
+    op = pdl.SIPOperator(pah.flatten(), keepalive=pah)
+    tol = 1e-12
+    for poly in range(oah.n_polytopes):
+        ref, got = oah.reinit(poly), op.reinit(poly)
+        assert got.n_q == ref.n_q
+        np.testing.assert_allclose(got.points, ref.points, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(got.JxW, ref.JxW, rtol=1e-14, atol=0)
+        np.testing.assert_allclose(got.values, ref.values, rtol=0, atol=tol * np.abs(ref.values).max())
+        np.testing.assert_allclose(got.grads, ref.grads, rtol=0, atol=tol * np.abs(ref.grads).max())
+        u, w, x = op.agglomerated_quadrature(poly)
+        np.testing.assert_allclose(x, ref.points, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(u, pah.real_to_unit(poly, ref.points), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(pah.unit_to_real(poly, u), ref.points, rtol=0, atol=1e-14)
+        lo, hi = oah.bbox(poly)
+        np.testing.assert_allclose(u, (ref.points - lo) / (hi - lo), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(w, ref.JxW, rtol=1e-14, atol=0)
+        # the element on the unit cell at the unit points reproduces the values (FE_DGQ / FE_AggloDGP evaluators)
+        vals, grads = pdl.fe_evaluate(pdl.FE_AGGLODGP if fe == "dgp" else pdl.FE_DGQ, dim, p, u)
+        np.testing.assert_allclose(vals, ref.values, rtol=0, atol=tol * np.abs(ref.values).max())
+        np.testing.assert_allclose(grads / (hi - lo), ref.grads, rtol=0, atol=tol * np.abs(ref.grads).max())
+        for f in range(oah.n_faces(poly)):
+            iface, side = pah.face_work_item(poly, f)
+            rf, gf = oah.reinit(poly, f), op.reinit_face(iface, side)
+            assert gf.n_q == rf.n_q
+            if side == 0:  # listed from this polytope: its own sub-face order
+                order = np.arange(rf.n_q)
+            else:  # the neighbour's list, aligned point by point with the listing side
+                nbp, nofn = oah.neighbor(poly, f), oah.neighbor_of_agglomerated_neighbor(poly, f)
+                assert pah.face_work_item(nbp, nofn) == (iface, 0)
+                other = oah.reinit(nbp, nofn)
+                assert np.abs(other.points - rf.points).max() < 1e-15  # reinit_cell_face_quad_pts
+                order = np.arange(rf.n_q)
+            np.testing.assert_allclose(gf.points, rf.points[order], rtol=0, atol=1e-15)
+            np.testing.assert_allclose(gf.normals, rf.normals[order], rtol=0, atol=1e-15)
+            np.testing.assert_allclose(gf.JxW, rf.JxW[order], rtol=1e-14, atol=0)
+            np.testing.assert_allclose(gf.values, rf.values[:, order], rtol=0, atol=tol * np.abs(rf.values).max())
+            np.testing.assert_allclose(gf.grads, rf.grads[:, order], rtol=0, atol=tol * np.abs(rf.grads).max())
+            if not oah.at_boundary(poly, f) and side == 0:
+                f0, f1 = op.reinit_interface(iface)
+                assert np.abs(f0.points - f1.points).max() == 0.0
+                assert np.abs(f0.normals + f1.normals).max() == 0.0
+
+
+def test_reference_style_loop_over_reinit_reproduces_the_assembled_matrix():
+    """The loop of PolyUtils::assemble_dg_matrix / examples/poisson.cc:745-905 written against the reinit() tables of
+    the library (host side, numpy) gives the matrix pd_assemble computes on the device."""
+    pdl = gpu()
+    dim, n, p, nq = 2, 8, 2, 3
+    oah, pah = both(dim, n, "random6", p, nq=nq, seed=4)
+    desc = pah.flatten()
+    op = pdl.SIPOperator(desc, keepalive=pah)
+    nd, N = pah.n_dofs_per_cell, pah.n_dofs
+    A = np.zeros((N, N))
+    C = 10.0 * (p + dim) * (p + 1)
+    for poly in range(pah.n_polytopes):
+        fev = op.reinit(poly)
+        dofs = pah.get_dof_indices(poly).astype(np.int64)
+        cell = np.einsum("iqd,jqd,q->ij", fev.grads, fev.grads, fev.JxW)
+        pen = C / pah.diameter(poly)
+        for f in range(pah.n_faces(poly)):
+            iface, side = pah.face_work_item(poly, f)
+            if pah.at_boundary(poly, f):
+                ff = op.reinit_face(iface, side)
+                gn = np.einsum("iqd,qd->iq", ff.grads, ff.normals)
+                cell += np.einsum("iq,jq,q->ij", -ff.values, gn, ff.JxW) + np.einsum("iq,jq,q->ij", -gn, ff.values, ff.JxW) \
+                    + pen * np.einsum("iq,jq,q->ij", ff.values, ff.values, ff.JxW)
+                continue
+            nbp = pah.neighbor(poly, f)
+            if not pah.master_cell(poly) < pah.master_cell(nbp):
+                continue
+            assert side == 0
+            f0, f1 = op.reinit_interface(iface)
+            nrm, w = f0.normals, f0.JxW
+            g0, g1 = np.einsum("iqd,qd->iq", f0.grads, nrm), np.einsum("iqd,qd->iq", f1.grads, nrm)
+            v0, v1 = f0.values, f1.values
+            E = lambda a, b: np.einsum("iq,jq,q->ij", a, b, w)
+            ndofs = pah.get_dof_indices(nbp).astype(np.int64)
+            A[np.ix_(dofs, dofs)] += -0.5 * E(g0, v0) - 0.5 * E(v0, g0) + pen * E(v0, v0)
+            A[np.ix_(dofs, ndofs)] += 0.5 * E(g0, v1) - 0.5 * E(v0, g1) - pen * E(v0, v1)
+            A[np.ix_(ndofs, dofs)] += -0.5 * E(g1, v0) + 0.5 * E(v1, g0) - pen * E(v1, v0)
+            A[np.ix_(ndofs, ndofs)] += 0.5 * E(g1, v1) + 0.5 * E(v1, g1) + pen * E(v1, v1)
+        A[np.ix_(dofs, dofs)] += cell
+    op.assemble()
+    got = op.scipy().toarray()
+    assert np.abs(got - A).max() <= 1e-12 * np.abs(A).max()
+    ref = po.assemble_dg_matrix(oah, degree=p).scipy().toarray()
+    assert np.abs(ref - A).max() <= 1e-12 * np.abs(A).max()
+
+
+def test_reference_style_cpp_loop_through_the_shim(tmp_path):
+    """tests/c_abi/shim_sip_loop.cpp: the SIP loop of examples/poisson.cc written against the header-only C++ shim
+    (reinit / reinit_interface / get_dof_indices / LinearOperatorMG-style vmult), compiled here and run on the GPU:
+    the host-assembled matrix equals pd_assemble's per entry (1e-12), in 2-D and 3-D."""
+    import subprocess
+
+    from test_host_mirror import build_shim_program
+
+    exe = build_shim_program(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHIM LOOP OK" in r.stdout, r.stdout + r.stderr
+    print(r.stdout)

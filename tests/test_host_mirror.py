@@ -237,6 +237,34 @@ def test_c_abi_from_plain_c(tmp_path):
     assert r.returncode == 0 and "C ABI OK" in r.stdout, r.stdout + r.stderr
 
 
+def build_shim_program(tmp_path):
+    """g++ -std=c++17 on tests/c_abi/shim_sip_loop.cpp against include/polydeal_b200_shim.hpp (no CUDA headers)."""
+    import shutil
+    import subprocess
+
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if cxx is None:
+        pytest.skip("no C++ compiler")
+    exe = str(tmp_path / "shim_sip_loop")
+    lib_dir = os.path.dirname(K.LIB_PATH)
+    subprocess.run([cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "shim_sip_loop.cpp"), "-L", lib_dir, "-lpolydeal_b200",
+                    "-Wl,-rpath," + lib_dir, "-o", exe], check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_cpp_shim_compiles_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/polydeal_b200_shim.hpp (the reference-named C++ surface) goes through a compiler; a reference-style
+    loop written against it walks the host mirror, and its first device call is refused without a GPU."""
+    import subprocess
+
+    exe = build_shim_program(tmp_path)
+    if K.lib().pd_device_count() > 0:
+        pytest.skip("a GPU is visible: the full loop runs in the -m gpu suite")
+    r = subprocess.run([exe, "--host"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "SHIM HOST OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_more_face_goldens_through_the_host_mirror(goldens):
     """continuous_face_02 (incl. the METIS scenario recovered from its golden), continuous_face_03,
     continuous_face_distorted_grid, reinit_cell_face_master_master, reinit_cell_face_quad_pts: face
