@@ -299,8 +299,19 @@ int pd_invalidate_quadrature(pd_handle *h);
 
 /* PolyUtils::assemble_dg_matrix (include/poly_utils.h:2000-2195).  Result: the
  * scalar-CSR value array of the reference pattern (ascending columns), kept on
- * the device inside the handle. */
+ * the device inside the handle.
+ * Two kernel families compute the same matrix (tests hold both to the oracle):
+ *   PD_PATH_TENSOR  every owned sub-cell is an axis-aligned box (checked on the device at
+ *                   pd_create / pd_upload): the quadrature sums factorise per sub-cell / sub-face
+ *                   into 1-D matrices and a block is a sum of Kronecker products (pd_cartesian.cu)
+ *   PD_PATH_DMMA    any mesh: rank-k updates over the agglomerated quadrature points on the FP64
+ *                   tensor cores (pd_assemble.cu)
+ * The environment variable PD_ASSEMBLE_KERNELS=generic forces PD_PATH_DMMA (measurements, tests). */
 int pd_assemble(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
+#define PD_PATH_DMMA 0
+#define PD_PATH_TENSOR 1
+/* which family the last pd_assemble ran (-1: none yet) */
+int pd_assembly_path(const pd_handle *h);
 
 int64_t pd_n_dofs(const pd_handle *h);        /* rows = owned DoFs */
 int64_t pd_n_source_dofs(const pd_handle *h); /* length of vmult source vectors = owned + ghost DoFs */

@@ -111,6 +111,7 @@ SIGNATURES = {
     "pd_agglomerated_quadrature": (C.c_int, [vp, i32, vp, vp, vp]),
     "pd_fe_evaluate": (C.c_int, [i32, i32, i32, i64, vp, vp, vp]),
     "pd_copy_array": (C.c_int, [vp, C.c_char_p, vp, P(i64)]),
+    "pd_assembly_path": (C.c_int, [vp]),
     "pd_launch_count": (i64, [vp]),
     "pd_last_kernel_ms": (C.c_int, [vp, P(C.c_float)]),
     "pd_quadrature_rule_1d": (C.c_int, [C.c_int, vp, vp]),

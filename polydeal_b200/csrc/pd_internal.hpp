@@ -164,6 +164,9 @@ struct pd_handle
 
   std::vector<int64_t> h_brow_ptr, h_subcell_ptr;
   std::vector<int32_t> h_bcol, h_dof_block, h_ifA, h_ifB;
+  bool                 cartesian = false; // every owned sub-cell is an axis-aligned box: tensor assembly path (pd_cartesian.cu)
+  pd::DevBuf<int>      cart_flag;
+  int                  last_assembly_path = -1; // 0: DMMA kernels on the agglomerated quadrature, 1: tensor path
   std::vector<double>  h_bbox;          // bounding boxes (reinit tables, pd_reinit.cu)
   pd::DevBuf<double>   reinit_scratch;  // tables of one polytope / face before they go to the caller
   uint64_t             fine_geo_hash = 0; // fine meshes: hash of the arrays the stencil / mapped operators derive from
@@ -234,6 +237,10 @@ namespace pd
   pd_handle *peer_handle(pd_peer *p);
   int      peer_status(pd_peer *p);
   void     peer_destroy(pd_peer *p);
+  // pd_cartesian.cu
+  bool check_axis_aligned(pd_handle *h);
+  bool cartesian_assembly_selected(const pd_handle *h);
+  void launch_assemble_cartesian(pd_handle *h, uint32_t flags, const pd_coefficients &coef);
   // pd_reinit.cu
   int64_t reinit_n_points(const pd_handle *h, int32_t poly);
   int64_t reinit_iface_n_points(const pd_handle *h, int32_t iface);

@@ -582,6 +582,11 @@ class SIPOperator:
         return out
 
     @property
+    def assembly_path(self):
+        """'tensor' (axis-aligned sub-cells, pd_cartesian.cu) or 'dmma' (pd_assemble.cu) for the last assemble()."""
+        return {0: "dmma", 1: "tensor"}.get(K.lib().pd_assembly_path(self._h))
+
+    @property
     def launch_count(self):
         return K.lib().pd_launch_count(self._h)
 

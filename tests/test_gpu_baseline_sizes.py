@@ -66,14 +66,19 @@ def groups_of_shape(shape, dim, n):
     ("B-blocks", 3, 64, "blocks8", 2, 3),
     ("B-metis", 3, 64, "metis512", 2, 3),
 ])
-def test_full_matrix_at_baseline_size(name, dim, n, shape, p, nq):
+@pytest.mark.parametrize("kernels", ["tensor", "dmma"])
+def test_full_matrix_at_baseline_size(name, dim, n, shape, p, nq, kernels, monkeypatch):
     import torch
 
     import polydeal_b200 as pdl
 
+    if kernels == "dmma":
+        monkeypatch.setenv("PD_ASSEMBLE_KERNELS", "generic")
+
     oah, pah = handlers(dim, n, groups_of_shape(shape, dim, n), p, nq)
     ref = po.assemble_dg_matrix(oah, degree=p, n_threads=16)
     op = pdl.assemble_dg_matrix(pah)
+    assert op.assembly_path == kernels
     rp, cols = op.pattern()
     orp, ocols, ovals = ref.csr()
     np.testing.assert_array_equal(rp, orp)  # sparsity bit exact
@@ -108,10 +113,14 @@ def test_full_matrix_at_baseline_size(name, dim, n, shape, p, nq):
     ("C", 128, 4, 3, 4, {}),
     ("D/8", 128, 4, 2, 3, dict(penalty_constant=40.0, mass_coeff=0.5)),
 ])
-def test_sampled_block_rows_at_baseline_size(name, n, b, p, nq, kw):
+@pytest.mark.parametrize("kernels", ["tensor", "dmma"])
+def test_sampled_block_rows_at_baseline_size(name, n, b, p, nq, kw, kernels, monkeypatch):
     import torch
 
     import polydeal_b200 as pdl
+
+    if kernels == "dmma":
+        monkeypatch.setenv("PD_ASSEMBLE_KERNELS", "generic")
 
     dim = 3
     oah, pah = handlers(dim, n, fast_block_groups(dim, n, b), p, nq)
@@ -123,7 +132,7 @@ def test_sampled_block_rows_at_baseline_size(name, n, b, p, nq, kw):
     pkw = dict(kw)
     pkw.setdefault("penalty_constant", -1.0)
     op = pdl.assemble_dg_matrix(pah, **pkw)
-    assert op.m() == oah.n_dofs
+    assert op.m() == oah.n_dofs and op.assembly_path == kernels
     dvals = torch.as_tensor(_DevView(op.values_device_ptr(), op.nnz), device="cuda")
     # pattern of the sampled rows from the host mirror (bit exact vs the oracle's block columns)
     d = op.desc

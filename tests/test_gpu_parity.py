@@ -99,9 +99,17 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("kernels", ["default", "generic"])
 @pytest.mark.parametrize("dim,n,shape,p,nq,distort,kw", CASES)
-def test_assembled_matrix_matches_oracle(dim, n, shape, p, nq, distort, kw):
+def test_assembled_matrix_matches_oracle(dim, n, shape, p, nq, distort, kw, kernels, monkeypatch):
+    """Both kernel families against the oracle: by default axis-aligned meshes take the tensor path
+    (pd_cartesian.cu: per-sub-cell sum factorisation) and distorted ones the DMMA kernels on the agglomerated
+    quadrature (pd_assemble.cu); PD_ASSEMBLE_KERNELS=generic runs the DMMA kernels everywhere."""
     pdl = gpu()
+    if kernels == "generic":
+        if distort is not None:
+            pytest.skip("distorted meshes take the DMMA kernels by default")
+        monkeypatch.setenv("PD_ASSEMBLE_KERNELS", "generic")
     oah, pah = both(dim, n, shape, p, nq=nq, distort=distort)
     okw = dict(kw)
     okw.setdefault("penalty_constant", None)
@@ -109,6 +117,7 @@ def test_assembled_matrix_matches_oracle(dim, n, shape, p, nq, distort, kw):
     pkw = dict(kw)
     pkw.setdefault("penalty_constant", -1.0)
     op = pdl.assemble_dg_matrix(pah, **pkw)
+    assert op.assembly_path == ("tensor" if distort is None and kernels == "default" else "dmma")
     rp, cols = op.pattern()
     orp, ocols, ovals = ref.csr()
     np.testing.assert_array_equal(rp, orp)      # sparsity bit exact
@@ -141,9 +150,12 @@ def test_assembled_matrix_matches_oracle(dim, n, shape, p, nq, distort, kw):
     np.testing.assert_allclose(dinv.cpu().numpy(), np.where(np.abs(diag) > 1e-10, 1.0 / diag, diag), rtol=1e-11)
 
 
-def test_assemble_flags_split_the_matrix():
+@pytest.mark.parametrize("kernels", ["default", "generic"])
+def test_assemble_flags_split_the_matrix(kernels, monkeypatch):
     """volume + boundary + interior parts add up to the full matrix."""
     pdl = gpu()
+    if kernels == "generic":
+        monkeypatch.setenv("PD_ASSEMBLE_KERNELS", "generic")
     from polydeal_b200 import ASSEMBLE_BOUNDARY, ASSEMBLE_INTERIOR, ASSEMBLE_VOLUME
 
     oah, pah = both(3, 4, "random5", 2, nq=3)
@@ -886,8 +898,13 @@ def test_interpolation_to_the_fine_mesh_space(dim, n, p, shape, distort):
     (3, 4, "random3", 3, 4, None, {}),
     (3, 4, "singletons", 2, 3, None, dict(with_boundary=False)),
 ])
-def test_assembly_with_fe_agglodgp(dim, n, shape, p, nq, distort, kw):
+@pytest.mark.parametrize("kernels", ["default", "generic"])
+def test_assembly_with_fe_agglodgp(dim, n, shape, p, nq, distort, kw, kernels, monkeypatch):
     """assemble_dg_matrix with FE_AggloDGP<dim>(p): C(p+dim, dim) Legendre products per polytope."""
+    if kernels == "generic":
+        if distort is not None:
+            pytest.skip("distorted meshes take the DMMA kernels by default")
+        monkeypatch.setenv("PD_ASSEMBLE_KERNELS", "generic")
     pdl = gpu()
     import math
     import torch

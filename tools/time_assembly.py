@@ -1,0 +1,18 @@
+import sys, json, statistics
+sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tools')
+import torch, numpy as np
+import polydeal_b200 as pdl
+from pd_workloads import CONFIGS, build_handler
+for name in sys.argv[1:]:
+    cfg=CONFIGS[name]
+    ah=build_handler(pdl,cfg,1)
+    desc=ah.flatten(penalty_constant=-1.0 if cfg["C"] is None else cfg["C"])
+    stream=torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    op=pdl.SIPOperator(desc,keepalive=ah); op.set_stream(stream.cuda_stream)
+    tot=[]; kms=[]
+    for s in range(6):
+        a,e=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+        a.record(stream); op.assemble(stiffness=1.0,mass=cfg["mass"]); e.record(stream); e.synchronize()
+        if s>=2: tot.append(a.elapsed_time(e)); kms.append(op.last_kernel_ms())
+    print(json.dumps({"config":name,"path":op.assembly_path,"assemble_ms":statistics.mean(tot),"dofs_per_s":op.m()/(statistics.mean(tot)*1e-3),"kernel_ms":kms[-1],"mem_GB":torch.cuda.max_memory_allocated()/1e9}))
+    del op
