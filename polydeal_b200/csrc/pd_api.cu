@@ -1186,6 +1186,8 @@ extern "C"
       {
         if (h->mf_ready && !h->force_generic_mf)
           launch_fine_operator(h, src, dst, add); // fine Cartesian mesh: sum-factorised stencil kernel
+        else if (cartesian_apply_available(h))
+          launch_cart_apply(h, src, dst, add); // axis-aligned sub-cells: sum factorisation per sub-cell / sub-face
         else
           {
             // agglomerated polytopes: regenerate the basis at the agglomerated quadrature points

@@ -28,9 +28,10 @@
 //                   order sub-cells, then adjacency list -- deterministic, no atomics, no partials
 //   k_cart_offdiag  one CTA per interior interface: M12 from cross matrices of the two bounding-box
 //                   bases, written to (A,B) and, transposed (M21 = M12^T), to (B,A)
-// Thread layout: thread (col, rg) owns the column col = (b,b',c,c') of the factorised block and
-// RPT = N1^2 / RG rows (a,a'); per item it forms its Y (x) Z entry from two shared-memory loads and
-// sweeps its rows with broadcast loads of X -- the 1-D matrices are the only shared-memory state.
+// Thread layout: thread (col, ig) owns the column col = (b,b',c,c') of the factorised block with all its
+// N1^2 rows (a,a') in registers; per item it forms its Y (x) Z entry from two shared-memory loads and sweeps
+// the rows with 16-byte broadcast loads of X -- the 1-D matrices are the only shared-memory state.  Small
+// elements deal the items of a chunk to IG item groups so that a CTA still has ~256 threads.
 // Roofline: the matrix is written once (8 n^2 bytes per block: config C 7.3 GB) => HBM-bound.
 // -----------------------------------------------------------------------------
 #include "pd_host.hpp"
@@ -95,12 +96,16 @@ namespace pd
     {
       using C                 = Cfg<DIM, DEGX>;
       static constexpr int N1 = C::N1, NX = N1 * N1, NYZ = ipow(NX, DIM - 1), NF = ipow(N1, DIM);
-      // row groups: threads = NYZ * RG, RPT rows each
-      static constexpr int RG   = NYZ >= 256 ? 1 : (NYZ * NX <= 1024 && NYZ < 64 ? NX : (NX % 3 == 0 ? 3 : (NX % 2 == 0 ? 2 : 1)));
-      static constexpr int RPT  = NX / RG;
-      static constexpr int NTHR = ((NYZ * RG + 31) / 32) * 32;
-      static constexpr int CH   = 16; // items per chunk
-      static_assert(NX % RG == 0, "row groups");
+      static constexpr int NXP = NX + (NX & 1); // slot stride: even, so that the X rows load as 16-byte pairs
+      static constexpr int CH  = 16;            // items per chunk
+      // thread (col, ig): column col = (b,b'[,c,c']) of the factorised block, all NX rows (a,a'); the items of a
+      // chunk are dealt to IG item groups (small elements: fills the CTA), summed through shared memory at the end
+      static constexpr int IG   = NYZ >= 128 ? 1 : (NYZ * 2 >= 128 ? 2 : (NYZ * 4 >= 128 ? 4 : (NYZ * 8 >= 128 ? 8 : 16)));
+      static constexpr int NTHR = ((NYZ * IG + 31) / 32) * 32;
+      // at least 24 resident warps per SM: the phases of a CTA (1-D matrices | accumulation) are separated by
+      // barriers, other CTAs fill the gaps
+      static constexpr int MINB = (768 / NTHR) < 1 ? 1 : ((768 / NTHR) > 8 ? 8 : (768 / NTHR));
+      static constexpr int ISTR = DIM * 2 * NXP;
     };
 
     // rows a of the 1-D matrices of one item along one axis, [a'] = 0..N1-1:
@@ -187,87 +192,115 @@ namespace pd
       hi                = A.verts[(int64_t)cv[(1 << DIM) - 1] * DIM + d];
     }
 
-    // acc[r] += X1[r] yz1 + X2[r] yz2 over the items of a chunk.  SL[item][d][2][NX]: slot 0 = M-like, slot 1 = K-like.
-    // kind[item]: 1 = cell (two terms), 2 = face (one term, F sits in slot 0 of its normal axis), 0 = empty.
+    // X rows of a slot into registers, 16 bytes at a time (the address is the same for every thread of the
+    // CTA: one broadcast wavefront per load)
+    template <int NX>
+    __device__ __forceinline__ void
+    load_rows(const double *src, double *x)
+    {
+#pragma unroll
+      for (int r = 0; r + 1 < NX; r += 2)
+        {
+          const double2 v = *reinterpret_cast<const double2 *>(src + r);
+          x[r]            = v.x;
+          x[r + 1]        = v.y;
+        }
+      if (NX & 1)
+        x[NX - 1] = src[NX - 1];
+    }
+
+    // acc[r] += X1[r] yz1 + X2[r] yz2 over the items ig, ig + IG, ... of a chunk.  SL[item][d][2][NXP]: slot 0 =
+    // M-like, slot 1 = K-like.  kind[item]: 1 = cell (two terms), 2 = face (one term, F sits in slot 0 of its
+    // normal axis).
     template <int DIM, int DEGX>
     __device__ __forceinline__ void
-    accumulate_chunk(const double *SL, const int *kind, const int cnt, const int col, const int rg, const double stiffness,
+    accumulate_chunk(const double *SL, const int *kind, const int cnt, const int col, const int ig, const double stiffness,
                      const double mass, double *acc)
     {
       using CC            = CartCfg<DIM, DEGX>;
-      constexpr int NX    = CC::NX, RPT = CC::RPT;
-      constexpr int ISTR  = DIM * 2 * NX;
+      constexpr int NX    = CC::NX, NXP = CC::NXP, ISTR = CC::ISTR, IG = CC::IG;
       const int     cb    = DIM == 3 ? col % NX : col; // (b,b')
       const int     cc    = DIM == 3 ? col / NX : 0;   // (c,c')
-      for (int it = 0; it < cnt; ++it)
+      for (int it = ig; it < cnt; it += IG)
         {
           const double *s  = SL + it * ISTR;
-          const int     kd = kind[it];
-          if (kd == 0)
-            continue;
-          const double m1 = s[(1 * 2 + 0) * NX + cb];
-          const double m2 = DIM == 3 ? s[(2 * 2 + 0) * NX + cc] : 1.;
+          const double m1 = s[(1 * 2 + 0) * NXP + cb];
+          const double m2 = DIM == 3 ? s[(2 * 2 + 0) * NXP + cc] : 1.;
           const double yz1 = m1 * m2;
-          if (kd == 1)
+          double       x[NX];
+          if (kind[it] == 1)
             {
-              const double k1  = s[(1 * 2 + 1) * NX + cb];
-              const double k2  = DIM == 3 ? s[(2 * 2 + 1) * NX + cc] : 0.;
+              const double k1  = s[(1 * 2 + 1) * NXP + cb];
+              const double k2  = DIM == 3 ? s[(2 * 2 + 1) * NXP + cc] : 0.;
               const double yz2 = stiffness * (k1 * m2 + m1 * k2) + mass * yz1;
               const double sy1 = stiffness * yz1;
-              const double *x1 = s + (0 * 2 + 1) * NX + rg * RPT; // K along x
-              const double *x0 = s + (0 * 2 + 0) * NX + rg * RPT; // M along x
+              load_rows<NX>(s + (0 * 2 + 1) * NXP, x); // K along x
 #pragma unroll
-              for (int r = 0; r < RPT; ++r)
-                acc[r] += x1[r] * sy1 + x0[r] * yz2;
+              for (int r = 0; r < NX; ++r)
+                acc[r] += x[r] * sy1;
+              load_rows<NX>(s + (0 * 2 + 0) * NXP, x); // M along x
+#pragma unroll
+              for (int r = 0; r < NX; ++r)
+                acc[r] += x[r] * yz2;
             }
           else
             {
-              const double *x0 = s + (0 * 2 + 0) * NX + rg * RPT;
+              load_rows<NX>(s + (0 * 2 + 0) * NXP, x);
 #pragma unroll
-              for (int r = 0; r < RPT; ++r)
-                acc[r] += x0[r] * yz1;
+              for (int r = 0; r < NX; ++r)
+                acc[r] += x[r] * yz1;
             }
         }
     }
 
-    // registers -> OUT[full row index][full column index] (shared, NF x (NF + 1))
+    // registers -> OUT[full row index][full column index] (shared, NF x (NF + 1)): item group 0 stores, the
+    // others add in turn (fixed order: deterministic)
     template <int DIM, int DEGX>
     __device__ __forceinline__ void
-    stage_block(double *OUT, const int col, const int rg, const double *acc)
+    stage_block(double *OUT, const int col, const int ig, const bool active, const double *acc)
     {
       using CC         = CartCfg<DIM, DEGX>;
-      constexpr int N1 = CC::N1, NX = CC::NX, RPT = CC::RPT, NF = CC::NF;
+      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, IG = CC::IG;
       const int     cb = DIM == 3 ? col % NX : col, cc = DIM == 3 ? col / NX : 0;
       const int     b = cb / N1, bp = cb % N1, c = cc / N1, cp = cc % N1;
-#pragma unroll
-      for (int r = 0; r < RPT; ++r)
+      for (int g = 0; g < IG; ++g)
         {
-          const int ra = rg * RPT + r;
-          const int a = ra / N1, ap = ra % N1;
-          const int i = a + N1 * (b + N1 * c), j = ap + N1 * (bp + N1 * cp);
-          OUT[i * (NF + 1) + j] = acc[r];
+          if (active && ig == g)
+            {
+#pragma unroll
+              for (int r = 0; r < NX; ++r)
+                {
+                  const int a = r / N1, ap = r % N1;
+                  const int i = a + N1 * (b + N1 * c), j = ap + N1 * (bp + N1 * cp);
+                  if (g == 0)
+                    OUT[i * (NF + 1) + j] = acc[r];
+                  else
+                    OUT[i * (NF + 1) + j] += acc[r];
+                }
+            }
+          __syncthreads();
         }
     }
 
     template <int DIM, int DEGX>
-    __global__ void __launch_bounds__(CartCfg<DIM, DEGX>::NTHR)
+    __global__ void __launch_bounds__(CartCfg<DIM, DEGX>::NTHR, CartCfg<DIM, DEGX>::MINB)
     k_cart_diag(const CartArgs A)
     {
       using C          = Cfg<DIM, DEGX>;
       using CC         = CartCfg<DIM, DEGX>;
-      constexpr int N1 = CC::N1, NX = CC::NX, NYZ = CC::NYZ, RG = CC::RG, RPT = CC::RPT, NF = CC::NF, CH = CC::CH, N = C::N;
-      constexpr int ISTR = DIM * 2 * NX;
-      __shared__ double SL[CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)];
-      __shared__ int    kind[CH];
-      const int tid = threadIdx.x;
-      const int col = tid % NYZ, rg = tid / NYZ;
-      const bool active = tid < NYZ * RG;
+      constexpr int N1 = CC::N1, NX = CC::NX, NXP = CC::NXP, NYZ = CC::NYZ, IG = CC::IG, NF = CC::NF, CH = CC::CH, N = C::N;
+      constexpr int ISTR = CC::ISTR;
+      __shared__ __align__(16) double SL[CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)];
+      __shared__ int                  kind[CH];
+      const int  tid = threadIdx.x;
+      const int  col = tid % NYZ, ig = tid / NYZ;
+      const bool active = tid < NYZ * IG;
 
       for (int p = blockIdx.x; p < A.np_own; p += gridDim.x)
         {
-          double acc[RPT];
+          double acc[NX];
 #pragma unroll
-          for (int r = 0; r < RPT; ++r)
+          for (int r = 0; r < NX; ++r)
             acc[r] = 0.;
           const double *bb = A.bbox + (int64_t)p * 2 * DIM;
           const int64_t s0 = A.subcell_ptr[p], s1 = A.subcell_ptr[p + 1];
@@ -341,24 +374,22 @@ namespace pd
                           if (d == 0 && a == 0)
                             kind[it] = 2;
                         }
-                      double *dst = SL + it * ISTR + d * 2 * NX + a * N1;
+                      double *dst = SL + it * ISTR + d * 2 * NXP + a * N1;
 #pragma unroll
                       for (int k = 0; k < N1; ++k)
                         {
-                          dst[k]      = M[k];
-                          dst[NX + k] = K[k];
+                          dst[k]       = M[k];
+                          dst[NXP + k] = K[k];
                         }
                     }
                   __syncthreads();
                   if (active)
-                    accumulate_chunk<DIM, DEGX>(SL, kind, cnt, col, rg, A.stiffness, A.mass, acc);
+                    accumulate_chunk<DIM, DEGX>(SL, kind, cnt, col, ig, A.stiffness, A.mass, acc);
                 }
             }
           // ---- epilogue: registers -> shared tile -> the diagonal block of the CSR rows
           __syncthreads();
-          if (active)
-            stage_block<DIM, DEGX>(SL, col, rg, acc);
-          __syncthreads();
+          stage_block<DIM, DEGX>(SL, col, ig, active, acc);
           const int64_t base   = A.diag_base[p];
           const int     stride = A.row_stride[A.dof_block[p]];
           for (int idx = tid; idx < N * N; idx += CC::NTHR)
@@ -372,27 +403,27 @@ namespace pd
     }
 
     template <int DIM, int DEGX>
-    __global__ void __launch_bounds__(CartCfg<DIM, DEGX>::NTHR)
+    __global__ void __launch_bounds__(CartCfg<DIM, DEGX>::NTHR, CartCfg<DIM, DEGX>::MINB)
     k_cart_offdiag(const CartArgs A)
     {
       using C          = Cfg<DIM, DEGX>;
       using CC         = CartCfg<DIM, DEGX>;
-      constexpr int N1 = CC::N1, NX = CC::NX, NYZ = CC::NYZ, RG = CC::RG, RPT = CC::RPT, NF = CC::NF, CH = CC::CH, N = C::N;
-      constexpr int ISTR = DIM * 2 * NX;
-      __shared__ double SL[CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)];
-      __shared__ int    kind[CH];
-      const int tid = threadIdx.x;
-      const int col = tid % NYZ, rg = tid / NYZ;
-      const bool active = tid < NYZ * RG;
+      constexpr int N1 = CC::N1, NX = CC::NX, NXP = CC::NXP, NYZ = CC::NYZ, IG = CC::IG, NF = CC::NF, CH = CC::CH, N = C::N;
+      constexpr int ISTR = CC::ISTR;
+      __shared__ __align__(16) double SL[CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)];
+      __shared__ int                  kind[CH];
+      const int  tid = threadIdx.x;
+      const int  col = tid % NYZ, ig = tid / NYZ;
+      const bool active = tid < NYZ * IG;
 
       for (int f = blockIdx.x; f < A.n_ifaces; f += gridDim.x)
         {
           const int32_t pa = A.ifA[f], pb = A.ifB[f];
           if (pb < 0)
             continue;
-          double acc[RPT];
+          double acc[NX];
 #pragma unroll
-          for (int r = 0; r < RPT; ++r)
+          for (int r = 0; r < NX; ++r)
             acc[r] = 0.;
           const double *ba = A.bbox + (int64_t)pa * 2 * DIM, *bbx = A.bbox + (int64_t)pb * 2 * DIM;
           const int64_t i0 = A.if_sub_ptr[f], i1 = A.if_sub_ptr[f + 1];
@@ -425,19 +456,17 @@ namespace pd
                     axis_rows_cross<C>(A.basis, A.quadf.x, A.quadf.w, A.nqf, lo, hi - lo, a_lo, a_ih, b_lo, b_ih, a, M);
                   if (d == 0 && a == 0)
                     kind[it] = 2;
-                  double *dst = SL + it * ISTR + d * 2 * NX + a * N1;
+                  double *dst = SL + it * ISTR + d * 2 * NXP + a * N1;
 #pragma unroll
                   for (int k = 0; k < N1; ++k)
                     dst[k] = M[k];
                 }
               __syncthreads();
               if (active)
-                accumulate_chunk<DIM, DEGX>(SL, kind, cnt, col, rg, 1., 0., acc);
+                accumulate_chunk<DIM, DEGX>(SL, kind, cnt, col, ig, 1., 0., acc);
             }
           __syncthreads();
-          if (active)
-            stage_block<DIM, DEGX>(SL, col, rg, acc);
-          __syncthreads();
+          stage_block<DIM, DEGX>(SL, col, ig, active, acc);
           const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
           const int     strideA = A.row_stride[A.dof_block[pa]];
           const int     strideB = baseBA >= 0 ? A.row_stride[A.dof_block[pb]] : 0;
@@ -452,6 +481,295 @@ namespace pd
             }
           __syncthreads();
         }
+    }
+
+    // -------------------------------------------------------------------------
+    // matrix-free apply on agglomerates of axis-aligned cells: y_P = sum over the same items of
+    // (X (x) Y (x) Z) x, by sum factorisation -- three 1-D contractions per item instead of a block.
+    //   sub-cell      (sigma (K.M.M + M.K.M + M.M.K) + f M.M.M) x_P     7 N1^4 multiply-adds
+    //   own face      (F in the slot of the normal axis, masses elsewhere) x_P
+    //   cross face    the same with cross matrices of the two bounding-box bases, applied to x_Q
+    // Thread (item j, line l): the j-th item of the chunk, one line of N1 coefficients per pass
+    // (z-pass: line (a,b); y-pass: (a,c); x-pass: (b,c)); intermediates of an item live in shared
+    // memory, the result line is accumulated in registers over the chunks and the item slots are
+    // summed in a fixed order at the end.  FE_DGQ only.
+    // -------------------------------------------------------------------------
+    struct CartApplyArgs
+    {
+      CartArgs      g;
+      const double *src;
+      double       *dst;
+      int           add;
+    };
+
+    template <int DIM, int DEGX>
+    struct ApplyCfg
+    {
+      using C                   = Cfg<DIM, DEGX>;
+      static constexpr int N1   = C::N1, NX = N1 * N1, NXP = NX + (NX & 1), NF = C::N;
+      static constexpr int NL   = ipow(N1, DIM - 1); // lines per item
+      static constexpr int CH   = 256 / NL;          // items per chunk
+      static constexpr int NTHR = ((CH * NL + 31) / 32) * 32;
+      static constexpr int MSTR = DIM * 2 * NXP;     // 1-D matrices of an item
+      static constexpr int WSTR = 2 * NF + 1;        // two intermediate tensors of an item (odd stride)
+    };
+
+    template <int DIM, int DEGX>
+    __global__ void __launch_bounds__(ApplyCfg<DIM, DEGX>::NTHR, 3)
+    k_cart_apply(const CartApplyArgs P)
+    {
+      using C          = Cfg<DIM, DEGX>;
+      using AC         = ApplyCfg<DIM, DEGX>;
+      constexpr int N1 = AC::N1, NXP = AC::NXP, NF = AC::NF, NL = AC::NL, CH = AC::CH, MSTR = AC::MSTR, WSTR = AC::WSTR;
+      const CartArgs &A = P.g;
+      extern __shared__ __align__(16) double smem[];
+      double *SM = smem;                  // [CH][MSTR]   1-D matrices, [d][slot][row a][a']
+      double *W  = SM + CH * MSTR;        // [CH][WSTR]   z-pass output (two tensors)
+      double *V  = W + CH * WSTR;         // [CH][WSTR]   y-pass output (two tensors)
+      const int tid = threadIdx.x;
+      const int j = tid / NL, l = tid % NL;
+      const bool active = tid < CH * NL;
+      const double sigma = A.stiffness, fmass = A.mass;
+
+      for (int p = blockIdx.x; p < A.np_own; p += gridDim.x)
+        {
+          double acc[N1];
+#pragma unroll
+          for (int k = 0; k < N1; ++k)
+            acc[k] = 0.;
+          const double *bb = A.bbox + (int64_t)p * 2 * DIM;
+          const int64_t own_base = (int64_t)A.dof_block[p] * NF;
+          const int64_t s0 = A.subcell_ptr[p], s1 = A.subcell_ptr[p + 1];
+          const int64_t k0 = A.padj_ptr[p], k1 = A.padj_ptr[p + 1];
+          // segments: the sub-cells, then per adjacency entry its own-side faces and (interior) its cross faces
+          for (int64_t seg = 2 * k0 - 1; seg < 2 * k1; ++seg)
+            {
+              int64_t i0, i1, f = -1;
+              int     side = 0, knd = 1;
+              bool    bnd = false;
+              const double *ob = bb; // bounding box of the column basis
+              int64_t       src_base = own_base;
+              if (seg < 2 * k0)
+                {
+                  if (!(A.flags & PD_ASSEMBLE_VOLUME))
+                    continue;
+                  i0 = s0;
+                  i1 = s1;
+                }
+              else
+                {
+                  const int64_t e = A.padj[seg >> 1];
+                  f               = e >> 1;
+                  side            = (int)(e & 1);
+                  bnd             = A.ifB[f] < 0;
+                  knd             = (seg & 1) ? 3 : 2;
+                  if (!(bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) : (A.flags & PD_ASSEMBLE_INTERIOR)) || (knd == 3 && bnd))
+                    continue;
+                  if (knd == 3)
+                    {
+                      const int32_t q = side ? A.ifA[f] : A.ifB[f];
+                      ob              = A.bbox + (int64_t)q * 2 * DIM;
+                      src_base        = (int64_t)A.dof_block[q] * NF;
+                    }
+                  i0 = A.if_sub_ptr[f];
+                  i1 = A.if_sub_ptr[f + 1];
+                }
+              for (int64_t c0 = i0; c0 < i1; c0 += CH)
+                {
+                  const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
+                  __syncthreads();
+                  // ---- 1-D matrices: thread = (item, axis, row)
+                  for (int w = tid; w < cnt * DIM * N1; w += AC::NTHR)
+                    {
+                      const int    it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
+                      double       M[N1], K[N1];
+                      const double r_lo = bb[d], r_ih = 1. / (bb[DIM + d] - bb[d]);
+                      const double c_lo = ob[d], c_ih = 1. / (ob[DIM + d] - ob[d]);
+                      double       lo, hi;
+                      if (knd == 1)
+                        {
+                          cell_box<DIM>(A, A.subcell_idx[c0 + it], d, lo, hi);
+                          axis_rows_mass<C>(A.basis, A.quad.x, A.quad.w, A.nq, lo, hi - lo, r_lo, r_ih, a, M, K);
+                        }
+                      else
+                        {
+                          const int64_t s  = c0 + it;
+                          const int     lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
+                          cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
+                          if (d == fd)
+                            {
+                              const double nrm = (fs ? 1. : -1.) * (side ? -1. : 1.); // outward normal of THIS polytope
+                              const double x = fs ? hi : lo, pen = A.sub_sigma[s];
+                              double       LR[N1], dLR[N1], LC[N1], dLC[N1];
+                              basis_1d<C>(A.basis, (x - r_lo) * r_ih, r_ih, LR, dLR);
+                              basis_1d<C>(A.basis, (x - c_lo) * c_ih, c_ih, LC, dLC);
+                              const double la = pick<N1>(LR, a), da = pick<N1>(dLR, a);
+                              const double cf = bnd ? 1. : 0.5;
+#pragma unroll
+                              for (int k = 0; k < N1; ++k)
+                                {
+                                  M[k] = knd == 2 ? sigma * (-cf * nrm * (da * LC[k] + la * dLC[k]) + pen * la * LC[k]) :
+                                                    sigma * (0.5 * nrm * (da * LC[k] - la * dLC[k]) - pen * la * LC[k]);
+                                  K[k] = 0.;
+                                }
+                            }
+                          else if (knd == 2)
+                            axis_rows_mass<C>(A.basis, A.quadf.x, A.quadf.w, A.nqf, lo, hi - lo, r_lo, r_ih, a, M, K);
+                          else
+                            axis_rows_cross<C>(A.basis, A.quadf.x, A.quadf.w, A.nqf, lo, hi - lo, r_lo, r_ih, c_lo, c_ih, a, M);
+                        }
+                      double *dst = SM + it * MSTR + d * 2 * NXP + a * N1;
+#pragma unroll
+                      for (int k = 0; k < N1; ++k)
+                        {
+                          dst[k]       = M[k];
+                          dst[NXP + k] = K[k];
+                        }
+                    }
+                  __syncthreads();
+                  const bool on = active && j < cnt;
+                  const double *m = SM + j * MSTR;
+                  double       *w1 = W + j * WSTR, *w2 = w1 + NF, *v1 = V + j * WSTR, *v2 = v1 + NF;
+                  double        in1[N1], in2[N1];
+                  if (DIM == 3)
+                    {
+                      // ---- z-pass: line (a, b) = l
+                      if (on)
+                        {
+#pragma unroll
+                          for (int k = 0; k < N1; ++k)
+                            in1[k] = P.src[src_base + l + NL * k];
+#pragma unroll
+                          for (int c = 0; c < N1; ++c)
+                            {
+                              double t1 = 0., t2 = 0.;
+#pragma unroll
+                              for (int k = 0; k < N1; ++k)
+                                {
+                                  t1 += m[(2 * 2 + 0) * NXP + c * N1 + k] * in1[k];
+                                  if (knd == 1)
+                                    t2 += m[(2 * 2 + 1) * NXP + c * N1 + k] * in1[k];
+                                }
+                              w1[l + NL * c] = t1;
+                              w2[l + NL * c] = t2;
+                            }
+                        }
+                      __syncthreads();
+                      // ---- y-pass: line (a, c): a = l % N1, c = l / N1
+                      if (on)
+                        {
+                          const int a = l % N1, c = l / N1;
+#pragma unroll
+                          for (int k = 0; k < N1; ++k)
+                            {
+                              in1[k] = w1[a + N1 * k + NL * c];
+                              in2[k] = w2[a + N1 * k + NL * c];
+                            }
+#pragma unroll
+                          for (int b = 0; b < N1; ++b)
+                            {
+                              double aa = 0., ab = 0., ba = 0.;
+#pragma unroll
+                              for (int k = 0; k < N1; ++k)
+                                {
+                                  const double my = m[(1 * 2 + 0) * NXP + b * N1 + k];
+                                  aa += my * in1[k];
+                                  if (knd == 1)
+                                    {
+                                      ab += m[(1 * 2 + 1) * NXP + b * N1 + k] * in1[k];
+                                      ba += my * in2[k];
+                                    }
+                                }
+                              v1[a + N1 * b + NL * c] = knd == 1 ? sigma * aa : 0.;
+                              v2[a + N1 * b + NL * c] = knd == 1 ? sigma * (ab + ba) + fmass * aa : aa;
+                            }
+                        }
+                      __syncthreads();
+                    }
+                  else
+                    {
+                      // ---- 2-D y-pass: line a = l
+                      if (on)
+                        {
+#pragma unroll
+                          for (int k = 0; k < N1; ++k)
+                            in1[k] = P.src[src_base + l + N1 * k];
+#pragma unroll
+                          for (int b = 0; b < N1; ++b)
+                            {
+                              double aa = 0., ab = 0.;
+#pragma unroll
+                              for (int k = 0; k < N1; ++k)
+                                {
+                                  aa += m[(1 * 2 + 0) * NXP + b * N1 + k] * in1[k];
+                                  if (knd == 1)
+                                    ab += m[(1 * 2 + 1) * NXP + b * N1 + k] * in1[k];
+                                }
+                              v1[l + N1 * b] = knd == 1 ? sigma * aa : 0.;
+                              v2[l + N1 * b] = knd == 1 ? sigma * ab + fmass * aa : aa;
+                            }
+                        }
+                      __syncthreads();
+                    }
+                  // ---- x-pass: line (b, c) = l -> the result line, accumulated in registers
+                  if (on)
+                    {
+#pragma unroll
+                      for (int k = 0; k < N1; ++k)
+                        {
+                          in1[k] = v1[k + N1 * l];
+                          in2[k] = v2[k + N1 * l];
+                        }
+#pragma unroll
+                      for (int ap = 0; ap < N1; ++ap)
+                        {
+                          double t = 0.;
+#pragma unroll
+                          for (int k = 0; k < N1; ++k)
+                            {
+                              t += m[(0 * 2 + 0) * NXP + ap * N1 + k] * in2[k];
+                              if (knd == 1)
+                                t += m[(0 * 2 + 1) * NXP + ap * N1 + k] * in1[k];
+                            }
+                          acc[ap] += t;
+                        }
+                    }
+                }
+            }
+          // ---- sum the item slots in a fixed order and write the rows of the polytope
+          __syncthreads();
+          if (active)
+            {
+#pragma unroll
+              for (int k = 0; k < N1; ++k)
+                W[j * (NF + 1) + k + N1 * l] = acc[k];
+            }
+          __syncthreads();
+          for (int i = tid; i < NF; i += AC::NTHR)
+            {
+              double t = 0.;
+              for (int jj = 0; jj < CH; ++jj)
+                t += W[jj * (NF + 1) + i];
+              double *o = P.dst + (int64_t)A.dof_block[p] * NF + i;
+              *o        = P.add ? *o + t : t;
+            }
+        }
+    }
+
+    template <int DIM, int DEGX>
+    void
+    run_cart_apply(pd_handle *h, const CartApplyArgs &a)
+    {
+      using AC = ApplyCfg<DIM, DEGX>;
+      auto         kern = k_cart_apply<DIM, DEGX>;
+      const size_t smem = sizeof(double) * (size_t)AC::CH * (AC::MSTR + 2 * AC::WSTR);
+      static_assert(AC::WSTR >= AC::NF + 1, "the slot sums alias the intermediates");
+      if (smem > 48 * 1024)
+        PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)std::min<int64_t>(h->np_own, (int64_t)h->sm_count * 16);
+      kern<<<grid, AC::NTHR, smem, h->stream>>>(a);
+      ++h->launches;
+      PD_CUDA(cudaGetLastError());
     }
 
     template <int DIM, int DEGX>
@@ -505,10 +823,71 @@ namespace pd
     return h->cartesian;
   }
 
+  static void
+  fill_cart_args(pd_handle *h, const uint32_t flags, const pd_coefficients &coef, CartArgs &a);
+
+  // matrix-free apply of the operator pd_set_operator describes on agglomerates of axis-aligned cells
+  bool
+  cartesian_apply_available(const pd_handle *h)
+  {
+    const char *e = getenv("PD_POLY_APPLY"); // "pointwise": the point-wise kernels everywhere (A/B measurements, tests)
+    if (e && e[0] == 'p')
+      return false;
+    return h->cartesian && h->fe_kind == PD_FE_DGQ;
+  }
+
+  void
+  launch_cart_apply(pd_handle *h, const double *src, double *dst, const bool add)
+  {
+    CartApplyArgs a{};
+    fill_cart_args(h, h->op_flags, h->op_coef, a.g);
+    a.src = src;
+    a.dst = dst;
+    a.add = add ? 1 : 0;
+    switch (h->dim * 10 + h->degree)
+      {
+        case 21: run_cart_apply<2, 1>(h, a); break;
+        case 22: run_cart_apply<2, 2>(h, a); break;
+        case 23: run_cart_apply<2, 3>(h, a); break;
+        case 24: run_cart_apply<2, 4>(h, a); break;
+        case 31: run_cart_apply<3, 1>(h, a); break;
+        case 32: run_cart_apply<3, 2>(h, a); break;
+        case 33: run_cart_apply<3, 3>(h, a); break;
+        default:
+          throw CudaError{cudaErrorNotSupported, "no tensor apply kernel for this (dim, degree)", __LINE__};
+      }
+  }
+
   void
   launch_assemble_cartesian(pd_handle *h, const uint32_t flags, const pd_coefficients &coef)
   {
     CartArgs a{};
+    fill_cart_args(h, flags, coef, a);
+    const int key = h->fe_kind * 100 + h->dim * 10 + h->degree;
+    switch (key)
+      {
+        case 121: run_cart<2, DGP_BASE + 1>(h, a); break;
+        case 122: run_cart<2, DGP_BASE + 2>(h, a); break;
+        case 123: run_cart<2, DGP_BASE + 3>(h, a); break;
+        case 124: run_cart<2, DGP_BASE + 4>(h, a); break;
+        case 131: run_cart<3, DGP_BASE + 1>(h, a); break;
+        case 132: run_cart<3, DGP_BASE + 2>(h, a); break;
+        case 133: run_cart<3, DGP_BASE + 3>(h, a); break;
+        case 21: run_cart<2, 1>(h, a); break;
+        case 22: run_cart<2, 2>(h, a); break;
+        case 23: run_cart<2, 3>(h, a); break;
+        case 24: run_cart<2, 4>(h, a); break;
+        case 31: run_cart<3, 1>(h, a); break;
+        case 32: run_cart<3, 2>(h, a); break;
+        case 33: run_cart<3, 3>(h, a); break;
+        default:
+          throw CudaError{cudaErrorNotSupported, "no assembly kernel for this (dim, degree)", __LINE__};
+      }
+  }
+
+  static void
+  fill_cart_args(pd_handle *h, const uint32_t flags, const pd_coefficients &coef, CartArgs &a)
+  {
     a.verts       = h->verts.p;
     a.cell_verts  = h->cell_verts.p;
     a.subcell_ptr = h->subcell_ptr.p;
@@ -555,25 +934,5 @@ namespace pd
               ++i;
             }
     }
-    const int key = h->fe_kind * 100 + h->dim * 10 + h->degree;
-    switch (key)
-      {
-        case 121: run_cart<2, DGP_BASE + 1>(h, a); break;
-        case 122: run_cart<2, DGP_BASE + 2>(h, a); break;
-        case 123: run_cart<2, DGP_BASE + 3>(h, a); break;
-        case 124: run_cart<2, DGP_BASE + 4>(h, a); break;
-        case 131: run_cart<3, DGP_BASE + 1>(h, a); break;
-        case 132: run_cart<3, DGP_BASE + 2>(h, a); break;
-        case 133: run_cart<3, DGP_BASE + 3>(h, a); break;
-        case 21: run_cart<2, 1>(h, a); break;
-        case 22: run_cart<2, 2>(h, a); break;
-        case 23: run_cart<2, 3>(h, a); break;
-        case 24: run_cart<2, 4>(h, a); break;
-        case 31: run_cart<3, 1>(h, a); break;
-        case 32: run_cart<3, 2>(h, a); break;
-        case 33: run_cart<3, 3>(h, a); break;
-        default:
-          throw CudaError{cudaErrorNotSupported, "no assembly kernel for this (dim, degree)", __LINE__};
-      }
   }
 } // namespace pd

@@ -241,6 +241,8 @@ namespace pd
   bool check_axis_aligned(pd_handle *h);
   bool cartesian_assembly_selected(const pd_handle *h);
   void launch_assemble_cartesian(pd_handle *h, uint32_t flags, const pd_coefficients &coef);
+  bool cartesian_apply_available(const pd_handle *h);
+  void launch_cart_apply(pd_handle *h, const double *src, double *dst, bool add);
   // pd_reinit.cu
   int64_t reinit_n_points(const pd_handle *h, int32_t poly);
   int64_t reinit_iface_n_points(const pd_handle *h, int32_t iface);

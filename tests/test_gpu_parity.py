@@ -511,11 +511,18 @@ def test_mapped_fine_mesh_unavailable_on_agglomerates():
     (3, 4, "random4", 1, 2, None, dict(stiffness_coeff=1e-4, mass_coeff=1.5e4, with_boundary=False)),
     (3, 4, "singletons", 2, 3, None, dict(penalty_constant=6.0, h_rule=3)),
 ])
-def test_polytopal_matrix_free_vmult(dim, n, shape, p, nq, distort, kw):
-    """PD_VMULT_MATRIX_FREE on genuine agglomerates: the basis is regenerated at the agglomerated
-    quadrature points and applied; same operator as the assembled one (checker: oracle matrix)."""
+@pytest.mark.parametrize("kernels", ["default", "pointwise"])
+def test_polytopal_matrix_free_vmult(dim, n, shape, p, nq, distort, kw, kernels, monkeypatch):
+    """PD_VMULT_MATRIX_FREE on genuine agglomerates, same operator as the assembled one (checker: oracle matrix).
+    Axis-aligned sub-cells: sum factorisation per sub-cell / sub-face (k_cart_apply); otherwise, and with
+    PD_POLY_APPLY=pointwise, the basis is regenerated at the agglomerated quadrature points (k_pw_*)."""
     pdl = gpu()
     import torch
+
+    if kernels == "pointwise":
+        if distort is not None:
+            pytest.skip("distorted meshes take the point-wise kernels by default")
+        monkeypatch.setenv("PD_POLY_APPLY", "pointwise")
 
     oah, pah = both(dim, n, shape, p, nq=nq, distort=distort)
     okw = dict(kw)

@@ -14,5 +14,16 @@ for name in sys.argv[1:]:
         a,e=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
         a.record(stream); op.assemble(stiffness=1.0,mass=cfg["mass"]); e.record(stream); e.synchronize()
         if s>=2: tot.append(a.elapsed_time(e)); kms.append(op.last_kernel_ms())
-    print(json.dumps({"config":name,"path":op.assembly_path,"assemble_ms":statistics.mean(tot),"dofs_per_s":op.m()/(statistics.mean(tot)*1e-3),"kernel_ms":kms[-1],"mem_GB":torch.cuda.max_memory_allocated()/1e9}))
+    N=op.m()
+    x=torch.from_numpy(np.sin(0.37*np.arange(N))).cuda(); y=torch.empty_like(x)
+    op.set_operator(pdl.ASSEMBLE_ALL,1.0,cfg["mass"])
+    res={}
+    for mode,key in ((pdl.VMULT_BLOCK_CSR,"csr_ms"),(pdl.VMULT_MATRIX_FREE,"mf_ms")):
+        for _ in range(2): op.vmult_ptr(y.data_ptr(),x.data_ptr(),mode=mode)
+        a,e=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(5): op.vmult_ptr(y.data_ptr(),x.data_ptr(),mode=mode)
+        e.record(stream); e.synchronize(); res[key]=a.elapsed_time(e)/5
+        res[key+"_sum"]=float(y.sum())
+    print(json.dumps({"vmult":res,"config":name,"path":op.assembly_path,"assemble_ms":statistics.mean(tot),"dofs_per_s":op.m()/(statistics.mean(tot)*1e-3),"kernel_ms":kms[-1],"mem_GB":torch.cuda.max_memory_allocated()/1e9}))
     del op
