@@ -63,7 +63,7 @@ def config_dict():
     """Identical in both arms (the driver compares them)."""
     return {"workload": WORKLOAD, "n_dofs_per_gpu": N_DOFS_PER_GPU, "n_polytopes_per_gpu": N_POLY_PER_GPU,
             "volume_q_points_per_gpu": N_POLY_PER_GPU * CFG["b"] ** 3 * NQ**DIM,
-            "l2": "inputs larger than L2 (4.3 GB of quadrature points per step); additionally flushed (512 MiB memset) between timed steps",
+            "l2": "flushed (512 MiB memset) between timed steps; the 7.3 GB matrix written per step does not fit L2 either",
             "step": "quadrature + volume + faces + diagonal gather, all device kernels"}
 
 
@@ -246,39 +246,107 @@ def traffic_of(kernel_key):
     return None
 
 
-def assembly_rooflines(desc, n, nq, kms, peaks, mass=False):
-    """One roofline block per kernel of the assembly step (algorithmic flops / bytes)."""
+def face_point_counts(desc, nq):
     dim = desc.dim
-    n_own = desc.n_owned_polytopes or desc.n_polytopes
-    Q = int(desc.poly_subcell_ptr[desc.n_polytopes]) * nq**dim
     B = np.ctypeslib.as_array(desc.iface_polyB, (desc.n_ifaces,))
     sp = np.ctypeslib.as_array(desc.iface_sub_ptr, (desc.n_ifaces + 1,))
     nsub = np.diff(sp)
-    qf_int = int(nsub[B >= 0].sum()) * nq ** (dim - 1)
-    qf_bnd = int(nsub[B < 0].sum()) * nq ** (dim - 1)
-    n_int, n_bnd = int((B >= 0).sum()), int((B < 0).sum())
+    return (int(nsub[B >= 0].sum()) * nq ** (dim - 1), int(nsub[B < 0].sum()) * nq ** (dim - 1), int((B >= 0).sum()),
+            int((B < 0).sum()), int(nsub[B >= 0].sum()), int(nsub[B < 0].sum()))
+
+
+def assembly_rooflines(desc, n, nq, kms, peaks, mass=False, path="dmma"):
+    """One roofline block per kernel of the assembly step.  `survey_*` = SURVEY 8d's algorithmic count of the
+    point-wise formulation (2 n^2 dim Q volume flops, 24 n^2 per interior face point); the tensor path computes the
+    same matrix with far fewer operations, so its kernels are held to the bytes they must move (the matrix is
+    written once) and to the FP64 pipe for the operations they actually issue."""
+    dim = desc.dim
+    n_own = desc.n_owned_polytopes or desc.n_polytopes
+    n_sub = int(desc.poly_subcell_ptr[desc.n_polytopes])
+    Q = n_sub * nq**dim
+    qf_int, qf_bnd, n_int, n_bnd, sf_int, sf_bnd = face_point_counts(desc, nq)
     ncomp = dim + (1 if mass else 0)
+    vol_flops = 2.0 * n * n * ncomp * Q
+    face_flops = 24.0 * n * n * qf_int + 6.0 * n * n * qf_bnd
     out = []
+    if path == "tensor":
+        n1 = round(n ** (1.0 / dim))
+        # k_cart_diag: per sub-cell two Kronecker terms, per own-side sub-face (2 per interior, 1 per boundary) one
+        diag_fma = n * n * (2.0 * n_sub + 2.0 * sf_int + sf_bnd)
+        off_fma = n * n * 1.0 * sf_int
+        geo = 48.0 + 8.0 * 2**dim  # cell index + 2^dim vertex indices + the two corner vertices
+        diag_bytes = 8.0 * n * n * n_own + geo * (n_sub + 2 * sf_int + sf_bnd)
+        off_bytes = 8.0 * n * n * 2 * n_int + (geo + 16.0) * sf_int
+        for name, ms, nbytes, fma, survey in (
+                (f"k_cart_diag<{dim},{desc.fe_degree}> (diagonal blocks: volume + own-side faces, Kronecker sums)", kms["volume"],
+                 diag_bytes, diag_fma, vol_flops + (face_flops - 12.0 * n * n * qf_int if qf_int else face_flops)),
+                (f"k_cart_offdiag<{dim},{desc.fe_degree}> (M12 and its transpose per interface)", kms["faces"], off_bytes,
+                 off_fma, 12.0 * n * n * qf_int)):
+            if ms <= 0:
+                continue
+            blk = hbm_block(name, nbytes, ms, peaks)
+            blk["issued_tflops"] = 2.0 * fma / (ms * 1e-3) / 1e12
+            blk["fp64_pipe_frac"] = blk["issued_tflops"] / peaks["fp64_tflops"]
+            blk["survey_algorithmic_flops_per_launch"] = survey
+            blk["survey_algorithmic_tflops"] = survey / (ms * 1e-3) / 1e12
+            blk["note"] = ("tensor path: bytes = the blocks written once + the mesh data read; issued_tflops = the Kronecker "
+                           "multiply-adds actually issued; survey_algorithmic_* = the point-wise count of SURVEY 8d the same "
+                           "result would cost (n1 = %d)" % n1)
+            out.append(blk)
+        return out
     out.append(tensor_block(f"k_volume<{dim},{desc.fe_degree}> (FP64 DMMA contraction, upper tiles only)",
-                            2.0 * n * n * ncomp * Q, kms["volume"], peaks,
+                            vol_flops, kms["volume"], peaks,
                             algorithmic_bytes_per_launch=8.0 * (dim + 1) * Q + 8.0 * n * n * n_own,
                             note="algorithmic flops = 2 n^2 dim Q (SURVEY 8d); the kernel issues only the upper triangle of 8x8 "
-                                 "tiles, so frac may exceed 1; frac_issued counts the DMMA flops actually issued",
-                            frac_issued=None))
-    out.append(tensor_block(f"k_faces<{dim},{desc.fe_degree}> (T + T^T form, FP64 DMMA)",
-                            24.0 * n * n * qf_int + 6.0 * n * n * qf_bnd, kms["faces"], peaks,
+                                 "tiles, so frac may exceed 1; frac_issued counts the DMMA flops actually issued"))
+    n_tiles = (n + 7) // 8
+    out[0]["frac_issued"] = out[0]["frac"] * (n_tiles * (n_tiles + 1) / 2) / (n_tiles * n_tiles)
+    out.append(tensor_block(f"k_faces<{dim},{desc.fe_degree}> (T + T^T form, FP64 DMMA)", face_flops, kms["faces"], peaks,
                             algorithmic_bytes_per_launch=8.0 * (2 * dim + 1) * (qf_int + qf_bnd) + 8.0 * n * n * (4 * n_int + n_bnd),
                             note="algorithmic flops = 24 n^2 per interior face point + 6 n^2 per boundary point (SURVEY 8d); "
                                  "the T + T^T form issues a third of that"))
+    out[1]["frac_issued"] = out[1]["frac"] / 3.0
     if kms.get("quadrature", 0) > 0:
         qbytes = 8.0 * (dim + 1) * Q + 8.0 * (2 * dim + 1) * (qf_int + qf_bnd) + (4.0 * 2**dim + 8.0 * dim) * desc.n_cells
         out.append(hbm_block("k_volume_quadrature + k_face_quadrature", qbytes, kms["quadrature"], peaks))
-    vol_items = None
     rbytes = 8.0 * n * n * (2 * n_own + 2 * n_int + n_bnd)
     out.append(hbm_block("k_reduce_diag (gather of the diagonal blocks)", rbytes, kms["reduce"], peaks,
                          note="reads >= one volume partial per polytope + M11/M22/boundary parts, writes the diagonal block"))
-    del vol_items
     return out
+
+
+def time_assembly_steps(op, stream, flush, steps, mass=0.0):
+    """Device-timed assembly steps of the path the environment selects: (ms per step, mean kernel ms)."""
+    import torch
+
+    kms, tot = {"volume": [], "faces": [], "reduce": [], "quadrature": []}, []
+    for s in range(steps + 2):
+        flush.zero_()
+        op.invalidate_quadrature()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        op.assemble(stiffness=1.0, mass=mass)
+        e.record(stream)
+        e.synchronize()
+        if s >= 2:
+            tot.append(a.elapsed_time(e))
+            for k, v in op.last_kernel_ms().items():
+                kms[k].append(v)
+    return statistics.mean(tot), {k: statistics.mean(v) for k, v in kms.items()}
+
+
+def generic_path_block(op, desc, n, nq, stream, flush, peaks, steps, mass=0.0):
+    """The DMMA kernels on the agglomerated quadrature (what a distorted mesh runs), forced on the same handle."""
+    os.environ["PD_ASSEMBLE_KERNELS"] = "generic"
+    try:
+        ms, kms = time_assembly_steps(op, stream, flush, steps, mass)
+        assert op.assembly_path == "dmma"
+    finally:
+        del os.environ["PD_ASSEMBLE_KERNELS"]
+    return {"what": "PD_ASSEMBLE_KERNELS=generic: rank-k updates over the agglomerated quadrature points on the FP64 tensor "
+                    "cores (pd_assemble.cu), the path of distorted meshes, on the same input",
+            "ms_per_step": ms, "dofs_per_s": op.m() / (ms * 1e-3), "kernel_ms": kms,
+            "rooflines": assembly_rooflines(desc, n, nq, kms, peaks, mass=bool(mass), path="dmma")}
 
 
 def run_gpu(args):
@@ -458,7 +526,11 @@ def run_gpu(args):
         dist.barrier()  # nobody unmaps while a neighbour may still pull
         peer.close()
     nblocks = int(desc.brow_ptr[desc.n_block_rows])
-    roofs = assembly_rooflines(desc, n, NQ, kms, read_peaks()) if rank == 0 else None
+    path = op.assembly_path
+    roofs = assembly_rooflines(desc, n, NQ, kms, read_peaks(), path=path) if rank == 0 else None
+    generic = None
+    if world == 1 and not args.no_extra_configs:
+        generic = generic_path_block(op, desc, n, NQ, stream, flush, read_peaks(), 3)
     n_ghost_poly = int(desc.n_polytopes - n_dofs // n)
     n_poly_own = n_dofs // n
     del op, x, y, bcg, xcg, keep, desc, desc0, part, out_host, ah, peer
@@ -488,10 +560,8 @@ def run_gpu(args):
     ms_per_step = t_ms / args.steps
     value = total_dofs / (ms_per_step * 1e-3)
     e2e_value = total_dofs / (t_e2e_ms * 1e-3)
-    vol = roofs[0]
-    vol["traffic"] = traffic_of("k_volume_C_bytes_per_launch")
-    n_tiles = (n + 7) // 8
-    vol["frac_issued"] = vol["frac"] * (n_tiles * (n_tiles + 1) / 2) / (n_tiles * n_tiles)
+    vol = max(roofs, key=lambda r: r["kernel_ms"])  # the dominant kernel of the step
+    vol["traffic"] = traffic_of(("k_cart_diag" if path == "tensor" else "k_volume") + "_C_bytes_per_launch")
     vm_bytes = 8.0 * n * n * nblocks + 4.0 * nblocks + 16.0 * n_dofs
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -510,6 +580,8 @@ def run_gpu(args):
                 "steps": e2e_steps, "checksum": checksum,
                 "serial_one_handle_value": total_dofs / (t_e2e_serial_ms * 1e-3)},
         "gpu_launches": int(launches),
+        "assembly_path": path + (" (every sub-cell an axis-aligned box: per-sub-cell sum factorisation, pd_cartesian.cu)"
+                                 if path == "tensor" else " (FP64 tensor-core contraction over the agglomerated quadrature)"),
         "clocks": clocks,
         "roofline": {k: vol[k] for k in vol if k != "kernel"} | {"kernel": vol["kernel"]},
         "rooflines": roofs,
@@ -539,6 +611,8 @@ def run_gpu(args):
     if mf3:
         mf3["roofline"] = hbm_block(mf3.pop("kernel"), 16.0 * mf3["n_dofs_per_gpu"], mf3["ms"], peaks)
         out["mf_vmult_dgq3"] = mf3
+    if generic:
+        out["generic_path"] = generic
     if world == 1 and not args.no_extra_configs:
         out["config_B"] = run_extra_config(pdl, "B", stream, peaks, steps=max(args.steps, 10))
         out["config_D"] = run_extra_config(pdl, "D", stream, peaks, steps=3)
@@ -619,20 +693,8 @@ def run_extra_config(pdl, name, stream, peaks, steps):
     op.set_stream(stream.cuda_stream)
     N, n = op.m(), op.n_dofs_per_cell
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
-    kms, tot = {"volume": [], "faces": [], "reduce": [], "quadrature": []}, []
-    for s in range(steps + 2):
-        flush.zero_()
-        op.invalidate_quadrature()
-        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        op.assemble(stiffness=1.0, mass=cfg["mass"])
-        e.record(stream)
-        e.synchronize()
-        if s >= 2:
-            tot.append(a.elapsed_time(e))
-            for k, v in op.last_kernel_ms().items():
-                kms[k].append(v)
-    kms = {k: statistics.mean(v) for k, v in kms.items()}
+    ms, kms = time_assembly_steps(op, stream, flush, steps, cfg["mass"])
+    path = op.assembly_path
     x = torch.from_numpy(src_values(N)).cuda()
     y = torch.empty_like(x)
     vm = []
@@ -646,11 +708,13 @@ def run_extra_config(pdl, name, stream, peaks, steps):
         if s >= 2:
             vm.append(a.elapsed_time(e))
     nblocks = int(desc.brow_ptr[desc.n_block_rows])
-    ms, vm_ms = statistics.mean(tot), statistics.mean(vm)
+    vm_ms = statistics.mean(vm)
     res = {"workload": f"{name}: {cfg['n']}^{cfg['dim']} cells -> {desc.n_polytopes} polytopes ({cfg['b']}^{cfg['dim']} blocks), "
                        f"FE_DGQ({cfg['p']}), QGauss({cfg['nq']})" + (", + reaction c=0.5, C=40" if cfg["mass"] else ""),
-           "n_dofs": N, "assemble_ms": ms, "dofs_per_s": N / (ms * 1e-3), "kernel_ms": kms, "host_setup_s": t_host,
-           "rooflines": assembly_rooflines(desc, n, cfg["nq"], kms, peaks, mass=bool(cfg["mass"])),
+           "n_dofs": N, "assembly_path": path, "assemble_ms": ms, "dofs_per_s": N / (ms * 1e-3), "kernel_ms": kms,
+           "host_setup_s": t_host,
+           "rooflines": assembly_rooflines(desc, n, cfg["nq"], kms, peaks, mass=bool(cfg["mass"]), path=path),
+           "generic_path": generic_path_block(op, desc, n, cfg["nq"], stream, flush, peaks, min(steps, 3), cfg["mass"]),
            "vmult_ms": vm_ms, "vmult_gdofs": N / (vm_ms * 1e-3) / 1e9,
            "vmult_roofline": hbm_block("k_spmv_block_row", 8.0 * n * n * nblocks + 4.0 * nblocks + 16.0 * N, vm_ms, peaks),
            "l2": "flushed between steps / applies"}
