@@ -447,7 +447,7 @@ namespace pd
             PD_CUDA(cudaMemcpy(h->if_sub_ptr.p, &zero, sizeof(zero), cudaMemcpyHostToDevice));
           }
         upload_descriptor(h, d);
-        h->cartesian = check_axis_aligned(h);
+        setup_cartesian(h, d);
 
         h->h_brow_ptr.assign(d.brow_ptr, d.brow_ptr + h->np_own + 1);
         h->h_bcol.assign(d.bcol_idx, d.bcol_idx + h->n_blocks);
@@ -649,7 +649,7 @@ extern "C"
           if (!(d->bbox[(size_t)p * 2 * d->dim + d->dim + k] > d->bbox[(size_t)p * 2 * d->dim + k]))
             throw Error(PD_ERR_INVALID, "pd_upload: degenerate bounding box");
       upload_descriptor(h, *d);
-      h->cartesian = check_axis_aligned(h); // waits for the upload (a 4-byte read-back): which assembly path applies
+      setup_cartesian(h, *d); // waits for the upload (an 8-byte read-back): which assembly path applies, bricks still valid?
       // fine-mesh operators (every polytope one cell): geometry tables, stencil records and tile plans are derived
       // from the coordinates and penalties -- re-derive them when those changed
       if (h->fe_kind == PD_FE_DGQ && h->n_subcells == h->np_own)

@@ -38,7 +38,13 @@
 #include "pd_internal.hpp"
 #include "pd_device.cuh"
 
+#include <algorithm>
+#include <array>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
 
 namespace pd
 {
@@ -65,18 +71,36 @@ namespace pd
       Basis1D        basis;
       Quad1D         quad, quadf;
       unsigned char  dof_abc[64][3]; // (a, b, c) of every DoF of the element
+      // bricks (see build_bricks): tensor-product sets of sub-cells / sub-faces whose sums factorise
+      const int64_t *cbk_ptr; // [np_own + 1] cell bricks of a polytope
+      const int32_t *cbk_iv;  // [n_cbk][2 dim]: (start, count) per axis into civ
+      const int32_t *civ;     // representative cell of every interval
+      const int64_t *fbk_ptr; // [n_ifaces + 1] face bricks of an interface / boundary face
+      const int32_t *fbk_s;   // [n_fbk] representative sub-face (plane, orientation, penalty)
+      const int32_t *fbk_iv;  // [n_fbk][2 (dim - 1)]: (start, count) per tangential axis into fiv
+      const int32_t *fiv;     // representative (A-side) cell of every tangential interval
     };
 
     // cells of the mesh that are NOT axis-aligned boxes in standard orientation (vertex v at lo + bit_k(v) (hi - lo))
+    // -> flags[0]; with bricks (cpos != nullptr): sub-cells / sub-faces whose box no longer is the product of their
+    // brick's representative intervals (vertices moved through pd_upload) -> flags[1]
     __global__ void __launch_bounds__(256)
     k_check_axis_aligned(const double *verts, const int32_t *cell_verts, const int32_t *subcell_idx, const int64_t n_sub,
-                         const int dim, int *n_bad)
+                         const int dim, int *flags, const int32_t *cpos, const int32_t *cbk_iv, const int32_t *civ,
+                         const int64_t n_subfaces, const int32_t *sub_cell, const int32_t *sub_face, const double *sub_sigma,
+                         const int32_t *fpos, const int32_t *fbk_s, const int32_t *fbk_iv, const int32_t *fiv)
     {
       const int vpc = 1 << dim;
-      int       bad = 0;
+      int       bad = 0, stale = 0;
+      auto      box = [&](const int32_t c, const int k, double &lo, double &hi) {
+        const int32_t *cv = cell_verts + (int64_t)c * vpc;
+        lo                = verts[(int64_t)cv[0] * dim + k];
+        hi                = verts[(int64_t)cv[vpc - 1] * dim + k];
+      };
       for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_sub; s += (int64_t)gridDim.x * blockDim.x)
         {
-          const int32_t *cv = cell_verts + (int64_t)subcell_idx[s] * vpc;
+          const int32_t  c  = subcell_idx[s];
+          const int32_t *cv = cell_verts + (int64_t)c * vpc;
           const double  *lo = verts + (int64_t)cv[0] * dim, *hi = verts + (int64_t)cv[vpc - 1] * dim;
           for (int k = 0; k < dim; ++k)
             bad |= !(hi[k] > lo[k]);
@@ -86,9 +110,45 @@ namespace pd
               for (int k = 0; k < dim; ++k)
                 bad |= x[k] != (((v >> k) & 1) ? hi[k] : lo[k]);
             }
+          if (cpos)
+            {
+              const int32_t *ps = cpos + s * (1 + dim);
+              for (int k = 0; k < dim; ++k)
+                {
+                  double rl, rh;
+                  box(civ[cbk_iv[(int64_t)ps[0] * 2 * dim + 2 * k] + ps[1 + k]], k, rl, rh);
+                  stale |= rl != lo[k] || rh != hi[k];
+                }
+            }
         }
-      if (__syncthreads_or(bad) && threadIdx.x == 0)
-        atomicAdd(n_bad, 1);
+      if (fpos)
+        for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_subfaces; s += (int64_t)gridDim.x * blockDim.x)
+          {
+            const int32_t *ps = fpos + s * dim;
+            const int32_t  rs = fbk_s[ps[0]];
+            const int      lf = sub_face[s], fd = lf >> 1;
+            stale |= lf != sub_face[rs] || sub_sigma[s] != sub_sigma[rs];
+            double l0, h0, l1, h1;
+            box(sub_cell[s], fd, l0, h0);
+            box(sub_cell[rs], fd, l1, h1);
+            stale |= ((lf & 1) ? h0 : l0) != ((lf & 1) ? h1 : l1);
+            for (int k = 0; k < dim; ++k)
+              if (k != fd)
+                {
+                  const int t = k < fd ? k : k - 1;
+                  box(sub_cell[s], k, l0, h0);
+                  box(fiv[fbk_iv[(int64_t)ps[0] * 2 * (dim - 1) + 2 * t] + ps[1 + t]], k, l1, h1);
+                  stale |= l0 != l1 || h0 != h1;
+                }
+          }
+      const int any_bad = __syncthreads_or(bad), any_stale = __syncthreads_or(stale);
+      if (threadIdx.x == 0)
+        {
+          if (any_bad)
+            atomicAdd(flags, 1);
+          if (any_stale)
+            atomicAdd(flags + 1, 1);
+        }
     }
 
     template <int DIM, int DEGX>
@@ -115,10 +175,7 @@ namespace pd
     axis_rows_mass(const Basis1D &B, const double *qx, const double *qw, const int nq, const double c_lo, const double eta,
                    const double b_lo, const double inv_h, const int a, double *M, double *K)
     {
-      constexpr int N1 = C::N1;
-#pragma unroll
-      for (int k = 0; k < N1; ++k)
-        M[k] = K[k] = 0.;
+      constexpr int N1 = C::N1; // accumulates: the caller zeroes M, K
       for (int q = 0; q < nq; ++q)
         {
           double       L[N1], dL[N1];
@@ -148,10 +205,7 @@ namespace pd
     axis_rows_cross(const Basis1D &B, const double *qx, const double *qw, const int nq, const double c_lo, const double eta,
                     const double a_lo, const double a_inv_h, const double b_lo, const double b_inv_h, const int a, double *M)
     {
-      constexpr int N1 = C::N1;
-#pragma unroll
-      for (int k = 0; k < N1; ++k)
-        M[k] = 0.;
+      constexpr int N1 = C::N1; // accumulates: the caller zeroes M
       for (int q = 0; q < nq; ++q)
         {
           double       LA[N1], dLA[N1], LB[N1], dLB[N1];
@@ -190,6 +244,41 @@ namespace pd
       const int32_t *cv = A.cell_verts + (int64_t)c * (1 << DIM);
       lo                = A.verts[(int64_t)cv[0] * DIM + d];
       hi                = A.verts[(int64_t)cv[(1 << DIM) - 1] * DIM + d];
+    }
+
+    // row a of the summed 1-D matrices of a brick along axis d: sum over its intervals (each read from the box of
+    // its representative cell) of the mass-like and stiffness-like sums; row basis = column basis (box b_lo, inv_h)
+    template <class C, int DIM>
+    __device__ __forceinline__ void
+    brick_rows_mass(const CartArgs &A, const int32_t *reps, const int start, const int count, const int d, const double *qx,
+                    const double *qw, const int nq, const double b_lo, const double inv_h, const int a, double *M, double *K)
+    {
+#pragma unroll
+      for (int k = 0; k < C::N1; ++k)
+        M[k] = K[k] = 0.;
+      for (int i = start; i < start + count; ++i)
+        {
+          double lo, hi;
+          cell_box<DIM>(A, reps[i], d, lo, hi);
+          axis_rows_mass<C>(A.basis, qx, qw, nq, lo, hi - lo, b_lo, inv_h, a, M, K);
+        }
+    }
+    // the same with a row basis (r_*) and another column basis (c_*)
+    template <class C, int DIM>
+    __device__ __forceinline__ void
+    brick_rows_cross(const CartArgs &A, const int32_t *reps, const int start, const int count, const int d, const double *qx,
+                     const double *qw, const int nq, const double r_lo, const double r_ih, const double c_lo, const double c_ih,
+                     const int a, double *M)
+    {
+#pragma unroll
+      for (int k = 0; k < C::N1; ++k)
+        M[k] = 0.;
+      for (int i = start; i < start + count; ++i)
+        {
+          double lo, hi;
+          cell_box<DIM>(A, reps[i], d, lo, hi);
+          axis_rows_cross<C>(A.basis, qx, qw, nq, lo, hi - lo, r_lo, r_ih, c_lo, c_ih, a, M);
+        }
     }
 
     // X rows of a slot into registers, 16 bytes at a time (the address is the same for every thread of the
@@ -303,9 +392,9 @@ namespace pd
           for (int r = 0; r < NX; ++r)
             acc[r] = 0.;
           const double *bb = A.bbox + (int64_t)p * 2 * DIM;
-          const int64_t s0 = A.subcell_ptr[p], s1 = A.subcell_ptr[p + 1];
+          const int64_t s0 = A.cbk_ptr[p], s1 = A.cbk_ptr[p + 1];
           const int64_t k0 = A.padj_ptr[p], k1 = A.padj_ptr[p + 1];
-          // segment -1: the sub-cells; segments k0..k1-1: the faces of the adjacency list
+          // segment -1: the cell bricks; segments k0..k1-1: the face bricks of the adjacency list
           for (int64_t seg = k0 - 1; seg < k1; ++seg)
             {
               int64_t i0, i1;
@@ -327,14 +416,14 @@ namespace pd
                   bnd             = A.ifB[f] < 0;
                   if (!(bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) : (A.flags & PD_ASSEMBLE_INTERIOR)))
                     continue;
-                  i0 = A.if_sub_ptr[f];
-                  i1 = A.if_sub_ptr[f + 1];
+                  i0 = A.fbk_ptr[f];
+                  i1 = A.fbk_ptr[f + 1];
                 }
               for (int64_t c0 = i0; c0 < i1; c0 += CH)
                 {
                   const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
                   __syncthreads(); // the previous chunk has been consumed
-                  // ---- 1-D matrices of the chunk's items: thread = (item, axis, row a)
+                  // ---- 1-D matrices of the chunk's bricks: thread = (brick, axis, row a)
                   for (int w = tid; w < cnt * DIM * N1; w += CC::NTHR)
                     {
                       const int it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
@@ -342,20 +431,19 @@ namespace pd
                       const double b_lo = bb[d], inv_h = 1. / (bb[DIM + d] - bb[d]);
                       if (seg < k0)
                         {
-                          double lo, hi;
-                          cell_box<DIM>(A, A.subcell_idx[c0 + it], d, lo, hi);
-                          axis_rows_mass<C>(A.basis, A.quad.x, A.quad.w, A.nq, lo, hi - lo, b_lo, inv_h, a, M, K);
+                          const int32_t *iv = A.cbk_iv + (c0 + it) * 2 * DIM + 2 * d;
+                          brick_rows_mass<C, DIM>(A, A.civ, iv[0], iv[1], d, A.quad.x, A.quad.w, A.nq, b_lo, inv_h, a, M, K);
                           if (d == 0 && a == 0)
                             kind[it] = 1;
                         }
                       else
                         {
-                          const int64_t s  = c0 + it;
+                          const int64_t s  = A.fbk_s[c0 + it];
                           const int     lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
-                          double        lo, hi;
-                          cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
                           if (d == fd)
                             {
+                              double lo, hi;
+                              cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
                               // own-side face term at the face coordinate: outward normal of THIS polytope
                               const double nrm = (fs ? 1. : -1.) * (side ? -1. : 1.);
                               const double cf  = bnd ? 1. : 0.5;
@@ -370,7 +458,10 @@ namespace pd
                                 }
                             }
                           else
-                            axis_rows_mass<C>(A.basis, A.quadf.x, A.quadf.w, A.nqf, lo, hi - lo, b_lo, inv_h, a, M, K);
+                            {
+                              const int32_t *iv = A.fbk_iv + (c0 + it) * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
+                              brick_rows_mass<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, b_lo, inv_h, a, M, K);
+                            }
                           if (d == 0 && a == 0)
                             kind[it] = 2;
                         }
@@ -426,7 +517,7 @@ namespace pd
           for (int r = 0; r < NX; ++r)
             acc[r] = 0.;
           const double *ba = A.bbox + (int64_t)pa * 2 * DIM, *bbx = A.bbox + (int64_t)pb * 2 * DIM;
-          const int64_t i0 = A.if_sub_ptr[f], i1 = A.if_sub_ptr[f + 1];
+          const int64_t i0 = A.fbk_ptr[f], i1 = A.fbk_ptr[f + 1];
           for (int64_t c0 = i0; c0 < i1; c0 += CH)
             {
               const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
@@ -434,15 +525,16 @@ namespace pd
               for (int w = tid; w < cnt * DIM * N1; w += CC::NTHR)
                 {
                   const int     it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
-                  const int64_t s  = c0 + it;
+                  const int64_t s  = A.fbk_s[c0 + it];
                   const int     lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
-                  double        lo, hi, M[N1];
-                  cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
+                  double        M[N1];
                   const double a_lo = ba[d], a_ih = 1. / (ba[DIM + d] - ba[d]);
                   const double b_lo = bbx[d], b_ih = 1. / (bbx[DIM + d] - bbx[d]);
                   if (d == fd)
                     {
                       // M12 = sum w [ 1/2 (dn phi0_i) phi1_j - 1/2 phi0_i (dn phi1_j) - pen phi0_i phi1_j ], n = A's normal
+                      double lo, hi;
+                      cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
                       const double nrm = fs ? 1. : -1., x = fs ? hi : lo, pen = A.sub_sigma[s];
                       double       LA[N1], dLA[N1], LB[N1], dLB[N1];
                       basis_1d<C>(A.basis, (x - a_lo) * a_ih, a_ih, LA, dLA);
@@ -453,7 +545,10 @@ namespace pd
                         M[k] = A.stiffness * (0.5 * nrm * (da * LB[k] - la * dLB[k]) - pen * la * LB[k]);
                     }
                   else
-                    axis_rows_cross<C>(A.basis, A.quadf.x, A.quadf.w, A.nqf, lo, hi - lo, a_lo, a_ih, b_lo, b_ih, a, M);
+                    {
+                      const int32_t *iv = A.fbk_iv + (c0 + it) * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
+                      brick_rows_cross<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, a_lo, a_ih, b_lo, b_ih, a, M);
+                    }
                   if (d == 0 && a == 0)
                     kind[it] = 2;
                   double *dst = SL + it * ISTR + d * 2 * NXP + a * N1;
@@ -539,7 +634,7 @@ namespace pd
             acc[k] = 0.;
           const double *bb = A.bbox + (int64_t)p * 2 * DIM;
           const int64_t own_base = (int64_t)A.dof_block[p] * NF;
-          const int64_t s0 = A.subcell_ptr[p], s1 = A.subcell_ptr[p + 1];
+          const int64_t s0 = A.cbk_ptr[p], s1 = A.cbk_ptr[p + 1];
           const int64_t k0 = A.padj_ptr[p], k1 = A.padj_ptr[p + 1];
           // segments: the sub-cells, then per adjacency entry its own-side faces and (interior) its cross faces
           for (int64_t seg = 2 * k0 - 1; seg < 2 * k1; ++seg)
@@ -571,33 +666,34 @@ namespace pd
                       ob              = A.bbox + (int64_t)q * 2 * DIM;
                       src_base        = (int64_t)A.dof_block[q] * NF;
                     }
-                  i0 = A.if_sub_ptr[f];
-                  i1 = A.if_sub_ptr[f + 1];
+                  i0 = A.fbk_ptr[f];
+                  i1 = A.fbk_ptr[f + 1];
                 }
               for (int64_t c0 = i0; c0 < i1; c0 += CH)
                 {
                   const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
                   __syncthreads();
-                  // ---- 1-D matrices: thread = (item, axis, row)
+                  // ---- 1-D matrices: thread = (brick, axis, row)
                   for (int w = tid; w < cnt * DIM * N1; w += AC::NTHR)
                     {
                       const int    it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
                       double       M[N1], K[N1];
                       const double r_lo = bb[d], r_ih = 1. / (bb[DIM + d] - bb[d]);
                       const double c_lo = ob[d], c_ih = 1. / (ob[DIM + d] - ob[d]);
-                      double       lo, hi;
                       if (knd == 1)
                         {
-                          cell_box<DIM>(A, A.subcell_idx[c0 + it], d, lo, hi);
-                          axis_rows_mass<C>(A.basis, A.quad.x, A.quad.w, A.nq, lo, hi - lo, r_lo, r_ih, a, M, K);
+                          const int32_t *iv = A.cbk_iv + (c0 + it) * 2 * DIM + 2 * d;
+                          brick_rows_mass<C, DIM>(A, A.civ, iv[0], iv[1], d, A.quad.x, A.quad.w, A.nq, r_lo, r_ih, a, M, K);
                         }
                       else
                         {
-                          const int64_t s  = c0 + it;
-                          const int     lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
-                          cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
+                          const int64_t  s  = A.fbk_s[c0 + it];
+                          const int      lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
+                          const int32_t *iv = A.fbk_iv + (c0 + it) * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
                           if (d == fd)
                             {
+                              double lo, hi;
+                              cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
                               const double nrm = (fs ? 1. : -1.) * (side ? -1. : 1.); // outward normal of THIS polytope
                               const double x = fs ? hi : lo, pen = A.sub_sigma[s];
                               double       LR[N1], dLR[N1], LC[N1], dLC[N1];
@@ -614,9 +710,15 @@ namespace pd
                                 }
                             }
                           else if (knd == 2)
-                            axis_rows_mass<C>(A.basis, A.quadf.x, A.quadf.w, A.nqf, lo, hi - lo, r_lo, r_ih, a, M, K);
+                            brick_rows_mass<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, a, M, K);
                           else
-                            axis_rows_cross<C>(A.basis, A.quadf.x, A.quadf.w, A.nqf, lo, hi - lo, r_lo, r_ih, c_lo, c_ih, a, M);
+                            {
+                              brick_rows_cross<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, c_lo, c_ih,
+                                                       a, M);
+#pragma unroll
+                              for (int k = 0; k < N1; ++k)
+                                K[k] = 0.;
+                            }
                         }
                       double *dst = SM + it * MSTR + d * 2 * NXP + a * N1;
 #pragma unroll
@@ -796,22 +898,318 @@ namespace pd
     }
   } // namespace
 
-  // every owned sub-cell an axis-aligned box?  (device scan of the uploaded mesh; one 4-byte read-back)
-  bool
-  check_axis_aligned(pd_handle *h)
+  // ---------------------------------------------------------------------------------------------------
+  // Bricks.  The sum over the sub-cells of a polytope of X_s (x) Y_s (x) Z_s factorises further wherever the
+  // sub-cells form a tensor-product set I x J x K of 1-D intervals:
+  //      sum_{(i,j,k) in I x J x K} X_i (x) Y_j (x) Z_k  =  (sum_I X_i) (x) (sum_J Y_j) (x) (sum_K Z_k),
+  // the 1-D sums being the composite Gauss sums over the member intervals -- the same numbers the reference adds
+  // up point by point, regrouped once more.  A polytope that is a box of b^dim cells (the `blocks` shape an R-tree
+  // extracts from a structured grid) is ONE brick; any other agglomerate decomposes greedily (pencils along x with
+  // equal index sets merge along y into slabs, equal slabs merge along z); a brick of one cell is the
+  // per-sub-cell form.  The sub-faces of an interface that lie in one plane with one penalty decompose the same way
+  // into rectangles.  Intervals are stored as REPRESENTATIVE CELLS (the kernel reads their current vertices), so
+  // moving vertices through pd_upload keeps the bricks valid as long as the tensor structure survives; a device
+  // scan (k_check_axis_aligned) verifies that and the bricks are rebuilt on the host otherwise.
+  // ---------------------------------------------------------------------------------------------------
+  namespace
   {
+    struct BrickBuilder
+    {
+      const pd_mesh_desc &d;
+      const int           dim, vpc;
+      std::vector<int64_t> cbk_ptr, fbk_ptr;
+      std::vector<int32_t> cbk_iv, civ, cpos, fbk_s, fbk_iv, fiv, fpos;
+      explicit BrickBuilder(const pd_mesh_desc &desc)
+        : d(desc)
+        , dim(desc.dim)
+        , vpc(1 << desc.dim)
+      {}
+      void
+      box(const int32_t c, const int k, double &lo, double &hi) const
+      {
+        const int32_t *cv = d.cell_verts + (size_t)c * vpc;
+        lo                = d.verts[(size_t)cv[0] * dim + k];
+        hi                = d.verts[(size_t)cv[vpc - 1] * dim + k];
+      }
+      // indices of the intervals of `cells` along axis k among the distinct ones; rep[i] = a cell with index i
+      int
+      index_axis(const int32_t *cells, const int n, const int k, std::vector<int> &idx, std::vector<int32_t> &rep) const
+      {
+        std::vector<std::pair<std::pair<double, double>, int>> key(n);
+        for (int i = 0; i < n; ++i)
+          {
+            box(cells[i], k, key[i].first.first, key[i].first.second);
+            key[i].second = i;
+          }
+        std::sort(key.begin(), key.end());
+        idx.assign(n, 0);
+        rep.clear();
+        for (int i = 0; i < n; ++i)
+          {
+            if (i == 0 || key[i].first != key[i - 1].first)
+              rep.push_back(cells[key[i].second]);
+            idx[key[i].second] = (int)rep.size() - 1;
+          }
+        return (int)rep.size();
+      }
+      // Decompose the index set {(i0[e], i1[e], i2[e])} (all distinct) into tensor-product bricks.  Emits, per
+      // brick, the index lists per axis through `emit(S0, S1, S2)`; ndim = 2 ignores i2.
+      template <class Emit>
+      void
+      decompose(const int n, const std::vector<int> *ix, const int *nx, const int ndim, Emit &&emit) const
+      {
+        const int64_t full = (int64_t)nx[0] * (ndim > 1 ? nx[1] : 1) * (ndim > 2 ? nx[2] : 1);
+        if (full == n)
+          { // a full tensor grid: one brick
+            std::vector<int> S[3];
+            for (int k = 0; k < ndim; ++k)
+              {
+                S[k].resize(nx[k]);
+                for (int i = 0; i < nx[k]; ++i)
+                  S[k][i] = i;
+              }
+            for (int k = ndim; k < 3; ++k)
+              S[k].assign(1, 0);
+            emit(S[0], S[1], S[2]);
+            return;
+          }
+        // pencils along axis 0: (i1, i2) -> sorted set of i0
+        std::map<std::pair<int, int>, std::vector<int>> pencil;
+        for (int e = 0; e < n; ++e)
+          pencil[{ndim > 2 ? ix[2][e] : 0, ndim > 1 ? ix[1][e] : 0}].push_back(ix[0][e]);
+        // slabs: for every i2, the i1's with the same pencil set
+        std::map<std::pair<int, std::vector<int>>, std::vector<int>> slab; // (i2, S0) -> S1
+        for (auto &pc : pencil)
+          {
+            std::sort(pc.second.begin(), pc.second.end());
+            slab[{pc.first.first, pc.second}].push_back(pc.first.second);
+          }
+        // bricks: the i2's with the same (S0, S1)
+        std::map<std::pair<std::vector<int>, std::vector<int>>, std::vector<int>> brick;
+        for (auto &sl : slab)
+          brick[{sl.first.second, sl.second}].push_back(sl.first.first);
+        for (auto &bk : brick)
+          emit(bk.first.first, bk.first.second, bk.second);
+      }
+      void
+      build(const int32_t np_own)
+      {
+        cbk_ptr.assign(1, 0);
+        cpos.assign((size_t)d.poly_subcell_ptr[np_own] * (1 + dim), 0);
+        std::vector<int>     ix[3];
+        std::vector<int32_t> rep[3];
+        for (int32_t p = 0; p < np_own; ++p)
+          {
+            const int64_t  s0 = d.poly_subcell_ptr[p];
+            const int      n  = (int)(d.poly_subcell_ptr[p + 1] - s0);
+            const int32_t *cells = d.poly_subcell_idx + s0;
+            if (n == 1)
+              { // one cell: one brick (fine meshes)
+                const int32_t b = (int32_t)(cbk_iv.size() / (2 * dim));
+                for (int k = 0; k < dim; ++k)
+                  {
+                    cbk_iv.push_back((int32_t)civ.size());
+                    cbk_iv.push_back(1);
+                    civ.push_back(cells[0]);
+                  }
+                cpos[(size_t)s0 * (1 + dim)] = b;
+                cbk_ptr.push_back((int64_t)(cbk_iv.size() / (2 * dim)));
+                continue;
+              }
+            int nx[3] = {1, 1, 1};
+            for (int k = 0; k < dim; ++k)
+              nx[k] = index_axis(cells, n, k, ix[k], rep[k]);
+            // (i0, i1, i2) -> position in the polytope's list, to write cpos
+            std::map<std::array<int, 3>, int> where;
+            const bool                        dense = (int64_t)nx[0] * nx[1] * nx[2] <= (int64_t)4 * n + 64;
+            std::vector<int>                  grid;
+            if (dense)
+              grid.assign((size_t)nx[0] * nx[1] * nx[2], -1);
+            for (int e = 0; e < n; ++e)
+              {
+                const int i0 = ix[0][e], i1 = dim > 1 ? ix[1][e] : 0, i2 = dim > 2 ? ix[2][e] : 0;
+                if (dense)
+                  grid[((size_t)i2 * nx[1] + i1) * nx[0] + i0] = e;
+                else
+                  where[{i0, i1, i2}] = e;
+              }
+            decompose(n, ix, nx, dim, [&](const std::vector<int> &S0, const std::vector<int> &S1, const std::vector<int> &S2) {
+              const int32_t           b = (int32_t)(cbk_iv.size() / (2 * dim));
+              const std::vector<int> *S[3] = {&S0, &S1, &S2};
+              for (int k = 0; k < dim; ++k)
+                {
+                  cbk_iv.push_back((int32_t)civ.size());
+                  cbk_iv.push_back((int32_t)S[k]->size());
+                  for (const int i : *S[k])
+                    civ.push_back(rep[k][i]);
+                }
+              for (size_t c = 0; c < S2.size(); ++c)
+                for (size_t bb = 0; bb < S1.size(); ++bb)
+                  for (size_t a = 0; a < S0.size(); ++a)
+                    {
+                      const int e = dense ? grid[((size_t)S2[c] * nx[1] + S1[bb]) * nx[0] + S0[a]] :
+                                            where.at({S0[a], S1[bb], S2[c]});
+                      int32_t  *ps = &cpos[(size_t)(s0 + e) * (1 + dim)];
+                      ps[0]        = b;
+                      ps[1]        = (int32_t)a;
+                      if (dim > 1)
+                        ps[2] = (int32_t)bb;
+                      if (dim > 2)
+                        ps[3] = (int32_t)c;
+                    }
+            });
+            cbk_ptr.push_back((int64_t)(cbk_iv.size() / (2 * dim)));
+          }
+        // faces: the sub-faces of an interface grouped by (orientation, plane, penalty), each group into rectangles
+        fbk_ptr.assign(1, 0);
+        const int64_t nsf = d.n_ifaces ? d.iface_sub_ptr[d.n_ifaces] : 0;
+        fpos.assign((size_t)nsf * dim, 0);
+        const int td = dim - 1;
+        for (int32_t f = 0; f < d.n_ifaces; ++f)
+          {
+            const int64_t s0 = d.iface_sub_ptr[f], s1 = d.iface_sub_ptr[f + 1];
+            if (s1 - s0 == 1)
+              { // one sub-face: one brick
+                fpos[(size_t)s0 * dim] = (int32_t)fbk_s.size();
+                fbk_s.push_back((int32_t)s0);
+                for (int t = 0; t < td; ++t)
+                  {
+                    fbk_iv.push_back((int32_t)fiv.size());
+                    fbk_iv.push_back(1);
+                    fiv.push_back(d.sub_cell[s0]);
+                  }
+                fbk_ptr.push_back((int64_t)fbk_s.size());
+                continue;
+              }
+            // group key: (local face, plane coordinate, penalty)
+            std::vector<std::pair<std::tuple<int, double, double>, int64_t>> key;
+            for (int64_t s = s0; s < s1; ++s)
+              {
+                const int lf = d.sub_face[s];
+                double    lo, hi;
+                box(d.sub_cell[s], lf >> 1, lo, hi);
+                key.push_back({{lf, (lf & 1) ? hi : lo, d.sub_sigma[s]}, s});
+              }
+            std::sort(key.begin(), key.end());
+            for (size_t g0 = 0; g0 < key.size();)
+              {
+                size_t g1 = g0;
+                while (g1 < key.size() && key[g1].first == key[g0].first)
+                  ++g1;
+                const int            n  = (int)(g1 - g0);
+                const int            fd = std::get<0>(key[g0].first) >> 1;
+                std::vector<int32_t> cells(n);
+                for (int e = 0; e < n; ++e)
+                  cells[e] = d.sub_cell[key[g0 + e].second];
+                int taxis[2] = {0, 0};
+                for (int k = 0, t = 0; k < dim; ++k)
+                  if (k != fd)
+                    taxis[t++] = k;
+                int nx[3] = {1, 1, 1};
+                for (int t = 0; t < td; ++t)
+                  nx[t] = index_axis(cells.data(), n, taxis[t], ix[t], rep[t]);
+                std::map<std::pair<int, int>, int> where;
+                for (int e = 0; e < n; ++e)
+                  where[{ix[0][e], td > 1 ? ix[1][e] : 0}] = e;
+                decompose(n, ix, nx, td, [&](const std::vector<int> &S0, const std::vector<int> &S1, const std::vector<int> &) {
+                  const int32_t           b = (int32_t)fbk_s.size();
+                  const std::vector<int> *S[2] = {&S0, &S1};
+                  fbk_s.push_back((int32_t)key[g0 + where.at({S0[0], S1[0]})].second);
+                  for (int t = 0; t < td; ++t)
+                    {
+                      fbk_iv.push_back((int32_t)fiv.size());
+                      fbk_iv.push_back((int32_t)S[t]->size());
+                      for (const int i : *S[t])
+                        fiv.push_back(rep[t][i]);
+                    }
+                  for (size_t bb = 0; bb < S1.size(); ++bb)
+                    for (size_t a = 0; a < S0.size(); ++a)
+                      {
+                        const int64_t s  = key[g0 + where.at({S0[a], S1[bb]})].second;
+                        int32_t      *ps = &fpos[(size_t)s * dim];
+                        ps[0]            = b;
+                        ps[1]            = (int32_t)a;
+                        if (td > 1)
+                          ps[2] = (int32_t)bb;
+                      }
+                });
+                g0 = g1;
+              }
+            fbk_ptr.push_back((int64_t)fbk_s.size());
+          }
+      }
+    };
+  } // namespace
+
+  // host: decompose into bricks and upload (pd_create; pd_upload when the device scan finds the bricks stale)
+  void
+  build_cartesian_bricks(pd_handle *h, const pd_mesh_desc &d)
+  {
+    BrickBuilder B(d);
+    B.build(h->np_own);
+    auto put = [](auto &buf, const auto &v) {
+      buf.alloc(std::max<size_t>(v.size(), 1));
+      if (!v.empty())
+        PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+    };
+    PD_CUDA(cudaStreamSynchronize(h->stream));
+    put(h->cbk_ptr, B.cbk_ptr);
+    put(h->cbk_iv, B.cbk_iv);
+    put(h->civ, B.civ);
+    put(h->cpos, B.cpos);
+    put(h->fbk_ptr, B.fbk_ptr);
+    put(h->fbk_s, B.fbk_s);
+    put(h->fbk_iv, B.fbk_iv);
+    put(h->fiv, B.fiv);
+    put(h->fpos, B.fpos);
+    h->n_cell_bricks = (int64_t)B.cbk_iv.size() / (2 * h->dim);
+    h->n_face_bricks = (int64_t)B.fbk_s.size();
+    h->bricks_ready  = true;
+    h->h_subcell_idx.assign(d.poly_subcell_idx, d.poly_subcell_idx + h->n_subcells);
+    h->h_sub_cell.assign(d.sub_cell, d.sub_cell + h->n_subfaces);
+    h->h_sub_face.assign(d.sub_face, d.sub_face + h->n_subfaces);
+  }
+
+  // Every owned sub-cell an axis-aligned box?  With bricks: do they still describe the mesh?  (device scan of the
+  // uploaded arrays; one 8-byte read-back.)  Returns the axis-alignment; *bricks_stale reports the second answer.
+  bool
+  check_axis_aligned(pd_handle *h, bool *bricks_stale)
+  {
+    if (bricks_stale)
+      *bricks_stale = false;
     if (h->n_subcells == 0)
       return false;
     if (!h->cart_flag.p)
-      h->cart_flag.alloc(1);
-    PD_CUDA(cudaMemsetAsync(h->cart_flag.p, 0, sizeof(int), h->stream));
-    const int grid = (int)std::min<int64_t>((h->n_subcells + 255) / 256, (int64_t)h->sm_count * 8);
+      h->cart_flag.alloc(2);
+    PD_CUDA(cudaMemsetAsync(h->cart_flag.p, 0, 2 * sizeof(int), h->stream));
+    const bool with_bricks = h->bricks_ready;
+    const int  grid        = (int)std::min<int64_t>((std::max(h->n_subcells, h->n_subfaces) + 255) / 256, (int64_t)h->sm_count * 8);
     k_check_axis_aligned<<<grid, 256, 0, h->stream>>>(h->verts.p, h->cell_verts.p, h->subcell_idx.p, h->n_subcells, h->dim,
-                                                       h->cart_flag.p);
-    int bad = 1;
-    PD_CUDA(cudaMemcpyAsync(&bad, h->cart_flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+                                                       h->cart_flag.p, with_bricks ? h->cpos.p : nullptr, h->cbk_iv.p, h->civ.p,
+                                                       h->n_subfaces, h->sub_cell.p, h->sub_face.p, h->sub_sigma.p,
+                                                       with_bricks ? h->fpos.p : nullptr, h->fbk_s.p, h->fbk_iv.p, h->fiv.p);
+    int flags[2] = {1, 1};
+    PD_CUDA(cudaMemcpyAsync(flags, h->cart_flag.p, sizeof flags, cudaMemcpyDeviceToHost, h->stream));
     PD_CUDA(cudaStreamSynchronize(h->stream));
-    return bad == 0;
+    if (bricks_stale)
+      *bricks_stale = flags[1] != 0;
+    return flags[0] == 0;
+  }
+
+  // pd_create / pd_upload: which assembly path applies, bricks (re)built when needed
+  void
+  setup_cartesian(pd_handle *h, const pd_mesh_desc &d)
+  {
+    bool stale = false;
+    // index arrays the bricks were built from: a changed list is a rebuild whatever the coordinates say
+    if (h->bricks_ready &&
+        (std::memcmp(h->h_subcell_idx.data(), d.poly_subcell_idx, sizeof(int32_t) * (size_t)h->n_subcells) != 0 ||
+         (h->n_subfaces > 0 && (std::memcmp(h->h_sub_cell.data(), d.sub_cell, sizeof(int32_t) * (size_t)h->n_subfaces) != 0 ||
+                                std::memcmp(h->h_sub_face.data(), d.sub_face, sizeof(int32_t) * (size_t)h->n_subfaces) != 0))))
+      h->bricks_ready = false;
+    h->cartesian = check_axis_aligned(h, &stale);
+    if (h->cartesian && (!h->bricks_ready || stale))
+      build_cartesian_bricks(h, d);
   }
 
   bool
@@ -917,6 +1315,13 @@ namespace pd
     a.basis       = h->basis;
     a.quad        = h->quad;
     a.quadf       = h->quadf;
+    a.cbk_ptr     = h->cbk_ptr.p;
+    a.cbk_iv      = h->cbk_iv.p;
+    a.civ         = h->civ.p;
+    a.fbk_ptr     = h->fbk_ptr.p;
+    a.fbk_s       = h->fbk_s.p;
+    a.fbk_iv      = h->fbk_iv.p;
+    a.fiv         = h->fiv.p;
     {
       // (a, b, c) of DoF i: FE_DGQ lexicographic; FE_AggloDGP in PolynomialSpace order (last coordinate outermost,
       // first fastest, total degree <= p: source/fe_agglodgp.cc:28-57)

@@ -166,6 +166,12 @@ struct pd_handle
   std::vector<int32_t> h_bcol, h_dof_block, h_ifA, h_ifB;
   bool                 cartesian = false; // every owned sub-cell is an axis-aligned box: tensor assembly path (pd_cartesian.cu)
   pd::DevBuf<int>      cart_flag;
+  // bricks of the tensor path (pd_cartesian.cu: build_cartesian_bricks)
+  pd::DevBuf<int64_t>  cbk_ptr, fbk_ptr;
+  pd::DevBuf<int32_t>  cbk_iv, civ, cpos, fbk_s, fbk_iv, fiv, fpos;
+  int64_t              n_cell_bricks = 0, n_face_bricks = 0;
+  bool                 bricks_ready = false;
+  std::vector<int32_t> h_subcell_idx, h_sub_cell, h_sub_face;
   int                  last_assembly_path = -1; // 0: DMMA kernels on the agglomerated quadrature, 1: tensor path
   std::vector<double>  h_bbox;          // bounding boxes (reinit tables, pd_reinit.cu)
   pd::DevBuf<double>   reinit_scratch;  // tables of one polytope / face before they go to the caller
@@ -238,7 +244,8 @@ namespace pd
   int      peer_status(pd_peer *p);
   void     peer_destroy(pd_peer *p);
   // pd_cartesian.cu
-  bool check_axis_aligned(pd_handle *h);
+  bool check_axis_aligned(pd_handle *h, bool *bricks_stale = nullptr);
+  void setup_cartesian(pd_handle *h, const pd_mesh_desc &d);
   bool cartesian_assembly_selected(const pd_handle *h);
   void launch_assemble_cartesian(pd_handle *h, uint32_t flags, const pd_coefficients &coef);
   bool cartesian_apply_available(const pd_handle *h);

@@ -3,12 +3,22 @@ sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tools')
 import torch, numpy as np
 import polydeal_b200 as pdl
 from pd_workloads import CONFIGS, build_handler
+import time
 for name in sys.argv[1:]:
+    shape="blocks"
+    if name.endswith("m"): name,shape=name[:-1],"metis"
     cfg=CONFIGS[name]
-    ah=build_handler(pdl,cfg,1)
+    if shape=="metis":
+        grid=pdl.Grid.hyper_cube(cfg["dim"],0.0,1.0,cfg["n"].bit_length()-1)
+        groups=pdl.metis_agglomerates(grid,(cfg["n"]//cfg["b"])**cfg["dim"])
+        ah=pdl.AgglomerationHandler(grid); ah.define_agglomerates(groups); ah.initialize_fe_values(cfg["nq"]); ah.distribute_agglomerated_dofs(pdl.FE_DGQ,cfg["p"])
+    else:
+        ah=build_handler(pdl,cfg,1)
+    t_create=time.time()
     desc=ah.flatten(penalty_constant=-1.0 if cfg["C"] is None else cfg["C"])
     stream=torch.cuda.Stream(); torch.cuda.set_stream(stream)
     op=pdl.SIPOperator(desc,keepalive=ah); op.set_stream(stream.cuda_stream)
+    t_create=time.time()-t_create
     tot=[]; kms=[]
     for s in range(6):
         a,e=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
@@ -25,5 +35,5 @@ for name in sys.argv[1:]:
         for _ in range(5): op.vmult_ptr(y.data_ptr(),x.data_ptr(),mode=mode)
         e.record(stream); e.synchronize(); res[key]=a.elapsed_time(e)/5
         res[key+"_sum"]=float(y.sum())
-    print(json.dumps({"vmult":res,"config":name,"path":op.assembly_path,"assemble_ms":statistics.mean(tot),"dofs_per_s":op.m()/(statistics.mean(tot)*1e-3),"kernel_ms":kms[-1],"mem_GB":torch.cuda.max_memory_allocated()/1e9}))
+    print(json.dumps({"shape":shape,"create_s":t_create,"n_ifaces":int(desc.n_ifaces),"vmult":res,"config":name,"path":op.assembly_path,"assemble_ms":statistics.mean(tot),"dofs_per_s":op.m()/(statistics.mean(tot)*1e-3),"kernel_ms":kms[-1],"mem_GB":torch.cuda.max_memory_allocated()/1e9}))
     del op
