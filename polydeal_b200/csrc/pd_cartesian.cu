@@ -379,8 +379,10 @@ namespace pd
       using CC         = CartCfg<DIM, DEGX>;
       constexpr int N1 = CC::N1, NX = CC::NX, NXP = CC::NXP, NYZ = CC::NYZ, IG = CC::IG, NF = CC::NF, CH = CC::CH, N = C::N;
       constexpr int ISTR = CC::ISTR;
+      constexpr int MAXE = 32; // entries (cells, adjacency entries) per batch of the item list
       __shared__ __align__(16) double SL[CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)];
-      __shared__ int                  kind[CH];
+      __shared__ int                  kind[CH], e_pre[MAXE + 1], e_meta[MAXE];
+      __shared__ int64_t              e_first[MAXE];
       const int  tid = threadIdx.x;
       const int  col = tid % NYZ, ig = tid / NYZ;
       const bool active = tid < NYZ * IG;
@@ -392,61 +394,82 @@ namespace pd
           for (int r = 0; r < NX; ++r)
             acc[r] = 0.;
           const double *bb = A.bbox + (int64_t)p * 2 * DIM;
-          const int64_t s0 = A.cbk_ptr[p], s1 = A.cbk_ptr[p + 1];
-          const int64_t k0 = A.padj_ptr[p], k1 = A.padj_ptr[p + 1];
-          // segment -1: the cell bricks; segments k0..k1-1: the face bricks of the adjacency list
-          for (int64_t seg = k0 - 1; seg < k1; ++seg)
+          const int64_t k0 = A.padj_ptr[p];
+          const int     n_adj = (int)(A.padj_ptr[p + 1] - k0);
+          // The bricks of the polytope as ONE item list: entry -1 = its cell bricks, entries 0 .. n_adj-1 = the face
+          // bricks of the adjacency list (batches of MAXE entries); chunks of CH items run across the entries.
+          for (int ebase = -1; ebase < n_adj; ebase += MAXE)
             {
-              int64_t i0, i1;
-              int     side = 0;
-              int64_t f    = -1;
-              bool    bnd  = false;
-              if (seg < k0)
+              __syncthreads();
+              for (int t = tid; t < MAXE; t += CC::NTHR)
                 {
-                  if (!(A.flags & PD_ASSEMBLE_VOLUME))
-                    continue;
-                  i0 = s0;
-                  i1 = s1;
+                  const int e = ebase + t;
+                  int       cnt = 0, meta = 0;
+                  int64_t   first = 0;
+                  if (e == -1)
+                    {
+                      if (A.flags & PD_ASSEMBLE_VOLUME)
+                        {
+                          first = A.cbk_ptr[p];
+                          cnt   = (int)(A.cbk_ptr[p + 1] - first);
+                          meta  = 1;
+                        }
+                    }
+                  else if (e < n_adj)
+                    {
+                      const int64_t pe  = A.padj[k0 + e], f = pe >> 1;
+                      const bool    bnd = A.ifB[f] < 0;
+                      if (bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) : (A.flags & PD_ASSEMBLE_INTERIOR))
+                        {
+                          first = A.fbk_ptr[f];
+                          cnt   = (int)(A.fbk_ptr[f + 1] - first);
+                          meta  = 2 | ((int)(pe & 1) << 2) | ((int)bnd << 3);
+                        }
+                    }
+                  e_first[t] = first;
+                  e_meta[t]  = meta;
+                  e_pre[t + 1] = cnt;
                 }
-              else
+              __syncthreads();
+              if (tid == 0)
                 {
-                  const int64_t e = A.padj[seg];
-                  f               = e >> 1;
-                  side            = (int)(e & 1);
-                  bnd             = A.ifB[f] < 0;
-                  if (!(bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) : (A.flags & PD_ASSEMBLE_INTERIOR)))
-                    continue;
-                  i0 = A.fbk_ptr[f];
-                  i1 = A.fbk_ptr[f + 1];
+                  e_pre[0] = 0;
+                  for (int t = 0; t < MAXE; ++t)
+                    e_pre[t + 1] += e_pre[t];
                 }
-              for (int64_t c0 = i0; c0 < i1; c0 += CH)
+              __syncthreads();
+              const int total = e_pre[MAXE];
+              for (int c0 = 0; c0 < total; c0 += CH)
                 {
-                  const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
+                  const int cnt = total - c0 < CH ? total - c0 : CH;
                   __syncthreads(); // the previous chunk has been consumed
                   // ---- 1-D matrices of the chunk's bricks: thread = (brick, axis, row a)
                   for (int w = tid; w < cnt * DIM * N1; w += CC::NTHR)
                     {
                       const int it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
-                      double    M[N1], K[N1];
-                      const double b_lo = bb[d], inv_h = 1. / (bb[DIM + d] - bb[d]);
-                      if (seg < k0)
+                      int       e  = 0;
+                      while (e_pre[e + 1] <= c0 + it)
+                        ++e;
+                      const int64_t brick = e_first[e] + (c0 + it - e_pre[e]);
+                      const int     meta  = e_meta[e];
+                      double        M[N1], K[N1];
+                      const double  b_lo = bb[d], inv_h = 1. / (bb[DIM + d] - bb[d]);
+                      if ((meta & 3) == 1)
                         {
-                          const int32_t *iv = A.cbk_iv + (c0 + it) * 2 * DIM + 2 * d;
+                          const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
                           brick_rows_mass<C, DIM>(A, A.civ, iv[0], iv[1], d, A.quad.x, A.quad.w, A.nq, b_lo, inv_h, a, M, K);
-                          if (d == 0 && a == 0)
-                            kind[it] = 1;
                         }
                       else
                         {
-                          const int64_t s  = A.fbk_s[c0 + it];
+                          const int64_t s  = A.fbk_s[brick];
                           const int     lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
                           if (d == fd)
                             {
                               double lo, hi;
                               cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
                               // own-side face term at the face coordinate: outward normal of THIS polytope
-                              const double nrm = (fs ? 1. : -1.) * (side ? -1. : 1.);
-                              const double cf  = bnd ? 1. : 0.5;
+                              const double nrm = (fs ? 1. : -1.) * ((meta & 4) ? -1. : 1.);
+                              const double cf  = (meta & 8) ? 1. : 0.5;
                               double       L[N1], dL[N1];
                               basis_1d<C>(A.basis, ((fs ? hi : lo) - b_lo) * inv_h, inv_h, L, dL);
                               const double la = pick<N1>(L, a), da = pick<N1>(dL, a), pen = A.sub_sigma[s];
@@ -459,12 +482,12 @@ namespace pd
                             }
                           else
                             {
-                              const int32_t *iv = A.fbk_iv + (c0 + it) * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
+                              const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
                               brick_rows_mass<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, b_lo, inv_h, a, M, K);
                             }
-                          if (d == 0 && a == 0)
-                            kind[it] = 2;
                         }
+                      if (d == 0 && a == 0)
+                        kind[it] = meta & 3;
                       double *dst = SL + it * ISTR + d * 2 * NXP + a * N1;
 #pragma unroll
                       for (int k = 0; k < N1; ++k)
@@ -621,6 +644,9 @@ namespace pd
       double *SM = smem;                  // [CH][MSTR]   1-D matrices, [d][slot][row a][a']
       double *W  = SM + CH * MSTR;        // [CH][WSTR]   z-pass output (two tensors)
       double *V  = W + CH * WSTR;         // [CH][WSTR]   y-pass output (two tensors)
+      constexpr int MAXE = 32;
+      __shared__ int     e_pre[MAXE + 1], e_meta[MAXE], e_poly[MAXE], it_kind[CH];
+      __shared__ int64_t e_first[MAXE], it_src[CH];
       const int tid = threadIdx.x;
       const int j = tid / NL, l = tid % NL;
       const bool active = tid < CH * NL;
@@ -633,63 +659,88 @@ namespace pd
           for (int k = 0; k < N1; ++k)
             acc[k] = 0.;
           const double *bb = A.bbox + (int64_t)p * 2 * DIM;
-          const int64_t own_base = (int64_t)A.dof_block[p] * NF;
-          const int64_t s0 = A.cbk_ptr[p], s1 = A.cbk_ptr[p + 1];
-          const int64_t k0 = A.padj_ptr[p], k1 = A.padj_ptr[p + 1];
-          // segments: the sub-cells, then per adjacency entry its own-side faces and (interior) its cross faces
-          for (int64_t seg = 2 * k0 - 1; seg < 2 * k1; ++seg)
+          const int64_t k0 = A.padj_ptr[p];
+          const int     n_adj = (int)(A.padj_ptr[p + 1] - k0);
+          // One item list per polytope: entry -1 = its cell bricks; entries 2 e / 2 e + 1 = the face bricks of
+          // adjacency entry e taken from its own side / from the neighbour's side (cross, interior only)
+          for (int ebase = -1; ebase < 2 * n_adj; ebase += MAXE)
             {
-              int64_t i0, i1, f = -1;
-              int     side = 0, knd = 1;
-              bool    bnd = false;
-              const double *ob = bb; // bounding box of the column basis
-              int64_t       src_base = own_base;
-              if (seg < 2 * k0)
+              __syncthreads();
+              for (int t = tid; t < MAXE; t += AC::NTHR)
                 {
-                  if (!(A.flags & PD_ASSEMBLE_VOLUME))
-                    continue;
-                  i0 = s0;
-                  i1 = s1;
-                }
-              else
-                {
-                  const int64_t e = A.padj[seg >> 1];
-                  f               = e >> 1;
-                  side            = (int)(e & 1);
-                  bnd             = A.ifB[f] < 0;
-                  knd             = (seg & 1) ? 3 : 2;
-                  if (!(bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) : (A.flags & PD_ASSEMBLE_INTERIOR)) || (knd == 3 && bnd))
-                    continue;
-                  if (knd == 3)
+                  const int e = ebase + t;
+                  int       cnt = 0, meta = 0, q = p;
+                  int64_t   first = 0;
+                  if (e == -1)
                     {
-                      const int32_t q = side ? A.ifA[f] : A.ifB[f];
-                      ob              = A.bbox + (int64_t)q * 2 * DIM;
-                      src_base        = (int64_t)A.dof_block[q] * NF;
+                      if (A.flags & PD_ASSEMBLE_VOLUME)
+                        {
+                          first = A.cbk_ptr[p];
+                          cnt   = (int)(A.cbk_ptr[p + 1] - first);
+                          meta  = 1;
+                        }
                     }
-                  i0 = A.fbk_ptr[f];
-                  i1 = A.fbk_ptr[f + 1];
+                  else if (e >= 0 && e < 2 * n_adj)
+                    {
+                      const int64_t pe  = A.padj[k0 + (e >> 1)], f = pe >> 1;
+                      const bool    bnd = A.ifB[f] < 0;
+                      const int     knd = (e & 1) ? 3 : 2, side = (int)(pe & 1);
+                      if ((bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) : (A.flags & PD_ASSEMBLE_INTERIOR)) && !(knd == 3 && bnd))
+                        {
+                          first = A.fbk_ptr[f];
+                          cnt   = (int)(A.fbk_ptr[f + 1] - first);
+                          meta  = knd | (side << 2) | ((int)bnd << 3);
+                          if (knd == 3)
+                            q = side ? A.ifA[f] : A.ifB[f];
+                        }
+                    }
+                  e_first[t]   = first;
+                  e_meta[t]    = meta;
+                  e_poly[t]    = q;
+                  e_pre[t + 1] = cnt;
                 }
-              for (int64_t c0 = i0; c0 < i1; c0 += CH)
+              __syncthreads();
+              if (tid == 0)
                 {
-                  const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
+                  e_pre[0] = 0;
+                  for (int t = 0; t < MAXE; ++t)
+                    e_pre[t + 1] += e_pre[t];
+                }
+              __syncthreads();
+              const int total = e_pre[MAXE];
+              for (int c0 = 0; c0 < total; c0 += CH)
+                {
+                  const int cnt = total - c0 < CH ? total - c0 : CH;
                   __syncthreads();
                   // ---- 1-D matrices: thread = (brick, axis, row)
                   for (int w = tid; w < cnt * DIM * N1; w += AC::NTHR)
                     {
-                      const int    it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
+                      const int it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
+                      int       e  = 0;
+                      while (e_pre[e + 1] <= c0 + it)
+                        ++e;
+                      const int64_t brick = e_first[e] + (c0 + it - e_pre[e]);
+                      const int     meta = e_meta[e], knd = meta & 3, side = (meta >> 2) & 1;
+                      const bool    bnd  = (meta & 8) != 0;
+                      const double *ob   = A.bbox + (int64_t)e_poly[e] * 2 * DIM; // bounding box of the column basis
+                      if (d == 0 && a == 0)
+                        {
+                          it_kind[it] = knd;
+                          it_src[it]  = (int64_t)A.dof_block[e_poly[e]] * NF;
+                        }
                       double       M[N1], K[N1];
                       const double r_lo = bb[d], r_ih = 1. / (bb[DIM + d] - bb[d]);
                       const double c_lo = ob[d], c_ih = 1. / (ob[DIM + d] - ob[d]);
                       if (knd == 1)
                         {
-                          const int32_t *iv = A.cbk_iv + (c0 + it) * 2 * DIM + 2 * d;
+                          const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
                           brick_rows_mass<C, DIM>(A, A.civ, iv[0], iv[1], d, A.quad.x, A.quad.w, A.nq, r_lo, r_ih, a, M, K);
                         }
                       else
                         {
-                          const int64_t  s  = A.fbk_s[c0 + it];
+                          const int64_t  s  = A.fbk_s[brick];
                           const int      lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
-                          const int32_t *iv = A.fbk_iv + (c0 + it) * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
+                          const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
                           if (d == fd)
                             {
                               double lo, hi;
@@ -729,7 +780,9 @@ namespace pd
                         }
                     }
                   __syncthreads();
-                  const bool on = active && j < cnt;
+                  const bool    on  = active && j < cnt;
+                  const int     knd = on ? it_kind[j] : 0;
+                  const int64_t src_base = on ? it_src[j] : 0;
                   const double *m = SM + j * MSTR;
                   double       *w1 = W + j * WSTR, *w2 = w1 + NF, *v1 = V + j * WSTR, *v2 = v1 + NF;
                   double        in1[N1], in2[N1];
