@@ -79,6 +79,14 @@ namespace pd
       const int32_t *fbk_s;   // [n_fbk] representative sub-face (plane, orientation, penalty)
       const int32_t *fbk_iv;  // [n_fbk][2 (dim - 1)]: (start, count) per tangential axis into fiv
       const int32_t *fiv;     // representative (A-side) cell of every tangential interval
+      // what the hot kernels read (refreshed from the representatives by k_refresh_bricks after every upload)
+      const double2 *civ_box, *fiv_box;     // (lo, hi) of every interval
+      const double  *fbk_plane, *fbk_sigma; // plane coordinate and penalty of a face brick
+      const int32_t *fbk_lf;                // its local face number (axis, side) seen from the listing polytope
+      // item list of a polytope: [pit_ptr[p], pit_diag_end[p]) cell bricks and own-side face bricks (the diagonal
+      // block), [pit_diag_end[p], pit_ptr[p + 1]) the cross face bricks (matrix-free apply only)
+      const int64_t *pit_ptr, *pit_diag_end;
+      const int32_t *pit_brick, *pit_meta, *pit_q; // meta = kind (1 cell, 2 own face, 3 cross face) | side << 2 | boundary << 3
     };
 
     // cells of the mesh that are NOT axis-aligned boxes in standard orientation (vertex v at lo + bit_k(v) (hi - lo))
@@ -160,11 +168,11 @@ namespace pd
       static constexpr int CH  = 16;            // items per chunk
       // thread (col, ig): column col = (b,b'[,c,c']) of the factorised block, all NX rows (a,a'); the items of a
       // chunk are dealt to IG item groups (small elements: fills the CTA), summed through shared memory at the end
-      static constexpr int IG   = NYZ >= 128 ? 1 : (NYZ * 2 >= 128 ? 2 : (NYZ * 4 >= 128 ? 4 : (NYZ * 8 >= 128 ? 8 : 16)));
+      static constexpr int IG   = NYZ >= 64 ? 1 : (NYZ * 2 >= 64 ? 2 : (NYZ * 4 >= 64 ? 4 : (NYZ * 8 >= 64 ? 8 : 16)));
       static constexpr int NTHR = ((NYZ * IG + 31) / 32) * 32;
       // at least 24 resident warps per SM: the phases of a CTA (1-D matrices | accumulation) are separated by
       // barriers, other CTAs fill the gaps
-      static constexpr int MINB = (768 / NTHR) < 1 ? 1 : ((768 / NTHR) > 8 ? 8 : (768 / NTHR));
+      static constexpr int MINB = (768 / NTHR) < 1 ? 1 : ((768 / NTHR) > 12 ? 12 : (768 / NTHR));
       static constexpr int ISTR = DIM * 2 * NXP;
     };
 
@@ -250,7 +258,7 @@ namespace pd
     // its representative cell) of the mass-like and stiffness-like sums; row basis = column basis (box b_lo, inv_h)
     template <class C, int DIM>
     __device__ __forceinline__ void
-    brick_rows_mass(const CartArgs &A, const int32_t *reps, const int start, const int count, const int d, const double *qx,
+    brick_rows_mass(const CartArgs &A, const double2 *boxes, const int start, const int count, const double *qx,
                     const double *qw, const int nq, const double b_lo, const double inv_h, const int a, double *M, double *K)
     {
 #pragma unroll
@@ -258,15 +266,14 @@ namespace pd
         M[k] = K[k] = 0.;
       for (int i = start; i < start + count; ++i)
         {
-          double lo, hi;
-          cell_box<DIM>(A, reps[i], d, lo, hi);
-          axis_rows_mass<C>(A.basis, qx, qw, nq, lo, hi - lo, b_lo, inv_h, a, M, K);
+          const double2 bx = boxes[i];
+          axis_rows_mass<C>(A.basis, qx, qw, nq, bx.x, bx.y - bx.x, b_lo, inv_h, a, M, K);
         }
     }
     // the same with a row basis (r_*) and another column basis (c_*)
     template <class C, int DIM>
     __device__ __forceinline__ void
-    brick_rows_cross(const CartArgs &A, const int32_t *reps, const int start, const int count, const int d, const double *qx,
+    brick_rows_cross(const CartArgs &A, const double2 *boxes, const int start, const int count, const double *qx,
                      const double *qw, const int nq, const double r_lo, const double r_ih, const double c_lo, const double c_ih,
                      const int a, double *M)
     {
@@ -275,9 +282,46 @@ namespace pd
         M[k] = 0.;
       for (int i = start; i < start + count; ++i)
         {
-          double lo, hi;
-          cell_box<DIM>(A, reps[i], d, lo, hi);
-          axis_rows_cross<C>(A.basis, qx, qw, nq, lo, hi - lo, r_lo, r_ih, c_lo, c_ih, a, M);
+          const double2 bx = boxes[i];
+          axis_rows_cross<C>(A.basis, qx, qw, nq, bx.x, bx.y - bx.x, r_lo, r_ih, c_lo, c_ih, a, M);
+        }
+    }
+
+    // cached geometry of the bricks from their representatives (after pd_create / every pd_upload)
+    __global__ void __launch_bounds__(256)
+    k_refresh_bricks(const double *verts, const int32_t *cell_verts, const int dim, const int64_t n_cbk, const int32_t *cbk_iv,
+                     const int32_t *civ, double2 *civ_box, const int64_t n_fbk, const int32_t *fbk_s, const int32_t *fbk_iv,
+                     const int32_t *fiv, double2 *fiv_box, const int32_t *sub_cell, const int32_t *sub_face,
+                     const double *sub_sigma, double *fbk_plane, double *fbk_sigma, int32_t *fbk_lf)
+    {
+      const int vpc = 1 << dim;
+      auto      box = [&](const int32_t c, const int k) {
+        const int32_t *cv = cell_verts + (int64_t)c * vpc;
+        return make_double2(verts[(int64_t)cv[0] * dim + k], verts[(int64_t)cv[vpc - 1] * dim + k]);
+      };
+      const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      for (int64_t w = t0; w < n_cbk * dim; w += stride)
+        {
+          const int     k  = (int)(w % dim);
+          const int32_t *iv = cbk_iv + (w / dim) * 2 * dim + 2 * k;
+          for (int i = iv[0]; i < iv[0] + iv[1]; ++i)
+            civ_box[i] = box(civ[i], k);
+        }
+      for (int64_t b = t0; b < n_fbk; b += stride)
+        {
+          const int32_t s  = fbk_s[b];
+          const int     lf = sub_face[s], fd = lf >> 1;
+          const double2 bx = box(sub_cell[s], fd);
+          fbk_plane[b]     = (lf & 1) ? bx.y : bx.x;
+          fbk_sigma[b]     = sub_sigma[s];
+          fbk_lf[b]        = lf;
+          for (int k = 0; k < dim; ++k)
+            if (k != fd)
+              {
+                const int32_t *iv = fbk_iv + b * 2 * (dim - 1) + 2 * (k < fd ? k : k - 1);
+                for (int i = iv[0]; i < iv[0] + iv[1]; ++i)
+                  fiv_box[i] = box(fiv[i], k);
+              }
         }
     }
 
@@ -312,6 +356,8 @@ namespace pd
       const int     cc    = DIM == 3 ? col / NX : 0;   // (c,c')
       for (int it = ig; it < cnt; it += IG)
         {
+          if (kind[it] == 0)
+            continue; // a term the flags switch off
           const double *s  = SL + it * ISTR;
           const double m1 = s[(1 * 2 + 0) * NXP + cb];
           const double m2 = DIM == 3 ? s[(2 * 2 + 0) * NXP + cc] : 1.;
@@ -379,10 +425,8 @@ namespace pd
       using CC         = CartCfg<DIM, DEGX>;
       constexpr int N1 = CC::N1, NX = CC::NX, NXP = CC::NXP, NYZ = CC::NYZ, IG = CC::IG, NF = CC::NF, CH = CC::CH, N = C::N;
       constexpr int ISTR = CC::ISTR;
-      constexpr int MAXE = 32; // entries (cells, adjacency entries) per batch of the item list
       __shared__ __align__(16) double SL[CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)];
-      __shared__ int                  kind[CH], e_pre[MAXE + 1], e_meta[MAXE];
-      __shared__ int64_t              e_first[MAXE];
+      __shared__ int                  kind[CH];
       const int  tid = threadIdx.x;
       const int  col = tid % NYZ, ig = tid / NYZ;
       const bool active = tid < NYZ * IG;
@@ -394,112 +438,66 @@ namespace pd
           for (int r = 0; r < NX; ++r)
             acc[r] = 0.;
           const double *bb = A.bbox + (int64_t)p * 2 * DIM;
-          const int64_t k0 = A.padj_ptr[p];
-          const int     n_adj = (int)(A.padj_ptr[p + 1] - k0);
-          // The bricks of the polytope as ONE item list: entry -1 = its cell bricks, entries 0 .. n_adj-1 = the face
-          // bricks of the adjacency list (batches of MAXE entries); chunks of CH items run across the entries.
-          for (int ebase = -1; ebase < n_adj; ebase += MAXE)
+          // the bricks of the polytope as one item list: its cell bricks, then the own-side face bricks of its adjacency
+          const int64_t i0 = A.pit_ptr[p], i1 = A.pit_diag_end[p];
+          for (int64_t c0 = i0; c0 < i1; c0 += CH)
             {
-              __syncthreads();
-              for (int t = tid; t < MAXE; t += CC::NTHR)
+              const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
+              __syncthreads(); // the previous chunk has been consumed
+              // ---- 1-D matrices of the chunk's bricks: thread = (brick, axis, row a)
+              for (int w = tid; w < cnt * DIM * N1; w += CC::NTHR)
                 {
-                  const int e = ebase + t;
-                  int       cnt = 0, meta = 0;
-                  int64_t   first = 0;
-                  if (e == -1)
+                  const int     it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
+                  const int64_t brick = A.pit_brick[c0 + it];
+                  const int     meta  = A.pit_meta[c0 + it];
+                  const bool    on    = (meta & 3) == 1 ? (A.flags & PD_ASSEMBLE_VOLUME) != 0 :
+                                        ((meta & 8) ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
+                  if (d == 0 && a == 0)
+                    kind[it] = on ? (meta & 3) : 0;
+                  if (!on)
+                    continue;
+                  double       M[N1], K[N1];
+                  const double b_lo = bb[d], inv_h = 1. / (bb[DIM + d] - bb[d]);
+                  if ((meta & 3) == 1)
                     {
-                      if (A.flags & PD_ASSEMBLE_VOLUME)
-                        {
-                          first = A.cbk_ptr[p];
-                          cnt   = (int)(A.cbk_ptr[p + 1] - first);
-                          meta  = 1;
-                        }
+                      const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
+                      brick_rows_mass<C, DIM>(A, A.civ_box, iv[0], iv[1], A.quad.x, A.quad.w, A.nq, b_lo, inv_h, a, M, K);
                     }
-                  else if (e < n_adj)
+                  else
                     {
-                      const int64_t pe  = A.padj[k0 + e], f = pe >> 1;
-                      const bool    bnd = A.ifB[f] < 0;
-                      if (bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) : (A.flags & PD_ASSEMBLE_INTERIOR))
+                      const int lf = A.fbk_lf[brick], fd = lf >> 1, fs = lf & 1;
+                      if (d == fd)
                         {
-                          first = A.fbk_ptr[f];
-                          cnt   = (int)(A.fbk_ptr[f + 1] - first);
-                          meta  = 2 | ((int)(pe & 1) << 2) | ((int)bnd << 3);
-                        }
-                    }
-                  e_first[t] = first;
-                  e_meta[t]  = meta;
-                  e_pre[t + 1] = cnt;
-                }
-              __syncthreads();
-              if (tid == 0)
-                {
-                  e_pre[0] = 0;
-                  for (int t = 0; t < MAXE; ++t)
-                    e_pre[t + 1] += e_pre[t];
-                }
-              __syncthreads();
-              const int total = e_pre[MAXE];
-              for (int c0 = 0; c0 < total; c0 += CH)
-                {
-                  const int cnt = total - c0 < CH ? total - c0 : CH;
-                  __syncthreads(); // the previous chunk has been consumed
-                  // ---- 1-D matrices of the chunk's bricks: thread = (brick, axis, row a)
-                  for (int w = tid; w < cnt * DIM * N1; w += CC::NTHR)
-                    {
-                      const int it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
-                      int       e  = 0;
-                      while (e_pre[e + 1] <= c0 + it)
-                        ++e;
-                      const int64_t brick = e_first[e] + (c0 + it - e_pre[e]);
-                      const int     meta  = e_meta[e];
-                      double        M[N1], K[N1];
-                      const double  b_lo = bb[d], inv_h = 1. / (bb[DIM + d] - bb[d]);
-                      if ((meta & 3) == 1)
-                        {
-                          const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
-                          brick_rows_mass<C, DIM>(A, A.civ, iv[0], iv[1], d, A.quad.x, A.quad.w, A.nq, b_lo, inv_h, a, M, K);
+                          // own-side face term at the face coordinate: outward normal of THIS polytope
+                          const double nrm = (fs ? 1. : -1.) * ((meta & 4) ? -1. : 1.);
+                          const double cf  = (meta & 8) ? 1. : 0.5;
+                          double       L[N1], dL[N1];
+                          basis_1d<C>(A.basis, (A.fbk_plane[brick] - b_lo) * inv_h, inv_h, L, dL);
+                          const double la = pick<N1>(L, a), da = pick<N1>(dL, a), pen = A.fbk_sigma[brick];
+#pragma unroll
+                          for (int k = 0; k < N1; ++k)
+                            {
+                              M[k] = A.stiffness * (-cf * nrm * (da * L[k] + la * dL[k]) + pen * la * L[k]);
+                              K[k] = 0.;
+                            }
                         }
                       else
                         {
-                          const int64_t s  = A.fbk_s[brick];
-                          const int     lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
-                          if (d == fd)
-                            {
-                              double lo, hi;
-                              cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
-                              // own-side face term at the face coordinate: outward normal of THIS polytope
-                              const double nrm = (fs ? 1. : -1.) * ((meta & 4) ? -1. : 1.);
-                              const double cf  = (meta & 8) ? 1. : 0.5;
-                              double       L[N1], dL[N1];
-                              basis_1d<C>(A.basis, ((fs ? hi : lo) - b_lo) * inv_h, inv_h, L, dL);
-                              const double la = pick<N1>(L, a), da = pick<N1>(dL, a), pen = A.sub_sigma[s];
-#pragma unroll
-                              for (int k = 0; k < N1; ++k)
-                                {
-                                  M[k] = A.stiffness * (-cf * nrm * (da * L[k] + la * dL[k]) + pen * la * L[k]);
-                                  K[k] = 0.;
-                                }
-                            }
-                          else
-                            {
-                              const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
-                              brick_rows_mass<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, b_lo, inv_h, a, M, K);
-                            }
-                        }
-                      if (d == 0 && a == 0)
-                        kind[it] = meta & 3;
-                      double *dst = SL + it * ISTR + d * 2 * NXP + a * N1;
-#pragma unroll
-                      for (int k = 0; k < N1; ++k)
-                        {
-                          dst[k]       = M[k];
-                          dst[NXP + k] = K[k];
+                          const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
+                          brick_rows_mass<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, b_lo, inv_h, a, M, K);
                         }
                     }
-                  __syncthreads();
-                  if (active)
-                    accumulate_chunk<DIM, DEGX>(SL, kind, cnt, col, ig, A.stiffness, A.mass, acc);
+                  double *dst = SL + it * ISTR + d * 2 * NXP + a * N1;
+#pragma unroll
+                  for (int k = 0; k < N1; ++k)
+                    {
+                      dst[k]       = M[k];
+                      dst[NXP + k] = K[k];
+                    }
                 }
+              __syncthreads();
+              if (active)
+                accumulate_chunk<DIM, DEGX>(SL, kind, cnt, col, ig, A.stiffness, A.mass, acc);
             }
           // ---- epilogue: registers -> shared tile -> the diagonal block of the CSR rows
           __syncthreads();
@@ -548,17 +546,15 @@ namespace pd
               for (int w = tid; w < cnt * DIM * N1; w += CC::NTHR)
                 {
                   const int     it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
-                  const int64_t s  = A.fbk_s[c0 + it];
-                  const int     lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
+                  const int64_t brick = c0 + it;
+                  const int     lf = A.fbk_lf[brick], fd = lf >> 1, fs = lf & 1;
                   double        M[N1];
                   const double a_lo = ba[d], a_ih = 1. / (ba[DIM + d] - ba[d]);
                   const double b_lo = bbx[d], b_ih = 1. / (bbx[DIM + d] - bbx[d]);
                   if (d == fd)
                     {
                       // M12 = sum w [ 1/2 (dn phi0_i) phi1_j - 1/2 phi0_i (dn phi1_j) - pen phi0_i phi1_j ], n = A's normal
-                      double lo, hi;
-                      cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
-                      const double nrm = fs ? 1. : -1., x = fs ? hi : lo, pen = A.sub_sigma[s];
+                      const double nrm = fs ? 1. : -1., x = A.fbk_plane[brick], pen = A.fbk_sigma[brick];
                       double       LA[N1], dLA[N1], LB[N1], dLB[N1];
                       basis_1d<C>(A.basis, (x - a_lo) * a_ih, a_ih, LA, dLA);
                       basis_1d<C>(A.basis, (x - b_lo) * b_ih, b_ih, LB, dLB);
@@ -569,8 +565,8 @@ namespace pd
                     }
                   else
                     {
-                      const int32_t *iv = A.fbk_iv + (c0 + it) * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
-                      brick_rows_cross<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, a_lo, a_ih, b_lo, b_ih, a, M);
+                      const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
+                      brick_rows_cross<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, a_lo, a_ih, b_lo, b_ih, a, M);
                     }
                   if (d == 0 && a == 0)
                     kind[it] = 2;
@@ -644,9 +640,8 @@ namespace pd
       double *SM = smem;                  // [CH][MSTR]   1-D matrices, [d][slot][row a][a']
       double *W  = SM + CH * MSTR;        // [CH][WSTR]   z-pass output (two tensors)
       double *V  = W + CH * WSTR;         // [CH][WSTR]   y-pass output (two tensors)
-      constexpr int MAXE = 32;
-      __shared__ int     e_pre[MAXE + 1], e_meta[MAXE], e_poly[MAXE], it_kind[CH];
-      __shared__ int64_t e_first[MAXE], it_src[CH];
+      __shared__ int     it_kind[CH];
+      __shared__ int64_t it_src[CH];
       const int tid = threadIdx.x;
       const int j = tid / NL, l = tid % NL;
       const bool active = tid < CH * NL;
@@ -659,94 +654,47 @@ namespace pd
           for (int k = 0; k < N1; ++k)
             acc[k] = 0.;
           const double *bb = A.bbox + (int64_t)p * 2 * DIM;
-          const int64_t k0 = A.padj_ptr[p];
-          const int     n_adj = (int)(A.padj_ptr[p + 1] - k0);
-          // One item list per polytope: entry -1 = its cell bricks; entries 2 e / 2 e + 1 = the face bricks of
-          // adjacency entry e taken from its own side / from the neighbour's side (cross, interior only)
-          for (int ebase = -1; ebase < 2 * n_adj; ebase += MAXE)
+          // one item list per polytope: cell bricks, own-side face bricks, cross face bricks (x_Q of the neighbour)
+          const int64_t i0 = A.pit_ptr[p], i1 = A.pit_ptr[p + 1];
             {
-              __syncthreads();
-              for (int t = tid; t < MAXE; t += AC::NTHR)
+              for (int64_t c0 = i0; c0 < i1; c0 += CH)
                 {
-                  const int e = ebase + t;
-                  int       cnt = 0, meta = 0, q = p;
-                  int64_t   first = 0;
-                  if (e == -1)
-                    {
-                      if (A.flags & PD_ASSEMBLE_VOLUME)
-                        {
-                          first = A.cbk_ptr[p];
-                          cnt   = (int)(A.cbk_ptr[p + 1] - first);
-                          meta  = 1;
-                        }
-                    }
-                  else if (e >= 0 && e < 2 * n_adj)
-                    {
-                      const int64_t pe  = A.padj[k0 + (e >> 1)], f = pe >> 1;
-                      const bool    bnd = A.ifB[f] < 0;
-                      const int     knd = (e & 1) ? 3 : 2, side = (int)(pe & 1);
-                      if ((bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) : (A.flags & PD_ASSEMBLE_INTERIOR)) && !(knd == 3 && bnd))
-                        {
-                          first = A.fbk_ptr[f];
-                          cnt   = (int)(A.fbk_ptr[f + 1] - first);
-                          meta  = knd | (side << 2) | ((int)bnd << 3);
-                          if (knd == 3)
-                            q = side ? A.ifA[f] : A.ifB[f];
-                        }
-                    }
-                  e_first[t]   = first;
-                  e_meta[t]    = meta;
-                  e_poly[t]    = q;
-                  e_pre[t + 1] = cnt;
-                }
-              __syncthreads();
-              if (tid == 0)
-                {
-                  e_pre[0] = 0;
-                  for (int t = 0; t < MAXE; ++t)
-                    e_pre[t + 1] += e_pre[t];
-                }
-              __syncthreads();
-              const int total = e_pre[MAXE];
-              for (int c0 = 0; c0 < total; c0 += CH)
-                {
-                  const int cnt = total - c0 < CH ? total - c0 : CH;
+                  const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
                   __syncthreads();
                   // ---- 1-D matrices: thread = (brick, axis, row)
                   for (int w = tid; w < cnt * DIM * N1; w += AC::NTHR)
                     {
-                      const int it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
-                      int       e  = 0;
-                      while (e_pre[e + 1] <= c0 + it)
-                        ++e;
-                      const int64_t brick = e_first[e] + (c0 + it - e_pre[e]);
-                      const int     meta = e_meta[e], knd = meta & 3, side = (meta >> 2) & 1;
+                      const int     it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
+                      const int64_t brick = A.pit_brick[c0 + it];
+                      const int     meta = A.pit_meta[c0 + it], knd = meta & 3, side = (meta >> 2) & 1;
                       const bool    bnd  = (meta & 8) != 0;
-                      const double *ob   = A.bbox + (int64_t)e_poly[e] * 2 * DIM; // bounding box of the column basis
+                      const int32_t q    = A.pit_q[c0 + it];
+                      const bool    enabled = knd == 1 ? (A.flags & PD_ASSEMBLE_VOLUME) != 0 :
+                                              (bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
+                      const double *ob   = A.bbox + (int64_t)q * 2 * DIM; // bounding box of the column basis
                       if (d == 0 && a == 0)
                         {
-                          it_kind[it] = knd;
-                          it_src[it]  = (int64_t)A.dof_block[e_poly[e]] * NF;
+                          it_kind[it] = enabled ? knd : 0;
+                          it_src[it]  = (int64_t)A.dof_block[q] * NF;
                         }
+                      if (!enabled)
+                        continue;
                       double       M[N1], K[N1];
                       const double r_lo = bb[d], r_ih = 1. / (bb[DIM + d] - bb[d]);
                       const double c_lo = ob[d], c_ih = 1. / (ob[DIM + d] - ob[d]);
                       if (knd == 1)
                         {
                           const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
-                          brick_rows_mass<C, DIM>(A, A.civ, iv[0], iv[1], d, A.quad.x, A.quad.w, A.nq, r_lo, r_ih, a, M, K);
+                          brick_rows_mass<C, DIM>(A, A.civ_box, iv[0], iv[1], A.quad.x, A.quad.w, A.nq, r_lo, r_ih, a, M, K);
                         }
                       else
                         {
-                          const int64_t  s  = A.fbk_s[brick];
-                          const int      lf = A.sub_face[s], fd = lf >> 1, fs = lf & 1;
+                          const int      lf = A.fbk_lf[brick], fd = lf >> 1, fs = lf & 1;
                           const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
                           if (d == fd)
                             {
-                              double lo, hi;
-                              cell_box<DIM>(A, A.sub_cell[s], d, lo, hi);
                               const double nrm = (fs ? 1. : -1.) * (side ? -1. : 1.); // outward normal of THIS polytope
-                              const double x = fs ? hi : lo, pen = A.sub_sigma[s];
+                              const double x = A.fbk_plane[brick], pen = A.fbk_sigma[brick];
                               double       LR[N1], dLR[N1], LC[N1], dLC[N1];
                               basis_1d<C>(A.basis, (x - r_lo) * r_ih, r_ih, LR, dLR);
                               basis_1d<C>(A.basis, (x - c_lo) * c_ih, c_ih, LC, dLC);
@@ -761,11 +709,11 @@ namespace pd
                                 }
                             }
                           else if (knd == 2)
-                            brick_rows_mass<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, a, M, K);
+                            brick_rows_mass<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, a, M, K);
                           else
                             {
-                              brick_rows_cross<C, DIM>(A, A.fiv, iv[0], iv[1], d, A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, c_lo, c_ih,
-                                                       a, M);
+                              brick_rows_cross<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, c_lo, c_ih, a,
+                                                       M);
 #pragma unroll
                               for (int k = 0; k < N1; ++k)
                                 K[k] = 0.;
@@ -780,8 +728,8 @@ namespace pd
                         }
                     }
                   __syncthreads();
-                  const bool    on  = active && j < cnt;
-                  const int     knd = on ? it_kind[j] : 0;
+                  const int     knd = (active && j < cnt) ? it_kind[j] : 0;
+                  const bool    on  = knd != 0;
                   const int64_t src_base = on ? it_src[j] : 0;
                   const double *m = SM + j * MSTR;
                   double       *w1 = W + j * WSTR, *w2 = w1 + NF, *v1 = V + j * WSTR, *v2 = v1 + NF;
@@ -1190,7 +1138,54 @@ namespace pd
               }
             fbk_ptr.push_back((int64_t)fbk_s.size());
           }
+        // item lists: per owned polytope its cell bricks, the own-side face bricks of its adjacency (interfaces in
+        // list order, A side then B side as in pd_create's adjacency), then the cross face bricks
+        std::vector<std::vector<int64_t>> adj(np_own);
+        for (int32_t f = 0; f < d.n_ifaces; ++f)
+          {
+            adj[d.iface_polyA[f]].push_back((int64_t)f * 2);
+            if (d.iface_polyB[f] >= 0 && d.iface_polyB[f] < np_own)
+              adj[d.iface_polyB[f]].push_back((int64_t)f * 2 + 1);
+          }
+        pit_ptr.assign(1, 0);
+        pit_diag_end.clear();
+        for (int32_t p = 0; p < np_own; ++p)
+          {
+            for (int64_t b = cbk_ptr[p]; b < cbk_ptr[p + 1]; ++b)
+              {
+                pit_brick.push_back((int32_t)b);
+                pit_meta.push_back(1);
+                pit_q.push_back(p);
+              }
+            for (const int64_t e : adj[p])
+              {
+                const int64_t f   = e >> 1;
+                const int     bnd = d.iface_polyB[f] < 0;
+                for (int64_t b = fbk_ptr[f]; b < fbk_ptr[f + 1]; ++b)
+                  {
+                    pit_brick.push_back((int32_t)b);
+                    pit_meta.push_back(2 | ((int)(e & 1) << 2) | (bnd << 3));
+                    pit_q.push_back(p);
+                  }
+              }
+            pit_diag_end.push_back((int64_t)pit_brick.size());
+            for (const int64_t e : adj[p])
+              {
+                const int64_t f = e >> 1;
+                if (d.iface_polyB[f] < 0)
+                  continue;
+                for (int64_t b = fbk_ptr[f]; b < fbk_ptr[f + 1]; ++b)
+                  {
+                    pit_brick.push_back((int32_t)b);
+                    pit_meta.push_back(3 | ((int)(e & 1) << 2));
+                    pit_q.push_back((e & 1) ? d.iface_polyA[f] : d.iface_polyB[f]);
+                  }
+              }
+            pit_ptr.push_back((int64_t)pit_brick.size());
+          }
       }
+      std::vector<int64_t> pit_ptr, pit_diag_end;
+      std::vector<int32_t> pit_brick, pit_meta, pit_q;
     };
   } // namespace
 
@@ -1215,6 +1210,16 @@ namespace pd
     put(h->fbk_iv, B.fbk_iv);
     put(h->fiv, B.fiv);
     put(h->fpos, B.fpos);
+    put(h->pit_ptr, B.pit_ptr);
+    put(h->pit_diag_end, B.pit_diag_end);
+    put(h->pit_brick, B.pit_brick);
+    put(h->pit_meta, B.pit_meta);
+    put(h->pit_q, B.pit_q);
+    h->civ_box.alloc(std::max<size_t>(B.civ.size(), 1));
+    h->fiv_box.alloc(std::max<size_t>(B.fiv.size(), 1));
+    h->fbk_plane.alloc(std::max<size_t>(B.fbk_s.size(), 1));
+    h->fbk_sigma.alloc(std::max<size_t>(B.fbk_s.size(), 1));
+    h->fbk_lf.alloc(std::max<size_t>(B.fbk_s.size(), 1));
     h->n_cell_bricks = (int64_t)B.cbk_iv.size() / (2 * h->dim);
     h->n_face_bricks = (int64_t)B.fbk_s.size();
     h->bricks_ready  = true;
@@ -1261,8 +1266,18 @@ namespace pd
                                 std::memcmp(h->h_sub_face.data(), d.sub_face, sizeof(int32_t) * (size_t)h->n_subfaces) != 0))))
       h->bricks_ready = false;
     h->cartesian = check_axis_aligned(h, &stale);
-    if (h->cartesian && (!h->bricks_ready || stale))
+    if (!h->cartesian)
+      return;
+    if (!h->bricks_ready || stale)
       build_cartesian_bricks(h, d);
+    // the coordinates the kernels read, from the representatives' current vertices
+    const int64_t work = std::max<int64_t>(h->n_cell_bricks * h->dim, h->n_face_bricks);
+    const int     grid = (int)std::min<int64_t>((work + 255) / 256, (int64_t)h->sm_count * 8);
+    k_refresh_bricks<<<std::max(grid, 1), 256, 0, h->stream>>>(
+      h->verts.p, h->cell_verts.p, h->dim, h->n_cell_bricks, h->cbk_iv.p, h->civ.p, h->civ_box.p, h->n_face_bricks, h->fbk_s.p,
+      h->fbk_iv.p, h->fiv.p, h->fiv_box.p, h->sub_cell.p, h->sub_face.p, h->sub_sigma.p, h->fbk_plane.p, h->fbk_sigma.p,
+      h->fbk_lf.p);
+    PD_CUDA(cudaGetLastError());
   }
 
   bool
@@ -1375,6 +1390,16 @@ namespace pd
     a.fbk_s       = h->fbk_s.p;
     a.fbk_iv      = h->fbk_iv.p;
     a.fiv         = h->fiv.p;
+    a.civ_box      = h->civ_box.p;
+    a.fiv_box      = h->fiv_box.p;
+    a.fbk_plane    = h->fbk_plane.p;
+    a.fbk_sigma    = h->fbk_sigma.p;
+    a.fbk_lf       = h->fbk_lf.p;
+    a.pit_ptr      = h->pit_ptr.p;
+    a.pit_diag_end = h->pit_diag_end.p;
+    a.pit_brick    = h->pit_brick.p;
+    a.pit_meta     = h->pit_meta.p;
+    a.pit_q        = h->pit_q.p;
     {
       // (a, b, c) of DoF i: FE_DGQ lexicographic; FE_AggloDGP in PolynomialSpace order (last coordinate outermost,
       // first fastest, total degree <= p: source/fe_agglodgp.cc:28-57)

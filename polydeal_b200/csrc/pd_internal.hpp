@@ -168,7 +168,10 @@ struct pd_handle
   pd::DevBuf<int>      cart_flag;
   // bricks of the tensor path (pd_cartesian.cu: build_cartesian_bricks)
   pd::DevBuf<int64_t>  cbk_ptr, fbk_ptr;
-  pd::DevBuf<int32_t>  cbk_iv, civ, cpos, fbk_s, fbk_iv, fiv, fpos;
+  pd::DevBuf<int32_t>  cbk_iv, civ, cpos, fbk_s, fbk_iv, fiv, fpos, fbk_lf, pit_brick, pit_meta, pit_q;
+  pd::DevBuf<int64_t>  pit_ptr, pit_diag_end;
+  pd::DevBuf<double2>  civ_box, fiv_box;
+  pd::DevBuf<double>   fbk_plane, fbk_sigma;
   int64_t              n_cell_bricks = 0, n_face_bricks = 0;
   bool                 bricks_ready = false;
   std::vector<int32_t> h_subcell_idx, h_sub_cell, h_sub_face;
