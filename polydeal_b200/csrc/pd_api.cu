@@ -1042,7 +1042,8 @@ extern "C"
     return guarded([&] {
       if (!h)
         throw Error(PD_ERR_INVALID, "null handle");
-      h->quad_valid = false;
+      h->quad_valid      = false;
+      h->brick_mat_valid = false; // the tensor path's analogue: cached brick geometry and 1-D matrices
     });
   }
 

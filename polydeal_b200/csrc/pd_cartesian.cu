@@ -87,6 +87,12 @@ namespace pd
       // block), [pit_diag_end[p], pit_ptr[p + 1]) the cross face bricks (matrix-free apply only)
       const int64_t *pit_ptr, *pit_diag_end;
       const int32_t *pit_brick, *pit_meta, *pit_q; // meta = kind (1 cell, 2 own face, 3 cross face) | side << 2 | boundary << 3
+      // the 1-D matrices of every brick (k_brick_matrices, once per geometry): what the hot kernels load
+      const int32_t *cbk_poly, *fbk_iface; // polytope of a cell brick, interface of a face brick
+      double        *cmat;                 // [n_cbk][dim][2][NXP]: mass-like and stiffness-like sums on the polytope's box
+      double        *fmat;                 // [n_fbk][3][dim][NXP]: own side A | own side B | cross (rows A, columns B); the
+                                           // normal axis holds the face factor WITHOUT the stiffness coefficient
+      int64_t        n_cbk, n_fbk;
     };
 
     // cells of the mesh that are NOT axis-aligned boxes in standard orientation (vertex v at lo + bit_k(v) (hi - lo))
@@ -417,6 +423,72 @@ namespace pd
         }
     }
 
+    // The 1-D matrices of all bricks, one thread per (brick, [which,] axis, row): they depend on the geometry, the
+    // element and the penalties only, so they are computed once per geometry (pd_create, pd_upload,
+    // pd_invalidate_quadrature) and shared by the assembly and every matrix-free apply.
+    template <int DIM, int DEGX>
+    __global__ void __launch_bounds__(128)
+    k_brick_matrices(const CartArgs A)
+    {
+      using C           = Cfg<DIM, DEGX>;
+      using CC          = CartCfg<DIM, DEGX>;
+      constexpr int N1  = CC::N1, NXP = CC::NXP;
+      const int64_t nc  = A.n_cbk * DIM * N1, nf = A.n_fbk * 3 * DIM * N1;
+      const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+      for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nc + nf; w += stride)
+        {
+          double M[N1], K[N1];
+          if (w < nc)
+            {
+              const int64_t brick = w / (DIM * N1);
+              const int     d = (int)((w / N1) % DIM), a = (int)(w % N1);
+              const double *bb = A.bbox + (int64_t)A.cbk_poly[brick] * 2 * DIM;
+              const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
+              brick_rows_mass<C, DIM>(A, A.civ_box, iv[0], iv[1], A.quad.x, A.quad.w, A.nq, bb[d], 1. / (bb[DIM + d] - bb[d]), a, M, K);
+              double *dst = A.cmat + (brick * DIM + d) * 2 * NXP + a * N1;
+#pragma unroll
+              for (int k = 0; k < N1; ++k)
+                {
+                  dst[k]       = M[k];
+                  dst[NXP + k] = K[k];
+                }
+              continue;
+            }
+          const int64_t v     = w - nc;
+          const int64_t brick = v / (3 * DIM * N1);
+          const int     which = (int)((v / (DIM * N1)) % 3), d = (int)((v / N1) % DIM), a = (int)(v % N1);
+          const int32_t f = A.fbk_iface[brick], pa = A.ifA[f], pb = A.ifB[f];
+          if (pb < 0 && which != 0)
+            continue; // a boundary face has one side
+          const int     lf = A.fbk_lf[brick], fd = lf >> 1, fs = lf & 1;
+          const double *ba = A.bbox + (int64_t)pa * 2 * DIM, *bbx = A.bbox + (int64_t)(pb < 0 ? pa : pb) * 2 * DIM;
+          const double *rb = which == 1 ? bbx : ba, *cb = which == 0 ? ba : bbx; // row / column basis
+          const double  r_lo = rb[d], r_ih = 1. / (rb[DIM + d] - rb[d]), c_lo = cb[d], c_ih = 1. / (cb[DIM + d] - cb[d]);
+          if (d == fd)
+            {
+              const double x = A.fbk_plane[brick], pen = A.fbk_sigma[brick], nA = fs ? 1. : -1.;
+              double       LR[N1], dLR[N1], LC[N1], dLC[N1];
+              basis_1d<C>(A.basis, (x - r_lo) * r_ih, r_ih, LR, dLR);
+              basis_1d<C>(A.basis, (x - c_lo) * c_ih, c_ih, LC, dLC);
+              const double la = pick<N1>(LR, a), da = pick<N1>(dLR, a);
+              const double cf = pb < 0 ? 1. : 0.5, nrm = which == 1 ? -nA : nA; // outward normal of the row polytope
+#pragma unroll
+              for (int k = 0; k < N1; ++k)
+                M[k] = which == 2 ? 0.5 * nA * (da * LC[k] - la * dLC[k]) - pen * la * LC[k] : // M12 (poly_utils.h:1900-1906)
+                                    -cf * nrm * (da * LC[k] + la * dLC[k]) + pen * la * LC[k];  // M11 / M22 / boundary
+            }
+          else
+            {
+              const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
+              brick_rows_cross<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, c_lo, c_ih, a, M);
+            }
+          double *dst = A.fmat + ((brick * 3 + which) * DIM + d) * NXP + a * N1;
+#pragma unroll
+          for (int k = 0; k < N1; ++k)
+            dst[k] = M[k];
+        }
+    }
+
     template <int DIM, int DEGX>
     __global__ void __launch_bounds__(CartCfg<DIM, DEGX>::NTHR, CartCfg<DIM, DEGX>::MINB)
     k_cart_diag(const CartArgs A)
@@ -444,56 +516,22 @@ namespace pd
             {
               const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
               __syncthreads(); // the previous chunk has been consumed
-              // ---- 1-D matrices of the chunk's bricks: thread = (brick, axis, row a)
-              for (int w = tid; w < cnt * DIM * N1; w += CC::NTHR)
+              // ---- the 1-D matrices of the chunk's bricks, from k_brick_matrices (face factor x stiffness coefficient)
+              for (int w = tid; w < cnt * ISTR; w += CC::NTHR)
                 {
-                  const int     it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
+                  const int     it = w / ISTR, r = w % ISTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
                   const int64_t brick = A.pit_brick[c0 + it];
                   const int     meta  = A.pit_meta[c0 + it];
                   const bool    on    = (meta & 3) == 1 ? (A.flags & PD_ASSEMBLE_VOLUME) != 0 :
                                         ((meta & 8) ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
-                  if (d == 0 && a == 0)
+                  if (r == 0)
                     kind[it] = on ? (meta & 3) : 0;
-                  if (!on)
-                    continue;
-                  double       M[N1], K[N1];
-                  const double b_lo = bb[d], inv_h = 1. / (bb[DIM + d] - bb[d]);
-                  if ((meta & 3) == 1)
-                    {
-                      const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
-                      brick_rows_mass<C, DIM>(A, A.civ_box, iv[0], iv[1], A.quad.x, A.quad.w, A.nq, b_lo, inv_h, a, M, K);
-                    }
-                  else
-                    {
-                      const int lf = A.fbk_lf[brick], fd = lf >> 1, fs = lf & 1;
-                      if (d == fd)
-                        {
-                          // own-side face term at the face coordinate: outward normal of THIS polytope
-                          const double nrm = (fs ? 1. : -1.) * ((meta & 4) ? -1. : 1.);
-                          const double cf  = (meta & 8) ? 1. : 0.5;
-                          double       L[N1], dL[N1];
-                          basis_1d<C>(A.basis, (A.fbk_plane[brick] - b_lo) * inv_h, inv_h, L, dL);
-                          const double la = pick<N1>(L, a), da = pick<N1>(dL, a), pen = A.fbk_sigma[brick];
-#pragma unroll
-                          for (int k = 0; k < N1; ++k)
-                            {
-                              M[k] = A.stiffness * (-cf * nrm * (da * L[k] + la * dL[k]) + pen * la * L[k]);
-                              K[k] = 0.;
-                            }
-                        }
-                      else
-                        {
-                          const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
-                          brick_rows_mass<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, b_lo, inv_h, a, M, K);
-                        }
-                    }
-                  double *dst = SL + it * ISTR + d * 2 * NXP + a * N1;
-#pragma unroll
-                  for (int k = 0; k < N1; ++k)
-                    {
-                      dst[k]       = M[k];
-                      dst[NXP + k] = K[k];
-                    }
+                  double v = 0.;
+                  if (on && (meta & 3) == 1)
+                    v = A.cmat[(brick * DIM + d) * 2 * NXP + slot * NXP + k];
+                  else if (on && slot == 0)
+                    v = A.fmat[((brick * 3 + ((meta >> 2) & 1)) * DIM + d) * NXP + k] * (d == (A.fbk_lf[brick] >> 1) ? A.stiffness : 1.);
+                  SL[w] = v;
                 }
               __syncthreads();
               if (active)
@@ -537,43 +575,18 @@ namespace pd
 #pragma unroll
           for (int r = 0; r < NX; ++r)
             acc[r] = 0.;
-          const double *ba = A.bbox + (int64_t)pa * 2 * DIM, *bbx = A.bbox + (int64_t)pb * 2 * DIM;
           const int64_t i0 = A.fbk_ptr[f], i1 = A.fbk_ptr[f + 1];
           for (int64_t c0 = i0; c0 < i1; c0 += CH)
             {
               const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
               __syncthreads();
-              for (int w = tid; w < cnt * DIM * N1; w += CC::NTHR)
+              for (int w = tid; w < cnt * ISTR; w += CC::NTHR)
                 {
-                  const int     it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
+                  const int     it = w / ISTR, r = w % ISTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
                   const int64_t brick = c0 + it;
-                  const int     lf = A.fbk_lf[brick], fd = lf >> 1, fs = lf & 1;
-                  double        M[N1];
-                  const double a_lo = ba[d], a_ih = 1. / (ba[DIM + d] - ba[d]);
-                  const double b_lo = bbx[d], b_ih = 1. / (bbx[DIM + d] - bbx[d]);
-                  if (d == fd)
-                    {
-                      // M12 = sum w [ 1/2 (dn phi0_i) phi1_j - 1/2 phi0_i (dn phi1_j) - pen phi0_i phi1_j ], n = A's normal
-                      const double nrm = fs ? 1. : -1., x = A.fbk_plane[brick], pen = A.fbk_sigma[brick];
-                      double       LA[N1], dLA[N1], LB[N1], dLB[N1];
-                      basis_1d<C>(A.basis, (x - a_lo) * a_ih, a_ih, LA, dLA);
-                      basis_1d<C>(A.basis, (x - b_lo) * b_ih, b_ih, LB, dLB);
-                      const double la = pick<N1>(LA, a), da = pick<N1>(dLA, a);
-#pragma unroll
-                      for (int k = 0; k < N1; ++k)
-                        M[k] = A.stiffness * (0.5 * nrm * (da * LB[k] - la * dLB[k]) - pen * la * LB[k]);
-                    }
-                  else
-                    {
-                      const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
-                      brick_rows_cross<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, a_lo, a_ih, b_lo, b_ih, a, M);
-                    }
-                  if (d == 0 && a == 0)
+                  if (r == 0)
                     kind[it] = 2;
-                  double *dst = SL + it * ISTR + d * 2 * NXP + a * N1;
-#pragma unroll
-                  for (int k = 0; k < N1; ++k)
-                    dst[k] = M[k];
+                  SL[w] = slot ? 0. : A.fmat[((brick * 3 + 2) * DIM + d) * NXP + k] * (d == (A.fbk_lf[brick] >> 1) ? A.stiffness : 1.);
                 }
               __syncthreads();
               if (active)
@@ -661,71 +674,30 @@ namespace pd
                 {
                   const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
                   __syncthreads();
-                  // ---- 1-D matrices: thread = (brick, axis, row)
-                  for (int w = tid; w < cnt * DIM * N1; w += AC::NTHR)
+                  // ---- the 1-D matrices of the chunk's bricks (k_brick_matrices); seen from side B a cross matrix is
+                  // the transpose of the stored one
+                  for (int w = tid; w < cnt * MSTR; w += AC::NTHR)
                     {
-                      const int     it = w / (DIM * N1), d = (w / N1) % DIM, a = w % N1;
+                      const int     it = w / MSTR, r = w % MSTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
                       const int64_t brick = A.pit_brick[c0 + it];
                       const int     meta = A.pit_meta[c0 + it], knd = meta & 3, side = (meta >> 2) & 1;
-                      const bool    bnd  = (meta & 8) != 0;
-                      const int32_t q    = A.pit_q[c0 + it];
                       const bool    enabled = knd == 1 ? (A.flags & PD_ASSEMBLE_VOLUME) != 0 :
-                                              (bnd ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
-                      const double *ob   = A.bbox + (int64_t)q * 2 * DIM; // bounding box of the column basis
-                      if (d == 0 && a == 0)
+                                              ((meta & 8) ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
+                      if (r == 0)
                         {
                           it_kind[it] = enabled ? knd : 0;
-                          it_src[it]  = (int64_t)A.dof_block[q] * NF;
+                          it_src[it]  = (int64_t)A.dof_block[A.pit_q[c0 + it]] * NF;
                         }
-                      if (!enabled)
-                        continue;
-                      double       M[N1], K[N1];
-                      const double r_lo = bb[d], r_ih = 1. / (bb[DIM + d] - bb[d]);
-                      const double c_lo = ob[d], c_ih = 1. / (ob[DIM + d] - ob[d]);
-                      if (knd == 1)
+                      double v = 0.;
+                      if (enabled && knd == 1)
+                        v = A.cmat[(brick * DIM + d) * 2 * NXP + slot * NXP + k];
+                      else if (enabled && slot == 0 && k < N1 * N1)
                         {
-                          const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
-                          brick_rows_mass<C, DIM>(A, A.civ_box, iv[0], iv[1], A.quad.x, A.quad.w, A.nq, r_lo, r_ih, a, M, K);
+                          const int kk = (knd == 3 && side) ? (k % N1) * N1 + k / N1 : k;
+                          v = A.fmat[((brick * 3 + (knd == 3 ? 2 : side)) * DIM + d) * NXP + kk] *
+                              (d == (A.fbk_lf[brick] >> 1) ? sigma : 1.);
                         }
-                      else
-                        {
-                          const int      lf = A.fbk_lf[brick], fd = lf >> 1, fs = lf & 1;
-                          const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
-                          if (d == fd)
-                            {
-                              const double nrm = (fs ? 1. : -1.) * (side ? -1. : 1.); // outward normal of THIS polytope
-                              const double x = A.fbk_plane[brick], pen = A.fbk_sigma[brick];
-                              double       LR[N1], dLR[N1], LC[N1], dLC[N1];
-                              basis_1d<C>(A.basis, (x - r_lo) * r_ih, r_ih, LR, dLR);
-                              basis_1d<C>(A.basis, (x - c_lo) * c_ih, c_ih, LC, dLC);
-                              const double la = pick<N1>(LR, a), da = pick<N1>(dLR, a);
-                              const double cf = bnd ? 1. : 0.5;
-#pragma unroll
-                              for (int k = 0; k < N1; ++k)
-                                {
-                                  M[k] = knd == 2 ? sigma * (-cf * nrm * (da * LC[k] + la * dLC[k]) + pen * la * LC[k]) :
-                                                    sigma * (0.5 * nrm * (da * LC[k] - la * dLC[k]) - pen * la * LC[k]);
-                                  K[k] = 0.;
-                                }
-                            }
-                          else if (knd == 2)
-                            brick_rows_mass<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, a, M, K);
-                          else
-                            {
-                              brick_rows_cross<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, c_lo, c_ih, a,
-                                                       M);
-#pragma unroll
-                              for (int k = 0; k < N1; ++k)
-                                K[k] = 0.;
-                            }
-                        }
-                      double *dst = SM + it * MSTR + d * 2 * NXP + a * N1;
-#pragma unroll
-                      for (int k = 0; k < N1; ++k)
-                        {
-                          dst[k]       = M[k];
-                          dst[NXP + k] = K[k];
-                        }
+                      SM[w] = v;
                     }
                   __syncthreads();
                   const int     knd = (active && j < cnt) ? it_kind[j] : 0;
@@ -877,10 +849,21 @@ namespace pd
 
     template <int DIM, int DEGX>
     void
+    run_brick_matrices(pd_handle *h, const CartArgs &a)
+    {
+      using CC           = CartCfg<DIM, DEGX>;
+      const int64_t work = (a.n_cbk + 3 * a.n_fbk) * DIM * CC::N1;
+      const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 127) / 128, (int64_t)h->sm_count * 32));
+      k_brick_matrices<DIM, DEGX><<<grid, 128, 0, h->stream>>>(a);
+      ++h->launches;
+      PD_CUDA(cudaGetLastError());
+    }
+
+    template <int DIM, int DEGX>
+    void
     run_cart(pd_handle *h, const CartArgs &a)
     {
       using CC = CartCfg<DIM, DEGX>;
-      PD_CUDA(cudaEventRecord(h->ev[0], h->stream));
       {
         const int grid = (int)std::min<int64_t>(h->np_own, (int64_t)h->sm_count * 16);
         k_cart_diag<DIM, DEGX><<<grid, CC::NTHR, 0, h->stream>>>(a);
@@ -1147,6 +1130,14 @@ namespace pd
             if (d.iface_polyB[f] >= 0 && d.iface_polyB[f] < np_own)
               adj[d.iface_polyB[f]].push_back((int64_t)f * 2 + 1);
           }
+        cbk_poly.resize((size_t)cbk_ptr[np_own]);
+        for (int32_t p = 0; p < np_own; ++p)
+          for (int64_t b = cbk_ptr[p]; b < cbk_ptr[p + 1]; ++b)
+            cbk_poly[(size_t)b] = p;
+        fbk_iface.resize(fbk_s.size());
+        for (int32_t f = 0; f < d.n_ifaces; ++f)
+          for (int64_t b = fbk_ptr[f]; b < fbk_ptr[f + 1]; ++b)
+            fbk_iface[(size_t)b] = f;
         pit_ptr.assign(1, 0);
         pit_diag_end.clear();
         for (int32_t p = 0; p < np_own; ++p)
@@ -1185,7 +1176,7 @@ namespace pd
           }
       }
       std::vector<int64_t> pit_ptr, pit_diag_end;
-      std::vector<int32_t> pit_brick, pit_meta, pit_q;
+      std::vector<int32_t> pit_brick, pit_meta, pit_q, cbk_poly, fbk_iface;
     };
   } // namespace
 
@@ -1215,6 +1206,16 @@ namespace pd
     put(h->pit_brick, B.pit_brick);
     put(h->pit_meta, B.pit_meta);
     put(h->pit_q, B.pit_q);
+    put(h->cbk_poly, B.cbk_poly);
+    put(h->fbk_iface, B.fbk_iface);
+    {
+      const int    nxp = h->n1 * h->n1 + ((h->n1 * h->n1) & 1);
+      const size_t nc = std::max<size_t>(B.cbk_poly.size() * h->dim * 2 * nxp, 1), nf = std::max<size_t>(B.fbk_s.size() * 3 * h->dim * nxp, 1);
+      h->cmat.alloc(nc);
+      h->fmat.alloc(nf);
+      PD_CUDA(cudaMemset(h->cmat.p, 0, nc * sizeof(double)));
+      PD_CUDA(cudaMemset(h->fmat.p, 0, nf * sizeof(double)));
+    }
     h->civ_box.alloc(std::max<size_t>(B.civ.size(), 1));
     h->fiv_box.alloc(std::max<size_t>(B.fiv.size(), 1));
     h->fbk_plane.alloc(std::max<size_t>(B.fbk_s.size(), 1));
@@ -1270,14 +1271,7 @@ namespace pd
       return;
     if (!h->bricks_ready || stale)
       build_cartesian_bricks(h, d);
-    // the coordinates the kernels read, from the representatives' current vertices
-    const int64_t work = std::max<int64_t>(h->n_cell_bricks * h->dim, h->n_face_bricks);
-    const int     grid = (int)std::min<int64_t>((work + 255) / 256, (int64_t)h->sm_count * 8);
-    k_refresh_bricks<<<std::max(grid, 1), 256, 0, h->stream>>>(
-      h->verts.p, h->cell_verts.p, h->dim, h->n_cell_bricks, h->cbk_iv.p, h->civ.p, h->civ_box.p, h->n_face_bricks, h->fbk_s.p,
-      h->fbk_iv.p, h->fiv.p, h->fiv_box.p, h->sub_cell.p, h->sub_face.p, h->sub_sigma.p, h->fbk_plane.p, h->fbk_sigma.p,
-      h->fbk_lf.p);
-    PD_CUDA(cudaGetLastError());
+    h->brick_mat_valid = false; // coordinates / penalties may have changed: the 1-D matrices are rebuilt on next use
   }
 
   bool
@@ -1291,6 +1285,46 @@ namespace pd
 
   static void
   fill_cart_args(pd_handle *h, const uint32_t flags, const pd_coefficients &coef, CartArgs &a);
+
+#define PD_CART_DISPATCH(FN, h, ...)                                                                     \
+  switch ((h)->fe_kind * 100 + (h)->dim * 10 + (h)->degree)                                                \
+    {                                                                                                      \
+      case 121: FN<2, DGP_BASE + 1>(__VA_ARGS__); break;                                                   \
+      case 122: FN<2, DGP_BASE + 2>(__VA_ARGS__); break;                                                   \
+      case 123: FN<2, DGP_BASE + 3>(__VA_ARGS__); break;                                                   \
+      case 124: FN<2, DGP_BASE + 4>(__VA_ARGS__); break;                                                   \
+      case 131: FN<3, DGP_BASE + 1>(__VA_ARGS__); break;                                                   \
+      case 132: FN<3, DGP_BASE + 2>(__VA_ARGS__); break;                                                   \
+      case 133: FN<3, DGP_BASE + 3>(__VA_ARGS__); break;                                                   \
+      case 21: FN<2, 1>(__VA_ARGS__); break;                                                               \
+      case 22: FN<2, 2>(__VA_ARGS__); break;                                                               \
+      case 23: FN<2, 3>(__VA_ARGS__); break;                                                               \
+      case 24: FN<2, 4>(__VA_ARGS__); break;                                                               \
+      case 31: FN<3, 1>(__VA_ARGS__); break;                                                               \
+      case 32: FN<3, 2>(__VA_ARGS__); break;                                                               \
+      case 33: FN<3, 3>(__VA_ARGS__); break;                                                               \
+      default:                                                                                             \
+        throw CudaError{cudaErrorNotSupported, "no tensor kernel for this (dim, degree)", __LINE__};       \
+    }
+
+  // the cached geometry of the bricks and their 1-D matrices, rebuilt after every change of the geometry
+  // (pd_create, pd_upload, pd_invalidate_quadrature: a benchmark step that starts from the flattened mesh pays for it)
+  static void
+  ensure_brick_matrices(pd_handle *h, const CartArgs &a)
+  {
+    if (h->brick_mat_valid)
+      return;
+    const int64_t work = std::max<int64_t>(h->n_cell_bricks * h->dim, h->n_face_bricks);
+    const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)h->sm_count * 8));
+    k_refresh_bricks<<<grid, 256, 0, h->stream>>>(h->verts.p, h->cell_verts.p, h->dim, h->n_cell_bricks, h->cbk_iv.p, h->civ.p,
+                                                   h->civ_box.p, h->n_face_bricks, h->fbk_s.p, h->fbk_iv.p, h->fiv.p, h->fiv_box.p,
+                                                   h->sub_cell.p, h->sub_face.p, h->sub_sigma.p, h->fbk_plane.p, h->fbk_sigma.p,
+                                                   h->fbk_lf.p);
+    ++h->launches;
+    PD_CUDA(cudaGetLastError());
+    PD_CART_DISPATCH(run_brick_matrices, h, h, a);
+    h->brick_mat_valid = true;
+  }
 
   // matrix-free apply of the operator pd_set_operator describes on agglomerates of axis-aligned cells
   bool
@@ -1307,6 +1341,7 @@ namespace pd
   {
     CartApplyArgs a{};
     fill_cart_args(h, h->op_flags, h->op_coef, a.g);
+    ensure_brick_matrices(h, a.g);
     a.src = src;
     a.dst = dst;
     a.add = add ? 1 : 0;
@@ -1329,26 +1364,9 @@ namespace pd
   {
     CartArgs a{};
     fill_cart_args(h, flags, coef, a);
-    const int key = h->fe_kind * 100 + h->dim * 10 + h->degree;
-    switch (key)
-      {
-        case 121: run_cart<2, DGP_BASE + 1>(h, a); break;
-        case 122: run_cart<2, DGP_BASE + 2>(h, a); break;
-        case 123: run_cart<2, DGP_BASE + 3>(h, a); break;
-        case 124: run_cart<2, DGP_BASE + 4>(h, a); break;
-        case 131: run_cart<3, DGP_BASE + 1>(h, a); break;
-        case 132: run_cart<3, DGP_BASE + 2>(h, a); break;
-        case 133: run_cart<3, DGP_BASE + 3>(h, a); break;
-        case 21: run_cart<2, 1>(h, a); break;
-        case 22: run_cart<2, 2>(h, a); break;
-        case 23: run_cart<2, 3>(h, a); break;
-        case 24: run_cart<2, 4>(h, a); break;
-        case 31: run_cart<3, 1>(h, a); break;
-        case 32: run_cart<3, 2>(h, a); break;
-        case 33: run_cart<3, 3>(h, a); break;
-        default:
-          throw CudaError{cudaErrorNotSupported, "no assembly kernel for this (dim, degree)", __LINE__};
-      }
+    PD_CUDA(cudaEventRecord(h->ev[0], h->stream)); // the 1-D matrices count as part of the diagonal kernel's slot
+    ensure_brick_matrices(h, a);
+    PD_CART_DISPATCH(run_cart, h, h, a);
   }
 
   static void
@@ -1400,6 +1418,12 @@ namespace pd
     a.pit_brick    = h->pit_brick.p;
     a.pit_meta     = h->pit_meta.p;
     a.pit_q        = h->pit_q.p;
+    a.cbk_poly     = h->cbk_poly.p;
+    a.fbk_iface    = h->fbk_iface.p;
+    a.cmat         = h->cmat.p;
+    a.fmat         = h->fmat.p;
+    a.n_cbk        = h->n_cell_bricks;
+    a.n_fbk        = h->n_face_bricks;
     {
       // (a, b, c) of DoF i: FE_DGQ lexicographic; FE_AggloDGP in PolynomialSpace order (last coordinate outermost,
       // first fastest, total degree <= p: source/fe_agglodgp.cc:28-57)

@@ -171,7 +171,9 @@ struct pd_handle
   pd::DevBuf<int32_t>  cbk_iv, civ, cpos, fbk_s, fbk_iv, fiv, fpos, fbk_lf, pit_brick, pit_meta, pit_q;
   pd::DevBuf<int64_t>  pit_ptr, pit_diag_end;
   pd::DevBuf<double2>  civ_box, fiv_box;
-  pd::DevBuf<double>   fbk_plane, fbk_sigma;
+  pd::DevBuf<double>   fbk_plane, fbk_sigma, cmat, fmat;
+  pd::DevBuf<int32_t>  cbk_poly, fbk_iface;
+  bool                 brick_mat_valid = false;
   int64_t              n_cell_bricks = 0, n_face_bricks = 0;
   bool                 bricks_ready = false;
   std::vector<int32_t> h_subcell_idx, h_sub_cell, h_sub_face;
