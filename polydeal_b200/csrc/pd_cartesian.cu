@@ -171,16 +171,32 @@ namespace pd
       using C                 = Cfg<DIM, DEGX>;
       static constexpr int N1 = C::N1, NX = N1 * N1, NYZ = ipow(NX, DIM - 1), NF = ipow(N1, DIM);
       static constexpr int NXP = NX + (NX & 1); // slot stride: even, so that the X rows load as 16-byte pairs
-      static constexpr int CH  = 16;            // items per chunk
-      // thread (col, ig): column col = (b,b'[,c,c']) of the factorised block, all NX rows (a,a'); the items of a
-      // chunk are dealt to IG item groups (small elements: fills the CTA), summed through shared memory at the end
-      static constexpr int IG   = NYZ >= 64 ? 1 : (NYZ * 2 >= 64 ? 2 : (NYZ * 4 >= 64 ? 4 : (NYZ * 8 >= 64 ? 8 : 16)));
-      static constexpr int NTHR = ((NYZ * IG + 31) / 32) * 32;
-      // at least 24 resident warps per SM: the phases of a CTA (1-D matrices | accumulation) are separated by
-      // barriers, other CTAs fill the gaps
-      static constexpr int MINB = (768 / NTHR) < 1 ? 1 : ((768 / NTHR) > 12 ? 12 : (768 / NTHR));
       static constexpr int ISTR = DIM * 2 * NXP;
+      // A work item (the diagonal block of a polytope / the M12 block of an interface) is computed by a GROUP of
+      // threads: thread t owns the columns t, t + GROUP, ... (CPT of them) of the factorised block -- column =
+      // (b,b'[,c,c']) -- with all NX rows (a,a') in registers.  Large elements (3-D p = 3: 256 columns): the whole
+      // CTA is one group.  Small elements: a WARP is a group, a CTA runs WPC independent work items at once and only
+      // warp-level barriers are used -- the work per block is a few hundred flops, what matters is how many blocks
+      // are in flight per SM.
+      static constexpr int GROUP = NYZ >= 128 ? ((NYZ + 31) / 32) * 32 : 32;
+      static constexpr int CPT   = (NYZ + GROUP - 1) / GROUP;
+      static constexpr int NTHR  = GROUP >= 128 ? GROUP : 256;
+      static constexpr int WPC   = NTHR / GROUP;
+      static constexpr int CH    = GROUP >= 128 ? 16 : 8; // items per chunk
+      static constexpr int MINB  = GROUP >= 128 ? 3 : 2;
+      // shared memory of a group: the chunk's 1-D matrices, later the staged block; + the kinds of the chunk's items
+      static constexpr int GSM   = (CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)) + CH / 2 + 2;
     };
+
+    template <int GROUP>
+    __device__ __forceinline__ void
+    group_sync()
+    {
+      if (GROUP == 32)
+        __syncwarp();
+      else
+        __syncthreads();
+    }
 
     // rows a of the 1-D matrices of one item along one axis, [a'] = 0..N1-1:
     //  cell / tangential axis:  M = eta sum_q w l_a l_a',  K = eta sum_q w l_a' l_a'' (derivatives per real length)
@@ -348,78 +364,92 @@ namespace pd
         x[NX - 1] = src[NX - 1];
     }
 
-    // acc[r] += X1[r] yz1 + X2[r] yz2 over the items ig, ig + IG, ... of a chunk.  SL[item][d][2][NXP]: slot 0 =
-    // M-like, slot 1 = K-like.  kind[item]: 1 = cell (two terms), 2 = face (one term, F sits in slot 0 of its
-    // normal axis).
+    // acc[k][r] += X1[r] yz1 + X2[r] yz2 over the items of a chunk, for the thread's columns k.
+    // SL[item][d][2][NXP]: slot 0 = M-like, slot 1 = K-like.  kind[item]: 1 = cell (two terms), 2 = face (one term,
+    // the face factor sits in slot 0 of its normal axis), 0 = switched off by the flags.
     template <int DIM, int DEGX>
     __device__ __forceinline__ void
-    accumulate_chunk(const double *SL, const int *kind, const int cnt, const int col, const int ig, const double stiffness,
-                     const double mass, double *acc)
+    accumulate_chunk(const double *SL, const int *kind, const int cnt, const int t, const double stiffness, const double mass,
+                     double (*acc)[CartCfg<DIM, DEGX>::NX])
     {
       using CC            = CartCfg<DIM, DEGX>;
-      constexpr int NX    = CC::NX, NXP = CC::NXP, ISTR = CC::ISTR, IG = CC::IG;
-      const int     cb    = DIM == 3 ? col % NX : col; // (b,b')
-      const int     cc    = DIM == 3 ? col / NX : 0;   // (c,c')
-      for (int it = ig; it < cnt; it += IG)
+      constexpr int NX    = CC::NX, NXP = CC::NXP, ISTR = CC::ISTR, GROUP = CC::GROUP, CPT = CC::CPT, NYZ = CC::NYZ;
+      for (int it = 0; it < cnt; ++it)
         {
-          if (kind[it] == 0)
-            continue; // a term the flags switch off
-          const double *s  = SL + it * ISTR;
-          const double m1 = s[(1 * 2 + 0) * NXP + cb];
-          const double m2 = DIM == 3 ? s[(2 * 2 + 0) * NXP + cc] : 1.;
-          const double yz1 = m1 * m2;
-          double       x[NX];
-          if (kind[it] == 1)
+          const int kd = kind[it];
+          if (kd == 0)
+            continue;
+          const double *s = SL + it * ISTR;
+          double        x[NX], yz1[CPT], yz2[CPT];
+#pragma unroll
+          for (int k = 0; k < CPT; ++k)
             {
-              const double k1  = s[(1 * 2 + 1) * NXP + cb];
-              const double k2  = DIM == 3 ? s[(2 * 2 + 1) * NXP + cc] : 0.;
-              const double yz2 = stiffness * (k1 * m2 + m1 * k2) + mass * yz1;
-              const double sy1 = stiffness * yz1;
+              const int col = t + k * GROUP;
+              const int cb = DIM == 3 ? col % NX : col, cc = DIM == 3 ? col / NX : 0;
+              yz1[k] = yz2[k] = 0.;
+              if (col < NYZ)
+                {
+                  const double m1 = s[(1 * 2 + 0) * NXP + cb];
+                  const double m2 = DIM == 3 ? s[(2 * 2 + 0) * NXP + cc] : 1.;
+                  yz1[k]          = m1 * m2;
+                  if (kd == 1)
+                    {
+                      const double k1 = s[(1 * 2 + 1) * NXP + cb];
+                      const double k2 = DIM == 3 ? s[(2 * 2 + 1) * NXP + cc] : 0.;
+                      yz2[k]          = stiffness * (k1 * m2 + m1 * k2) + mass * yz1[k];
+                      yz1[k] *= stiffness;
+                    }
+                }
+            }
+          if (kd == 1)
+            {
               load_rows<NX>(s + (0 * 2 + 1) * NXP, x); // K along x
 #pragma unroll
-              for (int r = 0; r < NX; ++r)
-                acc[r] += x[r] * sy1;
+              for (int k = 0; k < CPT; ++k)
+#pragma unroll
+                for (int r = 0; r < NX; ++r)
+                  acc[k][r] += x[r] * yz1[k];
               load_rows<NX>(s + (0 * 2 + 0) * NXP, x); // M along x
 #pragma unroll
-              for (int r = 0; r < NX; ++r)
-                acc[r] += x[r] * yz2;
+              for (int k = 0; k < CPT; ++k)
+#pragma unroll
+                for (int r = 0; r < NX; ++r)
+                  acc[k][r] += x[r] * yz2[k];
             }
           else
             {
               load_rows<NX>(s + (0 * 2 + 0) * NXP, x);
 #pragma unroll
-              for (int r = 0; r < NX; ++r)
-                acc[r] += x[r] * yz1;
+              for (int k = 0; k < CPT; ++k)
+#pragma unroll
+                for (int r = 0; r < NX; ++r)
+                  acc[k][r] += x[r] * yz1[k];
             }
         }
     }
 
-    // registers -> OUT[full row index][full column index] (shared, NF x (NF + 1)): item group 0 stores, the
-    // others add in turn (fixed order: deterministic)
+    // registers -> OUT[full row index][full column index] (shared, NF x (NF + 1))
     template <int DIM, int DEGX>
     __device__ __forceinline__ void
-    stage_block(double *OUT, const int col, const int ig, const bool active, const double *acc)
+    stage_block(double *OUT, const int t, const double (*acc)[CartCfg<DIM, DEGX>::NX])
     {
       using CC         = CartCfg<DIM, DEGX>;
-      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, IG = CC::IG;
-      const int     cb = DIM == 3 ? col % NX : col, cc = DIM == 3 ? col / NX : 0;
-      const int     b = cb / N1, bp = cb % N1, c = cc / N1, cp = cc % N1;
-      for (int g = 0; g < IG; ++g)
-        {
-          if (active && ig == g)
-            {
+      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, GROUP = CC::GROUP, CPT = CC::CPT, NYZ = CC::NYZ;
 #pragma unroll
-              for (int r = 0; r < NX; ++r)
-                {
-                  const int a = r / N1, ap = r % N1;
-                  const int i = a + N1 * (b + N1 * c), j = ap + N1 * (bp + N1 * cp);
-                  if (g == 0)
-                    OUT[i * (NF + 1) + j] = acc[r];
-                  else
-                    OUT[i * (NF + 1) + j] += acc[r];
-                }
+      for (int k = 0; k < CPT; ++k)
+        {
+          const int col = t + k * GROUP;
+          if (col >= NYZ)
+            continue;
+          const int cb = DIM == 3 ? col % NX : col, cc = DIM == 3 ? col / NX : 0;
+          const int b = cb / N1, bp = cb % N1, c = cc / N1, cp = cc % N1;
+#pragma unroll
+          for (int r = 0; r < NX; ++r)
+            {
+              const int a = r / N1, ap = r % N1;
+              const int i = a + N1 * (b + N1 * c), j = ap + N1 * (bp + N1 * cp);
+              OUT[i * (NF + 1) + j] = acc[k][r];
             }
-          __syncthreads();
         }
     }
 
@@ -489,60 +519,79 @@ namespace pd
         }
     }
 
+    // the chunk's 1-D matrices from k_brick_matrices into the group's shared memory (face factor x stiffness)
+    template <int DIM, int DEGX, bool OFFDIAG>
+    __device__ __forceinline__ void
+    load_chunk(const CartArgs &A, const int64_t c0, const int cnt, const int t, double *SL, int *kind)
+    {
+      using CC           = CartCfg<DIM, DEGX>;
+      constexpr int NXP  = CC::NXP, ISTR = CC::ISTR, GROUP = CC::GROUP;
+      for (int w = t; w < cnt * ISTR; w += GROUP)
+        {
+          const int it = w / ISTR, r = w % ISTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
+          double    v  = 0.;
+          if (OFFDIAG)
+            {
+              const int64_t brick = c0 + it;
+              if (r == 0)
+                kind[it] = 2;
+              if (slot == 0)
+                v = A.fmat[((brick * 3 + 2) * DIM + d) * NXP + k] * (d == (A.fbk_lf[brick] >> 1) ? A.stiffness : 1.);
+            }
+          else
+            {
+              const int64_t brick = A.pit_brick[c0 + it];
+              const int     meta  = A.pit_meta[c0 + it];
+              const bool    on    = (meta & 3) == 1 ? (A.flags & PD_ASSEMBLE_VOLUME) != 0 :
+                                    ((meta & 8) ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
+              if (r == 0)
+                kind[it] = on ? (meta & 3) : 0;
+              if (on && (meta & 3) == 1)
+                v = A.cmat[(brick * DIM + d) * 2 * NXP + slot * NXP + k];
+              else if (on && slot == 0)
+                v = A.fmat[((brick * 3 + ((meta >> 2) & 1)) * DIM + d) * NXP + k] * (d == (A.fbk_lf[brick] >> 1) ? A.stiffness : 1.);
+            }
+          SL[w] = v;
+        }
+    }
+
     template <int DIM, int DEGX>
     __global__ void __launch_bounds__(CartCfg<DIM, DEGX>::NTHR, CartCfg<DIM, DEGX>::MINB)
     k_cart_diag(const CartArgs A)
     {
       using C          = Cfg<DIM, DEGX>;
       using CC         = CartCfg<DIM, DEGX>;
-      constexpr int N1 = CC::N1, NX = CC::NX, NXP = CC::NXP, NYZ = CC::NYZ, IG = CC::IG, NF = CC::NF, CH = CC::CH, N = C::N;
-      constexpr int ISTR = CC::ISTR;
-      __shared__ __align__(16) double SL[CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)];
-      __shared__ int                  kind[CH];
-      const int  tid = threadIdx.x;
-      const int  col = tid % NYZ, ig = tid / NYZ;
-      const bool active = tid < NYZ * IG;
+      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, CH = CC::CH, N = C::N, GROUP = CC::GROUP, CPT = CC::CPT, WPC = CC::WPC;
+      extern __shared__ __align__(16) double cart_smem[];
+      const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
+      double   *SL   = cart_smem + g * CC::GSM;
+      int      *kind = reinterpret_cast<int *>(SL + CC::GSM - CH / 2 - 2);
 
-      for (int p = blockIdx.x; p < A.np_own; p += gridDim.x)
+      for (int64_t p = (int64_t)blockIdx.x * WPC + g; p < A.np_own; p += (int64_t)gridDim.x * WPC)
         {
-          double acc[NX];
+          double acc[CPT][NX];
 #pragma unroll
-          for (int r = 0; r < NX; ++r)
-            acc[r] = 0.;
-          const double *bb = A.bbox + (int64_t)p * 2 * DIM;
+          for (int k = 0; k < CPT; ++k)
+#pragma unroll
+            for (int r = 0; r < NX; ++r)
+              acc[k][r] = 0.;
           // the bricks of the polytope as one item list: its cell bricks, then the own-side face bricks of its adjacency
           const int64_t i0 = A.pit_ptr[p], i1 = A.pit_diag_end[p];
           for (int64_t c0 = i0; c0 < i1; c0 += CH)
             {
               const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
-              __syncthreads(); // the previous chunk has been consumed
-              // ---- the 1-D matrices of the chunk's bricks, from k_brick_matrices (face factor x stiffness coefficient)
-              for (int w = tid; w < cnt * ISTR; w += CC::NTHR)
-                {
-                  const int     it = w / ISTR, r = w % ISTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
-                  const int64_t brick = A.pit_brick[c0 + it];
-                  const int     meta  = A.pit_meta[c0 + it];
-                  const bool    on    = (meta & 3) == 1 ? (A.flags & PD_ASSEMBLE_VOLUME) != 0 :
-                                        ((meta & 8) ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
-                  if (r == 0)
-                    kind[it] = on ? (meta & 3) : 0;
-                  double v = 0.;
-                  if (on && (meta & 3) == 1)
-                    v = A.cmat[(brick * DIM + d) * 2 * NXP + slot * NXP + k];
-                  else if (on && slot == 0)
-                    v = A.fmat[((brick * 3 + ((meta >> 2) & 1)) * DIM + d) * NXP + k] * (d == (A.fbk_lf[brick] >> 1) ? A.stiffness : 1.);
-                  SL[w] = v;
-                }
-              __syncthreads();
-              if (active)
-                accumulate_chunk<DIM, DEGX>(SL, kind, cnt, col, ig, A.stiffness, A.mass, acc);
+              group_sync<GROUP>(); // the previous chunk / block has been consumed
+              load_chunk<DIM, DEGX, false>(A, c0, cnt, t, SL, kind);
+              group_sync<GROUP>();
+              accumulate_chunk<DIM, DEGX>(SL, kind, cnt, t, A.stiffness, A.mass, acc);
             }
           // ---- epilogue: registers -> shared tile -> the diagonal block of the CSR rows
-          __syncthreads();
-          stage_block<DIM, DEGX>(SL, col, ig, active, acc);
+          group_sync<GROUP>();
+          stage_block<DIM, DEGX>(SL, t, acc);
+          group_sync<GROUP>();
           const int64_t base   = A.diag_base[p];
           const int     stride = A.row_stride[A.dof_block[p]];
-          for (int idx = tid; idx < N * N; idx += CC::NTHR)
+          for (int idx = t; idx < N * N; idx += GROUP)
             {
               const int i = idx / N, j = idx - i * N;
               const int fi = A.dof_abc[i][0] + N1 * (A.dof_abc[i][1] + N1 * A.dof_abc[i][2]);
@@ -558,46 +607,39 @@ namespace pd
     {
       using C          = Cfg<DIM, DEGX>;
       using CC         = CartCfg<DIM, DEGX>;
-      constexpr int N1 = CC::N1, NX = CC::NX, NXP = CC::NXP, NYZ = CC::NYZ, IG = CC::IG, NF = CC::NF, CH = CC::CH, N = C::N;
-      constexpr int ISTR = CC::ISTR;
-      __shared__ __align__(16) double SL[CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)];
-      __shared__ int                  kind[CH];
-      const int  tid = threadIdx.x;
-      const int  col = tid % NYZ, ig = tid / NYZ;
-      const bool active = tid < NYZ * IG;
+      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, CH = CC::CH, N = C::N, GROUP = CC::GROUP, CPT = CC::CPT, WPC = CC::WPC;
+      extern __shared__ __align__(16) double cart_smem[];
+      const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
+      double   *SL   = cart_smem + g * CC::GSM;
+      int      *kind = reinterpret_cast<int *>(SL + CC::GSM - CH / 2 - 2);
 
-      for (int f = blockIdx.x; f < A.n_ifaces; f += gridDim.x)
+      for (int64_t f = (int64_t)blockIdx.x * WPC + g; f < A.n_ifaces; f += (int64_t)gridDim.x * WPC)
         {
           const int32_t pa = A.ifA[f], pb = A.ifB[f];
           if (pb < 0)
             continue;
-          double acc[NX];
+          double acc[CPT][NX];
 #pragma unroll
-          for (int r = 0; r < NX; ++r)
-            acc[r] = 0.;
+          for (int k = 0; k < CPT; ++k)
+#pragma unroll
+            for (int r = 0; r < NX; ++r)
+              acc[k][r] = 0.;
           const int64_t i0 = A.fbk_ptr[f], i1 = A.fbk_ptr[f + 1];
           for (int64_t c0 = i0; c0 < i1; c0 += CH)
             {
               const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
-              __syncthreads();
-              for (int w = tid; w < cnt * ISTR; w += CC::NTHR)
-                {
-                  const int     it = w / ISTR, r = w % ISTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
-                  const int64_t brick = c0 + it;
-                  if (r == 0)
-                    kind[it] = 2;
-                  SL[w] = slot ? 0. : A.fmat[((brick * 3 + 2) * DIM + d) * NXP + k] * (d == (A.fbk_lf[brick] >> 1) ? A.stiffness : 1.);
-                }
-              __syncthreads();
-              if (active)
-                accumulate_chunk<DIM, DEGX>(SL, kind, cnt, col, ig, 1., 0., acc);
+              group_sync<GROUP>();
+              load_chunk<DIM, DEGX, true>(A, c0, cnt, t, SL, kind);
+              group_sync<GROUP>();
+              accumulate_chunk<DIM, DEGX>(SL, kind, cnt, t, 1., 0., acc);
             }
-          __syncthreads();
-          stage_block<DIM, DEGX>(SL, col, ig, active, acc);
+          group_sync<GROUP>();
+          stage_block<DIM, DEGX>(SL, t, acc);
+          group_sync<GROUP>();
           const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
           const int     strideA = A.row_stride[A.dof_block[pa]];
           const int     strideB = baseBA >= 0 ? A.row_stride[A.dof_block[pb]] : 0;
-          for (int idx = tid; idx < N * N; idx += CC::NTHR)
+          for (int idx = t; idx < N * N; idx += GROUP)
             {
               const int i = idx / N, j = idx - i * N;
               const int fi = A.dof_abc[i][0] + N1 * (A.dof_abc[i][1] + N1 * A.dof_abc[i][2]);
@@ -606,7 +648,6 @@ namespace pd
               if (baseBA >= 0) // M21 = M12^T; coalesced over j as well: entry (i, j) of (B,A) is M12(j, i)
                 A.values[baseBA + (int64_t)i * strideB + j] = SL[fj * (NF + 1) + fi];
             }
-          __syncthreads();
         }
     }
 
@@ -863,17 +904,26 @@ namespace pd
     void
     run_cart(pd_handle *h, const CartArgs &a)
     {
-      using CC = CartCfg<DIM, DEGX>;
+      using CC            = CartCfg<DIM, DEGX>;
+      const size_t smem   = sizeof(double) * (size_t)CC::WPC * CC::GSM;
+      auto         kd = k_cart_diag<DIM, DEGX>, ko = k_cart_offdiag<DIM, DEGX>;
+      if (smem > 48 * 1024)
+        {
+          PD_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          PD_CUDA(cudaFuncSetAttribute(ko, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
       {
-        const int grid = (int)std::min<int64_t>(h->np_own, (int64_t)h->sm_count * 16);
-        k_cart_diag<DIM, DEGX><<<grid, CC::NTHR, 0, h->stream>>>(a);
+        const int64_t ctas = (h->np_own + CC::WPC - 1) / CC::WPC;
+        const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)h->sm_count * 16));
+        kd<<<grid, CC::NTHR, smem, h->stream>>>(a);
         ++h->launches;
       }
       PD_CUDA(cudaEventRecord(h->ev[1], h->stream));
       if ((a.flags & PD_ASSEMBLE_INTERIOR) && h->n_ifaces > 0)
         {
-          const int grid = (int)std::min<int64_t>(h->n_ifaces, (int64_t)h->sm_count * 16);
-          k_cart_offdiag<DIM, DEGX><<<grid, CC::NTHR, 0, h->stream>>>(a);
+          const int64_t ctas = (h->n_ifaces + CC::WPC - 1) / CC::WPC;
+          const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)h->sm_count * 16));
+          ko<<<grid, CC::NTHR, smem, h->stream>>>(a);
           ++h->launches;
         }
       PD_CUDA(cudaEventRecord(h->ev[2], h->stream));
@@ -882,18 +932,6 @@ namespace pd
     }
   } // namespace
 
-  // ---------------------------------------------------------------------------------------------------
-  // Bricks.  The sum over the sub-cells of a polytope of X_s (x) Y_s (x) Z_s factorises further wherever the
-  // sub-cells form a tensor-product set I x J x K of 1-D intervals:
-  //      sum_{(i,j,k) in I x J x K} X_i (x) Y_j (x) Z_k  =  (sum_I X_i) (x) (sum_J Y_j) (x) (sum_K Z_k),
-  // the 1-D sums being the composite Gauss sums over the member intervals -- the same numbers the reference adds
-  // up point by point, regrouped once more.  A polytope that is a box of b^dim cells (the `blocks` shape an R-tree
-  // extracts from a structured grid) is ONE brick; any other agglomerate decomposes greedily (pencils along x with
-  // equal index sets merge along y into slabs, equal slabs merge along z); a brick of one cell is the
-  // per-sub-cell form.  The sub-faces of an interface that lie in one plane with one penalty decompose the same way
-  // into rectangles.  Intervals are stored as REPRESENTATIVE CELLS (the kernel reads their current vertices), so
-  // moving vertices through pd_upload keeps the bricks valid as long as the tensor structure survives; a device
-  // scan (k_check_axis_aligned) verifies that and the bricks are rebuilt on the host otherwise.
   // ---------------------------------------------------------------------------------------------------
   namespace
   {
