@@ -255,7 +255,7 @@ def face_point_counts(desc, nq):
             int((B < 0).sum()), int(nsub[B >= 0].sum()), int(nsub[B < 0].sum()))
 
 
-def assembly_rooflines(desc, n, nq, kms, peaks, mass=False, path="dmma"):
+def assembly_rooflines(desc, n, nq, kms, peaks, mass=False, path="dmma", stats=None):
     """One roofline block per kernel of the assembly step.  `survey_*` = SURVEY 8d's algorithmic count of the
     point-wise formulation (2 n^2 dim Q volume flops, 24 n^2 per interior face point); the tensor path computes the
     same matrix with far fewer operations, so its kernels are held to the bytes they must move (the matrix is
@@ -271,12 +271,14 @@ def assembly_rooflines(desc, n, nq, kms, peaks, mass=False, path="dmma"):
     out = []
     if path == "tensor":
         n1 = round(n ** (1.0 / dim))
-        # k_cart_diag: per sub-cell two Kronecker terms, per own-side sub-face (2 per interior, 1 per boundary) one
-        diag_fma = n * n * (2.0 * n_sub + 2.0 * sf_int + sf_bnd)
-        off_fma = n * n * 1.0 * sf_int
-        geo = 48.0 + 8.0 * 2**dim  # cell index + 2^dim vertex indices + the two corner vertices
-        diag_bytes = 8.0 * n * n * n_own + geo * (n_sub + 2 * sf_int + sf_bnd)
-        off_bytes = 8.0 * n * n * 2 * n_int + (geo + 16.0) * sf_int
+        # per brick of a diagonal block two (cell) or one (face) Kronecker terms of n^2 multiply-adds; per face brick of
+        # an interface one; the bricks' 1-D matrices are read (about dim * 2 * N1^2 doubles per item)
+        st = stats or {"cell_bricks": n_sub, "face_bricks": sf_int + sf_bnd, "diag_items": n_sub + 2 * sf_int + sf_bnd}
+        diag_fma = n * n * (st["diag_items"] + st["cell_bricks"])
+        off_fma = n * n * 1.0 * st["face_bricks"] * (sf_int / max(sf_int + sf_bnd, 1))
+        item_bytes = 8.0 * dim * 2 * n1 * n1
+        diag_bytes = 8.0 * n * n * n_own + item_bytes * st["diag_items"]
+        off_bytes = 8.0 * n * n * 2 * n_int + 0.5 * item_bytes * st["face_bricks"]
         for name, ms, nbytes, fma, survey in (
                 (f"k_cart_diag<{dim},{desc.fe_degree}> (diagonal blocks: volume + own-side faces, Kronecker sums)", kms["volume"],
                  diag_bytes, diag_fma, vol_flops + (face_flops - 12.0 * n * n * qf_int if qf_int else face_flops)),
@@ -289,7 +291,8 @@ def assembly_rooflines(desc, n, nq, kms, peaks, mass=False, path="dmma"):
             blk["fp64_pipe_frac"] = blk["issued_tflops"] / peaks["fp64_tflops"]
             blk["survey_algorithmic_flops_per_launch"] = survey
             blk["survey_algorithmic_tflops"] = survey / (ms * 1e-3) / 1e12
-            blk["note"] = ("tensor path: bytes = the blocks written once + the mesh data read; issued_tflops = the Kronecker "
+            blk["bricks"] = st
+            blk["note"] = ("tensor path: bytes = the blocks written once + the bricks' 1-D matrices read; issued_tflops = the Kronecker "
                            "multiply-adds actually issued; survey_algorithmic_* = the point-wise count of SURVEY 8d the same "
                            "result would cost (n1 = %d)" % n1)
             out.append(blk)
@@ -527,7 +530,7 @@ def run_gpu(args):
         peer.close()
     nblocks = int(desc.brow_ptr[desc.n_block_rows])
     path = op.assembly_path
-    roofs = assembly_rooflines(desc, n, NQ, kms, read_peaks(), path=path) if rank == 0 else None
+    roofs = assembly_rooflines(desc, n, NQ, kms, read_peaks(), path=path, stats=op.tensor_path_stats()) if rank == 0 else None
     generic = None
     if world == 1 and not args.no_extra_configs:
         generic = generic_path_block(op, desc, n, NQ, stream, flush, read_peaks(), 3)
@@ -713,7 +716,8 @@ def run_extra_config(pdl, name, stream, peaks, steps):
                        f"FE_DGQ({cfg['p']}), QGauss({cfg['nq']})" + (", + reaction c=0.5, C=40" if cfg["mass"] else ""),
            "n_dofs": N, "assembly_path": path, "assemble_ms": ms, "dofs_per_s": N / (ms * 1e-3), "kernel_ms": kms,
            "host_setup_s": t_host,
-           "rooflines": assembly_rooflines(desc, n, cfg["nq"], kms, peaks, mass=bool(cfg["mass"]), path=path),
+           "rooflines": assembly_rooflines(desc, n, cfg["nq"], kms, peaks, mass=bool(cfg["mass"]), path=path,
+                                           stats=op.tensor_path_stats()),
            "generic_path": generic_path_block(op, desc, n, cfg["nq"], stream, flush, peaks, min(steps, 3), cfg["mass"]),
            "vmult_ms": vm_ms, "vmult_gdofs": N / (vm_ms * 1e-3) / 1e9,
            "vmult_roofline": hbm_block("k_spmv_block_row", 8.0 * n * n * nblocks + 4.0 * nblocks + 16.0 * N, vm_ms, peaks),

@@ -300,7 +300,7 @@ int pd_invalidate_quadrature(pd_handle *h);
 /* PolyUtils::assemble_dg_matrix (include/poly_utils.h:2000-2195).  Result: the
  * scalar-CSR value array of the reference pattern (ascending columns), kept on
  * the device inside the handle.
- * Two kernel families compute the same matrix (tests hold both to the oracle):
+ * Two kernel families compute the same matrix (the parity tests hold both to the CPU restatement of the reference):
  *   PD_PATH_TENSOR  every owned sub-cell is an axis-aligned box (checked on the device at
  *                   pd_create / pd_upload): the quadrature sums factorise per sub-cell / sub-face
  *                   into 1-D matrices and a block is a sum of Kronecker products (pd_cartesian.cu)
@@ -312,6 +312,9 @@ int pd_assemble(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
 #define PD_PATH_TENSOR 1
 /* which family the last pd_assemble ran (-1: none yet) */
 int pd_assembly_path(const pd_handle *h);
+/* the tensor path's work: stats4 = {axis-aligned (0/1), cell bricks, face bricks, items of all diagonal blocks}
+ * (a brick = a tensor-product set of sub-cells / coplanar sub-faces whose quadrature sums factorise, pd_cartesian.cu) */
+int pd_tensor_path_stats(const pd_handle *h, int64_t *stats4);
 
 int64_t pd_n_dofs(const pd_handle *h);        /* rows = owned DoFs */
 int64_t pd_n_source_dofs(const pd_handle *h); /* length of vmult source vectors = owned + ghost DoFs */

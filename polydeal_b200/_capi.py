@@ -112,6 +112,7 @@ SIGNATURES = {
     "pd_fe_evaluate": (C.c_int, [i32, i32, i32, i64, vp, vp, vp]),
     "pd_copy_array": (C.c_int, [vp, C.c_char_p, vp, P(i64)]),
     "pd_assembly_path": (C.c_int, [vp]),
+    "pd_tensor_path_stats": (C.c_int, [vp, vp]),
     "pd_launch_count": (i64, [vp]),
     "pd_last_kernel_ms": (C.c_int, [vp, P(C.c_float)]),
     "pd_quadrature_rule_1d": (C.c_int, [C.c_int, vp, vp]),

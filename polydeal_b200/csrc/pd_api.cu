@@ -1417,6 +1417,19 @@ extern "C"
     return h ? h->last_assembly_path : -1;
   }
 
+  int
+  pd_tensor_path_stats(const pd_handle *h, int64_t *stats4)
+  {
+    return guarded([&] {
+      if (!h || !stats4)
+        throw Error(PD_ERR_INVALID, "null argument");
+      stats4[0] = h->cartesian ? 1 : 0;
+      stats4[1] = h->n_cell_bricks;
+      stats4[2] = h->n_face_bricks;
+      stats4[3] = h->n_diag_items;
+    });
+  }
+
   int64_t
   pd_launch_count(const pd_handle *h)
   {

@@ -17,7 +17,7 @@
 // rank-structured sum with n^2 (2 + 1/S) multiply-adds per sub-cell instead of the 2 n^2 dim n_q^dim
 // of the point-wise contraction (p = 3: 8.2 k instead of 1.57 M flops per sub-cell).  The sums over the
 // quadrature points are the SAME sums the reference forms, regrouped; results agree to rounding
-// (tests: per block entry <= 1e-12 against the oracle, and against the DMMA kernels).
+// (tests: per block entry <= 1e-12 against the CPU restatement of the reference, and against the DMMA kernels).
 //
 // Applies when every owned sub-cell is an axis-aligned box in standard orientation (checked on the
 // device by k_check_axis_aligned at pd_create / pd_upload); distorted meshes take the DMMA kernels
@@ -1261,6 +1261,9 @@ namespace pd
     h->fbk_lf.alloc(std::max<size_t>(B.fbk_s.size(), 1));
     h->n_cell_bricks = (int64_t)B.cbk_iv.size() / (2 * h->dim);
     h->n_face_bricks = (int64_t)B.fbk_s.size();
+    h->n_diag_items  = 0;
+    for (int32_t p = 0; p < h->np_own; ++p)
+      h->n_diag_items += B.pit_diag_end[p] - B.pit_ptr[p];
     h->bricks_ready  = true;
     h->h_subcell_idx.assign(d.poly_subcell_idx, d.poly_subcell_idx + h->n_subcells);
     h->h_sub_cell.assign(d.sub_cell, d.sub_cell + h->n_subfaces);

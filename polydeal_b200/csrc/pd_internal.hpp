@@ -174,7 +174,7 @@ struct pd_handle
   pd::DevBuf<double>   fbk_plane, fbk_sigma, cmat, fmat;
   pd::DevBuf<int32_t>  cbk_poly, fbk_iface;
   bool                 brick_mat_valid = false;
-  int64_t              n_cell_bricks = 0, n_face_bricks = 0;
+  int64_t              n_cell_bricks = 0, n_face_bricks = 0, n_diag_items = 0;
   bool                 bricks_ready = false;
   std::vector<int32_t> h_subcell_idx, h_sub_cell, h_sub_face;
   int                  last_assembly_path = -1; // 0: DMMA kernels on the agglomerated quadrature, 1: tensor path

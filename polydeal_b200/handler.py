@@ -586,6 +586,12 @@ class SIPOperator:
         """'tensor' (axis-aligned sub-cells, pd_cartesian.cu) or 'dmma' (pd_assemble.cu) for the last assemble()."""
         return {0: "dmma", 1: "tensor"}.get(K.lib().pd_assembly_path(self._h))
 
+    def tensor_path_stats(self):
+        """dict(axis_aligned, cell_bricks, face_bricks, diag_items) of the tensor path (pd_tensor_path_stats)."""
+        st = (C.c_int64 * 4)()
+        K.check(K.lib().pd_tensor_path_stats(self._h, st))
+        return {"axis_aligned": bool(st[0]), "cell_bricks": int(st[1]), "face_bricks": int(st[2]), "diag_items": int(st[3])}
+
     @property
     def launch_count(self):
         return K.lib().pd_launch_count(self._h)
