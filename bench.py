@@ -353,6 +353,10 @@ def generic_path_block(op, desc, n, nq, stream, flush, peaks, steps, mass=0.0):
 
 
 def run_gpu(args):
+    # stdout carries exactly ONE JSON line: everything libraries print on fd 1 meanwhile (NCCL's version banner) goes to
+    # stderr; the line itself is written to the saved descriptor at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
 
     import polydeal_b200 as pdl
@@ -622,7 +626,7 @@ def run_gpu(args):
     if not args.no_cpu_baseline and world == 1:
         os.sched_setaffinity(0, affinity0)  # the CPU arm gets every core of the box
         out["cpu_baseline"] = cpu_baseline(CPU_STRIDE)
-    print(json.dumps(out))
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if dist:
         dist.destroy_process_group()
 
