@@ -182,10 +182,10 @@ namespace pd
       static constexpr int CPT   = (NYZ + GROUP - 1) / GROUP;
       static constexpr int NTHR  = GROUP >= 128 ? GROUP : 256;
       static constexpr int WPC   = NTHR / GROUP;
-      static constexpr int CH    = GROUP >= 128 ? 16 : 8; // items per chunk
+      static constexpr int CH    = 8; // items per chunk
       static constexpr int MINB  = GROUP >= 128 ? 3 : 2;
       // shared memory of a group: the chunk's 1-D matrices, later the staged block; + the kinds of the chunk's items
-      static constexpr int GSM   = (CH * ISTR > NF * (NF + 1) ? CH * ISTR : NF * (NF + 1)) + CH / 2 + 2;
+      static constexpr int GSM   = ((C::DGP && NF * (NF + 1) > CH * ISTR) ? NF * (NF + 1) : CH * ISTR) + CH / 2 + 2;
     };
 
     template <int GROUP>
@@ -453,6 +453,50 @@ namespace pd
         }
     }
 
+    // FE_DGQ: a thread's rows (a, a') for fixed a are N1 CONSECUTIVE entries of row i = (a,b,c) of the block (columns
+    // (a',b',c'), a' fastest), so the block goes straight from the registers to the CSR rows -- N1 = 4: one 32-byte
+    // sector per store pair, N1 = 2: 16 bytes -- without a shared-memory tile, a barrier or index arithmetic.
+    // TRANSPOSED: the same registers as the block's transpose (M21 = M12^T): row (a',b',c'), columns (a,b,c).
+    template <int DIM, int DEGX, bool TRANSPOSED>
+    __device__ __forceinline__ void
+    store_block_direct(double *base, const int stride, const int t, const double (*acc)[CartCfg<DIM, DEGX>::NX])
+    {
+      using CC         = CartCfg<DIM, DEGX>;
+      constexpr int N1 = CC::N1, NX = CC::NX, GROUP = CC::GROUP, CPT = CC::CPT, NYZ = CC::NYZ;
+#pragma unroll
+      for (int k = 0; k < CPT; ++k)
+        {
+          const int col = t + k * GROUP;
+          if (col >= NYZ)
+            continue;
+          const int cb = DIM == 3 ? col % NX : col, cc = DIM == 3 ? col / NX : 0;
+          const int b = cb / N1, bp = cb % N1, c = cc / N1, cp = cc % N1;
+          const int rowq = TRANSPOSED ? bp + N1 * cp : b + N1 * c;  // (b,c) part of the row index
+          const int colq = TRANSPOSED ? b + N1 * c : bp + N1 * cp;  // (b,c) part of the column index
+#pragma unroll
+          for (int a = 0; a < N1; ++a)
+            {
+              double *dst = base + (int64_t)(a + N1 * rowq) * stride + N1 * colq;
+              double  v[N1];
+#pragma unroll
+              for (int e = 0; e < N1; ++e)
+                v[e] = TRANSPOSED ? acc[k][e * N1 + a] : acc[k][a * N1 + e];
+              if (N1 % 2 == 0)
+                {
+#pragma unroll
+                  for (int e = 0; e < N1; e += 2)
+                    *reinterpret_cast<double2 *>(dst + e) = make_double2(v[e], v[e + 1]);
+                }
+              else
+                {
+#pragma unroll
+                  for (int e = 0; e < N1; ++e)
+                    dst[e] = v[e];
+                }
+            }
+        }
+    }
+
     // The 1-D matrices of all bricks, one thread per (brick, [which,] axis, row): they depend on the geometry, the
     // element and the penalties only, so they are computed once per geometry (pd_create, pd_upload,
     // pd_invalidate_quadrature) and shared by the assembly and every matrix-free apply.
@@ -585,12 +629,17 @@ namespace pd
               group_sync<GROUP>();
               accumulate_chunk<DIM, DEGX>(SL, kind, cnt, t, A.stiffness, A.mass, acc);
             }
-          // ---- epilogue: registers -> shared tile -> the diagonal block of the CSR rows
+          const int64_t base   = A.diag_base[p];
+          const int     stride = A.row_stride[A.dof_block[p]];
+          if (!C::DGP)
+            {
+              store_block_direct<DIM, DEGX, false>(A.values + base, stride, t, acc);
+              continue;
+            }
+          // ---- FE_AggloDGP (a sub-set of the tensor index set): registers -> shared tile -> the CSR rows
           group_sync<GROUP>();
           stage_block<DIM, DEGX>(SL, t, acc);
           group_sync<GROUP>();
-          const int64_t base   = A.diag_base[p];
-          const int     stride = A.row_stride[A.dof_block[p]];
           for (int idx = t; idx < N * N; idx += GROUP)
             {
               const int i = idx / N, j = idx - i * N;
@@ -633,12 +682,19 @@ namespace pd
               group_sync<GROUP>();
               accumulate_chunk<DIM, DEGX>(SL, kind, cnt, t, 1., 0., acc);
             }
-          group_sync<GROUP>();
-          stage_block<DIM, DEGX>(SL, t, acc);
-          group_sync<GROUP>();
           const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
           const int     strideA = A.row_stride[A.dof_block[pa]];
           const int     strideB = baseBA >= 0 ? A.row_stride[A.dof_block[pb]] : 0;
+          if (!C::DGP)
+            {
+              store_block_direct<DIM, DEGX, false>(A.values + baseAB, strideA, t, acc);
+              if (baseBA >= 0) // M21 = M12^T (B a ghost polytope: its rows live on another rank)
+                store_block_direct<DIM, DEGX, true>(A.values + baseBA, strideB, t, acc);
+              continue;
+            }
+          group_sync<GROUP>();
+          stage_block<DIM, DEGX>(SL, t, acc);
+          group_sync<GROUP>();
           for (int idx = t; idx < N * N; idx += GROUP)
             {
               const int i = idx / N, j = idx - i * N;

@@ -379,19 +379,35 @@ namespace pd
         vmult_dispatch(h, mode, x_full_dev, dst, add);
         return;
       }
+    // aux (high priority): publish -> pull -> the cells / block rows that read ghost data;
+    // main: the cells / block rows that do not -- both run concurrently and meet at the end, so the exchange and
+    // the small boundary kernel hide behind the interior work instead of following it
     PD_CUDA(cudaEventRecord(p->ev_fork, h->stream));
     PD_CUDA(cudaStreamWaitEvent(p->aux, p->ev_fork, 0));
     exchange_on(p, x_full_dev, p->aux);
+    {
+      cudaStream_t main_stream = h->stream;
+      h->stream                = p->aux; // the launch helpers enqueue on the handle's stream
+      try
+        {
+          if (split)
+            launch_fine_operator(h, x_full_dev, dst, add, 2);
+          else
+            launch_spmv(h, x_full_dev, dst, add, 2);
+        }
+      catch (...)
+        {
+          h->stream = main_stream;
+          throw;
+        }
+      h->stream = main_stream;
+    }
     PD_CUDA(cudaEventRecord(p->ev_join, p->aux));
     if (split)
       launch_fine_operator(h, x_full_dev, dst, add, 1);
     else
       launch_spmv(h, x_full_dev, dst, add, 1); // block rows without ghost columns
     PD_CUDA(cudaStreamWaitEvent(h->stream, p->ev_join, 0));
-    if (split)
-      launch_fine_operator(h, x_full_dev, dst, add, 2);
-    else
-      launch_spmv(h, x_full_dev, dst, add, 2);
   }
 
   void
