@@ -619,6 +619,8 @@ namespace pd
 #pragma unroll
             for (int r = 0; r < NX; ++r)
               acc[k][r] = 0.;
+          const int64_t base   = A.diag_base[p];
+          const int     stride = A.row_stride[A.dof_block[p]];
           // the bricks of the polytope as one item list: its cell bricks, then the own-side face bricks of its adjacency
           const int64_t i0 = A.pit_ptr[p], i1 = A.pit_diag_end[p];
           for (int64_t c0 = i0; c0 < i1; c0 += CH)
@@ -629,8 +631,6 @@ namespace pd
               group_sync<GROUP>();
               accumulate_chunk<DIM, DEGX>(SL, kind, cnt, t, A.stiffness, A.mass, acc);
             }
-          const int64_t base   = A.diag_base[p];
-          const int     stride = A.row_stride[A.dof_block[p]];
           if (!C::DGP)
             {
               store_block_direct<DIM, DEGX, false>(A.values + base, stride, t, acc);
@@ -667,6 +667,10 @@ namespace pd
           const int32_t pa = A.ifA[f], pb = A.ifB[f];
           if (pb < 0)
             continue;
+          // where the two blocks go: issued now, so that these dependent loads run under the matrix loads below
+          const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
+          const int     strideA = A.row_stride[A.dof_block[pa]];
+          const int     strideB = baseBA >= 0 ? A.row_stride[A.dof_block[pb]] : 0;
           double acc[CPT][NX];
 #pragma unroll
           for (int k = 0; k < CPT; ++k)
@@ -682,9 +686,6 @@ namespace pd
               group_sync<GROUP>();
               accumulate_chunk<DIM, DEGX>(SL, kind, cnt, t, 1., 0., acc);
             }
-          const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
-          const int     strideA = A.row_stride[A.dof_block[pa]];
-          const int     strideB = baseBA >= 0 ? A.row_stride[A.dof_block[pb]] : 0;
           if (!C::DGP)
             {
               store_block_direct<DIM, DEGX, false>(A.values + baseAB, strideA, t, acc);
