@@ -480,11 +480,15 @@ namespace pd
           bulk_g2s(sR + ci * RS, A.rec + (int64_t)cell_of(ci) * DIM, DIM * 64, bar);
           bytes += DIM * 64;
         }
-      if (RO == N && A.seq == nullptr && n_own == FINE_TILE && (s0 * N) % 2 == 0)
-        { // the own cells are one aligned contiguous range
+      // the own cells are one aligned contiguous range (always along the curve's own numbering; with a cell list --
+      // the interior / boundary split of a sharded apply -- whenever the tile's cells are consecutive)
+      const int64_t first_cell = cell_of(0);
+      const bool    contiguous = A.seq == nullptr || (int64_t)cell_of(n_own - 1) - first_cell == n_own - 1;
+      if (RO == N && contiguous && n_own == FINE_TILE && (first_cell * N) % 2 == 0)
+        {
           if (tid == 0)
             {
-              bulk_g2s(S, A.x + (int64_t)s0 * N, FINE_TILE * N * 8, bar);
+              bulk_g2s(S, A.x + first_cell * N, FINE_TILE * N * 8, bar);
               bytes += FINE_TILE * N * 8;
             }
         }

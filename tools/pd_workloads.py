@@ -59,12 +59,47 @@ def build_handler(pdl, cfg, world=1):
     if world == 1:
         grid = pdl.Grid.hyper_cube(dim, 0.0, 1.0, n.bit_length() - 1)
         groups = morton_block_groups(dim, n, b) if b > 1 else np.arange(n**dim, dtype=np.int32).reshape(-1, 1)
+    elif b == 1:
+        # fine mesh (every cell its own element): numbered along the Morton curve of the stacked box, as the cells of
+        # a p4est-distributed mesh are on every rank (the tiled fine-mesh kernel stages contiguous runs of the curve)
+        assert dim == 3 and (world & (world - 1)) == 0
+        grid = morton_numbered_box(pdl, n, n, n * world, (1.0, 1.0, float(world)))
+        groups = np.arange(n * n * n * world, dtype=np.int32).reshape(-1, 1)
     else:
         assert dim == 3
         grid = pdl.Grid.structured(dim, (n, n, n * world), 0.0, (1.0, 1.0, float(world)), order=1)
-        groups = lex_block_groups(n, n, n * world, b) if b > 1 else np.arange(n * n * n * world, dtype=np.int32).reshape(-1, 1)
+        groups = lex_block_groups(n, n, n * world, b)
     ah = pdl.AgglomerationHandler(grid)
     ah.define_agglomerates(groups)
     ah.initialize_fe_values(nq)
     ah.distribute_agglomerated_dofs(pdl.FE_DGQ, p)
     return ah
+
+
+def morton_numbered_box(pdl, nx, ny, nz, hi):
+    """An nx x ny x nz Cartesian hex grid on [0, hi] whose cells are numbered along the Morton (z-order) curve of the
+    whole box -- what a p4est-distributed deal.II mesh looks like on every rank -- as a pdl.Grid built from arrays
+    (vertices lexicographic, deal.II vertex order in a cell, neighbours behind the six faces).  nx, ny, nz powers of two."""
+    i, j, k = np.meshgrid(np.arange(nx, dtype=np.int64), np.arange(ny, dtype=np.int64), np.arange(nz, dtype=np.int64), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    key = np.zeros_like(i)
+    for b in range(max(nx, ny, nz).bit_length()):
+        key |= ((i >> b) & 1) << (3 * b) | ((j >> b) & 1) << (3 * b + 1) | ((k >> b) & 1) << (3 * b + 2)
+    order = np.argsort(key, kind="stable")
+    i, j, k = i[order], j[order], k[order]
+    n_cells = nx * ny * nz
+    cell_at = np.empty((nx, ny, nz), dtype=np.int64)
+    cell_at[i, j, k] = np.arange(n_cells)
+    vid = lambda a, b, c: (c * (ny + 1) + b) * (nx + 1) + a
+    cell_verts = np.stack([vid(i + (v & 1), j + ((v >> 1) & 1), k + ((v >> 2) & 1)) for v in range(8)], axis=1).astype(np.int32)
+    nbr = -np.ones((n_cells, 6), dtype=np.int32)
+    for f, (di, dj, dk) in enumerate([(-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)]):
+        a, b, c = i + di, j + dj, k + dk
+        ok = (a >= 0) & (a < nx) & (b >= 0) & (b < ny) & (c >= 0) & (c < nz)
+        nbr[ok, f] = cell_at[a[ok], b[ok], c[ok]]
+    x = np.linspace(0.0, hi[0], nx + 1)
+    y = np.linspace(0.0, hi[1], ny + 1)
+    z = np.linspace(0.0, hi[2], nz + 1)
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    verts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    return pdl.Grid.from_arrays(verts, cell_verts, nbr)
