@@ -733,198 +733,200 @@ namespace pd
       using C                   = Cfg<DIM, DEGX>;
       static constexpr int N1   = C::N1, NX = N1 * N1, NXP = NX + (NX & 1), NF = C::N;
       static constexpr int NL   = ipow(N1, DIM - 1); // lines per item
-      static constexpr int CH   = 256 / NL;          // items per chunk
-      static constexpr int NTHR = ((CH * NL + 31) / 32) * 32;
+      // a WARP per polytope, WPC polytopes per CTA in flight, warp barriers only: the work per polytope is a few
+      // thousand multiply-adds, what matters is how many polytopes an SM has in flight
+      static constexpr int GROUP = 32;
+      static constexpr int CH   = GROUP / NL;        // items a warp processes at once
+      static constexpr int NTHR = 256, WPC = NTHR / GROUP;
       static constexpr int MSTR = DIM * 2 * NXP;     // 1-D matrices of an item
       static constexpr int WSTR = 2 * NF + 1;        // two intermediate tensors of an item (odd stride)
+      static constexpr int GSM  = CH * (MSTR + 2 * WSTR) + 2 * CH + 2; // doubles of shared memory per warp
+      static_assert(NL <= 32, "a line per lane");
     };
 
     template <int DIM, int DEGX>
     __global__ void __launch_bounds__(ApplyCfg<DIM, DEGX>::NTHR, 3)
     k_cart_apply(const CartApplyArgs P)
     {
-      using C          = Cfg<DIM, DEGX>;
       using AC         = ApplyCfg<DIM, DEGX>;
-      constexpr int N1 = AC::N1, NXP = AC::NXP, NF = AC::NF, NL = AC::NL, CH = AC::CH, MSTR = AC::MSTR, WSTR = AC::WSTR;
+      constexpr int N1 = AC::N1, NXP = AC::NXP, NF = AC::NF, NL = AC::NL, CH = AC::CH, MSTR = AC::MSTR, WSTR = AC::WSTR,
+                    GROUP = AC::GROUP, WPC = AC::WPC;
       const CartArgs &A = P.g;
       extern __shared__ __align__(16) double smem[];
-      double *SM = smem;                  // [CH][MSTR]   1-D matrices, [d][slot][row a][a']
-      double *W  = SM + CH * MSTR;        // [CH][WSTR]   z-pass output (two tensors)
-      double *V  = W + CH * WSTR;         // [CH][WSTR]   y-pass output (two tensors)
-      __shared__ int     it_kind[CH];
-      __shared__ int64_t it_src[CH];
-      const int tid = threadIdx.x;
-      const int j = tid / NL, l = tid % NL;
-      const bool active = tid < CH * NL;
+      const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
+      double   *SM = smem + g * AC::GSM;   // [CH][MSTR]   1-D matrices, [d][slot][row a][a']
+      double   *W  = SM + CH * MSTR;       // [CH][WSTR]   z-pass output (two tensors)
+      double   *V  = W + CH * WSTR;        // [CH][WSTR]   y-pass output (two tensors)
+      int64_t  *it_src  = reinterpret_cast<int64_t *>(V + CH * WSTR); // [CH] first source entry of the item's input block
+      int      *it_kind = reinterpret_cast<int *>(it_src + CH);       // [CH] 1 cell, 2 own face, 3 cross face, 0 off
+      const int  j = t / NL, l = t % NL;
+      const bool active = t < CH * NL;
       const double sigma = A.stiffness, fmass = A.mass;
 
-      for (int p = blockIdx.x; p < A.np_own; p += gridDim.x)
+      for (int64_t p = (int64_t)blockIdx.x * WPC + g; p < A.np_own; p += (int64_t)gridDim.x * WPC)
         {
           double acc[N1];
 #pragma unroll
           for (int k = 0; k < N1; ++k)
             acc[k] = 0.;
-          const double *bb = A.bbox + (int64_t)p * 2 * DIM;
           // one item list per polytope: cell bricks, own-side face bricks, cross face bricks (x_Q of the neighbour)
           const int64_t i0 = A.pit_ptr[p], i1 = A.pit_ptr[p + 1];
+          for (int64_t c0 = i0; c0 < i1; c0 += CH)
             {
-              for (int64_t c0 = i0; c0 < i1; c0 += CH)
+              const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
+              __syncwarp();
+              // ---- the 1-D matrices of the chunk's bricks (k_brick_matrices); seen from side B a cross matrix is
+              // the transpose of the stored one
+              for (int w = t; w < cnt * MSTR; w += GROUP)
                 {
-                  const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
-                  __syncthreads();
-                  // ---- the 1-D matrices of the chunk's bricks (k_brick_matrices); seen from side B a cross matrix is
-                  // the transpose of the stored one
-                  for (int w = tid; w < cnt * MSTR; w += AC::NTHR)
+                  const int     it = w / MSTR, r = w % MSTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
+                  const int64_t brick = A.pit_brick[c0 + it];
+                  const int     meta = A.pit_meta[c0 + it], knd = meta & 3, side = (meta >> 2) & 1;
+                  const bool    enabled = knd == 1 ? (A.flags & PD_ASSEMBLE_VOLUME) != 0 :
+                                          ((meta & 8) ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
+                  if (r == 0)
                     {
-                      const int     it = w / MSTR, r = w % MSTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
-                      const int64_t brick = A.pit_brick[c0 + it];
-                      const int     meta = A.pit_meta[c0 + it], knd = meta & 3, side = (meta >> 2) & 1;
-                      const bool    enabled = knd == 1 ? (A.flags & PD_ASSEMBLE_VOLUME) != 0 :
-                                              ((meta & 8) ? (A.flags & PD_ASSEMBLE_BOUNDARY) != 0 : (A.flags & PD_ASSEMBLE_INTERIOR) != 0);
-                      if (r == 0)
-                        {
-                          it_kind[it] = enabled ? knd : 0;
-                          it_src[it]  = (int64_t)A.dof_block[A.pit_q[c0 + it]] * NF;
-                        }
-                      double v = 0.;
-                      if (enabled && knd == 1)
-                        v = A.cmat[(brick * DIM + d) * 2 * NXP + slot * NXP + k];
-                      else if (enabled && slot == 0 && k < N1 * N1)
-                        {
-                          const int kk = (knd == 3 && side) ? (k % N1) * N1 + k / N1 : k;
-                          v = A.fmat[((brick * 3 + (knd == 3 ? 2 : side)) * DIM + d) * NXP + kk] *
-                              (d == (A.fbk_lf[brick] >> 1) ? sigma : 1.);
-                        }
-                      SM[w] = v;
+                      it_kind[it] = enabled ? knd : 0;
+                      it_src[it]  = (int64_t)A.dof_block[A.pit_q[c0 + it]] * NF;
                     }
-                  __syncthreads();
-                  const int     knd = (active && j < cnt) ? it_kind[j] : 0;
-                  const bool    on  = knd != 0;
-                  const int64_t src_base = on ? it_src[j] : 0;
-                  const double *m = SM + j * MSTR;
-                  double       *w1 = W + j * WSTR, *w2 = w1 + NF, *v1 = V + j * WSTR, *v2 = v1 + NF;
-                  double        in1[N1], in2[N1];
-                  if (DIM == 3)
+                  double v = 0.;
+                  if (enabled && knd == 1)
+                    v = A.cmat[(brick * DIM + d) * 2 * NXP + slot * NXP + k];
+                  else if (enabled && slot == 0 && k < N1 * N1)
                     {
-                      // ---- z-pass: line (a, b) = l
-                      if (on)
-                        {
-#pragma unroll
-                          for (int k = 0; k < N1; ++k)
-                            in1[k] = P.src[src_base + l + NL * k];
-#pragma unroll
-                          for (int c = 0; c < N1; ++c)
-                            {
-                              double t1 = 0., t2 = 0.;
-#pragma unroll
-                              for (int k = 0; k < N1; ++k)
-                                {
-                                  t1 += m[(2 * 2 + 0) * NXP + c * N1 + k] * in1[k];
-                                  if (knd == 1)
-                                    t2 += m[(2 * 2 + 1) * NXP + c * N1 + k] * in1[k];
-                                }
-                              w1[l + NL * c] = t1;
-                              w2[l + NL * c] = t2;
-                            }
-                        }
-                      __syncthreads();
-                      // ---- y-pass: line (a, c): a = l % N1, c = l / N1
-                      if (on)
-                        {
-                          const int a = l % N1, c = l / N1;
-#pragma unroll
-                          for (int k = 0; k < N1; ++k)
-                            {
-                              in1[k] = w1[a + N1 * k + NL * c];
-                              in2[k] = w2[a + N1 * k + NL * c];
-                            }
-#pragma unroll
-                          for (int b = 0; b < N1; ++b)
-                            {
-                              double aa = 0., ab = 0., ba = 0.;
-#pragma unroll
-                              for (int k = 0; k < N1; ++k)
-                                {
-                                  const double my = m[(1 * 2 + 0) * NXP + b * N1 + k];
-                                  aa += my * in1[k];
-                                  if (knd == 1)
-                                    {
-                                      ab += m[(1 * 2 + 1) * NXP + b * N1 + k] * in1[k];
-                                      ba += my * in2[k];
-                                    }
-                                }
-                              v1[a + N1 * b + NL * c] = knd == 1 ? sigma * aa : 0.;
-                              v2[a + N1 * b + NL * c] = knd == 1 ? sigma * (ab + ba) + fmass * aa : aa;
-                            }
-                        }
-                      __syncthreads();
+                      const int kk = (knd == 3 && side) ? (k % N1) * N1 + k / N1 : k;
+                      v = A.fmat[((brick * 3 + (knd == 3 ? 2 : side)) * DIM + d) * NXP + kk] *
+                          (d == (A.fbk_lf[brick] >> 1) ? sigma : 1.);
                     }
-                  else
-                    {
-                      // ---- 2-D y-pass: line a = l
-                      if (on)
-                        {
-#pragma unroll
-                          for (int k = 0; k < N1; ++k)
-                            in1[k] = P.src[src_base + l + N1 * k];
-#pragma unroll
-                          for (int b = 0; b < N1; ++b)
-                            {
-                              double aa = 0., ab = 0.;
-#pragma unroll
-                              for (int k = 0; k < N1; ++k)
-                                {
-                                  aa += m[(1 * 2 + 0) * NXP + b * N1 + k] * in1[k];
-                                  if (knd == 1)
-                                    ab += m[(1 * 2 + 1) * NXP + b * N1 + k] * in1[k];
-                                }
-                              v1[l + N1 * b] = knd == 1 ? sigma * aa : 0.;
-                              v2[l + N1 * b] = knd == 1 ? sigma * ab + fmass * aa : aa;
-                            }
-                        }
-                      __syncthreads();
-                    }
-                  // ---- x-pass: line (b, c) = l -> the result line, accumulated in registers
+                  SM[w] = v;
+                }
+              __syncwarp();
+              const int     knd = (active && j < cnt) ? it_kind[j] : 0;
+              const bool    on  = knd != 0;
+              const int64_t src_base = on ? it_src[j] : 0;
+              const double *m = SM + j * MSTR;
+              double       *w1 = W + j * WSTR, *w2 = w1 + NF, *v1 = V + j * WSTR, *v2 = v1 + NF;
+              double        in1[N1], in2[N1];
+              if (DIM == 3)
+                {
+                  // ---- z-pass: line (a, b) = l
                   if (on)
                     {
 #pragma unroll
                       for (int k = 0; k < N1; ++k)
-                        {
-                          in1[k] = v1[k + N1 * l];
-                          in2[k] = v2[k + N1 * l];
-                        }
+                        in1[k] = P.src[src_base + l + NL * k];
 #pragma unroll
-                      for (int ap = 0; ap < N1; ++ap)
+                      for (int c = 0; c < N1; ++c)
                         {
-                          double t = 0.;
+                          double t1 = 0., t2 = 0.;
 #pragma unroll
                           for (int k = 0; k < N1; ++k)
                             {
-                              t += m[(0 * 2 + 0) * NXP + ap * N1 + k] * in2[k];
+                              t1 += m[(2 * 2 + 0) * NXP + c * N1 + k] * in1[k];
                               if (knd == 1)
-                                t += m[(0 * 2 + 1) * NXP + ap * N1 + k] * in1[k];
+                                t2 += m[(2 * 2 + 1) * NXP + c * N1 + k] * in1[k];
                             }
-                          acc[ap] += t;
+                          w1[l + NL * c] = t1;
+                          w2[l + NL * c] = t2;
                         }
+                    }
+                  __syncwarp();
+                  // ---- y-pass: line (a, c): a = l % N1, c = l / N1
+                  if (on)
+                    {
+                      const int a = l % N1, c = l / N1;
+#pragma unroll
+                      for (int k = 0; k < N1; ++k)
+                        {
+                          in1[k] = w1[a + N1 * k + NL * c];
+                          in2[k] = w2[a + N1 * k + NL * c];
+                        }
+#pragma unroll
+                      for (int b = 0; b < N1; ++b)
+                        {
+                          double aa = 0., ab = 0., ba = 0.;
+#pragma unroll
+                          for (int k = 0; k < N1; ++k)
+                            {
+                              const double my = m[(1 * 2 + 0) * NXP + b * N1 + k];
+                              aa += my * in1[k];
+                              if (knd == 1)
+                                {
+                                  ab += m[(1 * 2 + 1) * NXP + b * N1 + k] * in1[k];
+                                  ba += my * in2[k];
+                                }
+                            }
+                          v1[a + N1 * b + NL * c] = knd == 1 ? sigma * aa : 0.;
+                          v2[a + N1 * b + NL * c] = knd == 1 ? sigma * (ab + ba) + fmass * aa : aa;
+                        }
+                    }
+                  __syncwarp();
+                }
+              else
+                {
+                  // ---- 2-D y-pass: line a = l
+                  if (on)
+                    {
+#pragma unroll
+                      for (int k = 0; k < N1; ++k)
+                        in1[k] = P.src[src_base + l + N1 * k];
+#pragma unroll
+                      for (int b = 0; b < N1; ++b)
+                        {
+                          double aa = 0., ab = 0.;
+#pragma unroll
+                          for (int k = 0; k < N1; ++k)
+                            {
+                              aa += m[(1 * 2 + 0) * NXP + b * N1 + k] * in1[k];
+                              if (knd == 1)
+                                ab += m[(1 * 2 + 1) * NXP + b * N1 + k] * in1[k];
+                            }
+                          v1[l + N1 * b] = knd == 1 ? sigma * aa : 0.;
+                          v2[l + N1 * b] = knd == 1 ? sigma * ab + fmass * aa : aa;
+                        }
+                    }
+                  __syncwarp();
+                }
+              // ---- x-pass: line (b, c) = l -> the result line, accumulated in registers
+              if (on)
+                {
+#pragma unroll
+                  for (int k = 0; k < N1; ++k)
+                    {
+                      in1[k] = v1[k + N1 * l];
+                      in2[k] = v2[k + N1 * l];
+                    }
+#pragma unroll
+                  for (int ap = 0; ap < N1; ++ap)
+                    {
+                      double tt = 0.;
+#pragma unroll
+                      for (int k = 0; k < N1; ++k)
+                        {
+                          tt += m[(0 * 2 + 0) * NXP + ap * N1 + k] * in2[k];
+                          if (knd == 1)
+                            tt += m[(0 * 2 + 1) * NXP + ap * N1 + k] * in1[k];
+                        }
+                      acc[ap] += tt;
                     }
                 }
             }
           // ---- sum the item slots in a fixed order and write the rows of the polytope
-          __syncthreads();
+          __syncwarp();
           if (active)
             {
 #pragma unroll
               for (int k = 0; k < N1; ++k)
                 W[j * (NF + 1) + k + N1 * l] = acc[k];
             }
-          __syncthreads();
-          for (int i = tid; i < NF; i += AC::NTHR)
+          __syncwarp();
+          for (int i = t; i < NF; i += GROUP)
             {
-              double t = 0.;
+              double tt = 0.;
               for (int jj = 0; jj < CH; ++jj)
-                t += W[jj * (NF + 1) + i];
+                tt += W[jj * (NF + 1) + i];
               double *o = P.dst + (int64_t)A.dof_block[p] * NF + i;
-              *o        = P.add ? *o + t : t;
+              *o        = P.add ? *o + tt : tt;
             }
         }
     }
@@ -935,11 +937,12 @@ namespace pd
     {
       using AC = ApplyCfg<DIM, DEGX>;
       auto         kern = k_cart_apply<DIM, DEGX>;
-      const size_t smem = sizeof(double) * (size_t)AC::CH * (AC::MSTR + 2 * AC::WSTR);
+      const size_t smem = sizeof(double) * (size_t)AC::WPC * AC::GSM;
       static_assert(AC::WSTR >= AC::NF + 1, "the slot sums alias the intermediates");
       if (smem > 48 * 1024)
         PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int grid = (int)std::min<int64_t>(h->np_own, (int64_t)h->sm_count * 16);
+      const int64_t ctas = (h->np_own + AC::WPC - 1) / AC::WPC;
+      const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)h->sm_count * 16));
       kern<<<grid, AC::NTHR, smem, h->stream>>>(a);
       ++h->launches;
       PD_CUDA(cudaGetLastError());
