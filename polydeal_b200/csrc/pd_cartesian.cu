@@ -605,13 +605,14 @@ namespace pd
     {
       using C          = Cfg<DIM, DEGX>;
       using CC         = CartCfg<DIM, DEGX>;
-      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, CH = CC::CH, N = C::N, GROUP = CC::GROUP, CPT = CC::CPT, WPC = CC::WPC;
+      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, CH = CC::CH, N = C::N, GROUP = CC::GROUP, CPT = CC::CPT;
       extern __shared__ __align__(16) double cart_smem[];
       const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
       double   *SL   = cart_smem + g * CC::GSM;
       int      *kind = reinterpret_cast<int *>(SL + CC::GSM - CH / 2 - 2);
 
-      for (int64_t p = (int64_t)blockIdx.x * WPC + g; p < A.np_own; p += (int64_t)gridDim.x * WPC)
+      const int wpc = blockDim.x / GROUP;
+      for (int64_t p = (int64_t)blockIdx.x * wpc + g; p < A.np_own; p += (int64_t)gridDim.x * wpc)
         {
           double acc[CPT][NX];
 #pragma unroll
@@ -656,13 +657,14 @@ namespace pd
     {
       using C          = Cfg<DIM, DEGX>;
       using CC         = CartCfg<DIM, DEGX>;
-      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, CH = CC::CH, N = C::N, GROUP = CC::GROUP, CPT = CC::CPT, WPC = CC::WPC;
+      constexpr int N1 = CC::N1, NX = CC::NX, NF = CC::NF, CH = CC::CH, N = C::N, GROUP = CC::GROUP, CPT = CC::CPT;
       extern __shared__ __align__(16) double cart_smem[];
       const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
       double   *SL   = cart_smem + g * CC::GSM;
       int      *kind = reinterpret_cast<int *>(SL + CC::GSM - CH / 2 - 2);
 
-      for (int64_t f = (int64_t)blockIdx.x * WPC + g; f < A.n_ifaces; f += (int64_t)gridDim.x * WPC)
+      const int wpc = blockDim.x / GROUP;
+      for (int64_t f = (int64_t)blockIdx.x * wpc + g; f < A.n_ifaces; f += (int64_t)gridDim.x * wpc)
         {
           const int32_t pa = A.ifA[f], pb = A.ifB[f];
           if (pb < 0)
@@ -750,7 +752,7 @@ namespace pd
     {
       using AC         = ApplyCfg<DIM, DEGX>;
       constexpr int N1 = AC::N1, NXP = AC::NXP, NF = AC::NF, NL = AC::NL, CH = AC::CH, MSTR = AC::MSTR, WSTR = AC::WSTR,
-                    GROUP = AC::GROUP, WPC = AC::WPC;
+                    GROUP = AC::GROUP;
       const CartArgs &A = P.g;
       extern __shared__ __align__(16) double smem[];
       const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
@@ -763,7 +765,8 @@ namespace pd
       const bool active = t < CH * NL;
       const double sigma = A.stiffness, fmass = A.mass;
 
-      for (int64_t p = (int64_t)blockIdx.x * WPC + g; p < A.np_own; p += (int64_t)gridDim.x * WPC)
+      const int wpc = blockDim.x / GROUP; // fewer warps per CTA on small problems: more CTAs, every SM busy
+      for (int64_t p = (int64_t)blockIdx.x * wpc + g; p < A.np_own; p += (int64_t)gridDim.x * wpc)
         {
           double acc[N1];
 #pragma unroll
@@ -937,13 +940,16 @@ namespace pd
     {
       using AC = ApplyCfg<DIM, DEGX>;
       auto         kern = k_cart_apply<DIM, DEGX>;
-      const size_t smem = sizeof(double) * (size_t)AC::WPC * AC::GSM;
       static_assert(AC::WSTR >= AC::NF + 1, "the slot sums alias the intermediates");
-      if (smem > 48 * 1024)
-        PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int64_t ctas = (h->np_own + AC::WPC - 1) / AC::WPC;
+      // warps per CTA: eight on large problems, fewer when that would leave SMs without a CTA
+      int wpc = AC::WPC;
+      while (wpc > 1 && (h->np_own + wpc - 1) / wpc < (int64_t)h->sm_count * 4)
+        wpc /= 2;
+      const size_t smem = sizeof(double) * (size_t)wpc * AC::GSM;
+      PD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * AC::WPC * AC::GSM)));
+      const int64_t ctas = (h->np_own + wpc - 1) / wpc;
       const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)h->sm_count * 16));
-      kern<<<grid, AC::NTHR, smem, h->stream>>>(a);
+      kern<<<grid, wpc * AC::GROUP, smem, h->stream>>>(a);
       ++h->launches;
       PD_CUDA(cudaGetLastError());
     }
@@ -964,28 +970,28 @@ namespace pd
     void
     run_cart(pd_handle *h, const CartArgs &a)
     {
-      using CC            = CartCfg<DIM, DEGX>;
-      const size_t smem   = sizeof(double) * (size_t)CC::WPC * CC::GSM;
-      auto         kd = k_cart_diag<DIM, DEGX>, ko = k_cart_offdiag<DIM, DEGX>;
-      if (smem > 48 * 1024)
+      using CC = CartCfg<DIM, DEGX>;
+      auto kd = k_cart_diag<DIM, DEGX>, ko = k_cart_offdiag<DIM, DEGX>;
+      const size_t smem_max = sizeof(double) * (size_t)CC::WPC * CC::GSM;
+      if (smem_max > 48 * 1024)
         {
-          PD_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          PD_CUDA(cudaFuncSetAttribute(ko, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          PD_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+          PD_CUDA(cudaFuncSetAttribute(ko, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         }
-      {
-        const int64_t ctas = (h->np_own + CC::WPC - 1) / CC::WPC;
+      // work items per CTA (warp-granular kernels): eight on large problems, fewer when that would leave SMs idle
+      auto launch = [&](auto kern, const int64_t n_items) {
+        int wpc = CC::WPC;
+        while (wpc > 1 && (n_items + wpc - 1) / wpc < (int64_t)h->sm_count * 4)
+          wpc /= 2;
+        const int64_t ctas = (n_items + wpc - 1) / wpc;
         const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)h->sm_count * 16));
-        kd<<<grid, CC::NTHR, smem, h->stream>>>(a);
+        kern<<<grid, wpc * CC::GROUP, sizeof(double) * (size_t)wpc * CC::GSM, h->stream>>>(a);
         ++h->launches;
-      }
+      };
+      launch(kd, h->np_own);
       PD_CUDA(cudaEventRecord(h->ev[1], h->stream));
       if ((a.flags & PD_ASSEMBLE_INTERIOR) && h->n_ifaces > 0)
-        {
-          const int64_t ctas = (h->n_ifaces + CC::WPC - 1) / CC::WPC;
-          const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)h->sm_count * 16));
-          ko<<<grid, CC::NTHR, smem, h->stream>>>(a);
-          ++h->launches;
-        }
+        launch(ko, h->n_ifaces);
       PD_CUDA(cudaEventRecord(h->ev[2], h->stream));
       PD_CUDA(cudaEventRecord(h->ev[3], h->stream));
       PD_CUDA(cudaGetLastError());

@@ -462,7 +462,11 @@ namespace pd
           if (role == 0 && A.mass != 0.)
             mv = A.mass * A.vol[cell_of(ci)];
         }
-      __syncthreads(); // the mbarrier is initialised
+      // (the mbarrier is initialised behind this barrier.)  With a cell list -- a numbering that is not the curve's, or
+      // the interior / boundary split of a sharded apply -- the tile's own cells may still be one run of consecutive
+      // cells in list order: then one bulk copy stages them, as along the curve's own numbering
+      const int  first_cell = cell_of(0);
+      const bool contiguous = __syncthreads_and(!mine || cell_of(ci) == first_cell + ci) != 0;
       // ---- stage the coefficients (own + halo) and the own cells' records; everything is in flight at once
       uint32_t bytes = 0;
       for (int r = tid; r < nh; r += FINE_TILE_THREADS)
@@ -482,13 +486,11 @@ namespace pd
         }
       // the own cells are one aligned contiguous range (always along the curve's own numbering; with a cell list --
       // the interior / boundary split of a sharded apply -- whenever the tile's cells are consecutive)
-      const int64_t first_cell = cell_of(0);
-      const bool    contiguous = A.seq == nullptr || (int64_t)cell_of(n_own - 1) - first_cell == n_own - 1;
-      if (RO == N && contiguous && n_own == FINE_TILE && (first_cell * N) % 2 == 0)
+      if (RO == N && contiguous && n_own == FINE_TILE && ((int64_t)first_cell * N) % 2 == 0)
         {
           if (tid == 0)
             {
-              bulk_g2s(S, A.x + first_cell * N, FINE_TILE * N * 8, bar);
+              bulk_g2s(S, A.x + (int64_t)first_cell * N, FINE_TILE * N * 8, bar);
               bytes += FINE_TILE * N * 8;
             }
         }
