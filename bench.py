@@ -338,6 +338,17 @@ def time_assembly_steps(op, stream, flush, steps, mass=0.0):
     return statistics.mean(tot), {k: statistics.mean(v) for k, v in kms.items()}
 
 
+def serial_kernel_ms(op, stream, flush, steps, mass=0.0):
+    """Per-kernel device times with the tensor path's two kernels run one after the other (PD_CART_SERIAL): what the
+    rooflines of the individual kernels are computed from; the timed steps run them concurrently."""
+    os.environ["PD_CART_SERIAL"] = "1"
+    try:
+        ms, kms = time_assembly_steps(op, stream, flush, steps, mass)
+    finally:
+        del os.environ["PD_CART_SERIAL"]
+    return ms, kms
+
+
 def generic_path_block(op, desc, n, nq, stream, flush, peaks, steps, mass=0.0):
     """The DMMA kernels on the agglomerated quadrature (what a distorted mesh runs), forced on the same handle."""
     os.environ["PD_ASSEMBLE_KERNELS"] = "generic"
@@ -511,6 +522,7 @@ def run_gpu(args):
 
     t_pmf_ms = timer.per_call_ms(apply_pmf, max(3, reps // 3), warm=2)
     pmf_checksum = float(y.sum())
+    pmf_stats = op.tensor_path_stats()
     # the loop around vmult: Jacobi-preconditioned CG, device resident (CUDA graph); sharded: ghost exchange
     # and dot-product all-reduce over peer memory inside the graph.  24 iterations, no convergence test.
     bcg = torch.from_numpy(np.cos(0.23 * np.arange(n_dofs)) + 0.1).cuda()
@@ -534,7 +546,8 @@ def run_gpu(args):
         peer.close()
     nblocks = int(desc.brow_ptr[desc.n_block_rows])
     path = op.assembly_path
-    roofs = assembly_rooflines(desc, n, NQ, kms, read_peaks(), path=path, stats=op.tensor_path_stats()) if rank == 0 else None
+    serial_ms, kms_serial = serial_kernel_ms(op, stream, flush, 3) if path == "tensor" else (None, kms)
+    roofs = assembly_rooflines(desc, n, NQ, kms_serial, read_peaks(), path=path, stats=op.tensor_path_stats()) if rank == 0 else None
     generic = None
     if world == 1 and not args.no_extra_configs:
         generic = generic_path_block(op, desc, n, NQ, stream, flush, read_peaks(), 3)
@@ -593,6 +606,11 @@ def run_gpu(args):
         "roofline": {k: vol[k] for k in vol if k != "kernel"} | {"kernel": vol["kernel"]},
         "rooflines": roofs,
         "kernel_ms": kms,
+        "kernel_ms_serial": kms_serial,
+        "kernel_ms_note": ("tensor path: k_cart_diag and k_cart_offdiag run CONCURRENTLY in a timed step (kernel_ms: volume = the "
+                           "diagonal kernel, faces = what remains until the off-diagonal kernel ends); the rooflines use "
+                           "kernel_ms_serial, measured with PD_CART_SERIAL=1 (one after the other, %s ms per step)"
+                           % (("%.3f" % serial_ms) if serial_ms else "-")) if path == "tensor" else None,
         "vmult": {"metric": "SIP vmult GDoF/s (block-CSR apply of the assembled operator"
                             + (", incl. the ghost exchange over NVLink peer memory)" if world > 1 else ")"),
                   "value": total_dofs / (t_vm_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t_vm_ms,
@@ -601,9 +619,15 @@ def run_gpu(args):
                   "cg_ms_per_iteration": t_cg_ms,
                   "cg": "Jacobi-PCG around the block-CSR vmult, CUDA-graph replayed"
                         + ("; ghost exchange + dot-product all-reduce over NVLink peer memory inside the graph" if world > 1 else "")},
-        "poly_mf_vmult": {"metric": "matrix-free SIP vmult on the agglomerated polytopes, GDoF/s",
+        "poly_mf_vmult": {"metric": "matrix-free SIP vmult on the agglomerated polytopes, GDoF/s (sum-factorised per brick, "
+                                    "k_cart_apply; coefficients = the bricks' 1-D matrices)",
                           "value": total_dofs / (t_pmf_ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": t_pmf_ms,
-                          "checksum_rank0": pmf_checksum},
+                          "checksum_rank0": pmf_checksum, "bricks": pmf_stats,
+                          "roofline": hbm_block("k_cart_apply", 16.0 * n_dofs + 8.0 * DIM * 2 * (DEGREE + 1) ** 2 * pmf_stats["apply_items"],
+                                                t_pmf_ms, peaks,
+                                                note="bytes = 16 B/DoF (src read, dst written) + the 1-D matrices of every item "
+                                                     "(upper bound dim * 2 * N1^2 doubles each); the kernel is latency-bound, "
+                                                     "not bandwidth-bound: about 11 k multiply-adds per polytope")},
     }
     if world > 1:
         out["vmult"]["ms_with_nccl_exchange"] = t_vm_nccl_ms
@@ -702,6 +726,7 @@ def run_extra_config(pdl, name, stream, peaks, steps):
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
     ms, kms = time_assembly_steps(op, stream, flush, steps, cfg["mass"])
     path = op.assembly_path
+    kms_roof = serial_kernel_ms(op, stream, flush, min(steps, 3), cfg["mass"])[1] if path == "tensor" else kms
     x = torch.from_numpy(src_values(N)).cuda()
     y = torch.empty_like(x)
     vm = []
@@ -720,7 +745,8 @@ def run_extra_config(pdl, name, stream, peaks, steps):
                        f"FE_DGQ({cfg['p']}), QGauss({cfg['nq']})" + (", + reaction c=0.5, C=40" if cfg["mass"] else ""),
            "n_dofs": N, "assembly_path": path, "assemble_ms": ms, "dofs_per_s": N / (ms * 1e-3), "kernel_ms": kms,
            "host_setup_s": t_host,
-           "rooflines": assembly_rooflines(desc, n, cfg["nq"], kms, peaks, mass=bool(cfg["mass"]), path=path,
+           "kernel_ms_serial": kms_roof,
+           "rooflines": assembly_rooflines(desc, n, cfg["nq"], kms_roof, peaks, mass=bool(cfg["mass"]), path=path,
                                            stats=op.tensor_path_stats()),
            "generic_path": generic_path_block(op, desc, n, cfg["nq"], stream, flush, peaks, min(steps, 3), cfg["mass"]),
            "vmult_ms": vm_ms, "vmult_gdofs": N / (vm_ms * 1e-3) / 1e9,

@@ -312,9 +312,10 @@ int pd_assemble(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
 #define PD_PATH_TENSOR 1
 /* which family the last pd_assemble ran (-1: none yet) */
 int pd_assembly_path(const pd_handle *h);
-/* the tensor path's work: stats4 = {axis-aligned (0/1), cell bricks, face bricks, items of all diagonal blocks}
- * (a brick = a tensor-product set of sub-cells / coplanar sub-faces whose quadrature sums factorise, pd_cartesian.cu) */
-int pd_tensor_path_stats(const pd_handle *h, int64_t *stats4);
+/* the tensor path's work: stats5 = {axis-aligned (0/1), cell bricks, face bricks, items of all diagonal blocks,
+ * items of the matrix-free apply} (a brick = a tensor-product set of sub-cells / coplanar sub-faces whose quadrature
+ * sums factorise, pd_cartesian.cu) */
+int pd_tensor_path_stats(const pd_handle *h, int64_t *stats5);
 
 int64_t pd_n_dofs(const pd_handle *h);        /* rows = owned DoFs */
 int64_t pd_n_source_dofs(const pd_handle *h); /* length of vmult source vectors = owned + ghost DoFs */

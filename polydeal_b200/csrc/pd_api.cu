@@ -609,6 +609,12 @@ extern "C"
         cudaGraphExecDestroy(h->cg_graph1_exec);
       if (h->ev_order)
         cudaEventDestroy(h->ev_order);
+      if (h->ev_fork)
+        cudaEventDestroy(h->ev_fork);
+      if (h->ev_join)
+        cudaEventDestroy(h->ev_join);
+      if (h->aux_stream)
+        cudaStreamDestroy(h->aux_stream);
       for (auto &e : h->ev)
         if (e)
           cudaEventDestroy(e);
@@ -1418,15 +1424,16 @@ extern "C"
   }
 
   int
-  pd_tensor_path_stats(const pd_handle *h, int64_t *stats4)
+  pd_tensor_path_stats(const pd_handle *h, int64_t *stats5)
   {
     return guarded([&] {
-      if (!h || !stats4)
+      if (!h || !stats5)
         throw Error(PD_ERR_INVALID, "null argument");
-      stats4[0] = h->cartesian ? 1 : 0;
-      stats4[1] = h->n_cell_bricks;
-      stats4[2] = h->n_face_bricks;
-      stats4[3] = h->n_diag_items;
+      stats5[0] = h->cartesian ? 1 : 0;
+      stats5[1] = h->n_cell_bricks;
+      stats5[2] = h->n_face_bricks;
+      stats5[3] = h->n_diag_items;
+      stats5[4] = h->n_apply_items;
     });
   }
 

@@ -988,10 +988,37 @@ namespace pd
         kern<<<grid, wpc * CC::GROUP, sizeof(double) * (size_t)wpc * CC::GSM, h->stream>>>(a);
         ++h->launches;
       };
-      launch(kd, h->np_own);
-      PD_CUDA(cudaEventRecord(h->ev[1], h->stream));
-      if ((a.flags & PD_ASSEMBLE_INTERIOR) && h->n_ifaces > 0)
-        launch(ko, h->n_ifaces);
+      // The two kernels write disjoint blocks and bound differently (the diagonal one by latency, the off-diagonal
+      // one by the HBM write stream): they run CONCURRENTLY, the off-diagonal kernel on a second stream of the handle.
+      // PD_CART_SERIAL=1 runs them one after the other (per-kernel timings for the rooflines).
+      const bool        serial  = getenv("PD_CART_SERIAL") != nullptr;
+      const bool        offdiag = (a.flags & PD_ASSEMBLE_INTERIOR) && h->n_ifaces > 0;
+      if (offdiag && !serial)
+        {
+          if (!h->aux_stream)
+            {
+              PD_CUDA(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+              PD_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+              PD_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+            }
+          PD_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+          PD_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+          cudaStream_t main_stream = h->stream;
+          h->stream                = h->aux_stream;
+          launch(ko, h->n_ifaces);
+          h->stream = main_stream;
+          PD_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
+          launch(kd, h->np_own);
+          PD_CUDA(cudaEventRecord(h->ev[1], h->stream)); // (the diagonal kernel's end; the other kernel overlaps it)
+          PD_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        }
+      else
+        {
+          launch(kd, h->np_own);
+          PD_CUDA(cudaEventRecord(h->ev[1], h->stream));
+          if (offdiag)
+            launch(ko, h->n_ifaces);
+        }
       PD_CUDA(cudaEventRecord(h->ev[2], h->stream));
       PD_CUDA(cudaEventRecord(h->ev[3], h->stream));
       PD_CUDA(cudaGetLastError());
@@ -1330,6 +1357,7 @@ namespace pd
     h->n_diag_items  = 0;
     for (int32_t p = 0; p < h->np_own; ++p)
       h->n_diag_items += B.pit_diag_end[p] - B.pit_ptr[p];
+    h->n_apply_items = B.pit_ptr[h->np_own];
     h->bricks_ready  = true;
     h->h_subcell_idx.assign(d.poly_subcell_idx, d.poly_subcell_idx + h->n_subcells);
     h->h_sub_cell.assign(d.sub_cell, d.sub_cell + h->n_subfaces);

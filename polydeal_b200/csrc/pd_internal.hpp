@@ -174,7 +174,7 @@ struct pd_handle
   pd::DevBuf<double>   fbk_plane, fbk_sigma, cmat, fmat;
   pd::DevBuf<int32_t>  cbk_poly, fbk_iface;
   bool                 brick_mat_valid = false;
-  int64_t              n_cell_bricks = 0, n_face_bricks = 0, n_diag_items = 0;
+  int64_t              n_cell_bricks = 0, n_face_bricks = 0, n_diag_items = 0, n_apply_items = 0;
   bool                 bricks_ready = false;
   std::vector<int32_t> h_subcell_idx, h_sub_cell, h_sub_face;
   int                  last_assembly_path = -1; // 0: DMMA kernels on the agglomerated quadrature, 1: tensor path
@@ -190,6 +190,8 @@ struct pd_handle
   cudaStream_t stream     = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t  ev[5]      = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t aux_stream = nullptr; // the tensor path's off-diagonal kernel runs beside the diagonal one (pd_cartesian.cu)
+  cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t  ev_order   = nullptr; // orders the own stream behind a caller stream that cannot capture (pd_solver.cu)
   float        last_ms[4] = {0, 0, 0, 0};
   bool         quad_valid = false, assembled = false;

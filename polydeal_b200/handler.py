@@ -588,9 +588,10 @@ class SIPOperator:
 
     def tensor_path_stats(self):
         """dict(axis_aligned, cell_bricks, face_bricks, diag_items) of the tensor path (pd_tensor_path_stats)."""
-        st = (C.c_int64 * 4)()
+        st = (C.c_int64 * 5)()
         K.check(K.lib().pd_tensor_path_stats(self._h, st))
-        return {"axis_aligned": bool(st[0]), "cell_bricks": int(st[1]), "face_bricks": int(st[2]), "diag_items": int(st[3])}
+        return {"axis_aligned": bool(st[0]), "cell_bricks": int(st[1]), "face_bricks": int(st[2]), "diag_items": int(st[3]),
+                "apply_items": int(st[4])}
 
     @property
     def launch_count(self):
