@@ -183,7 +183,7 @@ namespace pd
       static constexpr int NTHR  = GROUP >= 128 ? GROUP : 256;
       static constexpr int WPC   = NTHR / GROUP;
       static constexpr int CH    = 8; // items per chunk
-      static constexpr int MINB  = GROUP >= 128 ? 3 : 2;
+      static constexpr int MINB  = GROUP >= 128 ? 4 : 2;
       // shared memory of a group: the chunk's 1-D matrices, later the staged block; + the kinds of the chunk's items
       static constexpr int GSM   = ((C::DGP && NF * (NF + 1) > CH * ISTR) ? NF * (NF + 1) : CH * ISTR) + CH / 2 + 2;
     };
@@ -481,7 +481,12 @@ namespace pd
 #pragma unroll
               for (int e = 0; e < N1; ++e)
                 v[e] = TRANSPOSED ? acc[k][e * N1 + a] : acc[k][a * N1 + e];
-              if (N1 % 2 == 0)
+              if (N1 == 4)
+                // one 32-byte sector per store (st.global.v4.f64 -> STG.E.256 on sm_100a); dst is 32-byte aligned:
+                // block bases and row strides are multiples of n = 64 doubles, the column offset a multiple of 4
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3])
+                             : "memory");
+              else if (N1 % 2 == 0)
                 {
 #pragma unroll
                   for (int e = 0; e < N1; e += 2)

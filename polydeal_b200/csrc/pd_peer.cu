@@ -379,6 +379,19 @@ namespace pd
         vmult_dispatch(h, mode, x_full_dev, dst, add);
         return;
       }
+    // measurements: PD_PEER_DEBUG_PART = 1 runs the interior part only, 2 the exchange + the boundary part only
+    const char *dbg = getenv("PD_PEER_DEBUG_PART");
+    if (dbg && dbg[0] == '1')
+      {
+        split ? launch_fine_operator(h, x_full_dev, dst, add, 1) : launch_spmv(h, x_full_dev, dst, add, 1);
+        return;
+      }
+    if (dbg && dbg[0] == '2')
+      {
+        exchange_on(p, x_full_dev, h->stream);
+        split ? launch_fine_operator(h, x_full_dev, dst, add, 2) : launch_spmv(h, x_full_dev, dst, add, 2);
+        return;
+      }
     // aux (high priority): publish -> pull -> the cells / block rows that read ghost data;
     // main: the cells / block rows that do not -- both run concurrently and meet at the end, so the exchange and
     // the small boundary kernel hide behind the interior work instead of following it

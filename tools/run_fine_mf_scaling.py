@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--cells", type=int, default=64)
     ap.add_argument("--degree", type=int, default=2)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--mesh", default="morton", choices=["morton", "lex"])
+    ap.add_argument("--partition", default="metis", choices=["metis", "slabs"])
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -38,17 +40,29 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c, p = args.cells, args.degree
     t0 = time.time()
-    grid = pdl.Grid.structured(3, (c, c, c * world), 0.0, (1.0, 1.0, float(world)), order=1)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from pd_workloads import morton_numbered_box
+
+    if args.mesh == "morton" and world > 1:
+        grid = morton_numbered_box(pdl, c, c, c * world, (1.0, 1.0, float(world)))
+    elif args.mesh == "morton":
+        grid = pdl.Grid.hyper_cube(3, 0.0, 1.0, c.bit_length() - 1)
+    else:
+        grid = pdl.Grid.structured(3, (c, c, c * world), 0.0, (1.0, 1.0, float(world)), order=1)
     ah = pdl.AgglomerationHandler(grid)
-    for cell in range(grid.n_cells):
-        ah.define_agglomerate([cell])
+    ah.define_agglomerates(np.arange(grid.n_cells, dtype=np.int32).reshape(-1, 1))
     ah.initialize_fe_values(p + 1)
     ah.distribute_agglomerated_dofs(pdl.FE_DGQ, p)
     C = max(p, 1) * (p + 1.0)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     if world > 1:
-        owner = (np.arange(grid.n_cells) // (c * c * c)).astype(np.int32)  # lexicographic cells: z-slabs
+        if args.partition == "metis":
+            owner = pdd.partition_by_metis(ah, world)
+        else:  # z-slabs
+            v, cv, _ = grid.arrays()
+            zc = v[cv].mean(axis=1)[:, 2]
+            owner = np.minimum((zc * 1.0).astype(np.int32), world - 1)
         dop = pdd.DistributedSIPOperator(ah, owner, rank, penalty_constant=C, h_rule=pdl.H_NORMAL_EXTENT)
         op, part = dop.op, dop.part
     else:
@@ -107,6 +121,12 @@ def main():
             return a.elapsed_time(b) / args.steps
         breakdown = {"exchange_only_ms": batch(lambda: peer.exchange(x)),
                      "local_apply_only_ms": batch(lambda: op.vmult_ptr(y.data_ptr(), x.data_ptr(), pdl.VMULT_MATRIX_FREE))}
+        for key, val in (("interior_part_only_ms", "1"), ("exchange_plus_boundary_part_ms", "2")):
+            os.environ["PD_PEER_DEBUG_PART"] = val
+            breakdown[key] = batch(lambda: peer.vmult(y, x, pdl.VMULT_MATRIX_FREE))
+            del os.environ["PD_PEER_DEBUG_PART"]
+        breakdown["owned_cells"] = int(part.n_owned)
+        breakdown["ghost_cells"] = int(part.n_ghost)
     checksum = float(y.sum())
     t = torch.tensor([t_peer, t_nccl, checksum], dtype=torch.float64, device="cuda")
     if world > 1:
