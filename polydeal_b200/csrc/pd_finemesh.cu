@@ -712,10 +712,17 @@ namespace pd
             lo[k]   = std::min(lo[k], a);
             hmin[k] = std::min(hmin[k], b - a);
           }
+      // integer cell coordinates q = floor(centre / h) in ABSOLUTE coordinates, shifted by a multiple of 2^20 cells: the
+      // curve is then the same whichever part of a mesh a rank holds (the restriction of a Morton-numbered global mesh
+      // to a rank is again in the curve's order: no permutation, contiguous tiles), and hyper_cube(-1, 1) splits at 0
+      std::vector<int64_t> q0(dim);
+      for (int k = 0; k < dim; ++k)
+        q0[k] = (int64_t)std::floor(std::floor(lo[k] / hmin[k]) / 1048576.) * 1048576;
       for (int32_t c = 0; c < h->np_own; ++c)
         for (int k = 0; k < dim; ++k)
           {
-            const uint64_t q = (uint64_t)std::min(2097151., std::floor((ctr[(size_t)c * dim + k] - lo[k]) / hmin[k]));
+            const int64_t  qa = (int64_t)std::floor(ctr[(size_t)c * dim + k] / hmin[k]) - q0[k];
+            const uint64_t q  = (uint64_t)std::min<int64_t>(2097151, std::max<int64_t>(0, qa));
             for (int b = 0; b < 21; ++b)
               key[c] |= ((q >> b) & 1u) << (b * dim + k);
           }
@@ -733,13 +740,22 @@ namespace pd
     std::vector<int32_t> inner, outer;
     if (h->np != h->np_own)
       {
+        // the split is made BLOCK by block of the curve (the tiles of the tiled kernel): a block one of whose cells reads
+        // ghost data goes to the boundary list as a whole, so that both lists consist of whole tiles -- full
+        // contiguous runs of the curve that one bulk copy stages -- instead of blocks with a layer missing
+        const int             split_bits = (dim == 3 ? 2 : (dim == 2 ? 3 : 6)) * dim;
+        std::vector<uint64_t> bnd_blocks;
         for (const int32_t c : morton_order)
-          {
-            bool ghost = false;
-            for (int f = 0; f < nfc; ++f)
-              ghost = ghost || nbr[(size_t)c * nfc + f] >= h->np_own;
-            (ghost ? outer : inner).push_back(c);
-          }
+          for (int f = 0; f < nfc; ++f)
+            if (nbr[(size_t)c * nfc + f] >= h->np_own)
+              {
+                if (bnd_blocks.empty() || bnd_blocks.back() != (key[c] >> split_bits))
+                  bnd_blocks.push_back(key[c] >> split_bits);
+                break;
+              }
+        std::sort(bnd_blocks.begin(), bnd_blocks.end());
+        for (const int32_t c : morton_order)
+          (std::binary_search(bnd_blocks.begin(), bnd_blocks.end(), key[c] >> split_bits) ? outer : inner).push_back(c);
         put(h->mf_list_interior, inner);
         put(h->mf_list_boundary, outer);
       }
