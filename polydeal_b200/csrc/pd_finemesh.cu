@@ -345,6 +345,7 @@ namespace pd
       double              *y;
       const int32_t       *seq;      // cells in processing order (nullptr: 0 .. n_seq-1)
       const int32_t       *tile_first; // [n_tiles + 1]: first sequence entry of a tile (at most FINE_TILE entries)
+      const int32_t       *tile_base;  // [n_tiles]: first cell of a tile whose cells are consecutive cell numbers, else -1
       const int32_t       *tile_ptr;   // [n_tiles + 1] into halo
       const int32_t       *halo;
       const uint16_t      *noff; // [n_seq][2 DIM]: first double of the neighbour's coefficients in shared memory
@@ -442,7 +443,9 @@ namespace pd
       const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
       const int s0 = A.tile_first[blockIdx.x], n_own = A.tile_first[blockIdx.x + 1] - s0;
       const int h0 = A.tile_ptr[blockIdx.x], nh = A.tile_ptr[blockIdx.x + 1] - h0;
-      auto      cell_of = [&](const int i) { return A.seq ? A.seq[s0 + i] : s0 + i; };
+      // cells of a tile: consecutive numbers from tile_base (one load per tile, one bulk copy stages them), else the list
+      const int tbase   = A.tile_base[blockIdx.x];
+      auto      cell_of = [&](const int i) { return tbase >= 0 ? tbase + i : A.seq[s0 + i]; };
 
       if (tid == 0)
         mbar_init(bar, FINE_TILE_THREADS);
@@ -462,11 +465,9 @@ namespace pd
           if (role == 0 && A.mass != 0.)
             mv = A.mass * A.vol[cell_of(ci)];
         }
-      // (the mbarrier is initialised behind this barrier.)  With a cell list -- a numbering that is not the curve's, or
-      // the interior / boundary split of a sharded apply -- the tile's own cells may still be one run of consecutive
-      // cells in list order: then one bulk copy stages them, as along the curve's own numbering
+      __syncthreads(); // the mbarrier is initialised
       const int  first_cell = cell_of(0);
-      const bool contiguous = __syncthreads_and(!mine || cell_of(ci) == first_cell + ci) != 0;
+      const bool contiguous = tbase >= 0;
       // ---- stage the coefficients (own + halo) and the own cells' records; everything is in flight at once
       uint32_t bytes = 0;
       for (int r = tid; r < nh; r += FINE_TILE_THREADS)
@@ -851,6 +852,20 @@ namespace pd
               continue; // tiles with large halos (four CTAs no longer fit an SM): the line-per-thread kernel takes this sequence
             auto &t = h->mf_tiles[part];
             put(t.tile_first, plan.tile_first);
+            {
+              std::vector<int32_t> base((size_t)plan.n_tiles, -1);
+              for (int32_t k = 0; k < plan.n_tiles; ++k)
+                {
+                  const int32_t s0 = plan.tile_first[k], n_own = plan.tile_first[k + 1] - s0;
+                  const int32_t c0 = seq ? (*seq)[s0] : s0;
+                  bool          run = true;
+                  for (int32_t i = 1; i < n_own && run; ++i)
+                    run = (seq ? (*seq)[s0 + i] : s0 + i) == c0 + i;
+                  if (run)
+                    base[k] = c0;
+                }
+              put(t.tile_base, base);
+            }
             put(t.tile_ptr, plan.tile_ptr);
             put(t.noff, plan.noff);
             if (plan.halo.empty())
@@ -940,6 +955,7 @@ namespace pd
       a.seq      = part == 0 ? h->mf_seq_all.p /* nullptr: the cells are numbered along the curve already */ :
                                (part == 1 ? h->mf_list_interior.p : h->mf_list_boundary.p);
       a.tile_first = t.tile_first.p;
+      a.tile_base  = t.tile_base.p;
       a.tile_ptr = t.tile_ptr.p;
       a.halo     = t.halo.p;
       a.noff     = t.noff.p;

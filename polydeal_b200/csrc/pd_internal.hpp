@@ -122,7 +122,7 @@ struct pd_handle
   // cell sequences (all owned cells, interior list, boundary list) and the premultiplied 1-D tables
   struct FineTiles
   {
-    pd::DevBuf<int32_t>  tile_first, tile_ptr, halo;
+    pd::DevBuf<int32_t>  tile_first, tile_ptr, halo, tile_base; // tile_base: first cell of a tile whose cells are consecutive, else -1
     pd::DevBuf<uint16_t> noff;
     int32_t              n_tiles = 0, max_halo = 0, zoff = 0, n_seq = 0;
     bool                 ok = false;
