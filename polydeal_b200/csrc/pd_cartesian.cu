@@ -178,6 +178,10 @@ namespace pd
       // CTA is one group.  Small elements: a WARP is a group, a CTA runs WPC independent work items at once and only
       // warp-level barriers are used -- the work per block is a few hundred flops, what matters is how many blocks
       // are in flight per SM.
+      // Which axis lives in the registers ("row axis"): x for even N1 -- a thread's N1 entries (a, 0..N1-1) are one
+      // 16- / 32-byte store -- and FE_AggloDGP; the LAST axis for odd N1, where the lanes then run over (a', b') fastest
+      // so that a warp's scalar stores cover runs of N1^(dim-1) consecutive entries of a row instead of one each.
+      static constexpr int RA    = (N1 % 2 == 0 || C::DGP) ? 0 : DIM - 1;
       static constexpr int GROUP = NYZ >= 128 ? ((NYZ + 31) / 32) * 32 : 32;
       static constexpr int CPT   = (NYZ + GROUP - 1) / GROUP;
       static constexpr int NTHR  = GROUP >= 128 ? GROUP : 256;
@@ -186,6 +190,37 @@ namespace pd
       static constexpr int MINB  = GROUP >= 128 ? 4 : 2;
       // shared memory of a group: the chunk's 1-D matrices, later the staged block; + the kinds of the chunk's items
       static constexpr int GSM   = ((C::DGP && NF * (NF + 1) > CH * ISTR) ? NF * (NF + 1) : CH * ISTR) + CH / 2 + 2;
+    };
+
+    // a column of the factorised block: the index pairs (i_d, i_d') of the two column axes ax1 < ax2 (2-D: one)
+    template <int DIM, int DEGX>
+    struct ColumnIndex
+    {
+      using CC = CartCfg<DIM, DEGX>;
+      int p1, p2;         // pair index i * N1 + i' along ax1 / ax2
+      int q[2][2];        // (i, i') along ax1, ax2
+      static constexpr int ax1 = CC::RA == 0 ? 1 : 0, ax2 = CC::RA == 0 ? 2 : 1;
+      __device__ __forceinline__ explicit ColumnIndex(const int col)
+      {
+        constexpr int N1 = CC::N1, NX = CC::NX;
+        if (CC::RA == 0)
+          {
+            p1 = DIM == 3 ? col % NX : col;
+            p2 = DIM == 3 ? col / NX : 0;
+          }
+        else if (DIM == 3)
+          { // lanes run over (a', b') fastest, then (a, b)
+            const int ap = col % N1, bp = (col / N1) % N1, a = (col / NX) % N1, b = col / (NX * N1);
+            p1 = a * N1 + ap;
+            p2 = b * N1 + bp;
+          }
+        else
+          {
+            p1 = (col / N1) * N1 + col % N1; // (a, a'): a' fastest
+            p2 = 0;
+          }
+        q[0][0] = p1 / N1, q[0][1] = p1 % N1, q[1][0] = p2 / N1, q[1][1] = p2 % N1;
+      }
     };
 
     template <int GROUP>
@@ -373,7 +408,8 @@ namespace pd
                      double (*acc)[CartCfg<DIM, DEGX>::NX])
     {
       using CC            = CartCfg<DIM, DEGX>;
-      constexpr int NX    = CC::NX, NXP = CC::NXP, ISTR = CC::ISTR, GROUP = CC::GROUP, CPT = CC::CPT, NYZ = CC::NYZ;
+      using CI            = ColumnIndex<DIM, DEGX>;
+      constexpr int NX    = CC::NX, NXP = CC::NXP, ISTR = CC::ISTR, GROUP = CC::GROUP, CPT = CC::CPT, NYZ = CC::NYZ, RA = CC::RA;
       for (int it = 0; it < cnt; ++it)
         {
           const int kd = kind[it];
@@ -385,17 +421,17 @@ namespace pd
           for (int k = 0; k < CPT; ++k)
             {
               const int col = t + k * GROUP;
-              const int cb = DIM == 3 ? col % NX : col, cc = DIM == 3 ? col / NX : 0;
               yz1[k] = yz2[k] = 0.;
               if (col < NYZ)
                 {
-                  const double m1 = s[(1 * 2 + 0) * NXP + cb];
-                  const double m2 = DIM == 3 ? s[(2 * 2 + 0) * NXP + cc] : 1.;
+                  const CI     ci(col);
+                  const double m1 = s[(CI::ax1 * 2 + 0) * NXP + ci.p1];
+                  const double m2 = DIM == 3 ? s[(CI::ax2 * 2 + 0) * NXP + ci.p2] : 1.;
                   yz1[k]          = m1 * m2;
                   if (kd == 1)
                     {
-                      const double k1 = s[(1 * 2 + 1) * NXP + cb];
-                      const double k2 = DIM == 3 ? s[(2 * 2 + 1) * NXP + cc] : 0.;
+                      const double k1 = s[(CI::ax1 * 2 + 1) * NXP + ci.p1];
+                      const double k2 = DIM == 3 ? s[(CI::ax2 * 2 + 1) * NXP + ci.p2] : 0.;
                       yz2[k]          = stiffness * (k1 * m2 + m1 * k2) + mass * yz1[k];
                       yz1[k] *= stiffness;
                     }
@@ -403,13 +439,13 @@ namespace pd
             }
           if (kd == 1)
             {
-              load_rows<NX>(s + (0 * 2 + 1) * NXP, x); // K along x
+              load_rows<NX>(s + (RA * 2 + 1) * NXP, x); // K along the row axis
 #pragma unroll
               for (int k = 0; k < CPT; ++k)
 #pragma unroll
                 for (int r = 0; r < NX; ++r)
                   acc[k][r] += x[r] * yz1[k];
-              load_rows<NX>(s + (0 * 2 + 0) * NXP, x); // M along x
+              load_rows<NX>(s + (RA * 2 + 0) * NXP, x); // M along the row axis
 #pragma unroll
               for (int k = 0; k < CPT; ++k)
 #pragma unroll
@@ -418,7 +454,7 @@ namespace pd
             }
           else
             {
-              load_rows<NX>(s + (0 * 2 + 0) * NXP, x);
+              load_rows<NX>(s + (RA * 2 + 0) * NXP, x);
 #pragma unroll
               for (int k = 0; k < CPT; ++k)
 #pragma unroll
@@ -441,8 +477,9 @@ namespace pd
           const int col = t + k * GROUP;
           if (col >= NYZ)
             continue;
-          const int cb = DIM == 3 ? col % NX : col, cc = DIM == 3 ? col / NX : 0;
-          const int b = cb / N1, bp = cb % N1, c = cc / N1, cp = cc % N1;
+          static_assert(CartCfg<DIM, DEGX>::RA == 0 || !Cfg<DIM, DEGX>::DGP, "the staged path keeps x in the registers");
+          const ColumnIndex<DIM, DEGX> ci(col);
+          const int b = ci.q[0][0], bp = ci.q[0][1], c = ci.q[1][0], cp = ci.q[1][1];
 #pragma unroll
           for (int r = 0; r < NX; ++r)
             {
@@ -469,8 +506,20 @@ namespace pd
           const int col = t + k * GROUP;
           if (col >= NYZ)
             continue;
-          const int cb = DIM == 3 ? col % NX : col, cc = DIM == 3 ? col / NX : 0;
-          const int b = cb / N1, bp = cb % N1, c = cc / N1, cp = cc % N1;
+          const ColumnIndex<DIM, DEGX> ci(col);
+          if (CC::RA != 0)
+            {
+              // registers = the pairs (c, c') of the last axis; the lanes run over (a', b') fastest: scalar stores, a warp
+              // covers runs of N1^(dim-1) consecutive entries of a row.  (The transposed block is a work item of its own.)
+              static_assert(CC::RA == 0 || !TRANSPOSED, "the transposed block is computed, not stored, on this path");
+              const int rowq = ci.q[0][0] + (DIM == 3 ? N1 * ci.q[1][0] : 0), colq = ci.q[0][1] + (DIM == 3 ? N1 * ci.q[1][1] : 0);
+              constexpr int NLAST = DIM == 3 ? N1 * N1 : N1; // stride of the last axis inside a row / column index
+#pragma unroll
+              for (int r = 0; r < NX; ++r)
+                base[(int64_t)(rowq + NLAST * (r / N1)) * stride + colq + NLAST * (r % N1)] = acc[k][r];
+              continue;
+            }
+          const int b = ci.q[0][0], bp = ci.q[0][1], c = ci.q[1][0], cp = ci.q[1][1];
           const int rowq = TRANSPOSED ? bp + N1 * cp : b + N1 * c;  // (b,c) part of the row index
           const int colq = TRANSPOSED ? b + N1 * c : bp + N1 * cp;  // (b,c) part of the column index
 #pragma unroll
@@ -486,17 +535,11 @@ namespace pd
                 // block bases and row strides are multiples of n = 64 doubles, the column offset a multiple of 4
                 asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3])
                              : "memory");
-              else if (N1 % 2 == 0)
+              else
                 {
 #pragma unroll
                   for (int e = 0; e < N1; e += 2)
                     *reinterpret_cast<double2 *>(dst + e) = make_double2(v[e], v[e + 1]);
-                }
-              else
-                {
-#pragma unroll
-                  for (int e = 0; e < N1; ++e)
-                    dst[e] = v[e];
                 }
             }
         }
@@ -571,10 +614,10 @@ namespace pd
     // the chunk's 1-D matrices from k_brick_matrices into the group's shared memory (face factor x stiffness)
     template <int DIM, int DEGX, bool OFFDIAG>
     __device__ __forceinline__ void
-    load_chunk(const CartArgs &A, const int64_t c0, const int cnt, const int t, double *SL, int *kind)
+    load_chunk(const CartArgs &A, const int64_t c0, const int cnt, const int t, double *SL, int *kind, const bool transpose = false)
     {
       using CC           = CartCfg<DIM, DEGX>;
-      constexpr int NXP  = CC::NXP, ISTR = CC::ISTR, GROUP = CC::GROUP;
+      constexpr int NXP  = CC::NXP, ISTR = CC::ISTR, GROUP = CC::GROUP, N1 = CC::N1;
       for (int w = t; w < cnt * ISTR; w += GROUP)
         {
           const int it = w / ISTR, r = w % ISTR, d = r / (2 * NXP), slot = (r / NXP) & 1, k = r % NXP;
@@ -584,8 +627,9 @@ namespace pd
               const int64_t brick = c0 + it;
               if (r == 0)
                 kind[it] = 2;
-              if (slot == 0)
-                v = A.fmat[((brick * 3 + 2) * DIM + d) * NXP + k] * (d == (A.fbk_lf[brick] >> 1) ? A.stiffness : 1.);
+              if (slot == 0 && k < N1 * N1) // (B,A) block: M21 = M12^T, i.e. every 1-D factor transposed
+                v = A.fmat[((brick * 3 + 2) * DIM + d) * NXP + (transpose ? (k % N1) * N1 + k / N1 : k)] *
+                    (d == (A.fbk_lf[brick] >> 1) ? A.stiffness : 1.);
             }
           else
             {
@@ -669,8 +713,13 @@ namespace pd
       int      *kind = reinterpret_cast<int *>(SL + CC::GSM - CH / 2 - 2);
 
       const int wpc = blockDim.x / GROUP;
-      for (int64_t f = (int64_t)blockIdx.x * wpc + g; f < A.n_ifaces; f += (int64_t)gridDim.x * wpc)
+      // even N1: one work item per interface stores M12 and, transposed, M21; odd N1: two work items, the second one
+      // computes M21 = M12^T from the transposed factors (cheap) so that both blocks are stored with the lanes along rows
+      constexpr int     WPI     = CC::RA == 0 ? 1 : 2;
+      for (int64_t w = (int64_t)blockIdx.x * wpc + g; w < (int64_t)A.n_ifaces * WPI; w += (int64_t)gridDim.x * wpc)
         {
+          const int64_t f  = w / WPI;
+          const bool    tr = WPI == 2 && (w & 1);
           const int32_t pa = A.ifA[f], pb = A.ifB[f];
           if (pb < 0)
             continue;
@@ -678,6 +727,8 @@ namespace pd
           const int64_t baseAB = A.if_baseAB[f], baseBA = A.if_baseBA[f];
           const int     strideA = A.row_stride[A.dof_block[pa]];
           const int     strideB = baseBA >= 0 ? A.row_stride[A.dof_block[pb]] : 0;
+          if (tr && baseBA < 0)
+            continue; // B a ghost polytope: its rows live on another rank
           double acc[CPT][NX];
 #pragma unroll
           for (int k = 0; k < CPT; ++k)
@@ -689,15 +740,20 @@ namespace pd
             {
               const int cnt = (int)(i1 - c0 < CH ? i1 - c0 : CH);
               group_sync<GROUP>();
-              load_chunk<DIM, DEGX, true>(A, c0, cnt, t, SL, kind);
+              load_chunk<DIM, DEGX, true>(A, c0, cnt, t, SL, kind, tr);
               group_sync<GROUP>();
               accumulate_chunk<DIM, DEGX>(SL, kind, cnt, t, 1., 0., acc);
             }
           if (!C::DGP)
             {
-              store_block_direct<DIM, DEGX, false>(A.values + baseAB, strideA, t, acc);
-              if (baseBA >= 0) // M21 = M12^T (B a ghost polytope: its rows live on another rank)
-                store_block_direct<DIM, DEGX, true>(A.values + baseBA, strideB, t, acc);
+              if (WPI == 2)
+                store_block_direct<DIM, DEGX, false>(A.values + (tr ? baseBA : baseAB), tr ? strideB : strideA, t, acc);
+              else
+                {
+                  store_block_direct<DIM, DEGX, false>(A.values + baseAB, strideA, t, acc);
+                  if (baseBA >= 0) // M21 = M12^T (B a ghost polytope: its rows live on another rank)
+                    store_block_direct<DIM, DEGX, CC::RA == 0>(A.values + baseBA, strideB, t, acc);
+                }
               continue;
             }
           group_sync<GROUP>();
@@ -998,6 +1054,7 @@ namespace pd
       // PD_CART_SERIAL=1 runs them one after the other (per-kernel timings for the rooflines).
       const bool        serial  = getenv("PD_CART_SERIAL") != nullptr;
       const bool        offdiag = (a.flags & PD_ASSEMBLE_INTERIOR) && h->n_ifaces > 0;
+      const int64_t n_off_items = (int64_t)h->n_ifaces * (CC::RA == 0 ? 1 : 2);
       if (offdiag && !serial)
         {
           if (!h->aux_stream)
@@ -1010,7 +1067,7 @@ namespace pd
           PD_CUDA(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
           cudaStream_t main_stream = h->stream;
           h->stream                = h->aux_stream;
-          launch(ko, h->n_ifaces);
+          launch(ko, n_off_items);
           h->stream = main_stream;
           PD_CUDA(cudaEventRecord(h->ev_join, h->aux_stream));
           launch(kd, h->np_own);
@@ -1022,7 +1079,7 @@ namespace pd
           launch(kd, h->np_own);
           PD_CUDA(cudaEventRecord(h->ev[1], h->stream));
           if (offdiag)
-            launch(ko, h->n_ifaces);
+            launch(ko, n_off_items);
         }
       PD_CUDA(cudaEventRecord(h->ev[2], h->stream));
       PD_CUDA(cudaEventRecord(h->ev[3], h->stream));
