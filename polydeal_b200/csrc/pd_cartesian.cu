@@ -545,31 +545,53 @@ namespace pd
         }
     }
 
-    // The 1-D matrices of all bricks, one thread per (brick, [which,] axis, row): they depend on the geometry, the
-    // element and the penalties only, so they are computed once per geometry (pd_create, pd_upload,
-    // pd_invalidate_quadrature) and shared by the assembly and every matrix-free apply.
+    // The 1-D matrices of all bricks, one thread per (brick, axis): they depend on the geometry, the element and the
+    // penalties only, so they are computed once per geometry (pd_create, pd_upload, pd_invalidate_quadrature) and
+    // shared by the assembly and every matrix-free apply.  A thread evaluates the basis (both bases for a face
+    // brick) once per quadrature point of its intervals and accumulates all its matrices as outer products.
     template <int DIM, int DEGX>
     __global__ void __launch_bounds__(128)
     k_brick_matrices(const CartArgs A)
     {
       using C           = Cfg<DIM, DEGX>;
       using CC          = CartCfg<DIM, DEGX>;
-      constexpr int N1  = CC::N1, NXP = CC::NXP;
-      const int64_t nc  = A.n_cbk * DIM * N1, nf = A.n_fbk * 3 * DIM * N1;
+      constexpr int N1  = CC::N1, NX = CC::NX, NXP = CC::NXP;
+      const int64_t nc  = A.n_cbk * DIM, nf = A.n_fbk * DIM;
       const int64_t stride = (int64_t)gridDim.x * blockDim.x;
       for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nc + nf; w += stride)
         {
-          double M[N1], K[N1];
           if (w < nc)
             {
-              const int64_t brick = w / (DIM * N1);
-              const int     d = (int)((w / N1) % DIM), a = (int)(w % N1);
-              const double *bb = A.bbox + (int64_t)A.cbk_poly[brick] * 2 * DIM;
+              const int64_t brick = w / DIM;
+              const int     d     = (int)(w % DIM);
+              const double *bb    = A.bbox + (int64_t)A.cbk_poly[brick] * 2 * DIM;
+              const double  b_lo = bb[d], inv_h = 1. / (bb[DIM + d] - bb[d]);
               const int32_t *iv = A.cbk_iv + brick * 2 * DIM + 2 * d;
-              brick_rows_mass<C, DIM>(A, A.civ_box, iv[0], iv[1], A.quad.x, A.quad.w, A.nq, bb[d], 1. / (bb[DIM + d] - bb[d]), a, M, K);
-              double *dst = A.cmat + (brick * DIM + d) * 2 * NXP + a * N1;
+              double         M[NX], K[NX];
 #pragma unroll
-              for (int k = 0; k < N1; ++k)
+              for (int k = 0; k < NX; ++k)
+                M[k] = K[k] = 0.;
+              for (int i = iv[0]; i < iv[0] + iv[1]; ++i)
+                {
+                  const double2 bx = A.civ_box[i];
+                  for (int q = 0; q < A.nq; ++q)
+                    {
+                      double L[N1], dL[N1];
+                      basis_1d<C>(A.basis, (bx.x + (bx.y - bx.x) * A.quad.x[q] - b_lo) * inv_h, inv_h, L, dL);
+                      const double wq = A.quad.w[q] * (bx.y - bx.x);
+#pragma unroll
+                      for (int a = 0; a < N1; ++a)
+#pragma unroll
+                        for (int k = 0; k < N1; ++k)
+                          {
+                            M[a * N1 + k] += wq * L[a] * L[k];
+                            K[a * N1 + k] += wq * dL[a] * dL[k];
+                          }
+                    }
+                }
+              double *dst = A.cmat + (brick * DIM + d) * 2 * NXP;
+#pragma unroll
+              for (int k = 0; k < NX; ++k)
                 {
                   dst[k]       = M[k];
                   dst[NXP + k] = K[k];
@@ -577,37 +599,70 @@ namespace pd
               continue;
             }
           const int64_t v     = w - nc;
-          const int64_t brick = v / (3 * DIM * N1);
-          const int     which = (int)((v / (DIM * N1)) % 3), d = (int)((v / N1) % DIM), a = (int)(v % N1);
+          const int64_t brick = v / DIM;
+          const int     d     = (int)(v % DIM);
           const int32_t f = A.fbk_iface[brick], pa = A.ifA[f], pb = A.ifB[f];
-          if (pb < 0 && which != 0)
-            continue; // a boundary face has one side
+          const bool    two = pb >= 0; // an interior interface: both own sides and the cross matrices
           const int     lf = A.fbk_lf[brick], fd = lf >> 1, fs = lf & 1;
-          const double *ba = A.bbox + (int64_t)pa * 2 * DIM, *bbx = A.bbox + (int64_t)(pb < 0 ? pa : pb) * 2 * DIM;
-          const double *rb = which == 1 ? bbx : ba, *cb = which == 0 ? ba : bbx; // row / column basis
-          const double  r_lo = rb[d], r_ih = 1. / (rb[DIM + d] - rb[d]), c_lo = cb[d], c_ih = 1. / (cb[DIM + d] - cb[d]);
+          const double *ba = A.bbox + (int64_t)pa * 2 * DIM, *bbx = A.bbox + (int64_t)(two ? pb : pa) * 2 * DIM;
+          const double  a_lo = ba[d], a_ih = 1. / (ba[DIM + d] - ba[d]), b_lo = bbx[d], b_ih = 1. / (bbx[DIM + d] - bbx[d]);
+          double        MA[NX], MB[NX], MX[NX]; // own side A | own side B | cross (rows A, columns B)
           if (d == fd)
             {
-              const double x = A.fbk_plane[brick], pen = A.fbk_sigma[brick], nA = fs ? 1. : -1.;
-              double       LR[N1], dLR[N1], LC[N1], dLC[N1];
-              basis_1d<C>(A.basis, (x - r_lo) * r_ih, r_ih, LR, dLR);
-              basis_1d<C>(A.basis, (x - c_lo) * c_ih, c_ih, LC, dLC);
-              const double la = pick<N1>(LR, a), da = pick<N1>(dLR, a);
-              const double cf = pb < 0 ? 1. : 0.5, nrm = which == 1 ? -nA : nA; // outward normal of the row polytope
+              const double x = A.fbk_plane[brick], pen = A.fbk_sigma[brick], nA = fs ? 1. : -1., cf = two ? 0.5 : 1.;
+              double       LA[N1], dLA[N1], LB[N1], dLB[N1];
+              basis_1d<C>(A.basis, (x - a_lo) * a_ih, a_ih, LA, dLA);
+              basis_1d<C>(A.basis, (x - b_lo) * b_ih, b_ih, LB, dLB);
 #pragma unroll
-              for (int k = 0; k < N1; ++k)
-                M[k] = which == 2 ? 0.5 * nA * (da * LC[k] - la * dLC[k]) - pen * la * LC[k] : // M12 (poly_utils.h:1900-1906)
-                                    -cf * nrm * (da * LC[k] + la * dLC[k]) + pen * la * LC[k];  // M11 / M22 / boundary
+              for (int a = 0; a < N1; ++a)
+#pragma unroll
+                for (int k = 0; k < N1; ++k)
+                  {
+                    // M11 / boundary, M22 (outward normal of B = -nA), M12 (include/poly_utils.h:1891-1922), per unit stiffness
+                    MA[a * N1 + k] = -cf * nA * (dLA[a] * LA[k] + LA[a] * dLA[k]) + pen * LA[a] * LA[k];
+                    MB[a * N1 + k] = cf * nA * (dLB[a] * LB[k] + LB[a] * dLB[k]) + pen * LB[a] * LB[k];
+                    MX[a * N1 + k] = 0.5 * nA * (dLA[a] * LB[k] - LA[a] * dLB[k]) - pen * LA[a] * LB[k];
+                  }
             }
           else
             {
-              const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
-              brick_rows_cross<C, DIM>(A, A.fiv_box, iv[0], iv[1], A.quadf.x, A.quadf.w, A.nqf, r_lo, r_ih, c_lo, c_ih, a, M);
-            }
-          double *dst = A.fmat + ((brick * 3 + which) * DIM + d) * NXP + a * N1;
 #pragma unroll
-          for (int k = 0; k < N1; ++k)
-            dst[k] = M[k];
+              for (int k = 0; k < NX; ++k)
+                MA[k] = MB[k] = MX[k] = 0.;
+              const int32_t *iv = A.fbk_iv + brick * 2 * (DIM - 1) + 2 * (d < fd ? d : d - 1);
+              for (int i = iv[0]; i < iv[0] + iv[1]; ++i)
+                {
+                  const double2 bx = A.fiv_box[i];
+                  for (int q = 0; q < A.nqf; ++q)
+                    {
+                      double       LA[N1], dLA[N1], LB[N1], dLB[N1];
+                      const double x = bx.x + (bx.y - bx.x) * A.quadf.x[q];
+                      basis_1d<C>(A.basis, (x - a_lo) * a_ih, a_ih, LA, dLA);
+                      basis_1d<C>(A.basis, (x - b_lo) * b_ih, b_ih, LB, dLB);
+                      const double wq = A.quadf.w[q] * (bx.y - bx.x);
+#pragma unroll
+                      for (int a = 0; a < N1; ++a)
+#pragma unroll
+                        for (int k = 0; k < N1; ++k)
+                          {
+                            MA[a * N1 + k] += wq * LA[a] * LA[k];
+                            MB[a * N1 + k] += wq * LB[a] * LB[k];
+                            MX[a * N1 + k] += wq * LA[a] * LB[k];
+                          }
+                    }
+                }
+            }
+          double *dst = A.fmat + (brick * 3 * DIM + d) * NXP;
+#pragma unroll
+          for (int k = 0; k < NX; ++k)
+            {
+              dst[k] = MA[k];
+              if (two)
+                {
+                  dst[DIM * NXP + k]     = MB[k];
+                  dst[2 * DIM * NXP + k] = MX[k];
+                }
+            }
         }
     }
 
@@ -1020,7 +1075,7 @@ namespace pd
     run_brick_matrices(pd_handle *h, const CartArgs &a)
     {
       using CC           = CartCfg<DIM, DEGX>;
-      const int64_t work = (a.n_cbk + 3 * a.n_fbk) * DIM * CC::N1;
+      const int64_t work = (a.n_cbk + a.n_fbk) * DIM;
       const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 127) / 128, (int64_t)h->sm_count * 32));
       k_brick_matrices<DIM, DEGX><<<grid, 128, 0, h->stream>>>(a);
       ++h->launches;

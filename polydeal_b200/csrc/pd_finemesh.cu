@@ -444,7 +444,7 @@ namespace pd
       const int s0 = A.tile_first[blockIdx.x], n_own = A.tile_first[blockIdx.x + 1] - s0;
       const int h0 = A.tile_ptr[blockIdx.x], nh = A.tile_ptr[blockIdx.x + 1] - h0;
       // cells of a tile: consecutive numbers from tile_base (one load per tile, one bulk copy stages them), else the list
-      const int tbase   = A.tile_base[blockIdx.x];
+      const int tbase   = A.seq ? A.tile_base[blockIdx.x] : s0; // (no list: the tile is the run s0 .. s0 + n_own - 1)
       auto      cell_of = [&](const int i) { return tbase >= 0 ? tbase + i : A.seq[s0 + i]; };
 
       if (tid == 0)
