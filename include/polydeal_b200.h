@@ -351,6 +351,13 @@ int pd_set_operator(pd_handle *h, uint32_t flags, const pd_coefficients *coef);
  *    whenever the matrix fits.
  * pd_force_generic_matrix_free(h, 1) selects the second kernel on fine meshes too (testing). */
 int pd_matrix_free_available(const pd_handle *h);
+/* which fine-mesh kernel the last PD_VMULT_MATRIX_FREE apply on a fine mesh launched (diagnostic; the tests use it to
+ * make sure the kernel they mean to check is the one that ran): 0 none yet, 1 line per thread (k_fine_sip), 2 tiled
+ * (k_fine_tile), 3 pipelined tiles on a uniform mesh (k_fine_stream) */
+#define PD_FINE_KERNEL_LINE 1
+#define PD_FINE_KERNEL_TILE 2
+#define PD_FINE_KERNEL_STREAM 3
+int pd_fine_kernel_last(const pd_handle *h);
 int pd_force_generic_matrix_free(pd_handle *h, int on);
 /* PD_VMULT_MAPPED_FINE: the reference's fine-mesh MatrixFree operators on GENERAL (Q1-mapped,
  * distorted) cells -- LaplaceOperatorDG / MonodomainOperatorDG with the standard mapped

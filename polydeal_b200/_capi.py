@@ -71,6 +71,7 @@ SIGNATURES = {
     "pd_matrix_free_available": (C.c_int, [vp]),
     "pd_force_generic_matrix_free": (C.c_int, [vp, C.c_int]),
     "pd_mapped_fine_available": (C.c_int, [vp]),
+    "pd_fine_kernel_last": (C.c_int, [vp]),
     "pd_transfer_create": (C.c_int, [vp, vp, C.c_void_p, C.POINTER(vp)]),
     "pd_transfer_create_to_cells": (C.c_int, [vp, C.POINTER(vp)]),
     "pd_transfer_destroy": (None, [vp]),

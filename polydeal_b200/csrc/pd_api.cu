@@ -1233,6 +1233,12 @@ extern "C"
   }
 
   int
+  pd_fine_kernel_last(const pd_handle *h)
+  {
+    return h ? h->mf_kernel_last : 0;
+  }
+
+  int
   pd_mapped_fine_available(const pd_handle *h)
   {
     return h && h->mp_ready ? 1 : 0;

@@ -182,6 +182,167 @@ namespace pd
         out[e] = acc0[e];
     }
 
+    // ---- the dense form of the line stencils on a UNIFORM mesh ------------------
+    // When all cells are the same box and the penalty depends only on (direction, interior / boundary side), the
+    // premultiplied line stencil of direction d is the same three N1 x N1 matrices for every cell,
+    //   out_line += A_d u_line + C_d0 n0_line + C_d1 n1_line      (n_s: the neighbour's line across side s)
+    // plus a correction dB_ds u_line when side s is a boundary face (a missing neighbour reads zeros, so C needs
+    // none).  All entries are kernel constants: a line costs 3 N1^2 multiply-adds with constant-bank operands
+    // instead of the N1^2 + 8 N1 + 10 dependent operations of the rank-one form in cell_lines, and the mass
+    // term f vol I rides on the diagonal of the last direction's A.
+    struct UniformLine
+    {
+      double cVol, cDi, Pi, Qi, cDb, Pb[2]; // FineRec's fields for an interior side (i) / a boundary side (b)
+    };
+    template <int DIM, int N1>
+    struct DenseTables
+    {
+      double Mh[N1 * N1];
+      double A[DIM][N1 * N1];     // persymmetric (the nodes are symmetric about 1/2): the kernel reads entries k <= N1^2-1-k only
+      double C[DIM][N1 * N1];     // across side 0; across side 1 it is the mirror image C[(N1-1-i) N1 + (N1-1-t)]
+      double dB[DIM][2][N1 * N1]; // (fewer distinct constants: they stay in uniform registers over the lines of a direction)
+    };
+    template <int DIM, int N1>
+    inline void
+    build_dense_tables(const TileTables<N1> &T, const UniformLine *U, const double mv, DenseTables<DIM, N1> &D)
+    {
+      // the part of the own-line matrix that side s contributes, with penalty P and derivative coefficient cD
+      auto side = [&](const int s, const double P, const double cD, const int i, const int t) {
+        const int    end = s == 0 ? 0 : N1 - 1;
+        const double dl  = t == end ? 1. : 0.;
+        return s == 0 ? T.ep[0][i] * (P * dl + cD * T.d[0][t]) + T.dp[0][i] * cD * dl :
+                        T.ep[1][i] * (P * dl - cD * T.d[1][t]) - T.dp[1][i] * cD * dl;
+      };
+      for (int k = 0; k < N1 * N1; ++k)
+        D.Mh[k] = T.Mh[k];
+      for (int d = 0; d < DIM; ++d)
+        for (int i = 0; i < N1; ++i)
+          for (int t = 0; t < N1; ++t)
+            {
+              const UniformLine &u = U[d];
+              const int          k = i * N1 + t;
+              D.A[d][k] = u.cVol * T.Shp[k] + side(0, u.Pi, u.cDi, i, t) + side(1, u.Pi, u.cDi, i, t) +
+                          ((d == DIM - 1 && i == t) ? mv : 0.);
+              for (int s = 0; s < 2; ++s)
+                D.dB[d][s][k] = side(s, u.Pb[s], u.cDb, i, t) - side(s, u.Pi, u.cDi, i, t);
+              const double l1 = t == N1 - 1 ? 1. : 0.;
+              D.C[d][k]       = T.ep[0][i] * (-u.Pi * l1 + u.Qi * T.d[1][t]) - T.dp[0][i] * u.cDi * l1;
+              // (across side 1: ep1 (-Pi l0 - Qi d0) + dp1 cDi l0 = the mirror image, as ep1, dp1, d1 mirror ep0, -dp0, -d0)
+            }
+    }
+
+    // role split of the dense form: a line costs about 3 N1^2 multiply-adds + 3 N1 loads, role 0 also does the mass
+    // passes (DIM N N1) and both ends of the exchange
+    template <int DIM, int N1>
+    constexpr int
+    dense_lines_of_role1()
+    {
+      constexpr int N = ipow(N1, DIM), L = DIM * (N / N1);
+      constexpr int line_cost = 3 * N1 * N1 + 3 * N1 + 4, mass_cost = DIM * N * N1 + 3 * N;
+      constexpr int nb = (L * line_cost + mass_cost + line_cost) / (2 * line_cost);
+      return nb > L ? L : nb;
+    }
+
+    // acc += the dense line stencils of the lines of `role` (role < 0: all lines).  u: the cell's coefficients (read
+    // line by line, not kept); nbv(d, s, e): coefficient e of the neighbour across face (d, s) (zeros where there
+    // is none); bnd[2 d + s]: that face is a boundary face.
+    template <int DIM, int N1, class Tab, class Nb>
+    PD_HD void
+    cell_lines_dense(const Tab &T, const int role, const double *u, Nb &&nbv, const bool *bnd, double *acc)
+    {
+      constexpr int N = ipow(N1, DIM), NL = N / N1, NB = dense_lines_of_role1<DIM, N1>();
+#pragma unroll
+      for (int d = 0; d < DIM; ++d)
+        {
+          const int stride = d == 0 ? 1 : (d == 1 ? N1 : N1 * N1);
+#pragma unroll
+          for (int j = 0; j < NL; ++j)
+            {
+              if (role >= 0 && (d * NL + j < NB) != (role == 1))
+                continue;
+              const int base = d == 0 ? j * N1 : (d == 1 ? (j % N1) + (j / N1) * N1 * N1 : j);
+              double    v[N1], n0[N1], n1[N1];
+#pragma unroll
+              for (int t = 0; t < N1; ++t)
+                {
+                  v[t]  = u[base + t * stride];
+                  n0[t] = nbv(d, 0, base + t * stride);
+                  n1[t] = nbv(d, 1, base + t * stride);
+                }
+#pragma unroll
+              for (int i = 0; i < N1; ++i)
+                {
+                  double sm = acc[base + i * stride];
+#pragma unroll
+                  for (int t = 0; t < N1; ++t)
+                    {
+                      const int k = i * N1 + t, km = N1 * N1 - 1 - k;
+                      sm += T.A[d][k < km ? k : km] * v[t];
+                    }
+#pragma unroll
+                  for (int t = 0; t < N1; ++t)
+                    sm += T.C[d][i * N1 + t] * n0[t];
+#pragma unroll
+                  for (int t = 0; t < N1; ++t)
+                    sm += T.C[d][N1 * N1 - 1 - (i * N1 + t)] * n1[t];
+                  acc[base + i * stride] = sm;
+                }
+            }
+          // boundary sides (rare): one branch per face, not per line -- the lines above stay one straight block that
+          // the scheduler can interleave; the own lines are read again
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            if (bnd[2 * d + s])
+              {
+                const double *ub = u;
+#if defined(__CUDA_ARCH__)
+                asm volatile("" : "+l"(ub)); // (keeps the compiler from holding the lines above in registers for this branch)
+#endif
+#pragma unroll
+                for (int j = 0; j < NL; ++j)
+                  {
+                    if (role >= 0 && (d * NL + j < NB) != (role == 1))
+                      continue;
+                    const int base = d == 0 ? j * N1 : (d == 1 ? (j % N1) + (j / N1) * N1 * N1 : j);
+                    double    v[N1];
+#pragma unroll
+                    for (int t = 0; t < N1; ++t)
+                      v[t] = ub[base + t * stride];
+#pragma unroll
+                    for (int i = 0; i < N1; ++i)
+                      {
+                        double sm = acc[base + i * stride];
+#pragma unroll
+                        for (int t = 0; t < N1; ++t)
+                          sm += T.dB[d][s][i * N1 + t] * v[t];
+                        acc[base + i * stride] = sm;
+                      }
+                  }
+              }
+        }
+    }
+
+    // the whole operator on one cell the way the pipelined kernel's two roles compose it
+    template <int DIM, int N1, class Tab, class Nb>
+    PD_HD void
+    cell_apply_dense(const Tab &T, const double *u, Nb &&nbv, const bool *bnd, double *out)
+    {
+      constexpr int N = ipow(N1, DIM);
+      double        acc0[N], acc1[N];
+#pragma unroll
+      for (int e = 0; e < N; ++e)
+        acc0[e] = acc1[e] = 0.;
+      cell_lines_dense<DIM, N1>(T, 0, u, nbv, bnd, acc0);
+      cell_lines_dense<DIM, N1>(T, 1, u, nbv, bnd, acc1);
+#pragma unroll
+      for (int e = 0; e < N; ++e)
+        acc0[e] += acc1[e];
+      cell_mass<DIM, N1>(T, acc0);
+#pragma unroll
+      for (int e = 0; e < N; ++e)
+        out[e] = acc0[e];
+    }
+
     // ---- tile plan -----------------------------------------------------------
     // A CTA of the tiled kernel takes TILE consecutive entries of a cell sequence (all owned cells, or the
     // interior / boundary lists of a sharded apply), stages their coefficients AND those of every

@@ -361,6 +361,20 @@ namespace pd
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
     }
     __device__ __forceinline__ void
+    cp_async16(void *smem, const void *gmem)
+    {
+      const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+    }
+    // arrive on the mbarrier once every cp.async this thread has issued so far has landed (the arrival is part of the
+    // barrier's initial count: .noinc)
+    __device__ __forceinline__ void
+    cp_async_mbar_arrive(uint64_t *bar)
+    {
+      const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(b) : "memory");
+    }
+    __device__ __forceinline__ void
     cp_async_wait_all()
     {
       asm volatile("cp.async.wait_all;" ::: "memory");
@@ -581,6 +595,247 @@ namespace pd
       }
     }
 
+    // ---------------------------------------------------------------------------------------
+    // The pipelined kernel: the tiles of k_fine_tile STREAMED through a ring of shared-memory stages.
+    //
+    // ncu on k_fine_tile (profiles/ncu_r01_fine_tile_summary.txt): warps active 24 %, long scoreboard the top
+    // stall -- a CTA lives through three dependent steps (tile metadata -> bulk copies -> arithmetic) and only
+    // four CTAs per SM overlap them.  Here the CTAs are persistent and warp-specialised:
+    //  * one PRODUCER warp walks the CTA's tiles (tile = blockIdx + k gridDim, so the tiles in flight at any time
+    //    are one contiguous run of the curve and share their halos in L2), reads the plan, and issues the bulk
+    //    copies of tile k + NS - 1 (own cells: one copy; halo cells: one copy each; the 16-bit neighbour offsets:
+    //    one copy) while the consumers work on tile k; completion on the stage's `full` mbarrier;
+    //  * four CONSUMER warps (two threads per cell, pd::fine::cell_lines / cell_mass as in k_fine_tile) wait on
+    //    `full`, apply the operator in registers, leave the result in the own rows, fence towards the async proxy
+    //    and arrive on the stage's `done` mbarrier;
+    //  * the producer then sends the own rows to y with ONE bulk store (cp.async.bulk shared -> global; the
+    //    add variant is cp.reduce.async.bulk .add.f64: every y entry has one writer, so it stays deterministic),
+    //    waits until the store has read the stage and refills it.
+    // No per-cell records: the kernel is for UNIFORM meshes (all cells the same box, one penalty per direction and
+    // face kind; pd_handle::mf_uniform), where the stencil coefficients are kernel constants and a face is a
+    // boundary face iff its neighbour offset points at the zero row.  Everything else runs k_fine_tile.
+    // Needs: every tile one contiguous run of cells starting on a 16-byte boundary with a multiple of four
+    // cells (FineTiles::stream_ok), N odd (own rows as in the vector), x and y 16-byte aligned.
+    // ---------------------------------------------------------------------------------------
+    constexpr int FINE_MAX_STAGES = 8, STREAM_HALO_PASSES = 1; // (at most FINE_TILE_THREADS halo cells per tile: one row per thread)
+    template <int DIM, int N1>
+    struct StreamArgs
+    {
+      fine::DenseTables<DIM, N1> T;
+      const double              *x;
+      double                    *y;
+      const int32_t             *tile_base; // [n_tiles] first cell of a tile (nullptr: tile * FINE_TILE)
+      const int32_t             *halo_pad;  // [n_tiles][max_halo] halo cells of a tile, padded with -1
+      const uint16_t            *noff;      // [n_tiles * FINE_TILE][2 DIM]
+      int64_t                    x_len;     // doubles that may be read from x
+      int32_t                    n_tiles, max_halo, zoff, n_stages;
+      int                        add;
+    };
+    constexpr size_t
+    stream_stage_bytes(const int dim, const int n, const int max_halo)
+    {
+      return tile_values_bytes(n, max_halo) + round16((size_t)FINE_TILE * 2 * dim * 2) + 16;
+    }
+    constexpr size_t
+    stream_smem_bytes(const int dim, const int n, const int max_halo, const int stages)
+    {
+      return stages * stream_stage_bytes(dim, n, max_halo) + 2 * FINE_MAX_STAGES * sizeof(uint64_t);
+    }
+    __device__ __forceinline__ void
+    mbar_wait(uint64_t *bar, const uint32_t parity)
+    {
+      for (int spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1 << 22))
+          __trap(); // a copy that never completes / a lost arrival would otherwise hang the device
+    }
+    __device__ __forceinline__ void
+    group_bar_sync(const int id)
+    {
+      asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(FINE_TILE_THREADS) : "memory");
+    }
+
+    // NG consumer groups of FINE_TILE_THREADS threads (group g takes the CTA's tiles g, g + NG, ...) and one helper
+    // warp.  Per stage two mbarriers: full (everything of the tile has landed), ready (result in the own rows).
+    //  * halo rows: gathered by the CONSUMERS -- as soon as a group is done reading stage s (tile it), its threads issue
+    //    the 16-byte cp.async chunks of tile it + NS into the same stage, one halo row per thread, completion counted
+    //    by cp.async.mbarrier.arrive on full[s]; the gather overlaps the rest of the group's tile (exchange, mass
+    //    passes) and the other groups' arithmetic.  Neither per-cell bulk copies (measured: the TMA unit of an SM
+    //    retires only ~40 of these 224-byte copies per microsecond) nor one gathering warp (measured: 6.5 us per tile,
+    //    too few loads in flight) keeps up with the consumers.
+    //  * own rows and the 16-bit neighbour offsets: one bulk copy each, issued by the helper warp once the bulk store
+    //    of the previous tile of that stage has read the rows.
+    template <int DIM, int DEG, int NG>
+    __global__ void __launch_bounds__(NG *FINE_TILE_THREADS + 32, NG <= 2 ? 2 : 1)
+      k_fine_stream(const __grid_constant__ StreamArgs<DIM, DEG + 1> A)
+    {
+      constexpr int N1  = DEG + 1;
+      constexpr int N   = ipow_(N1, DIM);
+      constexpr int NFC = 2 * DIM;
+      constexpr int RH  = fine::halo_row(N);
+      constexpr int RO  = fine::own_row(N);
+      static_assert(RO == N, "own rows are filled by one bulk copy: N odd");
+      constexpr uint32_t NOFFB = (uint32_t)round16((size_t)FINE_TILE * NFC * 2);
+      constexpr int      CPR   = (N + 2) / 2; // 16-byte chunks that cover N doubles from either alignment
+      static_assert(CPR * 2 <= RH, "a halo row holds the chunks");
+
+      extern __shared__ __align__(16) unsigned char smem[];
+      const int      NS          = A.n_stages;
+      const uint32_t vb          = (uint32_t)tile_values_bytes(N, A.max_halo);
+      const uint32_t stage_bytes = vb + NOFFB + 16;
+      uint64_t      *full = reinterpret_cast<uint64_t *>(smem + (size_t)NS * stage_bytes), *ready = full + FINE_MAX_STAGES;
+
+      // (the warp index through a broadcast shuffle: the compiler then knows that everything derived from it -- the
+      // warp's job, its group, its role -- is warp-uniform and keeps the 1-D matrices in uniform registers)
+      const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
+      if (tid == 0)
+        for (int s = 0; s < NS; ++s)
+          {
+            mbar_init(full + s, FINE_TILE_THREADS + 1); // the gathering group's threads + the bulk copies' transaction bytes
+            mbar_init(ready + s, FINE_TILE);
+          }
+      if (tid < N)
+        for (int s = 0; s < NS; ++s)
+          reinterpret_cast<double *>(smem + (size_t)s * stage_bytes)[A.zoff + tid] = 0.;
+      __syncthreads();
+      const int my_n = (int)blockIdx.x < A.n_tiles ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      auto      tile_of = [&](const int l) { return (int)blockIdx.x + l * (int)gridDim.x; };
+
+      if (warp == NG * (FINE_TILE_THREADS / 32))
+        { // ---- helper warp: own rows + neighbour offsets in (bulk copies), results out (bulk store)
+          if (lane == 0)
+            {
+              auto load_own = [&](const int l) {
+                const int      tile = tile_of(l), s = l % NS;
+                unsigned char *st   = smem + (size_t)s * stage_bytes;
+                const int      fc   = A.tile_base ? A.tile_base[tile] : tile * FINE_TILE;
+                bulk_g2s(st, A.x + (int64_t)fc * N, (uint32_t)FINE_TILE * N * 8, full + s);
+                bulk_g2s(st + vb, A.noff + (size_t)tile * FINE_TILE * NFC, (uint32_t)FINE_TILE * NFC * 2, full + s);
+                mbar_arrive_expect(full + s, (uint32_t)FINE_TILE * (N * 8 + NFC * 2));
+              };
+              for (int l = 0; l < NS && l < my_n; ++l)
+                load_own(l);
+              for (int Tt = 0; Tt < my_n; ++Tt)
+                {
+                  const int s    = Tt % NS, tile = tile_of(Tt);
+                  const int fc   = A.tile_base ? A.tile_base[tile] : tile * FINE_TILE; // (issued before the wait)
+                  mbar_wait(ready + s, (uint32_t)(Tt / NS) & 1u);
+                  double        *dst = A.y + (int64_t)fc * N;
+                  const uint32_t sz = (uint32_t)FINE_TILE * N * 8, src = (unsigned)__cvta_generic_to_shared(smem + (size_t)s * stage_bytes);
+                  if (A.add)
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                                 "r"(sz)
+                                 : "memory");
+                  else
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(sz)
+                                 : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                  if (Tt + NS < my_n)
+                    {
+                      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                      load_own(Tt + NS);
+                    }
+                }
+              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+        }
+      else
+        { // ---- consumers: group = tile in flight, thread = (role, cell) as in k_fine_tile
+          constexpr int WPG = FINE_TILE_THREADS / 32, WPR = FINE_TILE / 32; // warps per group / per role
+          const int     group = warp / WPG, role = (warp % WPG) / WPR, ci = (warp % WPR) * 32 + lane;
+          const int     gt = (warp % WPG) * 32 + lane; // thread of the group: gathers halo rows gt, gt + 128, ...
+          // the halo rows of tile l into its stage: one row per thread and pass, CPR chunks of 16 bytes from the 16-byte
+          // boundary below the cell
+          auto gather = [&](const int l, const int32_t (&hc)[STREAM_HALO_PASSES]) {
+            const int s = l % NS;
+            double   *S = reinterpret_cast<double *>(smem + (size_t)s * stage_bytes);
+#pragma unroll
+            for (int q = 0; q < STREAM_HALO_PASSES; ++q)
+              if (hc[q] >= 0)
+                {
+                  const int64_t a0  = ((int64_t)hc[q] * N) & ~(int64_t)1;
+                  double       *dst = S + FINE_TILE * RO + (gt + q * FINE_TILE_THREADS) * RH;
+#pragma unroll
+                  for (int c = 0; c < CPR - 1; ++c)
+                    cp_async16(dst + 2 * c, A.x + a0 + 2 * c);
+                  if (a0 + 2 * CPR <= A.x_len)
+                    cp_async16(dst + 2 * (CPR - 1), A.x + a0 + 2 * (CPR - 1));
+                  else // the vector ends inside the last chunk (its second double is not part of the cell)
+                    cp_async8(dst + 2 * (CPR - 1), A.x + a0 + 2 * (CPR - 1));
+                }
+            cp_async_mbar_arrive(full + s);
+          };
+          auto halo_cells = [&](const int l, int32_t (&hc)[STREAM_HALO_PASSES]) {
+#pragma unroll
+            for (int q = 0; q < STREAM_HALO_PASSES; ++q)
+              {
+                const int r = gt + q * FINE_TILE_THREADS;
+                hc[q]       = (l < my_n && r < A.max_halo) ? A.halo_pad[(size_t)tile_of(l) * A.max_halo + r] : -1;
+              }
+          };
+          int32_t hc[STREAM_HALO_PASSES];
+          // the first NS tiles: tile l by the group that will also process it (l % NG)
+          for (int l = group; l < NS && l < my_n; l += NG)
+            {
+              halo_cells(l, hc);
+              gather(l, hc);
+            }
+          for (int it = group; it < my_n; it += NG)
+            {
+              const int      s  = it % NS;
+              unsigned char *st = smem + (size_t)s * stage_bytes;
+              double        *S  = reinterpret_cast<double *>(st);
+              halo_cells(it + NS, hc); // (on its way while the lines are computed)
+              mbar_wait(full + s, (uint32_t)(it / NS) & 1u);
+              // (every tile of a sequence this kernel takes is full -- FineTiles::stream_ok --, so the whole group
+              // runs the same instruction stream: the 1-D matrices stay in uniform registers)
+              double        acc[N];
+              double *const own = S + ci * RO;
+              {
+                const uint16_t *np = reinterpret_cast<const uint16_t *>(st + vb) + ci * NFC;
+                const double   *nbp[NFC];
+                bool            bnd[NFC];
+#pragma unroll
+                for (int f = 0; f < NFC; ++f)
+                  {
+                    const uint32_t o = np[f];
+                    nbp[f]           = S + o;
+                    bnd[f]           = o == (uint32_t)A.zoff;
+                  }
+                auto nbv = [&](const int d, const int sd, const int k) { return nbp[2 * d + sd][k]; };
+#pragma unroll
+                for (int k = 0; k < N; ++k)
+                  acc[k] = 0.;
+                if (role == 0) // warp-uniform
+                  fine::cell_lines_dense<DIM, N1>(A.T, 0, own, nbv, bnd, acc);
+                else
+                  fine::cell_lines_dense<DIM, N1>(A.T, 1, own, nbv, bnd, acc);
+              }
+              group_bar_sync(group + 1); // every read of the staged coefficients is done: the own rows become the exchange / output staging
+              if (it + NS < my_n)
+                gather(it + NS, hc); // ... and the halo rows can take the next tile of this stage
+              if (role == 1)
+                {
+#pragma unroll
+                  for (int k = 0; k < N; ++k)
+                    own[k] = acc[k];
+                }
+              group_bar_sync(group + 1);
+              if (role == 0)
+                {
+#pragma unroll
+                  for (int k = 0; k < N; ++k)
+                    acc[k] += own[k];
+                  fine::cell_mass<DIM, N1>(A.T, acc);
+#pragma unroll
+                  for (int k = 0; k < N; ++k)
+                    own[k] = acc[k];
+                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the bulk store reads these rows
+                  mbar_arrive_expect(ready + s, 0);
+                }
+            }
+        }
+    }
+
     // host: l_a(x), l_a'(x)
     void
     lagrange_host(const Basis1D &B, const int n1, const double x, double *L, double *dL)
@@ -652,6 +907,34 @@ namespace pd
     for (char s : seen)
       if (!s)
         return; // a cell face without an interface entry: not a conforming singleton mesh
+    // uniform mesh?  (all cells -- owned and ghost -- the same box, one penalty per direction for the interior faces and
+    // one per (direction, side) for the boundary faces, to two units in the last place): the pipelined kernel then
+    // takes its stencil coefficients as kernel constants instead of per-cell records
+    {
+      auto &u    = h->mf_uniform;
+      u          = pd_handle::FineUniform{};
+      auto close = [](const double a, const double b) { return std::fabs(a - b) <= 4.5e-16 * std::max(std::fabs(a), std::fabs(b)); };
+      bool ok    = h->np_own > 0;
+      bool have_in[3] = {false, false, false}, have_bd[3][2] = {{false, false}, {false, false}, {false, false}};
+      for (int k = 0; k < dim && ok; ++k)
+        u.h[k] = cell_h[k];
+      for (int32_t c = 0; c < h->np && ok; ++c)
+        for (int k = 0; k < dim; ++k)
+          ok = ok && close(cell_h[(size_t)c * dim + k], u.h[k]);
+      for (int32_t c = 0; c < h->np_own && ok; ++c)
+        for (int f = 0; f < nfc; ++f)
+          {
+            const double sg = sigma[(size_t)c * nfc + f];
+            const bool   in = nbr[(size_t)c * nfc + f] >= 0;
+            double      &v  = in ? u.sig_in[f / 2] : u.sig_bd[f / 2][f % 2];
+            bool        &hv = in ? have_in[f / 2] : have_bd[f / 2][f % 2];
+            if (!hv)
+              v = sg, hv = true;
+            else
+              ok = ok && close(sg, v);
+          }
+      u.ok = ok;
+    }
     // the per-(cell, direction) stencil records
     std::vector<double> rec((size_t)h->np_own * dim * 6), vol((size_t)h->np_own);
     for (int32_t c = 0; c < h->np_own; ++c)
@@ -772,6 +1055,9 @@ namespace pd
       const char *env    = std::getenv("PD_FINE_KERNEL");
       const bool  faster = (dim == 3 && h->degree <= 2) || (dim == 2 && h->degree >= 2);
       h->mf_kernel = (env && std::strcmp(env, "line") == 0) ? 1 : ((env && std::strcmp(env, "tile") == 0) ? 0 : (faster ? 0 : 1));
+      // the pipelined kernel (k_fine_stream) takes over from the tiled one wherever it applies (uniform mesh, N odd,
+      // whole aligned tiles); PD_FINE_KERNEL=tile keeps the tiled kernel, =stream asks for the default policy
+      h->mf_stream = !(env && std::strcmp(env, "tile") == 0);
     }
     if (h->mf_kernel == 0 && h->n <= 27)
       {
@@ -873,6 +1159,29 @@ namespace pd
             put(t.halo, plan.halo);
             t.n_tiles = plan.n_tiles, t.max_halo = plan.max_halo, t.zoff = plan.zoff, t.n_seq = n_seq;
             t.ok = true;
+            {
+              // the pipelined kernel moves whole tiles with single bulk copies (own cells in, result out, neighbour offsets)
+              bool                 run_ok = h->n % 2 == 1 && stream_smem_bytes(dim, h->n, plan.max_halo, 2) <= 227 * 1024;
+              std::vector<int32_t> base_h((size_t)plan.n_tiles);
+              for (int32_t k = 0; k < plan.n_tiles && run_ok; ++k)
+                {
+                  const int32_t s0 = plan.tile_first[k], n_own = plan.tile_first[k + 1] - s0;
+                  const int32_t c0 = seq ? (*seq)[s0] : s0;
+                  run_ok           = n_own == FINE_TILE && ((int64_t)c0 * h->n) % 2 == 0;
+                  for (int32_t i = 1; i < n_own && run_ok; ++i)
+                    run_ok = (seq ? (*seq)[s0 + i] : s0 + i) == c0 + i;
+                }
+              run_ok = run_ok && plan.max_halo <= FINE_TILE_THREADS * STREAM_HALO_PASSES;
+              t.stream_ok = run_ok;
+              if (run_ok)
+                { // the halo lists at a fixed pitch: the load warp fetches them without waiting for tile_ptr
+                  std::vector<int32_t> pad((size_t)plan.n_tiles * std::max(1, plan.max_halo), -1);
+                  for (int32_t k = 0; k < plan.n_tiles; ++k)
+                    std::copy(plan.halo.begin() + plan.tile_ptr[k], plan.halo.begin() + plan.tile_ptr[k + 1],
+                              pad.begin() + (size_t)k * plan.max_halo);
+                  put(t.halo_pad, pad);
+                }
+            }
             if (part == 0 && seq)
               put(h->mf_seq_all, morton_order);
           }
@@ -973,11 +1282,120 @@ namespace pd
         }
       k_fine_tile<DIM, DEG><<<t.n_tiles, FINE_TILE_THREADS, smem, h->stream>>>(a);
     }
+    // the uniform mesh's dense line stencils with the operator's coefficient and term flags folded in
+    // (what k_fine_fold writes into the records of the other kernels)
+    template <int DIM, int N1>
+    void
+    uniform_dense_tables(const pd_handle *h, fine::DenseTables<DIM, N1> &D)
+    {
+      const auto          &u = h->mf_uniform;
+      fine::TileTables<N1> T;
+      static_assert(sizeof(T) == (2 * N1 * N1 + 6 * N1) * sizeof(double), "table layout");
+      std::memcpy(&T, h->mf_tile_tab_host.data(), sizeof(T));
+      fine::UniformLine U[DIM];
+      const double      c = h->op_coef.stiffness;
+      const bool        vol_on = (h->op_flags & PD_ASSEMBLE_VOLUME) != 0, in_on = (h->op_flags & PD_ASSEMBLE_INTERIOR) != 0,
+                 bd_on = (h->op_flags & PD_ASSEMBLE_BOUNDARY) != 0;
+      double vol = 1.;
+      for (int k = 0; k < DIM; ++k)
+        vol *= u.h[k];
+      for (int k = 0; k < DIM; ++k)
+        {
+          const double a = vol / u.h[k], cV = a / u.h[k];
+          U[k].cVol = vol_on ? c * cV : 0.;
+          U[k].cDi  = in_on ? c * (0.5 * cV) : 0.;
+          U[k].Pi   = in_on ? c * (a * u.sig_in[k]) : 0.;
+          U[k].Qi   = in_on ? c * (0.5 * a / u.h[k]) : 0.;
+          U[k].cDb  = bd_on ? c * cV : 0.;
+          for (int s = 0; s < 2; ++s)
+            U[k].Pb[s] = bd_on ? c * (a * u.sig_bd[k][s]) : 0.;
+        }
+      fine::build_dense_tables<DIM, N1>(T, U, vol_on ? h->op_coef.mass * vol : 0., D);
+    }
+
+    template <int DIM, int DEG>
+    void
+    launch_fine_stream(pd_handle *h, const double *src, double *dst, const bool add, const int part)
+    {
+      constexpr int       N1 = DEG + 1, N = ipow_(N1, DIM);
+      const auto         &t  = h->mf_tiles[part];
+      StreamArgs<DIM, N1> a;
+      uniform_dense_tables<DIM, N1>(h, a.T);
+      a.x          = src;
+      a.y          = dst;
+      // (no cell list: the cells are numbered along the curve already and a tile starts at its first sequence entry)
+      a.tile_base = (part == 0 && !h->mf_seq_all.p) ? nullptr : t.tile_base.p;
+      a.halo_pad  = t.halo_pad.p;
+      a.noff      = t.noff.p;
+      a.x_len     = (int64_t)h->np * N;
+      a.n_tiles   = t.n_tiles;
+      a.max_halo  = t.max_halo;
+      a.zoff      = t.zoff;
+      a.add       = add ? 1 : 0;
+      // consumer groups per CTA: PD_FINE_GROUPS (2..5), default: as many as the shared memory holds with one stage more
+      // than groups; stages: PD_FINE_STAGES, default groups + 1
+      static int groups_env = -1, stages_env = -1;
+      if (groups_env < 0)
+        {
+          const char *e = std::getenv("PD_FINE_GROUPS"), *f = std::getenv("PD_FINE_STAGES");
+          groups_env    = e ? std::min(5, std::max(2, std::atoi(e))) : 0;
+          stages_env    = f ? std::min(FINE_MAX_STAGES, std::max(2, std::atoi(f))) : 0;
+        }
+      const size_t cap = 227 * 1024;
+      int          groups = groups_env ? groups_env : 5;
+      while (groups > 2 && stream_smem_bytes(DIM, N, t.max_halo, groups + 1) > cap)
+        --groups;
+      int stages = stages_env ? stages_env : groups + 1;
+      const size_t per_cta_cap = groups <= 2 ? cap / 2 - 1024 : cap; // (two groups: two CTAs per SM)
+      while (stages > 2 && stream_smem_bytes(DIM, N, t.max_halo, stages) > per_cta_cap)
+        --stages;
+      a.n_stages        = stages;
+      const size_t smem = stream_smem_bytes(DIM, N, t.max_halo, stages);
+      auto go = [&](auto kernel, size_t &smem_set, const int threads) {
+        if (smem > smem_set)
+          {
+            PD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+          }
+        int per_sm = 1;
+        PD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+        const int grid = std::max(1, std::min(t.n_tiles, h->sm_count * std::max(1, per_sm)));
+        kernel<<<grid, threads, smem, h->stream>>>(a);
+      };
+      static size_t smem_set[6] = {0, 0, 0, 0, 0, 0}; // per instantiation
+      switch (groups)
+        {
+          case 2: go(k_fine_stream<DIM, DEG, 2>, smem_set[2], 2 * FINE_TILE_THREADS + 32); break;
+          case 3: go(k_fine_stream<DIM, DEG, 3>, smem_set[3], 3 * FINE_TILE_THREADS + 32); break;
+          case 4: go(k_fine_stream<DIM, DEG, 4>, smem_set[4], 4 * FINE_TILE_THREADS + 32); break;
+          default: go(k_fine_stream<DIM, DEG, 5>, smem_set[5], 5 * FINE_TILE_THREADS + 32); break;
+        }
+    }
   } // namespace
 
   void
   launch_fine_operator(pd_handle *h, const double *src, double *dst, const bool add, const int part)
   {
+    // the pipelined kernel: uniform mesh, whole aligned tiles, both vectors 16-byte aligned (bulk copies in and out)
+    if (h->mf_kernel == 0 && h->mf_stream && h->mf_uniform.ok && h->mf_tiles[part].ok && h->mf_tiles[part].stream_ok &&
+        reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0)
+      {
+        bool done = true;
+        switch (h->dim * 10 + h->degree)
+          {
+            case 22: launch_fine_stream<2, 2>(h, src, dst, add, part); break;
+            case 24: launch_fine_stream<2, 4>(h, src, dst, add, part); break;
+            case 32: launch_fine_stream<3, 2>(h, src, dst, add, part); break;
+            default: done = false;
+          }
+        if (done)
+          {
+            h->mf_kernel_last = PD_FINE_KERNEL_STREAM;
+            ++h->launches;
+            PD_CUDA(cudaGetLastError());
+            return;
+          }
+      }
     // (the tiled kernel fills its halo rows with 16-byte bulk copies: a source vector that is only 8-byte
     // aligned goes to the line-per-thread kernel)
     const bool tiled = h->mf_kernel == 0 && h->mf_tiles[part].ok && reinterpret_cast<uintptr_t>(src) % 16 == 0;
@@ -999,6 +1417,7 @@ namespace pd
         default:
           throw CudaError{cudaErrorNotSupported, "no fine-mesh operator kernel for this (dim, degree)", __LINE__};
       }
+    h->mf_kernel_last = tiled ? PD_FINE_KERNEL_TILE : PD_FINE_KERNEL_LINE;
     ++h->launches;
     PD_CUDA(cudaGetLastError());
   }

@@ -122,13 +122,25 @@ struct pd_handle
   // cell sequences (all owned cells, interior list, boundary list) and the premultiplied 1-D tables
   struct FineTiles
   {
+    pd::DevBuf<int32_t>  halo_pad; // [n_tiles][max_halo], -1 padded (pipelined kernel)
     pd::DevBuf<int32_t>  tile_first, tile_ptr, halo, tile_base; // tile_base: first cell of a tile whose cells are consecutive, else -1
     pd::DevBuf<uint16_t> noff;
     int32_t              n_tiles = 0, max_halo = 0, zoff = 0, n_seq = 0;
     bool                 ok = false;
+    bool                 stream_ok = false; // every tile one aligned contiguous run: the pipelined kernel (k_fine_stream) can take it
   };
+  // a uniform mesh (all cells the same box, one penalty per direction and face kind): the stencil coefficients are
+  // kernel constants and the pipelined kernel needs no per-cell records
+  struct FineUniform
+  {
+    bool   ok = false;
+    double h[3] = {1., 1., 1.}, sig_in[3] = {0., 0., 0.}, sig_bd[3][2] = {{0., 0.}, {0., 0.}, {0., 0.}};
+  };
+  FineUniform         mf_uniform;
   FineTiles           mf_tiles[3];
   std::vector<double> mf_tile_tab_host; // Mh | Mh^-1 Sh | Mh^-1 e0,e1 | Mh^-1 d0,d1 | d0,d1
+  bool                mf_stream = true;  // the pipelined kernel wherever it applies (PD_FINE_KERNEL=tile switches it off)
+  int                 mf_kernel_last = 0; // PD_FINE_KERNEL_* of the last launch
   int                 mf_kernel = 0;    // 0: tiled where available, 1: line-per-thread (default policy and PD_FINE_KERNEL in pd_finemesh.cu)
   // matrix-free fine-mesh operator on general (Q1-mapped) cells with the mapped basis, pd_mappedfine.cu
   bool                mp_ready = false, mp_geo_valid = false;

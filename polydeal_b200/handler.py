@@ -365,6 +365,11 @@ class SIPOperator:
         return bool(K.lib().pd_matrix_free_available(self._h))
 
     @property
+    def fine_kernel_last(self):
+        """Which fine-mesh kernel the last matrix-free apply launched: 0 none, 1 line, 2 tile, 3 stream."""
+        return int(K.lib().pd_fine_kernel_last(self._h))
+
+    @property
     def mapped_fine_available(self):
         """VMULT_MAPPED_FINE (mapped FE_DGQ basis on general hexes) can be applied."""
         return bool(K.lib().pd_mapped_fine_available(self._h))

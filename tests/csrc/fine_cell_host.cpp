@@ -24,10 +24,44 @@ namespace
       },
       mv, out);
   }
+
+  // the dense form on a uniform mesh: uni[dim][7] = cVol, cDi, Pi, Qi, cDb, Pb0, Pb1; bnd[2 dim]
+  template <int DIM, int N1>
+  void
+  run_dense(const double *tab, const double *u, const double *nb, const double *uni, const int *bnd, const double mv, double *out)
+  {
+    constexpr int            N = pd::fine::ipow(N1, DIM);
+    pd::fine::TileTables<N1> T;
+    std::memcpy(&T, tab, sizeof(T));
+    pd::fine::UniformLine U[DIM];
+    for (int d = 0; d < DIM; ++d)
+      U[d] = pd::fine::UniformLine{uni[7 * d], uni[7 * d + 1], uni[7 * d + 2], uni[7 * d + 3], uni[7 * d + 4], {uni[7 * d + 5], uni[7 * d + 6]}};
+    pd::fine::DenseTables<DIM, N1> D;
+    pd::fine::build_dense_tables<DIM, N1>(T, U, mv, D);
+    bool b[2 * DIM];
+    for (int f = 0; f < 2 * DIM; ++f)
+      b[f] = bnd[f] != 0;
+    pd::fine::cell_apply_dense<DIM, N1>(
+      D, u, [&](const int d, const int s, const int e) { return nb[(2 * d + s) * N + e]; }, b, out);
+  }
 } // namespace
 
 extern "C"
 {
+  int
+  fine_cell_dense_host(const int dim, const int n1, const double *tab, const double *u, const double *nb, const double *uni,
+                       const int *bnd, const double mv, double *out)
+  {
+    switch (dim * 10 + n1)
+      {
+        case 23: run_dense<2, 3>(tab, u, nb, uni, bnd, mv, out); return 0;
+        case 25: run_dense<2, 5>(tab, u, nb, uni, bnd, mv, out); return 0;
+        case 33: run_dense<3, 3>(tab, u, nb, uni, bnd, mv, out); return 0;
+        case 34: run_dense<3, 4>(tab, u, nb, uni, bnd, mv, out); return 0;
+        default: return -1;
+      }
+  }
+
   // tab: Mh | Mh^-1 Sh | Mh^-1 e0,e1 | Mh^-1 d0,d1 | d0,d1;  nb[2 dim][N];  coef[dim][7] = cVol, cD0, cD1, P0, P1, Q0, Q1
   int
   fine_cell_host(const int dim, const int n1, const double *tab, const double *u, const double *nb, const double *coef,
@@ -41,6 +75,7 @@ extern "C"
         case 25: run<2, 5>(tab, u, nb, coef, mv, out); return 0;
         case 32: run<3, 2>(tab, u, nb, coef, mv, out); return 0;
         case 33: run<3, 3>(tab, u, nb, coef, mv, out); return 0;
+        case 34: run<3, 4>(tab, u, nb, coef, mv, out); return 0;
         default: return -1;
       }
   }

@@ -91,6 +91,42 @@ def test_cell_apply_equals_dense_kronecker_form(lib, dim, p):
         assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("dim,p", [(2, 2), (2, 4), (3, 2), (3, 3)])
+def test_dense_uniform_form_equals_rank_one_form(lib, dim, p):
+    """cell_apply_dense (the pipelined kernel's arithmetic on a uniform mesh: dense N1 x N1 line matrices built by
+    build_dense_tables, boundary sides as a correction, mass term on the last direction's diagonal) equals
+    cell_apply fed the per-cell records a uniform mesh would have, for every combination of boundary sides."""
+    rng = np.random.default_rng(11 * dim + p)
+    n1, N = p + 1, (p + 1) ** dim
+    Mh, Sh, e, d = tables_1d(p)
+    tab = np.concatenate([Mh.ravel(), np.linalg.solve(Mh, Sh).ravel(), np.linalg.solve(Mh, e.T).T.ravel(),
+                          np.linalg.solve(Mh, d.T).T.ravel(), d.ravel()])
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for trial in range(1 << (2 * dim)):
+        bnd = np.array([(trial >> f) & 1 for f in range(2 * dim)], dtype=np.int32)
+        uni = rng.uniform(0.2, 2.0, (dim, 7))  # cVol, cDi, Pi, Qi, cDb, Pb0, Pb1
+        if trial % 5 == 3:
+            uni[:, 4:] = 0.0  # boundary term switched off
+        u = rng.standard_normal(N)
+        nb = rng.standard_normal((2 * dim, N))
+        coef = np.empty((dim, 7))  # cVol, cD0, cD1, P0, P1, Q0, Q1 as the records carry them
+        for k in range(dim):
+            b0, b1 = bnd[2 * k], bnd[2 * k + 1]
+            coef[k] = [uni[k, 0], uni[k, 4] if b0 else uni[k, 1], uni[k, 4] if b1 else uni[k, 1],
+                       uni[k, 5] if b0 else uni[k, 2], uni[k, 6] if b1 else uni[k, 2],
+                       0.0 if b0 else uni[k, 3], 0.0 if b1 else uni[k, 3]]
+            if b0:
+                nb[2 * k] = 0.0
+            if b1:
+                nb[2 * k + 1] = 0.0
+        mv = 0.0 if trial % 2 == 0 else 2.3
+        ref, out = np.empty(N), np.empty(N)
+        nbc, coefc, unic = np.ascontiguousarray(nb), np.ascontiguousarray(coef), np.ascontiguousarray(uni)
+        assert lib.fine_cell_host(dim, n1, dp(tab), dp(u), dp(nbc), dp(coefc), C.c_double(mv), dp(ref)) == 0
+        assert lib.fine_cell_dense_host(dim, n1, dp(tab), dp(u), dp(nbc), dp(unic), dp(bnd), C.c_double(mv), dp(out)) == 0
+        assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
 def grid_neighbours(shape, order):
     """neighbour table [cell][2 dim] of a Cartesian grid, cells numbered lexicographically or in Morton order"""
     dim = len(shape)

@@ -380,6 +380,56 @@ def test_fine_mesh_tiled_kernel_equals_line_kernel(dim, n, p, order, monkeypatch
         assert scale > 0 and (y["tile"] - y["line"]).abs().max().item() <= TOL * scale
 
 
+@pytest.mark.parametrize("dim,n,p,hi", [
+    (3, (8, 8, 8), 2, 1.0),             # eight tiles, every one with boundary faces
+    (3, (16, 16, 16), 2, (1.0, 0.5, 2.0)),  # 64 tiles (more than a CTA's ring of stages), anisotropic cells
+    (3, (4, 4, 4), 2, (0.5, 1.0, 1.0)),  # one tile without halo
+    (2, (32, 32), 2, 1.0),
+    (2, (32, 32), 4, (1.0, 3.0)),
+])
+def test_fine_mesh_pipelined_kernel(dim, n, p, hi, monkeypatch):
+    """k_fine_stream (uniform meshes: persistent CTAs, producer warp + ring of shared-memory stages, results
+    by bulk store / bulk reduce) is the kernel that runs on these meshes, and it agrees with the oracle's
+    matrix of the same form (include/utils.h:819-925, 1565-1659) per output, with the line kernel, for
+    Laplace and monodomain coefficients, vmult and vmult_add, whatever the number of stages."""
+    pdl = gpu()
+    import torch
+
+    ogrid = po.Grid(dim, n, 0.0, hi, 0)
+    groups = [[c] for c in range(ogrid.n_cells)]
+    oah = po.AgglomerationHandler(ogrid)
+    for g in groups:
+        oah.define_agglomerate(g)
+    oah.initialize_fe_values(p + 1)
+    oah.distribute_agglomerated_dofs(po.FE_DGQ, p)
+    C = max(p, 1) * (p + 1.0)
+    ops = {}
+    for kernel in ("stream", "line"):
+        monkeypatch.setenv("PD_FINE_KERNEL", kernel)
+        _, pah = product_handler(ogrid, groups, p, p + 1)
+        ops[kernel] = pdl.SIPOperator(pah.flatten(penalty_constant=C, h_rule=pdl.H_NORMAL_EXTENT), keepalive=pah)
+    x = torch.from_numpy(src_vector(ops["stream"].m())).cuda()
+    small = ogrid.n_cells <= 1024
+    for flags, kw in [(pdl.ASSEMBLE_ALL, {}),
+                      (pdl.ASSEMBLE_VOLUME | pdl.ASSEMBLE_INTERIOR, dict(with_boundary=False, stiffness_coeff=1e-4, mass_coeff=1.5e4)),
+                      (pdl.ASSEMBLE_INTERIOR | pdl.ASSEMBLE_BOUNDARY, None)]:
+        y = {}
+        for kernel, op in ops.items():
+            sc, mc = (kw or {}).get("stiffness_coeff", 1.0), (kw or {}).get("mass_coeff", 0.0)
+            op.set_operator(flags, sc, mc)
+            y[kernel] = torch.full_like(x, 0.25)
+            op.vmult(y[kernel], x, mode=pdl.VMULT_MATRIX_FREE)
+            op.vmult_add(y[kernel], x, mode=pdl.VMULT_MATRIX_FREE)
+            op.synchronize()
+        assert ops["stream"].fine_kernel_last == 3 and ops["line"].fine_kernel_last == 1
+        scale = y["line"].abs().max().item()
+        assert scale > 0 and (y["stream"] - y["line"]).abs().max().item() <= TOL * scale
+        if small and kw is not None:
+            ref = po.assemble_dg_matrix(oah, penalty_constant=C, h_rule=po.H_NORMAL_EXTENT, n_threads=4, **kw)
+            yref = 2 * ref.vmult(x.cpu().numpy())
+            assert np.abs(y["stream"].cpu().numpy() - yref).max() <= 2 * TOL * np.abs(yref).max()
+
+
 @pytest.mark.parametrize("dim,n,shape,p,nq,distort", [
     (2, 8, "random5", 1, 2, None),
     (2, 8, "blocks4", 2, 4, (0.2, 3)),

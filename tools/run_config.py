@@ -125,6 +125,7 @@ def main():
             geo_bytes = 8.0 * n**dim * ((dim * (dim + 1) // 2 + 1) * nq**dim + 2 * dim * (2 * dim + 1) * nq ** (dim - 1) + 2 * dim)
         print(json.dumps({"config": args.config, "cells": n**dim, "degree": p, "n_dofs": N, "host_setup_s": t_host,
                           "kernel": "mapped (general hexes)" if mapped else "Cartesian stencil",
+                          "fine_kernel_last": op.fine_kernel_last,
                           "GBs_with_geometry": (16.0 * N + geo_bytes) / (ms * 1e-3) / 1e9,
                           "frac_hbm_with_geometry": (16.0 * N + geo_bytes) / (ms * 1e-3) / 1e9 / 6543.4,
                           "mf_vmult_ms": ms, "mf_vmult_gdofs": N / (ms * 1e-3) / 1e9,
