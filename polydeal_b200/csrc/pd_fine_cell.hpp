@@ -443,6 +443,88 @@ namespace pd
         }
       return p;
     }
+    // ---- tile plan of the pipelined kernel (k_fine_stream) --------------------------------
+    // Same tiles, but the halo rows are packed like the own rows: n doubles apart (n odd), no alignment slack,
+    //   i * n + [0, n)              own cell i of the tile (i < TILE)
+    //   (TILE + r) * n + [0, n)     halo row r
+    //   zoff + [0, n)               zeros
+    // so that ALL rows a warp reads are an odd number of doubles apart (the 16-byte aligned rows of the other plan
+    // are an even number apart: rows r and r + 8 share their banks, measured 7 extra wavefronts per cell).  The rows
+    // are filled by 16-byte cp.async chunks all the same: a halo cell whose first coefficient sits on a 16-byte
+    // boundary of the vector ((cell * n) even) gets an EVEN row, the others an odd row -- source and destination then
+    // have the same alignment and the row is (n - 1) / 2 chunks of 16 bytes plus one of 8.  rows[tile][r] = cell or -1.
+    struct StreamPlan
+    {
+      int32_t               n_tiles = 0, max_rows = 0, zoff = 0;
+      std::vector<int32_t>  rows; // [n_tiles][max_rows]
+      std::vector<uint16_t> noff; // [n_tiles * tile][nfc]
+    };
+    // every tile must hold exactly `tile` sequence entries (the caller checks); n odd
+    inline StreamPlan
+    build_stream_plan(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
+                      const int tile, const int n)
+    {
+      if (n % 2 == 0 || n_seq % tile != 0)
+        throw std::invalid_argument("build_stream_plan: n odd and whole tiles only");
+      StreamPlan p;
+      p.n_tiles = n_seq / tile;
+      std::vector<std::vector<int32_t>> rows((size_t)p.n_tiles);
+      std::vector<int32_t>              row_of((size_t)n_cells_total, -1), own_of((size_t)n_cells_total, -1);
+      std::vector<int32_t>              noff_row((size_t)n_seq * nfc, -1); // >= 0: halo row, -2 - i: own cell i, -1: none
+      for (int32_t k = 0; k < p.n_tiles; ++k)
+        {
+          const int32_t s0 = k * tile;
+          auto         &R  = rows[(size_t)k];
+          int32_t       next[2] = {0, 1};
+          for (int32_t i = 0; i < tile; ++i)
+            own_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = i;
+          for (int f = 0; f < nfc; ++f) // face by face: the lanes of a warp, which read one face at a time, read different rows
+            for (int32_t i = 0; i < tile; ++i)
+              {
+                const int32_t c  = seq ? seq[s0 + i] : s0 + i;
+                const int32_t nb = nbr[(size_t)c * nfc + f];
+                if (nb < 0)
+                  continue;
+                if (nb >= n_cells_total)
+                  throw std::out_of_range("build_stream_plan: neighbour id out of range");
+                if (own_of[(size_t)nb] >= 0)
+                  {
+                    noff_row[(size_t)(s0 + i) * nfc + f] = -2 - own_of[(size_t)nb];
+                    continue;
+                  }
+                if (row_of[(size_t)nb] < 0)
+                  {
+                    const int par = (int)(((int64_t)nb * n) & 1);
+                    row_of[(size_t)nb] = next[par];
+                    next[par] += 2;
+                    if ((int32_t)R.size() <= row_of[(size_t)nb])
+                      R.resize((size_t)row_of[(size_t)nb] + 1, -1);
+                    R[(size_t)row_of[(size_t)nb]] = nb;
+                  }
+                noff_row[(size_t)(s0 + i) * nfc + f] = row_of[(size_t)nb];
+              }
+          for (int32_t i = 0; i < tile; ++i)
+            own_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = -1;
+          for (const int32_t c : R)
+            if (c >= 0)
+              row_of[(size_t)c] = -1;
+          p.max_rows = std::max<int32_t>(p.max_rows, (int32_t)R.size());
+        }
+      const int64_t zoff = (int64_t)(tile + p.max_rows) * n;
+      if (zoff + n >= 0xFFFF)
+        throw std::length_error("build_stream_plan: tile too large for 16-bit offsets");
+      p.zoff = (int32_t)zoff;
+      p.rows.assign((size_t)p.n_tiles * std::max<int32_t>(1, p.max_rows), -1);
+      for (int32_t k = 0; k < p.n_tiles; ++k)
+        std::copy(rows[(size_t)k].begin(), rows[(size_t)k].end(), p.rows.begin() + (size_t)k * p.max_rows);
+      p.noff.resize((size_t)n_seq * nfc);
+      for (size_t i = 0; i < p.noff.size(); ++i)
+        {
+          const int32_t r = noff_row[i];
+          p.noff[i]       = (uint16_t)(r == -1 ? p.zoff : (r <= -2 ? (-2 - r) * n : (tile + r) * n));
+        }
+      return p;
+    }
   } // namespace fine
 } // namespace pd
 

@@ -617,7 +617,7 @@ namespace pd
     // Needs: every tile one contiguous run of cells starting on a 16-byte boundary with a multiple of four
     // cells (FineTiles::stream_ok), N odd (own rows as in the vector), x and y 16-byte aligned.
     // ---------------------------------------------------------------------------------------
-    constexpr int FINE_MAX_STAGES = 8, STREAM_HALO_PASSES = 1; // (at most FINE_TILE_THREADS halo cells per tile: one row per thread)
+    constexpr int FINE_MAX_STAGES = 8; // (and at most FINE_TILE_THREADS halo cells per tile: one row per thread)
     template <int DIM, int N1>
     struct StreamArgs
     {
@@ -631,15 +631,21 @@ namespace pd
       int32_t                    n_tiles, max_halo, zoff, n_stages;
       int                        add;
     };
+    // shared memory of a stage: coefficients (own rows | halo rows | zeros, all n doubles apart: StreamPlan) | neighbour offsets
     constexpr size_t
-    stream_stage_bytes(const int dim, const int n, const int max_halo)
+    stream_values_bytes(const int n, const int max_rows)
     {
-      return tile_values_bytes(n, max_halo) + round16((size_t)FINE_TILE * 2 * dim * 2) + 16;
+      return round16(((size_t)(FINE_TILE + max_rows + 1) * n + 1) * sizeof(double));
+    }
+    constexpr size_t
+    stream_stage_bytes(const int dim, const int n, const int max_rows)
+    {
+      return stream_values_bytes(n, max_rows) + round16((size_t)FINE_TILE * 2 * dim * 2);
     }
     constexpr size_t
     stream_smem_bytes(const int dim, const int n, const int max_halo, const int stages)
     {
-      return stages * stream_stage_bytes(dim, n, max_halo) + 2 * FINE_MAX_STAGES * sizeof(uint64_t);
+      return stages * stream_stage_bytes(dim, n, max_halo) + FINE_MAX_STAGES * sizeof(uint64_t) + 32;
     }
     __device__ __forceinline__ void
     mbar_wait(uint64_t *bar, const uint32_t parity)
@@ -654,45 +660,52 @@ namespace pd
       asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(FINE_TILE_THREADS) : "memory");
     }
 
-    // NG consumer groups of FINE_TILE_THREADS threads (group g takes the CTA's tiles g, g + NG, ...) and one helper
-    // warp.  Per stage two mbarriers: full (everything of the tile has landed), ready (result in the own rows).
-    //  * halo rows: gathered by the CONSUMERS -- as soon as a group is done reading stage s (tile it), its threads issue
-    //    the 16-byte cp.async chunks of tile it + NS into the same stage, one halo row per thread, completion counted
-    //    by cp.async.mbarrier.arrive on full[s]; the gather overlaps the rest of the group's tile (exchange, mass
-    //    passes) and the other groups' arithmetic.  Neither per-cell bulk copies (measured: the TMA unit of an SM
-    //    retires only ~40 of these 224-byte copies per microsecond) nor one gathering warp (measured: 6.5 us per tile,
-    //    too few loads in flight) keeps up with the consumers.
-    //  * own rows and the 16-bit neighbour offsets: one bulk copy each, issued by the helper warp once the bulk store
-    //    of the previous tile of that stage has read the rows.
+    // NG groups of FINE_TILE_THREADS threads; a group works on one tile at a time (thread = (role, cell) as in
+    // k_fine_tile), the CTA's tiles are handed out in order to whichever group is free.  Per stage one mbarrier `full`
+    // (everything of the tile has landed).
+    //  * halo rows: gathered by the group itself -- as soon as it is done reading stage s (tile l), its threads issue the
+    //    16-byte cp.async chunks of tile l + NS into the same stage, one halo row per thread, completion counted by
+    //    cp.async.mbarrier.arrive on full[s]; the gather overlaps the rest of the group's tile (exchange, mass passes)
+    //    and the other groups' arithmetic.  Neither per-cell bulk copies (measured: the TMA unit of an SM retires only
+    //    ~40 of these 224-byte copies per microsecond) nor one gathering warp (measured: 6.5 us per tile, too few
+    //    loads in flight) keeps up.
+    //  * own rows in, neighbour offsets in, results out: one bulk copy each, issued by the group's first thread; the
+    //    refill of the own rows waits for the bulk store to have read them (checked at the top of the group's next
+    //    tile, when it no longer costs anything).
+    // No extra warp: registers are allocated to a CTA in units of four warps, and a 17th warp would cost every thread
+    // of four groups 32 registers.
+    constexpr int
+    stream_max_regs(const int ng)
+    {
+      return ng == 2 ? 128 : (ng == 3 ? 168 : (ng == 4 ? 128 : 96));
+    }
     template <int DIM, int DEG, int NG>
-    __global__ void __launch_bounds__(NG *FINE_TILE_THREADS + 32, NG <= 2 ? 2 : 1)
+    __global__ void __launch_bounds__(NG *FINE_TILE_THREADS) __maxnreg__(stream_max_regs(NG))
       k_fine_stream(const __grid_constant__ StreamArgs<DIM, DEG + 1> A)
     {
       constexpr int N1  = DEG + 1;
       constexpr int N   = ipow_(N1, DIM);
       constexpr int NFC = 2 * DIM;
-      constexpr int RH  = fine::halo_row(N);
-      constexpr int RO  = fine::own_row(N);
-      static_assert(RO == N, "own rows are filled by one bulk copy: N odd");
+      constexpr int RO  = N; // own and halo rows as in the vector (N odd), fine::StreamPlan
       constexpr uint32_t NOFFB = (uint32_t)round16((size_t)FINE_TILE * NFC * 2);
-      constexpr int      CPR   = (N + 2) / 2; // 16-byte chunks that cover N doubles from either alignment
-      static_assert(CPR * 2 <= RH, "a halo row holds the chunks");
+      static_assert(N % 2 == 1, "packed rows");
 
       extern __shared__ __align__(16) unsigned char smem[];
       const int      NS          = A.n_stages;
-      const uint32_t vb          = (uint32_t)tile_values_bytes(N, A.max_halo);
-      const uint32_t stage_bytes = vb + NOFFB + 16;
-      uint64_t      *full = reinterpret_cast<uint64_t *>(smem + (size_t)NS * stage_bytes), *ready = full + FINE_MAX_STAGES;
+      const uint32_t vb          = (uint32_t)stream_values_bytes(N, A.max_halo);
+      const uint32_t stage_bytes = vb + NOFFB;
+      uint64_t      *full        = reinterpret_cast<uint64_t *>(smem + (size_t)NS * stage_bytes);
+      int           *next_tile   = reinterpret_cast<int *>(full + FINE_MAX_STAGES); // [0]: next unclaimed tile of the CTA; [1 + g]: group g's claim
 
       // (the warp index through a broadcast shuffle: the compiler then knows that everything derived from it -- the
-      // warp's job, its group, its role -- is warp-uniform and keeps the 1-D matrices in uniform registers)
+      // warp's group, its role -- is warp-uniform and keeps the 1-D matrices in uniform registers)
       const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
       if (tid == 0)
-        for (int s = 0; s < NS; ++s)
-          {
+        {
+          for (int s = 0; s < NS; ++s)
             mbar_init(full + s, FINE_TILE_THREADS + 1); // the gathering group's threads + the bulk copies' transaction bytes
-            mbar_init(ready + s, FINE_TILE);
-          }
+          next_tile[0] = NG; // (the first NG tiles are taken by group number)
+        }
       if (tid < N)
         for (int s = 0; s < NS; ++s)
           reinterpret_cast<double *>(smem + (size_t)s * stage_bytes)[A.zoff + tid] = 0.;
@@ -700,27 +713,136 @@ namespace pd
       const int my_n = (int)blockIdx.x < A.n_tiles ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
       auto      tile_of = [&](const int l) { return (int)blockIdx.x + l * (int)gridDim.x; };
 
-      if (warp == NG * (FINE_TILE_THREADS / 32))
-        { // ---- helper warp: own rows + neighbour offsets in (bulk copies), results out (bulk store)
-          if (lane == 0)
+      constexpr int WPG = FINE_TILE_THREADS / 32, WPR = FINE_TILE / 32; // warps per group / per role
+      const int     group = warp / WPG, role = (warp % WPG) / WPR, ci = (warp % WPR) * 32 + lane;
+      const int     gt      = (warp % WPG) * 32 + lane; // thread of the group: gathers halo row gt
+      const bool    elected = gt == 0;                  // issues the group's bulk copies
+      // own rows + neighbour offsets of tile l into its stage
+      auto load_own = [&](const int l) {
+        const int      tile = tile_of(l), s = l % NS;
+        unsigned char *st   = smem + (size_t)s * stage_bytes;
+        const int      fc   = A.tile_base ? A.tile_base[tile] : tile * FINE_TILE;
+        bulk_g2s(st, A.x + (int64_t)fc * N, (uint32_t)FINE_TILE * N * 8, full + s);
+        bulk_g2s(st + vb, A.noff + (size_t)tile * FINE_TILE * NFC, (uint32_t)FINE_TILE * NFC * 2, full + s);
+        mbar_arrive_expect(full + s, (uint32_t)FINE_TILE * (N * 8 + NFC * 2));
+      };
+      // The halo rows of tile l into its stage.  Row and cell have the same 16-byte alignment (fine::StreamPlan), so a
+      // row is (N - 1) / 2 chunks of 16 bytes and one of 8 (the last of an even row, the first of an odd row).  N + 1
+      // consecutive lanes take the chunks of an (even, odd) pair of rows, PPP pairs per instruction: the shared-memory
+      // side of a cp.async costs one wavefront per contiguous 128 bytes, so lanes must write NEIGHBOURING chunks
+      // (one row per lane, the first version, took 30 wavefronts per instruction -- 43 % of all the kernel's
+      // shared-memory wavefronts).  The warps of the group take the passes round robin; lane q RPP + k of a warp has
+      // prefetched the cell of row k of the warp's pass q.
+      constexpr int PPP = 32 / (N + 1), RPP = 2 * PPP, HALF = (N + 1) / 2; // pairs / rows per pass, chunks per row
+      static_assert(PPP >= 1, "a pair of rows fits a warp");
+      const int  gw = warp % WPG; // warp of the group
+      const int  pair = lane / (N + 1), jj = lane % (N + 1), odd = jj >= HALF ? 1 : 0, chunk = odd ? jj - HALF : jj;
+      const bool gathers = lane < PPP * (N + 1);
+      const bool small   = odd ? chunk == 0 : chunk == HALF - 1;                          // the 8-byte chunk of the row
+      const int  coff    = odd ? (chunk == 0 ? 0 : 2 * chunk - 1) : 2 * chunk;           // first double of the chunk
+      const int  n_pass  = (A.max_halo + RPP - 1) / RPP;                                 // passes of the group
+      auto       gather  = [&](const int l, const int32_t hc) {
+        const int s = l % NS;
+        double   *S = reinterpret_cast<double *>(smem + (size_t)s * stage_bytes);
+        for (int q = 0; gw + q * WPG < n_pass; ++q)
+          {
+            const int32_t c   = __shfl_sync(0xffffffffu, hc, (q * RPP + 2 * pair + odd) & 31);
+            const int     row = (gw + q * WPG) * RPP + 2 * pair + odd;
+            if (gathers && c >= 0)
+              {
+                const double *src = A.x + (int64_t)c * N + coff;
+                double       *dst = S + (FINE_TILE + row) * RO + coff;
+                if (small)
+                  cp_async8(dst, src);
+                else
+                  cp_async16(dst, src);
+              }
+          }
+        cp_async_mbar_arrive(full + s);
+      };
+      auto halo_cell = [&](const int l) {
+        const int row = (gw + (lane / RPP) * WPG) * RPP + lane % RPP; // row lane % RPP of this warp's pass lane / RPP
+        return (l < my_n && lane < (32 / RPP) * RPP && row < A.max_halo) ? A.halo_pad[(size_t)tile_of(l) * A.max_halo + row] : -1;
+      };
+      // the first NS tiles: tile l by group l % NG
+      for (int l = group; l < NS && l < my_n; l += NG)
+        {
+          gather(l, halo_cell(l));
+          if (elected)
+            load_own(l);
+        }
+      int pend = -1; // (elected thread) tile whose bulk store may still be reading its stage
+      auto refill_own = [&]() {
+        if (pend >= 0)
+          {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (pend + NS < my_n)
+              load_own(pend + NS);
+            pend = -1;
+          }
+      };
+      for (int it = group; it < my_n;)
+        {
+          const int      s  = it % NS;
+          unsigned char *st = smem + (size_t)s * stage_bytes;
+          double        *S  = reinterpret_cast<double *>(st);
+          const int32_t  hc = halo_cell(it + NS); // (on its way while the lines are computed)
+          if (elected)
+            refill_own(); // (before any wait on a `full`: another group may be waiting for this refill)
+          mbar_wait(full + s, (uint32_t)(it / NS) & 1u);
+          // (every tile of a sequence this kernel takes is full -- FineTiles::stream_ok --, so the whole group
+          // runs the same instruction stream)
+          double        acc[N];
+          double *const own = S + ci * RO;
+          {
+            const uint16_t *np = reinterpret_cast<const uint16_t *>(st + vb) + ci * NFC;
+            const double   *nbp[NFC];
+            bool            bnd[NFC];
+#pragma unroll
+            for (int f = 0; f < NFC; ++f)
+              {
+                const uint32_t o = np[f];
+                nbp[f]           = S + o;
+                bnd[f]           = o == (uint32_t)A.zoff;
+              }
+            auto nbv = [&](const int d, const int sd, const int k) { return nbp[2 * d + sd][k]; };
+#pragma unroll
+            for (int k = 0; k < N; ++k)
+              acc[k] = 0.;
+            if (role == 0) // warp-uniform
+              fine::cell_lines_dense<DIM, N1>(A.T, 0, own, nbv, bnd, acc);
+            else
+              fine::cell_lines_dense<DIM, N1>(A.T, 1, own, nbv, bnd, acc);
+          }
+          group_bar_sync(group + 1); // every read of the staged coefficients is done: the own rows become the exchange / output staging
+          if (it + NS < my_n)
+            gather(it + NS, hc); // ... and the halo rows can take the next tile of this stage
+          if (role == 1)
             {
-              auto load_own = [&](const int l) {
-                const int      tile = tile_of(l), s = l % NS;
-                unsigned char *st   = smem + (size_t)s * stage_bytes;
-                const int      fc   = A.tile_base ? A.tile_base[tile] : tile * FINE_TILE;
-                bulk_g2s(st, A.x + (int64_t)fc * N, (uint32_t)FINE_TILE * N * 8, full + s);
-                bulk_g2s(st + vb, A.noff + (size_t)tile * FINE_TILE * NFC, (uint32_t)FINE_TILE * NFC * 2, full + s);
-                mbar_arrive_expect(full + s, (uint32_t)FINE_TILE * (N * 8 + NFC * 2));
-              };
-              for (int l = 0; l < NS && l < my_n; ++l)
-                load_own(l);
-              for (int Tt = 0; Tt < my_n; ++Tt)
+#pragma unroll
+              for (int k = 0; k < N; ++k)
+                own[k] = acc[k];
+            }
+          if (elected)
+            next_tile[1 + group] = atomicAdd(next_tile, 1);
+          group_bar_sync(group + 1);
+          const int it_next = next_tile[1 + group];
+          if (role == 0)
+            {
+#pragma unroll
+              for (int k = 0; k < N; ++k)
+                acc[k] += own[k];
+              fine::cell_mass<DIM, N1>(A.T, acc);
+#pragma unroll
+              for (int k = 0; k < N; ++k)
+                own[k] = acc[k];
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the bulk store reads these rows
+              asm volatile("bar.sync %0, %1;" ::"r"(NG + 1 + group), "n"(FINE_TILE) : "memory"); // the role's threads
+              if (elected)
                 {
-                  const int s    = Tt % NS, tile = tile_of(Tt);
-                  const int fc   = A.tile_base ? A.tile_base[tile] : tile * FINE_TILE; // (issued before the wait)
-                  mbar_wait(ready + s, (uint32_t)(Tt / NS) & 1u);
-                  double        *dst = A.y + (int64_t)fc * N;
-                  const uint32_t sz = (uint32_t)FINE_TILE * N * 8, src = (unsigned)__cvta_generic_to_shared(smem + (size_t)s * stage_bytes);
+                  const int      tile = tile_of(it);
+                  double        *dst  = A.y + (int64_t)(A.tile_base ? A.tile_base[tile] : tile * FINE_TILE) * N;
+                  const uint32_t sz = (uint32_t)FINE_TILE * N * 8, src = (unsigned)__cvta_generic_to_shared(st);
                   if (A.add)
                     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(src),
                                  "r"(sz)
@@ -729,110 +851,15 @@ namespace pd
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(sz)
                                  : "memory");
                   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                  if (Tt + NS < my_n)
-                    {
-                      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                      load_own(Tt + NS);
-                    }
+                  pend = it;
                 }
-              asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
+          it = it_next;
         }
-      else
-        { // ---- consumers: group = tile in flight, thread = (role, cell) as in k_fine_tile
-          constexpr int WPG = FINE_TILE_THREADS / 32, WPR = FINE_TILE / 32; // warps per group / per role
-          const int     group = warp / WPG, role = (warp % WPG) / WPR, ci = (warp % WPR) * 32 + lane;
-          const int     gt = (warp % WPG) * 32 + lane; // thread of the group: gathers halo rows gt, gt + 128, ...
-          // the halo rows of tile l into its stage: one row per thread and pass, CPR chunks of 16 bytes from the 16-byte
-          // boundary below the cell
-          auto gather = [&](const int l, const int32_t (&hc)[STREAM_HALO_PASSES]) {
-            const int s = l % NS;
-            double   *S = reinterpret_cast<double *>(smem + (size_t)s * stage_bytes);
-#pragma unroll
-            for (int q = 0; q < STREAM_HALO_PASSES; ++q)
-              if (hc[q] >= 0)
-                {
-                  const int64_t a0  = ((int64_t)hc[q] * N) & ~(int64_t)1;
-                  double       *dst = S + FINE_TILE * RO + (gt + q * FINE_TILE_THREADS) * RH;
-#pragma unroll
-                  for (int c = 0; c < CPR - 1; ++c)
-                    cp_async16(dst + 2 * c, A.x + a0 + 2 * c);
-                  if (a0 + 2 * CPR <= A.x_len)
-                    cp_async16(dst + 2 * (CPR - 1), A.x + a0 + 2 * (CPR - 1));
-                  else // the vector ends inside the last chunk (its second double is not part of the cell)
-                    cp_async8(dst + 2 * (CPR - 1), A.x + a0 + 2 * (CPR - 1));
-                }
-            cp_async_mbar_arrive(full + s);
-          };
-          auto halo_cells = [&](const int l, int32_t (&hc)[STREAM_HALO_PASSES]) {
-#pragma unroll
-            for (int q = 0; q < STREAM_HALO_PASSES; ++q)
-              {
-                const int r = gt + q * FINE_TILE_THREADS;
-                hc[q]       = (l < my_n && r < A.max_halo) ? A.halo_pad[(size_t)tile_of(l) * A.max_halo + r] : -1;
-              }
-          };
-          int32_t hc[STREAM_HALO_PASSES];
-          // the first NS tiles: tile l by the group that will also process it (l % NG)
-          for (int l = group; l < NS && l < my_n; l += NG)
-            {
-              halo_cells(l, hc);
-              gather(l, hc);
-            }
-          for (int it = group; it < my_n; it += NG)
-            {
-              const int      s  = it % NS;
-              unsigned char *st = smem + (size_t)s * stage_bytes;
-              double        *S  = reinterpret_cast<double *>(st);
-              halo_cells(it + NS, hc); // (on its way while the lines are computed)
-              mbar_wait(full + s, (uint32_t)(it / NS) & 1u);
-              // (every tile of a sequence this kernel takes is full -- FineTiles::stream_ok --, so the whole group
-              // runs the same instruction stream: the 1-D matrices stay in uniform registers)
-              double        acc[N];
-              double *const own = S + ci * RO;
-              {
-                const uint16_t *np = reinterpret_cast<const uint16_t *>(st + vb) + ci * NFC;
-                const double   *nbp[NFC];
-                bool            bnd[NFC];
-#pragma unroll
-                for (int f = 0; f < NFC; ++f)
-                  {
-                    const uint32_t o = np[f];
-                    nbp[f]           = S + o;
-                    bnd[f]           = o == (uint32_t)A.zoff;
-                  }
-                auto nbv = [&](const int d, const int sd, const int k) { return nbp[2 * d + sd][k]; };
-#pragma unroll
-                for (int k = 0; k < N; ++k)
-                  acc[k] = 0.;
-                if (role == 0) // warp-uniform
-                  fine::cell_lines_dense<DIM, N1>(A.T, 0, own, nbv, bnd, acc);
-                else
-                  fine::cell_lines_dense<DIM, N1>(A.T, 1, own, nbv, bnd, acc);
-              }
-              group_bar_sync(group + 1); // every read of the staged coefficients is done: the own rows become the exchange / output staging
-              if (it + NS < my_n)
-                gather(it + NS, hc); // ... and the halo rows can take the next tile of this stage
-              if (role == 1)
-                {
-#pragma unroll
-                  for (int k = 0; k < N; ++k)
-                    own[k] = acc[k];
-                }
-              group_bar_sync(group + 1);
-              if (role == 0)
-                {
-#pragma unroll
-                  for (int k = 0; k < N; ++k)
-                    acc[k] += own[k];
-                  fine::cell_mass<DIM, N1>(A.T, acc);
-#pragma unroll
-                  for (int k = 0; k < N; ++k)
-                    own[k] = acc[k];
-                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the bulk store reads these rows
-                  mbar_arrive_expect(ready + s, 0);
-                }
-            }
+      if (elected)
+        {
+          refill_own();
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
 
@@ -1160,27 +1187,37 @@ namespace pd
             t.n_tiles = plan.n_tiles, t.max_halo = plan.max_halo, t.zoff = plan.zoff, t.n_seq = n_seq;
             t.ok = true;
             {
-              // the pipelined kernel moves whole tiles with single bulk copies (own cells in, result out, neighbour offsets)
-              bool                 run_ok = h->n % 2 == 1 && stream_smem_bytes(dim, h->n, plan.max_halo, 2) <= 227 * 1024;
-              std::vector<int32_t> base_h((size_t)plan.n_tiles);
+              // the pipelined kernel moves whole tiles with single bulk copies (own cells in, result out, neighbour
+              // offsets) and has its own layout of the halo rows (fine::StreamPlan)
+              bool run_ok = h->mf_uniform.ok && h->n % 2 == 1;
               for (int32_t k = 0; k < plan.n_tiles && run_ok; ++k)
                 {
                   const int32_t s0 = plan.tile_first[k], n_own = plan.tile_first[k + 1] - s0;
                   const int32_t c0 = seq ? (*seq)[s0] : s0;
-                  run_ok           = n_own == FINE_TILE && ((int64_t)c0 * h->n) % 2 == 0;
+                  run_ok           = s0 == k * FINE_TILE && n_own == FINE_TILE && ((int64_t)c0 * h->n) % 2 == 0;
                   for (int32_t i = 1; i < n_own && run_ok; ++i)
                     run_ok = (seq ? (*seq)[s0 + i] : s0 + i) == c0 + i;
                 }
-              run_ok = run_ok && plan.max_halo <= FINE_TILE_THREADS * STREAM_HALO_PASSES;
-              t.stream_ok = run_ok;
+              t.stream_ok = false;
               if (run_ok)
-                { // the halo lists at a fixed pitch: the load warp fetches them without waiting for tile_ptr
-                  std::vector<int32_t> pad((size_t)plan.n_tiles * std::max(1, plan.max_halo), -1);
-                  for (int32_t k = 0; k < plan.n_tiles; ++k)
-                    std::copy(plan.halo.begin() + plan.tile_ptr[k], plan.halo.begin() + plan.tile_ptr[k + 1],
-                              pad.begin() + (size_t)k * plan.max_halo);
-                  put(t.halo_pad, pad);
-                }
+                try
+                  {
+                    const fine::StreamPlan sp =
+                      fine::build_stream_plan(n_seq, seq ? seq->data() : nullptr, nbr.data(), nfc, h->np, FINE_TILE, h->n);
+                    // (the gather: a warp's lanes hold the cells of 32 / rpp passes of rpp rows each, four warps per group)
+                    const int rpp = 2 * (32 / (h->n + 1));
+                    if (rpp >= 2 && sp.max_rows <= (FINE_TILE_THREADS / 32) * (32 / rpp) * rpp &&
+                        stream_smem_bytes(dim, h->n, sp.max_rows, 3) <= 227 * 1024)
+                      {
+                        put(t.halo_pad, sp.rows);
+                        put(t.noff_stream, sp.noff);
+                        t.stream_rows = sp.max_rows, t.stream_zoff = sp.zoff;
+                        t.stream_ok = true;
+                      }
+                  }
+                catch (const std::exception &)
+                  {
+                  }
             }
             if (part == 0 && seq)
               put(h->mf_seq_all, morton_order);
@@ -1326,11 +1363,11 @@ namespace pd
       // (no cell list: the cells are numbered along the curve already and a tile starts at its first sequence entry)
       a.tile_base = (part == 0 && !h->mf_seq_all.p) ? nullptr : t.tile_base.p;
       a.halo_pad  = t.halo_pad.p;
-      a.noff      = t.noff.p;
+      a.noff      = t.noff_stream.p;
       a.x_len     = (int64_t)h->np * N;
       a.n_tiles   = t.n_tiles;
-      a.max_halo  = t.max_halo;
-      a.zoff      = t.zoff;
+      a.max_halo  = t.stream_rows;
+      a.zoff      = t.stream_zoff;
       a.add       = add ? 1 : 0;
       // consumer groups per CTA: PD_FINE_GROUPS (2..5), default: as many as the shared memory holds with one stage more
       // than groups; stages: PD_FINE_STAGES, default groups + 1
@@ -1343,14 +1380,14 @@ namespace pd
         }
       const size_t cap = 227 * 1024;
       int          groups = groups_env ? groups_env : 5;
-      while (groups > 2 && stream_smem_bytes(DIM, N, t.max_halo, groups + 1) > cap)
+      while (groups > 2 && stream_smem_bytes(DIM, N, t.stream_rows, groups + 1) > cap)
         --groups;
       int stages = stages_env ? stages_env : groups + 1;
       const size_t per_cta_cap = groups <= 2 ? cap / 2 - 1024 : cap; // (two groups: two CTAs per SM)
-      while (stages > 2 && stream_smem_bytes(DIM, N, t.max_halo, stages) > per_cta_cap)
+      while (stages > 2 && stream_smem_bytes(DIM, N, t.stream_rows, stages) > per_cta_cap)
         --stages;
       a.n_stages        = stages;
-      const size_t smem = stream_smem_bytes(DIM, N, t.max_halo, stages);
+      const size_t smem = stream_smem_bytes(DIM, N, t.stream_rows, stages);
       auto go = [&](auto kernel, size_t &smem_set, const int threads) {
         if (smem > smem_set)
           {
@@ -1365,10 +1402,10 @@ namespace pd
       static size_t smem_set[6] = {0, 0, 0, 0, 0, 0}; // per instantiation
       switch (groups)
         {
-          case 2: go(k_fine_stream<DIM, DEG, 2>, smem_set[2], 2 * FINE_TILE_THREADS + 32); break;
-          case 3: go(k_fine_stream<DIM, DEG, 3>, smem_set[3], 3 * FINE_TILE_THREADS + 32); break;
-          case 4: go(k_fine_stream<DIM, DEG, 4>, smem_set[4], 4 * FINE_TILE_THREADS + 32); break;
-          default: go(k_fine_stream<DIM, DEG, 5>, smem_set[5], 5 * FINE_TILE_THREADS + 32); break;
+          case 2: go(k_fine_stream<DIM, DEG, 2>, smem_set[2], 2 * FINE_TILE_THREADS); break;
+          case 3: go(k_fine_stream<DIM, DEG, 3>, smem_set[3], 3 * FINE_TILE_THREADS); break;
+          case 4: go(k_fine_stream<DIM, DEG, 4>, smem_set[4], 4 * FINE_TILE_THREADS); break;
+          default: go(k_fine_stream<DIM, DEG, 5>, smem_set[5], 5 * FINE_TILE_THREADS); break;
         }
     }
   } // namespace

@@ -122,7 +122,9 @@ struct pd_handle
   // cell sequences (all owned cells, interior list, boundary list) and the premultiplied 1-D tables
   struct FineTiles
   {
-    pd::DevBuf<int32_t>  halo_pad; // [n_tiles][max_halo], -1 padded (pipelined kernel)
+    pd::DevBuf<int32_t>  halo_pad; // pipelined kernel (fine::StreamPlan): [n_tiles][stream_rows] halo cell of a row or -1
+    pd::DevBuf<uint16_t> noff_stream;
+    int32_t              stream_rows = 0, stream_zoff = 0;
     pd::DevBuf<int32_t>  tile_first, tile_ptr, halo, tile_base; // tile_base: first cell of a tile whose cells are consecutive, else -1
     pd::DevBuf<uint16_t> noff;
     int32_t              n_tiles = 0, max_halo = 0, zoff = 0, n_seq = 0;

@@ -80,6 +80,31 @@ extern "C"
       }
   }
 
+  // the pipelined kernel's plan; outputs sized by the caller: rows[n_tiles * rows_cap], noff[n_seq * nfc]
+  int
+  fine_stream_plan_host(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
+                        const int tile, const int n, const int32_t rows_cap, int32_t *max_rows, int32_t *zoff, int32_t *rows,
+                        uint16_t *noff)
+  {
+    try
+      {
+        const pd::fine::StreamPlan p = pd::fine::build_stream_plan(n_seq, seq, nbr, nfc, n_cells_total, tile, n);
+        if (p.max_rows > rows_cap)
+          return -2;
+        *max_rows = p.max_rows;
+        *zoff     = p.zoff;
+        for (int32_t k = 0; k < p.n_tiles; ++k)
+          for (int32_t r = 0; r < rows_cap; ++r)
+            rows[(size_t)k * rows_cap + r] = r < p.max_rows ? p.rows[(size_t)k * p.max_rows + r] : -1;
+        std::memcpy(noff, p.noff.data(), p.noff.size() * sizeof(uint16_t));
+        return 0;
+      }
+    catch (const std::exception &)
+      {
+        return -1;
+      }
+  }
+
   // outputs sized by the caller: tile_first[n_seq + 1], tile_ptr[n_seq + 1], noff[n_seq * nfc], halo[halo_cap]
   int
   fine_tile_plan_host(const int32_t n_seq, const int32_t *seq, const uint64_t *block_key, const int32_t *nbr, const int nfc,

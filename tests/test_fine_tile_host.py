@@ -249,3 +249,41 @@ def test_halo_bulk_copies_are_aligned_and_in_bounds(n):
     if ro == n:
         for t in range(5):
             assert (t * tile * n * 8) % 16 == 0 and (tile * n * 8) % 16 == 0
+
+
+@pytest.mark.parametrize("shape,tile,n", [((8, 8, 8), 64, 27), ((16, 16), 64, 9), ((16, 16), 64, 25), ((4, 4, 4), 64, 27)])
+def test_stream_plan_contract(lib, shape, tile, n):
+    """build_stream_plan (the pipelined kernel k_fine_stream): every neighbour offset points at the neighbour's own
+    row, at the halo row that holds it, or at the zero row; halo rows are packed n doubles apart, a cell whose first
+    coefficient is 16-byte aligned in the vector sits in an even row and the others in an odd row (source and
+    destination of the 16-byte cp.async chunks then have the same alignment), and no row is used twice."""
+    nbr = grid_neighbours(shape, "morton")
+    n_cells, nfc = nbr.shape
+    rows_cap = 128
+    n_tiles = n_cells // tile
+    rows = np.empty((n_tiles, rows_cap), dtype=np.int32)
+    noff = np.empty((n_cells, nfc), dtype=np.uint16)
+    max_rows, zoff = C.c_int32(), C.c_int32()
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)
+    nbrc = np.ascontiguousarray(nbr)
+    rc = lib.fine_stream_plan_host(n_cells, None, dp(nbrc), nfc, n_cells, tile, n, rows_cap, C.byref(max_rows), C.byref(zoff),
+                                   dp(rows), dp(noff))
+    assert rc == 0
+    assert zoff.value == (tile + max_rows.value) * n and max_rows.value <= 2 * 48 + 1
+    for k in range(n_tiles):
+        used = rows[k][rows[k] >= 0]
+        assert len(set(used.tolist())) == len(used)
+        for r in range(rows_cap):
+            c = rows[k, r]
+            if c >= 0:
+                assert (c * n) % 2 == r % 2 and not (k * tile <= c < (k + 1) * tile)
+        for i in range(tile):
+            cell = k * tile + i
+            for f in range(nfc):
+                nb, o = nbr[cell, f], int(noff[cell, f])
+                if nb < 0:
+                    assert o == zoff.value
+                elif k * tile <= nb < (k + 1) * tile:
+                    assert o == (nb - k * tile) * n
+                else:
+                    assert o % n == 0 and tile <= o // n < tile + max_rows.value and rows[k, o // n - tile] == nb
