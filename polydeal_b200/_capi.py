@@ -86,6 +86,7 @@ SIGNATURES = {
     "pd_peer_exchange": (C.c_int, [vp, C.c_void_p]),
     "pd_peer_vmult": (C.c_int, [vp, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "pd_peer_status": (C.c_int, [vp]),
+    "pd_peer_fused": (C.c_int, [vp]),
     "pd_peer_allreduce": (C.c_int, [vp, C.c_void_p, C.c_int]),
     "pd_estimate_lambda_max_sharded": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pd_chebyshev_smooth_sharded": (C.c_int, [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),

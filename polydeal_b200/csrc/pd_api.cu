@@ -948,6 +948,12 @@ extern "C"
     return guarded([&] { peer_vmult(p, mode, x_full_dev, dst_dev, add != 0); });
   }
   int
+  pd_peer_fused(pd_peer *p)
+  {
+    return peer_fused(p) ? 1 : 0;
+  }
+
+  int
   pd_peer_status(pd_peer *p)
   {
     return peer_status(p);

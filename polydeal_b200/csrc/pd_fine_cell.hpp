@@ -460,9 +460,12 @@ namespace pd
       std::vector<uint16_t> noff; // [n_tiles * tile][nfc]
     };
     // every tile must hold exactly `tile` sequence entries (the caller checks); n odd
+    // src_parity (optional, [n_cells_total]): whether a cell's coefficients start 8 bytes past a 16-byte boundary where
+    // the kernel reads them (default: (cell * n) & 1, the vector itself; ghost cells read straight from a peer's
+    // export buffer sit wherever that buffer has them)
     inline StreamPlan
     build_stream_plan(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
-                      const int tile, const int n)
+                      const int tile, const int n, const uint8_t *src_parity = nullptr)
     {
       if (n % 2 == 0 || n_seq % tile != 0)
         throw std::invalid_argument("build_stream_plan: n odd and whole tiles only");
@@ -494,7 +497,7 @@ namespace pd
                   }
                 if (row_of[(size_t)nb] < 0)
                   {
-                    const int par = (int)(((int64_t)nb * n) & 1);
+                    const int par = src_parity ? (src_parity[(size_t)nb] & 1) : (int)(((int64_t)nb * n) & 1);
                     row_of[(size_t)nb] = next[par];
                     next[par] += 2;
                     if ((int32_t)R.size() <= row_of[(size_t)nb])

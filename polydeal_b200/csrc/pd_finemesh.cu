@@ -630,6 +630,15 @@ namespace pd
       int64_t                    x_len;     // doubles that may be read from x
       int32_t                    n_tiles, max_halo, zoff, n_stages;
       int                        add;
+      // fused sharded apply (ghost_src != nullptr): halo cells >= np_own are read from the owner's export buffer over
+      // NVLink, tiles >= first_ghost_tile wait (once per warp) until the owners' epoch flags have reached this
+      // rank's exchange epoch
+      const double *const       *ghost_src;
+      int64_t                    parity_stride;
+      const unsigned long long  *epochs;
+      volatile unsigned long long *flags, *error_word;
+      const int32_t             *owners;
+      int32_t                    n_owners, np_own, first_ghost_tile;
     };
     // shared memory of a stage: coefficients (own rows | halo rows | zeros, all n doubles apart: StreamPlan) | neighbour offsets
     constexpr size_t
@@ -741,16 +750,40 @@ namespace pd
       const bool small   = odd ? chunk == 0 : chunk == HALF - 1;                          // the 8-byte chunk of the row
       const int  coff    = odd ? (chunk == 0 ? 0 : 2 * chunk - 1) : 2 * chunk;           // first double of the chunk
       const int  n_pass  = (A.max_halo + RPP - 1) / RPP;                                 // passes of the group
+      bool       ghosts_ready = A.ghost_src == nullptr;
+      int64_t    ghost_shift  = 0;
       auto       gather  = [&](const int l, const int32_t hc) {
         const int s = l % NS;
         double   *S = reinterpret_cast<double *>(smem + (size_t)s * stage_bytes);
+        if (!ghosts_ready && tile_of(l) >= A.first_ghost_tile)
+          { // (warp-uniform) the first tile of this warp that may read ghost cells: the owners must have published
+            const unsigned long long e = *A.epochs; // (bumped by this rank's publish, the kernel in front of this one)
+            if (lane < A.n_owners)
+              {
+                const long long t0 = clock64();
+                while (A.flags[A.owners[lane]] < e)
+                  {
+                    if (clock64() - t0 > 4000000000ll) // the peer is gone: report, do not hang
+                      {
+                        *A.error_word = 1ull;
+                        break;
+                      }
+                    __nanosleep(64);
+                  }
+              }
+            __threadfence_system();
+            __syncwarp();
+            ghost_shift  = (e & 1ull) ? A.parity_stride : 0;
+            ghosts_ready = true;
+          }
         for (int q = 0; gw + q * WPG < n_pass; ++q)
           {
             const int32_t c   = __shfl_sync(0xffffffffu, hc, (q * RPP + 2 * pair + odd) & 31);
             const int     row = (gw + q * WPG) * RPP + 2 * pair + odd;
             if (gathers && c >= 0)
               {
-                const double *src = A.x + (int64_t)c * N + coff;
+                const double *src =
+                  (A.ghost_src && c >= A.np_own ? A.ghost_src[c - A.np_own] + ghost_shift : A.x + (int64_t)c * N) + coff;
                 double       *dst = S + (FINE_TILE + row) * RO + coff;
                 if (small)
                   cp_async8(dst, src);
@@ -1049,6 +1082,9 @@ namespace pd
     h->mf_list_boundary.release();
     h->mf_seq_all.release();
     std::vector<int32_t> inner, outer;
+    h->mf_h_nbr = nbr;
+    h->mf_h_inner.clear(), h->mf_h_outer.clear();
+    h->mf_fused.ok = false;
     if (h->np != h->np_own)
       {
         // the split is made BLOCK by block of the curve (the tiles of the tiled kernel): a block one of whose cells reads
@@ -1067,6 +1103,7 @@ namespace pd
         std::sort(bnd_blocks.begin(), bnd_blocks.end());
         for (const int32_t c : morton_order)
           (std::binary_search(bnd_blocks.begin(), bnd_blocks.end(), key[c] >> split_bits) ? outer : inner).push_back(c);
+        h->mf_h_inner = inner, h->mf_h_outer = outer;
         put(h->mf_list_interior, inner);
         put(h->mf_list_boundary, outer);
       }
@@ -1141,6 +1178,7 @@ namespace pd
         bool unit = true;
         for (int i = 0; i < n1; ++i)
           unit = unit && std::fabs(e0[i] - (i == 0 ? 1. : 0.)) < 1e-14 && std::fabs(e0[n1 + i] - (i == n1 - 1 ? 1. : 0.)) < 1e-14;
+        h->mf_tiles[3].ok = h->mf_tiles[3].stream_ok = false;
         for (int part = 0; unit && part < 3; ++part)
           {
             const std::vector<int32_t> *seq = part == 0 ? (identity_order ? nullptr : &morton_order) : (part == 1 ? &inner : &outer);
@@ -1358,6 +1396,20 @@ namespace pd
       const auto         &t  = h->mf_tiles[part];
       StreamArgs<DIM, N1> a;
       uniform_dense_tables<DIM, N1>(h, a.T);
+      a.ghost_src = nullptr, a.parity_stride = 0, a.epochs = nullptr, a.flags = nullptr, a.error_word = nullptr, a.owners = nullptr;
+      a.n_owners = 0, a.np_own = h->np_own, a.first_ghost_tile = 0;
+      if (part == 3)
+        {
+          const auto &f      = h->mf_fused;
+          a.ghost_src        = f.ghost_src.p;
+          a.parity_stride    = f.parity_stride;
+          a.epochs           = f.epochs;
+          a.flags            = f.flags;
+          a.error_word       = f.error_word;
+          a.owners           = f.owners;
+          a.n_owners         = f.n_owners;
+          a.first_ghost_tile = f.first_ghost_tile;
+        }
       a.x          = src;
       a.y          = dst;
       // (no cell list: the cells are numbered along the curve already and a tile starts at its first sequence entry)
@@ -1458,5 +1510,88 @@ namespace pd
     h->mf_kernel_last = tiled ? PD_FINE_KERNEL_TILE : PD_FINE_KERNEL_LINE;
     ++h->launches;
     PD_CUDA(cudaGetLastError());
+  }
+
+  // The fused sharded apply: ONE launch of the pipelined kernel over the interior tiles followed by the boundary
+  // tiles.  The boundary tiles come last in every CTA's list; before a warp gathers the halo rows of the first of
+  // them it waits for the owners' epoch flags, and it reads the ghost cells' coefficients straight from the owners'
+  // export buffers over NVLink -- no pull kernel, no ghost section round trip, no second stream, no separate launch
+  // for the boundary cells (reference: update_ghost_values() inside MatrixFree::loop, include/utils.h:466-472).
+  bool
+  setup_fine_fused(pd_handle *h, const double *const *ghost_src_host, const int64_t parity_stride, const unsigned long long *epochs,
+                   unsigned long long *flags, unsigned long long *error_word, const int32_t *owners_dev, const int n_owners)
+  {
+    h->mf_fused.ok = false;
+    h->mf_tiles[3].ok = h->mf_tiles[3].stream_ok = false;
+    const int32_t n_ghost = h->np - h->np_own;
+    if (!h->mf_ready || !h->mf_stream || h->mf_kernel != 0 || !h->mf_uniform.ok || n_ghost <= 0 || !h->mf_tiles[1].stream_ok ||
+        !h->mf_tiles[2].stream_ok || h->n % 2 == 0 || n_owners > 32 || !(h->dim * 10 + h->degree == 22 || h->dim * 10 + h->degree == 24 || h->dim * 10 + h->degree == 32))
+      return false;
+    std::vector<int32_t> seq(h->mf_h_inner);
+    seq.insert(seq.end(), h->mf_h_outer.begin(), h->mf_h_outer.end());
+    const int            nfc = 2 * h->dim;
+    std::vector<uint8_t> par((size_t)h->np);
+    for (int32_t c = 0; c < h->np_own; ++c)
+      par[(size_t)c] = (uint8_t)(((int64_t)c * h->n) & 1);
+    for (int32_t g = 0; g < n_ghost; ++g)
+      par[(size_t)h->np_own + g] = (uint8_t)((reinterpret_cast<uintptr_t>(ghost_src_host[g]) / sizeof(double)) & 1);
+    fine::StreamPlan sp;
+    try
+      {
+        sp = fine::build_stream_plan((int32_t)seq.size(), seq.data(), h->mf_h_nbr.data(), nfc, h->np, FINE_TILE, h->n, par.data());
+      }
+    catch (const std::exception &)
+      {
+        return false;
+      }
+    const int rpp = 2 * (32 / (h->n + 1));
+    if (rpp < 2 || sp.max_rows > (FINE_TILE_THREADS / 32) * (32 / rpp) * rpp || stream_smem_bytes(h->dim, h->n, sp.max_rows, 3) > 227 * 1024)
+      return false;
+    auto put = [](auto &buf, const auto &v) {
+      buf.alloc(v.size());
+      PD_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice));
+    };
+    auto                &t = h->mf_tiles[3];
+    std::vector<int32_t> base((size_t)sp.n_tiles);
+    for (int32_t k = 0; k < sp.n_tiles; ++k)
+      base[(size_t)k] = seq[(size_t)k * FINE_TILE];
+    put(t.tile_base, base);
+    put(t.halo_pad, sp.rows);
+    put(t.noff_stream, sp.noff);
+    t.stream_rows = sp.max_rows, t.stream_zoff = sp.zoff, t.n_tiles = sp.n_tiles, t.n_seq = (int32_t)seq.size();
+    t.ok = false, t.stream_ok = true; // (the pipelined kernel only)
+    auto &f = h->mf_fused;
+    {
+      std::vector<const double *> gs(ghost_src_host, ghost_src_host + n_ghost);
+      put(f.ghost_src, gs);
+    }
+    f.parity_stride    = parity_stride;
+    f.epochs           = epochs;
+    f.flags            = flags;
+    f.error_word       = error_word;
+    f.owners           = owners_dev;
+    f.n_owners         = n_owners;
+    f.first_ghost_tile = (int32_t)(h->mf_h_inner.size() / FINE_TILE);
+    f.ok               = true;
+    return true;
+  }
+
+  bool
+  launch_fine_fused(pd_handle *h, const double *src, double *dst, const bool add)
+  {
+    if (!h->mf_fused.ok || !h->mf_tiles[3].stream_ok || reinterpret_cast<uintptr_t>(src) % 16 != 0 ||
+        reinterpret_cast<uintptr_t>(dst) % 16 != 0)
+      return false;
+    switch (h->dim * 10 + h->degree)
+      {
+        case 22: launch_fine_stream<2, 2>(h, src, dst, add, 3); break;
+        case 24: launch_fine_stream<2, 4>(h, src, dst, add, 3); break;
+        case 32: launch_fine_stream<3, 2>(h, src, dst, add, 3); break;
+        default: return false;
+      }
+    h->mf_kernel_last = PD_FINE_KERNEL_STREAM;
+    ++h->launches;
+    PD_CUDA(cudaGetLastError());
+    return true;
   }
 } // namespace pd

@@ -139,7 +139,23 @@ struct pd_handle
     double h[3] = {1., 1., 1.}, sig_in[3] = {0., 0., 0.}, sig_bd[3][2] = {{0., 0.}, {0., 0.}, {0., 0.}};
   };
   FineUniform         mf_uniform;
-  FineTiles           mf_tiles[3];
+  FineTiles           mf_tiles[4]; // all owned cells | interior list | boundary list | interior ++ boundary (fused sharded apply)
+  // host copies kept for the fused sharded apply's plan (built when the peer memory is connected, pd_peer.cu)
+  std::vector<int32_t> mf_h_nbr, mf_h_inner, mf_h_outer;
+  // the fused sharded apply (k_fine_stream over interior ++ boundary tiles, ghost rows read from the peers' export
+  // buffers once their epoch flags are up): set by setup_fine_fused
+  struct FineFused
+  {
+    bool                      ok = false;
+    int32_t                   first_ghost_tile = 0;
+    pd::DevBuf<const double *> ghost_src; // [n_ghost] coefficients of a ghost cell in its owner's export buffer, epoch parity 0
+    int64_t                   parity_stride = 0; // doubles between the two epoch copies
+    const unsigned long long *epochs = nullptr;
+    unsigned long long       *flags = nullptr, *error_word = nullptr;
+    const int32_t            *owners = nullptr;
+    int                       n_owners = 0;
+  };
+  FineFused mf_fused;
   std::vector<double> mf_tile_tab_host; // Mh | Mh^-1 Sh | Mh^-1 e0,e1 | Mh^-1 d0,d1 | d0,d1
   bool                mf_stream = true;  // the pipelined kernel wherever it applies (PD_FINE_KERNEL=tile switches it off)
   int                 mf_kernel_last = 0; // PD_FINE_KERNEL_* of the last launch
@@ -237,6 +253,11 @@ namespace pd
   // pd_finemesh.cu
   void setup_fine_operator(pd_handle *h, const pd_mesh_desc &d);
   void launch_fine_operator(pd_handle *h, const double *src, double *dst, bool add, int part = 0);
+  // fused sharded apply: plan over interior ++ boundary tiles; ghost_src_host[g] = device address of ghost cell g's
+  // coefficients (epoch parity 0) as mapped on this rank; returns whether the fused kernel can be used
+  bool setup_fine_fused(pd_handle *h, const double *const *ghost_src_host, int64_t parity_stride, const unsigned long long *epochs,
+                        unsigned long long *flags, unsigned long long *error_word, const int32_t *owners_dev, int n_owners);
+  bool launch_fine_fused(pd_handle *h, const double *src, double *dst, bool add);
   // pd_mappedfine.cu
   void setup_mapped_operator(pd_handle *h, const pd_mesh_desc &d);
   void launch_mapped_operator(pd_handle *h, const double *src, double *dst, bool add);
@@ -263,6 +284,7 @@ namespace pd
   void     peer_allreduce(pd_peer *p, double *scal_dev, int dst0, int nk);
   pd_handle *peer_handle(pd_peer *p);
   int      peer_status(pd_peer *p);
+  bool     peer_fused(pd_peer *p);
   void     peer_destroy(pd_peer *p);
   // pd_cartesian.cu
   bool check_axis_aligned(pd_handle *h, bool *bricks_stale = nullptr);

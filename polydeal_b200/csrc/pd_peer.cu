@@ -58,7 +58,21 @@ namespace
   __host__ __device__ inline size_t
   off_export(const int world)
   {
-    return off_red_vals(world) + (size_t)world * 2 * RED_MAX * sizeof(double);
+    return (off_red_vals(world) + (size_t)world * 2 * RED_MAX * sizeof(double) + 15) / 16 * 16;
+  }
+  // The export region: send block b, epoch parity pe, at double (2 b + pe) slot + shift(b) with slot = n rounded up
+  // to even and shift(b) = b & 1 for odd n.  Both epoch copies of a block then have the SAME 16-byte alignment, and
+  // consecutive blocks alternate -- what the fused fine-mesh apply needs to read ghost cells from here with 16-byte
+  // cp.async chunks into rows of matching alignment (pd_fine_cell.hpp: StreamPlan).
+  __host__ __device__ inline int64_t
+  export_slot(const int n)
+  {
+    return n + (n & 1);
+  }
+  __host__ __device__ inline int64_t
+  export_at(const int64_t b, const int parity, const int n)
+  {
+    return (2 * b + parity) * export_slot(n) + ((n & 1) ? (b & 1) : 0);
   }
 } // namespace
 
@@ -70,6 +84,9 @@ struct pd_peer
   std::vector<int64_t> send_ptr, recv_ptr;
   pd::DevBuf<int32_t>  send_blocks, recv_owner_of_block, d_neighbours, d_owners;
   pd::DevBuf<int64_t>  recv_src_block; // position of every ghost block inside its owner's send list
+  std::vector<int32_t> h_recv_owner;
+  std::vector<int64_t> h_recv_src;
+  bool                 fused = false; // the fused fine-mesh apply is set up (pd_finemesh.cu: setup_fine_fused)
   int64_t              n_send = 0, n_recv = 0;
   int                  n_neighbours = 0, n_owners = 0;
   // this rank's IPC buffer and device-side state
@@ -118,7 +135,7 @@ namespace pd
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
         {
           const int64_t b                         = i / n;
-          exp[(b * 2 + parity) * n + (i - b * n)] = x[(int64_t)send_blocks[b] * n + (i - b * n)];
+          exp[export_at(b, parity, n) + (i - b * n)] = x[(int64_t)send_blocks[b] * n + (i - b * n)];
         }
       // the last CTA to finish announces the epoch to every neighbour (all CTAs have read `epochs`
       // before taking their ticket, so bumping it here is safe)
@@ -163,7 +180,7 @@ namespace pd
         {
           const int64_t b   = i / n;
           const double *exp = reinterpret_cast<const double *>(peer_base[owner_of_block[b]] + off_export(world));
-          ghost[i]          = __ldcg(exp + (src_block[b] * 2 + parity) * n + (i - b * n));
+          ghost[i]          = __ldcg(exp + export_at(src_block[b], parity, n) + (i - b * n));
         }
     }
 
@@ -246,6 +263,7 @@ namespace pd
         if (recv_ptr[s + 1] > recv_ptr[s])
           owners.push_back(s);
       }
+    p->h_recv_owner = owner, p->h_recv_src = src;
     put(p->send_blocks, sb);
     put(p->recv_owner_of_block, owner);
     put(p->recv_src_block, src);
@@ -254,7 +272,7 @@ namespace pd
     p->n_neighbours = (int)nbrs.size();
     p->n_owners     = (int)owners.size();
     // the IPC-exportable buffer (plain cudaMalloc) and the local device state
-    const size_t bytes = off_export(world) + (size_t)std::max<int64_t>(1, 2 * p->n_send * h->n) * sizeof(double);
+    const size_t bytes = off_export(world) + (size_t)std::max<int64_t>(2, 2 * p->n_send * export_slot(h->n) + 2) * sizeof(double);
     PD_CUDA(cudaMalloc((void **)&p->ipc, bytes));
     PD_CUDA(cudaMemset(p->ipc, 0, bytes));
     PD_CUDA(cudaMalloc((void **)&p->epochs, 2 * sizeof(u64)));
@@ -309,6 +327,17 @@ namespace pd
     p->d_peer_base.alloc(p->world);
     PD_CUDA(cudaMemcpy(p->d_peer_base.p, p->peer_base.data(), sizeof(char *) * p->world, cudaMemcpyHostToDevice));
     p->connected = true;
+    // the fused fine-mesh apply reads ghost cells where their owners publish them
+    {
+      pd_handle                  *h = p->h;
+      std::vector<const double *> gs((size_t)p->n_recv);
+      for (int64_t g = 0; g < p->n_recv; ++g)
+        gs[(size_t)g] = reinterpret_cast<const double *>(p->peer_base[p->h_recv_owner[(size_t)g]] + off_export(p->world)) +
+                        export_at(p->h_recv_src[(size_t)g], 0, h->n);
+      u64 *flags = reinterpret_cast<u64 *>(p->ipc + off_flags(p->world));
+      p->fused   = p->n_recv > 0 && setup_fine_fused(h, gs.data(), export_slot(h->n), p->epochs, flags, flags + p->world,
+                                                   p->d_owners.p, p->n_owners);
+    }
   }
 
   static void
@@ -323,7 +352,7 @@ namespace pd
   void vmult_dispatch(pd_handle *h, int mode, const double *src, double *dst, bool add); // pd_api.cu
 
   static void
-  exchange_on(pd_peer *p, double *x_full_dev, cudaStream_t stream)
+  exchange_on(pd_peer *p, double *x_full_dev, cudaStream_t stream, const bool publish_only = false)
   {
     pd_handle *h = p->h;
     const int  n = h->n;
@@ -336,7 +365,7 @@ namespace pd
                                                     p->counter);
         ++h->launches;
       }
-    if (p->n_recv > 0)
+    if (p->n_recv > 0 && !publish_only)
       {
         const int grid = (int)std::min<int64_t>((p->n_recv * n + 255) / 256, (int64_t)h->sm_count * 4);
         k_peer_pull<<<grid, 256, 0, stream>>>(x_full_dev + (int64_t)h->np_own * n, p->recv_owner_of_block.p,
@@ -373,6 +402,24 @@ namespace pd
     // (measured on config B, a 16 us apply: 37 us unsplit, 39 us split)
     static const int64_t csr_min = getenv("PD_PEER_CSR_SPLIT_MIN_NNZ") ? atoll(getenv("PD_PEER_CSR_SPLIT_MIN_NNZ")) : (int64_t)16 * 1024 * 1024;
     const bool split_csr = !no_split && mode == PD_VMULT_BLOCK_CSR && h->nnz > csr_min && spmv_can_split(h);
+    // the fused path (uniform fine mesh, pipelined kernel): publish, then ONE kernel over all tiles whose boundary
+    // tiles wait for the owners' flags and read the ghost cells from the owners' export buffers.  The ghost section
+    // of x_full_dev is not written on this path.  PD_PEER_NO_FUSED keeps the split path (measurements, tests).
+    static const bool no_fused = getenv("PD_PEER_NO_FUSED") != nullptr;
+    if (split && p->fused && !no_fused && reinterpret_cast<uintptr_t>(x_full_dev) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0)
+      {
+        exchange_on(p, x_full_dev, h->stream, true);
+        if (launch_fine_fused(h, x_full_dev, dst, add))
+          return;
+        // (not launched after all: the ghost section still needs the pull)
+        const int grid = (int)std::min<int64_t>((p->n_recv * h->n + 255) / 256, (int64_t)h->sm_count * 4);
+        k_peer_pull<<<grid, 256, 0, h->stream>>>(x_full_dev + (int64_t)h->np_own * h->n, p->recv_owner_of_block.p,
+                                                    p->recv_src_block.p, p->n_recv, h->n, p->d_peer_base.p, p->rank, p->world,
+                                                    p->epochs, p->d_owners.p, p->n_owners);
+        ++h->launches;
+        vmult_dispatch(h, mode, x_full_dev, dst, add);
+        return;
+      }
     if (!split && !split_csr)
       {
         exchange_on(p, x_full_dev, h->stream);
@@ -438,6 +485,13 @@ namespace pd
   peer_handle(pd_peer *p)
   {
     return p ? p->h : nullptr;
+  }
+
+  bool
+  peer_fused(pd_peer *p)
+  {
+    static const bool no_fused = getenv("PD_PEER_NO_FUSED") != nullptr;
+    return p && p->fused && !no_fused;
   }
 
   int

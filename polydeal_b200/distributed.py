@@ -205,6 +205,11 @@ class PeerExchange:
     def ok(self):
         return K.lib().pd_peer_status(self._h) == 0
 
+    @property
+    def fused(self):
+        """pd_peer_vmult(MATRIX_FREE) runs the fused fine-mesh apply (one kernel, ghost cells read from the peers)."""
+        return bool(K.lib().pd_peer_fused(self._h))
+
     def allreduce(self, scalars):
         """In-place sum over the ranks of a CUDA float64 tensor of at most 4 entries."""
         assert scalars.is_cuda and scalars.numel() <= 4

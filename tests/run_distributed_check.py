@@ -128,10 +128,13 @@ def main():
                   f"{cg_info[-1][0]} its, relres {cg_info[-1][1]:.1e}, solution err {cg_info[-1][2]:.1e}", flush=True)
     # fine-mesh matrix-free operator (every cell its own element), sharded: pd_peer_vmult applies the cells
     # without ghost neighbours while the ghost blocks travel on a second stream
-    for dim, n, p in [(3, 8, 2), (2, 16, 3)]:
-        ogrid = po.Grid(dim, n, 0.0, 1.0, 1)
+    # (the last two cases: cells numbered along the Morton curve, as a p4est-distributed mesh has them on every rank,
+    # uniform -> the FUSED apply: one kernel, boundary tiles wait for the owners' flags and read the ghost cells from
+    # the owners' export buffers)
+    for dim, n, p, order in [(3, 8, 2, 1), (2, 16, 3, 1), (3, 16, 2, 0), (2, 64, 2, 0)]:
+        ogrid = po.Grid(dim, n, 0.0, 1.0, order)
         groups = [[c] for c in range(ogrid.n_cells)]
-        _, oah = oracle_handler(dim, n, groups, p, p + 1, order=1)
+        _, oah = oracle_handler(dim, n, groups, p, p + 1, order=order)
         _, pah = product_handler(oah.grid, groups, p, p + 1)
         C_ = max(p, 1) * (p + 1.0)
         A = po.assemble_dg_matrix(oah, penalty_constant=C_, h_rule=po.H_NORMAL_EXTENT, n_threads=4).scipy().tocsr()
@@ -152,6 +155,16 @@ def main():
                 dop.vmult(yd, xs * float(k), mode=pdl.VMULT_MATRIX_FREE)
                 stream.synchronize()
                 err = max(err, float(np.abs(yd.cpu().numpy() - k * y[rows]).max() / (k * np.abs(y).max())))
+            fused = dop.peer.fused
+            if order == 0 and world == 2:
+                assert fused and dop.op.fine_kernel_last == 3, (fused, dop.op.fine_kernel_last)
+            # applies back to back with ranks out of step (double-buffered export slots, epochs), then vmult_add
+            for k in range(5, 11):
+                if (rank + k) % 3 == 0:
+                    torch.cuda._sleep(2_000_000)
+                dop.vmult(yd, xs * float(k), mode=pdl.VMULT_MATRIX_FREE)
+            stream.synchronize()
+            err = max(err, float(np.abs(yd.cpu().numpy() - 10 * y[rows]).max() / (10 * np.abs(y).max())))
             assert dop.peer.ok()
             dist.barrier()
             dop.peer.close()
@@ -159,7 +172,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         worst = max(worst, float(t))
         if rank == 0:
-            print(f"fine-mesh MF dim={dim} n={n} p={p}: world={world} max rel err {float(t):.2e}", flush=True)
+            print(f"fine-mesh MF dim={dim} n={n} p={p} order={order}: world={world} fused={fused} max rel err {float(t):.2e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     assert worst <= 1e-12, worst
