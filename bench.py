@@ -573,6 +573,13 @@ def run_gpu(args):
 
     # ---- the second metric's own path: matrix-free fine-mesh SIP vmult, sharded like the polytopes ---------------
     mf = None if args.no_mf_vmult else mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, 2, reps)
+    mfz = None if (args.no_mf_vmult or world == 1) else mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, 2, reps, "zorder")
+    if mfz is not None:  # (max over ranks, like every other time of the line)
+        import torch
+
+        t_ = torch.tensor([mfz["ms"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        mfz["ms"] = float(t_.cpu()[0])
     mf3 = None
     if world == 1 and not args.no_mf_vmult:
         mf3 = mf_vmult_fine_mesh(pdl, pdd, stream, timer, 1, 0, None, 3, reps)
@@ -656,6 +663,12 @@ def run_gpu(args):
         mf["roofline"] = hbm_block(mf.pop("kernel"), 16.0 * mf["n_dofs_per_gpu"], t_mf_ms, peaks,
                                    note="algorithmic bytes = 16 B/DoF (read src, write dst; SURVEY 8d); per GPU")
         out["mf_vmult"] = mf
+        if mfz is not None:
+            tz = mfz["ms"]
+            mfz["value"] = mfz["total_dofs"] / (tz * 1e-3) / 1e9
+            mfz["roofline"] = hbm_block(mfz.pop("kernel"), 16.0 * mfz["n_dofs_per_gpu"], tz, peaks,
+                                        note="algorithmic bytes = 16 B/DoF (read src, write dst; SURVEY 8d); per GPU")
+            out["mf_vmult_zorder"] = mfz
     if mf3:
         mf3["roofline"] = hbm_block(mf3.pop("kernel"), 16.0 * mf3["n_dofs_per_gpu"], mf3["ms"], peaks)
         out["mf_vmult_dgq3"] = mf3
@@ -672,7 +685,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, p, reps):
+def mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, p, reps, partition="metis"):
     """The second metric of BASELINE.json: the matrix-free sum-factorised SIP vmult of examples/matrix_free_agglo.cc --
     Utils::MatrixFreeOperators::LaplaceOperatorDG (include/utils.h:819-925) on the fine hex mesh, 64^3 cells of
     FE_DGQ(p) per GPU -- through pd_vmult(PD_VMULT_MATRIX_FREE) / pd_peer_vmult, device vectors, `reps` applies back to
@@ -687,7 +700,9 @@ def mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, p, reps):
     if world == 1:
         op = pdl.SIPOperator(ah.flatten(**pen), keepalive=ah)
     else:
-        owner = pdd.partition_by_metis(ah, world)
+        # metis: GridTools::partition_triangulation as examples/matrix_free_agglo.cc:161 calls it (ragged cuts through the
+        # blocks of the curve); zorder: equal ranges of the Morton curve, what p4est / partition_triangulation_zorder give
+        owner = pdd.partition_by_metis(ah, world) if partition == "metis" else pdd.partition_by_blocks(ah, world)
         part = pdd.LocalPart(ah, owner, rank, **pen)
         op = pdl.SIPOperator(part.desc, keepalive=(ah, part))
     op.set_stream(stream.cuda_stream)
@@ -719,6 +734,9 @@ def mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, p, reps):
            "value": float(total.cpu()[0]) / (ms * 1e-3) / 1e9, "unit": "GDoF/s", "ms": ms, "n_dofs_per_gpu": N,
            "total_dofs": float(total.cpu()[0]), "applies": reps, "gpu_launches_per_apply": int(per_apply),
            "kernel": os.environ.get("PD_FINE_KERNEL", "default") + f" fine-mesh kernel, FE_DGQ<3>({p})",
+           "fine_kernel_last": {0: "none", 1: "k_fine_sip (line per thread)", 2: "k_fine_tile", 3: "k_fine_stream (pipelined tiles)"}[op.fine_kernel_last],
+           "partition": "single GPU" if world == 1 else partition,
+           "fused_exchange": bool(peer.fused) if peer is not None else None,
            "checksum_rank0": float(y.sum())}
     del l0
     if peer is not None:

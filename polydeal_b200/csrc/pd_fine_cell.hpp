@@ -444,48 +444,59 @@ namespace pd
       return p;
     }
     // ---- tile plan of the pipelined kernel (k_fine_stream) --------------------------------
-    // Same tiles, but the halo rows are packed like the own rows: n doubles apart (n odd), no alignment slack,
-    //   i * n + [0, n)              own cell i of the tile (i < TILE)
-    //   (TILE + r) * n + [0, n)     halo row r
+    // A tile is a run of at most TILE CONSECUTIVE cells (any length: the blocks a METIS partition cuts are partial;
+    // any alignment).  Its stage in shared memory, in doubles:
+    //   2 - par + i * n + [0, n)    own cell i: the run as it lies in the vector, one double lower when it starts 8
+    //                               bytes past a 16-byte boundary there (par = (first cell * n) & 1), so that shared
+    //                               memory and vector have the same 16-byte phase (bulk copies)
+    //   HB + r * n + [0, n)         halo row r, HB = 2 + TILE * n: the rows after the own rows of an aligned tile
     //   zoff + [0, n)               zeros
-    // so that ALL rows a warp reads are an odd number of doubles apart (the 16-byte aligned rows of the other plan
-    // are an even number apart: rows r and r + 8 share their banks, measured 7 extra wavefronts per cell).  The rows
-    // are filled by 16-byte cp.async chunks all the same: a halo cell whose first coefficient sits on a 16-byte
-    // boundary of the vector ((cell * n) even) gets an EVEN row, the others an odd row -- source and destination then
-    // have the same alignment and the row is (n - 1) / 2 chunks of 16 bytes plus one of 8.  rows[tile][r] = cell or -1.
+    // All rows are n doubles apart, n odd (the 16-byte aligned rows of the other plan are an even number apart: rows r
+    // and r + 8 share their banks).  The halo rows are filled by 16-byte cp.async chunks all the same: a halo cell
+    // whose first coefficient sits on a 16-byte boundary where it is read gets an EVEN row, the others an odd row --
+    // source and destination then have the same phase and the row is (n - 1) / 2 chunks of 16 bytes plus one of 8.
+    // rows[tile][r] = cell or -1.
     struct StreamPlan
     {
-      int32_t               n_tiles = 0, max_rows = 0, zoff = 0;
+      int32_t               n_tiles = 0, max_rows = 0, zoff = 0, halo_base = 0;
       std::vector<int32_t>  rows; // [n_tiles][max_rows]
-      std::vector<uint16_t> noff; // [n_tiles * tile][nfc]
+      std::vector<uint16_t> noff; // [n_seq][nfc]
     };
-    // every tile must hold exactly `tile` sequence entries (the caller checks); n odd
+    // tile_first[n_tiles + 1]: the tiles' sequence ranges; the cells of a tile must be consecutive numbers (checked).
     // src_parity (optional, [n_cells_total]): whether a cell's coefficients start 8 bytes past a 16-byte boundary where
-    // the kernel reads them (default: (cell * n) & 1, the vector itself; ghost cells read straight from a peer's
-    // export buffer sit wherever that buffer has them)
+    // the kernel reads them as a HALO cell (default: (cell * n) & 1, the vector itself; ghost cells read straight from
+    // a peer's export buffer sit wherever that buffer has them)
     inline StreamPlan
-    build_stream_plan(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
-                      const int tile, const int n, const uint8_t *src_parity = nullptr)
+    build_stream_plan(const int32_t n_seq, const int32_t *seq, const int32_t *tile_first, const int32_t n_tiles, const int32_t *nbr,
+                      const int nfc, const int32_t n_cells_total, const int tile, const int n, const uint8_t *src_parity = nullptr)
     {
-      if (n % 2 == 0 || n_seq % tile != 0)
-        throw std::invalid_argument("build_stream_plan: n odd and whole tiles only");
+      if (n % 2 == 0)
+        throw std::invalid_argument("build_stream_plan: n odd only");
       StreamPlan p;
-      p.n_tiles = n_seq / tile;
+      p.n_tiles   = n_tiles;
+      p.halo_base = tile * n + 2;
       std::vector<std::vector<int32_t>> rows((size_t)p.n_tiles);
       std::vector<int32_t>              row_of((size_t)n_cells_total, -1), own_of((size_t)n_cells_total, -1);
       std::vector<int32_t>              noff_row((size_t)n_seq * nfc, -1); // >= 0: halo row, -2 - i: own cell i, -1: none
+      std::vector<uint8_t>              tile_par((size_t)p.n_tiles, 0);
       for (int32_t k = 0; k < p.n_tiles; ++k)
         {
-          const int32_t s0 = k * tile;
-          auto         &R  = rows[(size_t)k];
-          int32_t       next[2] = {0, 1};
-          for (int32_t i = 0; i < tile; ++i)
-            own_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = i;
+          const int32_t s0 = tile_first[k], n_own = tile_first[k + 1] - s0;
+          if (n_own < 1 || n_own > tile)
+            throw std::invalid_argument("build_stream_plan: tile size");
+          const int32_t c0 = seq ? seq[s0] : s0;
+          for (int32_t i = 1; i < n_own; ++i)
+            if ((seq ? seq[s0 + i] : s0 + i) != c0 + i)
+              throw std::invalid_argument("build_stream_plan: the cells of a tile must be consecutive");
+          tile_par[(size_t)k] = (uint8_t)(((int64_t)c0 * n) & 1);
+          auto   &R           = rows[(size_t)k];
+          int32_t next[2]     = {0, 1};
+          for (int32_t i = 0; i < n_own; ++i)
+            own_of[(size_t)(c0 + i)] = i;
           for (int f = 0; f < nfc; ++f) // face by face: the lanes of a warp, which read one face at a time, read different rows
-            for (int32_t i = 0; i < tile; ++i)
+            for (int32_t i = 0; i < n_own; ++i)
               {
-                const int32_t c  = seq ? seq[s0 + i] : s0 + i;
-                const int32_t nb = nbr[(size_t)c * nfc + f];
+                const int32_t nb = nbr[(size_t)(c0 + i) * nfc + f];
                 if (nb < 0)
                   continue;
                 if (nb >= n_cells_total)
@@ -506,14 +517,14 @@ namespace pd
                   }
                 noff_row[(size_t)(s0 + i) * nfc + f] = row_of[(size_t)nb];
               }
-          for (int32_t i = 0; i < tile; ++i)
-            own_of[(size_t)(seq ? seq[s0 + i] : s0 + i)] = -1;
+          for (int32_t i = 0; i < n_own; ++i)
+            own_of[(size_t)(c0 + i)] = -1;
           for (const int32_t c : R)
             if (c >= 0)
               row_of[(size_t)c] = -1;
           p.max_rows = std::max<int32_t>(p.max_rows, (int32_t)R.size());
         }
-      const int64_t zoff = (int64_t)(tile + p.max_rows) * n;
+      const int64_t zoff = (int64_t)p.halo_base + (int64_t)p.max_rows * n;
       if (zoff + n >= 0xFFFF)
         throw std::length_error("build_stream_plan: tile too large for 16-bit offsets");
       p.zoff = (int32_t)zoff;
@@ -521,11 +532,12 @@ namespace pd
       for (int32_t k = 0; k < p.n_tiles; ++k)
         std::copy(rows[(size_t)k].begin(), rows[(size_t)k].end(), p.rows.begin() + (size_t)k * p.max_rows);
       p.noff.resize((size_t)n_seq * nfc);
-      for (size_t i = 0; i < p.noff.size(); ++i)
-        {
-          const int32_t r = noff_row[i];
-          p.noff[i]       = (uint16_t)(r == -1 ? p.zoff : (r <= -2 ? (-2 - r) * n : (tile + r) * n));
-        }
+      for (int32_t k = 0; k < p.n_tiles; ++k)
+        for (size_t i = (size_t)tile_first[k] * nfc; i < (size_t)tile_first[k + 1] * nfc; ++i)
+          {
+            const int32_t r = noff_row[i];
+            p.noff[i]       = (uint16_t)(r == -1 ? p.zoff : (r <= -2 ? 2 - tile_par[(size_t)k] + (-2 - r) * n : p.halo_base + r * n));
+          }
       return p;
     }
   } // namespace fine

@@ -125,6 +125,8 @@ struct pd_handle
     pd::DevBuf<int32_t>  halo_pad; // pipelined kernel (fine::StreamPlan): [n_tiles][stream_rows] halo cell of a row or -1
     pd::DevBuf<uint16_t> noff_stream;
     int32_t              stream_rows = 0, stream_zoff = 0;
+    bool                 stream_regular = false; // every tile FINE_TILE cells from a 16-byte boundary
+    std::vector<int32_t> h_tile_first, h_tile_base; // host copies (the fused sharded plan concatenates two sequences)
     pd::DevBuf<int32_t>  tile_first, tile_ptr, halo, tile_base; // tile_base: first cell of a tile whose cells are consecutive, else -1
     pd::DevBuf<uint16_t> noff;
     int32_t              n_tiles = 0, max_halo = 0, zoff = 0, n_seq = 0;

@@ -82,17 +82,18 @@ extern "C"
 
   // the pipelined kernel's plan; outputs sized by the caller: rows[n_tiles * rows_cap], noff[n_seq * nfc]
   int
-  fine_stream_plan_host(const int32_t n_seq, const int32_t *seq, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
-                        const int tile, const int n, const int32_t rows_cap, int32_t *max_rows, int32_t *zoff, int32_t *rows,
-                        uint16_t *noff)
+  fine_stream_plan_host(const int32_t n_seq, const int32_t *seq, const int32_t *tile_first, const int32_t n_tiles, const int32_t *nbr,
+                        const int nfc, const int32_t n_cells_total, const int tile, const int n, const int32_t rows_cap,
+                        int32_t *max_rows, int32_t *zoff, int32_t *halo_base, int32_t *rows, uint16_t *noff)
   {
     try
       {
-        const pd::fine::StreamPlan p = pd::fine::build_stream_plan(n_seq, seq, nbr, nfc, n_cells_total, tile, n);
+        const pd::fine::StreamPlan p = pd::fine::build_stream_plan(n_seq, seq, tile_first, n_tiles, nbr, nfc, n_cells_total, tile, n);
         if (p.max_rows > rows_cap)
           return -2;
-        *max_rows = p.max_rows;
-        *zoff     = p.zoff;
+        *max_rows  = p.max_rows;
+        *zoff      = p.zoff;
+        *halo_base = p.halo_base;
         for (int32_t k = 0; k < p.n_tiles; ++k)
           for (int32_t r = 0; r < rows_cap; ++r)
             rows[(size_t)k * rows_cap + r] = r < p.max_rows ? p.rows[(size_t)k * p.max_rows + r] : -1;

@@ -131,7 +131,9 @@ def main():
     # (the last two cases: cells numbered along the Morton curve, as a p4est-distributed mesh has them on every rank,
     # uniform -> the FUSED apply: one kernel, boundary tiles wait for the owners' flags and read the ghost cells from
     # the owners' export buffers)
-    for dim, n, p, order in [(3, 8, 2, 1), (2, 16, 3, 1), (3, 16, 2, 0), (2, 64, 2, 0)]:
+    for dim, n, p, order in [(3, 8, 2, 1), (2, 16, 3, 1), (3, 16, 2, 0), (2, 64, 2, 0), (3, 16, 2, 2)]:
+        metis = order == 2  # ... and the same with a METIS partition of the cells: ragged tiles along the cut
+        order = 0 if metis else order
         ogrid = po.Grid(dim, n, 0.0, 1.0, order)
         groups = [[c] for c in range(ogrid.n_cells)]
         _, oah = oracle_handler(dim, n, groups, p, p + 1, order=order)
@@ -140,7 +142,7 @@ def main():
         A = po.assemble_dg_matrix(oah, penalty_constant=C_, h_rule=po.H_NORMAL_EXTENT, n_threads=4).scipy().tocsr()
         x = src_vector(A.shape[0])
         y = A @ x
-        owner = pdd.partition_by_blocks(pah, world)
+        owner = pdd.partition_by_metis(pah, world) if metis else pdd.partition_by_blocks(pah, world)
         stream = torch.cuda.Stream()
         with torch.cuda.stream(stream):
             dop = pdd.DistributedSIPOperator(pah, owner, rank, penalty_constant=C_, h_rule=pdl.H_NORMAL_EXTENT)
@@ -172,7 +174,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         worst = max(worst, float(t))
         if rank == 0:
-            print(f"fine-mesh MF dim={dim} n={n} p={p} order={order}: world={world} fused={fused} max rel err {float(t):.2e}", flush=True)
+            print(f"fine-mesh MF dim={dim} n={n} p={p} order={order} metis={metis}: world={world} fused={fused} "
+                  f"max rel err {float(t):.2e}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     assert worst <= 1e-12, worst

@@ -251,39 +251,50 @@ def test_halo_bulk_copies_are_aligned_and_in_bounds(n):
             assert (t * tile * n * 8) % 16 == 0 and (tile * n * 8) % 16 == 0
 
 
-@pytest.mark.parametrize("shape,tile,n", [((8, 8, 8), 64, 27), ((16, 16), 64, 9), ((16, 16), 64, 25), ((4, 4, 4), 64, 27)])
-def test_stream_plan_contract(lib, shape, tile, n):
+@pytest.mark.parametrize("shape,tile,n,ragged", [((8, 8, 8), 64, 27, False), ((16, 16), 64, 9, False), ((16, 16), 64, 25, True),
+                                                  ((4, 4, 4), 64, 27, False), ((8, 8, 8), 64, 27, True)])
+def test_stream_plan_contract(lib, shape, tile, n, ragged):
     """build_stream_plan (the pipelined kernel k_fine_stream): every neighbour offset points at the neighbour's own
-    row, at the halo row that holds it, or at the zero row; halo rows are packed n doubles apart, a cell whose first
-    coefficient is 16-byte aligned in the vector sits in an even row and the others in an odd row (source and
-    destination of the 16-byte cp.async chunks then have the same alignment), and no row is used twice."""
+    row (shifted by the tile's 16-byte phase), at the halo row that holds it, or at the zero row; halo rows are packed
+    n doubles apart, a cell whose first coefficient is 16-byte aligned in the vector sits in an even row and the
+    others in an odd row (source and destination of the 16-byte cp.async chunks then have the same phase), and no
+    row is used twice.  ragged: tiles of any length and alignment (the blocks a METIS partition cuts)."""
     nbr = grid_neighbours(shape, "morton")
     n_cells, nfc = nbr.shape
     rows_cap = 128
-    n_tiles = n_cells // tile
+    if ragged:
+        rng = np.random.default_rng(5)
+        tf = [0]
+        while tf[-1] < n_cells:
+            tf.append(min(n_cells, tf[-1] + int(rng.integers(1, tile + 1))))
+    else:
+        tf = list(range(0, n_cells + 1, tile))
+    tf = np.array(tf, dtype=np.int32)
+    n_tiles = len(tf) - 1
     rows = np.empty((n_tiles, rows_cap), dtype=np.int32)
     noff = np.empty((n_cells, nfc), dtype=np.uint16)
-    max_rows, zoff = C.c_int32(), C.c_int32()
+    max_rows, zoff, hb = C.c_int32(), C.c_int32(), C.c_int32()
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
     nbrc = np.ascontiguousarray(nbr)
-    rc = lib.fine_stream_plan_host(n_cells, None, dp(nbrc), nfc, n_cells, tile, n, rows_cap, C.byref(max_rows), C.byref(zoff),
-                                   dp(rows), dp(noff))
+    rc = lib.fine_stream_plan_host(n_cells, None, dp(tf), n_tiles, dp(nbrc), nfc, n_cells, tile, n, rows_cap, C.byref(max_rows),
+                                   C.byref(zoff), C.byref(hb), dp(rows), dp(noff))
     assert rc == 0
-    assert zoff.value == (tile + max_rows.value) * n and max_rows.value <= 2 * 48 + 1
+    assert hb.value == tile * n + 2 and zoff.value == hb.value + max_rows.value * n
     for k in range(n_tiles):
+        lo, hi = int(tf[k]), int(tf[k + 1])
+        par = (lo * n) % 2
         used = rows[k][rows[k] >= 0]
         assert len(set(used.tolist())) == len(used)
         for r in range(rows_cap):
             c = rows[k, r]
             if c >= 0:
-                assert (c * n) % 2 == r % 2 and not (k * tile <= c < (k + 1) * tile)
-        for i in range(tile):
-            cell = k * tile + i
+                assert (c * n) % 2 == r % 2 and not (lo <= c < hi)
+        for cell in range(lo, hi):
             for f in range(nfc):
                 nb, o = nbr[cell, f], int(noff[cell, f])
                 if nb < 0:
                     assert o == zoff.value
-                elif k * tile <= nb < (k + 1) * tile:
-                    assert o == (nb - k * tile) * n
+                elif lo <= nb < hi:
+                    assert o == 2 - par + (nb - lo) * n
                 else:
-                    assert o % n == 0 and tile <= o // n < tile + max_rows.value and rows[k, o // n - tile] == nb
+                    assert (o - hb.value) % n == 0 and 0 <= (o - hb.value) // n < max_rows.value and rows[k, (o - hb.value) // n] == nb

@@ -658,6 +658,50 @@ def test_sharded_assembly_and_vmult_match_serial(world, dim, n, shape, p, kw):
     assert seen_rows == A.shape[0]
 
 
+@pytest.mark.parametrize("dim,n,p,world,how", [(3, 16, 2, 3, "metis"), (3, 8, 2, 2, "diagonal"), (2, 32, 2, 3, "metis"), (2, 32, 4, 2, "diagonal")])
+def test_sharded_fine_mesh_ragged_partition(dim, n, p, world, how):
+    """The fine-mesh matrix-free operator on the ranks of a partition that cuts through the 4x4x4 / 8x8 blocks of the
+    Morton curve (METIS, or a diagonal cut): the pipelined kernel k_fine_stream takes tiles of any length and 16-byte
+    phase (own runs by one bulk copy + single doubles, results likewise), ghost cells from the ghost section.
+    Ranks emulated one after the other; checker: the oracle's matrix of the same form (include/utils.h:819-925)."""
+    pdl = gpu()
+    import torch
+
+    from polydeal_b200 import distributed as pdd
+
+    ogrid = po.Grid(dim, n, 0.0, 1.0, 0)
+    groups = [[c] for c in range(ogrid.n_cells)]
+    _, oah = oracle_handler(dim, n, groups, p, p + 1, order=0)
+    _, pah = product_handler(oah.grid, groups, p, p + 1)
+    C_ = max(p, 1) * (p + 1.0)
+    A = po.assemble_dg_matrix(oah, penalty_constant=C_, h_rule=po.H_NORMAL_EXTENT, n_threads=4).scipy().tocsr()
+    x = src_vector(A.shape[0])
+    y = A @ x
+    if how == "metis":
+        owner = pdd.partition_by_metis(pah, world)
+    else:  # cells by the sum of their centre coordinates: every block near the cut is split
+        v, cv, _ = oah.grid.arrays()
+        ctr = v[cv].mean(axis=1).sum(axis=1)  # (polytope k is the cell k)
+        owner = np.minimum((ctr / ctr.max() * world * 0.999).astype(np.int32), world - 1)
+    streamed = 0
+    for rank in range(world):
+        part = pdd.LocalPart(pah, owner, rank, penalty_constant=C_, h_rule=pdl.H_NORMAL_EXTENT)
+        op = pdl.SIPOperator(part.desc, keepalive=(pah, part))
+        assert op.matrix_free_available
+        rows = part.owned_global_dofs()
+        cols = np.concatenate([rows, part.ghost_global_dofs()])
+        xd = torch.from_numpy(x[cols]).cuda()
+        yd = torch.full((len(rows),), 0.5, dtype=torch.float64, device="cuda")
+        op.vmult_ptr(yd.data_ptr(), xd.data_ptr(), mode=pdl.VMULT_MATRIX_FREE)
+        op.synchronize()
+        assert np.abs(yd.cpu().numpy() - y[rows]).max() <= TOL * np.abs(y).max()
+        op.vmult_ptr(yd.data_ptr(), xd.data_ptr(), mode=pdl.VMULT_MATRIX_FREE, add=True)
+        op.synchronize()
+        assert np.abs(yd.cpu().numpy() - 2 * y[rows]).max() <= 2 * TOL * np.abs(y).max()
+        streamed += op.fine_kernel_last == 3
+    assert streamed == world  # the pipelined kernel ran on every rank
+
+
 def test_poisson_golden_l2_error_on_gpu(goldens):
     """test/polydeal/poisson.cc / poisson.output: L2 error 0.00647702 with the matrix assembled
     by the CUDA path (RHS and error functional from the checker's tables, direct solve on the
