@@ -602,7 +602,9 @@ def run_gpu(args):
     value = total_dofs / (ms_per_step * 1e-3)
     e2e_value = total_dofs / (t_e2e_ms * 1e-3)
     vol = max(roofs, key=lambda r: r["kernel_ms"])  # the dominant kernel of the step
-    vol["traffic"] = traffic_of(("k_cart_diag" if path == "tensor" else "k_volume") + "_C_bytes_per_launch")
+    # DRAM bytes per launch from the committed ncu --set full capture of the same kernel on config C (1 GPU)
+    for r in roofs:
+        r["traffic"] = traffic_of(r["kernel"].split("<")[0] + "_C_bytes_per_launch") if world == 1 else None
     vm_bytes = 8.0 * n * n * nblocks + 4.0 * nblocks + 16.0 * n_dofs
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
