@@ -739,6 +739,7 @@ def mf_vmult_fine_mesh(pdl, pdd, stream, timer, world, rank, dist, p, reps, part
            "fine_kernel_last": {0: "none", 1: "k_fine_sip (line per thread)", 2: "k_fine_tile", 3: "k_fine_stream (pipelined tiles)"}[op.fine_kernel_last],
            "partition": "single GPU" if world == 1 else partition,
            "fused_exchange": bool(peer.fused) if peer is not None else None,
+           "fused_tiles": peer.fused_tiles if peer is not None else None,
            "checksum_rank0": float(y.sum())}
     del l0
     if peer is not None:

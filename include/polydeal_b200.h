@@ -277,10 +277,11 @@ int pd_peer_exchange(pd_peer *p, double *x_full_dev);
  * ghost data are applied while the ghost blocks travel on a second stream */
 int pd_peer_vmult(pd_peer *p, int mode, double *x_full_dev, double *dst_dev, int add);
 int pd_peer_status(pd_peer *p);
-/* 1 when pd_peer_vmult(PD_VMULT_MATRIX_FREE) runs the FUSED fine-mesh apply (uniform fine mesh whose cells are numbered
+/* > 0 when pd_peer_vmult(PD_VMULT_MATRIX_FREE) runs the FUSED fine-mesh apply (uniform fine mesh whose cells are numbered
  * along the Morton curve on every rank): after the publish ONE kernel applies all owned cells; the tiles next to a cut
  * come last, wait for the owners' epoch flags and read the ghost cells straight from the owners' export buffers over
- * NVLink.  The ghost section of x_full_dev is not written on that path. */
+ * NVLink.  The ghost section of x_full_dev is not written on that path.  The value is the number of tiles of that
+ * kernel's plan (blocks of the curve; a block whose halo would not fit the kernel's gather is split); 0: not fused. */
 int pd_peer_fused(pd_peer *p);
 /* sum of `count` <= 4 doubles (device memory, in place) over all ranks: one warp, stores into every
  * rank's mapped buffer + flag handshake; the result is bitwise identical on all ranks */

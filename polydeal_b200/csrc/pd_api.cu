@@ -950,7 +950,7 @@ extern "C"
   int
   pd_peer_fused(pd_peer *p)
   {
-    return peer_fused(p) ? 1 : 0;
+    return peer_fused(p);
   }
 
   int

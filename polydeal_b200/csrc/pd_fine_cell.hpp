@@ -540,6 +540,96 @@ namespace pd
           }
       return p;
     }
+    // Rows build_stream_plan gives the tile seq[s0, s1): its distinct halo cells by 16-byte phase -- even rows 0, 2, ..
+    // for the cells on a boundary, odd rows 1, 3, .. for the others -- so twice the larger class.  stamp: scratch of
+    // n_cells_total entries, none equal to id.
+    inline int32_t
+    stream_tile_rows(const int32_t *seq, const int32_t s0, const int32_t s1, const int32_t *nbr, const int nfc, const int n,
+                     const uint8_t *src_parity, std::vector<int32_t> &stamp, const int32_t id)
+    {
+      for (int32_t i = s0; i < s1; ++i)
+        stamp[(size_t)(seq ? seq[i] : i)] = id;
+      int32_t count[2] = {0, 0};
+      for (int32_t i = s0; i < s1; ++i)
+        for (int f = 0; f < nfc; ++f)
+          {
+            const int32_t nb = nbr[(size_t)(seq ? seq[i] : i) * nfc + f];
+            if (nb < 0 || nb >= (int32_t)stamp.size() || stamp[(size_t)nb] == id)
+              continue;
+            stamp[(size_t)nb] = id;
+            ++count[src_parity ? (src_parity[(size_t)nb] & 1) : (int)(((int64_t)nb * n) & 1)];
+          }
+      return std::max(count[0] > 0 ? 2 * count[0] - 1 : 0, 2 * count[1]);
+    }
+    // Tiles that would need more than max_rows halo rows are halved until they fit (a tile is any run of consecutive
+    // cells; one cell needs at most 2 nfc rows).  The ghost cells of the fused sharded apply lie in their owners'
+    // export buffers at whatever 16-byte phase those give them: a tile next to a cut most of whose halo cells share
+    // one phase needs twice as many rows as it has halo cells, more than the kernel's gather holds.  Returns the new
+    // tile_first.
+    inline std::vector<int32_t>
+    split_stream_tiles(const int32_t *seq, const int32_t *tile_first, const int32_t n_tiles, const int32_t *nbr, const int nfc,
+                       const int32_t n_cells_total, const int n, const uint8_t *src_parity, const int32_t max_rows)
+    {
+      if (max_rows < 2 * nfc)
+        throw std::invalid_argument("split_stream_tiles: max_rows below what one cell needs");
+      std::vector<int32_t> out, stamp((size_t)n_cells_total, -1), todo;
+      int32_t              id = 0;
+      for (int32_t k = 0; k < n_tiles; ++k)
+        {
+          // (pieces of the tile still to check, last first: they come out in sequence order)
+          todo.assign({tile_first[k + 1], tile_first[k]});
+          while (todo.size() >= 2)
+            {
+              const int32_t s0 = todo.back(), s1 = todo[todo.size() - 2];
+              if (s1 - s0 > 1 && stream_tile_rows(seq, s0, s1, nbr, nfc, n, src_parity, stamp, id++) > max_rows)
+                todo.insert(todo.end() - 1, s0 + (s1 - s0) / 2);
+              else
+                {
+                  out.push_back(s0);
+                  todo.pop_back();
+                }
+            }
+        }
+      out.push_back(tile_first[n_tiles]);
+      return out;
+    }
+    // The plan of the fused sharded apply: ONE tile sequence, the tiles of the interior list followed by those of the
+    // boundary list (the only ones that read ghost cells and therefore wait for the owners' epoch flags), tiles that
+    // would not fit the gather split.  src_parity as in build_stream_plan (own cells: (cell * n) & 1; ghost cells:
+    // where the owner's export buffer has them).
+    struct FusedPlan
+    {
+      std::vector<int32_t> seq, tile_first, tile_base;
+      int32_t              first_ghost_tile = 0;
+      StreamPlan           sp;
+    };
+    inline FusedPlan
+    build_fused_plan(const std::vector<int32_t> &inner, const std::vector<int32_t> &outer, const std::vector<int32_t> &inner_tile_first,
+                     const std::vector<int32_t> &outer_tile_first, const int32_t *nbr, const int nfc, const int32_t n_cells_total,
+                     const int tile, const int n, const uint8_t *src_parity, const int32_t max_rows)
+    {
+      if (inner_tile_first.empty() || outer_tile_first.empty() || inner_tile_first.back() != (int32_t)inner.size() ||
+          outer_tile_first.back() != (int32_t)outer.size())
+        throw std::invalid_argument("build_fused_plan: tile ranges do not cover the lists");
+      FusedPlan p;
+      p.seq = inner;
+      p.seq.insert(p.seq.end(), outer.begin(), outer.end());
+      std::vector<int32_t> tf(inner_tile_first);
+      for (size_t k = 1; k < outer_tile_first.size(); ++k)
+        tf.push_back(outer_tile_first[k] + (int32_t)inner.size());
+      p.tile_first = split_stream_tiles(p.seq.data(), tf.data(), (int32_t)tf.size() - 1, nbr, nfc, n_cells_total, n, src_parity, max_rows);
+      const int32_t n_tiles = (int32_t)p.tile_first.size() - 1;
+      p.tile_base.resize((size_t)n_tiles);
+      p.first_ghost_tile = n_tiles;
+      for (int32_t k = 0; k < n_tiles; ++k)
+        {
+          p.tile_base[(size_t)k] = p.seq[(size_t)p.tile_first[(size_t)k]];
+          if (p.tile_first[(size_t)k] >= (int32_t)inner.size() && k < p.first_ghost_tile)
+            p.first_ghost_tile = k;
+        }
+      p.sp = build_stream_plan((int32_t)p.seq.size(), p.seq.data(), p.tile_first.data(), n_tiles, nbr, nfc, n_cells_total, tile, n, src_parity);
+      return p;
+    }
   } // namespace fine
 } // namespace pd
 

@@ -1643,38 +1643,36 @@ namespace pd
     h->mf_fused.ok = false;
     h->mf_tiles[3].ok = h->mf_tiles[3].stream_ok = false;
     const int32_t n_ghost = h->np - h->np_own;
-    if (!h->mf_ready || !h->mf_stream || h->mf_kernel != 0 || !h->mf_uniform.ok || n_ghost <= 0 || !h->mf_tiles[1].stream_ok ||
-        !h->mf_tiles[2].stream_ok || h->n % 2 == 0 || n_owners > 32 || !(h->dim * 10 + h->degree == 22 || h->dim * 10 + h->degree == 24 || h->dim * 10 + h->degree == 32))
+    // (the interior / boundary lists themselves need not be streamable: their tiles are split here where the gather's
+    // row budget asks for it -- a METIS cut of 64^3 cells per rank leaves a few boundary tiles with 129 or 130 rows)
+    if (!h->mf_ready || !h->mf_stream || h->mf_kernel != 0 || !h->mf_uniform.ok || n_ghost <= 0 || !h->mf_tiles[1].ok ||
+        !h->mf_tiles[2].ok || h->n % 2 == 0 || n_owners > 32 || (int64_t)h->np * h->n >= INT32_MAX ||
+        !(h->dim * 10 + h->degree == 22 || h->dim * 10 + h->degree == 24 || h->dim * 10 + h->degree == 32))
       return false;
-    std::vector<int32_t> seq(h->mf_h_inner);
-    seq.insert(seq.end(), h->mf_h_outer.begin(), h->mf_h_outer.end());
-    // the tiles of the interior list followed by those of the boundary list
-    const auto          &t1 = h->mf_tiles[1], &t2 = h->mf_tiles[2];
-    std::vector<int32_t> tf(t1.h_tile_first), base(t1.h_tile_base);
-    if (tf.empty() || t2.h_tile_first.empty() || tf.back() != (int32_t)h->mf_h_inner.size())
-      return false;
-    for (size_t k = 1; k < t2.h_tile_first.size(); ++k)
-      tf.push_back(t2.h_tile_first[k] + (int32_t)h->mf_h_inner.size());
-    base.insert(base.end(), t2.h_tile_base.begin(), t2.h_tile_base.end());
-    const int32_t        n_tiles = (int32_t)tf.size() - 1;
     const int            nfc = 2 * h->dim;
     std::vector<uint8_t> par((size_t)h->np);
     for (int32_t c = 0; c < h->np_own; ++c)
       par[(size_t)c] = (uint8_t)(((int64_t)c * h->n) & 1);
     for (int32_t g = 0; g < n_ghost; ++g)
       par[(size_t)h->np_own + g] = (uint8_t)((reinterpret_cast<uintptr_t>(ghost_src_host[g]) / sizeof(double)) & 1);
-    fine::StreamPlan sp;
+    // (the gather: a warp's lanes hold the cells of 32 / rpp passes of rpp rows each, four warps per group)
+    const int     rpp      = 2 * (32 / (h->n + 1));
+    int32_t       max_rows = rpp >= 2 ? (FINE_TILE_THREADS / 32) * (32 / rpp) * rpp : 0;
+    if (const char *e = std::getenv("PD_FINE_FUSED_MAX_ROWS")) // (tests: a smaller budget, so that small meshes split their tiles too)
+      max_rows = std::min(max_rows, std::max(2 * nfc, std::atoi(e)));
+    fine::FusedPlan fp;
     try
       {
-        sp = fine::build_stream_plan((int32_t)seq.size(), seq.data(), tf.data(), n_tiles, h->mf_h_nbr.data(), nfc, h->np, FINE_TILE,
-                                     h->n, par.data());
+        fp = fine::build_fused_plan(h->mf_h_inner, h->mf_h_outer, h->mf_tiles[1].h_tile_first, h->mf_tiles[2].h_tile_first,
+                                    h->mf_h_nbr.data(), nfc, h->np, FINE_TILE, h->n, par.data(), max_rows);
       }
     catch (const std::exception &)
       {
         return false;
       }
-    const int rpp = 2 * (32 / (h->n + 1));
-    if (rpp < 2 || sp.max_rows > (FINE_TILE_THREADS / 32) * (32 / rpp) * rpp || stream_smem_bytes(h->dim, h->n, sp.max_rows, 3) > 227 * 1024)
+    const fine::StreamPlan     &sp   = fp.sp;
+    const std::vector<int32_t> &seq = fp.seq, &tf = fp.tile_first, &base = fp.tile_base;
+    if (sp.max_rows > max_rows || stream_smem_bytes(h->dim, h->n, sp.max_rows, 3) > 227 * 1024)
       return false;
     auto put = [](auto &buf, const auto &v) {
       buf.alloc(v.size());
@@ -1702,7 +1700,7 @@ namespace pd
     f.error_word       = error_word;
     f.owners           = owners_dev;
     f.n_owners         = n_owners;
-    f.first_ghost_tile = (int32_t)t1.h_tile_first.size() - 1;
+    f.first_ghost_tile = fp.first_ghost_tile;
     f.ok               = true;
     return true;
   }

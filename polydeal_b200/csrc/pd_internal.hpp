@@ -286,7 +286,7 @@ namespace pd
   void     peer_allreduce(pd_peer *p, double *scal_dev, int dst0, int nk);
   pd_handle *peer_handle(pd_peer *p);
   int      peer_status(pd_peer *p);
-  bool     peer_fused(pd_peer *p);
+  int      peer_fused(pd_peer *p); // tiles of the fused fine-mesh plan, 0: not fused
   void     peer_destroy(pd_peer *p);
   // pd_cartesian.cu
   bool check_axis_aligned(pd_handle *h, bool *bricks_stale = nullptr);

@@ -487,11 +487,11 @@ namespace pd
     return p ? p->h : nullptr;
   }
 
-  bool
+  int
   peer_fused(pd_peer *p)
   {
     static const bool no_fused = getenv("PD_PEER_NO_FUSED") != nullptr;
-    return p && p->fused && !no_fused;
+    return (p && p->fused && !no_fused) ? std::max(1, (int)p->h->mf_tiles[3].n_tiles) : 0;
   }
 
   int

@@ -210,6 +210,11 @@ class PeerExchange:
         """pd_peer_vmult(MATRIX_FREE) runs the fused fine-mesh apply (one kernel, ghost cells read from the peers)."""
         return bool(K.lib().pd_peer_fused(self._h))
 
+    @property
+    def fused_tiles(self):
+        """Tiles of the fused apply's plan (blocks of the curve, split where their halo exceeds the kernel's gather); 0: not fused."""
+        return int(K.lib().pd_peer_fused(self._h))
+
     def allreduce(self, scalars):
         """In-place sum over the ranks of a CUDA float64 tensor of at most 4 entries."""
         assert scalars.is_cuda and scalars.numel() <= 4

@@ -136,4 +136,38 @@ extern "C"
         return -1;
       }
   }
+  // The fused sharded plan (interior ++ boundary tiles, tiles split to the gather's row budget).  Outputs sized by the
+  // caller: seq[n_inner + n_outer], tile_first[n_inner + n_outer + 1], rows[n_tiles_out * max_rows] (queried through
+  // rows_cap: -2 when too small), noff[(n_inner + n_outer) * nfc].  unsplit_max_rows: what the unsplit tiles need.
+  int
+  fine_fused_plan_host(const int32_t n_inner, const int32_t *inner, const int32_t n_outer, const int32_t *outer, const int32_t n_t1,
+                       const int32_t *tf1, const int32_t n_t2, const int32_t *tf2, const int32_t *nbr, const int nfc,
+                       const int32_t n_cells_total, const int tile, const int n, const uint8_t *src_parity, const int32_t max_rows,
+                       int32_t *n_tiles, int32_t *first_ghost_tile, int32_t *plan_max_rows, int32_t *zoff, int32_t *unsplit_max_rows,
+                       int32_t *seq, int32_t *tile_first, int32_t *tile_base, int32_t *rows, const int64_t rows_cap, uint16_t *noff)
+  {
+    try
+      {
+        const std::vector<int32_t> in(inner, inner + n_inner), out(outer, outer + n_outer), t1(tf1, tf1 + n_t1 + 1), t2(tf2, tf2 + n_t2 + 1);
+        const pd::fine::FusedPlan  big = pd::fine::build_fused_plan(in, out, t1, t2, nbr, nfc, n_cells_total, tile, n, src_parity, 1 << 20);
+        *unsplit_max_rows          = big.sp.max_rows;
+        const pd::fine::FusedPlan p = pd::fine::build_fused_plan(in, out, t1, t2, nbr, nfc, n_cells_total, tile, n, src_parity, max_rows);
+        *n_tiles                    = (int32_t)p.tile_first.size() - 1;
+        *first_ghost_tile           = p.first_ghost_tile;
+        *plan_max_rows              = p.sp.max_rows;
+        *zoff                       = p.sp.zoff;
+        if ((int64_t)p.sp.rows.size() > rows_cap)
+          return -2;
+        std::memcpy(seq, p.seq.data(), p.seq.size() * sizeof(int32_t));
+        std::memcpy(tile_first, p.tile_first.data(), p.tile_first.size() * sizeof(int32_t));
+        std::memcpy(tile_base, p.tile_base.data(), p.tile_base.size() * sizeof(int32_t));
+        std::memcpy(rows, p.sp.rows.data(), p.sp.rows.size() * sizeof(int32_t));
+        std::memcpy(noff, p.sp.noff.data(), p.sp.noff.size() * sizeof(uint16_t));
+        return 0;
+      }
+    catch (const std::exception &)
+      {
+        return -1;
+      }
+  }
 }

@@ -131,9 +131,15 @@ def main():
     # (the last two cases: cells numbered along the Morton curve, as a p4est-distributed mesh has them on every rank,
     # uniform -> the FUSED apply: one kernel, boundary tiles wait for the owners' flags and read the ghost cells from
     # the owners' export buffers)
-    for dim, n, p, order in [(3, 8, 2, 1), (2, 16, 3, 1), (3, 16, 2, 0), (2, 64, 2, 0), (3, 16, 2, 2)]:
-        metis = order == 2  # ... and the same with a METIS partition of the cells: ragged tiles along the cut
+    # (order 3: METIS again with the fused plan's halo-row budget cut to 48 rows (PD_FINE_FUSED_MAX_ROWS), so that every
+    # tile is split -- what happens to a few boundary tiles of a ragged METIS cut at bench.py's size, where unsplit they need
+    # 129 / 130 of the gather's 128 rows)
+    for dim, n, p, order in [(3, 8, 2, 1), (2, 16, 3, 1), (3, 16, 2, 0), (2, 64, 2, 0), (3, 16, 2, 2), (3, 16, 2, 3)]:
+        metis, split_tiles = order >= 2, order == 3
         order = 0 if metis else order
+        os.environ.pop("PD_FINE_FUSED_MAX_ROWS", None)
+        if split_tiles:
+            os.environ["PD_FINE_FUSED_MAX_ROWS"] = "48"
         ogrid = po.Grid(dim, n, 0.0, 1.0, order)
         groups = [[c] for c in range(ogrid.n_cells)]
         _, oah = oracle_handler(dim, n, groups, p, p + 1, order=order)
@@ -160,6 +166,8 @@ def main():
             fused = dop.peer.fused
             if order == 0 and world == 2:
                 assert fused and dop.op.fine_kernel_last == 3, (fused, dop.op.fine_kernel_last)
+            if split_tiles and fused:  # (a whole 4^3 block needs 96 rows: every tile was split)
+                assert dop.peer.fused_tiles >= 2 * (dop.part.n_owned // 64), (dop.peer.fused_tiles, dop.part.n_owned)
             # applies back to back with ranks out of step (double-buffered export slots, epochs), then vmult_add
             for k in range(5, 11):
                 if (rank + k) % 3 == 0:
@@ -174,8 +182,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         worst = max(worst, float(t))
         if rank == 0:
-            print(f"fine-mesh MF dim={dim} n={n} p={p} order={order} metis={metis}: world={world} fused={fused} "
-                  f"max rel err {float(t):.2e}", flush=True)
+            print(f"fine-mesh MF dim={dim} n={n} p={p} order={order} metis={metis} split_tiles={split_tiles}: world={world} "
+                  f"fused={fused} max rel err {float(t):.2e}", flush=True)
+    os.environ.pop("PD_FINE_FUSED_MAX_ROWS", None)
     dist.barrier()
     dist.destroy_process_group()
     assert worst <= 1e-12, worst

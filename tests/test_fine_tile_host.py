@@ -298,3 +298,99 @@ def test_stream_plan_contract(lib, shape, tile, n, ragged):
                     assert o == 2 - par + (nb - lo) * n
                 else:
                     assert (o - hb.value) % n == 0 and 0 <= (o - hb.value) // n < max_rows.value and rows[k, (o - hb.value) // n] == nb
+
+
+def morton_coords(shape):
+    """cell coordinates in the Morton numbering of grid_neighbours(shape, "morton")"""
+    dim = len(shape)
+    coords = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), axis=-1).reshape(-1, dim)
+    key = np.zeros(len(coords), dtype=np.int64)
+    for b in range(10):
+        for k in range(dim):
+            key |= ((coords[:, k] >> b) & 1) << (b * dim + k)
+    return coords[np.argsort(key, kind="stable")]
+
+
+@pytest.mark.parametrize("shape,n,max_rows,ghost_phase", [((8, 8, 16), 27, 128, "same"), ((8, 8, 16), 27, 128, "alternate"),
+                                                          ((8, 8, 16), 27, 40, "same"), ((32, 32), 9, 30, "same"),
+                                                          ((32, 32), 25, 24, "alternate")])
+def test_fused_plan_splits_tiles_to_the_row_budget(lib, shape, n, max_rows, ghost_phase):
+    """build_fused_plan (the fused sharded apply, csrc/pd_finemesh.cu: setup_fine_fused): one tile sequence, interior
+    tiles then boundary tiles; a tile whose halo cells would need more than `max_rows` rows (ghost cells lie in their
+    owners' export buffers at whatever 16-byte phase those give them; a METIS cut of bench.py's sharded 64^3 mesh
+    leaves tiles with 129 / 130 rows against the gather's 128) is halved until it fits.  Contract: the tiles cover the
+    sequence in order, each one a run of consecutive cells, no interior tile reads a ghost cell, every neighbour offset
+    points at the own row / the halo row of matching phase / the zero row."""
+    dim = len(shape)
+    nbr_all = grid_neighbours(shape, "morton")
+    n_all, nfc = nbr_all.shape
+    # rank 0 owns a ragged half: cells of the curve whose (x + y [+ z]) coordinate sum lies below a staircase
+    coords = morton_coords(shape)
+    own_mask = coords.sum(axis=1) * 2 < sum(shape) + (coords[:, 0] % 3)
+    own = np.flatnonzero(own_mask)
+    local = np.full(n_all, -1, dtype=np.int64)
+    local[own] = np.arange(len(own))
+    ghosts = np.unique(nbr_all[own][(nbr_all[own] >= 0) & ~own_mask[np.maximum(nbr_all[own], 0)]])
+    local[ghosts] = len(own) + np.arange(len(ghosts))
+    n_own, n_total = len(own), len(own) + len(ghosts)
+    nbr = np.where(nbr_all[own] >= 0, local[np.maximum(nbr_all[own], 0)], -1).astype(np.int32)
+    assert (nbr[nbr_all[own] >= 0] >= 0).all()
+    # interior / boundary split by whole blocks of the curve, tiles = the owned cells of a block (consecutive numbers)
+    block = own // 64
+    reads_ghost = (nbr >= n_own).any(axis=1)
+    bnd = np.isin(block, np.unique(block[reads_ghost]))
+    inner, outer = np.flatnonzero(~bnd).astype(np.int32), np.flatnonzero(bnd).astype(np.int32)
+    assert len(inner) and len(outer)
+
+    def tiles(seq):
+        b = block[seq]
+        return np.concatenate([[0], np.flatnonzero(np.diff(b)) + 1, [len(seq)]]).astype(np.int32)
+
+    tf1, tf2 = tiles(inner), tiles(outer)
+    par = np.zeros(n_total, dtype=np.uint8)
+    par[:n_own] = (np.arange(n_own) * n) & 1
+    par[n_own:] = 1 if ghost_phase == "same" else (np.arange(len(ghosts)) & 1)
+    ns = n_own
+    seq, tf, base = np.zeros(ns, np.int32), np.zeros(ns + 1, np.int32), np.zeros(ns, np.int32)
+    rows, noff = np.full((ns + 1) * max_rows, -7, np.int32), np.zeros((ns, nfc), np.uint16)
+    nt, fg, mr, zoff, um = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)
+    nbrc = np.ascontiguousarray(nbr)
+    rc = lib.fine_fused_plan_host(len(inner), dp(inner), len(outer), dp(outer), len(tf1) - 1, dp(tf1), len(tf2) - 1, dp(tf2), dp(nbrc),
+                                  nfc, n_total, 64, n, dp(par), max_rows, C.byref(nt), C.byref(fg), C.byref(mr), C.byref(zoff),
+                                  C.byref(um), dp(seq), dp(tf), dp(base), dp(rows), C.c_int64(len(rows)), dp(noff))
+    assert rc == 0
+    n_tiles, R = nt.value, mr.value
+    assert R <= max_rows
+    if max_rows < 96:
+        assert um.value > max_rows and n_tiles > len(tf1) + len(tf2) - 2  # the case the split exists for
+    else:
+        assert um.value == R and n_tiles == len(tf1) + len(tf2) - 2  # nothing to split: the plan is the unsplit one
+    tf = tf[: n_tiles + 1]
+    assert tf[0] == 0 and tf[-1] == ns and (np.diff(tf) >= 1).all() and (np.diff(tf) <= 64).all()
+    assert (seq == np.concatenate([inner, outer])).all()
+    assert 0 < fg.value < n_tiles and tf[fg.value] == len(inner)
+    hb = 64 * n + 2
+    assert zoff.value == hb + R * n
+    rows = rows[: n_tiles * max(R, 1)].reshape(n_tiles, max(R, 1))
+    for k in range(n_tiles):
+        lo, hi = int(tf[k]), int(tf[k + 1])
+        c0 = int(seq[lo])
+        assert base[k] == c0 and (seq[lo:hi] == c0 + np.arange(hi - lo)).all()
+        tpar = (c0 * n) % 2
+        used = rows[k][rows[k] >= 0]
+        assert len(set(used.tolist())) == len(used)
+        for r, c in enumerate(rows[k]):
+            if c >= 0:
+                assert par[c] == r % 2 and not (c0 <= c < c0 + hi - lo)
+                assert k >= fg.value or c < n_own  # interior tiles never read a ghost cell
+        for i in range(lo, hi):
+            cell = int(seq[i])
+            for f in range(nfc):
+                nb, o = int(nbr[cell, f]), int(noff[i, f])
+                if nb < 0:
+                    assert o == zoff.value
+                elif c0 <= nb < c0 + hi - lo:
+                    assert o == 2 - tpar + (nb - c0) * n
+                else:
+                    assert (o - hb) % n == 0 and 0 <= (o - hb) // n < R and rows[k, (o - hb) // n] == nb
