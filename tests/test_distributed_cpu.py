@@ -266,3 +266,80 @@ def test_cut_interfaces_seen_from_both_ranks(name, n_ref, groups, owner):
             if not ah.at_boundary(p, f) and owner[p] != owner[ah.neighbor(p, f)]}
     assert {tuple(sorted(k)) for k in seen} == {tuple(sorted(k)) for k in want} and n_cut == len(want) // 2
     assert abs(volume - 1.0) < 1e-15 and abs(perimeter - 4.0) < 1e-15
+
+
+def _fused_plan_worker(rank, world, port, n, results):
+    """One rank of the fused sharded fine-mesh apply's HOST side (csrc/pd_peer.cu: peer_create / peer_connect,
+    csrc/pd_finemesh.cu: setup_fine_fused), with the all-gather PeerExchange does over gloo: where this rank will read
+    its ghost cells in the owners' export buffers is where the owners publish them, and the tile plan built from those
+    addresses' 16-byte phases obeys the kernel's contract (tools/fused_plan_check.py holds the emulation)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import fused_plan_check as fpc
+        import polydeal_b200 as pdl
+        from pd_workloads import build_handler
+        from polydeal_b200 import distributed as pdd
+
+        dim, p = 3, 2
+        nd = (p + 1) ** dim
+        ah = build_handler(pdl, dict(dim=dim, n=n, b=1, p=p, nq=p + 1), world)  # n x n x (n world) cells, Morton numbered
+        owner = pdd.partition_by_metis(ah, world)
+        part = pdd.LocalPart(ah, owner, rank, penalty_constant=6.0, h_rule=pdl.H_NORMAL_EXTENT)
+        n_own, n_total = part.n_owned, part.n_owned + part.n_ghost
+        # what PeerExchange.__init__ gathers: every rank's send offsets; here also the send lists themselves (global cells)
+        send_ptr = np.zeros(world + 1, dtype=np.int64)
+        send_ptr[1:] = np.cumsum(part.send_counts)
+        sent_global = np.concatenate([part.owned_global_block[b] for b in part.send_blocks]) if world > 1 else np.zeros(0)
+        all_ptr, all_sent = [None] * world, [None] * world
+        dist.all_gather_object(all_ptr, send_ptr.tolist())
+        dist.all_gather_object(all_sent, sent_global.tolist())
+        recv_ptr = np.zeros(world + 1, dtype=np.int64)
+        recv_ptr[1:] = np.cumsum(part.recv_counts)
+        # ghost g of owner s is block remote_off[s] + (g - recv_ptr[s]) of s's send list (peer_create): the same cell
+        par = np.zeros(n_total, dtype=np.uint8)
+        par[:n_own] = (np.arange(n_own, dtype=np.int64) * nd) & 1
+        n_owners = 0
+        for s in range(world):
+            cnt = int(recv_ptr[s + 1] - recv_ptr[s])
+            if cnt == 0:
+                continue
+            n_owners += 1
+            assert all_ptr[s][rank + 1] - all_ptr[s][rank] == cnt
+            b = all_ptr[s][rank] + np.arange(cnt)
+            np.testing.assert_array_equal(np.asarray(all_sent[s])[b], part.ghost_global_block[recv_ptr[s]:recv_ptr[s + 1]])
+            par[n_own + recv_ptr[s] + np.arange(cnt)] = b & 1  # export_at: block b sits at phase b & 1 (odd n)
+        assert n_owners >= (2 if world > 2 and 0 < rank < world - 1 else 1)
+        # the plan, with the row budget cut so that tiles are split
+        lib = fpc.host_lib()
+        nbr = fpc.neighbour_table(part.desc, dim)
+        key = fpc.morton_keys(part.desc, dim)
+        order = np.argsort(key, kind="stable").astype(np.int32)
+        assert (order == np.arange(n_own)).all()  # a rank's share of a Morton-numbered mesh is in curve order
+        blk = key >> np.uint64(2 * dim)
+        is_outer = np.isin(blk[order], np.unique(blk[(nbr >= n_own).any(axis=1)]))
+        inner, outer = order[~is_outer], order[is_outer]
+        assert len(inner) and len(outer)
+        tf1, _ = fpc.tile_first_of(lib, inner, key, nbr, n_total, nd, dim)
+        tf2, _ = fpc.tile_first_of(lib, outer, key, nbr, n_total, nd, dim)
+        for budget in (128, 48):
+            out = fpc.fused_plan(lib, inner, outer, tf1, tf2, nbr, n_total, nd, dim, par, budget)
+            assert out["rc"] == 0 and out["max_rows"] <= budget, out
+            assert 0 < out["first_ghost_tile"] < out["n_tiles"]
+            if budget == 48:
+                assert out["n_tiles"] > out["unsplit_tiles"] and out["unsplit_max_rows"] > 48
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_fine_mesh_plan_addresses_gloo(world):
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = _free_port()
+    mp.spawn(_fused_plan_worker, args=(world, port, 16, results), nprocs=world, join=True)
+    assert dict(results) == {r: "ok" for r in range(world)}
