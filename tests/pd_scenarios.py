@@ -248,47 +248,54 @@ def quad_mesh_from_gmsh(verts, quads_ccw, n_refine=0):
     return np.array(verts), np.array(cells, dtype=np.int32), nbr
 
 
-def hyper_ball_2d_refined_once():
-    """GridGenerator::hyper_ball<2>(tria) (centre 0, radius 1: the five-cell disc, inner square of half width
-    1 / (sqrt 2 (1 + sqrt 2)), SphericalManifold on the boundary) followed by refine_global(1), as in
-    test/polydeal/unstructured_grid.cc:30-32.  deal.II behaviours restated (pinned by that test's golden): the new
-    vertex of a boundary line lies on the circle, the one of an interior line at its mid-point, the one of a cell at
-    the transfinite interpolation of its 4 vertices (weight -1/4) and 4 new line vertices (+1/2)."""
-    a, r = 1.0 / (1.0 + np.sqrt(2.0)), 1.0 / np.sqrt(2.0)
+def hyper_ball_2d(radius=1.0, n_refine=1):
+    """GridGenerator::hyper_ball<2>(tria, {}, radius) (the five-cell disc, inner square of half width
+    radius / (sqrt 2 (1 + sqrt 2)), SphericalManifold on the boundary) followed by refine_global(n_refine), as in
+    test/polydeal/unstructured_grid.cc:30-32 and fe_collection_agglomeration.cc:119-122.  deal.II behaviours restated
+    (pinned by the first test's golden): the new vertex of a boundary line lies on the circle, the one of an interior
+    line at its mid-point, the one of a cell at the transfinite interpolation of its 4 vertices (weight -1/4) and 4
+    new line vertices (+1/2); children in the order of their parents (all leaves on one level: the active-cell order)."""
+    a, r = 1.0 / (1.0 + np.sqrt(2.0)), radius / np.sqrt(2.0)
     verts = [(-r, -r), (r, -r), (-r * a, -r * a), (r * a, -r * a), (-r * a, r * a), (r * a, r * a), (-r, r), (r, r)]
     cells = [[0, 1, 2, 3], [0, 2, 6, 4], [2, 3, 4, 5], [1, 7, 3, 5], [6, 4, 7, 5]]
     face_verts = [(0, 2), (1, 3), (0, 1), (2, 3)]
-    n_cells_at = {}
-    for c in cells:
-        for i, j in face_verts:
-            key = (min(c[i], c[j]), max(c[i], c[j]))
-            n_cells_at[key] = n_cells_at.get(key, 0) + 1
-    mid = {}
+    for _ in range(n_refine):
+        n_cells_at = {}
+        for c in cells:
+            for i, j in face_verts:
+                key = (min(c[i], c[j]), max(c[i], c[j]))
+                n_cells_at[key] = n_cells_at.get(key, 0) + 1
+        mid = {}
 
-    def midpoint(p, q):
-        key = (min(p, q), max(p, q))
-        if key not in mid:
-            m = 0.5 * (np.array(verts[p]) + np.array(verts[q]))
-            if n_cells_at[key] == 1:  # boundary line: SphericalManifold
-                m = m / np.linalg.norm(m)
-            verts.append(tuple(m))
-            mid[key] = len(verts) - 1
-        return mid[key]
+        def midpoint(p, q):
+            key = (min(p, q), max(p, q))
+            if key not in mid:
+                m = 0.5 * (np.array(verts[p]) + np.array(verts[q]))
+                if n_cells_at[key] == 1:  # boundary line: SphericalManifold
+                    m = m * (radius / np.linalg.norm(m))
+                verts.append(tuple(m))
+                mid[key] = len(verts) - 1
+            return mid[key]
 
-    children = []
-    for v0, v1, v2, v3 in cells:
-        m01, m02, m13, m23 = midpoint(v0, v1), midpoint(v0, v2), midpoint(v1, v3), midpoint(v2, v3)
-        P = lambda i: np.array(verts[i])
-        verts.append(tuple(-0.25 * (P(v0) + P(v1) + P(v2) + P(v3)) + 0.5 * (P(m01) + P(m02) + P(m13) + P(m23))))
-        c = len(verts) - 1
-        children += [[v0, m01, m02, c], [m01, v1, c, m13], [m02, c, v2, m23], [c, m13, m23, v3]]
+        children = []
+        for v0, v1, v2, v3 in cells:
+            m01, m02, m13, m23 = midpoint(v0, v1), midpoint(v0, v2), midpoint(v1, v3), midpoint(v2, v3)
+            P = lambda i: np.array(verts[i])
+            verts.append(tuple(-0.25 * (P(v0) + P(v1) + P(v2) + P(v3)) + 0.5 * (P(m01) + P(m02) + P(m13) + P(m23))))
+            c = len(verts) - 1
+            children += [[v0, m01, m02, c], [m01, v1, c, m13], [m02, c, v2, m23], [c, m13, m23, v3]]
+        cells = children
     edge = {}
-    for ci, cv in enumerate(children):
+    for ci, cv in enumerate(cells):
         for f, (i, j) in enumerate(face_verts):
             edge.setdefault((min(cv[i], cv[j]), max(cv[i], cv[j])), []).append((ci, f))
-    nbr = -np.ones((len(children), 4), dtype=np.int32)
+    nbr = -np.ones((len(cells), 4), dtype=np.int32)
     for sides in edge.values():
         if len(sides) == 2:
             (c0, f0), (c1, f1) = sides
             nbr[c0, f0], nbr[c1, f1] = c1, c0
-    return np.array(verts), np.array(children, dtype=np.int32), nbr
+    return np.array(verts), np.array(cells, dtype=np.int32), nbr
+
+
+def hyper_ball_2d_refined_once():
+    return hyper_ball_2d(1.0, 1)

@@ -284,3 +284,45 @@ def test_unstructured_grid_golden(goldens, which):
         perimeter += fv.JxW.sum()
         assert np.abs(fv.normals[0] - np.array(n_gold)).max() < 5e-7 * max(1.0, np.abs(n_gold).max()), (f, fv.normals[0])
     assert perimeter == pytest.approx(gold["perimeter"], rel=5e-6)
+
+
+@pytest.mark.parametrize("mesh", ["hyper_cube", "hyper_ball"])
+def test_fe_collection_agglomeration(mesh):
+    """test/polydeal/fe_collection_agglomeration.cc (golden: "Ok" twice): the agglomerates {3,6,9,12,13}, {15,36,37},
+    {57,60,54}, {25,19,22} + singletons on (:30-116) hyper_cube(-1,1) refined 3 times with QGauss<2>(1) and (:119-203)
+    hyper_ball(radius 2) refined 4 times (1280 cells, SphericalManifold on the boundary) with QGauss<2>(3): the JxW of
+    reinit(polytope) over all polytopes sum to GridTools::volume(tria, MappingQ1) -- the sum of the cells' areas -- and
+    every sub-cell is integrated exactly once (`total_sum == volume`, :110-113, 197-200)."""
+    special = [[3, 6, 9, 12, 13], [15, 36, 37], [57, 60, 54], [25, 19, 22]]
+    if mesh == "hyper_cube":
+        grid, nq = po.Grid.hyper_cube(2, -1, 1, 3), 1
+    else:
+        v, cv, nbr = sc.hyper_ball_2d(2.0, 4)
+        assert len(cv) == 5 * 4**4
+        grid, nq = po.Grid.from_arrays(v, cv, nbr), 3
+    v, cv, _ = grid.arrays()
+    # GridTools::volume with MappingQ1: shoelace area of every (bilinear) quadrilateral, vertices 0, 1, 3, 2 around it
+    q = v[cv][:, [0, 1, 3, 2], :]
+    x, y = q[..., 0], q[..., 1]
+    area = 0.5 * np.abs((x * np.roll(y, -1, axis=1) - np.roll(x, -1, axis=1) * y).sum(axis=1))
+    ah = po.AgglomerationHandler(grid)
+    flagged = {c for g in special for c in g}
+    for g in special:
+        ah.define_agglomerate(sorted(g))  # collect_cells_for_agglomeration: active-cell order (include/poly_utils.h:532-538)
+    for c in range(len(cv)):
+        if c not in flagged:
+            ah.define_agglomerate([c])
+    ah.initialize_fe_values(nq)
+    ah.distribute_agglomerated_dofs(po.FE_DGQ, 1)
+    total = 0.0
+    for p in range(ah.n_polytopes):
+        w = ah.reinit(p).JxW
+        cells = ah.get_agglomerate(p)
+        assert len(w) == len(cells) * nq * nq
+        assert w.sum() == pytest.approx(area[np.asarray(cells)].sum(), rel=1e-13)
+        total += w.sum()
+    assert ah.n_polytopes == len(cv) - len(flagged) + 4
+    if mesh == "hyper_cube":
+        assert total == 4.0  # (the reference compares with ==)
+    else:
+        assert total == pytest.approx(area.sum(), rel=1e-13) and 12.0 < total < 4 * np.pi
