@@ -498,8 +498,9 @@ typedef struct pdh_flatten_params
   int32_t visit_rule;
 } pdh_flatten_params;
 
-/* Flatten the agglomeration into a descriptor whose arrays stay owned by (and
- * valid as long as) the handler. */
+/* Flatten the agglomeration into a descriptor whose arrays stay owned by the handler: they are valid until the next
+ * pdh_flatten / pdh_flatten_local on the same handler (which reuses the storage) or its destruction.  pd_create copies
+ * everything it needs to the device, so a descriptor need not outlive that call. */
 int pdh_flatten(pdh_handler *ah, const pdh_flatten_params *prm, pd_mesh_desc *out);
 /* Where face f of polytope `poly` (the reference's face numbering, n_faces / neighbor / at_boundary) sits in
  * the work list of the LAST pdh_flatten: *iface = its entry, *side = 0 if `poly` is the listing (visiting)
@@ -515,7 +516,8 @@ int pdh_unit_to_real(const pdh_handler *ah, int32_t poly, int64_t n, const doubl
  * halo exchange.  Local block r of an owned polytope <-> owned_global_block[r] (ascending);
  * ghost k (local block n_owned + k) <-> ghost_global_block[k], owned by ghost_owner[k];
  * ghosts are grouped by owner rank (ascending) and ordered by global block inside a group.
- * Arrays stay owned by the handler. */
+ * Arrays stay owned by the handler and are valid until its next pdh_flatten / pdh_flatten_local (one rank's share at a
+ * time: emulating several ranks in one process means pd_create, or a copy, before flattening the next rank). */
 typedef struct pdh_local_info
 {
   int32_t        n_owned, n_ghost;

@@ -58,7 +58,11 @@ def partition_by_metis(ah: AgglomerationHandler, n_ranks: int) -> np.ndarray:
 
 
 class LocalPart:
-    """The local descriptor of one rank + the index maps of the halo exchange."""
+    """The local descriptor of one rank + the index maps of the halo exchange.
+
+    `desc` points into storage of the host handler that the next flatten / LocalPart on the same handler reuses
+    (pdh_flatten_local): create the SIPOperator (pd_create copies to the device) before building another rank's part
+    from the same handler.  The index maps (owned_global_block, ghost_*, send_blocks, counts) are copies."""
 
     def __init__(self, ah: AgglomerationHandler, owner: np.ndarray, rank: int, penalty_constant=-1.0,
                  h_rule=K.H_DIAMETER_OF_VISITOR, h_const=1.0, visit_rule=K.VISIT_BY_ID):
